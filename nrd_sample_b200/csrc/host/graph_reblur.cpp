@@ -1,0 +1,383 @@
+// REBLUR_DIFFUSE_SPECULAR pass graph and per-frame constants.
+// Pool layout and bindings: External/NRD/Source/Denoisers/Reblur_DiffuseSpecular.hpp:17-297.
+// Per-frame pass selection: External/NRD/Source/Reblur.cpp:98-199. Constants: Reblur.cpp:283-394.
+#include <algorithm>
+#include <cmath>
+
+#include "pass_graph.h"
+
+namespace nrdb {
+
+namespace {
+
+// Permanent pool (persists across frames) — 42 B/px
+enum P : uint16_t {
+    P_PREV_VIEWZ,
+    P_PREV_NORMAL_ROUGHNESS,
+    P_PREV_INTERNAL_DATA,
+    P_DIFF_HISTORY,
+    P_DIFF_FAST_HISTORY,
+    P_DIFF_STABILIZED_PING,
+    P_DIFF_STABILIZED_PONG,
+    P_SPEC_HISTORY,
+    P_SPEC_FAST_HISTORY,
+    P_SPEC_STABILIZED_PING,
+    P_SPEC_STABILIZED_PONG,
+    P_SPEC_HITDIST_TRACKING_PING,
+    P_SPEC_HITDIST_TRACKING_PONG,
+};
+
+// Transient pool (valid within one frame) — 28 B/px + tiles
+enum T : uint16_t { T_DATA1, T_DATA2, T_SPEC_HITDIST_TRACKING, T_DIFF_TMP2, T_DIFF_FAST, T_SPEC_TMP2, T_SPEC_FAST, T_TILES };
+
+// Index of each pass (and its permutations) in emission order; updateReblur() does arithmetic on these
+enum PassIndex : uint32_t {
+    PASS_CLASSIFY_TILES = 0,
+    PASS_HITDIST_RECONSTRUCTION = 1,  // 4 permutations: bit0 = prepass follows, bit1 = 5x5
+    PASS_PREPASS = 5,                 // 2: bit0 = reads reconstruction output
+    PASS_TEMPORAL_ACCUMULATION = 7,   // 8: bit0 = after prepass/reconstruction, bit1 = confidence inputs, bit2 = threshold mix
+    PASS_HISTORY_FIX = 15,
+    PASS_BLUR = 16,
+    PASS_POST_BLUR = 17,              // 2: bit0 = temporal stabilization follows
+    PASS_TEMPORAL_STABILIZATION = 19,
+    PASS_SPLIT_SCREEN = 20,
+    PASS_VALIDATION = 21,
+};
+
+const uint32_t kCb = sizeof(ReblurConstants);
+const char* const kSignal = "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE";
+
+}  // namespace
+
+void Graph::buildReblurDiffuseSpecular(DenoiserState& d) {
+    new (&d.settings.reblur) ReblurSettings();
+    d.settingsSize = sizeof(ReblurSettings);
+
+    const Format kRadiance = Format::RGBA16_SFLOAT, kFast = Format::R16_SFLOAT;
+    addPermanent(Format::R32_SFLOAT);            // prev viewZ
+    addPermanent(Format::R10_G10_B10_A2_UNORM);  // prev normal+roughness (must match IN_NORMAL_ROUGHNESS encoding)
+    addPermanent(Format::R16_UINT);              // prev internal data: 6b diff frames | 6b spec frames | 4b material
+    addPermanent(kRadiance);
+    addPermanent(kFast);
+    addPermanent(Format::R16_SFLOAT);
+    addPermanent(Format::R16_SFLOAT);
+    addPermanent(kRadiance);
+    addPermanent(kFast);
+    addPermanent(Format::R16_SFLOAT);
+    addPermanent(Format::R16_SFLOAT);
+    addPermanent(Format::R16_SFLOAT);
+    addPermanent(Format::R16_SFLOAT);
+
+    addTransient(Format::RG8_UNORM);
+    addTransient(Format::R32_UINT);
+    addTransient(Format::R16_SFLOAT);
+    addTransient(kRadiance);
+    addTransient(kFast);
+    addTransient(kRadiance);
+    addTransient(kFast);
+    addTransient(Format::R8_UNORM, 16);
+
+    auto U = [](ResourceType t) { return Slot::user(t); };
+    auto Pm = [](uint16_t i) { return Slot::perm(i); };
+    auto Tr = [](uint16_t i) { return Slot::tran(i); };
+    // The user's output textures double as scratch ("TEMP1") between passes
+    const Slot diffTemp1 = U(ResourceType::OUT_DIFF_RADIANCE_HITDIST), specTemp1 = U(ResourceType::OUT_SPEC_RADIANCE_HITDIST);
+    const Slot diffTemp2 = Tr(T_DIFF_TMP2), specTemp2 = Tr(T_SPEC_TMP2);
+    const Slot dummy = U(ResourceType::IN_VIEWZ);  // bound where an optional input is absent
+    const std::string sig = kSignal;
+
+    beginPass("REBLUR_DiffuseSpecular - Classify tiles");
+    in(U(ResourceType::IN_VIEWZ));
+    out(Tr(T_TILES));
+    emit("REBLUR_ClassifyTiles.cs.hlsl", 16, 16, kCb);
+
+    for (int i = 0; i < 4; i++) {
+        bool is5x5 = (i >> 1) & 1, prepassFollows = i & 1;
+        beginPass("REBLUR_DiffuseSpecular - Hit distance reconstruction");
+        in(Tr(T_TILES));
+        in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+        in(U(ResourceType::IN_VIEWZ));
+        in(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
+        in(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+        out(prepassFollows ? diffTemp2 : diffTemp1);
+        out(prepassFollows ? specTemp2 : specTemp1);
+        emit("REBLUR_HitDistReconstruction.cs.hlsl" + sig + (is5x5 ? "|MODE_5X5=1" : "|MODE_5X5=0"), 8, 16, kCb);
+    }
+
+    for (int i = 0; i < 2; i++) {
+        bool afterReconstruction = i & 1;
+        beginPass("REBLUR_DiffuseSpecular - Pre-pass");
+        in(Tr(T_TILES));
+        in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+        in(U(ResourceType::IN_VIEWZ));
+        in(afterReconstruction ? diffTemp2 : U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
+        in(afterReconstruction ? specTemp2 : U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+        out(diffTemp1);
+        out(specTemp1);
+        out(Tr(T_SPEC_HITDIST_TRACKING));
+        emit("REBLUR_PrePass.cs.hlsl" + sig, 16, 16, kCb);
+    }
+
+    for (int i = 0; i < 8; i++) {
+        bool hasMix = (i >> 2) & 1, hasConfidence = (i >> 1) & 1, afterPrepass = i & 1;
+        beginPass("REBLUR_DiffuseSpecular - Temporal accumulation");
+        in(Tr(T_TILES));
+        in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+        in(U(ResourceType::IN_VIEWZ));
+        in(U(ResourceType::IN_MV));
+        in(Pm(P_PREV_VIEWZ));
+        in(Pm(P_PREV_NORMAL_ROUGHNESS));
+        in(Pm(P_PREV_INTERNAL_DATA));
+        in(hasMix ? U(ResourceType::IN_DISOCCLUSION_THRESHOLD_MIX) : dummy);
+        in(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
+        in(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
+        in(afterPrepass ? diffTemp1 : U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
+        in(afterPrepass ? specTemp1 : U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+        in(Pm(P_DIFF_HISTORY));
+        in(Pm(P_SPEC_HISTORY));
+        in(Pm(P_DIFF_FAST_HISTORY));
+        in(Pm(P_SPEC_FAST_HISTORY));
+        in(Pm(P_SPEC_HITDIST_TRACKING_PING), Pm(P_SPEC_HITDIST_TRACKING_PONG));
+        in(Tr(T_SPEC_HITDIST_TRACKING));
+        out(Tr(T_DATA1));
+        out(diffTemp2);
+        out(specTemp2);
+        out(Tr(T_DIFF_FAST));
+        out(Tr(T_SPEC_FAST));
+        out(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
+        out(Tr(T_DATA2));
+        emit("REBLUR_TemporalAccumulation.cs.hlsl" + sig, 8, 16, kCb);
+    }
+
+    beginPass("REBLUR_DiffuseSpecular - History fix");
+    in(Tr(T_TILES));
+    in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+    in(Tr(T_DATA1));
+    in(U(ResourceType::IN_VIEWZ));
+    in(diffTemp2);
+    in(specTemp2);
+    in(Tr(T_DIFF_FAST));
+    in(Tr(T_SPEC_FAST));
+    in(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
+    out(diffTemp1);
+    out(specTemp1);
+    out(Pm(P_DIFF_FAST_HISTORY));
+    out(Pm(P_SPEC_FAST_HISTORY));
+    emit("REBLUR_HistoryFix.cs.hlsl" + sig, 8, 16, kCb);
+
+    beginPass("REBLUR_DiffuseSpecular - Blur");
+    in(Tr(T_TILES));
+    in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+    in(U(ResourceType::IN_VIEWZ));
+    in(Tr(T_DATA1));
+    in(diffTemp1);
+    in(specTemp1);
+    out(Pm(P_PREV_VIEWZ));
+    out(diffTemp2);
+    out(specTemp2);
+    emit("REBLUR_Blur.cs.hlsl" + sig, 8, 16, kCb);
+
+    for (int i = 0; i < 2; i++) {
+        bool stabilizationFollows = i & 1;
+        beginPass("REBLUR_DiffuseSpecular - Post-blur");
+        in(Tr(T_TILES));
+        in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+        in(Tr(T_DATA1));
+        in(Pm(P_PREV_VIEWZ));
+        in(diffTemp2);
+        in(specTemp2);
+        out(Pm(P_PREV_NORMAL_ROUGHNESS));
+        out(Pm(P_DIFF_HISTORY));
+        out(Pm(P_SPEC_HISTORY));
+        if (!stabilizationFollows) {
+            out(Pm(P_PREV_INTERNAL_DATA));
+            out(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
+            out(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
+        }
+        emit("REBLUR_PostBlur.cs.hlsl" + sig + (stabilizationFollows ? "|TEMPORAL_STABILIZATION=1" : "|TEMPORAL_STABILIZATION=0"), 8, 16, kCb);
+    }
+
+    beginPass("REBLUR_DiffuseSpecular - Temporal stabilization");
+    in(Tr(T_TILES));
+    in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+    in(Pm(P_PREV_VIEWZ));
+    in(Tr(T_DATA1));
+    in(Tr(T_DATA2));
+    in(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
+    in(Pm(P_DIFF_HISTORY));
+    in(Pm(P_SPEC_HISTORY));
+    in(Pm(P_DIFF_STABILIZED_PING), Pm(P_DIFF_STABILIZED_PONG));
+    in(Pm(P_SPEC_STABILIZED_PING), Pm(P_SPEC_STABILIZED_PONG));
+    out(U(ResourceType::IN_MV));  // bound read-write by the reference; only read by this pass
+    out(Pm(P_PREV_INTERNAL_DATA));
+    out(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
+    out(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
+    out(Pm(P_DIFF_STABILIZED_PONG), Pm(P_DIFF_STABILIZED_PING));
+    out(Pm(P_SPEC_STABILIZED_PONG), Pm(P_SPEC_STABILIZED_PING));
+    emit("REBLUR_TemporalStabilization.cs.hlsl" + sig, 8, 16, kCb);
+
+    beginPass("REBLUR_DiffuseSpecular - Split screen");
+    in(U(ResourceType::IN_VIEWZ));
+    in(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
+    in(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+    out(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
+    out(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
+    emit("REBLUR_SplitScreen.cs.hlsl" + sig, 8, 16, kCb);
+
+    beginPass("REBLUR_DiffuseSpecular - Validation");
+    in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+    in(U(ResourceType::IN_VIEWZ));
+    in(U(ResourceType::IN_MV));
+    in(Tr(T_DATA1));
+    in(Tr(T_DATA2));
+    in(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
+    in(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+    out(U(ResourceType::OUT_VALIDATION));
+    emit("REBLUR_Validation.cs.hlsl", 8, 16, kCb, GRID_FROM_RESOURCE, 1);
+}
+
+void Graph::updateReblur(const DenoiserState& d) {
+    const ReblurSettings& s = d.settings.reblur;
+    const bool reconstruct = s.hitDistanceReconstructionMode != HitDistanceReconstructionMode::OFF && s.checkerboardMode == CheckerboardMode::OFF;
+    const bool skipStabilization = s.maxStabilizedFrameNum == 0;
+    const bool skipPrePass = s.diffusePrepassBlurRadius == 0.0f && s.specularPrepassBlurRadius == 0.0f && s.checkerboardMode == CheckerboardMode::OFF;
+
+    auto push = [&](uint32_t pass) { fillReblurConstants(s, pushDispatch(d, pass)); };
+
+    if (m_common.splitScreen >= 1.0f) {
+        push(PASS_SPLIT_SCREEN);
+        return;
+    }
+    push(PASS_CLASSIFY_TILES);
+    if (reconstruct)
+        push(PASS_HITDIST_RECONSTRUCTION + (s.hitDistanceReconstructionMode == HitDistanceReconstructionMode::AREA_5X5 ? 2 : 0) + (skipPrePass ? 0 : 1));
+    if (!skipPrePass) push(PASS_PREPASS + (reconstruct ? 1 : 0));
+    push(PASS_TEMPORAL_ACCUMULATION + (m_common.isDisocclusionThresholdMixAvailable ? 4 : 0) + (m_common.isHistoryConfidenceAvailable ? 2 : 0) +
+         ((!skipPrePass || reconstruct) ? 1 : 0));
+    push(PASS_HISTORY_FIX);
+    push(PASS_BLUR);
+    push(PASS_POST_BLUR + (skipStabilization ? 0 : 1));
+    if (!skipStabilization) push(PASS_TEMPORAL_STABILIZATION);
+    if (m_common.splitScreen > 0.0f) push(PASS_SPLIT_SCREEN);
+    if (m_common.enableValidation) {
+        uint8_t* cb = (uint8_t*)pushDispatch(d, PASS_VALIDATION);
+        fillReblurConstants(s, cb);
+        // two trailing uints after the shared block: gHasDiffuse, gHasSpecular (the shared block's own tail padding is reused)
+        uint32_t flags[2] = {1, 1};
+        memcpy(cb + offsetof(ReblurConstants, _pad), flags, sizeof(flags));
+    }
+}
+
+void Graph::fillReblurConstants(const ReblurSettings& s, void* dst) {
+    if (!dst) return;
+    const CommonSettings& c = m_common;
+    const FrameState& f = m_frame;
+    const float resW = c.resourceSize[0], resH = c.resourceSize[1], resWp = c.resourceSizePrev[0], resHp = c.resourceSizePrev[1];
+    const float rectW = c.rectSize[0], rectH = c.rectSize[1], rectWp = c.rectSizePrev[0], rectHp = c.rectSizePrev[1];
+
+    const bool rectChanged = c.rectSize[0] != c.rectSizePrev[0] || c.rectSize[1] != c.rectSizePrev[1];
+    const bool reset = c.accumulationMode != AccumulationMode::CONTINUE;
+    const float unproject = 1.0f / (0.5f * rectH * f.projectY);
+    const float worstScale = std::min(rectW / resW, rectH / resH);
+    const float maxBlurRadius = s.maxBlurRadius * worstScale;
+    const float thresholdBonus = (1.0f + f.jitterDelta) / rectH;
+    const float stabilization = s.maxStabilizedFrameNum / (1.0f + s.maxStabilizedFrameNum);
+    const uint32_t maxFrames = std::min(s.maxAccumulatedFrameNum, REBLUR_MAX_HISTORY_FRAME_NUM);
+
+    uint32_t diffCheckerboard = 2, specCheckerboard = 2;
+    if (s.checkerboardMode == CheckerboardMode::BLACK) { diffCheckerboard = 0; specCheckerboard = 1; }
+    else if (s.checkerboardMode == CheckerboardMode::WHITE) { diffCheckerboard = 1; specCheckerboard = 0; }
+
+    ReblurConstants& k = *(ReblurConstants*)dst;
+    k.worldToClip = f.worldToClip;
+    k.viewToClip = f.viewToClip;
+    k.viewToWorld = f.viewToWorld;
+    k.worldToViewPrev = f.worldToViewPrev;
+    k.worldToClipPrev = f.worldToClipPrev;
+    k.worldPrevToWorld = f.worldPrevToWorld;
+    memcpy(k.rotatorPre, f.rotatorPre, 16);
+    memcpy(k.rotator, f.rotator, 16);
+    memcpy(k.rotatorPost, f.rotatorPost, 16);
+    memcpy(k.frustum, f.frustum, 16);
+    memcpy(k.frustumPrev, f.frustumPrev, 16);
+    for (int i = 0; i < 3; i++) {
+        k.cameraDelta[i] = f.cameraDelta[i];
+        k.viewVectorWorld[i] = f.viewDirection[i];
+        k.viewVectorWorldPrev[i] = f.viewDirectionPrev[i];
+        k.mvScale[i] = c.motionVectorScale[i];
+    }
+    k.hitDistSettings[0] = s.hitDistanceParameters.A;
+    k.hitDistSettings[1] = s.hitDistanceParameters.B;
+    k.hitDistSettings[2] = s.hitDistanceParameters.C;
+    k.mvScale[3] = c.isMotionVectorInWorldSpace ? 1.0f : 0.0f;
+    k.convergenceSettings[0] = s.convergenceSettings.s;
+    k.convergenceSettings[1] = s.convergenceSettings.b;
+    k.convergenceSettings[2] = s.convergenceSettings.p;
+    k.antilagSettings[0] = s.antilagSettings.luminanceSigmaScale;
+    k.antilagSettings[1] = s.antilagSettings.luminanceSensitivity;
+    k.resourceSize[0] = resW; k.resourceSize[1] = resH;
+    k.resourceSizeInv[0] = 1.0f / resW; k.resourceSizeInv[1] = 1.0f / resH;
+    k.resourceSizeInvPrev[0] = 1.0f / resWp; k.resourceSizeInvPrev[1] = 1.0f / resHp;
+    k.rectSize[0] = rectW; k.rectSize[1] = rectH;
+    k.rectSizeInv[0] = 1.0f / rectW; k.rectSizeInv[1] = 1.0f / rectH;
+    k.rectSizePrev[0] = rectWp; k.rectSizePrev[1] = rectHp;
+    k.resolutionScale[0] = rectW / resW; k.resolutionScale[1] = rectH / resH;
+    k.resolutionScalePrev[0] = rectWp / resWp; k.resolutionScalePrev[1] = rectHp / resHp;
+    k.rectOffset[0] = float(c.rectOrigin[0]) / resW; k.rectOffset[1] = float(c.rectOrigin[1]) / resH;
+    k.jitter[0] = c.cameraJitter[0]; k.jitter[1] = c.cameraJitter[1];
+    k.printfAt[0] = c.printfAt[0]; k.printfAt[1] = c.printfAt[1];
+    k.rectOrigin[0] = c.rectOrigin[0]; k.rectOrigin[1] = c.rectOrigin[1];
+    k.rectSizeMinusOne[0] = c.rectSize[0] - 1; k.rectSizeMinusOne[1] = c.rectSize[1] - 1;
+    k.disocclusionThreshold = c.disocclusionThreshold + thresholdBonus;
+    k.disocclusionThresholdAlternate = c.disocclusionThresholdAlternate + thresholdBonus;
+    k.cameraAttachedReflectionMaterialID = c.cameraAttachedReflectionMaterialID;
+    k.strandMaterialID = c.strandMaterialID;
+    k.strandThickness = c.strandThickness;
+    k.stabilizationStrength = reset ? 0.0f : stabilization;
+    k.debug = c.debug;
+    k.orthoMode = f.orthoMode;
+    k.unproject = unproject;
+    k.denoisingRange = c.denoisingRange;
+    k.planeDistSensitivity = s.planeDistanceSensitivity;
+    k.framerateScale = f.frameRateScale;
+    k.maxBlurRadius = std::max(maxBlurRadius, s.minBlurRadius);
+    k.minBlurRadius = s.minBlurRadius;
+    k.diffPrepassBlurRadius = s.diffusePrepassBlurRadius * worstScale;
+    k.specPrepassBlurRadius = s.specularPrepassBlurRadius * worstScale;
+    k.maxAccumulatedFrameNum = reset ? 0.0f : float(maxFrames);
+    k.maxFastAccumulatedFrameNum = reset ? 0.0f : float(s.maxFastAccumulatedFrameNum);
+    k.antiFirefly = s.enableAntiFirefly ? 1.0f : 0.0f;
+    k.lobeAngleFraction = s.lobeAngleFraction * s.lobeAngleFraction;  // squared on purpose (Reblur.cpp:367)
+    k.roughnessFraction = s.roughnessFraction;
+    k.historyFixFrameNum = (float)s.historyFixFrameNum;
+    k.historyFixBasePixelStride = (float)s.historyFixBasePixelStride;
+    k.historyFixAlternatePixelStride = (float)s.historyFixAlternatePixelStride;
+    k.historyFixAlternatePixelStrideMaterialID = c.historyFixAlternatePixelStrideMaterialID;
+    {
+        float t = std::max(maxBlurRadius, s.minBlurRadius) / 2.0f;
+        t = std::min(std::max(t, 0.0f), 1.0f);
+        k.fastHistoryClampingSigmaScale = 3.0f + (s.fastHistoryClampingSigmaScale - 3.0f) * t;
+    }
+    k.minRectDimMulUnproject = (float)std::min(c.rectSize[0], c.rectSize[1]) * unproject;
+    k.usePrepassNotOnlyForSpecularMotionEstimation = s.usePrepassOnlyForSpecularMotionEstimation ? 0.0f : 1.0f;
+    k.splitScreen = c.splitScreen;
+    k.splitScreenPrev = f.splitScreenPrev;
+    k.checkerboardResolveAccumSpeed = f.checkerboardResolveAccumSpeed;
+    k.viewZScale = c.viewZScale;
+    k.fireflySuppressorMinRelativeScale = s.fireflySuppressorMinRelativeScale;
+    k.minHitDistanceWeight = s.minHitDistanceWeight;
+    k.diffMinMaterial = s.minMaterialForDiffuse;
+    k.specMinMaterial = s.minMaterialForSpecular;
+    k.responsiveAccumulationInvRoughnessThreshold = 1.0f / std::max(s.responsiveAccumulationSettings.roughnessThreshold, 1e-3f);
+    k.responsiveAccumulationMinAccumulatedFrameNum = s.responsiveAccumulationSettings.minAccumulatedFrameNum;
+    k.hasHistoryConfidence = c.isHistoryConfidenceAvailable;
+    k.hasDisocclusionThresholdMix = c.isDisocclusionThresholdMixAvailable;
+    k.diffCheckerboard = diffCheckerboard;
+    k.specCheckerboard = specCheckerboard;
+    k.frameIndex = c.frameIndex;
+    k.isRectChanged = rectChanged ? 1 : 0;
+    k.resetHistory = reset ? 1 : 0;
+    k.returnHistoryLengthInsteadOfOcclusion = s.returnHistoryLengthInsteadOfOcclusion ? 1 : 0;
+}
+
+}  // namespace nrdb
