@@ -1,0 +1,90 @@
+/* nrdcu.h — C ABI of the CUDA (sm_100a) executor for NRD dispatch streams.
+ *
+ * This is the piece that replaces the reference's NRI-based executor, nrd::Integration
+ * (External/NRD/Integration/NRDIntegration.h:211-264, NRDIntegration.hpp:98-146 Recreate, :241-455 pool creation,
+ * :522-620 Denoise, :723-890 per-dispatch binding + CmdDispatch): it owns the permanent/transient texture pools,
+ * resolves every nrd::DispatchDesc binding to a pool or user texture and launches one hand-written CUDA kernel per
+ * dispatch, keyed by PipelineDesc::shaderIdentifier (NRDDescs.h:452-453). Plain pointers and sizes only — no torch,
+ * no C++ types — so the reference-side binding is a dozen lines.
+ *
+ * Texture contract ("bit-identical layout"): pitch-linear 2D arrays in device memory, texel encodings exactly the
+ * nrd::Format values (NRDDescs.h:264-322): IN_VIEWZ R32_SFLOAT, IN_MV RGBA16_SFLOAT, IN_NORMAL_ROUGHNESS
+ * R10_G10_B10_A2_UNORM, IN/OUT_*_RADIANCE_HITDIST RGBA16_SFLOAT (YCoCg + normalised hit distance), IN_PENUMBRA
+ * R16_SFLOAT, OUT_SHADOW_TRANSLUCENCY R8_UNORM. Rows must be 16-byte aligned (pitchBytes % 16 == 0).
+ *
+ * Every function returns an nrd::Result value as uint32_t (0 = SUCCESS, 1 = FAILURE, 2 = INVALID_ARGUMENT,
+ * 3 = UNSUPPORTED); nrdcuGetLastError() describes the last non-success on the calling thread.
+ * There is no CPU fallback: without a CUDA device every launching call returns FAILURE.
+ */
+#ifndef NRDCU_H
+#define NRDCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef NRDCU_API
+#    define NRDCU_API __attribute__((visibility("default")))
+#endif
+
+typedef struct nrdcuContext nrdcuContext; /* opaque: nrd::Instance + pools + stream state */
+
+/* One 2D texture in device memory. `format` is an nrd::Format value. Same layout as the oracle's view. */
+typedef struct nrdcuTexture {
+    void* data;
+    uint32_t width, height;
+    uint32_t pitchBytes;
+    uint32_t format;
+} nrdcuTexture;
+
+/* Flags of nrdcuCreate / nrdcuDispatch */
+enum {
+    NRDCU_FLAG_QUAD_INTRINSICS = 1u << 0, /* replay SM6.0 quad smoothing (NRD_SUPPORTS_QUAD_INTRINSICS=1, the reference default) */
+    NRDCU_FLAG_CUDA_GRAPH = 1u << 1,      /* replay steady-state frames from captured CUDA graphs (one per ping-pong parity) */
+    NRDCU_FLAG_ROBUST_MIRROR_TEST = 1u << 2, /* DEBUG: spatial taps use "left the screen" instead of the reference's bit-fragile any(uv != MirrorUv(uv)) */
+};
+#define NRDCU_DEFAULT_FLAGS (NRDCU_FLAG_QUAD_INTRINSICS)
+
+/* ---- low level: one pass ------------------------------------------------------------------------------------
+ * Replaces one NRDIntegration::_Dispatch (NRDIntegration.hpp:723-890). `textures` follow DispatchDesc::resources
+ * order (inputs then outputs); `constants` are DispatchDesc::constantBufferData (host memory, copied into the launch).
+ * `stream` is a cudaStream_t. Asynchronous. */
+NRDCU_API uint32_t nrdcuDispatch(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures,
+                                 uint32_t texturesNum, uint32_t flags, void* stream);
+
+/* ---- instance level ------------------------------------------------------------------------------------------
+ * nrdcuCreate           == Integration::Recreate: nrd::CreateInstance + pool allocation at `resourceWidth x Height`
+ *                          (instanceCreationDesc is a `const nrd::InstanceCreationDesc*`)
+ * nrdcuSetCommonSettings / nrdcuSetDenoiserSettings == the nrd:: calls of the same name (settings structs by pointer)
+ * nrdcuSetResource      == one slot of ResourceSnapshot (NRDIntegration.h:121-167): user texture for a ResourceType
+ * nrdcuDenoise          == Integration::Denoise: GetComputeDispatches + one kernel launch per dispatch on `stream`
+ * nrdcuGetPoolTexture   -- debug / parity tap on a pool texture (isPermanent != 0 -> permanent pool)
+ * nrdcuGetInstance      -- the underlying nrd::Instance*, for callers that want the descriptor API as well */
+NRDCU_API uint32_t nrdcuCreate(const void* instanceCreationDesc, uint16_t resourceWidth, uint16_t resourceHeight, int device, uint32_t flags, nrdcuContext** out);
+NRDCU_API void nrdcuDestroy(nrdcuContext* ctx);
+NRDCU_API uint32_t nrdcuSetCommonSettings(nrdcuContext* ctx, const void* commonSettings);
+NRDCU_API uint32_t nrdcuSetDenoiserSettings(nrdcuContext* ctx, uint32_t identifier, const void* denoiserSettings);
+NRDCU_API uint32_t nrdcuSetResource(nrdcuContext* ctx, uint32_t resourceType, const nrdcuTexture* texture);
+NRDCU_API uint32_t nrdcuDenoise(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream);
+NRDCU_API uint32_t nrdcuGetPoolTexture(nrdcuContext* ctx, int isPermanent, uint32_t index, nrdcuTexture* out);
+NRDCU_API void* nrdcuGetInstance(nrdcuContext* ctx);
+
+/* Host-buffer convenience used by plugin-style callers (the `e2e` path of bench.py): uploads the user inputs that
+ * were registered with nrdcuSetHostResource from pinned/pageable host memory, runs nrdcuDenoise, downloads the outputs.
+ * direction: 0 = input (H2D before the frame), 1 = output (D2H after the frame). Device staging is owned by ctx. */
+NRDCU_API uint32_t nrdcuSetHostResource(nrdcuContext* ctx, uint32_t resourceType, void* hostData, uint32_t width, uint32_t height, uint32_t pitchBytes,
+                                        uint32_t format, int direction);
+NRDCU_API uint32_t nrdcuDenoiseHost(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------------------------- */
+NRDCU_API const char* nrdcuGetLastError(void);
+NRDCU_API uint64_t nrdcuGetLaunchCount(void);           /* kernels launched by this library since load (all contexts) */
+NRDCU_API uint64_t nrdcuGetPoolBytes(nrdcuContext* ctx); /* device bytes held by the pools (README memory table analogue) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRDCU_H */

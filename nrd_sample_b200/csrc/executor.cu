@@ -1,0 +1,486 @@
+// CUDA executor for NRD dispatch streams (include/nrdcu.h). Host code only — the kernels live in kernels/*.cu.
+// Mirrors the reference's executor semantics (External/NRD/Integration/NRDIntegration.hpp): pools sized
+// resource / downsampleFactor (:246-318), bindings resolved per dispatch (:757-766), dispatches issued in order on one
+// queue (here: one CUDA stream, which gives the same "barrier between every pair of dependent dispatches").
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nrd_b200.h"
+#include "../../include/nrdcu.h"
+#include "kernels/reblur_common.cuh"
+#include "kernels/sigma_common.cuh"
+
+namespace nrdk {
+// kernels/*.cu
+void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t stream);
+void launchReblurClassifyTiles(const ReblurConstants&, const ClassifyTilesParams&, cudaStream_t);
+void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int flags, cudaStream_t);
+void launchReblurBlur(const ReblurConstants&, const BlurParams&, int flags, cudaStream_t);
+void launchReblurPostBlur(const ReblurConstants&, const PostBlurParams&, bool temporalStabilization, int flags, cudaStream_t);
+void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccumulationParams&, cudaStream_t);
+void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, bool quads, cudaStream_t);
+void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, cudaStream_t);
+uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
+}  // namespace nrdk
+
+using namespace nrd;
+
+namespace {
+
+thread_local std::string g_lastError;
+std::atomic<uint64_t> g_launchCount{0};
+
+uint32_t fail(Result r, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_lastError = buf;
+    return (uint32_t)r;
+}
+
+uint32_t bytesPerTexel(uint32_t fmt) {
+    switch ((Format)fmt) {
+        case Format::R8_UNORM: return 1;
+        case Format::RG8_UNORM: case Format::R16_UINT: case Format::R16_SFLOAT: return 2;
+        case Format::RGBA8_UNORM: case Format::RG16_SFLOAT: case Format::R32_UINT: case Format::R32_SFLOAT: case Format::R10_G10_B10_A2_UNORM: return 4;
+        case Format::RGBA16_SFLOAT: return 8;
+        default: return 0;
+    }
+}
+
+// Typed view construction with format checking
+struct Binder {
+    const nrdcuTexture* t;
+    uint32_t n, next = 0;
+    bool ok = true;
+    std::string* err;
+    const char* shader;
+    template <class V> V take(Format expect) {
+        V v{};
+        if (next >= n) {
+            ok = false;
+            return v;
+        }
+        const nrdcuTexture& x = t[next];
+        if (x.format != (uint32_t)expect || !x.data || (x.pitchBytes & 1u) || x.pitchBytes < x.width * bytesPerTexel(x.format)) {
+            if (ok) {
+                char buf[256];
+                snprintf(buf, sizeof(buf), "%s: binding %u has format %u pitch %u (expected format %u)", shader, next, x.format, x.pitchBytes, (uint32_t)expect);
+                *err = buf;
+            }
+            ok = false;
+        }
+        v.data = (uint8_t*)x.data;
+        v.w = (int)x.width;
+        v.h = (int)x.height;
+        v.pitch = (int)x.pitchBytes;
+        next++;
+        return v;
+    }
+    // optional inputs that are bound to a dummy (IN_VIEWZ) when disabled
+    nrdk::TexR32F takeDummy() { return take<nrdk::TexR32F>(Format::R32_SFLOAT); }
+};
+
+bool checkLaunch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_lastError = std::string(what) + ": " + cudaGetErrorString(e);
+        return false;
+    }
+    g_launchCount.fetch_add(1, std::memory_order_relaxed);
+    return true;
+}
+
+uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, uint32_t flags, cudaStream_t stream) {
+    using namespace nrdk;
+    if (constantsSize != sizeof(ReblurConstants) || !constants) return fail(Result::INVALID_ARGUMENT, "%s: expected %zu constant bytes, got %u", id.c_str(), sizeof(ReblurConstants), constantsSize);
+    ReblurConstants cb;
+    memcpy(&cb, constants, sizeof(cb));
+    if (cb.resolutionScale[0] != 1.0f || cb.resolutionScale[1] != 1.0f || cb.resolutionScalePrev[0] != 1.0f || cb.resolutionScalePrev[1] != 1.0f || cb.isRectChanged)
+        return fail(Result::UNSUPPORTED, "%s: dynamic resolution (rectSize != resourceSize) is not implemented", id.c_str());
+    if (cb.diffCheckerboard != 2 || cb.specCheckerboard != 2) return fail(Result::UNSUPPORTED, "%s: checkerboard modes are not implemented", id.c_str());
+    if (cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix) return fail(Result::UNSUPPORTED, "%s: confidence / disocclusion-threshold-mix inputs are not implemented", id.c_str());
+
+    const bool quads = flags & NRDCU_FLAG_QUAD_INTRINSICS;
+    const int kflags = (quads ? 1 : 0) | ((flags & NRDCU_FLAG_ROBUST_MIRROR_TEST) ? 2 : 0);
+    std::string err;
+    Binder b{tex, n, 0, true, &err, id.c_str()};
+    const char* kSig = "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE";
+    auto is = [&](const char* file, const char* suffix = "") { return id == std::string(file) + kSig + suffix; };
+    auto done = [&](uint32_t expected) -> uint32_t {
+        if (!b.ok || b.next != expected || n != expected) return fail(Result::INVALID_ARGUMENT, "%s", err.empty() ? (id + ": wrong number of textures").c_str() : err.c_str());
+        return 0xFFFFFFFFu;
+    };
+
+    if (id == "REBLUR_ClassifyTiles.cs.hlsl") {
+        ClassifyTilesParams p;
+        p.inViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.outTiles = b.take<TexR8>(Format::R8_UNORM);
+        uint32_t r = done(2);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurClassifyTiles(cb, p, stream);
+    } else if (is("REBLUR_PrePass.cs.hlsl")) {
+        PrePassParams p;
+        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outSpecHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
+        uint32_t r = done(8);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurPrePass(cb, p, kflags, stream);
+    } else if (is("REBLUR_TemporalAccumulation.cs.hlsl")) {
+        TemporalAccumulationParams p;
+        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.mv = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.prevViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.prevNormalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.prevInternalData = b.take<TexR16U>(Format::R16_UINT);
+        p.disocclusionThresholdMix = b.takeDummy();
+        p.diffConfidence = b.takeDummy();
+        p.specConfidence = b.takeDummy();
+        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.historyDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.historySpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.historyDiffFast = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.historySpecFast = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.prevSpecHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.inSpecHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outData1 = b.take<TexRG8>(Format::RG8_UNORM);
+        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outDiffFast = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outSpecFast = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outSpecHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outData2 = b.take<TexR32U>(Format::R32_UINT);
+        uint32_t r = done(25);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurTemporalAccumulation(cb, p, stream);
+    } else if (is("REBLUR_HistoryFix.cs.hlsl")) {
+        HistoryFixParams p;
+        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.data1 = b.take<TexRG8>(Format::RG8_UNORM);
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inDiffFast = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.inSpecFast = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.specHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outDiffFast = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outSpecFast = b.take<TexR16F>(Format::R16_SFLOAT);
+        uint32_t r = done(13);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurHistoryFix(cb, p, quads, stream);
+    } else if (is("REBLUR_Blur.cs.hlsl")) {
+        BlurParams p;
+        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.data1 = b.take<TexRG8>(Format::RG8_UNORM);
+        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        uint32_t r = done(9);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurBlur(cb, p, kflags, stream);
+    } else if (is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1") || is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0")) {
+        const bool ts = is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1");
+        PostBlurParams p = {};
+        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.data1 = b.take<TexRG8>(Format::RG8_UNORM);
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outNormalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        if (!ts) {
+            p.outInternalData = b.take<TexR16U>(Format::R16_UINT);
+            p.outDiffCopy = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+            p.outSpecCopy = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        }
+        uint32_t r = done(ts ? 9 : 12);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurPostBlur(cb, p, ts, kflags, stream);
+    } else if (is("REBLUR_TemporalStabilization.cs.hlsl")) {
+        TemporalStabilizationParams p;
+        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.data1 = b.take<TexRG8>(Format::RG8_UNORM);
+        p.data2 = b.take<TexR32U>(Format::R32_UINT);
+        p.specHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.historyDiffLuma = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.historySpecLuma = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.mv = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outInternalData = b.take<TexR16U>(Format::R16_UINT);
+        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outDiffLuma = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outSpecLuma = b.take<TexR16F>(Format::R16_SFLOAT);
+        uint32_t r = done(16);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurTemporalStabilization(cb, p, stream);
+    } else {
+        return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", id.c_str());
+    }
+    if (!checkLaunch(id.c_str())) return (uint32_t)Result::FAILURE;
+    return (uint32_t)Result::SUCCESS;
+}
+
+}  // namespace
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+extern "C" {
+
+NRDCU_API const char* nrdcuGetLastError(void) { return g_lastError.c_str(); }
+NRDCU_API uint64_t nrdcuGetLaunchCount(void) { return g_launchCount.load(); }
+
+NRDCU_API uint32_t nrdcuDispatch(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures, uint32_t texturesNum,
+                                 uint32_t flags, void* stream) {
+    if (!shaderIdentifier || (!textures && texturesNum)) return fail(Result::INVALID_ARGUMENT, "nrdcuDispatch: null argument");
+    const std::string id = shaderIdentifier;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (id.rfind("Clear.cs.hlsl", 0) == 0) {
+        if (texturesNum != 1 || !textures[0].data) return fail(Result::INVALID_ARGUMENT, "Clear: exactly one texture expected");
+        const nrdcuTexture& t = textures[0];
+        uint32_t bpp = bytesPerTexel(t.format);
+        if (!bpp) return fail(Result::UNSUPPORTED, "Clear: unsupported format %u", t.format);
+        nrdk::launchClear(t.data, (int)(t.width * bpp), (int)t.height, (int)t.pitchBytes, s);
+        return checkLaunch("Clear") ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
+    }
+    if (id.rfind("REBLUR_", 0) == 0) return dispatchReblur(id, constants, constantsSize, textures, texturesNum, flags, s);
+    if (id.rfind("SIGMA_", 0) == 0) {
+        std::string err;
+        uint32_t r = nrdk::dispatchSigma(id, constants, constantsSize, textures, texturesNum, s, err);
+        if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
+        return checkLaunch(id.c_str()) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
+    }
+    return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", shaderIdentifier);
+}
+
+}  // extern "C"
+
+// =================================================================================================================
+// Context: nrd::Instance + pools
+// =================================================================================================================
+struct HostBinding {
+    void* host = nullptr;
+    nrdcuTexture device = {};
+    uint32_t hostPitch = 0;
+    int direction = 0;
+    bool used = false;
+};
+
+struct nrdcuContext {
+    Instance* instance = nullptr;
+    int device = 0;
+    uint32_t flags = 0;
+    uint16_t width = 0, height = 0;
+    std::vector<nrdcuTexture> permanent, transient;
+    nrdcuTexture user[(size_t)ResourceType::MAX_NUM] = {};
+    HostBinding hostBindings[(size_t)ResourceType::MAX_NUM];
+    std::vector<void*> allocations;
+    uint64_t poolBytes = 0;
+    std::vector<nrdcuTexture> scratch;
+};
+
+namespace {
+
+bool allocTexture(nrdcuContext* ctx, uint32_t fmt, uint32_t w, uint32_t h, nrdcuTexture& out, bool countAsPool) {
+    uint32_t bpp = bytesPerTexel(fmt);
+    if (!bpp) {
+        g_lastError = "unsupported pool format " + std::to_string(fmt);
+        return false;
+    }
+    // 256-byte row pitch: every row starts on a full L2 sector group and satisfies TMA / 128-bit vector alignment
+    uint32_t pitch = (w * bpp + 255u) & ~255u;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)pitch * h);
+    if (e != cudaSuccess) {
+        g_lastError = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return false;
+    }
+    cudaMemset(p, 0, (size_t)pitch * h);
+    ctx->allocations.push_back(p);
+    if (countAsPool) ctx->poolBytes += (uint64_t)pitch * h;
+    out = {p, w, h, pitch, fmt};
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+NRDCU_API uint32_t nrdcuCreate(const void* instanceCreationDesc, uint16_t resourceWidth, uint16_t resourceHeight, int device, uint32_t flags, nrdcuContext** out) {
+    if (!instanceCreationDesc || !out || !resourceWidth || !resourceHeight) return fail(Result::INVALID_ARGUMENT, "nrdcuCreate: null or zero argument");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(Result::FAILURE, "nrdcuCreate: no CUDA device (%s) — this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(Result::INVALID_ARGUMENT, "nrdcuCreate: device %d out of range (%d devices)", device, count);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(Result::FAILURE, "cudaSetDevice: %s", cudaGetErrorString(e));
+
+    nrdcuContext* ctx = new nrdcuContext();
+    ctx->device = device;
+    ctx->flags = flags;
+    ctx->width = resourceWidth;
+    ctx->height = resourceHeight;
+    Result r = CreateInstance(*(const InstanceCreationDesc*)instanceCreationDesc, ctx->instance);
+    if (r != Result::SUCCESS) {
+        delete ctx;
+        return fail(r, "nrd::CreateInstance failed (%u)", (uint32_t)r);
+    }
+    const InstanceDesc& d = *GetInstanceDesc(*ctx->instance);
+    auto makePool = [&](const TextureDesc* descs, uint32_t n, std::vector<nrdcuTexture>& pool) {
+        pool.resize(n);
+        for (uint32_t i = 0; i < n; i++) {
+            uint32_t ds = descs[i].downsampleFactor;
+            if (!allocTexture(ctx, (uint32_t)descs[i].format, (resourceWidth + ds - 1) / ds, (resourceHeight + ds - 1) / ds, pool[i], true)) return false;
+        }
+        return true;
+    };
+    if (!makePool(d.permanentPool, d.permanentPoolSize, ctx->permanent) || !makePool(d.transientPool, d.transientPoolSize, ctx->transient)) {
+        nrdcuDestroy(ctx);
+        return (uint32_t)Result::FAILURE;
+    }
+    *out = ctx;
+    return (uint32_t)Result::SUCCESS;
+}
+
+NRDCU_API void nrdcuDestroy(nrdcuContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->allocations) cudaFree(p);
+    if (ctx->instance) DestroyInstance(*ctx->instance);
+    delete ctx;
+}
+
+NRDCU_API void* nrdcuGetInstance(nrdcuContext* ctx) { return ctx ? ctx->instance : nullptr; }
+NRDCU_API uint64_t nrdcuGetPoolBytes(nrdcuContext* ctx) { return ctx ? ctx->poolBytes : 0; }
+
+NRDCU_API uint32_t nrdcuSetCommonSettings(nrdcuContext* ctx, const void* commonSettings) {
+    if (!ctx || !commonSettings) return fail(Result::INVALID_ARGUMENT, "nrdcuSetCommonSettings: null argument");
+    const CommonSettings& cs = *(const CommonSettings*)commonSettings;
+    if (cs.resourceSize[0] != ctx->width || cs.resourceSize[1] != ctx->height)
+        return fail(Result::INVALID_ARGUMENT, "resourceSize %ux%u does not match the pools created at %ux%u", cs.resourceSize[0], cs.resourceSize[1], ctx->width, ctx->height);
+    Result r = SetCommonSettings(*ctx->instance, cs);
+    return r == Result::SUCCESS ? 0u : fail(r, "nrd::SetCommonSettings rejected the settings");
+}
+
+NRDCU_API uint32_t nrdcuSetDenoiserSettings(nrdcuContext* ctx, uint32_t identifier, const void* denoiserSettings) {
+    if (!ctx || !denoiserSettings) return fail(Result::INVALID_ARGUMENT, "nrdcuSetDenoiserSettings: null argument");
+    Result r = SetDenoiserSettings(*ctx->instance, identifier, denoiserSettings);
+    return r == Result::SUCCESS ? 0u : fail(r, "nrd::SetDenoiserSettings: unknown identifier %u", identifier);
+}
+
+NRDCU_API uint32_t nrdcuSetResource(nrdcuContext* ctx, uint32_t resourceType, const nrdcuTexture* texture) {
+    if (!ctx || !texture || resourceType >= (uint32_t)ResourceType::TRANSIENT_POOL) return fail(Result::INVALID_ARGUMENT, "nrdcuSetResource: bad slot %u", resourceType);
+    if (!texture->data || !bytesPerTexel(texture->format)) return fail(Result::INVALID_ARGUMENT, "nrdcuSetResource: null data or unsupported format %u", texture->format);
+    ctx->user[resourceType] = *texture;
+    return 0;
+}
+
+NRDCU_API uint32_t nrdcuGetPoolTexture(nrdcuContext* ctx, int isPermanent, uint32_t index, nrdcuTexture* out) {
+    if (!ctx || !out) return fail(Result::INVALID_ARGUMENT, "nrdcuGetPoolTexture: null argument");
+    const std::vector<nrdcuTexture>& pool = isPermanent ? ctx->permanent : ctx->transient;
+    if (index >= pool.size()) return fail(Result::INVALID_ARGUMENT, "pool index %u out of range", index);
+    *out = pool[index];
+    return 0;
+}
+
+NRDCU_API uint32_t nrdcuDenoise(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuDenoise: null context");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(Result::FAILURE, "cudaSetDevice: %s", cudaGetErrorString(e));
+    const DispatchDesc* dispatches = nullptr;
+    uint32_t n = 0;
+    Result r = GetComputeDispatches(*ctx->instance, identifiers, identifiersNum, dispatches, n);
+    if (r != Result::SUCCESS) return fail(r, "nrd::GetComputeDispatches failed (%u)", (uint32_t)r);
+    const InstanceDesc& d = *GetInstanceDesc(*ctx->instance);
+    for (uint32_t i = 0; i < n; i++) {
+        const DispatchDesc& dd = dispatches[i];
+        ctx->scratch.resize(dd.resourcesNum);
+        for (uint32_t k = 0; k < dd.resourcesNum; k++) {
+            const ResourceDesc& res = dd.resources[k];
+            if (res.type == ResourceType::PERMANENT_POOL)
+                ctx->scratch[k] = ctx->permanent[res.indexInPool];
+            else if (res.type == ResourceType::TRANSIENT_POOL)
+                ctx->scratch[k] = ctx->transient[res.indexInPool];
+            else {
+                ctx->scratch[k] = ctx->user[(uint32_t)res.type];
+                if (!ctx->scratch[k].data) return fail(Result::INVALID_ARGUMENT, "'%s' needs user resource %s, which was not set", dd.name, GetResourceTypeString(res.type));
+            }
+        }
+        uint32_t rc = nrdcuDispatch(d.pipelines[dd.pipelineIndex].shaderIdentifier, dd.constantBufferData, dd.constantBufferDataSize, ctx->scratch.data(), dd.resourcesNum,
+                                    ctx->flags, stream);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+NRDCU_API uint32_t nrdcuSetHostResource(nrdcuContext* ctx, uint32_t resourceType, void* hostData, uint32_t width, uint32_t height, uint32_t pitchBytes, uint32_t format,
+                                        int direction) {
+    if (!ctx || !hostData || resourceType >= (uint32_t)ResourceType::TRANSIENT_POOL) return fail(Result::INVALID_ARGUMENT, "nrdcuSetHostResource: bad argument");
+    uint32_t bpp = bytesPerTexel(format);
+    if (!bpp || pitchBytes < width * bpp) return fail(Result::INVALID_ARGUMENT, "nrdcuSetHostResource: bad format/pitch");
+    cudaSetDevice(ctx->device);
+    HostBinding& hb = ctx->hostBindings[resourceType];
+    if (!hb.used || hb.device.width != width || hb.device.height != height || hb.device.format != format) {
+        if (!allocTexture(ctx, format, width, height, hb.device, false)) return (uint32_t)Result::FAILURE;
+    }
+    hb.host = hostData;
+    hb.hostPitch = pitchBytes;
+    hb.direction = direction;
+    hb.used = true;
+    ctx->user[resourceType] = hb.device;
+    return 0;
+}
+
+NRDCU_API uint32_t nrdcuDenoiseHost(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuDenoiseHost: null context");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaSetDevice(ctx->device);
+    for (HostBinding& hb : ctx->hostBindings) {
+        if (!hb.used || hb.direction != 0) continue;
+        uint32_t rowBytes = hb.device.width * bytesPerTexel(hb.device.format);
+        cudaError_t e = cudaMemcpy2DAsync(hb.device.data, hb.device.pitchBytes, hb.host, hb.hostPitch, rowBytes, hb.device.height, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return fail(Result::FAILURE, "H2D copy: %s", cudaGetErrorString(e));
+    }
+    uint32_t rc = nrdcuDenoise(ctx, identifiers, identifiersNum, stream);
+    if (rc != 0) return rc;
+    for (HostBinding& hb : ctx->hostBindings) {
+        if (!hb.used || hb.direction != 1) continue;
+        uint32_t rowBytes = hb.device.width * bytesPerTexel(hb.device.format);
+        cudaError_t e = cudaMemcpy2DAsync(hb.host, hb.hostPitch, hb.device.data, hb.device.pitchBytes, rowBytes, hb.device.height, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return fail(Result::FAILURE, "D2H copy: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+}  // extern "C"

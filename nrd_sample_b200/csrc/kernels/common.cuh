@@ -1,0 +1,363 @@
+// Shared device code of the denoiser kernels: pitch-linear typed texture views with the D3D-style access
+// semantics the reference shaders rely on, and the math / weight helpers the three REBLUR spatial passes, temporal
+// accumulation, history fix and temporal stabilisation have in common.
+//
+// What each helper reproduces (file:line in /root/reference):
+//   MathLib        External/NRIFramework/External/MathLib/ml.hlsli  (Math 105-400, Geometry 477-672, Packing 1179-1215,
+//                  Filtering 1287-1414, Sequence 1620-1713, Rng 1752-1862, ImportanceSampling 2347-2405)
+//   NRD.hlsli      External/NRD/Shaders/NRD.hlsli:361-428, 559-573, 637-684
+//   Common.hlsli   External/NRD/Shaders/Common.hlsli:207-218, 253-277, 307-330, 346-364, 421-600
+// Texture semantics: Load out of bounds -> 0, store out of bounds dropped, samplers clamp to edge,
+// bilinear weights exact fp32, UNORM stores round to nearest, FP16 stores round to nearest even.
+#pragma once
+#include "../host/constants.h"
+#include "vecmath.cuh"
+
+namespace nrdk {
+
+using nrdb::Mat4;
+
+constexpr float NRD_EPS = 1e-6f;
+constexpr float NRD_INF = 1e6f;
+constexpr float NRD_NORMAL_ENCODING_ERROR = 0.75f / 255.0f;
+constexpr float NRD_ROUGHNESS_SENSITIVITY = 0.01f;
+constexpr float NRD_MAX_PERCENT_OF_LOBE_VOLUME = 0.75f;
+constexpr float ML_SMALL_EPS = 1e-15f;
+constexpr float ML_EPS = 1e-6f;
+
+// =================================================================================================================
+// Texture views. One struct per storage format so every access compiles to a single fixed-width LDG/STG.
+// =================================================================================================================
+struct TexView {
+    uint8_t* data;
+    int w, h, pitch;
+    NRD_DEV bool inside(int x, int y) const { return (unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h; }
+    template <class T> NRD_DEV const T* ptr(int x, int y) const { return (const T*)(data + (size_t)y * pitch) + x; }
+    template <class T> NRD_DEV T* ptrw(int x, int y) const { return (T*)(data + (size_t)y * pitch) + x; }
+    NRD_DEV int cx(int x) const { return clampi(x, 0, w - 1); }
+    NRD_DEV int cy(int y) const { return clampi(y, 0, h - 1); }
+};
+
+NRD_DEV uint32_t unormQ(float v, float maxv) { return (uint32_t)(saturate(v) * maxv + 0.5f); }
+
+struct TexR32F : TexView {
+    NRD_DEV float fetch(int x, int y) const { return __ldg(ptr<float>(x, y)); }
+    NRD_DEV float load(int x, int y) const { return inside(x, y) ? fetch(x, y) : 0.0f; }
+    NRD_DEV float fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
+    NRD_DEV void store(int x, int y, float v) const { if (inside(x, y)) *ptrw<float>(x, y) = v; }
+    NRD_DEV float sampleLinear(float2 uv) const {
+        float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
+        float fx = floorf(tx), fy = floorf(ty);
+        float wx = tx - fx, wy = ty - fy;
+        int x0 = (int)fx, y0 = (int)fy;
+        float a = fetchClamped(x0, y0), b = fetchClamped(x0 + 1, y0), c = fetchClamped(x0, y0 + 1), d = fetchClamped(x0 + 1, y0 + 1);
+        return lerp(lerp(a, b, wx), lerp(c, d, wx), wy);
+    }
+};
+
+struct TexR16F : TexView {
+    NRD_DEV float fetch(int x, int y) const { return __half2float(__ushort_as_half(__ldg(ptr<unsigned short>(x, y)))); }
+    NRD_DEV float load(int x, int y) const { return inside(x, y) ? fetch(x, y) : 0.0f; }
+    NRD_DEV float fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
+    NRD_DEV void store(int x, int y, float v) const { if (inside(x, y)) *ptrw<__half>(x, y) = __float2half_rn(v); }
+    NRD_DEV float sampleLinear(float2 uv) const {
+        float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
+        float fx = floorf(tx), fy = floorf(ty);
+        float wx = tx - fx, wy = ty - fy;
+        int x0 = (int)fx, y0 = (int)fy;
+        float a = fetchClamped(x0, y0), b = fetchClamped(x0 + 1, y0), c = fetchClamped(x0, y0 + 1), d = fetchClamped(x0 + 1, y0 + 1);
+        return lerp(lerp(a, b, wx), lerp(c, d, wx), wy);
+    }
+};
+
+struct TexRGBA16F : TexView {
+    NRD_DEV float4 fetch(int x, int y) const {
+        uint2 raw = __ldg(ptr<uint2>(x, y));
+        float2 lo = __half22float2(*reinterpret_cast<__half2*>(&raw.x));
+        float2 hi = __half22float2(*reinterpret_cast<__half2*>(&raw.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    NRD_DEV float4 load(int x, int y) const { return inside(x, y) ? fetch(x, y) : f4(0.0f); }
+    NRD_DEV float4 fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
+    NRD_DEV void store(int x, int y, float4 v) const {
+        if (!inside(x, y)) return;
+        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        uint2 raw;
+        raw.x = *reinterpret_cast<uint32_t*>(&lo);
+        raw.y = *reinterpret_cast<uint32_t*>(&hi);
+        *ptrw<uint2>(x, y) = raw;
+    }
+    NRD_DEV float4 sampleLinear(float2 uv) const {
+        float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
+        float fx = floorf(tx), fy = floorf(ty);
+        float wx = tx - fx, wy = ty - fy;
+        int x0 = (int)fx, y0 = (int)fy;
+        float4 a = fetchClamped(x0, y0), b = fetchClamped(x0 + 1, y0), c = fetchClamped(x0, y0 + 1), d = fetchClamped(x0 + 1, y0 + 1);
+        return lerp(lerp(a, b, wx), lerp(c, d, wx), wy);
+    }
+};
+
+// R10G10B10A2_UNORM normal + roughness + material
+struct TexNR : TexView {
+    NRD_DEV uint32_t fetchRaw(int x, int y) const { return __ldg(ptr<uint32_t>(x, y)); }
+    NRD_DEV uint32_t loadRaw(int x, int y) const { return inside(x, y) ? fetchRaw(x, y) : 0u; }
+    NRD_DEV uint32_t fetchRawClamped(int x, int y) const { return fetchRaw(cx(x), cy(y)); }
+    NRD_DEV void storeRaw(int x, int y, uint32_t v) const { if (inside(x, y)) *ptrw<uint32_t>(x, y) = v; }
+    static NRD_DEV float4 decode(uint32_t v) {
+        return make_float4((float)(v & 1023u) / 1023.0f, (float)((v >> 10) & 1023u) / 1023.0f, (float)((v >> 20) & 1023u) / 1023.0f, (float)(v >> 30) / 3.0f);
+    }
+};
+
+struct TexR8 : TexView {  // R8_UNORM
+    NRD_DEV float load(int x, int y) const { return inside(x, y) ? (float)__ldg(ptr<uint8_t>(x, y)) / 255.0f : 0.0f; }
+    NRD_DEV void store(int x, int y, float v) const { if (inside(x, y)) *ptrw<uint8_t>(x, y) = (uint8_t)unormQ(v, 255.0f); }
+};
+
+struct TexRG8 : TexView {  // RG8_UNORM
+    NRD_DEV float2 load(int x, int y) const {
+        if (!inside(x, y)) return f2(0.0f);
+        uchar2 v = __ldg(ptr<uchar2>(x, y));
+        return make_float2((float)v.x / 255.0f, (float)v.y / 255.0f);
+    }
+    NRD_DEV void store(int x, int y, float2 v) const {
+        if (inside(x, y)) *ptrw<uchar2>(x, y) = make_uchar2((unsigned char)unormQ(v.x, 255.0f), (unsigned char)unormQ(v.y, 255.0f));
+    }
+};
+
+struct TexR16U : TexView {
+    NRD_DEV uint32_t fetch(int x, int y) const { return __ldg(ptr<unsigned short>(x, y)); }
+    NRD_DEV uint32_t fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
+    NRD_DEV void store(int x, int y, uint32_t v) const { if (inside(x, y)) *ptrw<unsigned short>(x, y) = (unsigned short)v; }
+};
+
+struct TexR32U : TexView {
+    NRD_DEV uint32_t load(int x, int y) const { return inside(x, y) ? __ldg(ptr<uint32_t>(x, y)) : 0u; }
+    NRD_DEV void store(int x, int y, uint32_t v) const { if (inside(x, y)) *ptrw<uint32_t>(x, y) = v; }
+};
+
+// =================================================================================================================
+// Matrices as they sit in the constant buffer (column-major)
+// =================================================================================================================
+NRD_DEV float4 mulM4(const Mat4& M, float4 v) {
+    return make_float4(M.m[0] * v.x + M.m[4] * v.y + M.m[8] * v.z + M.m[12] * v.w, M.m[1] * v.x + M.m[5] * v.y + M.m[9] * v.z + M.m[13] * v.w,
+                       M.m[2] * v.x + M.m[6] * v.y + M.m[10] * v.z + M.m[14] * v.w, M.m[3] * v.x + M.m[7] * v.y + M.m[11] * v.z + M.m[15] * v.w);
+}
+NRD_DEV float3 rotate(const Mat4& M, float3 v) {  // (float3x3)M * v
+    return make_float3(M.m[0] * v.x + M.m[4] * v.y + M.m[8] * v.z, M.m[1] * v.x + M.m[5] * v.y + M.m[9] * v.z, M.m[2] * v.x + M.m[6] * v.y + M.m[10] * v.z);
+}
+NRD_DEV float3 rotateInverse(const Mat4& M, float3 v) {  // transpose((float3x3)M) * v
+    return make_float3(M.m[0] * v.x + M.m[1] * v.y + M.m[2] * v.z, M.m[4] * v.x + M.m[5] * v.y + M.m[6] * v.z, M.m[8] * v.x + M.m[9] * v.y + M.m[10] * v.z);
+}
+NRD_DEV float3 affine(const Mat4& M, float3 p) { return xyz(mulM4(M, f4(p, 1.0f))); }
+NRD_DEV float2 screenUv(const Mat4& worldToClip, float3 X) {  // Geometry::GetScreenUv, D3D origin
+    float4 clip = mulM4(worldToClip, f4(X, 1.0f));
+    return make_float2(clip.x / clip.w, clip.y / clip.w) * make_float2(0.5f, -0.5f) + 0.5f;
+}
+
+// =================================================================================================================
+// Math
+// =================================================================================================================
+NRD_DEV float linearStep(float a, float b, float x) { return saturate((x - a) / (b - a)); }
+NRD_DEV float smoothStep01(float x) { x = saturate(x); return x * x * (3.0f - x * 2.0f); }
+NRD_DEV float smoothStep(float a, float b, float x) { x = linearStep(a, b, x); return x * x * (3.0f - x * 2.0f); }
+NRD_DEV float pow01(float x, float y) { return powf(saturate(x), y); }
+NRD_DEV float sqrt01(float x) { return sqrtf(saturate(x)); }
+NRD_DEV float rsqrtSafe(float x) { return 1.0f / sqrtf(fmaxf(x, ML_SMALL_EPS)); }
+NRD_DEV float positiveRcp(float x) { return 1.0f / fmaxf(x, ML_SMALL_EPS); }
+NRD_DEV float acosApproxPositive(float x) { return lerp(1.567589f, 1.399331f, saturate(x)) * sqrtf(saturate(1.0f - x)); }
+NRD_DEV float degToRad(float x) { return x * (3.14159265358979323846f / 180.0f); }
+
+NRD_DEV float4 scaleRotator(float4 r, float2 s) { return make_float4(s.x * r.x, s.x * r.z, s.y * r.y, s.y * r.w); }
+NRD_DEV float2 rotate2(float4 r, float2 v) { return make_float2(v.x * r.x + v.y * r.y, v.x * r.z + v.y * r.w); }
+
+struct Basis { float3 T, B, N; };
+NRD_DEV Basis getBasis(float3 N) {
+    float sz = signFast(N.z);
+    float a = 1.0f / (sz + N.z);
+    float ya = N.y * a;
+    float b = N.x * ya;
+    float c = N.x * sz;
+    Basis r;
+    r.T = make_float3(c * N.x * a - 1.0f, sz * b, c);
+    r.B = make_float3(b, N.y * ya - sz, N.y);
+    r.N = N;
+    return r;
+}
+
+NRD_DEV float3 reconstructViewPosition(float2 uv, const float* frustum, float viewZ, float orthoMode) {
+    float s = orthoMode == 0.0f ? viewZ : orthoMode;
+    return make_float3((uv.x * frustum[2] + frustum[0]) * s, (uv.y * frustum[3] + frustum[1]) * s, viewZ);
+}
+
+// Packing::RgbaToUint( c, 6, 6, 4, 0 ) / UintToRgba for the 16-bit "internal data" word
+NRD_DEV uint32_t packInternal664(float r, float g, float b) {
+    return (uint32_t)(saturate(r) * 63.0f + 0.5f) | ((uint32_t)(saturate(g) * 63.0f + 0.5f) << 6) | ((uint32_t)(saturate(b) * 15.0f + 0.5f) << 12);
+}
+NRD_DEV float3 unpackInternalData(uint32_t p) {  // REBLUR_Common.hlsli:29-38 -> ( diff frames, spec frames, materialID )
+    float3 t = make_float3((float)(p & 63u) * (1.0f / 63.0f), (float)((p >> 6) & 63u) * (1.0f / 63.0f), (float)((p >> 12) & 15u) * (1.0f / 15.0f));
+    return make_float3(roundNe(t.x * 63.0f), roundNe(t.y * 63.0f), t.z * 15.0f);
+}
+
+struct Bilinear { float2 origin, weights; };
+NRD_DEV Bilinear getBilinearFilter(float2 uv, float2 texSize) {
+    float2 t = uv * texSize - 0.5f;
+    Bilinear r;
+    r.origin = floor2(t);
+    r.weights = saturate(t - r.origin);
+    return r;
+}
+NRD_DEV float applyBilinear(float s00, float s10, float s01, float s11, Bilinear f) {
+    return lerp(lerp(s00, s10, f.weights.x), lerp(s01, s11, f.weights.x), f.weights.y);
+}
+NRD_DEV float4 applyBilinear(float4 s00, float4 s10, float4 s01, float4 s11, Bilinear f) {
+    return lerp(lerp(s00, s10, f.weights.x), lerp(s01, s11, f.weights.x), f.weights.y);
+}
+NRD_DEV float4 bilinearCustomWeights(Bilinear f, float4 custom) {
+    float2 o = saturate(1.0f - f.weights);
+    return make_float4(custom.x * (o.x * o.y), custom.y * (f.weights.x * o.y), custom.z * (o.x * f.weights.y), custom.w * (f.weights.x * f.weights.y));
+}
+NRD_DEV float applyCustomWeights(float s00, float s10, float s01, float s11, float4 w) {
+    float sum = sum4(w);
+    return (s00 * w.x + s10 * w.y + s01 * w.z + s11 * w.w) * (sum < 0.0001f ? 0.0f : 1.0f / sum);
+}
+NRD_DEV float modifiedRoughnessFromNormalVariance(float roughness, float3 avgNormal) {
+    float l = length(avgNormal);
+    float kappa = saturate(1.0f - l * l) * positiveRcp(l * (3.0f - l * l));
+    return sqrt01(roughness * roughness + kappa);
+}
+
+// Sequence::Hash / HashCombine / Zorder and Rng::Hash
+NRD_DEV uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+NRD_DEV uint32_t explodeBits(uint32_t x) {
+    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+struct Rng {
+    uint32_t state;
+    NRD_DEV void init(uint32_t x, uint32_t y, uint32_t frame) {
+        uint32_t seed = hash32(frame + 0x035F9F29u);
+        uint32_t value = explodeBits(x) | (explodeBits(y) << 1);
+        state = seed ^ (hash32(value) + 0x9E3779B9u + (seed << 6) + (seed >> 2));
+    }
+    NRD_DEV float next() {
+        state = hash32(state);
+        return __uint_as_float((state >> 9) | 0x3F800000u) - 1.0f;
+    }
+};
+
+NRD_DEV float specularLobeTanHalfAngle(float roughness, float percentOfVolume) {
+    percentOfVolume = saturate(percentOfVolume);
+    return saturate(roughness) * sqrtf(percentOfVolume / (1.0f - percentOfVolume + ML_EPS));
+}
+NRD_DEV float4 specularDominantDirectionG2(float3 N, float3 V, float roughness) {
+    float NoV = fabsf(dot(N, V));
+    roughness = saturate(roughness);
+    float a = 0.298475f * logf(39.4115f - 39.0029f * roughness);
+    float factor = saturate(pow01(1.0f - NoV, 10.8649f) * (1.0f - a) + a);
+    float3 R = reflect(-V, N);
+    return f4(normalize(lerp(N, R, factor)), factor);
+}
+
+// NRD.hlsli
+NRD_DEV float4 unpackNormalRoughness(uint32_t raw, float& materialID) {
+    float4 p = TexNR::decode(raw);
+    float t = p.z * 2.0f - 1.0f;
+    float3 n;
+    n.x = p.x - p.y;
+    n.y = p.x + p.y - 1.0f;
+    n.z = (t < 0.0f ? -1.0f : 1.0f) * (1.0f - fabsf(n.x) - fabsf(n.y));
+    materialID = p.w * 3.0f;
+    n = n * (1.0f / sqrtf(dot(n, n) + 1e-9f));
+    return f4(n, fabsf(t));
+}
+NRD_DEV float4 unpackNormalRoughness(uint32_t raw) { float m; return unpackNormalRoughness(raw, m); }
+NRD_DEV float roughnessFromRaw(uint32_t raw) { return fabsf((float)((raw >> 20) & 1023u) / 1023.0f * 2.0f - 1.0f); }
+NRD_DEV float3 linearToYCoCg(float3 c) {
+    return make_float3(dot(c, make_float3(0.25f, 0.5f, 0.25f)), dot(c, make_float3(0.5f, 0.0f, -0.5f)), dot(c, make_float3(-0.25f, 0.5f, -0.25f)));
+}
+NRD_DEV float3 yCoCgToLinear(float3 c) {
+    float t = c.x - c.z;
+    return max3(make_float3(t + c.y, c.x + c.z, t - c.y), f3(0.0f));
+}
+NRD_DEV float specMagicCurve(float roughness, float power = 0.25f) {
+    return (1.0f - exp2f(-200.0f * roughness * roughness)) * powf(saturate(roughness), power);
+}
+NRD_DEV float hitDistanceNormalization(float viewZ, const float* p, float roughness) {
+    float smc = specMagicCurve(roughness, 0.5f);
+    return (p[0] + fabsf(viewZ) * p[1]) * lerp(p[2], 1.0f, smc);
+}
+
+// Common.hlsli
+NRD_DEV float stdDev(float m1, float m2) { return sqrtf(fabsf(m2 - m1 * m1)); }
+NRD_DEV bool compareMaterials(float m0, float m, float minm) { return fmaxf(m0, minm) == fmaxf(m, minm); }
+NRD_DEV float pixelRadiusToWorld(float unproject, float orthoMode, float pixelRadius, float viewZ) { return pixelRadius * unproject * lerp(viewZ, 1.0f, fabsf(orthoMode)); }
+NRD_DEV float frustumSizeAt(float minRectDimMulUnproject, float orthoMode, float viewZ) { return minRectDimMulUnproject * lerp(viewZ, 1.0f, fabsf(orthoMode)); }
+NRD_DEV float hitDistFactor(float hitDist, float frustumSize) { return saturate(hitDist / frustumSize); }
+NRD_DEV bool isInScreenNearest(float2 uv) { return uv.x > 0.0f && uv.y > 0.0f && uv.x < 1.0f && uv.y < 1.0f; }
+NRD_DEV float2 mirrorUv(float2 uv) {
+    float2 m = 1.0f - fabs2(1.0f - frac2(uv * 0.5f) * 2.0f);
+    return min2(m, f2(0.99999f));
+}
+NRD_DEV float4 isInScreenBilinear(float2 origin, float2 rectSize) {
+    float x0 = (origin.x >= 0.0f && origin.x < rectSize.x) ? 1.0f : 0.0f, y0 = (origin.y >= 0.0f && origin.y < rectSize.y) ? 1.0f : 0.0f;
+    float x1 = (origin.x + 1.0f >= 0.0f && origin.x + 1.0f < rectSize.x) ? 1.0f : 0.0f, y1 = (origin.y + 1.0f >= 0.0f && origin.y + 1.0f < rectSize.y) ? 1.0f : 0.0f;
+    return make_float4(x0 * y0, x1 * y0, x0 * y1, x1 * y1);
+}
+NRD_DEV float parallaxInPixels(float3 X, float2 uvForZeroParallax, const Mat4& worldToClip, float2 rectSize) {
+    return length((screenUv(worldToClip, X) - uvForZeroParallax) * rectSize);
+}
+NRD_DEV float3 getXvirtual(float hitDist, float curvature, float3 X, float3 Xprev, float3 N, float3 V, float roughness) {
+    float4 D = specularDominantDirectionG2(N, V, roughness);
+    float3 ray = xyz(D) * hitDist;
+    Basis b = getBasis(N);
+    float3 O = make_float3(dot(b.T, ray), dot(b.B, ray), -dot(b.N, ray));
+    float mag = 1.0f / (2.0f * curvature * O.z - 1.0f);
+    float NoV = fabsf(dot(N, V));
+    float f = length(X);
+    f *= saturate(1.0f - NoV);
+    f *= fmaxf(curvature, 0.0f);
+    f = 1.0f / (1.0f + f);
+    mag *= f;
+    float3 I = O * mag;
+    float dw = D.w * length(I);
+    float closeness = saturate(dw / (hitDist + NRD_EPS));
+    float3 x = lerp(Xprev, X, closeness);
+    return x + V * dw * signFast(mag);
+}
+NRD_DEV float normalWeightParam(float nonLinearAccumSpeed, float lobeAngleFraction, float roughness = 1.0f) {
+    float percentOfVolume = NRD_MAX_PERCENT_OF_LOBE_VOLUME * lerp(saturate(lobeAngleFraction), 1.0f, nonLinearAccumSpeed);
+    float tanHalfAngle = specularLobeTanHalfAngle(roughness, percentOfVolume);
+    float angle = fmaxf(atanf(tanHalfAngle), NRD_NORMAL_ENCODING_ERROR);
+    return 1.0f / angle;
+}
+NRD_DEV float2 geometryWeightParams(float planeDistSensitivity, float frustumSize, float3 Xv, float3 Nv) {
+    float a = 1.0f / (planeDistSensitivity * frustumSize);
+    return make_float2(a, -(dot(Nv, Xv) * a));
+}
+NRD_DEV float2 hitDistanceWeightParams(float hitDist, float nonLinearAccumSpeed) {
+    float a = 1.0f / nonLinearAccumSpeed;
+    return make_float2(a, -(hitDist * a));
+}
+NRD_DEV float2 roughnessWeightParams(float roughness, float fraction, float sensitivity = NRD_ROUGHNESS_SENSITIVITY) {
+    float a = 1.0f / lerp(sensitivity, 1.0f, saturate(roughness * fraction));
+    return make_float2(a, -(roughness * a));
+}
+NRD_DEV float2 relaxedRoughnessWeightParams(float m, float fraction = 1.0f, float sensitivity = NRD_ROUGHNESS_SENSITIVITY) {
+    float a = 1.0f / lerp(sensitivity, 1.0f, lerp(m * m, m, saturate(fraction)));
+    return make_float2(a, -(m * a));
+}
+NRD_DEV float expApprox(float x) { return 1.0f / (x * x - x + 1.0f); }
+NRD_DEV float exponentialWeight(float x, float px, float py) { return expApprox(-3.0f * fabsf(x * px + py)); }
+NRD_DEV float nonExponentialWeight(float x, float px, float py) { return smoothStep(1.0f, 0.0f, fabsf(x * px + py)); }
+NRD_DEV float gaussianWeight(float r) { return expf(-0.66f * r * r); }
+NRD_DEV float encodingAwareNormalWeight(float3 Ncurr, float3 Nprev, float maxAngle, float curvatureAngle, float thresholdAngle) {
+    float angle = acosApproxPositive(dot(Ncurr, Nprev));
+    float w = smoothStep01(1.0f - (angle - curvatureAngle - thresholdAngle) / maxAngle);
+    return smoothStep(0.05f, 0.95f, w);
+}
+NRD_DEV float disocclusionThresholdAt(float threshold, float frustumSize, float NoV) { return frustumSize * saturate(threshold / fmaxf(0.05f, NoV)); }
+
+}  // namespace nrdk

@@ -1,0 +1,175 @@
+// REBLUR helpers that read the per-frame constants (REBLUR_Common.hlsli:13-371, Common.hlsli:261-262, 567-572,
+// 604-658) and the launch-parameter blocks of the REBLUR kernels.
+#pragma once
+#include "common.cuh"
+
+namespace nrdk {
+
+using nrdb::ReblurConstants;
+
+constexpr float REBLUR_MAX_ACCUM_FRAME_NUM = 63.0f;
+constexpr float REBLUR_MAX_MATERIALID_NUM = 15.0f;
+constexpr float REBLUR_INVALID = -32768.0f;
+
+NRD_DEV float unpackViewZ(const ReblurConstants& cb, float z) { return fabsf(z * cb.viewZScale); }
+NRD_DEV bool inDenoisingRange(const ReblurConstants& cb, float z) { return z < cb.denoisingRange; }
+NRD_DEV float applyGeometryWeightLast(const ReblurConstants& cb, float w, float z, float NoX, float2 p) {
+    w *= nonExponentialWeight(NoX, p.x, p.y);
+    return !inDenoisingRange(cb, z) ? 0.0f : w;
+}
+
+NRD_DEV uint32_t packInternalData(const ReblurConstants& cb, float diffAccumSpeed, float specAccumSpeed, float materialID) {
+    diffAccumSpeed = fminf(diffAccumSpeed + 1.0f, cb.maxAccumulatedFrameNum);
+    specAccumSpeed = fminf(specAccumSpeed + 1.0f, cb.maxAccumulatedFrameNum);
+    return packInternal664(roundNe(diffAccumSpeed) / REBLUR_MAX_ACCUM_FRAME_NUM, roundNe(specAccumSpeed) / REBLUR_MAX_ACCUM_FRAME_NUM, materialID / REBLUR_MAX_MATERIALID_NUM);
+}
+NRD_DEV float2 packData1(float diffAccumSpeed, float specAccumSpeed) {
+    return make_float2(saturate(roundNe(diffAccumSpeed) / REBLUR_MAX_ACCUM_FRAME_NUM), saturate(roundNe(specAccumSpeed) / REBLUR_MAX_ACCUM_FRAME_NUM));
+}
+NRD_DEV float2 unpackData1(float2 p) { return make_float2(roundNe(p.x * REBLUR_MAX_ACCUM_FRAME_NUM), roundNe(p.y * REBLUR_MAX_ACCUM_FRAME_NUM)); }
+NRD_DEV uint32_t packData2(float fbits, float curvature, float virtualHistoryAmount, bool smbAllowCatRom) {
+    uint32_t p = (uint32_t)(fbits + 0.5f);
+    p |= (uint32_t)(saturate(virtualHistoryAmount) * 127.0f + 0.5f) << 8;
+    p |= smbAllowCatRom ? (1u << 15) : 0u;
+    p |= (uint32_t)__half_as_ushort(__float2half_rn(curvature)) << 16;
+    return p;
+}
+NRD_DEV float2 unpackData2(uint32_t p, uint32_t& bits, bool& smbAllowCatRom) {
+    bits = p & 0xFFu;
+    smbAllowCatRom = (p & (1u << 15)) != 0;
+    return make_float2((float)((p >> 8) & 127u) / 127.0f, __half2float(__ushort_as_half((unsigned short)(p >> 16))));
+}
+NRD_DEV float3 viewVector(const ReblurConstants& cb, float3 X, bool isViewSpace = false) {
+    return cb.orthoMode == 0.0f ? normalize(-X) : (isViewSpace ? make_float3(0, 0, -1) : make_float3(cb.viewVectorWorld[0], cb.viewVectorWorld[1], cb.viewVectorWorld[2]));
+}
+NRD_DEV float3 viewVectorPrev(const ReblurConstants& cb, float3 Xprev, float3 cameraDelta) {
+    return cb.orthoMode == 0.0f ? normalize(cameraDelta - Xprev) : make_float3(cb.viewVectorWorldPrev[0], cb.viewVectorWorldPrev[1], cb.viewVectorWorldPrev[2]);
+}
+NRD_DEV float minHitDistAccumSpeed(const ReblurConstants& cb, float roughness) {
+    return 1.0f / (1.0f + 0.5f * specMagicCurve(roughness) * cb.maxAccumulatedFrameNum);
+}
+NRD_DEV float responsiveFactor(const ReblurConstants& cb, float roughness) { return smoothStep01(fmaxf(roughness, 1e-3f) * cb.responsiveAccumulationInvRoughnessThreshold); }
+NRD_DEV float lumaScale(float currLuma, float newLuma) { return (newLuma + NRD_EPS) / (currLuma + NRD_EPS); }
+NRD_DEV float4 mixHistoryAndCurrent(const ReblurConstants& cb, float4 history, float4 current, float f, float roughness = 1.0f) {
+    float fw = fmaxf(f, minHitDistAccumSpeed(cb, roughness));
+    return make_float4(lerp(history.x, current.x, f), lerp(history.y, current.y, f), lerp(history.z, current.z, f), lerp(history.w, current.w, fw));
+}
+NRD_DEV float4 changeLuma(float4 c, float newLuma) {
+    float s = lumaScale(c.x, newLuma);
+    return make_float4(c.x * s, c.y * s, c.z * s, c.w);
+}
+NRD_DEV float4 clampNegativeToZero(float4 c) { return f4(linearToYCoCg(yCoCgToLinear(xyz(c))), saturate(c.w)); }
+NRD_DEV float computeAntilag(const ReblurConstants& cb, float h, float a, float sigma, float accumSpeed) {
+    float s = sigma * cb.antilagSettings[0];
+    float magic = cb.antilagSettings[1] * cb.framerateScale * cb.framerateScale;
+    float hc = clampf(h, a - s, a + s);
+    float d = fabsf(h - hc) / (fmaxf(h, hc) + NRD_EPS);
+    return 1.0f / (1.0f + d * accumSpeed / magic);
+}
+NRD_DEV void kernelBasis(float3 D, float3 N, float3& T, float3& B) {
+    Basis basis = getBasis(N);
+    T = basis.T;
+    B = basis.B;
+    if (fabsf(dot(D, N)) < 0.999f) {
+        float3 R = reflect(-D, N);
+        T = normalize(cross(N, R));
+        B = cross(R, T);
+    }
+}
+NRD_DEV float nonLinearAccumSpeedFast(const ReblurConstants& cb, float accumSpeed, float maxAccumSpeed, float confidence) {  // hasData = true
+    return fmaxf(1.0f - confidence, 1.0f / (1.0f + fminf(accumSpeed, maxAccumSpeed)));
+}
+NRD_DEV float advancedNonLinearAccumSpeed(const ReblurConstants& cb, float accumSpeed) {
+    float f = saturate(accumSpeed / (1.0f + cb.maxAccumulatedFrameNum * cb.convergenceSettings[2]));
+    float e = cb.convergenceSettings[0] * lerp(cb.convergenceSettings[1], 1.0f, f);
+    return 1.0f / (1.0f + e * accumSpeed);
+}
+NRD_DEV float2 temporalAccumulationParams(const ReblurConstants& cb, float footprintQuality, float accumSpeed, float antilag) {
+    float w = footprintQuality;
+    w *= 1.0f - advancedNonLinearAccumSpeed(cb, accumSpeed);
+    w *= antilag;
+    return make_float2(w, 1.0f + 3.0f * cb.framerateScale * w);
+}
+
+// 12-tap Catmull-Rom without corners as 5 bilinear fetches, falling back to custom-weighted bilinear (Common.hlsli:604-658)
+struct HistoryFilter {
+    float4 w;
+    float w4, sum;
+    float2 uv[5];
+    int ox, oy;
+    float4 custom;
+    NRD_DEV HistoryFilter(float2 samplePos, float2 invResourceSize, float4 customWeights, bool useBicubic) {
+        const float S = 0.5f;
+        float2 centerPos = floor2(samplePos - 0.5f) + 0.5f;
+        float2 f = saturate(samplePos - centerPos);
+        float2 w0 = f * (f * (-S * f + 2.0f * S) - S);
+        float2 w1 = f * (f * ((2.0f - S) * f - (3.0f - S))) + 1.0f;
+        float2 w2 = f * (f * (-(2.0f - S) * f + (3.0f - 2.0f * S)) + S);
+        float2 w3 = f * (f * (S * f - S));
+        float2 w12 = w1 + w2;
+        float2 tc = w2 / w12;
+        w = useBicubic ? make_float4(w12.x * w0.y, w0.x * w12.y, w12.x * w12.y, w3.x * w12.y) : customWeights;
+        w4 = useBicubic ? w12.x * w3.y : 0.0f;
+        sum = sum4(w) + w4;
+        uv[0] = (centerPos + (useBicubic ? make_float2(tc.x, -1.0f) : make_float2(0.0f, 0.0f))) * invResourceSize;
+        uv[1] = (centerPos + (useBicubic ? make_float2(-1.0f, tc.y) : make_float2(1.0f, 0.0f))) * invResourceSize;
+        uv[2] = (centerPos + (useBicubic ? make_float2(tc.x, tc.y) : make_float2(0.0f, 1.0f))) * invResourceSize;
+        uv[3] = (centerPos + (useBicubic ? make_float2(2.0f, tc.y) : make_float2(1.0f, 1.0f))) * invResourceSize;
+        uv[4] = (centerPos + (useBicubic ? make_float2(tc.x, 2.0f) : f)) * invResourceSize;
+        ox = (int)centerPos.x;
+        oy = (int)centerPos.y;
+        custom = customWeights;
+    }
+    template <class TEX> NRD_DEV auto color(const TEX& tex) const -> decltype(tex.sampleLinear(uv[0])) {
+        auto c = tex.sampleLinear(uv[0]) * w.x;
+        c += tex.sampleLinear(uv[1]) * w.y;
+        c += tex.sampleLinear(uv[2]) * w.z;
+        c += tex.sampleLinear(uv[3]) * w.w;
+        c += tex.sampleLinear(uv[4]) * w4;
+        return sum < 0.0001f ? c * 0.0f : c / sum;
+    }
+    NRD_DEV float bilinear(const TexR16F& tex) const {
+        float c = tex.load(ox, oy) * custom.x;
+        c += tex.load(ox + 1, oy) * custom.y;
+        c += tex.load(ox, oy + 1) * custom.z;
+        c += tex.load(ox + 1, oy + 1) * custom.w;
+        float s = sum4(custom);
+        return s < 0.0001f ? 0.0f : c / s;
+    }
+};
+
+// ---- launch parameter blocks (member order = shader register order = DispatchDesc::resources order) ----------
+struct ClassifyTilesParams {
+    TexR32F inViewZ;
+    TexR8 outTiles;
+};
+struct PrePassParams {
+    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
+    TexRGBA16F outDiff, outSpec; TexR16F outSpecHitDistForTracking;
+};
+struct BlurParams {
+    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRG8 data1; TexRGBA16F inDiff, inSpec;
+    TexR32F outViewZ; TexRGBA16F outDiff, outSpec;
+};
+struct PostBlurParams {
+    TexR8 tiles; TexNR normalRoughness; TexRG8 data1; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
+    TexNR outNormalRoughness; TexRGBA16F outDiff, outSpec;
+    TexR16U outInternalData; TexRGBA16F outDiffCopy, outSpecCopy;  // only bound when TEMPORAL_STABILIZATION = 0
+};
+struct TemporalAccumulationParams {
+    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F mv; TexR32F prevViewZ; TexNR prevNormalRoughness; TexR16U prevInternalData;
+    TexR32F disocclusionThresholdMix, diffConfidence, specConfidence;  // dummies (IN_VIEWZ) unless the optional inputs are enabled
+    TexRGBA16F inDiff, inSpec, historyDiff, historySpec; TexR16F historyDiffFast, historySpecFast, prevSpecHitDistForTracking, inSpecHitDistForTracking;
+    TexRG8 outData1; TexRGBA16F outDiff, outSpec; TexR16F outDiffFast, outSpecFast, outSpecHitDistForTracking; TexR32U outData2;
+};
+struct HistoryFixParams {
+    TexR8 tiles; TexNR normalRoughness; TexRG8 data1; TexR32F viewZ; TexRGBA16F inDiff, inSpec; TexR16F inDiffFast, inSpecFast, specHitDistForTracking;
+    TexRGBA16F outDiff, outSpec; TexR16F outDiffFast, outSpecFast;
+};
+struct TemporalStabilizationParams {
+    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRG8 data1; TexR32U data2; TexR16F specHitDistForTracking; TexRGBA16F inDiff, inSpec;
+    TexR16F historyDiffLuma, historySpecLuma;
+    TexRGBA16F mv; TexR16U outInternalData; TexRGBA16F outDiff, outSpec; TexR16F outDiffLuma, outSpecLuma;
+};
+
+}  // namespace nrdk

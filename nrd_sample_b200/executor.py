@@ -1,0 +1,195 @@
+"""ctypes binding of the CUDA executor C ABI (include/nrdcu.h) + a thin per-denoiser wrapper.
+
+torch is used for device memory and streams only; every pixel is produced by the hand-written kernels in
+csrc/kernels/*.cu behind `nrdcuDispatch` / `nrdcuDenoise`. If the library or a CUDA device is missing the calls
+raise — there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import build as _build
+from . import nrd_api as api
+
+
+class CuTexture(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("pitchBytes", C.c_uint32), ("format", C.c_uint32)]
+
+
+FLAG_QUAD_INTRINSICS = 1
+FLAG_CUDA_GRAPH = 2
+FLAG_ROBUST_MIRROR_TEST = 4
+
+NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
+                 "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuGetLastError", "nrdcuGetLaunchCount",
+                 "nrdcuGetPoolBytes")
+
+# nrd::Format -> (torch dtype, channels) for tensors handed to / returned by the executor
+FORMAT_STORAGE = {
+    api.Format.R8_UNORM: (torch.uint8, 1),
+    api.Format.RG8_UNORM: (torch.uint8, 2),
+    api.Format.RGBA8_UNORM: (torch.uint8, 4),
+    api.Format.R16_UINT: (torch.int16, 1),
+    api.Format.R16_SFLOAT: (torch.float16, 1),
+    api.Format.RGBA16_SFLOAT: (torch.float16, 4),
+    api.Format.R32_UINT: (torch.int32, 1),
+    api.Format.R32_SFLOAT: (torch.float32, 1),
+    api.Format.R10_G10_B10_A2_UNORM: (torch.int32, 1),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        L.nrdcuDispatch.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.POINTER(CuTexture), C.c_uint32, C.c_uint32, C.c_void_p]
+        L.nrdcuDispatch.restype = C.c_uint32
+        L.nrdcuCreate.argtypes = [C.c_void_p, C.c_uint16, C.c_uint16, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.nrdcuCreate.restype = C.c_uint32
+        L.nrdcuDestroy.argtypes = [C.c_void_p]
+        L.nrdcuDestroy.restype = None
+        L.nrdcuSetCommonSettings.argtypes = [C.c_void_p, C.c_void_p]
+        L.nrdcuSetCommonSettings.restype = C.c_uint32
+        L.nrdcuSetDenoiserSettings.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.nrdcuSetDenoiserSettings.restype = C.c_uint32
+        L.nrdcuSetResource.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(CuTexture)]
+        L.nrdcuSetResource.restype = C.c_uint32
+        L.nrdcuDenoise.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p]
+        L.nrdcuDenoise.restype = C.c_uint32
+        L.nrdcuGetPoolTexture.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(CuTexture)]
+        L.nrdcuGetPoolTexture.restype = C.c_uint32
+        L.nrdcuGetInstance.argtypes = [C.c_void_p]
+        L.nrdcuGetInstance.restype = C.c_void_p
+        L.nrdcuSetHostResource.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.nrdcuSetHostResource.restype = C.c_uint32
+        L.nrdcuDenoiseHost.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p]
+        L.nrdcuDenoiseHost.restype = C.c_uint32
+        L.nrdcuGetLastError.restype = C.c_char_p
+        L.nrdcuGetLaunchCount.restype = C.c_uint64
+        L.nrdcuGetPoolBytes.argtypes = [C.c_void_p]
+        L.nrdcuGetPoolBytes.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+class NrdcuError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise NrdcuError(f"{what}: {api.Result(rc).name}: {load().nrdcuGetLastError().decode()}")
+
+
+def launch_count() -> int:
+    return int(load().nrdcuGetLaunchCount())
+
+
+def texture_of(t: torch.Tensor, fmt: int) -> CuTexture:
+    """View a contiguous tensor (H, W[, C]) as an nrdcuTexture. The tensor must stay alive while the texture is in use."""
+    assert t.is_contiguous(), "textures are pitch-linear: tensor must be contiguous"
+    h, w = t.shape[0], t.shape[1]
+    return CuTexture(t.data_ptr(), w, h, w * api.FORMAT_BYTES[api.Format(fmt)], int(fmt))
+
+
+def alloc_texture(fmt: int, width: int, height: int, device) -> torch.Tensor:
+    dtype, ch = FORMAT_STORAGE[api.Format(fmt)]
+    # keep rows 16-byte aligned: width * bytes is a multiple of 16 for every width that is a multiple of 16 / bpp
+    shape = (height, width) if ch == 1 else (height, width, ch)
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
+def dispatch(shader: str, constants: bytes, textures: Sequence[CuTexture], flags: int = FLAG_QUAD_INTRINSICS, stream: Optional[torch.cuda.Stream] = None):
+    """One pass (== one nrd::DispatchDesc) on caller-provided device textures."""
+    arr = (CuTexture * len(textures))(*textures)
+    cb = C.create_string_buffer(constants, len(constants)) if constants else None
+    s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    _check(load().nrdcuDispatch(shader.encode(), cb, len(constants), arr, len(textures), flags, C.c_void_p(s)), f"nrdcuDispatch({shader})")
+
+
+class CudaDenoiser:
+    """nrdcuContext wrapper for ONE denoiser: pools live in the C++ context, user textures are torch CUDA tensors."""
+
+    def __init__(self, denoiser: int, width: int, height: int, identifier: int = 0, device: int = 0, flags: int = FLAG_QUAD_INTRINSICS):
+        self.width, self.height, self.identifier, self.denoiser, self.device = width, height, identifier, denoiser, device
+        L = load()
+        self._denoisers = (api.DenoiserDesc * 1)(api.DenoiserDesc(identifier, int(denoiser)))
+        desc = api.InstanceCreationDesc()
+        desc.denoisers = self._denoisers
+        desc.denoisersNum = 1
+        ctx = C.c_void_p()
+        _check(L.nrdcuCreate(C.byref(desc), width, height, device, flags, C.byref(ctx)), "nrdcuCreate")
+        self.ctx = ctx
+        self._keep: Dict[int, torch.Tensor] = {}
+        self._ids = (C.c_uint32 * 1)(identifier)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            load().nrdcuDestroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_user_texture(self, rtype: int, tensor: torch.Tensor, fmt: int):
+        assert tensor.is_cuda
+        tex = texture_of(tensor, fmt)
+        _check(load().nrdcuSetResource(self.ctx, int(rtype), C.byref(tex)), "nrdcuSetResource")
+        self._keep[int(rtype)] = tensor
+
+    def set_host_texture(self, rtype: int, tensor: torch.Tensor, fmt: int, is_output: bool):
+        """Plugin-style path: host buffer in, staging + copies inside nrdcuDenoiseHost."""
+        assert not tensor.is_cuda and tensor.is_contiguous()
+        h, w = tensor.shape[0], tensor.shape[1]
+        _check(load().nrdcuSetHostResource(self.ctx, int(rtype), C.c_void_p(tensor.data_ptr()), w, h, w * api.FORMAT_BYTES[api.Format(fmt)], int(fmt), 1 if is_output else 0),
+               "nrdcuSetHostResource")
+        self._keep[1000 + int(rtype)] = tensor
+
+    def set_common_settings(self, cs: api.CommonSettings):
+        _check(load().nrdcuSetCommonSettings(self.ctx, C.byref(cs)), "nrdcuSetCommonSettings")
+
+    def set_denoiser_settings(self, settings):
+        _check(load().nrdcuSetDenoiserSettings(self.ctx, self.identifier, C.byref(settings)), "nrdcuSetDenoiserSettings")
+
+    def denoise(self, stream: Optional[torch.cuda.Stream] = None):
+        s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        _check(load().nrdcuDenoise(self.ctx, self._ids, 1, C.c_void_p(s)), "nrdcuDenoise")
+
+    def denoise_host(self, stream: Optional[torch.cuda.Stream] = None):
+        s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        _check(load().nrdcuDenoiseHost(self.ctx, self._ids, 1, C.c_void_p(s)), "nrdcuDenoiseHost")
+
+    def pool_texture(self, permanent: bool, index: int) -> torch.Tensor:
+        """Copy of a pool texture (debug / parity tap)."""
+        tex = CuTexture()
+        _check(load().nrdcuGetPoolTexture(self.ctx, 1 if permanent else 0, index, C.byref(tex)), "nrdcuGetPoolTexture")
+        dtype, ch = FORMAT_STORAGE[api.Format(tex.format)]
+        out = alloc_texture(tex.format, tex.width, tex.height, f"cuda:{self.device}")
+        row = tex.width * api.FORMAT_BYTES[api.Format(tex.format)]
+        # cudaMemcpy2D through torch: wrap the pitched allocation as a byte tensor view
+        src = _as_byte_tensor(tex.data, tex.pitchBytes * tex.height, self.device).view(tex.height, tex.pitchBytes)[:, :row]
+        out.view(torch.uint8).view(tex.height, row).copy_(src)
+        return out
+
+    def pool_bytes(self) -> int:
+        return int(load().nrdcuGetPoolBytes(self.ctx))
+
+
+def _as_byte_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:
+    """Zero-copy uint8 view of raw device memory (via __cuda_array_interface__)."""
+
+    class _Raw:
+        pass
+
+    r = _Raw()
+    r.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(r, device=f"cuda:{device}")

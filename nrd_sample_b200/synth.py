@@ -1,0 +1,284 @@
+"""Seeded synthetic NRD inputs: the reference ships no pixel data, so tests and bench.py
+feed the denoisers an analytic "Bistro-shaped" scene — ground plane, back wall, boxes, spheres, ~25 % sky —
+rendered to exactly the textures NRDSample's path tracer would hand to NRD
+(Shaders/TraceOpaque.cs.hlsl:614-657,738-757: IN_VIEWZ R32F, IN_NORMAL_ROUGHNESS R10G10B10A2 via
+NRD_FrontEnd_PackNormalAndRoughness, IN_MV RGBA16F 2.5D, IN_*_RADIANCE_HITDIST RGBA16F via
+REBLUR_FrontEnd_PackRadianceAndNormHitDist), plus the matching nrd::CommonSettings camera matrices.
+
+Everything is torch tensor math so it runs on the CPU here and on the GPU for bench-sized frames; the
+generator is test/bench plumbing, not part of the denoiser.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, Tuple
+
+import torch
+
+from . import nrd_api as api
+
+SEED_BASE = 0x4E5244
+SKY_VIEWZ = 1.0e6           # > CommonSettings::denoisingRange (5e5): exercises the 16x16 sky-tile early-out
+HIT_DIST_PARAMS = (3.0, 0.1, 20.0)
+
+
+@dataclass
+class Camera:
+    view_to_clip: Tuple[float, ...]      # column-major 4x4
+    world_to_view: Tuple[float, ...]     # column-major 4x4
+    position: Tuple[float, float, float]
+    rotation: torch.Tensor               # 3x3 world->view (float64)
+    tan_half_fov_y: float
+    aspect: float
+
+
+def make_camera(frame: float, width: int, height: int, period: int = 0) -> Camera:
+    """D3D-style LH perspective, fovY 60 deg, reversed-Z infinite far. The camera drifts 0.02 units/frame along +x
+    and yaws 0.1 deg/frame; with `period` > 0 the path is a closed loop so a short ring of frames can be replayed."""
+    fov = math.radians(60.0)
+    t = 1.0 / math.tan(fov / 2.0)
+    a = width / height
+    near = 0.1
+    v2c = (t / a, 0, 0, 0, 0, t, 0, 0, 0, 0, 0, 1, 0, 0, near, 0)
+    if period:
+        ph = 2.0 * math.pi * (frame % period) / period
+        px, yaw = 0.02 * period / (2 * math.pi) * math.sin(ph), math.radians(0.1 * period / (2 * math.pi)) * math.cos(ph)
+    else:
+        px, yaw = 0.02 * frame, math.radians(0.1 * frame)
+    c, s = math.cos(yaw), math.sin(yaw)
+    R = torch.tensor([[c, 0.0, -s], [0.0, 1.0, 0.0], [s, 0.0, c]], dtype=torch.float64)
+    pos = torch.tensor([px, 1.5, -3.0], dtype=torch.float64)
+    M = torch.eye(4, dtype=torch.float64)
+    M[:3, :3] = R
+    M[:3, 3] = -(R @ pos)
+    w2v = tuple(float(x) for x in M.t().reshape(-1))
+    return Camera(v2c, w2v, (float(pos[0]), float(pos[1]), float(pos[2])), R, math.tan(fov / 2.0), a)
+
+
+def common_settings(frame_index: int, width: int, height: int, period: int = 0, **overrides) -> api.CommonSettings:
+    cur = make_camera(frame_index, width, height, period)
+    prev = make_camera(frame_index - 1 if frame_index > 0 or period else 0, width, height, period)
+    cs = api.CommonSettings()
+    cs.viewToClipMatrix = (C.c_float * 16)(*cur.view_to_clip)
+    cs.viewToClipMatrixPrev = (C.c_float * 16)(*prev.view_to_clip)
+    cs.worldToViewMatrix = (C.c_float * 16)(*cur.world_to_view)
+    cs.worldToViewMatrixPrev = (C.c_float * 16)(*prev.world_to_view)
+    cs.resourceSize = (C.c_uint16 * 2)(width, height)
+    cs.resourceSizePrev = (C.c_uint16 * 2)(width, height)
+    cs.rectSize = (C.c_uint16 * 2)(width, height)
+    cs.rectSizePrev = (C.c_uint16 * 2)(width, height)
+    cs.motionVectorScale = (C.c_float * 3)(1.0 / width, 1.0 / height, 1.0)
+    cs.frameIndex = frame_index
+    cs.timeDeltaBetweenFrames = 16.6   # removes the wall-clock dependence of gFramerateScale (InstanceImpl.cpp:439-443)
+    for k, v in overrides.items():
+        setattr(cs, k, v)
+    return cs
+
+
+# ------------------------------------------------------------------------------------------------
+# Scene
+# ------------------------------------------------------------------------------------------------
+def _scene():
+    """(kind, params, roughness, materialID). Fixed layout, units ~ metres."""
+    objs = [("plane_y", (0.0,), 0.5, 0), ("plane_z", (20.0, 7.5), 1.0, 0)]
+    rough = (0.05, 0.2, 0.5, 1.0)
+    for i in range(12):
+        cx = -11.0 + 2.0 * i + 0.3 * math.sin(3.1 * i)
+        cz = 4.0 + 1.3 * ((i * 7) % 11)
+        h = 0.6 + 0.25 * ((i * 5) % 7)
+        objs.append(("box", (cx - 0.6, 0.0, cz - 0.6, cx + 0.6, h, cz + 0.6), rough[i % 4], i % 2))
+    for i in range(6):
+        cx = -6.0 + 2.4 * i
+        cz = 3.0 + 1.1 * ((i * 3) % 5)
+        r = 0.45 + 0.1 * (i % 3)
+        objs.append(("sphere", (cx, r, cz, r), rough[(i + 1) % 4], (i + 1) % 2))
+    return objs
+
+
+def _raycast(cam: Camera, width: int, height: int, device, dtype=torch.float32):
+    ys, xs = torch.meshgrid(torch.arange(height, device=device, dtype=dtype), torch.arange(width, device=device, dtype=dtype), indexing="ij")
+    u = (xs + 0.5) / width
+    v = (ys + 0.5) / height
+    # view-space ray through the pixel centre, z = 1 (LH, +y up, uv.y down)
+    dvx = (u * 2.0 - 1.0) * (cam.tan_half_fov_y * cam.aspect)
+    dvy = (1.0 - v * 2.0) * cam.tan_half_fov_y
+    Rt = cam.rotation.t().to(device=device, dtype=dtype)          # view->world
+    dv = torch.stack([dvx, dvy, torch.ones_like(dvx)], -1)
+    d = dv @ Rt.t()
+    o = torch.tensor(cam.position, device=device, dtype=dtype)
+
+    inf = torch.full((height, width), float("inf"), device=device, dtype=dtype)
+    tbest = inf.clone()
+    nbest = torch.zeros(height, width, 3, device=device, dtype=dtype)
+    rough = torch.ones(height, width, device=device, dtype=dtype)
+    mat = torch.zeros(height, width, device=device, dtype=dtype)
+    eps = 1e-9
+
+    for kind, p, r, m in _scene():
+        if kind == "plane_y":
+            t = (p[0] - o[1]) / (d[..., 1] - eps)
+            n = torch.tensor([0.0, 1.0, 0.0], device=device, dtype=dtype).expand(height, width, 3)
+            ok = (t > 0) & (d[..., 1] < 0)
+        elif kind == "plane_z":
+            t = (p[0] - o[2]) / (d[..., 2] + eps)
+            hit_y = o[1] + t * d[..., 1]
+            n = torch.tensor([0.0, 0.0, -1.0], device=device, dtype=dtype).expand(height, width, 3)
+            ok = (t > 0) & (hit_y < p[1])
+        elif kind == "box":
+            lo = torch.tensor(p[:3], device=device, dtype=dtype)
+            hi = torch.tensor(p[3:], device=device, dtype=dtype)
+            inv = 1.0 / torch.where(d.abs() < 1e-9, torch.full_like(d, 1e-9), d)
+            t0 = (lo - o) * inv
+            t1 = (hi - o) * inv
+            tmin = torch.minimum(t0, t1)
+            tmax = torch.maximum(t0, t1)
+            tn, axis = tmin.max(-1)
+            tf = tmax.min(-1).values
+            ok = (tn < tf) & (tn > 0)
+            t = tn
+            n = torch.zeros(height, width, 3, device=device, dtype=dtype)
+            sgn = -torch.sign(torch.gather(d, -1, axis.unsqueeze(-1)))
+            n.scatter_(-1, axis.unsqueeze(-1), sgn)
+        else:  # sphere
+            c = torch.tensor(p[:3], device=device, dtype=dtype)
+            oc = o - c
+            dd = (d * d).sum(-1)
+            b = (d * oc).sum(-1)
+            cc = (oc * oc).sum() - p[3] * p[3]
+            disc = b * b - dd * cc
+            ok = disc > 0
+            t = (-b - torch.sqrt(disc.clamp_min(0))) / dd
+            ok = ok & (t > 0)
+            hitp = o + t.unsqueeze(-1) * d
+            n = (hitp - c) / p[3]
+        closer = ok & (t < tbest)
+        tbest = torch.where(closer, t, tbest)
+        nbest = torch.where(closer.unsqueeze(-1), n, nbest)
+        rough = torch.where(closer, torch.full_like(rough, r), rough)
+        mat = torch.where(closer, torch.full_like(mat, float(m)), mat)
+
+    hit = torch.isfinite(tbest)
+    tsafe = torch.where(hit, tbest, torch.zeros_like(tbest))
+    X = o + tsafe.unsqueeze(-1) * d
+    viewz = torch.where(hit, tsafe, torch.full_like(tbest, SKY_VIEWZ))   # ray has view-space z = 1 => viewZ = t
+    return dict(hit=hit, viewz=viewz, X=X, N=nbest, roughness=rough, material=mat, u=u, v=v, V=-d / d.norm(dim=-1, keepdim=True))
+
+
+# ------------------------------------------------------------------------------------------------
+# Packing (mirrors the front-end helpers of NRD.hlsli)
+# ------------------------------------------------------------------------------------------------
+def pack_normal_roughness(N: torch.Tensor, roughness: torch.Tensor, material: torch.Tensor) -> torch.Tensor:
+    """NRD_FrontEnd_PackNormalAndRoughness (NRD.hlsli:696-722, encoding 2) + R10G10B10A2_UNORM quantisation -> int32 (H, W)."""
+    n = N / (N.abs().sum(-1, keepdim=True) + 1e-20)
+    ry = n[..., 1] * 0.5 + 0.5
+    rx = n[..., 0] * 0.5 + ry
+    ry = ry - n[..., 0] * 0.5
+    rgh = roughness.clamp_min(1.5 / 512.0)
+    s = torch.where(n[..., 2] < 0, -rgh, rgh)
+    rz = s * 0.5 + 0.5
+    a = (material / 3.0).clamp(0, 1)
+
+    def q(x, m):
+        return torch.floor(x.clamp(0, 1) * m + 0.5).to(torch.int64)
+
+    word = q(rx, 1023.0) | (q(ry, 1023.0) << 10) | (q(rz, 1023.0) << 20) | (q(a, 3.0) << 30)
+    word = torch.where(word >= 2 ** 31, word - 2 ** 32, word)
+    return word.to(torch.int32)
+
+
+def spec_magic_curve(roughness: torch.Tensor, power: float) -> torch.Tensor:
+    return (1.0 - torch.exp2(-200.0 * roughness * roughness)) * roughness.clamp(0, 1).pow(power)
+
+
+def hit_dist_normalization(viewz: torch.Tensor, roughness: torch.Tensor, params=HIT_DIST_PARAMS) -> torch.Tensor:
+    """_REBLUR_GetHitDistanceNormalization (NRD.hlsli:568-573)."""
+    smc = spec_magic_curve(roughness, 0.5)
+    return (params[0] + viewz.abs() * params[1]) * (params[2] + (1.0 - params[2]) * smc)
+
+
+def pack_radiance_hitdist(rgb: torch.Tensor, norm_hit_dist: torch.Tensor) -> torch.Tensor:
+    """REBLUR_FrontEnd_PackRadianceAndNormHitDist(sanitize=true) (NRD.hlsli:815-826) -> float16 (H, W, 4)."""
+    rgb = torch.nan_to_num(rgb, nan=0.0, posinf=65504.0).clamp(0, 65504.0)
+    y = rgb[..., 0] * 0.25 + rgb[..., 1] * 0.5 + rgb[..., 2] * 0.25
+    co = rgb[..., 0] * 0.5 - rgb[..., 2] * 0.5
+    cg = -rgb[..., 0] * 0.25 + rgb[..., 1] * 0.5 - rgb[..., 2] * 0.25
+    return torch.stack([y, co, cg, norm_hit_dist.clamp(0, 1)], -1).to(torch.float16)
+
+
+def unpack_radiance(tex: torch.Tensor) -> torch.Tensor:
+    """REBLUR_BackEnd_UnpackRadianceAndNormHitDist: YCoCg -> linear RGB (NRD.hlsli:418-428)."""
+    t = tex.float()
+    tt = t[..., 0] - t[..., 2]
+    return torch.stack([tt + t[..., 1], t[..., 0] + t[..., 2], tt - t[..., 1]], -1).clamp_min(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Frame
+# ------------------------------------------------------------------------------------------------
+def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False) -> Dict[str, torch.Tensor]:
+    """All user inputs of REBLUR_DIFFUSE_SPECULAR for one frame, in their API storage formats."""
+    device = torch.device(device)
+    cam = make_camera(frame_index, width, height, period)
+    cam_prev = make_camera(frame_index - 1 if frame_index > 0 or period else 0, width, height, period)
+    g = _raycast(cam, width, height, device)
+    hit, viewz, X, N, rough, mat = g["hit"], g["viewz"], g["X"], g["N"], g["roughness"], g["material"]
+
+    # 2.5D motion: where was this (static) world point on screen last frame, and how far along view z
+    Rp = cam_prev.rotation.to(device=device, dtype=torch.float32)
+    pp = torch.tensor(cam_prev.position, device=device, dtype=torch.float32)
+    Xvp = (X - pp) @ Rp.t()
+    zp = Xvp[..., 2].clamp_min(1e-6)
+    up = (Xvp[..., 0] / zp / (cam_prev.tan_half_fov_y * cam_prev.aspect)) * 0.5 + 0.5
+    vp = 0.5 - (Xvp[..., 1] / zp / cam_prev.tan_half_fov_y) * 0.5
+    mvx = torch.where(hit, (up - g["u"]) * width, torch.zeros_like(up))
+    mvy = torch.where(hit, (vp - g["v"]) * height, torch.zeros_like(vp))
+    mvz = torch.where(hit, Xvp[..., 2] - viewz, torch.zeros_like(up))
+    mv = torch.stack([mvx, mvy, mvz, torch.zeros_like(mvx)], -1).to(torch.float16)
+
+    # clean signals: smooth lambert + a view-dependent lobe term, modulated by a smooth world-space pattern
+    L = torch.tensor([0.4, 0.8, -0.45], device=device, dtype=torch.float32)
+    L = L / L.norm()
+    ndl = (N * L).sum(-1).clamp_min(0)
+    checker = 0.75 + 0.25 * torch.sin(X[..., 0] * 0.9) * torch.cos(X[..., 2] * 0.7)   # smooth "lighting" variation (inputs are albedo-demodulated)
+    tint_d = torch.tensor([1.0, 0.9, 0.75], device=device)
+    tint_s = torch.tensor([0.8, 0.9, 1.0], device=device)
+    diff_clean = ((ndl + 0.1) * checker).unsqueeze(-1) * tint_d
+    V = g["V"]
+    R = 2.0 * (N * V).sum(-1, keepdim=True) * N - V
+    rdl = (R * L).sum(-1).clamp_min(0)
+    shin = 2.0 / (rough * rough).clamp_min(1e-3)
+    spec_clean = (rdl.pow(shin.clamp_max(64.0)) * 2.0 + 0.05).unsqueeze(-1) * tint_s
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(SEED_BASE + frame_index)
+
+    def rnd():
+        return torch.rand(height, width, device=device, generator=gen)
+
+    def noisy(clean):
+        e = -torch.log(1.0 - rnd() * 0.999999)                 # Exp(1): 1-spp-like multiplicative noise, mean 1
+        fire = torch.where(rnd() < 0.002, torch.full_like(e, 50.0), torch.ones_like(e))
+        return clean * (e * fire).unsqueeze(-1)
+
+    diff_noisy = noisy(diff_clean)
+    spec_noisy = noisy(spec_clean)
+    hit_t_d = (0.1 + 9.9 * rnd()) * 2.0
+    hit_t_s = (0.1 + 9.9 * rnd()) * (1.0 + rough)
+    nhd_d = (hit_t_d / hit_dist_normalization(viewz, torch.ones_like(rough))).clamp(0, 1)
+    nhd_s = (hit_t_s / hit_dist_normalization(viewz, rough)).clamp(0, 1)
+
+    zero4 = torch.zeros(height, width, 4, device=device, dtype=torch.float16)
+    out = {
+        "IN_VIEWZ": viewz.contiguous(),
+        "IN_NORMAL_ROUGHNESS": pack_normal_roughness(N, rough, mat).contiguous(),
+        "IN_MV": mv.contiguous(),
+        "IN_DIFF_RADIANCE_HITDIST": torch.where(hit[..., None], pack_radiance_hitdist(diff_noisy, nhd_d), zero4).contiguous(),
+        "IN_SPEC_RADIANCE_HITDIST": torch.where(hit[..., None], pack_radiance_hitdist(spec_noisy, nhd_s), zero4).contiguous(),
+    }
+    if with_clean:
+        out["_clean_diff"] = diff_clean
+        out["_clean_spec"] = spec_clean
+        out["_hit"] = hit
+    return out

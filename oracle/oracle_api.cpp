@@ -1,0 +1,119 @@
+// TEST INFRASTRUCTURE — CPU oracle (see hlsl_like.h). C entry point used by tests/, smoke() and bench.py's CPU legs.
+// One call replays one nrd::DispatchDesc on host memory: the shader is selected by the same `shaderIdentifier`
+// string the product's CUDA executor keys on, textures arrive in DispatchDesc::resources order.
+#include <omp.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "reblur_passes.h"
+
+namespace orc {
+// sigma_passes.cpp
+int sigmaDispatch(const std::string& id, const void* cb, uint32_t cbSize, Tex* t, uint32_t n, int gridW, int gridH);
+}  // namespace orc
+
+using namespace orc;
+
+static bool startsWith(const std::string& s, const char* p) { return s.compare(0, strlen(p), p) == 0; }
+
+extern "C" {
+
+// flags: bit0 = replay SM6.0 quad intrinsics (NRD_SUPPORTS_QUAD_INTRINSICS = 1, the reference default)
+//        bit1 = robust "tap left the screen" test instead of the bit-fragile any( uv != MirrorUv( uv ) ) (strict parity runs)
+// returns 0 on success, 1 unknown shader, 2 bad arguments
+__attribute__((visibility("default"))) int nrd_oracle_dispatch(const char* shaderIdentifier, const void* constants, uint32_t constantsSize,
+                                                                const OracleTexture* textures, uint32_t texturesNum, uint32_t gridW, uint32_t gridH,
+                                                                uint32_t flags) {
+    if (!shaderIdentifier || (!textures && texturesNum)) return 2;
+    std::string id = shaderIdentifier;
+    Tex t[32];
+    if (texturesNum > 32) return 2;
+    for (uint32_t i = 0; i < texturesNum; i++) t[i] = Tex(textures[i]);
+    const bool quads = flags & 1u, robust = flags & 2u;
+    const int gw = (int)gridW, gh = (int)gridH;
+
+    if (startsWith(id, "Clear.cs.hlsl")) {
+        if (texturesNum != 1) return 2;
+        clearTexture(t[0]);
+        return 0;
+    }
+    if (startsWith(id, "REBLUR_")) {
+        if (constantsSize != sizeof(ReblurCB)) return 2;
+        const ReblurCB& cb = *(const ReblurCB*)constants;
+        if (startsWith(id, "REBLUR_ClassifyTiles.cs.hlsl")) {
+            if (texturesNum != 2) return 2;
+            reblurClassifyTiles(cb, t[0], t[1], gw, gh);
+            return 0;
+        }
+        if (id == "REBLUR_PrePass.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
+            if (texturesNum != 8) return 2;
+            reblurPrePass(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], gw, gh, robust);
+            return 0;
+        }
+        if (id == "REBLUR_TemporalAccumulation.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
+            if (texturesNum != 25) return 2;
+            TaTextures a = {&t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6], &t[7], &t[8], &t[9], &t[10], &t[11], &t[12], &t[13], &t[14], &t[15], &t[16], &t[17],
+                            &t[18], &t[19], &t[20], &t[21], &t[22], &t[23], &t[24]};
+            reblurTemporalAccumulation(cb, a, gw, gh);
+            return 0;
+        }
+        if (id == "REBLUR_HistoryFix.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
+            if (texturesNum != 13) return 2;
+            HfTextures a = {&t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6], &t[7], &t[8], &t[9], &t[10], &t[11], &t[12]};
+            reblurHistoryFix(cb, a, gw, gh, quads);
+            return 0;
+        }
+        if (id == "REBLUR_Blur.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
+            if (texturesNum != 9) return 2;
+            reblurBlur(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], gw, gh, quads, robust);
+            return 0;
+        }
+        if (id == "REBLUR_PostBlur.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|TEMPORAL_STABILIZATION=1") {
+            if (texturesNum != 9) return 2;
+            reblurPostBlur(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], nullptr, nullptr, nullptr, true, gw, gh, quads, robust);
+            return 0;
+        }
+        if (id == "REBLUR_PostBlur.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|TEMPORAL_STABILIZATION=0") {
+            if (texturesNum != 12) return 2;
+            reblurPostBlur(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], &t[9], &t[10], &t[11], false, gw, gh, quads, robust);
+            return 0;
+        }
+        if (id == "REBLUR_TemporalStabilization.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
+            if (texturesNum != 16) return 2;
+            TsTextures a = {&t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6], &t[7], &t[8], &t[9], &t[10], &t[11], &t[12], &t[13], &t[14], &t[15]};
+            reblurTemporalStabilization(cb, a, gw, gh);
+            return 0;
+        }
+        return 1;
+    }
+    if (startsWith(id, "SIGMA_")) return sigmaDispatch(id, constants, constantsSize, t, texturesNum, gw, gh);
+    return 1;
+}
+
+__attribute__((visibility("default"))) void nrd_oracle_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
+__attribute__((visibility("default"))) int nrd_oracle_max_threads() { return omp_get_max_threads(); }
+
+// Spot-check hooks for tests/test_oracle_math.py (compared against MathLib compiled from the reference tree)
+__attribute__((visibility("default"))) uint16_t nrd_oracle_f32tof16(float f) { return f32tof16(f); }
+__attribute__((visibility("default"))) float nrd_oracle_f16tof32(uint16_t h) { return f16tof32(h); }
+__attribute__((visibility("default"))) uint32_t nrd_oracle_hash(uint32_t x) { return Sequence::Hash(x); }
+__attribute__((visibility("default"))) float nrd_oracle_rng_first(uint32_t x, uint32_t y, uint32_t frame) {
+    RngHash r;
+    r.Initialize(x, y, frame);
+    return r.GetFloat();
+}
+__attribute__((visibility("default"))) void nrd_oracle_pack_normal_roughness(const float* n, float roughness, float materialID, float* out4) {
+    float4 p = NRD_FrontEnd_PackNormalAndRoughness(float3(n[0], n[1], n[2]), roughness, materialID);
+    out4[0] = p.x; out4[1] = p.y; out4[2] = p.z; out4[3] = p.w;
+}
+__attribute__((visibility("default"))) void nrd_oracle_unpack_normal_roughness(const float* p4, float* out5) {
+    float m;
+    float4 r = NRD_FrontEnd_UnpackNormalAndRoughness(float4(p4[0], p4[1], p4[2], p4[3]), m);
+    out5[0] = r.x; out5[1] = r.y; out5[2] = r.z; out5[3] = r.w; out5[4] = m;
+}
+__attribute__((visibility("default"))) float nrd_oracle_hitdist_normalization(float viewZ, float A, float B, float C, float roughness) {
+    return _REBLUR_GetHitDistanceNormalization(viewZ, float3(A, B, C), roughness);
+}
+}
