@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Headline benchmark: denoised Mpixels/s of the REBLUR_DIFFUSE_SPECULAR pass chain at 2560x1440 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--width 2560 --height 1440]
+
+A "step" is one nrdcuDenoise of one synthetic frame (7 passes: classify tiles, pre-pass, temporal accumulation,
+history fix, blur, post-blur, temporal stabilisation) in steady state. `value` times K steps with the frame's inputs
+already in HBM (CUDA events on the launch stream, barrier + synchronize on both sides, max over ranks); `e2e` times the
+same K steps through the host-buffer entry point nrdcuDenoiseHost: pinned host inputs -> H2D -> 7 kernels -> D2H of both
+denoised outputs, every step. N > 1 (torchrun): every rank denoises its own independent stream of frames (replicas, no
+data-path collective — REBLUR frames shard as independent streams, BASELINE.json config 5), `value` is the aggregate.
+
+`--impl reference`: the reference has no CPU (or CUDA) implementation of this path — its HLSL cannot be built or run
+here — so this arm times the oracle's CPU restatement of the same chain (oracle/, "port") on all host cores, on a
+bounded sample of the workload (a 1280x720 stream of the same synthetic scene), rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoised Mpixels/s (REBLUR diff+spec, 1440p)"
+UNIT = "Mpixels/s"
+# Compulsory bytes per pixel per pass (every bound texel read once, every output written once; SURVEY.md App. B / DESIGN.md)
+PASS_BYTES_PER_PIXEL = {
+    "Classify tiles": 4, "Pre-pass": 42, "Temporal accumulation": 94, "History fix": 52, "Blur": 46, "Post-blur": 46, "Temporal stabilization": 66,
+}
+CHAIN_BYTES_PER_PIXEL = sum(PASS_BYTES_PER_PIXEL.values())  # 350
+PUBLISHED_MPX_S = 3.6864 / 2.55e-3  # NRD/README.md:30: REBLUR_DIFFUSE_SPECULAR 2.55 ms @1440p on RTX 4080
+RING = 4  # distinct frames cycled through (4 x 118 MB of inputs at 1440p >> 126 MB L2)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons, sampled every 200 ms while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle's restatement of the chain on all host cores (the reference ships no CPU path)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from nrd_sample_b200 import nrd_api as api, synth
+    from oracle import runner
+
+    W, H = 1280, 720  # bounded sample: a quarter-size stream of the same scene (cost per pixel is resolution independent)
+    threads = os.cpu_count() or 1
+    runner.lib().nrd_oracle_set_threads(threads)
+    den = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H)
+    out_d = runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H)
+    out_s = runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H)
+    den.set_user_texture(api.ResourceType.OUT_DIFF_RADIANCE_HITDIST, out_d)
+    den.set_user_texture(api.ResourceType.OUT_SPEC_RADIANCE_HITDIST, out_s)
+    frames = [synth.reblur_frame(i, W, H, period=RING) for i in range(RING)]
+
+    def step(i):
+        for k, v in frames[i % RING].items():
+            den.set_user_texture(getattr(api.ResourceType, k), v)
+        den.denoise(synth.common_settings(i, W, H, period=RING))
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    value = W * H * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "REBLUR_DIFFUSE_SPECULAR full pass chain, 2560x1440, synthetic 1spp noisy radiance + G-buffer", "denoiser": "REBLUR_DIFFUSE_SPECULAR",
+                   "resolution": [args.width, args.height], "settings": "library defaults"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steady-state frames of a {W}x{H} stream of the same synthetic scene (oracle restatement, all host threads)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference's REBLUR implementation is HLSL compute (no CPU/CUDA path, not buildable here); this arm is oracle/'s CPU port of it",
+    }
+    print(json.dumps(line))
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from nrd_sample_b200 import executor as ex, nrd_api as api, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the denoiser has no CPU fallback (use --impl reference for the CPU oracle arm)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    W, H = args.width, args.height
+    px = W * H
+    RT = api.ResourceType
+    FMT = {"IN_VIEWZ": api.Format.R32_SFLOAT, "IN_NORMAL_ROUGHNESS": api.Format.R10_G10_B10_A2_UNORM, "IN_MV": api.Format.RGBA16_SFLOAT,
+           "IN_DIFF_RADIANCE_HITDIST": api.Format.RGBA16_SFLOAT, "IN_SPEC_RADIANCE_HITDIST": api.Format.RGBA16_SFLOAT}
+
+    # every rank gets its own stream of frames (different seeds per rank via the frame index offset)
+    frames = [synth.reblur_frame(i + 1000 * rank, W, H, device=dev, period=RING) for i in range(RING)]
+    host_frames = [{k: v.cpu().pin_memory() for k, v in f.items()} for f in frames]
+    out_d = ex.alloc_texture(api.Format.RGBA16_SFLOAT, W, H, dev)
+    out_s = ex.alloc_texture(api.Format.RGBA16_SFLOAT, W, H, dev)
+    host_out_d = torch.zeros(H, W, 4, dtype=torch.float16).pin_memory()
+    host_out_s = torch.zeros(H, W, 4, dtype=torch.float16).pin_memory()
+
+    den = ex.CudaDenoiser(api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, device=local)
+    stream = torch.cuda.current_stream()
+
+    def settings(i):
+        return synth.common_settings(i + 1000 * rank, W, H, period=RING)
+
+    def step_device(i):
+        for k, v in frames[i % RING].items():
+            den.set_user_texture(getattr(RT, k), v, FMT[k])
+        den.set_user_texture(RT.OUT_DIFF_RADIANCE_HITDIST, out_d, api.Format.RGBA16_SFLOAT)
+        den.set_user_texture(RT.OUT_SPEC_RADIANCE_HITDIST, out_s, api.Format.RGBA16_SFLOAT)
+        den.set_common_settings(settings(i))
+        den.denoise(stream)
+
+    def step_host(i):
+        for k, v in host_frames[i % RING].items():
+            den.set_host_texture(getattr(RT, k), v, FMT[k], is_output=False)
+        den.set_host_texture(RT.OUT_DIFF_RADIANCE_HITDIST, host_out_d, api.Format.RGBA16_SFLOAT, is_output=True)
+        den.set_host_texture(RT.OUT_SPEC_RADIANCE_HITDIST, host_out_s, api.Format.RGBA16_SFLOAT, is_output=True)
+        den.set_common_settings(settings(i))
+        den.denoise_host(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, first, profile=False):
+        for i in range(first, first + args.warmup):
+            step_fn(i)
+        barrier()
+        if profile:
+            den.reset_profile()
+            den.set_profiling(True)
+        launches0 = ex.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(first + args.warmup, first + args.warmup + args.steps):
+            step_fn(i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ex.launch_count() - launches0
+        prof = den.profile() if profile else {}
+        den.set_profiling(False)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, prof
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev, launches, prof = timed(step_device, 0, profile=True)
+    clocks = sampler.stop() if sampler else None
+    ms_host, _, _ = timed(step_host, args.warmup + args.steps)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        total_px = px * args.steps * world
+        value = total_px / (ms_dev * 1e-3) / 1e6
+        e2e_value = total_px / (ms_host * 1e-3) / 1e6
+        passes = {}
+        for name, (tot, cnt) in prof.items():
+            short = name.split(" - ")[-1]
+            if cnt and short in PASS_BYTES_PER_PIXEL:
+                avg_ms = tot / cnt
+                gbs = PASS_BYTES_PER_PIXEL[short] * px / (avg_ms * 1e-3) / 1e9
+                passes[short] = {"avg_us": round(avg_ms * 1e3, 2), "alg_bytes_per_px": PASS_BYTES_PER_PIXEL[short], "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        dom = max(passes, key=lambda k: passes[k]["avg_us"]) if passes else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if dom and os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(f"{W}x{H}", {}).get(dom)
+            except Exception:
+                traffic = None
+        chain_gbs = CHAIN_BYTES_PER_PIXEL * px / (ms_dev / args.steps * 1e-3) / 1e9
+        roofline = None
+        if dom:
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": passes[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": passes[dom]["frac"], "traffic": traffic,
+                        "peak_source": peak_src, "alg_bytes_per_launch": PASS_BYTES_PER_PIXEL[dom] * px,
+                        "chain": {"alg_bytes_per_px": CHAIN_BYTES_PER_PIXEL, "achieved": round(chain_gbs, 1), "frac": round(chain_gbs / peak, 4)}, "passes": passes,
+                        "note": "REBLUR is ALU-bound on B200 (30-40 FLOP per algorithmic byte vs a ~10 FLOP/B fp32 ridge); see DESIGN.md"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / world / PUBLISHED_MPX_S if (W, H) == (2560, 1440) else None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"REBLUR_DIFFUSE_SPECULAR full pass chain, {W}x{H}, synthetic 1spp noisy radiance + G-buffer", "denoiser": "REBLUR_DIFFUSE_SPECULAR",
+                       "resolution": [W, H], "settings": "library defaults (prepass on, hit-distance reconstruction off, anti-firefly on, stabilization on)",
+                       "streams_per_gpu": 1, "parallelism": f"replicas x{world} (independent frame streams, no collective)",
+                       "l2_policy": f"ring of {RING} distinct frames: {RING * 32 * px // 2**20} MiB of inputs + pools > 126 MB L2",
+                       "baseline_note": "vs_baseline = per-GPU value / 1446 Mpx/s (RTX 4080, NRD README, default settings + 3x3 hit-distance reconstruction)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * px, "d2h_bytes_per_step": 16 * px, "ms_per_step": ms_host / args.steps},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+        }
+        # CPU baseline: the oracle port on this box's host cores, bounded sample (N=1 only)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    den.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    import torch  # noqa: F401
+    from nrd_sample_b200 import nrd_api as api, synth
+    from oracle import runner
+
+    W, H, warm, steps = 1280, 720, 4, 8
+    threads = os.cpu_count() or 1
+    runner.lib().nrd_oracle_set_threads(threads)
+    den = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H)
+    den.set_user_texture(api.ResourceType.OUT_DIFF_RADIANCE_HITDIST, runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H))
+    den.set_user_texture(api.ResourceType.OUT_SPEC_RADIANCE_HITDIST, runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H))
+    frames = [synth.reblur_frame(i, W, H, period=RING) for i in range(RING)]
+    t0 = 0.0
+    for i in range(warm + steps):
+        if i == warm:
+            t0 = time.perf_counter()
+        for k, v in frames[i % RING].items():
+            den.set_user_texture(getattr(api.ResourceType, k), v)
+        den.denoise(synth.common_settings(i, W, H, period=RING))
+    dt = time.perf_counter() - t0
+    return {"value": W * H * steps / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} steady-state frames of a {W}x{H} stream of the same synthetic scene (oracle/ CPU restatement, OpenMP over rows)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--width", type=int, default=2560)
+    ap.add_argument("--height", type=int, default=1440)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

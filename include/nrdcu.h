@@ -79,6 +79,14 @@ NRDCU_API uint32_t nrdcuSetHostResource(nrdcuContext* ctx, uint32_t resourceType
                                         uint32_t format, int direction);
 NRDCU_API uint32_t nrdcuDenoiseHost(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream);
 
+/* ---- per-pass timing -----------------------------------------------------------------------------------------
+ * With profiling on, nrdcuDenoise brackets every dispatch with CUDA events on `stream`; nrdcuResolveProfile
+ * synchronises and accumulates them per pass name (DispatchDesc::name). Used by bench.py for the live roofline. */
+NRDCU_API uint32_t nrdcuSetProfiling(nrdcuContext* ctx, int enabled);
+NRDCU_API uint32_t nrdcuResolveProfile(nrdcuContext* ctx);
+NRDCU_API uint32_t nrdcuGetProfileEntry(nrdcuContext* ctx, uint32_t index, const char** name, double* totalMs, uint64_t* count);
+NRDCU_API void nrdcuResetProfile(nrdcuContext* ctx);
+
 /* ---- introspection ------------------------------------------------------------------------------------------- */
 NRDCU_API const char* nrdcuGetLastError(void);
 NRDCU_API uint64_t nrdcuGetLaunchCount(void);           /* kernels launched by this library since load (all contexts) */

@@ -307,6 +307,13 @@ struct nrdcuContext {
     std::vector<void*> allocations;
     uint64_t poolBytes = 0;
     std::vector<nrdcuTexture> scratch;
+    // per-dispatch CUDA-event timing (bench.py's live roofline measurement)
+    struct ProfileEntry { const char* name; double totalMs = 0; uint64_t count = 0; };
+    struct PendingTiming { const char* name; cudaEvent_t start, stop; };
+    bool profiling = false;
+    std::vector<ProfileEntry> profile;
+    std::vector<PendingTiming> pending;
+    std::vector<cudaEvent_t> freeEvents;
 };
 
 namespace {
@@ -437,11 +444,70 @@ NRDCU_API uint32_t nrdcuDenoise(nrdcuContext* ctx, const uint32_t* identifiers, 
                 if (!ctx->scratch[k].data) return fail(Result::INVALID_ARGUMENT, "'%s' needs user resource %s, which was not set", dd.name, GetResourceTypeString(res.type));
             }
         }
+        cudaEvent_t evStart = nullptr, evStop = nullptr;
+        if (ctx->profiling) {
+            auto grab = [&]() {
+                cudaEvent_t ev;
+                if (!ctx->freeEvents.empty()) { ev = ctx->freeEvents.back(); ctx->freeEvents.pop_back(); }
+                else cudaEventCreate(&ev);
+                return ev;
+            };
+            evStart = grab();
+            evStop = grab();
+            cudaEventRecord(evStart, (cudaStream_t)stream);
+        }
         uint32_t rc = nrdcuDispatch(d.pipelines[dd.pipelineIndex].shaderIdentifier, dd.constantBufferData, dd.constantBufferDataSize, ctx->scratch.data(), dd.resourcesNum,
                                     ctx->flags, stream);
+        if (ctx->profiling) {
+            cudaEventRecord(evStop, (cudaStream_t)stream);
+            ctx->pending.push_back({dd.name, evStart, evStop});
+        }
         if (rc != 0) return rc;
     }
     return 0;
+}
+
+NRDCU_API uint32_t nrdcuSetProfiling(nrdcuContext* ctx, int enabled) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuSetProfiling: null context");
+    ctx->profiling = enabled != 0;
+    return 0;
+}
+
+// Synchronises the device, folds all pending per-dispatch timings into the per-pass totals and returns the number of passes seen
+NRDCU_API uint32_t nrdcuResolveProfile(nrdcuContext* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& t : ctx->pending) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess) {
+            nrdcuContext::ProfileEntry* e = nullptr;
+            for (auto& pe : ctx->profile)
+                if (pe.name == t.name || !strcmp(pe.name, t.name)) e = &pe;
+            if (!e) {
+                ctx->profile.push_back({t.name});
+                e = &ctx->profile.back();
+            }
+            e->totalMs += ms;
+            e->count++;
+        }
+        ctx->freeEvents.push_back(t.start);
+        ctx->freeEvents.push_back(t.stop);
+    }
+    ctx->pending.clear();
+    return (uint32_t)ctx->profile.size();
+}
+
+NRDCU_API uint32_t nrdcuGetProfileEntry(nrdcuContext* ctx, uint32_t index, const char** name, double* totalMs, uint64_t* count) {
+    if (!ctx || index >= ctx->profile.size()) return fail(Result::INVALID_ARGUMENT, "nrdcuGetProfileEntry: index out of range");
+    if (name) *name = ctx->profile[index].name;
+    if (totalMs) *totalMs = ctx->profile[index].totalMs;
+    if (count) *count = ctx->profile[index].count;
+    return 0;
+}
+
+NRDCU_API void nrdcuResetProfile(nrdcuContext* ctx) {
+    if (ctx) ctx->profile.clear();
 }
 
 NRDCU_API uint32_t nrdcuSetHostResource(nrdcuContext* ctx, uint32_t resourceType, void* hostData, uint32_t width, uint32_t height, uint32_t pitchBytes, uint32_t format,

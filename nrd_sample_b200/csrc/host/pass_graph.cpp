@@ -253,10 +253,12 @@ static void rotator(float out[4], float angle) {
     out[0] = c; out[1] = s; out[2] = -s; out[3] = c;
 }
 
-// Sequence::Weyl1D (ml.hlsli:1712): frac(p + float(n * 10368889) / 2^24), uint32 wrap-around on the product
+// Sequence::Weyl1D (ml.hlsli:1712): frac(p + float(n * 10368889) / exp2(24)), uint32 wrap-around on the product.
+// Compiled as C++ the reference evaluates exp2() and therefore the sum and frac() in double (tests/test_oracle_math.py
+// pins this against the reference MathLib), which matters once n * 10368889 / 2^24 reaches the hundreds.
 static float weyl1D(float p, uint32_t n) {
-    float x = p + float(n * 10368889u) / 16777216.0f;
-    return x - std::floor(x);
+    double x = (double)p + (double)float(n * 10368889u) / 16777216.0;
+    return (float)(x - std::floor(x));
 }
 
 Result Graph::setCommonSettings(const CommonSettings& cs) {

@@ -25,7 +25,7 @@ FLAG_ROBUST_MIRROR_TEST = 4
 
 NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
                  "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuGetLastError", "nrdcuGetLaunchCount",
-                 "nrdcuGetPoolBytes")
+                 "nrdcuGetPoolBytes", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile")
 
 # nrd::Format -> (torch dtype, channels) for tensors handed to / returned by the executor
 FORMAT_STORAGE = {
@@ -74,6 +74,14 @@ def load() -> C.CDLL:
         L.nrdcuGetLaunchCount.restype = C.c_uint64
         L.nrdcuGetPoolBytes.argtypes = [C.c_void_p]
         L.nrdcuGetPoolBytes.restype = C.c_uint64
+        L.nrdcuSetProfiling.argtypes = [C.c_void_p, C.c_int]
+        L.nrdcuSetProfiling.restype = C.c_uint32
+        L.nrdcuResolveProfile.argtypes = [C.c_void_p]
+        L.nrdcuResolveProfile.restype = C.c_uint32
+        L.nrdcuGetProfileEntry.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.nrdcuGetProfileEntry.restype = C.c_uint32
+        L.nrdcuResetProfile.argtypes = [C.c_void_p]
+        L.nrdcuResetProfile.restype = None
         _lib = L
     return _lib
 
@@ -178,6 +186,22 @@ class CudaDenoiser:
         # cudaMemcpy2D through torch: wrap the pitched allocation as a byte tensor view
         src = _as_byte_tensor(tex.data, tex.pitchBytes * tex.height, self.device).view(tex.height, tex.pitchBytes)[:, :row]
         out.view(torch.uint8).view(tex.height, row).copy_(src)
+        return out
+
+    def set_profiling(self, enabled: bool):
+        _check(load().nrdcuSetProfiling(self.ctx, 1 if enabled else 0), "nrdcuSetProfiling")
+
+    def reset_profile(self):
+        load().nrdcuResetProfile(self.ctx)
+
+    def profile(self) -> Dict[str, tuple]:
+        """{pass name: (total ms, launches)} accumulated since the last reset (synchronises the device)."""
+        n = load().nrdcuResolveProfile(self.ctx)
+        out = {}
+        for i in range(n):
+            name, ms, cnt = C.c_char_p(), C.c_double(), C.c_uint64()
+            _check(load().nrdcuGetProfileEntry(self.ctx, i, C.byref(name), C.byref(ms), C.byref(cnt)), "nrdcuGetProfileEntry")
+            out[name.value.decode()] = (ms.value, cnt.value)
         return out
 
     def pool_bytes(self) -> int:

@@ -22,3 +22,6 @@ g++ -std=c++17 -O2 -fPIC -shared -mssse3 -msse4.1 -w \
     "$NRD/Source/Reference.cpp" "$NRD/Source/Timer.cpp" "$NRD/Source/Wrapper.cpp" \
     -o "$OUT/libnrd_ref.so"
 echo "built $OUT/libnrd_ref.so"
+# MathLib spot-check library: the reference's ml.hlsli compiled as C++ behind C wrappers (oracle/ref_shim/ml_wrappers.cpp)
+g++ -std=c++17 -O2 -fPIC -shared -mssse3 -msse4.1 -w -fvisibility=hidden -I "$ML" "$HERE/ref_shim/ml_wrappers.cpp" -o "$OUT/libml_ref.so"
+echo "built $OUT/libml_ref.so"

@@ -1,0 +1,75 @@
+"""The drop-in boundary: libnrd_b200.so loads on a CPU-only box and exports every symbol include/*.h declares,
+with the POD sizes of the reference headers (External/NRD/Include/NRD.h:60-79, NRDDescs.h, NRDSettings.h)."""
+import ctypes as C
+import os
+import re
+
+from nrd_sample_b200 import executor, nrd_api as api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header, pattern):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(pattern, text)))
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    lib = C.CDLL(product_lib)
+    nrd_syms = _declared("nrd_b200.h", r"NRD_API [^;(]*?\b(\w+)\(")
+    cu_syms = _declared("nrdcu.h", r"NRDCU_API [^;(]*?\b(nrdcu\w+)\(")
+    assert set(nrd_syms) == set(api.EXPORTED_SYMBOLS)
+    assert set(cu_syms) == set(executor.NRDCU_SYMBOLS)
+    for s in nrd_syms + cu_syms:
+        assert hasattr(lib, s), f"missing export {s}"
+
+
+def test_pod_sizes_match_reference_headers():
+    # measured by compiling the reference headers with g++ 13.3 (x86-64); static_asserted in include/nrd_b200.h too
+    assert C.sizeof(api.CommonSettings) == 432
+    assert C.sizeof(api.ReblurSettings) == 120
+    assert C.sizeof(api.SigmaSettings) == 20
+    assert C.sizeof(api.DispatchDesc) == 56
+    assert C.sizeof(api.PipelineDesc) == 320
+    assert C.sizeof(api.ResourceDesc) == 12
+    assert C.sizeof(api.InstanceDesc) == 112
+    assert C.sizeof(api.LibraryDesc) == 40
+    assert C.sizeof(api.InstanceCreationDesc) == 48
+
+
+def test_library_desc_and_strings(host_library):
+    d = host_library.library_desc()
+    assert (d.versionMajor, d.versionMinor) == (4, 17)
+    assert d.normalEncoding == 2 and d.roughnessEncoding == 1  # R10G10B10A2, linear roughness
+    sup = host_library.supported_denoisers()
+    assert int(api.Denoiser.REBLUR_DIFFUSE_SPECULAR) in sup and int(api.Denoiser.SIGMA_SHADOW) in sup
+    assert host_library.lib.GetDenoiserString(int(api.Denoiser.REBLUR_DIFFUSE_SPECULAR)) == b"REBLUR_DIFFUSE_SPECULAR"
+    assert host_library.lib.GetResourceTypeString(int(api.ResourceType.IN_VIEWZ)) == b"IN_VIEWZ"
+
+
+def test_error_behaviour(host_library):
+    # unsupported denoiser -> UNSUPPORTED (InstanceImpl.cpp:95-102); duplicate identifiers -> NON_UNIQUE_IDENTIFIER (:104-108)
+    inst = api.NrdInstance(host_library, [(0, api.Denoiser.REFERENCE)])
+    assert inst.result == api.Result.UNSUPPORTED
+    inst = api.NrdInstance(host_library, [(3, api.Denoiser.REBLUR_DIFFUSE_SPECULAR), (3, api.Denoiser.SIGMA_SHADOW)])
+    assert inst.result == api.Result.NON_UNIQUE_IDENTIFIER
+    inst = api.NrdInstance(host_library, [(1, api.Denoiser.REBLUR_DIFFUSE_SPECULAR)])
+    assert inst.result == api.Result.SUCCESS
+    # empty identifier list -> SUCCESS with 0 dispatches (:492-497); unknown identifier for settings -> INVALID_ARGUMENT (:484)
+    r, d = inst.get_compute_dispatches([])
+    assert r == api.Result.SUCCESS and d == []
+    assert inst.set_denoiser_settings(99, api.ReblurSettings()) == api.Result.INVALID_ARGUMENT
+    # invalid common settings (zero sizes) -> INVALID_ARGUMENT (:279-328, 453)
+    assert inst.set_common_settings(api.CommonSettings()) == api.Result.INVALID_ARGUMENT
+
+
+def test_executor_fails_loudly_without_gpu(product_lib):
+    import torch
+    if torch.cuda.is_available():
+        return
+    try:
+        executor.CudaDenoiser(api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 64, 64)
+    except executor.NrdcuError as e:
+        assert "no CUDA device" in str(e)
+    else:
+        raise AssertionError("nrdcuCreate must fail without a CUDA device (no CPU fallback)")

@@ -1,0 +1,105 @@
+"""Pins the host pass graph against the reference host library (External/NRD/Source/*.cpp compiled unmodified into
+oracle/_ref/libnrd_ref.so): InstanceDesc, pools, shader identifiers, per-frame dispatch order, bindings, ping-pong parity,
+grids, constant-buffer bytes. When /root/reference is not mounted (GPU box) the same streams are checked against the
+JSON snapshot tests/golden/dispatch_streams.json, which tests/golden/make_dispatch_golden.py wrote from the reference build."""
+import ctypes as C
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from nrd_sample_b200 import nrd_api as api, synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dispatch_streams.json")
+
+CASES = [
+    ("reblur_1080p", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 1920, 1080, None),
+    ("reblur_1440p", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 2560, 1440, None),
+    ("reblur_720p_recon_nots", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 1280, 720, "recon_nots"),
+    ("reblur_odd_noprepass", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 1000, 562, "noprepass"),
+    ("sigma_512", api.Denoiser.SIGMA_SHADOW, 512, 512, "sigma"),
+    ("sigma_nostab", api.Denoiser.SIGMA_SHADOW, 640, 360, "sigma_nostab"),
+]
+
+
+def _settings(kind):
+    if kind == "recon_nots":
+        return api.ReblurSettings(hitDistanceReconstructionMode=1, maxStabilizedFrameNum=0)
+    if kind == "noprepass":
+        return api.ReblurSettings(diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0, enableAntiFirefly=False)
+    if kind == "sigma":
+        return api.SigmaSettings(lightDirection=(C.c_float * 3)(0.0, 0.0, 1.0))
+    if kind == "sigma_nostab":
+        return api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0)
+    return None
+
+
+def capture(lib, denoiser, w, h, kind, frames=4):
+    """Everything observable through the descriptor API, as plain python."""
+    inst = api.NrdInstance(lib, [(7, denoiser)])
+    assert inst.result == api.Result.SUCCESS
+    d = inst.desc()
+    pd = d.descriptorPoolDesc
+    out = {
+        "desc": [d.constantBufferAndSamplersSpaceIndex, d.resourcesSpaceIndex, d.constantBufferRegisterIndex, d.samplersBaseRegisterIndex, d.resourcesBaseRegisterIndex,
+                 d.constantBufferMaxDataSize, d.samplersNum, d.pipelinesNum, d.permanentPoolSize, d.transientPoolSize],
+        "descriptor_pool": [pd.perSetTexturesMaxNum, pd.perSetStorageTexturesMaxNum, pd.totalTexturesNum, pd.totalStorageTexturesNum, pd.setsMaxNum],
+        "pools": [list(map(list, p)) for p in inst.pools()],
+        "shaders": inst.shader_identifiers(),
+        "ranges": [[(d.pipelines[i].resourceRanges[j].descriptorType, d.pipelines[i].resourceRanges[j].descriptorsNum) for j in range(d.pipelines[i].resourceRangesNum)]
+                   for i in range(d.pipelinesNum)],
+        "frames": [],
+    }
+    out["ranges"] = [[list(x) for x in r] for r in out["ranges"]]
+    s = _settings(kind)
+    for f in range(frames):
+        cs = synth.common_settings(f, w, h)
+        if f == 2:
+            cs.cameraJitter = (C.c_float * 2)(0.25, -0.125)
+        r1 = inst.set_common_settings(cs)
+        if s is not None:
+            inst.set_denoiser_settings(7, s)
+        r2, disp = inst.get_compute_dispatches([7])
+        out["frames"].append({"results": [int(r1), int(r2)], "dispatches": [
+            {"name": x.name, "shader": x.shader, "bindings": [[b.descriptor, b.type, b.index] for b in x.bindings], "grid": list(x.grid),
+             "pipeline": x.pipeline_index, "cb_same_as_prev": x.constants_match_previous, "cb": x.constants.hex()} for x in disp]})
+    return out
+
+
+def assert_same(mine, ref, label):
+    for key in ("desc", "descriptor_pool", "pools", "shaders", "ranges"):
+        assert mine[key] == ref[key], f"{label}: {key} differs"
+    assert len(mine["frames"]) == len(ref["frames"])
+    for f, (fm, fr) in enumerate(zip(mine["frames"], ref["frames"])):
+        assert fm["results"] == fr["results"], f"{label} frame {f}: result codes"
+        assert len(fm["dispatches"]) == len(fr["dispatches"]), f"{label} frame {f}: dispatch count"
+        for i, (a, b) in enumerate(zip(fm["dispatches"], fr["dispatches"])):
+            for key in ("name", "shader", "bindings", "grid", "pipeline", "cb_same_as_prev"):
+                assert a[key] == b[key], f"{label} frame {f} dispatch {i} ({b['name']}): {key}: {a[key]} != {b[key]}"
+            ca, cbb = bytes.fromhex(a["cb"]), bytes.fromhex(b["cb"])
+            assert len(ca) == len(cbb)
+            if not ca:
+                continue
+            ia, ib = np.frombuffer(ca, np.uint32), np.frombuffer(cbb, np.uint32)
+            fa, fb = np.frombuffer(ca, np.float32), np.frombuffer(cbb, np.float32)
+            differ = np.nonzero(ia != ib)[0]
+            # integers and almost all floats are bit-identical; rotators (MathLib's own sin/cos) and sums that cancel to ~0
+            # may differ in the last bits
+            assert len(differ) <= 16, f"{label} frame {f} dispatch {i}: {len(differ)} constant words differ"
+            for k in differ:
+                assert abs(fa[k] - fb[k]) <= 1e-6 + 1e-6 * abs(fb[k]), f"{label} frame {f} dispatch {i} word {k}: {fa[k]!r} vs {fb[k]!r}"
+
+
+@pytest.mark.parametrize("label,denoiser,w,h,kind", CASES)
+def test_stream_matches_reference_library(host_library, reference_host_library, label, denoiser, w, h, kind):
+    assert_same(capture(host_library, denoiser, w, h, kind), capture(reference_host_library, denoiser, w, h, kind), label)
+
+
+@pytest.mark.parametrize("label,denoiser,w,h,kind", CASES)
+def test_stream_matches_golden_snapshot(host_library, label, denoiser, w, h, kind):
+    if not os.path.exists(GOLDEN):
+        pytest.skip("golden snapshot not generated")
+    golden = json.load(open(GOLDEN))
+    assert_same(capture(host_library, denoiser, w, h, kind), golden[label], label)
