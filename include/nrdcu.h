@@ -10,7 +10,7 @@
  * Texture contract ("bit-identical layout"): pitch-linear 2D arrays in device memory, texel encodings exactly the
  * nrd::Format values (NRDDescs.h:264-322): IN_VIEWZ R32_SFLOAT, IN_MV RGBA16_SFLOAT, IN_NORMAL_ROUGHNESS
  * R10_G10_B10_A2_UNORM, IN/OUT_*_RADIANCE_HITDIST RGBA16_SFLOAT (YCoCg + normalised hit distance), IN_PENUMBRA
- * R16_SFLOAT, OUT_SHADOW_TRANSLUCENCY R8_UNORM. Rows must be 16-byte aligned (pitchBytes % 16 == 0).
+ * R16_SFLOAT, OUT_SHADOW_TRANSLUCENCY R8_UNORM. `data` and `pitchBytes` must be multiples of the texel size (pools owned by the executor use a 256-byte row pitch).
  *
  * Every function returns an nrd::Result value as uint32_t (0 = SUCCESS, 1 = FAILURE, 2 = INVALID_ARGUMENT,
  * 3 = UNSUPPORTED); nrdcuGetLastError() describes the last non-success on the calling thread.

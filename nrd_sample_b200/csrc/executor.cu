@@ -70,7 +70,7 @@ struct Binder {
             return v;
         }
         const nrdcuTexture& x = t[next];
-        if (x.format != (uint32_t)expect || !x.data || (x.pitchBytes & 1u) || x.pitchBytes < x.width * bytesPerTexel(x.format)) {
+        if (x.format != (uint32_t)expect || !x.data || (x.pitchBytes % bytesPerTexel(x.format)) != 0 || x.pitchBytes < x.width * bytesPerTexel(x.format)) {
             if (ok) {
                 char buf[256];
                 snprintf(buf, sizeof(buf), "%s: binding %u has format %u pitch %u (expected format %u)", shader, next, x.format, x.pitchBytes, (uint32_t)expect);

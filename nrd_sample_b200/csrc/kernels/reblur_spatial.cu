@@ -23,10 +23,13 @@ enum { DIFF = 0, SPEC = 1 };
 
 constexpr int BLOCK_W = 32, BLOCK_H = 8;
 
-static __device__ __constant__ float cSpecial8[8][3] = {
-    {-1.0f, 0.0f, 1.0f}, {0.0f, 1.0f, 1.0f}, {1.0f, 0.0f, 1.0f}, {0.0f, -1.0f, 1.0f},
-    {-0.35355339059327373f, 0.35355339059327373f, 0.5f}, {0.35355339059327373f, 0.35355339059327373f, 0.5f},
-    {0.35355339059327373f, -0.35355339059327373f, 0.5f}, {-0.35355339059327373f, -0.35355339059327373f, 0.5f}};
+// g_Special8 (Common.hlsli:207-218) as compile-time immediates: the tap loop is fully unrolled, so offsets fold into
+// FFMA immediates and the per-tap gaussian weight exp(-0.66 z^2), z in {1, 0.5}, becomes a literal.
+constexpr float kQ = 0.35355339059327373f;  // 0.25 * sqrt(2)
+__device__ constexpr float kSpecial8X[8] = {-1.0f, 0.0f, 1.0f, 0.0f, -kQ, kQ, kQ, -kQ};
+__device__ constexpr float kSpecial8Y[8] = {0.0f, 1.0f, 0.0f, -1.0f, kQ, kQ, -kQ, -kQ};
+constexpr float kGaussOuter = 0.5168513209367337f;  // exp(-0.66f * 1.0 * 1.0)
+constexpr float kGaussInner = 0.8478936985286916f;  // exp(-0.66f * 0.5 * 0.5)
 
 struct Center {
     int px, py;
@@ -124,7 +127,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
 
 #pragma unroll
         for (int n = 0; n < 8; n++) {
-            const float ox = cSpecial8[n][0], oy = cSpecial8[n][1], oz = cSpecial8[n][2];
+            const float ox = kSpecial8X[n], oy = kSpecial8Y[n];
 
             float2 uv;
             if (SCREEN_SPACE) {
@@ -141,16 +144,16 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             // outcome hangs on the last mantissa bits of uv (see DESIGN.md "chaotic predicates"); the robust variant
             // (debug flag, used by the strict parity tests) asks the intended question: did the tap leave the screen?
             bool mirrored = robustMirrorTest ? (uv.x < 0.0f || uv.y < 0.0f || uv.x >= 1.0f || uv.y >= 1.0f) : (uv.x != muv.x || uv.y != muv.y);
-            float w = mirrored ? 1.0f : gaussianWeight(oz);
+            float w = mirrored ? 1.0f : (n < 4 ? kGaussOuter : kGaussInner);
 
             float2 posf = muv * rectSize;
             int tx = (int)posf.x, ty = (int)posf.y;
 
-            float zs = unpackViewZ(cb, viewZTex.load(tx, ty));
+            float zs = unpackViewZ(cb, viewZTex.fetch(tx, ty));  // mirrorUv() < 1 keeps every tap inside the rect: no bounds checks
             float3 Xvs = reconstructViewPosition(make_float2(tx + 0.5f, ty + 0.5f) * rectSizeInv, cb.frustum, zs, cb.orthoMode);
 
             float materialIDs;
-            float4 Ns = unpackNormalRoughness(nrTex.loadRaw(tx, ty), materialIDs);
+            float4 Ns = unpackNormalRoughness(nrTex.fetchRaw(tx, ty), materialIDs);
 
             float angle = acosApproxPositive(dot(s.N, xyz(Ns)));
             float NoX = dot(s.Nv, Xvs);
@@ -160,7 +163,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             if (LOBE == SPEC) w *= nonExponentialWeight(Ns.w, roughParams.x, roughParams.y);
             w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
 
-            float4 smp = input.load(tx, ty);
+            float4 smp = input.fetch(tx, ty);
             smp = w == 0.0f ? f4(0.0f) : smp;
 
             if (PASS == PRE_PASS && LOBE == SPEC) {

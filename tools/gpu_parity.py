@@ -1,5 +1,5 @@
 import sys, time, torch, ctypes as C
-sys.path.insert(0, '.')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nrd_sample_b200 import nrd_api as api, synth, executor as ex
 from oracle import runner
 from tests.util import compare
