@@ -262,6 +262,8 @@ NRD_DEV float4 specularDominantDirectionG2(float3 N, float3 V, float roughness) 
 }
 
 // NRD.hlsli
+// materialID = alpha * 3 with alpha the 2-bit UNORM channel; ONE expression everywhere so equal IDs compare equal
+NRD_DEV float materialFromRaw(uint32_t raw) { return (float)(raw >> 30) * (1.0f / 3.0f) * 3.0f; }
 NRD_DEV float4 unpackNormalRoughness(uint32_t raw, float& materialID) {
     float4 p = TexNR::decode(raw);
     float t = p.z * 2.0f - 1.0f;
@@ -269,7 +271,7 @@ NRD_DEV float4 unpackNormalRoughness(uint32_t raw, float& materialID) {
     n.x = p.x - p.y;
     n.y = p.x + p.y - 1.0f;
     n.z = (t < 0.0f ? -1.0f : 1.0f) * (1.0f - fabsf(n.x) - fabsf(n.y));
-    materialID = p.w * 3.0f;
+    materialID = materialFromRaw(raw);
     n = n * (1.0f / sqrtf(dot(n, n) + 1e-9f));
     return f4(n, fabsf(t));
 }

@@ -26,7 +26,8 @@ constexpr int HF_BORDER = 4;  // REBLUR_ANTI_FIREFLY_FILTER_RADIUS
 constexpr int HF_TILE_W = BLOCK_W + 2 * HF_BORDER, HF_TILE_H = BLOCK_H + 2 * HF_BORDER;
 
 template <int LOBE>
-NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p, const float (*sLuma)[HF_TILE_W], int px, int py, float strideIn, float frameNum,
+NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p, const float (*sLuma)[HF_TILE_W], const float2 (*sRow)[HF_TILE_H][BLOCK_W], bool tileHasSky,
+                            int px, int py, float strideIn, float frameNum,
                             float frameNumAvgNorm, float viewZ, float materialID, float3 N, float roughness, float3 Nv, float3 Xv, float frustumSize, float2 pixelUv) {
     const TexRGBA16F& in = LOBE == DIFF ? p.inDiff : p.inSpec;
     const TexRGBA16F& out = LOBE == DIFF ? p.outDiff : p.outSpec;
@@ -106,22 +107,42 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
     // Local variance: 5x5 for the fast-history clamp, 9x9 minus the central 3x3 for the anti-firefly clamp
     float fastM1 = fastCenter, fastM2 = fastCenter * fastCenter;
     float antiFireflyM1 = 0.0f, antiFireflyM2 = 0.0f;
+    if (!tileHasSky) {
+        // Separable box sums: the CTA already reduced every tile row over the 3 / 5 / 9 wide windows (packed { v, v^2 });
+        // each thread adds 3 + 5 + 9 row sums with FADD2 instead of walking 80 texels. The centre texel enters the
+        // reference's sums as `fastCenter`, not as its stored value, hence the "- centre" terms.
+        const int x = threadIdx.x, y = threadIdx.y + HF_BORDER;
+        float2 s3 = sRow[0][y][x], s5 = sRow[1][y][x], s9 = sRow[2][y][x];
 #pragma unroll
-    for (int j = -HF_BORDER; j <= HF_BORDER; j++)
-#pragma unroll
-        for (int i = -HF_BORDER; i <= HF_BORDER; i++) {
-            if (i == 0 && j == 0) continue;
-            float d = sLuma[sy + j][sx + i];
-            d = d == REBLUR_INVALID ? fastCenter : d;
-            if (abs(i) <= 2 && abs(j) <= 2) {
-                fastM1 += d;
-                fastM2 += d * d;
-            }
-            if (!(abs(i) <= 1 && abs(j) <= 1)) {
-                antiFireflyM1 += d;
-                antiFireflyM2 += d * d;
-            }
+        for (int j = 1; j <= HF_BORDER; j++) {
+            if (j <= 1) s3 = __fadd2_rn(s3, __fadd2_rn(sRow[0][y - j][x], sRow[0][y + j][x]));
+            if (j <= 2) s5 = __fadd2_rn(s5, __fadd2_rn(sRow[1][y - j][x], sRow[1][y + j][x]));
+            s9 = __fadd2_rn(s9, __fadd2_rn(sRow[2][y - j][x], sRow[2][y + j][x]));
         }
+        const float vc = sLuma[sy][sx];
+        fastM1 += s5.x - vc;
+        fastM2 += s5.y - vc * vc;
+        antiFireflyM1 = s9.x - s3.x;
+        antiFireflyM2 = s9.y - s3.y;
+    } else {
+        // Tiles touching the sky keep the reference's per-texel walk: invalid texels are replaced by this pixel's own value
+#pragma unroll 1
+        for (int j = -HF_BORDER; j <= HF_BORDER; j++)
+#pragma unroll
+            for (int i = -HF_BORDER; i <= HF_BORDER; i++) {
+                if (i == 0 && j == 0) continue;
+                float d = sLuma[sy + j][sx + i];
+                d = d == REBLUR_INVALID ? fastCenter : d;
+                if (abs(i) <= 2 && abs(j) <= 2) {
+                    fastM1 += d;
+                    fastM2 += d * d;
+                }
+                if (!(abs(i) <= 1 && abs(j) <= 1)) {
+                    antiFireflyM1 += d;
+                    antiFireflyM2 += d * d;
+                }
+            }
+    }
 
     if (cb.antiFirefly != 0.0f) {
         const float invNorm = 1.0f / ((HF_BORDER * 2 + 1) * (HF_BORDER * 2 + 1) - 3 * 3);
@@ -147,20 +168,43 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HistoryFixParams p, int quads) {
     __shared__ float sDiffLuma[HF_TILE_H][HF_TILE_W];
     __shared__ float sSpecLuma[HF_TILE_H][HF_TILE_W];
+    // row sums of { v, v^2 } over windows of 3 / 5 / 9 texels centred on the 32 interior columns, per lobe
+    __shared__ float2 sDiffRow[3][HF_TILE_H][BLOCK_W];
+    __shared__ float2 sSpecRow[3][HF_TILE_H][BLOCK_W];
 
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int tid = threadIdx.y * BLOCK_W + threadIdx.x;
+    int sawSky = 0;
     {
         const int baseX = blockIdx.x * BLOCK_W - HF_BORDER, baseY = blockIdx.y * BLOCK_H - HF_BORDER;
-        const int tid = threadIdx.y * BLOCK_W + threadIdx.x;
         for (int i = tid; i < HF_TILE_W * HF_TILE_H; i += BLOCK_W * BLOCK_H) {
             int sx = i % HF_TILE_W, sy = i / HF_TILE_W;
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
             bool sky = !inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.load(gx, gy)));
+            sawSky |= sky ? 1 : 0;
             sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : p.inDiffFast.load(gx, gy);
             sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : p.inSpecFast.load(gx, gy);
         }
     }
-    __syncthreads();
+    const bool tileHasSky = __syncthreads_or(sawSky) != 0;  // also the barrier that publishes the tile
+    if (!tileHasSky) {
+        for (int i = tid; i < HF_TILE_H * BLOCK_W; i += BLOCK_W * BLOCK_H) {
+            const int x = i % BLOCK_W, y = i / BLOCK_W, c = x + HF_BORDER;
+            auto sq = [](float v) { return make_float2(v, v * v); };
+            auto rowSums = [&](const float(*t)[HF_TILE_W], float2(*r)[HF_TILE_H][BLOCK_W]) {
+                float2 a = __fadd2_rn(sq(t[y][c]), __fadd2_rn(sq(t[y][c - 1]), sq(t[y][c + 1])));
+                r[0][y][x] = a;
+                a = __fadd2_rn(a, __fadd2_rn(sq(t[y][c - 2]), sq(t[y][c + 2])));
+                r[1][y][x] = a;
+                a = __fadd2_rn(a, __fadd2_rn(sq(t[y][c - 3]), sq(t[y][c + 3])));
+                a = __fadd2_rn(a, __fadd2_rn(sq(t[y][c - 4]), sq(t[y][c + 4])));
+                r[2][y][x] = a;
+            };
+            rowSums(sDiffLuma, sDiffRow);
+            rowSums(sSpecLuma, sSpecRow);
+        }
+        __syncthreads();
+    }
 
     // Quad exchange first (HistoryFix.cs.hlsl:56-74): all lanes stay until it is done
     const bool skyTile = p.tiles.load(px >> 4, py >> 4) != 0.0f;
@@ -192,8 +236,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const
     stride *= 2.0f / 2.0f;
     stride *= materialID == cb.historyFixAlternatePixelStrideMaterialID ? cb.historyFixAlternatePixelStride : cb.historyFixBasePixelStride;
 
-    historyFixLobe<DIFF>(cb, p, sDiffLuma, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
-    historyFixLobe<SPEC>(cb, p, sSpecLuma, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+    historyFixLobe<DIFF>(cb, p, sDiffLuma, sDiffRow, tileHasSky, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+    historyFixLobe<SPEC>(cb, p, sSpecLuma, sSpecRow, tileHasSky, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
 }
 
 // ===============================================================================================================
@@ -224,7 +268,10 @@ NRD_DEV void lumaMoments3x3(const float (*sLuma)[TS_TILE_W], float& luma, float&
 }
 }  // namespace
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurTemporalStabilizationKernel(const __grid_constant__ ReblurConstants cb,
+#ifndef TS_MIN_BLOCKS
+#    define TS_MIN_BLOCKS 3  // 512-thread CTAs: 40 regs + a small spill (3 CTAs / SM) beats 64 regs (2 CTAs) by 12 % on B200
+#endif
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTemporalStabilizationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                        const __grid_constant__ TemporalStabilizationParams p) {
     __shared__ float sDiffLuma[TS_TILE_H][TS_TILE_W];
     __shared__ float sSpecLuma[TS_TILE_H][TS_TILE_W];

@@ -12,6 +12,11 @@
 // radius: they hit L1/L2, not HBM, so no shared-memory staging is attempted (a TMA box cannot follow a per-pixel
 // rotated, mirrored, lobe-projected footprint). Diffuse and specular share the centre set-up and run back to back
 // in one kernel so G-buffer lines fetched by one lobe are still in L1 for the other.
+//
+// The kernels are issue-bound on fp32 arithmetic (ncu: ~80 % issue-slot utilisation, DRAM < 5 %), so the tap loop is
+// written for Blackwell's packed fp32x2 pipe: taps n and n+4 (outer / inner ring of g_Special8) advance in lock step as
+// the two lanes of FFMA2 / FMUL2 / FADD2 (pairmath.cuh); only loads, conversions, MUFU and min/max/abs stay scalar.
+#include "pairmath.cuh"
 #include "reblur_common.cuh"
 
 namespace nrdk {
@@ -22,9 +27,13 @@ enum { PRE_PASS = 0, BLUR = 1, POST_BLUR = 2 };
 enum { DIFF = 0, SPEC = 1 };
 
 constexpr int BLOCK_W = 32, BLOCK_H = 8;
+#ifndef SPATIAL_MIN_BLOCKS
+#    define SPATIAL_MIN_BLOCKS 4  // resident CTAs per SM the register allocator must leave room for: 64 regs + a 32-48 B spill beats
+                                 // 80 regs (3 CTAs) and 124 regs (2 CTAs) by 5 % / 13 % on B200 (profiles/README.md)
+#endif
 
-// g_Special8 (Common.hlsli:207-218) as compile-time immediates: the tap loop is fully unrolled, so offsets fold into
-// FFMA immediates and the per-tap gaussian weight exp(-0.66 z^2), z in {1, 0.5}, becomes a literal.
+// g_Special8 (Common.hlsli:207-218) as compile-time immediates: the pair loop is fully unrolled, offsets fold into the
+// instruction stream and the per-tap gaussian weight exp(-0.66 z^2), z in {1, 0.5}, becomes a literal.
 constexpr float kQ = 0.35355339059327373f;  // 0.25 * sqrt(2)
 __device__ constexpr float kSpecial8X[8] = {-1.0f, 0.0f, 1.0f, 0.0f, -kQ, kQ, kQ, -kQ};
 __device__ constexpr float kSpecial8Y[8] = {0.0f, 1.0f, 0.0f, -1.0f, kQ, kQ, -kQ, -kQ};
@@ -52,6 +61,17 @@ NRD_DEV void setupCenter(const ReblurConstants& cb, Center& s, const TexNR& norm
     s.rotator = make_float4(baseRotator[0], baseRotator[1], baseRotator[2], baseRotator[3]);
 }
 
+// Math::SmoothStep( 1, 0, |y| ) for a pair
+NRD_DEV P2 nonExponentialWeight2(P2 y) {
+    P2 s = oneMinusAbsSat2(y);
+    return (s * s) * fma2(s, -2.0f, 3.0f);
+}
+// ExpApprox( -3 |y| ) = 1 / ( x^2 - x + 1 ), x = -3 |y|
+NRD_DEV P2 exponentialWeight2(P2 y) {
+    P2 x = absMul2(y, -3.0f);
+    return rcp2(fma2(x, x, fma2(x, -1.0f, 1.0f)));
+}
+
 // One lobe of one spatial pass for one pixel
 template <int PASS, int LOBE>
 NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const TexR32F& viewZTex, const TexNR& nrTex, const TexRGBA16F& input,
@@ -68,8 +88,14 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
     float4 result = input.load(s.px, s.py);
 
     if (PASS != PRE_PASS || MAX_BLUR_RADIUS != 0.0f) {
-        Rng rng;
-        if (PASS == PRE_PASS && LOBE == SPEC) rng.init((uint32_t)s.px, (uint32_t)s.py, cb.frameIndex);
+        // Stochastic tracking decisions of the specular pre-pass consume one random number per tap, in tap order
+        float rnd[8];
+        if (PASS == PRE_PASS && LOBE == SPEC) {
+            Rng rng;
+            rng.init((uint32_t)s.px, (uint32_t)s.py, cb.frameIndex);
+#pragma unroll
+            for (int n = 0; n < 8; n++) rnd[n] = rng.next();
+        }
 
         constexpr float radiusScale = PASS == POST_BLUR ? 2.0f : 1.0f;
         constexpr float fractionScale = PASS == PRE_PASS ? 2.0f : (PASS == BLUR ? 1.0f : 0.5f);
@@ -94,15 +120,18 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             blurRadius = fminf(blurRadius, lobeRadius);
         }
 
-        float2 geomParams = geometryWeightParams(cb.planeDistSensitivity, s.frustumSize, s.Xv, s.Nv);
-        float normalParam = normalWeightParam(NLAS, cb.lobeAngleFraction, ROUGHNESS) / fractionScale;
-        float2 roughParams = roughnessWeightParams(ROUGHNESS, cb.roughnessFraction * fractionScale);
-        float2 hitDistParams = hitDistanceWeightParams(result.w, NLAS);
+        const float2 geomParams = geometryWeightParams(cb.planeDistSensitivity, s.frustumSize, s.Xv, s.Nv);
+        const float normalParam = normalWeightParam(NLAS, cb.lobeAngleFraction, ROUGHNESS) / fractionScale;
+        const float2 roughParams = roughnessWeightParams(ROUGHNESS, cb.roughnessFraction * fractionScale);
+        const float2 hitDistParams = hitDistanceWeightParams(result.w, NLAS);
         float minHitDistWeight = cb.minHitDistanceWeight * fractionScale * smc;
         if (PASS != PRE_PASS) minHitDistWeight *= NLAS;
+        const float centerMaterial = fmaxf(s.materialID, MIN_MATERIAL);
 
+        // Tap placement. Screen space: uv = pixelUv + R * offset with the blur-radius-scaled rotator R. World space:
+        // clip = M * ( Xv + T o.x + B o.y ) is expanded once per pixel into C + A o.x + B' o.y (rows x, y, w of M only).
         float4 scaledRotator = f4(0.0f);
-        float3 Tv = f3(0.0f), Bv = f3(0.0f);
+        float3 clipC = f3(0.0f), clipA = f3(0.0f), clipB = f3(0.0f);
         if (SCREEN_SPACE) {
             float2 skew = f2(1.0f);
             if (PASS != PRE_PASS && LOBE == DIFF) {
@@ -118,72 +147,138 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             skewFactor = lerp(1.0f, skewFactor, bentFactor);
             float3 bentDv = normalize(lerp(s.Nv, xyz(Dv), bentFactor));
             float worldRadius = pixelRadiusToWorld(cb.unproject, cb.orthoMode, blurRadius, s.viewZ);
+            float3 Tv, Bv;
             kernelBasis(bentDv, s.Nv, Tv, Bv);
             Tv *= worldRadius * skewFactor;
             Bv *= worldRadius / skewFactor;
+            const Mat4& M = cb.viewToClip;
+            auto rows = [&](float3 v, float w) {
+                return make_float3(M.m[0] * v.x + M.m[4] * v.y + M.m[8] * v.z + M.m[12] * w, M.m[1] * v.x + M.m[5] * v.y + M.m[9] * v.z + M.m[13] * w,
+                                   M.m[3] * v.x + M.m[7] * v.y + M.m[11] * v.z + M.m[15] * w);
+            };
+            clipC = rows(s.Xv, 1.0f);
+            clipA = rows(Tv, 0.0f);
+            clipB = rows(Bv, 0.0f);
         }
+
+        // view-space ray through the centre of texel (tx, ty): ray = ( tx + 0.5 ) / rect * frustum.zw + frustum.xy, folded into one FMA
+        const float rayMulX = rectSizeInv.x * cb.frustum[2], rayAddX = 0.5f * rectSizeInv.x * cb.frustum[2] + cb.frustum[0];
+        const float rayMulY = rectSizeInv.y * cb.frustum[3], rayAddY = 0.5f * rectSizeInv.y * cb.frustum[3] + cb.frustum[1];
+        const bool perspective = cb.orthoMode == 0.0f;
 
         float hitDistForTracking = hitDist == 0.0f ? NRD_INF : hitDist;
+        P2 sum2(0.0f);
+        P2 accX(0.0f), accY(0.0f), accZ(0.0f), accW(0.0f);
 
 #pragma unroll
-        for (int n = 0; n < 8; n++) {
-            const float ox = kSpecial8X[n], oy = kSpecial8Y[n];
+        for (int pair = 0; pair < 4; pair++) {
+            const int na = pair, nb = pair + 4;
+            const P2 OX(kSpecial8X[na], kSpecial8X[nb]), OY(kSpecial8Y[na], kSpecial8Y[nb]);
 
-            float2 uv;
+            P2 ux, uy;
             if (SCREEN_SPACE) {
-                uv = s.pixelUv + rotate2(scaledRotator, make_float2(ox, oy));
+                ux = fma2(OY, scaledRotator.y, fma2(OX, scaledRotator.x, P2(s.pixelUv.x)));
+                uy = fma2(OY, scaledRotator.w, fma2(OX, scaledRotator.z, P2(s.pixelUv.y)));
             } else {
-                float2 o = rotate2(s.rotator, make_float2(ox, oy));
-                float3 p = s.Xv + Tv * o.x + Bv * o.y;
-                float4 clip = mulM4(cb.viewToClip, f4(p, 1.0f));
-                uv = make_float2(clip.x / clip.w, -(clip.y / clip.w)) * 0.5f + 0.5f;
+                // rotated unit offsets are uniform per tap
+                P2 ox = fma2(OY, s.rotator.y, OX * s.rotator.x), oy = fma2(OY, s.rotator.w, OX * s.rotator.z);
+                P2 cx = fma2(oy, clipB.x, fma2(ox, clipA.x, P2(clipC.x)));
+                P2 cy = fma2(oy, clipB.y, fma2(ox, clipA.y, P2(clipC.y)));
+                P2 cw = fma2(oy, clipB.z, fma2(ox, clipA.z, P2(clipC.z)));
+                P2 iw = rcp2(cw) * 0.5f;
+                ux = fma2(cx, iw, 0.5f);
+                uy = fma2(cy * -1.0f, iw, 0.5f);
             }
 
-            float2 muv = mirrorUv(uv);
+            // MirrorUv (Common.hlsli:312-318): 1 - | 1 - frac( uv / 2 ) * 2 |, capped below 1
+            P2 hx = ux * 0.5f, hy = uy * 0.5f;
+            P2 mx = min2(oneMinusAbsSat2(fma2(hx - floor2(hx), -2.0f, 1.0f)), 0.99999f);
+            P2 my = min2(oneMinusAbsSat2(fma2(hy - floor2(hy), -2.0f, 1.0f)), 0.99999f);
             // Reference predicate: any( uv != mirrorUv ). For in-screen taps mirrorUv = 1 - ( 1 - uv ) re-rounds uv, so the
-            // outcome hangs on the last mantissa bits of uv (see DESIGN.md "chaotic predicates"); the robust variant
-            // (debug flag, used by the strict parity tests) asks the intended question: did the tap leave the screen?
-            bool mirrored = robustMirrorTest ? (uv.x < 0.0f || uv.y < 0.0f || uv.x >= 1.0f || uv.y >= 1.0f) : (uv.x != muv.x || uv.y != muv.y);
-            float w = mirrored ? 1.0f : (n < 4 ? kGaussOuter : kGaussInner);
+            // outcome hangs on the last mantissa bits of uv (DESIGN.md "chaotic predicates"); the robust variant (debug
+            // flag, used by the strict parity tests) asks the intended question: did the tap leave the screen?
+            bool mirA, mirB;
+            if (robustMirrorTest) {
+                mirA = ux.a() < 0.0f || uy.a() < 0.0f || ux.a() >= 1.0f || uy.a() >= 1.0f;
+                mirB = ux.b() < 0.0f || uy.b() < 0.0f || ux.b() >= 1.0f || uy.b() >= 1.0f;
+            } else {
+                mirA = ux.a() != mx.a() || uy.a() != my.a();
+                mirB = ux.b() != mx.b() || uy.b() != my.b();
+            }
+            P2 w(mirA ? 1.0f : kGaussOuter, mirB ? 1.0f : kGaussInner);
 
-            float2 posf = muv * rectSize;
-            int tx = (int)posf.x, ty = (int)posf.y;
+            // texel coordinates: mirrorUv() < 1 keeps every tap inside the rect, so fetches need no bounds checks
+            P2 fx = floor2(mx * rectSize.x), fy = floor2(my * rectSize.y);
+            const int txa = (int)fx.a(), tya = (int)fy.a(), txb = (int)fx.b(), tyb = (int)fy.b();
 
-            float zs = unpackViewZ(cb, viewZTex.fetch(tx, ty));  // mirrorUv() < 1 keeps every tap inside the rect: no bounds checks
-            float3 Xvs = reconstructViewPosition(make_float2(tx + 0.5f, ty + 0.5f) * rectSizeInv, cb.frustum, zs, cb.orthoMode);
+            const float zRawA = viewZTex.fetch(txa, tya), zRawB = viewZTex.fetch(txb, tyb);
+            const uint32_t nrA = nrTex.fetchRaw(txa, tya), nrB = nrTex.fetchRaw(txb, tyb);
+            float4 smpA = input.fetch(txa, tya), smpB = input.fetch(txb, tyb);
 
-            float materialIDs;
-            float4 Ns = unpackNormalRoughness(nrTex.fetchRaw(tx, ty), materialIDs);
+            P2 zs = absMul2(P2(zRawA, zRawB), fabsf(cb.viewZScale));  // UnpackViewZ: | z * scale |
+            P2 rx = fma2(fx, rayMulX, rayAddX), ry = fma2(fy, rayMulY, rayAddY);
+            P2 sxy = perspective ? zs : P2(cb.orthoMode);
 
-            float angle = acosApproxPositive(dot(s.N, xyz(Ns)));
-            float NoX = dot(s.Nv, Xvs);
+            // normal + roughness + material of both taps (NRD.hlsli:387-400, 656-684)
+            P2 px10((float)(nrA & 1023u), (float)(nrB & 1023u)), py10((float)((nrA >> 10) & 1023u), (float)((nrB >> 10) & 1023u));
+            P2 pz10((float)((nrA >> 20) & 1023u), (float)((nrB >> 20) & 1023u));
+            px10 = px10 * (1.0f / 1023.0f);
+            py10 = py10 * (1.0f / 1023.0f);
+            P2 t = fma2(pz10, 2.0f / 1023.0f, -1.0f);
+            P2 nx = px10 - py10, ny = (px10 + py10) + -1.0f;
+            // ( 1 - |nx| ) - |ny| with the sign of t: scalar FADDs so the |.| modifiers fold into the instructions
+            const float nzA = (1.0f - fabsf(nx.a())) - fabsf(ny.a()), nzB = (1.0f - fabsf(nx.b())) - fabsf(ny.b());
+            P2 nz(t.a() < 0.0f ? -nzA : nzA, t.b() < 0.0f ? -nzB : nzB);
+            P2 invLen = rsqrt2(fma2(nz, nz, fma2(ny, ny, fma2(nx, nx, 1e-9f))));
+            P2 cosa = fma2(nz, s.N.z, fma2(ny, s.N.y, nx * s.N.x)) * invLen;
+            P2 roughS = abs2(t);
+            const float matA = fmaxf(materialFromRaw(nrA), MIN_MATERIAL), matB = fmaxf(materialFromRaw(nrB), MIN_MATERIAL);
 
-            w *= compareMaterials(s.materialID, materialIDs, MIN_MATERIAL) ? 1.0f : 0.0f;
-            w *= nonExponentialWeight(angle, normalParam, 0.0f);
-            if (LOBE == SPEC) w *= nonExponentialWeight(Ns.w, roughParams.x, roughParams.y);
-            w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
+            // Math::AcosApproxPositive
+            P2 cs = sat2(cosa);
+            P2 angle = fma2(cs, 1.399331f - 1.567589f, 1.567589f) * sqrt2(satOneMinus2(cosa));
 
-            float4 smp = input.fetch(tx, ty);
-            smp = w == 0.0f ? f4(0.0f) : smp;
+            w = sel2(matA == centerMaterial, matB == centerMaterial, w, P2(0.0f));
+            w = w * nonExponentialWeight2(angle * normalParam);
+            if (LOBE == SPEC) w = w * nonExponentialWeight2(fma2(roughS, roughParams.x, roughParams.y));
+            // plane distance: NoX = dot( Nv, Xvs ), Xvs = ( ray.xy * sxy, zs )
+            P2 NoX = fma2(zs, s.Nv.z, sxy * fma2(ry, s.Nv.y, rx * s.Nv.x));
+            w = w * nonExponentialWeight2(fma2(NoX, geomParams.x, geomParams.y));
+            w = sel2(zs.a() < cb.denoisingRange, zs.b() < cb.denoisingRange, w, P2(0.0f));
+
+            // Denanify
+            if (w.a() == 0.0f) smpA = f4(0.0f);
+            if (w.b() == 0.0f) smpB = f4(0.0f);
+            P2 sw(smpA.w, smpB.w);
 
             if (PASS == PRE_PASS && LOBE == SPEC) {
-                float hs = smp.w * hitDistanceNormalization(zs, cb.hitDistSettings, Ns.w);
-                float geometryWeight = w * s.NoV * (hs != 0.0f ? 1.0f : 0.0f);
-                if (rng.next() < geometryWeight) hitDistForTracking = fminf(hitDistForTracking, hs);
+                // hit distance for tracking: stochastic min over taps weighted by their geometry weight
+                P2 smcS(specMagicCurve(roughS.a(), 0.5f), specMagicCurve(roughS.b(), 0.5f));
+                P2 hs = sw * (fma2(zs, cb.hitDistSettings[1], cb.hitDistSettings[0]) * fma2(smcS, 1.0f - cb.hitDistSettings[2], cb.hitDistSettings[2]));
+                P2 geometryWeight = w * s.NoV;
+                if (hs.a() != 0.0f && rnd[na] < geometryWeight.a()) hitDistForTracking = fminf(hitDistForTracking, hs.a());
+                if (hs.b() != 0.0f && rnd[nb] < geometryWeight.b()) hitDistForTracking = fminf(hitDistForTracking, hs.b());
 
-                w *= cb.usePrepassNotOnlyForSpecularMotionEstimation;
+                w = w * cb.usePrepassNotOnlyForSpecularMotionEstimation;
 
-                float d = length(Xvs - s.Xv) + NRD_EPS;
-                float t = hs / (d + hitDist);
-                w *= lerp(saturate(t), 1.0f, linearStep(0.5f, 1.0f, ROUGHNESS));
+                P2 dx = fma2(rx, sxy, -s.Xv.x), dy = fma2(ry, sxy, -s.Xv.y), dz = zs - s.Xv.z;
+                P2 d = sqrt2(fma2(dz, dz, fma2(dy, dy, dx * dx))) + NRD_EPS;
+                P2 tt = mulSat2(hs, rcp2(d + hitDist));
+                float k = linearStep(0.5f, 1.0f, ROUGHNESS);
+                w = w * fma2(tt, 1.0f - k, k);  // lerp( saturate( t ), 1, k ) = t ( 1 - k ) + k
             }
 
-            w *= minHitDistWeight + exponentialWeight(smp.w, hitDistParams.x, hitDistParams.y);
+            w = w * (exponentialWeight2(fma2(sw, hitDistParams.x, hitDistParams.y)) + minHitDistWeight);
 
-            sum += w;
-            result += smp * w;
+            sum2 = sum2 + w;
+            accX = fma2(P2(smpA.x, smpB.x), w, accX);
+            accY = fma2(P2(smpA.y, smpB.y), w, accY);
+            accZ = fma2(P2(smpA.z, smpB.z), w, accZ);
+            accW = fma2(sw, w, accW);
         }
 
+        sum += sum2.a() + sum2.b();
+        result += make_float4(accX.a() + accX.b(), accY.a() + accY.b(), accZ.a() + accZ.b(), accW.a() + accW.b());
         result *= positiveRcp(sum);
         if (PASS != PRE_PASS) result.w = hitDist / hitDistScale;
         if (PASS == PRE_PASS && LOBE == SPEC) outSpecHitDistForTracking->store(s.px, s.py, hitDistForTracking == NRD_INF ? 0.0f : hitDistForTracking);
@@ -209,7 +304,7 @@ __global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_co
     if (threadIdx.x == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags) {
     const bool robust = (flags & 2) != 0;
     Center s;
     s.px = blockIdx.x * BLOCK_W + threadIdx.x;
@@ -237,7 +332,7 @@ NRD_DEV float2 quadSmoothedAccumSpeed(const ReblurConstants& cb, float2 data1, f
     return n;
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
     s.px = blockIdx.x * BLOCK_W + threadIdx.x;
@@ -260,7 +355,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurBlurKernel(const __gri
 }
 
 template <bool TEMPORAL_STABILIZATION>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
     s.px = blockIdx.x * BLOCK_W + threadIdx.x;

@@ -39,7 +39,10 @@ NRD_DEV uint4 gather4(const TexR16U& t, int x0, int y0) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurTemporalAccumulationKernel(const __grid_constant__ ReblurConstants cb,
+#ifndef TA_MIN_BLOCKS
+#    define TA_MIN_BLOCKS 3  // 80 regs + 88 B spill (3 CTAs / SM): 450 us vs 514 us at 128 regs (2 CTAs) for a 1440p frame on B200
+#endif
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTemporalAccumulationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                       const __grid_constant__ TemporalAccumulationParams p) {
     __shared__ float4 sNormalHitDist[TILE_H][TILE_W];
 
