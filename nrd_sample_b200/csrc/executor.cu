@@ -81,7 +81,7 @@ struct Binder {
         v.data = (uint8_t*)x.data;
         v.w = (int)x.width;
         v.h = (int)x.height;
-        v.pitch = (int)x.pitchBytes;
+        v.pitch = (int)(x.pitchBytes / (bytesPerTexel(x.format) ? bytesPerTexel(x.format) : 1u));  // in texels (see TexView)
         next++;
         return v;
     }

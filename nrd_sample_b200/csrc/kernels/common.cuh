@@ -25,15 +25,27 @@ constexpr float NRD_MAX_PERCENT_OF_LOBE_VOLUME = 0.75f;
 constexpr float ML_SMALL_EPS = 1e-15f;
 constexpr float ML_EPS = 1e-6f;
 
+// CTA order (Common.hlsli:125-136, NRD_CTA_ORDER_REVERSED / _DEFAULT): consecutive passes walk the tile grid in opposite
+// directions, so a pass starts on the tiles its producer wrote last and still finds them in the 126 MB L2.
+// NRD_CTA_REV_MASK bits: 0 PrePass, 1 TemporalAccumulation, 2 HistoryFix, 3 Blur, 4 PostBlur, 5 TemporalStabilization.
+#ifndef NRD_CTA_REV_MASK
+#define NRD_CTA_REV_MASK 0x35  // the reference's pattern: PrePass, HistoryFix, PostBlur, TemporalStabilization reversed
+#endif
+template <int BIT> NRD_DEV int2 ctaTile() {
+    if ((NRD_CTA_REV_MASK >> BIT) & 1) return make_int2((int)(gridDim.x - 1u - blockIdx.x), (int)(gridDim.y - 1u - blockIdx.y));
+    return make_int2((int)blockIdx.x, (int)blockIdx.y);
+}
+
 // =================================================================================================================
 // Texture views. One struct per storage format so every access compiles to a single fixed-width LDG/STG.
 // =================================================================================================================
 struct TexView {
     uint8_t* data;
-    int w, h, pitch;
+    int w, h, pitch;  // pitch in TEXELS (the executor divides the byte pitch by the texel size): address = base + (y * pitch + x) * sizeof(T)
     NRD_DEV bool inside(int x, int y) const { return (unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h; }
-    template <class T> NRD_DEV const T* ptr(int x, int y) const { return (const T*)(data + (size_t)y * pitch) + x; }
-    template <class T> NRD_DEV T* ptrw(int x, int y) const { return (T*)(data + (size_t)y * pitch) + x; }
+    // one 32-bit IMAD for the texel index + one IMAD.WIDE for the address (textures are < 2^31 texels)
+    template <class T> NRD_DEV const T* ptr(int x, int y) const { return reinterpret_cast<const T*>(data) + (y * pitch + x); }
+    template <class T> NRD_DEV T* ptrw(int x, int y) const { return reinterpret_cast<T*>(data) + (y * pitch + x); }
     NRD_DEV int cx(int x) const { return clampi(x, 0, w - 1); }
     NRD_DEV int cy(int y) const { return clampi(y, 0, h - 1); }
 };
@@ -71,12 +83,13 @@ struct TexR16F : TexView {
 };
 
 struct TexRGBA16F : TexView {
-    NRD_DEV float4 fetch(int x, int y) const {
-        uint2 raw = __ldg(ptr<uint2>(x, y));
+    NRD_DEV uint2 fetchRaw(int x, int y) const { return __ldg(ptr<uint2>(x, y)); }
+    static NRD_DEV float4 decode(uint2 raw) {
         float2 lo = __half22float2(*reinterpret_cast<__half2*>(&raw.x));
         float2 hi = __half22float2(*reinterpret_cast<__half2*>(&raw.y));
         return make_float4(lo.x, lo.y, hi.x, hi.y);
     }
+    NRD_DEV float4 fetch(int x, int y) const { return decode(fetchRaw(x, y)); }
     NRD_DEV float4 load(int x, int y) const { return inside(x, y) ? fetch(x, y) : f4(0.0f); }
     NRD_DEV float4 fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
     NRD_DEV void store(int x, int y, float4 v) const {

@@ -172,11 +172,12 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const
     __shared__ float2 sDiffRow[3][HF_TILE_H][BLOCK_W];
     __shared__ float2 sSpecRow[3][HF_TILE_H][BLOCK_W];
 
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int2 cta = ctaTile<2>();
+    const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
     const int tid = threadIdx.y * BLOCK_W + threadIdx.x;
     int sawSky = 0;
     {
-        const int baseX = blockIdx.x * BLOCK_W - HF_BORDER, baseY = blockIdx.y * BLOCK_H - HF_BORDER;
+        const int baseX = cta.x * BLOCK_W - HF_BORDER, baseY = cta.y * BLOCK_H - HF_BORDER;
         for (int i = tid; i < HF_TILE_W * HF_TILE_H; i += BLOCK_W * BLOCK_H) {
             int sx = i % HF_TILE_W, sy = i / HF_TILE_W;
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
@@ -276,9 +277,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
     __shared__ float sDiffLuma[TS_TILE_H][TS_TILE_W];
     __shared__ float sSpecLuma[TS_TILE_H][TS_TILE_W];
 
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int2 cta = ctaTile<5>();
+    const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
     {
-        const int baseX = blockIdx.x * BLOCK_W - TS_BORDER, baseY = blockIdx.y * BLOCK_H - TS_BORDER;
+        const int baseX = cta.x * BLOCK_W - TS_BORDER, baseY = cta.y * BLOCK_H - TS_BORDER;
         const int tid = threadIdx.y * BLOCK_W + threadIdx.x;
         for (int i = tid; i < TS_TILE_W * TS_TILE_H; i += BLOCK_W * BLOCK_H) {
             int sx = i % TS_TILE_W, sy = i / TS_TILE_W;

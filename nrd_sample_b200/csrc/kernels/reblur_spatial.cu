@@ -126,7 +126,10 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
         const float2 hitDistParams = hitDistanceWeightParams(result.w, NLAS);
         float minHitDistWeight = cb.minHitDistanceWeight * fractionScale * smc;
         if (PASS != PRE_PASS) minHitDistWeight *= NLAS;
-        const float centerMaterial = fmaxf(s.materialID, MIN_MATERIAL);
+        // CompareMaterials( m0, m, minm ) = max( m0, minm ) == max( m, minm ) on the 2-bit IDs k0, k in 0..3 is
+        // ( k == k0 ) || max( k, k0 ) <= minm: integer compares, and no work at all when minm >= 3 (the default is 4)
+        const uint32_t centerK = (uint32_t)(s.materialID + 0.5f);
+        const bool materialsAlwaysMatch = MIN_MATERIAL >= 3.0f;
 
         // Tap placement. Screen space: uv = pixelUv + R * offset with the blur-radius-scaled rotator R. World space:
         // clip = M * ( Xv + T o.x + B o.y ) is expanded once per pixel into C + A o.x + B' o.y (rows x, y, w of M only).
@@ -213,7 +216,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
 
             const float zRawA = viewZTex.fetch(txa, tya), zRawB = viewZTex.fetch(txb, tyb);
             const uint32_t nrA = nrTex.fetchRaw(txa, tya), nrB = nrTex.fetchRaw(txb, tyb);
-            float4 smpA = input.fetch(txa, tya), smpB = input.fetch(txb, tyb);
+            uint2 rawA = input.fetchRaw(txa, tya), rawB = input.fetchRaw(txb, tyb);
 
             P2 zs = absMul2(P2(zRawA, zRawB), fabsf(cb.viewZScale));  // UnpackViewZ: | z * scale |
             P2 rx = fma2(fx, rayMulX, rayAddX), ry = fma2(fy, rayMulY, rayAddY);
@@ -232,13 +235,18 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             P2 invLen = rsqrt2(fma2(nz, nz, fma2(ny, ny, fma2(nx, nx, 1e-9f))));
             P2 cosa = fma2(nz, s.N.z, fma2(ny, s.N.y, nx * s.N.x)) * invLen;
             P2 roughS = abs2(t);
-            const float matA = fmaxf(materialFromRaw(nrA), MIN_MATERIAL), matB = fmaxf(materialFromRaw(nrB), MIN_MATERIAL);
+            bool matchA = true, matchB = true;
+            if (!materialsAlwaysMatch) {
+                const uint32_t ka = nrA >> 30, kb = nrB >> 30;
+                matchA = ka == centerK || (float)max(ka, centerK) <= MIN_MATERIAL;
+                matchB = kb == centerK || (float)max(kb, centerK) <= MIN_MATERIAL;
+            }
 
             // Math::AcosApproxPositive
             P2 cs = sat2(cosa);
             P2 angle = fma2(cs, 1.399331f - 1.567589f, 1.567589f) * sqrt2(satOneMinus2(cosa));
 
-            w = sel2(matA == centerMaterial, matB == centerMaterial, w, P2(0.0f));
+            if (!materialsAlwaysMatch) w = sel2(matchA, matchB, w, P2(0.0f));
             w = w * nonExponentialWeight2(angle * normalParam);
             if (LOBE == SPEC) w = w * nonExponentialWeight2(fma2(roughS, roughParams.x, roughParams.y));
             // plane distance: NoX = dot( Nv, Xvs ), Xvs = ( ray.xy * sxy, zs )
@@ -246,9 +254,10 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             w = w * nonExponentialWeight2(fma2(NoX, geomParams.x, geomParams.y));
             w = sel2(zs.a() < cb.denoisingRange, zs.b() < cb.denoisingRange, w, P2(0.0f));
 
-            // Denanify
-            if (w.a() == 0.0f) smpA = f4(0.0f);
-            if (w.b() == 0.0f) smpB = f4(0.0f);
+            // Denanify, on the packed fp16 words (2 selects per tap instead of 4)
+            if (w.a() == 0.0f) rawA = make_uint2(0u, 0u);
+            if (w.b() == 0.0f) rawB = make_uint2(0u, 0u);
+            const float4 smpA = TexRGBA16F::decode(rawA), smpB = TexRGBA16F::decode(rawB);
             P2 sw(smpA.w, smpB.w);
 
             if (PASS == PRE_PASS && LOBE == SPEC) {
@@ -307,8 +316,9 @@ __global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_co
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags) {
     const bool robust = (flags & 2) != 0;
     Center s;
-    s.px = blockIdx.x * BLOCK_W + threadIdx.x;
-    s.py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int2 cta = ctaTile<0>();
+    s.px = cta.x * BLOCK_W + threadIdx.x;
+    s.py = cta.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(s.px >> 4, s.py >> 4) != 0.0f || s.px > cb.rectSizeMinusOne[0] || s.py > cb.rectSizeMinusOne[1]) return;
     s.viewZ = unpackViewZ(cb, p.viewZ.load(s.px, s.py));
     if (!inDenoisingRange(cb, s.viewZ)) return;
@@ -335,8 +345,9 @@ NRD_DEV float2 quadSmoothedAccumSpeed(const ReblurConstants& cb, float2 data1, f
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
-    s.px = blockIdx.x * BLOCK_W + threadIdx.x;
-    s.py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int2 cta = ctaTile<3>();
+    s.px = cta.x * BLOCK_W + threadIdx.x;
+    s.py = cta.y * BLOCK_H + threadIdx.y;
 
     // viewZ (sky included) is copied for the next pass and the next frame
     float viewZpacked = p.viewZ.load(s.px, s.py);
@@ -358,8 +369,9 @@ template <bool TEMPORAL_STABILIZATION>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
-    s.px = blockIdx.x * BLOCK_W + threadIdx.x;
-    s.py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int2 cta = ctaTile<4>();
+    s.px = cta.x * BLOCK_W + threadIdx.x;
+    s.py = cta.y * BLOCK_H + threadIdx.y;
 
     bool skyTile = p.tiles.load(s.px >> 4, s.py >> 4) != 0.0f;
     s.data1 = unpackData1(p.data1.load(s.px, s.py));

@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
                                                                                       const __grid_constant__ TemporalAccumulationParams p) {
     __shared__ float4 sNormalHitDist[TILE_H][TILE_W];
 
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int2 cta = ctaTile<1>();
+    const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
     const float2 rectSize = make_float2(cb.rectSize[0], cb.rectSize[1]);
     const float2 rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
     const float2 rectSizePrev = make_float2(cb.rectSizePrev[0], cb.rectSizePrev[1]);
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
 
     // ---- Preload (TA:38-66): { N, hit distance for tracking or INF } of the clamped 34x10 neighbourhood ----
     {
-        const int baseX = blockIdx.x * BLOCK_W - BORDER, baseY = blockIdx.y * BLOCK_H - BORDER;
+        const int baseX = cta.x * BLOCK_W - BORDER, baseY = cta.y * BLOCK_H - BORDER;
         const int tid = threadIdx.y * BLOCK_W + threadIdx.x;
         for (int i = tid; i < TILE_W * TILE_H; i += BLOCK_W * BLOCK_H) {
             int sx = i % TILE_W, sy = i / TILE_W;
