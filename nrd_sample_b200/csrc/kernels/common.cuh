@@ -57,6 +57,7 @@ struct TexR32F : TexView {
     NRD_DEV float load(int x, int y) const { return inside(x, y) ? fetch(x, y) : 0.0f; }
     NRD_DEV float fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
     NRD_DEV void store(int x, int y, float v) const { if (inside(x, y)) *ptrw<float>(x, y) = v; }
+    NRD_DEV float sampleNearest(float2 uv) const { return fetchClamped((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
     NRD_DEV float sampleLinear(float2 uv) const {
         float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
         float fx = floorf(tx), fy = floorf(ty);
@@ -72,6 +73,7 @@ struct TexR16F : TexView {
     NRD_DEV float load(int x, int y) const { return inside(x, y) ? fetch(x, y) : 0.0f; }
     NRD_DEV float fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
     NRD_DEV void store(int x, int y, float v) const { if (inside(x, y)) *ptrw<__half>(x, y) = __float2half_rn(v); }
+    NRD_DEV float sampleNearest(float2 uv) const { return fetchClamped((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
     NRD_DEV float sampleLinear(float2 uv) const {
         float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
         float fx = floorf(tx), fy = floorf(ty);
@@ -122,8 +124,19 @@ struct TexNR : TexView {
 };
 
 struct TexR8 : TexView {  // R8_UNORM
-    NRD_DEV float load(int x, int y) const { return inside(x, y) ? (float)__ldg(ptr<uint8_t>(x, y)) / 255.0f : 0.0f; }
+    NRD_DEV float fetch(int x, int y) const { return (float)__ldg(ptr<uint8_t>(x, y)) / 255.0f; }
+    NRD_DEV float load(int x, int y) const { return inside(x, y) ? fetch(x, y) : 0.0f; }
+    NRD_DEV float fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
     NRD_DEV void store(int x, int y, float v) const { if (inside(x, y)) *ptrw<uint8_t>(x, y) = (uint8_t)unormQ(v, 255.0f); }
+    NRD_DEV float sampleNearest(float2 uv) const { return fetchClamped((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
+    NRD_DEV float sampleLinear(float2 uv) const {
+        float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
+        float fx = floorf(tx), fy = floorf(ty);
+        float wx = tx - fx, wy = ty - fy;
+        int x0 = (int)fx, y0 = (int)fy;
+        float a = fetchClamped(x0, y0), b = fetchClamped(x0 + 1, y0), c = fetchClamped(x0, y0 + 1), d = fetchClamped(x0 + 1, y0 + 1);
+        return lerp(lerp(a, b, wx), lerp(c, d, wx), wy);
+    }
 };
 
 struct TexRG8 : TexView {  // RG8_UNORM
@@ -135,6 +148,31 @@ struct TexRG8 : TexView {  // RG8_UNORM
     NRD_DEV void store(int x, int y, float2 v) const {
         if (inside(x, y)) *ptrw<uchar2>(x, y) = make_uchar2((unsigned char)unormQ(v.x, 255.0f), (unsigned char)unormQ(v.y, 255.0f));
     }
+    NRD_DEV float2 fetchClamped(int x, int y) const {
+        uchar2 v = __ldg(ptr<uchar2>(cx(x), cy(y)));
+        return make_float2((float)v.x / 255.0f, (float)v.y / 255.0f);
+    }
+    NRD_DEV float2 sampleLinear(float2 uv) const {
+        float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
+        float fx = floorf(tx), fy = floorf(ty);
+        float wx = tx - fx, wy = ty - fy;
+        int x0 = (int)fx, y0 = (int)fy;
+        float2 a = fetchClamped(x0, y0), b = fetchClamped(x0 + 1, y0), c = fetchClamped(x0, y0 + 1), d = fetchClamped(x0 + 1, y0 + 1);
+        return lerp(lerp(a, b, wx), lerp(c, d, wx), wy);
+    }
+};
+
+struct TexRGBA8 : TexView {  // RGBA8_UNORM
+    NRD_DEV float4 load(int x, int y) const {
+        if (!inside(x, y)) return f4(0.0f);
+        uchar4 v = __ldg(ptr<uchar4>(x, y));
+        return make_float4((float)v.x / 255.0f, (float)v.y / 255.0f, (float)v.z / 255.0f, (float)v.w / 255.0f);
+    }
+    NRD_DEV void store(int x, int y, float4 v) const {
+        if (inside(x, y))
+            *ptrw<uchar4>(x, y) = make_uchar4((unsigned char)unormQ(v.x, 255.0f), (unsigned char)unormQ(v.y, 255.0f), (unsigned char)unormQ(v.z, 255.0f),
+                                              (unsigned char)unormQ(v.w, 255.0f));
+    }
 };
 
 struct TexR16U : TexView {
@@ -145,6 +183,7 @@ struct TexR16U : TexView {
 
 struct TexR32U : TexView {
     NRD_DEV uint32_t load(int x, int y) const { return inside(x, y) ? __ldg(ptr<uint32_t>(x, y)) : 0u; }
+    NRD_DEV uint32_t fetchClamped(int x, int y) const { return __ldg(ptr<uint32_t>(cx(x), cy(y))); }
     NRD_DEV void store(int x, int y, uint32_t v) const { if (inside(x, y)) *ptrw<uint32_t>(x, y) = v; }
 };
 

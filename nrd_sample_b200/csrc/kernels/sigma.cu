@@ -1,4 +1,11 @@
-// SIGMA_SHADOW passes on sm_100a — not implemented yet; the executor reports UNSUPPORTED for these shaders.
+// SIGMA_SHADOW passes on sm_100a (TRANSLUCENCY = 0): ClassifyTiles, SmoothTiles, Copy, Blur (first pass / post-blur),
+// TemporalStabilization, SplitScreen. One kernel per reference dispatch, one thread per pixel, CTA = 32x8 pixels for the
+// per-pixel passes (a 32-pixel row per warp: coalesced R16F / R32F / R8 rows), 5x5 neighbourhoods through shared memory.
+//
+// Reference (External/NRD/Shaders): SIGMA_ClassifyTiles.cs.hlsl:24-91, SIGMA_SmoothTiles.cs.hlsl:21-58,
+// SIGMA_Copy.cs.hlsl:19-32, SIGMA_Blur.cs.hlsl:21-286, SIGMA_TemporalStabilization.cs.hlsl:21-236,
+// SIGMA_SplitScreen.cs.hlsl:21-45. The reference groups are 8x16 (16x16 for the tile passes); the CUDA grid is laid out
+// differently but every pixel computes the same function of the same texels.
 #include <string>
 
 #include "../../../include/nrd_b200.h"
@@ -6,8 +13,508 @@
 #include "sigma_common.cuh"
 
 namespace nrdk {
-uint32_t dispatchSigma(const std::string& id, const void*, uint32_t, const nrdcuTexture*, uint32_t, cudaStream_t, std::string& err) {
-    err = "no CUDA kernel for shader '" + id + "' yet";
-    return (uint32_t)nrd::Result::UNSUPPORTED;
+
+namespace {
+
+constexpr int BLOCK_W = 32, BLOCK_H = 8;
+constexpr int TILE_W = BLOCK_W + 2 * SIGMA_BORDER, TILE_H = BLOCK_H + 2 * SIGMA_BORDER;
+
+// g_Special8 (Common.hlsli:207-218)
+__constant__ float3 kSpecial8[8] = {{-1.0f, 0.0f, 1.0f},
+                                    {0.0f, 1.0f, 1.0f},
+                                    {1.0f, 0.0f, 1.0f},
+                                    {0.0f, -1.0f, 1.0f},
+                                    {-0.25f * 1.41421356237309504880f, 0.25f * 1.41421356237309504880f, 0.5f},
+                                    {0.25f * 1.41421356237309504880f, 0.25f * 1.41421356237309504880f, 0.5f},
+                                    {0.25f * 1.41421356237309504880f, -0.25f * 1.41421356237309504880f, 0.5f},
+                                    {-0.25f * 1.41421356237309504880f, -0.25f * 1.41421356237309504880f, 0.5f}};
+
+NRD_DEV float applyGeometryWeightLast(const SigmaConstants& cb, float w, float z, float NoX, float2 params) {
+    w *= nonExponentialWeight(NoX, params.x, params.y);
+    return !sigmaInRange(cb, z) ? 0.0f : w;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// One CTA of 256 threads per 16x16 tile; the three 9-bit counters of the reference's s_Mask become block-wide counts
+__global__ void __launch_bounds__(256) sigmaClassifyTilesKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaClassifyTilesParams p) {
+    __shared__ uint32_t sRadius[8];
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int px = tx * 16 + (threadIdx.x & 15), py = ty * 16 + (threadIdx.x >> 4);
+    const float h = p.penumbra.load(px, py);
+    const float viewZ = sigmaUnpackViewZ(cb, p.viewZ.load(px, py));
+    const bool isInf = !sigmaInRange(cb, viewZ), isShadow = h == 0.0f, isLit = sigmaIsLit(h);
+    const int nLit = __syncthreads_count(isLit || isInf || isShadow);
+    const int nUmbra = __syncthreads_count(!isLit || isInf || isShadow);
+    const int nInf = __syncthreads_count(isInf);
+    const float hitDist = (isLit || isInf) ? 0.0f : h;
+    const float pixelSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, 1.0f, viewZ);
+    const float radius = sigmaKernelRadiusInPixels(hitDist, pixelSize);
+    // radii are >= 0: the float order is the order of the bit patterns (InterlockedMax on asuint in the reference)
+    const uint32_t warpMax = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(fmaxf(radius, 0.0f)));
+    if ((threadIdx.x & 31) == 0) sRadius[threadIdx.x >> 5] = warpMax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t m = sRadius[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) m = max(m, sRadius[i]);
+        const bool lit = nLit == 256, umbra = nUmbra == 256, inf = nInf == 256;
+        p.outTiles.store(tx, ty, make_float4((lit || umbra) ? 0.0f : 1.0f, saturate(__uint_as_float(m) / 16.0f), inf ? 1.0f : 0.0f, 0.0f));
+    }
+}
+
+// One thread per tile texel
+__global__ void __launch_bounds__(256) sigmaSmoothTilesKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaSmoothTilesParams p) {
+    const int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    const float4 center = p.tiles.load(x, y);
+    const float k = 1.01f / (center.y + 0.01f);
+    float blurry = 0.0f, sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j <= 2; j++)
+#pragma unroll
+        for (int i = 0; i <= 2; i++) {
+            const float d2 = (float)((i - 1) * (i - 1) + (j - 1) * (j - 1));  // length( float2( i, j ) - 1 ) ^ 2
+            const float w = exp2f(-k * d2);
+            blurry += p.tiles.load(clampi(x + i - 1, 0, cb.tilesSizeMinusOne[0]), clampi(y + j - 1, 0, cb.tilesSizeMinusOne[1])).x * w;
+            sum += w;
+        }
+    p.outTiles.store(x, y, make_float2(center.z, blurry / sum));
+}
+
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaCopyParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const float isSky = p.tiles.load(px >> 4, py >> 4).x;
+    if ((isSky != 0.0f && !cb.isRectChanged) || !p.history.inside(px, py)) return;
+    *p.outHistory.ptrw<uint8_t>(px, py) = __ldg(p.history.ptr<uint8_t>(px, py));
+    p.outHistoryLength.store(px, py, p.historyLength.load(px, py));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <bool FIRST_PASS>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaBlurParams p) {
+    __shared__ float2 sPenumbraViewZ[TILE_H][TILE_W];
+    __shared__ float sShadow[FIRST_PASS ? 1 : TILE_H][FIRST_PASS ? 1 : TILE_W];
+
+    // CTA order: first pass default, post-blur reversed (SIGMA_Blur.cs.hlsl:51-55)
+    const int bx = FIRST_PASS ? (int)blockIdx.x : (int)(gridDim.x - 1u - blockIdx.x), by = FIRST_PASS ? (int)blockIdx.y : (int)(gridDim.y - 1u - blockIdx.y);
+    const int px = bx * BLOCK_W + threadIdx.x, py = by * BLOCK_H + threadIdx.y;
+
+    // The CTA covers two 16x16 tiles of one tile row
+    const float skyL = p.tiles.load((bx * BLOCK_W) >> 4, py >> 4).x, skyR = p.tiles.load((bx * BLOCK_W + 16) >> 4, py >> 4).x;
+    if (skyL != 0.0f && skyR != 0.0f) return;
+
+    {
+        const int baseX = bx * BLOCK_W - SIGMA_BORDER, baseY = by * BLOCK_H - SIGMA_BORDER;
+        const int tid = threadIdx.y * BLOCK_W + threadIdx.x;
+        for (int i = tid; i < TILE_W * TILE_H; i += BLOCK_W * BLOCK_H) {
+            const int sx = i % TILE_W, sy = i / TILE_W;
+            const int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
+            sPenumbraViewZ[sy][sx] = make_float2(p.penumbra.load(gx, gy), sigmaUnpackViewZ(cb, p.viewZ.load(gx, gy)));
+            if (!FIRST_PASS) {
+                const float s = p.shadow.load(gx, gy);
+                sShadow[sy][sx] = s * s;  // SIGMA_BackEnd_UnpackShadow
+            }
+        }
+    }
+    __syncthreads();
+
+    const float isSky = threadIdx.x < 16 ? skyL : skyR;
+    if (isSky != 0.0f || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1]) return;
+
+    const int smx = threadIdx.x + SIGMA_BORDER, smy = threadIdx.y + SIGMA_BORDER;
+    const float2 centerData = sPenumbraViewZ[smy][smx];
+    const float centerPenumbra = centerData.x, viewZ = centerData.y;
+    if (!sigmaInRange(cb, viewZ)) return;
+
+    const float2 rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
+    const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * rectSizeInv;
+    const float tileValue = sigmaTileValue(p.tiles, pixelUv * make_float2(cb.resolutionScale[0], cb.resolutionScale[1]));
+
+    auto shadowAt = [&](int y, int x, float penum) -> float {
+        if (FIRST_PASS) return sigmaIsLit(penum) ? 1.0f : 0.0f;
+        return sShadow[FIRST_PASS ? 0 : y][FIRST_PASS ? 0 : x];
+    };
+
+    if (tileValue == 0.0f || centerPenumbra == 0.0f) {
+        if (FIRST_PASS || cb.stabilizationStrength != 0.0f) p.outPenumbra.store(px, py, centerPenumbra);
+        p.outShadow.store(px, py, sigmaPackShadow(shadowAt(smy, smx, centerPenumbra)));
+        return;
+    }
+
+    const float3 Xv = reconstructViewPosition(pixelUv, cb.frustum, viewZ, cb.orthoMode);
+    const float3 N = xyz(unpackNormalRoughness(p.normalRoughness.loadRaw(px, py)));
+    const float3 Nv = rotate(cb.worldToView, N);
+
+    const float pixelSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, 1.0f, viewZ);
+    const float frustumSize = frustumSizeAt(cb.minRectDimMulUnproject, cb.orthoMode, viewZ);
+    const float3 Vv = cb.orthoMode == 0.0f ? normalize(-Xv) : make_float3(0.0f, 0.0f, -1.0f);
+    const float NoV = fabsf(dot(Nv, Vv));
+    const float2 geomParams = geometryWeightParams(cb.planeDistSensitivity, frustumSize, Xv, Nv);
+
+    // Estimate penumbra size and filter shadow ( dense 5x5 )
+    float sumX = 0.0f, sumY = 0.0f, penumbra = 0.0f, result = 0.0f, centerTap = 0.0f;
+#pragma unroll
+    for (int j = 0; j <= SIGMA_BORDER * 2; j++)
+#pragma unroll
+        for (int i = 0; i <= SIGMA_BORDER * 2; i++) {
+            const float2 data = sPenumbraViewZ[threadIdx.y + j][threadIdx.x + i];
+            const float penum = data.x, zs = data.y;
+            const float s = shadowAt(threadIdx.y + j, threadIdx.x + i, penum);
+            float w = 1.0f;
+            if (i == SIGMA_BORDER && j == SIGMA_BORDER)
+                centerTap = s;
+            else {
+                const float2 o = make_float2((float)(i - SIGMA_BORDER), (float)(j - SIGMA_BORDER));
+                const float2 uv = pixelUv + o * rectSizeInv;
+                const float3 Xvs = reconstructViewPosition(uv, cb.frustum, zs, cb.orthoMode);
+                const float NoX = dot(Nv, Xvs);
+                w *= sigmaBothLitOrUnlit(centerPenumbra, penum);
+                w *= gaussianWeight(length(o / (float)SIGMA_BORDER));
+                w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
+            }
+            result += w == 0.0f ? 0.0f : s * w;
+            sumX += w;
+            w *= pixelSize / (pixelSize + penum);
+            w *= sigmaIsLit(penum) ? 0.0f : 1.0f;
+            penumbra += w == 0.0f ? 0.0f : penum * w;
+            sumY += w;
+        }
+    result /= sumX;
+    sumX = 1.0f;
+    penumbra /= fmaxf(sumY, NRD_EPS);
+    sumY = sumY != 0.0f ? 1.0f : 0.0f;
+
+    // Avoid blurry result if penumbra size < NRD_BORDER
+    const float penumbraInPixels = penumbra / pixelSize;
+    float f = smoothStep(0.0f, (float)SIGMA_BORDER, penumbraInPixels);
+    result = lerp(centerTap, result, f);
+
+    // Sparse pass: avoid unnecessary weight increase for the unfiltered center sample if the blur radius is small
+    f = lerp(4.0f, 1.0f, f);
+    result *= f;
+    penumbra *= f;
+    sumX *= f;
+    sumY *= f;
+
+    const float blurRadius = sigmaKernelRadiusInPixels(penumbra, pixelSize, tileValue);
+    const float* rot = FIRST_PASS ? cb.rotator : cb.rotatorPost;  // SIGMA_ROTATOR_MODE = NRD_FRAME
+    const float4 rotator = make_float4(rot[0], rot[1], rot[2], rot[3]);
+
+    float2 skew = lerp(f2(1.0f) - fabs2(make_float2(Nv.x, Nv.y)), f2(1.0f), NoV);
+    skew = skew / fmaxf(skew.x, skew.y);
+    skew = skew * (rectSizeInv * blurRadius);
+    const float4 scaledRotator = scaleRotator(rotator, skew);
+
+    const float invEstimatedPenumbra = 1.0f / fmaxf(penumbra, NRD_EPS);
+    const float2 rectSize = make_float2(cb.rectSize[0], cb.rectSize[1]);
+    const float2 resolutionScale = make_float2(cb.resolutionScale[0], cb.resolutionScale[1]);
+    const float2 uvMax = resolutionScale - 0.5f * make_float2(cb.resourceSizeInv[0], cb.resourceSizeInv[1]);
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+        const float3 offset = kSpecial8[n];
+        float2 uv = pixelUv + rotate2(scaledRotator, make_float2(offset.x, offset.y));
+        uv = (floor2(uv * rectSize) + 0.5f) * rectSizeInv;  // snap to the pixel center
+        const float2 uvScaled = min2(uv * resolutionScale, uvMax);  // ClampUvToViewport (Common.hlsli:242)
+
+        const float penum = p.penumbra.sampleNearest(uvScaled);
+        const float zs = sigmaUnpackViewZ(cb, p.viewZ.sampleNearest(uvScaled));
+        const float3 Xvs = reconstructViewPosition(uv, cb.frustum, zs, cb.orthoMode);
+        float s;
+        if (FIRST_PASS)
+            s = sigmaIsLit(penum) ? 1.0f : 0.0f;
+        else {
+            s = p.shadow.sampleNearest(uvScaled);
+            s *= s;
+        }
+
+        const float NoX = dot(Nv, Xvs);
+        float w = isInScreenNearest(uv) ? 1.0f : 0.0f;
+        w *= sigmaBothLitOrUnlit(centerPenumbra, penum);
+        w *= gaussianWeight(offset.z);
+        w *= saturate(penum * invEstimatedPenumbra);  // avoid umbra leaking inside wide penumbra
+        w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
+
+        result += w == 0.0f ? 0.0f : s * w;
+        sumX += w;
+        w *= pixelSize / (pixelSize + penum);
+        w *= sigmaIsLit(penum) ? 0.0f : 1.0f;
+        penumbra += w == 0.0f ? 0.0f : penum * w;
+        sumY += w;
+    }
+
+    result /= sumX;
+    penumbra = sumY == 0.0f ? centerPenumbra : penumbra / sumY;
+
+    if (FIRST_PASS || cb.stabilizationStrength != 0.0f) p.outPenumbra.store(px, py, penumbra);
+    p.outShadow.store(px, py, sigmaPackShadow(result));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+NRD_DEV uint32_t packViewZAndHistoryLength(float viewZ, float historyLength) {
+    return (__float_as_uint(viewZ) & ~7u) | min((uint32_t)(historyLength + 0.5f), 7u);
+}
+
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaTemporalStabilizationKernel(const __grid_constant__ SigmaConstants cb,
+                                                                                    const __grid_constant__ SigmaTemporalStabilizationParams p) {
+    __shared__ float sShadow[TILE_H][TILE_W];
+    __shared__ float sPenumbra[TILE_H][TILE_W];
+
+    const int bx = blockIdx.x, by = blockIdx.y;  // NRD_CTA_ORDER_DEFAULT
+    const int px = bx * BLOCK_W + threadIdx.x, py = by * BLOCK_H + threadIdx.y;
+    const float skyL = p.tiles.load((bx * BLOCK_W) >> 4, py >> 4).x, skyR = p.tiles.load((bx * BLOCK_W + 16) >> 4, py >> 4).x;
+    if (skyL != 0.0f && skyR != 0.0f) return;
+    {
+        const int baseX = bx * BLOCK_W - SIGMA_BORDER, baseY = by * BLOCK_H - SIGMA_BORDER;
+        const int tid = threadIdx.y * BLOCK_W + threadIdx.x;
+        for (int i = tid; i < TILE_W * TILE_H; i += BLOCK_W * BLOCK_H) {
+            const int sx = i % TILE_W, sy = i / TILE_W;
+            const int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
+            const float s = p.shadow.load(gx, gy);
+            sShadow[sy][sx] = s * s;
+            sPenumbra[sy][sx] = p.penumbra.load(gx, gy);
+        }
+    }
+    __syncthreads();
+
+    const float isSky = threadIdx.x < 16 ? skyL : skyR;
+    const float viewZ = sigmaUnpackViewZ(cb, p.viewZ.load(px, py));
+    if (isSky != 0.0f || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1] || !sigmaInRange(cb, viewZ)) return;
+
+    const int smx = threadIdx.x + SIGMA_BORDER, smy = threadIdx.y + SIGMA_BORDER;
+    const float centerPenumbra = sPenumbra[smy][smx];
+    const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
+    const float tileValue = sigmaTileValue(p.tiles, pixelUv * make_float2(cb.resolutionScale[0], cb.resolutionScale[1]));
+
+    if (tileValue == 0.0f || centerPenumbra == 0.0f) {  // hard shadow / fully lit: nothing to stabilise
+        p.outShadow.store(px, py, sigmaPackShadow(sShadow[smy][smx]));
+        p.outHistoryLength.store(px, py, packViewZAndHistoryLength(viewZ, SIGMA_MAX_ACCUM_FRAME_NUM));
+        return;
+    }
+
+    // Local variance
+    float sum = 0.0f, m1 = 0.0f, m2 = 0.0f, input = 0.0f;
+#pragma unroll
+    for (int j = 0; j <= SIGMA_BORDER * 2; j++)
+#pragma unroll
+        for (int i = 0; i <= SIGMA_BORDER * 2; i++) {
+            const float s = sShadow[threadIdx.y + j][threadIdx.x + i];
+            float w = 1.0f;
+            if (i == SIGMA_BORDER && j == SIGMA_BORDER)
+                input = s;
+            else {
+                const float penum = sPenumbra[threadIdx.y + j][threadIdx.x + i];
+                w = sigmaBothLitOrUnlit(centerPenumbra, penum);
+                w *= gaussianWeight(length(make_float2((float)(i - SIGMA_BORDER), (float)(j - SIGMA_BORDER)) / (float)SIGMA_BORDER));
+            }
+            m1 += s * w;
+            m2 += s * s * w;
+            sum += w;
+        }
+    m1 /= sum;
+    m2 /= sum;
+    float sigma = stdDev(m1, m2);
+
+    // Current and previous positions
+    const float3 Xv = reconstructViewPosition(pixelUv, cb.frustum, viewZ, cb.orthoMode);
+    const float3 X = rotateInverse(cb.worldToView, Xv);
+    const float4 mvRaw = p.mv.load(px, py);
+    float3 mv = make_float3(mvRaw.x * cb.mvScale[0], mvRaw.y * cb.mvScale[1], mvRaw.z * cb.mvScale[2]);
+    float3 Xprev = X;
+    float2 smbPixelUv = pixelUv + make_float2(mv.x, mv.y);
+    if (cb.mvScale[3] == 0.0f) {
+        if (cb.mvScale[2] == 0.0f) mv.z = affine(cb.worldToViewPrev, X).z - viewZ;
+        const float viewZprev = viewZ + mv.z;
+        const float3 Xvprevlocal = reconstructViewPosition(smbPixelUv, cb.frustumPrev, viewZprev, cb.orthoMode);
+        Xprev = rotateInverse(cb.worldToViewPrev, Xvprevlocal) + make_float3(cb.cameraDelta[0], cb.cameraDelta[1], cb.cameraDelta[2]);
+    } else {
+        Xprev = Xprev + mv;
+        smbPixelUv = screenUv(cb.worldToClipPrev, Xprev);
+    }
+
+    // History length: 2x2 footprint of { viewZ with the length in the low 3 bits }
+    const float2 rectSizePrev = make_float2(cb.rectSizePrev[0], cb.rectSizePrev[1]);
+    const Bilinear smbFilter = getBilinearFilter(smbPixelUv, rectSizePrev);
+    const int ox = (int)smbFilter.origin.x, oy = (int)smbFilter.origin.y;
+    const uint32_t d00 = p.historyLength.fetchClamped(ox, oy), d10 = p.historyLength.fetchClamped(ox + 1, oy);
+    const uint32_t d01 = p.historyLength.fetchClamped(ox, oy + 1), d11 = p.historyLength.fetchClamped(ox + 1, oy + 1);
+    const float4 prevViewZ = make_float4(__uint_as_float(d00 & ~7u), __uint_as_float(d10 & ~7u), __uint_as_float(d01 & ~7u), __uint_as_float(d11 & ~7u));
+    const float4 prevHistoryLength = make_float4((float)(d00 & 7u), (float)(d10 & 7u), (float)(d01 & 7u), (float)(d11 & 7u));
+
+    const float frustumSize = frustumSizeAt(cb.minRectDimMulUnproject, cb.orthoMode, viewZ);
+    float4 disocclusionThreshold = f4(disocclusionThresholdAt(SIGMA_DISOCCLUSION_THRESHOLD, frustumSize, 1.0f));
+    disocclusionThreshold = disocclusionThreshold * isInScreenBilinear(smbFilter.origin, rectSizePrev);
+    disocclusionThreshold = disocclusionThreshold - NRD_EPS;
+
+    const float3 Xvprev = affine(cb.worldToViewPrev, Xprev);
+    const float4 planeDist = make_float4(fabsf(prevViewZ.x - Xvprev.z), fabsf(prevViewZ.y - Xvprev.z), fabsf(prevViewZ.z - Xvprev.z), fabsf(prevViewZ.w - Xvprev.z));
+    // step( planeDist, threshold ): 1 where threshold >= planeDist
+    const float4 occlusion = make_float4(disocclusionThreshold.x >= planeDist.x ? 1.0f : 0.0f, disocclusionThreshold.y >= planeDist.y ? 1.0f : 0.0f,
+                                         disocclusionThreshold.z >= planeDist.z ? 1.0f : 0.0f, disocclusionThreshold.w >= planeDist.w ? 1.0f : 0.0f);
+    const float4 occlusionWeights = bilinearCustomWeights(smbFilter, occlusion);
+    float historyLength = applyCustomWeights(prevHistoryLength.x, prevHistoryLength.y, prevHistoryLength.z, prevHistoryLength.w, occlusionWeights);
+
+    // Sample history
+    const bool isCatRomAllowed = sum4(occlusionWeights) > 3.5f;
+    const HistoryFilter hf(saturate(smbPixelUv) * rectSizePrev, make_float2(cb.resourceSizeInvPrev[0], cb.resourceSizeInvPrev[1]), occlusionWeights, isCatRomAllowed);
+    float history = hf.color(p.history);
+    history = saturate(history);
+    history *= history;
+
+    // Clamp history
+    sigma *= lerp(SIGMA_TS_SIGMA_SCALE, 1.0f, 1.0f / (1.0f + historyLength));
+    float historyClamped = fminf(fmaxf(history, m1 - sigma), m1 + sigma);
+
+    // Antilag
+    float antilag = sqrt01(fabsf(historyClamped - history));
+    antilag = saturate(1.0f - antilag);
+    historyLength *= antilag;
+
+    const float historyWeight = historyLength / (1.0f + historyLength);
+    const float streetMagic = 0.6f * historyWeight * antilag;
+    historyClamped = lerp(historyClamped, history, streetMagic);
+
+    const float result = lerp(input, historyClamped, fminf(cb.stabilizationStrength, historyWeight));
+    historyLength = fminf(historyLength + 1.0f, SIGMA_MAX_ACCUM_FRAME_NUM);
+
+    p.outShadow.store(px, py, sigmaPackShadow(result));
+    p.outHistoryLength.store(px, py, packViewZAndHistoryLength(viewZ, historyLength));
+}
+
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaSplitScreenKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaSplitScreenParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
+    if (u > cb.splitScreen || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1]) return;
+    const float viewZ = sigmaUnpackViewZ(cb, p.viewZ.load(px, py));
+    const float s = sigmaIsLit(p.penumbra.load(px, py)) ? 1.0f : 0.0f;
+    p.outShadow.store(px, py, sigmaInRange(cb, viewZ) ? s : 0.0f);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dispatch by shader identifier (called by the executor). Returns an nrd::Result; `err` explains a failure.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+uint32_t bytesOf(nrd::Format f) {
+    switch (f) {
+        case nrd::Format::R8_UNORM: return 1;
+        case nrd::Format::RG8_UNORM: case nrd::Format::R16_SFLOAT: return 2;
+        case nrd::Format::RGBA16_SFLOAT: return 8;
+        default: return 4;
+    }
+}
+struct SigmaBinder {
+    const nrdcuTexture* t;
+    uint32_t n, next;
+    bool ok;
+    std::string* err;
+    const std::string* id;
+    template <class V> V take(nrd::Format expect) {
+        V v{};
+        if (next >= n) {
+            ok = false;
+            return v;
+        }
+        const nrdcuTexture& x = t[next];
+        const uint32_t bpp = bytesOf(expect);
+        if (x.format != (uint32_t)expect || !x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
+            if (ok) *err = *id + ": binding " + std::to_string(next) + " has format " + std::to_string(x.format) + " (expected " + std::to_string((uint32_t)expect) + ")";
+            ok = false;
+        }
+        v.data = (uint8_t*)x.data;
+        v.w = (int)x.width;
+        v.h = (int)x.height;
+        v.pitch = (int)(x.pitchBytes / bpp);
+        next++;
+        return v;
+    }
+};
+}  // namespace
+
+uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, cudaStream_t stream, std::string& err) {
+    using nrd::Format;
+    using nrd::Result;
+    if (constantsSize != sizeof(SigmaConstants) || !constants) {
+        err = id + ": expected " + std::to_string(sizeof(SigmaConstants)) + " constant bytes";
+        return (uint32_t)Result::INVALID_ARGUMENT;
+    }
+    SigmaConstants cb;
+    memcpy(&cb, constants, sizeof(cb));
+    if (cb.resolutionScale[0] != 1.0f || cb.resolutionScale[1] != 1.0f || cb.isRectChanged || cb.rectOrigin[0] || cb.rectOrigin[1]) {
+        err = id + ": dynamic resolution (rectSize != resourceSize) is not implemented";
+        return (uint32_t)Result::UNSUPPORTED;
+    }
+    SigmaBinder b{tex, n, 0, true, &err, &id};
+    auto bad = [&](uint32_t expected) {
+        if (b.ok && b.next == expected && n == expected) return false;
+        if (err.empty()) err = id + ": wrong number of textures";
+        return true;
+    };
+    const dim3 block(BLOCK_W, BLOCK_H);
+    const dim3 pixelGrid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, (cb.rectSizeMinusOne[1] + BLOCK_H) / BLOCK_H);
+    const int tilesW = cb.tilesSizeMinusOne[0] + 1, tilesH = cb.tilesSizeMinusOne[1] + 1;
+
+    if (id == "SIGMA_ClassifyTiles.cs.hlsl|TRANSLUCENCY=0") {
+        SigmaClassifyTilesParams p;
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outTiles = b.take<TexRGBA8>(Format::RGBA8_UNORM);
+        if (bad(3)) return (uint32_t)Result::INVALID_ARGUMENT;
+        sigmaClassifyTilesKernel<<<dim3(tilesW, tilesH), 256, 0, stream>>>(cb, p);
+    } else if (id == "SIGMA_SmoothTiles.cs.hlsl") {
+        SigmaSmoothTilesParams p;
+        p.tiles = b.take<TexRGBA8>(Format::RGBA8_UNORM);
+        p.outTiles = b.take<TexRG8>(Format::RG8_UNORM);
+        if (bad(2)) return (uint32_t)Result::INVALID_ARGUMENT;
+        sigmaSmoothTilesKernel<<<dim3((tilesW + 15) / 16, (tilesH + 15) / 16), 256, 0, stream>>>(cb, p);
+    } else if (id == "SIGMA_Copy.cs.hlsl") {
+        SigmaCopyParams p;
+        p.tiles = b.take<TexRG8>(Format::RG8_UNORM);
+        p.history = b.take<TexR8>(Format::R8_UNORM);
+        p.historyLength = b.take<TexR32U>(Format::R32_UINT);
+        p.outHistory = b.take<TexR8>(Format::R8_UNORM);
+        p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
+        if (bad(5)) return (uint32_t)Result::INVALID_ARGUMENT;
+        sigmaCopyKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=1" || id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=0") {
+        const bool first = id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=1";
+        SigmaBlurParams p = {};
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.tiles = b.take<TexRG8>(Format::RG8_UNORM);
+        if (!first) p.shadow = b.take<TexR8>(Format::R8_UNORM);
+        p.outPenumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outShadow = b.take<TexR8>(Format::R8_UNORM);
+        if (bad(first ? 6 : 7)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (first)
+            sigmaBlurKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p);
+        else
+            sigmaBlurKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "SIGMA_TemporalStabilization.cs.hlsl|TRANSLUCENCY=0") {
+        SigmaTemporalStabilizationParams p;
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.mv = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.shadow = b.take<TexR8>(Format::R8_UNORM);
+        p.history = b.take<TexR8>(Format::R8_UNORM);
+        p.historyLength = b.take<TexR32U>(Format::R32_UINT);
+        p.tiles = b.take<TexRG8>(Format::RG8_UNORM);
+        p.outShadow = b.take<TexR8>(Format::R8_UNORM);
+        p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
+        if (bad(9)) return (uint32_t)Result::INVALID_ARGUMENT;
+        sigmaTemporalStabilizationKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "SIGMA_SplitScreen.cs.hlsl|TRANSLUCENCY=0") {
+        SigmaSplitScreenParams p;
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outShadow = b.take<TexR8>(Format::R8_UNORM);
+        if (bad(3)) return (uint32_t)Result::INVALID_ARGUMENT;
+        sigmaSplitScreenKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else {
+        err = "no CUDA kernel for shader '" + id + "'";
+        return (uint32_t)Result::UNSUPPORTED;
+    }
+    return (uint32_t)Result::SUCCESS;
+}
+
 }  // namespace nrdk

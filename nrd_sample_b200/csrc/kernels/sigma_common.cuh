@@ -1,3 +1,65 @@
-// SIGMA helpers and launch-parameter blocks (filled in with the SIGMA kernels).
+// SIGMA_SHADOW helpers and launch-parameter blocks.
+// Reference: External/NRD/Shaders/SIGMA_Common.hlsli:13-95, SIGMA_Config.hlsli:11-42 (switches at their defaults:
+// 5x5 radius-estimation and temporal kernels, sparse blur, screen-space sampling, early out in TS, CatRom history).
 #pragma once
-#include "common.cuh"
+#include "reblur_common.cuh"  // HistoryFilter (Common.hlsli:604-658) is shared with REBLUR
+
+namespace nrdk {
+
+using nrdb::SigmaConstants;
+
+constexpr float SIGMA_MAX_PIXEL_RADIUS = 32.0f;
+constexpr float SIGMA_TS_SIGMA_SCALE = 3.0f;
+constexpr float SIGMA_MAX_ACCUM_FRAME_NUM = 7.0f;
+constexpr float SIGMA_DISOCCLUSION_THRESHOLD = 0.02f;  // NRD_DISOCCLUSION_THRESHOLD, Common.hlsli:63
+constexpr float NRD_FP16_MAX = 65504.0f;
+constexpr int SIGMA_BORDER = 2;  // Blur and TemporalStabilization both use the 5x5 neighbourhood
+
+NRD_DEV float sigmaUnpackViewZ(const SigmaConstants& cb, float z) { return fabsf(z * cb.viewZScale); }
+NRD_DEV bool sigmaInRange(const SigmaConstants& cb, float z) { return z < cb.denoisingRange; }
+NRD_DEV bool sigmaIsLit(float p) { return p >= NRD_FP16_MAX; }
+NRD_DEV float sigmaPackShadow(float s) { return sqrt01(s); }
+NRD_DEV float sigmaBothLitOrUnlit(float p1, float p2) { return ((p1 == 0.0f) == (p2 == 0.0f)) ? 1.0f : 0.0f; }
+// GetKernelRadiusInPixels: fminf / fmaxf are IEEE minNum / maxNum like the HLSL intrinsics (0 / 0 -> lower bound)
+NRD_DEV float sigmaKernelRadiusInPixels(float hitDist, float unprojectZ, float scale = 1.0f) {
+    float unclamped = hitDist / unprojectZ * scale;
+    float minRadius = fminf(unclamped, 2.0f);
+    return fminf(fmaxf(unclamped, minRadius), SIGMA_MAX_PIXEL_RADIUS);
+}
+
+// TextureCubic( gIn_Tiles, uv ).y — B-spline reconstruction from four bilinear taps (SIGMA_Common.hlsli:46-95)
+NRD_DEV float3 sigmaCubicAxis(float f) {
+    const float k = 1.0f / 6.0f;
+    float f2 = f * f, f3 = f2 * f;
+    float px = k * (-f3 + 3.0f * f2 - 3.0f * f + 1.0f);
+    float py = k * (3.0f * f3 - 6.0f * f2 + 4.0f);
+    float pz = k * (-3.0f * f3 + 3.0f * f2 + 3.0f * f + 1.0f);
+    float pw = k * f3;
+    return make_float3(1.0f + f - py / (px + py), 1.0f - f + pw / (pz + pw), px + py);
+}
+NRD_DEV float sigmaTileValue(const TexRG8& tiles, float2 uv) {
+    float2 size = make_float2((float)tiles.w, (float)tiles.h);
+    float2 f = frac2(uv * size - 0.5f);
+    float3 xw = sigmaCubicAxis(f.x), yw = sigmaCubicAxis(f.y);
+    float dx = -1.0f / size.x, dy = -1.0f / size.y;
+    float u10 = uv.x + xw.x * dx, u00 = uv.x - xw.y * dx;
+    float v1 = uv.y + yw.x * dy, v0 = uv.y - yw.y * dy;
+    float c00 = tiles.sampleLinear(make_float2(u00, v0)).y, c10 = tiles.sampleLinear(make_float2(u10, v0)).y;
+    float c01 = tiles.sampleLinear(make_float2(u00, v1)).y, c11 = tiles.sampleLinear(make_float2(u10, v1)).y;
+    c00 = lerp(c00, c01, yw.z);
+    c10 = lerp(c10, c11, yw.z);
+    return lerp(c00, c10, xw.z);
+}
+
+// ---- launch parameter blocks (member order = shader register order = DispatchDesc::resources order) ----------
+struct SigmaClassifyTilesParams { TexR32F viewZ; TexR16F penumbra; TexRGBA8 outTiles; };
+struct SigmaSmoothTilesParams { TexRGBA8 tiles; TexRG8 outTiles; };
+struct SigmaCopyParams { TexRG8 tiles; TexR8 history; TexR32U historyLength; TexR8 outHistory; TexR32U outHistoryLength; };
+struct SigmaBlurParams { TexR32F viewZ; TexNR normalRoughness; TexR16F penumbra; TexRG8 tiles; TexR8 shadow; TexR16F outPenumbra; TexR8 outShadow; };
+struct SigmaTemporalStabilizationParams {
+    TexR32F viewZ; TexRGBA16F mv; TexR16F penumbra; TexR8 shadow; TexR8 history; TexR32U historyLength; TexRG8 tiles;
+    TexR8 outShadow; TexR32U outHistoryLength;
+};
+struct SigmaSplitScreenParams { TexR32F viewZ; TexR16F penumbra; TexR8 outShadow; };
+
+}  // namespace nrdk

@@ -80,8 +80,9 @@ def common_settings(frame_index: int, width: int, height: int, period: int = 0, 
 # ------------------------------------------------------------------------------------------------
 # Scene
 # ------------------------------------------------------------------------------------------------
-def _scene():
-    """(kind, params, roughness, materialID). Fixed layout, units ~ metres."""
+def _scene(shadow_casters: bool = False):
+    """(kind, params, roughness, materialID). Fixed layout, units ~ metres. `shadow_casters` adds off-screen occluders
+    (a floating slab and two beams) that only shadow rays see, so a good part of the ground lies in wide penumbra."""
     objs = [("plane_y", (0.0,), 0.5, 0), ("plane_z", (20.0, 7.5), 1.0, 0)]
     rough = (0.05, 0.2, 0.5, 1.0)
     for i in range(12):
@@ -94,21 +95,17 @@ def _scene():
         cz = 3.0 + 1.1 * ((i * 3) % 5)
         r = 0.45 + 0.1 * (i % 3)
         objs.append(("sphere", (cx, r, cz, r), rough[(i + 1) % 4], (i + 1) % 2))
+    if shadow_casters:
+        objs.append(("box", (-7.0, 3.0, 2.0, -1.0, 3.2, 9.0), 1.0, 0))
+        objs.append(("box", (1.0, 5.0, 1.0, 1.4, 5.4, 16.0), 1.0, 0))
+        objs.append(("box", (4.0, 2.0, 0.0, 9.0, 2.2, 0.6), 1.0, 0))
     return objs
 
 
-def _raycast(cam: Camera, width: int, height: int, device, dtype=torch.float32):
-    ys, xs = torch.meshgrid(torch.arange(height, device=device, dtype=dtype), torch.arange(width, device=device, dtype=dtype), indexing="ij")
-    u = (xs + 0.5) / width
-    v = (ys + 0.5) / height
-    # view-space ray through the pixel centre, z = 1 (LH, +y up, uv.y down)
-    dvx = (u * 2.0 - 1.0) * (cam.tan_half_fov_y * cam.aspect)
-    dvy = (1.0 - v * 2.0) * cam.tan_half_fov_y
-    Rt = cam.rotation.t().to(device=device, dtype=dtype)          # view->world
-    dv = torch.stack([dvx, dvy, torch.ones_like(dvx)], -1)
-    d = dv @ Rt.t()
-    o = torch.tensor(cam.position, device=device, dtype=dtype)
-
+def _intersect(o: torch.Tensor, d: torch.Tensor, shadow_casters: bool = False):
+    """Nearest hit of the rays o + t d (o, d: H x W x 3) with the scene: (t or inf, normal, roughness, materialID)."""
+    height, width = d.shape[0], d.shape[1]
+    device, dtype = d.device, d.dtype
     inf = torch.full((height, width), float("inf"), device=device, dtype=dtype)
     tbest = inf.clone()
     nbest = torch.zeros(height, width, 3, device=device, dtype=dtype)
@@ -116,14 +113,14 @@ def _raycast(cam: Camera, width: int, height: int, device, dtype=torch.float32):
     mat = torch.zeros(height, width, device=device, dtype=dtype)
     eps = 1e-9
 
-    for kind, p, r, m in _scene():
+    for kind, p, r, m in _scene(shadow_casters):
         if kind == "plane_y":
-            t = (p[0] - o[1]) / (d[..., 1] - eps)
+            t = (p[0] - o[..., 1]) / (d[..., 1] - eps)
             n = torch.tensor([0.0, 1.0, 0.0], device=device, dtype=dtype).expand(height, width, 3)
             ok = (t > 0) & (d[..., 1] < 0)
         elif kind == "plane_z":
-            t = (p[0] - o[2]) / (d[..., 2] + eps)
-            hit_y = o[1] + t * d[..., 1]
+            t = (p[0] - o[..., 2]) / (d[..., 2] + eps)
+            hit_y = o[..., 1] + t * d[..., 1]
             n = torch.tensor([0.0, 0.0, -1.0], device=device, dtype=dtype).expand(height, width, 3)
             ok = (t > 0) & (hit_y < p[1])
         elif kind == "box":
@@ -146,7 +143,7 @@ def _raycast(cam: Camera, width: int, height: int, device, dtype=torch.float32):
             oc = o - c
             dd = (d * d).sum(-1)
             b = (d * oc).sum(-1)
-            cc = (oc * oc).sum() - p[3] * p[3]
+            cc = (oc * oc).sum(-1) - p[3] * p[3]
             disc = b * b - dd * cc
             ok = disc > 0
             t = (-b - torch.sqrt(disc.clamp_min(0))) / dd
@@ -158,6 +155,23 @@ def _raycast(cam: Camera, width: int, height: int, device, dtype=torch.float32):
         nbest = torch.where(closer.unsqueeze(-1), n, nbest)
         rough = torch.where(closer, torch.full_like(rough, r), rough)
         mat = torch.where(closer, torch.full_like(mat, float(m)), mat)
+
+    return tbest, nbest, rough, mat
+
+
+def _raycast(cam: Camera, width: int, height: int, device, dtype=torch.float32):
+    ys, xs = torch.meshgrid(torch.arange(height, device=device, dtype=dtype), torch.arange(width, device=device, dtype=dtype), indexing="ij")
+    u = (xs + 0.5) / width
+    v = (ys + 0.5) / height
+    # view-space ray through the pixel centre, z = 1 (LH, +y up, uv.y down)
+    dvx = (u * 2.0 - 1.0) * (cam.tan_half_fov_y * cam.aspect)
+    dvy = (1.0 - v * 2.0) * cam.tan_half_fov_y
+    Rt = cam.rotation.t().to(device=device, dtype=dtype)          # view->world
+    dv = torch.stack([dvx, dvy, torch.ones_like(dvx)], -1)
+    d = dv @ Rt.t()
+    o = torch.tensor(cam.position, device=device, dtype=dtype)
+
+    tbest, nbest, rough, mat = _intersect(o.expand(height, width, 3), d)
 
     hit = torch.isfinite(tbest)
     tsafe = torch.where(hit, tbest, torch.zeros_like(tbest))
@@ -280,5 +294,62 @@ def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period
     if with_clean:
         out["_clean_diff"] = diff_clean
         out["_clean_spec"] = spec_clean
+        out["_hit"] = hit
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# SIGMA_SHADOW inputs
+# ------------------------------------------------------------------------------------------------
+SIGMA_LIGHT_DIRECTION = (0.6, 0.5, 0.2)       # direction TO the light (not normalised)
+SIGMA_TAN_ANGULAR_RADIUS = math.tan(math.radians(5.0))
+FP16_MAX = 65504.0
+
+
+def sigma_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False) -> Dict[str, torch.Tensor]:
+    """All user inputs of SIGMA_SHADOW for one frame: IN_VIEWZ, IN_NORMAL_ROUGHNESS, IN_MV as for REBLUR plus IN_PENUMBRA
+    (R16F) = SIGMA_FrontEnd_PackPenumbra (NRD.hlsli:974-980) of a 1-spp shadow ray towards a disk light: 0 where the
+    surface faces away from the light, FP16_MAX where the ray escapes, distance-to-occluder * tan(angular radius) / 2 otherwise."""
+    device = torch.device(device)
+    base = reblur_frame(frame_index, width, height, device, period)
+    cam = make_camera(frame_index, width, height, period)
+    g = _raycast(cam, width, height, device)
+    hit, X, N = g["hit"], g["X"], g["N"]
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(SEED_BASE + 0x5147 + frame_index)
+    L = torch.tensor(SIGMA_LIGHT_DIRECTION, device=device, dtype=torch.float32)
+    L = L / L.norm()
+    # orthonormal frame around L, uniform sample of the light disk
+    up = torch.tensor([0.0, 0.0, 1.0], device=device)
+    T = torch.linalg.cross(up, L)
+    T = T / T.norm()
+    B = torch.linalg.cross(L, T)
+    o = X + N * 1e-3
+
+    def shadow_ray():
+        r = torch.sqrt(torch.rand(height, width, device=device, generator=gen)) * SIGMA_TAN_ANGULAR_RADIUS
+        phi = torch.rand(height, width, device=device, generator=gen) * (2.0 * math.pi)
+        d = L + (r * torch.cos(phi)).unsqueeze(-1) * T + (r * torch.sin(phi)).unsqueeze(-1) * B
+        d = d / d.norm(dim=-1, keepdim=True)
+        return _intersect(o, d, shadow_casters=True)[0]
+
+    t = shadow_ray()
+    ndl = (N * L).sum(-1)
+    dist = torch.where(torch.isfinite(t), t, torch.full_like(t, FP16_MAX))
+    penumbra = torch.where(dist >= FP16_MAX, torch.full_like(dist, FP16_MAX), (dist * SIGMA_TAN_ANGULAR_RADIUS * 0.5).clamp_max(32768.0))
+    penumbra = torch.where(ndl <= 0.0, torch.zeros_like(penumbra), penumbra)
+    penumbra = torch.where(hit, penumbra, torch.full_like(penumbra, FP16_MAX))
+    out = {
+        "IN_VIEWZ": base["IN_VIEWZ"],
+        "IN_NORMAL_ROUGHNESS": base["IN_NORMAL_ROUGHNESS"],
+        "IN_MV": base["IN_MV"],
+        "IN_PENUMBRA": penumbra.to(torch.float16).contiguous(),
+    }
+    if with_clean:   # converged visibility: mean over 48 more light samples
+        vis = torch.zeros_like(ndl)
+        for _ in range(48):
+            vis += (~torch.isfinite(shadow_ray())).float()
+        out["_clean_visibility"] = torch.where(ndl <= 0.0, torch.zeros_like(vis), vis / 48.0)
         out["_hit"] = hit
     return out

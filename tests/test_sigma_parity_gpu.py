@@ -1,0 +1,137 @@
+"""GPU parity of the CUDA SIGMA_SHADOW path against the CPU oracle, through the C ABI (nrdcuDispatch / nrdcuDenoise).
+Tolerances (ours — the reference states none): UNORM8 planes (shadow, tiles) within +-1 LSB on >= 99.9 % of texels,
+R16F penumbra |a-b| <= 1e-3 + 2^-9 |b| on >= 99.9 % of texels, history-length plane (viewZ bits | 3-bit length) identical
+on >= 99.9 % of texels; closed loop over frames: shadow within +-1 LSB on >= 99.5 % of texels and PSNR >= 45 dB."""
+import os
+
+import pytest
+import torch
+
+from nrd_sample_b200 import nrd_api as api, synth
+from tests.util import compare
+
+pytestmark = pytest.mark.gpu
+R8 = api.Format.R8_UNORM
+RT = api.ResourceType
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sigma_96x64.pt")
+
+
+@pytest.fixture(scope="module")
+def ex():
+    from nrd_sample_b200 import executor
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    executor.load()
+    return executor
+
+
+@pytest.fixture(scope="module")
+def runner():
+    from oracle import runner as r
+    return r
+
+
+@pytest.mark.parametrize("w,h", [(208, 120), (320, 192)])
+def test_per_pass_parity(ex, runner, w, h):
+    """Every dispatch of 5 frames replayed on the GPU from the oracle's own pre-dispatch textures (208x120 is not a multiple of the
+    16-pixel tile nor of the 32x8 CTA: partial tiles, clamped shared-memory aprons)."""
+    orc = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.SIGMA_SHADOW, w, h)
+    orc.set_user_texture(RT.OUT_SHADOW_TRANSLUCENCY, runner.alloc_texture(R8, w, h))
+    worst, snap = {}, {}
+
+    def before(i, d, keys, den):
+        snap["t"] = [den.textures[k].clone() for k in keys]
+
+    def after(i, d, keys, den):
+        gpu = [t.to("cuda:0") for t in snap["t"]]
+        ex.dispatch(d.shader, d.constants, [ex.texture_of(g, den.formats[k]) for g, k in zip(gpu, keys)])
+        torch.cuda.synchronize()
+        for j, (b, k) in enumerate(zip(d.bindings, keys)):
+            if b.descriptor != int(api.DescriptorType.STORAGE_TEXTURE):
+                continue
+            r = compare(gpu[j], den.textures[k], den.formats[k], layout="sigma")
+            key = (d.shader, j, api.Format(den.formats[k]).name)
+            if key not in worst or r["frac_bad"] > worst[key]["frac_bad"]:
+                worst[key] = r
+
+    for f in range(5):
+        for k, v in synth.sigma_frame(f, w, h).items():
+            orc.set_user_texture(getattr(RT, k), v)
+        orc.denoise(synth.common_settings(f, w, h), before_dispatch=before, on_dispatch=after)
+
+    shaders = {k[0].split("|")[0] for k in worst}
+    assert {"SIGMA_ClassifyTiles.cs.hlsl", "SIGMA_SmoothTiles.cs.hlsl", "SIGMA_Copy.cs.hlsl", "SIGMA_Blur.cs.hlsl", "SIGMA_TemporalStabilization.cs.hlsl"} <= shaders
+    for key, r in worst.items():
+        assert r["frac_bad"] <= 1e-3, f"{key}: {r}"
+
+
+def test_closed_loop_and_golden(ex, runner):
+    g = torch.load(GOLDEN)
+    for (w, h, n, golden) in ((g["width"], g["height"], len(g["inputs"]), True), (256, 144, 10, False)):
+        cud = ex.CudaDenoiser(api.Denoiser.SIGMA_SHADOW, w, h)
+        orc = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.SIGMA_SHADOW, w, h)
+        go, co = ex.alloc_texture(R8, w, h, "cuda:0"), runner.alloc_texture(R8, w, h)
+        cud.set_user_texture(RT.OUT_SHADOW_TRANSLUCENCY, go, R8)
+        orc.set_user_texture(RT.OUT_SHADOW_TRANSLUCENCY, co)
+        keep = {}
+        for f in range(n):
+            frame = {k: v.clone() for k, v in g["inputs"][f].items()} if golden else synth.sigma_frame(f, w, h)
+            for k, v in frame.items():
+                rt = getattr(RT, k)
+                orc.set_user_texture(rt, v)
+                keep[k] = v.to("cuda:0")
+                cud.set_user_texture(rt, keep[k], runner.USER_FORMATS[rt])
+            cs = synth.common_settings(f, w, h)
+            orc.denoise(cs)
+            cud.set_common_settings(cs)
+            cud.denoise()
+            torch.cuda.synchronize()
+            r = compare(go, co, R8)
+            assert r["frac_bad"] <= 5e-3 and r["psnr"] >= 45.0, f"{w}x{h} frame {f}: {r}"
+            if golden:
+                r = compare(go, g["outputs"][f], R8)
+                assert r["frac_bad"] <= 5e-3 and r["psnr"] >= 45.0, f"golden frame {f}: {r}"
+        cud.close()
+
+
+def test_full_size_invariants_1440p(ex):
+    """Size-independent properties at 2560x1440: determinism, black stays black, lit stays lit, error against the converged
+    visibility drops by > 8 dB, history length reaches its 3-bit cap on static surfaces."""
+    w, h, n = 2560, 1440, 8
+    fmts = {"IN_VIEWZ": api.Format.R32_SFLOAT, "IN_NORMAL_ROUGHNESS": api.Format.R10_G10_B10_A2_UNORM, "IN_MV": api.Format.RGBA16_SFLOAT,
+            "IN_PENUMBRA": api.Format.R16_SFLOAT}
+    outs = []
+    for rep in range(2):
+        cud = ex.CudaDenoiser(api.Denoiser.SIGMA_SHADOW, w, h)
+        out = ex.alloc_texture(R8, w, h, "cuda:0")
+        cud.set_user_texture(RT.OUT_SHADOW_TRANSLUCENCY, out, R8)
+        for f in range(n):
+            frame = synth.sigma_frame(f, w, h, device="cuda:0", with_clean=(f == n - 1 and rep == 0))
+            for k, v in frame.items():
+                if not k.startswith("_"):
+                    cud.set_user_texture(getattr(RT, k), v, fmts[k])
+            cud.set_common_settings(synth.common_settings(f, w, h))
+            cud.denoise()
+            torch.cuda.synchronize()
+        outs.append(out.clone())
+        if rep == 0:
+            m, clean = frame["_hit"], frame["_clean_visibility"]
+            pen = frame["IN_PENUMBRA"].float()
+            noisy = (pen >= synth.FP16_MAX).float()
+            shadow = (out.float() / 255.0) ** 2
+            mse_out, mse_in = ((shadow - clean) ** 2)[m].mean(), ((noisy - clean) ** 2)[m].mean()
+            assert mse_out * 6.3 < mse_in, (mse_in.item(), mse_out.item())
+            assert (out[m & (pen == 0.0)] == 0).all()
+            hl = cud.pool_texture(True, 0)
+            assert ((hl & 7)[m] >= 1).all() and ((hl & 7)[m].float().mean() > 5.0)
+        cud.close()
+    assert torch.equal(outs[0], outs[1]), "two runs on the same inputs must agree bit for bit"
+
+
+def test_errors_are_reported(ex):
+    t = ex.alloc_texture(api.Format.R32_SFLOAT, 64, 64, "cuda:0")
+    with pytest.raises(ex.NrdcuError):   # wrong constant-buffer size
+        ex.dispatch("SIGMA_SmoothTiles.cs.hlsl", b"\0" * 16, [ex.texture_of(t, api.Format.R32_SFLOAT)] * 2)
+    with pytest.raises(ex.NrdcuError):   # wrong formats
+        ex.dispatch("SIGMA_SmoothTiles.cs.hlsl", b"\0" * 528, [ex.texture_of(t, api.Format.R32_SFLOAT)] * 2)
+    with pytest.raises(ex.NrdcuError, match="UNSUPPORTED"):
+        ex.dispatch("SIGMA_Blur.cs.hlsl|TRANSLUCENCY=1|FIRST_PASS=1", b"\0" * 528, [])

@@ -8,10 +8,15 @@ import torch
 from nrd_sample_b200 import nrd_api as api
 
 
-def decode(t: torch.Tensor, fmt: int) -> torch.Tensor:
-    """Storage tensor -> float tensor (H, W, C) of decoded channel values (integers stay integers-as-float)."""
+def decode(t: torch.Tensor, fmt: int, layout: str = "reblur") -> torch.Tensor:
+    """Storage tensor -> float tensor (H, W, C) of decoded channel values (integers stay integers-as-float).
+    `layout` selects the meaning of R32_UINT planes: "reblur" = REBLUR data2, "sigma" = asuint(viewZ) & ~7 | history length."""
     t = t.detach().cpu()
     f = api.Format(fmt)
+    if f == api.Format.R32_UINT and layout == "sigma":
+        v = t.to(torch.int64) & 0xFFFFFFFF
+        z = ((v & 0xFFFFFFF8) - ((v & 0x80000000) << 1)).to(torch.int32).view(torch.float32)   # two's complement back to int32 bits
+        return torch.stack([z, (v & 7).float()], -1)
     if f == api.Format.R10_G10_B10_A2_UNORM:
         v = t.to(torch.int64) & 0xFFFFFFFF
         return torch.stack([(v & 1023), (v >> 10) & 1023, (v >> 20) & 1023, (v >> 30) & 3], -1).float()
@@ -26,10 +31,10 @@ def decode(t: torch.Tensor, fmt: int) -> torch.Tensor:
     return x if x.dim() == 3 else x.unsqueeze(-1)
 
 
-def compare(a: torch.Tensor, b: torch.Tensor, fmt: int, atol=1e-3, rtol=2 ** -9):
+def compare(a: torch.Tensor, b: torch.Tensor, fmt: int, atol=1e-3, rtol=2 ** -9, layout: str = "reblur"):
     """a = under test, b = oracle. Returns dict(frac_bad, max_abs, psnr, n)."""
     f = api.Format(fmt)
-    da, db = decode(a, fmt), decode(b, fmt)
+    da, db = decode(a, fmt, layout), decode(b, fmt, layout)
     assert da.shape == db.shape, (da.shape, db.shape)
     both_nan = torch.isnan(da) & torch.isnan(db)
     da = torch.where(both_nan, torch.zeros_like(da), da)
@@ -39,6 +44,8 @@ def compare(a: torch.Tensor, b: torch.Tensor, fmt: int, atol=1e-3, rtol=2 ** -9)
         bad = diff > 1.0
     elif f == api.Format.R16_UINT:
         bad = diff > 0.0
+    elif f == api.Format.R32_UINT and layout == "sigma":
+        bad = diff > 0.0                                                     # viewZ bits and 3-bit history length: identical
     elif f == api.Format.R32_UINT:
         bad = diff > 0.0
         bad[..., 1] = diff[..., 1] > 1.0                                     # 7-bit virtual history amount: +-1 LSB

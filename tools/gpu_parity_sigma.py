@@ -1,0 +1,73 @@
+"""GPU box helper: per-dispatch and closed-loop parity of the CUDA SIGMA_SHADOW path against the CPU oracle.
+usage: python tools/gpu_parity_sigma.py W H FRAMES"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nrd_sample_b200 import nrd_api as api, synth, executor as ex  # noqa: E402
+from oracle import runner  # noqa: E402
+from tests.util import compare  # noqa: E402
+
+W, H, N = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+dev = "cuda:0"
+RT = api.ResourceType
+R8 = api.Format.R8_UNORM
+host = runner.default_host_library()
+
+orc = runner.OracleDenoiser(host, api.Denoiser.SIGMA_SHADOW, W, H)
+orc.set_user_texture(RT.OUT_SHADOW_TRANSLUCENCY, runner.alloc_texture(R8, W, H))
+worst = {}
+
+
+def before(i, d, keys, den):
+    den._snap = [den.textures[k].clone() for k in keys]
+
+
+def after(i, d, keys, den):
+    if d.name.startswith("Clear"):
+        return
+    gpu = [t.to(dev) for t in den._snap]
+    texs = [ex.texture_of(g, den.formats[k]) for g, k in zip(gpu, keys)]
+    ex.dispatch(d.shader, d.constants, texs)
+    torch.cuda.synchronize()
+    for j, (b, k) in enumerate(zip(d.bindings, keys)):
+        if b.descriptor != 1:
+            continue
+        r = compare(gpu[j], den.textures[k], den.formats[k], layout="sigma")
+        key = (d.name.split(" - ")[-1], d.shader.split("|")[-1][:14], j, api.Format(den.formats[k]).name)
+        w = worst.get(key)
+        if w is None or r["frac_bad"] > w["frac_bad"]:
+            worst[key] = r
+
+
+for f in range(N):
+    fr = synth.sigma_frame(f, W, H)
+    for k, v in fr.items():
+        orc.set_user_texture(getattr(RT, k), v)
+    orc.denoise(synth.common_settings(f, W, H), before_dispatch=before, on_dispatch=after)
+for k, r in worst.items():
+    print(f"{k[0]:24s} {k[1]:14s} binding {k[2]:2d} {k[3]:14s} frac_bad {r['frac_bad']:.2e} max_abs {r['max_abs']:.3e} psnr {r['psnr']:.1f}")
+
+# closed loop through nrdcuDenoise
+cud = ex.CudaDenoiser(api.Denoiser.SIGMA_SHADOW, W, H)
+orc2 = runner.OracleDenoiser(host, api.Denoiser.SIGMA_SHADOW, W, H)
+o2 = runner.alloc_texture(R8, W, H)
+orc2.set_user_texture(RT.OUT_SHADOW_TRANSLUCENCY, o2)
+g = ex.alloc_texture(R8, W, H, dev)
+cud.set_user_texture(RT.OUT_SHADOW_TRANSLUCENCY, g, R8)
+for f in range(max(N, 10)):
+    fr = synth.sigma_frame(f, W, H)
+    gfr = {k: v.to(dev) for k, v in fr.items()}
+    for k, v in fr.items():
+        orc2.set_user_texture(getattr(RT, k), v)
+        cud.set_user_texture(getattr(RT, k), gfr[k], runner.USER_FORMATS[getattr(RT, k)])
+    cs = synth.common_settings(f, W, H)
+    orc2.denoise(cs)
+    cud.set_common_settings(cs)
+    cud.denoise()
+    torch.cuda.synchronize()
+    r = compare(g, o2, R8)
+    print(f"closed loop frame {f}: shadow psnr {r['psnr']:.1f} bad(>1 LSB) {r['frac_bad']:.2e} max_abs {r['max_abs']:.1f} LSB")
+print("launches", ex.launch_count())
