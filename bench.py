@@ -38,6 +38,19 @@ PUBLISHED_MPX_S = 3.6864 / 2.55e-3  # NRD/README.md:30: REBLUR_DIFFUSE_SPECULAR 
 RING = 4  # distinct frames cycled through (4 x 118 MB of inputs at 1440p >> 126 MB L2)
 
 
+def usable_cores() -> int:
+    """Host threads this process may really use: the scheduler affinity capped by the cgroup CPU quota (the GPU boxes expose
+    128 logical CPUs with a 16-CPU quota — 128 OpenMP threads would only oversubscribe it)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -87,7 +100,7 @@ def run_reference(args):
     from oracle import runner
 
     W, H = 1280, 720  # bounded sample: a quarter-size stream of the same scene (cost per pixel is resolution independent)
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     runner.lib().nrd_oracle_set_threads(threads)
     den = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H)
     out_d = runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H)
@@ -262,7 +275,7 @@ def cpu_baseline():
     from oracle import runner
 
     W, H, warm, steps = 1280, 720, 4, 8
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     runner.lib().nrd_oracle_set_threads(threads)
     den = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H)
     den.set_user_texture(api.ResourceType.OUT_DIFF_RADIANCE_HITDIST, runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H))

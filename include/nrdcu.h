@@ -54,6 +54,10 @@ enum {
  * `stream` is a cudaStream_t. Asynchronous. */
 NRDCU_API uint32_t nrdcuDispatch(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures,
                                  uint32_t texturesNum, uint32_t flags, void* stream);
+/* Same, restricted to the rect rows [rowBegin, rowEnd) (rowBegin a multiple of 16; rowEnd is clamped to the rect). Every texture is
+ * still the whole frame: a strip reads rows outside its range (the halo) and writes only rows inside it. REBLUR passes only. */
+NRDCU_API uint32_t nrdcuDispatchRows(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures,
+                                     uint32_t texturesNum, uint32_t flags, void* stream, uint32_t rowBegin, uint32_t rowEnd);
 
 /* ---- instance level ------------------------------------------------------------------------------------------
  * nrdcuCreate           == Integration::Recreate: nrd::CreateInstance + pool allocation at `resourceWidth x Height`
@@ -69,6 +73,15 @@ NRDCU_API uint32_t nrdcuSetCommonSettings(nrdcuContext* ctx, const void* commonS
 NRDCU_API uint32_t nrdcuSetDenoiserSettings(nrdcuContext* ctx, uint32_t identifier, const void* denoiserSettings);
 NRDCU_API uint32_t nrdcuSetResource(nrdcuContext* ctx, uint32_t resourceType, const nrdcuTexture* texture);
 NRDCU_API uint32_t nrdcuDenoise(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream);
+/* One frame tiled over several GPUs as horizontal strips (there is no counterpart in NRDIntegration: the reference runs one queue on
+ * one device). Like nrdcuDenoise, but every pass computes only rows [rowBegin, rowEnd); after each dispatch has been enqueued
+ * `afterDispatch` (may be NULL) is called with the dispatch's resolved textures and a flag per texture telling whether the pass wrote
+ * it, so the caller can trade the seam rows of those textures with the neighbouring strips (nrd_sample_b200/tiling.py: NCCL
+ * send/recv on the same stream) before the next pass reads them. */
+typedef void (*nrdcuDispatchCallback)(void* userArg, uint32_t dispatchIndex, const char* passName, const nrdcuTexture* textures, const uint8_t* isStorage,
+                                      uint32_t texturesNum);
+NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream, uint32_t rowBegin, uint32_t rowEnd,
+                                    nrdcuDispatchCallback afterDispatch, void* userArg);
 NRDCU_API uint32_t nrdcuGetPoolTexture(nrdcuContext* ctx, int isPermanent, uint32_t index, nrdcuTexture* out);
 NRDCU_API void* nrdcuGetInstance(nrdcuContext* ctx);
 

@@ -19,13 +19,13 @@
 namespace nrdk {
 // kernels/*.cu
 void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t stream);
-void launchReblurClassifyTiles(const ReblurConstants&, const ClassifyTilesParams&, cudaStream_t);
-void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int flags, cudaStream_t);
-void launchReblurBlur(const ReblurConstants&, const BlurParams&, int flags, cudaStream_t);
-void launchReblurPostBlur(const ReblurConstants&, const PostBlurParams&, bool temporalStabilization, int flags, cudaStream_t);
-void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccumulationParams&, cudaStream_t);
-void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, bool quads, cudaStream_t);
-void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, cudaStream_t);
+void launchReblurClassifyTiles(const ReblurConstants&, const ClassifyTilesParams&, Rows, cudaStream_t);
+void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int flags, Rows, cudaStream_t);
+void launchReblurBlur(const ReblurConstants&, const BlurParams&, int flags, Rows, cudaStream_t);
+void launchReblurPostBlur(const ReblurConstants&, const PostBlurParams&, bool temporalStabilization, int flags, Rows, cudaStream_t);
+void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccumulationParams&, Rows, cudaStream_t);
+void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, bool quads, Rows, cudaStream_t);
+void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, Rows, cudaStream_t);
 uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
 }  // namespace nrdk
 
@@ -99,7 +99,8 @@ bool checkLaunch(const char* what) {
     return true;
 }
 
-uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, uint32_t flags, cudaStream_t stream) {
+uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, uint32_t flags, nrdk::Rows rows,
+                        cudaStream_t stream) {
     using namespace nrdk;
     if (constantsSize != sizeof(ReblurConstants) || !constants) return fail(Result::INVALID_ARGUMENT, "%s: expected %zu constant bytes, got %u", id.c_str(), sizeof(ReblurConstants), constantsSize);
     ReblurConstants cb;
@@ -126,7 +127,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outTiles = b.take<TexR8>(Format::R8_UNORM);
         uint32_t r = done(2);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurClassifyTiles(cb, p, stream);
+        launchReblurClassifyTiles(cb, p, rows, stream);
     } else if (is("REBLUR_PrePass.cs.hlsl")) {
         PrePassParams p;
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
@@ -139,7 +140,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
         uint32_t r = done(8);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurPrePass(cb, p, kflags, stream);
+        launchReblurPrePass(cb, p, kflags, rows, stream);
     } else if (is("REBLUR_TemporalAccumulation.cs.hlsl")) {
         TemporalAccumulationParams p;
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
@@ -169,7 +170,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outData2 = b.take<TexR32U>(Format::R32_UINT);
         uint32_t r = done(25);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurTemporalAccumulation(cb, p, stream);
+        launchReblurTemporalAccumulation(cb, p, rows, stream);
     } else if (is("REBLUR_HistoryFix.cs.hlsl")) {
         HistoryFixParams p;
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
@@ -187,7 +188,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecFast = b.take<TexR16F>(Format::R16_SFLOAT);
         uint32_t r = done(13);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurHistoryFix(cb, p, quads, stream);
+        launchReblurHistoryFix(cb, p, quads, rows, stream);
     } else if (is("REBLUR_Blur.cs.hlsl")) {
         BlurParams p;
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
@@ -201,7 +202,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
         uint32_t r = done(9);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurBlur(cb, p, kflags, stream);
+        launchReblurBlur(cb, p, kflags, rows, stream);
     } else if (is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1") || is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0")) {
         const bool ts = is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1");
         PostBlurParams p = {};
@@ -221,7 +222,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         }
         uint32_t r = done(ts ? 9 : 12);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurPostBlur(cb, p, ts, kflags, stream);
+        launchReblurPostBlur(cb, p, ts, kflags, rows, stream);
     } else if (is("REBLUR_TemporalStabilization.cs.hlsl")) {
         TemporalStabilizationParams p;
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
@@ -242,7 +243,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecLuma = b.take<TexR16F>(Format::R16_SFLOAT);
         uint32_t r = done(16);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurTemporalStabilization(cb, p, stream);
+        launchReblurTemporalStabilization(cb, p, rows, stream);
     } else {
         return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", id.c_str());
     }
@@ -260,12 +261,17 @@ extern "C" {
 NRDCU_API const char* nrdcuGetLastError(void) { return g_lastError.c_str(); }
 NRDCU_API uint64_t nrdcuGetLaunchCount(void) { return g_launchCount.load(); }
 
-NRDCU_API uint32_t nrdcuDispatch(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures, uint32_t texturesNum,
-                                 uint32_t flags, void* stream) {
+NRDCU_API uint32_t nrdcuDispatchRows(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures, uint32_t texturesNum,
+                                     uint32_t flags, void* stream, uint32_t rowBegin, uint32_t rowEnd) {
     if (!shaderIdentifier || (!textures && texturesNum)) return fail(Result::INVALID_ARGUMENT, "nrdcuDispatch: null argument");
+    if (rowBegin % 16u) return fail(Result::INVALID_ARGUMENT, "nrdcuDispatchRows: rowBegin %u is not a multiple of 16", rowBegin);
     const std::string id = shaderIdentifier;
     cudaStream_t s = (cudaStream_t)stream;
-    if (id.rfind("Clear.cs.hlsl", 0) == 0) {
+    nrdk::Rows rows;
+    rows.begin = (int)rowBegin;
+    rows.end = rowEnd > 0x7FFFFFFFu ? 0x7FFFFFFF : (int)rowEnd;
+    const bool partial = rowBegin != 0 || rowEnd != 0xFFFFFFFFu;
+    if (id.rfind("Clear.cs.hlsl", 0) == 0) {  // clears always cover the whole texture (frame 0 only)
         if (texturesNum != 1 || !textures[0].data) return fail(Result::INVALID_ARGUMENT, "Clear: exactly one texture expected");
         const nrdcuTexture& t = textures[0];
         uint32_t bpp = bytesPerTexel(t.format);
@@ -273,14 +279,20 @@ NRDCU_API uint32_t nrdcuDispatch(const char* shaderIdentifier, const void* const
         nrdk::launchClear(t.data, (int)(t.width * bpp), (int)t.height, (int)t.pitchBytes, s);
         return checkLaunch("Clear") ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
     }
-    if (id.rfind("REBLUR_", 0) == 0) return dispatchReblur(id, constants, constantsSize, textures, texturesNum, flags, s);
+    if (id.rfind("REBLUR_", 0) == 0) return dispatchReblur(id, constants, constantsSize, textures, texturesNum, flags, rows, s);
     if (id.rfind("SIGMA_", 0) == 0) {
+        if (partial) return fail(Result::UNSUPPORTED, "%s: row ranges (multi-GPU strips) are implemented for REBLUR only", shaderIdentifier);
         std::string err;
         uint32_t r = nrdk::dispatchSigma(id, constants, constantsSize, textures, texturesNum, s, err);
         if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
         return checkLaunch(id.c_str()) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
     }
     return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", shaderIdentifier);
+}
+
+NRDCU_API uint32_t nrdcuDispatch(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures, uint32_t texturesNum,
+                                 uint32_t flags, void* stream) {
+    return nrdcuDispatchRows(shaderIdentifier, constants, constantsSize, textures, texturesNum, flags, stream, 0u, 0xFFFFFFFFu);
 }
 
 }  // extern "C"
@@ -307,6 +319,7 @@ struct nrdcuContext {
     std::vector<void*> allocations;
     uint64_t poolBytes = 0;
     std::vector<nrdcuTexture> scratch;
+    std::vector<uint8_t> scratchIsStorage;
     // per-dispatch CUDA-event timing (bench.py's live roofline measurement)
     struct ProfileEntry { const char* name; double totalMs = 0; uint64_t count = 0; };
     struct PendingTiming { const char* name; cudaEvent_t start, stop; };
@@ -422,6 +435,11 @@ NRDCU_API uint32_t nrdcuGetPoolTexture(nrdcuContext* ctx, int isPermanent, uint3
 }
 
 NRDCU_API uint32_t nrdcuDenoise(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream) {
+    return nrdcuDenoiseRows(ctx, identifiers, identifiersNum, stream, 0u, 0xFFFFFFFFu, nullptr, nullptr);
+}
+
+NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream, uint32_t rowBegin, uint32_t rowEnd,
+                                    nrdcuDispatchCallback afterDispatch, void* userArg) {
     if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuDenoise: null context");
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return fail(Result::FAILURE, "cudaSetDevice: %s", cudaGetErrorString(e));
@@ -456,13 +474,19 @@ NRDCU_API uint32_t nrdcuDenoise(nrdcuContext* ctx, const uint32_t* identifiers, 
             evStop = grab();
             cudaEventRecord(evStart, (cudaStream_t)stream);
         }
-        uint32_t rc = nrdcuDispatch(d.pipelines[dd.pipelineIndex].shaderIdentifier, dd.constantBufferData, dd.constantBufferDataSize, ctx->scratch.data(), dd.resourcesNum,
-                                    ctx->flags, stream);
+        uint32_t rc = nrdcuDispatchRows(d.pipelines[dd.pipelineIndex].shaderIdentifier, dd.constantBufferData, dd.constantBufferDataSize, ctx->scratch.data(),
+                                        dd.resourcesNum, ctx->flags, stream, rowBegin, rowEnd);
         if (ctx->profiling) {
             cudaEventRecord(evStop, (cudaStream_t)stream);
             ctx->pending.push_back({dd.name, evStart, evStop});
         }
         if (rc != 0) return rc;
+        if (afterDispatch) {
+            // which bindings the dispatch wrote (storage textures): what a strip has to trade with its neighbours
+            ctx->scratchIsStorage.resize(dd.resourcesNum);
+            for (uint32_t k = 0; k < dd.resourcesNum; k++) ctx->scratchIsStorage[k] = dd.resources[k].descriptorType == DescriptorType::STORAGE_TEXTURE ? 1 : 0;
+            afterDispatch(userArg, i, dd.name, ctx->scratch.data(), ctx->scratchIsStorage.data(), dd.resourcesNum);
+        }
     }
     return 0;
 }

@@ -31,9 +31,24 @@ constexpr float ML_EPS = 1e-6f;
 #ifndef NRD_CTA_REV_MASK
 #define NRD_CTA_REV_MASK 0x35  // the reference's pattern: PrePass, HistoryFix, PostBlur, TemporalStabilization reversed
 #endif
-template <int BIT> NRD_DEV int2 ctaTile() {
-    if ((NRD_CTA_REV_MASK >> BIT) & 1) return make_int2((int)(gridDim.x - 1u - blockIdx.x), (int)(gridDim.y - 1u - blockIdx.y));
-    return make_int2((int)blockIdx.x, (int)blockIdx.y);
+// `ctaY0`: first CTA row of the launch when only a strip of rows is computed (multi-GPU strips, nrdcuDenoiseRows)
+template <int BIT> NRD_DEV int2 ctaTile(int ctaY0) {
+    if ((NRD_CTA_REV_MASK >> BIT) & 1) return make_int2((int)(gridDim.x - 1u - blockIdx.x), ctaY0 + (int)(gridDim.y - 1u - blockIdx.y));
+    return make_int2((int)blockIdx.x, ctaY0 + (int)blockIdx.y);
+}
+
+// Rows [begin, end) of the rect a launch covers; begin must be a multiple of 16 (tile- and CTA-aligned)
+struct Rows {
+    int begin = 0, end = 0x7FFFFFFF;
+};
+struct RowGrid {
+    int ctaY0;
+    unsigned count;
+};
+inline RowGrid rowGrid(Rows r, int rectHeight, int blockHeight) {
+    const int b = r.begin < 0 ? 0 : r.begin, e = r.end < rectHeight ? r.end : rectHeight;
+    if (e <= b) return {0, 0u};
+    return {b / blockHeight, (unsigned)((e - b + blockHeight - 1) / blockHeight)};
 }
 
 // =================================================================================================================

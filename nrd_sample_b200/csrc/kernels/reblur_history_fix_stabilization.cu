@@ -165,14 +165,14 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
 }
 }  // namespace
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HistoryFixParams p, int quads) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HistoryFixParams p, int quads, int ctaY0) {
     __shared__ float sDiffLuma[HF_TILE_H][HF_TILE_W];
     __shared__ float sSpecLuma[HF_TILE_H][HF_TILE_W];
     // row sums of { v, v^2 } over windows of 3 / 5 / 9 texels centred on the 32 interior columns, per lobe
     __shared__ float2 sDiffRow[3][HF_TILE_H][BLOCK_W];
     __shared__ float2 sSpecRow[3][HF_TILE_H][BLOCK_W];
 
-    const int2 cta = ctaTile<2>();
+    const int2 cta = ctaTile<2>(ctaY0);
     const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
     const int tid = threadIdx.y * BLOCK_W + threadIdx.x;
     int sawSky = 0;
@@ -273,11 +273,11 @@ NRD_DEV void lumaMoments3x3(const float (*sLuma)[TS_TILE_W], float& luma, float&
 #    define TS_MIN_BLOCKS 3  // 512-thread CTAs: 40 regs + a small spill (3 CTAs / SM) beats 64 regs (2 CTAs) by 12 % on B200
 #endif
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTemporalStabilizationKernel(const __grid_constant__ ReblurConstants cb,
-                                                                                       const __grid_constant__ TemporalStabilizationParams p) {
+                                                                                       const __grid_constant__ TemporalStabilizationParams p, int ctaY0) {
     __shared__ float sDiffLuma[TS_TILE_H][TS_TILE_W];
     __shared__ float sSpecLuma[TS_TILE_H][TS_TILE_W];
 
-    const int2 cta = ctaTile<5>();
+    const int2 cta = ctaTile<5>(ctaY0);
     const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
     {
         const int baseX = cta.x * BLOCK_W - TS_BORDER, baseY = cta.y * BLOCK_H - TS_BORDER;
@@ -437,13 +437,17 @@ void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t s
     clearKernel<<<dim3(blocksX, height), 256, 0, stream>>>((uint8_t*)data, rowBytes, height, pitch);
 }
 
-void launchReblurHistoryFix(const ReblurConstants& cb, const HistoryFixParams& p, bool quads, cudaStream_t stream) {
-    dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, (cb.rectSizeMinusOne[1] + BLOCK_H) / BLOCK_H);
-    reblurHistoryFixKernel<<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, quads ? 1 : 0);
+void launchReblurHistoryFix(const ReblurConstants& cb, const HistoryFixParams& p, bool quads, Rows rows, cudaStream_t stream) {
+    const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
+    if (!g.count) return;
+    dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
+    reblurHistoryFixKernel<<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
 }
-void launchReblurTemporalStabilization(const ReblurConstants& cb, const TemporalStabilizationParams& p, cudaStream_t stream) {
-    dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, (cb.rectSizeMinusOne[1] + BLOCK_H) / BLOCK_H);
-    reblurTemporalStabilizationKernel<<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p);
+void launchReblurTemporalStabilization(const ReblurConstants& cb, const TemporalStabilizationParams& p, Rows rows, cudaStream_t stream) {
+    const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
+    if (!g.count) return;
+    dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
+    reblurTemporalStabilizationKernel<<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
 }
 
 }  // namespace nrdk

@@ -305,18 +305,18 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
 
 // ---------------------------------------------------------------------------------------------------------------
 // One CTA of 256 threads per 16x16 tile: each thread tests one pixel, the verdict is a block-wide AND.
-__global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ ClassifyTilesParams p) {
-    int tx = blockIdx.x, ty = blockIdx.y;
+__global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ ClassifyTilesParams p, int ctaY0) {
+    int tx = blockIdx.x, ty = ctaY0 + blockIdx.y;
     int px = tx * 16 + (threadIdx.x & 15), py = ty * 16 + (threadIdx.x >> 4);
     float viewZ = unpackViewZ(cb, p.inViewZ.load(px, py));
     int allSky = __syncthreads_and(!inDenoisingRange(cb, viewZ));
     if (threadIdx.x == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags, int ctaY0) {
     const bool robust = (flags & 2) != 0;
     Center s;
-    const int2 cta = ctaTile<0>();
+    const int2 cta = ctaTile<0>(ctaY0);
     s.px = cta.x * BLOCK_W + threadIdx.x;
     s.py = cta.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(s.px >> 4, s.py >> 4) != 0.0f || s.px > cb.rectSizeMinusOne[0] || s.py > cb.rectSizeMinusOne[1]) return;
@@ -342,10 +342,10 @@ NRD_DEV float2 quadSmoothedAccumSpeed(const ReblurConstants& cb, float2 data1, f
     return n;
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
-    const int2 cta = ctaTile<3>();
+    const int2 cta = ctaTile<3>(ctaY0);
     s.px = cta.x * BLOCK_W + threadIdx.x;
     s.py = cta.y * BLOCK_H + threadIdx.y;
 
@@ -366,10 +366,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBl
 }
 
 template <bool TEMPORAL_STABILIZATION>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
-    const int2 cta = ctaTile<4>();
+    const int2 cta = ctaTile<4>(ctaY0);
     s.px = cta.x * BLOCK_W + threadIdx.x;
     s.py = cta.y * BLOCK_H + threadIdx.y;
 
@@ -391,23 +391,29 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPo
 // ---------------------------------------------------------------------------------------------------------------
 // Host launchers (called by the executor)
 // ---------------------------------------------------------------------------------------------------------------
-static dim3 pixelGrid(const ReblurConstants& cb) { return dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, (cb.rectSizeMinusOne[1] + BLOCK_H) / BLOCK_H); }
-
-void launchReblurClassifyTiles(const ReblurConstants& cb, const ClassifyTilesParams& p, cudaStream_t stream) {
-    dim3 grid((cb.rectSizeMinusOne[0] + 16) / 16, (cb.rectSizeMinusOne[1] + 16) / 16);
-    reblurClassifyTilesKernel<<<grid, 256, 0, stream>>>(cb, p);
+void launchReblurClassifyTiles(const ReblurConstants& cb, const ClassifyTilesParams& p, Rows rows, cudaStream_t stream) {
+    const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, 16);
+    if (!g.count) return;
+    reblurClassifyTilesKernel<<<dim3((cb.rectSizeMinusOne[0] + 16) / 16, g.count), 256, 0, stream>>>(cb, p, g.ctaY0);
 }
-void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int flags, cudaStream_t stream) {
-    reblurPrePassKernel<<<pixelGrid(cb), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags);
+void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int flags, Rows rows, cudaStream_t stream) {
+    const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
+    if (!g.count) return;
+    reblurPrePassKernel<<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
 }
-void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int flags, cudaStream_t stream) {
-    reblurBlurKernel<<<pixelGrid(cb), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags);
+void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int flags, Rows rows, cudaStream_t stream) {
+    const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
+    if (!g.count) return;
+    reblurBlurKernel<<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
 }
-void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, bool temporalStabilization, int flags, cudaStream_t stream) {
+void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, bool temporalStabilization, int flags, Rows rows, cudaStream_t stream) {
+    const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
+    if (!g.count) return;
+    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
     if (temporalStabilization)
-        reblurPostBlurKernel<true><<<pixelGrid(cb), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags);
+        reblurPostBlurKernel<true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
     else
-        reblurPostBlurKernel<false><<<pixelGrid(cb), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags);
+        reblurPostBlurKernel<false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
 }
 
 }  // namespace nrdk

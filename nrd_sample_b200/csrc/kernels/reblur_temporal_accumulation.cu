@@ -43,10 +43,10 @@ NRD_DEV uint4 gather4(const TexR16U& t, int x0, int y0) {
 #    define TA_MIN_BLOCKS 3  // 80 regs + 88 B spill (3 CTAs / SM): 450 us vs 514 us at 128 regs (2 CTAs) for a 1440p frame on B200
 #endif
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTemporalAccumulationKernel(const __grid_constant__ ReblurConstants cb,
-                                                                                      const __grid_constant__ TemporalAccumulationParams p) {
+                                                                                      const __grid_constant__ TemporalAccumulationParams p, int ctaY0) {
     __shared__ float4 sNormalHitDist[TILE_H][TILE_W];
 
-    const int2 cta = ctaTile<1>();
+    const int2 cta = ctaTile<1>(ctaY0);
     const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
     const float2 rectSize = make_float2(cb.rectSize[0], cb.rectSize[1]);
     const float2 rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
@@ -570,9 +570,11 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
     p.outData1.store(px, py, packData1(diffAccumSpeed, specAccumSpeedCorrected));
 }
 
-void launchReblurTemporalAccumulation(const ReblurConstants& cb, const TemporalAccumulationParams& p, cudaStream_t stream) {
-    dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, (cb.rectSizeMinusOne[1] + BLOCK_H) / BLOCK_H);
-    reblurTemporalAccumulationKernel<<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p);
+void launchReblurTemporalAccumulation(const ReblurConstants& cb, const TemporalAccumulationParams& p, Rows rows, cudaStream_t stream) {
+    const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
+    if (!g.count) return;
+    dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
+    reblurTemporalAccumulationKernel<<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
 }
 
 }  // namespace nrdk

@@ -23,7 +23,7 @@ FLAG_QUAD_INTRINSICS = 1
 FLAG_CUDA_GRAPH = 2
 FLAG_ROBUST_MIRROR_TEST = 4
 
-NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
+NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
                  "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuGetLastError", "nrdcuGetLaunchCount",
                  "nrdcuGetPoolBytes", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile")
 
@@ -40,6 +40,9 @@ FORMAT_STORAGE = {
     api.Format.R10_G10_B10_A2_UNORM: (torch.int32, 1),
 }
 
+# void (*nrdcuDispatchCallback)(void* userArg, uint32_t dispatchIndex, const char* passName, const nrdcuTexture*, const uint8_t* isStorage, uint32_t n)
+DISPATCH_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_char_p, C.POINTER(CuTexture), C.POINTER(C.c_uint8), C.c_uint32)
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -50,6 +53,10 @@ def load() -> C.CDLL:
         L = C.CDLL(path)
         L.nrdcuDispatch.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.POINTER(CuTexture), C.c_uint32, C.c_uint32, C.c_void_p]
         L.nrdcuDispatch.restype = C.c_uint32
+        L.nrdcuDispatchRows.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.POINTER(CuTexture), C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.nrdcuDispatchRows.restype = C.c_uint32
+        L.nrdcuDenoiseRows.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, DISPATCH_CALLBACK, C.c_void_p]
+        L.nrdcuDenoiseRows.restype = C.c_uint32
         L.nrdcuCreate.argtypes = [C.c_void_p, C.c_uint16, C.c_uint16, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
         L.nrdcuCreate.restype = C.c_uint32
         L.nrdcuDestroy.argtypes = [C.c_void_p]
@@ -113,12 +120,16 @@ def alloc_texture(fmt: int, width: int, height: int, device) -> torch.Tensor:
     return torch.zeros(shape, dtype=dtype, device=device)
 
 
-def dispatch(shader: str, constants: bytes, textures: Sequence[CuTexture], flags: int = FLAG_QUAD_INTRINSICS, stream: Optional[torch.cuda.Stream] = None):
-    """One pass (== one nrd::DispatchDesc) on caller-provided device textures."""
+def dispatch(shader: str, constants: bytes, textures: Sequence[CuTexture], flags: int = FLAG_QUAD_INTRINSICS, stream: Optional[torch.cuda.Stream] = None,
+             rows: Optional[Sequence[int]] = None):
+    """One pass (== one nrd::DispatchDesc) on caller-provided device textures; `rows` = (begin, end) restricts it to a strip."""
     arr = (CuTexture * len(textures))(*textures)
     cb = C.create_string_buffer(constants, len(constants)) if constants else None
     s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
-    _check(load().nrdcuDispatch(shader.encode(), cb, len(constants), arr, len(textures), flags, C.c_void_p(s)), f"nrdcuDispatch({shader})")
+    if rows is None:
+        _check(load().nrdcuDispatch(shader.encode(), cb, len(constants), arr, len(textures), flags, C.c_void_p(s)), f"nrdcuDispatch({shader})")
+    else:
+        _check(load().nrdcuDispatchRows(shader.encode(), cb, len(constants), arr, len(textures), flags, C.c_void_p(s), rows[0], rows[1]), f"nrdcuDispatchRows({shader})")
 
 
 class CudaDenoiser:

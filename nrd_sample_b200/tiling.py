@@ -1,0 +1,138 @@
+"""One frame tiled over N GPUs as horizontal strips with halo exchange at the seams
+(BASELINE.json config 3: REBLUR_DIFFUSE_SPECULAR 3840x2160 over 2/4/8 B200).
+
+Layout. Every rank owns a full-resolution nrdcuContext (pools are 0.6 GB at 4K — memory is not the constraint) but
+computes only the rows [y0, y1) of its strip in every pass (`nrdcuDenoiseRows`). Strip boundaries are multiples of 16
+rows, so the 16x16 sky-tile classification and every CTA (32x8 / 32x16 pixels) are strip-local. The noisy inputs are
+provided full frame (a tiled renderer would render its strip plus the apron).
+
+Exchange. A pass reads its inputs through gathers that reach up to 60 rows away (post-blur: 2 x maxBlurRadius;
+history fix: 2 x 14 + 4; temporal passes: motion vector + 2), and what it reads was written by an earlier pass — or by
+the previous frame — on the NEIGHBOUR rank for rows outside the strip. So after every dispatch each rank sends the
+`halo` rows at the edges of its strip of every texture the dispatch wrote to the neighbour above / below, and receives
+the neighbour's rows into the apron of its own copy: one batched NCCL send/recv group per pass over NVLink, 6-7 per
+frame. With halo >= the largest reach the N-GPU result is bit-identical to the single-GPU frame (tests/test_tiling.py
+checks exactly that, on gloo with the CPU oracle standing in for the kernels and on NCCL with the real ones).
+
+Bound on temporal reach: history is fetched at pixel + motion; HALO_ROWS - 2 = 62 rows of vertical motion per frame
+are covered, beyond that a strip would need a taller halo (`halo_rows=`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+TILE = 16
+HALO_ROWS = 64
+
+
+def strip_rows(height: int, world: int) -> List[Tuple[int, int]]:
+    """Rows [y0, y1) of each rank's strip: whole 16-row tile rows, as even as possible, last strip takes the ragged end."""
+    tiles = (height + TILE - 1) // TILE
+    if world > tiles:
+        raise ValueError(f"{world} strips need at least {world} tile rows, the frame has {tiles}")
+    base, extra = divmod(tiles, world)
+    out, t = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((t * TILE, min((t + n) * TILE, height)))
+        t += n
+    return out
+
+
+def _scaled(rows: Tuple[int, int], halo: int, tex_height: int, full_height: int) -> Tuple[int, int, int]:
+    """Strip rows and halo in the row units of a texture that may be downsampled (tiles: 1/16)."""
+    if tex_height == full_height:
+        return rows[0], rows[1], halo
+    ds = (full_height + tex_height - 1) // tex_height
+    return rows[0] // ds, min((rows[1] + ds - 1) // ds, tex_height), (halo + ds - 1) // ds
+
+
+def exchange_halos(planes: Sequence[torch.Tensor], strips: Sequence[Tuple[int, int]], rank: int, full_height: int, halo: int = HALO_ROWS,
+                   group: Optional[dist.ProcessGroup] = None) -> int:
+    """Send the edge rows of this rank's strip of every plane to the neighbours and receive theirs into the apron.
+
+    `planes`: 2-D row-major views [rows, row_bytes_or_elems] of whole textures (row slices are contiguous, so every
+    message is one contiguous block). Works on CUDA tensors (NCCL) and CPU tensors (gloo). Returns the bytes sent."""
+    world = len(strips)
+    if world == 1:
+        return 0
+    ops, sent = [], 0
+    for p in planes:
+        assert p.dim() == 2 and p.is_contiguous()
+        y0, y1, h = _scaled(strips[rank], halo, p.shape[0], full_height)
+        for nb, send_rows, recv_rows in ((rank - 1, (y0, min(y0 + h, y1)), (max(y0 - h, 0), y0)), (rank + 1, (max(y1 - h, y0), y1), (y1, min(y1 + h, p.shape[0])))):
+            if nb < 0 or nb >= world:
+                continue
+            # the neighbour's strip must be at least as tall as the halo it supplies, or rows would come from two ranks away
+            ny0, ny1, _ = _scaled(strips[nb], halo, p.shape[0], full_height)
+            assert ny1 - ny0 >= recv_rows[1] - recv_rows[0] and y1 - y0 >= send_rows[1] - send_rows[0], "strip shorter than the halo"
+            if send_rows[1] > send_rows[0]:
+                s = p[send_rows[0]:send_rows[1]]
+                ops.append(dist.P2POp(dist.isend, s, nb, group))
+                sent += s.numel() * s.element_size()
+            if recv_rows[1] > recv_rows[0]:
+                ops.append(dist.P2POp(dist.irecv, p[recv_rows[0]:recv_rows[1]], nb, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return sent
+
+
+def exchange_halos_local(plane_sets: Sequence[Sequence[torch.Tensor]], strips: Sequence[Tuple[int, int]], full_height: int, halo: int = HALO_ROWS) -> None:
+    """The same row trade between strips that live in ONE process (plane_sets[r][i] = plane i of strip r): plain copies.
+    Used to run several strips on a single GPU (tests, debugging) — the row arithmetic is shared with `exchange_halos`."""
+    world = len(strips)
+    for r in range(world - 1):
+        for up, down in zip(plane_sets[r], plane_sets[r + 1]):
+            _, seam, h = _scaled(strips[r], halo, up.shape[0], full_height)   # seam = first row of strip r + 1
+            u0, _, _ = _scaled(strips[r], halo, up.shape[0], full_height)
+            _, d1, _ = _scaled(strips[r + 1], halo, up.shape[0], full_height)
+            down[max(seam - h, u0):seam] = up[max(seam - h, u0):seam]        # bottom rows of strip r -> apron above strip r + 1
+            up[seam:min(seam + h, d1)] = down[seam:min(seam + h, d1)]        # top rows of strip r + 1 -> apron below strip r
+
+
+class TiledDenoiser:
+    """N ranks, one frame: rank r denoises the rows of strip r and trades seam rows with its neighbours after every pass.
+    Construct on every rank of an initialised process group (backend nccl); call `denoise()` in lockstep."""
+
+    def __init__(self, denoiser: int, width: int, height: int, rank: int, world: int, device: int = 0, halo_rows: int = HALO_ROWS, flags: Optional[int] = None,
+                 group: Optional[dist.ProcessGroup] = None):
+        from . import executor as ex
+        self.ex = ex
+        self.rank, self.world, self.height, self.width, self.halo, self.group = rank, world, height, width, halo_rows, group
+        self.strips = strip_rows(height, world)
+        self.rows = self.strips[rank]
+        if world > 1 and min(b - a for a, b in self.strips) < halo_rows:
+            raise ValueError(f"strips of {min(b - a for a, b in self.strips)} rows are shorter than the {halo_rows}-row halo")
+        self.den = ex.CudaDenoiser(denoiser, width, height, device=device, flags=ex.FLAG_QUAD_INTRINSICS if flags is None else flags)
+        self.device = device
+        self.bytes_sent = 0
+        self.on_pass: Optional[Callable[[int, str], None]] = None
+        self._cb = ex.DISPATCH_CALLBACK(self._after_dispatch)
+
+    # the executor calls this after it has enqueued dispatch `index` on the stream
+    def _after_dispatch(self, user, index, name, textures, is_storage, n):
+        planes = []
+        for i in range(n):
+            if is_storage[i]:
+                t = textures[i]
+                planes.append(self.ex._as_byte_tensor(t.data, t.pitchBytes * t.height, self.device).view(t.height, t.pitchBytes))
+        self.bytes_sent += exchange_halos(planes, self.strips, self.rank, self.height, self.halo, self.group)
+        if self.on_pass:
+            self.on_pass(index, name.decode() if name else "")
+
+    def __getattr__(self, item):  # set_user_texture, set_common_settings, set_denoiser_settings, pool_texture, profiling ...
+        return getattr(self.den, item)
+
+    def denoise(self, stream: Optional[torch.cuda.Stream] = None):
+        s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        L = self.ex.load()
+        cb = self._cb if self.world > 1 else self.ex.DISPATCH_CALLBACK()
+        self.ex._check(L.nrdcuDenoiseRows(self.den.ctx, self.den._ids, 1, C.c_void_p(s), self.rows[0], self.rows[1], cb, None), "nrdcuDenoiseRows")
+
+    def close(self):
+        self.den.close()

@@ -216,3 +216,62 @@ def test_missing_resource_and_bad_format_are_reported(ex):
     with pytest.raises(ex.NrdcuError, match="UNSUPPORTED"):
         ex.dispatch("RELAX_Atrous.cs.hlsl", b"", [])
     cud.close()
+
+
+def test_two_strips_on_one_gpu_equal_the_whole_frame(ex, runner):
+    """nrdcuDispatchRows + the halo plan of nrd_sample_b200/tiling.py, emulated on ONE GPU: two full-size texture sets, each pass
+    computes rows [0, y) on set A and [y, H) on set B, rows a strip does not own are poisoned and only the 64-row halo is copied
+    across the seam. The strips must reproduce the single-launch frame bit for bit (the multi-GPU run is tools/tiled_check.py)."""
+    from nrd_sample_b200 import tiling
+    w, h, frames = 256, 208, 5
+    dev = "cuda:0"
+    host = runner.default_host_library()
+    strips = tiling.strip_rows(h, 2)
+    inst = api.NrdInstance(host, [(0, api.Denoiser.REBLUR_DIFFUSE_SPECULAR)])
+    perm, tran = inst.pools()
+
+    def texture_set():
+        t = {}
+        for kind, pool in ((RT.PERMANENT_POOL, perm), (RT.TRANSIENT_POOL, tran)):
+            for i, (fmt, ds) in enumerate(pool):
+                t[(int(kind), i)] = (ex.alloc_texture(fmt, (w + ds - 1) // ds, (h + ds - 1) // ds, dev), fmt)
+        for rt in (RT.OUT_DIFF_RADIANCE_HITDIST, RT.OUT_SPEC_RADIANCE_HITDIST):
+            t[(int(rt), 0)] = (ex.alloc_texture(F16, w, h, dev), F16)
+        return t
+
+    sets = [texture_set(), texture_set(), texture_set()]   # strip A, strip B, whole frame
+    pools = (int(RT.PERMANENT_POOL), int(RT.TRANSIENT_POOL))
+    for f in range(frames):
+        frame = synth.reblur_frame(f, w, h)
+        for s in sets:
+            for k, v in frame.items():
+                rt = getattr(RT, k)
+                s[(int(rt), 0)] = (v.to(dev), runner.USER_FORMATS[rt])
+        assert inst.set_common_settings(synth.common_settings(f, w, h)) == api.Result.SUCCESS
+        r, dispatches = inst.get_compute_dispatches([0])
+        assert r == api.Result.SUCCESS
+        for d in dispatches:
+            keys = [(b.type, b.index) if b.type in pools else (b.type, 0) for b in d.bindings]
+            for si, rows in ((0, strips[0]), (1, strips[1]), (2, None)):
+                tex = [ex.texture_of(*sets[si][k]) for k in keys]
+                ex.dispatch(d.shader, d.constants, tex, flags=ex.FLAG_QUAD_INTRINSICS | ex.FLAG_ROBUST_MIRROR_TEST, rows=rows)
+            if d.shader.startswith("Clear"):
+                continue
+            planes = [[], []]
+            for b, k in zip(d.bindings, keys):
+                if b.descriptor != int(api.DescriptorType.STORAGE_TEXTURE):
+                    continue
+                for si in (0, 1):
+                    t = sets[si][k][0]
+                    p = t.view(torch.uint8).view(t.shape[0], -1)
+                    y0, y1, _ = tiling._scaled(strips[si], tiling.HALO_ROWS, p.shape[0], h)
+                    p[:y0] = 0xFF
+                    p[y1:] = 0xFF
+                    planes[si].append(p)
+            tiling.exchange_halos_local(planes, strips, h)
+        torch.cuda.synchronize()
+        for rt in (RT.OUT_DIFF_RADIANCE_HITDIST, RT.OUT_SPEC_RADIANCE_HITDIST):
+            whole = sets[2][(int(rt), 0)][0]
+            for si, (y0, y1) in enumerate(strips):
+                got = sets[si][(int(rt), 0)][0]
+                assert torch.equal(got[y0:y1].view(torch.int16), whole[y0:y1].view(torch.int16)), f"frame {f} strip {si} {rt}"

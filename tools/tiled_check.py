@@ -1,0 +1,96 @@
+"""Multi-GPU strip tiling on real GPUs (BASELINE.json config 3). Run under torchrun, one rank per GPU:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/tiled_check.py [W H [FRAMES [STEPS]]]
+
+1. parity: FRAMES frames of REBLUR_DIFFUSE_SPECULAR at WxH denoised as N strips with NCCL halo exchange must equal, row for row
+   and bit for bit, the same frames denoised whole on one GPU (every rank computes the whole-frame run itself);
+2. timing: STEPS steady-state frames, CUDA events on the launch stream, barrier on both sides, max over ranks."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nrd_sample_b200 import executor as ex, nrd_api as api, synth, tiling  # noqa: E402
+
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 3840
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 2160
+FRAMES = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+STEPS = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = f"cuda:{local}"
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device(dev))
+RT, F16 = api.ResourceType, api.Format.RGBA16_SFLOAT
+FMT = {"IN_VIEWZ": api.Format.R32_SFLOAT, "IN_NORMAL_ROUGHNESS": api.Format.R10_G10_B10_A2_UNORM, "IN_MV": F16, "IN_DIFF_RADIANCE_HITDIST": F16, "IN_SPEC_RADIANCE_HITDIST": F16}
+RING = 4
+frames = [synth.reblur_frame(i, W, H, device=dev, period=RING) for i in range(RING)]
+
+
+def make(cls, *a):
+    den = cls(*a)
+    outs = [ex.alloc_texture(F16, W, H, dev), ex.alloc_texture(F16, W, H, dev)]
+    den.set_user_texture(RT.OUT_DIFF_RADIANCE_HITDIST, outs[0], F16)
+    den.set_user_texture(RT.OUT_SPEC_RADIANCE_HITDIST, outs[1], F16)
+    return den, outs
+
+
+def step(den, i):
+    for k, v in frames[i % RING].items():
+        den.set_user_texture(getattr(RT, k), v.clone() if k == "IN_MV" else v, FMT[k])   # IN_MV is bound read-write by TS
+    den.set_common_settings(synth.common_settings(i, W, H, period=RING))
+    den.denoise()
+
+
+tiled, t_out = make(tiling.TiledDenoiser, api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, rank, world, local)
+whole, w_out = make(ex.CudaDenoiser, api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, 0, local)
+y0, y1 = tiled.rows
+ok = True
+for i in range(FRAMES):
+    step(tiled, i)
+    step(whole, i)
+    torch.cuda.synchronize()
+    for a, b in zip(t_out, w_out):
+        same = torch.equal(a[y0:y1].view(torch.int16), b[y0:y1].view(torch.int16))
+        if not same:
+            d = (a[y0:y1].float() - b[y0:y1].float()).abs()
+            print(f"rank {rank} frame {i}: strip rows [{y0},{y1}) differ from the whole-frame run: {int((d > 0).any(-1).sum())} px, max {d.max().item():.4g}", flush=True)
+        ok &= same
+flag = torch.tensor([1 if ok else 0], device=dev)
+if world > 1:
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+whole.close()
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+stream = torch.cuda.current_stream()
+for i in range(FRAMES, FRAMES + 6):
+    step(tiled, i)
+barrier()
+sent0 = tiled.bytes_sent
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stream)
+for i in range(FRAMES + 6, FRAMES + 6 + STEPS):
+    step(tiled, i)
+e1.record(stream)
+barrier()
+ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+if rank == 0:
+    per = float(ms.item()) / STEPS
+    print(json.dumps({"check": "tiled strips == whole frame (bit exact)", "passed": bool(flag.item()), "n_gpus": world, "resolution": [W, H], "strips": tiled.strips,
+                      "halo_rows": tiled.halo, "ms_per_frame": per, "mpixels_per_s": W * H / per / 1e3,
+                      "halo_bytes_sent_per_frame_rank0": (tiled.bytes_sent - sent0) // STEPS}))
+tiled.close()
+if world > 1:
+    dist.destroy_process_group()
+sys.exit(0 if flag.item() else 1)
