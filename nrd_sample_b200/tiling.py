@@ -28,6 +28,25 @@ import torch.distributed as dist
 TILE = 16
 HALO_ROWS = 64
 
+# Rows of apron each written texture needs on the neighbour, by (pass, binding index in DispatchDesc::resources). The default is
+# HALO_ROWS; entries below are smaller because every later reader of that texture stays closer to its own pixel:
+#   0  = only ever read at the pixel itself (or not at all: the final outputs, IN_MV which temporal stabilisation binds read-write)
+#   2  = read through a 1-texel shared-memory border,  8 = 9x9 luma window of history fix,
+#   32 = history-fix 5x5 taps with stride <= 14 (2 x 14 = 28) and blur taps (maxBlurRadius = 30).
+# Post-blur reaches 2 x 30 = 60 rows and everything that survives into the next frame is fetched at pixel + motion: HALO_ROWS.
+HALO_TABLE = {
+    "Classify tiles": {1: 0},
+    "Pre-pass": {5: 0, 6: 0, 7: 2},
+    "Temporal accumulation": {19: 32, 20: 32, 21: 8, 22: 8, 24: 0},
+    "History fix": {9: 32, 10: 32},
+    "Temporal stabilization": {10: 0, 12: 0, 13: 0},
+}
+
+
+def halo_rows_for(pass_name: str, binding: int, default: int = HALO_ROWS) -> int:
+    """Apron rows for output `binding` of the pass called '<denoiser> - <pass_name>' (never more than `default`)."""
+    return min(default, HALO_TABLE.get(pass_name.split(" - ")[-1], {}).get(binding, default))
+
 
 def strip_rows(height: int, world: int) -> List[Tuple[int, int]]:
     """Rows [y0, y1) of each rank's strip: whole 16-row tile rows, as even as possible, last strip takes the ragged end."""
@@ -51,24 +70,22 @@ def _scaled(rows: Tuple[int, int], halo: int, tex_height: int, full_height: int)
     return rows[0] // ds, min((rows[1] + ds - 1) // ds, tex_height), (halo + ds - 1) // ds
 
 
-def exchange_halos(planes: Sequence[torch.Tensor], strips: Sequence[Tuple[int, int]], rank: int, full_height: int, halo: int = HALO_ROWS,
-                   group: Optional[dist.ProcessGroup] = None) -> int:
-    """Send the edge rows of this rank's strip of every plane to the neighbours and receive theirs into the apron.
-
-    `planes`: 2-D row-major views [rows, row_bytes_or_elems] of whole textures (row slices are contiguous, so every
-    message is one contiguous block). Works on CUDA tensors (NCCL) and CPU tensors (gloo). Returns the bytes sent."""
+def build_exchange(planes: Sequence[torch.Tensor], strips: Sequence[Tuple[int, int]], rank: int, full_height: int, halo=HALO_ROWS,
+                   group: Optional[dist.ProcessGroup] = None):
+    """The send / recv list of one halo trade: ([P2POp], bytes sent). `halo` is one row count or one per plane."""
     world = len(strips)
-    if world == 1:
-        return 0
     ops, sent = [], 0
-    for p in planes:
+    halos = [halo] * len(planes) if isinstance(halo, int) else list(halo)
+    for p, hp in zip(planes, halos):
         assert p.dim() == 2 and p.is_contiguous()
-        y0, y1, h = _scaled(strips[rank], halo, p.shape[0], full_height)
+        if world == 1 or hp <= 0:
+            continue
+        y0, y1, h = _scaled(strips[rank], hp, p.shape[0], full_height)
         for nb, send_rows, recv_rows in ((rank - 1, (y0, min(y0 + h, y1)), (max(y0 - h, 0), y0)), (rank + 1, (max(y1 - h, y0), y1), (y1, min(y1 + h, p.shape[0])))):
             if nb < 0 or nb >= world:
                 continue
             # the neighbour's strip must be at least as tall as the halo it supplies, or rows would come from two ranks away
-            ny0, ny1, _ = _scaled(strips[nb], halo, p.shape[0], full_height)
+            ny0, ny1, _ = _scaled(strips[nb], hp, p.shape[0], full_height)
             assert ny1 - ny0 >= recv_rows[1] - recv_rows[0] and y1 - y0 >= send_rows[1] - send_rows[0], "strip shorter than the halo"
             if send_rows[1] > send_rows[0]:
                 s = p[send_rows[0]:send_rows[1]]
@@ -76,21 +93,34 @@ def exchange_halos(planes: Sequence[torch.Tensor], strips: Sequence[Tuple[int, i
                 sent += s.numel() * s.element_size()
             if recv_rows[1] > recv_rows[0]:
                 ops.append(dist.P2POp(dist.irecv, p[recv_rows[0]:recv_rows[1]], nb, group))
+    return ops, sent
+
+
+def exchange_halos(planes: Sequence[torch.Tensor], strips: Sequence[Tuple[int, int]], rank: int, full_height: int, halo=HALO_ROWS,
+                   group: Optional[dist.ProcessGroup] = None) -> int:
+    """Send the edge rows of this rank's strip of every plane to the neighbours and receive theirs into the apron.
+
+    `planes`: 2-D row-major views [rows, row_bytes_or_elems] of whole textures (row slices are contiguous, so every
+    message is one contiguous block). Works on CUDA tensors (NCCL) and CPU tensors (gloo). Returns the bytes sent."""
+    ops, sent = build_exchange(planes, strips, rank, full_height, halo, group)
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
     return sent
 
 
-def exchange_halos_local(plane_sets: Sequence[Sequence[torch.Tensor]], strips: Sequence[Tuple[int, int]], full_height: int, halo: int = HALO_ROWS) -> None:
+def exchange_halos_local(plane_sets: Sequence[Sequence[torch.Tensor]], strips: Sequence[Tuple[int, int]], full_height: int, halo=HALO_ROWS) -> None:
     """The same row trade between strips that live in ONE process (plane_sets[r][i] = plane i of strip r): plain copies.
     Used to run several strips on a single GPU (tests, debugging) — the row arithmetic is shared with `exchange_halos`."""
     world = len(strips)
+    halos = [halo] * len(plane_sets[0]) if isinstance(halo, int) else list(halo)
     for r in range(world - 1):
-        for up, down in zip(plane_sets[r], plane_sets[r + 1]):
-            _, seam, h = _scaled(strips[r], halo, up.shape[0], full_height)   # seam = first row of strip r + 1
-            u0, _, _ = _scaled(strips[r], halo, up.shape[0], full_height)
-            _, d1, _ = _scaled(strips[r + 1], halo, up.shape[0], full_height)
+        for up, down, hp in zip(plane_sets[r], plane_sets[r + 1], halos):
+            if hp <= 0:
+                continue
+            _, seam, h = _scaled(strips[r], hp, up.shape[0], full_height)   # seam = first row of strip r + 1
+            u0, _, _ = _scaled(strips[r], hp, up.shape[0], full_height)
+            _, d1, _ = _scaled(strips[r + 1], hp, up.shape[0], full_height)
             down[max(seam - h, u0):seam] = up[max(seam - h, u0):seam]        # bottom rows of strip r -> apron above strip r + 1
             up[seam:min(seam + h, d1)] = down[seam:min(seam + h, d1)]        # top rows of strip r + 1 -> apron below strip r
 
@@ -100,7 +130,7 @@ class TiledDenoiser:
     Construct on every rank of an initialised process group (backend nccl); call `denoise()` in lockstep."""
 
     def __init__(self, denoiser: int, width: int, height: int, rank: int, world: int, device: int = 0, halo_rows: int = HALO_ROWS, flags: Optional[int] = None,
-                 group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, use_table: bool = True):
         from . import executor as ex
         self.ex = ex
         self.rank, self.world, self.height, self.width, self.halo, self.group = rank, world, height, width, halo_rows, group
@@ -111,17 +141,28 @@ class TiledDenoiser:
         self.den = ex.CudaDenoiser(denoiser, width, height, device=device, flags=ex.FLAG_QUAD_INTRINSICS if flags is None else flags)
         self.device = device
         self.bytes_sent = 0
+        self.use_table = use_table
+        self._plans = {}
         self.on_pass: Optional[Callable[[int, str], None]] = None
         self._cb = ex.DISPATCH_CALLBACK(self._after_dispatch)
 
     # the executor calls this after it has enqueued dispatch `index` on the stream
     def _after_dispatch(self, user, index, name, textures, is_storage, n):
-        planes = []
-        for i in range(n):
-            if is_storage[i]:
-                t = textures[i]
-                planes.append(self.ex._as_byte_tensor(t.data, t.pitchBytes * t.height, self.device).view(t.height, t.pitchBytes))
-        self.bytes_sent += exchange_halos(planes, self.strips, self.rank, self.height, self.halo, self.group)
+        # pools ping-pong between two bindings at most, so the send / recv list of a (pass, pointers) pair is built once
+        pass_name = name.decode() if name else ""
+        wanted = [(i, halo_rows_for(pass_name, i, self.halo) if self.use_table else self.halo) for i in range(n) if is_storage[i]]
+        wanted = [(i, h) for i, h in wanted if h > 0]
+        key = (name, tuple(textures[i].data for i, _ in wanted))
+        plan = self._plans.get(key)
+        if plan is None:
+            planes = [self.ex._as_byte_tensor(textures[i].data, textures[i].pitchBytes * textures[i].height, self.device).view(textures[i].height, textures[i].pitchBytes)
+                      for i, _ in wanted]
+            plan = self._plans[key] = build_exchange(planes, self.strips, self.rank, self.height, [h for _, h in wanted], self.group)
+        ops, sent = plan
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.bytes_sent += sent
         if self.on_pass:
             self.on_pass(index, name.decode() if name else "")
 

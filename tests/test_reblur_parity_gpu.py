@@ -257,10 +257,11 @@ def test_two_strips_on_one_gpu_equal_the_whole_frame(ex, runner):
                 ex.dispatch(d.shader, d.constants, tex, flags=ex.FLAG_QUAD_INTRINSICS | ex.FLAG_ROBUST_MIRROR_TEST, rows=rows)
             if d.shader.startswith("Clear"):
                 continue
-            planes = [[], []]
-            for b, k in zip(d.bindings, keys):
+            planes, halos = [[], []], []
+            for j, (b, k) in enumerate(zip(d.bindings, keys)):
                 if b.descriptor != int(api.DescriptorType.STORAGE_TEXTURE):
                     continue
+                halos.append(tiling.halo_rows_for(d.name, j))   # per-texture apron table of tiling.py
                 for si in (0, 1):
                     t = sets[si][k][0]
                     p = t.view(torch.uint8).view(t.shape[0], -1)
@@ -268,7 +269,7 @@ def test_two_strips_on_one_gpu_equal_the_whole_frame(ex, runner):
                     p[:y0] = 0xFF
                     p[y1:] = 0xFF
                     planes[si].append(p)
-            tiling.exchange_halos_local(planes, strips, h)
+            tiling.exchange_halos_local(planes, strips, h, halos)
         torch.cuda.synchronize()
         for rt in (RT.OUT_DIFF_RADIANCE_HITDIST, RT.OUT_SPEC_RADIANCE_HITDIST):
             whole = sets[2][(int(rt), 0)][0]

@@ -66,17 +66,19 @@ def _rank_main(rank, world, port, w, h, frames, halo, result_dir):
         def after(i, d, keys, self):
             if d.shader.startswith("Clear"):
                 return  # every rank clears its whole copy
-            planes = []
-            for b, k in zip(d.bindings, keys):
+            planes, halos = [], []
+            for j, (b, k) in enumerate(zip(d.bindings, keys)):
                 if b.descriptor != int(api.DescriptorType.STORAGE_TEXTURE):
                     continue
                 t = self.textures[k]
                 p = t.view(torch.uint8).view(t.shape[0], -1)
                 ty0, ty1, _ = tiling._scaled((y0, y1), halo, p.shape[0], h)
-                p[:ty0] = 0xFF   # poison: 0xFFFF is a NaN in fp16, 255 in UNORM, an impossible history word
-                p[ty1:] = 0xFF
+                if k[0] != int(RT.IN_MV):   # bound read-write by temporal stabilisation but only written on clear frames: stays an input
+                    p[:ty0] = 0xFF          # poison: 0xFFFF is a NaN in fp16, 255 in UNORM, an impossible history word
+                    p[ty1:] = 0xFF
                 planes.append(p)
-            tiling.exchange_halos(planes, strips, rank, h, halo)
+                halos.append(tiling.halo_rows_for(d.name, j, halo))   # the per-texture table of tiling.py, capped by `halo`
+            tiling.exchange_halos(planes, strips, rank, h, halos)
 
         outs = []
         for f in range(frames):
