@@ -112,13 +112,16 @@ private:
     void finalize();
     void flipPingPong(const DenoiserState& d);
 
-    // graph_reblur.cpp / graph_sigma.cpp
+    // graph_reblur.cpp / graph_sigma.cpp / graph_relax.cpp
     void buildReblurDiffuseSpecular(DenoiserState& d);
     void updateReblur(const DenoiserState& d);
     void fillReblurConstants(const ReblurSettings& s, void* dst);
     void buildSigmaShadow(DenoiserState& d);
     void updateSigma(const DenoiserState& d);
     void fillSigmaConstants(const SigmaSettings& s, void* dst);
+    void buildRelaxDiffuseSpecularSh(DenoiserState& d);
+    void updateRelax(const DenoiserState& d);
+    void* fillRelaxConstants(const RelaxSettings& s, void* dst);
 
     std::vector<DenoiserState> m_denoisers;
     std::vector<TextureDesc> m_permanentPool, m_transientPool;

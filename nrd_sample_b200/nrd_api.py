@@ -255,6 +255,47 @@ class ReblurSettings(C.Structure):
             setattr(self, k, v)
 
 
+class RelaxSettings(C.Structure):
+    """nrd::RelaxSettings (NRDSettings.h:361-452), 148 bytes."""
+    _fields_ = [("antilagAccelerationAmount", C.c_float), ("antilagSpatialSigmaScale", C.c_float), ("antilagTemporalSigmaScale", C.c_float), ("antilagResetAmount", C.c_float),
+                ("diffuseMaxAccumulatedFrameNum", C.c_uint32), ("specularMaxAccumulatedFrameNum", C.c_uint32),
+                ("diffuseMaxFastAccumulatedFrameNum", C.c_uint32), ("specularMaxFastAccumulatedFrameNum", C.c_uint32),
+                ("historyFixFrameNum", C.c_uint32), ("historyFixBasePixelStride", C.c_uint32), ("historyFixAlternatePixelStride", C.c_uint32),
+                ("historyFixEdgeStoppingNormalPower", C.c_float), ("fastHistoryClampingSigmaScale", C.c_float),
+                ("diffusePrepassBlurRadius", C.c_float), ("specularPrepassBlurRadius", C.c_float), ("minHitDistanceWeight", C.c_float),
+                ("spatialVarianceEstimationHistoryThreshold", C.c_uint32), ("diffusePhiLuminance", C.c_float), ("specularPhiLuminance", C.c_float),
+                ("lobeAngleFraction", C.c_float), ("roughnessFraction", C.c_float), ("specularVarianceBoost", C.c_float), ("specularLobeAngleSlack", C.c_float),
+                ("atrousIterationNum", C.c_uint32), ("diffuseMinLuminanceWeight", C.c_float), ("specularMinLuminanceWeight", C.c_float), ("depthThreshold", C.c_float),
+                ("confidenceDrivenRelaxationMultiplier", C.c_float), ("confidenceDrivenLuminanceEdgeStoppingRelaxation", C.c_float),
+                ("confidenceDrivenNormalEdgeStoppingRelaxation", C.c_float), ("luminanceEdgeStoppingRelaxation", C.c_float),
+                ("normalEdgeStoppingRelaxation", C.c_float), ("roughnessEdgeStoppingRelaxation", C.c_float),
+                ("checkerboardMode", C.c_uint8), ("hitDistanceReconstructionMode", C.c_uint8),
+                ("minMaterialForDiffuse", C.c_float), ("minMaterialForSpecular", C.c_float), ("enableAntiFirefly", C.c_bool), ("enableRoughnessEdgeStopping", C.c_bool)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.antilagAccelerationAmount, self.antilagSpatialSigmaScale, self.antilagTemporalSigmaScale, self.antilagResetAmount = 0.3, 4.5, 0.5, 0.5
+        self.diffuseMaxAccumulatedFrameNum = self.specularMaxAccumulatedFrameNum = 30
+        self.diffuseMaxFastAccumulatedFrameNum = self.specularMaxFastAccumulatedFrameNum = 6
+        self.historyFixFrameNum = 3
+        self.historyFixBasePixelStride = self.historyFixAlternatePixelStride = 14
+        self.historyFixEdgeStoppingNormalPower = 8.0
+        self.fastHistoryClampingSigmaScale = 2.0
+        self.diffusePrepassBlurRadius, self.specularPrepassBlurRadius = 30.0, 50.0
+        self.minHitDistanceWeight = 0.1
+        self.spatialVarianceEstimationHistoryThreshold = 3
+        self.diffusePhiLuminance, self.specularPhiLuminance = 2.0, 1.0
+        self.lobeAngleFraction, self.roughnessFraction = 0.5, 0.15
+        self.specularLobeAngleSlack = 0.15
+        self.atrousIterationNum = 5
+        self.depthThreshold = 0.003
+        self.luminanceEdgeStoppingRelaxation, self.normalEdgeStoppingRelaxation, self.roughnessEdgeStoppingRelaxation = 0.5, 0.3, 1.0
+        self.minMaterialForDiffuse = self.minMaterialForSpecular = 4.0
+        self.enableRoughnessEdgeStopping = True
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
 class SigmaSettings(C.Structure):
     _fields_ = [("lightDirection", C.c_float * 3), ("planeDistanceSensitivity", C.c_float), ("maxStabilizedFrameNum", C.c_uint32)]
 
@@ -266,7 +307,7 @@ class SigmaSettings(C.Structure):
             setattr(self, k, v)
 
 
-assert C.sizeof(CommonSettings) == 432 and C.sizeof(ReblurSettings) == 120 and C.sizeof(SigmaSettings) == 20
+assert C.sizeof(CommonSettings) == 432 and C.sizeof(ReblurSettings) == 120 and C.sizeof(SigmaSettings) == 20 and C.sizeof(RelaxSettings) == 148
 assert C.sizeof(DispatchDesc) == 56 and C.sizeof(PipelineDesc) == 320 and C.sizeof(InstanceDesc) == 112
 
 EXPORTED_SYMBOLS = ("CreateInstance", "DestroyInstance", "GetLibraryDesc", "GetInstanceDesc", "SetCommonSettings",

@@ -21,6 +21,9 @@ CASES = [
     ("reblur_odd_noprepass", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 1000, 562, "noprepass"),
     ("sigma_512", api.Denoiser.SIGMA_SHADOW, 512, 512, "sigma"),
     ("sigma_nostab", api.Denoiser.SIGMA_SHADOW, 640, 360, "sigma_nostab"),
+    ("relax_sh_1440p", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 2560, 1440, None),
+    ("relax_sh_odd_firefly_recon", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 1000, 562, "relax_firefly_recon"),
+    ("relax_sh_8_iterations", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 640, 360, "relax_8"),
 ]
 
 
@@ -33,6 +36,11 @@ def _settings(kind):
         return api.SigmaSettings(lightDirection=(C.c_float * 3)(0.0, 0.0, 1.0))
     if kind == "sigma_nostab":
         return api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0)
+    if kind == "relax_firefly_recon":
+        return api.RelaxSettings(enableAntiFirefly=True, hitDistanceReconstructionMode=2, atrousIterationNum=4, diffuseMinLuminanceWeight=0.1, specularLobeAngleSlack=0.3,
+                                 diffuseMaxAccumulatedFrameNum=40, historyFixFrameNum=2)
+    if kind == "relax_8":
+        return api.RelaxSettings(atrousIterationNum=8, diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0, enableRoughnessEdgeStopping=False)
     return None
 
 
