@@ -85,6 +85,23 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
 NRDCU_API uint32_t nrdcuGetPoolTexture(nrdcuContext* ctx, int isPermanent, uint32_t index, nrdcuTexture* out);
 NRDCU_API void* nrdcuGetInstance(nrdcuContext* ctx);
 
+/* ---- strips over peer memory -----------------------------------------------------------------------------------
+ * The B200-native seam exchange for nrdcuDenoiseRows: one process per GPU, neighbouring strips map each other's textures
+ * through CUDA IPC and every pass pushes its seam rows straight into the neighbours' copies over NVLink, then raises a flag
+ * the neighbour spins on before its next pass (csrc/kernels/peer_halo.cu) — no host round trip, no collective library.
+ *   1. every rank: nrdcuCreate; nrdcuAllocSharedTexture for each user texture the denoiser WRITES (OUT_*), bound with
+ *      nrdcuSetResource like any other texture; optional nrdcuTileSetHalo rules (apron rows per pass / binding, default 64)
+ *   2. every rank: nrdcuTileExport -> a blob of IPC handles; ranks trade blobs (torch.distributed / MPI / a pipe: plumbing)
+ *   3. every rank: nrdcuTileAttach(blob of the rank above, blob of the rank below)  (NULL at the top / bottom of the frame)
+ *   4. per frame, in lockstep: nrdcuDenoiseRows(ctx, ..., rowBegin, rowEnd, NULL, NULL)
+ * nrdcuTileGetStatus: bytes pushed so far and a non-zero error if a wait for a neighbour timed out (~4 s). */
+NRDCU_API uint32_t nrdcuAllocSharedTexture(nrdcuContext* ctx, uint32_t format, uint32_t width, uint32_t height, nrdcuTexture* out);
+NRDCU_API uint32_t nrdcuTileExportSize(nrdcuContext* ctx);
+NRDCU_API uint32_t nrdcuTileExport(nrdcuContext* ctx, void* blob, uint32_t blobSize);
+NRDCU_API uint32_t nrdcuTileAttach(nrdcuContext* ctx, const void* blobAbove, const void* blobBelow, uint32_t blobSize);
+NRDCU_API uint32_t nrdcuTileSetHalo(nrdcuContext* ctx, const char* passName /* NULL: set the default */, uint32_t binding, uint32_t rows);
+NRDCU_API uint32_t nrdcuTileGetStatus(nrdcuContext* ctx, uint64_t* bytesPushed, uint32_t* error);
+
 /* Host-buffer convenience used by plugin-style callers (the `e2e` path of bench.py): uploads the user inputs that
  * were registered with nrdcuSetHostResource from pinned/pageable host memory, runs nrdcuDenoise, downloads the outputs.
  * direction: 0 = input (H2D before the frame), 1 = output (D2H after the frame). Device staging is owned by ctx. */

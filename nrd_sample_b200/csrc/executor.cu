@@ -14,6 +14,7 @@
 #include "../../include/nrd_b200.h"
 #include "../../include/nrdcu.h"
 #include "kernels/reblur_common.cuh"
+#include "kernels/peer_halo.cuh"
 #include "kernels/sigma_common.cuh"
 
 namespace nrdk {
@@ -320,6 +321,19 @@ struct nrdcuContext {
     uint64_t poolBytes = 0;
     std::vector<nrdcuTexture> scratch;
     std::vector<uint8_t> scratchIsStorage;
+    // multi-GPU strips over peer memory (nrdcuTile*): textures of the two neighbouring strips mapped through CUDA IPC
+    struct HaloRule { std::string pass; uint32_t binding, rows; };
+    struct Tile {
+        bool attached = false;
+        std::vector<nrdcuTexture> exported;   // permanent pool, transient pool, shared user textures — the order of the export blob
+        std::vector<void*> peerBase[2];       // [0] = neighbour above, [1] = below: base of its copy of exported[i]
+        uint32_t* flags = nullptr;            // this GPU's two flag words: [0] written by the neighbour above, [1] below
+        uint32_t* peerFlags[2] = {nullptr, nullptr};
+        uint32_t* hostError = nullptr;        // pinned, mapped: set by the wait kernel on timeout
+        uint32_t seq = 0, defaultHalo = 64;
+        std::vector<HaloRule> rules;
+        uint64_t bytesPushed = 0;
+    } tile;
     // per-dispatch CUDA-event timing (bench.py's live roofline measurement)
     struct ProfileEntry { const char* name; double totalMs = 0; uint64_t count = 0; };
     struct PendingTiming { const char* name; cudaEvent_t start, stop; };
@@ -352,9 +366,171 @@ bool allocTexture(nrdcuContext* ctx, uint32_t fmt, uint32_t w, uint32_t h, nrdcu
     return true;
 }
 
+// Seam traffic of one dispatch in peer mode: rows of every written texture that the neighbours' later passes reach into go straight
+// into the neighbours' copies, then flag + wait (kernels/peer_halo.cu). Every dispatch signals and waits, with or without rows to
+// push: that keeps neighbouring strips within one pass of each other, which is what makes writing into their aprons safe.
+uint32_t pushHalos(nrdcuContext* ctx, const DispatchDesc& dd, uint32_t rowBegin, uint32_t rowEnd, cudaStream_t stream) {
+    nrdcuContext::Tile& t = ctx->tile;
+    const uint32_t fullH = ctx->height;
+    const uint32_t y0 = rowBegin, y1 = rowEnd < fullH ? rowEnd : fullH;
+    const char* dash = strstr(dd.name, " - ");
+    const char* passName = dash ? dash + 3 : dd.name;
+    nrdk::HaloSegments segs;
+    segs.n = 0;
+    for (uint32_t k = 0; k < dd.resourcesNum; k++) {
+        if (dd.resources[k].descriptorType != DescriptorType::STORAGE_TEXTURE) continue;
+        uint32_t halo = t.defaultHalo;
+        for (const auto& r : t.rules)
+            if (r.binding == k && r.pass == passName) halo = r.rows < t.defaultHalo ? r.rows : t.defaultHalo;
+        if (!halo || !strncmp(dd.name, "Clear", 5)) continue;  // clears cover the whole texture on every GPU
+        const nrdcuTexture& tex = ctx->scratch[k];
+        size_t idx = t.exported.size();
+        for (size_t i = 0; i < t.exported.size(); i++)
+            if (t.exported[i].data == tex.data) idx = i;
+        if (idx == t.exported.size())
+            return fail(Result::INVALID_ARGUMENT, "'%s' writes binding %u into a texture the neighbouring strips cannot see: in peer mode user outputs must come from nrdcuAllocSharedTexture",
+                        dd.name, k);
+        const uint32_t ds = (fullH + tex.height - 1) / tex.height;
+        const uint32_t ty0 = y0 / ds, ty1 = std::min<uint32_t>((y1 + ds - 1) / ds, tex.height), h = (halo + ds - 1) / ds;
+        const uint32_t up1 = std::min(ty0 + h, ty1), down0 = ty1 > ty0 + h ? ty1 - h : ty0;
+        const uint32_t range[2][2] = {{ty0, up1}, {down0, ty1}};  // rows for the neighbour above / below
+        for (int d = 0; d < 2; d++) {
+            if (!t.peerFlags[d] || range[d][1] <= range[d][0]) continue;
+            if (segs.n >= nrdk::kMaxHaloSegments) return fail(Result::FAILURE, "'%s': too many halo segments", dd.name);
+            const size_t off = (size_t)range[d][0] * tex.pitchBytes, bytes = (size_t)(range[d][1] - range[d][0]) * tex.pitchBytes;
+            segs.s[segs.n++] = {(const uint8_t*)tex.data + off, (uint8_t*)t.peerBase[d][idx] + off, (uint32_t)(bytes / 16), 0u};
+            t.bytesPushed += bytes;
+        }
+    }
+    t.seq++;
+    nrdk::launchHaloPush(segs, stream);
+    nrdk::launchHaloSignal(t.peerFlags[0] ? t.peerFlags[0] + 1 : nullptr, t.peerFlags[1] ? t.peerFlags[1] + 0 : nullptr, t.seq, stream);
+    nrdk::launchHaloWait(t.flags, t.seq, t.peerFlags[0] != nullptr, t.peerFlags[1] != nullptr, t.hostError, stream);
+    if (!checkLaunch("halo push")) return (uint32_t)Result::FAILURE;
+    return 0;
+}
+
+struct TileExportEntry {
+    cudaIpcMemHandle_t handle;
+    uint64_t bytes;
+};
+
 }  // namespace
 
 extern "C" {
+
+// ---- strips over peer memory ---------------------------------------------------------------------------------------
+NRDCU_API uint32_t nrdcuAllocSharedTexture(nrdcuContext* ctx, uint32_t format, uint32_t width, uint32_t height, nrdcuTexture* out) {
+    if (!ctx || !out) return fail(Result::INVALID_ARGUMENT, "nrdcuAllocSharedTexture: null argument");
+    if (ctx->tile.attached) return fail(Result::INVALID_ARGUMENT, "nrdcuAllocSharedTexture: allocate before nrdcuTileExport / nrdcuTileAttach");
+    cudaSetDevice(ctx->device);
+    nrdcuTexture t = {};
+    if (!allocTexture(ctx, format, width, height, t, false)) return (uint32_t)Result::FAILURE;
+    ctx->tile.exported.push_back(t);  // appended behind the pools when the export list is built
+    *out = t;
+    return 0;
+}
+
+static void buildExportList(nrdcuContext* ctx) {
+    std::vector<nrdcuTexture> shared;
+    shared.swap(ctx->tile.exported);
+    // keep only genuine shared textures (anything that is not already a pool texture), pools first
+    std::vector<nrdcuTexture> list = ctx->permanent;
+    list.insert(list.end(), ctx->transient.begin(), ctx->transient.end());
+    const size_t pools = list.size();
+    for (const nrdcuTexture& s : shared) {
+        bool isPool = false;
+        for (size_t i = 0; i < pools; i++) isPool |= list[i].data == s.data;
+        if (!isPool) list.push_back(s);
+    }
+    ctx->tile.exported.swap(list);
+}
+
+NRDCU_API uint32_t nrdcuTileExportSize(nrdcuContext* ctx) {
+    if (!ctx) return 0;
+    buildExportList(ctx);
+    return (uint32_t)(sizeof(uint32_t) * 2 + (ctx->tile.exported.size() + 1) * sizeof(TileExportEntry));
+}
+
+NRDCU_API uint32_t nrdcuTileExport(nrdcuContext* ctx, void* blob, uint32_t blobSize) {
+    if (!ctx || !blob) return fail(Result::INVALID_ARGUMENT, "nrdcuTileExport: null argument");
+    if (blobSize < nrdcuTileExportSize(ctx)) return fail(Result::INVALID_ARGUMENT, "nrdcuTileExport: blob too small");
+    cudaSetDevice(ctx->device);
+    nrdcuContext::Tile& t = ctx->tile;
+    if (!t.flags) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, 256) != cudaSuccess) return fail(Result::FAILURE, "nrdcuTileExport: cudaMalloc failed");
+        cudaMemset(p, 0, 256);
+        ctx->allocations.push_back(p);
+        t.flags = (uint32_t*)p;
+        if (cudaHostAlloc((void**)&t.hostError, sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) return fail(Result::FAILURE, "nrdcuTileExport: cudaHostAlloc failed");
+        *t.hostError = 0;
+    }
+    uint8_t* w = (uint8_t*)blob;
+    const uint32_t header[2] = {0x4E524454u, (uint32_t)t.exported.size()};
+    memcpy(w, header, sizeof(header));
+    w += sizeof(header);
+    for (size_t i = 0; i <= t.exported.size(); i++) {
+        TileExportEntry e = {};
+        void* ptr = i < t.exported.size() ? t.exported[i].data : (void*)t.flags;
+        e.bytes = i < t.exported.size() ? (uint64_t)t.exported[i].pitchBytes * t.exported[i].height : 256;
+        cudaError_t err = cudaIpcGetMemHandle(&e.handle, ptr);
+        if (err != cudaSuccess) return fail(Result::FAILURE, "cudaIpcGetMemHandle: %s", cudaGetErrorString(err));
+        memcpy(w, &e, sizeof(e));
+        w += sizeof(e);
+    }
+    cudaDeviceSynchronize();  // the memset of the flag words has landed before anybody maps them
+    return 0;
+}
+
+// blobAbove / blobBelow: the export blobs of the ranks owning the strips above / below this one (NULL at the frame edges)
+NRDCU_API uint32_t nrdcuTileAttach(nrdcuContext* ctx, const void* blobAbove, const void* blobBelow, uint32_t blobSize) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuTileAttach: null context");
+    nrdcuContext::Tile& t = ctx->tile;
+    if (!t.flags) return fail(Result::INVALID_ARGUMENT, "nrdcuTileAttach: call nrdcuTileExport first");
+    cudaSetDevice(ctx->device);
+    const void* blobs[2] = {blobAbove, blobBelow};
+    for (int d = 0; d < 2; d++) {
+        if (!blobs[d]) continue;
+        const uint8_t* r = (const uint8_t*)blobs[d];
+        uint32_t header[2];
+        memcpy(header, r, sizeof(header));
+        r += sizeof(header);
+        if (header[0] != 0x4E524454u || header[1] != t.exported.size() || blobSize < sizeof(header) + (header[1] + 1) * sizeof(TileExportEntry))
+            return fail(Result::INVALID_ARGUMENT, "nrdcuTileAttach: neighbour blob does not match this context (%u textures vs %zu)", header[1], t.exported.size());
+        t.peerBase[d].assign(t.exported.size(), nullptr);
+        for (size_t i = 0; i <= t.exported.size(); i++) {
+            TileExportEntry e;
+            memcpy(&e, r, sizeof(e));
+            r += sizeof(e);
+            void* mapped = nullptr;
+            cudaError_t err = cudaIpcOpenMemHandle(&mapped, e.handle, cudaIpcMemLazyEnablePeerAccess);
+            if (err != cudaSuccess) return fail(Result::FAILURE, "cudaIpcOpenMemHandle (texture %zu of the neighbour %s): %s", i, d ? "below" : "above", cudaGetErrorString(err));
+            if (i < t.exported.size())
+                t.peerBase[d][i] = mapped;
+            else
+                t.peerFlags[d] = (uint32_t*)mapped;
+        }
+    }
+    t.attached = true;
+    return 0;
+}
+
+NRDCU_API uint32_t nrdcuTileSetHalo(nrdcuContext* ctx, const char* passName, uint32_t binding, uint32_t rows) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuTileSetHalo: null context");
+    if (!passName)
+        ctx->tile.defaultHalo = rows;
+    else
+        ctx->tile.rules.push_back({passName, binding, rows});
+    return 0;
+}
+
+NRDCU_API uint32_t nrdcuTileGetStatus(nrdcuContext* ctx, uint64_t* bytesPushed, uint32_t* error) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuTileGetStatus: null context");
+    if (bytesPushed) *bytesPushed = ctx->tile.bytesPushed;
+    if (error) *error = ctx->tile.hostError ? *(volatile uint32_t*)ctx->tile.hostError : 0u;
+    return 0;
+}
 
 NRDCU_API uint32_t nrdcuCreate(const void* instanceCreationDesc, uint16_t resourceWidth, uint16_t resourceHeight, int device, uint32_t flags, nrdcuContext** out) {
     if (!instanceCreationDesc || !out || !resourceWidth || !resourceHeight) return fail(Result::INVALID_ARGUMENT, "nrdcuCreate: null or zero argument");
@@ -396,6 +572,12 @@ NRDCU_API void nrdcuDestroy(nrdcuContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    for (int d = 0; d < 2; d++) {
+        for (void* p : ctx->tile.peerBase[d])
+            if (p) cudaIpcCloseMemHandle(p);
+        if (ctx->tile.peerFlags[d]) cudaIpcCloseMemHandle(ctx->tile.peerFlags[d]);
+    }
+    if (ctx->tile.hostError) cudaFreeHost(ctx->tile.hostError);
     for (void* p : ctx->allocations) cudaFree(p);
     if (ctx->instance) DestroyInstance(*ctx->instance);
     delete ctx;
@@ -481,6 +663,10 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
             ctx->pending.push_back({dd.name, evStart, evStop});
         }
         if (rc != 0) return rc;
+        if (ctx->tile.attached) {
+            rc = pushHalos(ctx, dd, rowBegin, rowEnd, (cudaStream_t)stream);
+            if (rc != 0) return rc;
+        }
         if (afterDispatch) {
             // which bindings the dispatch wrote (storage textures): what a strip has to trade with its neighbours
             ctx->scratchIsStorage.resize(dd.resourcesNum);

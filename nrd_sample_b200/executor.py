@@ -23,7 +23,8 @@ FLAG_QUAD_INTRINSICS = 1
 FLAG_CUDA_GRAPH = 2
 FLAG_ROBUST_MIRROR_TEST = 4
 
-NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
+NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdcuAllocSharedTexture", "nrdcuTileExportSize", "nrdcuTileExport", "nrdcuTileAttach",
+                 "nrdcuTileSetHalo", "nrdcuTileGetStatus", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
                  "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuGetLastError", "nrdcuGetLaunchCount",
                  "nrdcuGetPoolBytes", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile")
 
@@ -57,6 +58,18 @@ def load() -> C.CDLL:
         L.nrdcuDispatchRows.restype = C.c_uint32
         L.nrdcuDenoiseRows.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, DISPATCH_CALLBACK, C.c_void_p]
         L.nrdcuDenoiseRows.restype = C.c_uint32
+        L.nrdcuAllocSharedTexture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(CuTexture)]
+        L.nrdcuAllocSharedTexture.restype = C.c_uint32
+        L.nrdcuTileExportSize.argtypes = [C.c_void_p]
+        L.nrdcuTileExportSize.restype = C.c_uint32
+        L.nrdcuTileExport.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.nrdcuTileExport.restype = C.c_uint32
+        L.nrdcuTileAttach.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.nrdcuTileAttach.restype = C.c_uint32
+        L.nrdcuTileSetHalo.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32]
+        L.nrdcuTileSetHalo.restype = C.c_uint32
+        L.nrdcuTileGetStatus.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.nrdcuTileGetStatus.restype = C.c_uint32
         L.nrdcuCreate.argtypes = [C.c_void_p, C.c_uint16, C.c_uint16, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
         L.nrdcuCreate.restype = C.c_uint32
         L.nrdcuDestroy.argtypes = [C.c_void_p]

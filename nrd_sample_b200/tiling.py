@@ -14,6 +14,12 @@ the neighbour's rows into the apron of its own copy: one batched NCCL send/recv 
 frame. With halo >= the largest reach the N-GPU result is bit-identical to the single-GPU frame (tests/test_tiling.py
 checks exactly that, on gloo with the CPU oracle standing in for the kernels and on NCCL with the real ones).
 
+Two transports. `mode="peer"` (default on GPUs): neighbouring ranks map each other's textures through CUDA IPC and the
+executor itself stores the seam rows into the neighbours' copies over NVLink after every pass, then raises a flag the
+neighbour spins on (csrc/kernels/peer_halo.cu): three tiny launches per pass, nothing on the host. `mode="nccl"`: the
+same rows through torch.distributed batched send/recv from a per-dispatch callback — the portable baseline (also what
+the gloo CPU tests exercise), ~0.1 ms slower per pass.
+
 Bound on temporal reach: history is fetched at pixel + motion; HALO_ROWS - 2 = 62 rows of vertical motion per frame
 are covered, beyond that a strip would need a taller halo (`halo_rows=`).
 """
@@ -130,7 +136,7 @@ class TiledDenoiser:
     Construct on every rank of an initialised process group (backend nccl); call `denoise()` in lockstep."""
 
     def __init__(self, denoiser: int, width: int, height: int, rank: int, world: int, device: int = 0, halo_rows: int = HALO_ROWS, flags: Optional[int] = None,
-                 group: Optional[dist.ProcessGroup] = None, use_table: bool = True):
+                 group: Optional[dist.ProcessGroup] = None, use_table: bool = True, mode: str = "peer"):
         from . import executor as ex
         self.ex = ex
         self.rank, self.world, self.height, self.width, self.halo, self.group = rank, world, height, width, halo_rows, group
@@ -143,6 +149,9 @@ class TiledDenoiser:
         self.bytes_sent = 0
         self.use_table = use_table
         self._plans = {}
+        self.mode = mode if world > 1 else "single"
+        self._attached = False
+        self._shared = []
         self.on_pass: Optional[Callable[[int, str], None]] = None
         self._cb = ex.DISPATCH_CALLBACK(self._after_dispatch)
 
@@ -166,13 +175,59 @@ class TiledDenoiser:
         if self.on_pass:
             self.on_pass(index, name.decode() if name else "")
 
+    # ---- peer mode -----------------------------------------------------------------------------------------------
+    def shared_texture(self, rtype: int, fmt: int) -> torch.Tensor:
+        """Allocate a user texture the denoiser WRITES (OUT_*) inside the context, so that the neighbouring strips can map it, bind
+        it to `rtype` and return a tensor view [H, W(, C)] of it (rows are 256-byte aligned: the view may be strided)."""
+        from . import nrd_api as api
+        ex = self.ex
+        tex = ex.CuTexture()
+        ex._check(ex.load().nrdcuAllocSharedTexture(self.den.ctx, int(fmt), self.width, self.height, C.byref(tex)), "nrdcuAllocSharedTexture")
+        ex._check(ex.load().nrdcuSetResource(self.den.ctx, int(rtype), C.byref(tex)), "nrdcuSetResource")
+        dtype, ch = ex.FORMAT_STORAGE[api.Format(fmt)]
+        raw = ex._as_byte_tensor(tex.data, tex.pitchBytes * tex.height, self.device).view(dtype)
+        pitch_elems = tex.pitchBytes // raw.element_size()
+        view = raw.as_strided((self.height, self.width, ch), (pitch_elems, ch, 1)) if ch > 1 else raw.as_strided((self.height, self.width), (pitch_elems, 1))
+        self._shared.append(view)
+        return view
+
+    def attach_peers(self):
+        """Trade IPC handles with the neighbouring ranks and map their textures (collective: call on every rank, once, after all
+        shared textures exist and before the first denoise)."""
+        if self.mode != "peer" or self._attached:
+            return
+        ex, L = self.ex, self.ex.load()
+        if self.use_table:
+            for pass_name, table in HALO_TABLE.items():
+                for binding, rows in table.items():
+                    ex._check(L.nrdcuTileSetHalo(self.den.ctx, pass_name.encode(), binding, min(rows, self.halo)), "nrdcuTileSetHalo")
+        ex._check(L.nrdcuTileSetHalo(self.den.ctx, None, 0, self.halo), "nrdcuTileSetHalo")
+        size = L.nrdcuTileExportSize(self.den.ctx)
+        blob = C.create_string_buffer(size)
+        ex._check(L.nrdcuTileExport(self.den.ctx, blob, size), "nrdcuTileExport")
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, bytes(blob.raw), group=self.group)
+        above = C.create_string_buffer(blobs[self.rank - 1], size) if self.rank > 0 else None
+        below = C.create_string_buffer(blobs[self.rank + 1], size) if self.rank + 1 < self.world else None
+        ex._check(L.nrdcuTileAttach(self.den.ctx, above, below, size), "nrdcuTileAttach")
+        dist.barrier(group=self.group)   # nobody pushes before everybody has mapped
+        self._attached = True
+
+    def status(self):
+        """(bytes pushed to the neighbours so far, error code of the flag wait: 0 = fine)."""
+        b, e = C.c_uint64(), C.c_uint32()
+        self.ex._check(self.ex.load().nrdcuTileGetStatus(self.den.ctx, C.byref(b), C.byref(e)), "nrdcuTileGetStatus")
+        return int(b.value), int(e.value)
+
     def __getattr__(self, item):  # set_user_texture, set_common_settings, set_denoiser_settings, pool_texture, profiling ...
         return getattr(self.den, item)
 
     def denoise(self, stream: Optional[torch.cuda.Stream] = None):
         s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
         L = self.ex.load()
-        cb = self._cb if self.world > 1 else self.ex.DISPATCH_CALLBACK()
+        if self.mode == "peer" and not self._attached:
+            self.attach_peers()
+        cb = self._cb if self.mode == "nccl" else self.ex.DISPATCH_CALLBACK()
         self.ex._check(L.nrdcuDenoiseRows(self.den.ctx, self.den._ids, 1, C.c_void_p(s), self.rows[0], self.rows[1], cb, None), "nrdcuDenoiseRows")
 
     def close(self):

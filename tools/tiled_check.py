@@ -19,6 +19,7 @@ W = int(sys.argv[1]) if len(sys.argv) > 1 else 3840
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 2160
 FRAMES = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 STEPS = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+MODE = sys.argv[5] if len(sys.argv) > 5 else "peer"   # "peer": seam rows pushed over NVLink peer memory by the executor; "nccl": torch.distributed send/recv
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dev = f"cuda:{local}"
@@ -30,8 +31,12 @@ RING = 4
 frames = [synth.reblur_frame(i, W, H, device=dev, period=RING) for i in range(RING)]
 
 
-def make(cls, *a):
-    den = cls(*a)
+def make(cls, *a, **kw):
+    den = cls(*a, **kw)
+    if kw.get("mode") == "peer" and world > 1:   # outputs live in the context so that the neighbouring strips can map them
+        outs = [den.shared_texture(RT.OUT_DIFF_RADIANCE_HITDIST, F16), den.shared_texture(RT.OUT_SPEC_RADIANCE_HITDIST, F16)]
+        den.attach_peers()
+        return den, outs
     outs = [ex.alloc_texture(F16, W, H, dev), ex.alloc_texture(F16, W, H, dev)]
     den.set_user_texture(RT.OUT_DIFF_RADIANCE_HITDIST, outs[0], F16)
     den.set_user_texture(RT.OUT_SPEC_RADIANCE_HITDIST, outs[1], F16)
@@ -45,7 +50,7 @@ def step(den, i):
     den.denoise()
 
 
-tiled, t_out = make(tiling.TiledDenoiser, api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, rank, world, local)
+tiled, t_out = make(tiling.TiledDenoiser, api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, rank, world, local, mode=MODE)
 whole, w_out = make(ex.CudaDenoiser, api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, 0, local)
 y0, y1 = tiled.rows
 ok = True
@@ -75,7 +80,7 @@ stream = torch.cuda.current_stream()
 for i in range(FRAMES, FRAMES + 6):
     step(tiled, i)
 barrier()
-sent0 = tiled.bytes_sent
+sent0 = tiled.bytes_sent + tiled.status()[0]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(stream)
 for i in range(FRAMES + 6, FRAMES + 6 + STEPS):
@@ -89,7 +94,7 @@ if rank == 0:
     per = float(ms.item()) / STEPS
     print(json.dumps({"check": "tiled strips == whole frame (bit exact)", "passed": bool(flag.item()), "n_gpus": world, "resolution": [W, H], "strips": tiled.strips,
                       "halo_rows": tiled.halo, "ms_per_frame": per, "mpixels_per_s": W * H / per / 1e3,
-                      "halo_bytes_sent_per_frame_rank0": (tiled.bytes_sent - sent0) // STEPS}))
+                      "mode": tiled.mode, "halo_bytes_sent_per_frame_rank0": (tiled.bytes_sent + tiled.status()[0] - sent0) // STEPS, "wait_error": tiled.status()[1]}))
 tiled.close()
 if world > 1:
     dist.destroy_process_group()
