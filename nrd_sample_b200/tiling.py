@@ -54,18 +54,54 @@ def halo_rows_for(pass_name: str, binding: int, default: int = HALO_ROWS) -> int
     return min(default, HALO_TABLE.get(pass_name.split(" - ")[-1], {}).get(binding, default))
 
 
-def strip_rows(height: int, world: int) -> List[Tuple[int, int]]:
-    """Rows [y0, y1) of each rank's strip: whole 16-row tile rows, as even as possible, last strip takes the ragged end."""
+def strip_rows(height: int, world: int, weights: Optional[Sequence[float]] = None, min_rows: int = 0) -> List[Tuple[int, int]]:
+    """Rows [y0, y1) of each rank's strip: whole 16-row tile rows, the last strip takes the ragged end.
+
+    Without `weights` the tile rows are split evenly. With `weights` (one cost per 16-row tile row, e.g. the number of pixels in
+    denoising range — sky costs nothing, see `tile_row_weights`) the cuts sit where the cumulative cost crosses k / world of the
+    total, so that every GPU gets the same amount of work rather than the same number of rows; `min_rows` keeps every strip at
+    least as tall as the halo its neighbours read from it."""
     tiles = (height + TILE - 1) // TILE
     if world > tiles:
         raise ValueError(f"{world} strips need at least {world} tile rows, the frame has {tiles}")
-    base, extra = divmod(tiles, world)
+    min_tiles = max(1, (min_rows + TILE - 1) // TILE)
+    if weights is None:
+        base, extra = divmod(tiles, world)
+        counts = [base + (1 if r < extra else 0) for r in range(world)]
+    else:
+        w = [float(x) for x in weights]
+        if len(w) != tiles:
+            raise ValueError(f"expected {tiles} tile-row weights, got {len(w)}")
+        total = sum(w) or 1.0
+        cuts, acc, t = [0], 0.0, 0
+        for k in range(1, world):
+            target = total * k / world
+            while t < tiles and acc + w[t] * 0.5 < target:
+                acc += w[t]
+                t += 1
+            t = min(max(t, cuts[-1] + min_tiles), tiles - (world - k) * min_tiles)   # leave room for the strips still to come
+            acc = sum(w[:t])
+            cuts.append(t)
+        cuts.append(tiles)
+        counts = [b - a for a, b in zip(cuts, cuts[1:])]
+    if min(counts) < 1:
+        raise ValueError("a strip came out empty")
     out, t = [], 0
-    for r in range(world):
-        n = base + (1 if r < extra else 0)
+    for n in counts:
         out.append((t * TILE, min((t + n) * TILE, height)))
         t += n
     return out
+
+
+def tile_row_weights(viewz: torch.Tensor, denoising_range: float = 5e5, floor: float = 0.03) -> List[float]:
+    """Cost of each 16-row tile row of a frame: the fraction of its pixels inside the denoising range (every pass early-outs on sky
+    tiles / pixels), plus a small floor for the fixed per-row cost. Every rank holds the full IN_VIEWZ, so all ranks derive the same cuts."""
+    h = viewz.shape[0]
+    inside = (viewz.abs() < denoising_range).float().mean(dim=1)
+    pad = (-h) % TILE
+    if pad:
+        inside = torch.cat([inside, inside.new_zeros(pad)])
+    return (inside.view(-1, TILE).mean(dim=1) + floor).tolist()
 
 
 def _scaled(rows: Tuple[int, int], halo: int, tex_height: int, full_height: int) -> Tuple[int, int, int]:
@@ -136,11 +172,11 @@ class TiledDenoiser:
     Construct on every rank of an initialised process group (backend nccl); call `denoise()` in lockstep."""
 
     def __init__(self, denoiser: int, width: int, height: int, rank: int, world: int, device: int = 0, halo_rows: int = HALO_ROWS, flags: Optional[int] = None,
-                 group: Optional[dist.ProcessGroup] = None, use_table: bool = True, mode: str = "peer"):
+                 group: Optional[dist.ProcessGroup] = None, use_table: bool = True, mode: str = "peer", row_weights: Optional[Sequence[float]] = None):
         from . import executor as ex
         self.ex = ex
         self.rank, self.world, self.height, self.width, self.halo, self.group = rank, world, height, width, halo_rows, group
-        self.strips = strip_rows(height, world)
+        self.strips = strip_rows(height, world, row_weights, halo_rows if world > 1 else 0)
         self.rows = self.strips[rank]
         if world > 1 and min(b - a for a, b in self.strips) < halo_rows:
             raise ValueError(f"strips of {min(b - a for a, b in self.strips)} rows are shorter than the {halo_rows}-row halo")

@@ -29,6 +29,20 @@ def test_strip_rows():
         tiling.strip_rows(32, 4)
 
 
+def test_balanced_strips_follow_the_work():
+    """Sky rows cost nothing: cuts by cumulative denoising-range pixels give every rank the same work, not the same height."""
+    h = 544
+    w = tiling.tile_row_weights(synth.reblur_frame(0, 320, h)["IN_VIEWZ"])
+    assert len(w) == h // 16 and w[0] < 0.1 < w[-2]   # sky on top, geometry below
+    for world in (2, 4):
+        s = tiling.strip_rows(h, world, w, min_rows=64)
+        assert s[0][0] == 0 and s[-1][1] == h and all(a[1] == b[0] for a, b in zip(s, s[1:])) and all(a % 16 == 0 for a, _ in s)
+        assert all(b - a >= 64 for a, b in s)
+        work = [sum(w[a // 16:(b + 15) // 16]) for a, b in s]
+        even = [sum(w[a // 16:(b + 15) // 16]) for a, b in tiling.strip_rows(h, world)]
+        assert max(work) < max(even) * 0.85 and max(work) / (sum(work) / world) < 1.2
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -20,6 +20,7 @@ H = int(sys.argv[2]) if len(sys.argv) > 2 else 2160
 FRAMES = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 STEPS = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 MODE = sys.argv[5] if len(sys.argv) > 5 else "peer"   # "peer": seam rows pushed over NVLink peer memory by the executor; "nccl": torch.distributed send/recv
+SPLIT = sys.argv[6] if len(sys.argv) > 6 else "balanced"   # "balanced": cuts by denoising-range pixels per tile row; "even": equal row counts
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dev = f"cuda:{local}"
@@ -50,7 +51,8 @@ def step(den, i):
     den.denoise()
 
 
-tiled, t_out = make(tiling.TiledDenoiser, api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, rank, world, local, mode=MODE)
+weights = tiling.tile_row_weights(frames[0]["IN_VIEWZ"]) if SPLIT == "balanced" else None   # same on every rank: all hold the full input frame
+tiled, t_out = make(tiling.TiledDenoiser, api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, rank, world, local, mode=MODE, row_weights=weights)
 whole, w_out = make(ex.CudaDenoiser, api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, 0, local)
 y0, y1 = tiled.rows
 ok = True
@@ -94,7 +96,7 @@ if rank == 0:
     per = float(ms.item()) / STEPS
     print(json.dumps({"check": "tiled strips == whole frame (bit exact)", "passed": bool(flag.item()), "n_gpus": world, "resolution": [W, H], "strips": tiled.strips,
                       "halo_rows": tiled.halo, "ms_per_frame": per, "mpixels_per_s": W * H / per / 1e3,
-                      "mode": tiled.mode, "halo_bytes_sent_per_frame_rank0": (tiled.bytes_sent + tiled.status()[0] - sent0) // STEPS, "wait_error": tiled.status()[1]}))
+                      "mode": tiled.mode, "split": SPLIT, "halo_bytes_sent_per_frame_rank0": (tiled.bytes_sent + tiled.status()[0] - sent0) // STEPS, "wait_error": tiled.status()[1]}))
 tiled.close()
 if world > 1:
     dist.destroy_process_group()
