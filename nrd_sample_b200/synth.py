@@ -353,3 +353,63 @@ def sigma_frame(frame_index: int, width: int, height: int, device="cpu", period:
         out["_clean_visibility"] = torch.where(ndl <= 0.0, torch.zeros_like(vis), vis / 48.0)
         out["_hit"] = hit
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# RELAX_DIFFUSE_SPECULAR_SH inputs
+# ------------------------------------------------------------------------------------------------
+def relax_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False) -> Dict[str, torch.Tensor]:
+    """All user inputs of RELAX_DIFFUSE_SPECULAR_SH for one frame (BASELINE.json config 2): the G-buffer and motion of `reblur_frame`,
+    un-normalised radiance + hit distance in IN_*_SH0 and `direction * luminance` in IN_*_SH1, both RGBA16F, packed like
+    RELAX_FrontEnd_PackSh (NRD.hlsli:925-941). Directions: cosine-weighted around N (diffuse), jittered mirror direction (specular)."""
+    device = torch.device(device)
+    cam = make_camera(frame_index, width, height, period)
+    g = _raycast(cam, width, height, device)
+    base = reblur_frame(frame_index, width, height, device, period, with_clean=True)
+    hit, N, V, rough = g["hit"], g["N"], g["V"], g["roughness"]
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(SEED_BASE + 0x52454C + frame_index)
+
+    def rnd():
+        return torch.rand(height, width, device=device, generator=gen)
+
+    def noisy(clean):
+        # RELAX stores squared luminance (2nd moments) in fp16: radiance is capped at 200 the way a renderer caps fireflies before
+        # handing them to RELAX, so that luminance^2 stays below 65504 (an Inf there would spread through the a-trous passes)
+        e = -torch.log(1.0 - rnd() * 0.999999)
+        fire = torch.where(rnd() < 0.002, torch.full_like(e, 50.0), torch.ones_like(e))
+        return (clean * (e * fire).unsqueeze(-1)).clamp_max(200.0)
+
+    def around(axis, spread):
+        d = axis + spread.unsqueeze(-1) * (torch.stack([rnd(), rnd(), rnd()], -1) * 2.0 - 1.0)
+        return d / d.norm(dim=-1, keepdim=True).clamp_min(1e-6)
+
+    diff = noisy(base["_clean_diff"])
+    spec = noisy(base["_clean_spec"])
+    R = 2.0 * (N * V).sum(-1, keepdim=True) * N - V
+    dir_d = around(N, torch.full_like(rough, 0.8))
+    dir_s = around(R, rough * 0.7 + 0.02)
+    hit_t_d = (0.1 + 9.9 * rnd()) * 2.0
+    hit_t_s = (0.1 + 9.9 * rnd()) * (1.0 + rough)
+    lum = torch.tensor([0.2126, 0.7152, 0.0722], device=device)
+    zero4 = torch.zeros(height, width, 4, device=device, dtype=torch.float16)
+
+    def sh0(rad, t):
+        return torch.where(hit[..., None], torch.cat([rad.clamp(0, FP16_MAX), t.unsqueeze(-1)], -1).to(torch.float16), zero4).contiguous()
+
+    def sh1(rad, d):
+        return torch.where(hit[..., None], torch.cat([d * (rad * lum).sum(-1, keepdim=True), torch.zeros_like(d[..., :1])], -1).to(torch.float16), zero4).contiguous()
+
+    out = {
+        "IN_VIEWZ": base["IN_VIEWZ"],
+        "IN_NORMAL_ROUGHNESS": base["IN_NORMAL_ROUGHNESS"],
+        "IN_MV": base["IN_MV"],
+        "IN_DIFF_SH0": sh0(diff, hit_t_d),
+        "IN_DIFF_SH1": sh1(diff, dir_d),
+        "IN_SPEC_SH0": sh0(spec, hit_t_s),
+        "IN_SPEC_SH1": sh1(spec, dir_s),
+    }
+    if with_clean:
+        out["_clean_diff"], out["_clean_spec"], out["_hit"] = base["_clean_diff"], base["_clean_spec"], hit
+    return out

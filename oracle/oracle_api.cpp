@@ -12,6 +12,8 @@
 namespace orc {
 // sigma_passes.cpp
 int sigmaDispatch(const std::string& id, const void* cb, uint32_t cbSize, Tex* t, uint32_t n, int gridW, int gridH);
+// relax_passes.cpp
+int relaxDispatch(const std::string& id, const void* cb, uint32_t cbSize, Tex* t, uint32_t n, int gridW, int gridH);
 }  // namespace orc
 
 using namespace orc;
@@ -28,8 +30,8 @@ __attribute__((visibility("default"))) int nrd_oracle_dispatch(const char* shade
                                                                 uint32_t flags) {
     if (!shaderIdentifier || (!textures && texturesNum)) return 2;
     std::string id = shaderIdentifier;
-    Tex t[32];
-    if (texturesNum > 32) return 2;
+    Tex t[40];
+    if (texturesNum > 40) return 2;
     for (uint32_t i = 0; i < texturesNum; i++) t[i] = Tex(textures[i]);
     const bool quads = flags & 1u, robust = flags & 2u;
     const int gw = (int)gridW, gh = (int)gridH;
@@ -89,6 +91,7 @@ __attribute__((visibility("default"))) int nrd_oracle_dispatch(const char* shade
         return 1;
     }
     if (startsWith(id, "SIGMA_")) return sigmaDispatch(id, constants, constantsSize, t, texturesNum, gw, gh);
+    if (startsWith(id, "RELAX_")) return relaxDispatch(id, constants, constantsSize, t, texturesNum, gw, gh);
     return 1;
 }
 

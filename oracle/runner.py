@@ -73,6 +73,14 @@ USER_FORMATS = {
     api.ResourceType.IN_SPEC_RADIANCE_HITDIST: api.Format.RGBA16_SFLOAT,
     api.ResourceType.OUT_DIFF_RADIANCE_HITDIST: api.Format.RGBA16_SFLOAT,
     api.ResourceType.OUT_SPEC_RADIANCE_HITDIST: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.IN_DIFF_SH0: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.IN_DIFF_SH1: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.IN_SPEC_SH0: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.IN_SPEC_SH1: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.OUT_DIFF_SH0: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.OUT_DIFF_SH1: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.OUT_SPEC_SH0: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.OUT_SPEC_SH1: api.Format.RGBA16_SFLOAT,
     api.ResourceType.IN_PENUMBRA: api.Format.R16_SFLOAT,
     api.ResourceType.OUT_SHADOW_TRANSLUCENCY: api.Format.R8_UNORM,
 }
