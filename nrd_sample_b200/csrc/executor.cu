@@ -28,6 +28,7 @@ void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccu
 void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, bool quads, Rows, cudaStream_t);
 void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, Rows, cudaStream_t);
 uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
+uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
 }  // namespace nrdk
 
 using namespace nrd;
@@ -285,6 +286,13 @@ NRDCU_API uint32_t nrdcuDispatchRows(const char* shaderIdentifier, const void* c
         if (partial) return fail(Result::UNSUPPORTED, "%s: row ranges (multi-GPU strips) are implemented for REBLUR only", shaderIdentifier);
         std::string err;
         uint32_t r = nrdk::dispatchSigma(id, constants, constantsSize, textures, texturesNum, s, err);
+        if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
+        return checkLaunch(id.c_str()) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
+    }
+    if (id.rfind("RELAX_", 0) == 0) {
+        if (partial) return fail(Result::UNSUPPORTED, "%s: row ranges (multi-GPU strips) are implemented for REBLUR only", shaderIdentifier);
+        std::string err;
+        uint32_t r = nrdk::dispatchRelax(id, constants, constantsSize, textures, texturesNum, s, err);
         if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
         return checkLaunch(id.c_str()) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
     }

@@ -109,6 +109,7 @@ struct TexRGBA16F : TexView {
     NRD_DEV float4 fetch(int x, int y) const { return decode(fetchRaw(x, y)); }
     NRD_DEV float4 load(int x, int y) const { return inside(x, y) ? fetch(x, y) : f4(0.0f); }
     NRD_DEV float4 fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
+    NRD_DEV float4 sampleNearest(float2 uv) const { return fetchClamped((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
     NRD_DEV void store(int x, int y, float4 v) const {
         if (!inside(x, y)) return;
         __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
@@ -132,6 +133,7 @@ struct TexNR : TexView {
     NRD_DEV uint32_t fetchRaw(int x, int y) const { return __ldg(ptr<uint32_t>(x, y)); }
     NRD_DEV uint32_t loadRaw(int x, int y) const { return inside(x, y) ? fetchRaw(x, y) : 0u; }
     NRD_DEV uint32_t fetchRawClamped(int x, int y) const { return fetchRaw(cx(x), cy(y)); }
+    NRD_DEV uint32_t sampleNearestRaw(float2 uv) const { return fetchRawClamped((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
     NRD_DEV void storeRaw(int x, int y, uint32_t v) const { if (inside(x, y)) *ptrw<uint32_t>(x, y) = v; }
     static NRD_DEV float4 decode(uint32_t v) {
         return make_float4((float)(v & 1023u) / 1023.0f, (float)((v >> 10) & 1023u) / 1023.0f, (float)((v >> 20) & 1023u) / 1023.0f, (float)(v >> 30) / 3.0f);
@@ -178,10 +180,19 @@ struct TexRG8 : TexView {  // RG8_UNORM
 };
 
 struct TexRGBA8 : TexView {  // RGBA8_UNORM
-    NRD_DEV float4 load(int x, int y) const {
-        if (!inside(x, y)) return f4(0.0f);
+    NRD_DEV float4 fetch(int x, int y) const {
         uchar4 v = __ldg(ptr<uchar4>(x, y));
         return make_float4((float)v.x / 255.0f, (float)v.y / 255.0f, (float)v.z / 255.0f, (float)v.w / 255.0f);
+    }
+    NRD_DEV float4 load(int x, int y) const { return inside(x, y) ? fetch(x, y) : f4(0.0f); }
+    NRD_DEV float4 fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
+    NRD_DEV float4 sampleLinear(float2 uv) const {
+        float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
+        float fx = floorf(tx), fy = floorf(ty);
+        float wx = tx - fx, wy = ty - fy;
+        int x0 = (int)fx, y0 = (int)fy;
+        float4 a = fetchClamped(x0, y0), b = fetchClamped(x0 + 1, y0), c = fetchClamped(x0, y0 + 1), d = fetchClamped(x0 + 1, y0 + 1);
+        return lerp(lerp(a, b, wx), lerp(c, d, wx), wy);
     }
     NRD_DEV void store(int x, int y, float4 v) const {
         if (inside(x, y))

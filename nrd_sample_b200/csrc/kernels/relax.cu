@@ -1,0 +1,1349 @@
+// RELAX_DIFFUSE_SPECULAR_SH passes on sm_100a (NRD_SIGNAL = BOTH, NRD_MODE = SH): ClassifyTiles, PrePass,
+// TemporalAccumulation, HistoryFix, HistoryClamping, Copy, AntiFirefly, AtrousSmem, Atrous. One kernel per reference
+// dispatch, one thread per pixel, CTA = 32x8 pixels (a 32-pixel row per warp: coalesced RGBA16F rows).
+//
+// Reference (External/NRD/Shaders): RELAX_ClassifyTiles.cs.hlsl:21-51, RELAX_PrePass.cs.hlsl:21-385,
+// RELAX_TemporalAccumulation.cs.hlsl:21-942, RELAX_HistoryFix.cs.hlsl:21-163, RELAX_HistoryClamping.cs.hlsl:21-354,
+// RELAX_Copy.cs.hlsl:21-34, RELAX_AntiFirefly.cs.hlsl:21-216, RELAX_AtrousSmem.cs.hlsl:21-484, RELAX_Atrous.cs.hlsl:21-260,
+// helpers RELAX_Common.hlsli:11-185. Build switches of the reference's default build: no checkerboard, no confidence /
+// disocclusion-threshold-mix inputs (rejected with UNSUPPORTED), NRD_USE_PREV_WORLD_SPACE_MATRIX = 0.
+// First version: the 3x3 / 5x5 neighbourhoods the reference stages in groupshared memory are read through L1 here
+// (clamped fetches); the arithmetic follows the shaders statement by statement.
+#include <string>
+
+#include "../../../include/nrd_b200.h"
+#include "../../../include/nrdcu.h"
+#include "reblur_common.cuh"  // HistoryFilter
+
+namespace nrdk {
+
+using nrdb::RelaxConstants;
+
+namespace {
+
+constexpr int BLOCK_W = 32, BLOCK_H = 8;
+constexpr float RELAX_NORMAL_ULP = 1.5f / 255.0f;
+constexpr float RELAX_MAX_ACCUM_FRAME_NUM = 255.0f;
+constexpr float RELAX_ANTILAG_ACCELERATION_AMOUNT_SCALE = 10.0f;
+constexpr float NRD_FP16_MAX_F = 65504.0f;
+
+__constant__ float3 kPoisson8[8] = {{-0.4706069f, -0.4427112f, +0.6461146f}, {-0.9057375f, +0.3003471f, +0.9542373f}, {-0.3487388f, +0.4037880f, +0.5335386f},
+                                    {+0.1023042f, +0.6439373f, +0.6520134f}, {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
+                                    {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
+
+// ---- small helpers ------------------------------------------------------------------------------------------------
+NRD_DEV float luminance(float3 x) { return dot(x, make_float3(0.2126f, 0.7152f, 0.0722f)); }
+NRD_DEV float3 rgbToYCoCg(float3 x) { return make_float3(dot(x, make_float3(0.25f, 0.5f, 0.25f)), dot(x, make_float3(0.5f, 0.0f, -0.5f)), dot(x, make_float3(-0.25f, 0.5f, -0.25f))); }
+NRD_DEV float3 yCoCgToRgb(float3 x) { float t = x.x - x.z; return make_float3(t + x.y, x.x + x.z, t - x.y); }
+NRD_DEV float3 min3v(float3 a, float3 b) { return make_float3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+NRD_DEV float4 max4v(float4 a, float b) { return make_float4(fmaxf(a.x, b), fmaxf(a.y, b), fmaxf(a.z, b), fmaxf(a.w, b)); }
+NRD_DEV float4 clamp4v(float4 a, float lo, float hi) { return make_float4(fminf(fmaxf(a.x, lo), hi), fminf(fmaxf(a.y, lo), hi), fminf(fmaxf(a.z, lo), hi), fminf(fmaxf(a.w, lo), hi)); }
+NRD_DEV float3 clamp3v(float3 a, float3 lo, float3 hi) { return min3v(max3(a, lo), hi); }
+NRD_DEV float3 sqrt3v(float3 a) { return make_float3(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z)); }
+NRD_DEV float bayer4x4(uint32_t x, uint32_t y, uint32_t frameIndex) {
+    const uint32_t px = x & 3u, py = y & 3u;
+    const uint32_t b = ((py & 1u) << 2) | ((px & 1u) << 3) | ((py & 2u) >> 1) | (px & 2u);
+    return ((float)((b + frameIndex) & 0xFu) + 0.5f) / 16.0f;
+}
+NRD_DEV float pow5(float x) { return pow01(1.0f - x, 5.0f); }
+NRD_DEV float3 safeNormalize(float3 v) { return v * (1.0f / sqrtf(dot(v, v) + 1e-9f)); }
+NRD_DEV float4 unpackPrevNormalRoughness(float4 p) { return f4(safeNormalize(xyz(p) * 2.0f - 1.0f), p.w); }
+NRD_DEV float4 packPrevNormalRoughness(float4 nr) { return f4(xyz(nr) * 0.5f + 0.5f, nr.w); }
+NRD_DEV float customWeightsFloat(float s00, float s10, float s01, float s11, float4 w) {
+    float o = s00 * w.x;
+    o += s10 * w.y;
+    o += s01 * w.z;
+    o += s11 * w.w;
+    const float sum = sum4(w);
+    return sum < 0.0001f ? 0.0f : o * (1.0f / sum);
+}
+NRD_DEV float3 customWeightsSH(const TexRGBA16F& t, int x, int y, float4 w) {
+    float3 o = xyz(t.load(x, y)) * w.x;
+    o += xyz(t.load(x + 1, y)) * w.y;
+    o += xyz(t.load(x, y + 1)) * w.z;
+    o += xyz(t.load(x + 1, y + 1)) * w.w;
+    const float sum = sum4(w);
+    return sum < 0.0001f ? f3(0.0f) : o * (1.0f / sum);
+}
+NRD_DEV float planeDistanceWeight(float3 centerWorldPos, float3 centerNormal, float centerViewZ, float3 sampleWorldPos, float threshold) {
+    return fabsf(dot(sampleWorldPos - centerWorldPos, centerNormal)) / centerViewZ > threshold ? 0.0f : 1.0f;
+}
+NRD_DEV float planeDistanceWeightAtrous(float3 centerWorldPos, float3 centerNormal, float3 sampleWorldPos, float threshold) {
+    return fabsf(dot(sampleWorldPos - centerWorldPos, centerNormal)) < threshold ? 1.0f : 0.0f;
+}
+NRD_DEV float relaxSpecLobeTanHalfAngle(float roughness, float percentOfVolume = 0.75f) {
+    roughness = saturate(roughness);
+    percentOfVolume = saturate(percentOfVolume);
+    return roughness * roughness * percentOfVolume / (1.0f - percentOfVolume + NRD_EPS);
+}
+NRD_DEV float2 normalWeightParamsAtrous(float roughness, float numFramesInHistory, float confidence, float normalEdgeStoppingRelaxation, float lobeAngleFraction, float lobeAngleSlack) {
+    float relaxation = saturate(numFramesInHistory / 5.0f);
+    relaxation *= lerp(1.0f, confidence, normalEdgeStoppingRelaxation);
+    const float f = 0.9f + 0.1f * relaxation;
+    float angle = atanf(relaxSpecLobeTanHalfAngle(roughness, lobeAngleFraction));
+    angle *= 10.0f - 9.0f * relaxation;
+    angle += lobeAngleSlack;
+    angle = fminf(3.14159265358979323846f * 0.5f, angle);
+    return make_float2(angle, f);
+}
+NRD_DEV float specularNormalWeightAtrous(float2 params0, float3 n0, float3 n, float3 v0, float3 v) {
+    const float cosa = fminf(dot(n0, n), dot(v0, v));
+    float a = acosApproxPositive(cosa);
+    a = smoothStep(0.0f, params0.x, a);
+    return saturate(1.0f - a * params0.y);
+}
+NRD_DEV float normalWeightParam2(float roughness, float angleFraction) { return 1.0f / fmaxf(atanf(relaxSpecLobeTanHalfAngle(roughness, angleFraction)), RELAX_NORMAL_ULP); }
+NRD_DEV float thinLens(float O, float curvature) { return O / (2.0f * curvature * O + 1.0f); }
+NRD_DEV float computeWeight(float x, float px, float py) { return nonExponentialWeight(x, px, py); }
+NRD_DEV float strandThickness(float strandThicknessV, float pixelSize) { return saturate(0.5f * pixelSize / (strandThicknessV + NRD_EPS)); }
+
+NRD_DEV float relaxViewZ(const RelaxConstants& cb, float z) { return fabsf(z * cb.viewZScale); }
+NRD_DEV bool relaxInRange(const RelaxConstants& cb, float z) { return z < cb.denoisingRange; }
+NRD_DEV float3 worldPosFrom(const RelaxConstants& cb, float2 clip, float viewZ, const float* fwd, const float* right, const float* up) {
+    const float3 F = make_float3(fwd[0], fwd[1], fwd[2]), R = make_float3(right[0], right[1], right[2]), U = make_float3(up[0], up[1], up[2]);
+    if (cb.orthoMode == 0.0f) return viewZ * (F + R * clip.x - U * clip.y);
+    return viewZ * F + R * clip.x - U * clip.y;
+}
+NRD_DEV float3 currentWorldPosClip(const RelaxConstants& cb, float2 clip, float viewZ) { return worldPosFrom(cb, clip, viewZ, cb.frustumForward, cb.frustumRight, cb.frustumUp); }
+NRD_DEV float3 currentWorldPosPixel(const RelaxConstants& cb, int px, int py, float viewZ) {
+    const float2 clip = (make_float2((float)px, (float)py) + 0.5f) * make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]) * 2.0f - 1.0f;
+    return currentWorldPosClip(cb, clip, viewZ);
+}
+NRD_DEV float3 previousWorldPosClip(const RelaxConstants& cb, float2 clip, float viewZ) { return worldPosFrom(cb, clip, viewZ, cb.prevFrustumForward, cb.prevFrustumRight, cb.prevFrustumUp); }
+NRD_DEV float3 previousWorldPosPixel(const RelaxConstants& cb, int px, int py, float viewZ) {
+    const float2 clip = (make_float2((float)px, (float)py) + 0.5f) * (f2(1.0f) / make_float2(cb.rectSizePrev[0], cb.rectSizePrev[1])) * 2.0f - 1.0f;
+    return previousWorldPosClip(cb, clip, viewZ);
+}
+NRD_DEV float2 clampUvToViewport(const RelaxConstants& cb, float2 uv) {
+    const float2 scale = make_float2(cb.resolutionScale[0], cb.resolutionScale[1]);
+    return min2(uv * scale, scale - 0.5f * make_float2(cb.resourceSizeInv[0], cb.resourceSizeInv[1]));
+}
+NRD_DEV float4 gatherR32(const TexR32F& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
+NRD_DEV float4 gatherR8(const TexR8& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
+NRD_DEV float4 gatherR16(const TexR16F& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
+NRD_DEV void storeSh(const TexRGBA16F& t, int x, int y, float3 v) { t.store(x, y, f4(v, 0.0f)); }
+
+// ---- parameter blocks (member order = DispatchDesc::resources order) ------------------------------------------------------------
+struct RelaxClassifyParams { TexR32F viewZ; TexR8 outTiles; };
+struct RelaxPrePassParams { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, specSh, diffSh, outSpec, outDiff, outSpecSh, outDiffSh; };
+struct RelaxTaParams {
+    TexR8 tiles; TexRGBA16F mv; TexNR normalRoughness; TexR32F viewZ; TexR32F mixDummy; TexRGBA8 prevNormalRoughness; TexR32F prevViewZ; TexR8 prevHistoryLength, prevMaterialID;
+    TexRGBA16F spec, diff, historySpecFast, historyDiffFast, historySpec, historyDiff; TexR16F prevSpecHitDist; TexR32F specConfDummy, diffConfDummy;
+    TexRGBA16F specSh, diffSh, historySpecShFast, historyDiffShFast, historySpecSh, historyDiffSh;
+    TexR8 outHistoryLength; TexRGBA16F outSpec, outDiff, outSpecFast, outDiffFast; TexR16F outSpecHitDist; TexR8 outSpecReprojectionConfidence;
+    TexRGBA16F outSpecSh, outDiffSh, outSpecShFast, outDiffShFast;
+};
+struct RelaxHistoryFixParams { TexR8 tiles, historyLength; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, specSh, diffSh, outSpec, outDiff, outSpecSh, outDiffSh; };
+struct RelaxHistoryClampingParams {
+    TexR8 tiles; TexR32F viewZ; TexR8 historyLength; TexRGBA16F specNoisy, diffNoisy, spec, diff, specFast, diffFast, specSh, diffSh, specShFast, diffShFast;
+    TexR8 outHistoryLength; TexRGBA16F outSpec, outDiff, outSpecFast, outDiffFast, outSpecSh, outDiffSh, outSpecShFast, outDiffShFast;
+};
+struct RelaxCopyParams { TexRGBA16F spec, diff, outSpec, outDiff; };
+struct RelaxAntiFireflyParams { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, outSpec, outDiff; };
+struct RelaxAtrousParams {
+    TexR8 tiles, historyLength; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff; TexR8 specReprojectionConfidence; TexR32F specConfDummy, diffConfDummy; TexRGBA16F specSh, diffSh;
+    TexRGBA16F outSpec, outDiff; TexRGBA8 outNormalRoughness; TexR8 outMaterialID; TexR32F outViewZ; TexRGBA16F outSpecSh, outDiffSh;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxClassifyParams p) {
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int px = tx * 16 + (threadIdx.x & 15), py = ty * 16 + (threadIdx.x >> 4);
+    const int sky = __syncthreads_count(!relaxInRange(cb, fabsf(p.viewZ.load(px, py))));
+    if (threadIdx.x == 0) p.outTiles.store(tx, ty, sky == 256 ? 1.0f : 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxPrePassParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
+    if (!relaxInRange(cb, centerViewZ)) return;
+
+    float centerMaterialID;
+    const float4 centerNormalRoughness = unpackNormalRoughness(p.normalRoughness.loadRaw(px, py), centerMaterialID);
+    const float3 centerNormal = xyz(centerNormalRoughness);
+    const float centerRoughness = centerNormalRoughness.w;
+    const float3 centerWorldPos = currentWorldPosPixel(cb, px, py, centerViewZ);
+    const float4 rotator = make_float4(cb.rotatorPre[0], cb.rotatorPre[1], cb.rotatorPre[2], cb.rotatorPre[3]);
+    const float2 rectSize = make_float2((float)cb.rectSize[0], (float)cb.rectSize[1]), rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
+    const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * rectSizeInv;
+    const float minRectDim = (float)min(cb.rectSize[0], cb.rectSize[1]);
+    const float planeZ = cb.orthoMode == 0.0f ? centerViewZ : 1.0f;
+
+    // ---- diffuse ----
+    float4 diffuseIllumination = p.diff.load(px, py);
+    float3 diffuseSH = xyz(p.diffSh.load(px, py));
+    if (cb.diffBlurRadius > 0.0f) {
+        const float frustumSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, minRectDim, centerViewZ);
+        const float hitDist = diffuseIllumination.w == 0.0f ? 1.0f : diffuseIllumination.w;
+        float blurRadius = cb.diffBlurRadius * hitDistFactor(hitDist, frustumSize);
+        if (diffuseIllumination.w == 0.0f) blurRadius = fmaxf(blurRadius, 1.0f);
+        const float normalWeightParam = normalWeightParam2(1.0f, 0.25f * cb.lobeAngleFraction);
+        const float2 hitDistanceWeightP = hitDistanceWeightParams(diffuseIllumination.w, 1.0f / 9.0f);
+        float weightSum = 1.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float3 offset = kPoisson8[i];
+            float2 uv = pixelUv * rectSize + rotate2(rotator, make_float2(offset.x, offset.y)) * blurRadius;
+            uv = floor2(uv) + 0.5f;
+            uv = uv * rectSizeInv;
+            const float2 uvScaled = clampUvToViewport(cb, uv);
+
+            float sampleMaterialID;
+            const float3 sampleNormal = xyz(unpackNormalRoughness(p.normalRoughness.sampleNearestRaw(uvScaled), sampleMaterialID));
+            const float sampleViewZ = relaxViewZ(cb, p.viewZ.sampleNearest(uvScaled));
+            const float3 sampleWorldPos = currentWorldPosClip(cb, uv * 2.0f - 1.0f, sampleViewZ);
+
+            float sampleWeight = isInScreenNearest(uv) ? 1.0f : 0.0f;
+            sampleWeight *= relaxInRange(cb, sampleViewZ) ? 1.0f : 0.0f;
+            sampleWeight *= compareMaterials(centerMaterialID, sampleMaterialID, cb.diffMinMaterial) ? 1.0f : 0.0f;
+            sampleWeight *= planeDistanceWeight(centerWorldPos, centerNormal, planeZ, sampleWorldPos, cb.depthThreshold);
+            sampleWeight *= computeWeight(acosApproxPositive(dot(centerNormal, sampleNormal)), normalWeightParam, 0.0f);
+
+            float4 sampleDiffuse = p.diff.sampleNearest(uvScaled);
+            if (sampleWeight == 0.0f) sampleDiffuse = f4(0.0f);
+            sampleWeight *= lerp(cb.minHitDistanceWeight, 1.0f, exponentialWeight(sampleDiffuse.w, hitDistanceWeightP.x, hitDistanceWeightP.y));
+            sampleWeight *= gaussianWeight(offset.z);
+
+            weightSum += sampleWeight;
+            diffuseIllumination += sampleDiffuse * sampleWeight;
+            float3 sampleSH = xyz(p.diffSh.sampleNearest(uvScaled));
+            if (sampleWeight == 0.0f) sampleSH = f3(0.0f);
+            diffuseSH += sampleSH * sampleWeight;
+        }
+        diffuseIllumination = diffuseIllumination / weightSum;
+        diffuseSH = diffuseSH / weightSum;
+    }
+    p.outDiff.store(px, py, clamp4v(diffuseIllumination, 0.0f, NRD_FP16_MAX_F));
+    storeSh(p.outDiffSh, px, py, clamp3v(diffuseSH, f3(-NRD_FP16_MAX_F), f3(NRD_FP16_MAX_F)));
+
+    // ---- specular ----
+    Rng rng;
+    rng.init((uint32_t)px, (uint32_t)py, cb.frameIndex);
+    float4 specularIllumination = p.spec.load(px, py);
+    float3 specularSH = xyz(p.specSh.load(px, py));
+    specularIllumination.w = fmaxf(0.0f, fminf(cb.denoisingRange, specularIllumination.w));
+    if (cb.specBlurRadius > 0.0f) {
+        const float3 viewVector = cb.orthoMode == 0.0f ? normalize(-centerWorldPos) : make_float3(cb.frustumForward[0], cb.frustumForward[1], cb.frustumForward[2]);
+        const float4 D = specularDominantDirectionG2(centerNormal, viewVector, centerRoughness);
+        const float NoD = fabsf(dot(centerNormal, xyz(D)));
+        const float frustumSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, minRectDim, centerViewZ);
+        const float hitDist = specularIllumination.w == 0.0f ? 1.0f : specularIllumination.w;
+        const float smc = specMagicCurve(centerRoughness);
+        float blurRadius = cb.specBlurRadius * hitDistFactor(hitDist * NoD, frustumSize) * smc;
+        const float lobeRadius = hitDist * NoD * specularLobeTanHalfAngle(centerRoughness, 0.75f);
+        const float minBlurRadius = lobeRadius / pixelRadiusToWorld(cb.unproject, cb.orthoMode, 1.0f, centerViewZ + hitDist * D.w);
+        blurRadius = fminf(blurRadius, minBlurRadius);
+        if (specularIllumination.w == 0.0f) blurRadius = fmaxf(blurRadius, 1.0f);
+
+        const float normalWeightParam = normalWeightParam2(centerRoughness, 0.5f * cb.lobeAngleFraction);
+        const float2 hitDistanceWeightP = hitDistanceWeightParams(specularIllumination.w, 1.0f / 9.0f);
+        const float2 roughnessWeightP = roughnessWeightParams(centerRoughness, cb.roughnessFraction);
+        const float specMinHitDistanceWeight = specularIllumination.w == 0.0f ? 1.0f : cb.minHitDistanceWeight * smc;
+        const float specularHitT = specularIllumination.w == 0.0f ? cb.denoisingRange : specularIllumination.w;
+        const float NoV = fabsf(dot(centerNormal, viewVector));
+        float minHitT = specularHitT == 0.0f ? NRD_INF : specularHitT;
+        float weightSum = 1.0f;
+        const float roughnessLerp = linearStep(0.5f, 1.0f, centerRoughness);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float3 offset = kPoisson8[i];
+            float2 uv = pixelUv * rectSize + rotate2(rotator, make_float2(offset.x, offset.y)) * blurRadius;
+            uv = floor2(uv) + 0.5f;
+            uv = uv * rectSizeInv;
+            const float2 uvScaled = clampUvToViewport(cb, uv);
+
+            float sampleMaterialID;
+            const float4 sampleNormalRoughness = unpackNormalRoughness(p.normalRoughness.sampleNearestRaw(uvScaled), sampleMaterialID);
+            const float3 sampleNormal = xyz(sampleNormalRoughness);
+            const float sampleViewZ = relaxViewZ(cb, p.viewZ.sampleNearest(uvScaled));
+
+            float sampleWeight = isInScreenNearest(uv) ? 1.0f : 0.0f;
+            sampleWeight *= relaxInRange(cb, sampleViewZ) ? 1.0f : 0.0f;
+            sampleWeight *= compareMaterials(centerMaterialID, sampleMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
+            sampleWeight *= computeWeight(sampleNormalRoughness.w, roughnessWeightP.x, roughnessWeightP.y);
+            sampleWeight *= computeWeight(acosApproxPositive(dot(centerNormal, sampleNormal)), normalWeightParam, 0.0f);
+            const float3 sampleWorldPos = currentWorldPosClip(cb, uv * 2.0f - 1.0f, sampleViewZ);
+            sampleWeight *= planeDistanceWeight(centerWorldPos, centerNormal, planeZ, sampleWorldPos, cb.depthThreshold);
+
+            float4 sampleSpecular = p.spec.sampleNearest(uvScaled);
+            if (sampleWeight == 0.0f) sampleSpecular = f4(0.0f);
+            if (rng.next() < sampleWeight * NoV) minHitT = fminf(minHitT, sampleSpecular.w == 0.0f ? NRD_INF : sampleSpecular.w);
+
+            sampleWeight *= lerp(specMinHitDistanceWeight, 1.0f, exponentialWeight(sampleSpecular.w, hitDistanceWeightP.x, hitDistanceWeightP.y));
+            sampleWeight *= gaussianWeight(offset.z);
+            const float d = length(sampleWorldPos - centerWorldPos);
+            const float t = sampleSpecular.w / (specularIllumination.w + d);
+            sampleWeight *= lerp(saturate(t), 1.0f, roughnessLerp);
+
+            weightSum += sampleWeight;
+            specularIllumination.x += sampleSpecular.x * sampleWeight;
+            specularIllumination.y += sampleSpecular.y * sampleWeight;
+            specularIllumination.z += sampleSpecular.z * sampleWeight;
+            float3 sampleSH = xyz(p.specSh.sampleNearest(uvScaled));
+            if (sampleWeight == 0.0f) sampleSH = f3(0.0f);
+            specularSH += sampleSH * sampleWeight;
+        }
+        specularIllumination = f4(xyz(specularIllumination) / weightSum, minHitT == NRD_INF ? 0.0f : minHitT);
+        specularSH = specularSH / weightSum;
+    }
+    p.outSpec.store(px, py, clamp4v(specularIllumination, 0.0f, NRD_FP16_MAX_F));
+    storeSh(p.outSpecSh, px, py, clamp3v(specularSH, f3(-NRD_FP16_MAX_F), f3(NRD_FP16_MAX_F)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    const float currentLinearZ = relaxViewZ(cb, p.viewZ.load(px, py));
+    if (!relaxInRange(cb, currentLinearZ)) return;
+
+    const float2 rectSize = make_float2((float)cb.rectSize[0], (float)cb.rectSize[1]), rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
+    const float2 rectSizePrev = make_float2(cb.rectSizePrev[0], cb.rectSizePrev[1]), resourceSizeInvPrev = make_float2(cb.resourceSizeInvPrev[0], cb.resourceSizeInvPrev[1]);
+    const float2 resolutionScalePrev = rectSizePrev * resourceSizeInvPrev;
+    const float3 cameraDelta = make_float3(cb.cameraDelta[0], cb.cameraDelta[1], cb.cameraDelta[2]);
+    const float minRectDim = (float)min(cb.rectSize[0], cb.rectSize[1]);
+    const int maxX = cb.rectSize[0] - 1, maxY = cb.rectSize[1] - 1;
+    // Preload( ) of the shader: { normal, spec hitT } at the rect-clamped position
+    auto preload = [&](int x, int y) -> float4 {
+        const int gx = clampi(x, 0, maxX), gy = clampi(y, 0, maxY);
+        return f4(xyz(unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy))), p.spec.load(gx, gy).w);
+    };
+
+    float currentMaterialID;
+    const float4 currentNormalRoughness = unpackNormalRoughness(p.normalRoughness.loadRaw(px, py), currentMaterialID);
+    const float3 currentNormal = xyz(currentNormalRoughness);
+    const float currentRoughness = currentNormalRoughness.w;
+
+    const float3 currentWorldPos = currentWorldPosPixel(cb, px, py, currentLinearZ);
+    const float3 fwd = make_float3(cb.frustumForward[0], cb.frustumForward[1], cb.frustumForward[2]);
+    const float3 currentViewVector = cb.orthoMode == 0.0f ? currentWorldPos : currentLinearZ * normalize(fwd);
+    const float3 V = -normalize(currentViewVector);
+    const float NoV = fabsf(dot(currentNormal, V));
+
+    const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * rectSizeInv;
+    const float4 mvRaw = p.mv.load(px, py);
+    float3 mv = make_float3(mvRaw.x * cb.mvScale[0], mvRaw.y * cb.mvScale[1], mvRaw.z * cb.mvScale[2]);
+    float3 prevWorldPos = currentWorldPos;
+    float2 prevUVSMB = pixelUv + make_float2(mv.x, mv.y);
+    if (cb.mvScale[3] == 0.0f) {
+        if (cb.mvScale[2] == 0.0f) mv.z = affine(cb.worldToViewPrev, currentWorldPos).z - currentLinearZ;
+        prevWorldPos = previousWorldPosClip(cb, prevUVSMB * 2.0f - 1.0f, currentLinearZ + mv.z) + cameraDelta;
+    } else {
+        prevWorldPos = prevWorldPos + mv;
+        prevUVSMB = screenUv(cb.worldToClipPrev, prevWorldPos);
+    }
+
+    const float3 diffuseIllumination = xyz(p.diff.load(px, py));
+    const float3 diffuseSH = xyz(p.diffSh.load(px, py));
+    const float4 specularIllumination = p.spec.load(px, py);
+    const float3 specularSH = xyz(p.specSh.load(px, py));
+
+    const float hitTM1 = preload(px, py).w;
+    float minHitDist3x3 = hitTM1 == 0.0f ? NRD_INF : hitTM1;
+    float3 currentNormalAveraged = currentNormal;
+#pragma unroll
+    for (int i = -1; i <= 1; i++)
+#pragma unroll
+        for (int j = -1; j <= 1; j++) {
+            if (i == 0 && j == 0) continue;
+            const float4 n = preload(px + i, py + j);
+            minHitDist3x3 = fminf(minHitDist3x3, n.w == 0.0f ? NRD_INF : n.w);
+            currentNormalAveraged += xyz(n);
+        }
+    currentNormalAveraged = currentNormalAveraged / 9.0f;
+    const float currentRoughnessModified = modifiedRoughnessFromNormalVariance(currentRoughness, currentNormalAveraged);
+
+    const float specular1stMoment = luminance(xyz(specularIllumination)), specular2ndMoment = specular1stMoment * specular1stMoment;
+    const float diffuse1stMoment = luminance(diffuseIllumination), diffuse2ndMoment = diffuse1stMoment * diffuse1stMoment;
+
+    const float smbParallaxInPixels1 = parallaxInPixels(prevWorldPos + cameraDelta, cb.orthoMode == 0.0f ? prevUVSMB : pixelUv, cb.worldToClipPrev, rectSize);
+    const float smbParallaxInPixels2 = parallaxInPixels(prevWorldPos - cameraDelta, cb.orthoMode == 0.0f ? pixelUv : prevUVSMB, cb.worldToClip, rectSize);
+    const float smbParallaxInPixelsMax = fmaxf(smbParallaxInPixels1, smbParallaxInPixels2), smbParallaxInPixelsMin = fminf(smbParallaxInPixels1, smbParallaxInPixels2);
+    const float pixelSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, 1.0f, currentLinearZ);
+
+    float disocclusionThresholdMix = 0.0f;
+    if (currentMaterialID == cb.strandMaterialID) disocclusionThresholdMix = strandThickness(cb.strandThickness, pixelSize);
+    float disocclusionThreshold = lerp(cb.disocclusionThreshold, cb.disocclusionThresholdAlternate, disocclusionThresholdMix);
+    if (currentMaterialID == cb.strandMaterialID) disocclusionThreshold = lerp(0.25f, disocclusionThreshold, smoothStep01(smbParallaxInPixelsMax));
+
+    // ---- surface-motion based history (TA:48-236) ----
+    float footprintQuality, historyLength, SMBReprojectionFound, prevReflectionHitTSMB;
+    float4 prevDiffuseSMB, prevSpecularSMB;
+    float3 prevDiffuseSMBResponsive, prevSpecularSMBResponsive, prevDiffuseSH, prevDiffuseResponsiveSH, prevSpecularSMBSH, prevSpecularSMBResponsiveSH;
+    {
+        const float3 smbNormal = normalize(currentNormalAveraged);
+        const float2 prevPixelPosFloat = prevUVSMB * rectSizePrev;
+        const float2 fl = floor2(prevPixelPosFloat - 0.5f);
+        const int ox = (int)fl.x, oy = (int)fl.y;
+        Bilinear bilinear;
+        bilinear.origin = fl;
+        bilinear.weights = frac2(prevPixelPosFloat - 0.5f);
+
+        auto unpack4 = [&](float4 z) { return make_float4(relaxViewZ(cb, z.x), relaxViewZ(cb, z.y), relaxViewZ(cb, z.z), relaxViewZ(cb, z.w)); };
+        const float4 z00 = unpack4(gatherR32(p.prevViewZ, ox - 1, oy - 1)), z10 = unpack4(gatherR32(p.prevViewZ, ox + 1, oy - 1));
+        const float4 z01 = unpack4(gatherR32(p.prevViewZ, ox - 1, oy + 1)), z11 = unpack4(gatherR32(p.prevViewZ, ox + 1, oy + 1));
+        const float4 m00 = gatherR8(p.prevMaterialID, ox - 1, oy - 1) * 255.0f, m10 = gatherR8(p.prevMaterialID, ox + 1, oy - 1) * 255.0f;
+        const float4 m01 = gatherR8(p.prevMaterialID, ox - 1, oy + 1) * 255.0f, m11 = gatherR8(p.prevMaterialID, ox + 1, oy + 1) * 255.0f;
+
+        const float frustumSize = pixelSize * minRectDim;
+        const float slopeScale = 1.0f / lerp(lerp(0.05f, 1.0f, NoV), 1.0f, saturate(smbParallaxInPixelsMax / 30.0f));
+        float4 thr = f4(saturate(disocclusionThreshold * slopeScale) * frustumSize);
+        thr = thr * isInScreenBilinear(fl, rectSizePrev);
+        thr = thr - NRD_EPS;
+
+        const float pz = affine(cb.worldToViewPrev, prevWorldPos).z;
+        const float minMaterial = fminf(cb.specMinMaterial, cb.diffMinMaterial);
+        auto valid = [&](float z, float t, float mat) -> float { return (t >= fabsf(z - pz) ? 1.0f : 0.0f) * (compareMaterials(currentMaterialID, mat, minMaterial) ? 1.0f : 0.0f); };
+        const float3 tv0 = make_float3(valid(z00.y, thr.x, m00.y), valid(z00.z, thr.x, m00.z), valid(z00.w, thr.x, m00.w));
+        const float3 tv1 = make_float3(valid(z10.x, thr.y, m10.x), valid(z10.z, thr.y, m10.z), valid(z10.w, thr.y, m10.w));
+        const float3 tv2 = make_float3(valid(z01.x, thr.z, m01.x), valid(z01.y, thr.z, m01.y), valid(z01.w, thr.z, m01.w));
+        const float3 tv3 = make_float3(valid(z11.x, thr.w, m11.x), valid(z11.y, thr.w, m11.y), valid(z11.z, thr.w, m11.z));
+        const float3 tvSum = tv0 + tv1 + tv2 + tv3;
+        float bicubicFootprintValid = (tvSum.x + tvSum.y + tvSum.z) > 11.5f ? 1.0f : 0.0f;
+        float4 bilinearTapsValid = make_float4(tv0.z, tv1.y, tv2.y, tv3.x);
+
+        const float2 uv = (fl + 1.0f) * resourceSizeInvPrev;
+        const float3 prevNormalFlat = xyz(unpackPrevNormalRoughness(p.prevNormalRoughness.sampleLinear(uv)));
+        if (dot(smbNormal, prevNormalFlat) < 0.0f) {
+            bilinearTapsValid = f4(0.0f);
+            bicubicFootprintValid = 0.0f;
+        }
+        const float4 bilinearCustomW = bilinearCustomWeights(bilinear, bilinearTapsValid);
+        const bool useBicubic = bicubicFootprintValid > 0.0f;
+
+        const HistoryFilter hf(prevPixelPosFloat, resourceSizeInvPrev, bilinearCustomW, useBicubic);
+        prevDiffuseSMB = max4v(hf.color(p.historyDiff), 0.0f);
+        prevSpecularSMB = max4v(hf.color(p.historySpec), 0.0f);
+        prevDiffuseSMBResponsive = max3(xyz(hf.color(p.historyDiffFast)), f3(0.0f));
+        prevSpecularSMBResponsive = max3(xyz(hf.color(p.historySpecFast)), f3(0.0f));
+
+        prevDiffuseSH = customWeightsSH(p.historyDiffSh, ox, oy, bilinearCustomW);
+        prevDiffuseResponsiveSH = customWeightsSH(p.historyDiffShFast, ox, oy, bilinearCustomW);
+        prevSpecularSMBSH = customWeightsSH(p.historySpecSh, ox, oy, bilinearCustomW);
+        prevSpecularSMBResponsiveSH = customWeightsSH(p.historySpecShFast, ox, oy, bilinearCustomW);
+
+        const float4 prevHistoryLengths = gatherR8(p.prevHistoryLength, ox, oy);
+        historyLength = 255.0f * customWeightsFloat(prevHistoryLengths.x, prevHistoryLengths.y, prevHistoryLengths.z, prevHistoryLengths.w, bilinearCustomW);
+        const float4 prevHitTs = gatherR16(p.prevSpecHitDist, ox, oy);
+        prevReflectionHitTSMB = fmaxf(0.001f, customWeightsFloat(prevHitTs.x, prevHitTs.y, prevHitTs.z, prevHitTs.w, bilinearCustomW));
+
+        SMBReprojectionFound = bicubicFootprintValid > 0.0f ? 2.0f : 1.0f;
+        footprintQuality = bicubicFootprintValid > 0.0f ? 1.0f : sum4(bilinearCustomW);
+        if (!(bilinearTapsValid.x != 0.0f || bilinearTapsValid.y != 0.0f || bilinearTapsValid.z != 0.0f || bilinearTapsValid.w != 0.0f)) {
+            SMBReprojectionFound = 0.0f;
+            footprintQuality = 0.0f;
+        }
+    }
+
+    historyLength = fminf(RELAX_MAX_ACCUM_FRAME_NUM, historyLength + 1.0f);
+    const float3 prevFwd = make_float3(cb.prevFrustumForward[0], cb.prevFrustumForward[1], cb.prevFrustumForward[2]);
+    const float3 Vprev = cb.orthoMode == 0.0f ? -normalize(prevWorldPos - cameraDelta) : -normalize(prevFwd);
+    const float NoVprev = fabsf(dot(currentNormal, Vprev));
+    float sizeQuality = (NoVprev + 1e-3f) / (NoV + 1e-3f);
+    sizeQuality *= sizeQuality;
+    sizeQuality *= sizeQuality;
+    footprintQuality *= lerp(0.1f, 1.0f, saturate(sizeQuality + fabsf(cb.orthoMode)));
+    if (footprintQuality < 1.0f) historyLength = fmaxf(historyLength * sqrtf(footprintQuality), 1.0f);
+    historyLength = cb.resetHistory != 0 ? 1.0f : historyLength;
+    historyLength = fminf(historyLength, 1.0f + fmaxf(cb.diffMaxAccumulatedFrameNum, cb.specMaxAccumulatedFrameNum));
+
+    // ---- diffuse ----
+    {
+        const float diffuseAlpha = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (cb.diffMaxAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+        const float diffuseAlphaResponsive = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (cb.diffMaxFastAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+        p.outDiff.store(px, py, lerp(prevDiffuseSMB, f4(diffuseIllumination, diffuse2ndMoment), diffuseAlpha));
+        p.outDiffFast.store(px, py, f4(lerp(prevDiffuseSMBResponsive, diffuseIllumination, diffuseAlphaResponsive), 0.0f));
+        storeSh(p.outDiffSh, px, py, lerp(prevDiffuseSH, diffuseSH, diffuseAlpha));
+        storeSh(p.outDiffShFast, px, py, lerp(prevDiffuseResponsiveSH, diffuseSH, diffuseAlphaResponsive));
+    }
+    p.outHistoryLength.store(px, py, historyLength / 255.0f);
+
+    // ---- specular ----
+    const float specHistoryFrames = fminf(cb.specMaxAccumulatedFrameNum, historyLength);
+    const float specHistoryResponsiveFrames = fminf(cb.specMaxFastAccumulatedFrameNum, historyLength);
+    const float hitDist = minHitDist3x3 == NRD_INF ? 0.0f : minHitDist3x3;
+
+    float curvature = 0.0f;
+    {
+        const float2 uvForZeroParallax = cb.orthoMode == 0.0f ? prevUVSMB : pixelUv;
+        float2 deltaUv = uvForZeroParallax - screenUv(cb.worldToClipPrev, prevWorldPos + cameraDelta);
+        deltaUv = deltaUv * rectSize;
+        deltaUv = deltaUv / fmaxf(smbParallaxInPixels1, 1.0f / 256.0f);
+
+        auto edgePoint = [&](float2 d) -> float3 {
+            const float3 x = currentWorldPosClip(cb, (pixelUv + d * rectSizeInv) * 2.0f - 1.0f, 1.0f);
+            const float3 v = cb.orthoMode == 0.0f ? normalize(-x) : fwd;
+            const float3 o = cb.orthoMode == 0.0f ? f3(0.0f) : x;
+            return o + v * dot(currentWorldPos - o, currentNormal) / dot(currentNormal, v);  // line-plane intersection
+        };
+        const float3 x10 = edgePoint(make_float2(1.0f, 0.0f)), x01 = edgePoint(make_float2(0.0f, 1.0f));
+        const float3 n10 = xyz(preload(px + 1, py)), n01 = xyz(preload(px, py + 1));
+
+        float2 w = fabs2(deltaUv) + 1.0f / 256.0f;
+        w = w / (w.x + w.y);
+        float3 x = x10 * w.x + x01 * w.y;
+        float3 n = normalize(n10 * w.x + n01 * w.y);
+
+        const float dither = bayer4x4((uint32_t)px, (uint32_t)py, cb.frameIndex);
+        const float edgeFix = 1.0f - pow5(NoV);
+        float deltaUvLenFixed = smbParallaxInPixelsMin;
+        deltaUvLenFixed *= 1.0f + edgeFix * (1.0f + cb.framerateScale * dither);
+        float2 motionUvHigh = pixelUv + deltaUvLenFixed * deltaUv * rectSizeInv;
+        motionUvHigh = (floor2(motionUvHigh * rectSize) + 0.5f) * rectSizeInv;
+        if (deltaUvLenFixed > 1.0f && isInScreenNearest(motionUvHigh)) {
+            const float2 uvScaled = clampUvToViewport(cb, motionUvHigh);
+            const float zHigh = relaxViewZ(cb, p.viewZ.sampleNearest(uvScaled));
+            const float3 xHigh = currentWorldPosClip(cb, motionUvHigh * 2.0f - 1.0f, zHigh);
+            const float3 nHigh = xyz(unpackNormalRoughness(p.normalRoughness.sampleNearestRaw(uvScaled)));
+            const float2 gp = geometryWeightParams(0.04f, minRectDim * pixelSize, currentWorldPos, currentNormal);
+            float wg = nonExponentialWeight(dot(currentNormal, xHigh), gp.x, gp.y);
+            wg = !relaxInRange(cb, zHigh) ? 0.0f : wg;
+            const bool cmp = wg > 0.5f;
+            n = cmp ? nHigh : n;
+            x = cmp ? xHigh : x;
+        }
+        const float3 edge = x - currentWorldPos;
+        curvature = dot(n - currentNormal, edge) / dot(edge, edge);
+        if (curvature < 0.0f) {
+            const float2 uv1 = screenUv(cb.worldToClipPrev, getXvirtual(hitDist, curvature, currentWorldPos, currentWorldPos, currentNormal, V, currentRoughness));
+            const float2 uv2 = screenUv(cb.worldToClipPrev, currentWorldPos);
+            const float a = length((uv1 - uv2) * rectSize);
+            curvature *= a < 5.0f * smbParallaxInPixelsMax + rectSizeInv.x ? 1.0f : 0.0f;
+        }
+    }
+
+    const float3 virtualWorldPos = getXvirtual(hitDist, curvature, currentWorldPos, prevWorldPos, currentNormal, V, currentRoughness);
+
+    // ---- virtual-motion based history (TA:239-357) ----
+    float4 prevSpecularVMB = f4(0.0f), prevSpecularVMBResponsive = f4(0.0f);
+    float3 prevNormalVMB = currentNormal, prevSpecularVMBSH = f3(0.0f), prevSpecularVMBResponsiveSH = f3(0.0f);
+    float prevRoughnessVMB = 0.0f, prevReflectionHitTVMB = cb.denoisingRange, VMBReprojectionFound;
+    float2 prevUVVMB;
+    {
+        const float4 clip = mulM4(cb.worldToClipPrev, f4(virtualWorldPos, 1.0f));
+        prevUVVMB = make_float2(clip.x / clip.w, clip.y / clip.w) * make_float2(0.5f, -0.5f) + 0.5f;
+        prevUVVMB = currentMaterialID == cb.cameraAttachedReflectionMaterialID ? prevUVSMB : prevUVVMB;
+        const float2 prevVirtualPixelPosFloat = prevUVVMB * rectSizePrev;
+        const float2 fl = floor2(prevVirtualPixelPosFloat - 0.5f);
+        const int ox = (int)fl.x, oy = (int)fl.y;
+        Bilinear bilinear;
+        bilinear.origin = fl;
+        bilinear.weights = frac2(prevVirtualPixelPosFloat - 0.5f);
+
+        const float3 cwp = currentWorldPos - cameraDelta;
+        float4 thr = f4(disocclusionThreshold * (cb.orthoMode == 0.0f ? currentLinearZ : 1.0f));
+        thr = thr * isInScreenBilinear(fl, rectSizePrev);
+        thr = thr - NRD_EPS;
+
+        const float4 zr = gatherR32(p.prevViewZ, ox, oy);
+        const float4 prevMaterialIDs = gatherR8(p.prevMaterialID, ox, oy) * 255.0f;
+        auto tapValid = [&](int dx, int dy, float zraw, float t, float mat) -> float {
+            const float3 q = previousWorldPosPixel(cb, ox + dx, oy + dy, relaxViewZ(cb, zraw));
+            const float v = fabsf(dot(cwp - q, currentNormal)) > t ? 0.0f : 1.0f;
+            return v * (compareMaterials(currentMaterialID, mat, cb.specMinMaterial) ? 1.0f : 0.0f);
+        };
+        const float4 tapsValid = make_float4(tapValid(0, 0, zr.x, thr.x, prevMaterialIDs.x), tapValid(1, 0, zr.y, thr.y, prevMaterialIDs.y), tapValid(0, 1, zr.z, thr.z, prevMaterialIDs.z),
+                                             tapValid(1, 1, zr.w, thr.w, prevMaterialIDs.w));
+        const bool anyValid = tapsValid.x != 0.0f || tapsValid.y != 0.0f || tapsValid.z != 0.0f || tapsValid.w != 0.0f;
+        const bool allValid = tapsValid.x != 0.0f && tapsValid.y != 0.0f && tapsValid.z != 0.0f && tapsValid.w != 0.0f;
+        if (anyValid) {
+            const float4 bilinearCustomW = bilinearCustomWeights(bilinear, tapsValid);
+            const bool useBicubic = SMBReprojectionFound == 2.0f && allValid;
+            const HistoryFilter hf(prevVirtualPixelPosFloat, resourceSizeInvPrev, bilinearCustomW, useBicubic);
+            prevSpecularVMB = max4v(hf.color(p.historySpec), 0.0f);
+            prevSpecularVMBResponsive = max4v(hf.color(p.historySpecFast), 0.0f);
+            prevSpecularVMBSH = customWeightsSH(p.historySpecSh, ox, oy, bilinearCustomW);
+            prevSpecularVMBResponsiveSH = customWeightsSH(p.historySpecShFast, ox, oy, bilinearCustomW);
+            prevReflectionHitTVMB = fmaxf(0.001f, p.prevSpecHitDist.sampleLinear(prevUVVMB * resolutionScalePrev));
+            const float4 prevNR = unpackPrevNormalRoughness(p.prevNormalRoughness.sampleLinear(prevUVVMB * resolutionScalePrev));
+            prevNormalVMB = xyz(prevNR);
+            prevRoughnessVMB = prevNR.w;
+        }
+        VMBReprojectionFound = allValid ? 1.0f : 0.0f;
+    }
+
+    const float4 D = specularDominantDirectionG2(currentNormal, V, currentRoughnessModified);
+    float virtualHistoryAmount = VMBReprojectionFound * D.w;
+    virtualHistoryAmount *= cb.orthoMode == 0.0f ? 1.0f : 0.75f;
+    virtualHistoryAmount *= dot(prevNormalVMB, currentNormalAveraged) > 0.0f ? 1.0f : 0.0f;
+
+    float2 uvDiff = prevUVVMB - prevUVSMB;
+    const float uvDiffLengthInPixels = length(uvDiff * rectSize);
+    float tanCurvature = fabsf(curvature * pixelSize);
+    tanCurvature *= fmaxf(uvDiffLengthInPixels / fmaxf(NoV, 0.01f), 1.0f);
+    const float curvatureAngle = atanf(tanCurvature);
+
+    const float lobeHalfAngle = fmaxf(atanf(relaxSpecLobeTanHalfAngle(currentRoughnessModified)), RELAX_NORMAL_ULP);
+    const float normalWeight = encodingAwareNormalWeight(currentNormal, prevNormalVMB, lobeHalfAngle, curvatureAngle, RELAX_NORMAL_ULP);
+    virtualHistoryAmount *= lerp(1.0f - saturate(uvDiffLengthInPixels), 1.0f, normalWeight);
+
+    const float2 relaxedRoughnessP = relaxedRoughnessWeightParams(currentRoughness * currentRoughness, cb.roughnessFraction);
+    float virtualRoughnessWeight = computeWeight(prevRoughnessVMB * prevRoughnessVMB, relaxedRoughnessP.x, relaxedRoughnessP.y);
+    virtualRoughnessWeight = lerp(1.0f - saturate(uvDiffLengthInPixels), 1.0f, virtualRoughnessWeight);
+    virtualHistoryAmount *= cb.orthoMode == 0.0f ? virtualRoughnessWeight : 1.0f;
+    float specVMBConfidence = virtualRoughnessWeight * 0.9f + 0.1f;
+
+    uvDiff = uvDiff * rsqrtSafe(dot(uvDiff, uvDiff));
+    uvDiff = uvDiff / rectSizePrev;
+    uvDiff = uvDiff * (saturate(uvDiffLengthInPixels / 0.1f) + uvDiffLengthInPixels / 2.0f);
+    const float2 backUV1 = prevUVVMB + 1.0f * uvDiff, backUV2 = prevUVVMB + 2.0f * uvDiff;
+    const float4 backNR1 = unpackPrevNormalRoughness(p.prevNormalRoughness.sampleLinear(backUV1 * resolutionScalePrev));
+    const float4 backNR2 = unpackPrevNormalRoughness(p.prevNormalRoughness.sampleLinear(backUV2 * resolutionScalePrev));
+    float prevPrevNormalWeight = isInScreenNearest(backUV1) ? encodingAwareNormalWeight(prevNormalVMB, xyz(backNR1), lobeHalfAngle, curvatureAngle * 2.0f, RELAX_NORMAL_ULP) : 1.0f;
+    prevPrevNormalWeight *= isInScreenNearest(backUV2) ? encodingAwareNormalWeight(prevNormalVMB, xyz(backNR2), lobeHalfAngle, curvatureAngle * 3.0f, RELAX_NORMAL_ULP) : 1.0f;
+    virtualHistoryAmount *= 0.33f + 0.67f * prevPrevNormalWeight;
+    specVMBConfidence *= 0.33f + 0.67f * prevPrevNormalWeight;
+    float rw = computeWeight(backNR1.w * backNR1.w, relaxedRoughnessP.x, relaxedRoughnessP.y);
+    rw *= computeWeight(backNR2.w * backNR2.w, relaxedRoughnessP.x, relaxedRoughnessP.y);
+    virtualHistoryAmount *= cb.orthoMode == 0.0f ? rw * 0.9f + 0.1f : 1.0f;
+
+    const float SMC = specMagicCurve(currentRoughnessModified);
+    const float hitDistC = lerp(specularIllumination.w, prevReflectionHitTSMB, SMC);
+    const float hitDist1 = thinLens(hitDistC, curvature), hitDist2 = thinLens(prevReflectionHitTVMB, curvature);
+    const float maxDist = fmaxf(hitDist1, hitDist2);
+    const float dHitT = fabsf(hitDist1 - hitDist2);
+    const float dHitTMultiplier = lerp(20.0f, 0.0f, SMC);
+    float virtualHistoryHitDistConfidence = 1.0f - saturate(dHitTMultiplier * dHitT / (currentLinearZ + maxDist));
+    virtualHistoryHitDistConfidence = lerp(virtualHistoryHitDistConfidence, 1.0f, SMC);
+
+    const float virtualWorldPosLength = length(virtualWorldPos);
+    const float hitDistForTrackingPrev = prevSpecularVMBResponsive.w;
+    const float3 prevVirtualWorldPos = getXvirtual(hitDistForTrackingPrev, curvature, currentWorldPos, prevWorldPos, currentNormal, V, currentRoughness);
+    const float virtualWorldPosLengthPrev = length(prevVirtualWorldPos);
+    float2 prevUVVMBTest = screenUv(cb.worldToClipPrev, prevVirtualWorldPos);
+    prevUVVMBTest = currentMaterialID == cb.cameraAttachedReflectionMaterialID ? prevUVSMB : prevUVVMBTest;
+    const float lobeTanHalfAngle = fmaxf(relaxSpecLobeTanHalfAngle(currentRoughness, 0.6f), 0.5f * rectSizeInv.x);
+    const float unproj1 = fminf(hitDist, hitDistForTrackingPrev) / pixelRadiusToWorld(cb.unproject, cb.orthoMode, 1.0f, fmaxf(virtualWorldPosLength, virtualWorldPosLengthPrev));
+    const float lobeRadiusInPixels = lobeTanHalfAngle * unproj1;
+    const float deltaParallaxInPixels = length((prevUVVMBTest - prevUVVMB) * rectSize);
+    virtualHistoryHitDistConfidence *= smoothStep(lobeRadiusInPixels + 0.25f, 0.0f, deltaParallaxInPixels);
+
+    const float specSMBConfidence = (SMBReprojectionFound > 0.0f ? 1.0f : 0.0f) * encodingAwareNormalWeight(V, Vprev, lobeHalfAngle * NoV / cb.framerateScale, 0.0f, 0.0f);
+    float specSMBAlpha = 1.0f - specSMBConfidence;
+    specSMBAlpha = fmaxf(specSMBAlpha, 1.0f / (1.0f + specHistoryFrames));
+    const float specSMBResponsiveAlpha = fmaxf(specSMBAlpha, 1.0f / (1.0f + specHistoryResponsiveFrames));
+
+    const float3 accSMBrgb = lerp(xyz(prevSpecularSMB), xyz(specularIllumination), specSMBAlpha);
+    const float accSMBw = lerp(prevReflectionHitTSMB, specularIllumination.w, fmaxf(specSMBAlpha, 0.1f));
+    const float accM2SMB = lerp(prevSpecularSMB.w, specular2ndMoment, specSMBAlpha);
+    const float3 accSMBResponsive = lerp(prevSpecularSMBResponsive, xyz(specularIllumination), specSMBResponsiveAlpha);
+
+    float specVMBAlpha = 1.0f - specVMBConfidence;
+    float specVMBResponsiveAlpha = 1.0f - specVMBConfidence * virtualHistoryHitDistConfidence;
+    float specVMBHitTAlpha = specVMBResponsiveAlpha;
+    specVMBAlpha = fmaxf(specVMBAlpha, 1.0f / (1.0f + specHistoryFrames));
+    specVMBResponsiveAlpha = fmaxf(specVMBResponsiveAlpha, 1.0f / (1.0f + specHistoryResponsiveFrames));
+    specVMBHitTAlpha = fmaxf(specVMBHitTAlpha, 1.0f / (1.0f + specHistoryFrames));
+
+    const float3 accVMBrgb = lerp(xyz(prevSpecularVMB), xyz(specularIllumination), specVMBAlpha);
+    const float accVMBw = lerp(prevReflectionHitTVMB, specularIllumination.w, fmaxf(specVMBHitTAlpha, 0.1f));
+    const float accM2VMB = lerp(prevSpecularVMB.w, specular2ndMoment, specVMBAlpha);
+    const float3 accVMBResponsive = lerp(xyz(prevSpecularVMBResponsive), xyz(specularIllumination), specVMBResponsiveAlpha);
+
+    virtualHistoryAmount *= saturate(specVMBConfidence / (specSMBConfidence + NRD_EPS));
+
+    const float accumulatedReflectionHitT = lerp(accSMBw, accVMBw, virtualHistoryAmount);
+    const float3 accumulatedSpecular = lerp(accSMBrgb, accVMBrgb, virtualHistoryAmount);
+    const float3 accumulatedSpecularResponsive = lerp(accSMBResponsive, accVMBResponsive, virtualHistoryAmount);
+    float accumulatedSpecular2ndMoment = lerp(accM2SMB, accM2VMB, virtualHistoryAmount);
+
+    const float3 accSMBSH = lerp(prevSpecularSMBSH, specularSH, specSMBAlpha), accSMBRespSH = lerp(prevSpecularSMBResponsiveSH, specularSH, specSMBResponsiveAlpha);
+    const float3 accVMBSH = lerp(prevSpecularVMBSH, specularSH, specVMBAlpha), accVMBRespSH = lerp(prevSpecularVMBResponsiveSH, specularSH, specVMBResponsiveAlpha);
+    storeSh(p.outSpecSh, px, py, lerp(accSMBSH, accVMBSH, virtualHistoryAmount));
+    storeSh(p.outSpecShFast, px, py, lerp(accSMBRespSH, accVMBRespSH, virtualHistoryAmount));
+
+    const float specularHistoryConfidence = lerp(specSMBConfidence, specVMBConfidence, virtualHistoryAmount);
+    if (accumulatedSpecular2ndMoment == 0.0f) accumulatedSpecular2ndMoment = cb.specVarianceBoost * (1.0f - specularHistoryConfidence);
+
+    p.outSpec.store(px, py, f4(accumulatedSpecular, accumulatedSpecular2ndMoment));
+    p.outSpecFast.store(px, py, f4(accumulatedSpecularResponsive, hitDist));
+    p.outSpecHitDist.store(px, py, accumulatedReflectionHitT);
+    p.outSpecReprojectionConfidence.store(px, py, specularHistoryConfidence);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryFixParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
+    const float historyLength = 255.0f * p.historyLength.load(px, py);
+    if (!relaxInRange(cb, centerViewZ) || historyLength > cb.historyFixFrameNum || cb.historyFixFrameNum == 1.0f) return;
+
+    float centerMaterialID;
+    const float4 centerNormalRoughness = unpackNormalRoughness(p.normalRoughness.loadRaw(px, py), centerMaterialID);
+    const float3 centerNormal = xyz(centerNormalRoughness);
+    const float3 centerWorldPos = currentWorldPosPixel(cb, px, py, centerViewZ);
+    const float3 centerV = -normalize(centerWorldPos);
+    const float depthThreshold = cb.depthThreshold * (cb.orthoMode == 0.0f ? centerViewZ : 1.0f);
+    const float2 rectSize = make_float2((float)cb.rectSize[0], (float)cb.rectSize[1]), rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
+
+    float4 diffuseSum = p.diff.load(px, py), specularSum = p.spec.load(px, py);
+    float3 diffuseSumSH = xyz(p.diffSh.load(px, py)), specularSumSH = xyz(p.specSh.load(px, py));
+    float diffuseWSum = 1.0f, specularWSum = 1.0f;
+    const float2 specularNormalWeightP = normalWeightParamsAtrous(centerNormalRoughness.w, 5.0f, 1.0f, 0.0f, cb.lobeAngleFraction, cb.specLobeAngleSlack);
+    const float normalPower = fmaxf(cb.historyFixEdgeStoppingNormalPower, 0.01f);
+
+    const float baseStride = centerMaterialID == cb.historyFixAlternatePixelStrideMaterialID ? cb.historyFixAlternatePixelStride : cb.historyFixBasePixelStride;
+    const float r = roundNe(baseStride / (1.0f + historyLength));
+    for (int j = -2; j <= 2; j++)
+        for (int i = -2; i <= 2; i++) {
+            if (i == 0 && j == 0) continue;
+            int sx = (int)((float)px + (float)i * r), sy = (int)((float)py + (float)j * r);
+            const float2 uv = mirrorUv(make_float2((float)sx + 0.5f, (float)sy + 0.5f) * rectSizeInv);
+            sx = (int)(uv.x * rectSize.x);
+            sy = (int)(uv.y * rectSize.y);
+
+            float sampleMaterialID;
+            const float3 sampleNormal = xyz(unpackNormalRoughness(p.normalRoughness.loadRaw(sx, sy), sampleMaterialID));
+            const float sampleViewZ = relaxViewZ(cb, p.viewZ.load(sx, sy));
+            const float3 sampleWorldPos = currentWorldPosPixel(cb, sx, sy, sampleViewZ);
+            float geometryWeight = planeDistanceWeightAtrous(centerWorldPos, centerNormal, sampleWorldPos, depthThreshold);
+            geometryWeight = relaxInRange(cb, sampleViewZ) ? geometryWeight : 0.0f;
+
+            float diffuseW = geometryWeight;
+            diffuseW *= powf(fmaxf(0.01f, dot(centerNormal, sampleNormal)), normalPower);
+            diffuseW *= compareMaterials(sampleMaterialID, centerMaterialID, cb.diffMinMaterial) ? 1.0f : 0.0f;
+            if (diffuseW > 1e-4f) {
+                diffuseSum += p.diff.load(sx, sy) * diffuseW;
+                diffuseSumSH += xyz(p.diffSh.load(sx, sy)) * diffuseW;
+                diffuseWSum += diffuseW;
+            }
+            const float3 sampleV = -normalize(sampleWorldPos + cb.roughnessEdgeStoppingRelaxation * centerWorldPos);
+            float specularW = geometryWeight;
+            specularW *= specularNormalWeightAtrous(specularNormalWeightP, centerNormal, sampleNormal, centerV, sampleV);
+            specularW *= compareMaterials(sampleMaterialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
+            if (specularW > 1e-4f) {
+                specularSum += p.spec.load(sx, sy) * specularW;
+                specularSumSH += xyz(p.specSh.load(sx, sy)) * specularW;
+                specularWSum += specularW;
+            }
+        }
+    p.outDiff.store(px, py, diffuseSum / diffuseWSum);
+    storeSh(p.outDiffSh, px, py, diffuseSumSH / diffuseWSum);
+    p.outSpec.store(px, py, specularSum / specularWSum);
+    storeSh(p.outSpecSh, px, py, specularSumSH / specularWSum);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One lobe of history clamping (the specular and diffuse halves of the shader differ in three constants only)
+template <bool SPEC>
+NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const TexR32F& viewZ, int px, int py, float historyLength, const TexRGBA16F& noisyTex, const TexRGBA16F& slowTex,
+                                 const TexRGBA16F& fastTex, const TexRGBA16F& shTex, const TexRGBA16F& shFastTex, const TexRGBA16F& outSlow, const TexRGBA16F& outFast,
+                                 const TexRGBA16F& outSh, const TexRGBA16F& outShFast, float maxFast, float maxSlow) {
+    const int maxX = cb.rectSize[0] - 1, maxY = cb.rectSize[1] - 1;
+    float3 m1 = f3(0.0f), m2 = f3(0.0f), noisyM1 = f3(0.0f);
+    float noisyM2 = 0.0f, sum = 0.0f;
+    for (int dx = -2; dx <= 2; dx++)
+        for (int dy = -2; dy <= 2; dy++) {
+            const int x = clampi(px + dx, 0, maxX), y = clampi(py + dy, 0, maxY);
+            if (relaxInRange(cb, viewZ.load(x, y))) {  // raw viewZ, as in the shader's Preload( )
+                const float3 s = rgbToYCoCg(xyz(fastTex.load(x, y)));
+                m1 += s;
+                m2 += s * s;
+                const float3 n = xyz(noisyTex.load(x, y));
+                const float l = luminance(n);
+                noisyM1 += n;
+                noisyM2 += l * l;
+                sum += 1.0f;
+            }
+        }
+    m1 = m1 / sum;
+    m2 = m2 / sum;
+    noisyM1 = noisyM1 / sum;
+    noisyM2 /= sum;
+    const float3 sigma = sqrt3v(max3(f3(0.0f), m2 - m1 * m1));
+    float3 colorMin = m1 - cb.fastHistoryClampingSigmaScale * sigma, colorMax = m1 + cb.fastHistoryClampingSigmaScale * sigma;
+
+    const float4 fastCenterRaw = fastTex.load(px, py);
+    const float3 responsiveCenterYCoCg = rgbToYCoCg(xyz(fastCenterRaw));
+    colorMin = min3v(colorMin, responsiveCenterYCoCg);
+    colorMax = max3(colorMax, responsiveCenterYCoCg);
+
+    const float4 slow = slowTex.load(px, py);
+    const float3 slowYCoCg = rgbToYCoCg(xyz(slow));
+    float3 clampedYCoCg = slowYCoCg;
+    if (maxFast < maxSlow) clampedYCoCg = clamp3v(slowYCoCg, colorMin, colorMax);
+    const float3 clamped = yCoCgToRgb(clampedYCoCg);
+
+    float4 outSlowV = f4(clamped, slow.w);
+    const float3 responsiveCenter = yCoCgToRgb(responsiveCenterYCoCg);
+    float4 outFastV = f4(responsiveCenter, SPEC ? fastCenterRaw.w : 0.0f);
+    const bool fixed = historyLength <= cb.historyFixFrameNum;
+    if (fixed) outSlowV = SPEC ? outFastV : f4(xyz(outFastV), outSlowV.w);
+
+    float clampingFactor = (clampedYCoCg.x - slowYCoCg.x) == 0.0f ? 0.0f : saturate((clampedYCoCg.x - slowYCoCg.x) / (responsiveCenterYCoCg.x - slowYCoCg.x));
+    if (fixed) clampingFactor = 1.0f;
+
+    float historyDifferenceL = (SPEC ? 0.33f : 1.0f) * RELAX_ANTILAG_ACCELERATION_AMOUNT_SCALE * cb.historyAccelerationAmount * luminance(fabs3(responsiveCenter - xyz(slow)));
+    historyDifferenceL *= clampingFactor;
+    if (fixed) historyDifferenceL = 0.0f;
+
+    const float3 distanceToNoisy = noisyM1 - responsiveCenter;
+    const float distanceToNoisyL = luminance(fabs3(distanceToNoisy));
+    float3 acceleration = distanceToNoisyL == 0.0f ? f3(0.0f) : distanceToNoisy * historyDifferenceL / distanceToNoisyL;
+    const float accelerationL = luminance(fabs3(acceleration));
+    const float accelerationRatio = accelerationL == 0.0f ? 0.0f : distanceToNoisyL / accelerationL;
+    if (accelerationRatio < 1.0f) acceleration = acceleration * accelerationRatio;
+    if (accelerationRatio <= 0.0f) acceleration = f3(0.0f);
+    outSlowV = f4(xyz(outSlowV) + acceleration, outSlowV.w);
+    outFastV = f4(xyz(outFastV) + acceleration, outFastV.w);
+
+    const float slowL = luminance(xyz(slow));
+    const float noisyInputL = luminance(noisyM1);
+    const float temporalSigma = cb.historyResetTemporalSigmaScale * sqrtf(fmaxf(0.0f, noisyM2 - noisyInputL * noisyInputL));
+    const float spatialSigma = cb.historyResetSpatialSigmaScale * sigma.x;
+    float resetAmount = (SPEC ? 0.5f : 1.0f) * cb.historyResetAmount * fmaxf(0.0f, fabsf(slowL - noisyInputL) - spatialSigma - temporalSigma) /
+                        (1.0e-6f + fmaxf(slowL, noisyInputL) + spatialSigma + temporalSigma);
+    resetAmount = saturate(resetAmount);
+    const float3 noisyCenter = xyz(noisyTex.load(px, py));
+    outSlowV = f4(lerp(xyz(outSlowV), noisyCenter, resetAmount), outSlowV.w);
+    outFastV = f4(lerp(xyz(outFastV), noisyCenter, resetAmount), outFastV.w);
+
+    const float outL = luminance(xyz(outSlowV));
+    outSlowV.w = fmaxf(0.0f, outSlowV.w + (outL * outL - slowL * slowL));
+
+    outSlow.store(px, py, outSlowV);
+    outFast.store(px, py, outFastV);
+    const float3 sh = xyz(shTex.load(px, py)), shFast = xyz(shFastTex.load(px, py));
+    storeSh(outSh, px, py, lerp(sh, shFast, clampingFactor));
+    storeSh(outShFast, px, py, shFast);
+}
+
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    if (!relaxInRange(cb, p.viewZ.load(px, py))) return;
+    const float historyLength = 255.0f * p.historyLength.load(px, py);
+    historyClampingLobe<true>(cb, p.viewZ, px, py, historyLength, p.specNoisy, p.spec, p.specFast, p.specSh, p.specShFast, p.outSpec, p.outSpecFast, p.outSpecSh, p.outSpecShFast,
+                              cb.specMaxFastAccumulatedFrameNum, cb.specMaxAccumulatedFrameNum);
+    historyClampingLobe<false>(cb, p.viewZ, px, py, historyLength, p.diffNoisy, p.diff, p.diffFast, p.diffSh, p.diffShFast, p.outDiff, p.outDiffFast, p.outDiffSh, p.outDiffShFast,
+                               cb.diffMaxFastAccumulatedFrameNum, cb.diffMaxAccumulatedFrameNum);
+    p.outHistoryLength.store(px, py, historyLength / 255.0f);
+}
+
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxCopyKernel(const __grid_constant__ RelaxCopyParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    if (!p.outSpec.inside(px, py)) return;
+    *p.outSpec.ptrw<uint2>(px, py) = p.spec.inside(px, py) ? p.spec.fetchRaw(px, py) : make_uint2(0u, 0u);
+    *p.outDiff.ptrw<uint2>(px, py) = p.diff.inside(px, py) ? p.diff.fetchRaw(px, py) : make_uint2(0u, 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+NRD_DEV float4 rcrs(const RelaxConstants& cb, const TexNR& normalRoughness, const TexRGBA16F& tex, int px, int py, float minMaterial, float centerMaterialID) {
+    const float4 center = tex.load(px, py);
+    const float centerL = luminance(xyz(center));
+    float maxL = -1.0f, minL = 1.0e6f;
+    int maxXc = px, maxYc = py, minXc = px, minYc = py;
+#pragma unroll
+    for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+        for (int xx = -1; xx <= 1; xx++) {
+            const int x = px + xx, y = py + yy;
+            if ((xx == 0 && yy == 0) || x < 0 || y < 0 || x >= cb.rectSize[0] || y >= cb.rectSize[1]) continue;
+            const float sampleL = luminance(xyz(tex.load(x, y)));
+            if (compareMaterials(materialFromRaw(normalRoughness.loadRaw(x, y)), centerMaterialID, minMaterial)) {
+                if (sampleL > maxL) { maxL = sampleL; maxXc = x; maxYc = y; }
+                if (sampleL < minL) { minL = sampleL; minXc = x; minYc = y; }
+            }
+        }
+    int sx = px, sy = py;
+    if (centerL > maxL) { sx = maxXc; sy = maxYc; }
+    if (centerL < minL) { sx = minXc; sy = minYc; }
+    return f4(xyz(tex.load(sx, sy)), center.w);
+}
+
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAntiFireflyParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    if (!relaxInRange(cb, relaxViewZ(cb, p.viewZ.load(px, py)))) return;
+    const float centerMaterialID = materialFromRaw(p.normalRoughness.loadRaw(px, py));
+    p.outSpec.store(px, py, rcrs(cb, p.normalRoughness, p.spec, px, py, cb.specMinMaterial, centerMaterialID));
+    p.outDiff.store(px, py, rcrs(cb, p.normalRoughness, p.diff, px, py, cb.diffMinMaterial, centerMaterialID));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct AtrousTexel {
+    float4 spec, diff, nr;
+    float3 specSh, diffSh, worldPos;
+    float materialID;
+};
+NRD_DEV AtrousTexel atrousFetch(const RelaxConstants& cb, const RelaxAtrousParams& p, int x, int y) {
+    const int gx = clampi(x, 0, cb.rectSize[0] - 1), gy = clampi(y, 0, cb.rectSize[1] - 1);
+    AtrousTexel r;
+    r.spec = p.spec.load(gx, gy);
+    r.diff = p.diff.load(gx, gy);
+    r.specSh = xyz(p.specSh.load(gx, gy));
+    r.diffSh = xyz(p.diffSh.load(gx, gy));
+    r.nr = unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy), r.materialID);
+    r.worldPos = currentWorldPosPixel(cb, gx, gy, relaxViewZ(cb, p.viewZ.load(gx, gy)));
+    return r;
+}
+
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const float isSky = p.tiles.load(px >> 4, py >> 4);
+    const float viewZpacked = p.viewZ.load(px, py);
+    p.outViewZ.store(px, py, viewZpacked);
+    const AtrousTexel ctr = atrousFetch(cb, p, px, py);
+    float4 normalRoughness = ctr.nr;
+    const float centerViewZ = relaxViewZ(cb, viewZpacked);
+    if (!relaxInRange(cb, centerViewZ)) normalRoughness = f4(1.0f / 255.0f);
+    p.outNormalRoughness.store(px, py, packPrevNormalRoughness(normalRoughness));
+    const float3 centerWorldPos = ctr.worldPos;
+    const float centerMaterialID = ctr.materialID;
+    p.outMaterialID.store(px, py, centerMaterialID / 255.0f);
+
+    if (isSky != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    if (!relaxInRange(cb, centerViewZ)) return;
+
+    const float3 centerNormal = xyz(normalRoughness);
+    const float centerRoughness = normalRoughness.w;
+    const float historyLength = 255.0f * p.historyLength.load(px, py);
+    const float kGauss[2] = {0.44198f, 0.27901f};
+
+    if (historyLength >= cb.historyThreshold) {
+        const float kernel[2][2] = {{1.0f / 4.0f, 1.0f / 8.0f}, {1.0f / 8.0f, 1.0f / 16.0f}};
+        float4 specularSumV = f4(0.0f), diffuseSumV = f4(0.0f);
+        AtrousTexel nb[3][3];
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) nb[dy + 1][dx + 1] = (dx == 0 && dy == 0) ? ctr : atrousFetch(cb, p, px + dx, py + dy);
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++)
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const float k = kernel[dx < 0 ? -dx : dx][dy < 0 ? -dy : dy];
+                specularSumV += nb[dy + 1][dx + 1].spec * k;
+                diffuseSumV += nb[dy + 1][dx + 1].diff * k;
+            }
+        const float s1 = luminance(xyz(specularSumV)), d1 = luminance(xyz(diffuseSumV));
+        const float centerSpecularVar = fmaxf(0.0f, specularSumV.w - s1 * s1), centerDiffuseVar = fmaxf(0.0f, diffuseSumV.w - d1 * d1);
+
+        const float centerSpecularLuminance = luminance(xyz(ctr.spec));
+        const float specularPhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, cb.specPhiLuminance * sqrtf(centerSpecularVar));
+        const float2 roughnessWeightP = roughnessWeightParams(centerRoughness, cb.roughnessFraction);
+        const float specularReprojectionConfidence = p.specReprojectionConfidence.load(px, py);
+        const float specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, cb.luminanceEdgeStoppingRelaxation);
+        const float specularNormalWeightParamSimplified = normalWeightParam2(1.0f, cb.lobeAngleFraction);
+        const float2 specularNormalWeightP = normalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, cb.normalEdgeStoppingRelaxation, cb.lobeAngleFraction,
+                                                                      cb.specLobeAngleSlack);
+        const float3 centerV = -normalize(centerWorldPos);
+        const float centerDiffuseLuminance = luminance(xyz(ctr.diff));
+        const float diffusePhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, cb.diffPhiLuminance * sqrtf(centerDiffuseVar));
+        const float diffuseNormalWeightParam = normalWeightParam2(1.0f, cb.lobeAngleFraction);
+        const float depthThreshold = cb.depthThreshold * (cb.orthoMode == 0.0f ? centerViewZ : 1.0f);
+
+        float sumWSpecular = 0.0f, sumWDiffuse = 0.0f;
+        float4 sumSpecular = f4(0.0f), sumDiffuse = f4(0.0f);
+        float3 sumSpecularSH = f3(0.0f), sumDiffuseSH = f3(0.0f);
+#pragma unroll
+        for (int j = -1; j <= 1; j++)
+#pragma unroll
+            for (int i = -1; i <= 1; i++) {
+                const int x = px + i, y = py + j;
+                const bool isCenter = i == 0 && j == 0;
+                const bool isInside = x >= 0 && y >= 0 && x < cb.rectSize[0] && y < cb.rectSize[1];
+                const float kernelW = isInside ? kGauss[i < 0 ? -i : i] * kGauss[j < 0 ? -j : j] : 0.0f;
+                const AtrousTexel& s = nb[j + 1][i + 1];
+                const float3 sampleNormal = xyz(s.nr);
+                float geometryW = planeDistanceWeightAtrous(centerWorldPos, centerNormal, s.worldPos, depthThreshold);
+                geometryW *= kernelW;
+
+                const float angles = acosApproxPositive(dot(centerNormal, sampleNormal));
+                const float3 sampleV = -normalize(s.worldPos + cb.roughnessEdgeStoppingRelaxation * centerWorldPos);
+                const float normalWSpecularSimplified = computeWeight(angles, specularNormalWeightParamSimplified, 0.0f);
+                const float normalWSpecular = specularNormalWeightAtrous(specularNormalWeightP, centerNormal, sampleNormal, centerV, sampleV);
+                const float roughnessWSpecular = computeWeight(s.nr.w, roughnessWeightP.x, roughnessWeightP.y);
+                float specularLuminanceW = fabsf(centerSpecularLuminance - luminance(xyz(s.spec))) * specularPhiLIlluminationInv;
+                specularLuminanceW = fminf(cb.specMaxLuminanceRelativeDifference, specularLuminanceW);
+                specularLuminanceW *= specularLuminanceWeightRelaxation;
+                float wSpecular = geometryW * expf(-specularLuminanceW);
+                wSpecular *= cb.roughnessEdgeStoppingEnabled ? (normalWSpecular * roughnessWSpecular) : normalWSpecularSimplified;
+                wSpecular *= compareMaterials(s.materialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
+                wSpecular = isCenter ? kernelW : wSpecular;
+                sumWSpecular += wSpecular;
+                sumSpecular += wSpecular * s.spec;
+                sumSpecularSH += wSpecular * s.specSh;
+
+                const float normalWDiffuse = computeWeight(angles, diffuseNormalWeightParam, 0.0f);
+                float diffuseLuminanceW = fabsf(centerDiffuseLuminance - luminance(xyz(s.diff))) * diffusePhiLIlluminationInv;
+                diffuseLuminanceW = fminf(cb.diffMaxLuminanceRelativeDifference, diffuseLuminanceW);
+                float wDiffuse = geometryW * normalWDiffuse * expf(-diffuseLuminanceW);
+                wDiffuse *= compareMaterials(s.materialID, centerMaterialID, cb.diffMinMaterial) ? 1.0f : 0.0f;
+                wDiffuse = isCenter ? kernelW : wDiffuse;
+                sumWDiffuse += wDiffuse;
+                sumDiffuse += wDiffuse * s.diff;
+                sumDiffuseSH += wDiffuse * s.diffSh;
+            }
+        sumWSpecular = fmaxf(sumWSpecular, 1e-6f);
+        sumSpecular = sumSpecular / sumWSpecular;
+        const float sp1 = luminance(xyz(sumSpecular));
+        p.outSpec.store(px, py, f4(xyz(sumSpecular), fmaxf(0.0f, sumSpecular.w - sp1 * sp1)));
+        storeSh(p.outSpecSh, px, py, sumSpecularSH / sumWSpecular);
+        sumWDiffuse = fmaxf(sumWDiffuse, 1e-6f);
+        sumDiffuse = sumDiffuse / sumWDiffuse;
+        const float dp1 = luminance(xyz(sumDiffuse));
+        p.outDiff.store(px, py, f4(xyz(sumDiffuse), fmaxf(0.0f, sumDiffuse.w - dp1 * dp1)));
+        storeSh(p.outDiffSh, px, py, sumDiffuseSH / sumWDiffuse);
+    } else {
+        float sumWS = 0.0f, sumS1 = 0.0f, sumS2 = 0.0f, sumWD = 0.0f, sumD1 = 0.0f, sumD2 = 0.0f;
+        float3 sumS = f3(0.0f), sumD = f3(0.0f), sumSSH = f3(0.0f), sumDSH = f3(0.0f);
+        const float diffuseNormalWeightParam = normalWeightParam2(1.0f, cb.lobeAngleFraction);
+        for (int cx = -2; cx <= 2; cx++)
+            for (int cy = -2; cy <= 2; cy++) {
+                const AtrousTexel s = atrousFetch(cb, p, px + cx, py + cy);
+                const float normalW = computeWeight(acosApproxPositive(dot(centerNormal, xyz(s.nr))), diffuseNormalWeightParam, 0.0f);
+                const float specularW = normalW * (compareMaterials(s.materialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f);
+                sumWS += specularW;
+                sumS += xyz(s.spec) * specularW;
+                sumS1 += luminance(xyz(s.spec)) * specularW;
+                sumS2 += s.spec.w * specularW;
+                sumSSH += s.specSh * specularW;
+                const float diffuseW = normalW * (compareMaterials(s.materialID, centerMaterialID, cb.diffMinMaterial) ? 1.0f : 0.0f);
+                sumWD += diffuseW;
+                sumD += xyz(s.diff) * diffuseW;
+                sumD1 += luminance(xyz(s.diff)) * diffuseW;
+                sumD2 += s.diff.w * diffuseW;
+                sumDSH += s.diffSh * diffuseW;
+            }
+        const float boost = fmaxf(1.0f, 4.0f / (historyLength + 1.0f));
+        sumWS = fmaxf(sumWS, 1e-6f);
+        sumS = sumS / sumWS;
+        sumS1 /= sumWS;
+        sumS2 /= sumWS;
+        p.outSpec.store(px, py, f4(sumS, fmaxf(0.0f, sumS2 - sumS1 * sumS1) * boost));
+        storeSh(p.outSpecSh, px, py, sumSSH / sumWS);
+        sumWD = fmaxf(sumWD, 1e-6f);
+        sumD = sumD / sumWD;
+        sumD1 /= sumWD;
+        sumD2 /= sumWD;
+        p.outDiff.store(px, py, f4(sumD, fmaxf(0.0f, sumD2 - sumD1 * sumD1) * boost));
+        storeSh(p.outDiffSh, px, py, sumDSH / sumWD);
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
+    if (!relaxInRange(cb, centerViewZ)) return;
+
+    float centerMaterialID;
+    const float4 centerNormalRoughness = unpackNormalRoughness(p.normalRoughness.loadRaw(px, py), centerMaterialID);
+    const float3 centerNormal = xyz(centerNormalRoughness);
+    const float centerRoughness = centerNormalRoughness.w;
+    const float historyLength = 255.0f * p.historyLength.load(px, py);
+    const float stepSize = (float)cb.stepSize;
+    const float kGauss[2] = {0.44198f, 0.27901f};
+
+    float diffuseLobeAngleFraction = 1.0f / sqrtf(stepSize);  // NRD_MODE == SH
+    diffuseLobeAngleFraction = lerp(0.99f, diffuseLobeAngleFraction, saturate(historyLength / 5.0f));
+
+    const float4 centerSpecular = p.spec.load(px, py);
+    const float centerSpecularLuminance = luminance(xyz(centerSpecular));
+    const float specularPhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, cb.specPhiLuminance * sqrtf(centerSpecular.w));
+    const float2 roughnessWeightP = roughnessWeightParams(centerRoughness, cb.roughnessFraction);
+    const float specularReprojectionConfidence = p.specReprojectionConfidence.load(px, py);
+    float specularLuminanceWeightRelaxation = 1.0f;
+    if (cb.stepSize <= 4) specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, cb.luminanceEdgeStoppingRelaxation);
+    const float specularNormalWeightParamSimplified = normalWeightParam2(1.0f, diffuseLobeAngleFraction);
+    const float2 specularNormalWeightP = normalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, cb.normalEdgeStoppingRelaxation, cb.lobeAngleFraction,
+                                                                  cb.specLobeAngleSlack);
+    float sumWSpecular = 0.44198f * 0.44198f;
+    float4 sumSpecular = centerSpecular * make_float4(sumWSpecular, sumWSpecular, sumWSpecular, sumWSpecular * sumWSpecular);
+    float3 sumSpecularSH = xyz(p.specSh.load(px, py)) * sumWSpecular;
+
+    const float4 centerDiffuse = p.diff.load(px, py);
+    const float centerDiffuseLuminance = luminance(xyz(centerDiffuse));
+    const float diffusePhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, cb.diffPhiLuminance * sqrtf(centerDiffuse.w));
+    const float diffuseNormalWeightParam = normalWeightParam2(1.0f, diffuseLobeAngleFraction);
+    float sumWDiffuse = 0.44198f * 0.44198f;
+    float4 sumDiffuse = centerDiffuse * make_float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse);
+    float3 sumDiffuseSH = xyz(p.diffSh.load(px, py)) * sumWDiffuse;
+
+    const float3 centerWorldPos = currentWorldPosPixel(cb, px, py, centerViewZ);
+    const float3 centerV = -normalize(centerWorldPos);
+    const float depthThreshold = cb.depthThreshold * (cb.orthoMode == 0.0f ? centerViewZ : 1.0f);
+
+    int offX = 0, offY = 0;
+    if (cb.stepSize > 4) {
+        Rng rng;
+        rng.init((uint32_t)px, (uint32_t)py, cb.frameIndex);
+        const float rx = rng.next(), ry = rng.next();
+        offX = (int)(stepSize * 0.5f * (rx - 0.5f));
+        offY = (int)(stepSize * 0.5f * (ry - 0.5f));
+    }
+#pragma unroll
+    for (int j = -1; j <= 1; j++)
+#pragma unroll
+        for (int i = -1; i <= 1; i++) {
+            if (i == 0 && j == 0) continue;
+            const int x = px + offX + i * (int)cb.stepSize, y = py + offY + j * (int)cb.stepSize;
+            const bool isInside = x >= 0 && y >= 0 && x < cb.rectSize[0] && y < cb.rectSize[1];
+            const float kernelW = kGauss[i < 0 ? -i : i] * kGauss[j < 0 ? -j : j];
+
+            float sampleMaterialID;
+            const float4 sampleNormalRoughness = unpackNormalRoughness(p.normalRoughness.loadRaw(x, y), sampleMaterialID);
+            const float3 sampleNormal = xyz(sampleNormalRoughness);
+            const float sampleViewZ = relaxViewZ(cb, p.viewZ.load(x, y));
+            const float3 sampleWorldPos = currentWorldPosPixel(cb, x, y, sampleViewZ);
+            float geometryW = planeDistanceWeightAtrous(centerWorldPos, centerNormal, sampleWorldPos, depthThreshold);
+            geometryW *= kernelW;
+            geometryW *= (isInside && relaxInRange(cb, sampleViewZ)) ? 1.0f : 0.0f;
+
+            const float3 sampleV = -normalize(sampleWorldPos + cb.roughnessEdgeStoppingRelaxation * centerWorldPos);
+            const float angles = acosApproxPositive(dot(centerNormal, sampleNormal));
+            const float normalWSpecularSimplified = computeWeight(angles, specularNormalWeightParamSimplified, 0.0f);
+            const float normalWSpecular = specularNormalWeightAtrous(specularNormalWeightP, centerNormal, sampleNormal, centerV, sampleV);
+            const float roughnessWSpecular = computeWeight(sampleNormalRoughness.w, roughnessWeightP.x, roughnessWeightP.y);
+            float wSpecular = geometryW * (cb.roughnessEdgeStoppingEnabled ? (normalWSpecular * roughnessWSpecular) : normalWSpecularSimplified);
+            wSpecular *= compareMaterials(sampleMaterialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
+            if (wSpecular > 1e-4f) {
+                const float4 s = p.spec.load(x, y);
+                float lw = fabsf(centerSpecularLuminance - luminance(xyz(s))) * specularPhiLIlluminationInv;
+                lw = fminf(cb.specMaxLuminanceRelativeDifference, lw);
+                lw *= specularLuminanceWeightRelaxation;
+                wSpecular *= expf(-lw);
+                sumWSpecular += wSpecular;
+                sumSpecular += make_float4(wSpecular, wSpecular, wSpecular, wSpecular * wSpecular) * s;
+                sumSpecularSH += xyz(p.specSh.load(x, y)) * wSpecular;
+            }
+
+            const float normalWDiffuse = computeWeight(angles, diffuseNormalWeightParam, 0.0f);
+            float wDiffuse = geometryW * normalWDiffuse;
+            wDiffuse *= compareMaterials(sampleMaterialID, centerMaterialID, cb.diffMinMaterial) ? 1.0f : 0.0f;
+            if (wDiffuse > 1e-4f) {
+                const float4 s = p.diff.load(x, y);
+                float lw = fabsf(centerDiffuseLuminance - luminance(xyz(s))) * diffusePhiLIlluminationInv;
+                lw = fminf(cb.diffMaxLuminanceRelativeDifference, lw);
+                wDiffuse *= expf(-lw);
+                sumWDiffuse += wDiffuse;
+                sumDiffuse += make_float4(wDiffuse, wDiffuse, wDiffuse, wDiffuse * wDiffuse) * s;
+                sumDiffuseSH += xyz(p.diffSh.load(x, y)) * wDiffuse;
+            }
+        }
+    const float currHistoryLength = fmaxf(historyLength - 1.0f, 0.0f);
+    float4 filteredSpecular = sumSpecular / make_float4(sumWSpecular, sumWSpecular, sumWSpecular, sumWSpecular * sumWSpecular);
+    if (cb.isLastPass == 1) filteredSpecular = f4(linearToYCoCg(xyz(filteredSpecular)), currHistoryLength);
+    storeSh(p.outSpecSh, px, py, sumSpecularSH / sumWSpecular);
+    p.outSpec.store(px, py, filteredSpecular);
+    float4 filteredDiffuse = sumDiffuse / make_float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse);
+    if (cb.isLastPass == 1) filteredDiffuse = f4(linearToYCoCg(xyz(filteredDiffuse)), currHistoryLength);
+    storeSh(p.outDiffSh, px, py, sumDiffuseSH / sumWDiffuse);
+    p.outDiff.store(px, py, filteredDiffuse);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+uint32_t bytesOf(nrd::Format f) {
+    switch (f) {
+        case nrd::Format::R8_UNORM: return 1;
+        case nrd::Format::RG8_UNORM: case nrd::Format::R16_SFLOAT: case nrd::Format::R16_UINT: return 2;
+        case nrd::Format::RGBA16_SFLOAT: return 8;
+        default: return 4;
+    }
+}
+struct RelaxBinder {
+    const nrdcuTexture* t;
+    uint32_t n, next;
+    bool ok;
+    std::string* err;
+    const std::string* id;
+    template <class V> V take(nrd::Format expect) {
+        V v{};
+        if (next >= n) {
+            ok = false;
+            return v;
+        }
+        const nrdcuTexture& x = t[next];
+        const uint32_t bpp = bytesOf(expect);
+        if (x.format != (uint32_t)expect || !x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
+            if (ok) *err = *id + ": binding " + std::to_string(next) + " has format " + std::to_string(x.format) + " (expected " + std::to_string((uint32_t)expect) + ")";
+            ok = false;
+        }
+        v.data = (uint8_t*)x.data;
+        v.w = (int)x.width;
+        v.h = (int)x.height;
+        v.pitch = (int)(x.pitchBytes / bpp);
+        next++;
+        return v;
+    }
+};
+
+}  // namespace
+
+// Dispatch by shader identifier (called by the executor). Returns an nrd::Result; `err` explains a failure.
+uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, cudaStream_t stream, std::string& err) {
+    using nrd::Format;
+    using nrd::Result;
+    if (constantsSize != sizeof(RelaxConstants) || !constants) {
+        err = id + ": expected " + std::to_string(sizeof(RelaxConstants)) + " constant bytes";
+        return (uint32_t)Result::INVALID_ARGUMENT;
+    }
+    RelaxConstants cb;
+    memcpy(&cb, constants, sizeof(cb));
+    if (cb.resolutionScale[0] != 1.0f || cb.resolutionScale[1] != 1.0f || cb.rectOrigin[0] || cb.rectOrigin[1] || cb.rectSizePrev[0] != (float)cb.rectSize[0] ||
+        cb.rectSizePrev[1] != (float)cb.rectSize[1]) {
+        err = id + ": dynamic resolution (rectSize != resourceSize) is not implemented";
+        return (uint32_t)Result::UNSUPPORTED;
+    }
+    if (cb.diffCheckerboard != 2 || cb.specCheckerboard != 2 || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix) {
+        err = id + ": checkerboard modes and confidence / disocclusion-threshold-mix inputs are not implemented";
+        return (uint32_t)Result::UNSUPPORTED;
+    }
+    RelaxBinder b{tex, n, 0, true, &err, &id};
+    auto bad = [&](uint32_t expected) {
+        if (b.ok && b.next == expected && n == expected) return false;
+        if (err.empty()) err = id + ": wrong number of textures";
+        return true;
+    };
+    const Format F16 = Format::RGBA16_SFLOAT, R8 = Format::R8_UNORM, R32 = Format::R32_SFLOAT, NR = Format::R10_G10_B10_A2_UNORM;
+    const dim3 block(BLOCK_W, BLOCK_H);
+    const dim3 pixelGrid((cb.rectSize[0] + BLOCK_W - 1) / BLOCK_W, (cb.rectSize[1] + BLOCK_H - 1) / BLOCK_H);
+    const std::string sig = "|NRD_SIGNAL=BOTH|NRD_MODE=SH";
+
+    if (id == "RELAX_ClassifyTiles.cs.hlsl") {
+        RelaxClassifyParams p;
+        p.viewZ = b.take<TexR32F>(R32);
+        p.outTiles = b.take<TexR8>(R8);
+        if (bad(2)) return (uint32_t)Result::INVALID_ARGUMENT;
+        relaxClassifyTilesKernel<<<dim3((cb.rectSize[0] + 15) / 16, (cb.rectSize[1] + 15) / 16), 256, 0, stream>>>(cb, p);
+    } else if (id == "RELAX_PrePass.cs.hlsl" + sig) {
+        RelaxPrePassParams p;
+        p.tiles = b.take<TexR8>(R8);
+        p.normalRoughness = b.take<TexNR>(NR);
+        p.viewZ = b.take<TexR32F>(R32);
+        p.spec = b.take<TexRGBA16F>(F16);
+        p.diff = b.take<TexRGBA16F>(F16);
+        p.specSh = b.take<TexRGBA16F>(F16);
+        p.diffSh = b.take<TexRGBA16F>(F16);
+        p.outSpec = b.take<TexRGBA16F>(F16);
+        p.outDiff = b.take<TexRGBA16F>(F16);
+        p.outSpecSh = b.take<TexRGBA16F>(F16);
+        p.outDiffSh = b.take<TexRGBA16F>(F16);
+        if (bad(11)) return (uint32_t)Result::INVALID_ARGUMENT;
+        relaxPrePassKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "RELAX_TemporalAccumulation.cs.hlsl" + sig) {
+        RelaxTaParams p;
+        p.tiles = b.take<TexR8>(R8);
+        p.mv = b.take<TexRGBA16F>(F16);
+        p.normalRoughness = b.take<TexNR>(NR);
+        p.viewZ = b.take<TexR32F>(R32);
+        p.mixDummy = b.take<TexR32F>(R32);
+        p.prevNormalRoughness = b.take<TexRGBA8>(Format::RGBA8_UNORM);
+        p.prevViewZ = b.take<TexR32F>(R32);
+        p.prevHistoryLength = b.take<TexR8>(R8);
+        p.prevMaterialID = b.take<TexR8>(R8);
+        p.spec = b.take<TexRGBA16F>(F16);
+        p.diff = b.take<TexRGBA16F>(F16);
+        p.historySpecFast = b.take<TexRGBA16F>(F16);
+        p.historyDiffFast = b.take<TexRGBA16F>(F16);
+        p.historySpec = b.take<TexRGBA16F>(F16);
+        p.historyDiff = b.take<TexRGBA16F>(F16);
+        p.prevSpecHitDist = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.specConfDummy = b.take<TexR32F>(R32);
+        p.diffConfDummy = b.take<TexR32F>(R32);
+        p.specSh = b.take<TexRGBA16F>(F16);
+        p.diffSh = b.take<TexRGBA16F>(F16);
+        p.historySpecShFast = b.take<TexRGBA16F>(F16);
+        p.historyDiffShFast = b.take<TexRGBA16F>(F16);
+        p.historySpecSh = b.take<TexRGBA16F>(F16);
+        p.historyDiffSh = b.take<TexRGBA16F>(F16);
+        p.outHistoryLength = b.take<TexR8>(R8);
+        p.outSpec = b.take<TexRGBA16F>(F16);
+        p.outDiff = b.take<TexRGBA16F>(F16);
+        p.outSpecFast = b.take<TexRGBA16F>(F16);
+        p.outDiffFast = b.take<TexRGBA16F>(F16);
+        p.outSpecHitDist = b.take<TexR16F>(Format::R16_SFLOAT);
+        p.outSpecReprojectionConfidence = b.take<TexR8>(R8);
+        p.outSpecSh = b.take<TexRGBA16F>(F16);
+        p.outDiffSh = b.take<TexRGBA16F>(F16);
+        p.outSpecShFast = b.take<TexRGBA16F>(F16);
+        p.outDiffShFast = b.take<TexRGBA16F>(F16);
+        if (bad(35)) return (uint32_t)Result::INVALID_ARGUMENT;
+        relaxTemporalAccumulationKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "RELAX_HistoryFix.cs.hlsl" + sig) {
+        RelaxHistoryFixParams p;
+        p.tiles = b.take<TexR8>(R8);
+        p.historyLength = b.take<TexR8>(R8);
+        p.normalRoughness = b.take<TexNR>(NR);
+        p.viewZ = b.take<TexR32F>(R32);
+        p.spec = b.take<TexRGBA16F>(F16);
+        p.diff = b.take<TexRGBA16F>(F16);
+        p.specSh = b.take<TexRGBA16F>(F16);
+        p.diffSh = b.take<TexRGBA16F>(F16);
+        p.outSpec = b.take<TexRGBA16F>(F16);
+        p.outDiff = b.take<TexRGBA16F>(F16);
+        p.outSpecSh = b.take<TexRGBA16F>(F16);
+        p.outDiffSh = b.take<TexRGBA16F>(F16);
+        if (bad(12)) return (uint32_t)Result::INVALID_ARGUMENT;
+        relaxHistoryFixKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "RELAX_HistoryClamping.cs.hlsl" + sig) {
+        RelaxHistoryClampingParams p;
+        p.tiles = b.take<TexR8>(R8);
+        p.viewZ = b.take<TexR32F>(R32);
+        p.historyLength = b.take<TexR8>(R8);
+        TexRGBA16F* ins[10] = {&p.specNoisy, &p.diffNoisy, &p.spec, &p.diff, &p.specFast, &p.diffFast, &p.specSh, &p.diffSh, &p.specShFast, &p.diffShFast};
+        for (TexRGBA16F* t : ins) *t = b.take<TexRGBA16F>(F16);
+        p.outHistoryLength = b.take<TexR8>(R8);
+        TexRGBA16F* outs[8] = {&p.outSpec, &p.outDiff, &p.outSpecFast, &p.outDiffFast, &p.outSpecSh, &p.outDiffSh, &p.outSpecShFast, &p.outDiffShFast};
+        for (TexRGBA16F* t : outs) *t = b.take<TexRGBA16F>(F16);
+        if (bad(22)) return (uint32_t)Result::INVALID_ARGUMENT;
+        relaxHistoryClampingKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "RELAX_Copy.cs.hlsl" + sig) {
+        RelaxCopyParams p;
+        p.spec = b.take<TexRGBA16F>(F16);
+        p.diff = b.take<TexRGBA16F>(F16);
+        p.outSpec = b.take<TexRGBA16F>(F16);
+        p.outDiff = b.take<TexRGBA16F>(F16);
+        if (bad(4)) return (uint32_t)Result::INVALID_ARGUMENT;
+        relaxCopyKernel<<<pixelGrid, block, 0, stream>>>(p);
+    } else if (id == "RELAX_AntiFirefly.cs.hlsl" + sig) {
+        RelaxAntiFireflyParams p;
+        p.tiles = b.take<TexR8>(R8);
+        p.normalRoughness = b.take<TexNR>(NR);
+        p.viewZ = b.take<TexR32F>(R32);
+        p.spec = b.take<TexRGBA16F>(F16);
+        p.diff = b.take<TexRGBA16F>(F16);
+        p.outSpec = b.take<TexRGBA16F>(F16);
+        p.outDiff = b.take<TexRGBA16F>(F16);
+        if (bad(7)) return (uint32_t)Result::INVALID_ARGUMENT;
+        relaxAntiFireflyKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "RELAX_AtrousSmem.cs.hlsl" + sig || id == "RELAX_Atrous.cs.hlsl" + sig) {
+        const bool smem = id == "RELAX_AtrousSmem.cs.hlsl" + sig;
+        RelaxAtrousParams p = {};
+        p.tiles = b.take<TexR8>(R8);
+        p.historyLength = b.take<TexR8>(R8);
+        p.normalRoughness = b.take<TexNR>(NR);
+        p.viewZ = b.take<TexR32F>(R32);
+        p.spec = b.take<TexRGBA16F>(F16);
+        p.diff = b.take<TexRGBA16F>(F16);
+        p.specReprojectionConfidence = b.take<TexR8>(R8);
+        p.specConfDummy = b.take<TexR32F>(R32);
+        p.diffConfDummy = b.take<TexR32F>(R32);
+        p.specSh = b.take<TexRGBA16F>(F16);
+        p.diffSh = b.take<TexRGBA16F>(F16);
+        p.outSpec = b.take<TexRGBA16F>(F16);
+        p.outDiff = b.take<TexRGBA16F>(F16);
+        if (smem) {
+            p.outNormalRoughness = b.take<TexRGBA8>(Format::RGBA8_UNORM);
+            p.outMaterialID = b.take<TexR8>(R8);
+            p.outViewZ = b.take<TexR32F>(R32);
+        }
+        p.outSpecSh = b.take<TexRGBA16F>(F16);
+        p.outDiffSh = b.take<TexRGBA16F>(F16);
+        if (bad(smem ? 18 : 15)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (smem)
+            relaxAtrousSmemKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+        else
+            relaxAtrousKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else {
+        err = "no CUDA kernel for shader '" + id + "'";
+        return (uint32_t)Result::UNSUPPORTED;
+    }
+    return (uint32_t)Result::SUCCESS;
+}
+
+}  // namespace nrdk
