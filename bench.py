@@ -37,6 +37,23 @@ CHAIN_BYTES_PER_PIXEL = sum(PASS_BYTES_PER_PIXEL.values())  # 350
 PUBLISHED_MPX_S = 3.6864 / 2.55e-3  # NRD/README.md:30: REBLUR_DIFFUSE_SPECULAR 2.55 ms @1440p on RTX 4080
 RING = 4  # distinct frames cycled through (4 x 118 MB of inputs at 1440p >> 126 MB L2)
 
+# Secondary workloads (`--denoiser relax|sigma`): BASELINE.json configs 2 and 0/1', same harness, own metric name. Compulsory bytes per pixel per
+# pass from SURVEY.md App. B; published RTX 4080 times from External/NRD/README.md:32,34.
+WORKLOADS = {
+    "reblur": dict(denoiser="REBLUR_DIFFUSE_SPECULAR", frame="reblur_frame", metric=METRIC, published_ms=2.55,
+                   outputs=(("OUT_DIFF_RADIANCE_HITDIST", "RGBA16_SFLOAT"), ("OUT_SPEC_RADIANCE_HITDIST", "RGBA16_SFLOAT")),
+                   pass_bytes=PASS_BYTES_PER_PIXEL, what="REBLUR_DIFFUSE_SPECULAR full pass chain, {w}x{h}, synthetic 1spp noisy radiance + G-buffer"),
+    "relax": dict(denoiser="RELAX_DIFFUSE_SPECULAR_SH", frame="relax_frame", metric="denoised Mpixels/s (RELAX diff+spec SH, 1440p)", published_ms=4.80,
+                  outputs=(("OUT_DIFF_SH0", "RGBA16_SFLOAT"), ("OUT_DIFF_SH1", "RGBA16_SFLOAT"), ("OUT_SPEC_SH0", "RGBA16_SFLOAT"), ("OUT_SPEC_SH1", "RGBA16_SFLOAT")),
+                  pass_bytes={"Classify tiles": 4, "Pre-pass": 72, "Temporal accumulation": 200, "History fix": 5, "History clamping": 150, "A-trous (SMEM)": 83, "A-trous": 74},
+                  what="RELAX_DIFFUSE_SPECULAR_SH full pass chain (5 a-trous iterations), {w}x{h}, synthetic SH radiance + G-buffer"),
+    "sigma": dict(denoiser="SIGMA_SHADOW", frame="sigma_frame", metric="denoised Mpixels/s (SIGMA shadow, 1440p)", published_ms=0.40,
+                  outputs=(("OUT_SHADOW_TRANSLUCENCY", "R8_UNORM"),),
+                  pass_bytes={"Classify tiles": 6, "Smooth tiles": 0, "Copy": 10, "Blur": 13, "Post-blur": 14, "Temporal stabilization": 25},
+                  what="SIGMA_SHADOW full pass chain, {w}x{h}, synthetic 1spp penumbra + G-buffer"),
+}
+INPUT_FORMATS = {"IN_VIEWZ": "R32_SFLOAT", "IN_NORMAL_ROUGHNESS": "R10_G10_B10_A2_UNORM", "IN_PENUMBRA": "R16_SFLOAT"}   # everything else RGBA16_SFLOAT
+
 
 def usable_cores() -> int:
     """Host threads this process may really use: the scheduler affinity capped by the cgroup CPU quota (the GPU boxes expose
@@ -102,12 +119,11 @@ def run_reference(args):
     W, H = 1280, 720  # bounded sample: a quarter-size stream of the same scene (cost per pixel is resolution independent)
     threads = usable_cores()
     runner.lib().nrd_oracle_set_threads(threads)
-    den = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H)
-    out_d = runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H)
-    out_s = runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H)
-    den.set_user_texture(api.ResourceType.OUT_DIFF_RADIANCE_HITDIST, out_d)
-    den.set_user_texture(api.ResourceType.OUT_SPEC_RADIANCE_HITDIST, out_s)
-    frames = [synth.reblur_frame(i, W, H, period=RING) for i in range(RING)]
+    wl = WORKLOADS[args.denoiser]
+    den = runner.OracleDenoiser(runner.default_host_library(), getattr(api.Denoiser, wl["denoiser"]), W, H)
+    for name, fmt in wl["outputs"]:
+        den.set_user_texture(getattr(api.ResourceType, name), runner.alloc_texture(getattr(api.Format, fmt), W, H))
+    frames = [getattr(synth, wl["frame"])(i, W, H, period=RING) for i in range(RING)]
 
     def step(i):
         for k, v in frames[i % RING].items():
@@ -122,15 +138,14 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = W * H * args.steps / dt / 1e6
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "REBLUR_DIFFUSE_SPECULAR full pass chain, 2560x1440, synthetic 1spp noisy radiance + G-buffer", "denoiser": "REBLUR_DIFFUSE_SPECULAR",
-                   "resolution": [args.width, args.height], "settings": "library defaults"},
+        "config": {"workload": wl["what"].format(w=args.width, h=args.height), "denoiser": wl["denoiser"], "resolution": [args.width, args.height], "settings": "library defaults"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steady-state frames of a {W}x{H} stream of the same synthetic scene (oracle restatement, all host threads)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference's REBLUR implementation is HLSL compute (no CPU/CUDA path, not buildable here); this arm is oracle/'s CPU port of it",
+        "note": "the reference's denoisers are HLSL compute (no CPU/CUDA path, not buildable here); this arm is oracle/'s CPU port of the same chain",
     }
     print(json.dumps(line))
 
@@ -153,18 +168,21 @@ def run_product(args):
     W, H = args.width, args.height
     px = W * H
     RT = api.ResourceType
-    FMT = {"IN_VIEWZ": api.Format.R32_SFLOAT, "IN_NORMAL_ROUGHNESS": api.Format.R10_G10_B10_A2_UNORM, "IN_MV": api.Format.RGBA16_SFLOAT,
-           "IN_DIFF_RADIANCE_HITDIST": api.Format.RGBA16_SFLOAT, "IN_SPEC_RADIANCE_HITDIST": api.Format.RGBA16_SFLOAT}
+    wl = WORKLOADS[args.denoiser]
+    pass_bytes = wl["pass_bytes"]
+
+    def fmt_of(name):
+        return getattr(api.Format, INPUT_FORMATS.get(name, "RGBA16_SFLOAT"))
 
     # every rank gets its own stream of frames (different seeds per rank via the frame index offset)
-    frames = [synth.reblur_frame(i + 1000 * rank, W, H, device=dev, period=RING) for i in range(RING)]
+    frames = [getattr(synth, wl["frame"])(i + 1000 * rank, W, H, device=dev, period=RING) for i in range(RING)]
     host_frames = [{k: v.cpu().pin_memory() for k, v in f.items()} for f in frames]
-    out_d = ex.alloc_texture(api.Format.RGBA16_SFLOAT, W, H, dev)
-    out_s = ex.alloc_texture(api.Format.RGBA16_SFLOAT, W, H, dev)
-    host_out_d = torch.zeros(H, W, 4, dtype=torch.float16).pin_memory()
-    host_out_s = torch.zeros(H, W, 4, dtype=torch.float16).pin_memory()
+    outs = [(getattr(RT, name), getattr(api.Format, fmt), ex.alloc_texture(getattr(api.Format, fmt), W, H, dev)) for name, fmt in wl["outputs"]]
+    host_outs = [torch.zeros_like(t, device="cpu").pin_memory() for _, _, t in outs]
+    in_bytes = sum(v.numel() * v.element_size() for v in frames[0].values())
+    out_bytes = sum(t.numel() * t.element_size() for _, _, t in outs)
 
-    den = ex.CudaDenoiser(api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, device=local)
+    den = ex.CudaDenoiser(getattr(api.Denoiser, wl["denoiser"]), W, H, device=local)
     stream = torch.cuda.current_stream()
 
     def settings(i):
@@ -172,17 +190,17 @@ def run_product(args):
 
     def step_device(i):
         for k, v in frames[i % RING].items():
-            den.set_user_texture(getattr(RT, k), v, FMT[k])
-        den.set_user_texture(RT.OUT_DIFF_RADIANCE_HITDIST, out_d, api.Format.RGBA16_SFLOAT)
-        den.set_user_texture(RT.OUT_SPEC_RADIANCE_HITDIST, out_s, api.Format.RGBA16_SFLOAT)
+            den.set_user_texture(getattr(RT, k), v, fmt_of(k))
+        for rt, fmt, t in outs:
+            den.set_user_texture(rt, t, fmt)
         den.set_common_settings(settings(i))
         den.denoise(stream)
 
     def step_host(i):
         for k, v in host_frames[i % RING].items():
-            den.set_host_texture(getattr(RT, k), v, FMT[k], is_output=False)
-        den.set_host_texture(RT.OUT_DIFF_RADIANCE_HITDIST, host_out_d, api.Format.RGBA16_SFLOAT, is_output=True)
-        den.set_host_texture(RT.OUT_SPEC_RADIANCE_HITDIST, host_out_s, api.Format.RGBA16_SFLOAT, is_output=True)
+            den.set_host_texture(getattr(RT, k), v, fmt_of(k), is_output=False)
+        for (rt, fmt, _), h in zip(outs, host_outs):
+            den.set_host_texture(rt, h, fmt, is_output=True)
         den.set_common_settings(settings(i))
         den.denoise_host(stream)
 
@@ -230,10 +248,11 @@ def run_product(args):
         passes = {}
         for name, (tot, cnt) in prof.items():
             short = name.split(" - ")[-1]
-            if cnt and short in PASS_BYTES_PER_PIXEL:
+            if cnt and short in pass_bytes:
                 avg_ms = tot / cnt
-                gbs = PASS_BYTES_PER_PIXEL[short] * px / (avg_ms * 1e-3) / 1e9
-                passes[short] = {"avg_us": round(avg_ms * 1e3, 2), "alg_bytes_per_px": PASS_BYTES_PER_PIXEL[short], "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+                gbs = pass_bytes[short] * px / (avg_ms * 1e-3) / 1e9
+                passes[short] = {"avg_us": round(avg_ms * 1e3, 2), "launches_per_step": cnt // args.steps, "alg_bytes_per_px": pass_bytes[short], "achieved_gbs": round(gbs, 1),
+                                 "frac": round(gbs / peak, 4)}
         dom = max(passes, key=lambda k: passes[k]["avg_us"]) if passes else None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
@@ -242,34 +261,36 @@ def run_product(args):
                 traffic = json.load(open(tpath)).get(f"{W}x{H}", {}).get(dom)
             except Exception:
                 traffic = None
-        chain_gbs = CHAIN_BYTES_PER_PIXEL * px / (ms_dev / args.steps * 1e-3) / 1e9
+        chain_bytes = sum(pass_bytes[k] * v["launches_per_step"] for k, v in passes.items())
+        chain_gbs = chain_bytes * px / (ms_dev / args.steps * 1e-3) / 1e9
         roofline = None
         if dom:
             roofline = {"bound": "hbm", "kernel": dom, "achieved": passes[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": passes[dom]["frac"], "traffic": traffic,
-                        "peak_source": peak_src, "alg_bytes_per_launch": PASS_BYTES_PER_PIXEL[dom] * px,
-                        "chain": {"alg_bytes_per_px": CHAIN_BYTES_PER_PIXEL, "achieved": round(chain_gbs, 1), "frac": round(chain_gbs / peak, 4)}, "passes": passes,
-                        "note": "REBLUR is ALU-bound on B200 (30-40 FLOP per algorithmic byte vs a ~10 FLOP/B fp32 ridge); see DESIGN.md"}
+                        "peak_source": peak_src, "alg_bytes_per_launch": pass_bytes[dom] * px,
+                        "chain": {"alg_bytes_per_px": chain_bytes, "achieved": round(chain_gbs, 1), "frac": round(chain_gbs / peak, 4)}, "passes": passes,
+                        "note": "the chains are FP32-issue bound on B200 (30-40 FLOP per algorithmic byte vs a ~10 FLOP/B fp32 ridge); see DESIGN.md"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / world / PUBLISHED_MPX_S if (W, H) == (2560, 1440) else None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"REBLUR_DIFFUSE_SPECULAR full pass chain, {W}x{H}, synthetic 1spp noisy radiance + G-buffer", "denoiser": "REBLUR_DIFFUSE_SPECULAR",
-                       "resolution": [W, H], "settings": "library defaults (prepass on, hit-distance reconstruction off, anti-firefly on, stabilization on)",
+            "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / world / (3.6864 / (wl["published_ms"] * 1e-3)) if (W, H) == (2560, 1440) else None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["what"].format(w=W, h=H), "denoiser": wl["denoiser"],
+                       "resolution": [W, H], "settings": "library defaults",
                        "streams_per_gpu": 1, "parallelism": f"replicas x{world} (independent frame streams, no collective)",
-                       "l2_policy": f"ring of {RING} distinct frames: {RING * 32 * px // 2**20} MiB of inputs + pools > 126 MB L2",
-                       "baseline_note": "vs_baseline = per-GPU value / 1446 Mpx/s (RTX 4080, NRD README, default settings + 3x3 hit-distance reconstruction)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * px, "d2h_bytes_per_step": 16 * px, "ms_per_step": ms_host / args.steps},
+                       "l2_policy": f"ring of {RING} distinct frames: {RING * in_bytes // 2**20} MiB of inputs + pools > 126 MB L2",
+                       "baseline_note": f"vs_baseline = per-GPU value / ({wl['published_ms']} ms per 1440p frame on an RTX 4080, NRD README)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_host / args.steps},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
         }
         # CPU baseline: the oracle port on this box's host cores, bounded sample (N=1 only)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline(args.denoiser)
         print(json.dumps(line))
     den.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline():
+def cpu_baseline(which="reblur"):
     import torch  # noqa: F401
     from nrd_sample_b200 import nrd_api as api, synth
     from oracle import runner
@@ -277,10 +298,11 @@ def cpu_baseline():
     W, H, warm, steps = 1280, 720, 4, 8
     threads = usable_cores()
     runner.lib().nrd_oracle_set_threads(threads)
-    den = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H)
-    den.set_user_texture(api.ResourceType.OUT_DIFF_RADIANCE_HITDIST, runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H))
-    den.set_user_texture(api.ResourceType.OUT_SPEC_RADIANCE_HITDIST, runner.alloc_texture(api.Format.RGBA16_SFLOAT, W, H))
-    frames = [synth.reblur_frame(i, W, H, period=RING) for i in range(RING)]
+    wl = WORKLOADS[which]
+    den = runner.OracleDenoiser(runner.default_host_library(), getattr(api.Denoiser, wl["denoiser"]), W, H)
+    for name, fmt in wl["outputs"]:
+        den.set_user_texture(getattr(api.ResourceType, name), runner.alloc_texture(getattr(api.Format, fmt), W, H))
+    frames = [getattr(synth, wl["frame"])(i, W, H, period=RING) for i in range(RING)]
     t0 = 0.0
     for i in range(warm + steps):
         if i == warm:
@@ -302,6 +324,7 @@ def main():
     ap.add_argument("--width", type=int, default=2560)
     ap.add_argument("--height", type=int, default=1440)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--denoiser", default="reblur", choices=sorted(WORKLOADS), help="reblur = the headline workload (default); relax / sigma = BASELINE.json configs 2 and 0")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
