@@ -1,6 +1,6 @@
 """Runs N frames of one denoiser at WxH on cuda:0 — the workload ncu attaches to (see profiles/README.md) — and prints
 the per-pass CUDA-event times of the last N - 4 frames.
-  ncu --set full -k regex:reblur -s 63 -c 7 ... python tools/profile_frame.py 2560 1440 10 [reblur|sigma]"""
+  ncu --set full -k regex:reblur -s 63 -c 7 ... python tools/profile_frame.py 2560 1440 10 [reblur|sigma|relax]"""
 import os
 import sys
 
@@ -15,7 +15,13 @@ F16 = api.Format.RGBA16_SFLOAT
 RT = api.ResourceType
 FMT = {"IN_VIEWZ": api.Format.R32_SFLOAT, "IN_NORMAL_ROUGHNESS": api.Format.R10_G10_B10_A2_UNORM, "IN_MV": F16, "IN_DIFF_RADIANCE_HITDIST": F16, "IN_SPEC_RADIANCE_HITDIST": F16,
        "IN_PENUMBRA": api.Format.R16_SFLOAT}
-if WHAT == "sigma":
+if WHAT == "relax":
+    frames = [synth.relax_frame(i, W, H, device=dev, period=4) for i in range(4)]
+    den = ex.CudaDenoiser(api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, W, H)
+    outs = [ex.alloc_texture(F16, W, H, dev) for _ in range(4)]
+    for rt, t in zip((RT.OUT_DIFF_SH0, RT.OUT_DIFF_SH1, RT.OUT_SPEC_SH0, RT.OUT_SPEC_SH1), outs):
+        den.set_user_texture(rt, t, F16)
+elif WHAT == "sigma":
     frames = [synth.sigma_frame(i, W, H, device=dev, period=4) for i in range(4)]
     den = ex.CudaDenoiser(api.Denoiser.SIGMA_SHADOW, W, H)
     outs = [ex.alloc_texture(api.Format.R8_UNORM, W, H, dev)]
@@ -32,7 +38,7 @@ for i in range(N):
         torch.cuda.synchronize()
         den.set_profiling(True)
     for k, v in frames[i % 4].items():
-        den.set_user_texture(getattr(RT, k), v, FMT[k])
+        den.set_user_texture(getattr(RT, k), v, FMT.get(k, F16))
     den.set_common_settings(synth.common_settings(i, W, H, period=4))
     den.denoise()
 torch.cuda.synchronize()
@@ -41,7 +47,7 @@ total = 0.0
 for name, (tot, cnt) in prof.items():
     if cnt:
         print(f"{name:44s} {tot / cnt * 1e3:9.2f} us  x{cnt}")
-        total += tot / cnt
+        total += tot / (N - 4)   # per frame: the a-trous pass runs several times per frame
 if prof:
     print(f"frame total {total * 1e3:.1f} us = {W * H / total / 1e3:.0f} Mpx/s")
 print("done", ex.launch_count())
