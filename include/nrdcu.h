@@ -108,6 +108,11 @@ NRDCU_API uint32_t nrdcuTileGetStatus(nrdcuContext* ctx, uint64_t* bytesPushed, 
 NRDCU_API uint32_t nrdcuSetHostResource(nrdcuContext* ctx, uint32_t resourceType, void* hostData, uint32_t width, uint32_t height, uint32_t pitchBytes,
                                         uint32_t format, int direction);
 NRDCU_API uint32_t nrdcuDenoiseHost(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream);
+/* Same work, pipelined over PCIe: the upload of the NEXT call's inputs (second device buffer, own copy stream) and the download of the
+ * PREVIOUS call's outputs (from a staging copy, own copy stream) overlap this call's kernels on `stream`. Returns once everything is
+ * enqueued. Host outputs are complete, and host inputs may be reused, after nrdcuHostFlush( ctx, stream ) followed by a wait on `stream`. */
+NRDCU_API uint32_t nrdcuDenoiseHostPipelined(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream);
+NRDCU_API uint32_t nrdcuHostFlush(nrdcuContext* ctx, void* stream);
 
 /* ---- per-pass timing -----------------------------------------------------------------------------------------
  * With profiling on, nrdcuDenoise brackets every dispatch with CUDA events on `stream`; nrdcuResolveProfile

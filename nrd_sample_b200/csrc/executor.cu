@@ -311,7 +311,8 @@ NRDCU_API uint32_t nrdcuDispatch(const char* shaderIdentifier, const void* const
 // =================================================================================================================
 struct HostBinding {
     void* host = nullptr;
-    nrdcuTexture device = {};
+    nrdcuTexture device = {};     // what the kernels bind (inputs: buffer 0)
+    nrdcuTexture deviceAlt = {};  // pipelined path: input buffer 1 / output staging the D2H copy reads from
     uint32_t hostPitch = 0;
     int direction = 0;
     bool used = false;
@@ -329,6 +330,13 @@ struct nrdcuContext {
     uint64_t poolBytes = 0;
     std::vector<nrdcuTexture> scratch;
     std::vector<uint8_t> scratchIsStorage;
+    // pipelined host path (nrdcuDenoiseHostPipelined): copies on their own streams, double-buffered inputs
+    struct HostPipe {
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        cudaEvent_t inReady[2] = {}, inConsumed[2] = {}, outCopied = nullptr, d2hDone = nullptr;
+        bool consumedValid[2] = {false, false}, d2hValid = false;
+        uint64_t frame = 0;
+    } pipe;
     // multi-GPU strips over peer memory (nrdcuTile*): textures of the two neighbouring strips mapped through CUDA IPC
     struct HaloRule { std::string pass; uint32_t binding, rows; };
     struct Tile {
@@ -586,6 +594,16 @@ NRDCU_API void nrdcuDestroy(nrdcuContext* ctx) {
         if (ctx->tile.peerFlags[d]) cudaIpcCloseMemHandle(ctx->tile.peerFlags[d]);
     }
     if (ctx->tile.hostError) cudaFreeHost(ctx->tile.hostError);
+    if (ctx->pipe.h2d) {
+        cudaStreamDestroy(ctx->pipe.h2d);
+        cudaStreamDestroy(ctx->pipe.d2h);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(ctx->pipe.inReady[i]);
+            cudaEventDestroy(ctx->pipe.inConsumed[i]);
+        }
+        cudaEventDestroy(ctx->pipe.outCopied);
+        cudaEventDestroy(ctx->pipe.d2hDone);
+    }
     for (void* p : ctx->allocations) cudaFree(p);
     if (ctx->instance) DestroyInstance(*ctx->instance);
     delete ctx;
@@ -746,15 +764,89 @@ NRDCU_API uint32_t nrdcuSetHostResource(nrdcuContext* ctx, uint32_t resourceType
     return 0;
 }
 
+// Pipelined variant of nrdcuDenoiseHost: the H2D copy of frame i + 1 (own stream, second input buffer) and the D2H copy of frame
+// i - 1 (own stream, from a staging copy of the outputs) overlap the kernels of frame i on `stream`. The call returns as soon as
+// everything is enqueued; host outputs of this call are complete after nrdcuHostFlush( ctx, stream ) + a wait on `stream`.
+// The host input buffers must stay untouched until then as well.
+NRDCU_API uint32_t nrdcuDenoiseHostPipelined(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuDenoiseHostPipelined: null context");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaSetDevice(ctx->device);
+    nrdcuContext::HostPipe& pp = ctx->pipe;
+    if (!pp.h2d) {
+        cudaStreamCreateWithFlags(&pp.h2d, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&pp.d2h, cudaStreamNonBlocking);
+        for (int i = 0; i < 2; i++) {
+            cudaEventCreateWithFlags(&pp.inReady[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&pp.inConsumed[i], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&pp.outCopied, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&pp.d2hDone, cudaEventDisableTiming);
+    }
+    const int b = (int)(pp.frame & 1);
+    // second buffers on first use
+    for (HostBinding& hb : ctx->hostBindings) {
+        if (!hb.used || hb.deviceAlt.data) continue;
+        if (!allocTexture(ctx, hb.device.format, hb.device.width, hb.device.height, hb.deviceAlt, false)) return (uint32_t)Result::FAILURE;
+    }
+    // inputs of this frame -> input buffer b, once the frame that last read buffer b (two calls ago) has consumed it
+    if (pp.consumedValid[b]) cudaStreamWaitEvent(pp.h2d, pp.inConsumed[b], 0);
+    for (size_t slot = 0; slot < (size_t)ResourceType::MAX_NUM; slot++) {
+        HostBinding& hb = ctx->hostBindings[slot];
+        if (!hb.used || hb.direction != 0) continue;
+        const nrdcuTexture& dst = b ? hb.deviceAlt : hb.device;
+        const uint32_t rowBytes = dst.width * bytesPerTexel(dst.format);
+        cudaError_t e = cudaMemcpy2DAsync(dst.data, dst.pitchBytes, hb.host, hb.hostPitch, rowBytes, dst.height, cudaMemcpyHostToDevice, pp.h2d);
+        if (e != cudaSuccess) return fail(Result::FAILURE, "H2D copy: %s", cudaGetErrorString(e));
+        ctx->user[slot] = dst;
+    }
+    cudaEventRecord(pp.inReady[b], pp.h2d);
+    cudaStreamWaitEvent(s, pp.inReady[b], 0);
+    uint32_t rc = nrdcuDenoise(ctx, identifiers, identifiersNum, stream);
+    if (rc != 0) return rc;
+    cudaEventRecord(pp.inConsumed[b], s);
+    pp.consumedValid[b] = true;
+    // outputs: device-to-device into the staging copy (after the previous D2H has finished reading it), then D2H on its own stream
+    if (pp.d2hValid) cudaStreamWaitEvent(s, pp.d2hDone, 0);
+    for (HostBinding& hb : ctx->hostBindings) {
+        if (!hb.used || hb.direction != 1) continue;
+        const uint32_t rowBytes = hb.device.width * bytesPerTexel(hb.device.format);
+        cudaError_t e = cudaMemcpy2DAsync(hb.deviceAlt.data, hb.deviceAlt.pitchBytes, hb.device.data, hb.device.pitchBytes, rowBytes, hb.device.height, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return fail(Result::FAILURE, "D2D copy: %s", cudaGetErrorString(e));
+    }
+    cudaEventRecord(pp.outCopied, s);
+    cudaStreamWaitEvent(pp.d2h, pp.outCopied, 0);
+    for (HostBinding& hb : ctx->hostBindings) {
+        if (!hb.used || hb.direction != 1) continue;
+        const uint32_t rowBytes = hb.device.width * bytesPerTexel(hb.device.format);
+        cudaError_t e = cudaMemcpy2DAsync(hb.host, hb.hostPitch, hb.deviceAlt.data, hb.deviceAlt.pitchBytes, rowBytes, hb.device.height, cudaMemcpyDeviceToHost, pp.d2h);
+        if (e != cudaSuccess) return fail(Result::FAILURE, "D2H copy: %s", cudaGetErrorString(e));
+    }
+    cudaEventRecord(pp.d2hDone, pp.d2h);
+    pp.d2hValid = true;
+    pp.frame++;
+    return 0;
+}
+
+// Makes `stream` wait for every copy the pipelined path has in flight (call before reading host outputs / stopping a timer)
+NRDCU_API uint32_t nrdcuHostFlush(nrdcuContext* ctx, void* stream) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuHostFlush: null context");
+    if (ctx->pipe.d2hValid) cudaStreamWaitEvent((cudaStream_t)stream, ctx->pipe.d2hDone, 0);
+    return 0;
+}
+
 NRDCU_API uint32_t nrdcuDenoiseHost(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream) {
     if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuDenoiseHost: null context");
     cudaStream_t s = (cudaStream_t)stream;
     cudaSetDevice(ctx->device);
-    for (HostBinding& hb : ctx->hostBindings) {
+    if (ctx->pipe.d2hValid) cudaStreamWaitEvent(s, ctx->pipe.d2hDone, 0);  // a pipelined call may still be downloading
+    for (size_t slot = 0; slot < (size_t)ResourceType::MAX_NUM; slot++) {
+        HostBinding& hb = ctx->hostBindings[slot];
         if (!hb.used || hb.direction != 0) continue;
         uint32_t rowBytes = hb.device.width * bytesPerTexel(hb.device.format);
         cudaError_t e = cudaMemcpy2DAsync(hb.device.data, hb.device.pitchBytes, hb.host, hb.hostPitch, rowBytes, hb.device.height, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) return fail(Result::FAILURE, "H2D copy: %s", cudaGetErrorString(e));
+        ctx->user[slot] = hb.device;  // the pipelined path may have left the slot on the second input buffer
     }
     uint32_t rc = nrdcuDenoise(ctx, identifiers, identifiersNum, stream);
     if (rc != 0) return rc;

@@ -25,7 +25,7 @@ FLAG_ROBUST_MIRROR_TEST = 4
 
 NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdcuAllocSharedTexture", "nrdcuTileExportSize", "nrdcuTileExport", "nrdcuTileAttach",
                  "nrdcuTileSetHalo", "nrdcuTileGetStatus", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
-                 "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuGetLastError", "nrdcuGetLaunchCount",
+                 "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuDenoiseHostPipelined", "nrdcuHostFlush", "nrdcuGetLastError", "nrdcuGetLaunchCount",
                  "nrdcuGetPoolBytes", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile")
 
 # nrd::Format -> (torch dtype, channels) for tensors handed to / returned by the executor
@@ -90,6 +90,10 @@ def load() -> C.CDLL:
         L.nrdcuSetHostResource.restype = C.c_uint32
         L.nrdcuDenoiseHost.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p]
         L.nrdcuDenoiseHost.restype = C.c_uint32
+        L.nrdcuDenoiseHostPipelined.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p]
+        L.nrdcuDenoiseHostPipelined.restype = C.c_uint32
+        L.nrdcuHostFlush.argtypes = [C.c_void_p, C.c_void_p]
+        L.nrdcuHostFlush.restype = C.c_uint32
         L.nrdcuGetLastError.restype = C.c_char_p
         L.nrdcuGetLaunchCount.restype = C.c_uint64
         L.nrdcuGetPoolBytes.argtypes = [C.c_void_p]
@@ -199,6 +203,15 @@ class CudaDenoiser:
     def denoise_host(self, stream: Optional[torch.cuda.Stream] = None):
         s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
         _check(load().nrdcuDenoiseHost(self.ctx, self._ids, 1, C.c_void_p(s)), "nrdcuDenoiseHost")
+
+    def denoise_host_pipelined(self, stream: Optional[torch.cuda.Stream] = None):
+        """Host buffers in / out with the PCIe copies of neighbouring frames overlapping the kernels; call host_flush() before reading outputs."""
+        s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        _check(load().nrdcuDenoiseHostPipelined(self.ctx, self._ids, 1, C.c_void_p(s)), "nrdcuDenoiseHostPipelined")
+
+    def host_flush(self, stream: Optional[torch.cuda.Stream] = None):
+        s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        _check(load().nrdcuHostFlush(self.ctx, C.c_void_p(s)), "nrdcuHostFlush")
 
     def pool_texture(self, permanent: bool, index: int) -> torch.Tensor:
         """Copy of a pool texture (debug / parity tap)."""

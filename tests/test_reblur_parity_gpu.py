@@ -276,3 +276,43 @@ def test_two_strips_on_one_gpu_equal_the_whole_frame(ex, runner):
             for si, (y0, y1) in enumerate(strips):
                 got = sets[si][(int(rt), 0)][0]
                 assert torch.equal(got[y0:y1].view(torch.int16), whole[y0:y1].view(torch.int16)), f"frame {f} strip {si} {rt}"
+
+
+def test_pipelined_host_path_matches_device_path(ex, runner):
+    """nrdcuDenoiseHostPipelined (uploads / downloads of neighbouring frames overlapping the kernels, double-buffered inputs) must hand
+    back, frame by frame, exactly the bits of nrdcuDenoise on resident textures."""
+    w, h, n = 320, 192, 6
+    a = ex.CudaDenoiser(api.Denoiser.REBLUR_DIFFUSE_SPECULAR, w, h)
+    b = ex.CudaDenoiser(api.Denoiser.REBLUR_DIFFUSE_SPECULAR, w, h)
+    od, os_ = ex.alloc_texture(F16, w, h, "cuda:0"), ex.alloc_texture(F16, w, h, "cuda:0")
+    a.set_user_texture(RT.OUT_DIFF_RADIANCE_HITDIST, od, F16)
+    a.set_user_texture(RT.OUT_SPEC_RADIANCE_HITDIST, os_, F16)
+    want, got, keep_host = [], [], []
+    keep = {}
+    for f in range(n):
+        frame = synth.reblur_frame(f, w, h)
+        host = {k: v.clone().pin_memory() for k, v in frame.items()}
+        hd, hs = torch.zeros(h, w, 4, dtype=torch.float16).pin_memory(), torch.zeros(h, w, 4, dtype=torch.float16).pin_memory()
+        keep_host.append(host)
+        for k, v in frame.items():
+            rt = getattr(RT, k)
+            keep[k] = v.to("cuda:0")
+            a.set_user_texture(rt, keep[k], runner.USER_FORMATS[rt])
+            b.set_host_texture(rt, host[k], runner.USER_FORMATS[rt], is_output=False)
+        b.set_host_texture(RT.OUT_DIFF_RADIANCE_HITDIST, hd, F16, is_output=True)
+        b.set_host_texture(RT.OUT_SPEC_RADIANCE_HITDIST, hs, F16, is_output=True)
+        cs = synth.common_settings(f, w, h)
+        a.set_common_settings(cs)
+        b.set_common_settings(cs)
+        a.denoise()
+        b.denoise_host_pipelined()   # no synchronisation between frames: copies of frame f + 1 overlap the kernels of frame f
+        torch.cuda.current_stream().synchronize()   # stream only: the copy streams of `b` keep running
+        want.append((od.cpu().clone(), os_.cpu().clone()))
+        got.append((hd, hs))
+    b.host_flush()
+    torch.cuda.synchronize()
+    for f in range(n):
+        assert torch.equal(want[f][0].view(torch.int16), got[f][0].view(torch.int16)), f"frame {f} diffuse"
+        assert torch.equal(want[f][1].view(torch.int16), got[f][1].view(torch.int16)), f"frame {f} specular"
+    a.close()
+    b.close()
