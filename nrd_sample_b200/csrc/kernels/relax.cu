@@ -293,7 +293,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParams p) {
+#ifndef RELAX_TA_MIN_BLOCKS
+#define RELAX_TA_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParams p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float currentLinearZ = relaxViewZ(cb, p.viewZ.load(px, py));
@@ -881,7 +884,10 @@ NRD_DEV AtrousTexel atrousFetch(const RelaxConstants& cb, const RelaxAtrousParam
     return r;
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParams p) {
+#ifndef RELAX_ATROUS_SMEM_MIN_BLOCKS
+#define RELAX_ATROUS_SMEM_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParams p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     const float isSky = p.tiles.load(px >> 4, py >> 4);
     const float viewZpacked = p.viewZ.load(px, py);
@@ -906,18 +912,16 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousSmemKernel(const 
     if (historyLength >= cb.historyThreshold) {
         const float kernel[2][2] = {{1.0f / 4.0f, 1.0f / 8.0f}, {1.0f / 8.0f, 1.0f / 16.0f}};
         float4 specularSumV = f4(0.0f), diffuseSumV = f4(0.0f);
-        AtrousTexel nb[3][3];
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++) nb[dy + 1][dx + 1] = (dx == 0 && dy == 0) ? ctr : atrousFetch(cb, p, px + dx, py + dy);
+        // two sweeps over the 3x3 neighbourhood (variance first, then the filter): the second sweep re-reads through L1 instead of
+        // keeping nine fat texels in registers
 #pragma unroll
         for (int dx = -1; dx <= 1; dx++)
 #pragma unroll
             for (int dy = -1; dy <= 1; dy++) {
+                const int gx = clampi(px + dx, 0, cb.rectSize[0] - 1), gy = clampi(py + dy, 0, cb.rectSize[1] - 1);
                 const float k = kernel[dx < 0 ? -dx : dx][dy < 0 ? -dy : dy];
-                specularSumV += nb[dy + 1][dx + 1].spec * k;
-                diffuseSumV += nb[dy + 1][dx + 1].diff * k;
+                specularSumV += p.spec.load(gx, gy) * k;
+                diffuseSumV += p.diff.load(gx, gy) * k;
             }
         const float s1 = luminance(xyz(specularSumV)), d1 = luminance(xyz(diffuseSumV));
         const float centerSpecularVar = fmaxf(0.0f, specularSumV.w - s1 * s1), centerDiffuseVar = fmaxf(0.0f, diffuseSumV.w - d1 * d1);
@@ -947,7 +951,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousSmemKernel(const 
                 const bool isCenter = i == 0 && j == 0;
                 const bool isInside = x >= 0 && y >= 0 && x < cb.rectSize[0] && y < cb.rectSize[1];
                 const float kernelW = isInside ? kGauss[i < 0 ? -i : i] * kGauss[j < 0 ? -j : j] : 0.0f;
-                const AtrousTexel& s = nb[j + 1][i + 1];
+                const AtrousTexel s = isCenter ? ctr : atrousFetch(cb, p, x, y);
                 const float3 sampleNormal = xyz(s.nr);
                 float geometryW = planeDistanceWeightAtrous(centerWorldPos, centerNormal, s.worldPos, depthThreshold);
                 geometryW *= kernelW;
