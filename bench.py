@@ -271,7 +271,7 @@ def run_product(args):
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if dom and os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(f"{W}x{H}", {}).get(dom)
+                traffic = json.load(open(tpath)).get(f"{W}x{H}" if args.denoiser == "reblur" else f"{args.denoiser} {W}x{H}", {}).get(dom)
             except Exception:
                 traffic = None
         chain_bytes = sum(pass_bytes[k] * v["launches_per_step"] for k, v in passes.items())

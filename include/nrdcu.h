@@ -43,7 +43,8 @@ typedef struct nrdcuTexture {
 /* Flags of nrdcuCreate / nrdcuDispatch */
 enum {
     NRDCU_FLAG_QUAD_INTRINSICS = 1u << 0, /* replay SM6.0 quad smoothing (NRD_SUPPORTS_QUAD_INTRINSICS=1, the reference default) */
-    NRDCU_FLAG_CUDA_GRAPH = 1u << 1,      /* replay steady-state frames from captured CUDA graphs (one per ping-pong parity) */
+    NRDCU_FLAG_CUDA_GRAPH = 1u << 1,      /* reserved, ignored: every pass takes new constants each frame, so a replayed graph would need all of its
+                                             kernel nodes patched per frame — no gain over 7-10 launches while the chains are GPU-bound */
     NRDCU_FLAG_ROBUST_MIRROR_TEST = 1u << 2, /* DEBUG: spatial taps use "left the screen" instead of the reference's bit-fragile any(uv != MirrorUv(uv)) */
 };
 #define NRDCU_DEFAULT_FLAGS (NRDCU_FLAG_QUAD_INTRINSICS)
