@@ -7,8 +7,9 @@
 // RELAX_Copy.cs.hlsl:21-34, RELAX_AntiFirefly.cs.hlsl:21-216, RELAX_AtrousSmem.cs.hlsl:21-484, RELAX_Atrous.cs.hlsl:21-260,
 // helpers RELAX_Common.hlsli:11-185. Build switches of the reference's default build: no checkerboard, no confidence /
 // disocclusion-threshold-mix inputs (rejected with UNSUPPORTED), NRD_USE_PREV_WORLD_SPACE_MATRIX = 0.
-// First version: the 3x3 / 5x5 neighbourhoods the reference stages in groupshared memory are read through L1 here
-// (clamped fetches); the arithmetic follows the shaders statement by statement.
+// History clamping and the first a-trous pass stage their 5x5 neighbourhoods in shared memory like the reference (36x12 texels per
+// 32x8 CTA, colour-space conversions / normal decode / world positions done once per texel); the 3x3 of temporal accumulation and
+// anti-firefly go through L1. The arithmetic follows the shaders statement by statement.
 #include <string>
 
 #include "../../../include/nrd_b200.h"
@@ -730,25 +731,30 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One lobe of history clamping (the specular and diffuse halves of the shader differ in three constants only)
+// History clamping: the 5x5 neighbourhood of { responsive history in YCoCg, validity } and { noisy input, luminance^2 } lives in shared
+// memory (36x12 texels per 32x8 CTA), converted once per texel instead of once per tap.
+constexpr int HC_BORDER = 2, HC_TILE_W = BLOCK_W + 2 * HC_BORDER, HC_TILE_H = BLOCK_H + 2 * HC_BORDER;
+
+// One lobe (the specular and diffuse halves of the shader differ in three constants only)
 template <bool SPEC>
-NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const TexR32F& viewZ, int px, int py, float historyLength, const TexRGBA16F& noisyTex, const TexRGBA16F& slowTex,
-                                 const TexRGBA16F& fastTex, const TexRGBA16F& shTex, const TexRGBA16F& shFastTex, const TexRGBA16F& outSlow, const TexRGBA16F& outFast,
-                                 const TexRGBA16F& outSh, const TexRGBA16F& outShFast, float maxFast, float maxSlow) {
-    const int maxX = cb.rectSize[0] - 1, maxY = cb.rectSize[1] - 1;
+NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)[HC_TILE_W], const float4 (*sNoisy)[HC_TILE_W], int px, int py, float historyLength,
+                                 const TexRGBA16F& slowTex, const TexRGBA16F& fastTex, const TexRGBA16F& shTex, const TexRGBA16F& shFastTex, const TexRGBA16F& outSlow,
+                                 const TexRGBA16F& outFast, const TexRGBA16F& outSh, const TexRGBA16F& outShFast, float maxFast, float maxSlow) {
+    const int sx = threadIdx.x + HC_BORDER, sy = threadIdx.y + HC_BORDER;
     float3 m1 = f3(0.0f), m2 = f3(0.0f), noisyM1 = f3(0.0f);
     float noisyM2 = 0.0f, sum = 0.0f;
+#pragma unroll
     for (int dx = -2; dx <= 2; dx++)
+#pragma unroll
         for (int dy = -2; dy <= 2; dy++) {
-            const int x = clampi(px + dx, 0, maxX), y = clampi(py + dy, 0, maxY);
-            if (relaxInRange(cb, viewZ.load(x, y))) {  // raw viewZ, as in the shader's Preload( )
-                const float3 s = rgbToYCoCg(xyz(fastTex.load(x, y)));
-                m1 += s;
-                m2 += s * s;
-                const float3 n = xyz(noisyTex.load(x, y));
-                const float l = luminance(n);
-                noisyM1 += n;
-                noisyM2 += l * l;
+            const float4 f = sFast[sy + dy][sx + dx];
+            if (f.w != 0.0f) {
+                const float3 c = xyz(f);
+                m1 += c;
+                m2 += c * c;
+                const float4 n = sNoisy[sy + dy][sx + dx];
+                noisyM1 += xyz(n);
+                noisyM2 += n.w;
                 sum += 1.0f;
             }
         }
@@ -759,8 +765,8 @@ NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const TexR32F& viewZ,
     const float3 sigma = sqrt3v(max3(f3(0.0f), m2 - m1 * m1));
     float3 colorMin = m1 - cb.fastHistoryClampingSigmaScale * sigma, colorMax = m1 + cb.fastHistoryClampingSigmaScale * sigma;
 
-    const float4 fastCenterRaw = fastTex.load(px, py);
-    const float3 responsiveCenterYCoCg = rgbToYCoCg(xyz(fastCenterRaw));
+    const float3 responsiveCenterYCoCg = xyz(sFast[sy][sx]);
+    const float responsiveCenterAlpha = SPEC ? fastTex.load(px, py).w : 0.0f;
     colorMin = min3v(colorMin, responsiveCenterYCoCg);
     colorMax = max3(colorMax, responsiveCenterYCoCg);
 
@@ -772,7 +778,7 @@ NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const TexR32F& viewZ,
 
     float4 outSlowV = f4(clamped, slow.w);
     const float3 responsiveCenter = yCoCgToRgb(responsiveCenterYCoCg);
-    float4 outFastV = f4(responsiveCenter, SPEC ? fastCenterRaw.w : 0.0f);
+    float4 outFastV = f4(responsiveCenter, responsiveCenterAlpha);
     const bool fixed = historyLength <= cb.historyFixFrameNum;
     if (fixed) outSlowV = SPEC ? outFastV : f4(xyz(outFastV), outSlowV.w);
 
@@ -800,7 +806,7 @@ NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const TexR32F& viewZ,
     float resetAmount = (SPEC ? 0.5f : 1.0f) * cb.historyResetAmount * fmaxf(0.0f, fabsf(slowL - noisyInputL) - spatialSigma - temporalSigma) /
                         (1.0e-6f + fmaxf(slowL, noisyInputL) + spatialSigma + temporalSigma);
     resetAmount = saturate(resetAmount);
-    const float3 noisyCenter = xyz(noisyTex.load(px, py));
+    const float3 noisyCenter = xyz(sNoisy[sy][sx]);
     outSlowV = f4(lerp(xyz(outSlowV), noisyCenter, resetAmount), outSlowV.w);
     outFastV = f4(lerp(xyz(outFastV), noisyCenter, resetAmount), outFastV.w);
 
@@ -815,13 +821,34 @@ NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const TexR32F& viewZ,
 }
 
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParams p) {
+    __shared__ float4 sSpecFast[HC_TILE_H][HC_TILE_W], sSpecNoisy[HC_TILE_H][HC_TILE_W], sDiffFast[HC_TILE_H][HC_TILE_W], sDiffNoisy[HC_TILE_H][HC_TILE_W];
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
-    if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
-    if (!relaxInRange(cb, p.viewZ.load(px, py))) return;
+    // the CTA covers two 16x16 tiles of one tile row
+    const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
+    if (skyL != 0.0f && skyR != 0.0f) return;
+    {
+        const int baseX = blockIdx.x * BLOCK_W - HC_BORDER, baseY = blockIdx.y * BLOCK_H - HC_BORDER;
+        const int maxX = cb.rectSize[0] - 1, maxY = cb.rectSize[1] - 1;
+        for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < HC_TILE_W * HC_TILE_H; i += BLOCK_W * BLOCK_H) {
+            const int tx = i % HC_TILE_W, ty = i / HC_TILE_W;
+            const int gx = clampi(baseX + tx, 0, maxX), gy = clampi(baseY + ty, 0, maxY);
+            const float valid = relaxInRange(cb, p.viewZ.load(gx, gy)) ? 1.0f : 0.0f;  // raw viewZ, as in the shader's Preload( )
+            const float3 sn = xyz(p.specNoisy.load(gx, gy)), dn = xyz(p.diffNoisy.load(gx, gy));
+            const float sl = luminance(sn), dl = luminance(dn);
+            sSpecFast[ty][tx] = f4(rgbToYCoCg(xyz(p.specFast.load(gx, gy))), valid);
+            sSpecNoisy[ty][tx] = f4(sn, sl * sl);
+            sDiffFast[ty][tx] = f4(rgbToYCoCg(xyz(p.diffFast.load(gx, gy))), valid);
+            sDiffNoisy[ty][tx] = f4(dn, dl * dl);
+        }
+    }
+    __syncthreads();
+    const float isSky = threadIdx.x < 16 ? skyL : skyR;
+    if (isSky != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    if (sSpecFast[threadIdx.y + HC_BORDER][threadIdx.x + HC_BORDER].w == 0.0f) return;
     const float historyLength = 255.0f * p.historyLength.load(px, py);
-    historyClampingLobe<true>(cb, p.viewZ, px, py, historyLength, p.specNoisy, p.spec, p.specFast, p.specSh, p.specShFast, p.outSpec, p.outSpecFast, p.outSpecSh, p.outSpecShFast,
+    historyClampingLobe<true>(cb, sSpecFast, sSpecNoisy, px, py, historyLength, p.spec, p.specFast, p.specSh, p.specShFast, p.outSpec, p.outSpecFast, p.outSpecSh, p.outSpecShFast,
                               cb.specMaxFastAccumulatedFrameNum, cb.specMaxAccumulatedFrameNum);
-    historyClampingLobe<false>(cb, p.viewZ, px, py, historyLength, p.diffNoisy, p.diff, p.diffFast, p.diffSh, p.diffShFast, p.outDiff, p.outDiffFast, p.outDiffSh, p.outDiffShFast,
+    historyClampingLobe<false>(cb, sDiffFast, sDiffNoisy, px, py, historyLength, p.diff, p.diffFast, p.diffSh, p.diffShFast, p.outDiff, p.outDiffFast, p.outDiffSh, p.outDiffShFast,
                                cb.diffMaxFastAccumulatedFrameNum, cb.diffMaxAccumulatedFrameNum);
     p.outHistoryLength.store(px, py, historyLength / 255.0f);
 }
@@ -884,15 +911,48 @@ NRD_DEV AtrousTexel atrousFetch(const RelaxConstants& cb, const RelaxAtrousParam
     return r;
 }
 
+constexpr int AT_BORDER = 2, AT_TILE_W = BLOCK_W + 2 * AT_BORDER, AT_TILE_H = BLOCK_H + 2 * AT_BORDER;
 #ifndef RELAX_ATROUS_SMEM_MIN_BLOCKS
 #define RELAX_ATROUS_SMEM_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParams p) {
+    // the reference's groupshared tile: 36x12 texels of { illumination + 2nd moment, SH1, normal + roughness, world position + material }
+    __shared__ float4 sSpec[AT_TILE_H][AT_TILE_W], sDiff[AT_TILE_H][AT_TILE_W], sNr[AT_TILE_H][AT_TILE_W], sPosMat[AT_TILE_H][AT_TILE_W], sSpecSh[AT_TILE_H][AT_TILE_W],
+        sDiffSh[AT_TILE_H][AT_TILE_W];
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
-    const float isSky = p.tiles.load(px >> 4, py >> 4);
+    const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
+    const float isSky = threadIdx.x < 16 ? skyL : skyR;
     const float viewZpacked = p.viewZ.load(px, py);
     p.outViewZ.store(px, py, viewZpacked);
-    const AtrousTexel ctr = atrousFetch(cb, p, px, py);
+    const bool skipTile = skyL != 0.0f && skyR != 0.0f;  // nothing to filter in this CTA: only the prev-frame planes are written
+    if (!skipTile) {
+        const int baseX = blockIdx.x * BLOCK_W - AT_BORDER, baseY = blockIdx.y * BLOCK_H - AT_BORDER;
+        for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < AT_TILE_W * AT_TILE_H; i += BLOCK_W * BLOCK_H) {
+            const int tx = i % AT_TILE_W, ty = i / AT_TILE_W;
+            const AtrousTexel t = atrousFetch(cb, p, baseX + tx, baseY + ty);
+            sSpec[ty][tx] = t.spec;
+            sDiff[ty][tx] = t.diff;
+            sNr[ty][tx] = t.nr;
+            sPosMat[ty][tx] = f4(t.worldPos, t.materialID);
+            sSpecSh[ty][tx] = f4(t.specSh, 0.0f);
+            sDiffSh[ty][tx] = f4(t.diffSh, 0.0f);
+        }
+    }
+    __syncthreads();
+    const int smx = threadIdx.x + AT_BORDER, smy = threadIdx.y + AT_BORDER;
+    auto texel = [&](int dx, int dy) -> AtrousTexel {
+        AtrousTexel t;
+        t.spec = sSpec[smy + dy][smx + dx];
+        t.diff = sDiff[smy + dy][smx + dx];
+        t.nr = sNr[smy + dy][smx + dx];
+        const float4 pm = sPosMat[smy + dy][smx + dx];
+        t.worldPos = xyz(pm);
+        t.materialID = pm.w;
+        t.specSh = xyz(sSpecSh[smy + dy][smx + dx]);
+        t.diffSh = xyz(sDiffSh[smy + dy][smx + dx]);
+        return t;
+    };
+    const AtrousTexel ctr = skipTile ? atrousFetch(cb, p, px, py) : texel(0, 0);
     float4 normalRoughness = ctr.nr;
     const float centerViewZ = relaxViewZ(cb, viewZpacked);
     if (!relaxInRange(cb, centerViewZ)) normalRoughness = f4(1.0f / 255.0f);
@@ -912,16 +972,14 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
     if (historyLength >= cb.historyThreshold) {
         const float kernel[2][2] = {{1.0f / 4.0f, 1.0f / 8.0f}, {1.0f / 8.0f, 1.0f / 16.0f}};
         float4 specularSumV = f4(0.0f), diffuseSumV = f4(0.0f);
-        // two sweeps over the 3x3 neighbourhood (variance first, then the filter): the second sweep re-reads through L1 instead of
-        // keeping nine fat texels in registers
+        // two sweeps over the 3x3 neighbourhood: variance first, then the filter
 #pragma unroll
         for (int dx = -1; dx <= 1; dx++)
 #pragma unroll
             for (int dy = -1; dy <= 1; dy++) {
-                const int gx = clampi(px + dx, 0, cb.rectSize[0] - 1), gy = clampi(py + dy, 0, cb.rectSize[1] - 1);
                 const float k = kernel[dx < 0 ? -dx : dx][dy < 0 ? -dy : dy];
-                specularSumV += p.spec.load(gx, gy) * k;
-                diffuseSumV += p.diff.load(gx, gy) * k;
+                specularSumV += sSpec[smy + dy][smx + dx] * k;
+                diffuseSumV += sDiff[smy + dy][smx + dx] * k;
             }
         const float s1 = luminance(xyz(specularSumV)), d1 = luminance(xyz(diffuseSumV));
         const float centerSpecularVar = fmaxf(0.0f, specularSumV.w - s1 * s1), centerDiffuseVar = fmaxf(0.0f, diffuseSumV.w - d1 * d1);
@@ -951,7 +1009,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
                 const bool isCenter = i == 0 && j == 0;
                 const bool isInside = x >= 0 && y >= 0 && x < cb.rectSize[0] && y < cb.rectSize[1];
                 const float kernelW = isInside ? kGauss[i < 0 ? -i : i] * kGauss[j < 0 ? -j : j] : 0.0f;
-                const AtrousTexel s = isCenter ? ctr : atrousFetch(cb, p, x, y);
+                const AtrousTexel s = texel(i, j);
                 const float3 sampleNormal = xyz(s.nr);
                 float geometryW = planeDistanceWeightAtrous(centerWorldPos, centerNormal, s.worldPos, depthThreshold);
                 geometryW *= kernelW;
@@ -998,7 +1056,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
         const float diffuseNormalWeightParam = normalWeightParam2(1.0f, cb.lobeAngleFraction);
         for (int cx = -2; cx <= 2; cx++)
             for (int cy = -2; cy <= 2; cy++) {
-                const AtrousTexel s = atrousFetch(cb, p, px + cx, py + cy);
+                const AtrousTexel s = texel(cx, cy);
                 const float normalW = computeWeight(acosApproxPositive(dot(centerNormal, xyz(s.nr))), diffuseNormalWeightParam, 0.0f);
                 const float specularW = normalW * (compareMaterials(s.materialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f);
                 sumWS += specularW;
