@@ -176,7 +176,12 @@ def run_product(args):
         return getattr(api.Format, INPUT_FORMATS.get(name, "RGBA16_SFLOAT"))
 
     # every rank gets its own stream of frames (different seeds per rank via the frame index offset)
-    frames = [getattr(synth, wl["frame"])(i + 1000 * rank, W, H, device=dev, period=RING) for i in range(RING)]
+    recon = {"off": 0, "3x3": 1, "5x5": 2}[args.hitdist_reconstruction]
+    extra = {"holes": True} if recon else {}
+    if recon:
+        assert args.denoiser == "reblur", "--hitdist-reconstruction applies to the REBLUR workload"
+        pass_bytes = dict(pass_bytes, **{"Hit distance reconstruction": 40})
+    frames = [getattr(synth, wl["frame"])(i + 1000 * rank, W, H, device=dev, period=RING, **extra) for i in range(RING)]
     host_frames = [{k: v.cpu().pin_memory() for k, v in f.items()} for f in frames]
     outs = [(getattr(RT, name), getattr(api.Format, fmt), ex.alloc_texture(getattr(api.Format, fmt), W, H, dev)) for name, fmt in wl["outputs"]]
     host_outs = [torch.zeros_like(t, device="cpu").pin_memory() for _, _, t in outs]
@@ -184,6 +189,8 @@ def run_product(args):
     out_bytes = sum(t.numel() * t.element_size() for _, _, t in outs)
 
     den = ex.CudaDenoiser(getattr(api.Denoiser, wl["denoiser"]), W, H, device=local)
+    if recon:
+        den.set_denoiser_settings(api.ReblurSettings(hitDistanceReconstructionMode=recon))
     stream = torch.cuda.current_stream()
 
     def settings(i):
@@ -287,7 +294,8 @@ def run_product(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": value / world / (3.6864 / (wl["published_ms"] * 1e-3)) if (W, H) == (2560, 1440) else None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["what"].format(w=W, h=H), "denoiser": wl["denoiser"],
-                       "resolution": [W, H], "settings": "library defaults",
+                       "resolution": [W, H],
+                       "settings": "library defaults" if not recon else f"library defaults + hitDistanceReconstructionMode = AREA_{args.hitdist_reconstruction.upper()} (the NRD README's setting), one lobe traced per pixel",
                        "streams_per_gpu": 1, "parallelism": f"replicas x{world} (independent frame streams, no collective)",
                        "l2_policy": f"ring of {RING} distinct frames: {RING * in_bytes // 2**20} MiB of inputs + pools > 126 MB L2",
                        "baseline_note": f"vs_baseline = per-GPU value / ({wl['published_ms']} ms per 1440p frame on an RTX 4080, NRD README)"},
@@ -339,6 +347,8 @@ def main():
     ap.add_argument("--width", type=int, default=2560)
     ap.add_argument("--height", type=int, default=1440)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hitdist-reconstruction", default="off", choices=["off", "3x3", "5x5"],
+                    help="REBLUR only: run with ReblurSettings::hitDistanceReconstructionMode (the README's 2.55 ms was taken with 3x3) on inputs with one lobe per pixel")
     ap.add_argument("--denoiser", default="reblur", choices=sorted(WORKLOADS), help="reblur = the headline workload (default); relax / sigma = BASELINE.json configs 2 and 0")
     args = ap.parse_args()
     if args.warmup < 3:

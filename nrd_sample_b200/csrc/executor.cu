@@ -21,6 +21,7 @@ namespace nrdk {
 // kernels/*.cu
 void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t stream);
 void launchReblurClassifyTiles(const ReblurConstants&, const ClassifyTilesParams&, Rows, cudaStream_t);
+void launchReblurHitDistReconstruction(const ReblurConstants&, const HitDistReconstructionParams&, bool is5x5, Rows, cudaStream_t);
 void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int flags, Rows, cudaStream_t);
 void launchReblurBlur(const ReblurConstants&, const BlurParams&, int flags, Rows, cudaStream_t);
 void launchReblurPostBlur(const ReblurConstants&, const PostBlurParams&, bool temporalStabilization, int flags, Rows, cudaStream_t);
@@ -130,6 +131,18 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         uint32_t r = done(2);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurClassifyTiles(cb, p, rows, stream);
+    } else if (is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=0") || is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1")) {
+        HitDistReconstructionParams p;
+        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        uint32_t r = done(7);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurHitDistReconstruction(cb, p, is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), rows, stream);
     } else if (is("REBLUR_PrePass.cs.hlsl")) {
         PrePassParams p;
         p.tiles = b.take<TexR8>(Format::R8_UNORM);

@@ -143,6 +143,10 @@ struct ClassifyTilesParams {
     TexR32F inViewZ;
     TexR8 outTiles;
 };
+struct HitDistReconstructionParams {
+    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
+    TexRGBA16F outDiff, outSpec;
+};
 struct PrePassParams {
     TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexRGBA16F outDiff, outSpec; TexR16F outSpecHitDistForTracking;

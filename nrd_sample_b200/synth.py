@@ -231,8 +231,10 @@ def unpack_radiance(tex: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # Frame
 # ------------------------------------------------------------------------------------------------
-def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False) -> Dict[str, torch.Tensor]:
-    """All user inputs of REBLUR_DIFFUSE_SPECULAR for one frame, in their API storage formats."""
+def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, holes: bool = False) -> Dict[str, torch.Tensor]:
+    """All user inputs of REBLUR_DIFFUSE_SPECULAR for one frame, in their API storage formats. `holes`: probabilistic lobe sampling as in
+    NRDSample — every pixel traced only one lobe this frame (checkerboard flipping per frame), the other lobe has hit distance 0 and
+    relies on ReblurSettings::hitDistanceReconstructionMode."""
     device = torch.device(device)
     cam = make_camera(frame_index, width, height, period)
     cam_prev = make_camera(frame_index - 1 if frame_index > 0 or period else 0, width, height, period)
@@ -282,6 +284,12 @@ def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period
     hit_t_s = (0.1 + 9.9 * rnd()) * (1.0 + rough)
     nhd_d = (hit_t_d / hit_dist_normalization(viewz, torch.ones_like(rough))).clamp(0, 1)
     nhd_s = (hit_t_s / hit_dist_normalization(viewz, rough)).clamp(0, 1)
+
+    if holes:
+        ys, xs = torch.meshgrid(torch.arange(height, device=device), torch.arange(width, device=device), indexing="ij")
+        checker = ((xs + ys + frame_index) & 1).bool()
+        nhd_d = torch.where(checker, nhd_d, torch.zeros_like(nhd_d))
+        nhd_s = torch.where(checker, torch.zeros_like(nhd_s), nhd_s)
 
     zero4 = torch.zeros(height, width, 4, device=device, dtype=torch.float16)
     out = {

@@ -49,6 +49,12 @@ __attribute__((visibility("default"))) int nrd_oracle_dispatch(const char* shade
             reblurClassifyTiles(cb, t[0], t[1], gw, gh);
             return 0;
         }
+        if (id == "REBLUR_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=0" ||
+            id == "REBLUR_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=1") {
+            if (texturesNum != 7) return 2;
+            reblurHitDistReconstruction(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], gw, gh, id.back() == '1' ? 2 : 1);
+            return 0;
+        }
         if (id == "REBLUR_PrePass.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
             if (texturesNum != 8) return 2;
             reblurPrePass(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], gw, gh, robust);

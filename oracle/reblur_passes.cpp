@@ -227,6 +227,81 @@ static void spatialCenter(const ReblurCtx& c, SpatialCommon& s, const Tex& gIn_N
     s.rotator = baseRotator;  // *_ROTATOR_MODE = NRD_FRAME: the per-frame rotator is used as is (common:282-305)
 }
 
+// REBLUR_HitDistReconstruction.cs.hlsl:21-167 (NRD_SIGNAL = BOTH, RADIANCE, REBLUR_USE_DECOMPRESSED_HIT_DIST_IN_RECONSTRUCTION = 0,
+// REBLUR_PERFORMANCE_MODE = 0). `border` = 1 (3x3) or 2 (5x5). The shared-memory tile holds f( clamp( pos, 0, rectSizeMinusOne ) ).
+void reblurHitDistReconstruction(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec,
+                                 Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, int border) {
+    ReblurCtx c(cb);
+    auto clampPos = [&](int& x, int& y) {
+        x = x < 0 ? 0 : (x > cb.gRectSizeMinusOne.x ? cb.gRectSizeMinusOne.x : x);
+        y = y < 0 ? 0 : (y > cb.gRectSizeMinusOne.y ? cb.gRectSizeMinusOne.y : y);
+    };
+    auto hitDistViewZ = [&](int x, int y) {  // Preload( ): { diff hitDist, spec hitDist, viewZ }, hit distances zeroed outside the denoising range
+        clampPos(x, y);
+        float viewZ = c.UnpackViewZ(gIn_ViewZ.load(x, y).x);
+        float2 hitDist = float2(gIn_Diff.load(x, y).w, gIn_Spec.load(x, y).w);
+        if (!c.IsInDenoisingRange(viewZ)) hitDist = float2(0.0f);
+        return float3(hitDist.x, hitDist.y, viewZ);
+    };
+    auto normalRoughness = [&](int x, int y) {
+        clampPos(x, y);
+        return NRD_FrontEnd_UnpackNormalAndRoughness(gIn_Normal_Roughness.load(x, y));
+    };
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = 0; py < gridH * 16; py++)
+        for (int px = 0; px < gridW * 8; px++) {
+            float isSky = gIn_Tiles.load(px >> 4, py >> 4).x;
+            if (isSky != 0.0f || px > cb.gRectSizeMinusOne.x || py > cb.gRectSizeMinusOne.y) continue;
+            float3 center = hitDistViewZ(px, py);
+            if (!c.IsInDenoisingRange(center.z)) continue;
+
+            float4 nr = normalRoughness(px, py);
+            float3 N = nr.xyz();
+            float roughness = nr.w;
+            float2 pixelUv = float2(px + 0.5f, py + 0.5f) * cb.gRectSizeInv;
+            float3 Xv = Geometry::ReconstructViewPosition(pixelUv, cb.gFrustum, center.z, cb.gOrthoMode);
+            float3 Nv = Geometry::RotateVectorInverse(cb.gViewToWorld, N);
+            float frustumSize = GetFrustumSize(cb.gMinRectDimMulUnproject, cb.gOrthoMode, center.z);
+            float2 geometryWeightParams = GetGeometryWeightParams(cb.gPlaneDistSensitivity, frustumSize, Xv, Nv);
+            float2 relaxedRoughnessWeightParams = GetRelaxedRoughnessWeightParams(roughness * roughness);
+            float diffNormalWeightParam = GetNormalWeightParam(1.0f, 1.0f);
+            float specNormalWeightParam = GetNormalWeightParam(1.0f, 1.0f, roughness);
+
+            float2 sum = float2(center.x != 0.0f ? 1000.0f : 0.0f, center.y != 0.0f ? 1000.0f : 0.0f);
+            float2 acc = float2(center.x, center.y) * sum;
+            for (int j = 0; j <= border * 2; j++)
+                for (int i = 0; i <= border * 2; i++) {
+                    float2 o = float2(float(i - border), float(j - border));
+                    if (o.x == 0.0f && o.y == 0.0f) continue;
+                    int sx = px + i - border, sy = py + j - border;
+                    float3 data = hitDistViewZ(sx, sy);
+
+                    float2 uv = pixelUv + o * cb.gRectSizeInv;
+                    float w = IsInScreenNearest(uv);
+                    w *= GetGaussianWeight(length(o) * 0.5f);
+                    float3 Xvs = Geometry::ReconstructViewPosition(uv, cb.gFrustum, data.z, cb.gOrthoMode);
+                    float NoX = dot(Nv, Xvs);
+                    w *= ComputeWeight(NoX, geometryWeightParams.x, geometryWeightParams.y);
+
+                    float4 snr = normalRoughness(sx, sy);
+                    float angle = Math::AcosApproxPositive(dot(N, snr.xyz()));
+                    float2 ww = float2(w);
+                    ww.x *= ComputeExponentialWeight(angle, diffNormalWeightParam, 0.0f);
+                    ww.y *= ComputeExponentialWeight(angle, specNormalWeightParam, 0.0f);
+                    ww.y *= ComputeExponentialWeight(snr.w * snr.w, relaxedRoughnessWeightParams.x, relaxedRoughnessWeightParams.y);
+                    ww.x = data.x == 0.0f ? 0.0f : ww.x;
+                    ww.y = data.y == 0.0f ? 0.0f : ww.y;
+
+                    acc += float2(data.x, data.y) * ww;
+                    sum += ww;
+                }
+            acc = acc / max(sum, float2(NRD_EPS));
+            float4 diff = gIn_Diff.load(px, py), spec = gIn_Spec.load(px, py);
+            gOut_Diff.store(px, py, float4(diff.xyz(), acc.x));
+            gOut_Spec.store(px, py, float4(spec.xyz(), acc.y));
+        }
+}
+
 void reblurPrePass(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec,
                    Tex& gOut_Diff, Tex& gOut_Spec, Tex& gOut_SpecHitDistForTracking, int gridW, int gridH, bool robust) {
     ReblurCtx c(cb);

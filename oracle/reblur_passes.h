@@ -24,6 +24,8 @@ struct TsTextures {
 };
 
 void reblurClassifyTiles(const ReblurCB& cb, const Tex& gIn_ViewZ, Tex& gOut_Tiles, int gridW, int gridH);
+void reblurHitDistReconstruction(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec,
+                                 Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, int border);
 void reblurPrePass(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec,
                    Tex& gOut_Diff, Tex& gOut_Spec, Tex& gOut_SpecHitDistForTracking, int gridW, int gridH, bool robustMirrorTest);
 void reblurBlur(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Data1, const Tex& gIn_Diff,

@@ -110,3 +110,39 @@ def test_restart_resets_history():
     # gMaxAccumulatedFrameNum = 0 on reset frames (Reblur.cpp:364): min(n + 1, 0) -> history length 0 everywhere
     assert ((idata & 63)[fr["_hit"]] == 0).all()
     assert len(den.last_dispatches) == 7  # RESTART does not inject clears, CLEAR_AND_RESTART does
+
+
+def test_hit_distance_reconstruction_fills_holes():
+    """ReblurSettings::hitDistanceReconstructionMode (the NRD README's benchmark setting): with one lobe traced per pixel the other lobe's
+    normalised hit distance arrives as 0; the 3x3 / 5x5 pass replaces it by a weighted average of same-surface neighbours and leaves the
+    radiance untouched. Checked on the dispatch itself."""
+    w, h = 128, 80
+    for mode, shader_tail in ((1, "MODE_5X5=0"), (2, "MODE_5X5=1")):
+        den, od, os_ = make(w, h)
+        s = api.ReblurSettings(hitDistanceReconstructionMode=mode)
+        seen = {}
+
+        def before(i, d, keys, self):
+            if d.shader.endswith(shader_tail) and "HitDistReconstruction" in d.shader:
+                seen["in"] = [self.textures[k].clone() for k in keys]
+
+        def after(i, d, keys, self):
+            if d.shader.endswith(shader_tail) and "HitDistReconstruction" in d.shader:
+                seen["out"] = [self.textures[k].clone() for k in keys]
+
+        fr = synth.reblur_frame(0, w, h, holes=True)
+        feed(den, fr)
+        den.denoise(synth.common_settings(0, w, h), settings=s, before_dispatch=before, on_dispatch=after)
+        assert "out" in seen, "the reconstruction pass must be in the dispatch list"
+        viewz = seen["in"][2]
+        inside = viewz < 5e5
+        for lobe in (0, 1):
+            src, dst = seen["in"][3 + lobe].float(), seen["out"][5 + lobe].float()
+            holes = inside & (src[..., 3] == 0)
+            assert holes.float().mean() > 0.2
+            assert torch.equal(dst[..., :3][inside], src[..., :3][inside]), "radiance passes through"
+            filled = (dst[..., 3][holes] > 0).float().mean().item()
+            assert filled > 0.97, f"mode {mode} lobe {lobe}: only {filled:.3f} of the holes got a hit distance"
+            # where data existed the result stays within the local range (the centre tap weighs 1000)
+            had = inside & (src[..., 3] > 0)
+            assert (dst[..., 3][had] - src[..., 3][had]).abs().max() < 0.05

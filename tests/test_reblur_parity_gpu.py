@@ -316,3 +316,46 @@ def test_pipelined_host_path_matches_device_path(ex, runner):
         assert torch.equal(want[f][1].view(torch.int16), got[f][1].view(torch.int16)), f"frame {f} specular"
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_hit_distance_reconstruction_parity(ex, runner, mode):
+    """ReblurSettings::hitDistanceReconstructionMode = AREA_3X3 / AREA_5X5 (REBLUR_HitDistReconstruction.cs.hlsl, the NRD README's
+    benchmark setting) on inputs where every pixel traced one lobe only: the pass itself replayed from the oracle's pre-dispatch
+    textures, then the closed loop over 6 frames."""
+    w, h = 208, 120
+    settings = api.ReblurSettings(hitDistanceReconstructionMode=mode)
+    cud, orc, g, c = make_pair(ex, runner, w, h, True)
+    flags = ex.FLAG_QUAD_INTRINSICS | ex.FLAG_ROBUST_MIRROR_TEST
+    snap, seen = {}, []
+
+    def before(i, d, keys, den):
+        if "HitDistReconstruction" in d.shader:
+            snap["t"] = [den.textures[k].clone() for k in keys]
+
+    def after(i, d, keys, den):
+        if "HitDistReconstruction" not in d.shader:
+            return
+        assert d.shader.endswith(f"MODE_5X5={mode - 1}")
+        gpu = [t.to("cuda:0") for t in snap["t"]]
+        ex.dispatch(d.shader, d.constants, [ex.texture_of(t, den.formats[k]) for t, k in zip(gpu, keys)], flags=flags)
+        torch.cuda.synchronize()
+        for j in (5, 6):
+            r = compare(gpu[j], den.textures[keys[j]], den.formats[keys[j]])
+            assert r["frac_bad"] <= 1e-4 and r["psnr"] >= 70.0, f"lobe {j - 5}: {r}"
+            seen.append(r)
+
+    keep = {}
+    cud.set_denoiser_settings(settings)
+    for f in range(6):
+        feed_both(cud, orc, runner, synth.reblur_frame(f, w, h, holes=True), keep)
+        cs = synth.common_settings(f, w, h)
+        orc.denoise(cs, settings=settings, before_dispatch=before, on_dispatch=after)
+        cud.set_common_settings(cs)
+        cud.denoise()
+        torch.cuda.synchronize()
+        for k in ("d", "s"):
+            r = compare(g[k], c[k], F16)
+            assert r["psnr"] >= 60.0 and r["frac_bad"] <= 2e-3, f"mode {mode} frame {f} {k}: {r}"
+    assert len(seen) == 12
+    cud.close()
