@@ -118,7 +118,7 @@ inline float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z;
 inline float dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 inline float length(float2 a) { return std::sqrt(dot(a, a)); }
 inline float length(float3 a) { return std::sqrt(dot(a, a)); }
-inline float3 normalize(float3 a) { return a / length(a); }
+inline float3 normalize(float3 a) { return a * rsqrt(dot(a, a)); }   // DXC lowers normalize to v * rsqrt( dot( v, v ) )
 inline float3 cross(float3 a, float3 b) { return float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 inline float3 reflect(float3 i, float3 n) { return i - 2.0f * n * dot(i, n); }
 

@@ -19,6 +19,8 @@ from nrd_sample_b200 import nrd_api as api
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_LIB_PATH = os.path.join(HERE, "_ref", "libnrd_ref.so")
+# the reference's own compute shaders compiled as C++ ( oracle/ref_build_shaders.py ): what pins the oracle's pixel math
+REF_SHADERS_PATH = os.path.join(HERE, "_ref", "libnrd_refshaders.so")
 
 
 class OracleTexture(C.Structure):
@@ -33,6 +35,12 @@ def build(force: bool = False) -> str:
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/External/NRD/Source") and not os.path.exists(REF_LIB_PATH):
         subprocess.check_call([os.path.join(HERE, "ref_build.sh")], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/External/NRD/Shaders"):
+        shim = os.path.join(HERE, "ref_shim")
+        deps = [os.path.join(shim, f) for f in os.listdir(shim)] + [os.path.join(HERE, "ref_build_shaders.py")]
+        if force or not os.path.exists(REF_SHADERS_PATH) or any(os.path.getmtime(d) > os.path.getmtime(REF_SHADERS_PATH) for d in deps):
+            import sys
+            subprocess.check_call([sys.executable, os.path.join(HERE, "ref_build_shaders.py")], stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 
@@ -49,6 +57,29 @@ def lib() -> C.CDLL:
         _lib.nrd_oracle_set_threads.argtypes = [C.c_int]
         _lib.nrd_oracle_max_threads.restype = C.c_int
     return _lib
+
+
+_ref_shaders = None
+
+
+def ref_shaders() -> Optional[C.CDLL]:
+    """libnrd_refshaders.so (prebuilt in this container from /root/reference; travels to the GPU box), or None when it was never built."""
+    global _ref_shaders
+    if _ref_shaders is None:
+        build()
+        if not os.path.exists(REF_SHADERS_PATH):
+            return None
+        _ref_shaders = C.CDLL(REF_SHADERS_PATH)
+        _ref_shaders.nrd_refshader_dispatch.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.POINTER(OracleTexture), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        _ref_shaders.nrd_refshader_dispatch.restype = C.c_int
+        _ref_shaders.nrd_refshader_name.restype = C.c_char_p
+        _ref_shaders.nrd_refshader_name.argtypes = [C.c_int]
+    return _ref_shaders
+
+
+def ref_shader_names() -> List[str]:
+    L = ref_shaders()
+    return [L.nrd_refshader_name(i).decode() for i in range(L.nrd_refshader_count())] if L else []
 
 
 # nrd::Format -> (torch dtype, channels)
@@ -101,7 +132,10 @@ def tex_desc(t: torch.Tensor, fmt: int) -> OracleTexture:
 class OracleDenoiser:
     """nrd::Instance + pools + oracle replay for ONE denoiser on host memory."""
 
-    def __init__(self, host_lib: api.NrdLibrary, denoiser: int, width: int, height: int, identifier: int = 0, quads: bool = True, robust_mirror_test: bool = False):
+    def __init__(self, host_lib: api.NrdLibrary, denoiser: int, width: int, height: int, identifier: int = 0, quads: bool = True, robust_mirror_test: bool = False,
+                 engine: str = "oracle"):
+        """engine: "oracle" = the hand-written restatement (liboracle.so); "reference" = the reference's shaders compiled as C++."""
+        self.engine = engine
         self.width, self.height, self.identifier, self.denoiser = width, height, identifier, denoiser
         self.instance = api.NrdInstance(host_lib, [(identifier, denoiser)])
         assert self.instance.result == api.Result.SUCCESS, self.instance.result
@@ -134,15 +168,18 @@ class OracleDenoiser:
         r, dispatches = self.instance.get_compute_dispatches([self.identifier])
         assert r == api.Result.SUCCESS, r
         self.last_dispatches = dispatches
-        L = lib()
+        if self.engine == "reference":
+            fn = ref_shaders().nrd_refshader_dispatch
+        else:
+            fn = lib().nrd_oracle_dispatch
         for i, d in enumerate(dispatches):
             keys = [self._resolve(b) for b in d.bindings]
             if before_dispatch:
                 before_dispatch(i, d, keys, self)
             arr = (OracleTexture * len(keys))(*[tex_desc(self.textures[k], self.formats[k]) for k in keys])
             cb = C.create_string_buffer(d.constants, len(d.constants)) if d.constants else None
-            rc = L.nrd_oracle_dispatch(d.shader.encode(), cb, len(d.constants), arr, len(keys), d.grid[0], d.grid[1], self.flags)
-            assert rc == 0, f"oracle dispatch failed rc={rc} for {d.shader}"
+            rc = fn(d.shader.encode(), cb, len(d.constants), arr, len(keys), d.grid[0], d.grid[1], self.flags)
+            assert rc == 0, f"{self.engine} dispatch failed rc={rc} for {d.shader}"
             if on_dispatch:
                 on_dispatch(i, d, keys, self)
         return dispatches

@@ -1,0 +1,136 @@
+"""Pins the CPU oracle's pixel math against the REFERENCE'S OWN SHADERS: External/NRD/Shaders/*.cs.hlsl (+ MathLib's ml.hlsli) compiled as
+C++ from where they lie under /root/reference into oracle/_ref/libnrd_refshaders.so (oracle/ref_build_shaders.py, oracle/ref_shim/hlsl_cpu.h).
+Every dispatch of every frame is replayed by both engines from the same pre-dispatch textures; every written texture must be bit-identical
+(both are fp32 CPU code without FMA contraction, so there is no tolerance to hide behind).
+
+The prebuilt .so travels to the GPU box; when it is absent and the reference tree is not mounted the tests skip and the committed fixtures
+(tests/golden/refshaders_*.pt, written by tests/golden/make_refshader_golden.py from the same engine) take over."""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+from nrd_sample_b200 import nrd_api as api, synth
+from oracle import runner
+
+RT = api.ResourceType
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+DENOISERS = {
+    "reblur": (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, synth.reblur_frame, ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST")),
+    "sigma": (api.Denoiser.SIGMA_SHADOW, synth.sigma_frame, ("OUT_SHADOW_TRANSLUCENCY",)),
+    "relax": (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, synth.relax_frame, ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1")),
+}
+
+# ( label, denoiser, width, height, frames, denoiser settings, extra frame kwargs )
+CASES = [
+    ("reblur_default", "reblur", 96, 64, 6, None, {}),
+    ("reblur_odd_size", "reblur", 100, 75, 4, None, {}),
+    ("reblur_recon3x3", "reblur", 96, 64, 4, lambda: api.ReblurSettings(hitDistanceReconstructionMode=1), {"holes": True}),
+    ("reblur_recon5x5", "reblur", 96, 64, 3, lambda: api.ReblurSettings(hitDistanceReconstructionMode=2), {"holes": True}),
+    ("reblur_no_stabilization", "reblur", 96, 64, 4, lambda: api.ReblurSettings(maxStabilizedFrameNum=0), {}),
+    ("reblur_no_prepass_no_antifirefly", "reblur", 96, 64, 4, lambda: api.ReblurSettings(diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0, enableAntiFirefly=False), {}),
+    ("sigma_default", "sigma", 96, 64, 5, None, {}),
+    ("sigma_odd_size", "sigma", 100, 75, 3, None, {}),
+    ("sigma_no_stabilization", "sigma", 96, 64, 3, lambda: api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0), {}),
+    ("relax_default", "relax", 96, 64, 5, None, {}),
+    ("relax_odd_size", "relax", 100, 75, 3, None, {}),
+    ("relax_antifirefly_3_iterations", "relax", 96, 64, 4, lambda: api.RelaxSettings(enableAntiFirefly=True, atrousIterationNum=3), {}),
+    ("relax_8_iterations_no_prepass", "relax", 96, 64, 3, lambda: api.RelaxSettings(atrousIterationNum=8, diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0,
+                                                                                  enableRoughnessEdgeStopping=False), {}),
+]
+
+
+def make_denoiser(which, w, h, engine="oracle"):
+    den_id, _, outputs = DENOISERS[which]
+    den = runner.OracleDenoiser(runner.default_host_library(), den_id, w, h, engine=engine)
+    for o in outputs:
+        den.set_user_texture(getattr(RT, o), runner.alloc_texture(runner.USER_FORMATS[getattr(RT, o)], w, h))
+    return den
+
+
+needs_refshaders = pytest.mark.skipif(runner.ref_shaders() is None, reason="oracle/_ref/libnrd_refshaders.so not built (reference tree not mounted)")
+
+
+@needs_refshaders
+def test_every_shader_the_host_library_emits_is_compiled_from_the_reference():
+    names = set(runner.ref_shader_names())
+    for which, (den_id, _, _) in DENOISERS.items():
+        inst = api.NrdInstance(runner.default_host_library(), [(0, den_id)])
+        for s in set(inst.shader_identifiers()):
+            if "Validation" in s:
+                continue   # debug overlay, out of scope
+            assert s in names, f"{s} is not in libnrd_refshaders.so"
+
+
+@needs_refshaders
+@pytest.mark.parametrize("label,which,w,h,frames,make_settings,frame_kwargs", CASES, ids=[c[0] for c in CASES])
+def test_oracle_is_bit_identical_to_the_reference_shaders_per_dispatch(label, which, w, h, frames, make_settings, frame_kwargs):
+    den = make_denoiser(which, w, h)
+    fn = runner.ref_shaders().nrd_refshader_dispatch
+    snap, checked, seen = {}, [0], set()
+
+    def before(i, d, keys, self):
+        snap["t"] = [self.textures[k].clone() for k in keys]
+
+    def after(i, d, keys, self):
+        ref = snap["t"]
+        arr = (runner.OracleTexture * len(keys))(*[runner.tex_desc(t, self.formats[k]) for t, k in zip(ref, keys)])
+        cb = C.create_string_buffer(d.constants, len(d.constants)) if d.constants else None
+        rc = fn(d.shader.encode(), cb, len(d.constants), arr, len(keys), d.grid[0], d.grid[1], 0)
+        assert rc == 0, f"reference shader {d.shader} rc={rc}"
+        seen.add(d.shader)
+        for j, (b, k) in enumerate(zip(d.bindings, keys)):
+            if b.descriptor != int(api.DescriptorType.STORAGE_TEXTURE):
+                assert torch.equal(ref[j], self.textures[k]), f"{d.name}: input {j} was modified"
+                continue
+            same = torch.equal(ref[j], self.textures[k])
+            if not same:
+                a, o = ref[j].float().flatten(), self.textures[k].float().flatten()
+                bad = (ref[j] != self.textures[k]).float().mean().item()
+                raise AssertionError(f"{label} frame {frame} {d.name} ({d.shader}) output {j}: {bad:.2e} of the texels differ, max |d| {(a - o).abs().max().item():.3g}")
+            checked[0] += 1
+
+    settings = make_settings() if make_settings else None
+    for frame in range(frames):
+        for k, v in DENOISERS[which][1](frame, w, h, **frame_kwargs).items():
+            den.set_user_texture(getattr(RT, k), v)
+        den.denoise(synth.common_settings(frame, w, h), settings=settings, before_dispatch=before, on_dispatch=after)
+    assert checked[0] >= frames * 5
+    assert any("Clear" in s for s in seen) and len(seen) >= 6
+
+
+@needs_refshaders
+@pytest.mark.parametrize("which", ["reblur", "sigma", "relax"])
+def test_closed_loop_with_the_reference_shaders_as_the_engine(which):
+    """The whole recurrence (history feedback) executed by the reference's shaders, against the oracle: final outputs identical."""
+    w, h, frames = 112, 80, 5
+    a, b = make_denoiser(which, w, h, "oracle"), make_denoiser(which, w, h, "reference")
+    for frame in range(frames):
+        fr = DENOISERS[which][1](frame, w, h)
+        cs = synth.common_settings(frame, w, h)
+        for den in (a, b):
+            for k, v in fr.items():
+                den.set_user_texture(getattr(RT, k), v)
+            den.denoise(cs)
+        for o in DENOISERS[which][2]:
+            key = (int(getattr(RT, o)), 0)
+            assert torch.equal(a.textures[key], b.textures[key]), f"{which} frame {frame} {o}"
+
+
+@pytest.mark.parametrize("which", ["reblur", "sigma", "relax"])
+def test_oracle_reproduces_the_committed_reference_shader_outputs(which):
+    """Runs everywhere (GPU box included): the fixture holds the outputs the reference's shaders produced in this container."""
+    path = os.path.join(GOLDEN_DIR, f"refshaders_{which}_80x48.pt")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    g = torch.load(path)
+    w, h = g["width"], g["height"]
+    den = make_denoiser(which, w, h)
+    for frame in range(g["frames"]):
+        for k, v in DENOISERS[which][1](frame, w, h).items():
+            den.set_user_texture(getattr(RT, k), v)
+        den.denoise(synth.common_settings(frame, w, h))
+    for o, ref in g["outputs"].items():
+        assert torch.equal(den.textures[(int(getattr(RT, o)), 0)], ref), f"{which} {o} differs from the reference-shader fixture"
