@@ -3,7 +3,8 @@
 //
 // Minimal HLSL-flavoured scalar vector types so the pass restatements in this directory can follow the
 // reference shaders (External/NRD/Shaders/*.hlsl*) line by line. Plain fp32, no intrinsics, no SIMD.
-// PARITY UNPINNED at the pixel level: the reference ships no golden images.
+// PINNED: bit-identical, dispatch by dispatch, to the reference's own shaders compiled as C++
+// (oracle/_ref/libnrd_refshaders.so, tests/test_oracle_vs_reference_shaders.py).
 #pragma once
 #include <cmath>
 #include <cstdint>

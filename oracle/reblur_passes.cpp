@@ -1,6 +1,6 @@
-// TEST INFRASTRUCTURE — CPU oracle (see hlsl_like.h). PARITY UNPINNED at pixel level: the reference ships no
-// golden images; this file is a hand restatement of the HLSL, pinned only through the reference host library's
-// dispatch streams/constants (tests/test_dispatch_stream.py) and MathLib spot checks (tests/test_oracle_math.py).
+// TEST INFRASTRUCTURE — CPU oracle (see hlsl_like.h). A hand restatement of the HLSL.
+// PINNED: bit-identical, dispatch by dispatch, to the reference's own shaders compiled as C++
+// (oracle/_ref/libnrd_refshaders.so, tests/test_oracle_vs_reference_shaders.py).
 //
 // REBLUR_DIFFUSE_SPECULAR passes (NRD_SIGNAL=BOTH, NRD_MODE=RADIANCE), one scalar function per compute shader:
 //   ClassifyTiles          External/NRD/Shaders/REBLUR_ClassifyTiles.cs.hlsl:21-55

@@ -65,7 +65,12 @@ def transform(text: str, identifier: str, namespace: str) -> str:
     # arguments have side effects are ml.hlsli's uint2( GetUint( ), GetUint( ) ) / uint4( GetUint2( ), GetUint2( ) ) -> braces fix the order
     text = re.sub(r"\b(uint[24])\s*\(\s*(GetUint2?\s*\([^()]*\))\s*,\s*(GetUint2?\s*\([^()]*\))\s*\)", r"\1{ \2, \3 }", text)
 
-    text = re.sub(r"\bgroupshared\b", "static thread_local", text)
+    # groupshared T name[ .. ][ .. ]; -> thread_local storage ( one OS thread executes a group ) that the runtime zero-fills per group
+    text = re.sub(r"\bgroupshared\s+([A-Za-z_]\w*)\s+(\w+)\s*((?:\[[^\]]*\]\s*)*);",
+                  lambda k: f"static thread_local {k.group(1)} {k.group(2)}{k.group(3)}; static hlsl::SmemRegistrar _smem_{k.group(2)}( &g_module, []() -> void* {{ return (void*)&{k.group(2)}; }}, sizeof( {k.group(2)} ) );",
+                  text)
+    if re.search(r"\bgroupshared\b", text):
+        raise SystemExit(f"{identifier}: unparsed groupshared declaration")
     # ( Type )0 zero-initialisation of structs
     text = re.sub(r"=\s*\(\s*([A-Z]\w*)\s*\)\s*0\s*;", r"= \1();", text)
 

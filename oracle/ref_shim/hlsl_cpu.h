@@ -404,10 +404,16 @@ template <class T> struct RWTexture2D {
 
 // ------------------------------------------------------------------------------------------------ per-shader registry
 struct ConstReg { void* p; int kind; };   // kind: number of 32-bit words ( 1..4 ), 16 = float4x4
+struct SmemReg { void* (*address)(); size_t bytes; };   // a groupshared array: thread_local, so its address is asked for on the executing thread
 struct ShaderModule {
     std::vector<ConstReg> constants;
     std::vector<TexData*> srv, uav;
+    std::vector<SmemReg> smem;
 };
+// Group-shared memory starts every group zero-filled. ( On a GPU it starts with leftovers: the RELAX / REBLUR shaders skip their preload on sky
+// tiles and still read it — e.g. RELAX_AtrousSmem.cs.hlsl:145-150 writes gOut_MaterialID from it — so those texels are garbage by design;
+// zero makes them reproducible. )
+struct SmemRegistrar { SmemRegistrar(ShaderModule* m, void* (*address)(), size_t bytes) { m->smem.push_back({address, bytes}); } };
 struct ConstRegistrar {
     template <class T> ConstRegistrar(ShaderModule* m, T* p) {
         int kind = 0;
@@ -480,7 +486,7 @@ template <class D, class V> inline void InterlockedMax(D& d, const V& v) { if ((
 template <class D, class V> inline void InterlockedMin(D& d, const V& v) { if ((D)v < d) d = (D)v; }
 template <class D, class V> inline void InterlockedOr(D& d, const V& v) { d = (D)(d | (D)v); }
 
-void runGroup(void (*entry)(uint3, uint3, uint3, uint), uint3 groupID, uint3 groupSize, bool useFibers);
+void runGroup(const ShaderModule& module, void (*entry)(uint3, uint3, uint3, uint), uint3 groupID, uint3 groupSize, bool useFibers);
 
 // what one compiled shader permutation exports
 struct ShaderEntry {

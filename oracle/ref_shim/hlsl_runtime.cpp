@@ -25,8 +25,9 @@ static void fiberMain() {
     f.state = 2;   // returns to g.sched through uc_link
 }
 
-void runGroup(void (*entry)(uint3, uint3, uint3, uint), uint3 groupID, uint3 groupSize, bool useFibers) {
+void runGroup(const ShaderModule& module, void (*entry)(uint3, uint3, uint3, uint), uint3 groupID, uint3 groupSize, bool useFibers) {
     GroupRun& g = t_group;
+    for (const SmemReg& r : module.smem) memset(r.address(), 0, r.bytes);
     g.entry = entry; g.groupID = groupID; g.groupSize = groupSize; g.useFibers = useFibers;
     const int n = (int)(groupSize.x * groupSize.y * groupSize.z);
     if (!useFibers) {
@@ -84,7 +85,7 @@ __attribute__((visibility("default"))) int nrd_refshader_dispatch(const char* sh
     const uint3 gs(e.gx, e.gy, e.gz);
     const long groups = (long)gridW * (long)gridH;
 #pragma omp parallel for schedule(dynamic, 1)
-    for (long k = 0; k < groups; k++) runGroup(e.entry, uint3((uint)(k % gridW), (uint)(k / gridW), 0u), gs, e.useFibers);
+    for (long k = 0; k < groups; k++) runGroup(m, e.entry, uint3((uint)(k % gridW), (uint)(k / gridW), 0u), gs, e.useFibers);
     return 0;
 }
 __attribute__((visibility("default"))) int nrd_refshader_count() { return (int)registry().size(); }

@@ -1,5 +1,6 @@
-// TEST INFRASTRUCTURE — CPU oracle (see hlsl_like.h). NOT part of the product; parity unpinned at the pixel level
-// (the reference's HLSL cannot be executed here).
+// TEST INFRASTRUCTURE — CPU oracle (see hlsl_like.h). NOT part of the product.
+// PINNED: bit-identical, dispatch by dispatch, to the reference's own shaders compiled as C++
+// (oracle/_ref/libnrd_refshaders.so, tests/test_oracle_vs_reference_shaders.py).
 //
 // RELAX_DIFFUSE_SPECULAR_SH (NRD_SIGNAL = BOTH, NRD_MODE = SH) restated from /root/reference/External/NRD/Shaders:
 //   RELAX_ClassifyTiles.cs.hlsl:21-51, RELAX_PrePass.cs.hlsl:21-385, RELAX_TemporalAccumulation.cs.hlsl:21-942,

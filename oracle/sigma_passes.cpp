@@ -1,5 +1,6 @@
-// TEST INFRASTRUCTURE — CPU oracle (see hlsl_like.h). NOT part of the product; parity unpinned at the pixel level
-// (the reference's HLSL cannot be executed here).
+// TEST INFRASTRUCTURE — CPU oracle (see hlsl_like.h). NOT part of the product.
+// PINNED: bit-identical, dispatch by dispatch, to the reference's own shaders compiled as C++
+// (oracle/_ref/libnrd_refshaders.so, tests/test_oracle_vs_reference_shaders.py).
 //
 // SIGMA_SHADOW (TRANSLUCENCY = 0) restated from /root/reference/External/NRD/Shaders:
 //   SIGMA_ClassifyTiles.cs.hlsl:24-91, SIGMA_SmoothTiles.cs.hlsl:21-58, SIGMA_Copy.cs.hlsl:19-32,

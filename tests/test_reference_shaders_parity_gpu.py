@@ -1,0 +1,129 @@
+"""CUDA executor against the REFERENCE'S OWN SHADERS (External/NRD/Shaders/*.cs.hlsl compiled as C++ into oracle/_ref/libnrd_refshaders.so,
+prebuilt in the build container) — no hand-written oracle in between.
+
+* per dispatch: every pass of 4 frames replayed through nrdcuDispatch from the reference engine's own pre-dispatch textures;
+* closed loop: nrdcuDenoise over 8 frames against the reference shaders running the whole recurrence.
+The reference engine has the reference's bit-fragile predicates (DESIGN.md "chaotic predicates"), so REBLUR runs in faithful mode here;
+the strict-mode numbers live in tests/test_reblur_parity_gpu.py."""
+import json
+import os
+
+import pytest
+import torch
+
+from nrd_sample_b200 import nrd_api as api, synth
+from tests.util import compare
+
+pytestmark = pytest.mark.gpu
+RT = api.ResourceType
+
+CASES = {
+    "reblur": (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, "reblur_frame", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur"),
+    "sigma": (api.Denoiser.SIGMA_SHADOW, "sigma_frame", ("OUT_SHADOW_TRANSLUCENCY",), "sigma"),
+    "relax": (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, "relax_frame", ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur"),
+}
+# worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
+LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0)}
+
+
+@pytest.fixture(scope="module")
+def ex():
+    from nrd_sample_b200 import executor
+    assert torch.cuda.is_available()
+    return executor
+
+
+@pytest.fixture(scope="module")
+def runner():
+    from oracle import runner as r
+    if r.ref_shaders() is None:
+        pytest.skip("oracle/_ref/libnrd_refshaders.so was not shipped")
+    return r
+
+
+def reference_engine(runner, which, w, h):
+    den_id, _, outputs, _ = CASES[which]
+    den = runner.OracleDenoiser(runner.default_host_library(), den_id, w, h, engine="reference")
+    for o in outputs:
+        den.set_user_texture(getattr(RT, o), runner.alloc_texture(runner.USER_FORMATS[getattr(RT, o)], w, h))
+    return den
+
+
+@pytest.mark.parametrize("which", list(CASES))
+def test_each_dispatch_against_the_reference_shaders(ex, runner, which):
+    w, h, frames = 208, 120, 4
+    ref = reference_engine(runner, which, w, h)
+    flags = ex.FLAG_QUAD_INTRINSICS
+    snap, worst = {}, {}
+
+    def before(i, d, keys, den):
+        snap["t"] = [den.textures[k].clone() for k in keys]
+
+    def after(i, d, keys, den):
+        gpu = [t.to("cuda:0") for t in snap["t"]]
+        ex.dispatch(d.shader, d.constants, [ex.texture_of(g, den.formats[k]) for g, k in zip(gpu, keys)], flags=flags)
+        torch.cuda.synchronize()
+        for j, (b, k) in enumerate(zip(d.bindings, keys)):
+            if b.descriptor != int(api.DescriptorType.STORAGE_TEXTURE):
+                continue
+            fmt = den.formats[k]
+            r = compare(gpu[j], den.textures[k], fmt, layout=CASES[which][3])
+            key = (d.name, j, api.Format(fmt).name)
+            if key not in worst or r["frac_bad"] > worst[key]["frac_bad"]:
+                worst[key] = r
+
+    for f in range(frames):
+        for k, v in getattr(synth, CASES[which][1])(f, w, h).items():
+            ref.set_user_texture(getattr(RT, k), v)
+        ref.denoise(synth.common_settings(f, w, h), before_dispatch=before, on_dispatch=after)
+
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump({" | ".join(map(str, k)): {"frac_bad": v["frac_bad"], "psnr": v["psnr"], "max_abs": v["max_abs"]} for k, v in worst.items()},
+              open(f"gpurun_out/refshader_per_dispatch_{which}.json", "w"), indent=1)
+    limit = LIMITS[which][0]
+    for key, r in worst.items():
+        spatial = which == "reblur" and any(p in key[0] for p in ("Pre-pass", "Blur", "Post-blur"))
+        if spatial and key[2] == "RGBA16_SFLOAT":
+            # the reference's tap weight is 1 instead of the Gaussian when any( uv != MirrorUv( uv ) ), which is decided by the last mantissa bit
+            # of the tap position ( DESIGN.md "chaotic predicates" ): an FMA-contracting GPU flips it on a third of the taps, so texel-wise
+            # agreement is not defined for these passes in faithful mode — the image is ( measured: 60-74 dB )
+            assert r["psnr"] >= 55.0, f"{key}: {r}"
+            continue
+        lim = 5e-2 if (which == "reblur" and key[2] == "R32_UINT") else limit   # data2's fp16 curvature on the static first frame, see test_reblur_parity_gpu
+        assert r["frac_bad"] <= lim, f"{key}: {r}"
+
+
+@pytest.mark.parametrize("which", list(CASES))
+def test_closed_loop_against_the_reference_shaders(ex, runner, which):
+    w, h, frames = 256, 144, 8
+    den_id, frame_fn, outputs, _ = CASES[which]
+    ref = reference_engine(runner, which, w, h)
+    cud = ex.CudaDenoiser(den_id, w, h, flags=ex.FLAG_QUAD_INTRINSICS)
+    gout = {}
+    for o in outputs:
+        fmt = runner.USER_FORMATS[getattr(RT, o)]
+        gout[o] = ex.alloc_texture(fmt, w, h, "cuda:0")
+        cud.set_user_texture(getattr(RT, o), gout[o], fmt)
+    keep, log = {}, []
+    for f in range(frames):
+        for k, v in getattr(synth, frame_fn)(f, w, h).items():
+            rt = getattr(RT, k)
+            ref.set_user_texture(rt, v)
+            keep[k] = v.to("cuda:0")
+            cud.set_user_texture(rt, keep[k], runner.USER_FORMATS[rt])
+        cs = synth.common_settings(f, w, h)
+        ref.denoise(cs)
+        cud.set_common_settings(cs)
+        cud.denoise()
+        torch.cuda.synchronize()
+        for o in outputs:
+            fmt = runner.USER_FORMATS[getattr(RT, o)]
+            g, c = gout[o], ref.textures[(int(getattr(RT, o)), 0)]
+            if o.endswith("SH1"):
+                g, c = g[..., :3], c[..., :3]
+            r = compare(g, c, fmt, layout=CASES[which][3])
+            log.append((f, o, r["psnr"], r["frac_bad"]))
+            assert r["psnr"] >= LIMITS[which][1], f"{which} frame {f} {o}: {r}"
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(log, open(f"gpurun_out/refshader_closed_loop_{which}.json", "w"))
+    cud.close()

@@ -1,5 +1,5 @@
 """CPU-side checks of the RELAX_DIFFUSE_SPECULAR_SH oracle (oracle/relax_passes.cpp) and of the synthetic SH input generator:
-regression fixture, dispatch list, denoising quality and invariants (no reference pixels exist — parity unpinned)."""
+regression fixture, dispatch list, denoising quality and invariants (the pin against the reference's shaders is tests/test_oracle_vs_reference_shaders.py)."""
 import os
 
 import torch

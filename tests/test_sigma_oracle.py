@@ -1,5 +1,5 @@
 """CPU-side checks of the SIGMA_SHADOW oracle (oracle/sigma_passes.cpp) and of the synthetic shadow generator:
-a regression fixture, behavioural properties (no reference pixels exist — parity unpinned), and
+a regression fixture, behavioural properties (the pin against the reference's shaders is tests/test_oracle_vs_reference_shaders.py), and
 BASELINE.json config 0: the single-pass SIGMA blur on a 512x512 tile as a CPU scalar run."""
 import ctypes as C
 import os
