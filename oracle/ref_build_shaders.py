@@ -53,7 +53,7 @@ IDENTIFIERS = [
     "RELAX_Atrous.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=SH",
     "RELAX_SplitScreen.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=SH",
 ]
-CXXFLAGS = ["-std=c++20", "-O1", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fvisibility=hidden", "-w", "-fmax-errors=25", "-I", SHIM]
+CXXFLAGS = ["-std=c++20", "-O2", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fvisibility=hidden", "-w", "-fmax-errors=25", "-I", SHIM]
 
 
 def cxx_for(identifier: str) -> str:

@@ -74,6 +74,7 @@ def ref_shaders() -> Optional[C.CDLL]:
         _ref_shaders.nrd_refshader_dispatch.restype = C.c_int
         _ref_shaders.nrd_refshader_name.restype = C.c_char_p
         _ref_shaders.nrd_refshader_name.argtypes = [C.c_int]
+        _ref_shaders.nrd_refshader_set_threads.argtypes = [C.c_int]
     return _ref_shaders
 
 
