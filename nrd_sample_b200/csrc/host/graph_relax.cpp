@@ -1,5 +1,5 @@
-// RELAX_DIFFUSE_SPECULAR_SH pass graph and per-frame constants.
-// Pool layout and bindings: External/NRD/Source/Denoisers/Relax_DiffuseSpecularSh.hpp:13-382.
+// RELAX_DIFFUSE_SPECULAR_SH / RELAX_DIFFUSE_SPECULAR pass graphs and per-frame constants.
+// Pool layout and bindings: External/NRD/Source/Denoisers/Relax_DiffuseSpecularSh.hpp:13-382, Relax_DiffuseSpecular.hpp:13-312.
 // Per-frame pass selection: External/NRD/Source/Relax.cpp:186-296. Constants: Relax.cpp:52-184.
 #include <algorithm>
 #include <cmath>
@@ -62,11 +62,13 @@ const uint32_t kCb = sizeof(RelaxConstants);
 
 }  // namespace
 
-void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
+// RELAX_DIFFUSE_SPECULAR is the same graph without the SH1 textures (Relax_DiffuseSpecular.hpp:13-312): the pool enums above are the SH
+// ones, `Pm` / `Tr` compact them when `sh` is false.
+void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
     new (&d.settings.relax) RelaxSettings();
     d.settingsSize = sizeof(RelaxSettings);
 
-    for (int i = 0; i < 8; i++) addPermanent(Format::RGBA16_SFLOAT);  // spec / diff x { normal, responsive } x { SH0, SH1 } history
+    for (int i = 0; i < (sh ? 8 : 4); i++) addPermanent(Format::RGBA16_SFLOAT);  // spec / diff x { normal, responsive } ( x { SH0, SH1 } ) history
     addPermanent(Format::R16_SFLOAT);   // reflection hit T (ping)
     addPermanent(Format::R16_SFLOAT);   // reflection hit T (pong)
     addPermanent(Format::R8_UNORM);     // history length
@@ -74,24 +76,38 @@ void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
     addPermanent(Format::R8_UNORM);     // prev material ID
     addPermanent(Format::R32_SFLOAT);   // prev viewZ
 
-    for (int i = 0; i < 8; i++) addTransient(Format::RGBA16_SFLOAT);
+    for (int i = 0; i < (sh ? 8 : 4); i++) addTransient(Format::RGBA16_SFLOAT);
     addTransient(Format::R8_UNORM);      // specular reprojection confidence
     addTransient(Format::R8_UNORM, 16);  // tiles
     addTransient(Format::R8_UNORM);      // history length
 
-    auto U = [](ResourceType t) { return Slot::user(t); };
-    auto Pm = [](uint16_t i) { return Slot::perm(i); };
-    auto Tr = [](uint16_t i) { return Slot::tran(i); };
+    auto U = [sh](ResourceType t) {
+        if (!sh) {
+            if (t == ResourceType::IN_SPEC_SH0) t = ResourceType::IN_SPEC_RADIANCE_HITDIST;
+            else if (t == ResourceType::IN_DIFF_SH0) t = ResourceType::IN_DIFF_RADIANCE_HITDIST;
+            else if (t == ResourceType::OUT_SPEC_SH0) t = ResourceType::OUT_SPEC_RADIANCE_HITDIST;
+            else if (t == ResourceType::OUT_DIFF_SH0) t = ResourceType::OUT_DIFF_RADIANCE_HITDIST;
+        }
+        return Slot::user(t);
+    };
+    // without SH1: transients keep their order; the permanent histories are spec, diff, spec responsive, diff responsive (Relax_DiffuseSpecular.hpp:17-22)
+    auto Pm = [sh](uint16_t i) {
+        static const uint16_t kNoSh[8] = {0, 0, 2, 2, 1, 1, 3, 3};
+        return Slot::perm(sh ? i : (uint16_t)(i < 8 ? kNoSh[i] : i - 4));
+    };
+    auto Tr = [sh](uint16_t i) { return Slot::tran(sh ? i : (uint16_t)(i < 8 ? i / 2 : i - 4)); };
     const Slot dummy = U(ResourceType::IN_VIEWZ);
-    const std::string sig = "|NRD_SIGNAL=BOTH|NRD_MODE=SH";
+    const std::string sig = sh ? "|NRD_SIGNAL=BOTH|NRD_MODE=SH" : "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE";
+    const std::string prefix = sh ? "RELAX_DiffuseSpecularSh - " : "RELAX_DiffuseSpecular - ";
+    auto name = [&](const char* pass) { return intern(prefix + pass); };
 
-    beginPass("RELAX_DiffuseSpecularSh - Classify tiles");
+    beginPass(name("Classify tiles"));
     in(U(ResourceType::IN_VIEWZ));
     out(Tr(T_TILES));
     emit("RELAX_ClassifyTiles.cs.hlsl", 16, 16, kCb);
 
     for (int i = 0; i < 2; i++) {
-        beginPass("RELAX_DiffuseSpecularSh - Hit distance reconstruction");
+        beginPass(name("Hit distance reconstruction"));
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(U(ResourceType::IN_VIEWZ));
@@ -104,24 +120,24 @@ void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
 
     for (int i = 0; i < 2; i++) {
         const bool afterReconstruction = i & 1;
-        beginPass("RELAX_DiffuseSpecularSh - Pre-pass");
+        beginPass(name("Pre-pass"));
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(U(ResourceType::IN_VIEWZ));
         in(afterReconstruction ? Tr(T_SPEC_ILLUM_PING) : U(ResourceType::IN_SPEC_SH0));
         in(afterReconstruction ? Tr(T_DIFF_ILLUM_PING) : U(ResourceType::IN_DIFF_SH0));
-        in(U(ResourceType::IN_SPEC_SH1));
-        in(U(ResourceType::IN_DIFF_SH1));
+        if (sh) in(U(ResourceType::IN_SPEC_SH1));
+        if (sh) in(U(ResourceType::IN_DIFF_SH1));
         out(U(ResourceType::OUT_SPEC_SH0));
         out(U(ResourceType::OUT_DIFF_SH0));
-        out(U(ResourceType::OUT_SPEC_SH1));
-        out(U(ResourceType::OUT_DIFF_SH1));
+        if (sh) out(U(ResourceType::OUT_SPEC_SH1));
+        if (sh) out(U(ResourceType::OUT_DIFF_SH1));
         emit("RELAX_PrePass.cs.hlsl" + sig, 16, 16, kCb);
     }
 
     for (int i = 0; i < 4; i++) {
         const bool hasMix = (i >> 1) & 1, hasConfidence = i & 1;
-        beginPass("RELAX_DiffuseSpecularSh - Temporal accumulation");
+        beginPass(name("Temporal accumulation"));
         in(Tr(T_TILES));
         in(U(ResourceType::IN_MV));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
@@ -140,12 +156,12 @@ void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
         in(Pm(P_REFLECTION_HIT_T_PREV), Pm(P_REFLECTION_HIT_T_CURR));
         in(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
         in(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
-        in(U(ResourceType::OUT_SPEC_SH1));
-        in(U(ResourceType::OUT_DIFF_SH1));
-        in(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV_SH1));
-        in(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV_SH1));
-        in(Pm(P_SPEC_ILLUM_PREV_SH1));
-        in(Pm(P_DIFF_ILLUM_PREV_SH1));
+        if (sh) in(U(ResourceType::OUT_SPEC_SH1));
+        if (sh) in(U(ResourceType::OUT_DIFF_SH1));
+        if (sh) in(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV_SH1));
+        if (sh) in(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV_SH1));
+        if (sh) in(Pm(P_SPEC_ILLUM_PREV_SH1));
+        if (sh) in(Pm(P_DIFF_ILLUM_PREV_SH1));
         out(Tr(T_HISTORY_LENGTH));
         out(Tr(T_SPEC_ILLUM_PING));
         out(Tr(T_DIFF_ILLUM_PING));
@@ -153,29 +169,29 @@ void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
         out(Tr(T_DIFF_ILLUM_PONG));
         out(Pm(P_REFLECTION_HIT_T_CURR), Pm(P_REFLECTION_HIT_T_PREV));
         out(Tr(T_SPEC_REPROJECTION_CONFIDENCE));
-        out(Tr(T_SPEC_ILLUM_PING_SH1));
-        out(Tr(T_DIFF_ILLUM_PING_SH1));
-        out(Tr(T_SPEC_ILLUM_PONG_SH1));
-        out(Tr(T_DIFF_ILLUM_PONG_SH1));
+        if (sh) out(Tr(T_SPEC_ILLUM_PING_SH1));
+        if (sh) out(Tr(T_DIFF_ILLUM_PING_SH1));
+        if (sh) out(Tr(T_SPEC_ILLUM_PONG_SH1));
+        if (sh) out(Tr(T_DIFF_ILLUM_PONG_SH1));
         emit("RELAX_TemporalAccumulation.cs.hlsl" + sig, 8, 16, kCb);
     }
 
-    beginPass("RELAX_DiffuseSpecularSh - History fix");
+    beginPass(name("History fix"));
     in(Tr(T_TILES));
     in(Tr(T_HISTORY_LENGTH));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(U(ResourceType::IN_VIEWZ));
     in(Tr(T_SPEC_ILLUM_PING));  // normal history
     in(Tr(T_DIFF_ILLUM_PING));
-    in(Tr(T_SPEC_ILLUM_PING_SH1));
-    in(Tr(T_DIFF_ILLUM_PING_SH1));
+    if (sh) in(Tr(T_SPEC_ILLUM_PING_SH1));
+    if (sh) in(Tr(T_DIFF_ILLUM_PING_SH1));
     out(Tr(T_SPEC_ILLUM_PONG));  // responsive history
     out(Tr(T_DIFF_ILLUM_PONG));
-    out(Tr(T_SPEC_ILLUM_PONG_SH1));
-    out(Tr(T_DIFF_ILLUM_PONG_SH1));
+    if (sh) out(Tr(T_SPEC_ILLUM_PONG_SH1));
+    if (sh) out(Tr(T_DIFF_ILLUM_PONG_SH1));
     emit("RELAX_HistoryFix.cs.hlsl" + sig, 8, 8, kCb);
 
-    beginPass("RELAX_DiffuseSpecularSh - History clamping");
+    beginPass(name("History clamping"));
     in(Tr(T_TILES));
     in(U(ResourceType::IN_VIEWZ));
     in(Tr(T_HISTORY_LENGTH));
@@ -185,29 +201,29 @@ void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
     in(Tr(T_DIFF_ILLUM_PING));
     in(Tr(T_SPEC_ILLUM_PONG));
     in(Tr(T_DIFF_ILLUM_PONG));
-    in(Tr(T_SPEC_ILLUM_PING_SH1));
-    in(Tr(T_DIFF_ILLUM_PING_SH1));
-    in(Tr(T_SPEC_ILLUM_PONG_SH1));
-    in(Tr(T_DIFF_ILLUM_PONG_SH1));
+    if (sh) in(Tr(T_SPEC_ILLUM_PING_SH1));
+    if (sh) in(Tr(T_DIFF_ILLUM_PING_SH1));
+    if (sh) in(Tr(T_SPEC_ILLUM_PONG_SH1));
+    if (sh) in(Tr(T_DIFF_ILLUM_PONG_SH1));
     out(Pm(P_HISTORY_LENGTH_PREV));
     out(Pm(P_SPEC_ILLUM_PREV));
     out(Pm(P_DIFF_ILLUM_PREV));
     out(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV));
     out(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV));
-    out(Pm(P_SPEC_ILLUM_PREV_SH1));
-    out(Pm(P_DIFF_ILLUM_PREV_SH1));
-    out(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV_SH1));
-    out(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV_SH1));
+    if (sh) out(Pm(P_SPEC_ILLUM_PREV_SH1));
+    if (sh) out(Pm(P_DIFF_ILLUM_PREV_SH1));
+    if (sh) out(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV_SH1));
+    if (sh) out(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV_SH1));
     emit("RELAX_HistoryClamping.cs.hlsl" + sig, 8, 8, kCb);
 
-    beginPass("RELAX_DiffuseSpecularSh - Copy");
+    beginPass(name("Copy"));
     in(Pm(P_SPEC_ILLUM_PREV));
     in(Pm(P_DIFF_ILLUM_PREV));
     out(U(ResourceType::OUT_SPEC_SH0));
     out(U(ResourceType::OUT_DIFF_SH0));
     emit("RELAX_Copy.cs.hlsl" + sig, 8, 8, kCb);
 
-    beginPass("RELAX_DiffuseSpecularSh - Anti-firefly");
+    beginPass(name("Anti-firefly"));
     in(Tr(T_TILES));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(U(ResourceType::IN_VIEWZ));
@@ -221,7 +237,7 @@ void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
         const bool hasConfidence = i & 1;
         for (uint32_t j = 0; j < kAtrousVariants; j++) {
             const bool smem = j == 0, even = j % 2 == 0, last = j > 2;
-            beginPass(smem ? "RELAX_DiffuseSpecularSh - A-trous (SMEM)" : "RELAX_DiffuseSpecularSh - A-trous");
+            beginPass(smem ? name("A-trous (SMEM)") : name("A-trous"));
             in(Tr(T_TILES));
             in(Tr(T_HISTORY_LENGTH));
             in(U(ResourceType::IN_NORMAL_ROUGHNESS));
@@ -237,11 +253,11 @@ void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
             in(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
             in(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
             if (smem) {
-                in(Pm(P_SPEC_ILLUM_PREV_SH1));
-                in(Pm(P_DIFF_ILLUM_PREV_SH1));
+                if (sh) in(Pm(P_SPEC_ILLUM_PREV_SH1));
+                if (sh) in(Pm(P_DIFF_ILLUM_PREV_SH1));
             } else {
-                in(even ? Tr(T_SPEC_ILLUM_PONG_SH1) : Tr(T_SPEC_ILLUM_PING_SH1));
-                in(even ? Tr(T_DIFF_ILLUM_PONG_SH1) : Tr(T_DIFF_ILLUM_PING_SH1));
+                if (sh) in(even ? Tr(T_SPEC_ILLUM_PONG_SH1) : Tr(T_SPEC_ILLUM_PING_SH1));
+                if (sh) in(even ? Tr(T_DIFF_ILLUM_PONG_SH1) : Tr(T_DIFF_ILLUM_PING_SH1));
             }
             if (last) {
                 out(U(ResourceType::OUT_SPEC_SH0));
@@ -256,11 +272,11 @@ void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
                 out(Pm(P_VIEWZ_PREV));
             }
             if (last) {
-                out(U(ResourceType::OUT_SPEC_SH1));
-                out(U(ResourceType::OUT_DIFF_SH1));
+                if (sh) out(U(ResourceType::OUT_SPEC_SH1));
+                if (sh) out(U(ResourceType::OUT_DIFF_SH1));
             } else {
-                out(even ? Tr(T_SPEC_ILLUM_PING_SH1) : Tr(T_SPEC_ILLUM_PONG_SH1));
-                out(even ? Tr(T_DIFF_ILLUM_PING_SH1) : Tr(T_DIFF_ILLUM_PONG_SH1));
+                if (sh) out(even ? Tr(T_SPEC_ILLUM_PING_SH1) : Tr(T_SPEC_ILLUM_PONG_SH1));
+                if (sh) out(even ? Tr(T_DIFF_ILLUM_PING_SH1) : Tr(T_DIFF_ILLUM_PONG_SH1));
             }
             if (smem)
                 emit("RELAX_AtrousSmem.cs.hlsl" + sig, 8, 8, kCb);
@@ -269,19 +285,19 @@ void Graph::buildRelaxDiffuseSpecularSh(DenoiserState& d) {
         }
     }
 
-    beginPass("RELAX_DiffuseSpecularSh - Split screen");
+    beginPass(name("Split screen"));
     in(U(ResourceType::IN_VIEWZ));
     in(U(ResourceType::IN_DIFF_SH0));
     in(U(ResourceType::IN_SPEC_SH0));
-    in(U(ResourceType::IN_DIFF_SH1));
-    in(U(ResourceType::IN_SPEC_SH1));
+    if (sh) in(U(ResourceType::IN_DIFF_SH1));
+    if (sh) in(U(ResourceType::IN_SPEC_SH1));
     out(U(ResourceType::OUT_DIFF_SH0));
     out(U(ResourceType::OUT_SPEC_SH0));
-    out(U(ResourceType::OUT_DIFF_SH1));
-    out(U(ResourceType::OUT_SPEC_SH1));
+    if (sh) out(U(ResourceType::OUT_DIFF_SH1));
+    if (sh) out(U(ResourceType::OUT_SPEC_SH1));
     emit("RELAX_SplitScreen.cs.hlsl" + sig, 8, 16, kCb);
 
-    beginPass("RELAX_DiffuseSpecularSh - Validation");
+    beginPass(name("Validation"));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(U(ResourceType::IN_VIEWZ));
     in(U(ResourceType::IN_MV));

@@ -40,6 +40,7 @@ static bool contains(const Identifier* ids, uint32_t n, Identifier id) {
 // which is the reference's own answer for a denoiser missing from LibraryDesc (InstanceImpl.cpp:95-102).
 static const Denoiser kSupported[] = {
     Denoiser::REBLUR_DIFFUSE_SPECULAR,
+    Denoiser::RELAX_DIFFUSE_SPECULAR,
     Denoiser::RELAX_DIFFUSE_SPECULAR_SH,
     Denoiser::SIGMA_SHADOW,
 };
@@ -155,7 +156,8 @@ Result Graph::create(const InstanceCreationDesc& desc) {
         switch (dd.denoiser) {
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: buildReblurDiffuseSpecular(d); break;
             case Denoiser::SIGMA_SHADOW: buildSigmaShadow(d); break;
-            case Denoiser::RELAX_DIFFUSE_SPECULAR_SH: buildRelaxDiffuseSpecularSh(d); break;
+            case Denoiser::RELAX_DIFFUSE_SPECULAR_SH: buildRelaxDiffuseSpecular(d, true); break;
+            case Denoiser::RELAX_DIFFUSE_SPECULAR: buildRelaxDiffuseSpecular(d, false); break;
             default: return Result::INVALID_ARGUMENT;
         }
         d.swapNum = m_swaps.size() - d.firstSwap;
@@ -450,7 +452,8 @@ Result Graph::getComputeDispatches(const Identifier* ids, uint32_t idsNum, const
         switch (d.desc.denoiser) {
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: updateReblur(d); break;
             case Denoiser::SIGMA_SHADOW: updateSigma(d); break;
-            case Denoiser::RELAX_DIFFUSE_SPECULAR_SH: updateRelax(d); break;
+            case Denoiser::RELAX_DIFFUSE_SPECULAR_SH:
+            case Denoiser::RELAX_DIFFUSE_SPECULAR: updateRelax(d); break;
             default: break;
         }
     }

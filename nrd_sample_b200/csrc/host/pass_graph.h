@@ -6,6 +6,7 @@
 #pragma once
 
 #include <cstring>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -119,7 +120,7 @@ private:
     void buildSigmaShadow(DenoiserState& d);
     void updateSigma(const DenoiserState& d);
     void fillSigmaConstants(const SigmaSettings& s, void* dst);
-    void buildRelaxDiffuseSpecularSh(DenoiserState& d);
+    void buildRelaxDiffuseSpecular(DenoiserState& d, bool sh);
     void updateRelax(const DenoiserState& d);
     void* fillRelaxConstants(const RelaxSettings& s, void* dst);
 
@@ -138,6 +139,12 @@ private:
     uint8_t* m_constantData = nullptr;
     size_t m_constantOffset = 0;
     size_t m_clearPass[2] = {};
+    std::deque<std::string> m_names;   // pass names built at run time ( interned: finalize() groups permutations by name pointer )
+    const char* intern(const std::string& s) {
+        for (const std::string& n : m_names) if (n == s) return n.c_str();
+        m_names.push_back(s);
+        return m_names.back().c_str();
+    }
     const char* m_passName = nullptr;
     size_t m_passFirstResource = 0;
     uint16_t m_permanentBase = 0, m_transientBase = 0;

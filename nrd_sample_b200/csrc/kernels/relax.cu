@@ -1,4 +1,4 @@
-// RELAX_DIFFUSE_SPECULAR_SH passes on sm_100a (NRD_SIGNAL = BOTH, NRD_MODE = SH): ClassifyTiles, PrePass,
+// RELAX_DIFFUSE_SPECULAR_SH and RELAX_DIFFUSE_SPECULAR passes on sm_100a (NRD_SIGNAL = BOTH, NRD_MODE = SH / RADIANCE, template <bool SH>): ClassifyTiles, PrePass,
 // TemporalAccumulation, HistoryFix, HistoryClamping, Copy, AntiFirefly, AtrousSmem, Atrous. One kernel per reference
 // dispatch, one thread per pixel, CTA = 32x8 pixels (a 32-pixel row per warp: coalesced RGBA16F rows).
 //
@@ -58,7 +58,10 @@ NRD_DEV float customWeightsFloat(float s00, float s10, float s01, float s11, flo
     const float sum = sum4(w);
     return sum < 0.0001f ? 0.0f : o * (1.0f / sum);
 }
+// SH = false is RELAX_DIFFUSE_SPECULAR ( NRD_MODE = RADIANCE ): the SH1 textures are not bound, every access to them compiles away
+template <bool SH>
 NRD_DEV float3 customWeightsSH(const TexRGBA16F& t, int x, int y, float4 w) {
+    if constexpr (!SH) return f3(0.0f);
     float3 o = xyz(t.load(x, y)) * w.x;
     o += xyz(t.load(x + 1, y)) * w.y;
     o += xyz(t.load(x, y + 1)) * w.z;
@@ -122,7 +125,9 @@ NRD_DEV float2 clampUvToViewport(const RelaxConstants& cb, float2 uv) {
 NRD_DEV float4 gatherR32(const TexR32F& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
 NRD_DEV float4 gatherR8(const TexR8& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
 NRD_DEV float4 gatherR16(const TexR16F& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
-NRD_DEV void storeSh(const TexRGBA16F& t, int x, int y, float3 v) { t.store(x, y, f4(v, 0.0f)); }
+template <bool SH> NRD_DEV void storeSh(const TexRGBA16F& t, int x, int y, float3 v) { if constexpr (SH) t.store(x, y, f4(v, 0.0f)); }
+template <bool SH> NRD_DEV float3 loadSh(const TexRGBA16F& t, int x, int y) { if constexpr (SH) return xyz(t.load(x, y)); else return f3(0.0f); }
+template <bool SH> NRD_DEV float3 sampleNearestSh(const TexRGBA16F& t, float2 uv) { if constexpr (SH) return xyz(t.sampleNearest(uv)); else return f3(0.0f); }
 
 // ---- parameter blocks (member order = DispatchDesc::resources order) ------------------------------------------------------------
 struct RelaxClassifyParams { TexR32F viewZ; TexR8 outTiles; };
@@ -155,6 +160,7 @@ __global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+template <bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxPrePassParams p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
 
     // ---- diffuse ----
     float4 diffuseIllumination = p.diff.load(px, py);
-    float3 diffuseSH = xyz(p.diffSh.load(px, py));
+    float3 diffuseSH = loadSh<SH>(p.diffSh, px, py);
     if (cb.diffBlurRadius > 0.0f) {
         const float frustumSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, minRectDim, centerViewZ);
         const float hitDist = diffuseIllumination.w == 0.0f ? 1.0f : diffuseIllumination.w;
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
 
             weightSum += sampleWeight;
             diffuseIllumination += sampleDiffuse * sampleWeight;
-            float3 sampleSH = xyz(p.diffSh.sampleNearest(uvScaled));
+            float3 sampleSH = sampleNearestSh<SH>(p.diffSh, uvScaled);
             if (sampleWeight == 0.0f) sampleSH = f3(0.0f);
             diffuseSH += sampleSH * sampleWeight;
         }
@@ -217,13 +223,13 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
         diffuseSH = diffuseSH / weightSum;
     }
     p.outDiff.store(px, py, clamp4v(diffuseIllumination, 0.0f, NRD_FP16_MAX_F));
-    storeSh(p.outDiffSh, px, py, clamp3v(diffuseSH, f3(-NRD_FP16_MAX_F), f3(NRD_FP16_MAX_F)));
+    storeSh<SH>(p.outDiffSh, px, py, clamp3v(diffuseSH, f3(-NRD_FP16_MAX_F), f3(NRD_FP16_MAX_F)));
 
     // ---- specular ----
     Rng rng;
     rng.init((uint32_t)px, (uint32_t)py, cb.frameIndex);
     float4 specularIllumination = p.spec.load(px, py);
-    float3 specularSH = xyz(p.specSh.load(px, py));
+    float3 specularSH = loadSh<SH>(p.specSh, px, py);
     specularIllumination.w = fmaxf(0.0f, fminf(cb.denoisingRange, specularIllumination.w));
     if (cb.specBlurRadius > 0.0f) {
         const float3 viewVector = cb.orthoMode == 0.0f ? normalize(-centerWorldPos) : make_float3(cb.frustumForward[0], cb.frustumForward[1], cb.frustumForward[2]);
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
             specularIllumination.x += sampleSpecular.x * sampleWeight;
             specularIllumination.y += sampleSpecular.y * sampleWeight;
             specularIllumination.z += sampleSpecular.z * sampleWeight;
-            float3 sampleSH = xyz(p.specSh.sampleNearest(uvScaled));
+            float3 sampleSH = sampleNearestSh<SH>(p.specSh, uvScaled);
             if (sampleWeight == 0.0f) sampleSH = f3(0.0f);
             specularSH += sampleSH * sampleWeight;
         }
@@ -290,13 +296,14 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
         specularSH = specularSH / weightSum;
     }
     p.outSpec.store(px, py, clamp4v(specularIllumination, 0.0f, NRD_FP16_MAX_F));
-    storeSh(p.outSpecSh, px, py, clamp3v(specularSH, f3(-NRD_FP16_MAX_F), f3(NRD_FP16_MAX_F)));
+    storeSh<SH>(p.outSpecSh, px, py, clamp3v(specularSH, f3(-NRD_FP16_MAX_F), f3(NRD_FP16_MAX_F)));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef RELAX_TA_MIN_BLOCKS
 #define RELAX_TA_MIN_BLOCKS 3
 #endif
+template <bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParams p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
@@ -340,9 +347,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
     }
 
     const float3 diffuseIllumination = xyz(p.diff.load(px, py));
-    const float3 diffuseSH = xyz(p.diffSh.load(px, py));
+    const float3 diffuseSH = loadSh<SH>(p.diffSh, px, py);
     const float4 specularIllumination = p.spec.load(px, py);
-    const float3 specularSH = xyz(p.specSh.load(px, py));
+    const float3 specularSH = loadSh<SH>(p.specSh, px, py);
 
     const float hitTM1 = preload(px, py).w;
     float minHitDist3x3 = hitTM1 == 0.0f ? NRD_INF : hitTM1;
@@ -423,10 +430,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
         prevDiffuseSMBResponsive = max3(xyz(hf.color(p.historyDiffFast)), f3(0.0f));
         prevSpecularSMBResponsive = max3(xyz(hf.color(p.historySpecFast)), f3(0.0f));
 
-        prevDiffuseSH = customWeightsSH(p.historyDiffSh, ox, oy, bilinearCustomW);
-        prevDiffuseResponsiveSH = customWeightsSH(p.historyDiffShFast, ox, oy, bilinearCustomW);
-        prevSpecularSMBSH = customWeightsSH(p.historySpecSh, ox, oy, bilinearCustomW);
-        prevSpecularSMBResponsiveSH = customWeightsSH(p.historySpecShFast, ox, oy, bilinearCustomW);
+        prevDiffuseSH = customWeightsSH<SH>(p.historyDiffSh, ox, oy, bilinearCustomW);
+        prevDiffuseResponsiveSH = customWeightsSH<SH>(p.historyDiffShFast, ox, oy, bilinearCustomW);
+        prevSpecularSMBSH = customWeightsSH<SH>(p.historySpecSh, ox, oy, bilinearCustomW);
+        prevSpecularSMBResponsiveSH = customWeightsSH<SH>(p.historySpecShFast, ox, oy, bilinearCustomW);
 
         const float4 prevHistoryLengths = gatherR8(p.prevHistoryLength, ox, oy);
         historyLength = 255.0f * customWeightsFloat(prevHistoryLengths.x, prevHistoryLengths.y, prevHistoryLengths.z, prevHistoryLengths.w, bilinearCustomW);
@@ -459,8 +466,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
         const float diffuseAlphaResponsive = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (cb.diffMaxFastAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
         p.outDiff.store(px, py, lerp(prevDiffuseSMB, f4(diffuseIllumination, diffuse2ndMoment), diffuseAlpha));
         p.outDiffFast.store(px, py, f4(lerp(prevDiffuseSMBResponsive, diffuseIllumination, diffuseAlphaResponsive), 0.0f));
-        storeSh(p.outDiffSh, px, py, lerp(prevDiffuseSH, diffuseSH, diffuseAlpha));
-        storeSh(p.outDiffShFast, px, py, lerp(prevDiffuseResponsiveSH, diffuseSH, diffuseAlphaResponsive));
+        storeSh<SH>(p.outDiffSh, px, py, lerp(prevDiffuseSH, diffuseSH, diffuseAlpha));
+        storeSh<SH>(p.outDiffShFast, px, py, lerp(prevDiffuseResponsiveSH, diffuseSH, diffuseAlphaResponsive));
     }
     p.outHistoryLength.store(px, py, historyLength / 255.0f);
 
@@ -558,8 +565,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
             const HistoryFilter hf(prevVirtualPixelPosFloat, resourceSizeInvPrev, bilinearCustomW, useBicubic);
             prevSpecularVMB = max4v(hf.color(p.historySpec), 0.0f);
             prevSpecularVMBResponsive = max4v(hf.color(p.historySpecFast), 0.0f);
-            prevSpecularVMBSH = customWeightsSH(p.historySpecSh, ox, oy, bilinearCustomW);
-            prevSpecularVMBResponsiveSH = customWeightsSH(p.historySpecShFast, ox, oy, bilinearCustomW);
+            prevSpecularVMBSH = customWeightsSH<SH>(p.historySpecSh, ox, oy, bilinearCustomW);
+            prevSpecularVMBResponsiveSH = customWeightsSH<SH>(p.historySpecShFast, ox, oy, bilinearCustomW);
             prevReflectionHitTVMB = fmaxf(0.001f, p.prevSpecHitDist.sampleLinear(prevUVVMB * resolutionScalePrev));
             const float4 prevNR = unpackPrevNormalRoughness(p.prevNormalRoughness.sampleLinear(prevUVVMB * resolutionScalePrev));
             prevNormalVMB = xyz(prevNR);
@@ -655,8 +662,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
 
     const float3 accSMBSH = lerp(prevSpecularSMBSH, specularSH, specSMBAlpha), accSMBRespSH = lerp(prevSpecularSMBResponsiveSH, specularSH, specSMBResponsiveAlpha);
     const float3 accVMBSH = lerp(prevSpecularVMBSH, specularSH, specVMBAlpha), accVMBRespSH = lerp(prevSpecularVMBResponsiveSH, specularSH, specVMBResponsiveAlpha);
-    storeSh(p.outSpecSh, px, py, lerp(accSMBSH, accVMBSH, virtualHistoryAmount));
-    storeSh(p.outSpecShFast, px, py, lerp(accSMBRespSH, accVMBRespSH, virtualHistoryAmount));
+    storeSh<SH>(p.outSpecSh, px, py, lerp(accSMBSH, accVMBSH, virtualHistoryAmount));
+    storeSh<SH>(p.outSpecShFast, px, py, lerp(accSMBRespSH, accVMBRespSH, virtualHistoryAmount));
 
     const float specularHistoryConfidence = lerp(specSMBConfidence, specVMBConfidence, virtualHistoryAmount);
     if (accumulatedSpecular2ndMoment == 0.0f) accumulatedSpecular2ndMoment = cb.specVarianceBoost * (1.0f - specularHistoryConfidence);
@@ -668,6 +675,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+template <bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryFixParams p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
@@ -684,7 +692,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const 
     const float2 rectSize = make_float2((float)cb.rectSize[0], (float)cb.rectSize[1]), rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
 
     float4 diffuseSum = p.diff.load(px, py), specularSum = p.spec.load(px, py);
-    float3 diffuseSumSH = xyz(p.diffSh.load(px, py)), specularSumSH = xyz(p.specSh.load(px, py));
+    float3 diffuseSumSH = loadSh<SH>(p.diffSh, px, py), specularSumSH = loadSh<SH>(p.specSh, px, py);
     float diffuseWSum = 1.0f, specularWSum = 1.0f;
     const float2 specularNormalWeightP = normalWeightParamsAtrous(centerNormalRoughness.w, 5.0f, 1.0f, 0.0f, cb.lobeAngleFraction, cb.specLobeAngleSlack);
     const float normalPower = fmaxf(cb.historyFixEdgeStoppingNormalPower, 0.01f);
@@ -711,7 +719,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const 
             diffuseW *= compareMaterials(sampleMaterialID, centerMaterialID, cb.diffMinMaterial) ? 1.0f : 0.0f;
             if (diffuseW > 1e-4f) {
                 diffuseSum += p.diff.load(sx, sy) * diffuseW;
-                diffuseSumSH += xyz(p.diffSh.load(sx, sy)) * diffuseW;
+                diffuseSumSH += loadSh<SH>(p.diffSh, sx, sy) * diffuseW;
                 diffuseWSum += diffuseW;
             }
             const float3 sampleV = -normalize(sampleWorldPos + cb.roughnessEdgeStoppingRelaxation * centerWorldPos);
@@ -720,14 +728,14 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const 
             specularW *= compareMaterials(sampleMaterialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
             if (specularW > 1e-4f) {
                 specularSum += p.spec.load(sx, sy) * specularW;
-                specularSumSH += xyz(p.specSh.load(sx, sy)) * specularW;
+                specularSumSH += loadSh<SH>(p.specSh, sx, sy) * specularW;
                 specularWSum += specularW;
             }
         }
     p.outDiff.store(px, py, diffuseSum / diffuseWSum);
-    storeSh(p.outDiffSh, px, py, diffuseSumSH / diffuseWSum);
+    storeSh<SH>(p.outDiffSh, px, py, diffuseSumSH / diffuseWSum);
     p.outSpec.store(px, py, specularSum / specularWSum);
-    storeSh(p.outSpecSh, px, py, specularSumSH / specularWSum);
+    storeSh<SH>(p.outSpecSh, px, py, specularSumSH / specularWSum);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -736,7 +744,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const 
 constexpr int HC_BORDER = 2, HC_TILE_W = BLOCK_W + 2 * HC_BORDER, HC_TILE_H = BLOCK_H + 2 * HC_BORDER;
 
 // One lobe (the specular and diffuse halves of the shader differ in three constants only)
-template <bool SPEC>
+template <bool SPEC, bool SH>
 NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)[HC_TILE_W], const float4 (*sNoisy)[HC_TILE_W], int px, int py, float historyLength,
                                  const TexRGBA16F& slowTex, const TexRGBA16F& fastTex, const TexRGBA16F& shTex, const TexRGBA16F& shFastTex, const TexRGBA16F& outSlow,
                                  const TexRGBA16F& outFast, const TexRGBA16F& outSh, const TexRGBA16F& outShFast, float maxFast, float maxSlow) {
@@ -815,11 +823,12 @@ NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)
 
     outSlow.store(px, py, outSlowV);
     outFast.store(px, py, outFastV);
-    const float3 sh = xyz(shTex.load(px, py)), shFast = xyz(shFastTex.load(px, py));
-    storeSh(outSh, px, py, lerp(sh, shFast, clampingFactor));
-    storeSh(outShFast, px, py, shFast);
+    const float3 sh = loadSh<SH>(shTex, px, py), shFast = loadSh<SH>(shFastTex, px, py);
+    storeSh<SH>(outSh, px, py, lerp(sh, shFast, clampingFactor));
+    storeSh<SH>(outShFast, px, py, shFast);
 }
 
+template <bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParams p) {
     __shared__ float4 sSpecFast[HC_TILE_H][HC_TILE_W], sSpecNoisy[HC_TILE_H][HC_TILE_W], sDiffFast[HC_TILE_H][HC_TILE_W], sDiffNoisy[HC_TILE_H][HC_TILE_W];
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
@@ -846,9 +855,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(c
     if (isSky != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     if (sSpecFast[threadIdx.y + HC_BORDER][threadIdx.x + HC_BORDER].w == 0.0f) return;
     const float historyLength = 255.0f * p.historyLength.load(px, py);
-    historyClampingLobe<true>(cb, sSpecFast, sSpecNoisy, px, py, historyLength, p.spec, p.specFast, p.specSh, p.specShFast, p.outSpec, p.outSpecFast, p.outSpecSh, p.outSpecShFast,
+    historyClampingLobe<true, SH>(cb, sSpecFast, sSpecNoisy, px, py, historyLength, p.spec, p.specFast, p.specSh, p.specShFast, p.outSpec, p.outSpecFast, p.outSpecSh, p.outSpecShFast,
                               cb.specMaxFastAccumulatedFrameNum, cb.specMaxAccumulatedFrameNum);
-    historyClampingLobe<false>(cb, sDiffFast, sDiffNoisy, px, py, historyLength, p.diff, p.diffFast, p.diffSh, p.diffShFast, p.outDiff, p.outDiffFast, p.outDiffSh, p.outDiffShFast,
+    historyClampingLobe<false, SH>(cb, sDiffFast, sDiffNoisy, px, py, historyLength, p.diff, p.diffFast, p.diffSh, p.diffShFast, p.outDiff, p.outDiffFast, p.outDiffSh, p.outDiffShFast,
                                cb.diffMaxFastAccumulatedFrameNum, cb.diffMaxAccumulatedFrameNum);
     p.outHistoryLength.store(px, py, historyLength / 255.0f);
 }
@@ -899,13 +908,14 @@ struct AtrousTexel {
     float3 specSh, diffSh, worldPos;
     float materialID;
 };
+template <bool SH>
 NRD_DEV AtrousTexel atrousFetch(const RelaxConstants& cb, const RelaxAtrousParams& p, int x, int y) {
     const int gx = clampi(x, 0, cb.rectSize[0] - 1), gy = clampi(y, 0, cb.rectSize[1] - 1);
     AtrousTexel r;
     r.spec = p.spec.load(gx, gy);
     r.diff = p.diff.load(gx, gy);
-    r.specSh = xyz(p.specSh.load(gx, gy));
-    r.diffSh = xyz(p.diffSh.load(gx, gy));
+    r.specSh = loadSh<SH>(p.specSh, gx, gy);
+    r.diffSh = loadSh<SH>(p.diffSh, gx, gy);
     r.nr = unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy), r.materialID);
     r.worldPos = currentWorldPosPixel(cb, gx, gy, relaxViewZ(cb, p.viewZ.load(gx, gy)));
     return r;
@@ -915,10 +925,11 @@ constexpr int AT_BORDER = 2, AT_TILE_W = BLOCK_W + 2 * AT_BORDER, AT_TILE_H = BL
 #ifndef RELAX_ATROUS_SMEM_MIN_BLOCKS
 #define RELAX_ATROUS_SMEM_MIN_BLOCKS 4
 #endif
+template <bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParams p) {
     // the reference's groupshared tile: 36x12 texels of { illumination + 2nd moment, SH1, normal + roughness, world position + material }
-    __shared__ float4 sSpec[AT_TILE_H][AT_TILE_W], sDiff[AT_TILE_H][AT_TILE_W], sNr[AT_TILE_H][AT_TILE_W], sPosMat[AT_TILE_H][AT_TILE_W], sSpecSh[AT_TILE_H][AT_TILE_W],
-        sDiffSh[AT_TILE_H][AT_TILE_W];
+    __shared__ float4 sSpec[AT_TILE_H][AT_TILE_W], sDiff[AT_TILE_H][AT_TILE_W], sNr[AT_TILE_H][AT_TILE_W], sPosMat[AT_TILE_H][AT_TILE_W];
+    __shared__ float4 sSpecSh[SH ? AT_TILE_H : 1][SH ? AT_TILE_W : 1], sDiffSh[SH ? AT_TILE_H : 1][SH ? AT_TILE_W : 1];
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
     const float isSky = threadIdx.x < 16 ? skyL : skyR;
@@ -929,13 +940,15 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
         const int baseX = blockIdx.x * BLOCK_W - AT_BORDER, baseY = blockIdx.y * BLOCK_H - AT_BORDER;
         for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < AT_TILE_W * AT_TILE_H; i += BLOCK_W * BLOCK_H) {
             const int tx = i % AT_TILE_W, ty = i / AT_TILE_W;
-            const AtrousTexel t = atrousFetch(cb, p, baseX + tx, baseY + ty);
+            const AtrousTexel t = atrousFetch<SH>(cb, p, baseX + tx, baseY + ty);
             sSpec[ty][tx] = t.spec;
             sDiff[ty][tx] = t.diff;
             sNr[ty][tx] = t.nr;
             sPosMat[ty][tx] = f4(t.worldPos, t.materialID);
-            sSpecSh[ty][tx] = f4(t.specSh, 0.0f);
-            sDiffSh[ty][tx] = f4(t.diffSh, 0.0f);
+            if constexpr (SH) {
+                sSpecSh[ty][tx] = f4(t.specSh, 0.0f);
+                sDiffSh[ty][tx] = f4(t.diffSh, 0.0f);
+            }
         }
     }
     __syncthreads();
@@ -948,11 +961,15 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
         const float4 pm = sPosMat[smy + dy][smx + dx];
         t.worldPos = xyz(pm);
         t.materialID = pm.w;
-        t.specSh = xyz(sSpecSh[smy + dy][smx + dx]);
-        t.diffSh = xyz(sDiffSh[smy + dy][smx + dx]);
+        if constexpr (SH) {
+            t.specSh = xyz(sSpecSh[smy + dy][smx + dx]);
+            t.diffSh = xyz(sDiffSh[smy + dy][smx + dx]);
+        } else {
+            t.specSh = t.diffSh = f3(0.0f);
+        }
         return t;
     };
-    const AtrousTexel ctr = skipTile ? atrousFetch(cb, p, px, py) : texel(0, 0);
+    const AtrousTexel ctr = skipTile ? atrousFetch<SH>(cb, p, px, py) : texel(0, 0);
     float4 normalRoughness = ctr.nr;
     const float centerViewZ = relaxViewZ(cb, viewZpacked);
     if (!relaxInRange(cb, centerViewZ)) normalRoughness = f4(1.0f / 255.0f);
@@ -1044,12 +1061,12 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
         sumSpecular = sumSpecular / sumWSpecular;
         const float sp1 = luminance(xyz(sumSpecular));
         p.outSpec.store(px, py, f4(xyz(sumSpecular), fmaxf(0.0f, sumSpecular.w - sp1 * sp1)));
-        storeSh(p.outSpecSh, px, py, sumSpecularSH / sumWSpecular);
+        storeSh<SH>(p.outSpecSh, px, py, sumSpecularSH / sumWSpecular);
         sumWDiffuse = fmaxf(sumWDiffuse, 1e-6f);
         sumDiffuse = sumDiffuse / sumWDiffuse;
         const float dp1 = luminance(xyz(sumDiffuse));
         p.outDiff.store(px, py, f4(xyz(sumDiffuse), fmaxf(0.0f, sumDiffuse.w - dp1 * dp1)));
-        storeSh(p.outDiffSh, px, py, sumDiffuseSH / sumWDiffuse);
+        storeSh<SH>(p.outDiffSh, px, py, sumDiffuseSH / sumWDiffuse);
     } else {
         float sumWS = 0.0f, sumS1 = 0.0f, sumS2 = 0.0f, sumWD = 0.0f, sumD1 = 0.0f, sumD2 = 0.0f;
         float3 sumS = f3(0.0f), sumD = f3(0.0f), sumSSH = f3(0.0f), sumDSH = f3(0.0f);
@@ -1077,16 +1094,17 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
         sumS1 /= sumWS;
         sumS2 /= sumWS;
         p.outSpec.store(px, py, f4(sumS, fmaxf(0.0f, sumS2 - sumS1 * sumS1) * boost));
-        storeSh(p.outSpecSh, px, py, sumSSH / sumWS);
+        storeSh<SH>(p.outSpecSh, px, py, sumSSH / sumWS);
         sumWD = fmaxf(sumWD, 1e-6f);
         sumD = sumD / sumWD;
         sumD1 /= sumWD;
         sumD2 /= sumWD;
         p.outDiff.store(px, py, f4(sumD, fmaxf(0.0f, sumD2 - sumD1 * sumD1) * boost));
-        storeSh(p.outDiffSh, px, py, sumDSH / sumWD);
+        storeSh<SH>(p.outDiffSh, px, py, sumDSH / sumWD);
     }
 }
 
+template <bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParams p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
@@ -1101,7 +1119,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __gr
     const float stepSize = (float)cb.stepSize;
     const float kGauss[2] = {0.44198f, 0.27901f};
 
-    float diffuseLobeAngleFraction = 1.0f / sqrtf(stepSize);  // NRD_MODE == SH
+    float diffuseLobeAngleFraction = (SH ? 1.0f : cb.lobeAngleFraction) / sqrtf(stepSize);  // RELAX_Atrous.cs.hlsl:46-49
     diffuseLobeAngleFraction = lerp(0.99f, diffuseLobeAngleFraction, saturate(historyLength / 5.0f));
 
     const float4 centerSpecular = p.spec.load(px, py);
@@ -1116,7 +1134,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __gr
                                                                   cb.specLobeAngleSlack);
     float sumWSpecular = 0.44198f * 0.44198f;
     float4 sumSpecular = centerSpecular * make_float4(sumWSpecular, sumWSpecular, sumWSpecular, sumWSpecular * sumWSpecular);
-    float3 sumSpecularSH = xyz(p.specSh.load(px, py)) * sumWSpecular;
+    float3 sumSpecularSH = loadSh<SH>(p.specSh, px, py) * sumWSpecular;
 
     const float4 centerDiffuse = p.diff.load(px, py);
     const float centerDiffuseLuminance = luminance(xyz(centerDiffuse));
@@ -1124,7 +1142,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __gr
     const float diffuseNormalWeightParam = normalWeightParam2(1.0f, diffuseLobeAngleFraction);
     float sumWDiffuse = 0.44198f * 0.44198f;
     float4 sumDiffuse = centerDiffuse * make_float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse);
-    float3 sumDiffuseSH = xyz(p.diffSh.load(px, py)) * sumWDiffuse;
+    float3 sumDiffuseSH = loadSh<SH>(p.diffSh, px, py) * sumWDiffuse;
 
     const float3 centerWorldPos = currentWorldPosPixel(cb, px, py, centerViewZ);
     const float3 centerV = -normalize(centerWorldPos);
@@ -1171,7 +1189,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __gr
                 wSpecular *= expf(-lw);
                 sumWSpecular += wSpecular;
                 sumSpecular += make_float4(wSpecular, wSpecular, wSpecular, wSpecular * wSpecular) * s;
-                sumSpecularSH += xyz(p.specSh.load(x, y)) * wSpecular;
+                sumSpecularSH += loadSh<SH>(p.specSh, x, y) * wSpecular;
             }
 
             const float normalWDiffuse = computeWeight(angles, diffuseNormalWeightParam, 0.0f);
@@ -1184,17 +1202,17 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __gr
                 wDiffuse *= expf(-lw);
                 sumWDiffuse += wDiffuse;
                 sumDiffuse += make_float4(wDiffuse, wDiffuse, wDiffuse, wDiffuse * wDiffuse) * s;
-                sumDiffuseSH += xyz(p.diffSh.load(x, y)) * wDiffuse;
+                sumDiffuseSH += loadSh<SH>(p.diffSh, x, y) * wDiffuse;
             }
         }
     const float currHistoryLength = fmaxf(historyLength - 1.0f, 0.0f);
     float4 filteredSpecular = sumSpecular / make_float4(sumWSpecular, sumWSpecular, sumWSpecular, sumWSpecular * sumWSpecular);
-    if (cb.isLastPass == 1) filteredSpecular = f4(linearToYCoCg(xyz(filteredSpecular)), currHistoryLength);
-    storeSh(p.outSpecSh, px, py, sumSpecularSH / sumWSpecular);
+    if (cb.isLastPass == 1) filteredSpecular = f4(SH ? linearToYCoCg(xyz(filteredSpecular)) : xyz(filteredSpecular), currHistoryLength);   // YCoCg output in SH mode only
+    storeSh<SH>(p.outSpecSh, px, py, sumSpecularSH / sumWSpecular);
     p.outSpec.store(px, py, filteredSpecular);
     float4 filteredDiffuse = sumDiffuse / make_float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse);
-    if (cb.isLastPass == 1) filteredDiffuse = f4(linearToYCoCg(xyz(filteredDiffuse)), currHistoryLength);
-    storeSh(p.outDiffSh, px, py, sumDiffuseSH / sumWDiffuse);
+    if (cb.isLastPass == 1) filteredDiffuse = f4(SH ? linearToYCoCg(xyz(filteredDiffuse)) : xyz(filteredDiffuse), currHistoryLength);
+    storeSh<SH>(p.outDiffSh, px, py, sumDiffuseSH / sumWDiffuse);
     p.outDiff.store(px, py, filteredDiffuse);
 }
 
@@ -1264,7 +1282,11 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
     const Format F16 = Format::RGBA16_SFLOAT, R8 = Format::R8_UNORM, R32 = Format::R32_SFLOAT, NR = Format::R10_G10_B10_A2_UNORM;
     const dim3 block(BLOCK_W, BLOCK_H);
     const dim3 pixelGrid((cb.rectSize[0] + BLOCK_W - 1) / BLOCK_W, (cb.rectSize[1] + BLOCK_H - 1) / BLOCK_H);
-    const std::string sig = "|NRD_SIGNAL=BOTH|NRD_MODE=SH";
+    // "|NRD_SIGNAL=BOTH|NRD_MODE=SH" ( RELAX_DIFFUSE_SPECULAR_SH ) or "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE" ( RELAX_DIFFUSE_SPECULAR: same passes, no SH1 textures )
+    const bool sh = id.find("|NRD_MODE=SH") != std::string::npos;
+    const std::string sig = sh ? "|NRD_SIGNAL=BOTH|NRD_MODE=SH" : "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE";
+    auto takeSh = [&](TexRGBA16F& t) { if (sh) t = b.take<TexRGBA16F>(F16); else t = TexRGBA16F(); };
+    const uint32_t noSh = sh ? 0u : 1u;   // multiplies the number of SH1 bindings a pass loses
 
     if (id == "RELAX_ClassifyTiles.cs.hlsl") {
         RelaxClassifyParams p;
@@ -1279,14 +1301,14 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.viewZ = b.take<TexR32F>(R32);
         p.spec = b.take<TexRGBA16F>(F16);
         p.diff = b.take<TexRGBA16F>(F16);
-        p.specSh = b.take<TexRGBA16F>(F16);
-        p.diffSh = b.take<TexRGBA16F>(F16);
+        takeSh(p.specSh);
+        takeSh(p.diffSh);
         p.outSpec = b.take<TexRGBA16F>(F16);
         p.outDiff = b.take<TexRGBA16F>(F16);
-        p.outSpecSh = b.take<TexRGBA16F>(F16);
-        p.outDiffSh = b.take<TexRGBA16F>(F16);
-        if (bad(11)) return (uint32_t)Result::INVALID_ARGUMENT;
-        relaxPrePassKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+        takeSh(p.outSpecSh);
+        takeSh(p.outDiffSh);
+        if (bad(11 - 4 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (sh) relaxPrePassKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxPrePassKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
     } else if (id == "RELAX_TemporalAccumulation.cs.hlsl" + sig) {
         RelaxTaParams p;
         p.tiles = b.take<TexR8>(R8);
@@ -1307,12 +1329,12 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.prevSpecHitDist = b.take<TexR16F>(Format::R16_SFLOAT);
         p.specConfDummy = b.take<TexR32F>(R32);
         p.diffConfDummy = b.take<TexR32F>(R32);
-        p.specSh = b.take<TexRGBA16F>(F16);
-        p.diffSh = b.take<TexRGBA16F>(F16);
-        p.historySpecShFast = b.take<TexRGBA16F>(F16);
-        p.historyDiffShFast = b.take<TexRGBA16F>(F16);
-        p.historySpecSh = b.take<TexRGBA16F>(F16);
-        p.historyDiffSh = b.take<TexRGBA16F>(F16);
+        takeSh(p.specSh);
+        takeSh(p.diffSh);
+        takeSh(p.historySpecShFast);
+        takeSh(p.historyDiffShFast);
+        takeSh(p.historySpecSh);
+        takeSh(p.historyDiffSh);
         p.outHistoryLength = b.take<TexR8>(R8);
         p.outSpec = b.take<TexRGBA16F>(F16);
         p.outDiff = b.take<TexRGBA16F>(F16);
@@ -1320,12 +1342,12 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.outDiffFast = b.take<TexRGBA16F>(F16);
         p.outSpecHitDist = b.take<TexR16F>(Format::R16_SFLOAT);
         p.outSpecReprojectionConfidence = b.take<TexR8>(R8);
-        p.outSpecSh = b.take<TexRGBA16F>(F16);
-        p.outDiffSh = b.take<TexRGBA16F>(F16);
-        p.outSpecShFast = b.take<TexRGBA16F>(F16);
-        p.outDiffShFast = b.take<TexRGBA16F>(F16);
-        if (bad(35)) return (uint32_t)Result::INVALID_ARGUMENT;
-        relaxTemporalAccumulationKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+        takeSh(p.outSpecSh);
+        takeSh(p.outDiffSh);
+        takeSh(p.outSpecShFast);
+        takeSh(p.outDiffShFast);
+        if (bad(35 - 10 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (sh) relaxTemporalAccumulationKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxTemporalAccumulationKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
     } else if (id == "RELAX_HistoryFix.cs.hlsl" + sig) {
         RelaxHistoryFixParams p;
         p.tiles = b.take<TexR8>(R8);
@@ -1334,26 +1356,30 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.viewZ = b.take<TexR32F>(R32);
         p.spec = b.take<TexRGBA16F>(F16);
         p.diff = b.take<TexRGBA16F>(F16);
-        p.specSh = b.take<TexRGBA16F>(F16);
-        p.diffSh = b.take<TexRGBA16F>(F16);
+        takeSh(p.specSh);
+        takeSh(p.diffSh);
         p.outSpec = b.take<TexRGBA16F>(F16);
         p.outDiff = b.take<TexRGBA16F>(F16);
-        p.outSpecSh = b.take<TexRGBA16F>(F16);
-        p.outDiffSh = b.take<TexRGBA16F>(F16);
-        if (bad(12)) return (uint32_t)Result::INVALID_ARGUMENT;
-        relaxHistoryFixKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+        takeSh(p.outSpecSh);
+        takeSh(p.outDiffSh);
+        if (bad(12 - 4 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (sh) relaxHistoryFixKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxHistoryFixKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
     } else if (id == "RELAX_HistoryClamping.cs.hlsl" + sig) {
         RelaxHistoryClampingParams p;
         p.tiles = b.take<TexR8>(R8);
         p.viewZ = b.take<TexR32F>(R32);
         p.historyLength = b.take<TexR8>(R8);
-        TexRGBA16F* ins[10] = {&p.specNoisy, &p.diffNoisy, &p.spec, &p.diff, &p.specFast, &p.diffFast, &p.specSh, &p.diffSh, &p.specShFast, &p.diffShFast};
+        TexRGBA16F* ins[6] = {&p.specNoisy, &p.diffNoisy, &p.spec, &p.diff, &p.specFast, &p.diffFast};
         for (TexRGBA16F* t : ins) *t = b.take<TexRGBA16F>(F16);
+        TexRGBA16F* insSh[4] = {&p.specSh, &p.diffSh, &p.specShFast, &p.diffShFast};
+        for (TexRGBA16F* t : insSh) takeSh(*t);
         p.outHistoryLength = b.take<TexR8>(R8);
-        TexRGBA16F* outs[8] = {&p.outSpec, &p.outDiff, &p.outSpecFast, &p.outDiffFast, &p.outSpecSh, &p.outDiffSh, &p.outSpecShFast, &p.outDiffShFast};
+        TexRGBA16F* outs[4] = {&p.outSpec, &p.outDiff, &p.outSpecFast, &p.outDiffFast};
         for (TexRGBA16F* t : outs) *t = b.take<TexRGBA16F>(F16);
-        if (bad(22)) return (uint32_t)Result::INVALID_ARGUMENT;
-        relaxHistoryClampingKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+        TexRGBA16F* outsSh[4] = {&p.outSpecSh, &p.outDiffSh, &p.outSpecShFast, &p.outDiffShFast};
+        for (TexRGBA16F* t : outsSh) takeSh(*t);
+        if (bad(22 - 8 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (sh) relaxHistoryClampingKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxHistoryClampingKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
     } else if (id == "RELAX_Copy.cs.hlsl" + sig) {
         RelaxCopyParams p;
         p.spec = b.take<TexRGBA16F>(F16);
@@ -1385,8 +1411,8 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.specReprojectionConfidence = b.take<TexR8>(R8);
         p.specConfDummy = b.take<TexR32F>(R32);
         p.diffConfDummy = b.take<TexR32F>(R32);
-        p.specSh = b.take<TexRGBA16F>(F16);
-        p.diffSh = b.take<TexRGBA16F>(F16);
+        takeSh(p.specSh);
+        takeSh(p.diffSh);
         p.outSpec = b.take<TexRGBA16F>(F16);
         p.outDiff = b.take<TexRGBA16F>(F16);
         if (smem) {
@@ -1394,13 +1420,14 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
             p.outMaterialID = b.take<TexR8>(R8);
             p.outViewZ = b.take<TexR32F>(R32);
         }
-        p.outSpecSh = b.take<TexRGBA16F>(F16);
-        p.outDiffSh = b.take<TexRGBA16F>(F16);
-        if (bad(smem ? 18 : 15)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (smem)
-            relaxAtrousSmemKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
-        else
-            relaxAtrousKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+        takeSh(p.outSpecSh);
+        takeSh(p.outDiffSh);
+        if (bad((smem ? 18 : 15) - 4 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (smem) {
+            if (sh) relaxAtrousSmemKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxAtrousSmemKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+        } else {
+            if (sh) relaxAtrousKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxAtrousKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+        }
     } else {
         err = "no CUDA kernel for shader '" + id + "'";
         return (uint32_t)Result::UNSUPPORTED;

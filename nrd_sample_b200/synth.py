@@ -366,7 +366,7 @@ def sigma_frame(frame_index: int, width: int, height: int, device="cpu", period:
 # ------------------------------------------------------------------------------------------------
 # RELAX_DIFFUSE_SPECULAR_SH inputs
 # ------------------------------------------------------------------------------------------------
-def relax_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False) -> Dict[str, torch.Tensor]:
+def relax_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, sh: bool = True) -> Dict[str, torch.Tensor]:
     """All user inputs of RELAX_DIFFUSE_SPECULAR_SH for one frame (BASELINE.json config 2): the G-buffer and motion of `reblur_frame`,
     un-normalised radiance + hit distance in IN_*_SH0 and `direction * luminance` in IN_*_SH1, both RGBA16F, packed like
     RELAX_FrontEnd_PackSh (NRD.hlsli:925-941). Directions: cosine-weighted around N (diffuse), jittered mirror direction (specular)."""
@@ -418,6 +418,9 @@ def relax_frame(frame_index: int, width: int, height: int, device="cpu", period:
         "IN_SPEC_SH0": sh0(spec, hit_t_s),
         "IN_SPEC_SH1": sh1(spec, dir_s),
     }
+    if not sh:   # RELAX_DIFFUSE_SPECULAR (NRD_MODE = RADIANCE): the same radiance + hit distance, no SH1 textures
+        out["IN_DIFF_RADIANCE_HITDIST"], out["IN_SPEC_RADIANCE_HITDIST"] = out.pop("IN_DIFF_SH0"), out.pop("IN_SPEC_SH0")
+        del out["IN_DIFF_SH1"], out["IN_SPEC_SH1"]
     if with_clean:
         out["_clean_diff"], out["_clean_spec"], out["_hit"] = base["_clean_diff"], base["_clean_spec"], hit
     return out

@@ -52,6 +52,21 @@ IDENTIFIERS = [
     "RELAX_AtrousSmem.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=SH",
     "RELAX_Atrous.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=SH",
     "RELAX_SplitScreen.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=SH",
+    # RELAX_DIFFUSE_SPECULAR ( what NRDSample instantiates as shipped )
+    "RELAX_PrePass.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE",
+    "RELAX_TemporalAccumulation.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE",
+    "RELAX_HistoryFix.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE",
+    "RELAX_HistoryClamping.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE",
+    "RELAX_Copy.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE",
+    "RELAX_AntiFirefly.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE",
+    "RELAX_AtrousSmem.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE",
+    "RELAX_Atrous.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE",
+    "RELAX_SplitScreen.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE",
+    # SIGMA_SHADOW_TRANSLUCENCY
+    "SIGMA_ClassifyTiles.cs.hlsl|TRANSLUCENCY=1", "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=1|FIRST_PASS=1", "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=1|FIRST_PASS=0",
+    "SIGMA_TemporalStabilization.cs.hlsl|TRANSLUCENCY=1", "SIGMA_SplitScreen.cs.hlsl|TRANSLUCENCY=1",
+    # REFERENCE
+    "REFERENCE_TemporalAccumulation.cs.hlsl", "REFERENCE_Copy.cs.hlsl",
 ]
 CXXFLAGS = ["-std=c++20", "-O2", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fvisibility=hidden", "-w", "-fmax-errors=25", "-I", SHIM]
 

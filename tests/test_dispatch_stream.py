@@ -24,6 +24,8 @@ CASES = [
     ("relax_sh_1440p", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 2560, 1440, None),
     ("relax_sh_odd_firefly_recon", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 1000, 562, "relax_firefly_recon"),
     ("relax_sh_8_iterations", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 640, 360, "relax_8"),
+    ("relax_1440p", api.Denoiser.RELAX_DIFFUSE_SPECULAR, 2560, 1440, None),
+    ("relax_odd_firefly_recon", api.Denoiser.RELAX_DIFFUSE_SPECULAR, 1000, 562, "relax_firefly_recon"),
 ]
 
 

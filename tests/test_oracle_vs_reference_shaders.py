@@ -22,6 +22,10 @@ DENOISERS = {
     "sigma": (api.Denoiser.SIGMA_SHADOW, synth.sigma_frame, ("OUT_SHADOW_TRANSLUCENCY",)),
     "relax": (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, synth.relax_frame, ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1")),
 }
+# denoisers the CUDA executor covers beyond the three the oracle restates: the reference shaders are their only CPU engine
+REFERENCE_ONLY = {
+    "relax_nosh": (api.Denoiser.RELAX_DIFFUSE_SPECULAR, lambda *a, **k: synth.relax_frame(*a, sh=False, **k), ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST")),
+}
 
 # ( label, denoiser, width, height, frames, denoiser settings, extra frame kwargs )
 CASES = [
@@ -43,7 +47,7 @@ CASES = [
 
 
 def make_denoiser(which, w, h, engine="oracle"):
-    den_id, _, outputs = DENOISERS[which]
+    den_id, _, outputs = {**DENOISERS, **REFERENCE_ONLY}[which]
     den = runner.OracleDenoiser(runner.default_host_library(), den_id, w, h, engine=engine)
     for o in outputs:
         den.set_user_texture(getattr(RT, o), runner.alloc_texture(runner.USER_FORMATS[getattr(RT, o)], w, h))

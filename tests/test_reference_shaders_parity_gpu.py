@@ -21,9 +21,17 @@ CASES = {
     "reblur": (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, "reblur_frame", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur"),
     "sigma": (api.Denoiser.SIGMA_SHADOW, "sigma_frame", ("OUT_SHADOW_TRANSLUCENCY",), "sigma"),
     "relax": (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, "relax_frame", ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur"),
+    # NRD_MODE = RADIANCE: what NRDSample instantiates as shipped (Shaders/Shared.hlsli:16); the reference shaders are the only CPU engine for it
+    "relax_nosh": (api.Denoiser.RELAX_DIFFUSE_SPECULAR, "relax_frame_nosh", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur"),
 }
+
+
+def frame_of(name, f, w, h):
+    if name == "relax_frame_nosh":
+        return synth.relax_frame(f, w, h, sh=False)
+    return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0)}
+LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0)}
 
 
 @pytest.fixture(scope="module")
@@ -73,7 +81,7 @@ def test_each_dispatch_against_the_reference_shaders(ex, runner, which):
                 worst[key] = r
 
     for f in range(frames):
-        for k, v in getattr(synth, CASES[which][1])(f, w, h).items():
+        for k, v in frame_of(CASES[which][1], f, w, h).items():
             ref.set_user_texture(getattr(RT, k), v)
         ref.denoise(synth.common_settings(f, w, h), before_dispatch=before, on_dispatch=after)
 
@@ -106,7 +114,7 @@ def test_closed_loop_against_the_reference_shaders(ex, runner, which):
         cud.set_user_texture(getattr(RT, o), gout[o], fmt)
     keep, log = {}, []
     for f in range(frames):
-        for k, v in getattr(synth, frame_fn)(f, w, h).items():
+        for k, v in frame_of(frame_fn, f, w, h).items():
             rt = getattr(RT, k)
             ref.set_user_texture(rt, v)
             keep[k] = v.to("cuda:0")
