@@ -1,8 +1,10 @@
-// SIGMA_SHADOW pass graph and per-frame constants.
-// Pool layout and bindings: External/NRD/Source/Denoisers/Sigma_Shadow.hpp:13-165.
+// SIGMA_SHADOW / SIGMA_SHADOW_TRANSLUCENCY pass graph and per-frame constants.
+// Pool layout and bindings: External/NRD/Source/Denoisers/Sigma_Shadow.hpp:13-165, Sigma_ShadowTranslucency.hpp:13-168
+// (RGBA8 shadow+translucency textures, IN_TRANSLUCENCY bound to ClassifyTiles / Blur / SplitScreen, TRANSLUCENCY=1 permutations).
 // Per-frame pass selection: External/NRD/Source/Sigma.cpp:25-85. Constants: Sigma.cpp:87-140.
 #include <algorithm>
 #include <cmath>
+#include <string>
 
 #include "pass_graph.h"
 
@@ -23,7 +25,10 @@ enum PassIndex : uint32_t {
 const uint32_t kCb = sizeof(SigmaConstants);
 }  // namespace
 
-void Graph::buildSigmaShadow(DenoiserState& d) {
+void Graph::buildSigmaShadow(DenoiserState& d, bool translucency) {
+    const Format shadowFormat = translucency ? Format::RGBA8_UNORM : Format::R8_UNORM;
+    const std::string tr = translucency ? "|TRANSLUCENCY=1" : "|TRANSLUCENCY=0";
+    const std::string name = translucency ? "SIGMA_ShadowTranslucency" : "SIGMA_Shadow";
     new (&d.settings.sigma) SigmaSettings();
     d.settingsSize = sizeof(SigmaSettings);
 
@@ -31,9 +36,9 @@ void Graph::buildSigmaShadow(DenoiserState& d) {
 
     addTransient(Format::R16_SFLOAT);       // penumbra ping
     addTransient(Format::R16_SFLOAT);       // penumbra pong
-    addTransient(Format::R8_UNORM);         // shadow ping
-    addTransient(Format::R8_UNORM);         // shadow pong
-    addTransient(Format::R8_UNORM);         // history copy
+    addTransient(shadowFormat);             // shadow ( + translucency ) ping
+    addTransient(shadowFormat);             // shadow ( + translucency ) pong
+    addTransient(shadowFormat);             // history copy
     addTransient(Format::R32_UINT);         // history-length copy
     addTransient(Format::RGBA8_UNORM, 16);  // tiles
     addTransient(Format::RG8_UNORM, 16);    // smoothed tiles
@@ -42,18 +47,19 @@ void Graph::buildSigmaShadow(DenoiserState& d) {
     auto Pm = [](uint16_t i) { return Slot::perm(i); };
     auto Tr = [](uint16_t i) { return Slot::tran(i); };
 
-    beginPass("SIGMA_Shadow - Classify tiles");
+    beginPass(intern(name + " - Classify tiles"));
     in(U(ResourceType::IN_VIEWZ));
     in(U(ResourceType::IN_PENUMBRA));
+    if (translucency) in(U(ResourceType::IN_TRANSLUCENCY));
     out(Tr(T_TILES));
-    emit("SIGMA_ClassifyTiles.cs.hlsl|TRANSLUCENCY=0", 16, 16, kCb);
+    emit(("SIGMA_ClassifyTiles.cs.hlsl" + tr).c_str(), 16, 16, kCb);
 
-    beginPass("SIGMA_Shadow - Smooth tiles");
+    beginPass(intern(name + " - Smooth tiles"));
     in(Tr(T_TILES));
     out(Tr(T_SMOOTHED_TILES));
     emit("SIGMA_SmoothTiles.cs.hlsl", 16, 16, kCb, 16, 1);
 
-    beginPass("SIGMA_Shadow - Copy");
+    beginPass(intern(name + " - Copy"));
     in(Tr(T_SMOOTHED_TILES));
     in(U(ResourceType::OUT_SHADOW_TRANSLUCENCY));
     in(Pm(P_HISTORY_LENGTH));
@@ -61,18 +67,19 @@ void Graph::buildSigmaShadow(DenoiserState& d) {
     out(Tr(T_HISTORY_LENGTH));
     emit("SIGMA_Copy.cs.hlsl", 8, 16, kCb, GRID_FROM_PREV_RECT, 1);
 
-    beginPass("SIGMA_Shadow - Blur");
+    beginPass(intern(name + " - Blur"));
     in(U(ResourceType::IN_VIEWZ));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(U(ResourceType::IN_PENUMBRA));
     in(Tr(T_SMOOTHED_TILES));
+    if (translucency) in(U(ResourceType::IN_TRANSLUCENCY));
     out(Tr(T_DATA_1));
     out(Tr(T_TEMP_1));
-    emit("SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=1", 8, 16, kCb);
+    emit(("SIGMA_Blur.cs.hlsl" + tr + "|FIRST_PASS=1").c_str(), 8, 16, kCb);
 
     for (int i = 0; i < 2; i++) {
         bool stabilizationFollows = i & 1;
-        beginPass("SIGMA_Shadow - Post-blur");
+        beginPass(intern(name + " - Post-blur"));
         in(U(ResourceType::IN_VIEWZ));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(Tr(T_DATA_1));
@@ -80,10 +87,10 @@ void Graph::buildSigmaShadow(DenoiserState& d) {
         in(Tr(T_TEMP_1));
         out(Tr(T_DATA_2));
         out(stabilizationFollows ? Tr(T_TEMP_2) : U(ResourceType::OUT_SHADOW_TRANSLUCENCY));
-        emit("SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=0", 8, 16, kCb);
+        emit(("SIGMA_Blur.cs.hlsl" + tr + "|FIRST_PASS=0").c_str(), 8, 16, kCb);
     }
 
-    beginPass("SIGMA_Shadow - Temporal stabilization");
+    beginPass(intern(name + " - Temporal stabilization"));
     in(U(ResourceType::IN_VIEWZ));
     in(U(ResourceType::IN_MV));
     in(Tr(T_DATA_2));
@@ -93,13 +100,14 @@ void Graph::buildSigmaShadow(DenoiserState& d) {
     in(Tr(T_SMOOTHED_TILES));
     out(U(ResourceType::OUT_SHADOW_TRANSLUCENCY));
     out(Pm(P_HISTORY_LENGTH));
-    emit("SIGMA_TemporalStabilization.cs.hlsl|TRANSLUCENCY=0", 8, 16, kCb);
+    emit(("SIGMA_TemporalStabilization.cs.hlsl" + tr).c_str(), 8, 16, kCb);
 
-    beginPass("SIGMA_Shadow - Split screen");
+    beginPass(intern(name + " - Split screen"));
     in(U(ResourceType::IN_VIEWZ));
     in(U(ResourceType::IN_PENUMBRA));
+    if (translucency) in(U(ResourceType::IN_TRANSLUCENCY));
     out(U(ResourceType::OUT_SHADOW_TRANSLUCENCY));
-    emit("SIGMA_SplitScreen.cs.hlsl|TRANSLUCENCY=0", 8, 16, kCb);
+    emit(("SIGMA_SplitScreen.cs.hlsl" + tr).c_str(), 8, 16, kCb);
 }
 
 void Graph::updateSigma(const DenoiserState& d) {

@@ -43,6 +43,7 @@ static const Denoiser kSupported[] = {
     Denoiser::RELAX_DIFFUSE_SPECULAR,
     Denoiser::RELAX_DIFFUSE_SPECULAR_SH,
     Denoiser::SIGMA_SHADOW,
+    Denoiser::SIGMA_SHADOW_TRANSLUCENCY,
 };
 
 const LibraryDesc& libraryDesc() {
@@ -155,7 +156,8 @@ Result Graph::create(const InstanceCreationDesc& desc) {
 
         switch (dd.denoiser) {
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: buildReblurDiffuseSpecular(d); break;
-            case Denoiser::SIGMA_SHADOW: buildSigmaShadow(d); break;
+            case Denoiser::SIGMA_SHADOW: buildSigmaShadow(d, false); break;
+            case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: buildSigmaShadow(d, true); break;
             case Denoiser::RELAX_DIFFUSE_SPECULAR_SH: buildRelaxDiffuseSpecular(d, true); break;
             case Denoiser::RELAX_DIFFUSE_SPECULAR: buildRelaxDiffuseSpecular(d, false); break;
             default: return Result::INVALID_ARGUMENT;
@@ -451,7 +453,8 @@ Result Graph::getComputeDispatches(const Identifier* ids, uint32_t idsNum, const
         flipPingPong(d);
         switch (d.desc.denoiser) {
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: updateReblur(d); break;
-            case Denoiser::SIGMA_SHADOW: updateSigma(d); break;
+            case Denoiser::SIGMA_SHADOW:
+            case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: updateSigma(d); break;
             case Denoiser::RELAX_DIFFUSE_SPECULAR_SH:
             case Denoiser::RELAX_DIFFUSE_SPECULAR: updateRelax(d); break;
             default: break;

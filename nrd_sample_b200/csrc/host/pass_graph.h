@@ -117,7 +117,7 @@ private:
     void buildReblurDiffuseSpecular(DenoiserState& d);
     void updateReblur(const DenoiserState& d);
     void fillReblurConstants(const ReblurSettings& s, void* dst);
-    void buildSigmaShadow(DenoiserState& d);
+    void buildSigmaShadow(DenoiserState& d, bool translucency);
     void updateSigma(const DenoiserState& d);
     void fillSigmaConstants(const SigmaSettings& s, void* dst);
     void buildRelaxDiffuseSpecular(DenoiserState& d, bool sh);

@@ -186,6 +186,7 @@ struct TexRGBA8 : TexView {  // RGBA8_UNORM
     }
     NRD_DEV float4 load(int x, int y) const { return inside(x, y) ? fetch(x, y) : f4(0.0f); }
     NRD_DEV float4 fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
+    NRD_DEV float4 sampleNearest(float2 uv) const { return fetchClamped((int)floorf(uv.x * (float)w), (int)floorf(uv.y * (float)h)); }
     NRD_DEV float4 sampleLinear(float2 uv) const {
         float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
         float fx = floorf(tx), fy = floorf(ty);

@@ -1,4 +1,4 @@
-// SIGMA_SHADOW passes on sm_100a (TRANSLUCENCY = 0): ClassifyTiles, SmoothTiles, Copy, Blur (first pass / post-blur),
+// SIGMA_SHADOW / SIGMA_SHADOW_TRANSLUCENCY passes on sm_100a (kernels templated on TRANSLUCENCY: SIGMA_TYPE = float / float4): ClassifyTiles, SmoothTiles, Copy, Blur (first pass / post-blur),
 // TemporalStabilization, SplitScreen. One kernel per reference dispatch, one thread per pixel, CTA = 32x8 pixels for the
 // per-pixel passes (a 32-pixel row per warp: coalesced R16F / R32F / R8 rows), 5x5 neighbourhoods through shared memory.
 //
@@ -7,6 +7,7 @@
 // SIGMA_SplitScreen.cs.hlsl:21-45. The reference groups are 8x16 (16x16 for the tile passes); the CUDA grid is laid out
 // differently but every pixel computes the same function of the same texels.
 #include <string>
+#include <type_traits>
 
 #include "../../../include/nrd_b200.h"
 #include "../../../include/nrdcu.h"
@@ -36,6 +37,7 @@ NRD_DEV float applyGeometryWeightLast(const SigmaConstants& cb, float w, float z
 
 // ---------------------------------------------------------------------------------------------------------------
 // One CTA of 256 threads per 16x16 tile; the three 9-bit counters of the reference's s_Mask become block-wide counts
+template <bool TR>
 __global__ void __launch_bounds__(256) sigmaClassifyTilesKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaClassifyTilesParams p) {
     __shared__ uint32_t sRadius[8];
     const int tx = blockIdx.x, ty = blockIdx.y;
@@ -44,7 +46,12 @@ __global__ void __launch_bounds__(256) sigmaClassifyTilesKernel(const __grid_con
     const float viewZ = sigmaUnpackViewZ(cb, p.viewZ.load(px, py));
     const bool isInf = !sigmaInRange(cb, viewZ), isShadow = h == 0.0f, isLit = sigmaIsLit(h);
     const int nLit = __syncthreads_count(isLit || isInf || isShadow);
-    const int nUmbra = __syncthreads_count(!isLit || isInf || isShadow);
+    bool isOpaque = true;
+    if (TR) {  // SIGMA_ClassifyTiles.cs.hlsl:55-58
+        const float4 st = p.translucency.load(px, py);
+        isOpaque = dot(make_float3(st.y, st.z, st.w), make_float3(0.2126f, 0.7152f, 0.0722f)) < 0.003f;
+    }
+    const int nUmbra = __syncthreads_count((!isLit && isOpaque) || isInf || isShadow);
     const int nInf = __syncthreads_count(isInf);
     const float hitDist = (isLit || isInf) ? 0.0f : h;
     const float pixelSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, 1.0f, viewZ);
@@ -80,19 +87,25 @@ __global__ void __launch_bounds__(256) sigmaSmoothTilesKernel(const __grid_const
     p.outTiles.store(x, y, make_float2(center.z, blurry / sum));
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaCopyParams p) {
+template <class ST>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaCopyParams<ST> p) {
+    using Raw = typename std::conditional<std::is_same<ST, TexR8>::value, uint8_t, uint32_t>::type;
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     const float isSky = p.tiles.load(px >> 4, py >> 4).x;
     if ((isSky != 0.0f && !cb.isRectChanged) || !p.history.inside(px, py)) return;
-    *p.outHistory.ptrw<uint8_t>(px, py) = __ldg(p.history.ptr<uint8_t>(px, py));
+    *p.outHistory.template ptrw<Raw>(px, py) = __ldg(p.history.template ptr<Raw>(px, py));
     p.outHistoryLength.store(px, py, p.historyLength.load(px, py));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <bool FIRST_PASS>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaBlurParams p) {
+template <bool FIRST_PASS, bool TR>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid_constant__ SigmaConstants cb,
+                                                                   const __grid_constant__ SigmaBlurParams<typename SigmaSignal<TR>::Tex> p) {
+    using SG = SigmaSignal<TR>;
+    using S = typename SG::T;
+    constexpr bool SHADOW_FROM_PENUMBRA = FIRST_PASS && !TR;  // s = IsLit( penumbra ): no shadow texture bound (SIGMA_Blur.cs.hlsl:35-39)
     __shared__ float2 sPenumbraViewZ[TILE_H][TILE_W];
-    __shared__ float sShadow[FIRST_PASS ? 1 : TILE_H][FIRST_PASS ? 1 : TILE_W];
+    __shared__ S sShadow[SHADOW_FROM_PENUMBRA ? 1 : TILE_H][SHADOW_FROM_PENUMBRA ? 1 : TILE_W];
 
     // CTA order: first pass default, post-blur reversed (SIGMA_Blur.cs.hlsl:51-55)
     const int bx = FIRST_PASS ? (int)blockIdx.x : (int)(gridDim.x - 1u - blockIdx.x), by = FIRST_PASS ? (int)blockIdx.y : (int)(gridDim.y - 1u - blockIdx.y);
@@ -109,9 +122,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
             const int sx = i % TILE_W, sy = i / TILE_W;
             const int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
             sPenumbraViewZ[sy][sx] = make_float2(p.penumbra.load(gx, gy), sigmaUnpackViewZ(cb, p.viewZ.load(gx, gy)));
-            if (!FIRST_PASS) {
-                const float s = p.shadow.load(gx, gy);
-                sShadow[sy][sx] = s * s;  // SIGMA_BackEnd_UnpackShadow
+            if (!SHADOW_FROM_PENUMBRA) {
+                const S s = p.shadow.load(gx, gy);
+                sShadow[SHADOW_FROM_PENUMBRA ? 0 : sy][SHADOW_FROM_PENUMBRA ? 0 : sx] = FIRST_PASS ? s : s * s;  // SIGMA_BackEnd_UnpackShadow
             }
         }
     }
@@ -129,9 +142,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
     const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * rectSizeInv;
     const float tileValue = sigmaTileValue(p.tiles, pixelUv * make_float2(cb.resolutionScale[0], cb.resolutionScale[1]));
 
-    auto shadowAt = [&](int y, int x, float penum) -> float {
-        if (FIRST_PASS) return sigmaIsLit(penum) ? 1.0f : 0.0f;
-        return sShadow[FIRST_PASS ? 0 : y][FIRST_PASS ? 0 : x];
+    auto shadowAt = [&](int y, int x, float penum) -> S {
+        if (SHADOW_FROM_PENUMBRA) return SG::splat(sigmaIsLit(penum) ? 1.0f : 0.0f);
+        return sShadow[SHADOW_FROM_PENUMBRA ? 0 : y][SHADOW_FROM_PENUMBRA ? 0 : x];
     };
 
     if (tileValue == 0.0f || centerPenumbra == 0.0f) {
@@ -151,14 +164,15 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
     const float2 geomParams = geometryWeightParams(cb.planeDistSensitivity, frustumSize, Xv, Nv);
 
     // Estimate penumbra size and filter shadow ( dense 5x5 )
-    float sumX = 0.0f, sumY = 0.0f, penumbra = 0.0f, result = 0.0f, centerTap = 0.0f;
+    float sumX = 0.0f, sumY = 0.0f, penumbra = 0.0f;
+    S result = SG::splat(0.0f), centerTap = SG::splat(0.0f);
 #pragma unroll
     for (int j = 0; j <= SIGMA_BORDER * 2; j++)
 #pragma unroll
         for (int i = 0; i <= SIGMA_BORDER * 2; i++) {
             const float2 data = sPenumbraViewZ[threadIdx.y + j][threadIdx.x + i];
             const float penum = data.x, zs = data.y;
-            const float s = shadowAt(threadIdx.y + j, threadIdx.x + i, penum);
+            const S s = shadowAt(threadIdx.y + j, threadIdx.x + i, penum);
             float w = 1.0f;
             if (i == SIGMA_BORDER && j == SIGMA_BORDER)
                 centerTap = s;
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
                 w *= gaussianWeight(length(o / (float)SIGMA_BORDER));
                 w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
             }
-            result += w == 0.0f ? 0.0f : s * w;
+            result += w == 0.0f ? SG::splat(0.0f) : s * w;
             sumX += w;
             w *= pixelSize / (pixelSize + penum);
             w *= sigmaIsLit(penum) ? 0.0f : 1.0f;
@@ -218,12 +232,12 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
         const float penum = p.penumbra.sampleNearest(uvScaled);
         const float zs = sigmaUnpackViewZ(cb, p.viewZ.sampleNearest(uvScaled));
         const float3 Xvs = reconstructViewPosition(uv, cb.frustum, zs, cb.orthoMode);
-        float s;
-        if (FIRST_PASS)
-            s = sigmaIsLit(penum) ? 1.0f : 0.0f;
+        S s;
+        if (SHADOW_FROM_PENUMBRA)
+            s = SG::splat(sigmaIsLit(penum) ? 1.0f : 0.0f);
         else {
             s = p.shadow.sampleNearest(uvScaled);
-            s *= s;
+            if (!FIRST_PASS) s *= s;
         }
 
         const float NoX = dot(Nv, Xvs);
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
         w *= saturate(penum * invEstimatedPenumbra);  // avoid umbra leaking inside wide penumbra
         w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
 
-        result += w == 0.0f ? 0.0f : s * w;
+        result += w == 0.0f ? SG::splat(0.0f) : s * w;
         sumX += w;
         w *= pixelSize / (pixelSize + penum);
         w *= sigmaIsLit(penum) ? 0.0f : 1.0f;
@@ -253,9 +267,12 @@ NRD_DEV uint32_t packViewZAndHistoryLength(float viewZ, float historyLength) {
     return (__float_as_uint(viewZ) & ~7u) | min((uint32_t)(historyLength + 0.5f), 7u);
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaTemporalStabilizationKernel(const __grid_constant__ SigmaConstants cb,
-                                                                                    const __grid_constant__ SigmaTemporalStabilizationParams p) {
-    __shared__ float sShadow[TILE_H][TILE_W];
+template <bool TR>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H)
+    sigmaTemporalStabilizationKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaTemporalStabilizationParams<typename SigmaSignal<TR>::Tex> p) {
+    using SG = SigmaSignal<TR>;
+    using S = typename SG::T;
+    __shared__ S sShadow[TILE_H][TILE_W];
     __shared__ float sPenumbra[TILE_H][TILE_W];
 
     const int bx = blockIdx.x, by = blockIdx.y;  // NRD_CTA_ORDER_DEFAULT
@@ -268,7 +285,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaTemporalStabilizationKe
         for (int i = tid; i < TILE_W * TILE_H; i += BLOCK_W * BLOCK_H) {
             const int sx = i % TILE_W, sy = i / TILE_W;
             const int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
-            const float s = p.shadow.load(gx, gy);
+            const S s = p.shadow.load(gx, gy);
             sShadow[sy][sx] = s * s;
             sPenumbra[sy][sx] = p.penumbra.load(gx, gy);
         }
@@ -291,12 +308,13 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaTemporalStabilizationKe
     }
 
     // Local variance
-    float sum = 0.0f, m1 = 0.0f, m2 = 0.0f, input = 0.0f;
+    float sum = 0.0f;
+    S m1 = SG::splat(0.0f), m2 = SG::splat(0.0f), input = SG::splat(0.0f);
 #pragma unroll
     for (int j = 0; j <= SIGMA_BORDER * 2; j++)
 #pragma unroll
         for (int i = 0; i <= SIGMA_BORDER * 2; i++) {
-            const float s = sShadow[threadIdx.y + j][threadIdx.x + i];
+            const S s = sShadow[threadIdx.y + j][threadIdx.x + i];
             float w = 1.0f;
             if (i == SIGMA_BORDER && j == SIGMA_BORDER)
                 input = s;
@@ -311,7 +329,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaTemporalStabilizationKe
         }
     m1 /= sum;
     m2 /= sum;
-    float sigma = stdDev(m1, m2);
+    S sigma = SG::stdDev(m1, m2);
 
     // Current and previous positions
     const float3 Xv = reconstructViewPosition(pixelUv, cb.frustum, viewZ, cb.orthoMode);
@@ -355,16 +373,16 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaTemporalStabilizationKe
     // Sample history
     const bool isCatRomAllowed = sum4(occlusionWeights) > 3.5f;
     const HistoryFilter hf(saturate(smbPixelUv) * rectSizePrev, make_float2(cb.resourceSizeInvPrev[0], cb.resourceSizeInvPrev[1]), occlusionWeights, isCatRomAllowed);
-    float history = hf.color(p.history);
+    S history = hf.color(p.history);
     history = saturate(history);
     history *= history;
 
     // Clamp history
     sigma *= lerp(SIGMA_TS_SIGMA_SCALE, 1.0f, 1.0f / (1.0f + historyLength));
-    float historyClamped = fminf(fmaxf(history, m1 - sigma), m1 + sigma);
+    S historyClamped = SG::clamp(history, m1 - sigma, m1 + sigma);
 
-    // Antilag
-    float antilag = sqrt01(fabsf(historyClamped - history));
+    // Antilag ( on the shadow channel: SIGMA_TemporalStabilization.cs.hlsl:183 )
+    float antilag = sqrt01(fabsf(SG::x(historyClamped) - SG::x(history)));
     antilag = saturate(1.0f - antilag);
     historyLength *= antilag;
 
@@ -372,20 +390,27 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaTemporalStabilizationKe
     const float streetMagic = 0.6f * historyWeight * antilag;
     historyClamped = lerp(historyClamped, history, streetMagic);
 
-    const float result = lerp(input, historyClamped, fminf(cb.stabilizationStrength, historyWeight));
+    const S result = lerp(input, historyClamped, fminf(cb.stabilizationStrength, historyWeight));
     historyLength = fminf(historyLength + 1.0f, SIGMA_MAX_ACCUM_FRAME_NUM);
 
     p.outShadow.store(px, py, sigmaPackShadow(result));
     p.outHistoryLength.store(px, py, packViewZAndHistoryLength(viewZ, historyLength));
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaSplitScreenKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaSplitScreenParams p) {
+template <bool TR>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaSplitScreenKernel(const __grid_constant__ SigmaConstants cb,
+                                                                          const __grid_constant__ SigmaSplitScreenParams<typename SigmaSignal<TR>::Tex> p) {
+    using SG = SigmaSignal<TR>;
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
     if (u > cb.splitScreen || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1]) return;
     const float viewZ = sigmaUnpackViewZ(cb, p.viewZ.load(px, py));
-    const float s = sigmaIsLit(p.penumbra.load(px, py)) ? 1.0f : 0.0f;
-    p.outShadow.store(px, py, sigmaInRange(cb, viewZ) ? s : 0.0f);
+    typename SG::T s;
+    if (TR)
+        s = p.translucency.load(px, py);
+    else
+        s = SG::splat(sigmaIsLit(p.penumbra.load(px, py)) ? 1.0f : 0.0f);
+    p.outShadow.store(px, py, s * (sigmaInRange(cb, viewZ) ? 1.0f : 0.0f));
 }
 
 }  // namespace
@@ -453,13 +478,19 @@ uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t co
     const dim3 pixelGrid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, (cb.rectSizeMinusOne[1] + BLOCK_H) / BLOCK_H);
     const int tilesW = cb.tilesSizeMinusOne[0] + 1, tilesH = cb.tilesSizeMinusOne[1] + 1;
 
-    if (id == "SIGMA_ClassifyTiles.cs.hlsl|TRANSLUCENCY=0") {
-        SigmaClassifyTilesParams p;
+    const bool tr = id.find("|TRANSLUCENCY=1") != std::string::npos;
+    auto is = [&](const char* file, const char* suffix = "") { return id == std::string(file) + (tr ? "|TRANSLUCENCY=1" : "|TRANSLUCENCY=0") + suffix; };
+    if (is("SIGMA_ClassifyTiles.cs.hlsl")) {
+        SigmaClassifyTilesParams p = {};
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+        if (tr) p.translucency = b.take<TexRGBA8>(Format::RGBA8_UNORM);
         p.outTiles = b.take<TexRGBA8>(Format::RGBA8_UNORM);
-        if (bad(3)) return (uint32_t)Result::INVALID_ARGUMENT;
-        sigmaClassifyTilesKernel<<<dim3(tilesW, tilesH), 256, 0, stream>>>(cb, p);
+        if (bad(tr ? 4 : 3)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (tr)
+            sigmaClassifyTilesKernel<true><<<dim3(tilesW, tilesH), 256, 0, stream>>>(cb, p);
+        else
+            sigmaClassifyTilesKernel<false><<<dim3(tilesW, tilesH), 256, 0, stream>>>(cb, p);
     } else if (id == "SIGMA_SmoothTiles.cs.hlsl") {
         SigmaSmoothTilesParams p;
         p.tiles = b.take<TexRGBA8>(Format::RGBA8_UNORM);
@@ -467,49 +498,76 @@ uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t co
         if (bad(2)) return (uint32_t)Result::INVALID_ARGUMENT;
         sigmaSmoothTilesKernel<<<dim3((tilesW + 15) / 16, (tilesH + 15) / 16), 256, 0, stream>>>(cb, p);
     } else if (id == "SIGMA_Copy.cs.hlsl") {
-        SigmaCopyParams p;
-        p.tiles = b.take<TexRG8>(Format::RG8_UNORM);
-        p.history = b.take<TexR8>(Format::R8_UNORM);
-        p.historyLength = b.take<TexR32U>(Format::R32_UINT);
-        p.outHistory = b.take<TexR8>(Format::R8_UNORM);
-        p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
-        if (bad(5)) return (uint32_t)Result::INVALID_ARGUMENT;
-        sigmaCopyKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
-    } else if (id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=1" || id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=0") {
-        const bool first = id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=1";
-        SigmaBlurParams p = {};
-        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
-        p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.tiles = b.take<TexRG8>(Format::RG8_UNORM);
-        if (!first) p.shadow = b.take<TexR8>(Format::R8_UNORM);
-        p.outPenumbra = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outShadow = b.take<TexR8>(Format::R8_UNORM);
-        if (bad(first ? 6 : 7)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (first)
-            sigmaBlurKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p);
-        else
-            sigmaBlurKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
-    } else if (id == "SIGMA_TemporalStabilization.cs.hlsl|TRANSLUCENCY=0") {
-        SigmaTemporalStabilizationParams p;
-        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.mv = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.shadow = b.take<TexR8>(Format::R8_UNORM);
-        p.history = b.take<TexR8>(Format::R8_UNORM);
-        p.historyLength = b.take<TexR32U>(Format::R32_UINT);
-        p.tiles = b.take<TexRG8>(Format::RG8_UNORM);
-        p.outShadow = b.take<TexR8>(Format::R8_UNORM);
-        p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
-        if (bad(9)) return (uint32_t)Result::INVALID_ARGUMENT;
-        sigmaTemporalStabilizationKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
-    } else if (id == "SIGMA_SplitScreen.cs.hlsl|TRANSLUCENCY=0") {
-        SigmaSplitScreenParams p;
-        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outShadow = b.take<TexR8>(Format::R8_UNORM);
-        if (bad(3)) return (uint32_t)Result::INVALID_ARGUMENT;
-        sigmaSplitScreenKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+        // one shader for both variants (gIn_History is declared float4): the history's own format picks the texel width
+        const bool wide = n > 1 && tex[1].format == (uint32_t)Format::RGBA8_UNORM;
+        auto run = [&](auto sig) -> bool {
+            using SG = decltype(sig);
+            SigmaCopyParams<typename SG::Tex> p;
+            p.tiles = b.take<TexRG8>(Format::RG8_UNORM);
+            p.history = b.take<typename SG::Tex>(SG::format);
+            p.historyLength = b.take<TexR32U>(Format::R32_UINT);
+            p.outHistory = b.take<typename SG::Tex>(SG::format);
+            p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
+            if (bad(5)) return false;
+            sigmaCopyKernel<typename SG::Tex><<<pixelGrid, block, 0, stream>>>(cb, p);
+            return true;
+        };
+        if (!(wide ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
+    } else if (is("SIGMA_Blur.cs.hlsl", "|FIRST_PASS=1") || is("SIGMA_Blur.cs.hlsl", "|FIRST_PASS=0")) {
+        const bool first = is("SIGMA_Blur.cs.hlsl", "|FIRST_PASS=1");
+        auto run = [&](auto sig) -> bool {
+            using SG = decltype(sig);
+            constexpr bool TR = std::is_same<SG, SigmaSignal<true>>::value;
+            SigmaBlurParams<typename SG::Tex> p = {};
+            p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+            p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+            p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+            p.tiles = b.take<TexRG8>(Format::RG8_UNORM);
+            const bool hasShadow = !first || TR;  // SIGMA_Blur.resources.hlsli:25-27
+            if (hasShadow) p.shadow = b.take<typename SG::Tex>(SG::format);
+            p.outPenumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+            p.outShadow = b.take<typename SG::Tex>(SG::format);
+            if (bad(hasShadow ? 7 : 6)) return false;
+            if (first)
+                sigmaBlurKernel<true, TR><<<pixelGrid, block, 0, stream>>>(cb, p);
+            else
+                sigmaBlurKernel<false, TR><<<pixelGrid, block, 0, stream>>>(cb, p);
+            return true;
+        };
+        if (!(tr ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
+    } else if (is("SIGMA_TemporalStabilization.cs.hlsl")) {
+        auto run = [&](auto sig) -> bool {
+            using SG = decltype(sig);
+            constexpr bool TR = std::is_same<SG, SigmaSignal<true>>::value;
+            SigmaTemporalStabilizationParams<typename SG::Tex> p;
+            p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+            p.mv = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+            p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+            p.shadow = b.take<typename SG::Tex>(SG::format);
+            p.history = b.take<typename SG::Tex>(SG::format);
+            p.historyLength = b.take<TexR32U>(Format::R32_UINT);
+            p.tiles = b.take<TexRG8>(Format::RG8_UNORM);
+            p.outShadow = b.take<typename SG::Tex>(SG::format);
+            p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
+            if (bad(9)) return false;
+            sigmaTemporalStabilizationKernel<TR><<<pixelGrid, block, 0, stream>>>(cb, p);
+            return true;
+        };
+        if (!(tr ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
+    } else if (is("SIGMA_SplitScreen.cs.hlsl")) {
+        auto run = [&](auto sig) -> bool {
+            using SG = decltype(sig);
+            constexpr bool TR = std::is_same<SG, SigmaSignal<true>>::value;
+            SigmaSplitScreenParams<typename SG::Tex> p = {};
+            p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+            p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
+            if (TR) p.translucency = b.take<typename SG::Tex>(SG::format);
+            p.outShadow = b.take<typename SG::Tex>(SG::format);
+            if (bad(TR ? 4 : 3)) return false;
+            sigmaSplitScreenKernel<TR><<<pixelGrid, block, 0, stream>>>(cb, p);
+            return true;
+        };
+        if (!(tr ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
     } else {
         err = "no CUDA kernel for shader '" + id + "'";
         return (uint32_t)Result::UNSUPPORTED;

@@ -2,6 +2,7 @@
 // Reference: External/NRD/Shaders/SIGMA_Common.hlsli:13-95, SIGMA_Config.hlsli:11-42 (switches at their defaults:
 // 5x5 radius-estimation and temporal kernels, sparse blur, screen-space sampling, early out in TS, CatRom history).
 #pragma once
+#include "../../../include/nrd_b200.h"
 #include "reblur_common.cuh"  // HistoryFilter (Common.hlsli:604-658) is shared with REBLUR
 
 namespace nrdk {
@@ -19,6 +20,30 @@ NRD_DEV float sigmaUnpackViewZ(const SigmaConstants& cb, float z) { return fabsf
 NRD_DEV bool sigmaInRange(const SigmaConstants& cb, float z) { return z < cb.denoisingRange; }
 NRD_DEV bool sigmaIsLit(float p) { return p >= NRD_FP16_MAX; }
 NRD_DEV float sigmaPackShadow(float s) { return sqrt01(s); }
+NRD_DEV float4 sigmaPackShadow(float4 s) { return make_float4(sqrt01(s.x), sqrt01(s.y), sqrt01(s.z), sqrt01(s.w)); }
+
+// SIGMA_TYPE (SIGMA_Config.hlsli:37-42): float for SIGMA_SHADOW, float4 = { shadow, translucency.rgb } for SIGMA_SHADOW_TRANSLUCENCY
+template <bool TRANSLUCENCY> struct SigmaSignal;
+template <> struct SigmaSignal<false> {
+    using T = float;
+    using Tex = TexR8;
+    static constexpr nrd::Format format = nrd::Format::R8_UNORM;
+    static NRD_DEV T splat(float v) { return v; }
+    static NRD_DEV float x(T s) { return s; }
+    static NRD_DEV T stdDev(T m1, T m2) { return nrdk::stdDev(m1, m2); }
+    static NRD_DEV T clamp(T v, T lo, T hi) { return fminf(fmaxf(v, lo), hi); }
+};
+template <> struct SigmaSignal<true> {
+    using T = float4;
+    using Tex = TexRGBA8;
+    static constexpr nrd::Format format = nrd::Format::RGBA8_UNORM;
+    static NRD_DEV T splat(float v) { return make_float4(v, v, v, v); }
+    static NRD_DEV float x(T s) { return s.x; }
+    static NRD_DEV T stdDev(T m1, T m2) { return make_float4(nrdk::stdDev(m1.x, m2.x), nrdk::stdDev(m1.y, m2.y), nrdk::stdDev(m1.z, m2.z), nrdk::stdDev(m1.w, m2.w)); }
+    static NRD_DEV T clamp(T v, T lo, T hi) {
+        return make_float4(fminf(fmaxf(v.x, lo.x), hi.x), fminf(fmaxf(v.y, lo.y), hi.y), fminf(fmaxf(v.z, lo.z), hi.z), fminf(fmaxf(v.w, lo.w), hi.w));
+    }
+};
 NRD_DEV float sigmaBothLitOrUnlit(float p1, float p2) { return ((p1 == 0.0f) == (p2 == 0.0f)) ? 1.0f : 0.0f; }
 // GetKernelRadiusInPixels: fminf / fmaxf are IEEE minNum / maxNum like the HLSL intrinsics (0 / 0 -> lower bound)
 NRD_DEV float sigmaKernelRadiusInPixels(float hitDist, float unprojectZ, float scale = 1.0f) {
@@ -52,14 +77,15 @@ NRD_DEV float sigmaTileValue(const TexRG8& tiles, float2 uv) {
 }
 
 // ---- launch parameter blocks (member order = shader register order = DispatchDesc::resources order) ----------
-struct SigmaClassifyTilesParams { TexR32F viewZ; TexR16F penumbra; TexRGBA8 outTiles; };
+struct SigmaClassifyTilesParams { TexR32F viewZ; TexR16F penumbra; TexRGBA8 translucency; TexRGBA8 outTiles; };
 struct SigmaSmoothTilesParams { TexRGBA8 tiles; TexRG8 outTiles; };
-struct SigmaCopyParams { TexRG8 tiles; TexR8 history; TexR32U historyLength; TexR8 outHistory; TexR32U outHistoryLength; };
-struct SigmaBlurParams { TexR32F viewZ; TexNR normalRoughness; TexR16F penumbra; TexRG8 tiles; TexR8 shadow; TexR16F outPenumbra; TexR8 outShadow; };
-struct SigmaTemporalStabilizationParams {
-    TexR32F viewZ; TexRGBA16F mv; TexR16F penumbra; TexR8 shadow; TexR8 history; TexR32U historyLength; TexRG8 tiles;
-    TexR8 outShadow; TexR32U outHistoryLength;
+// `ST` = SigmaSignal<TRANSLUCENCY>::Tex: R8 shadow or RGBA8 shadow + translucency
+template <class ST> struct SigmaCopyParams { TexRG8 tiles; ST history; TexR32U historyLength; ST outHistory; TexR32U outHistoryLength; };
+template <class ST> struct SigmaBlurParams { TexR32F viewZ; TexNR normalRoughness; TexR16F penumbra; TexRG8 tiles; ST shadow; TexR16F outPenumbra; ST outShadow; };
+template <class ST> struct SigmaTemporalStabilizationParams {
+    TexR32F viewZ; TexRGBA16F mv; TexR16F penumbra; ST shadow; ST history; TexR32U historyLength; TexRG8 tiles;
+    ST outShadow; TexR32U outHistoryLength;
 };
-struct SigmaSplitScreenParams { TexR32F viewZ; TexR16F penumbra; TexR8 outShadow; };
+template <class ST> struct SigmaSplitScreenParams { TexR32F viewZ; TexR16F penumbra; ST translucency; ST outShadow; };
 
 }  // namespace nrdk

@@ -314,7 +314,7 @@ SIGMA_TAN_ANGULAR_RADIUS = math.tan(math.radians(5.0))
 FP16_MAX = 65504.0
 
 
-def sigma_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False) -> Dict[str, torch.Tensor]:
+def sigma_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, translucency: bool = False) -> Dict[str, torch.Tensor]:
     """All user inputs of SIGMA_SHADOW for one frame: IN_VIEWZ, IN_NORMAL_ROUGHNESS, IN_MV as for REBLUR plus IN_PENUMBRA
     (R16F) = SIGMA_FrontEnd_PackPenumbra (NRD.hlsli:974-980) of a 1-spp shadow ray towards a disk light: 0 where the
     surface faces away from the light, FP16_MAX where the ray escapes, distance-to-occluder * tan(angular radius) / 2 otherwise."""
@@ -354,6 +354,16 @@ def sigma_frame(frame_index: int, width: int, height: int, device="cpu", period:
         "IN_MV": base["IN_MV"],
         "IN_PENUMBRA": penumbra.to(torch.float16).contiguous(),
     }
+    if translucency:
+        # SIGMA_SHADOW_TRANSLUCENCY: IN_TRANSLUCENCY (RGBA8, as NRDSample creates it) = SIGMA_FrontEnd_PackTranslucency (NRD.hlsli:994-1001):
+        # x = the shadow ray escaped, yzw = tint of the occluder it went through: 40 % of the blocked rays hit a "stained glass" occluder
+        lit = dist >= FP16_MAX
+        u = torch.rand(height, width, device=device, generator=gen)
+        glass = (~lit) & (torch.rand(height, width, device=device, generator=gen) < 0.4)
+        tint = torch.tensor([0.9, 0.45, 0.2], device=device) * (0.5 + 0.5 * u).unsqueeze(-1)
+        rgb = torch.where(lit.unsqueeze(-1), torch.ones_like(tint), torch.where(glass.unsqueeze(-1), tint, torch.zeros_like(tint)))
+        packed = torch.cat([lit.float().unsqueeze(-1), rgb.clamp(0.0, 1.0)], dim=-1)
+        out["IN_TRANSLUCENCY"] = (packed * 255.0 + 0.5).to(torch.uint8).contiguous()
     if with_clean:   # converged visibility: mean over 48 more light samples
         vis = torch.zeros_like(ndl)
         for _ in range(48):

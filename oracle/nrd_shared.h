@@ -90,6 +90,7 @@ inline float2 GetScreenUv(const float4x4& worldToClip, float3 X) {  // ml:659, D
 // Color, Packing, Filtering, Sequence, Rng, ImportanceSampling
 // ------------------------------------------------------------------------------------------------------------
 namespace Color {
+inline float Luminance(float3 x) { return dot(x, float3(0.2126f, 0.7152f, 0.0722f)); }  // ml:712-717
 inline float Clamp(float m1, float sigma, float c) { return clamp(c, m1 - sigma, m1 + sigma); }  // ml:1101
 }
 

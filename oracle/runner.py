@@ -114,7 +114,8 @@ USER_FORMATS = {
     api.ResourceType.OUT_SPEC_SH0: api.Format.RGBA16_SFLOAT,
     api.ResourceType.OUT_SPEC_SH1: api.Format.RGBA16_SFLOAT,
     api.ResourceType.IN_PENUMBRA: api.Format.R16_SFLOAT,
-    api.ResourceType.OUT_SHADOW_TRANSLUCENCY: api.Format.R8_UNORM,
+    api.ResourceType.OUT_SHADOW_TRANSLUCENCY: api.Format.R8_UNORM,   # RGBA8_UNORM for SIGMA_SHADOW_TRANSLUCENCY ( pass fmt= explicitly )
+    api.ResourceType.IN_TRANSLUCENCY: api.Format.RGBA8_UNORM,
 }
 
 

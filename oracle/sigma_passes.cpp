@@ -2,7 +2,7 @@
 // PINNED: bit-identical, dispatch by dispatch, to the reference's own shaders compiled as C++
 // (oracle/_ref/libnrd_refshaders.so, tests/test_oracle_vs_reference_shaders.py).
 //
-// SIGMA_SHADOW (TRANSLUCENCY = 0) restated from /root/reference/External/NRD/Shaders:
+// SIGMA_SHADOW / SIGMA_SHADOW_TRANSLUCENCY (TRANSLUCENCY = 0 / 1: SIGMA_TYPE = float / float4, SIGMA_Config.hlsli:37-42) restated from /root/reference/External/NRD/Shaders:
 //   SIGMA_ClassifyTiles.cs.hlsl:24-91, SIGMA_SmoothTiles.cs.hlsl:21-58, SIGMA_Copy.cs.hlsl:19-32,
 //   SIGMA_Blur.cs.hlsl:21-286 (FIRST_PASS = 1 / 0), SIGMA_TemporalStabilization.cs.hlsl:21-236,
 //   SIGMA_SplitScreen.cs.hlsl:21-45, helpers SIGMA_Common.hlsli:13-95, switches SIGMA_Config.hlsli:11-42.
@@ -39,6 +39,29 @@ const int TS_BORDER = 2;                     // SIGMA_5X5_TEMPORAL_KERNEL = 1
 inline float PackShadow(float s) { return Math::Sqrt01(s); }     // SIGMA_Common.hlsli:13
 inline bool IsLit(float p) { return p >= NRD_FP16_MAX; }         // :14
 inline float UnpackShadow(float s) { return s * s; }             // NRD.hlsli:1010
+inline float4 PackShadow(float4 s) { return float4(Math::Sqrt01(s.x), Math::Sqrt01(s.y), Math::Sqrt01(s.z), Math::Sqrt01(s.w)); }
+inline float4 UnpackShadow(float4 s) { return s * s; }
+inline float StdDevS(float m1, float m2) { return GetStdDev(m1, m2); }
+inline float4 StdDevS(float4 m1, float4 m2) { return float4(GetStdDev(m1.x, m2.x), GetStdDev(m1.y, m2.y), GetStdDev(m1.z, m2.z), GetStdDev(m1.w, m2.w)); }
+inline float ClampS(float x, float lo, float hi) { return clamp(x, lo, hi); }
+inline float4 ClampS(float4 x, float4 lo, float4 hi) { return min(max(x, lo), hi); }
+
+// SIGMA_TYPE (SIGMA_Config.hlsli:37-42): float, or float4 = { shadow, translucency.rgb }
+template <bool TRANSLUCENCY> struct Sig;
+template <> struct Sig<false> {
+    using T = float;
+    static T get(float4 texel) { return texel.x; }
+    static float4 texel(T s) { return float4(s, 0, 0, 0); }
+    static T splat(float v) { return v; }
+    static float x(T s) { return s; }
+};
+template <> struct Sig<true> {
+    using T = float4;
+    static T get(float4 texel) { return texel; }
+    static float4 texel(T s) { return s; }
+    static T splat(float v) { return float4(v); }
+    static float x(T s) { return s.x; }
+};
 
 // SIGMA_Common.hlsli:21-34. min / clamp are IEEE minNum / maxNum like the HLSL intrinsics: 0 / 0 (texels outside the
 // resource read viewZ = 0) collapses to the lower bound instead of propagating the NaN
@@ -110,7 +133,8 @@ inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v
 
 // ---------------------------------------------------------------------------------------------------------------
 // SIGMA_ClassifyTiles.cs.hlsl:24-91 — one 16x16 tile per group
-void classifyTiles(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Penumbra, Tex& gOut_Tiles, int gridW, int gridH) {
+template <bool TRANSLUCENCY>
+void classifyTiles(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Penumbra, const Tex* gIn_Shadow_Translucency, Tex& gOut_Tiles, int gridW, int gridH) {
     Ctx c(cb);
 #pragma omp parallel for schedule(dynamic, 1)
     for (int ty = 0; ty < gridH; ty++)
@@ -125,8 +149,13 @@ void classifyTiles(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Penum
                     bool isInf = !c.IsInDenoisingRange(viewZ);
                     bool isShadow = h == 0.0f;
                     bool isLit = IsLit(h);
+                    bool isOpaque = true;
+                    if (TRANSLUCENCY) {
+                        float4 st = gIn_Shadow_Translucency->load(px, py);
+                        isOpaque = Color::Luminance(float3(st.y, st.z, st.w)) < 0.003f;
+                    }
                     nLit += (isLit || isInf || isShadow) ? 1 : 0;
-                    nUmbra += (!isLit || isInf || isShadow) ? 1 : 0;  // isOpaque = true without translucency
+                    nUmbra += ((!isLit && isOpaque) || isInf || isShadow) ? 1 : 0;
                     nInf += isInf ? 1 : 0;
                     float hitDist = (isLit || isInf) ? 0.0f : h;
                     float pixelSize = PixelRadiusToWorld(cb.gUnproject, cb.gOrthoMode, 1.0f, viewZ);
@@ -179,18 +208,22 @@ void copy(const SigmaCB& cb, const Tex& gIn_Tiles, const Tex& gIn_History, const
 }
 
 // SIGMA_Blur.cs.hlsl:21-286
+template <bool TRANSLUCENCY>
 void blur(const SigmaCB& cb, bool firstPass, const Tex& gIn_ViewZ, const Tex& gIn_Normal_Roughness, const Tex& gIn_Penumbra, const Tex& gIn_Tiles,
           const Tex* gIn_Shadow_Translucency, Tex& gOut_Penumbra, Tex& gOut_Shadow_Translucency, int gridW, int gridH) {
+    using SG = Sig<TRANSLUCENCY>;
+    using S = typename SG::T;
     Ctx c(cb);
     // Preload( ) of the shader: { penumbra, viewZ }, shadow at the rect-clamped position
     auto preloadPV = [&](int x, int y) {
         int gx = clampi(x, 0, cb.gRectSizeMinusOne.x), gy = clampi(y, 0, cb.gRectSizeMinusOne.y);
         return float2(gIn_Penumbra.load(gx, gy).x, c.UnpackViewZ(gIn_ViewZ.load(gx, gy).x));
     };
-    auto preloadS = [&](int x, int y, float penumbra) {
+    auto preloadS = [&](int x, int y, float penumbra) -> S {
         int gx = clampi(x, 0, cb.gRectSizeMinusOne.x), gy = clampi(y, 0, cb.gRectSizeMinusOne.y);
-        if (firstPass) return float(IsLit(penumbra));
-        return UnpackShadow(gIn_Shadow_Translucency->load(gx, gy).x);
+        if (firstPass && !TRANSLUCENCY) return SG::splat(float(IsLit(penumbra)));
+        S s = SG::get(gIn_Shadow_Translucency->load(gx, gy));
+        return firstPass ? s : UnpackShadow(s);
     };
 #pragma omp parallel for schedule(dynamic, 4)
     for (int py = 0; py < gridH * 16; py++)
@@ -208,7 +241,7 @@ void blur(const SigmaCB& cb, bool firstPass, const Tex& gIn_ViewZ, const Tex& gI
 
             if (tileValue == 0.0f || centerPenumbra == 0.0f) {
                 if (firstPass || cb.gStabilizationStrength != 0.0f) gOut_Penumbra.store(px, py, float4(centerPenumbra, 0, 0, 0));
-                gOut_Shadow_Translucency.store(px, py, float4(PackShadow(preloadS(px, py, centerPenumbra)), 0, 0, 0));
+                gOut_Shadow_Translucency.store(px, py, SG::texel(PackShadow(preloadS(px, py, centerPenumbra))));
                 continue;
             }
 
@@ -225,13 +258,14 @@ void blur(const SigmaCB& cb, bool firstPass, const Tex& gIn_ViewZ, const Tex& gI
 
             // Estimate penumbra size and filter shadow ( dense )
             float2 sum = float2(0.0f);
-            float penumbra = 0.0f, result = 0.0f, centerTap = 0.0f;
+            float penumbra = 0.0f;
+            S result = SG::splat(0.0f), centerTap = SG::splat(0.0f);
             for (int j = 0; j <= BLUR_BORDER * 2; j++)
                 for (int i = 0; i <= BLUR_BORDER * 2; i++) {
                     int sx = px + i - BLUR_BORDER, sy = py + j - BLUR_BORDER;
                     float2 data = preloadPV(sx, sy);
                     float penum = data.x, zs = data.y;
-                    float s = preloadS(sx, sy, penum);
+                    S s = preloadS(sx, sy, penum);
                     float w = 1.0f;
                     if (i == BLUR_BORDER && j == BLUR_BORDER)
                         centerTap = s;
@@ -244,14 +278,14 @@ void blur(const SigmaCB& cb, bool firstPass, const Tex& gIn_ViewZ, const Tex& gI
                         w *= GetGaussianWeight(length(o / float(BLUR_BORDER)));
                         w = c.ApplyGeometryWeightLast(w, zs, NoX, geometryWeightParams);
                     }
-                    result += w == 0.0f ? 0.0f : s * w;
+                    result = result + (w == 0.0f ? SG::splat(0.0f) : s * w);
                     sum.x += w;
                     w *= pixelSize / (pixelSize + penum);
                     w *= float(!IsLit(penum));
                     penumbra += w == 0.0f ? 0.0f : penum * w;
                     sum.y += w;
                 }
-            result /= sum.x;
+            result = result / sum.x;
             sum.x = 1.0f;
             penumbra /= max(sum.y, NRD_EPS);
             sum.y = float(sum.y != 0.0f);
@@ -263,7 +297,7 @@ void blur(const SigmaCB& cb, bool firstPass, const Tex& gIn_ViewZ, const Tex& gI
 
             // SIGMA_USE_SPARSE_BLUR = 1
             f = lerp(4.0f, 1.0f, f);
-            result *= f;
+            result = result * f;
             penumbra *= f;
             sum = sum * f;
 
@@ -287,7 +321,13 @@ void blur(const SigmaCB& cb, bool firstPass, const Tex& gIn_ViewZ, const Tex& gI
                 float penum = gIn_Penumbra.sampleNearest(uvScaled).x;
                 float zs = c.UnpackViewZ(gIn_ViewZ.sampleNearest(uvScaled).x);
                 float3 Xvs = Geometry::ReconstructViewPosition(uv, cb.gFrustum, zs, cb.gOrthoMode);
-                float s = firstPass ? float(IsLit(penum)) : UnpackShadow(gIn_Shadow_Translucency->sampleNearest(uvScaled).x);
+                S s;
+                if (firstPass && !TRANSLUCENCY)
+                    s = SG::splat(float(IsLit(penum)));
+                else {
+                    s = SG::get(gIn_Shadow_Translucency->sampleNearest(uvScaled));
+                    if (!firstPass) s = UnpackShadow(s);
+                }
 
                 float NoX = dot(Nv, Xvs);
                 float w = IsInScreenNearest(uv);
@@ -296,7 +336,7 @@ void blur(const SigmaCB& cb, bool firstPass, const Tex& gIn_ViewZ, const Tex& gI
                 w *= saturate(penum * invEstimatedPenumbra);  // avoid umbra leaking inside wide penumbra
                 w = c.ApplyGeometryWeightLast(w, zs, NoX, geometryWeightParams);
 
-                result += w == 0.0f ? 0.0f : s * w;
+                result = result + (w == 0.0f ? SG::splat(0.0f) : s * w);
                 sum.x += w;
                 w *= pixelSize / (pixelSize + penum);
                 w *= float(!IsLit(penum));
@@ -304,11 +344,11 @@ void blur(const SigmaCB& cb, bool firstPass, const Tex& gIn_ViewZ, const Tex& gI
                 sum.y += w;
             }
 
-            result /= sum.x;
+            result = result / sum.x;
             penumbra = sum.y == 0.0f ? centerPenumbra : penumbra / sum.y;
 
             if (firstPass || cb.gStabilizationStrength != 0.0f) gOut_Penumbra.store(px, py, float4(penumbra, 0, 0, 0));
-            gOut_Shadow_Translucency.store(px, py, float4(PackShadow(result), 0, 0, 0));
+            gOut_Shadow_Translucency.store(px, py, SG::texel(PackShadow(result)));
         }
 }
 
@@ -320,13 +360,16 @@ inline uint32_t PackViewZAndHistoryLength(float viewZ, float historyLength) {  /
 }
 
 // SIGMA_TemporalStabilization.cs.hlsl:53-236
+template <bool TRANSLUCENCY>
 void temporalStabilization(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Mv, const Tex& gIn_Penumbra, const Tex& gIn_Shadow_Translucency,
                            const Tex& gIn_History, const Tex& gIn_HistoryLength, const Tex& gIn_Tiles, Tex& gOut_Shadow_Translucency, Tex& gOut_HistoryLength,
                            int gridW, int gridH) {
+    using SG = Sig<TRANSLUCENCY>;
+    using S = typename SG::T;
     Ctx c(cb);
-    auto preloadS = [&](int x, int y) {
+    auto preloadS = [&](int x, int y) -> S {
         int gx = clampi(x, 0, cb.gRectSizeMinusOne.x), gy = clampi(y, 0, cb.gRectSizeMinusOne.y);
-        return UnpackShadow(gIn_Shadow_Translucency.load(gx, gy).x);
+        return UnpackShadow(SG::get(gIn_Shadow_Translucency.load(gx, gy)));
     };
     auto preloadP = [&](int x, int y) {
         int gx = clampi(x, 0, cb.gRectSizeMinusOne.x), gy = clampi(y, 0, cb.gRectSizeMinusOne.y);
@@ -344,17 +387,18 @@ void temporalStabilization(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& g
             float tileValue = TextureCubic(gIn_Tiles, pixelUv * cb.gResolutionScale).y;
             bool isHardShadow = tileValue == 0.0f || centerPenumbra == 0.0f;  // NRD_USE_TILE_CHECK = SIGMA_USE_EARLY_OUT_IN_TS = 1
             if (isHardShadow) {
-                gOut_Shadow_Translucency.store(px, py, float4(PackShadow(preloadS(px, py)), 0, 0, 0));
+                gOut_Shadow_Translucency.store(px, py, SG::texel(PackShadow(preloadS(px, py))));
                 gOut_HistoryLength.storeUint(px, py, PackViewZAndHistoryLength(viewZ, SIGMA_MAX_ACCUM_FRAME_NUM));
                 continue;
             }
 
             // Local variance
-            float sum = 0.0f, m1 = 0.0f, m2 = 0.0f, input = 0.0f;
+            float sum = 0.0f;
+            S m1 = SG::splat(0.0f), m2 = SG::splat(0.0f), input = SG::splat(0.0f);
             for (int j = 0; j <= TS_BORDER * 2; j++)
                 for (int i = 0; i <= TS_BORDER * 2; i++) {
                     int sx = px + i - TS_BORDER, sy = py + j - TS_BORDER;
-                    float s = preloadS(sx, sy);
+                    S s = preloadS(sx, sy);
                     float w = 1.0f;
                     if (i == TS_BORDER && j == TS_BORDER)
                         input = s;
@@ -363,13 +407,13 @@ void temporalStabilization(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& g
                         w = AreBothLitOrUnlit(centerPenumbra, penum);
                         w *= GetGaussianWeight(length(float2(float(i - TS_BORDER), float(j - TS_BORDER)) / float(TS_BORDER)));
                     }
-                    m1 += s * w;
-                    m2 += s * s * w;
+                    m1 = m1 + s * w;
+                    m2 = m2 + s * s * w;
                     sum += w;
                 }
-            m1 /= sum;
-            m2 /= sum;
-            float sigma = GetStdDev(m1, m2);
+            m1 = m1 / sum;
+            m2 = m2 / sum;
+            S sigma = StdDevS(m1, m2);
 
             // Current and previous positions
             float3 Xv = Geometry::ReconstructViewPosition(pixelUv, cb.gFrustum, viewZ, cb.gOrthoMode);
@@ -412,17 +456,17 @@ void temporalStabilization(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& g
             // Sample history
             bool isCatRomAllowed = dot(smbOcclusionWeights, float4(1.0f)) > 3.5f;
             HistoryFilter hf(saturate(smbPixelUv) * cb.gRectSizePrev, cb.gResourceSizeInvPrev, smbOcclusionWeights, isCatRomAllowed);
-            float history = hf.color(gIn_History).x;
+            S history = SG::get(hf.color(gIn_History));
             history = saturate(history);
             history = UnpackShadow(history);
 
             // Clamp history
-            sigma *= lerp(SIGMA_TS_SIGMA_SCALE, 1.0f, 1.0f / (1.0f + historyLength));
-            float inputMin = m1 - sigma, inputMax = m1 + sigma;
-            float historyClamped = clamp(history, inputMin, inputMax);
+            sigma = sigma * lerp(SIGMA_TS_SIGMA_SCALE, 1.0f, 1.0f / (1.0f + historyLength));
+            S inputMin = m1 - sigma, inputMax = m1 + sigma;
+            S historyClamped = ClampS(history, inputMin, inputMax);
 
             // Antilag ( SIGMA_ADJUST_HISTORY_LENGTH_BY_ANTILAG = 1 )
-            float antilag = std::fabs(historyClamped - history);
+            float antilag = std::fabs(SG::x(historyClamped) - SG::x(history));
             antilag = Math::Sqrt01(antilag);
             antilag = saturate(1.0f - antilag);
             historyLength *= antilag;
@@ -431,24 +475,26 @@ void temporalStabilization(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& g
             float streetMagic = 0.6f * historyWeight * antilag;
             historyClamped = lerp(historyClamped, history, streetMagic);
 
-            float result = lerp(input, historyClamped, min(cb.gStabilizationStrength, historyWeight));
+            S result = lerp(input, historyClamped, min(cb.gStabilizationStrength, historyWeight));
             historyLength = min(historyLength + 1.0f, SIGMA_MAX_ACCUM_FRAME_NUM);
 
-            gOut_Shadow_Translucency.store(px, py, float4(PackShadow(result), 0, 0, 0));
+            gOut_Shadow_Translucency.store(px, py, SG::texel(PackShadow(result)));
             gOut_HistoryLength.storeUint(px, py, PackViewZAndHistoryLength(viewZ, historyLength));
         }
 }
 
 // SIGMA_SplitScreen.cs.hlsl:21-45
-void splitScreen(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Penumbra, Tex& gOut_Shadow_Translucency, int gridW, int gridH) {
+template <bool TRANSLUCENCY>
+void splitScreen(const SigmaCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Penumbra, const Tex* gIn_Shadow_Translucency, Tex& gOut_Shadow_Translucency, int gridW, int gridH) {
+    using SG = Sig<TRANSLUCENCY>;
     Ctx c(cb);
     for (int py = 0; py < gridH * 16; py++)
         for (int px = 0; px < gridW * 8; px++) {
             float2 pixelUv = float2(px + 0.5f, py + 0.5f) * cb.gRectSizeInv;
             if (pixelUv.x > cb.gSplitScreen || px > cb.gRectSizeMinusOne.x || py > cb.gRectSizeMinusOne.y) continue;
             float viewZ = c.UnpackViewZ(gIn_ViewZ.load(px, py).x);
-            float s = float(IsLit(gIn_Penumbra.load(px, py).x));
-            gOut_Shadow_Translucency.store(px, py, float4(s * float(c.IsInDenoisingRange(viewZ)), 0, 0, 0));
+            typename SG::T s = TRANSLUCENCY ? SG::get(gIn_Shadow_Translucency->load(px, py)) : SG::splat(float(IsLit(gIn_Penumbra.load(px, py).x)));
+            gOut_Shadow_Translucency.store(px, py, SG::texel(s * float(c.IsInDenoisingRange(viewZ))));
         }
 }
 
@@ -460,7 +506,12 @@ int sigmaDispatch(const std::string& id, const void* constants, uint32_t cbSize,
     const SigmaCB& cb = *(const SigmaCB*)constants;
     if (id == "SIGMA_ClassifyTiles.cs.hlsl|TRANSLUCENCY=0") {
         if (n != 3) return 2;
-        classifyTiles(cb, t[0], t[1], t[2], gridW, gridH);
+        classifyTiles<false>(cb, t[0], t[1], nullptr, t[2], gridW, gridH);
+        return 0;
+    }
+    if (id == "SIGMA_ClassifyTiles.cs.hlsl|TRANSLUCENCY=1") {
+        if (n != 4) return 2;
+        classifyTiles<true>(cb, t[0], t[1], &t[2], t[3], gridW, gridH);
         return 0;
     }
     if (id == "SIGMA_SmoothTiles.cs.hlsl") {
@@ -475,22 +526,35 @@ int sigmaDispatch(const std::string& id, const void* constants, uint32_t cbSize,
     }
     if (id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=1") {
         if (n != 6) return 2;
-        blur(cb, true, t[0], t[1], t[2], t[3], nullptr, t[4], t[5], gridW, gridH);
+        blur<false>(cb, true, t[0], t[1], t[2], t[3], nullptr, t[4], t[5], gridW, gridH);
         return 0;
     }
     if (id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=0|FIRST_PASS=0") {
         if (n != 7) return 2;
-        blur(cb, false, t[0], t[1], t[2], t[3], &t[4], t[5], t[6], gridW, gridH);
+        blur<false>(cb, false, t[0], t[1], t[2], t[3], &t[4], t[5], t[6], gridW, gridH);
         return 0;
     }
-    if (id == "SIGMA_TemporalStabilization.cs.hlsl|TRANSLUCENCY=0") {
+    if (id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=1|FIRST_PASS=1" || id == "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=1|FIRST_PASS=0") {
+        if (n != 7) return 2;
+        blur<true>(cb, id.back() == '1', t[0], t[1], t[2], t[3], &t[4], t[5], t[6], gridW, gridH);
+        return 0;
+    }
+    if (id == "SIGMA_TemporalStabilization.cs.hlsl|TRANSLUCENCY=0" || id == "SIGMA_TemporalStabilization.cs.hlsl|TRANSLUCENCY=1") {
         if (n != 9) return 2;
-        temporalStabilization(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], gridW, gridH);
+        if (id.back() == '1')
+            temporalStabilization<true>(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], gridW, gridH);
+        else
+            temporalStabilization<false>(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], gridW, gridH);
         return 0;
     }
     if (id == "SIGMA_SplitScreen.cs.hlsl|TRANSLUCENCY=0") {
         if (n != 3) return 2;
-        splitScreen(cb, t[0], t[1], t[2], gridW, gridH);
+        splitScreen<false>(cb, t[0], t[1], nullptr, t[2], gridW, gridH);
+        return 0;
+    }
+    if (id == "SIGMA_SplitScreen.cs.hlsl|TRANSLUCENCY=1") {
+        if (n != 4) return 2;
+        splitScreen<true>(cb, t[0], t[1], &t[2], t[3], gridW, gridH);
         return 0;
     }
     return 1;

@@ -21,6 +21,8 @@ CASES = [
     ("reblur_odd_noprepass", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 1000, 562, "noprepass"),
     ("sigma_512", api.Denoiser.SIGMA_SHADOW, 512, 512, "sigma"),
     ("sigma_nostab", api.Denoiser.SIGMA_SHADOW, 640, 360, "sigma_nostab"),
+    ("sigma_translucency_1080p", api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, 1920, 1080, "sigma"),
+    ("sigma_translucency_nostab", api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, 1000, 562, "sigma_nostab"),
     ("relax_sh_1440p", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 2560, 1440, None),
     ("relax_sh_odd_firefly_recon", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 1000, 562, "relax_firefly_recon"),
     ("relax_sh_8_iterations", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 640, 360, "relax_8"),

@@ -21,7 +21,10 @@ DENOISERS = {
     "reblur": (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, synth.reblur_frame, ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST")),
     "sigma": (api.Denoiser.SIGMA_SHADOW, synth.sigma_frame, ("OUT_SHADOW_TRANSLUCENCY",)),
     "relax": (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, synth.relax_frame, ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1")),
+    "sigma_tr": (api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, lambda *a, **k: synth.sigma_frame(*a, translucency=True, **k), ("OUT_SHADOW_TRANSLUCENCY",)),
 }
+# user-texture formats that differ from runner.USER_FORMATS for a denoiser
+OUTPUT_FORMATS = {"sigma_tr": {"OUT_SHADOW_TRANSLUCENCY": api.Format.RGBA8_UNORM}}
 # denoisers the CUDA executor covers beyond the three the oracle restates: the reference shaders are their only CPU engine
 REFERENCE_ONLY = {
     "relax_nosh": (api.Denoiser.RELAX_DIFFUSE_SPECULAR, lambda *a, **k: synth.relax_frame(*a, sh=False, **k), ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST")),
@@ -38,6 +41,8 @@ CASES = [
     ("sigma_default", "sigma", 96, 64, 5, None, {}),
     ("sigma_odd_size", "sigma", 100, 75, 3, None, {}),
     ("sigma_no_stabilization", "sigma", 96, 64, 3, lambda: api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0), {}),
+    ("sigma_translucency_default", "sigma_tr", 96, 64, 5, None, {}),
+    ("sigma_translucency_odd_size_no_stabilization", "sigma_tr", 100, 75, 3, lambda: api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0), {}),
     ("relax_default", "relax", 96, 64, 5, None, {}),
     ("relax_odd_size", "relax", 100, 75, 3, None, {}),
     ("relax_antifirefly_3_iterations", "relax", 96, 64, 4, lambda: api.RelaxSettings(enableAntiFirefly=True, atrousIterationNum=3), {}),
@@ -50,7 +55,8 @@ def make_denoiser(which, w, h, engine="oracle"):
     den_id, _, outputs = {**DENOISERS, **REFERENCE_ONLY}[which]
     den = runner.OracleDenoiser(runner.default_host_library(), den_id, w, h, engine=engine)
     for o in outputs:
-        den.set_user_texture(getattr(RT, o), runner.alloc_texture(runner.USER_FORMATS[getattr(RT, o)], w, h))
+        fmt = OUTPUT_FORMATS.get(which, {}).get(o, runner.USER_FORMATS[getattr(RT, o)])
+        den.set_user_texture(getattr(RT, o), runner.alloc_texture(fmt, w, h), fmt)
     return den
 
 
@@ -106,7 +112,7 @@ def test_oracle_is_bit_identical_to_the_reference_shaders_per_dispatch(label, wh
 
 
 @needs_refshaders
-@pytest.mark.parametrize("which", ["reblur", "sigma", "relax"])
+@pytest.mark.parametrize("which", ["reblur", "sigma", "relax", "sigma_tr"])
 def test_closed_loop_with_the_reference_shaders_as_the_engine(which):
     """The whole recurrence (history feedback) executed by the reference's shaders, against the oracle: final outputs identical."""
     w, h, frames = 112, 80, 5

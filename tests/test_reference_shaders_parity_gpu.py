@@ -23,15 +23,24 @@ CASES = {
     "relax": (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, "relax_frame", ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur"),
     # NRD_MODE = RADIANCE: what NRDSample instantiates as shipped (Shaders/Shared.hlsli:16); the reference shaders are the only CPU engine for it
     "relax_nosh": (api.Denoiser.RELAX_DIFFUSE_SPECULAR, "relax_frame_nosh", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur"),
+    # what NRDSample instantiates by default ( SIGMA_TRANSLUCENCY = 1, Source/NRDSample.cpp:49 )
+    "sigma_tr": (api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, "sigma_frame_tr", ("OUT_SHADOW_TRANSLUCENCY",), "sigma"),
 }
+OUTPUT_FORMATS = {"sigma_tr": {"OUT_SHADOW_TRANSLUCENCY": api.Format.RGBA8_UNORM}}
+
+
+def out_format(which, o, runner):
+    return OUTPUT_FORMATS.get(which, {}).get(o, runner.USER_FORMATS[getattr(RT, o)])
 
 
 def frame_of(name, f, w, h):
     if name == "relax_frame_nosh":
         return synth.relax_frame(f, w, h, sh=False)
+    if name == "sigma_frame_tr":
+        return synth.sigma_frame(f, w, h, translucency=True)
     return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0)}
+LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0)}
 
 
 @pytest.fixture(scope="module")
@@ -53,7 +62,8 @@ def reference_engine(runner, which, w, h):
     den_id, _, outputs, _ = CASES[which]
     den = runner.OracleDenoiser(runner.default_host_library(), den_id, w, h, engine="reference")
     for o in outputs:
-        den.set_user_texture(getattr(RT, o), runner.alloc_texture(runner.USER_FORMATS[getattr(RT, o)], w, h))
+        fmt = out_format(which, o, runner)
+        den.set_user_texture(getattr(RT, o), runner.alloc_texture(fmt, w, h), fmt)
     return den
 
 
@@ -109,7 +119,7 @@ def test_closed_loop_against_the_reference_shaders(ex, runner, which):
     cud = ex.CudaDenoiser(den_id, w, h, flags=ex.FLAG_QUAD_INTRINSICS)
     gout = {}
     for o in outputs:
-        fmt = runner.USER_FORMATS[getattr(RT, o)]
+        fmt = out_format(which, o, runner)
         gout[o] = ex.alloc_texture(fmt, w, h, "cuda:0")
         cud.set_user_texture(getattr(RT, o), gout[o], fmt)
     keep, log = {}, []
@@ -125,7 +135,7 @@ def test_closed_loop_against_the_reference_shaders(ex, runner, which):
         cud.denoise()
         torch.cuda.synchronize()
         for o in outputs:
-            fmt = runner.USER_FORMATS[getattr(RT, o)]
+            fmt = out_format(which, o, runner)
             g, c = gout[o], ref.textures[(int(getattr(RT, o)), 0)]
             if o.endswith("SH1"):
                 g, c = g[..., :3], c[..., :3]
