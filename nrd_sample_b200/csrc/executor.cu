@@ -110,7 +110,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
     memcpy(&cb, constants, sizeof(cb));
     if (cb.resolutionScale[0] != 1.0f || cb.resolutionScale[1] != 1.0f || cb.resolutionScalePrev[0] != 1.0f || cb.resolutionScalePrev[1] != 1.0f || cb.isRectChanged)
         return fail(Result::UNSUPPORTED, "%s: dynamic resolution (rectSize != resourceSize) is not implemented", id.c_str());
-    if (cb.diffCheckerboard != 2 || cb.specCheckerboard != 2) return fail(Result::UNSUPPORTED, "%s: checkerboard modes are not implemented", id.c_str());
+    if ((cb.diffCheckerboard == 2) != (cb.specCheckerboard == 2)) return fail(Result::INVALID_ARGUMENT, "%s: checkerboard constants %u / %u", id.c_str(), cb.diffCheckerboard, cb.specCheckerboard);
     if (cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix) return fail(Result::UNSUPPORTED, "%s: confidence / disocclusion-threshold-mix inputs are not implemented", id.c_str());
 
     const bool quads = flags & NRDCU_FLAG_QUAD_INTRINSICS;

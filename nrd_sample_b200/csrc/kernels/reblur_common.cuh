@@ -76,8 +76,12 @@ NRD_DEV void kernelBasis(float3 D, float3 N, float3& T, float3& B) {
         B = cross(R, T);
     }
 }
-NRD_DEV float nonLinearAccumSpeedFast(const ReblurConstants& cb, float accumSpeed, float maxAccumSpeed, float confidence) {  // hasData = true
-    return fmaxf(1.0f - confidence, 1.0f / (1.0f + fminf(accumSpeed, maxAccumSpeed)));
+// pixels the checkerboard did not trace this frame accumulate faster ( REBLUR_Common.hlsli:302-303 )
+NRD_DEV float checkerboardResolveAccumSpeed(const ReblurConstants& cb, float nonLinearAccumSpeed, bool hasData) {
+    return hasData ? nonLinearAccumSpeed : nonLinearAccumSpeed * lerp(1.0f - cb.checkerboardResolveAccumSpeed, 1.0f, nonLinearAccumSpeed);
+}
+NRD_DEV float nonLinearAccumSpeedFast(const ReblurConstants& cb, float accumSpeed, float maxAccumSpeed, float confidence, bool hasData) {
+    return checkerboardResolveAccumSpeed(cb, fmaxf(1.0f - confidence, 1.0f / (1.0f + fminf(accumSpeed, maxAccumSpeed))), hasData);
 }
 NRD_DEV float advancedNonLinearAccumSpeed(const ReblurConstants& cb, float accumSpeed) {
     float f = saturate(accumSpeed / (1.0f + cb.maxAccumulatedFrameNum * cb.convergenceSettings[2]));

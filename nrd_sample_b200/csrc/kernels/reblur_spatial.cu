@@ -48,6 +48,14 @@ struct Center {
     float4 rotator;
 };
 
+// Checkerboard resolve state of the pre-pass (REBLUR_PrePass.cs.hlsl:52-67): parity of the pixel, half-width x of its row
+// neighbours and their disocclusion weights
+struct Resolve {
+    uint32_t checkerboard;
+    int x0, x1;
+    float2 wc;
+};
+
 NRD_DEV void setupCenter(const ReblurConstants& cb, Center& s, const TexNR& normalRoughness, const float* baseRotator) {
     float4 nr = unpackNormalRoughness(normalRoughness.loadRaw(s.px, s.py), s.materialID);
     s.N = xyz(nr);
@@ -73,9 +81,13 @@ NRD_DEV P2 exponentialWeight2(P2 y) {
 }
 
 // One lobe of one spatial pass for one pixel
-template <int PASS, int LOBE>
+// CB: checkerboard input (pre-pass only): `input` is half width, holds the pixels whose parity equals `cbMode` this frame
+template <int PASS, int LOBE, bool CB = false>
 NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const TexR32F& viewZTex, const TexNR& nrTex, const TexRGBA16F& input,
-                           const TexRGBA16F& output, const TexR16F* outSpecHitDistForTracking, const TexRGBA16F* outputCopy, bool temporalStabilization, bool robustMirrorTest) {
+                           const TexRGBA16F& output, const TexR16F* outSpecHitDistForTracking, const TexRGBA16F* outputCopy, bool temporalStabilization, bool robustMirrorTest,
+                           const Resolve* resolve = nullptr) {
+    static_assert(!CB || PASS == PRE_PASS, "only the pre-pass reads checkerboarded input");
+    const uint32_t cbMode = CB ? (LOBE == DIFF ? cb.diffCheckerboard : cb.specCheckerboard) : 2u;
     const float ROUGHNESS = LOBE == DIFF ? 1.0f : s.roughness;
     const float NLAS = LOBE == DIFF ? s.nonLinearAccumSpeed.x : s.nonLinearAccumSpeed.y;
     const float MIN_MATERIAL = LOBE == DIFF ? cb.diffMinMaterial : cb.specMinMaterial;
@@ -85,7 +97,11 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
     const float2 rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
 
     float sum = 1.0f;
-    float4 result = input.load(s.px, s.py);
+    float4 result = input.load(CB ? s.px >> 1 : s.px, s.py);
+    if (CB && resolve->checkerboard != cbMode) {
+        sum = 0.0f;
+        result = f4(0.0f);
+    }
 
     if (PASS != PRE_PASS || MAX_BLUR_RADIUS != 0.0f) {
         // Stochastic tracking decisions of the specular pre-pass consume one random number per tap, in tap order
@@ -212,11 +228,30 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
 
             // texel coordinates: mirrorUv() < 1 keeps every tap inside the rect, so fetches need no bounds checks
             P2 fx = floor2(mx * rectSize.x), fy = floor2(my * rectSize.y);
-            const int txa = (int)fx.a(), tya = (int)fy.a(), txb = (int)fx.b(), tyb = (int)fy.b();
+            int txa = (int)fx.a(), txb = (int)fx.b();
+            const int tya = (int)fy.a(), tyb = (int)fy.b();
+            int ixa = txa, ixb = txb;  // x in the (possibly half-width) input
+            if (CB) {
+                // Move to a pixel that was traced this frame: taps n = pair (even / odd) and n + 4 share the shift direction
+                const int shift = (pair & 1) == 0 ? -1 : 1;
+                txa += (((uint32_t)(txa ^ tya) ^ cb.frameIndex) & 1u) != cbMode ? shift : 0;
+                txb += (((uint32_t)(txb ^ tyb) ^ cb.frameIndex) & 1u) != cbMode ? shift : 0;
+                ixa = txa >> 1;
+                ixb = txb >> 1;
+                // a tap pushed off the rect is invalid; it fetches the clamped texel and gets zero weight
+                if (txa < 0 || txa > cb.rectSizeMinusOne[0]) w = P2(0.0f, w.b());
+                if (txb < 0 || txb > cb.rectSizeMinusOne[0]) w = P2(w.a(), 0.0f);
+                const int cxa = clampi(txa, 0, cb.rectSizeMinusOne[0]), cxb = clampi(txb, 0, cb.rectSizeMinusOne[0]);
+                fx = P2((float)txa, (float)txb);
+                txa = cxa;
+                txb = cxb;
+                ixa = clampi(ixa, 0, input.w - 1);
+                ixb = clampi(ixb, 0, input.w - 1);
+            }
 
             const float zRawA = viewZTex.fetch(txa, tya), zRawB = viewZTex.fetch(txb, tyb);
             const uint32_t nrA = nrTex.fetchRaw(txa, tya), nrB = nrTex.fetchRaw(txb, tyb);
-            uint2 rawA = input.fetchRaw(txa, tya), rawB = input.fetchRaw(txb, tyb);
+            uint2 rawA = input.fetchRaw(ixa, tya), rawB = input.fetchRaw(ixb, tyb);
 
             P2 zs = absMul2(P2(zRawA, zRawB), fabsf(cb.viewZScale));  // UnpackViewZ: | z * scale |
             P2 rx = fma2(fx, rayMulX, rayAddX), ry = fma2(fy, rayMulY, rayAddY);
@@ -293,6 +328,14 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
         if (PASS == PRE_PASS && LOBE == SPEC) outSpecHitDistForTracking->store(s.px, s.py, hitDistForTracking == NRD_INF ? 0.0f : hitDistForTracking);
     }
 
+    // Checkerboard resolve ( if the pre-pass found nothing ): the traced row neighbours, REBLUR_Common_SpatialFilter.hlsli:294-316
+    if (CB && sum == 0.0f) {
+        float4 s0 = input.load(resolve->x0, s.py), s1 = input.load(resolve->x1, s.py);
+        if (resolve->wc.x == 0.0f) s0 = f4(0.0f);
+        if (resolve->wc.y == 0.0f) s1 = f4(0.0f);
+        result = s0 * resolve->wc.x + s1 * resolve->wc.y;
+    }
+
     output.store(s.px, s.py, result);
 
     if (PASS == POST_BLUR && !temporalStabilization) {
@@ -313,6 +356,7 @@ __global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_co
     if (threadIdx.x == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
 }
 
+template <bool CB>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags, int ctaY0) {
     const bool robust = (flags & 2) != 0;
     Center s;
@@ -325,8 +369,21 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPr
     setupCenter(cb, s, p.normalRoughness, cb.rotatorPre);
     s.nonLinearAccumSpeed = f2(1.0f / (1.0f + 10.0f));
     s.data1 = f2(0.0f);
-    spatialFilter<PRE_PASS, DIFF>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust);
-    spatialFilter<PRE_PASS, SPEC>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust);
+    Resolve r = {};
+    if (CB) {
+        r.checkerboard = ((uint32_t)(s.px ^ s.py) ^ cb.frameIndex) & 1u;
+        const int x0 = max(s.px - 1, 0), x1 = min(s.px + 1, cb.rectSizeMinusOne[0]);
+        const float viewZ0 = unpackViewZ(cb, p.viewZ.load(x0, s.py)), viewZ1 = unpackViewZ(cb, p.viewZ.load(x1, s.py));
+        const float threshold = disocclusionThresholdAt(0.02f, s.frustumSize, s.NoV);  // NRD_DISOCCLUSION_THRESHOLD
+        float2 wc = make_float2(threshold >= fabsf(viewZ0 - s.viewZ) ? 1.0f : 0.0f, threshold >= fabsf(viewZ1 - s.viewZ) ? 1.0f : 0.0f);
+        if (!inDenoisingRange(cb, viewZ0) || s.px < 1) wc.x = 0.0f;
+        if (!inDenoisingRange(cb, viewZ1) || s.px >= cb.rectSizeMinusOne[0]) wc.y = 0.0f;
+        r.wc = wc * positiveRcp(wc.x + wc.y);
+        r.x0 = x0 >> 1;
+        r.x1 = x1 >> 1;
+    }
+    spatialFilter<PRE_PASS, DIFF, CB>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r);
+    spatialFilter<PRE_PASS, SPEC, CB>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r);
 }
 
 // Non-linear accumulation speed with the quad-neighbour smoothing of REBLUR_Blur.cs.hlsl:40-59 (lanes x^1, x^2 of the row)
@@ -399,7 +456,11 @@ void launchReblurClassifyTiles(const ReblurConstants& cb, const ClassifyTilesPar
 void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    reblurPrePassKernel<<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
+    if (cb.diffCheckerboard != 2u || cb.specCheckerboard != 2u)  // CheckerboardMode::BLACK / WHITE set both (Reblur.cpp:301-313)
+        reblurPrePassKernel<true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    else
+        reblurPrePassKernel<false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
 }
 void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);

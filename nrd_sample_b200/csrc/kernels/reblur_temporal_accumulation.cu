@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         if (cb.hasHistoryConfidence) smbSpecHistoryConfidence = fminf(smbSpecHistoryConfidence, saturate(p.specConfidence.sampleLinear(smbPixelUv)));
         smbSpecAccumSpeed *= lerp(smbSpecHistoryConfidence, 1.0f, 1.0f / (1.0f + smbSpecAccumSpeed));
 
+        // Checkerboard ( RADIANCE mode: the pre-pass has already resolved the half-width input, only the accumulation speed changes; TA:329-357 )
+        const bool specHasData = cb.specCheckerboard == 2u || (((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u) == cb.specCheckerboard;
         const float4 spec = p.inSpec.load(px, py);
 
         // Curvature estimation along predicted motion (TA:387-467)
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         // Accumulation
         specAccumSpeedCorrected = lerp(smbSpecAccumSpeed_NoHistoryFix, vmbSpecAccumSpeed_NoHistoryFix, virtualHistoryAmount);
         const float specAccumSpeed = lerp(smbSpecAccumSpeed, vmbSpecAccumSpeed, virtualHistoryAmount);
-        const float specNonLinearAccumSpeed = 1.0f / (1.0f + specAccumSpeed);
+        const float specNonLinearAccumSpeed = checkerboardResolveAccumSpeed(cb, 1.0f / (1.0f + specAccumSpeed), specHasData);
 
         float4 specResult = mixHistoryAndCurrent(cb, specHistory, spec, specNonLinearAccumSpeed, roughness);
 
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
             if (materialID == cb.strandMaterialID) maxFastAccumulatedFrameNum = fmaxf(maxFastAccumulatedFrameNum, cb.maxAccumulatedFrameNum / 5.0f);
 
             float specHistoryConfidence = lerp(surfaceHistoryConfidence, virtualHistoryConfidence, virtualHistoryAmount);
-            float fastNonLinearAccumSpeed = nonLinearAccumSpeedFast(cb, specAccumSpeed, maxFastAccumulatedFrameNum, specHistoryConfidence);
+            float fastNonLinearAccumSpeed = nonLinearAccumSpeedFast(cb, specAccumSpeed, maxFastAccumulatedFrameNum, specHistoryConfidence, specHasData);
             float fastResult = lerp(specFastHistory, spec.x, fastNonLinearAccumSpeed);
             float fastClamped = fminf(fastResult, specHistory.x * specMaxRelativeIntensity * 4.0f);
             fastResult = lerp(fastResult, fastClamped, specAntifireflyFactor);
@@ -538,13 +540,14 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         if (cb.hasHistoryConfidence) diffHistoryConfidence = fminf(diffHistoryConfidence, saturate(p.diffConfidence.sampleLinear(smbPixelUv)));
         diffAccumSpeed *= lerp(diffHistoryConfidence, 1.0f, 1.0f / (1.0f + diffAccumSpeed));
 
+        const bool diffHasData = cb.diffCheckerboard == 2u || (((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u) == cb.diffCheckerboard;
         const float4 diff = p.inDiff.load(px, py);
 
         HistoryFilter hf(saturate(smbPixelUv) * rectSizePrev, resourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom);
         const float4 diffHistory = clampNegativeToZero(hf.color(p.historyDiff));
         const float diffFastHistory = fmaxf(hf.bilinear(p.historyDiffFast), 0.0f);
 
-        const float diffNonLinearAccumSpeed = 1.0f / (1.0f + diffAccumSpeed);
+        const float diffNonLinearAccumSpeed = checkerboardResolveAccumSpeed(cb, 1.0f / (1.0f + diffAccumSpeed), diffHasData);
         float4 diffResult = mixHistoryAndCurrent(cb, diffHistory, diff, diffNonLinearAccumSpeed);
 
         const float diffMaxRelativeIntensity = cb.fireflySuppressorMinRelativeScale + 38.0f / (diffAccumSpeed + 1.0f);
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         diffResult.w = lerp(diffResult.w, fminf(diffResult.w, diffHistory.w * hitDistMaxRelativeIntensity), diffAntifireflyFactor);
         p.outDiff.store(px, py, diffResult);
 
-        float fastNonLinearAccumSpeed = 1.0f / (1.0f + fminf(diffAccumSpeed, cb.maxFastAccumulatedFrameNum));
+        float fastNonLinearAccumSpeed = checkerboardResolveAccumSpeed(cb, 1.0f / (1.0f + fminf(diffAccumSpeed, cb.maxFastAccumulatedFrameNum)), diffHasData);
         float fastResult = lerp(diffFastHistory, diff.x, fastNonLinearAccumSpeed);
         float fastClamped = fminf(fastResult, diffHistory.x * diffMaxRelativeIntensity * 4.0f);
         fastResult = lerp(fastResult, fastClamped, diffAntifireflyFactor);

@@ -231,7 +231,20 @@ def unpack_radiance(tex: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # Frame
 # ------------------------------------------------------------------------------------------------
-def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, holes: bool = False) -> Dict[str, torch.Tensor]:
+def checkerboard_pack(full: torch.Tensor, mode: int, frame_index: int) -> torch.Tensor:
+    """Half-width texture holding the pixels a checkerboarded tracer produced this frame: texel (x >> 1, y) = full[y, x] for the pixels with
+    Sequence::CheckerBoard( ( x, y ), frameIndex ) == mode (ml.hlsli:1620; NRDSettings.h CheckerboardMode: BLACK -> diffuse 0 / specular 1,
+    WHITE -> diffuse 1 / specular 0, Reblur.cpp:301-313). The width must be even."""
+    h, w = full.shape[0], full.shape[1]
+    assert w % 2 == 0
+    ys = torch.arange(h, device=full.device)
+    b = (mode ^ ys ^ frame_index) & 1                                      # x parity carrying data in row y
+    xs = 2 * torch.arange(w // 2, device=full.device)[None, :] + b[:, None]
+    return full[ys[:, None], xs].contiguous()
+
+
+def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, holes: bool = False,
+                 checkerboard: int = 0) -> Dict[str, torch.Tensor]:
     """All user inputs of REBLUR_DIFFUSE_SPECULAR for one frame, in their API storage formats. `holes`: probabilistic lobe sampling as in
     NRDSample — every pixel traced only one lobe this frame (checkerboard flipping per frame), the other lobe has hit distance 0 and
     relies on ReblurSettings::hitDistanceReconstructionMode."""
@@ -299,6 +312,10 @@ def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period
         "IN_DIFF_RADIANCE_HITDIST": torch.where(hit[..., None], pack_radiance_hitdist(diff_noisy, nhd_d), zero4).contiguous(),
         "IN_SPEC_RADIANCE_HITDIST": torch.where(hit[..., None], pack_radiance_hitdist(spec_noisy, nhd_s), zero4).contiguous(),
     }
+    if checkerboard:   # nrd::CheckerboardMode: 1 = BLACK, 2 = WHITE
+        diff_mode, spec_mode = (0, 1) if checkerboard == 1 else (1, 0)
+        out["IN_DIFF_RADIANCE_HITDIST"] = checkerboard_pack(out["IN_DIFF_RADIANCE_HITDIST"], diff_mode, frame_index)
+        out["IN_SPEC_RADIANCE_HITDIST"] = checkerboard_pack(out["IN_SPEC_RADIANCE_HITDIST"], spec_mode, frame_index)
     if with_clean:
         out["_clean_diff"] = diff_clean
         out["_clean_spec"] = spec_clean

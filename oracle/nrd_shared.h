@@ -368,6 +368,7 @@ inline float GetEncodingAwareNormalWeight(float3 Ncurr, float3 Nprev, float maxA
     w = Math::SmoothStep(0.05f, 0.95f, w);
     return w;
 }
+const float NRD_DISOCCLUSION_THRESHOLD = 0.02f;  // common:63
 inline float GetDisocclusionThreshold(float disocclusionThreshold, float frustumSize, float NoV) {  // common:595
     return frustumSize * saturate(disocclusionThreshold / max(0.05f, NoV));
 }

@@ -55,10 +55,14 @@ struct SpatialCommon {
     float3 N, Nv, Xv, Vv;
     float2 pixelUv, nonLinearAccumSpeed, data1;
     float4 rotator;
+    // checkerboard resolve of the pre-pass ( REBLUR_PrePass.cs.hlsl:52-67 ): parity of the pixel, half-res x of the left / right neighbours, their weights
+    uint32_t checkerboard = 0;
+    int checkerboardX0 = 0, checkerboardX1 = 0;
+    float2 wc = float2(0.0f);
 };
 
-// REBLUR_Common_SpatialFilter.hlsli, one lobe. Checkerboard modes are off in this denoiser configuration
-// (gDiffCheckerboard == gSpecCheckerboard == 2), so the resolve branches reduce to the plain path.
+// REBLUR_Common_SpatialFilter.hlsli, one lobe. Checkerboard ( gDiffCheckerboard / gSpecCheckerboard != 2 ) only concerns the pre-pass:
+// its input is half width, taps move to a pixel that was traced this frame, and pixels without data are resolved from their row neighbours.
 template <int PASS, int LOBE>
 static void spatialFilter(const ReblurCtx& c, const SpatialCommon& s, const Tex& gIn_ViewZ, const Tex& gIn_Normal_Roughness, const Tex& INPUT, Tex& OUTPUT,
                           Tex* gOut_SpecHitDistForTracking, Tex* OUTPUT_COPY, bool temporalStabilization, bool robustMirrorTest) {
@@ -69,9 +73,15 @@ static void spatialFilter(const ReblurCtx& c, const SpatialCommon& s, const Tex&
     const float MAX_BLUR_RADIUS = PASS == PRE_PASS ? (LOBE == DIFF ? cb.gDiffPrepassBlurRadius : cb.gSpecPrepassBlurRadius) : cb.gMaxBlurRadius;
     const bool USE_SCREEN_SPACE = LOBE == DIFF;  // REBLUR_USE_SCREEN_SPACE_SAMPLING_FOR_DIFFUSE = 1, ..._FOR_SPECULAR = 0
 
+    const uint32_t CHECKERBOARD = PASS == PRE_PASS ? (LOBE == DIFF ? cb.gDiffCheckerboard : cb.gSpecCheckerboard) : 2u;
+
     float sum = 1.0f;
-    float4 result = INPUT.load(s.px, s.py);
+    float4 result = INPUT.load(CHECKERBOARD == 2 ? s.px : s.px >> 1, s.py);
     RngHash rng;
+    if (CHECKERBOARD != 2 && s.checkerboard != CHECKERBOARD) {
+        sum = 0.0f;
+        result = float4(0.0f);
+    }
 
     bool runFilter = PASS != PRE_PASS || MAX_BLUR_RADIUS != 0.0f;
     if (runFilter) {
@@ -160,6 +170,15 @@ static void spatialFilter(const ReblurCtx& c, const SpatialCommon& s, const Tex&
             float2 posf = mirrorUv * cb.gRectSize;
             int2 pos = int2((int)posf.x, (int)posf.y);
 
+            // Move to a "valid" pixel in checkerboard mode
+            int checkerboardX = pos.x;
+            if (CHECKERBOARD != 2) {
+                int shift = ((n & 0x1) == 0) ? -1 : 1;
+                pos.x += Sequence::CheckerBoard((uint32_t)pos.x, (uint32_t)pos.y, cb.gFrameIndex) != CHECKERBOARD ? shift : 0;
+                checkerboardX = pos.x >> 1;
+                w = (pos.x < 0 || pos.x > cb.gRectSizeMinusOne.x) ? 0.0f : w;
+            }
+
             // Fetch data (PostBlur reads the copy of viewZ made by Blur — same texels)
             float zs = c.UnpackViewZ(gIn_ViewZ.load(pos).x);
             float3 Xvs = Geometry::ReconstructViewPosition(float2(pos.x + 0.5f, pos.y + 0.5f) * cb.gRectSizeInv, cb.gFrustum, zs, cb.gOrthoMode);
@@ -175,7 +194,7 @@ static void spatialFilter(const ReblurCtx& c, const SpatialCommon& s, const Tex&
             if (LOBE == SPEC) w *= ComputeWeight(Ns.w, roughnessWeightParams.x, roughnessWeightParams.y);
             w = c.ApplyGeometryWeightLast(w, zs, NoX, geometryWeightParams);
 
-            float4 smp = INPUT.load(pos);
+            float4 smp = INPUT.load(checkerboardX, pos.y);
             smp = w == 0.0f ? float4(0.0f) : smp;  // Denanify
 
             if (PASS == PRE_PASS && LOBE == SPEC) {
@@ -202,6 +221,15 @@ static void spatialFilter(const ReblurCtx& c, const SpatialCommon& s, const Tex&
         if (PASS != PRE_PASS) result.w = hitDist / hitDistScale;
 
         if (PASS == PRE_PASS && LOBE == SPEC) gOut_SpecHitDistForTracking->store(s.px, s.py, float4(hitDistForTracking == NRD_INF ? 0.0f : hitDistForTracking));
+    }
+
+    // Checkerboard resolve ( if pre-pass failed )
+    if (PASS == PRE_PASS && sum == 0.0f) {
+        float4 s0 = INPUT.load(s.checkerboardX0, s.py);
+        float4 s1 = INPUT.load(s.checkerboardX1, s.py);
+        s0 = s.wc.x == 0.0f ? float4(0.0f) : s0;
+        s1 = s.wc.y == 0.0f ? float4(0.0f) : s1;
+        result = s0 * s.wc.x + s1 * s.wc.y;
     }
 
     OUTPUT.store(s.px, s.py, result);
@@ -319,6 +347,19 @@ void reblurPrePass(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Norm
             spatialCenter(c, s, gIn_Normal_Roughness, cb.gRotatorPre);
             s.nonLinearAccumSpeed = float2(1.0f / (1.0f + 10.0f));
             s.data1 = float2(0.0f);
+            {  // Checkerboard resolve ( REBLUR_PrePass.cs.hlsl:52-67 )
+                s.checkerboard = Sequence::CheckerBoard((uint32_t)px, (uint32_t)py, cb.gFrameIndex);
+                int x0 = std::max(px - 1, 0), x1 = std::min(px + 1, cb.gRectSizeMinusOne.x);
+                float viewZ0 = c.UnpackViewZ(gIn_ViewZ.load(x0, py).x), viewZ1 = c.UnpackViewZ(gIn_ViewZ.load(x1, py).x);
+                float threshold = GetDisocclusionThreshold(NRD_DISOCCLUSION_THRESHOLD, s.frustumSize, s.NoV);
+                float2 wc = float2(step(std::fabs(viewZ0 - s.viewZ), threshold), step(std::fabs(viewZ1 - s.viewZ), threshold));
+                wc.x = (!c.IsInDenoisingRange(viewZ0) || px < 1) ? 0.0f : wc.x;
+                wc.y = (!c.IsInDenoisingRange(viewZ1) || px >= cb.gRectSizeMinusOne.x) ? 0.0f : wc.y;
+                wc *= Math::PositiveRcp(wc.x + wc.y);
+                s.wc = wc;
+                s.checkerboardX0 = x0 >> 1;
+                s.checkerboardX1 = x1 >> 1;
+            }
             spatialFilter<PRE_PASS, DIFF>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Diff, gOut_Diff, nullptr, nullptr, true, robust);
             spatialFilter<PRE_PASS, SPEC>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Spec, gOut_Spec, &gOut_SpecHitDistForTracking, nullptr, true, robust);
         }
@@ -613,7 +654,8 @@ static void taPixel(const ReblurCtx& c, const TaTextures& t, int px, int py) {
         }
         smbSpecAccumSpeed *= lerp(smbSpecHistoryConfidence, 1.0f, 1.0f / (1.0f + smbSpecAccumSpeed));
 
-        const bool specHasData = true;  // checkerboard off
+        const uint32_t checkerboard = Sequence::CheckerBoard((uint32_t)px, (uint32_t)py, cb.gFrameIndex);
+        const bool specHasData = cb.gSpecCheckerboard == 2 || checkerboard == cb.gSpecCheckerboard;  // RADIANCE: the pre-pass has resolved the input already
         float4 spec = t.gIn_Spec->load(px, py);
 
         // Curvature estimation along predicted motion (TA:387-467)
@@ -910,6 +952,7 @@ static void taPixel(const ReblurCtx& c, const TaTextures& t, int px, int py) {
         specAccumSpeedCorrected = lerp(smbSpecAccumSpeed_NoHistoryFix, vmbSpecAccumSpeed_NoHistoryFix, virtualHistoryAmount);
         float specAccumSpeed = lerp(smbSpecAccumSpeed, vmbSpecAccumSpeed, virtualHistoryAmount);
         float specNonLinearAccumSpeed = 1.0f / (1.0f + specAccumSpeed);
+        if (!specHasData) specNonLinearAccumSpeed *= lerp(1.0f - cb.gCheckerboardResolveAccumSpeed, 1.0f, specNonLinearAccumSpeed);
 
         float4 specResult = c.MixHistoryAndCurrent(specHistory, spec, specNonLinearAccumSpeed, roughness);
 
@@ -953,6 +996,7 @@ static void taPixel(const ReblurCtx& c, const TaTextures& t, int px, int py) {
         }
         diffAccumSpeed *= lerp(diffHistoryConfidence, 1.0f, 1.0f / (1.0f + diffAccumSpeed));
 
+        const bool diffHasData = cb.gDiffCheckerboard == 2 || Sequence::CheckerBoard((uint32_t)px, (uint32_t)py, cb.gFrameIndex) == cb.gDiffCheckerboard;
         float4 diff = t.gIn_Diff->load(px, py);
 
         float4 diffHistory;
@@ -966,6 +1010,7 @@ static void taPixel(const ReblurCtx& c, const TaTextures& t, int px, int py) {
         }
 
         float diffNonLinearAccumSpeed = 1.0f / (1.0f + diffAccumSpeed);
+        if (!diffHasData) diffNonLinearAccumSpeed *= lerp(1.0f - cb.gCheckerboardResolveAccumSpeed, 1.0f, diffNonLinearAccumSpeed);
         float4 diffResult = c.MixHistoryAndCurrent(diffHistory, diff, diffNonLinearAccumSpeed);
 
         float diffMaxRelativeIntensity = cb.gFireflySuppressorMinRelativeScale + REBLUR_FIREFLY_SUPPRESSOR_MAX_RELATIVE_INTENSITY / (diffAccumSpeed + 1.0f);
@@ -985,6 +1030,7 @@ static void taPixel(const ReblurCtx& c, const TaTextures& t, int px, int py) {
         {  // Fast history
             float diffFastAccumSpeed = min(diffAccumSpeed, cb.gMaxFastAccumulatedFrameNum);
             float diffFastNonLinearAccumSpeed = 1.0f / (1.0f + diffFastAccumSpeed);
+            if (!diffHasData) diffFastNonLinearAccumSpeed *= lerp(1.0f - cb.gCheckerboardResolveAccumSpeed, 1.0f, diffFastNonLinearAccumSpeed);
             float diffFastResult = lerp(diffFastHistory, ReblurCtx::GetLuma(diff), diffFastNonLinearAccumSpeed);
             float diffFastClamped = min(diffFastResult, ReblurCtx::GetLuma(diffHistory) * diffMaxRelativeIntensity * REBLUR_FIREFLY_SUPPRESSOR_FAST_RELATIVE_INTENSITY);
             diffFastResult = lerp(diffFastResult, diffFastClamped, diffAntifireflyFactor);

@@ -32,7 +32,6 @@ static_assert(sizeof(SigmaCB) == 528, "SIGMA cbuffer is 528 bytes");
 const float SIGMA_MAX_PIXEL_RADIUS = 32.0f;  // SIGMA_Config.hlsli:33
 const float SIGMA_TS_SIGMA_SCALE = 3.0f;     // :34
 const float SIGMA_MAX_ACCUM_FRAME_NUM = 7;   // :35
-const float NRD_DISOCCLUSION_THRESHOLD = 0.02f;  // Common.hlsli:63
 const int BLUR_BORDER = 2;                   // SIGMA_5X5_BLUR_RADIUS_ESTIMATION_KERNEL = 1
 const int TS_BORDER = 2;                     // SIGMA_5X5_TEMPORAL_KERNEL = 1
 

@@ -38,6 +38,9 @@ CASES = [
     ("reblur_recon5x5", "reblur", 96, 64, 3, lambda: api.ReblurSettings(hitDistanceReconstructionMode=2), {"holes": True}),
     ("reblur_no_stabilization", "reblur", 96, 64, 4, lambda: api.ReblurSettings(maxStabilizedFrameNum=0), {}),
     ("reblur_no_prepass_no_antifirefly", "reblur", 96, 64, 4, lambda: api.ReblurSettings(diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0, enableAntiFirefly=False), {}),
+    ("reblur_checkerboard_white", "reblur", 96, 64, 5, lambda: api.ReblurSettings(checkerboardMode=2), {"checkerboard": 2}),
+    ("reblur_checkerboard_black_no_prepass_radius", "reblur", 100, 76, 4, lambda: api.ReblurSettings(checkerboardMode=1, diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0),
+     {"checkerboard": 1}),
     ("sigma_default", "sigma", 96, 64, 5, None, {}),
     ("sigma_odd_size", "sigma", 100, 75, 3, None, {}),
     ("sigma_no_stabilization", "sigma", 96, 64, 3, lambda: api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0), {}),

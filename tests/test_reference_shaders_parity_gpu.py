@@ -26,6 +26,9 @@ CASES = {
     # what NRDSample instantiates by default ( SIGMA_TRANSLUCENCY = 1, Source/NRDSample.cpp:49 )
     "sigma_tr": (api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, "sigma_frame_tr", ("OUT_SHADOW_TRANSLUCENCY",), "sigma"),
 }
+# NRDSample's default tracing mode is RESOLUTION_HALF => CheckerboardMode::WHITE ( Source/NRDSample.cpp:267, 545 )
+CASES["reblur_cb"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, "reblur_frame_cb", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
+SETTINGS = {"reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
 OUTPUT_FORMATS = {"sigma_tr": {"OUT_SHADOW_TRANSLUCENCY": api.Format.RGBA8_UNORM}}
 
 
@@ -36,11 +39,13 @@ def out_format(which, o, runner):
 def frame_of(name, f, w, h):
     if name == "relax_frame_nosh":
         return synth.relax_frame(f, w, h, sh=False)
+    if name == "reblur_frame_cb":
+        return synth.reblur_frame(f, w, h, checkerboard=2)
     if name == "sigma_frame_tr":
         return synth.sigma_frame(f, w, h, translucency=True)
     return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0)}
+LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0)}
 
 
 @pytest.fixture(scope="module")
@@ -93,21 +98,21 @@ def test_each_dispatch_against_the_reference_shaders(ex, runner, which):
     for f in range(frames):
         for k, v in frame_of(CASES[which][1], f, w, h).items():
             ref.set_user_texture(getattr(RT, k), v)
-        ref.denoise(synth.common_settings(f, w, h), before_dispatch=before, on_dispatch=after)
+        ref.denoise(synth.common_settings(f, w, h), settings=SETTINGS[which]() if which in SETTINGS else None, before_dispatch=before, on_dispatch=after)
 
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump({" | ".join(map(str, k)): {"frac_bad": v["frac_bad"], "psnr": v["psnr"], "max_abs": v["max_abs"]} for k, v in worst.items()},
               open(f"gpurun_out/refshader_per_dispatch_{which}.json", "w"), indent=1)
     limit = LIMITS[which][0]
     for key, r in worst.items():
-        spatial = which == "reblur" and any(p in key[0] for p in ("Pre-pass", "Blur", "Post-blur"))
+        spatial = which.startswith("reblur") and any(p in key[0] for p in ("Pre-pass", "Blur", "Post-blur"))
         if spatial and key[2] == "RGBA16_SFLOAT":
             # the reference's tap weight is 1 instead of the Gaussian when any( uv != MirrorUv( uv ) ), which is decided by the last mantissa bit
             # of the tap position ( DESIGN.md "chaotic predicates" ): an FMA-contracting GPU flips it on a third of the taps, so texel-wise
             # agreement is not defined for these passes in faithful mode — the image is ( measured: 60-74 dB )
             assert r["psnr"] >= 55.0, f"{key}: {r}"
             continue
-        lim = 5e-2 if (which == "reblur" and key[2] == "R32_UINT") else limit   # data2's fp16 curvature on the static first frame, see test_reblur_parity_gpu
+        lim = 5e-2 if (which.startswith("reblur") and key[2] == "R32_UINT") else limit   # data2's fp16 curvature on the static first frame, see test_reblur_parity_gpu
         assert r["frac_bad"] <= lim, f"{key}: {r}"
 
 
@@ -130,8 +135,10 @@ def test_closed_loop_against_the_reference_shaders(ex, runner, which):
             keep[k] = v.to("cuda:0")
             cud.set_user_texture(rt, keep[k], runner.USER_FORMATS[rt])
         cs = synth.common_settings(f, w, h)
-        ref.denoise(cs)
+        ref.denoise(cs, settings=SETTINGS[which]() if which in SETTINGS else None)
         cud.set_common_settings(cs)
+        if which in SETTINGS:
+            cud.set_denoiser_settings(SETTINGS[which]())
         cud.denoise()
         torch.cuda.synchronize()
         for o in outputs:
