@@ -59,6 +59,26 @@ uint32_t bytesPerTexel(uint32_t fmt) {
     }
 }
 
+// Formats an application may use for the single-channel guide inputs (confidence, disocclusion-threshold mix): first channel only
+bool guideFormat(uint32_t fmt, uint32_t& kind, uint32_t& bpp) {
+    using K = nrdk::TexAnyX;
+    switch ((Format)fmt) {
+        case Format::R8_UNORM: kind = K::UNORM8; bpp = 1; return true;
+        case Format::RG8_UNORM: kind = K::UNORM8; bpp = 2; return true;
+        case Format::RGBA8_UNORM: kind = K::UNORM8; bpp = 4; return true;
+        case Format::R16_UNORM: kind = K::UNORM16; bpp = 2; return true;
+        case Format::RG16_UNORM: kind = K::UNORM16; bpp = 4; return true;
+        case Format::RGBA16_UNORM: kind = K::UNORM16; bpp = 8; return true;
+        case Format::R16_SFLOAT: kind = K::HALF; bpp = 2; return true;
+        case Format::RG16_SFLOAT: kind = K::HALF; bpp = 4; return true;
+        case Format::RGBA16_SFLOAT: kind = K::HALF; bpp = 8; return true;
+        case Format::R32_SFLOAT: kind = K::FLOAT; bpp = 4; return true;
+        case Format::RG32_SFLOAT: kind = K::FLOAT; bpp = 8; return true;
+        case Format::RGBA32_SFLOAT: kind = K::FLOAT; bpp = 16; return true;
+        default: return false;
+    }
+}
+
 // Typed view construction with format checking
 struct Binder {
     const nrdcuTexture* t;
@@ -88,8 +108,32 @@ struct Binder {
         next++;
         return v;
     }
-    // optional inputs that are bound to a dummy (IN_VIEWZ) when disabled
-    nrdk::TexR32F takeDummy() { return take<nrdk::TexR32F>(Format::R32_SFLOAT); }
+    // optional single-channel guides: IN_VIEWZ as a dummy when disabled, otherwise whatever the application owns (any size, see guideFormat)
+    nrdk::TexAnyX takeGuide() {
+        nrdk::TexAnyX v{};
+        if (next >= n) {
+            ok = false;
+            return v;
+        }
+        const nrdcuTexture& x = t[next];
+        uint32_t kind = 0, bpp = 1;
+        if (!guideFormat(x.format, kind, bpp) || !x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
+            if (ok) {
+                char buf[256];
+                snprintf(buf, sizeof(buf), "%s: binding %u (single-channel guide) has unsupported format %u / pitch %u", shader, next, x.format, x.pitchBytes);
+                *err = buf;
+            }
+            ok = false;
+        }
+        v.data = (uint8_t*)x.data;
+        v.w = (int)x.width;
+        v.h = (int)x.height;
+        v.pitch = (int)(x.pitchBytes / bpp);
+        v.kind = kind;
+        v.bytesPerTexel = bpp;
+        next++;
+        return v;
+    }
 };
 
 bool checkLaunch(const char* what) {
@@ -111,7 +155,6 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
     if (cb.resolutionScale[0] != 1.0f || cb.resolutionScale[1] != 1.0f || cb.resolutionScalePrev[0] != 1.0f || cb.resolutionScalePrev[1] != 1.0f || cb.isRectChanged)
         return fail(Result::UNSUPPORTED, "%s: dynamic resolution (rectSize != resourceSize) is not implemented", id.c_str());
     if ((cb.diffCheckerboard == 2) != (cb.specCheckerboard == 2)) return fail(Result::INVALID_ARGUMENT, "%s: checkerboard constants %u / %u", id.c_str(), cb.diffCheckerboard, cb.specCheckerboard);
-    if (cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix) return fail(Result::UNSUPPORTED, "%s: confidence / disocclusion-threshold-mix inputs are not implemented", id.c_str());
 
     const bool quads = flags & NRDCU_FLAG_QUAD_INTRINSICS;
     const int kflags = (quads ? 1 : 0) | ((flags & NRDCU_FLAG_ROBUST_MIRROR_TEST) ? 2 : 0);
@@ -165,9 +208,9 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.prevViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.prevNormalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.prevInternalData = b.take<TexR16U>(Format::R16_UINT);
-        p.disocclusionThresholdMix = b.takeDummy();
-        p.diffConfidence = b.takeDummy();
-        p.specConfidence = b.takeDummy();
+        p.disocclusionThresholdMix = b.takeGuide();
+        p.diffConfidence = b.takeGuide();
+        p.specConfidence = b.takeGuide();
         p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
         p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
         p.historyDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);

@@ -202,6 +202,33 @@ struct TexRGBA8 : TexView {  // RGBA8_UNORM
     }
 };
 
+// First channel of an application-owned guide texture (IN_DIFF_CONFIDENCE / IN_SPEC_CONFIDENCE / IN_DISOCCLUSION_THRESHOLD_MIX): the
+// reference declares them Texture2D<float>, so the application may bind any format and any size (NRDSample binds an RGBA16F texture at
+// SHARC resolution). Read a few times per pixel at most, so the format switch is a uniform branch, not a template parameter.
+struct TexAnyX : TexView {
+    enum Kind : uint32_t { UNORM8 = 0, UNORM16 = 1, HALF = 2, FLOAT = 3 };
+    uint32_t kind, bytesPerTexel;  // `pitch` stays in texels
+    NRD_DEV float fetch(int x, int y) const {
+        const uint8_t* at = data + (size_t)(y * pitch + x) * bytesPerTexel;
+        switch (kind) {
+            case UNORM8: return (float)__ldg(at) / 255.0f;
+            case UNORM16: return (float)__ldg(reinterpret_cast<const unsigned short*>(at)) / 65535.0f;
+            case HALF: return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(at))));
+            default: return __ldg(reinterpret_cast<const float*>(at));
+        }
+    }
+    NRD_DEV float load(int x, int y) const { return inside(x, y) ? fetch(x, y) : 0.0f; }
+    NRD_DEV float fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }
+    NRD_DEV float sampleLinear(float2 uv) const {
+        float tx = uv.x * (float)w - 0.5f, ty = uv.y * (float)h - 0.5f;
+        float fx = floorf(tx), fy = floorf(ty);
+        float wx = tx - fx, wy = ty - fy;
+        int x0 = (int)fx, y0 = (int)fy;
+        float a = fetchClamped(x0, y0), b = fetchClamped(x0 + 1, y0), c = fetchClamped(x0, y0 + 1), d = fetchClamped(x0 + 1, y0 + 1);
+        return lerp(lerp(a, b, wx), lerp(c, d, wx), wy);
+    }
+};
+
 struct TexR16U : TexView {
     NRD_DEV uint32_t fetch(int x, int y) const { return __ldg(ptr<unsigned short>(x, y)); }
     NRD_DEV uint32_t fetchClamped(int x, int y) const { return fetch(cx(x), cy(y)); }

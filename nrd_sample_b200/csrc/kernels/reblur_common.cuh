@@ -166,7 +166,7 @@ struct PostBlurParams {
 };
 struct TemporalAccumulationParams {
     TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F mv; TexR32F prevViewZ; TexNR prevNormalRoughness; TexR16U prevInternalData;
-    TexR32F disocclusionThresholdMix, diffConfidence, specConfidence;  // dummies (IN_VIEWZ) unless the optional inputs are enabled
+    TexAnyX disocclusionThresholdMix, diffConfidence, specConfidence;  // dummies (IN_VIEWZ) unless the optional inputs are enabled
     TexRGBA16F inDiff, inSpec, historyDiff, historySpec; TexR16F historyDiffFast, historySpecFast, prevSpecHitDistForTracking, inSpecHitDistForTracking;
     TexRG8 outData1; TexRGBA16F outDiff, outSpec; TexR16F outDiffFast, outSpecFast, outSpecHitDistForTracking; TexR32U outData2;
 };

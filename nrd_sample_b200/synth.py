@@ -244,7 +244,7 @@ def checkerboard_pack(full: torch.Tensor, mode: int, frame_index: int) -> torch.
 
 
 def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, holes: bool = False,
-                 checkerboard: int = 0) -> Dict[str, torch.Tensor]:
+                 checkerboard: int = 0, guides: bool = False) -> Dict[str, torch.Tensor]:
     """All user inputs of REBLUR_DIFFUSE_SPECULAR for one frame, in their API storage formats. `holes`: probabilistic lobe sampling as in
     NRDSample — every pixel traced only one lobe this frame (checkerboard flipping per frame), the other lobe has hit distance 0 and
     relies on ReblurSettings::hitDistanceReconstructionMode."""
@@ -312,6 +312,18 @@ def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period
         "IN_DIFF_RADIANCE_HITDIST": torch.where(hit[..., None], pack_radiance_hitdist(diff_noisy, nhd_d), zero4).contiguous(),
         "IN_SPEC_RADIANCE_HITDIST": torch.where(hit[..., None], pack_radiance_hitdist(spec_noisy, nhd_s), zero4).contiguous(),
     }
+    if guides:
+        # Optional single-channel guides ( CommonSettings::isHistoryConfidenceAvailable / isDisocclusionThresholdMixAvailable ). NRD declares them
+        # Texture2D<float> and samples the confidences by uv, so size and format are the application's: NRDSample binds an RGBA16F texture at
+        # SHARC resolution ( Source/NRDSample.cpp:457-462, 2990 ). Here: diffuse confidence RGBA16F at half resolution, specular R8 at full
+        # resolution, the threshold mix R16F — three different formats through the same kernel path.
+        hw, hh = (width + 1) // 2, (height + 1) // 2
+        yy, xx = torch.meshgrid(torch.arange(hh, device=device), torch.arange(hw, device=device), indexing="ij")
+        conf_d = (0.55 + 0.45 * torch.sin(0.37 * xx + 0.11 * frame_index) * torch.cos(0.23 * yy)).clamp(0, 1)
+        out["IN_DIFF_CONFIDENCE"] = torch.stack([conf_d, 1.0 - conf_d, torch.zeros_like(conf_d), torch.ones_like(conf_d)], -1).to(torch.float16).contiguous()
+        conf_s = (rnd() * 1.3).clamp(0, 1)
+        out["IN_SPEC_CONFIDENCE"] = (conf_s * 255.0 + 0.5).to(torch.uint8).contiguous()
+        out["IN_DISOCCLUSION_THRESHOLD_MIX"] = (rough > 0.3).to(torch.float16).contiguous()
     if checkerboard:   # nrd::CheckerboardMode: 1 = BLACK, 2 = WHITE
         diff_mode, spec_mode = (0, 1) if checkerboard == 1 else (1, 0)
         out["IN_DIFF_RADIANCE_HITDIST"] = checkerboard_pack(out["IN_DIFF_RADIANCE_HITDIST"], diff_mode, frame_index)

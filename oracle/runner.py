@@ -116,6 +116,10 @@ USER_FORMATS = {
     api.ResourceType.IN_PENUMBRA: api.Format.R16_SFLOAT,
     api.ResourceType.OUT_SHADOW_TRANSLUCENCY: api.Format.R8_UNORM,   # RGBA8_UNORM for SIGMA_SHADOW_TRANSLUCENCY ( pass fmt= explicitly )
     api.ResourceType.IN_TRANSLUCENCY: api.Format.RGBA8_UNORM,
+    # the application's choice ( Texture2D<float> in the shaders ); these are what synth.reblur_frame( guides=True ) makes
+    api.ResourceType.IN_DIFF_CONFIDENCE: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.IN_SPEC_CONFIDENCE: api.Format.R8_UNORM,
+    api.ResourceType.IN_DISOCCLUSION_THRESHOLD_MIX: api.Format.R16_SFLOAT,
 }
 
 

@@ -41,6 +41,9 @@ CASES = [
     ("reblur_checkerboard_white", "reblur", 96, 64, 5, lambda: api.ReblurSettings(checkerboardMode=2), {"checkerboard": 2}),
     ("reblur_checkerboard_black_no_prepass_radius", "reblur", 100, 76, 4, lambda: api.ReblurSettings(checkerboardMode=1, diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0),
      {"checkerboard": 1}),
+    # "cs_*" keys go to CommonSettings, the rest to the frame generator
+    ("reblur_confidence_and_threshold_mix", "reblur", 96, 64, 5, None, {"guides": True, "cs_isHistoryConfidenceAvailable": True, "cs_isDisocclusionThresholdMixAvailable": True}),
+    ("reblur_confidence_checkerboard", "reblur", 96, 64, 4, lambda: api.ReblurSettings(checkerboardMode=2), {"guides": True, "checkerboard": 2, "cs_isHistoryConfidenceAvailable": True}),
     ("sigma_default", "sigma", 96, 64, 5, None, {}),
     ("sigma_odd_size", "sigma", 100, 75, 3, None, {}),
     ("sigma_no_stabilization", "sigma", 96, 64, 3, lambda: api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0), {}),
@@ -106,10 +109,12 @@ def test_oracle_is_bit_identical_to_the_reference_shaders_per_dispatch(label, wh
             checked[0] += 1
 
     settings = make_settings() if make_settings else None
+    cs_kwargs = {k[3:]: v for k, v in frame_kwargs.items() if k.startswith("cs_")}
+    frame_kwargs = {k: v for k, v in frame_kwargs.items() if not k.startswith("cs_")}
     for frame in range(frames):
         for k, v in DENOISERS[which][1](frame, w, h, **frame_kwargs).items():
             den.set_user_texture(getattr(RT, k), v)
-        den.denoise(synth.common_settings(frame, w, h), settings=settings, before_dispatch=before, on_dispatch=after)
+        den.denoise(synth.common_settings(frame, w, h, **cs_kwargs), settings=settings, before_dispatch=before, on_dispatch=after)
     assert checked[0] >= frames * 5
     assert any("Clear" in s for s in seen) and len(seen) >= 6
 

@@ -28,7 +28,10 @@ CASES = {
 }
 # NRDSample's default tracing mode is RESOLUTION_HALF => CheckerboardMode::WHITE ( Source/NRDSample.cpp:267, 545 )
 CASES["reblur_cb"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, "reblur_frame_cb", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
-SETTINGS = {"reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
+# ... and it feeds history confidence by default ( m_Settings.confidence = true, :296, 3866 ): guides of three formats / two sizes + checkerboard
+CASES["reblur_guides_cb"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, "reblur_frame_guides_cb", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
+SETTINGS = {"reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_guides_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
+COMMON = {"reblur_guides_cb": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True)}
 OUTPUT_FORMATS = {"sigma_tr": {"OUT_SHADOW_TRANSLUCENCY": api.Format.RGBA8_UNORM}}
 
 
@@ -39,13 +42,15 @@ def out_format(which, o, runner):
 def frame_of(name, f, w, h):
     if name == "relax_frame_nosh":
         return synth.relax_frame(f, w, h, sh=False)
+    if name == "reblur_frame_guides_cb":
+        return synth.reblur_frame(f, w, h, checkerboard=2, guides=True)
     if name == "reblur_frame_cb":
         return synth.reblur_frame(f, w, h, checkerboard=2)
     if name == "sigma_frame_tr":
         return synth.sigma_frame(f, w, h, translucency=True)
     return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0)}
+LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0)}
 
 
 @pytest.fixture(scope="module")
@@ -98,7 +103,7 @@ def test_each_dispatch_against_the_reference_shaders(ex, runner, which):
     for f in range(frames):
         for k, v in frame_of(CASES[which][1], f, w, h).items():
             ref.set_user_texture(getattr(RT, k), v)
-        ref.denoise(synth.common_settings(f, w, h), settings=SETTINGS[which]() if which in SETTINGS else None, before_dispatch=before, on_dispatch=after)
+        ref.denoise(synth.common_settings(f, w, h, **COMMON.get(which, {})), settings=SETTINGS[which]() if which in SETTINGS else None, before_dispatch=before, on_dispatch=after)
 
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump({" | ".join(map(str, k)): {"frac_bad": v["frac_bad"], "psnr": v["psnr"], "max_abs": v["max_abs"]} for k, v in worst.items()},
@@ -134,7 +139,7 @@ def test_closed_loop_against_the_reference_shaders(ex, runner, which):
             ref.set_user_texture(rt, v)
             keep[k] = v.to("cuda:0")
             cud.set_user_texture(rt, keep[k], runner.USER_FORMATS[rt])
-        cs = synth.common_settings(f, w, h)
+        cs = synth.common_settings(f, w, h, **COMMON.get(which, {}))
         ref.denoise(cs, settings=SETTINGS[which]() if which in SETTINGS else None)
         cud.set_common_settings(cs)
         if which in SETTINGS:
