@@ -23,6 +23,7 @@ void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t s
 void launchReblurClassifyTiles(const ReblurConstants&, const ClassifyTilesParams&, Rows, cudaStream_t);
 void launchReblurHitDistReconstruction(const ReblurConstants&, const HitDistReconstructionParams&, bool is5x5, Rows, cudaStream_t);
 void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int flags, Rows, cudaStream_t);
+void launchReblurSplitScreen(const ReblurConstants&, const SplitScreenParams&, Rows, cudaStream_t);
 void launchReblurBlur(const ReblurConstants&, const BlurParams&, int flags, Rows, cudaStream_t);
 void launchReblurPostBlur(const ReblurConstants&, const PostBlurParams&, bool temporalStabilization, int flags, Rows, cudaStream_t);
 void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccumulationParams&, Rows, cudaStream_t);
@@ -30,6 +31,8 @@ void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, boo
 void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, Rows, cudaStream_t);
 uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
 uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
+uint32_t dispatchReference(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, uint32_t gridW, uint32_t gridH, cudaStream_t stream,
+                           std::string& err);
 }  // namespace nrdk
 
 using namespace nrd;
@@ -55,6 +58,7 @@ uint32_t bytesPerTexel(uint32_t fmt) {
         case Format::RG8_UNORM: case Format::R16_UINT: case Format::R16_SFLOAT: return 2;
         case Format::RGBA8_UNORM: case Format::RG16_SFLOAT: case Format::R32_UINT: case Format::R32_SFLOAT: case Format::R10_G10_B10_A2_UNORM: return 4;
         case Format::RGBA16_SFLOAT: return 8;
+        case Format::RGBA32_SFLOAT: return 16;
         default: return 0;
     }
 }
@@ -186,6 +190,16 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         uint32_t r = done(7);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurHitDistReconstruction(cb, p, is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), rows, stream);
+    } else if (is("REBLUR_SplitScreen.cs.hlsl")) {
+        SplitScreenParams p;
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        uint32_t r = done(5);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurSplitScreen(cb, p, rows, stream);
     } else if (is("REBLUR_PrePass.cs.hlsl")) {
         PrePassParams p;
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
@@ -349,6 +363,13 @@ NRDCU_API uint32_t nrdcuDispatchRows(const char* shaderIdentifier, const void* c
         if (partial) return fail(Result::UNSUPPORTED, "%s: row ranges (multi-GPU strips) are implemented for REBLUR only", shaderIdentifier);
         std::string err;
         uint32_t r = nrdk::dispatchRelax(id, constants, constantsSize, textures, texturesNum, s, err);
+        if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
+        return checkLaunch(id.c_str()) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
+    }
+    if (id.rfind("REFERENCE_", 0) == 0) {
+        if (partial) return fail(Result::UNSUPPORTED, "%s: row ranges (multi-GPU strips) are implemented for REBLUR only", shaderIdentifier);
+        std::string err;
+        uint32_t r = nrdk::dispatchReference(id, constants, constantsSize, textures, texturesNum, 0u, 0u, s, err);
         if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
         return checkLaunch(id.c_str()) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
     }

@@ -224,4 +224,13 @@ struct RelaxConstants {
 };
 static_assert(sizeof(RelaxConstants) == 720, "RELAX cbuffer must stay 720 bytes");
 
+// REFERENCE_TemporalAccumulation.resources.hlsli:10-17, REFERENCE_Copy.resources.hlsli:10-18
+struct ReferenceAccumulateConstants {
+    float accumSpeed, debug, viewZScale, denoisingRange;
+};
+struct ReferenceCopyConstants {
+    float rectSizeInv[2], splitScreen, debug, viewZScale, denoisingRange;
+};
+static_assert(sizeof(ReferenceAccumulateConstants) == 16 && sizeof(ReferenceCopyConstants) == 24, "REFERENCE cbuffers");
+
 }  // namespace nrdb

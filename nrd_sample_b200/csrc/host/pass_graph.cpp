@@ -44,6 +44,7 @@ static const Denoiser kSupported[] = {
     Denoiser::RELAX_DIFFUSE_SPECULAR_SH,
     Denoiser::SIGMA_SHADOW,
     Denoiser::SIGMA_SHADOW_TRANSLUCENCY,
+    Denoiser::REFERENCE,
 };
 
 const LibraryDesc& libraryDesc() {
@@ -158,6 +159,7 @@ Result Graph::create(const InstanceCreationDesc& desc) {
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: buildReblurDiffuseSpecular(d); break;
             case Denoiser::SIGMA_SHADOW: buildSigmaShadow(d, false); break;
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: buildSigmaShadow(d, true); break;
+            case Denoiser::REFERENCE: buildReference(d); break;
             case Denoiser::RELAX_DIFFUSE_SPECULAR_SH: buildRelaxDiffuseSpecular(d, true); break;
             case Denoiser::RELAX_DIFFUSE_SPECULAR: buildRelaxDiffuseSpecular(d, false); break;
             default: return Result::INVALID_ARGUMENT;
@@ -455,6 +457,7 @@ Result Graph::getComputeDispatches(const Identifier* ids, uint32_t idsNum, const
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: updateReblur(d); break;
             case Denoiser::SIGMA_SHADOW:
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: updateSigma(d); break;
+            case Denoiser::REFERENCE: updateReference(d); break;
             case Denoiser::RELAX_DIFFUSE_SPECULAR_SH:
             case Denoiser::RELAX_DIFFUSE_SPECULAR: updateRelax(d); break;
             default: break;

@@ -123,6 +123,8 @@ private:
     void buildRelaxDiffuseSpecular(DenoiserState& d, bool sh);
     void updateRelax(const DenoiserState& d);
     void* fillRelaxConstants(const RelaxSettings& s, void* dst);
+    void buildReference(DenoiserState& d);
+    void updateReference(const DenoiserState& d);
 
     std::vector<DenoiserState> m_denoisers;
     std::vector<TextureDesc> m_permanentPool, m_transientPool;
@@ -151,6 +153,7 @@ private:
     InstanceDesc m_desc = {};
     CommonSettings m_common = {};
     FrameState m_frame = {};
+    uint32_t m_accumulatedFrameNum = 0;  // REFERENCE denoiser (InstanceImpl::m_AccumulatedFrameNum)
     bool m_firstUse = true;
     double m_lastTimeMs = -1.0;
     float m_smoothedDeltaMs = 16.6f;

@@ -147,6 +147,10 @@ struct ClassifyTilesParams {
     TexR32F inViewZ;
     TexR8 outTiles;
 };
+struct SplitScreenParams {
+    TexR32F viewZ; TexRGBA16F inDiff, inSpec;
+    TexRGBA16F outDiff, outSpec;
+};
 struct HitDistReconstructionParams {
     TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexRGBA16F outDiff, outSpec;

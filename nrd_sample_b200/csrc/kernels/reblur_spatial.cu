@@ -445,6 +445,16 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPo
     spatialFilter<POST_BLUR, SPEC>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust);
 }
 
+// REBLUR_SplitScreen.cs.hlsl:21-56: the noisy input (range-masked) left of CommonSettings::splitScreen
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurSplitScreenKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ SplitScreenParams p, int ctaY0) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (ctaY0 + blockIdx.y) * BLOCK_H + threadIdx.y;
+    const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
+    if (u > cb.splitScreen || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1]) return;
+    const float inRange = inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.load(px, py))) ? 1.0f : 0.0f;
+    p.outDiff.store(px, py, p.inDiff.load(px >> (cb.diffCheckerboard != 2u ? 1 : 0), py) * inRange);
+    p.outSpec.store(px, py, p.inSpec.load(px >> (cb.specCheckerboard != 2u ? 1 : 0), py) * inRange);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Host launchers (called by the executor)
 // ---------------------------------------------------------------------------------------------------------------
@@ -452,6 +462,11 @@ void launchReblurClassifyTiles(const ReblurConstants& cb, const ClassifyTilesPar
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, 16);
     if (!g.count) return;
     reblurClassifyTilesKernel<<<dim3((cb.rectSizeMinusOne[0] + 16) / 16, g.count), 256, 0, stream>>>(cb, p, g.ctaY0);
+}
+void launchReblurSplitScreen(const ReblurConstants& cb, const SplitScreenParams& p, Rows rows, cudaStream_t stream) {
+    const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
+    if (!g.count) return;
+    reblurSplitScreenKernel<<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
 }
 void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);

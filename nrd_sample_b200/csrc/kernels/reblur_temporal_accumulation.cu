@@ -42,6 +42,8 @@ NRD_DEV uint4 gather4(const TexR16U& t, int x0, int y0) {
 #ifndef TA_MIN_BLOCKS
 #    define TA_MIN_BLOCKS 3  // 80 regs + 88 B spill (3 CTAs / SM): 450 us vs 514 us at 128 regs (2 CTAs) for a 1440p frame on B200
 #endif
+// OPTIONAL: checkerboard resolve speed-up and the application's guide textures (confidence, threshold mix); compiled out of the plain kernel
+template <bool OPTIONAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTemporalAccumulationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                       const __grid_constant__ TemporalAccumulationParams p, int ctaY0) {
     __shared__ float4 sNormalHitDist[TILE_H][TILE_W];
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
 
     float disocclusionThresholdMix = 0.0f;
     if (materialID == cb.strandMaterialID) disocclusionThresholdMix = saturate(0.5f * pixelSize / (cb.strandThickness + NRD_EPS));
-    if (cb.hasDisocclusionThresholdMix) disocclusionThresholdMix = p.disocclusionThresholdMix.load(px, py);
+    if (OPTIONAL && cb.hasDisocclusionThresholdMix) disocclusionThresholdMix = p.disocclusionThresholdMix.load(px, py);
     float disocclusionThreshold = lerp(cb.disocclusionThreshold, cb.disocclusionThresholdAlternate, disocclusionThresholdMix);
     if (materialID == cb.strandMaterialID) disocclusionThreshold = lerp(0.25f, disocclusionThreshold, smoothStep01(smbParallaxInPixelsMax));
 
@@ -223,11 +225,11 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
     float specAccumSpeedCorrected, curvature, virtualHistoryAmount;
     {
         float smbSpecHistoryConfidence = smbFootprintQuality;
-        if (cb.hasHistoryConfidence) smbSpecHistoryConfidence = fminf(smbSpecHistoryConfidence, saturate(p.specConfidence.sampleLinear(smbPixelUv)));
+        if (OPTIONAL && cb.hasHistoryConfidence) smbSpecHistoryConfidence = fminf(smbSpecHistoryConfidence, saturate(p.specConfidence.sampleLinear(smbPixelUv)));
         smbSpecAccumSpeed *= lerp(smbSpecHistoryConfidence, 1.0f, 1.0f / (1.0f + smbSpecAccumSpeed));
 
         // Checkerboard ( RADIANCE mode: the pre-pass has already resolved the half-width input, only the accumulation speed changes; TA:329-357 )
-        const bool specHasData = cb.specCheckerboard == 2u || (((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u) == cb.specCheckerboard;
+        const bool specHasData = !OPTIONAL || cb.specCheckerboard == 2u || (((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u) == cb.specCheckerboard;
         const float4 spec = p.inSpec.load(px, py);
 
         // Curvature estimation along predicted motion (TA:387-467)
@@ -376,7 +378,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
 
             float vmbFootprintQuality = sqrt01(applyBilinear(vmbOcclusion.x, vmbOcclusion.y, vmbOcclusion.z, vmbOcclusion.w, vmbBilinearFilter));
             float vmbSpecHistoryConfidence = vmbFootprintQuality;
-            if (cb.hasHistoryConfidence) vmbSpecHistoryConfidence = fminf(vmbSpecHistoryConfidence, saturate(p.specConfidence.sampleLinear(vmbPixelUv)));
+            if (OPTIONAL && cb.hasHistoryConfidence) vmbSpecHistoryConfidence = fminf(vmbSpecHistoryConfidence, saturate(p.specConfidence.sampleLinear(vmbPixelUv)));
             vmbSpecAccumSpeed *= lerp(vmbSpecHistoryConfidence, 1.0f, 1.0f / (1.0f + vmbSpecAccumSpeed));
 
             vmbAllowCatRom = sum4(vmbOcclusion) > 3.5f && smbAllowCatRom;
@@ -537,10 +539,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
     // =============================================================================================== Diffuse
     {
         float diffHistoryConfidence = smbFootprintQuality;
-        if (cb.hasHistoryConfidence) diffHistoryConfidence = fminf(diffHistoryConfidence, saturate(p.diffConfidence.sampleLinear(smbPixelUv)));
+        if (OPTIONAL && cb.hasHistoryConfidence) diffHistoryConfidence = fminf(diffHistoryConfidence, saturate(p.diffConfidence.sampleLinear(smbPixelUv)));
         diffAccumSpeed *= lerp(diffHistoryConfidence, 1.0f, 1.0f / (1.0f + diffAccumSpeed));
 
-        const bool diffHasData = cb.diffCheckerboard == 2u || (((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u) == cb.diffCheckerboard;
+        const bool diffHasData = !OPTIONAL || cb.diffCheckerboard == 2u || (((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u) == cb.diffCheckerboard;
         const float4 diff = p.inDiff.load(px, py);
 
         HistoryFilter hf(saturate(smbPixelUv) * rectSizePrev, resourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom);
@@ -577,7 +579,10 @@ void launchReblurTemporalAccumulation(const ReblurConstants& cb, const TemporalA
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    reblurTemporalAccumulationKernel<<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+    if (cb.specCheckerboard != 2u || cb.diffCheckerboard != 2u || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix)
+        reblurTemporalAccumulationKernel<true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+    else
+        reblurTemporalAccumulationKernel<false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
 }
 
 }  // namespace nrdk

@@ -39,6 +39,7 @@ FORMAT_STORAGE = {
     api.Format.R32_UINT: (torch.int32, 1),
     api.Format.R32_SFLOAT: (torch.float32, 1),
     api.Format.R10_G10_B10_A2_UNORM: (torch.int32, 1),
+    api.Format.RGBA32_SFLOAT: (torch.float32, 4),
 }
 
 # void (*nrdcuDispatchCallback)(void* userArg, uint32_t dispatchIndex, const char* passName, const nrdcuTexture*, const uint8_t* isStorage, uint32_t n)

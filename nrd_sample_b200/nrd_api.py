@@ -87,12 +87,14 @@ class Format(enum.IntEnum):
     RGBA16_SFLOAT = 27
     R32_UINT = 28
     R32_SFLOAT = 30
+    RG32_SFLOAT = 33
+    RGBA32_SFLOAT = 39
     R10_G10_B10_A2_UNORM = 40
 
 
 FORMAT_BYTES = {
     Format.R8_UNORM: 1, Format.RG8_UNORM: 2, Format.RGBA8_UNORM: 4, Format.R16_UINT: 2, Format.R16_SFLOAT: 2,
-    Format.RG16_SFLOAT: 4, Format.RGBA16_SFLOAT: 8, Format.R32_UINT: 4, Format.R32_SFLOAT: 4, Format.R10_G10_B10_A2_UNORM: 4,
+    Format.RG16_SFLOAT: 4, Format.RGBA16_SFLOAT: 8, Format.R32_UINT: 4, Format.R32_SFLOAT: 4, Format.R10_G10_B10_A2_UNORM: 4, Format.RGBA32_SFLOAT: 16,
 }
 
 
@@ -292,6 +294,17 @@ class RelaxSettings(C.Structure):
         self.luminanceEdgeStoppingRelaxation, self.normalEdgeStoppingRelaxation, self.roughnessEdgeStoppingRelaxation = 0.5, 0.3, 1.0
         self.minMaterialForDiffuse = self.minMaterialForSpecular = 4.0
         self.enableRoughnessEdgeStopping = True
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class ReferenceSettings(C.Structure):
+    """nrd::ReferenceSettings (NRDSettings.h:483-487)."""
+    _fields_ = [("maxAccumulatedFrameNum", C.c_uint32)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.maxAccumulatedFrameNum = 120
         for k, v in kw.items():
             setattr(self, k, v)
 

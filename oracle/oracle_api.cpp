@@ -18,6 +18,48 @@ int relaxDispatch(const std::string& id, const void* cb, uint32_t cbSize, Tex* t
 
 using namespace orc;
 
+// REFERENCE_TemporalAccumulation.cs.hlsl:18-28, REFERENCE_Copy.cs.hlsl:18-27 (16x16 groups; constants: REFERENCE_*.resources.hlsli:10-18)
+static int referenceDispatch(const std::string& id, const void* constants, uint32_t cbSize, Tex* t, uint32_t n, int gridW, int gridH) {
+    if (n != 2) return 2;
+    const float* c = (const float*)constants;
+    if (id == "REFERENCE_TemporalAccumulation.cs.hlsl") {
+        if (cbSize != 16) return 2;
+        const float gAccumSpeed = c[0];
+        for (int y = 0; y < gridH * 16; y++)
+            for (int x = 0; x < gridW * 16; x++) {
+                float4 input = t[0].load(x, y), history = t[1].load(x, y);
+                t[1].store(x, y, lerp(history, input, gAccumSpeed));
+            }
+        return 0;
+    }
+    if (id == "REFERENCE_Copy.cs.hlsl") {
+        if (cbSize != 24) return 2;
+        const float2 gRectSizeInv = float2(c[0], c[1]);
+        const float gSplitScreen = c[2];
+        for (int y = 0; y < gridH * 16; y++)
+            for (int x = 0; x < gridW * 16; x++) {
+                float2 pixelUv = float2(x + 0.5f, y + 0.5f) * gRectSizeInv;
+                if (pixelUv.x > gSplitScreen) t[1].store(x, y, t[0].load(x, y));
+            }
+        return 0;
+    }
+    return 1;
+}
+
+// REBLUR_SplitScreen.cs.hlsl:21-56 (NRD_SIGNAL = BOTH, NRD_MODE = RADIANCE): the noisy input left of the split line
+static void reblurSplitScreen(const ReblurCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec, Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH) {
+    ReblurCtx c(cb);
+    for (int py = 0; py < gridH * 16; py++)
+        for (int px = 0; px < gridW * 8; px++) {
+            float2 pixelUv = float2(px + 0.5f, py + 0.5f) * cb.gRectSizeInv;
+            if (pixelUv.x > cb.gSplitScreen || px > cb.gRectSizeMinusOne.x || py > cb.gRectSizeMinusOne.y) continue;
+            float viewZ = c.UnpackViewZ(gIn_ViewZ.load(px, py).x);
+            float inRange = float(c.IsInDenoisingRange(viewZ));
+            gOut_Diff.store(px, py, gIn_Diff.load(px >> (cb.gDiffCheckerboard != 2 ? 1 : 0), py) * inRange);
+            gOut_Spec.store(px, py, gIn_Spec.load(px >> (cb.gSpecCheckerboard != 2 ? 1 : 0), py) * inRange);
+        }
+}
+
 static bool startsWith(const std::string& s, const char* p) { return s.compare(0, strlen(p), p) == 0; }
 
 extern "C" {
@@ -88,6 +130,11 @@ __attribute__((visibility("default"))) int nrd_oracle_dispatch(const char* shade
             reblurPostBlur(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], &t[9], &t[10], &t[11], false, gw, gh, quads, robust);
             return 0;
         }
+        if (id == "REBLUR_SplitScreen.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
+            if (texturesNum != 5) return 2;
+            reblurSplitScreen(cb, t[0], t[1], t[2], t[3], t[4], gw, gh);
+            return 0;
+        }
         if (id == "REBLUR_TemporalStabilization.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
             if (texturesNum != 16) return 2;
             TsTextures a = {&t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6], &t[7], &t[8], &t[9], &t[10], &t[11], &t[12], &t[13], &t[14], &t[15]};
@@ -98,6 +145,7 @@ __attribute__((visibility("default"))) int nrd_oracle_dispatch(const char* shade
     }
     if (startsWith(id, "SIGMA_")) return sigmaDispatch(id, constants, constantsSize, t, texturesNum, gw, gh);
     if (startsWith(id, "RELAX_")) return relaxDispatch(id, constants, constantsSize, t, texturesNum, gw, gh);
+    if (startsWith(id, "REFERENCE_")) return referenceDispatch(id, constants, constantsSize, t, texturesNum, gw, gh);
     return 1;
 }
 

@@ -94,6 +94,7 @@ FORMAT_STORAGE = {
     api.Format.R32_UINT: (torch.int32, 1),
     api.Format.R32_SFLOAT: (torch.float32, 1),
     api.Format.R10_G10_B10_A2_UNORM: (torch.int32, 1),
+    api.Format.RGBA32_SFLOAT: (torch.float32, 4),
 }
 
 # Formats of the user-provided resources as NRDSample creates them (Source/NRDSample.cpp:2913-3002)
@@ -116,6 +117,8 @@ USER_FORMATS = {
     api.ResourceType.IN_PENUMBRA: api.Format.R16_SFLOAT,
     api.ResourceType.OUT_SHADOW_TRANSLUCENCY: api.Format.R8_UNORM,   # RGBA8_UNORM for SIGMA_SHADOW_TRANSLUCENCY ( pass fmt= explicitly )
     api.ResourceType.IN_TRANSLUCENCY: api.Format.RGBA8_UNORM,
+    api.ResourceType.IN_SIGNAL: api.Format.RGBA16_SFLOAT,    # NRDSample's "Composed" ( Source/NRDSample.cpp:484-485, 2944 )
+    api.ResourceType.OUT_SIGNAL: api.Format.RGBA16_SFLOAT,
     # the application's choice ( Texture2D<float> in the shaders ); these are what synth.reblur_frame( guides=True ) makes
     api.ResourceType.IN_DIFF_CONFIDENCE: api.Format.RGBA16_SFLOAT,
     api.ResourceType.IN_SPEC_CONFIDENCE: api.Format.R8_UNORM,

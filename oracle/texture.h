@@ -22,6 +22,7 @@ enum Fmt : uint32_t {  // numeric values = nrd::Format
     FMT_RGBA16_SFLOAT = 27,
     FMT_R32_UINT = 28,
     FMT_R32_SFLOAT = 30,
+    FMT_RGBA32_SFLOAT = 39,
     FMT_R10_G10_B10_A2_UNORM = 40,
 };
 
@@ -56,6 +57,7 @@ struct Tex {
             case FMT_RG16_SFLOAT: { uint16_t v[2]; memcpy(v, at(x, y, 4), 4); return float4(f16tof32(v[0]), f16tof32(v[1]), 0, 1); }
             case FMT_RGBA16_SFLOAT: { uint16_t v[4]; memcpy(v, at(x, y, 8), 8); return float4(f16tof32(v[0]), f16tof32(v[1]), f16tof32(v[2]), f16tof32(v[3])); }
             case FMT_R32_SFLOAT: { float v; memcpy(&v, at(x, y, 4), 4); return float4(v, 0, 0, 1); }
+            case FMT_RGBA32_SFLOAT: { float v[4]; memcpy(v, at(x, y, 16), 16); return float4(v[0], v[1], v[2], v[3]); }
             case FMT_R10_G10_B10_A2_UNORM: {
                 uint32_t v; memcpy(&v, at(x, y, 4), 4);
                 return float4((v & 1023u) / 1023.0f, ((v >> 10) & 1023u) / 1023.0f, ((v >> 20) & 1023u) / 1023.0f, (v >> 30) / 3.0f);
@@ -101,6 +103,7 @@ struct Tex {
             case FMT_RG16_SFLOAT: { uint16_t q[2] = {f32tof16(v.x), f32tof16(v.y)}; memcpy(at(x, y, 4), q, 4); break; }
             case FMT_RGBA16_SFLOAT: { uint16_t q[4] = {f32tof16(v.x), f32tof16(v.y), f32tof16(v.z), f32tof16(v.w)}; memcpy(at(x, y, 8), q, 8); break; }
             case FMT_R32_SFLOAT: memcpy(at(x, y, 4), &v.x, 4); break;
+            case FMT_RGBA32_SFLOAT: { float q[4] = {v.x, v.y, v.z, v.w}; memcpy(at(x, y, 16), q, 16); break; }
             case FMT_R10_G10_B10_A2_UNORM: {
                 uint32_t q = unormEncode(v.x, 1023.0f) | (unormEncode(v.y, 1023.0f) << 10) | (unormEncode(v.z, 1023.0f) << 20) | (unormEncode(v.w, 3.0f) << 30);
                 memcpy(at(x, y, 4), &q, 4);
@@ -121,6 +124,7 @@ struct Tex {
             case FMT_R8_UNORM: return 1;
             case FMT_RG8_UNORM: case FMT_R16_UINT: case FMT_R16_SFLOAT: return 2;
             case FMT_RGBA16_SFLOAT: return 8;
+            case FMT_RGBA32_SFLOAT: return 16;
             default: return 4;
         }
     }

@@ -19,6 +19,10 @@ CASES = [
     ("reblur_1440p", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 2560, 1440, None),
     ("reblur_720p_recon_nots", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 1280, 720, "recon_nots"),
     ("reblur_odd_noprepass", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 1000, 562, "noprepass"),
+    ("reblur_checkerboard_guides_split", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 1280, 720, "reblur_cb_guides_split"),
+    ("reblur_split_only", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 640, 360, "split_only"),
+    ("reference_720p", api.Denoiser.REFERENCE, 1280, 720, "reference"),
+    ("reference_static_camera", api.Denoiser.REFERENCE, 640, 360, "reference_static"),
     ("sigma_512", api.Denoiser.SIGMA_SHADOW, 512, 512, "sigma"),
     ("sigma_nostab", api.Denoiser.SIGMA_SHADOW, 640, 360, "sigma_nostab"),
     ("sigma_translucency_1080p", api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, 1920, 1080, "sigma"),
@@ -31,7 +35,19 @@ CASES = [
 ]
 
 
+# CommonSettings overrides per case kind; "static" freezes the camera so the REFERENCE frame counter advances
+COMMON = {
+    "reblur_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.4),
+    "split_only": dict(splitScreen=1.0),
+    "reference": dict(splitScreen=0.25),
+}
+
+
 def _settings(kind):
+    if kind == "reblur_cb_guides_split":
+        return api.ReblurSettings(checkerboardMode=2)
+    if kind == "reference_static":
+        return api.ReferenceSettings(maxAccumulatedFrameNum=2)
     if kind == "recon_nots":
         return api.ReblurSettings(hitDistanceReconstructionMode=1, maxStabilizedFrameNum=0)
     if kind == "noprepass":
@@ -67,8 +83,9 @@ def capture(lib, denoiser, w, h, kind, frames=4):
     out["ranges"] = [[list(x) for x in r] for r in out["ranges"]]
     s = _settings(kind)
     for f in range(frames):
-        cs = synth.common_settings(f, w, h)
-        if f == 2:
+        cs = synth.common_settings(0 if kind == "reference_static" else f, w, h, **COMMON.get(kind, {}))
+        cs.frameIndex = f
+        if f == 2 and kind != "reference_static":
             cs.cameraJitter = (C.c_float * 2)(0.25, -0.125)
         r1 = inst.set_common_settings(cs)
         if s is not None:

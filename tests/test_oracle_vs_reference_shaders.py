@@ -21,6 +21,7 @@ DENOISERS = {
     "reblur": (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, synth.reblur_frame, ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST")),
     "sigma": (api.Denoiser.SIGMA_SHADOW, synth.sigma_frame, ("OUT_SHADOW_TRANSLUCENCY",)),
     "relax": (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, synth.relax_frame, ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1")),
+    "reference": (api.Denoiser.REFERENCE, synth.reference_frame, ("OUT_SIGNAL",)),
     "sigma_tr": (api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, lambda *a, **k: synth.sigma_frame(*a, translucency=True, **k), ("OUT_SHADOW_TRANSLUCENCY",)),
 }
 # user-texture formats that differ from runner.USER_FORMATS for a denoiser
@@ -44,6 +45,11 @@ CASES = [
     # "cs_*" keys go to CommonSettings, the rest to the frame generator
     ("reblur_confidence_and_threshold_mix", "reblur", 96, 64, 5, None, {"guides": True, "cs_isHistoryConfidenceAvailable": True, "cs_isDisocclusionThresholdMixAvailable": True}),
     ("reblur_confidence_checkerboard", "reblur", 96, 64, 4, lambda: api.ReblurSettings(checkerboardMode=2), {"guides": True, "checkerboard": 2, "cs_isHistoryConfidenceAvailable": True}),
+    ("reblur_split_screen", "reblur", 96, 64, 3, None, {"cs_splitScreen": 0.4}),
+    ("reblur_split_screen_checkerboard_full", "reblur", 96, 64, 2, lambda: api.ReblurSettings(checkerboardMode=1), {"checkerboard": 1, "cs_splitScreen": 1.0}),
+    # "cs_static": the camera of frame 0 every frame, so the REFERENCE accumulator actually accumulates ( Reference.hpp:62-68 )
+    ("reference_static_camera_split", "reference", 100, 75, 5, lambda: api.ReferenceSettings(maxAccumulatedFrameNum=3), {"cs_static": True, "cs_splitScreen": 0.3}),
+    ("reference_moving_camera", "reference", 96, 64, 3, None, {}),
     ("sigma_default", "sigma", 96, 64, 5, None, {}),
     ("sigma_odd_size", "sigma", 100, 75, 3, None, {}),
     ("sigma_no_stabilization", "sigma", 96, 64, 3, lambda: api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0), {}),
@@ -114,9 +120,13 @@ def test_oracle_is_bit_identical_to_the_reference_shaders_per_dispatch(label, wh
     for frame in range(frames):
         for k, v in DENOISERS[which][1](frame, w, h, **frame_kwargs).items():
             den.set_user_texture(getattr(RT, k), v)
-        den.denoise(synth.common_settings(frame, w, h, **cs_kwargs), settings=settings, before_dispatch=before, on_dispatch=after)
-    assert checked[0] >= frames * 5
-    assert any("Clear" in s for s in seen) and len(seen) >= 6
+        static = cs_kwargs.get("static", False)
+        cs = synth.common_settings(0 if static else frame, w, h, **{k: v for k, v in cs_kwargs.items() if k != "static"})
+        cs.frameIndex = frame
+        den.denoise(cs, settings=settings, before_dispatch=before, on_dispatch=after)
+    few = which == "reference" or cs_kwargs.get("splitScreen", 0.0) >= 1.0    # chains of one or two passes
+    assert checked[0] >= frames * (1 if few else 5)
+    assert any("Clear" in s for s in seen) and len(seen) >= (2 if few else 6)
 
 
 @needs_refshaders

@@ -30,8 +30,19 @@ CASES = {
 CASES["reblur_cb"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, "reblur_frame_cb", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
 # ... and it feeds history confidence by default ( m_Settings.confidence = true, :296, 3866 ): guides of three formats / two sizes + checkerboard
 CASES["reblur_guides_cb"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, "reblur_frame_guides_cb", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
-SETTINGS = {"reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_guides_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
-COMMON = {"reblur_guides_cb": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True)}
+CASES["reblur_split"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, "reblur_frame_cb", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
+# REFERENCE: static camera so that the accumulator accumulates ( Reference.hpp:62-68 )
+CASES["reference"] = (api.Denoiser.REFERENCE, "reference_frame", ("OUT_SIGNAL",), "reblur")
+SETTINGS = {"reblur_split": lambda: api.ReblurSettings(checkerboardMode=2), "reference": lambda: api.ReferenceSettings(maxAccumulatedFrameNum=5), "reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_guides_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
+COMMON = {"reblur_guides_cb": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True), "reblur_split": dict(splitScreen=0.35),
+          "reference": dict(splitScreen=0.2)}
+STATIC_CAMERA = {"reference"}
+
+
+def common_of(which, f, w, h):
+    cs = synth.common_settings(0 if which in STATIC_CAMERA else f, w, h, **COMMON.get(which, {}))
+    cs.frameIndex = f
+    return cs
 OUTPUT_FORMATS = {"sigma_tr": {"OUT_SHADOW_TRANSLUCENCY": api.Format.RGBA8_UNORM}}
 
 
@@ -50,7 +61,7 @@ def frame_of(name, f, w, h):
         return synth.sigma_frame(f, w, h, translucency=True)
     return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0)}
+LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0), "reblur_split": (3e-2, 45.0), "reference": (1e-3, 80.0)}
 
 
 @pytest.fixture(scope="module")
@@ -103,7 +114,7 @@ def test_each_dispatch_against_the_reference_shaders(ex, runner, which):
     for f in range(frames):
         for k, v in frame_of(CASES[which][1], f, w, h).items():
             ref.set_user_texture(getattr(RT, k), v)
-        ref.denoise(synth.common_settings(f, w, h, **COMMON.get(which, {})), settings=SETTINGS[which]() if which in SETTINGS else None, before_dispatch=before, on_dispatch=after)
+        ref.denoise(common_of(which, f, w, h), settings=SETTINGS[which]() if which in SETTINGS else None, before_dispatch=before, on_dispatch=after)
 
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump({" | ".join(map(str, k)): {"frac_bad": v["frac_bad"], "psnr": v["psnr"], "max_abs": v["max_abs"]} for k, v in worst.items()},
@@ -139,7 +150,7 @@ def test_closed_loop_against_the_reference_shaders(ex, runner, which):
             ref.set_user_texture(rt, v)
             keep[k] = v.to("cuda:0")
             cud.set_user_texture(rt, keep[k], runner.USER_FORMATS[rt])
-        cs = synth.common_settings(f, w, h, **COMMON.get(which, {}))
+        cs = common_of(which, f, w, h)
         ref.denoise(cs, settings=SETTINGS[which]() if which in SETTINGS else None)
         cud.set_common_settings(cs)
         if which in SETTINGS:
