@@ -63,26 +63,6 @@ uint32_t bytesPerTexel(uint32_t fmt) {
     }
 }
 
-// Formats an application may use for the single-channel guide inputs (confidence, disocclusion-threshold mix): first channel only
-bool guideFormat(uint32_t fmt, uint32_t& kind, uint32_t& bpp) {
-    using K = nrdk::TexAnyX;
-    switch ((Format)fmt) {
-        case Format::R8_UNORM: kind = K::UNORM8; bpp = 1; return true;
-        case Format::RG8_UNORM: kind = K::UNORM8; bpp = 2; return true;
-        case Format::RGBA8_UNORM: kind = K::UNORM8; bpp = 4; return true;
-        case Format::R16_UNORM: kind = K::UNORM16; bpp = 2; return true;
-        case Format::RG16_UNORM: kind = K::UNORM16; bpp = 4; return true;
-        case Format::RGBA16_UNORM: kind = K::UNORM16; bpp = 8; return true;
-        case Format::R16_SFLOAT: kind = K::HALF; bpp = 2; return true;
-        case Format::RG16_SFLOAT: kind = K::HALF; bpp = 4; return true;
-        case Format::RGBA16_SFLOAT: kind = K::HALF; bpp = 8; return true;
-        case Format::R32_SFLOAT: kind = K::FLOAT; bpp = 4; return true;
-        case Format::RG32_SFLOAT: kind = K::FLOAT; bpp = 8; return true;
-        case Format::RGBA32_SFLOAT: kind = K::FLOAT; bpp = 16; return true;
-        default: return false;
-    }
-}
-
 // Typed view construction with format checking
 struct Binder {
     const nrdcuTexture* t;
@@ -120,8 +100,7 @@ struct Binder {
             return v;
         }
         const nrdcuTexture& x = t[next];
-        uint32_t kind = 0, bpp = 1;
-        if (!guideFormat(x.format, kind, bpp) || !x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
+        if (!nrdk::bindGuide(x.format, x.data, x.width, x.height, x.pitchBytes, v)) {
             if (ok) {
                 char buf[256];
                 snprintf(buf, sizeof(buf), "%s: binding %u (single-channel guide) has unsupported format %u / pitch %u", shader, next, x.format, x.pitchBytes);
@@ -129,12 +108,6 @@ struct Binder {
             }
             ok = false;
         }
-        v.data = (uint8_t*)x.data;
-        v.w = (int)x.width;
-        v.h = (int)x.height;
-        v.pitch = (int)(x.pitchBytes / bpp);
-        v.kind = kind;
-        v.bytesPerTexel = bpp;
         next++;
         return v;
     }

@@ -10,6 +10,7 @@
 // Texture semantics: Load out of bounds -> 0, store out of bounds dropped, samplers clamp to edge,
 // bilinear weights exact fp32, UNORM stores round to nearest, FP16 stores round to nearest even.
 #pragma once
+#include "../../../include/nrd_b200.h"
 #include "../host/constants.h"
 #include "vecmath.cuh"
 
@@ -228,6 +229,35 @@ struct TexAnyX : TexView {
         return lerp(lerp(a, b, wx), lerp(c, d, wx), wy);
     }
 };
+
+// Host side: view of an application texture as a single-channel guide; false if the format is not one of the supported ones
+inline bool bindGuide(uint32_t format, void* data, uint32_t width, uint32_t height, uint32_t pitchBytes, TexAnyX& v) {
+    using F = nrd::Format;
+    uint32_t kind, bpp;
+    switch ((F)format) {
+        case F::R8_UNORM: kind = TexAnyX::UNORM8; bpp = 1; break;
+        case F::RG8_UNORM: kind = TexAnyX::UNORM8; bpp = 2; break;
+        case F::RGBA8_UNORM: kind = TexAnyX::UNORM8; bpp = 4; break;
+        case F::R16_UNORM: kind = TexAnyX::UNORM16; bpp = 2; break;
+        case F::RG16_UNORM: kind = TexAnyX::UNORM16; bpp = 4; break;
+        case F::RGBA16_UNORM: kind = TexAnyX::UNORM16; bpp = 8; break;
+        case F::R16_SFLOAT: kind = TexAnyX::HALF; bpp = 2; break;
+        case F::RG16_SFLOAT: kind = TexAnyX::HALF; bpp = 4; break;
+        case F::RGBA16_SFLOAT: kind = TexAnyX::HALF; bpp = 8; break;
+        case F::R32_SFLOAT: kind = TexAnyX::FLOAT; bpp = 4; break;
+        case F::RG32_SFLOAT: kind = TexAnyX::FLOAT; bpp = 8; break;
+        case F::RGBA32_SFLOAT: kind = TexAnyX::FLOAT; bpp = 16; break;
+        default: return false;
+    }
+    if (!data || (pitchBytes % bpp) != 0 || pitchBytes < width * bpp) return false;
+    v.data = (uint8_t*)data;
+    v.w = (int)width;
+    v.h = (int)height;
+    v.pitch = (int)(pitchBytes / bpp);
+    v.kind = kind;
+    v.bytesPerTexel = bpp;
+    return true;
+}
 
 struct TexR16U : TexView {
     NRD_DEV uint32_t fetch(int x, int y) const { return __ldg(ptr<unsigned short>(x, y)); }

@@ -5,8 +5,8 @@
 // Reference (External/NRD/Shaders): RELAX_ClassifyTiles.cs.hlsl:21-51, RELAX_PrePass.cs.hlsl:21-385,
 // RELAX_TemporalAccumulation.cs.hlsl:21-942, RELAX_HistoryFix.cs.hlsl:21-163, RELAX_HistoryClamping.cs.hlsl:21-354,
 // RELAX_Copy.cs.hlsl:21-34, RELAX_AntiFirefly.cs.hlsl:21-216, RELAX_AtrousSmem.cs.hlsl:21-484, RELAX_Atrous.cs.hlsl:21-260,
-// helpers RELAX_Common.hlsli:11-185. Build switches of the reference's default build: no checkerboard, no confidence /
-// disocclusion-threshold-mix inputs (rejected with UNSUPPORTED), NRD_USE_PREV_WORLD_SPACE_MATRIX = 0.
+// RELAX_SplitScreen.cs.hlsl:21-62, helpers RELAX_Common.hlsli:11-185. Build switches of the reference's default build
+// (NRD_USE_PREV_WORLD_SPACE_MATRIX = 0); checkerboard modes, history-confidence and disocclusion-threshold-mix inputs included.
 // History clamping and the first a-trous pass stage their 5x5 neighbourhoods in shared memory like the reference (36x12 texels per
 // 32x8 CTA, colour-space conversions / normal decode / world positions done once per texel); the 3x3 of temporal accumulation and
 // anti-firefly go through L1. The arithmetic follows the shaders statement by statement.
@@ -133,8 +133,8 @@ template <bool SH> NRD_DEV float3 sampleNearestSh(const TexRGBA16F& t, float2 uv
 struct RelaxClassifyParams { TexR32F viewZ; TexR8 outTiles; };
 struct RelaxPrePassParams { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, specSh, diffSh, outSpec, outDiff, outSpecSh, outDiffSh; };
 struct RelaxTaParams {
-    TexR8 tiles; TexRGBA16F mv; TexNR normalRoughness; TexR32F viewZ; TexR32F mixDummy; TexRGBA8 prevNormalRoughness; TexR32F prevViewZ; TexR8 prevHistoryLength, prevMaterialID;
-    TexRGBA16F spec, diff, historySpecFast, historyDiffFast, historySpec, historyDiff; TexR16F prevSpecHitDist; TexR32F specConfDummy, diffConfDummy;
+    TexR8 tiles; TexRGBA16F mv; TexNR normalRoughness; TexR32F viewZ; TexAnyX mixDummy; TexRGBA8 prevNormalRoughness; TexR32F prevViewZ; TexR8 prevHistoryLength, prevMaterialID;
+    TexRGBA16F spec, diff, historySpecFast, historyDiffFast, historySpec, historyDiff; TexR16F prevSpecHitDist; TexAnyX specConfDummy, diffConfDummy;
     TexRGBA16F specSh, diffSh, historySpecShFast, historyDiffShFast, historySpecSh, historyDiffSh;
     TexR8 outHistoryLength; TexRGBA16F outSpec, outDiff, outSpecFast, outDiffFast; TexR16F outSpecHitDist; TexR8 outSpecReprojectionConfidence;
     TexRGBA16F outSpecSh, outDiffSh, outSpecShFast, outDiffShFast;
@@ -147,7 +147,7 @@ struct RelaxHistoryClampingParams {
 struct RelaxCopyParams { TexRGBA16F spec, diff, outSpec, outDiff; };
 struct RelaxAntiFireflyParams { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, outSpec, outDiff; };
 struct RelaxAtrousParams {
-    TexR8 tiles, historyLength; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff; TexR8 specReprojectionConfidence; TexR32F specConfDummy, diffConfDummy; TexRGBA16F specSh, diffSh;
+    TexR8 tiles, historyLength; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff; TexR8 specReprojectionConfidence; TexAnyX specConfDummy, diffConfDummy; TexRGBA16F specSh, diffSh;
     TexRGBA16F outSpec, outDiff; TexRGBA8 outNormalRoughness; TexR8 outMaterialID; TexR32F outViewZ; TexRGBA16F outSpecSh, outDiffSh;
 };
 
@@ -160,7 +160,25 @@ __global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <bool SH>
+// Confidence-driven relaxation of the a-trous edge stopping ( RELAX_AtrousSmem.cs.hlsl:201-215, 239-251; RELAX_Atrous.cs.hlsl:67-80, 107-119 ):
+// returns { r for the normal weights, r for the luminance weight }
+NRD_DEV float2 confidenceDrivenRelaxation(const RelaxConstants& cb, const TexAnyX& confidence, float2 pixelUv) {
+    const float relaxation = saturate(cb.confidenceDrivenRelaxationMultiplier * (1.0f - saturate(confidence.sampleLinear(pixelUv))));
+    return make_float2(saturate(relaxation * cb.confidenceDrivenNormalEdgeStoppingRelaxation), saturate(relaxation * cb.confidenceDrivenLuminanceEdgeStoppingRelaxation));
+}
+
+// RELAX_Common.hlsli:164-165
+NRD_DEV float bilateralWeight(float z, float zc) { return linearStep(0.03f, 0.0f, fabsf(z - zc) * (1.0f / fmaxf(z, zc))); }
+// ApplyCheckerboardShift ( Common.hlsli:332-342 ) on a pixel-centre position: move a tap to a pixel that was traced this frame
+NRD_DEV float2 applyCheckerboardShift(float2 pos, uint32_t mode, int counter, uint32_t frameIndex) {
+    const uint32_t checkerboard = (((uint32_t)(pos.x + 16384.0f) ^ (uint32_t)(pos.y + 16384.0f)) ^ frameIndex) & 1u;
+    const float shift = (counter & 1) == 0 ? -1.0f : 1.0f;
+    pos.x += (checkerboard != mode && mode != 2u) ? shift : 0.0f;
+    return pos;
+}
+
+// CB: checkerboarded inputs ( CheckerboardMode::BLACK / WHITE ): the traced pixels sit in the left half of the input textures
+template <bool SH, bool CB>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxPrePassParams p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
@@ -178,9 +196,43 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
     const float minRectDim = (float)min(cb.rectSize[0], cb.rectSize[1]);
     const float planeZ = cb.orthoMode == 0.0f ? centerViewZ : 1.0f;
 
+    // Checkerboard resolve weights ( RELAX_PrePass.cs.hlsl:39-72 )
+    uint32_t checkerboard = 0;
+    int cbX0 = 0, cbX1 = 0;
+    float materialID0 = 0.0f, materialID1 = 0.0f;
+    float2 resolveWeights = f2(1.0f);
+    if (CB) {
+        checkerboard = ((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u;
+        cbX0 = max(px - 1, 0);
+        cbX1 = min(px + 1, cb.rectSize[0] - 1);
+        const float viewZ0 = relaxViewZ(cb, p.viewZ.load(cbX0, py)), viewZ1 = relaxViewZ(cb, p.viewZ.load(cbX1, py));
+        materialID0 = materialFromRaw(p.normalRoughness.loadRaw(cbX0, py));
+        materialID1 = materialFromRaw(p.normalRoughness.loadRaw(cbX1, py));
+        resolveWeights = make_float2(bilateralWeight(viewZ0, centerViewZ), bilateralWeight(viewZ1, centerViewZ));
+        if (!relaxInRange(cb, viewZ0) || px < 1) resolveWeights.x = 0.0f;
+        if (!relaxInRange(cb, viewZ1) || px > cb.rectSize[0] - 2) resolveWeights.y = 0.0f;
+        cbX0 >>= 1;
+        cbX1 >>= 1;
+    }
+    // the traced row neighbours of a pixel the checkerboard skipped this frame ( :101-125, 238-262 )
+    auto resolve = [&](const TexRGBA16F& tex, const TexRGBA16F& texSh, float minMaterial, float4& illumination, float3& sh) {
+        float2 wc = resolveWeights;
+        wc.x *= compareMaterials(centerMaterialID, materialID0, minMaterial) ? 1.0f : 0.0f;
+        wc.y *= compareMaterials(centerMaterialID, materialID1, minMaterial) ? 1.0f : 0.0f;
+        wc = wc * positiveRcp(wc.x + wc.y);
+        float4 a = tex.load(cbX0, py), b = tex.load(cbX1, py);
+        float3 aSh = loadSh<SH>(texSh, cbX0, py), bSh = loadSh<SH>(texSh, cbX1, py);
+        if (wc.x == 0.0f) { a = f4(0.0f); aSh = f3(0.0f); }
+        if (wc.y == 0.0f) { b = f4(0.0f); bSh = f3(0.0f); }
+        illumination = a * wc.x + b * wc.y;
+        sh = aSh * wc.x + bSh * wc.y;
+    };
+
     // ---- diffuse ----
-    float4 diffuseIllumination = p.diff.load(px, py);
-    float3 diffuseSH = loadSh<SH>(p.diffSh, px, py);
+    const bool diffCb = CB && cb.diffCheckerboard != 2u;
+    float4 diffuseIllumination = p.diff.load(diffCb ? px >> 1 : px, py);
+    float3 diffuseSH = loadSh<SH>(p.diffSh, diffCb ? px >> 1 : px, py);
+    if (diffCb && checkerboard != cb.diffCheckerboard) resolve(p.diff, p.diffSh, cb.diffMinMaterial, diffuseIllumination, diffuseSH);
     if (cb.diffBlurRadius > 0.0f) {
         const float frustumSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, minRectDim, centerViewZ);
         const float hitDist = diffuseIllumination.w == 0.0f ? 1.0f : diffuseIllumination.w;
@@ -194,8 +246,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
             const float3 offset = kPoisson8[i];
             float2 uv = pixelUv * rectSize + rotate2(rotator, make_float2(offset.x, offset.y)) * blurRadius;
             uv = floor2(uv) + 0.5f;
+            if (CB) uv = applyCheckerboardShift(uv, cb.diffCheckerboard, i, cb.frameIndex);
             uv = uv * rectSizeInv;
             const float2 uvScaled = clampUvToViewport(cb, uv);
+            const float2 uvInput = make_float2(diffCb ? uvScaled.x * 0.5f : uvScaled.x, uvScaled.y);
 
             float sampleMaterialID;
             const float3 sampleNormal = xyz(unpackNormalRoughness(p.normalRoughness.sampleNearestRaw(uvScaled), sampleMaterialID));
@@ -208,14 +262,14 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
             sampleWeight *= planeDistanceWeight(centerWorldPos, centerNormal, planeZ, sampleWorldPos, cb.depthThreshold);
             sampleWeight *= computeWeight(acosApproxPositive(dot(centerNormal, sampleNormal)), normalWeightParam, 0.0f);
 
-            float4 sampleDiffuse = p.diff.sampleNearest(uvScaled);
+            float4 sampleDiffuse = p.diff.sampleNearest(uvInput);
             if (sampleWeight == 0.0f) sampleDiffuse = f4(0.0f);
             sampleWeight *= lerp(cb.minHitDistanceWeight, 1.0f, exponentialWeight(sampleDiffuse.w, hitDistanceWeightP.x, hitDistanceWeightP.y));
             sampleWeight *= gaussianWeight(offset.z);
 
             weightSum += sampleWeight;
             diffuseIllumination += sampleDiffuse * sampleWeight;
-            float3 sampleSH = sampleNearestSh<SH>(p.diffSh, uvScaled);
+            float3 sampleSH = sampleNearestSh<SH>(p.diffSh, uvInput);
             if (sampleWeight == 0.0f) sampleSH = f3(0.0f);
             diffuseSH += sampleSH * sampleWeight;
         }
@@ -228,8 +282,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
     // ---- specular ----
     Rng rng;
     rng.init((uint32_t)px, (uint32_t)py, cb.frameIndex);
-    float4 specularIllumination = p.spec.load(px, py);
-    float3 specularSH = loadSh<SH>(p.specSh, px, py);
+    const bool specCb = CB && cb.specCheckerboard != 2u;
+    float4 specularIllumination = p.spec.load(specCb ? px >> 1 : px, py);
+    float3 specularSH = loadSh<SH>(p.specSh, specCb ? px >> 1 : px, py);
+    if (specCb && checkerboard != cb.specCheckerboard) resolve(p.spec, p.specSh, cb.specMinMaterial, specularIllumination, specularSH);
     specularIllumination.w = fmaxf(0.0f, fminf(cb.denoisingRange, specularIllumination.w));
     if (cb.specBlurRadius > 0.0f) {
         const float3 viewVector = cb.orthoMode == 0.0f ? normalize(-centerWorldPos) : make_float3(cb.frustumForward[0], cb.frustumForward[1], cb.frustumForward[2]);
@@ -258,8 +314,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
             const float3 offset = kPoisson8[i];
             float2 uv = pixelUv * rectSize + rotate2(rotator, make_float2(offset.x, offset.y)) * blurRadius;
             uv = floor2(uv) + 0.5f;
+            if (CB) uv = applyCheckerboardShift(uv, cb.specCheckerboard, i, cb.frameIndex);
             uv = uv * rectSizeInv;
             const float2 uvScaled = clampUvToViewport(cb, uv);
+            const float2 uvInput = make_float2(specCb ? uvScaled.x * 0.5f : uvScaled.x, uvScaled.y);
 
             float sampleMaterialID;
             const float4 sampleNormalRoughness = unpackNormalRoughness(p.normalRoughness.sampleNearestRaw(uvScaled), sampleMaterialID);
@@ -274,7 +332,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
             const float3 sampleWorldPos = currentWorldPosClip(cb, uv * 2.0f - 1.0f, sampleViewZ);
             sampleWeight *= planeDistanceWeight(centerWorldPos, centerNormal, planeZ, sampleWorldPos, cb.depthThreshold);
 
-            float4 sampleSpecular = p.spec.sampleNearest(uvScaled);
+            float4 sampleSpecular = p.spec.sampleNearest(uvInput);
             if (sampleWeight == 0.0f) sampleSpecular = f4(0.0f);
             if (rng.next() < sampleWeight * NoV) minHitT = fminf(minHitT, sampleSpecular.w == 0.0f ? NRD_INF : sampleSpecular.w);
 
@@ -288,7 +346,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
             specularIllumination.x += sampleSpecular.x * sampleWeight;
             specularIllumination.y += sampleSpecular.y * sampleWeight;
             specularIllumination.z += sampleSpecular.z * sampleWeight;
-            float3 sampleSH = sampleNearestSh<SH>(p.specSh, uvScaled);
+            float3 sampleSH = sampleNearestSh<SH>(p.specSh, uvInput);
             if (sampleWeight == 0.0f) sampleSH = f3(0.0f);
             specularSH += sampleSH * sampleWeight;
         }
@@ -303,11 +361,13 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
 #ifndef RELAX_TA_MIN_BLOCKS
 #define RELAX_TA_MIN_BLOCKS 3
 #endif
-template <bool SH>
+// OPT: checkerboard resolve speed-up and the application's guide textures ( confidence, threshold mix ); compiled out of the plain kernel
+template <bool SH, bool OPT>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParams p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float currentLinearZ = relaxViewZ(cb, p.viewZ.load(px, py));
+    const uint32_t checkerboard = ((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u;
     if (!relaxInRange(cb, currentLinearZ)) return;
 
     const float2 rectSize = make_float2((float)cb.rectSize[0], (float)cb.rectSize[1]), rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
@@ -376,6 +436,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
 
     float disocclusionThresholdMix = 0.0f;
     if (currentMaterialID == cb.strandMaterialID) disocclusionThresholdMix = strandThickness(cb.strandThickness, pixelSize);
+    if (OPT && cb.hasDisocclusionThresholdMix) disocclusionThresholdMix = p.mixDummy.load(px, py);
     float disocclusionThreshold = lerp(cb.disocclusionThreshold, cb.disocclusionThresholdAlternate, disocclusionThresholdMix);
     if (currentMaterialID == cb.strandMaterialID) disocclusionThreshold = lerp(0.25f, disocclusionThreshold, smoothStep01(smbParallaxInPixelsMax));
 
@@ -462,8 +523,18 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
 
     // ---- diffuse ----
     {
-        const float diffuseAlpha = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (cb.diffMaxAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
-        const float diffuseAlphaResponsive = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (cb.diffMaxFastAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+        float diffMaxAccumulatedFrameNum = cb.diffMaxAccumulatedFrameNum, diffMaxFastAccumulatedFrameNum = cb.diffMaxFastAccumulatedFrameNum;
+        if (OPT && cb.hasHistoryConfidence) {  // TA:599-604
+            const float inDiffConfidence = saturate(p.diffConfDummy.sampleLinear(prevUVSMB));
+            diffMaxAccumulatedFrameNum *= inDiffConfidence;
+            diffMaxFastAccumulatedFrameNum *= inDiffConfidence;
+        }
+        float diffuseAlpha = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (diffMaxAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+        float diffuseAlphaResponsive = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (diffMaxFastAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+        if (OPT && cb.diffCheckerboard != 2u && checkerboard != cb.diffCheckerboard && historyLength > 1.0f) {  // TA:611-620
+            diffuseAlpha *= 1.0f - cb.checkerboardResolveAccumSpeed;
+            diffuseAlphaResponsive *= 1.0f - cb.checkerboardResolveAccumSpeed;
+        }
         p.outDiff.store(px, py, lerp(prevDiffuseSMB, f4(diffuseIllumination, diffuse2ndMoment), diffuseAlpha));
         p.outDiffFast.store(px, py, f4(lerp(prevDiffuseSMBResponsive, diffuseIllumination, diffuseAlphaResponsive), 0.0f));
         storeSh<SH>(p.outDiffSh, px, py, lerp(prevDiffuseSH, diffuseSH, diffuseAlpha));
@@ -472,8 +543,14 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
     p.outHistoryLength.store(px, py, historyLength / 255.0f);
 
     // ---- specular ----
-    const float specHistoryFrames = fminf(cb.specMaxAccumulatedFrameNum, historyLength);
-    const float specHistoryResponsiveFrames = fminf(cb.specMaxFastAccumulatedFrameNum, historyLength);
+    float specMaxAccumulatedFrameNum = cb.specMaxAccumulatedFrameNum, specMaxFastAccumulatedFrameNum = cb.specMaxFastAccumulatedFrameNum;
+    if (OPT && cb.hasHistoryConfidence) {  // TA:642-647
+        const float inSpecConfidence = saturate(p.specConfDummy.sampleLinear(prevUVSMB));
+        specMaxAccumulatedFrameNum *= inSpecConfidence;
+        specMaxFastAccumulatedFrameNum *= inSpecConfidence;
+    }
+    const float specHistoryFrames = fminf(specMaxAccumulatedFrameNum, historyLength);
+    const float specHistoryResponsiveFrames = fminf(specMaxFastAccumulatedFrameNum, historyLength);
     const float hitDist = minHitDist3x3 == NRD_INF ? 0.0f : minHitDist3x3;
 
     float curvature = 0.0f;
@@ -634,7 +711,14 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
     const float specSMBConfidence = (SMBReprojectionFound > 0.0f ? 1.0f : 0.0f) * encodingAwareNormalWeight(V, Vprev, lobeHalfAngle * NoV / cb.framerateScale, 0.0f, 0.0f);
     float specSMBAlpha = 1.0f - specSMBConfidence;
     specSMBAlpha = fmaxf(specSMBAlpha, 1.0f / (1.0f + specHistoryFrames));
-    const float specSMBResponsiveAlpha = fmaxf(specSMBAlpha, 1.0f / (1.0f + specHistoryResponsiveFrames));
+    float specSMBResponsiveAlpha = fmaxf(specSMBAlpha, 1.0f / (1.0f + specHistoryResponsiveFrames));
+    // pixels the checkerboard skipped this frame accumulate faster while the camera is (nearly) static ( TA:866-875, 893-899 )
+    const bool specResolved = OPT && cb.specCheckerboard != 2u && checkerboard != cb.specCheckerboard && smbParallaxInPixelsMax < 0.5f;
+    if (specResolved) {
+        const float k = 1.0f - cb.checkerboardResolveAccumSpeed * (SMBReprojectionFound > 0.0f ? 1.0f : 0.0f);
+        specSMBAlpha *= k;
+        specSMBResponsiveAlpha *= k;
+    }
 
     const float3 accSMBrgb = lerp(xyz(prevSpecularSMB), xyz(specularIllumination), specSMBAlpha);
     const float accSMBw = lerp(prevReflectionHitTSMB, specularIllumination.w, fmaxf(specSMBAlpha, 0.1f));
@@ -647,6 +731,12 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
     specVMBAlpha = fmaxf(specVMBAlpha, 1.0f / (1.0f + specHistoryFrames));
     specVMBResponsiveAlpha = fmaxf(specVMBResponsiveAlpha, 1.0f / (1.0f + specHistoryResponsiveFrames));
     specVMBHitTAlpha = fmaxf(specVMBHitTAlpha, 1.0f / (1.0f + specHistoryFrames));
+    if (specResolved) {
+        const float k = 1.0f - cb.checkerboardResolveAccumSpeed * (VMBReprojectionFound > 0.0f ? 1.0f : 0.0f);
+        specVMBAlpha *= k;
+        specVMBResponsiveAlpha *= k;
+        specVMBHitTAlpha *= k;
+    }
 
     const float3 accVMBrgb = lerp(xyz(prevSpecularVMB), xyz(specularIllumination), specVMBAlpha);
     const float accVMBw = lerp(prevReflectionHitTVMB, specularIllumination.w, fmaxf(specVMBHitTAlpha, 0.1f));
@@ -903,6 +993,26 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// RELAX_SplitScreen.cs.hlsl:21-62: the noisy input (range-masked; radiance converted to YCoCg in SH mode) left of CommonSettings::splitScreen
+struct RelaxSplitScreenParams { TexR32F viewZ; TexRGBA16F diff, spec, diffSh, specSh, outDiff, outSpec, outDiffSh, outSpecSh; };
+template <bool SH>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxSplitScreenKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxSplitScreenParams p) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
+    if (u > cb.splitScreen || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    const float inRange = relaxInRange(cb, relaxViewZ(cb, p.viewZ.load(px, py))) ? 1.0f : 0.0f;
+    const int dx = px >> (cb.diffCheckerboard != 2u ? 1 : 0), sx = px >> (cb.specCheckerboard != 2u ? 1 : 0);
+    float4 diff = p.diff.load(dx, py), spec = p.spec.load(sx, py);
+    if (SH) {
+        diff = f4(linearToYCoCg(xyz(diff)), diff.w);
+        spec = f4(linearToYCoCg(xyz(spec)), spec.w);
+    }
+    p.outDiff.store(px, py, diff * inRange);
+    p.outSpec.store(px, py, spec * inRange);
+    storeSh<SH>(p.outDiffSh, px, py, loadSh<SH>(p.diffSh, dx, py) * inRange);
+    storeSh<SH>(p.outSpecSh, px, py, loadSh<SH>(p.specSh, sx, py) * inRange);
+}
+
 struct AtrousTexel {
     float4 spec, diff, nr;
     float3 specSh, diffSh, worldPos;
@@ -1005,14 +1115,25 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
         const float specularPhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, cb.specPhiLuminance * sqrtf(centerSpecularVar));
         const float2 roughnessWeightP = roughnessWeightParams(centerRoughness, cb.roughnessFraction);
         const float specularReprojectionConfidence = p.specReprojectionConfidence.load(px, py);
-        const float specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, cb.luminanceEdgeStoppingRelaxation);
-        const float specularNormalWeightParamSimplified = normalWeightParam2(1.0f, cb.lobeAngleFraction);
-        const float2 specularNormalWeightP = normalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, cb.normalEdgeStoppingRelaxation, cb.lobeAngleFraction,
+        float specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, cb.luminanceEdgeStoppingRelaxation);
+        float diffuseLobeAngleFraction = cb.lobeAngleFraction, diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = cb.lobeAngleFraction;
+        float specularLobeAngleFraction = cb.lobeAngleFraction, diffuseLuminanceWeightRelaxation = 1.0f;
+        if (cb.hasHistoryConfidence) {
+            const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
+            const float2 rs = confidenceDrivenRelaxation(cb, p.specConfDummy, pixelUv), rd = confidenceDrivenRelaxation(cb, p.diffConfDummy, pixelUv);
+            diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = lerp(diffuseLobeAngleFraction, 1.0f, rs.x);
+            specularLobeAngleFraction = lerp(specularLobeAngleFraction, 1.0f, rs.x);
+            specularLuminanceWeightRelaxation *= 1.0f - rs.y;
+            diffuseLobeAngleFraction = lerp(diffuseLobeAngleFraction, 1.0f, rd.x);
+            diffuseLuminanceWeightRelaxation = 1.0f - rd.y;
+        }
+        const float specularNormalWeightParamSimplified = normalWeightParam2(1.0f, diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight);
+        const float2 specularNormalWeightP = normalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, cb.normalEdgeStoppingRelaxation, specularLobeAngleFraction,
                                                                       cb.specLobeAngleSlack);
         const float3 centerV = -normalize(centerWorldPos);
         const float centerDiffuseLuminance = luminance(xyz(ctr.diff));
         const float diffusePhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, cb.diffPhiLuminance * sqrtf(centerDiffuseVar));
-        const float diffuseNormalWeightParam = normalWeightParam2(1.0f, cb.lobeAngleFraction);
+        const float diffuseNormalWeightParam = normalWeightParam2(1.0f, diffuseLobeAngleFraction);
         const float depthThreshold = cb.depthThreshold * (cb.orthoMode == 0.0f ? centerViewZ : 1.0f);
 
         float sumWSpecular = 0.0f, sumWDiffuse = 0.0f;
@@ -1050,6 +1171,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
                 const float normalWDiffuse = computeWeight(angles, diffuseNormalWeightParam, 0.0f);
                 float diffuseLuminanceW = fabsf(centerDiffuseLuminance - luminance(xyz(s.diff))) * diffusePhiLIlluminationInv;
                 diffuseLuminanceW = fminf(cb.diffMaxLuminanceRelativeDifference, diffuseLuminanceW);
+                diffuseLuminanceW *= diffuseLuminanceWeightRelaxation;
                 float wDiffuse = geometryW * normalWDiffuse * expf(-diffuseLuminanceW);
                 wDiffuse *= compareMaterials(s.materialID, centerMaterialID, cb.diffMinMaterial) ? 1.0f : 0.0f;
                 wDiffuse = isCenter ? kernelW : wDiffuse;
@@ -1129,8 +1251,19 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __gr
     const float specularReprojectionConfidence = p.specReprojectionConfidence.load(px, py);
     float specularLuminanceWeightRelaxation = 1.0f;
     if (cb.stepSize <= 4) specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, cb.luminanceEdgeStoppingRelaxation);
-    const float specularNormalWeightParamSimplified = normalWeightParam2(1.0f, diffuseLobeAngleFraction);
-    const float2 specularNormalWeightP = normalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, cb.normalEdgeStoppingRelaxation, cb.lobeAngleFraction,
+    float diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = diffuseLobeAngleFraction, specularLobeAngleFraction = cb.lobeAngleFraction;
+    float diffuseLuminanceWeightRelaxation = 1.0f;
+    if (cb.hasHistoryConfidence) {
+        const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
+        const float2 rs = confidenceDrivenRelaxation(cb, p.specConfDummy, pixelUv), rd = confidenceDrivenRelaxation(cb, p.diffConfDummy, pixelUv);
+        diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = lerp(diffuseLobeAngleFraction, 1.0f, rs.x);
+        specularLobeAngleFraction = lerp(specularLobeAngleFraction, 1.0f, rs.x);
+        specularLuminanceWeightRelaxation *= 1.0f - rs.y;
+        diffuseLobeAngleFraction = lerp(diffuseLobeAngleFraction, 1.0f, rd.x);
+        diffuseLuminanceWeightRelaxation = 1.0f - rd.y;
+    }
+    const float specularNormalWeightParamSimplified = normalWeightParam2(1.0f, diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight);
+    const float2 specularNormalWeightP = normalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, cb.normalEdgeStoppingRelaxation, specularLobeAngleFraction,
                                                                   cb.specLobeAngleSlack);
     float sumWSpecular = 0.44198f * 0.44198f;
     float4 sumSpecular = centerSpecular * make_float4(sumWSpecular, sumWSpecular, sumWSpecular, sumWSpecular * sumWSpecular);
@@ -1199,6 +1332,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __gr
                 const float4 s = p.diff.load(x, y);
                 float lw = fabsf(centerDiffuseLuminance - luminance(xyz(s))) * diffusePhiLIlluminationInv;
                 lw = fminf(cb.diffMaxLuminanceRelativeDifference, lw);
+                lw *= diffuseLuminanceWeightRelaxation;
                 wDiffuse *= expf(-lw);
                 sumWDiffuse += wDiffuse;
                 sumDiffuse += make_float4(wDiffuse, wDiffuse, wDiffuse, wDiffuse * wDiffuse) * s;
@@ -1250,6 +1384,21 @@ struct RelaxBinder {
         next++;
         return v;
     }
+    // optional single-channel guides ( IN_VIEWZ as a dummy when disabled, otherwise the application's texture: any size, see bindGuide )
+    TexAnyX takeGuide() {
+        TexAnyX v{};
+        if (next >= n) {
+            ok = false;
+            return v;
+        }
+        const nrdcuTexture& x = t[next];
+        if (!bindGuide(x.format, x.data, x.width, x.height, x.pitchBytes, v)) {
+            if (ok) *err = *id + ": binding " + std::to_string(next) + " (single-channel guide) has unsupported format " + std::to_string(x.format);
+            ok = false;
+        }
+        next++;
+        return v;
+    }
 };
 
 }  // namespace
@@ -1269,10 +1418,11 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         err = id + ": dynamic resolution (rectSize != resourceSize) is not implemented";
         return (uint32_t)Result::UNSUPPORTED;
     }
-    if (cb.diffCheckerboard != 2 || cb.specCheckerboard != 2 || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix) {
-        err = id + ": checkerboard modes and confidence / disocclusion-threshold-mix inputs are not implemented";
-        return (uint32_t)Result::UNSUPPORTED;
+    if ((cb.diffCheckerboard == 2) != (cb.specCheckerboard == 2)) {
+        err = id + ": inconsistent checkerboard constants";
+        return (uint32_t)Result::INVALID_ARGUMENT;
     }
+    const bool checkerboarded = cb.diffCheckerboard != 2;
     RelaxBinder b{tex, n, 0, true, &err, &id};
     auto bad = [&](uint32_t expected) {
         if (b.ok && b.next == expected && n == expected) return false;
@@ -1308,14 +1458,18 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         takeSh(p.outSpecSh);
         takeSh(p.outDiffSh);
         if (bad(11 - 4 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) relaxPrePassKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxPrePassKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+        if (checkerboarded) {
+            if (sh) relaxPrePassKernel<true, true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxPrePassKernel<false, true><<<pixelGrid, block, 0, stream>>>(cb, p);
+        } else {
+            if (sh) relaxPrePassKernel<true, false><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxPrePassKernel<false, false><<<pixelGrid, block, 0, stream>>>(cb, p);
+        }
     } else if (id == "RELAX_TemporalAccumulation.cs.hlsl" + sig) {
         RelaxTaParams p;
         p.tiles = b.take<TexR8>(R8);
         p.mv = b.take<TexRGBA16F>(F16);
         p.normalRoughness = b.take<TexNR>(NR);
         p.viewZ = b.take<TexR32F>(R32);
-        p.mixDummy = b.take<TexR32F>(R32);
+        p.mixDummy = b.takeGuide();
         p.prevNormalRoughness = b.take<TexRGBA8>(Format::RGBA8_UNORM);
         p.prevViewZ = b.take<TexR32F>(R32);
         p.prevHistoryLength = b.take<TexR8>(R8);
@@ -1327,8 +1481,8 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.historySpec = b.take<TexRGBA16F>(F16);
         p.historyDiff = b.take<TexRGBA16F>(F16);
         p.prevSpecHitDist = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.specConfDummy = b.take<TexR32F>(R32);
-        p.diffConfDummy = b.take<TexR32F>(R32);
+        p.specConfDummy = b.takeGuide();
+        p.diffConfDummy = b.takeGuide();
         takeSh(p.specSh);
         takeSh(p.diffSh);
         takeSh(p.historySpecShFast);
@@ -1347,7 +1501,11 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         takeSh(p.outSpecShFast);
         takeSh(p.outDiffShFast);
         if (bad(35 - 10 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) relaxTemporalAccumulationKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxTemporalAccumulationKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+        if (checkerboarded || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix) {
+            if (sh) relaxTemporalAccumulationKernel<true, true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxTemporalAccumulationKernel<false, true><<<pixelGrid, block, 0, stream>>>(cb, p);
+        } else {
+            if (sh) relaxTemporalAccumulationKernel<true, false><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxTemporalAccumulationKernel<false, false><<<pixelGrid, block, 0, stream>>>(cb, p);
+        }
     } else if (id == "RELAX_HistoryFix.cs.hlsl" + sig) {
         RelaxHistoryFixParams p;
         p.tiles = b.take<TexR8>(R8);
@@ -1380,6 +1538,19 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         for (TexRGBA16F* t : outsSh) takeSh(*t);
         if (bad(22 - 8 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (sh) relaxHistoryClampingKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxHistoryClampingKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "RELAX_SplitScreen.cs.hlsl" + sig) {
+        RelaxSplitScreenParams p;
+        p.viewZ = b.take<TexR32F>(R32);
+        p.diff = b.take<TexRGBA16F>(F16);
+        p.spec = b.take<TexRGBA16F>(F16);
+        takeSh(p.diffSh);
+        takeSh(p.specSh);
+        p.outDiff = b.take<TexRGBA16F>(F16);
+        p.outSpec = b.take<TexRGBA16F>(F16);
+        takeSh(p.outDiffSh);
+        takeSh(p.outSpecSh);
+        if (bad(9 - 4 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (sh) relaxSplitScreenKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxSplitScreenKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
     } else if (id == "RELAX_Copy.cs.hlsl" + sig) {
         RelaxCopyParams p;
         p.spec = b.take<TexRGBA16F>(F16);
@@ -1409,8 +1580,8 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.spec = b.take<TexRGBA16F>(F16);
         p.diff = b.take<TexRGBA16F>(F16);
         p.specReprojectionConfidence = b.take<TexR8>(R8);
-        p.specConfDummy = b.take<TexR32F>(R32);
-        p.diffConfDummy = b.take<TexR32F>(R32);
+        p.specConfDummy = b.takeGuide();
+        p.diffConfDummy = b.takeGuide();
         takeSh(p.specSh);
         takeSh(p.diffSh);
         p.outSpec = b.take<TexRGBA16F>(F16);

@@ -232,15 +232,18 @@ def unpack_radiance(tex: torch.Tensor) -> torch.Tensor:
 # Frame
 # ------------------------------------------------------------------------------------------------
 def checkerboard_pack(full: torch.Tensor, mode: int, frame_index: int) -> torch.Tensor:
-    """Half-width texture holding the pixels a checkerboarded tracer produced this frame: texel (x >> 1, y) = full[y, x] for the pixels with
-    Sequence::CheckerBoard( ( x, y ), frameIndex ) == mode (ml.hlsli:1620; NRDSettings.h CheckerboardMode: BLACK -> diffuse 0 / specular 1,
-    WHITE -> diffuse 1 / specular 0, Reblur.cpp:301-313). The width must be even."""
+    """Checkerboarded input as NRD expects it: a texture of the full resource size whose LEFT HALF holds the pixels the tracer produced this
+    frame — texel (x >> 1, y) = full[y, x] for the pixels with Sequence::CheckerBoard( ( x, y ), frameIndex ) == mode (ml.hlsli:1620;
+    CheckerboardMode::BLACK -> diffuse 0 / specular 1, WHITE -> diffuse 1 / specular 0, Reblur.cpp:301-313). The shaders address it both with
+    integer loads (pos.x >> 1) and with uv.x * 0.5 (RELAX_PrePass.cs.hlsl:167), hence the full width. The width must be even."""
     h, w = full.shape[0], full.shape[1]
     assert w % 2 == 0
     ys = torch.arange(h, device=full.device)
     b = (mode ^ ys ^ frame_index) & 1                                      # x parity carrying data in row y
     xs = 2 * torch.arange(w // 2, device=full.device)[None, :] + b[:, None]
-    return full[ys[:, None], xs].contiguous()
+    out = torch.zeros_like(full)
+    out[:, : w // 2] = full[ys[:, None], xs]
+    return out.contiguous()
 
 
 def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, holes: bool = False,
@@ -410,14 +413,15 @@ def sigma_frame(frame_index: int, width: int, height: int, device="cpu", period:
 # ------------------------------------------------------------------------------------------------
 # RELAX_DIFFUSE_SPECULAR_SH inputs
 # ------------------------------------------------------------------------------------------------
-def relax_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, sh: bool = True) -> Dict[str, torch.Tensor]:
+def relax_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, sh: bool = True, checkerboard: int = 0,
+                guides: bool = False) -> Dict[str, torch.Tensor]:
     """All user inputs of RELAX_DIFFUSE_SPECULAR_SH for one frame (BASELINE.json config 2): the G-buffer and motion of `reblur_frame`,
     un-normalised radiance + hit distance in IN_*_SH0 and `direction * luminance` in IN_*_SH1, both RGBA16F, packed like
     RELAX_FrontEnd_PackSh (NRD.hlsli:925-941). Directions: cosine-weighted around N (diffuse), jittered mirror direction (specular)."""
     device = torch.device(device)
     cam = make_camera(frame_index, width, height, period)
     g = _raycast(cam, width, height, device)
-    base = reblur_frame(frame_index, width, height, device, period, with_clean=True)
+    base = reblur_frame(frame_index, width, height, device, period, with_clean=True, guides=guides)
     hit, N, V, rough = g["hit"], g["N"], g["V"], g["roughness"]
 
     gen = torch.Generator(device=device)
@@ -462,6 +466,15 @@ def relax_frame(frame_index: int, width: int, height: int, device="cpu", period:
         "IN_SPEC_SH0": sh0(spec, hit_t_s),
         "IN_SPEC_SH1": sh1(spec, dir_s),
     }
+    if guides:
+        for k in ("IN_DIFF_CONFIDENCE", "IN_SPEC_CONFIDENCE", "IN_DISOCCLUSION_THRESHOLD_MIX"):
+            out[k] = base[k]
+    if checkerboard:   # nrd::CheckerboardMode: 1 = BLACK, 2 = WHITE; SH1 travels with its SH0
+        diff_mode, spec_mode = (0, 1) if checkerboard == 1 else (1, 0)
+        for k in ("IN_DIFF_SH0", "IN_DIFF_SH1"):
+            out[k] = checkerboard_pack(out[k], diff_mode, frame_index)
+        for k in ("IN_SPEC_SH0", "IN_SPEC_SH1"):
+            out[k] = checkerboard_pack(out[k], spec_mode, frame_index)
     if not sh:   # RELAX_DIFFUSE_SPECULAR (NRD_MODE = RADIANCE): the same radiance + hit distance, no SH1 textures
         out["IN_DIFF_RADIANCE_HITDIST"], out["IN_SPEC_RADIANCE_HITDIST"] = out.pop("IN_DIFF_SH0"), out.pop("IN_SPEC_SH0")
         del out["IN_DIFF_SH1"], out["IN_SPEC_SH1"]

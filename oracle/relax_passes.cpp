@@ -7,7 +7,7 @@
 //   RELAX_HistoryFix.cs.hlsl:21-163, RELAX_HistoryClamping.cs.hlsl:21-354, RELAX_Copy.cs.hlsl:21-34,
 //   RELAX_AntiFirefly.cs.hlsl:21-216, RELAX_AtrousSmem.cs.hlsl:21-484, RELAX_Atrous.cs.hlsl:21-260,
 //   helpers RELAX_Common.hlsli:11-185, constants RELAX_Config.hlsli:11-102.
-// Build switches as in the reference's default build: no checkerboard, no confidence / disocclusion-mix inputs
+// Build switches as in the reference's default build; checkerboard, confidence and disocclusion-threshold-mix inputs are restated
 // (the executor rejects those), NRD_USE_PREV_WORLD_SPACE_MATRIX = 0, R10G10B10A2 normals (material IDs on).
 // Shared-memory tiles of the shaders hold f( clamp( pos, 0, rectSize - 1 ) ); the restatement reads the clamped texel.
 #include <cmath>
@@ -166,7 +166,10 @@ void classifyTiles(const RelaxCB& cb, const Tex& gIn_ViewZ, Tex& gOut_Tiles, int
         }
 }
 
-// RELAX_PrePass.cs.hlsl:21-385 (no checkerboard)
+// RELAX_Common.hlsli:164-165
+inline float GetBilateralWeight(float z, float zc) { return Math::LinearStep(0.03f, 0.0f, std::fabs(z - zc) * rcp(max(z, zc))); }
+
+// RELAX_PrePass.cs.hlsl:21-385
 void prePass(const RelaxCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Spec, const Tex& gIn_Diff, const Tex& gIn_SpecSh,
              const Tex& gIn_DiffSh, Tex& gOut_Spec, Tex& gOut_Diff, Tex& gOut_SpecSh, Tex& gOut_DiffSh, int gridW, int gridH) {
     Ctx c(cb);
@@ -186,9 +189,53 @@ void prePass(const RelaxCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roug
             float4 rotator = cb.gRotatorPre;  // NRD_FRAME
             float2 pixelUv = float2(px + 0.5f, py + 0.5f) * cb.gRectSizeInv;
 
+            // Checkerboard resolve weights ( :39-72 )
+            const uint32_t checkerboard = Sequence::CheckerBoard((uint32_t)px, (uint32_t)py, cb.gFrameIndex);
+            int cbX0 = std::max(px - 1, 0), cbX1 = std::min(px + 1, cb.gRectSize.x - 1);
+            float materialID0 = 0.0f, materialID1 = 0.0f;
+            float2 checkerboardResolveWeights = float2(1.0f);
+            if (cb.gSpecCheckerboard != 2 || cb.gDiffCheckerboard != 2) {
+                float viewZ0 = c.UnpackViewZ(gIn_ViewZ.load(cbX0, py).x), viewZ1 = c.UnpackViewZ(gIn_ViewZ.load(cbX1, py).x);
+                unpackNR(gIn_Normal_Roughness, cbX0, py, materialID0);
+                unpackNR(gIn_Normal_Roughness, cbX1, py, materialID1);
+                checkerboardResolveWeights = float2(GetBilateralWeight(viewZ0, centerViewZ), GetBilateralWeight(viewZ1, centerViewZ));
+                checkerboardResolveWeights.x = (!c.IsInDenoisingRange(viewZ0) || px < 1) ? 0.0f : checkerboardResolveWeights.x;
+                checkerboardResolveWeights.y = (!c.IsInDenoisingRange(viewZ1) || px > cb.gRectSize.x - 2) ? 0.0f : checkerboardResolveWeights.y;
+            }
+            cbX0 >>= 1;
+            cbX1 >>= 1;
+            // ApplyCheckerboardShift ( Common.hlsli:332-342 ) on a pixel-centre position
+            auto applyCheckerboardShift = [&](float2 pos, uint32_t mode, int counter) {
+                float2 posPositive = pos + 16384.0f;
+                uint32_t cbd = Sequence::CheckerBoard((uint32_t)posPositive.x, (uint32_t)posPositive.y, cb.gFrameIndex);
+                float shift = ((counter & 0x1) == 0) ? -1.0f : 1.0f;
+                pos.x += shift * float(cbd != mode && mode != 2);
+                return pos;
+            };
+
             // ---- diffuse ----
-            float4 diffuseIllumination = gIn_Diff.load(px, py);
-            float3 diffuseSH = gIn_DiffSh.load(px, py).xyz();
+            bool diffHasData = true;
+            int diffX = px;
+            if (cb.gDiffCheckerboard != 2) {
+                diffHasData = checkerboard == cb.gDiffCheckerboard;
+                diffX >>= 1;
+            }
+            float4 diffuseIllumination = gIn_Diff.load(diffX, py);
+            float3 diffuseSH = gIn_DiffSh.load(diffX, py).xyz();
+            if (!diffHasData) {
+                float2 wc = checkerboardResolveWeights;
+                wc.x *= float(CompareMaterials(centerMaterialID, materialID0, cb.gDiffMinMaterial));
+                wc.y *= float(CompareMaterials(centerMaterialID, materialID1, cb.gDiffMinMaterial));
+                wc *= Math::PositiveRcp(wc.x + wc.y);
+                float4 d0 = gIn_Diff.load(cbX0, py), d1 = gIn_Diff.load(cbX1, py);
+                if (wc.x == 0.0f) d0 = float4(0.0f);
+                if (wc.y == 0.0f) d1 = float4(0.0f);
+                diffuseIllumination = d0 * wc.x + d1 * wc.y;
+                float3 d0SH = gIn_DiffSh.load(cbX0, py).xyz(), d1SH = gIn_DiffSh.load(cbX1, py).xyz();
+                if (wc.x == 0.0f) d0SH = float3(0.0f);
+                if (wc.y == 0.0f) d1SH = float3(0.0f);
+                diffuseSH = d0SH * wc.x + d1SH * wc.y;
+            }
             if (cb.gDiffBlurRadius > 0.0f) {
                 float frustumSize = PixelRadiusToWorld(cb.gUnproject, cb.gOrthoMode, (float)std::min(cb.gRectSize.x, cb.gRectSize.y), centerViewZ);
                 float hitDist = diffuseIllumination.w == 0.0f ? 1.0f : diffuseIllumination.w;
@@ -203,8 +250,10 @@ void prePass(const RelaxCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roug
                     float3 offset = g_Poisson8[i];
                     float2 uv = pixelUv * rectSize + Geometry::RotateVector(rotator, float2(offset.x, offset.y)) * blurRadius;
                     uv = floor(uv) + 0.5f;
+                    uv = applyCheckerboardShift(uv, cb.gDiffCheckerboard, i);
                     uv = uv * cb.gRectSizeInv;
                     float2 uvScaled = c.ClampUvToViewport(uv);
+                    float2 checkerboardUvScaled = float2(uvScaled.x * (cb.gDiffCheckerboard != 2 ? 0.5f : 1.0f), uvScaled.y);
 
                     float sampleMaterialID;
                     float3 sampleNormal = NRD_FrontEnd_UnpackNormalAndRoughness(gIn_Normal_Roughness.sampleNearest(uvScaled), sampleMaterialID).xyz();
@@ -218,14 +267,14 @@ void prePass(const RelaxCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roug
                     float angle = Math::AcosApproxPositive(dot(centerNormal, sampleNormal));
                     sampleWeight *= ComputeWeight(angle, normalWeightParam, 0.0f);
 
-                    float4 sampleDiffuseIllumination = gIn_Diff.sampleNearest(uvScaled);
+                    float4 sampleDiffuseIllumination = gIn_Diff.sampleNearest(checkerboardUvScaled);
                     if (sampleWeight == 0.0f) sampleDiffuseIllumination = float4(0.0f);  // Denanify
                     sampleWeight *= lerp(diffMinHitDistanceWeight, 1.0f, ComputeExponentialWeight(sampleDiffuseIllumination.w, hitDistanceWeightParams.x, hitDistanceWeightParams.y));
                     sampleWeight *= GetGaussianWeight(offset.z);
 
                     weightSum += sampleWeight;
                     diffuseIllumination += sampleDiffuseIllumination * sampleWeight;
-                    float3 sampleDiffuseSH = gIn_DiffSh.sampleNearest(uvScaled).xyz();
+                    float3 sampleDiffuseSH = gIn_DiffSh.sampleNearest(checkerboardUvScaled).xyz();
                     if (sampleWeight == 0.0f) sampleDiffuseSH = float3(0.0f);
                     diffuseSH += sampleDiffuseSH * sampleWeight;
                 }
@@ -238,8 +287,28 @@ void prePass(const RelaxCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roug
             // ---- specular ----
             RngHash rng;
             rng.Initialize((uint32_t)px, (uint32_t)py, cb.gFrameIndex);
-            float4 specularIllumination = gIn_Spec.load(px, py);
-            float3 specularSH = gIn_SpecSh.load(px, py).xyz();
+            bool specHasData = true;
+            int specX = px;
+            if (cb.gSpecCheckerboard != 2) {
+                specHasData = checkerboard == cb.gSpecCheckerboard;
+                specX >>= 1;
+            }
+            float4 specularIllumination = gIn_Spec.load(specX, py);
+            float3 specularSH = gIn_SpecSh.load(specX, py).xyz();
+            if (!specHasData) {
+                float2 wc = checkerboardResolveWeights;
+                wc.x *= float(CompareMaterials(centerMaterialID, materialID0, cb.gSpecMinMaterial));
+                wc.y *= float(CompareMaterials(centerMaterialID, materialID1, cb.gSpecMinMaterial));
+                wc *= Math::PositiveRcp(wc.x + wc.y);
+                float4 s0 = gIn_Spec.load(cbX0, py), s1 = gIn_Spec.load(cbX1, py);
+                if (wc.x == 0.0f) s0 = float4(0.0f);
+                if (wc.y == 0.0f) s1 = float4(0.0f);
+                specularIllumination = s0 * wc.x + s1 * wc.y;
+                float3 s0SH = gIn_SpecSh.load(cbX0, py).xyz(), s1SH = gIn_SpecSh.load(cbX1, py).xyz();
+                if (wc.x == 0.0f) s0SH = float3(0.0f);
+                if (wc.y == 0.0f) s1SH = float3(0.0f);
+                specularSH = s0SH * wc.x + s1SH * wc.y;
+            }
             specularIllumination.w = max(0.0f, min(cb.gDenoisingRange, specularIllumination.w));
             if (cb.gSpecBlurRadius > 0.0f) {
                 float3 viewVector = cb.gOrthoMode == 0.0f ? normalize(-centerWorldPos) : cb.gFrustumForward.xyz();
@@ -268,8 +337,10 @@ void prePass(const RelaxCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roug
                     float3 offset = g_Poisson8[i];
                     float2 uv = pixelUv * rectSize + Geometry::RotateVector(rotator, float2(offset.x, offset.y)) * blurRadius;
                     uv = floor(uv) + 0.5f;
+                    uv = applyCheckerboardShift(uv, cb.gSpecCheckerboard, i);
                     uv = uv * cb.gRectSizeInv;
                     float2 uvScaled = c.ClampUvToViewport(uv);
+                    float2 checkerboardUvScaled = float2(uvScaled.x * (cb.gSpecCheckerboard != 2 ? 0.5f : 1.0f), uvScaled.y);
 
                     float sampleMaterialID;
                     float4 sampleNormalRoughness = NRD_FrontEnd_UnpackNormalAndRoughness(gIn_Normal_Roughness.sampleNearest(uvScaled), sampleMaterialID);
@@ -286,7 +357,7 @@ void prePass(const RelaxCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roug
                     float3 sampleWorldPos = c.GetCurrentWorldPosFromClipSpaceXY(uv * 2.0f - 1.0f, sampleViewZ);
                     sampleWeight *= GetPlaneDistanceWeight(centerWorldPos, centerNormal, cb.gOrthoMode == 0.0f ? centerViewZ : 1.0f, sampleWorldPos, cb.gDepthThreshold);
 
-                    float4 sampleSpecularIllumination = gIn_Spec.sampleNearest(uvScaled);
+                    float4 sampleSpecularIllumination = gIn_Spec.sampleNearest(checkerboardUvScaled);
                     if (sampleWeight == 0.0f) sampleSpecularIllumination = float4(0.0f);
                     if (rng.GetFloat() < sampleWeight * NoV) minHitT = min(minHitT, sampleSpecularIllumination.w == 0.0f ? NRD_INF : sampleSpecularIllumination.w);
 
@@ -302,7 +373,7 @@ void prePass(const RelaxCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roug
                     weightSum += sampleWeight;
                     float3 rgb = specularIllumination.xyz() + sampleSpecularIllumination.xyz() * sampleWeight;
                     specularIllumination = float4(rgb, specularIllumination.w);
-                    float3 sampleSpecularSH = gIn_SpecSh.sampleNearest(uvScaled).xyz();
+                    float3 sampleSpecularSH = gIn_SpecSh.sampleNearest(checkerboardUvScaled).xyz();
                     if (sampleWeight == 0.0f) sampleSpecularSH = float3(0.0f);
                     specularSH += sampleSpecularSH * sampleWeight;
                 }
@@ -401,6 +472,7 @@ void temporalAccumulation(const RelaxCB& cb, const TaTex& t, int gridW, int grid
 
             float disocclusionThresholdMix = 0.0f;
             if (currentMaterialID == cb.gStrandMaterialID) disocclusionThresholdMix = NRD_GetNormalizedStrandThickness(cb.gStrandThickness, pixelSize);
+            if (cb.gHasDisocclusionThresholdMix) disocclusionThresholdMix = t.gIn_DisocclusionThresholdMix->load(px, py).x;
             float disocclusionThreshold = lerp(cb.gDisocclusionThreshold, cb.gDisocclusionThresholdAlternate, disocclusionThresholdMix);
             if (currentMaterialID == cb.gStrandMaterialID) {
                 float mediumParallax = Math::SmoothStep01(smbParallaxInPixelsMax);
@@ -507,10 +579,23 @@ void temporalAccumulation(const RelaxCB& cb, const TaTex& t, int gridW, int grid
             float maxAccumulatedFrameNum = 1.0f + max(cb.gDiffMaxAccumulatedFrameNum, cb.gSpecMaxAccumulatedFrameNum);
             historyLength = min(historyLength, maxAccumulatedFrameNum);
 
+            const uint32_t checkerboard = Sequence::CheckerBoard((uint32_t)px, (uint32_t)py, cb.gFrameIndex);
+
             // ---- diffuse ----
             {
-                float diffuseAlpha = SMBReprojectionFound > 0.0f ? max(1.0f / (cb.gDiffMaxAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
-                float diffuseAlphaResponsive = SMBReprojectionFound > 0.0f ? max(1.0f / (cb.gDiffMaxFastAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+                float diffMaxAccumulatedFrameNum = cb.gDiffMaxAccumulatedFrameNum, diffMaxFastAccumulatedFrameNum = cb.gDiffMaxFastAccumulatedFrameNum;
+                if (cb.gHasHistoryConfidence) {
+                    float inDiffConfidence = saturate(t.gIn_DiffConfidence->sampleLinear(prevUVSMB).x);
+                    diffMaxAccumulatedFrameNum *= inDiffConfidence;
+                    diffMaxFastAccumulatedFrameNum *= inDiffConfidence;
+                }
+                float diffuseAlpha = SMBReprojectionFound > 0.0f ? max(1.0f / (diffMaxAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+                float diffuseAlphaResponsive = SMBReprojectionFound > 0.0f ? max(1.0f / (diffMaxFastAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+                const bool diffHasData = cb.gDiffCheckerboard == 2 || checkerboard == cb.gDiffCheckerboard;
+                if (!diffHasData && historyLength > 1.0f) {
+                    diffuseAlpha *= 1.0f - cb.gCheckerboardResolveAccumSpeed;
+                    diffuseAlphaResponsive *= 1.0f - cb.gCheckerboardResolveAccumSpeed;
+                }
                 float4 accumulated = lerp(prevDiffuseIlluminationAnd2ndMomentSMB, float4(diffuseIllumination, diffuse2ndMoment), diffuseAlpha);
                 float3 accumulatedResponsive = lerp(prevDiffuseIlluminationAnd2ndMomentSMBResponsive, diffuseIllumination, diffuseAlphaResponsive);
                 t.gOut_Diff->store(px, py, accumulated);
@@ -521,8 +606,14 @@ void temporalAccumulation(const RelaxCB& cb, const TaTex& t, int gridW, int grid
             t.gOut_HistoryLength->store(px, py, float4(historyLength / 255.0f, 0, 0, 0));
 
             // ---- specular ----
-            float specHistoryFrames = min(cb.gSpecMaxAccumulatedFrameNum, historyLength);
-            float specHistoryResponsiveFrames = min(cb.gSpecMaxFastAccumulatedFrameNum, historyLength);
+            float specMaxAccumulatedFrameNum = cb.gSpecMaxAccumulatedFrameNum, specMaxFastAccumulatedFrameNum = cb.gSpecMaxFastAccumulatedFrameNum;
+            if (cb.gHasHistoryConfidence) {
+                float inSpecConfidence = saturate(t.gIn_SpecConfidence->sampleLinear(prevUVSMB).x);
+                specMaxAccumulatedFrameNum *= inSpecConfidence;
+                specMaxFastAccumulatedFrameNum *= inSpecConfidence;
+            }
+            float specHistoryFrames = min(specMaxAccumulatedFrameNum, historyLength);
+            float specHistoryResponsiveFrames = min(specMaxFastAccumulatedFrameNum, historyLength);
             float hitDist = minHitDist3x3 == NRD_INF ? 0.0f : minHitDist3x3;
 
             // curvature along the direction of motion (TA:633-717)
@@ -700,6 +791,11 @@ void temporalAccumulation(const RelaxCB& cb, const TaTex& t, int gridW, int grid
             float specSMBResponsiveAlpha = 1.0f - specSMBConfidence;
             specSMBAlpha = max(specSMBAlpha, 1.0f / (1.0f + specHistoryFrames));
             specSMBResponsiveAlpha = max(specSMBAlpha, 1.0f / (1.0f + specHistoryResponsiveFrames));
+            const bool specHasData = cb.gSpecCheckerboard == 2 || checkerboard == cb.gSpecCheckerboard;
+            if (!specHasData && smbParallaxInPixelsMax < 0.5f) {
+                specSMBAlpha *= 1.0f - cb.gCheckerboardResolveAccumSpeed * (SMBReprojectionFound > 0.0f ? 1.0f : 0.0f);
+                specSMBResponsiveAlpha *= 1.0f - cb.gCheckerboardResolveAccumSpeed * (SMBReprojectionFound > 0.0f ? 1.0f : 0.0f);
+            }
 
             float3 accumulatedSpecularSMBrgb = lerp(prevSpecularIlluminationAnd2ndMomentSMB.xyz(), specularIllumination.xyz(), specSMBAlpha);
             float accumulatedSpecularSMBw = lerp(prevReflectionHitTSMB, specularIllumination.w, max(specSMBAlpha, 0.1f));
@@ -713,6 +809,11 @@ void temporalAccumulation(const RelaxCB& cb, const TaTex& t, int gridW, int grid
             specVMBAlpha = max(specVMBAlpha, 1.0f / (1.0f + specHistoryFrames));
             specVMBResponsiveAlpha = max(specVMBResponsiveAlpha, 1.0f / (1.0f + specHistoryResponsiveFrames));
             specVMBHitTAlpha = max(specVMBHitTAlpha, 1.0f / (1.0f + specHistoryFrames));
+            if (!specHasData && smbParallaxInPixelsMax < 0.5f) {
+                specVMBAlpha *= 1.0f - cb.gCheckerboardResolveAccumSpeed * (VMBReprojectionFound > 0.0f ? 1.0f : 0.0f);
+                specVMBResponsiveAlpha *= 1.0f - cb.gCheckerboardResolveAccumSpeed * (VMBReprojectionFound > 0.0f ? 1.0f : 0.0f);
+                specVMBHitTAlpha *= 1.0f - cb.gCheckerboardResolveAccumSpeed * (VMBReprojectionFound > 0.0f ? 1.0f : 0.0f);
+            }
 
             float3 accumulatedSpecularVMBrgb = lerp(prevSpecularVMB.xyz(), specularIllumination.xyz(), specVMBAlpha);
             float accumulatedSpecularVMBw = lerp(prevReflectionHitTVMB, specularIllumination.w, max(specVMBHitTAlpha, 0.1f));
@@ -1039,12 +1140,30 @@ void atrousSmem(const RelaxCB& cb, const AtTex& t, int gridW, int gridH) {
                 float2 roughnessWeightParams = GetRoughnessWeightParams(centerRoughness, cb.gRoughnessFraction);
                 float specularReprojectionConfidence = t.gIn_SpecReprojectionConfidence->load(px, py).x;
                 float specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, cb.gLuminanceEdgeStoppingRelaxation);
-                float specularNormalWeightParamSimplified = GetNormalWeightParam2(1.0f, diffuseLobeAngleFraction);
+                float diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = diffuseLobeAngleFraction, specularLobeAngleFraction = cb.gLobeAngleFraction;
+                const float2 pixelUv = float2(px + 0.5f, py + 0.5f) * cb.gRectSizeInv;
+                if (cb.gHasHistoryConfidence) {  // :201-215
+                    float relax = saturate(cb.gConfidenceDrivenRelaxationMultiplier * (1.0f - saturate(t.gIn_SpecConfidence->sampleLinear(pixelUv).x)));
+                    float r = saturate(relax * cb.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+                    diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = lerp(diffuseLobeAngleFraction, 1.0f, r);
+                    specularLobeAngleFraction = lerp(specularLobeAngleFraction, 1.0f, r);
+                    r = saturate(relax * cb.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+                    specularLuminanceWeightRelaxation *= 1.0f - r;
+                }
+                float specularNormalWeightParamSimplified = GetNormalWeightParam2(1.0f, diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight);
                 float2 specularNormalWeightParams = GetNormalWeightParams_ATrous(centerRoughness, historyLength, specularReprojectionConfidence, cb.gNormalEdgeStoppingRelaxation,
-                                                                                 cb.gLobeAngleFraction, cb.gSpecLobeAngleSlack);
+                                                                                 specularLobeAngleFraction, cb.gSpecLobeAngleSlack);
                 float3 centerV = -normalize(centerWorldPos);
                 float centerDiffuseLuminance = Luminance(ctr.diff.xyz());
                 float diffusePhiLIlluminationInv = 1.0f / max(1.0e-4f, cb.gDiffPhiLuminance * std::sqrt(centerDiffuseVar));
+                float diffuseLuminanceWeightRelaxation = 1.0f;
+                if (cb.gHasHistoryConfidence) {  // :239-251
+                    float relax = saturate(cb.gConfidenceDrivenRelaxationMultiplier * (1.0f - saturate(t.gIn_DiffConfidence->sampleLinear(pixelUv).x)));
+                    float r = saturate(relax * cb.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+                    diffuseLobeAngleFraction = lerp(diffuseLobeAngleFraction, 1.0f, r);
+                    r = saturate(relax * cb.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+                    diffuseLuminanceWeightRelaxation = 1.0f - r;
+                }
                 float diffuseNormalWeightParam = GetNormalWeightParam2(1.0f, diffuseLobeAngleFraction);
                 float depthThreshold = cb.gDepthThreshold * (cb.gOrthoMode == 0.0f ? centerViewZ : 1.0f);
 
@@ -1081,6 +1200,7 @@ void atrousSmem(const RelaxCB& cb, const AtTex& t, int gridW, int gridH) {
                         float normalWDiffuse = ComputeWeight(angles, diffuseNormalWeightParam, 0.0f);
                         float diffuseLuminanceW = std::fabs(centerDiffuseLuminance - Luminance(s.diff.xyz())) * diffusePhiLIlluminationInv;
                         diffuseLuminanceW = min(cb.gDiffMaxLuminanceRelativeDifference, diffuseLuminanceW);
+                        diffuseLuminanceW *= diffuseLuminanceWeightRelaxation;
                         float wDiffuse = geometryW * normalWDiffuse * std::exp(-diffuseLuminanceW);
                         wDiffuse *= float(CompareMaterials(s.materialID, centerMaterialID, cb.gDiffMinMaterial));
                         wDiffuse = isCenter ? kernelW : wDiffuse;
@@ -1164,9 +1284,19 @@ void atrous(const RelaxCB& cb, const AtTex& t, int gridW, int gridH) {
             float specularReprojectionConfidence = t.gIn_SpecReprojectionConfidence->load(px, py).x;
             float specularLuminanceWeightRelaxation = 1.0f;
             if (cb.gStepSize <= 4) specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, cb.gLuminanceEdgeStoppingRelaxation);
-            float specularNormalWeightParamSimplified = GetNormalWeightParam2(1.0f, diffuseLobeAngleFraction);
+            float diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = diffuseLobeAngleFraction, specularLobeAngleFraction = cb.gLobeAngleFraction;
+            const float2 pixelUv = float2(px + 0.5f, py + 0.5f) * cb.gRectSizeInv;
+            if (cb.gHasHistoryConfidence) {  // RELAX_Atrous.cs.hlsl:67-80
+                float relax = saturate(cb.gConfidenceDrivenRelaxationMultiplier * (1.0f - saturate(t.gIn_SpecConfidence->sampleLinear(pixelUv).x)));
+                float r = saturate(relax * cb.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+                diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = lerp(diffuseLobeAngleFraction, 1.0f, r);
+                specularLobeAngleFraction = lerp(specularLobeAngleFraction, 1.0f, r);
+                r = saturate(relax * cb.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+                specularLuminanceWeightRelaxation *= 1.0f - r;
+            }
+            float specularNormalWeightParamSimplified = GetNormalWeightParam2(1.0f, diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight);
             float2 specularNormalWeightParams = GetNormalWeightParams_ATrous(centerRoughness, historyLength, specularReprojectionConfidence, cb.gNormalEdgeStoppingRelaxation,
-                                                                             cb.gLobeAngleFraction, cb.gSpecLobeAngleSlack);
+                                                                             specularLobeAngleFraction, cb.gSpecLobeAngleSlack);
             float sumWSpecular = 0.44198f * 0.44198f;
             float4 sumSpecular = centerSpecular * float4(sumWSpecular, sumWSpecular, sumWSpecular, sumWSpecular * sumWSpecular);
             float3 sumSpecularSH = t.gIn_SpecSh->load(px, py).xyz() * sumWSpecular;
@@ -1174,6 +1304,14 @@ void atrous(const RelaxCB& cb, const AtTex& t, int gridW, int gridH) {
             float4 centerDiffuse = t.gIn_Diff_Variance->load(px, py);
             float centerDiffuseLuminance = Luminance(centerDiffuse.xyz());
             float diffusePhiLIlluminationInv = 1.0f / max(1.0e-4f, cb.gDiffPhiLuminance * std::sqrt(centerDiffuse.w));
+            float diffuseLuminanceWeightRelaxation = 1.0f;
+            if (cb.gHasHistoryConfidence) {  // :107-119
+                float relax = saturate(cb.gConfidenceDrivenRelaxationMultiplier * (1.0f - saturate(t.gIn_DiffConfidence->sampleLinear(pixelUv).x)));
+                float r = saturate(relax * cb.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+                diffuseLobeAngleFraction = lerp(diffuseLobeAngleFraction, 1.0f, r);
+                r = saturate(relax * cb.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+                diffuseLuminanceWeightRelaxation = 1.0f - r;
+            }
             float diffuseNormalWeightParam = GetNormalWeightParam2(1.0f, diffuseLobeAngleFraction);
             float sumWDiffuse = 0.44198f * 0.44198f;
             float4 sumDiffuse = centerDiffuse * float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse);
@@ -1232,6 +1370,7 @@ void atrous(const RelaxCB& cb, const AtTex& t, int gridW, int gridH) {
                         float4 s = t.gIn_Diff_Variance->load(x, y);
                         float lw = std::fabs(centerDiffuseLuminance - Luminance(s.xyz())) * diffusePhiLIlluminationInv;
                         lw = min(cb.gDiffMaxLuminanceRelativeDifference, lw);
+                        lw *= diffuseLuminanceWeightRelaxation;
                         wDiffuse *= std::exp(-lw);
                         sumWDiffuse += wDiffuse;
                         sumDiffuse += float4(wDiffuse, wDiffuse, wDiffuse, wDiffuse * wDiffuse) * s;
@@ -1250,17 +1389,41 @@ void atrous(const RelaxCB& cb, const AtTex& t, int gridW, int gridH) {
         }
 }
 
+// RELAX_SplitScreen.cs.hlsl:21-62 (NRD_SIGNAL = BOTH, NRD_MODE = SH)
+void splitScreen(const RelaxCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec, const Tex& gIn_DiffSh, const Tex& gIn_SpecSh, Tex& gOut_Diff, Tex& gOut_Spec,
+                 Tex& gOut_DiffSh, Tex& gOut_SpecSh, int gridW, int gridH) {
+    Ctx c(cb);
+    for (int py = 0; py < gridH * 16; py++)
+        for (int px = 0; px < gridW * 8; px++) {
+            float2 pixelUv = float2(px + 0.5f, py + 0.5f) * cb.gRectSizeInv;
+            if (pixelUv.x > cb.gSplitScreen || px >= cb.gRectSize.x || py >= cb.gRectSize.y) continue;
+            float inRange = float(c.IsInDenoisingRange(c.UnpackViewZ(gIn_ViewZ.load(px, py).x)));
+            int dx = px >> (cb.gDiffCheckerboard != 2 ? 1 : 0), sx = px >> (cb.gSpecCheckerboard != 2 ? 1 : 0);
+            float4 diff = gIn_Diff.load(dx, py), spec = gIn_Spec.load(sx, py);
+            diff = float4(_NRD_LinearToYCoCg(diff.xyz()), diff.w);
+            spec = float4(_NRD_LinearToYCoCg(spec.xyz()), spec.w);
+            gOut_Diff.store(px, py, diff * inRange);
+            gOut_Spec.store(px, py, spec * inRange);
+            gOut_DiffSh.store(px, py, float4(gIn_DiffSh.load(dx, py).xyz() * inRange, 0.0f));
+            gOut_SpecSh.store(px, py, float4(gIn_SpecSh.load(sx, py).xyz() * inRange, 0.0f));
+        }
+}
+
 }  // namespace
 
 // returns 0 on success, 1 unknown shader, 2 bad arguments (same contract as nrd_oracle_dispatch)
 int relaxDispatch(const std::string& id, const void* constants, uint32_t cbSize, Tex* t, uint32_t n, int gridW, int gridH) {
     if (cbSize != sizeof(RelaxCB)) return 2;
     const RelaxCB& cb = *(const RelaxCB*)constants;
-    if (cb.gHasHistoryConfidence || cb.gHasDisocclusionThresholdMix || cb.gDiffCheckerboard != 2 || cb.gSpecCheckerboard != 2) return 1;  // not restated
     const std::string sig = "|NRD_SIGNAL=BOTH|NRD_MODE=SH";
     if (id == "RELAX_ClassifyTiles.cs.hlsl") {
         if (n != 2) return 2;
         classifyTiles(cb, t[0], t[1], gridW, gridH);
+        return 0;
+    }
+    if (id == "RELAX_SplitScreen.cs.hlsl" + sig) {
+        if (n != 9) return 2;
+        splitScreen(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], gridW, gridH);
         return 0;
     }
     if (id == "RELAX_PrePass.cs.hlsl" + sig) {

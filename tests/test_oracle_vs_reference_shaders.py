@@ -56,6 +56,10 @@ CASES = [
     ("sigma_translucency_default", "sigma_tr", 96, 64, 5, None, {}),
     ("sigma_translucency_odd_size_no_stabilization", "sigma_tr", 100, 75, 3, lambda: api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0), {}),
     ("relax_default", "relax", 96, 64, 5, None, {}),
+    ("relax_split_screen_checkerboard", "relax", 96, 64, 3, lambda: api.RelaxSettings(checkerboardMode=2), {"checkerboard": 2, "cs_splitScreen": 0.45}),
+    ("relax_checkerboard_white", "relax", 96, 64, 4, lambda: api.RelaxSettings(checkerboardMode=2), {"checkerboard": 2}),
+    ("relax_checkerboard_black_guides", "relax", 100, 76, 4, lambda: api.RelaxSettings(checkerboardMode=1, enableAntiFirefly=True),
+     {"checkerboard": 1, "guides": True, "cs_isHistoryConfidenceAvailable": True, "cs_isDisocclusionThresholdMixAvailable": True}),
     ("relax_odd_size", "relax", 100, 75, 3, None, {}),
     ("relax_antifirefly_3_iterations", "relax", 96, 64, 4, lambda: api.RelaxSettings(enableAntiFirefly=True, atrousIterationNum=3), {}),
     ("relax_8_iterations_no_prepass", "relax", 96, 64, 3, lambda: api.RelaxSettings(atrousIterationNum=8, diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0,
