@@ -993,6 +993,78 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// RELAX_HitDistReconstruction.cs.hlsl:21-158 ( 3x3 / 5x5 ): hit distances of pixels whose ray carried none ( hitDist = 0 ) are rebuilt from
+// the neighbours on the same surface. The ( 32 + 2B ) x ( 8 + 2B ) neighbourhood of { normal } and { spec hitDist, diff hitDist, viewZ } is
+// staged in shared memory, normals decoded once per texel. One permutation serves SH and RADIANCE ( only .w of the SH0 textures changes ).
+struct RelaxHitDistReconstructionParams { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, outSpec, outDiff; };
+template <int BORDER>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHitDistReconstructionKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHitDistReconstructionParams p) {
+    constexpr int TW = BLOCK_W + 2 * BORDER, TH = BLOCK_H + 2 * BORDER;
+    __shared__ float3 sNormal[TH][TW];
+    __shared__ float3 sHitDistViewZ[TH][TW];
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
+    if (skyL != 0.0f && skyR != 0.0f) return;
+    {
+        const int baseX = blockIdx.x * BLOCK_W - BORDER, baseY = blockIdx.y * BLOCK_H - BORDER;
+        for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < TW * TH; i += BLOCK_W * BLOCK_H) {
+            const int tx = i % TW, ty = i / TW;
+            const int gx = clampi(baseX + tx, 0, cb.rectSize[0] - 1), gy = clampi(baseY + ty, 0, cb.rectSize[1] - 1);
+            sNormal[ty][tx] = xyz(unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy)));
+            sHitDistViewZ[ty][tx] = make_float3(p.spec.load(gx, gy).w, p.diff.load(gx, gy).w, relaxViewZ(cb, p.viewZ.load(gx, gy)));
+        }
+    }
+    __syncthreads();
+    const float isSky = threadIdx.x < 16 ? skyL : skyR;
+    if (isSky != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    const float3 center = sHitDistViewZ[threadIdx.y + BORDER][threadIdx.x + BORDER];
+    const float centerViewZ = center.z;
+    if (!relaxInRange(cb, centerViewZ)) return;
+
+    const float4 normalAndRoughness = unpackNormalRoughness(p.normalRoughness.loadRaw(px, py));
+    const float3 centerNormal = xyz(normalAndRoughness);
+    const float centerRoughness = normalAndRoughness.w;
+    const float2 rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
+    const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * rectSizeInv;
+    const float2 relaxedRoughnessP = relaxedRoughnessWeightParams(centerRoughness * centerRoughness);
+    const float specularNormalWeightParam = normalWeightParam(1.0f, 1.0f, centerRoughness), diffuseNormalWeightParam = normalWeightParam(1.0f, 1.0f);
+    // the shader weights every tap by the CENTER roughness ( :121 ): a per-pixel constant
+    const float roughnessW = exponentialWeight(centerRoughness * centerRoughness, relaxedRoughnessP.x, relaxedRoughnessP.y);
+
+    float sumSpecularWeight = center.x != 0.0f ? 1000.0f : 0.0f, sumDiffuseWeight = center.y != 0.0f ? 1000.0f : 0.0f;
+    float sumSpecularHitDist = center.x * sumSpecularWeight, sumDiffuseHitDist = center.y * sumDiffuseWeight;
+#pragma unroll
+    for (int j = 0; j <= BORDER * 2; j++)
+#pragma unroll
+        for (int i = 0; i <= BORDER * 2; i++) {
+            if (i == BORDER && j == BORDER) continue;
+            const float2 o = make_float2((float)(i - BORDER), (float)(j - BORDER));
+            const float3 sampleNormal = sNormal[threadIdx.y + j][threadIdx.x + i];
+            const float3 data = sHitDistViewZ[threadIdx.y + j][threadIdx.x + i];
+            const float angle = acosApproxPositive(dot(centerNormal, sampleNormal));
+            float w = isInScreenNearest(pixelUv + o * rectSizeInv) ? 1.0f : 0.0f;
+            w *= relaxInRange(cb, data.z) ? 1.0f : 0.0f;
+            w *= gaussianWeight(length(o) * 0.5f);
+            w *= bilateralWeight(data.z, centerViewZ);
+
+            float specularWeight = w * exponentialWeight(angle, specularNormalWeightParam, 0.0f);
+            specularWeight *= roughnessW;
+            const float sampleSpecularHitDist = specularWeight == 0.0f ? 0.0f : data.x;
+            specularWeight *= sampleSpecularHitDist != 0.0f ? 1.0f : 0.0f;
+            sumSpecularHitDist += sampleSpecularHitDist * specularWeight;
+            sumSpecularWeight += specularWeight;
+
+            float diffuseWeight = w * exponentialWeight(angle, diffuseNormalWeightParam, 0.0f);
+            const float sampleDiffuseHitDist = diffuseWeight == 0.0f ? 0.0f : data.y;
+            diffuseWeight *= sampleDiffuseHitDist != 0.0f ? 1.0f : 0.0f;
+            sumDiffuseHitDist += diffuseWeight == 0.0f ? 0.0f : sampleDiffuseHitDist * diffuseWeight;
+            sumDiffuseWeight += diffuseWeight;
+        }
+    const float4 spec = p.spec.load(px, py), diff = p.diff.load(px, py);
+    p.outSpec.store(px, py, make_float4(spec.x, spec.y, spec.z, sumSpecularHitDist / fmaxf(sumSpecularWeight, 1e-6f)));
+    p.outDiff.store(px, py, make_float4(diff.x, diff.y, diff.z, sumDiffuseHitDist / fmaxf(sumDiffuseWeight, 1e-6f)));
+}
+
 // RELAX_SplitScreen.cs.hlsl:21-62: the noisy input (range-masked; radiance converted to YCoCg in SH mode) left of CommonSettings::splitScreen
 struct RelaxSplitScreenParams { TexR32F viewZ; TexRGBA16F diff, spec, diffSh, specSh, outDiff, outSpec, outDiffSh, outSpecSh; };
 template <bool SH>
@@ -1538,6 +1610,20 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         for (TexRGBA16F* t : outsSh) takeSh(*t);
         if (bad(22 - 8 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (sh) relaxHistoryClampingKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxHistoryClampingKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+    } else if (id == "RELAX_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=0" || id == "RELAX_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=1") {
+        RelaxHitDistReconstructionParams p;
+        p.tiles = b.take<TexR8>(R8);
+        p.normalRoughness = b.take<TexNR>(NR);
+        p.viewZ = b.take<TexR32F>(R32);
+        p.spec = b.take<TexRGBA16F>(F16);
+        p.diff = b.take<TexRGBA16F>(F16);
+        p.outSpec = b.take<TexRGBA16F>(F16);
+        p.outDiff = b.take<TexRGBA16F>(F16);
+        if (bad(7)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (id.back() == '1')
+            relaxHitDistReconstructionKernel<2><<<pixelGrid, block, 0, stream>>>(cb, p);
+        else
+            relaxHitDistReconstructionKernel<1><<<pixelGrid, block, 0, stream>>>(cb, p);
     } else if (id == "RELAX_SplitScreen.cs.hlsl" + sig) {
         RelaxSplitScreenParams p;
         p.viewZ = b.take<TexR32F>(R32);

@@ -414,7 +414,7 @@ def sigma_frame(frame_index: int, width: int, height: int, device="cpu", period:
 # RELAX_DIFFUSE_SPECULAR_SH inputs
 # ------------------------------------------------------------------------------------------------
 def relax_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, sh: bool = True, checkerboard: int = 0,
-                guides: bool = False) -> Dict[str, torch.Tensor]:
+                guides: bool = False, holes: bool = False) -> Dict[str, torch.Tensor]:
     """All user inputs of RELAX_DIFFUSE_SPECULAR_SH for one frame (BASELINE.json config 2): the G-buffer and motion of `reblur_frame`,
     un-normalised radiance + hit distance in IN_*_SH0 and `direction * luminance` in IN_*_SH1, both RGBA16F, packed like
     RELAX_FrontEnd_PackSh (NRD.hlsli:925-941). Directions: cosine-weighted around N (diffuse), jittered mirror direction (specular)."""
@@ -466,6 +466,11 @@ def relax_frame(frame_index: int, width: int, height: int, device="cpu", period:
         "IN_SPEC_SH0": sh0(spec, hit_t_s),
         "IN_SPEC_SH1": sh1(spec, dir_s),
     }
+    if holes:   # probabilistic lobe sampling: each pixel traced one lobe, the other one has no hit distance ( HitDistanceReconstructionMode )
+        ys, xs = torch.meshgrid(torch.arange(height, device=device), torch.arange(width, device=device), indexing="ij")
+        checker = ((xs + ys + frame_index) & 1).bool()
+        out["IN_DIFF_SH0"][..., 3] = torch.where(checker, out["IN_DIFF_SH0"][..., 3], torch.zeros_like(out["IN_DIFF_SH0"][..., 3]))
+        out["IN_SPEC_SH0"][..., 3] = torch.where(checker, torch.zeros_like(out["IN_SPEC_SH0"][..., 3]), out["IN_SPEC_SH0"][..., 3])
     if guides:
         for k in ("IN_DIFF_CONFIDENCE", "IN_SPEC_CONFIDENCE", "IN_DISOCCLUSION_THRESHOLD_MIX"):
             out[k] = base[k]

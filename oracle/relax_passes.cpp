@@ -151,6 +151,7 @@ struct Ctx {
 };
 
 float4 unpackNR(const Tex& t, int x, int y, float& materialID) { return NRD_FrontEnd_UnpackNormalAndRoughness(t.load(x, y), materialID); }
+float4 unpackNR(const Tex& t, int x, int y) { float m; return unpackNR(t, x, y, m); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // RELAX_ClassifyTiles.cs.hlsl:21-51
@@ -1389,6 +1390,73 @@ void atrous(const RelaxCB& cb, const AtTex& t, int gridW, int gridH) {
         }
 }
 
+// RELAX_HitDistReconstruction.cs.hlsl:21-158 (NRD_SIGNAL = BOTH; one permutation serves SH and RADIANCE: only the .w of the SH0 / radiance
+// textures is touched). `border` = 1 (3x3) or 2 (5x5); the shared-memory tile holds f( clamp( pos, 0, rectSize - 1 ) ). 8x8 groups.
+void hitDistReconstruction(const RelaxCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Spec, const Tex& gIn_Diff, Tex& gOut_Spec,
+                           Tex& gOut_Diff, int gridW, int gridH, int border) {
+    Ctx c(cb);
+    auto clampX = [&](int x) { return std::min(std::max(x, 0), cb.gRectSize.x - 1); };
+    auto clampY = [&](int y) { return std::min(std::max(y, 0), cb.gRectSize.y - 1); };
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = 0; py < gridH * 8; py++)
+        for (int px = 0; px < gridW * 8; px++) {
+            if (gIn_Tiles.load(px >> 4, py >> 4).x != 0.0f || px >= cb.gRectSize.x || py >= cb.gRectSize.y) continue;
+            float centerViewZ = c.UnpackViewZ(gIn_ViewZ.load(px, py).x);
+            if (!c.IsInDenoisingRange(centerViewZ)) continue;
+            float2 pixelUv = float2(px + 0.5f, py + 0.5f) * cb.gRectSizeInv;
+            float4 normalAndRoughness = unpackNR(gIn_Normal_Roughness, px, py);
+            float3 centerNormal = normalAndRoughness.xyz();
+            float centerRoughness = normalAndRoughness.w;
+
+            float4 centerSpec = gIn_Spec.load(px, py), centerDiff = gIn_Diff.load(px, py);
+            float centerSpecularHitDist = centerSpec.w, centerDiffuseHitDist = centerDiff.w;
+            float2 relaxedRoughnessWeightParams = GetRelaxedRoughnessWeightParams(centerRoughness * centerRoughness);
+            float specularNormalWeightParam = GetNormalWeightParam(1.0f, 1.0f, centerRoughness);
+            float sumSpecularWeight = 1000.0f * float(centerSpecularHitDist != 0.0f);
+            float sumSpecularHitDist = centerSpecularHitDist * sumSpecularWeight;
+            float diffuseNormalWeightParam = GetNormalWeightParam(1.0f, 1.0f);
+            float sumDiffuseWeight = 1000.0f * float(centerDiffuseHitDist != 0.0f);
+            float sumDiffuseHitDist = centerDiffuseHitDist * sumDiffuseWeight;
+
+            for (int dy = -border; dy <= border; dy++)
+                for (int dx = -border; dx <= border; dx++) {
+                    if (dx == 0 && dy == 0) continue;
+                    int sx = clampX(px + dx), sy = clampY(py + dy);
+                    float3 sampleNormal = unpackNR(gIn_Normal_Roughness, sx, sy).xyz();
+                    float sampleViewZ = c.UnpackViewZ(gIn_ViewZ.load(sx, sy).x);
+                    float angle = Math::AcosApproxPositive(dot(centerNormal, sampleNormal));
+                    float2 o = float2((float)dx, (float)dy);
+
+                    float w = IsInScreenNearest(pixelUv + o * cb.gRectSizeInv);
+                    w *= float(c.IsInDenoisingRange(sampleViewZ));
+                    w *= GetGaussianWeight(length(o) * 0.5f);
+                    w *= GetBilateralWeight(sampleViewZ, centerViewZ);
+
+                    float specularWeight = w;
+                    specularWeight *= ComputeExponentialWeight(angle, specularNormalWeightParam, 0.0f);
+                    // ( the shader weights by the CENTER roughness here, :121 )
+                    specularWeight *= ComputeExponentialWeight(normalAndRoughness.w * normalAndRoughness.w, relaxedRoughnessWeightParams.x, relaxedRoughnessWeightParams.y);
+                    float sampleSpecularHitDist = gIn_Spec.load(sx, sy).w;
+                    if (specularWeight == 0.0f) sampleSpecularHitDist = 0.0f;
+                    specularWeight *= float(sampleSpecularHitDist != 0.0f);
+                    sumSpecularHitDist += sampleSpecularHitDist * specularWeight;
+                    sumSpecularWeight += specularWeight;
+
+                    float diffuseWeight = w;
+                    diffuseWeight *= ComputeExponentialWeight(angle, diffuseNormalWeightParam, 0.0f);
+                    float sampleDiffuseHitDist = gIn_Diff.load(sx, sy).w;
+                    if (diffuseWeight == 0.0f) sampleDiffuseHitDist = 0.0f;
+                    diffuseWeight *= float(sampleDiffuseHitDist != 0.0f);
+                    sumDiffuseHitDist += diffuseWeight == 0.0f ? 0.0f : sampleDiffuseHitDist * diffuseWeight;
+                    sumDiffuseWeight += diffuseWeight;
+                }
+            sumSpecularHitDist /= max(sumSpecularWeight, 1e-6f);
+            gOut_Spec.store(px, py, float4(centerSpec.xyz(), sumSpecularHitDist));
+            sumDiffuseHitDist /= max(sumDiffuseWeight, 1e-6f);
+            gOut_Diff.store(px, py, float4(centerDiff.xyz(), sumDiffuseHitDist));
+        }
+}
+
 // RELAX_SplitScreen.cs.hlsl:21-62 (NRD_SIGNAL = BOTH, NRD_MODE = SH)
 void splitScreen(const RelaxCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec, const Tex& gIn_DiffSh, const Tex& gIn_SpecSh, Tex& gOut_Diff, Tex& gOut_Spec,
                  Tex& gOut_DiffSh, Tex& gOut_SpecSh, int gridW, int gridH) {
@@ -1419,6 +1487,11 @@ int relaxDispatch(const std::string& id, const void* constants, uint32_t cbSize,
     if (id == "RELAX_ClassifyTiles.cs.hlsl") {
         if (n != 2) return 2;
         classifyTiles(cb, t[0], t[1], gridW, gridH);
+        return 0;
+    }
+    if (id == "RELAX_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=0" || id == "RELAX_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=1") {
+        if (n != 7) return 2;
+        hitDistReconstruction(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], gridW, gridH, id.back() == '1' ? 2 : 1);
         return 0;
     }
     if (id == "RELAX_SplitScreen.cs.hlsl" + sig) {

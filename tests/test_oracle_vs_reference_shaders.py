@@ -56,6 +56,9 @@ CASES = [
     ("sigma_translucency_default", "sigma_tr", 96, 64, 5, None, {}),
     ("sigma_translucency_odd_size_no_stabilization", "sigma_tr", 100, 75, 3, lambda: api.SigmaSettings(lightDirection=(C.c_float * 3)(0.3, 0.8, -0.5), maxStabilizedFrameNum=0), {}),
     ("relax_default", "relax", 96, 64, 5, None, {}),
+    ("relax_recon3x3", "relax", 96, 64, 3, lambda: api.RelaxSettings(hitDistanceReconstructionMode=1), {"holes": True}),
+    ("relax_recon5x5_odd_size_no_prepass", "relax", 100, 75, 3, lambda: api.RelaxSettings(hitDistanceReconstructionMode=2, diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0),
+     {"holes": True}),
     ("relax_split_screen_checkerboard", "relax", 96, 64, 3, lambda: api.RelaxSettings(checkerboardMode=2), {"checkerboard": 2, "cs_splitScreen": 0.45}),
     ("relax_checkerboard_white", "relax", 96, 64, 4, lambda: api.RelaxSettings(checkerboardMode=2), {"checkerboard": 2}),
     ("relax_checkerboard_black_guides", "relax", 100, 76, 4, lambda: api.RelaxSettings(checkerboardMode=1, enableAntiFirefly=True),

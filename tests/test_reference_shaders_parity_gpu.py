@@ -36,7 +36,10 @@ CASES["reference"] = (api.Denoiser.REFERENCE, "reference_frame", ("OUT_SIGNAL",)
 # RELAX as NRDSample drives it by default: checkerboard WHITE + history confidence; SH and RADIANCE variants, with a split screen on the SH one
 CASES["relax_cb_guides_split"] = (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, "relax_frame_cb_guides", ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur")
 CASES["relax_nosh_cb_guides"] = (api.Denoiser.RELAX_DIFFUSE_SPECULAR, "relax_frame_nosh_cb_guides", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
-SETTINGS = {"relax_cb_guides_split": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True), "relax_nosh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2),
+CASES["relax_nosh_recon5x5"] = (api.Denoiser.RELAX_DIFFUSE_SPECULAR, "relax_frame_nosh_holes", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
+CASES["relax_recon3x3"] = (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, "relax_frame_holes", ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur")
+SETTINGS = {"relax_nosh_recon5x5": lambda: api.RelaxSettings(hitDistanceReconstructionMode=2), "relax_recon3x3": lambda: api.RelaxSettings(hitDistanceReconstructionMode=1),
+            "relax_cb_guides_split": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True), "relax_nosh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2),
             "reblur_split": lambda: api.ReblurSettings(checkerboardMode=2), "reference": lambda: api.ReferenceSettings(maxAccumulatedFrameNum=5), "reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_guides_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
 COMMON = {"relax_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.3),
           "relax_nosh_cb_guides": dict(isHistoryConfidenceAvailable=True),
@@ -59,6 +62,10 @@ def out_format(which, o, runner):
 def frame_of(name, f, w, h):
     if name == "relax_frame_nosh":
         return synth.relax_frame(f, w, h, sh=False)
+    if name == "relax_frame_holes":
+        return synth.relax_frame(f, w, h, holes=True)
+    if name == "relax_frame_nosh_holes":
+        return synth.relax_frame(f, w, h, sh=False, holes=True)
     if name == "relax_frame_cb_guides":
         return synth.relax_frame(f, w, h, checkerboard=2, guides=True)
     if name == "relax_frame_nosh_cb_guides":
@@ -71,7 +78,7 @@ def frame_of(name, f, w, h):
         return synth.sigma_frame(f, w, h, translucency=True)
     return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0), "reblur_split": (3e-2, 45.0), "reference": (1e-3, 80.0), "relax_cb_guides_split": (2e-3, 60.0), "relax_nosh_cb_guides": (2e-3, 60.0)}
+LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0), "reblur_split": (3e-2, 45.0), "reference": (1e-3, 80.0), "relax_cb_guides_split": (2e-3, 60.0), "relax_nosh_cb_guides": (2e-3, 60.0), "relax_nosh_recon5x5": (2e-3, 60.0), "relax_recon3x3": (2e-3, 60.0)}
 
 
 @pytest.fixture(scope="module")
