@@ -1,5 +1,5 @@
-// REBLUR_DIFFUSE_SPECULAR pass graph and per-frame constants.
-// Pool layout and bindings: External/NRD/Source/Denoisers/Reblur_DiffuseSpecular.hpp:17-297.
+// REBLUR_DIFFUSE / REBLUR_SPECULAR / REBLUR_DIFFUSE_SPECULAR pass graphs and per-frame constants.
+// Pool layout and bindings: External/NRD/Source/Denoisers/Reblur_Diffuse.hpp, Reblur_Specular.hpp, Reblur_DiffuseSpecular.hpp.
 // Per-frame pass selection: External/NRD/Source/Reblur.cpp:98-199. Constants: Reblur.cpp:283-394.
 #include <algorithm>
 #include <cmath>
@@ -9,26 +9,6 @@
 namespace nrdb {
 
 namespace {
-
-// Permanent pool (persists across frames) — 42 B/px
-enum P : uint16_t {
-    P_PREV_VIEWZ,
-    P_PREV_NORMAL_ROUGHNESS,
-    P_PREV_INTERNAL_DATA,
-    P_DIFF_HISTORY,
-    P_DIFF_FAST_HISTORY,
-    P_DIFF_STABILIZED_PING,
-    P_DIFF_STABILIZED_PONG,
-    P_SPEC_HISTORY,
-    P_SPEC_FAST_HISTORY,
-    P_SPEC_STABILIZED_PING,
-    P_SPEC_STABILIZED_PONG,
-    P_SPEC_HITDIST_TRACKING_PING,
-    P_SPEC_HITDIST_TRACKING_PONG,
-};
-
-// Transient pool (valid within one frame) — 28 B/px + tiles
-enum T : uint16_t { T_DATA1, T_DATA2, T_SPEC_HITDIST_TRACKING, T_DIFF_TMP2, T_DIFF_FAST, T_SPEC_TMP2, T_SPEC_FAST, T_TILES };
 
 // Index of each pass (and its permutations) in emission order; updateReblur() does arithmetic on these
 enum PassIndex : uint32_t {
@@ -45,37 +25,58 @@ enum PassIndex : uint32_t {
 };
 
 const uint32_t kCb = sizeof(ReblurConstants);
-const char* const kSignal = "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE";
+
+bool hasDiffuse(Denoiser d) { return d == Denoiser::REBLUR_DIFFUSE || d == Denoiser::REBLUR_DIFFUSE_SPECULAR; }
+bool hasSpecular(Denoiser d) { return d == Denoiser::REBLUR_SPECULAR || d == Denoiser::REBLUR_DIFFUSE_SPECULAR; }
 
 }  // namespace
 
-void Graph::buildReblurDiffuseSpecular(DenoiserState& d) {
+// One builder for REBLUR_DIFFUSE / REBLUR_SPECULAR / REBLUR_DIFFUSE_SPECULAR (NRD_MODE = RADIANCE): the reference's three .hpp files are the
+// same graph with the bindings of the absent lobe removed (Reblur_Diffuse.hpp:15-249, Reblur_Specular.hpp:15-260, Reblur_DiffuseSpecular.hpp:17-297).
+// Pool layout: permanent = prev viewZ / normal+roughness / internal data, then per lobe { history, fast history, stabilized luma ping / pong },
+// then the specular hit-distance-for-tracking ping / pong; transient = data1 (RG8 for both lobes, R8 for one), data2 (R32_UINT, R8_UINT without
+// specular), hit distance for tracking (specular), per lobe { tmp2, fast history }, tiles.
+void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
     new (&d.settings.reblur) ReblurSettings();
     d.settingsSize = sizeof(ReblurSettings);
 
     const Format kRadiance = Format::RGBA16_SFLOAT, kFast = Format::R16_SFLOAT;
-    addPermanent(Format::R32_SFLOAT);            // prev viewZ
-    addPermanent(Format::R10_G10_B10_A2_UNORM);  // prev normal+roughness (must match IN_NORMAL_ROUGHNESS encoding)
-    addPermanent(Format::R16_UINT);              // prev internal data: 6b diff frames | 6b spec frames | 4b material
-    addPermanent(kRadiance);
-    addPermanent(kFast);
-    addPermanent(Format::R16_SFLOAT);
-    addPermanent(Format::R16_SFLOAT);
-    addPermanent(kRadiance);
-    addPermanent(kFast);
-    addPermanent(Format::R16_SFLOAT);
-    addPermanent(Format::R16_SFLOAT);
-    addPermanent(Format::R16_SFLOAT);
-    addPermanent(Format::R16_SFLOAT);
+    uint16_t nPerm = 0, nTran = 0;
+    auto perm = [&](Format f) { addPermanent(f); return nPerm++; };
+    auto tran = [&](Format f, uint16_t ds = 1) { addTransient(f, ds); return nTran++; };
+    const uint16_t P_PREV_VIEWZ = perm(Format::R32_SFLOAT);
+    const uint16_t P_PREV_NORMAL_ROUGHNESS = perm(Format::R10_G10_B10_A2_UNORM);  // must match the IN_NORMAL_ROUGHNESS encoding
+    const uint16_t P_PREV_INTERNAL_DATA = perm(Format::R16_UINT);                 // 6b diff frames | 6b spec frames | 4b material
+    uint16_t P_DIFF_HISTORY = 0, P_DIFF_FAST_HISTORY = 0, P_DIFF_STABILIZED_PING = 0, P_DIFF_STABILIZED_PONG = 0;
+    uint16_t P_SPEC_HISTORY = 0, P_SPEC_FAST_HISTORY = 0, P_SPEC_STABILIZED_PING = 0, P_SPEC_STABILIZED_PONG = 0, P_SPEC_HITDIST_TRACKING_PING = 0, P_SPEC_HITDIST_TRACKING_PONG = 0;
+    if (diff) {
+        P_DIFF_HISTORY = perm(kRadiance);
+        P_DIFF_FAST_HISTORY = perm(kFast);
+        P_DIFF_STABILIZED_PING = perm(Format::R16_SFLOAT);
+        P_DIFF_STABILIZED_PONG = perm(Format::R16_SFLOAT);
+    }
+    if (spec) {
+        P_SPEC_HISTORY = perm(kRadiance);
+        P_SPEC_FAST_HISTORY = perm(kFast);
+        P_SPEC_STABILIZED_PING = perm(Format::R16_SFLOAT);
+        P_SPEC_STABILIZED_PONG = perm(Format::R16_SFLOAT);
+        P_SPEC_HITDIST_TRACKING_PING = perm(Format::R16_SFLOAT);
+        P_SPEC_HITDIST_TRACKING_PONG = perm(Format::R16_SFLOAT);
+    }
 
-    addTransient(Format::RG8_UNORM);
-    addTransient(Format::R32_UINT);
-    addTransient(Format::R16_SFLOAT);
-    addTransient(kRadiance);
-    addTransient(kFast);
-    addTransient(kRadiance);
-    addTransient(kFast);
-    addTransient(Format::R8_UNORM, 16);
+    const uint16_t T_DATA1 = tran(diff && spec ? Format::RG8_UNORM : Format::R8_UNORM);
+    const uint16_t T_DATA2 = tran(spec ? Format::R32_UINT : Format::R8_UINT);
+    uint16_t T_SPEC_HITDIST_TRACKING = 0, T_DIFF_TMP2 = 0, T_DIFF_FAST = 0, T_SPEC_TMP2 = 0, T_SPEC_FAST = 0;
+    if (spec) T_SPEC_HITDIST_TRACKING = tran(Format::R16_SFLOAT);
+    if (diff) {
+        T_DIFF_TMP2 = tran(kRadiance);
+        T_DIFF_FAST = tran(kFast);
+    }
+    if (spec) {
+        T_SPEC_TMP2 = tran(kRadiance);
+        T_SPEC_FAST = tran(kFast);
+    }
+    const uint16_t T_TILES = tran(Format::R8_UNORM, 16);
 
     auto U = [](ResourceType t) { return Slot::user(t); };
     auto Pm = [](uint16_t i) { return Slot::perm(i); };
@@ -84,43 +85,50 @@ void Graph::buildReblurDiffuseSpecular(DenoiserState& d) {
     const Slot diffTemp1 = U(ResourceType::OUT_DIFF_RADIANCE_HITDIST), specTemp1 = U(ResourceType::OUT_SPEC_RADIANCE_HITDIST);
     const Slot diffTemp2 = Tr(T_DIFF_TMP2), specTemp2 = Tr(T_SPEC_TMP2);
     const Slot dummy = U(ResourceType::IN_VIEWZ);  // bound where an optional input is absent
-    const std::string sig = kSignal;
+    const std::string sig = std::string("|NRD_SIGNAL=") + (diff && spec ? "BOTH" : (diff ? "DIFF" : "SPEC")) + "|NRD_MODE=RADIANCE";
+    const std::string prefix = std::string("REBLUR_") + (diff && spec ? "DiffuseSpecular" : (diff ? "Diffuse" : "Specular")) + " - ";
+    auto name = [&](const char* pass) { return intern(prefix + pass); };
+    // bind helpers: a lobe's binding exists only when the denoiser has that lobe
+    auto inD = [&](Slot s, Slot swap = Slot()) { if (diff) in(s, swap); };
+    auto inS = [&](Slot s, Slot swap = Slot()) { if (spec) in(s, swap); };
+    auto outD = [&](Slot s, Slot swap = Slot()) { if (diff) out(s, swap); };
+    auto outS = [&](Slot s, Slot swap = Slot()) { if (spec) out(s, swap); };
 
-    beginPass("REBLUR_DiffuseSpecular - Classify tiles");
+    beginPass(name("Classify tiles"));
     in(U(ResourceType::IN_VIEWZ));
     out(Tr(T_TILES));
     emit("REBLUR_ClassifyTiles.cs.hlsl", 16, 16, kCb);
 
     for (int i = 0; i < 4; i++) {
         bool is5x5 = (i >> 1) & 1, prepassFollows = i & 1;
-        beginPass("REBLUR_DiffuseSpecular - Hit distance reconstruction");
+        beginPass(name("Hit distance reconstruction"));
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(U(ResourceType::IN_VIEWZ));
-        in(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
-        in(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
-        out(prepassFollows ? diffTemp2 : diffTemp1);
-        out(prepassFollows ? specTemp2 : specTemp1);
+        inD(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
+        inS(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+        outD(prepassFollows ? diffTemp2 : diffTemp1);
+        outS(prepassFollows ? specTemp2 : specTemp1);
         emit("REBLUR_HitDistReconstruction.cs.hlsl" + sig + (is5x5 ? "|MODE_5X5=1" : "|MODE_5X5=0"), 8, 16, kCb);
     }
 
     for (int i = 0; i < 2; i++) {
         bool afterReconstruction = i & 1;
-        beginPass("REBLUR_DiffuseSpecular - Pre-pass");
+        beginPass(name("Pre-pass"));
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(U(ResourceType::IN_VIEWZ));
-        in(afterReconstruction ? diffTemp2 : U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
-        in(afterReconstruction ? specTemp2 : U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
-        out(diffTemp1);
-        out(specTemp1);
-        out(Tr(T_SPEC_HITDIST_TRACKING));
+        inD(afterReconstruction ? diffTemp2 : U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
+        inS(afterReconstruction ? specTemp2 : U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+        outD(diffTemp1);
+        outS(specTemp1);
+        outS(Tr(T_SPEC_HITDIST_TRACKING));
         emit("REBLUR_PrePass.cs.hlsl" + sig, 16, 16, kCb);
     }
 
     for (int i = 0; i < 8; i++) {
         bool hasMix = (i >> 2) & 1, hasConfidence = (i >> 1) & 1, afterPrepass = i & 1;
-        beginPass("REBLUR_DiffuseSpecular - Temporal accumulation");
+        beginPass(name("Temporal accumulation"));
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(U(ResourceType::IN_VIEWZ));
@@ -129,109 +137,110 @@ void Graph::buildReblurDiffuseSpecular(DenoiserState& d) {
         in(Pm(P_PREV_NORMAL_ROUGHNESS));
         in(Pm(P_PREV_INTERNAL_DATA));
         in(hasMix ? U(ResourceType::IN_DISOCCLUSION_THRESHOLD_MIX) : dummy);
-        in(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
-        in(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
-        in(afterPrepass ? diffTemp1 : U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
-        in(afterPrepass ? specTemp1 : U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
-        in(Pm(P_DIFF_HISTORY));
-        in(Pm(P_SPEC_HISTORY));
-        in(Pm(P_DIFF_FAST_HISTORY));
-        in(Pm(P_SPEC_FAST_HISTORY));
-        in(Pm(P_SPEC_HITDIST_TRACKING_PING), Pm(P_SPEC_HITDIST_TRACKING_PONG));
-        in(Tr(T_SPEC_HITDIST_TRACKING));
+        inD(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
+        inS(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
+        inD(afterPrepass ? diffTemp1 : U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
+        inS(afterPrepass ? specTemp1 : U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+        inD(Pm(P_DIFF_HISTORY));
+        inS(Pm(P_SPEC_HISTORY));
+        inD(Pm(P_DIFF_FAST_HISTORY));
+        inS(Pm(P_SPEC_FAST_HISTORY));
+        inS(Pm(P_SPEC_HITDIST_TRACKING_PING), Pm(P_SPEC_HITDIST_TRACKING_PONG));
+        inS(Tr(T_SPEC_HITDIST_TRACKING));
         out(Tr(T_DATA1));
-        out(diffTemp2);
-        out(specTemp2);
-        out(Tr(T_DIFF_FAST));
-        out(Tr(T_SPEC_FAST));
-        out(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
+        outD(diffTemp2);
+        outS(specTemp2);
+        outD(Tr(T_DIFF_FAST));
+        outS(Tr(T_SPEC_FAST));
+        outS(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
         out(Tr(T_DATA2));
         emit("REBLUR_TemporalAccumulation.cs.hlsl" + sig, 8, 16, kCb);
     }
 
-    beginPass("REBLUR_DiffuseSpecular - History fix");
+    beginPass(name("History fix"));
     in(Tr(T_TILES));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(Tr(T_DATA1));
     in(U(ResourceType::IN_VIEWZ));
-    in(diffTemp2);
-    in(specTemp2);
-    in(Tr(T_DIFF_FAST));
-    in(Tr(T_SPEC_FAST));
-    in(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
-    out(diffTemp1);
-    out(specTemp1);
-    out(Pm(P_DIFF_FAST_HISTORY));
-    out(Pm(P_SPEC_FAST_HISTORY));
+    inD(diffTemp2);
+    inS(specTemp2);
+    inD(Tr(T_DIFF_FAST));
+    inS(Tr(T_SPEC_FAST));
+    inS(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
+    outD(diffTemp1);
+    outS(specTemp1);
+    outD(Pm(P_DIFF_FAST_HISTORY));
+    outS(Pm(P_SPEC_FAST_HISTORY));
     emit("REBLUR_HistoryFix.cs.hlsl" + sig, 8, 16, kCb);
 
-    beginPass("REBLUR_DiffuseSpecular - Blur");
+    beginPass(name("Blur"));
     in(Tr(T_TILES));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(U(ResourceType::IN_VIEWZ));
     in(Tr(T_DATA1));
-    in(diffTemp1);
-    in(specTemp1);
+    inD(diffTemp1);
+    inS(specTemp1);
     out(Pm(P_PREV_VIEWZ));
-    out(diffTemp2);
-    out(specTemp2);
+    outD(diffTemp2);
+    outS(specTemp2);
     emit("REBLUR_Blur.cs.hlsl" + sig, 8, 16, kCb);
 
     for (int i = 0; i < 2; i++) {
         bool stabilizationFollows = i & 1;
-        beginPass("REBLUR_DiffuseSpecular - Post-blur");
+        beginPass(name("Post-blur"));
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(Tr(T_DATA1));
         in(Pm(P_PREV_VIEWZ));
-        in(diffTemp2);
-        in(specTemp2);
+        inD(diffTemp2);
+        inS(specTemp2);
         out(Pm(P_PREV_NORMAL_ROUGHNESS));
-        out(Pm(P_DIFF_HISTORY));
-        out(Pm(P_SPEC_HISTORY));
+        outD(Pm(P_DIFF_HISTORY));
+        outS(Pm(P_SPEC_HISTORY));
         if (!stabilizationFollows) {
             out(Pm(P_PREV_INTERNAL_DATA));
-            out(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
-            out(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
+            outD(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
+            outS(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
         }
         emit("REBLUR_PostBlur.cs.hlsl" + sig + (stabilizationFollows ? "|TEMPORAL_STABILIZATION=1" : "|TEMPORAL_STABILIZATION=0"), 8, 16, kCb);
     }
 
-    beginPass("REBLUR_DiffuseSpecular - Temporal stabilization");
+    beginPass(name("Temporal stabilization"));
     in(Tr(T_TILES));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(Pm(P_PREV_VIEWZ));
     in(Tr(T_DATA1));
     in(Tr(T_DATA2));
-    in(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
-    in(Pm(P_DIFF_HISTORY));
-    in(Pm(P_SPEC_HISTORY));
-    in(Pm(P_DIFF_STABILIZED_PING), Pm(P_DIFF_STABILIZED_PONG));
-    in(Pm(P_SPEC_STABILIZED_PING), Pm(P_SPEC_STABILIZED_PONG));
+    inS(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
+    inD(Pm(P_DIFF_HISTORY));
+    inS(Pm(P_SPEC_HISTORY));
+    inD(Pm(P_DIFF_STABILIZED_PING), Pm(P_DIFF_STABILIZED_PONG));
+    inS(Pm(P_SPEC_STABILIZED_PING), Pm(P_SPEC_STABILIZED_PONG));
     out(U(ResourceType::IN_MV));  // bound read-write by the reference; only read by this pass
     out(Pm(P_PREV_INTERNAL_DATA));
-    out(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
-    out(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
-    out(Pm(P_DIFF_STABILIZED_PONG), Pm(P_DIFF_STABILIZED_PING));
-    out(Pm(P_SPEC_STABILIZED_PONG), Pm(P_SPEC_STABILIZED_PING));
+    outD(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
+    outS(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
+    outD(Pm(P_DIFF_STABILIZED_PONG), Pm(P_DIFF_STABILIZED_PING));
+    outS(Pm(P_SPEC_STABILIZED_PONG), Pm(P_SPEC_STABILIZED_PING));
     emit("REBLUR_TemporalStabilization.cs.hlsl" + sig, 8, 16, kCb);
 
-    beginPass("REBLUR_DiffuseSpecular - Split screen");
+    beginPass(name("Split screen"));
     in(U(ResourceType::IN_VIEWZ));
-    in(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
-    in(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
-    out(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
-    out(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
+    inD(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
+    inS(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+    outD(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
+    outS(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
     emit("REBLUR_SplitScreen.cs.hlsl" + sig, 8, 16, kCb);
 
-    beginPass("REBLUR_DiffuseSpecular - Validation");
+    // REBLUR_ADD_VALIDATION_DISPATCH (Reblur.cpp:65-78): a single-lobe denoiser binds its input in both lobe slots
+    beginPass(name("Validation"));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(U(ResourceType::IN_VIEWZ));
     in(U(ResourceType::IN_MV));
     in(Tr(T_DATA1));
     in(Tr(T_DATA2));
-    in(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
-    in(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+    in(U(diff ? ResourceType::IN_DIFF_RADIANCE_HITDIST : ResourceType::IN_SPEC_RADIANCE_HITDIST));
+    in(U(spec ? ResourceType::IN_SPEC_RADIANCE_HITDIST : ResourceType::IN_DIFF_RADIANCE_HITDIST));
     out(U(ResourceType::OUT_VALIDATION));
     emit("REBLUR_Validation.cs.hlsl", 8, 16, kCb, GRID_FROM_RESOURCE, 1);
 }
@@ -240,7 +249,8 @@ void Graph::updateReblur(const DenoiserState& d) {
     const ReblurSettings& s = d.settings.reblur;
     const bool reconstruct = s.hitDistanceReconstructionMode != HitDistanceReconstructionMode::OFF && s.checkerboardMode == CheckerboardMode::OFF;
     const bool skipStabilization = s.maxStabilizedFrameNum == 0;
-    const bool skipPrePass = s.diffusePrepassBlurRadius == 0.0f && s.specularPrepassBlurRadius == 0.0f && s.checkerboardMode == CheckerboardMode::OFF;
+    const bool diff = hasDiffuse(d.desc.denoiser), spec = hasSpecular(d.desc.denoiser);
+    const bool skipPrePass = (s.diffusePrepassBlurRadius == 0.0f || !diff) && (s.specularPrepassBlurRadius == 0.0f || !spec) && s.checkerboardMode == CheckerboardMode::OFF;
 
     auto push = [&](uint32_t pass) { fillReblurConstants(s, pushDispatch(d, pass)); };
 
@@ -263,7 +273,7 @@ void Graph::updateReblur(const DenoiserState& d) {
         uint8_t* cb = (uint8_t*)pushDispatch(d, PASS_VALIDATION);
         fillReblurConstants(s, cb);
         // two trailing uints after the shared block: gHasDiffuse, gHasSpecular (the shared block's own tail padding is reused)
-        uint32_t flags[2] = {1, 1};
+        uint32_t flags[2] = {diff ? 1u : 0u, spec ? 1u : 0u};
         memcpy(cb + offsetof(ReblurConstants, _pad), flags, sizeof(flags));
     }
 }

@@ -39,6 +39,8 @@ static bool contains(const Identifier* ids, uint32_t n, Identifier id) {
 // The denoisers this build implements end to end (graph + CUDA kernels). Everything else is UNSUPPORTED,
 // which is the reference's own answer for a denoiser missing from LibraryDesc (InstanceImpl.cpp:95-102).
 static const Denoiser kSupported[] = {
+    Denoiser::REBLUR_DIFFUSE,
+    Denoiser::REBLUR_SPECULAR,
     Denoiser::REBLUR_DIFFUSE_SPECULAR,
     Denoiser::RELAX_DIFFUSE_SPECULAR,
     Denoiser::RELAX_DIFFUSE_SPECULAR_SH,
@@ -156,7 +158,9 @@ Result Graph::create(const InstanceCreationDesc& desc) {
         size_t firstResource = m_resources.size();
 
         switch (dd.denoiser) {
-            case Denoiser::REBLUR_DIFFUSE_SPECULAR: buildReblurDiffuseSpecular(d); break;
+            case Denoiser::REBLUR_DIFFUSE: buildReblur(d, true, false); break;
+            case Denoiser::REBLUR_SPECULAR: buildReblur(d, false, true); break;
+            case Denoiser::REBLUR_DIFFUSE_SPECULAR: buildReblur(d, true, true); break;
             case Denoiser::SIGMA_SHADOW: buildSigmaShadow(d, false); break;
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: buildSigmaShadow(d, true); break;
             case Denoiser::REFERENCE: buildReference(d); break;
@@ -454,6 +458,8 @@ Result Graph::getComputeDispatches(const Identifier* ids, uint32_t idsNum, const
         if (!contains(ids, idsNum, d.desc.identifier)) continue;
         flipPingPong(d);
         switch (d.desc.denoiser) {
+            case Denoiser::REBLUR_DIFFUSE:
+            case Denoiser::REBLUR_SPECULAR:
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: updateReblur(d); break;
             case Denoiser::SIGMA_SHADOW:
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: updateSigma(d); break;

@@ -65,6 +65,11 @@ IDENTIFIERS = [
     # SIGMA_SHADOW_TRANSLUCENCY
     "SIGMA_ClassifyTiles.cs.hlsl|TRANSLUCENCY=1", "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=1|FIRST_PASS=1", "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=1|FIRST_PASS=0",
     "SIGMA_TemporalStabilization.cs.hlsl|TRANSLUCENCY=1", "SIGMA_SplitScreen.cs.hlsl|TRANSLUCENCY=1",
+    # REBLUR_DIFFUSE / REBLUR_SPECULAR
+] + [f"{f}|NRD_SIGNAL={sig}|NRD_MODE=RADIANCE{suffix}" for sig in ("DIFF", "SPEC") for f, suffix in (
+    ("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=0"), ("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), ("REBLUR_PrePass.cs.hlsl", ""),
+    ("REBLUR_TemporalAccumulation.cs.hlsl", ""), ("REBLUR_HistoryFix.cs.hlsl", ""), ("REBLUR_Blur.cs.hlsl", ""), ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0"),
+    ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1"), ("REBLUR_TemporalStabilization.cs.hlsl", ""), ("REBLUR_SplitScreen.cs.hlsl", ""))] + [
     # REFERENCE
     "REFERENCE_TemporalAccumulation.cs.hlsl", "REFERENCE_Copy.cs.hlsl",
 ]

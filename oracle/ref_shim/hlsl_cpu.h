@@ -301,14 +301,14 @@ template <class A, class B, class = std::enable_if_t<Tr<A>::num && Tr<B>::num>> 
 
 // ------------------------------------------------------------------------------------------------ textures
 enum Format : uint32_t {  // numeric values = nrd::Format ( NRDDescs.h )
-    R8_UNORM = 0, RG8_UNORM = 4, RGBA8_UNORM = 8, R16_UINT = 15, R16_SFLOAT = 17, RG16_SFLOAT = 22, RGBA16_SFLOAT = 27, R32_UINT = 28, R32_SFLOAT = 30, RGBA32_SFLOAT = 39, R10_G10_B10_A2_UNORM = 40,
+    R8_UNORM = 0, R8_UINT = 2, RG8_UNORM = 4, RGBA8_UNORM = 8, R16_UINT = 15, R16_SFLOAT = 17, RG16_SFLOAT = 22, RGBA16_SFLOAT = 27, R32_UINT = 28, R32_SFLOAT = 30, RGBA32_SFLOAT = 39, R10_G10_B10_A2_UNORM = 40,
 };
 struct HostTexture { void* data; uint32_t width, height, pitchBytes, format; };   // same layout as the oracle's OracleTexture
 
 struct TexData {
     uint8_t* data = nullptr; int w = 0, h = 0, pitch = 0; uint32_t fmt = 0;
     bool inside(int x, int y) const { return x >= 0 && y >= 0 && x < w && y < h; }
-    int bpp() const { switch (fmt) { case R8_UNORM: return 1; case RG8_UNORM: case R16_UINT: case R16_SFLOAT: return 2; case RGBA16_SFLOAT: return 8; case RGBA32_SFLOAT: return 16; default: return 4; } }
+    int bpp() const { switch (fmt) { case R8_UNORM: case R8_UINT: return 1; case RG8_UNORM: case R16_UINT: case R16_SFLOAT: return 2; case RGBA16_SFLOAT: return 8; case RGBA32_SFLOAT: return 16; default: return 4; } }
     uint8_t* at(int x, int y) const { return data + (size_t)y * pitch + (size_t)x * bpp(); }
     float4 fetch(int x, int y) const {
         const uint8_t* p = at(x, y);
@@ -322,6 +322,7 @@ struct TexData {
             case R32_SFLOAT: { float v; memcpy(&v, p, 4); return float4(v, 0, 0, 1); }
             case RGBA32_SFLOAT: { float v[4]; memcpy(v, p, 16); return float4(v[0], v[1], v[2], v[3]); }
             case R10_G10_B10_A2_UNORM: { uint32_t v; memcpy(&v, p, 4); return float4((v & 1023u) / 1023.0f, ((v >> 10) & 1023u) / 1023.0f, ((v >> 20) & 1023u) / 1023.0f, (v >> 30) / 3.0f); }
+            case R8_UINT: return float4(floatOf((uint32_t)p[0]), 0, 0, 0);
             case R16_UINT: { uint16_t v; memcpy(&v, p, 2); return float4(floatOf(v), 0, 0, 0); }      // raw bits travel in .x for <uint> views
             case R32_UINT: { uint32_t v; memcpy(&v, p, 4); return float4(floatOf(v), 0, 0, 0); }
             default: return float4(0.0f);
@@ -341,6 +342,7 @@ struct TexData {
             case R32_SFLOAT: memcpy(p, &v.x, 4); break;
             case RGBA32_SFLOAT: { float q[4] = {v.x, v.y, v.z, v.w}; memcpy(p, q, 16); break; }
             case R10_G10_B10_A2_UNORM: { uint32_t q = unorm(v.x, 1023.0f) | (unorm(v.y, 1023.0f) << 10) | (unorm(v.z, 1023.0f) << 20) | (unorm(v.w, 3.0f) << 30); memcpy(p, &q, 4); break; }
+            case R8_UINT: { uint32_t q = bitsOf(v.x); p[0] = (uint8_t)(q > 255u ? 255u : q); break; }   // D3D clamps integer stores to the format's range
             case R16_UINT: { uint16_t q = (uint16_t)bitsOf(v.x); memcpy(p, &q, 2); break; }
             case R32_UINT: { uint32_t q = bitsOf(v.x); memcpy(p, &q, 4); break; }
             default: break;

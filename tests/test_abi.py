@@ -49,7 +49,7 @@ def test_library_desc_and_strings(host_library):
 
 def test_error_behaviour(host_library):
     # unsupported denoiser -> UNSUPPORTED (InstanceImpl.cpp:95-102); duplicate identifiers -> NON_UNIQUE_IDENTIFIER (:104-108)
-    inst = api.NrdInstance(host_library, [(0, api.Denoiser.REFERENCE)])
+    inst = api.NrdInstance(host_library, [(0, api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION)])
     assert inst.result == api.Result.UNSUPPORTED
     inst = api.NrdInstance(host_library, [(3, api.Denoiser.REBLUR_DIFFUSE_SPECULAR), (3, api.Denoiser.SIGMA_SHADOW)])
     assert inst.result == api.Result.NON_UNIQUE_IDENTIFIER

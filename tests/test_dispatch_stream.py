@@ -23,6 +23,11 @@ CASES = [
     ("reblur_split_only", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 640, 360, "split_only"),
     ("reference_720p", api.Denoiser.REFERENCE, 1280, 720, "reference"),
     ("reference_static_camera", api.Denoiser.REFERENCE, 640, 360, "reference_static"),
+    ("reblur_diffuse_1080p", api.Denoiser.REBLUR_DIFFUSE, 1920, 1080, None),
+    ("reblur_diffuse_recon_nots", api.Denoiser.REBLUR_DIFFUSE, 1000, 562, "recon_nots"),
+    ("reblur_specular_1080p", api.Denoiser.REBLUR_SPECULAR, 1920, 1080, None),
+    ("reblur_specular_cb_guides_split", api.Denoiser.REBLUR_SPECULAR, 1280, 720, "reblur_cb_guides_split"),
+    ("reblur_specular_noprepass", api.Denoiser.REBLUR_SPECULAR, 640, 360, "noprepass"),
     ("sigma_512", api.Denoiser.SIGMA_SHADOW, 512, 512, "sigma"),
     ("sigma_nostab", api.Denoiser.SIGMA_SHADOW, 640, 360, "sigma_nostab"),
     ("sigma_translucency_1080p", api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, 1920, 1080, "sigma"),
