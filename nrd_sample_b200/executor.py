@@ -31,6 +31,7 @@ NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdc
 # nrd::Format -> (torch dtype, channels) for tensors handed to / returned by the executor
 FORMAT_STORAGE = {
     api.Format.R8_UNORM: (torch.uint8, 1),
+    api.Format.R8_UINT: (torch.uint8, 1),
     api.Format.RG8_UNORM: (torch.uint8, 2),
     api.Format.RGBA8_UNORM: (torch.uint8, 4),
     api.Format.R16_UINT: (torch.int16, 1),

@@ -46,17 +46,17 @@ static int referenceDispatch(const std::string& id, const void* constants, uint3
     return 1;
 }
 
-// REBLUR_SplitScreen.cs.hlsl:21-56 (NRD_SIGNAL = BOTH, NRD_MODE = RADIANCE): the noisy input left of the split line
-static void reblurSplitScreen(const ReblurCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec, Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH) {
-    ReblurCtx c(cb);
+// REBLUR_SplitScreen.cs.hlsl:21-56 (NRD_MODE = RADIANCE): the noisy input left of the split line
+static void reblurSplitScreen(const ReblurCB& cb, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec, Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, int signal) {
+    ReblurCtx c(cb, signal);
     for (int py = 0; py < gridH * 16; py++)
         for (int px = 0; px < gridW * 8; px++) {
             float2 pixelUv = float2(px + 0.5f, py + 0.5f) * cb.gRectSizeInv;
             if (pixelUv.x > cb.gSplitScreen || px > cb.gRectSizeMinusOne.x || py > cb.gRectSizeMinusOne.y) continue;
             float viewZ = c.UnpackViewZ(gIn_ViewZ.load(px, py).x);
             float inRange = float(c.IsInDenoisingRange(viewZ));
-            gOut_Diff.store(px, py, gIn_Diff.load(px >> (cb.gDiffCheckerboard != 2 ? 1 : 0), py) * inRange);
-            gOut_Spec.store(px, py, gIn_Spec.load(px >> (cb.gSpecCheckerboard != 2 ? 1 : 0), py) * inRange);
+            if (c.hasDiff()) gOut_Diff.store(px, py, gIn_Diff.load(px >> (cb.gDiffCheckerboard != 2 ? 1 : 0), py) * inRange);
+            if (c.hasSpec()) gOut_Spec.store(px, py, gIn_Spec.load(px >> (cb.gSpecCheckerboard != 2 ? 1 : 0), py) * inRange);
         }
 }
 
@@ -91,54 +91,79 @@ __attribute__((visibility("default"))) int nrd_oracle_dispatch(const char* shade
             reblurClassifyTiles(cb, t[0], t[1], gw, gh);
             return 0;
         }
-        if (id == "REBLUR_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=0" ||
-            id == "REBLUR_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=1") {
-            if (texturesNum != 7) return 2;
-            reblurHitDistReconstruction(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], gw, gh, id.back() == '1' ? 2 : 1);
+        // "<file>|NRD_SIGNAL=<DIFF|SPEC|BOTH>|NRD_MODE=RADIANCE<suffix>": a single-lobe permutation binds only its own lobe's textures
+        // (REBLUR_*.resources.hlsli), so the compact list is spread over the full slot table: C = always bound, D / S = lobe-only
+        int signal = 0;
+        const char* sigNames[4] = {nullptr, "|NRD_SIGNAL=DIFF|NRD_MODE=RADIANCE", "|NRD_SIGNAL=SPEC|NRD_MODE=RADIANCE", "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE"};
+        std::string file, suffix;
+        for (int k = 1; k <= 3 && !signal; k++) {
+            size_t at = id.find(sigNames[k]);
+            if (at != std::string::npos) {
+                signal = k;
+                file = id.substr(0, at);
+                suffix = id.substr(at + strlen(sigNames[k]));
+            }
+        }
+        if (!signal) return 1;
+        static Tex absent;  // never dereferenced: every access to a missing lobe is behind hasDiff() / hasSpec()
+        Tex* f[25];
+        auto spread = [&](const char* slots) -> bool {
+            uint32_t next = 0;
+            size_t n = strlen(slots);
+            for (size_t i = 0; i < n; i++) {
+                const bool bound = slots[i] == 'C' || (slots[i] == 'D' && (signal & 1)) || (slots[i] == 'S' && (signal & 2));
+                if (bound && next >= texturesNum) return false;
+                f[i] = bound ? &t[next++] : &absent;
+            }
+            return next == texturesNum;
+        };
+        if (file == "REBLUR_HitDistReconstruction.cs.hlsl" && (suffix == "|MODE_5X5=0" || suffix == "|MODE_5X5=1")) {
+            if (!spread("CCCDSDS")) return 2;
+            reblurHitDistReconstruction(cb, *f[0], *f[1], *f[2], *f[3], *f[4], *f[5], *f[6], gw, gh, suffix.back() == '1' ? 2 : 1, signal);
             return 0;
         }
-        if (id == "REBLUR_PrePass.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
-            if (texturesNum != 8) return 2;
-            reblurPrePass(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], gw, gh, robust);
+        if (file == "REBLUR_PrePass.cs.hlsl" && suffix.empty()) {
+            if (!spread("CCCDSDSS")) return 2;
+            reblurPrePass(cb, *f[0], *f[1], *f[2], *f[3], *f[4], *f[5], *f[6], *f[7], gw, gh, robust, signal);
             return 0;
         }
-        if (id == "REBLUR_TemporalAccumulation.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
-            if (texturesNum != 25) return 2;
-            TaTextures a = {&t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6], &t[7], &t[8], &t[9], &t[10], &t[11], &t[12], &t[13], &t[14], &t[15], &t[16], &t[17],
-                            &t[18], &t[19], &t[20], &t[21], &t[22], &t[23], &t[24]};
-            reblurTemporalAccumulation(cb, a, gw, gh);
+        if (file == "REBLUR_TemporalAccumulation.cs.hlsl" && suffix.empty()) {
+            if (!spread("CCCCCCCCDSDSDSDSSSCDSDSSC")) return 2;
+            TaTextures a = {f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], f[9], f[10], f[11], f[12], f[13], f[14], f[15], f[16], f[17],
+                            f[18], f[19], f[20], f[21], f[22], f[23], f[24]};
+            reblurTemporalAccumulation(cb, a, gw, gh, signal);
             return 0;
         }
-        if (id == "REBLUR_HistoryFix.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
-            if (texturesNum != 13) return 2;
-            HfTextures a = {&t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6], &t[7], &t[8], &t[9], &t[10], &t[11], &t[12]};
-            reblurHistoryFix(cb, a, gw, gh, quads);
+        if (file == "REBLUR_HistoryFix.cs.hlsl" && suffix.empty()) {
+            if (!spread("CCCCDSDSSDSDS")) return 2;
+            HfTextures a = {f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], f[9], f[10], f[11], f[12]};
+            reblurHistoryFix(cb, a, gw, gh, quads, signal);
             return 0;
         }
-        if (id == "REBLUR_Blur.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
-            if (texturesNum != 9) return 2;
-            reblurBlur(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], gw, gh, quads, robust);
+        if (file == "REBLUR_Blur.cs.hlsl" && suffix.empty()) {
+            if (!spread("CCCCDSCDS")) return 2;
+            reblurBlur(cb, *f[0], *f[1], *f[2], *f[3], *f[4], *f[5], *f[6], *f[7], *f[8], gw, gh, quads, robust, signal);
             return 0;
         }
-        if (id == "REBLUR_PostBlur.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|TEMPORAL_STABILIZATION=1") {
-            if (texturesNum != 9) return 2;
-            reblurPostBlur(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], nullptr, nullptr, nullptr, true, gw, gh, quads, robust);
+        if (file == "REBLUR_PostBlur.cs.hlsl" && suffix == "|TEMPORAL_STABILIZATION=1") {
+            if (!spread("CCCCDSCDS")) return 2;
+            reblurPostBlur(cb, *f[0], *f[1], *f[2], *f[3], *f[4], *f[5], *f[6], *f[7], *f[8], nullptr, nullptr, nullptr, true, gw, gh, quads, robust, signal);
             return 0;
         }
-        if (id == "REBLUR_PostBlur.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|TEMPORAL_STABILIZATION=0") {
-            if (texturesNum != 12) return 2;
-            reblurPostBlur(cb, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], &t[9], &t[10], &t[11], false, gw, gh, quads, robust);
+        if (file == "REBLUR_PostBlur.cs.hlsl" && suffix == "|TEMPORAL_STABILIZATION=0") {
+            if (!spread("CCCCDSCDSCDS")) return 2;
+            reblurPostBlur(cb, *f[0], *f[1], *f[2], *f[3], *f[4], *f[5], *f[6], *f[7], *f[8], f[9], f[10], f[11], false, gw, gh, quads, robust, signal);
             return 0;
         }
-        if (id == "REBLUR_SplitScreen.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
-            if (texturesNum != 5) return 2;
-            reblurSplitScreen(cb, t[0], t[1], t[2], t[3], t[4], gw, gh);
+        if (file == "REBLUR_SplitScreen.cs.hlsl" && suffix.empty()) {
+            if (!spread("CDSDS")) return 2;
+            reblurSplitScreen(cb, *f[0], *f[1], *f[2], *f[3], *f[4], gw, gh, signal);
             return 0;
         }
-        if (id == "REBLUR_TemporalStabilization.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") {
-            if (texturesNum != 16) return 2;
-            TsTextures a = {&t[0], &t[1], &t[2], &t[3], &t[4], &t[5], &t[6], &t[7], &t[8], &t[9], &t[10], &t[11], &t[12], &t[13], &t[14], &t[15]};
-            reblurTemporalStabilization(cb, a, gw, gh);
+        if (file == "REBLUR_TemporalStabilization.cs.hlsl" && suffix.empty()) {
+            if (!spread("CCCCCSDSDSCCDSDS")) return 2;
+            TsTextures a = {f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], f[9], f[10], f[11], f[12], f[13], f[14], f[15]};
+            reblurTemporalStabilization(cb, a, gw, gh, signal);
             return 0;
         }
         return 1;

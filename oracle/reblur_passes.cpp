@@ -258,8 +258,8 @@ static void spatialCenter(const ReblurCtx& c, SpatialCommon& s, const Tex& gIn_N
 // REBLUR_HitDistReconstruction.cs.hlsl:21-167 (NRD_SIGNAL = BOTH, RADIANCE, REBLUR_USE_DECOMPRESSED_HIT_DIST_IN_RECONSTRUCTION = 0,
 // REBLUR_PERFORMANCE_MODE = 0). `border` = 1 (3x3) or 2 (5x5). The shared-memory tile holds f( clamp( pos, 0, rectSizeMinusOne ) ).
 void reblurHitDistReconstruction(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec,
-                                 Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, int border) {
-    ReblurCtx c(cb);
+                                 Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, int border, int signal) {
+    ReblurCtx c(cb, signal);
     auto clampPos = [&](int& x, int& y) {
         x = x < 0 ? 0 : (x > cb.gRectSizeMinusOne.x ? cb.gRectSizeMinusOne.x : x);
         y = y < 0 ? 0 : (y > cb.gRectSizeMinusOne.y ? cb.gRectSizeMinusOne.y : y);
@@ -267,7 +267,9 @@ void reblurHitDistReconstruction(const ReblurCB& cb, const Tex& gIn_Tiles, const
     auto hitDistViewZ = [&](int x, int y) {  // Preload( ): { diff hitDist, spec hitDist, viewZ }, hit distances zeroed outside the denoising range
         clampPos(x, y);
         float viewZ = c.UnpackViewZ(gIn_ViewZ.load(x, y).x);
-        float2 hitDist = float2(gIn_Diff.load(x, y).w, gIn_Spec.load(x, y).w);
+        float2 hitDist = float2(0.0f);  // :33-48: the lobe the denoiser does not have stays 0
+        if (c.hasDiff()) hitDist.x = gIn_Diff.load(x, y).w;
+        if (c.hasSpec()) hitDist.y = gIn_Spec.load(x, y).w;
         if (!c.IsInDenoisingRange(viewZ)) hitDist = float2(0.0f);
         return float3(hitDist.x, hitDist.y, viewZ);
     };
@@ -324,15 +326,14 @@ void reblurHitDistReconstruction(const ReblurCB& cb, const Tex& gIn_Tiles, const
                     sum += ww;
                 }
             acc = acc / max(sum, float2(NRD_EPS));
-            float4 diff = gIn_Diff.load(px, py), spec = gIn_Spec.load(px, py);
-            gOut_Diff.store(px, py, float4(diff.xyz(), acc.x));
-            gOut_Spec.store(px, py, float4(spec.xyz(), acc.y));
+            if (c.hasDiff()) gOut_Diff.store(px, py, float4(gIn_Diff.load(px, py).xyz(), acc.x));  // :150-166
+            if (c.hasSpec()) gOut_Spec.store(px, py, float4(gIn_Spec.load(px, py).xyz(), acc.y));
         }
 }
 
 void reblurPrePass(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec,
-                   Tex& gOut_Diff, Tex& gOut_Spec, Tex& gOut_SpecHitDistForTracking, int gridW, int gridH, bool robust) {
-    ReblurCtx c(cb);
+                   Tex& gOut_Diff, Tex& gOut_Spec, Tex& gOut_SpecHitDistForTracking, int gridW, int gridH, bool robust, int signal) {
+    ReblurCtx c(cb, signal);
     const int W = gridW * 16, H = gridH * 16;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int py = 0; py < H; py++)
@@ -360,15 +361,15 @@ void reblurPrePass(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Norm
                 s.checkerboardX0 = x0 >> 1;
                 s.checkerboardX1 = x1 >> 1;
             }
-            spatialFilter<PRE_PASS, DIFF>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Diff, gOut_Diff, nullptr, nullptr, true, robust);
-            spatialFilter<PRE_PASS, SPEC>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Spec, gOut_Spec, &gOut_SpecHitDistForTracking, nullptr, true, robust);
+            if (c.hasDiff()) spatialFilter<PRE_PASS, DIFF>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Diff, gOut_Diff, nullptr, nullptr, true, robust);  // :75-79
+            if (c.hasSpec()) spatialFilter<PRE_PASS, SPEC>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Spec, gOut_Spec, &gOut_SpecHitDistForTracking, nullptr, true, robust);  // :81-85
         }
 }
 
 // Value each lane holds when the quad exchange happens in Blur / PostBlur
 static float2 blurNonLinearAccumSpeed(const ReblurCtx& c, const Tex& gIn_Data1, const Tex& viewZTex, int px, int py, float2* data1Out, float* viewZOut) {
     float4 d = gIn_Data1.load(px, py);
-    float2 data1 = ReblurCtx::UnpackData1(float2(d.x, d.y));
+    float2 data1 = ReblurCtx::UnpackData1(float2(d.x, d.y), c.signal);
     float2 n = float2(c.GetAdvancedNonLinearAccumSpeed(data1.x), c.GetAdvancedNonLinearAccumSpeed(data1.y));
     float viewZ = c.UnpackViewZ(viewZTex.load(px, py).x);
     if (!c.IsInDenoisingRange(viewZ)) n = float2(0.0f);
@@ -380,8 +381,8 @@ static float2 blurNonLinearAccumSpeed(const ReblurCtx& c, const Tex& gIn_Data1, 
 template <int PASS>
 static void blurLike(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Data1, const Tex& gIn_Diff,
                      const Tex& gIn_Spec, Tex* gOut_ViewZ, Tex* gOut_Normal_Roughness, Tex* gOut_InternalData, Tex& gOut_Diff, Tex& gOut_Spec, Tex* gOut_DiffCopy,
-                     Tex* gOut_SpecCopy, bool temporalStabilization, int gridW, int gridH, bool quads, bool robust) {
-    ReblurCtx c(cb);
+                     Tex* gOut_SpecCopy, bool temporalStabilization, int gridW, int gridH, bool quads, bool robust, int signal) {
+    ReblurCtx c(cb, signal);
     const int W = gridW * 8, H = gridH * 16;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int py = 0; py < H; py++)
@@ -411,22 +412,22 @@ static void blurLike(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_No
                 gOut_Normal_Roughness->store(px, py, gIn_Normal_Roughness.load(px, py));  // same format: re-quantisation is the identity
                 if (!temporalStabilization) gOut_InternalData->storeUint(px, py, c.PackInternalData(s.data1.x, s.data1.y, s.materialID));
             }
-            spatialFilter<PASS, DIFF>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Diff, gOut_Diff, nullptr, gOut_DiffCopy, temporalStabilization, robust);
-            spatialFilter<PASS, SPEC>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Spec, gOut_Spec, nullptr, gOut_SpecCopy, temporalStabilization, robust);
+            if (c.hasDiff()) spatialFilter<PASS, DIFF>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Diff, gOut_Diff, nullptr, gOut_DiffCopy, temporalStabilization, robust);
+            if (c.hasSpec()) spatialFilter<PASS, SPEC>(c, s, gIn_ViewZ, gIn_Normal_Roughness, gIn_Spec, gOut_Spec, nullptr, gOut_SpecCopy, temporalStabilization, robust);
         }
 }
 
 void reblurBlur(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Data1, const Tex& gIn_Diff,
-                const Tex& gIn_Spec, Tex& gOut_ViewZ, Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, bool quads, bool robust) {
+                const Tex& gIn_Spec, Tex& gOut_ViewZ, Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, bool quads, bool robust, int signal) {
     blurLike<BLUR>(cb, gIn_Tiles, gIn_Normal_Roughness, gIn_ViewZ, gIn_Data1, gIn_Diff, gIn_Spec, &gOut_ViewZ, nullptr, nullptr, gOut_Diff, gOut_Spec, nullptr, nullptr,
-                   true, gridW, gridH, quads, robust);
+                   true, gridW, gridH, quads, robust, signal);
 }
 
 void reblurPostBlur(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_Data1, const Tex& gIn_ViewZ, const Tex& gIn_Diff,
                     const Tex& gIn_Spec, Tex& gOut_Normal_Roughness, Tex& gOut_Diff, Tex& gOut_Spec, Tex* gOut_InternalData, Tex* gOut_DiffCopy, Tex* gOut_SpecCopy,
-                    bool temporalStabilization, int gridW, int gridH, bool quads, bool robust) {
+                    bool temporalStabilization, int gridW, int gridH, bool quads, bool robust, int signal) {
     blurLike<POST_BLUR>(cb, gIn_Tiles, gIn_Normal_Roughness, gIn_ViewZ, gIn_Data1, gIn_Diff, gIn_Spec, nullptr, &gOut_Normal_Roughness, gOut_InternalData, gOut_Diff,
-                        gOut_Spec, gOut_DiffCopy, gOut_SpecCopy, temporalStabilization, gridW, gridH, quads, robust);
+                        gOut_Spec, gOut_DiffCopy, gOut_SpecCopy, temporalStabilization, gridW, gridH, quads, robust, signal);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -440,6 +441,7 @@ float4 taPreload(const ReblurCtx& c, const TaTextures& t, int gx, int gy) {
     gx = clampi(gx, 0, cb.gRectSizeMinusOne.x);
     gy = clampi(gy, 0, cb.gRectSizeMinusOne.y);
     float3 N = unpackNR(*t.gIn_Normal_Roughness, gx, gy).xyz();
+    if (!c.hasSpec()) return float4(N, 0.0f);  // TA:43-63: the tracking distance is a specular-only quantity
     float4 spec = t.gIn_Spec->load(gx, gy);
     float hitDist = cb.gSpecPrepassBlurRadius == 0.0f ? spec.w : t.gIn_SpecHitDistForTracking->load(gx, gy).x;
     float viewZ = c.UnpackViewZ(t.gIn_ViewZ->load(gx, gy).x);
@@ -504,10 +506,12 @@ static void taPixel(const ReblurCtx& c, const TaTextures& t, int px, int py) {
     RngHash rng;
     rng.Initialize((uint32_t)px, (uint32_t)py, cb.gFrameIndex);
 
-    hitDistForTracking = hitDistForTracking == NRD_INF ? 0.0f : hitDistForTracking;
-    float hitDistNormalization = _REBLUR_GetHitDistanceNormalization(viewZ, cb.gHitDistSettings.xyz(), roughness);
-    hitDistForTracking *= cb.gSpecPrepassBlurRadius == 0.0f ? hitDistNormalization : 1.0f;
-    t.gOut_SpecHitDistForTracking->store(px, py, float4(hitDistForTracking));
+    const float hitDistNormalization = _REBLUR_GetHitDistanceNormalization(viewZ, cb.gHitDistSettings.xyz(), roughness);
+    if (c.hasSpec()) {  // TA:123-142
+        hitDistForTracking = hitDistForTracking == NRD_INF ? 0.0f : hitDistForTracking;
+        hitDistForTracking *= cb.gSpecPrepassBlurRadius == 0.0f ? hitDistNormalization : 1.0f;
+        t.gOut_SpecHitDistForTracking->store(px, py, float4(hitDistForTracking));
+    }
 
     // Previous position and surface motion uv
     float4 mvRaw = t.gIn_Mv->load(px, py);
@@ -645,8 +649,8 @@ static void taPixel(const ReblurCtx& c, const TaTextures& t, int px, int py) {
     smbFootprintQuality *= sizeQuality;
 
     // ---------------------------------------------------------------------------------------------- Specular
-    float specAccumSpeedCorrected, curvature, virtualHistoryAmount;
-    {
+    float specAccumSpeedCorrected = 0.0f, curvature = 0.0f, virtualHistoryAmount = 0.0f;  // TA:869-873 for a diffuse-only denoiser
+    if (c.hasSpec()) {
         float smbSpecHistoryConfidence = smbFootprintQuality;
         if (cb.gHasHistoryConfidence) {
             float confidence = saturate(t.gIn_SpecConfidence->sampleLinear(smbPixelUv).x);
@@ -985,10 +989,11 @@ static void taPixel(const ReblurCtx& c, const TaTextures& t, int px, int py) {
         }
     }
 
-    t.gOut_Data2->storeUint(px, py, ReblurCtx::PackData2(fbits, curvature, virtualHistoryAmount, smbAllowCatRom));
+    t.gOut_Data2->storeUint(px, py, ReblurCtx::PackData2(fbits, curvature, virtualHistoryAmount, smbAllowCatRom, c.signal));
 
     // ---------------------------------------------------------------------------------------------- Diffuse
-    {
+    if (!c.hasDiff()) diffAccumSpeed = 0.0f;  // TA:972-974
+    else {
         float diffHistoryConfidence = smbFootprintQuality;
         if (cb.gHasHistoryConfidence) {
             float confidence = saturate(t.gIn_DiffConfidence->sampleLinear(smbPixelUv).x);
@@ -1038,12 +1043,12 @@ static void taPixel(const ReblurCtx& c, const TaTextures& t, int px, int py) {
         }
     }
 
-    float2 d1 = ReblurCtx::PackData1(diffAccumSpeed, specAccumSpeedCorrected);
+    float2 d1 = ReblurCtx::PackData1(diffAccumSpeed, specAccumSpeedCorrected, c.signal);
     t.gOut_Data1->store(px, py, float4(d1.x, d1.y, 0, 0));
 }
 
-void reblurTemporalAccumulation(const ReblurCB& cb, const TaTextures& t, int gridW, int gridH) {
-    ReblurCtx c(cb);
+void reblurTemporalAccumulation(const ReblurCB& cb, const TaTextures& t, int gridW, int gridH, int signal) {
+    ReblurCtx c(cb, signal);
     const int W = gridW * 8, H = gridH * 16;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int py = 0; py < H; py++)
@@ -1069,7 +1074,7 @@ float hfSmemLuma(const ReblurCtx& c, const HfTextures& t, const Tex& fast, int g
 // value each lane contributes to the quad exchange: ( frameNum < gHistoryFixFrameNum )
 float2 hfStridePreQuad(const ReblurCtx& c, const HfTextures& t, int px, int py, float2* frameNumOut, float* viewZOut) {
     float4 d = t.gIn_Data1->load(px, py);
-    float2 frameNum = ReblurCtx::UnpackData1(float2(d.x, d.y));
+    float2 frameNum = ReblurCtx::UnpackData1(float2(d.x, d.y), c.signal);
     float viewZ = c.UnpackViewZ(t.gIn_ViewZ->load(px, py).x);
     if (!c.IsInDenoisingRange(viewZ)) frameNum = float2((float)REBLUR_MAX_ACCUM_FRAME_NUM);
     if (frameNumOut) *frameNumOut = frameNum;
@@ -1138,7 +1143,7 @@ static void hfLobe(const ReblurCtx& c, const HfTextures& t, int px, int py, floa
                 if (LOBE == SPEC) w *= ComputeExponentialWeight(Ns.w * Ns.w, relaxedRoughnessWeightParams.x, relaxedRoughnessWeightParams.y);
 
                 float4 d1 = t.gIn_Data1->load(pos);
-                float2 fn = ReblurCtx::UnpackData1(float2(d1.x, d1.y));
+                float2 fn = ReblurCtx::UnpackData1(float2(d1.x, d1.y), c.signal);
                 w *= 1.0f + (LOBE == DIFF ? fn.x : fn.y);
 
                 w = c.ApplyGeometryWeightLast(w, zs, NoX, geometryWeightParams);
@@ -1206,8 +1211,8 @@ static void hfLobe(const ReblurCtx& c, const HfTextures& t, int px, int py, floa
     OUT.store(px, py, v);
 }
 
-void reblurHistoryFix(const ReblurCB& cb, const HfTextures& t, int gridW, int gridH, bool quads) {
-    ReblurCtx c(cb);
+void reblurHistoryFix(const ReblurCB& cb, const HfTextures& t, int gridW, int gridH, bool quads, int signal) {
+    ReblurCtx c(cb, signal);
     const int W = gridW * 8, H = gridH * 16;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int py = 0; py < H; py++)
@@ -1243,8 +1248,8 @@ void reblurHistoryFix(const ReblurCB& cb, const HfTextures& t, int gridW, int gr
             stride *= 2.0f / 2.0f;  // REBLUR_HISTORY_FIX_FILTER_RADIUS = 2
             stride *= materialID == cb.gHistoryFixAlternatePixelStrideMaterialID ? cb.gHistoryFixAlternatePixelStride : cb.gHistoryFixBasePixelStride;
 
-            hfLobe<DIFF>(c, t, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
-            hfLobe<SPEC>(c, t, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+            if (c.hasDiff()) hfLobe<DIFF>(c, t, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+            if (c.hasSpec()) hfLobe<SPEC>(c, t, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
         }
 }
 
@@ -1309,8 +1314,8 @@ static void tsPixel(const ReblurCtx& c, const TsTextures& t, int px, int py) {
     uint32_t bits;
     bool smbAllowCatRom;
     float4 d1 = t.gIn_Data1->load(px, py);
-    float2 data1 = ReblurCtx::UnpackData1(float2(d1.x, d1.y));
-    float2 data2 = ReblurCtx::UnpackData2(t.gIn_Data2->loadUint(px, py), bits, smbAllowCatRom);
+    float2 data1 = ReblurCtx::UnpackData1(float2(d1.x, d1.y), c.signal);
+    float2 data2 = ReblurCtx::UnpackData2(t.gIn_Data2->loadUint(px, py), bits, smbAllowCatRom, c.signal);
 
     Filtering::Bilinear smbBilinearFilter = Filtering::GetBilinearFilter(smbPixelUv, cb.gRectSizePrev);
     float4 smbOcclusion = float4(float((bits & 1u) != 0), float((bits & 2u) != 0), float((bits & 4u) != 0), float((bits & 8u) != 0));
@@ -1319,7 +1324,7 @@ static void tsPixel(const ReblurCtx& c, const TsTextures& t, int px, int py) {
     smbFootprintQuality = Math::Sqrt01(smbFootprintQuality);
 
     // Diffuse
-    {
+    if (c.hasDiff()) {
         float diffLuma, diffLumaM1, diffLumaSigma;
         tsMoments(c, t, *t.gIn_Diff, px, py, diffLuma, diffLumaM1, diffLumaSigma);
 
@@ -1350,7 +1355,7 @@ static void tsPixel(const ReblurCtx& c, const TsTextures& t, int px, int py) {
     }
 
     // Specular
-    {
+    if (c.hasSpec()) {
         float specLuma, specLumaM1, specLumaSigma;
         tsMoments(c, t, *t.gIn_Spec, px, py, specLuma, specLumaM1, specLumaSigma);
 
@@ -1414,8 +1419,8 @@ static void tsPixel(const ReblurCtx& c, const TsTextures& t, int px, int py) {
     t.gOut_InternalData->storeUint(px, py, c.PackInternalData(data1.x, data1.y, materialID));
 }
 
-void reblurTemporalStabilization(const ReblurCB& cb, const TsTextures& t, int gridW, int gridH) {
-    ReblurCtx c(cb);
+void reblurTemporalStabilization(const ReblurCB& cb, const TsTextures& t, int gridW, int gridH, int signal) {
+    ReblurCtx c(cb, signal);
     const int W = gridW * 8, H = gridH * 16;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int py = 0; py < H; py++)

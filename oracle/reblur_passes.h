@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE — CPU oracle (see hlsl_like.h). Binding tables and entry points of reblur_passes.cpp.
 // Member order == shader register order == DispatchDesc::resources order (REBLUR_*.resources.hlsli).
+// `signal` = NRD_SIGNAL of the permutation (1 DIFF, 2 SPEC, 3 BOTH): bindings of the lobe a denoiser does not have are never touched.
 #pragma once
 #include "reblur_shared.h"
 
@@ -25,17 +26,17 @@ struct TsTextures {
 
 void reblurClassifyTiles(const ReblurCB& cb, const Tex& gIn_ViewZ, Tex& gOut_Tiles, int gridW, int gridH);
 void reblurHitDistReconstruction(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec,
-                                 Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, int border);
+                                 Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, int border, int signal = 3);
 void reblurPrePass(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Diff, const Tex& gIn_Spec,
-                   Tex& gOut_Diff, Tex& gOut_Spec, Tex& gOut_SpecHitDistForTracking, int gridW, int gridH, bool robustMirrorTest);
+                   Tex& gOut_Diff, Tex& gOut_Spec, Tex& gOut_SpecHitDistForTracking, int gridW, int gridH, bool robustMirrorTest, int signal = 3);
 void reblurBlur(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_ViewZ, const Tex& gIn_Data1, const Tex& gIn_Diff,
-                const Tex& gIn_Spec, Tex& gOut_ViewZ, Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, bool quads, bool robustMirrorTest);
+                const Tex& gIn_Spec, Tex& gOut_ViewZ, Tex& gOut_Diff, Tex& gOut_Spec, int gridW, int gridH, bool quads, bool robustMirrorTest, int signal = 3);
 void reblurPostBlur(const ReblurCB& cb, const Tex& gIn_Tiles, const Tex& gIn_Normal_Roughness, const Tex& gIn_Data1, const Tex& gIn_ViewZ, const Tex& gIn_Diff,
                     const Tex& gIn_Spec, Tex& gOut_Normal_Roughness, Tex& gOut_Diff, Tex& gOut_Spec, Tex* gOut_InternalData, Tex* gOut_DiffCopy, Tex* gOut_SpecCopy,
-                    bool temporalStabilization, int gridW, int gridH, bool quads, bool robustMirrorTest);
-void reblurTemporalAccumulation(const ReblurCB& cb, const TaTextures& t, int gridW, int gridH);
-void reblurHistoryFix(const ReblurCB& cb, const HfTextures& t, int gridW, int gridH, bool quads);
-void reblurTemporalStabilization(const ReblurCB& cb, const TsTextures& t, int gridW, int gridH);
+                    bool temporalStabilization, int gridW, int gridH, bool quads, bool robustMirrorTest, int signal = 3);
+void reblurTemporalAccumulation(const ReblurCB& cb, const TaTextures& t, int gridW, int gridH, int signal = 3);
+void reblurHistoryFix(const ReblurCB& cb, const HfTextures& t, int gridW, int gridH, bool quads, int signal = 3);
+void reblurTemporalStabilization(const ReblurCB& cb, const TsTextures& t, int gridW, int gridH, int signal = 3);
 void clearTexture(Tex& out);
 
 }  // namespace orc

@@ -43,7 +43,10 @@ static const float REBLUR_MAX_PERCENT_OF_LOBE_VOLUME_FOR_PRE_PASS = 0.3f;
 // Everything below closes over one frame's constants, the way the shaders see the cbuffer as globals.
 struct ReblurCtx {
     const ReblurCB& cb;
-    explicit ReblurCtx(const ReblurCB& c) : cb(c) {}
+    const int signal;  // NRD_SIGNAL: 1 = DIFF, 2 = SPEC, 3 = BOTH (NRD.hlsli:338-339)
+    explicit ReblurCtx(const ReblurCB& c, int sig = 3) : cb(c), signal(sig) {}
+    bool hasDiff() const { return (signal & 1) != 0; }
+    bool hasSpec() const { return (signal & 2) != 0; }
 
     float UnpackViewZ(float z) const { return std::fabs(z * cb.gViewZScale); }            // common:261
     bool IsInDenoisingRange(float z) const { return z < cb.gDenoisingRange; }             // common:262 (false for NaN)
@@ -66,20 +69,29 @@ struct ReblurCtx {
         float4 t = Packing::UintToRgba(p, 6, 6, 4, 0);
         return float3(hlsl_round(t.x * REBLUR_MAX_ACCUM_FRAME_NUM), hlsl_round(t.y * REBLUR_MAX_ACCUM_FRAME_NUM), t.z * REBLUR_MAX_MATERIALID_NUM);
     }
-    static float2 PackData1(float diffAccumSpeed, float specAccumSpeed) {  // :42
-        return float2(saturate(hlsl_round(diffAccumSpeed) / REBLUR_MAX_ACCUM_FRAME_NUM), saturate(hlsl_round(specAccumSpeed) / REBLUR_MAX_ACCUM_FRAME_NUM));
+    // `signal` = NRD_SIGNAL of the permutation: a specular-only denoiser keeps its one value in .x of an R8_UNORM texture (:48-51, :58-61),
+    // a diffuse-only one stores data2 in 8 bits with the CatRom flag in bit 4 instead of 15 (:69-73)
+    static float2 PackData1(float diffAccumSpeed, float specAccumSpeed, int signal = 3) {  // :42
+        float2 r = float2(saturate(hlsl_round(diffAccumSpeed) / REBLUR_MAX_ACCUM_FRAME_NUM), saturate(hlsl_round(specAccumSpeed) / REBLUR_MAX_ACCUM_FRAME_NUM));
+        if (!(signal & 1)) r.x = r.y;
+        return r;
     }
-    static float2 UnpackData1(float2 p) { return float2(hlsl_round(p.x * REBLUR_MAX_ACCUM_FRAME_NUM), hlsl_round(p.y * REBLUR_MAX_ACCUM_FRAME_NUM)); }  // :56
-    static uint32_t PackData2(float fbits, float curvature, float virtualHistoryAmount, bool smbAllowCatRom) {  // :75 (NRD_SPEC: bit 15)
+    static float2 UnpackData1(float2 p, int signal = 3) {  // :56
+        if (!(signal & 1)) p.y = p.x;
+        return float2(hlsl_round(p.x * REBLUR_MAX_ACCUM_FRAME_NUM), hlsl_round(p.y * REBLUR_MAX_ACCUM_FRAME_NUM));
+    }
+    static uint32_t PackData2(float fbits, float curvature, float virtualHistoryAmount, bool smbAllowCatRom, int signal = 3) {  // :75
+        const uint32_t smbAllowCatRomBit = (signal & 2) ? 15u : 4u;
         uint32_t p = (uint32_t)(fbits + 0.5f);
         p |= (uint32_t)(saturate(virtualHistoryAmount) * 127.0f + 0.5f) << 8;
-        p |= smbAllowCatRom ? (1u << 15) : 0u;
+        p |= smbAllowCatRom ? (1u << smbAllowCatRomBit) : 0u;
         p |= (uint32_t)f32tof16(curvature) << 16;
         return p;
     }
-    static float2 UnpackData2(uint32_t p, uint32_t& bits, bool& smbAllowCatRom) {  // :92
+    static float2 UnpackData2(uint32_t p, uint32_t& bits, bool& smbAllowCatRom, int signal = 3) {  // :92
+        const uint32_t smbAllowCatRomBit = (signal & 2) ? 15u : 4u;
         bits = p & 0xFFu;
-        smbAllowCatRom = (p & (1u << 15)) != 0;
+        smbAllowCatRom = (p & (1u << smbAllowCatRomBit)) != 0;
         return float2(float((p >> 8) & 127u) / 127.0f, f16tof32(p >> 16));
     }
     float3 GetViewVector(float3 X, bool isViewSpace = false) const {  // :105

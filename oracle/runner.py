@@ -86,6 +86,7 @@ def ref_shader_names() -> List[str]:
 # nrd::Format -> (torch dtype, channels)
 FORMAT_STORAGE = {
     api.Format.R8_UNORM: (torch.uint8, 1),
+    api.Format.R8_UINT: (torch.uint8, 1),
     api.Format.RG8_UNORM: (torch.uint8, 2),
     api.Format.RGBA8_UNORM: (torch.uint8, 4),
     api.Format.R16_UINT: (torch.int16, 1),

@@ -14,6 +14,7 @@ namespace orc {
 
 enum Fmt : uint32_t {  // numeric values = nrd::Format
     FMT_R8_UNORM = 0,
+    FMT_R8_UINT = 2,
     FMT_RG8_UNORM = 4,
     FMT_RGBA8_UNORM = 8,
     FMT_R16_UINT = 15,
@@ -66,6 +67,7 @@ struct Tex {
         }
     }
     uint32_t fetchUint(int x, int y) const {
+        if (fmt == FMT_R8_UINT) return *at(x, y, 1);
         if (fmt == FMT_R16_UINT) { uint16_t v; memcpy(&v, at(x, y, 2), 2); return v; }
         if (fmt == FMT_R32_UINT) { uint32_t v; memcpy(&v, at(x, y, 4), 4); return v; }
         return 0;
@@ -115,13 +117,14 @@ struct Tex {
     void store(int2 p, float4 v) { store(p.x, p.y, v); }
     void storeUint(int x, int y, uint32_t v) {
         if (!inside(x, y)) return;
-        if (fmt == FMT_R16_UINT) { uint16_t q = (uint16_t)v; memcpy(at(x, y, 2), &q, 2); }
+        if (fmt == FMT_R8_UINT) *at(x, y, 1) = (uint8_t)(v > 255u ? 255u : v);  // D3D clamps integer stores to the format's range
+        else if (fmt == FMT_R16_UINT) { uint16_t q = (uint16_t)v; memcpy(at(x, y, 2), &q, 2); }
         else if (fmt == FMT_R32_UINT) memcpy(at(x, y, 4), &v, 4);
     }
     // raw copy of one texel between same-format textures (used where a shader forwards a packed value untouched)
     int bytesPerTexel() const {
         switch (fmt) {
-            case FMT_R8_UNORM: return 1;
+            case FMT_R8_UNORM: case FMT_R8_UINT: return 1;
             case FMT_RG8_UNORM: case FMT_R16_UINT: case FMT_R16_SFLOAT: return 2;
             case FMT_RGBA16_SFLOAT: return 8;
             case FMT_RGBA32_SFLOAT: return 16;

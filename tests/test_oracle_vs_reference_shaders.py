@@ -17,8 +17,16 @@ from oracle import runner
 RT = api.ResourceType
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
+def one_lobe(lobe):
+    """synth.reblur_frame without the inputs of the other lobe ( REBLUR_DIFFUSE / REBLUR_SPECULAR )"""
+    other = "SPEC" if lobe == "DIFF" else "DIFF"
+    return lambda *a, **k: {key: v for key, v in synth.reblur_frame(*a, **k).items() if f"_{other}_" not in key}
+
+
 DENOISERS = {
     "reblur": (api.Denoiser.REBLUR_DIFFUSE_SPECULAR, synth.reblur_frame, ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST")),
+    "reblur_diff": (api.Denoiser.REBLUR_DIFFUSE, one_lobe("DIFF"), ("OUT_DIFF_RADIANCE_HITDIST",)),
+    "reblur_spec": (api.Denoiser.REBLUR_SPECULAR, one_lobe("SPEC"), ("OUT_SPEC_RADIANCE_HITDIST",)),
     "sigma": (api.Denoiser.SIGMA_SHADOW, synth.sigma_frame, ("OUT_SHADOW_TRANSLUCENCY",)),
     "relax": (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, synth.relax_frame, ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1")),
     "reference": (api.Denoiser.REFERENCE, synth.reference_frame, ("OUT_SIGNAL",)),
@@ -47,6 +55,14 @@ CASES = [
     ("reblur_confidence_checkerboard", "reblur", 96, 64, 4, lambda: api.ReblurSettings(checkerboardMode=2), {"guides": True, "checkerboard": 2, "cs_isHistoryConfidenceAvailable": True}),
     ("reblur_split_screen", "reblur", 96, 64, 3, None, {"cs_splitScreen": 0.4}),
     ("reblur_split_screen_checkerboard_full", "reblur", 96, 64, 2, lambda: api.ReblurSettings(checkerboardMode=1), {"checkerboard": 1, "cs_splitScreen": 1.0}),
+    ("reblur_diffuse_default", "reblur_diff", 96, 64, 5, None, {}),
+    ("reblur_diffuse_recon3x3_no_stabilization_odd_size", "reblur_diff", 100, 75, 4, lambda: api.ReblurSettings(hitDistanceReconstructionMode=1, maxStabilizedFrameNum=0), {"holes": True}),
+    ("reblur_diffuse_checkerboard_guides_split", "reblur_diff", 96, 64, 4, lambda: api.ReblurSettings(checkerboardMode=2),
+     {"guides": True, "checkerboard": 2, "cs_isHistoryConfidenceAvailable": True, "cs_isDisocclusionThresholdMixAvailable": True, "cs_splitScreen": 0.4}),
+    ("reblur_specular_default", "reblur_spec", 96, 64, 5, None, {}),
+    ("reblur_specular_recon5x5_no_stabilization_odd_size", "reblur_spec", 100, 75, 4, lambda: api.ReblurSettings(hitDistanceReconstructionMode=2, maxStabilizedFrameNum=0), {"holes": True}),
+    ("reblur_specular_checkerboard_guides_no_prepass", "reblur_spec", 96, 64, 4, lambda: api.ReblurSettings(checkerboardMode=1, specularPrepassBlurRadius=0.0),
+     {"guides": True, "checkerboard": 1, "cs_isHistoryConfidenceAvailable": True, "cs_isDisocclusionThresholdMixAvailable": True}),
     # "cs_static": the camera of frame 0 every frame, so the REFERENCE accumulator actually accumulates ( Reference.hpp:62-68 )
     ("reference_static_camera_split", "reference", 100, 75, 5, lambda: api.ReferenceSettings(maxAccumulatedFrameNum=3), {"cs_static": True, "cs_splitScreen": 0.3}),
     ("reference_moving_camera", "reference", 96, 64, 3, None, {}),
@@ -137,7 +153,7 @@ def test_oracle_is_bit_identical_to_the_reference_shaders_per_dispatch(label, wh
 
 
 @needs_refshaders
-@pytest.mark.parametrize("which", ["reblur", "sigma", "relax", "sigma_tr"])
+@pytest.mark.parametrize("which", ["reblur", "reblur_diff", "reblur_spec", "sigma", "relax", "sigma_tr"])
 def test_closed_loop_with_the_reference_shaders_as_the_engine(which):
     """The whole recurrence (history feedback) executed by the reference's shaders, against the oracle: final outputs identical."""
     w, h, frames = 112, 80, 5
