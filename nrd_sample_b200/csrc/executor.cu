@@ -21,14 +21,14 @@ namespace nrdk {
 // kernels/*.cu
 void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t stream);
 void launchReblurClassifyTiles(const ReblurConstants&, const ClassifyTilesParams&, Rows, cudaStream_t);
-void launchReblurHitDistReconstruction(const ReblurConstants&, const HitDistReconstructionParams&, bool is5x5, Rows, cudaStream_t);
-void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int flags, Rows, cudaStream_t);
-void launchReblurSplitScreen(const ReblurConstants&, const SplitScreenParams&, Rows, cudaStream_t);
-void launchReblurBlur(const ReblurConstants&, const BlurParams&, int flags, Rows, cudaStream_t);
-void launchReblurPostBlur(const ReblurConstants&, const PostBlurParams&, bool temporalStabilization, int flags, Rows, cudaStream_t);
-void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccumulationParams&, Rows, cudaStream_t);
-void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, bool quads, Rows, cudaStream_t);
-void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, Rows, cudaStream_t);
+void launchReblurHitDistReconstruction(const ReblurConstants&, const HitDistReconstructionParams&, int signal, bool is5x5, Rows, cudaStream_t);
+void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int signal, int flags, Rows, cudaStream_t);
+void launchReblurSplitScreen(const ReblurConstants&, const SplitScreenParams&, int signal, Rows, cudaStream_t);
+void launchReblurBlur(const ReblurConstants&, const BlurParams&, int signal, int flags, Rows, cudaStream_t);
+void launchReblurPostBlur(const ReblurConstants&, const PostBlurParams&, int signal, bool temporalStabilization, int flags, Rows, cudaStream_t);
+void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccumulationParams&, int signal, Rows, cudaStream_t);
+void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, int signal, bool quads, Rows, cudaStream_t);
+void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, int signal, Rows, cudaStream_t);
 uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
 uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
 uint32_t dispatchReference(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, uint32_t gridW, uint32_t gridH, cudaStream_t stream,
@@ -54,7 +54,7 @@ uint32_t fail(Result r, const char* fmt, ...) {
 
 uint32_t bytesPerTexel(uint32_t fmt) {
     switch ((Format)fmt) {
-        case Format::R8_UNORM: return 1;
+        case Format::R8_UNORM: case Format::R8_UINT: return 1;
         case Format::RG8_UNORM: case Format::R16_UINT: case Format::R16_SFLOAT: return 2;
         case Format::RGBA8_UNORM: case Format::RG16_SFLOAT: case Format::R32_UINT: case Format::R32_SFLOAT: case Format::R10_G10_B10_A2_UNORM: return 4;
         case Format::RGBA16_SFLOAT: return 8;
@@ -137,57 +137,78 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
     const int kflags = (quads ? 1 : 0) | ((flags & NRDCU_FLAG_ROBUST_MIRROR_TEST) ? 2 : 0);
     std::string err;
     Binder b{tex, n, 0, true, &err, id.c_str()};
-    const char* kSig = "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE";
-    auto is = [&](const char* file, const char* suffix = "") { return id == std::string(file) + kSig + suffix; };
+    // "<file>|NRD_SIGNAL=<DIFF|SPEC|BOTH>|NRD_MODE=RADIANCE<suffix>" (InstanceImpl.h:59-67). REBLUR_DIFFUSE / REBLUR_SPECULAR bind only their own lobe's
+    // textures (REBLUR_*.resources.hlsli): takeD / takeS consume a binding only when the permutation has that lobe
+    int signal = 0;
+    std::string kSig;
+    for (int k = 1; k <= 3 && !signal; k++) {
+        const std::string candidate = std::string("|NRD_SIGNAL=") + (k == 1 ? "DIFF" : (k == 2 ? "SPEC" : "BOTH")) + "|NRD_MODE=RADIANCE";
+        if (id.find(candidate) != std::string::npos) {
+            signal = k;
+            kSig = candidate;
+        }
+    }
+    const bool hasDiff = (signal & 1) != 0, hasSpec = (signal & 2) != 0;
+    const uint32_t lobes = (hasDiff ? 1u : 0u) + (hasSpec ? 1u : 0u);
+    auto is = [&](const char* file, const char* suffix = "") { return signal != 0 && id == std::string(file) + kSig + suffix; };
     auto done = [&](uint32_t expected) -> uint32_t {
         if (!b.ok || b.next != expected || n != expected) return fail(Result::INVALID_ARGUMENT, "%s", err.empty() ? (id + ": wrong number of textures").c_str() : err.c_str());
         return 0xFFFFFFFFu;
     };
+    auto takeD16 = [&]() { return hasDiff ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
+    auto takeS16 = [&]() { return hasSpec ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
+    auto takeDF = [&]() { return hasDiff ? b.take<TexR16F>(Format::R16_SFLOAT) : TexR16F{}; };
+    auto takeSF = [&]() { return hasSpec ? b.take<TexR16F>(Format::R16_SFLOAT) : TexR16F{}; };
+    // data1: RG8_UNORM for two lobes, R8_UNORM for one (Reblur.cpp: DATA1 format); P has `data1` + `data1R8` or `outData1` + `outData1R8`
+    auto takeData1 = [&](TexRG8& both, TexR8& single) {
+        if (lobes == 2) both = b.take<TexRG8>(Format::RG8_UNORM);
+        else single = b.take<TexR8>(Format::R8_UNORM);
+    };
 
     if (id == "REBLUR_ClassifyTiles.cs.hlsl") {
-        ClassifyTilesParams p;
+        ClassifyTilesParams p = {};
         p.inViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.outTiles = b.take<TexR8>(Format::R8_UNORM);
         uint32_t r = done(2);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurClassifyTiles(cb, p, rows, stream);
     } else if (is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=0") || is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1")) {
-        HitDistReconstructionParams p;
+        HitDistReconstructionParams p = {};
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        uint32_t r = done(7);
+        p.inDiff = takeD16();
+        p.inSpec = takeS16();
+        p.outDiff = takeD16();
+        p.outSpec = takeS16();
+        uint32_t r = done(3 + 2 * lobes);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurHitDistReconstruction(cb, p, is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), rows, stream);
+        launchReblurHitDistReconstruction(cb, p, signal, is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), rows, stream);
     } else if (is("REBLUR_SplitScreen.cs.hlsl")) {
-        SplitScreenParams p;
+        SplitScreenParams p = {};
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        uint32_t r = done(5);
+        p.inDiff = takeD16();
+        p.inSpec = takeS16();
+        p.outDiff = takeD16();
+        p.outSpec = takeS16();
+        uint32_t r = done(1 + 2 * lobes);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurSplitScreen(cb, p, rows, stream);
+        launchReblurSplitScreen(cb, p, signal, rows, stream);
     } else if (is("REBLUR_PrePass.cs.hlsl")) {
-        PrePassParams p;
+        PrePassParams p = {};
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outSpecHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
-        uint32_t r = done(8);
+        p.inDiff = takeD16();
+        p.inSpec = takeS16();
+        p.outDiff = takeD16();
+        p.outSpec = takeS16();
+        p.outSpecHitDistForTracking = takeSF();
+        uint32_t r = done(3 + 2 * lobes + (hasSpec ? 1 : 0));
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurPrePass(cb, p, kflags, rows, stream);
+        launchReblurPrePass(cb, p, signal, kflags, rows, stream);
     } else if (is("REBLUR_TemporalAccumulation.cs.hlsl")) {
-        TemporalAccumulationParams p;
+        TemporalAccumulationParams p = {};
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
@@ -196,99 +217,101 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.prevNormalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.prevInternalData = b.take<TexR16U>(Format::R16_UINT);
         p.disocclusionThresholdMix = b.takeGuide();
-        p.diffConfidence = b.takeGuide();
-        p.specConfidence = b.takeGuide();
-        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.historyDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.historySpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.historyDiffFast = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.historySpecFast = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.prevSpecHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.inSpecHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outData1 = b.take<TexRG8>(Format::RG8_UNORM);
-        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outDiffFast = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outSpecFast = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outSpecHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outData2 = b.take<TexR32U>(Format::R32_UINT);
-        uint32_t r = done(25);
+        if (hasDiff) p.diffConfidence = b.takeGuide();
+        if (hasSpec) p.specConfidence = b.takeGuide();
+        p.inDiff = takeD16();
+        p.inSpec = takeS16();
+        p.historyDiff = takeD16();
+        p.historySpec = takeS16();
+        p.historyDiffFast = takeDF();
+        p.historySpecFast = takeSF();
+        p.prevSpecHitDistForTracking = takeSF();
+        p.inSpecHitDistForTracking = takeSF();
+        takeData1(p.outData1, p.outData1R8);
+        p.outDiff = takeD16();
+        p.outSpec = takeS16();
+        p.outDiffFast = takeDF();
+        p.outSpecFast = takeSF();
+        p.outSpecHitDistForTracking = takeSF();
+        if (hasSpec) p.outData2 = b.take<TexR32U>(Format::R32_UINT);
+        else p.outData2R8 = b.take<TexR8U>(Format::R8_UINT);
+        uint32_t r = done(10 + 6 * lobes + (hasSpec ? 3 : 0));
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurTemporalAccumulation(cb, p, rows, stream);
+        launchReblurTemporalAccumulation(cb, p, signal, rows, stream);
     } else if (is("REBLUR_HistoryFix.cs.hlsl")) {
-        HistoryFixParams p;
+        HistoryFixParams p = {};
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
-        p.data1 = b.take<TexRG8>(Format::RG8_UNORM);
+        takeData1(p.data1, p.data1R8);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.inDiffFast = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.inSpecFast = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.specHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outDiffFast = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outSpecFast = b.take<TexR16F>(Format::R16_SFLOAT);
-        uint32_t r = done(13);
+        p.inDiff = takeD16();
+        p.inSpec = takeS16();
+        p.inDiffFast = takeDF();
+        p.inSpecFast = takeSF();
+        p.specHitDistForTracking = takeSF();
+        p.outDiff = takeD16();
+        p.outSpec = takeS16();
+        p.outDiffFast = takeDF();
+        p.outSpecFast = takeSF();
+        uint32_t r = done(4 + 4 * lobes + (hasSpec ? 1 : 0));
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurHistoryFix(cb, p, quads, rows, stream);
+        launchReblurHistoryFix(cb, p, signal, quads, rows, stream);
     } else if (is("REBLUR_Blur.cs.hlsl")) {
-        BlurParams p;
+        BlurParams p = {};
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.data1 = b.take<TexRG8>(Format::RG8_UNORM);
-        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        takeData1(p.data1, p.data1R8);
+        p.inDiff = takeD16();
+        p.inSpec = takeS16();
         p.outViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        uint32_t r = done(9);
+        p.outDiff = takeD16();
+        p.outSpec = takeS16();
+        uint32_t r = done(5 + 2 * lobes);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurBlur(cb, p, kflags, rows, stream);
+        launchReblurBlur(cb, p, signal, kflags, rows, stream);
     } else if (is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1") || is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0")) {
         const bool ts = is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1");
         PostBlurParams p = {};
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
-        p.data1 = b.take<TexRG8>(Format::RG8_UNORM);
+        takeData1(p.data1, p.data1R8);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.inDiff = takeD16();
+        p.inSpec = takeS16();
         p.outNormalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
-        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        p.outDiff = takeD16();
+        p.outSpec = takeS16();
         if (!ts) {
             p.outInternalData = b.take<TexR16U>(Format::R16_UINT);
-            p.outDiffCopy = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-            p.outSpecCopy = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+            p.outDiffCopy = takeD16();
+            p.outSpecCopy = takeS16();
         }
-        uint32_t r = done(ts ? 9 : 12);
+        uint32_t r = done(ts ? 5 + 2 * lobes : 6 + 3 * lobes);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurPostBlur(cb, p, ts, kflags, rows, stream);
+        launchReblurPostBlur(cb, p, signal, ts, kflags, rows, stream);
     } else if (is("REBLUR_TemporalStabilization.cs.hlsl")) {
-        TemporalStabilizationParams p;
+        TemporalStabilizationParams p = {};
         p.tiles = b.take<TexR8>(Format::R8_UNORM);
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.data1 = b.take<TexRG8>(Format::RG8_UNORM);
-        p.data2 = b.take<TexR32U>(Format::R32_UINT);
-        p.specHitDistForTracking = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.inDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.inSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.historyDiffLuma = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.historySpecLuma = b.take<TexR16F>(Format::R16_SFLOAT);
+        takeData1(p.data1, p.data1R8);
+        if (hasSpec) p.data2 = b.take<TexR32U>(Format::R32_UINT);
+        else p.data2R8 = b.take<TexR8U>(Format::R8_UINT);
+        p.specHitDistForTracking = takeSF();
+        p.inDiff = takeD16();
+        p.inSpec = takeS16();
+        p.historyDiffLuma = takeDF();
+        p.historySpecLuma = takeSF();
         p.mv = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
         p.outInternalData = b.take<TexR16U>(Format::R16_UINT);
-        p.outDiff = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outSpec = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
-        p.outDiffLuma = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outSpecLuma = b.take<TexR16F>(Format::R16_SFLOAT);
-        uint32_t r = done(16);
+        p.outDiff = takeD16();
+        p.outSpec = takeS16();
+        p.outDiffLuma = takeDF();
+        p.outSpecLuma = takeSF();
+        uint32_t r = done(7 + 4 * lobes + (hasSpec ? 1 : 0));
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurTemporalStabilization(cb, p, rows, stream);
+        launchReblurTemporalStabilization(cb, p, signal, rows, stream);
     } else {
         return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", id.c_str());
     }

@@ -265,6 +265,11 @@ struct TexR16U : TexView {
     NRD_DEV void store(int x, int y, uint32_t v) const { if (inside(x, y)) *ptrw<unsigned short>(x, y) = (unsigned short)v; }
 };
 
+struct TexR8U : TexView {  // R8_UINT; integer stores saturate to the format's range like D3D / Vulkan image stores
+    NRD_DEV uint32_t load(int x, int y) const { return inside(x, y) ? (uint32_t)__ldg(ptr<uint8_t>(x, y)) : 0u; }
+    NRD_DEV void store(int x, int y, uint32_t v) const { if (inside(x, y)) *ptrw<uint8_t>(x, y) = (uint8_t)(v > 255u ? 255u : v); }
+};
+
 struct TexR32U : TexView {
     NRD_DEV uint32_t load(int x, int y) const { return inside(x, y) ? __ldg(ptr<uint32_t>(x, y)) : 0u; }
     NRD_DEV uint32_t fetchClamped(int x, int y) const { return __ldg(ptr<uint32_t>(cx(x), cy(y))); }

@@ -1,6 +1,8 @@
 // REBLUR helpers that read the per-frame constants (REBLUR_Common.hlsli:13-371, Common.hlsli:261-262, 567-572,
 // 604-658) and the launch-parameter blocks of the REBLUR kernels.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace nrdk {
@@ -10,6 +12,16 @@ using nrdb::ReblurConstants;
 constexpr float REBLUR_MAX_ACCUM_FRAME_NUM = 63.0f;
 constexpr float REBLUR_MAX_MATERIALID_NUM = 15.0f;
 constexpr float REBLUR_INVALID = -32768.0f;
+
+// NRD_SIGNAL of a permutation (NRD.hlsli:338-339): kernels are templated on it, the bindings of the lobe a denoiser does not have
+// (REBLUR_DIFFUSE / REBLUR_SPECULAR) stay zero-initialised and are never touched
+enum : int { SIGNAL_DIFF = 1, SIGNAL_SPEC = 2, SIGNAL_BOTH = 3 };
+// host side of the launchers: run `call( std::integral_constant< int, SIGNAL > )` for the run-time NRD_SIGNAL
+template <class F> inline void withSignal(int signal, F&& call) {
+    if (signal == SIGNAL_DIFF) call(std::integral_constant<int, SIGNAL_DIFF>());
+    else if (signal == SIGNAL_SPEC) call(std::integral_constant<int, SIGNAL_SPEC>());
+    else call(std::integral_constant<int, SIGNAL_BOTH>());
+}
 
 NRD_DEV float unpackViewZ(const ReblurConstants& cb, float z) { return fabsf(z * cb.viewZScale); }
 NRD_DEV bool inDenoisingRange(const ReblurConstants& cb, float z) { return z < cb.denoisingRange; }
@@ -38,6 +50,32 @@ NRD_DEV float2 unpackData2(uint32_t p, uint32_t& bits, bool& smbAllowCatRom) {
     bits = p & 0xFFu;
     smbAllowCatRom = (p & (1u << 15)) != 0;
     return make_float2((float)((p >> 8) & 127u) / 127.0f, __half2float(__ushort_as_half((unsigned short)(p >> 16))));
+}
+// Single-lobe denoisers keep data1 in an R8_UNORM texture holding their one accumulation speed ( REBLUR_Common.hlsli:48-51, 58-61 ) and a
+// diffuse-only one keeps data2 in 8 bits with the CatRom flag in bit 4 instead of 15 ( :69-73 ). P = any launch-parameter block below.
+template <int SIGNAL, class P> NRD_DEV float2 loadData1(const P& p, int x, int y) {
+    if constexpr (SIGNAL == SIGNAL_BOTH) return unpackData1(p.data1.load(x, y));
+    else {
+        const float v = roundNe(p.data1R8.load(x, y) * REBLUR_MAX_ACCUM_FRAME_NUM);
+        return make_float2(v, SIGNAL == SIGNAL_DIFF ? 0.0f : v);
+    }
+}
+template <int SIGNAL, class P> NRD_DEV void storeData1(const P& p, int x, int y, float diffAccumSpeed, float specAccumSpeed) {
+    const float2 r = packData1(diffAccumSpeed, specAccumSpeed);
+    if constexpr (SIGNAL == SIGNAL_BOTH) p.outData1.store(x, y, r);
+    else p.outData1R8.store(x, y, SIGNAL == SIGNAL_DIFF ? r.x : r.y);
+}
+template <int SIGNAL, class P> NRD_DEV void storeData2(const P& p, int x, int y, float fbits, float curvature, float virtualHistoryAmount, bool smbAllowCatRom) {
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) p.outData2.store(x, y, packData2(fbits, curvature, virtualHistoryAmount, smbAllowCatRom));
+    else p.outData2R8.store(x, y, (uint32_t)(fbits + 0.5f) | (smbAllowCatRom ? (1u << 4) : 0u));  // curvature = virtualHistoryAmount = 0
+}
+template <int SIGNAL, class P> NRD_DEV float2 loadData2(const P& p, int x, int y, uint32_t& bits, bool& smbAllowCatRom) {
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) return unpackData2(p.data2.load(x, y), bits, smbAllowCatRom);
+    else {
+        bits = p.data2R8.load(x, y);
+        smbAllowCatRom = (bits & (1u << 4)) != 0;
+        return make_float2(0.0f, 0.0f);
+    }
 }
 NRD_DEV float3 viewVector(const ReblurConstants& cb, float3 X, bool isViewSpace = false) {
     return cb.orthoMode == 0.0f ? normalize(-X) : (isViewSpace ? make_float3(0, 0, -1) : make_float3(cb.viewVectorWorld[0], cb.viewVectorWorld[1], cb.viewVectorWorld[2]));
@@ -159,29 +197,35 @@ struct PrePassParams {
     TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexRGBA16F outDiff, outSpec; TexR16F outSpecHitDistForTracking;
 };
+// `data1R8` / `data2R8` / `outData1R8` / `outData2R8`: the single-lobe formats of data1 / data2 (bound instead of the two-lobe view)
 struct BlurParams {
     TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRG8 data1; TexRGBA16F inDiff, inSpec;
     TexR32F outViewZ; TexRGBA16F outDiff, outSpec;
+    TexR8 data1R8;
 };
 struct PostBlurParams {
     TexR8 tiles; TexNR normalRoughness; TexRG8 data1; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexNR outNormalRoughness; TexRGBA16F outDiff, outSpec;
     TexR16U outInternalData; TexRGBA16F outDiffCopy, outSpecCopy;  // only bound when TEMPORAL_STABILIZATION = 0
+    TexR8 data1R8;
 };
 struct TemporalAccumulationParams {
     TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F mv; TexR32F prevViewZ; TexNR prevNormalRoughness; TexR16U prevInternalData;
     TexAnyX disocclusionThresholdMix, diffConfidence, specConfidence;  // dummies (IN_VIEWZ) unless the optional inputs are enabled
     TexRGBA16F inDiff, inSpec, historyDiff, historySpec; TexR16F historyDiffFast, historySpecFast, prevSpecHitDistForTracking, inSpecHitDistForTracking;
     TexRG8 outData1; TexRGBA16F outDiff, outSpec; TexR16F outDiffFast, outSpecFast, outSpecHitDistForTracking; TexR32U outData2;
+    TexR8 outData1R8; TexR8U outData2R8;
 };
 struct HistoryFixParams {
     TexR8 tiles; TexNR normalRoughness; TexRG8 data1; TexR32F viewZ; TexRGBA16F inDiff, inSpec; TexR16F inDiffFast, inSpecFast, specHitDistForTracking;
     TexRGBA16F outDiff, outSpec; TexR16F outDiffFast, outSpecFast;
+    TexR8 data1R8;
 };
 struct TemporalStabilizationParams {
     TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRG8 data1; TexR32U data2; TexR16F specHitDistForTracking; TexRGBA16F inDiff, inSpec;
     TexR16F historyDiffLuma, historySpecLuma;
     TexRGBA16F mv; TexR16U outInternalData; TexRGBA16F outDiff, outSpec; TexR16F outDiffLuma, outSpecLuma;
+    TexR8 data1R8; TexR8U data2R8;
 };
 
 }  // namespace nrdk

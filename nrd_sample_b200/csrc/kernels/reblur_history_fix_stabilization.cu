@@ -1,4 +1,4 @@
-// REBLUR HistoryFix and TemporalStabilization on sm_100a (NRD_SIGNAL=BOTH, NRD_MODE=RADIANCE), plus Clear.
+// REBLUR HistoryFix and TemporalStabilization on sm_100a (NRD_MODE=RADIANCE; NRD_SIGNAL = DIFF / SPEC / BOTH is a template parameter), plus Clear.
 //
 // Replaces External/NRD/Shaders/REBLUR_HistoryFix.cs.hlsl:44-506 (sparse 5x5-minus-corners cross-bilateral
 // reconstruction for pixels with < historyFixFrameNum frames of history, then 9x9 anti-firefly and 5x5 fast-history
@@ -25,7 +25,7 @@ namespace {
 constexpr int HF_BORDER = 4;  // REBLUR_ANTI_FIREFLY_FILTER_RADIUS
 constexpr int HF_TILE_W = BLOCK_W + 2 * HF_BORDER, HF_TILE_H = BLOCK_H + 2 * HF_BORDER;
 
-template <int LOBE>
+template <int LOBE, int SIGNAL>
 NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p, const float (*sLuma)[HF_TILE_W], const float2 (*sRow)[HF_TILE_H][BLOCK_W], bool tileHasSky,
                             int px, int py, float strideIn, float frameNum,
                             float frameNumAvgNorm, float viewZ, float materialID, float3 N, float roughness, float3 Nv, float3 Xv, float frustumSize, float2 pixelUv) {
@@ -81,7 +81,7 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
                 w *= exponentialWeight(angle, normalParam, 0.0f);
                 if (LOBE == SPEC) w *= exponentialWeight(Ns.w * Ns.w, roughParams.x, roughParams.y);
 
-                float2 fn = unpackData1(p.data1.load(tx, ty));
+                float2 fn = loadData1<SIGNAL>(p, tx, ty);
                 w *= 1.0f + (LOBE == DIFF ? fn.x : fn.y);
                 w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
 
@@ -165,12 +165,14 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
 }
 }  // namespace
 
+template <int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HistoryFixParams p, int quads, int ctaY0) {
-    __shared__ float sDiffLuma[HF_TILE_H][HF_TILE_W];
-    __shared__ float sSpecLuma[HF_TILE_H][HF_TILE_W];
+    constexpr bool HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0, HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0;
+    __shared__ float sDiffLuma[HAS_DIFF ? HF_TILE_H : 1][HF_TILE_W];
+    __shared__ float sSpecLuma[HAS_SPEC ? HF_TILE_H : 1][HF_TILE_W];
     // row sums of { v, v^2 } over windows of 3 / 5 / 9 texels centred on the 32 interior columns, per lobe
-    __shared__ float2 sDiffRow[3][HF_TILE_H][BLOCK_W];
-    __shared__ float2 sSpecRow[3][HF_TILE_H][BLOCK_W];
+    __shared__ float2 sDiffRow[3][HAS_DIFF ? HF_TILE_H : 1][BLOCK_W];
+    __shared__ float2 sSpecRow[3][HAS_SPEC ? HF_TILE_H : 1][BLOCK_W];
 
     const int2 cta = ctaTile<2>(ctaY0);
     const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
@@ -183,8 +185,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
             bool sky = !inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.load(gx, gy)));
             sawSky |= sky ? 1 : 0;
-            sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : p.inDiffFast.load(gx, gy);
-            sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : p.inSpecFast.load(gx, gy);
+            if constexpr (HAS_DIFF) sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : p.inDiffFast.load(gx, gy);
+            if constexpr (HAS_SPEC) sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : p.inSpecFast.load(gx, gy);
         }
     }
     const bool tileHasSky = __syncthreads_or(sawSky) != 0;  // also the barrier that publishes the tile
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const
         for (int i = tid; i < HF_TILE_H * BLOCK_W; i += BLOCK_W * BLOCK_H) {
             const int x = i % BLOCK_W, y = i / BLOCK_W, c = x + HF_BORDER;
             auto sq = [](float v) { return make_float2(v, v * v); };
-            auto rowSums = [&](const float(*t)[HF_TILE_W], float2(*r)[HF_TILE_H][BLOCK_W]) {
+            auto rowSums = [&](const float(*t)[HF_TILE_W], auto* r) {
                 float2 a = __fadd2_rn(sq(t[y][c]), __fadd2_rn(sq(t[y][c - 1]), sq(t[y][c + 1])));
                 r[0][y][x] = a;
                 a = __fadd2_rn(a, __fadd2_rn(sq(t[y][c - 2]), sq(t[y][c + 2])));
@@ -201,15 +203,15 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const
                 a = __fadd2_rn(a, __fadd2_rn(sq(t[y][c - 4]), sq(t[y][c + 4])));
                 r[2][y][x] = a;
             };
-            rowSums(sDiffLuma, sDiffRow);
-            rowSums(sSpecLuma, sSpecRow);
+            if constexpr (HAS_DIFF) rowSums(sDiffLuma, sDiffRow);
+            if constexpr (HAS_SPEC) rowSums(sSpecLuma, sSpecRow);
         }
         __syncthreads();
     }
 
     // Quad exchange first (HistoryFix.cs.hlsl:56-74): all lanes stay until it is done
     const bool skyTile = p.tiles.load(px >> 4, py >> 4) != 0.0f;
-    float2 frameNum = unpackData1(p.data1.load(px, py));
+    float2 frameNum = loadData1<SIGNAL>(p, px, py);
     const float viewZ = unpackViewZ(cb, p.viewZ.load(px, py));
     if (!inDenoisingRange(cb, viewZ)) frameNum = f2(REBLUR_MAX_ACCUM_FRAME_NUM);
     float2 stride = make_float2(frameNum.x < cb.historyFixFrameNum ? 1.0f : 0.0f, frameNum.y < cb.historyFixFrameNum ? 1.0f : 0.0f);
@@ -237,8 +239,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const
     stride *= 2.0f / 2.0f;
     stride *= materialID == cb.historyFixAlternatePixelStrideMaterialID ? cb.historyFixAlternatePixelStride : cb.historyFixBasePixelStride;
 
-    historyFixLobe<DIFF>(cb, p, sDiffLuma, sDiffRow, tileHasSky, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
-    historyFixLobe<SPEC>(cb, p, sSpecLuma, sSpecRow, tileHasSky, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+    if constexpr (HAS_DIFF) historyFixLobe<DIFF, SIGNAL>(cb, p, sDiffLuma, sDiffRow, tileHasSky, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+    if constexpr (HAS_SPEC) historyFixLobe<SPEC, SIGNAL>(cb, p, sSpecLuma, sSpecRow, tileHasSky, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
 }
 
 // ===============================================================================================================
@@ -272,10 +274,12 @@ NRD_DEV void lumaMoments3x3(const float (*sLuma)[TS_TILE_W], float& luma, float&
 #ifndef TS_MIN_BLOCKS
 #    define TS_MIN_BLOCKS 3  // 512-thread CTAs: 40 regs + a small spill (3 CTAs / SM) beats 64 regs (2 CTAs) by 12 % on B200
 #endif
+template <int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTemporalStabilizationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                        const __grid_constant__ TemporalStabilizationParams p, int ctaY0) {
-    __shared__ float sDiffLuma[TS_TILE_H][TS_TILE_W];
-    __shared__ float sSpecLuma[TS_TILE_H][TS_TILE_W];
+    constexpr bool HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0, HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0;
+    __shared__ float sDiffLuma[HAS_DIFF ? TS_TILE_H : 1][TS_TILE_W];
+    __shared__ float sSpecLuma[HAS_SPEC ? TS_TILE_H : 1][TS_TILE_W];
 
     const int2 cta = ctaTile<5>(ctaY0);
     const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
@@ -286,8 +290,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
             int sx = i % TS_TILE_W, sy = i / TS_TILE_W;
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
             bool sky = !inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.load(gx, gy)));
-            sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : p.inDiff.load(gx, gy).x;
-            sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : p.inSpec.load(gx, gy).x;
+            if constexpr (HAS_DIFF) sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : p.inDiff.load(gx, gy).x;
+            if constexpr (HAS_SPEC) sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : p.inSpec.load(gx, gy).x;
         }
     }
     __syncthreads();
@@ -325,8 +329,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
 
     uint32_t bits;
     bool smbAllowCatRom;
-    float2 data1 = unpackData1(p.data1.load(px, py));
-    const float2 data2 = unpackData2(p.data2.load(px, py), bits, smbAllowCatRom);
+    float2 data1 = loadData1<SIGNAL>(p, px, py);
+    const float2 data2 = loadData2<SIGNAL>(p, px, py, bits, smbAllowCatRom);
 
     const Bilinear smbBilinearFilter = getBilinearFilter(smbPixelUv, rectSizePrev);
     const float4 smbOcclusion = make_float4((bits & 1u) != 0, (bits & 2u) != 0, (bits & 4u) != 0, (bits & 8u) != 0);
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
     const float smbFootprintQuality = sqrt01(applyBilinear(smbOcclusion.x, smbOcclusion.y, smbOcclusion.z, smbOcclusion.w, smbBilinearFilter));
 
     // ---- Diffuse ----
-    {
+    if constexpr (HAS_DIFF) {
         float luma, m1, sigma;
         lumaMoments3x3(sDiffLuma, luma, m1, sigma);
         if (data1.x < cb.historyFixFrameNum) luma = fminf(luma, m1 * (1.2f + 1.0f / (1.0f + data1.x)));
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
     }
 
     // ---- Specular ----
-    {
+    if constexpr (HAS_SPEC) {
         float luma, m1, sigma;
         lumaMoments3x3(sSpecLuma, luma, m1, sigma);
         if (data1.y < cb.historyFixFrameNum) luma = fminf(luma, m1 * (1.2f + 1.0f / (1.0f + data1.y)));
@@ -437,17 +441,17 @@ void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t s
     clearKernel<<<dim3(blocksX, height), 256, 0, stream>>>((uint8_t*)data, rowBytes, height, pitch);
 }
 
-void launchReblurHistoryFix(const ReblurConstants& cb, const HistoryFixParams& p, bool quads, Rows rows, cudaStream_t stream) {
+void launchReblurHistoryFix(const ReblurConstants& cb, const HistoryFixParams& p, int signal, bool quads, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    reblurHistoryFixKernel<<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
+    withSignal(signal, [&](auto sig) { reblurHistoryFixKernel<decltype(sig)::value><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0); });
 }
-void launchReblurTemporalStabilization(const ReblurConstants& cb, const TemporalStabilizationParams& p, Rows rows, cudaStream_t stream) {
+void launchReblurTemporalStabilization(const ReblurConstants& cb, const TemporalStabilizationParams& p, int signal, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    reblurTemporalStabilizationKernel<<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+    withSignal(signal, [&](auto sig) { reblurTemporalStabilizationKernel<decltype(sig)::value><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0); });
 }
 
 }  // namespace nrdk

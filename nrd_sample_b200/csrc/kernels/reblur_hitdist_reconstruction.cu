@@ -1,6 +1,7 @@
 // REBLUR_HitDistReconstruction (3x3 / 5x5): fills in the hit distance of pixels whose ray carried none (hitDist = 0) from the
 // neighbours on the same surface. Reference: External/NRD/Shaders/REBLUR_HitDistReconstruction.cs.hlsl:21-167
-// (NRD_SIGNAL = BOTH, RADIANCE, REBLUR_USE_DECOMPRESSED_HIT_DIST_IN_RECONSTRUCTION = 0, REBLUR_PERFORMANCE_MODE = 0).
+// (RADIANCE, REBLUR_USE_DECOMPRESSED_HIT_DIST_IN_RECONSTRUCTION = 0, REBLUR_PERFORMANCE_MODE = 0; NRD_SIGNAL is a uniform run-time argument:
+// a single-lobe denoiser leaves the other lobe's hit distance at 0 and its textures untouched).
 // CTA = 32x8 pixels; the { normal, roughness } and { diff hitDist, spec hitDist, viewZ } of the (32 + 2B) x (8 + 2B) neighbourhood
 // are staged in shared memory (B = 1 or 2), normals decoded once per texel.
 #include "reblur_common.cuh"
@@ -12,7 +13,8 @@ constexpr int BLOCK_W = 32, BLOCK_H = 8;
 
 template <int BORDER>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHitDistReconstructionKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HitDistReconstructionParams p,
-                                                                                     int ctaY0) {
+                                                                                     int signal, int ctaY0) {
+    const bool hasDiff = (signal & SIGNAL_DIFF) != 0, hasSpec = (signal & SIGNAL_SPEC) != 0;
     constexpr int TW = BLOCK_W + 2 * BORDER, TH = BLOCK_H + 2 * BORDER;
     __shared__ float4 sNormalRoughness[TH][TW];
     __shared__ float4 sHitDistViewZ[TH][TW];
@@ -29,7 +31,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHitDistReconstructionK
             const float viewZ = unpackViewZ(cb, p.viewZ.load(gx, gy));
             sNormalRoughness[ty][tx] = unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy));
             const bool inRange = inDenoisingRange(cb, viewZ);
-            sHitDistViewZ[ty][tx] = make_float4(inRange ? p.inDiff.load(gx, gy).w : 0.0f, inRange ? p.inSpec.load(gx, gy).w : 0.0f, viewZ, 0.0f);
+            sHitDistViewZ[ty][tx] = make_float4(inRange && hasDiff ? p.inDiff.load(gx, gy).w : 0.0f, inRange && hasSpec ? p.inSpec.load(gx, gy).w : 0.0f, viewZ, 0.0f);
         }
     }
     __syncthreads();
@@ -84,20 +86,25 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHitDistReconstructionK
     acc.x /= fmaxf(sum.x, NRD_EPS);
     acc.y /= fmaxf(sum.y, NRD_EPS);
 
-    const float4 diff = p.inDiff.load(px, py), spec = p.inSpec.load(px, py);
-    p.outDiff.store(px, py, make_float4(diff.x, diff.y, diff.z, acc.x));
-    p.outSpec.store(px, py, make_float4(spec.x, spec.y, spec.z, acc.y));
+    if (hasDiff) {
+        const float4 diff = p.inDiff.load(px, py);
+        p.outDiff.store(px, py, make_float4(diff.x, diff.y, diff.z, acc.x));
+    }
+    if (hasSpec) {
+        const float4 spec = p.inSpec.load(px, py);
+        p.outSpec.store(px, py, make_float4(spec.x, spec.y, spec.z, acc.y));
+    }
 }
 }  // namespace
 
-void launchReblurHitDistReconstruction(const ReblurConstants& cb, const HitDistReconstructionParams& p, bool is5x5, Rows rows, cudaStream_t stream) {
+void launchReblurHitDistReconstruction(const ReblurConstants& cb, const HitDistReconstructionParams& p, int signal, bool is5x5, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
     if (is5x5)
-        reblurHitDistReconstructionKernel<2><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        reblurHitDistReconstructionKernel<2><<<grid, block, 0, stream>>>(cb, p, signal, g.ctaY0);
     else
-        reblurHitDistReconstructionKernel<1><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        reblurHitDistReconstructionKernel<1><<<grid, block, 0, stream>>>(cb, p, signal, g.ctaY0);
 }
 
 }  // namespace nrdk

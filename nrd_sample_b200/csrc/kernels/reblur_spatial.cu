@@ -1,4 +1,5 @@
-// REBLUR spatial passes on sm_100a: ClassifyTiles, PrePass, Blur, PostBlur (NRD_SIGNAL=BOTH, NRD_MODE=RADIANCE).
+// REBLUR spatial passes on sm_100a: ClassifyTiles, PrePass, Blur, PostBlur (NRD_MODE=RADIANCE; NRD_SIGNAL = DIFF / SPEC / BOTH as a template
+// parameter: REBLUR_DIFFUSE and REBLUR_SPECULAR run the same code with the other lobe compiled out).
 //
 // What they replace: External/NRD/Shaders/REBLUR_ClassifyTiles.cs.hlsl:21-55, REBLUR_PrePass.cs.hlsl:21-86,
 // REBLUR_Blur.cs.hlsl:21-92, REBLUR_PostBlur.cs.hlsl:21-95 and their shared body
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_co
     if (threadIdx.x == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
 }
 
-template <bool CB>
+template <bool CB, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags, int ctaY0) {
     const bool robust = (flags & 2) != 0;
     Center s;
@@ -382,8 +383,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPr
         r.x0 = x0 >> 1;
         r.x1 = x1 >> 1;
     }
-    spatialFilter<PRE_PASS, DIFF, CB>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r);
-    spatialFilter<PRE_PASS, SPEC, CB>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r);
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<PRE_PASS, DIFF, CB>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r);
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<PRE_PASS, SPEC, CB>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r);
 }
 
 // Non-linear accumulation speed with the quad-neighbour smoothing of REBLUR_Blur.cs.hlsl:40-59 (lanes x^1, x^2 of the row)
@@ -399,6 +400,7 @@ NRD_DEV float2 quadSmoothedAccumSpeed(const ReblurConstants& cb, float2 data1, f
     return n;
 }
 
+template <int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
@@ -412,17 +414,17 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBl
 
     // No lane leaves before the quad exchange; lanes of sky tiles / outside the rect only feed their own quads
     bool skyTile = p.tiles.load(s.px >> 4, s.py >> 4) != 0.0f;
-    s.data1 = unpackData1(p.data1.load(s.px, s.py));
+    s.data1 = loadData1<SIGNAL>(p, s.px, s.py);
     s.viewZ = unpackViewZ(cb, viewZpacked);
     s.nonLinearAccumSpeed = quadSmoothedAccumSpeed(cb, s.data1, s.viewZ, quads);
     if (skyTile || !inDenoisingRange(cb, s.viewZ) || s.px > cb.rectSizeMinusOne[0] || s.py > cb.rectSizeMinusOne[1]) return;
 
     setupCenter(cb, s, p.normalRoughness, cb.rotator);
-    spatialFilter<BLUR, DIFF>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust);
-    spatialFilter<BLUR, SPEC>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust);
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<BLUR, DIFF>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust);
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<BLUR, SPEC>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust);
 }
 
-template <bool TEMPORAL_STABILIZATION>
+template <bool TEMPORAL_STABILIZATION, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPo
     s.py = cta.y * BLOCK_H + threadIdx.y;
 
     bool skyTile = p.tiles.load(s.px >> 4, s.py >> 4) != 0.0f;
-    s.data1 = unpackData1(p.data1.load(s.px, s.py));
+    s.data1 = loadData1<SIGNAL>(p, s.px, s.py);
     s.viewZ = unpackViewZ(cb, p.viewZ.load(s.px, s.py));
     s.nonLinearAccumSpeed = quadSmoothedAccumSpeed(cb, s.data1, s.viewZ, quads);
     if (skyTile || !inDenoisingRange(cb, s.viewZ) || s.px > cb.rectSizeMinusOne[0] || s.py > cb.rectSizeMinusOne[1]) return;
@@ -441,18 +443,18 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPo
     p.outNormalRoughness.storeRaw(s.px, s.py, p.normalRoughness.loadRaw(s.px, s.py));
     if (!TEMPORAL_STABILIZATION) p.outInternalData.store(s.px, s.py, packInternalData(cb, s.data1.x, s.data1.y, s.materialID));
 
-    spatialFilter<POST_BLUR, DIFF>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust);
-    spatialFilter<POST_BLUR, SPEC>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust);
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<POST_BLUR, DIFF>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust);
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<POST_BLUR, SPEC>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust);
 }
 
 // REBLUR_SplitScreen.cs.hlsl:21-56: the noisy input (range-masked) left of CommonSettings::splitScreen
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurSplitScreenKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ SplitScreenParams p, int ctaY0) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurSplitScreenKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ SplitScreenParams p, int signal, int ctaY0) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (ctaY0 + blockIdx.y) * BLOCK_H + threadIdx.y;
     const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
     if (u > cb.splitScreen || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1]) return;
     const float inRange = inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.load(px, py))) ? 1.0f : 0.0f;
-    p.outDiff.store(px, py, p.inDiff.load(px >> (cb.diffCheckerboard != 2u ? 1 : 0), py) * inRange);
-    p.outSpec.store(px, py, p.inSpec.load(px >> (cb.specCheckerboard != 2u ? 1 : 0), py) * inRange);
+    if (signal & SIGNAL_DIFF) p.outDiff.store(px, py, p.inDiff.load(px >> (cb.diffCheckerboard != 2u ? 1 : 0), py) * inRange);
+    if (signal & SIGNAL_SPEC) p.outSpec.store(px, py, p.inSpec.load(px >> (cb.specCheckerboard != 2u ? 1 : 0), py) * inRange);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -463,33 +465,41 @@ void launchReblurClassifyTiles(const ReblurConstants& cb, const ClassifyTilesPar
     if (!g.count) return;
     reblurClassifyTilesKernel<<<dim3((cb.rectSizeMinusOne[0] + 16) / 16, g.count), 256, 0, stream>>>(cb, p, g.ctaY0);
 }
-void launchReblurSplitScreen(const ReblurConstants& cb, const SplitScreenParams& p, Rows rows, cudaStream_t stream) {
+void launchReblurSplitScreen(const ReblurConstants& cb, const SplitScreenParams& p, int signal, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    reblurSplitScreenKernel<<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+    reblurSplitScreenKernel<<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, signal, g.ctaY0);
 }
-void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int flags, Rows rows, cudaStream_t stream) {
+void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int signal, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    if (cb.diffCheckerboard != 2u || cb.specCheckerboard != 2u)  // CheckerboardMode::BLACK / WHITE set both (Reblur.cpp:301-313)
-        reblurPrePassKernel<true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
-    else
-        reblurPrePassKernel<false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    withSignal(signal, [&](auto sig) {
+        constexpr int S = decltype(sig)::value;
+        if (cb.diffCheckerboard != 2u || cb.specCheckerboard != 2u)  // CheckerboardMode::BLACK / WHITE set both (Reblur.cpp:301-313)
+            reblurPrePassKernel<true, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        else
+            reblurPrePassKernel<false, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    });
 }
-void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int flags, Rows rows, cudaStream_t stream) {
+void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int signal, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    reblurBlurKernel<<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    withSignal(signal, [&](auto sig) {
+        reblurBlurKernel<decltype(sig)::value><<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    });
 }
-void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, bool temporalStabilization, int flags, Rows rows, cudaStream_t stream) {
+void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, int signal, bool temporalStabilization, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    if (temporalStabilization)
-        reblurPostBlurKernel<true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
-    else
-        reblurPostBlurKernel<false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    withSignal(signal, [&](auto sig) {
+        constexpr int S = decltype(sig)::value;
+        if (temporalStabilization)
+            reblurPostBlurKernel<true, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        else
+            reblurPostBlurKernel<false, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    });
 }
 
 }  // namespace nrdk

@@ -1,4 +1,4 @@
-// REBLUR temporal accumulation on sm_100a (NRD_SIGNAL=BOTH, NRD_MODE=RADIANCE).
+// REBLUR temporal accumulation on sm_100a (NRD_MODE=RADIANCE; NRD_SIGNAL = DIFF / SPEC / BOTH is a template parameter).
 //
 // Replaces External/NRD/Shaders/REBLUR_TemporalAccumulation.cs.hlsl:68-995: surface-motion and virtual (specular)
 // motion reprojection with per-tap occlusion tests on the previous frame's viewZ / normals / material IDs, thin-lens
@@ -43,7 +43,7 @@ NRD_DEV uint4 gather4(const TexR16U& t, int x0, int y0) {
 #    define TA_MIN_BLOCKS 3  // 80 regs + 88 B spill (3 CTAs / SM): 450 us vs 514 us at 128 regs (2 CTAs) for a 1440p frame on B200
 #endif
 // OPTIONAL: checkerboard resolve speed-up and the application's guide textures (confidence, threshold mix); compiled out of the plain kernel
-template <bool OPTIONAL>
+template <bool OPTIONAL, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTemporalAccumulationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                       const __grid_constant__ TemporalAccumulationParams p, int ctaY0) {
     __shared__ float4 sNormalHitDist[TILE_H][TILE_W];
@@ -65,9 +65,12 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
             int sx = i % TILE_W, sy = i / TILE_W;
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
             float3 N = xyz(unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy)));
-            float hitDist = cb.specPrepassBlurRadius == 0.0f ? p.inSpec.load(gx, gy).w : p.inSpecHitDistForTracking.load(gx, gy);
-            float z = unpackViewZ(cb, p.viewZ.load(gx, gy));
-            sNormalHitDist[sy][sx] = f4(N, (hitDist == 0.0f || !inDenoisingRange(cb, z)) ? NRD_INF : hitDist);
+            if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) {
+                float hitDist = cb.specPrepassBlurRadius == 0.0f ? p.inSpec.load(gx, gy).w : p.inSpecHitDistForTracking.load(gx, gy);
+                float z = unpackViewZ(cb, p.viewZ.load(gx, gy));
+                sNormalHitDist[sy][sx] = f4(N, (hitDist == 0.0f || !inDenoisingRange(cb, z)) ? NRD_INF : hitDist);
+            } else
+                sNormalHitDist[sy][sx] = f4(N, 0.0f);  // the tracking distance is a specular-only quantity (TA:43-63)
         }
     }
     __syncthreads();
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
     hitDistForTracking = hitDistForTracking == NRD_INF ? 0.0f : hitDistForTracking;
     const float hitDistNormalization = hitDistanceNormalization(viewZ, cb.hitDistSettings, roughness);
     hitDistForTracking *= cb.specPrepassBlurRadius == 0.0f ? hitDistNormalization : 1.0f;
-    p.outSpecHitDistForTracking.store(px, py, hitDistForTracking);
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) p.outSpecHitDistForTracking.store(px, py, hitDistForTracking);
 
     // Previous position and surface motion uv
     float4 mvRaw = p.mv.load(px, py);
@@ -222,8 +225,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
     smbFootprintQuality *= sizeQuality;
 
     // =============================================================================================== Specular
-    float specAccumSpeedCorrected, curvature, virtualHistoryAmount;
-    {
+    float specAccumSpeedCorrected = 0.0f, curvature = 0.0f, virtualHistoryAmount = 0.0f;  // what a diffuse-only denoiser packs (TA:869-873)
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) {
         float smbSpecHistoryConfidence = smbFootprintQuality;
         if (OPTIONAL && cb.hasHistoryConfidence) smbSpecHistoryConfidence = fminf(smbSpecHistoryConfidence, saturate(p.specConfidence.sampleLinear(smbPixelUv)));
         smbSpecAccumSpeed *= lerp(smbSpecHistoryConfidence, 1.0f, 1.0f / (1.0f + smbSpecAccumSpeed));
@@ -534,10 +537,11 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         }
     }
 
-    p.outData2.store(px, py, packData2(fbits, curvature, virtualHistoryAmount, smbAllowCatRom));
+    storeData2<SIGNAL>(p, px, py, fbits, curvature, virtualHistoryAmount, smbAllowCatRom);
 
     // =============================================================================================== Diffuse
-    {
+    if constexpr ((SIGNAL & SIGNAL_DIFF) == 0) diffAccumSpeed = 0.0f;  // TA:972-974
+    else {
         float diffHistoryConfidence = smbFootprintQuality;
         if (OPTIONAL && cb.hasHistoryConfidence) diffHistoryConfidence = fminf(diffHistoryConfidence, saturate(p.diffConfidence.sampleLinear(smbPixelUv)));
         diffAccumSpeed *= lerp(diffHistoryConfidence, 1.0f, 1.0f / (1.0f + diffAccumSpeed));
@@ -572,17 +576,20 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         p.outDiffFast.store(px, py, fastResult);
     }
 
-    p.outData1.store(px, py, packData1(diffAccumSpeed, specAccumSpeedCorrected));
+    storeData1<SIGNAL>(p, px, py, diffAccumSpeed, specAccumSpeedCorrected);
 }
 
-void launchReblurTemporalAccumulation(const ReblurConstants& cb, const TemporalAccumulationParams& p, Rows rows, cudaStream_t stream) {
+void launchReblurTemporalAccumulation(const ReblurConstants& cb, const TemporalAccumulationParams& p, int signal, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    if (cb.specCheckerboard != 2u || cb.diffCheckerboard != 2u || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix)
-        reblurTemporalAccumulationKernel<true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
-    else
-        reblurTemporalAccumulationKernel<false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+    withSignal(signal, [&](auto sig) {
+        constexpr int S = decltype(sig)::value;
+        if (cb.specCheckerboard != 2u || cb.diffCheckerboard != 2u || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix)
+            reblurTemporalAccumulationKernel<true, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+        else
+            reblurTemporalAccumulationKernel<false, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+    });
 }
 
 }  // namespace nrdk

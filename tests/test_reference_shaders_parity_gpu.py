@@ -38,10 +38,19 @@ CASES["relax_cb_guides_split"] = (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, "relax
 CASES["relax_nosh_cb_guides"] = (api.Denoiser.RELAX_DIFFUSE_SPECULAR, "relax_frame_nosh_cb_guides", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
 CASES["relax_nosh_recon5x5"] = (api.Denoiser.RELAX_DIFFUSE_SPECULAR, "relax_frame_nosh_holes", ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "reblur")
 CASES["relax_recon3x3"] = (api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, "relax_frame_holes", ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur")
-SETTINGS = {"relax_nosh_recon5x5": lambda: api.RelaxSettings(hitDistanceReconstructionMode=2), "relax_recon3x3": lambda: api.RelaxSettings(hitDistanceReconstructionMode=1),
+# REBLUR_DIFFUSE / REBLUR_SPECULAR ( NRD_SIGNAL = DIFF / SPEC permutations: R8 data1, 8-bit data2 for diffuse ); the second pair runs them the way
+# NRDSample would ( checkerboard WHITE + confidence ) resp. with hit-distance reconstruction and without stabilization
+CASES["reblur_diff"] = (api.Denoiser.REBLUR_DIFFUSE, "reblur_frame_diff", ("OUT_DIFF_RADIANCE_HITDIST",), "reblur")
+CASES["reblur_spec"] = (api.Denoiser.REBLUR_SPECULAR, "reblur_frame_spec", ("OUT_SPEC_RADIANCE_HITDIST",), "reblur")
+CASES["reblur_diff_cb_guides"] = (api.Denoiser.REBLUR_DIFFUSE, "reblur_frame_diff_cb_guides", ("OUT_DIFF_RADIANCE_HITDIST",), "reblur")
+CASES["reblur_spec_recon_nots"] = (api.Denoiser.REBLUR_SPECULAR, "reblur_frame_spec_holes", ("OUT_SPEC_RADIANCE_HITDIST",), "reblur")
+SETTINGS = {"reblur_diff_cb_guides": lambda: api.ReblurSettings(checkerboardMode=2),
+            "reblur_spec_recon_nots": lambda: api.ReblurSettings(hitDistanceReconstructionMode=1, maxStabilizedFrameNum=0),
+            "relax_nosh_recon5x5": lambda: api.RelaxSettings(hitDistanceReconstructionMode=2), "relax_recon3x3": lambda: api.RelaxSettings(hitDistanceReconstructionMode=1),
             "relax_cb_guides_split": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True), "relax_nosh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2),
             "reblur_split": lambda: api.ReblurSettings(checkerboardMode=2), "reference": lambda: api.ReferenceSettings(maxAccumulatedFrameNum=5), "reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_guides_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
-COMMON = {"relax_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.3),
+COMMON = {"reblur_diff_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
+          "relax_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.3),
           "relax_nosh_cb_guides": dict(isHistoryConfidenceAvailable=True),
           "reblur_guides_cb": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True), "reblur_split": dict(splitScreen=0.35),
           "reference": dict(splitScreen=0.2)}
@@ -60,6 +69,10 @@ def out_format(which, o, runner):
 
 
 def frame_of(name, f, w, h):
+    for lobe, other in (("diff", "_SPEC_"), ("spec", "_DIFF_")):   # single-lobe denoisers: the other lobe's inputs do not exist
+        if name.startswith(f"reblur_frame_{lobe}"):
+            kw = dict(checkerboard=2, guides=True) if name.endswith("_cb_guides") else (dict(holes=True) if name.endswith("_holes") else {})
+            return {k: v for k, v in synth.reblur_frame(f, w, h, **kw).items() if other not in k}
     if name == "relax_frame_nosh":
         return synth.relax_frame(f, w, h, sh=False)
     if name == "relax_frame_holes":
@@ -78,7 +91,7 @@ def frame_of(name, f, w, h):
         return synth.sigma_frame(f, w, h, translucency=True)
     return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0), "reblur_split": (3e-2, 45.0), "reference": (1e-3, 80.0), "relax_cb_guides_split": (2e-3, 60.0), "relax_nosh_cb_guides": (2e-3, 60.0), "relax_nosh_recon5x5": (2e-3, 60.0), "relax_recon3x3": (2e-3, 60.0)}
+LIMITS = {"reblur_diff": (3e-2, 45.0), "reblur_spec": (3e-2, 45.0), "reblur_diff_cb_guides": (3e-2, 45.0), "reblur_spec_recon_nots": (3e-2, 45.0), "reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0), "reblur_split": (3e-2, 45.0), "reference": (1e-3, 80.0), "relax_cb_guides_split": (2e-3, 60.0), "relax_nosh_cb_guides": (2e-3, 60.0), "relax_nosh_recon5x5": (2e-3, 60.0), "relax_recon3x3": (2e-3, 60.0)}
 
 
 @pytest.fixture(scope="module")

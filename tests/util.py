@@ -42,7 +42,7 @@ def compare(a: torch.Tensor, b: torch.Tensor, fmt: int, atol=1e-3, rtol=2 ** -9,
     diff = (da - db).abs()
     if f in (api.Format.R8_UNORM, api.Format.RG8_UNORM, api.Format.RGBA8_UNORM, api.Format.R10_G10_B10_A2_UNORM):
         bad = diff > 1.0
-    elif f == api.Format.R16_UINT:
+    elif f in (api.Format.R16_UINT, api.Format.R8_UINT):
         bad = diff > 0.0
     elif f == api.Format.R32_UINT and layout == "sigma":
         bad = diff > 0.0                                                     # viewZ bits and 3-bit history length: identical
