@@ -133,14 +133,20 @@ NRD_DEV float2 temporalAccumulationParams(const ReblurConstants& cb, float footp
     return make_float2(w, 1.0f + 3.0f * cb.framerateScale * w);
 }
 
-// 12-tap Catmull-Rom without corners as 5 bilinear fetches, falling back to custom-weighted bilinear (Common.hlsli:604-658)
+// 12-tap Catmull-Rom without corners, falling back to custom-weighted bilinear (Common.hlsli:604-658). The reference issues 5 hardware
+// bilinear fetches at ( tc.x, -1 ), ( -1, tc.y ), ( tc.x, tc.y ), ( 2, tc.y ), ( tc.x, 2 ) around the footprint origin; four of them sit
+// exactly on a texel row or column, so of the 20 texels a bilinear unit would touch only the 12 of the 4x4-minus-corners footprint carry
+// weight. They are fetched directly ( clamp addressing, like the sampler ) and blended with the same lerps the sampler would do: 12
+// loads + 8 lerps per texture instead of 20 loads + 15 lerps. The bilinear fallback reads its 4 texels. `invResourceSize` must be
+// 1 / the size of the sampled texture ( static resolution ).
 struct HistoryFilter {
     float4 w;
     float w4, sum;
-    float2 uv[5];
+    float2 tc;
     int ox, oy;
+    bool bicubic;
     float4 custom;
-    NRD_DEV HistoryFilter(float2 samplePos, float2 invResourceSize, float4 customWeights, bool useBicubic) {
+    NRD_DEV HistoryFilter(float2 samplePos, float2 /*invResourceSize*/, float4 customWeights, bool useBicubic) {
         const float S = 0.5f;
         float2 centerPos = floor2(samplePos - 0.5f) + 0.5f;
         float2 f = saturate(samplePos - centerPos);
@@ -149,25 +155,31 @@ struct HistoryFilter {
         float2 w2 = f * (f * (-(2.0f - S) * f + (3.0f - 2.0f * S)) + S);
         float2 w3 = f * (f * (S * f - S));
         float2 w12 = w1 + w2;
-        float2 tc = w2 / w12;
+        tc = w2 / w12;
         w = useBicubic ? make_float4(w12.x * w0.y, w0.x * w12.y, w12.x * w12.y, w3.x * w12.y) : customWeights;
         w4 = useBicubic ? w12.x * w3.y : 0.0f;
         sum = sum4(w) + w4;
-        uv[0] = (centerPos + (useBicubic ? make_float2(tc.x, -1.0f) : make_float2(0.0f, 0.0f))) * invResourceSize;
-        uv[1] = (centerPos + (useBicubic ? make_float2(-1.0f, tc.y) : make_float2(1.0f, 0.0f))) * invResourceSize;
-        uv[2] = (centerPos + (useBicubic ? make_float2(tc.x, tc.y) : make_float2(0.0f, 1.0f))) * invResourceSize;
-        uv[3] = (centerPos + (useBicubic ? make_float2(2.0f, tc.y) : make_float2(1.0f, 1.0f))) * invResourceSize;
-        uv[4] = (centerPos + (useBicubic ? make_float2(tc.x, 2.0f) : f)) * invResourceSize;
         ox = (int)centerPos.x;
         oy = (int)centerPos.y;
+        bicubic = useBicubic;
         custom = customWeights;
     }
-    template <class TEX> NRD_DEV auto color(const TEX& tex) const -> decltype(tex.sampleLinear(uv[0])) {
-        auto c = tex.sampleLinear(uv[0]) * w.x;
-        c += tex.sampleLinear(uv[1]) * w.y;
-        c += tex.sampleLinear(uv[2]) * w.z;
-        c += tex.sampleLinear(uv[3]) * w.w;
-        c += tex.sampleLinear(uv[4]) * w4;
+    template <class TEX> NRD_DEV auto color(const TEX& tex) const -> decltype(tex.fetchClamped(0, 0)) {
+        const int x0 = tex.cx(ox), x1 = tex.cx(ox + 1), y0 = tex.cy(oy), y1 = tex.cy(oy + 1);
+        decltype(tex.fetchClamped(0, 0)) c;
+        if (bicubic) {
+            const int xm = tex.cx(ox - 1), x2 = tex.cx(ox + 2), ym = tex.cy(oy - 1), y2 = tex.cy(oy + 2);
+            c = lerp(tex.fetch(x0, ym), tex.fetch(x1, ym), tc.x) * w.x;
+            c += lerp(tex.fetch(xm, y0), tex.fetch(xm, y1), tc.y) * w.y;
+            c += lerp(lerp(tex.fetch(x0, y0), tex.fetch(x1, y0), tc.x), lerp(tex.fetch(x0, y1), tex.fetch(x1, y1), tc.x), tc.y) * w.z;
+            c += lerp(tex.fetch(x2, y0), tex.fetch(x2, y1), tc.y) * w.w;
+            c += lerp(tex.fetch(x0, y2), tex.fetch(x1, y2), tc.x) * w4;
+        } else {
+            c = tex.fetch(x0, y0) * w.x;
+            c += tex.fetch(x1, y0) * w.y;
+            c += tex.fetch(x0, y1) * w.z;
+            c += tex.fetch(x1, y1) * w.w;
+        }
         return sum < 0.0001f ? c * 0.0f : c / sum;
     }
     NRD_DEV float bilinear(const TexR16F& tex) const {

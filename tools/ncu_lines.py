@@ -1,8 +1,10 @@
 """Attribute executed warp instructions of one kernel (from an .ncu-rep SASS page) to CUDA source lines (nvdisasm -g line info).
-  python tools/ncu_lines.py gpurun_out/x.ncu-rep build/kernels_reblur_spatial.cu.o reblurBlurKernel [top]"""
+  python tools/ncu_lines.py gpurun_out/x.ncu-rep build/kernels_reblur_spatial.cu.o reblurBlurKernel [top] [mangled-substring]
+The optional mangled substring picks one template instantiation in the object file, e.g. reblurBlurKernelILi3E for <SIGNAL_BOTH>."""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 rep, obj, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+section = sys.argv[5] if len(sys.argv) > 5 else kern
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -12,7 +14,7 @@ line_of = {}
 inside, cur = False, None
 for l in dis:
     if l.startswith("//---------------------") and ".text." in l:
-        inside = kern in l
+        inside = section in l
         continue
     if not inside:
         continue
