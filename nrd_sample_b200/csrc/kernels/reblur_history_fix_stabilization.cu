@@ -165,8 +165,11 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
 }
 }  // namespace
 
+#ifndef HF_MIN_BLOCKS
+#    define HF_MIN_BLOCKS 3  // 512-thread CTAs: 40 regs (3 CTAs / SM) 153 us vs 156 us at 57 regs (2 CTAs)
+#endif
 template <int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HistoryFixParams p, int quads, int ctaY0) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, HF_MIN_BLOCKS) reblurHistoryFixKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HistoryFixParams p, int quads, int ctaY0) {
     constexpr bool HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0, HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0;
     __shared__ float sDiffLuma[HAS_DIFF ? HF_TILE_H : 1][HF_TILE_W];
     __shared__ float sSpecLuma[HAS_SPEC ? HF_TILE_H : 1][HF_TILE_W];
@@ -183,10 +186,14 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHistoryFixKernel(const
         for (int i = tid; i < HF_TILE_W * HF_TILE_H; i += BLOCK_W * BLOCK_H) {
             int sx = i % HF_TILE_W, sy = i / HF_TILE_W;
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
-            bool sky = !inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.load(gx, gy)));
+            // the coordinates are clamped to the rect: plain fetches, issued together with the viewZ load instead of behind its sky test
+            float dFast = 0.0f, sFast = 0.0f;
+            if constexpr (HAS_DIFF) dFast = p.inDiffFast.fetch(gx, gy);
+            if constexpr (HAS_SPEC) sFast = p.inSpecFast.fetch(gx, gy);
+            bool sky = !inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.fetch(gx, gy)));
             sawSky |= sky ? 1 : 0;
-            if constexpr (HAS_DIFF) sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : p.inDiffFast.load(gx, gy);
-            if constexpr (HAS_SPEC) sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : p.inSpecFast.load(gx, gy);
+            if constexpr (HAS_DIFF) sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : dFast;
+            if constexpr (HAS_SPEC) sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : sFast;
         }
     }
     const bool tileHasSky = __syncthreads_or(sawSky) != 0;  // also the barrier that publishes the tile
@@ -289,9 +296,13 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
         for (int i = tid; i < TS_TILE_W * TS_TILE_H; i += BLOCK_W * BLOCK_H) {
             int sx = i % TS_TILE_W, sy = i / TS_TILE_W;
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
-            bool sky = !inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.load(gx, gy)));
-            if constexpr (HAS_DIFF) sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : p.inDiff.load(gx, gy).x;
-            if constexpr (HAS_SPEC) sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : p.inSpec.load(gx, gy).x;
+            // clamped coordinates: plain fetches of the luma half-words, issued together with the viewZ load
+            float dLuma = 0.0f, sLuma = 0.0f;
+            if constexpr (HAS_DIFF) dLuma = __half2float(__ushort_as_half(__ldg(p.inDiff.template ptr<unsigned short>(gx * 4, gy * 4) )));
+            if constexpr (HAS_SPEC) sLuma = __half2float(__ushort_as_half(__ldg(p.inSpec.template ptr<unsigned short>(gx * 4, gy * 4) )));
+            bool sky = !inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.fetch(gx, gy)));
+            if constexpr (HAS_DIFF) sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : dLuma;
+            if constexpr (HAS_SPEC) sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : sLuma;
         }
     }
     __syncthreads();

@@ -40,7 +40,7 @@ NRD_DEV uint4 gather4(const TexR16U& t, int x0, int y0) {
 }  // namespace
 
 #ifndef TA_MIN_BLOCKS
-#    define TA_MIN_BLOCKS 3  // 80 regs + 88 B spill (3 CTAs / SM): 450 us vs 514 us at 128 regs (2 CTAs) for a 1440p frame on B200
+#    define TA_MIN_BLOCKS 4  // 64 regs (4 CTAs / SM): 383 us vs 401 us at 80 regs (3 CTAs) and 467 us at 128 regs (2 CTAs) for a 1440p frame on B200
 #endif
 // OPTIONAL: checkerboard resolve speed-up and the application's guide textures (confidence, threshold mix); compiled out of the plain kernel
 template <bool OPTIONAL, int SIGNAL>

@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
 
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef RELAX_TA_MIN_BLOCKS
-#define RELAX_TA_MIN_BLOCKS 3
+#define RELAX_TA_MIN_BLOCKS 4  // 64 regs: 612 us vs 652 us at 80 regs (3 CTAs) and 714 us at 128 regs (2 CTAs) per 1440p frame
 #endif
 // OPT: checkerboard resolve speed-up and the application's guide textures ( confidence, threshold mix ); compiled out of the plain kernel
 template <bool SH, bool OPT>

@@ -7,6 +7,7 @@ raise — there is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -52,7 +53,7 @@ _lib: Optional[C.CDLL] = None
 def load() -> C.CDLL:
     global _lib
     if _lib is None:
-        path = _build.build()
+        path = os.environ.get("NRD_B200_LIB") or _build.build()   # NRD_B200_LIB: a prebuilt variant (tools/build_variant.py), experiments only
         L = C.CDLL(path)
         L.nrdcuDispatch.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.POINTER(CuTexture), C.c_uint32, C.c_uint32, C.c_void_p]
         L.nrdcuDispatch.restype = C.c_uint32
