@@ -123,6 +123,23 @@ NRDCU_API uint32_t nrdcuResolveProfile(nrdcuContext* ctx);
 NRDCU_API uint32_t nrdcuGetProfileEntry(nrdcuContext* ctx, uint32_t index, const char** name, double* totalMs, uint64_t* count);
 NRDCU_API void nrdcuResetProfile(nrdcuContext* ctx);
 
+/* ---- front end / back end on the device ( SURVEY.md 8(f).2 ) ---------------------------------------------------------
+ * The application-side helpers of NRD.hlsli as CUDA: include/nrd_frontend.cuh holds the functions ( host + device ), these entry points run
+ * them over whole frames for renderers that keep fp32 results in linear device buffers ( tightly packed, width * height texels ).
+ * Replaces the packing at NRDSample Shaders/TraceOpaque.cs.hlsl:738-757 and the unpacking at Shaders/Composition.cs.hlsl:85-118.
+ *   mode 0 = REBLUR ( YCoCg radiance, hit distance normalised with ReblurSettings::hitDistanceParameters { A, B, C } ), 1 = RELAX.
+ * Return values are nrd::Result; nrdcuFrontEndGetLastError describes the last failure of these calls. All calls are asynchronous on `stream`
+ * except nrdcuFrontEndProbe. */
+NRDCU_API uint32_t nrdcuFrontEndPackNormalRoughness(const float* normalRoughness /* float4: N.xyz, linear roughness */, const float* materialID /* 0..3, may be NULL */,
+                                                    const nrdcuTexture* outNormalRoughness /* R10_G10_B10_A2_UNORM */, void* stream);
+NRDCU_API uint32_t nrdcuFrontEndPackRadianceHitDist(uint32_t mode, const float* radianceHitDist /* float4: linear radiance, hit distance */, const nrdcuTexture* viewZ /* R32_SFLOAT, REBLUR */,
+                                                    const nrdcuTexture* normalRoughness /* specular lobe of REBLUR */, uint32_t isSpecular, const float* hitDistParams3,
+                                                    const nrdcuTexture* out /* RGBA16_SFLOAT */, void* stream);
+NRDCU_API uint32_t nrdcuBackEndUnpackRadiance(uint32_t mode, const nrdcuTexture* in /* RGBA16_SFLOAT */, float* outRadiance /* float4: linear radiance, .w as stored */, void* stream);
+/* Verification hook: nrd_sample_b200/csrc/frontend_probe.inl ( every function of nrd_frontend.cuh ) over n columns; in6 / out21 are HOST arrays of DEVICE pointers to n float4 each. */
+NRDCU_API uint32_t nrdcuFrontEndProbe(const float* const* in6, float* const* out21, uint32_t n, void* stream);
+NRDCU_API const char* nrdcuFrontEndGetLastError(void);
+
 /* ---- introspection ------------------------------------------------------------------------------------------- */
 NRDCU_API const char* nrdcuGetLastError(void);
 NRDCU_API uint64_t nrdcuGetLaunchCount(void);           /* kernels launched by this library since load (all contexts) */

@@ -25,6 +25,8 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ] + os.environ.get("NRD_B200_NVCC_EXTRA", "").split()  # experiments only, e.g. NRD_B200_NVCC_EXTRA=-use_fast_math
+# HBM-bound data-movement kernels whose arithmetic should match the host build of the same header bit for bit: IEEE division / sqrt, no FMA contraction
+PRECISE_FILES = {"frontend.cu"}
 HOST_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-Wall", "-Wextra"]
 
 
@@ -75,7 +77,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
             continue
         if src.endswith(".cu"):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            flags = [f for f in NVCC_FLAGS if f != "-use_fast_math"] + ["-fmad=false"] if os.path.basename(src) in PRECISE_FILES else NVCC_FLAGS
+            cmd = [_nvcc()] + flags + ["-c", src, "-o", obj]
         else:
             cmd = ["g++"] + HOST_FLAGS + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -321,6 +321,10 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
 
 }  // namespace
 
+namespace nrdk {
+void countLaunch() { g_launchCount.fetch_add(1, std::memory_order_relaxed); }  // kernels launched by frontend.cu
+}
+
 // =================================================================================================================
 // C ABI
 // =================================================================================================================

@@ -27,7 +27,8 @@ FLAG_ROBUST_MIRROR_TEST = 4
 NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdcuAllocSharedTexture", "nrdcuTileExportSize", "nrdcuTileExport", "nrdcuTileAttach",
                  "nrdcuTileSetHalo", "nrdcuTileGetStatus", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
                  "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuDenoiseHostPipelined", "nrdcuHostFlush", "nrdcuGetLastError", "nrdcuGetLaunchCount",
-                 "nrdcuGetPoolBytes", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile")
+                 "nrdcuGetPoolBytes", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile",
+                 "nrdcuFrontEndPackNormalRoughness", "nrdcuFrontEndPackRadianceHitDist", "nrdcuBackEndUnpackRadiance", "nrdcuFrontEndProbe", "nrdcuFrontEndGetLastError")
 
 # nrd::Format -> (torch dtype, channels) for tensors handed to / returned by the executor
 FORMAT_STORAGE = {
@@ -257,3 +258,69 @@ def _as_byte_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:
     r = _Raw()
     r.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
     return torch.as_tensor(r, device=f"cuda:{device}")
+
+
+# ------------------------------------------------------------------------------------------------
+# Front end / back end on the device (include/nrd_frontend.cuh, csrc/kernels/frontend.cu)
+# ------------------------------------------------------------------------------------------------
+def _frontend_check(rc: int, what: str):
+    if rc != 0:
+        raise NrdcuError(f"{what}: {api.Result(rc).name}: {load().nrdcuFrontEndGetLastError().decode()}")
+
+
+def frontend_probe(inputs: Sequence[torch.Tensor], device="cuda:0"):
+    """Runs csrc/frontend_probe.inl on the device: `inputs` = 6 (n, 4) fp32 tensors, returns 21 (n, 4) fp32 device tensors."""
+    L = load()
+    L.nrdcuFrontEndProbe.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]
+    L.nrdcuFrontEndGetLastError.restype = C.c_char_p
+    n = inputs[0].shape[0]
+    dev_in = [t.to(device=device, dtype=torch.float32).contiguous() for t in inputs]
+    outs = [torch.zeros(n, 4, dtype=torch.float32, device=device) for _ in range(21)]
+    torch.cuda.synchronize()
+    rc = L.nrdcuFrontEndProbe((C.c_void_p * 6)(*[t.data_ptr() for t in dev_in]), (C.c_void_p * 21)(*[t.data_ptr() for t in outs]), n, None)
+    _frontend_check(rc, "nrdcuFrontEndProbe")
+    return outs
+
+
+def frontend_pack_normal_roughness(normal_roughness: torch.Tensor, material_id: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(H, W, 4) fp32 { N, linear roughness } (+ (H, W) fp32 material IDs 0..3) -> IN_NORMAL_ROUGHNESS (H, W) int32 texels."""
+    L = load()
+    L.nrdcuFrontEndPackNormalRoughness.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CuTexture), C.c_void_p]
+    L.nrdcuFrontEndGetLastError.restype = C.c_char_p
+    h, w = normal_roughness.shape[:2]
+    out = alloc_texture(api.Format.R10_G10_B10_A2_UNORM, w, h, normal_roughness.device)
+    tex = texture_of(out, api.Format.R10_G10_B10_A2_UNORM)
+    rc = L.nrdcuFrontEndPackNormalRoughness(normal_roughness.contiguous().data_ptr(), material_id.contiguous().data_ptr() if material_id is not None else None, C.byref(tex),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _frontend_check(rc, "nrdcuFrontEndPackNormalRoughness")
+    return out
+
+
+def frontend_pack_radiance_hitdist(mode: int, radiance_hitdist: torch.Tensor, viewz: Optional[torch.Tensor] = None, normal_roughness: Optional[torch.Tensor] = None,
+                                   is_specular: bool = False, hit_dist_params=(3.0, 0.1, 20.0)) -> torch.Tensor:
+    """(H, W, 4) fp32 { linear radiance, hit distance } -> IN_*_RADIANCE_HITDIST (H, W, 4) fp16. mode 0 = REBLUR (needs viewz, and normal_roughness for specular), 1 = RELAX."""
+    L = load()
+    L.nrdcuFrontEndPackRadianceHitDist.argtypes = [C.c_uint32, C.c_void_p, C.POINTER(CuTexture), C.POINTER(CuTexture), C.c_uint32, C.POINTER(C.c_float), C.POINTER(CuTexture), C.c_void_p]
+    L.nrdcuFrontEndGetLastError.restype = C.c_char_p
+    h, w = radiance_hitdist.shape[:2]
+    out = alloc_texture(api.Format.RGBA16_SFLOAT, w, h, radiance_hitdist.device)
+    tz = C.byref(texture_of(viewz, api.Format.R32_SFLOAT)) if viewz is not None else None
+    tn = C.byref(texture_of(normal_roughness, api.Format.R10_G10_B10_A2_UNORM)) if normal_roughness is not None else None
+    to = texture_of(out, api.Format.RGBA16_SFLOAT)
+    rc = L.nrdcuFrontEndPackRadianceHitDist(mode, radiance_hitdist.contiguous().data_ptr(), tz, tn, 1 if is_specular else 0, (C.c_float * 3)(*hit_dist_params), C.byref(to),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _frontend_check(rc, "nrdcuFrontEndPackRadianceHitDist")
+    return out
+
+
+def backend_unpack_radiance(mode: int, texture: torch.Tensor) -> torch.Tensor:
+    """OUT_*_RADIANCE_HITDIST (H, W, 4) fp16 -> (H, W, 4) fp32 { linear radiance, .w as stored }."""
+    L = load()
+    L.nrdcuBackEndUnpackRadiance.argtypes = [C.c_uint32, C.POINTER(CuTexture), C.c_void_p, C.c_void_p]
+    L.nrdcuFrontEndGetLastError.restype = C.c_char_p
+    h, w = texture.shape[:2]
+    out = torch.empty(h, w, 4, dtype=torch.float32, device=texture.device)
+    tex = texture_of(texture, api.Format.RGBA16_SFLOAT)
+    rc = L.nrdcuBackEndUnpackRadiance(mode, C.byref(tex), out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _frontend_check(rc, "nrdcuBackEndUnpackRadiance")
+    return out

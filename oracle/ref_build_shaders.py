@@ -72,6 +72,8 @@ IDENTIFIERS = [
     ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1"), ("REBLUR_TemporalStabilization.cs.hlsl", ""), ("REBLUR_SplitScreen.cs.hlsl", ""))] + [
     # REFERENCE
     "REFERENCE_TemporalAccumulation.cs.hlsl", "REFERENCE_Copy.cs.hlsl",
+    # ours: calls the application-side functions of the reference's NRD.hlsli ( oracle/ref_shim/Shaders/NRD_FrontEndProbe.cs.hlsl )
+    "NRD_FrontEndProbe.cs.hlsl",
 ]
 CXXFLAGS = ["-std=c++20", "-O2", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fvisibility=hidden", "-w", "-fmax-errors=25", "-I", SHIM]
 
@@ -80,7 +82,7 @@ def cxx_for(identifier: str) -> str:
     parts = identifier.split("|")
     defines = [f"-D{p}" for p in parts[1:]]
     cpp = ["gcc", "-E", "-P", "-undef", "-nostdinc", "-x", "c", "-include", os.path.join(SHIM, "hlsl_engine_macros.h"), "-I", SHADERS, "-I", ML, "-I", SHIM] + defines + [
-        os.path.join(SHADERS, parts[0])]
+        os.path.join(SHADERS if os.path.exists(os.path.join(SHADERS, parts[0])) else os.path.join(SHIM, "Shaders"), parts[0])]
     pre = subprocess.run(cpp, capture_output=True, text=True)
     if pre.returncode:
         raise RuntimeError(f"{identifier}: preprocessing failed\n{pre.stderr}")

@@ -30,6 +30,7 @@ class OracleTexture(C.Structure):
 def build(force: bool = False) -> str:
     """Compile the oracle (and, when the reference tree is mounted, oracle/_ref). Returns the .so path."""
     srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cpp", ".h"))]
+    srcs += [os.path.join(HERE, "..", "include", "nrd_frontend.cuh"), os.path.join(HERE, "..", "nrd_sample_b200", "csrc", "frontend_probe.inl")]   # frontend_probe.cpp
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
@@ -38,6 +39,7 @@ def build(force: bool = False) -> str:
     if os.path.isdir("/root/reference/External/NRD/Shaders"):
         shim = os.path.join(HERE, "ref_shim")
         deps = [os.path.join(shim, f) for f in os.listdir(shim)] + [os.path.join(HERE, "ref_build_shaders.py")]
+        deps += [os.path.join(shim, "Shaders", f) for f in os.listdir(os.path.join(shim, "Shaders"))]
         if force or not os.path.exists(REF_SHADERS_PATH) or any(os.path.getmtime(d) > os.path.getmtime(REF_SHADERS_PATH) for d in deps):
             import sys
             subprocess.check_call([sys.executable, os.path.join(HERE, "ref_build_shaders.py")], stdout=subprocess.DEVNULL)
