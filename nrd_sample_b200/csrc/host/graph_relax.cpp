@@ -62,24 +62,55 @@ const uint32_t kCb = sizeof(RelaxConstants);
 
 }  // namespace
 
-// RELAX_DIFFUSE_SPECULAR is the same graph without the SH1 textures (Relax_DiffuseSpecular.hpp:13-312): the pool enums above are the SH
-// ones, `Pm` / `Tr` compact them when `sh` is false.
-void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
+// One graph for the six RELAX denoisers: RELAX_DIFFUSE_SPECULAR( _SH ) (Relax_DiffuseSpecular( Sh ).hpp), RELAX_DIFFUSE( _SH ) (Relax_Diffuse( Sh ).hpp) and
+// RELAX_SPECULAR( _SH ) (Relax_Specular( Sh ).hpp). The single-lobe ones are the two-lobe graph without the other lobe's textures and bindings; the
+// RADIANCE ones are the SH graph without the SH1 textures. The pool enums above name the textures, `Pm` / `Tr` map them to the pool order of the
+// denoiser at hand.
+void Graph::buildRelax(DenoiserState& d, bool diff, bool spec, bool sh) {
     new (&d.settings.relax) RelaxSettings();
     d.settingsSize = sizeof(RelaxSettings);
 
-    for (int i = 0; i < (sh ? 8 : 4); i++) addPermanent(Format::RGBA16_SFLOAT);  // spec / diff x { normal, responsive } ( x { SH0, SH1 } ) history
-    addPermanent(Format::R16_SFLOAT);   // reflection hit T (ping)
-    addPermanent(Format::R16_SFLOAT);   // reflection hit T (pong)
-    addPermanent(Format::R8_UNORM);     // history length
-    addPermanent(Format::RGBA8_UNORM);  // prev normal + roughness
-    addPermanent(Format::R8_UNORM);     // prev material ID
-    addPermanent(Format::R32_SFLOAT);   // prev viewZ
+    uint16_t permIndex[16], tranIndex[16];
+    for (int i = 0; i < 16; i++) permIndex[i] = tranIndex[i] = 0xFFFF;
+    uint16_t nPerm = 0, nTran = 0;  // denoiser-local pool indices, in allocation order
+    auto perm = [&](uint16_t which, Format f) { addPermanent(f); permIndex[which] = nPerm++; };
+    auto tran = [&](uint16_t which, Format f, uint16_t downsample = 1) { addTransient(f, downsample); tranIndex[which] = nTran++; };
+    const Format kIllum = Format::RGBA16_SFLOAT;
+    if (diff && spec && !sh) {  // Relax_DiffuseSpecular.hpp:17-22: lobes interleaved
+        perm(P_SPEC_ILLUM_PREV, kIllum);
+        perm(P_DIFF_ILLUM_PREV, kIllum);
+        perm(P_SPEC_ILLUM_RESPONSIVE_PREV, kIllum);
+        perm(P_DIFF_ILLUM_RESPONSIVE_PREV, kIllum);
+    } else {                    // lobe-major: { normal, ( SH1 ), responsive, ( SH1 ) } per lobe, specular first
+        for (int lobe = 0; lobe < 2; lobe++) {
+            if (!(lobe == 0 ? spec : diff)) continue;
+            const uint16_t base = lobe == 0 ? P_SPEC_ILLUM_PREV : P_DIFF_ILLUM_PREV;
+            perm(base + 0, kIllum);
+            if (sh) perm(base + 1, kIllum);
+            perm(base + 2, kIllum);
+            if (sh) perm(base + 3, kIllum);
+        }
+    }
+    if (spec) {
+        perm(P_REFLECTION_HIT_T_CURR, Format::R16_SFLOAT);
+        perm(P_REFLECTION_HIT_T_PREV, Format::R16_SFLOAT);
+    }
+    perm(P_HISTORY_LENGTH_PREV, Format::R8_UNORM);
+    perm(P_NORMAL_ROUGHNESS_PREV, Format::RGBA8_UNORM);
+    perm(P_MATERIAL_ID_PREV, Format::R8_UNORM);
+    perm(P_VIEWZ_PREV, Format::R32_SFLOAT);
 
-    for (int i = 0; i < (sh ? 8 : 4); i++) addTransient(Format::RGBA16_SFLOAT);
-    addTransient(Format::R8_UNORM);      // specular reprojection confidence
-    addTransient(Format::R8_UNORM, 16);  // tiles
-    addTransient(Format::R8_UNORM);      // history length
+    for (int lobe = 0; lobe < 2; lobe++) {  // { ping, ( SH1 ), pong, ( SH1 ) } per lobe, specular first
+        if (!(lobe == 0 ? spec : diff)) continue;
+        const uint16_t base = lobe == 0 ? T_SPEC_ILLUM_PING : T_DIFF_ILLUM_PING;
+        tran(base + 0, kIllum);
+        if (sh) tran(base + 1, kIllum);
+        tran(base + 2, kIllum);
+        if (sh) tran(base + 3, kIllum);
+    }
+    if (spec) tran(T_SPEC_REPROJECTION_CONFIDENCE, Format::R8_UNORM);
+    tran(T_TILES, Format::R8_UNORM, 16);
+    tran(T_HISTORY_LENGTH, Format::R8_UNORM);
 
     auto U = [sh](ResourceType t) {
         if (!sh) {
@@ -90,16 +121,18 @@ void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
         }
         return Slot::user(t);
     };
-    // without SH1: transients keep their order; the permanent histories are spec, diff, spec responsive, diff responsive (Relax_DiffuseSpecular.hpp:17-22)
-    auto Pm = [sh](uint16_t i) {
-        static const uint16_t kNoSh[8] = {0, 0, 2, 2, 1, 1, 3, 3};
-        return Slot::perm(sh ? i : (uint16_t)(i < 8 ? kNoSh[i] : i - 4));
-    };
-    auto Tr = [sh](uint16_t i) { return Slot::tran(sh ? i : (uint16_t)(i < 8 ? i / 2 : i - 4)); };
+    auto Pm = [&](uint16_t i) { return Slot::perm(permIndex[i]); };
+    auto Tr = [&](uint16_t i) { return Slot::tran(tranIndex[i]); };
     const Slot dummy = U(ResourceType::IN_VIEWZ);
-    const std::string sig = sh ? "|NRD_SIGNAL=BOTH|NRD_MODE=SH" : "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE";
-    const std::string prefix = sh ? "RELAX_DiffuseSpecularSh - " : "RELAX_DiffuseSpecular - ";
+    const std::string signal = std::string("|NRD_SIGNAL=") + (diff && spec ? "BOTH" : (diff ? "DIFF" : "SPEC"));
+    const std::string sig = signal + (sh ? "|NRD_MODE=SH" : "|NRD_MODE=RADIANCE");
+    const std::string prefix = std::string("RELAX_") + (diff && spec ? "DiffuseSpecular" : (diff ? "Diffuse" : "Specular")) + (sh ? "Sh - " : " - ");
     auto name = [&](const char* pass) { return intern(prefix + pass); };
+    // a lobe's binding exists only when the denoiser has that lobe
+    auto inS = [&](Slot s, Slot swap = Slot()) { if (spec) in(s, swap); };
+    auto inD = [&](Slot s, Slot swap = Slot()) { if (diff) in(s, swap); };
+    auto outS = [&](Slot s, Slot swap = Slot()) { if (spec) out(s, swap); };
+    auto outD = [&](Slot s, Slot swap = Slot()) { if (diff) out(s, swap); };
 
     beginPass(name("Classify tiles"));
     in(U(ResourceType::IN_VIEWZ));
@@ -111,11 +144,11 @@ void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(U(ResourceType::IN_VIEWZ));
-        in(U(ResourceType::IN_SPEC_SH0));
-        in(U(ResourceType::IN_DIFF_SH0));
-        out(Tr(T_SPEC_ILLUM_PING));
-        out(Tr(T_DIFF_ILLUM_PING));
-        emit(std::string("RELAX_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE") + (i ? "|MODE_5X5=1" : "|MODE_5X5=0"), 8, 8, kCb);
+        inS(U(ResourceType::IN_SPEC_SH0));
+        inD(U(ResourceType::IN_DIFF_SH0));
+        outS(Tr(T_SPEC_ILLUM_PING));
+        outD(Tr(T_DIFF_ILLUM_PING));
+        emit("RELAX_HitDistReconstruction.cs.hlsl" + signal + "|NRD_MODE=RADIANCE" + (i ? "|MODE_5X5=1" : "|MODE_5X5=0"), 8, 8, kCb);
     }
 
     for (int i = 0; i < 2; i++) {
@@ -124,14 +157,14 @@ void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(U(ResourceType::IN_VIEWZ));
-        in(afterReconstruction ? Tr(T_SPEC_ILLUM_PING) : U(ResourceType::IN_SPEC_SH0));
-        in(afterReconstruction ? Tr(T_DIFF_ILLUM_PING) : U(ResourceType::IN_DIFF_SH0));
-        if (sh) in(U(ResourceType::IN_SPEC_SH1));
-        if (sh) in(U(ResourceType::IN_DIFF_SH1));
-        out(U(ResourceType::OUT_SPEC_SH0));
-        out(U(ResourceType::OUT_DIFF_SH0));
-        if (sh) out(U(ResourceType::OUT_SPEC_SH1));
-        if (sh) out(U(ResourceType::OUT_DIFF_SH1));
+        inS(afterReconstruction ? Tr(T_SPEC_ILLUM_PING) : U(ResourceType::IN_SPEC_SH0));
+        inD(afterReconstruction ? Tr(T_DIFF_ILLUM_PING) : U(ResourceType::IN_DIFF_SH0));
+        if (sh) inS(U(ResourceType::IN_SPEC_SH1));
+        if (sh) inD(U(ResourceType::IN_DIFF_SH1));
+        outS(U(ResourceType::OUT_SPEC_SH0));
+        outD(U(ResourceType::OUT_DIFF_SH0));
+        if (sh) outS(U(ResourceType::OUT_SPEC_SH1));
+        if (sh) outD(U(ResourceType::OUT_DIFF_SH1));
         emit("RELAX_PrePass.cs.hlsl" + sig, 16, 16, kCb);
     }
 
@@ -147,32 +180,32 @@ void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
         in(Pm(P_VIEWZ_PREV));
         in(Pm(P_HISTORY_LENGTH_PREV));
         in(Pm(P_MATERIAL_ID_PREV));
-        in(U(ResourceType::OUT_SPEC_SH0));
-        in(U(ResourceType::OUT_DIFF_SH0));
-        in(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV));
-        in(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV));
-        in(Pm(P_SPEC_ILLUM_PREV));
-        in(Pm(P_DIFF_ILLUM_PREV));
-        in(Pm(P_REFLECTION_HIT_T_PREV), Pm(P_REFLECTION_HIT_T_CURR));
-        in(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
-        in(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
-        if (sh) in(U(ResourceType::OUT_SPEC_SH1));
-        if (sh) in(U(ResourceType::OUT_DIFF_SH1));
-        if (sh) in(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV_SH1));
-        if (sh) in(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV_SH1));
-        if (sh) in(Pm(P_SPEC_ILLUM_PREV_SH1));
-        if (sh) in(Pm(P_DIFF_ILLUM_PREV_SH1));
+        inS(U(ResourceType::OUT_SPEC_SH0));
+        inD(U(ResourceType::OUT_DIFF_SH0));
+        inS(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV));
+        inD(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV));
+        inS(Pm(P_SPEC_ILLUM_PREV));
+        inD(Pm(P_DIFF_ILLUM_PREV));
+        inS(Pm(P_REFLECTION_HIT_T_PREV), Pm(P_REFLECTION_HIT_T_CURR));
+        inS(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
+        inD(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
+        if (sh) inS(U(ResourceType::OUT_SPEC_SH1));
+        if (sh) inD(U(ResourceType::OUT_DIFF_SH1));
+        if (sh) inS(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV_SH1));
+        if (sh) inD(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV_SH1));
+        if (sh) inS(Pm(P_SPEC_ILLUM_PREV_SH1));
+        if (sh) inD(Pm(P_DIFF_ILLUM_PREV_SH1));
         out(Tr(T_HISTORY_LENGTH));
-        out(Tr(T_SPEC_ILLUM_PING));
-        out(Tr(T_DIFF_ILLUM_PING));
-        out(Tr(T_SPEC_ILLUM_PONG));
-        out(Tr(T_DIFF_ILLUM_PONG));
-        out(Pm(P_REFLECTION_HIT_T_CURR), Pm(P_REFLECTION_HIT_T_PREV));
-        out(Tr(T_SPEC_REPROJECTION_CONFIDENCE));
-        if (sh) out(Tr(T_SPEC_ILLUM_PING_SH1));
-        if (sh) out(Tr(T_DIFF_ILLUM_PING_SH1));
-        if (sh) out(Tr(T_SPEC_ILLUM_PONG_SH1));
-        if (sh) out(Tr(T_DIFF_ILLUM_PONG_SH1));
+        outS(Tr(T_SPEC_ILLUM_PING));
+        outD(Tr(T_DIFF_ILLUM_PING));
+        outS(Tr(T_SPEC_ILLUM_PONG));
+        outD(Tr(T_DIFF_ILLUM_PONG));
+        outS(Pm(P_REFLECTION_HIT_T_CURR), Pm(P_REFLECTION_HIT_T_PREV));
+        outS(Tr(T_SPEC_REPROJECTION_CONFIDENCE));
+        if (sh) outS(Tr(T_SPEC_ILLUM_PING_SH1));
+        if (sh) outD(Tr(T_DIFF_ILLUM_PING_SH1));
+        if (sh) outS(Tr(T_SPEC_ILLUM_PONG_SH1));
+        if (sh) outD(Tr(T_DIFF_ILLUM_PONG_SH1));
         emit("RELAX_TemporalAccumulation.cs.hlsl" + sig, 8, 16, kCb);
     }
 
@@ -181,56 +214,56 @@ void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
     in(Tr(T_HISTORY_LENGTH));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(U(ResourceType::IN_VIEWZ));
-    in(Tr(T_SPEC_ILLUM_PING));  // normal history
-    in(Tr(T_DIFF_ILLUM_PING));
-    if (sh) in(Tr(T_SPEC_ILLUM_PING_SH1));
-    if (sh) in(Tr(T_DIFF_ILLUM_PING_SH1));
-    out(Tr(T_SPEC_ILLUM_PONG));  // responsive history
-    out(Tr(T_DIFF_ILLUM_PONG));
-    if (sh) out(Tr(T_SPEC_ILLUM_PONG_SH1));
-    if (sh) out(Tr(T_DIFF_ILLUM_PONG_SH1));
+    inS(Tr(T_SPEC_ILLUM_PING));  // normal history
+    inD(Tr(T_DIFF_ILLUM_PING));
+    if (sh) inS(Tr(T_SPEC_ILLUM_PING_SH1));
+    if (sh) inD(Tr(T_DIFF_ILLUM_PING_SH1));
+    outS(Tr(T_SPEC_ILLUM_PONG));  // responsive history
+    outD(Tr(T_DIFF_ILLUM_PONG));
+    if (sh) outS(Tr(T_SPEC_ILLUM_PONG_SH1));
+    if (sh) outD(Tr(T_DIFF_ILLUM_PONG_SH1));
     emit("RELAX_HistoryFix.cs.hlsl" + sig, 8, 8, kCb);
 
     beginPass(name("History clamping"));
     in(Tr(T_TILES));
     in(U(ResourceType::IN_VIEWZ));
     in(Tr(T_HISTORY_LENGTH));
-    in(U(ResourceType::OUT_SPEC_SH0));  // noisy input with the pre-blur applied
-    in(U(ResourceType::OUT_DIFF_SH0));
-    in(Tr(T_SPEC_ILLUM_PING));
-    in(Tr(T_DIFF_ILLUM_PING));
-    in(Tr(T_SPEC_ILLUM_PONG));
-    in(Tr(T_DIFF_ILLUM_PONG));
-    if (sh) in(Tr(T_SPEC_ILLUM_PING_SH1));
-    if (sh) in(Tr(T_DIFF_ILLUM_PING_SH1));
-    if (sh) in(Tr(T_SPEC_ILLUM_PONG_SH1));
-    if (sh) in(Tr(T_DIFF_ILLUM_PONG_SH1));
+    inS(U(ResourceType::OUT_SPEC_SH0));  // noisy input with the pre-blur applied
+    inD(U(ResourceType::OUT_DIFF_SH0));
+    inS(Tr(T_SPEC_ILLUM_PING));
+    inD(Tr(T_DIFF_ILLUM_PING));
+    inS(Tr(T_SPEC_ILLUM_PONG));
+    inD(Tr(T_DIFF_ILLUM_PONG));
+    if (sh) inS(Tr(T_SPEC_ILLUM_PING_SH1));
+    if (sh) inD(Tr(T_DIFF_ILLUM_PING_SH1));
+    if (sh) inS(Tr(T_SPEC_ILLUM_PONG_SH1));
+    if (sh) inD(Tr(T_DIFF_ILLUM_PONG_SH1));
     out(Pm(P_HISTORY_LENGTH_PREV));
-    out(Pm(P_SPEC_ILLUM_PREV));
-    out(Pm(P_DIFF_ILLUM_PREV));
-    out(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV));
-    out(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV));
-    if (sh) out(Pm(P_SPEC_ILLUM_PREV_SH1));
-    if (sh) out(Pm(P_DIFF_ILLUM_PREV_SH1));
-    if (sh) out(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV_SH1));
-    if (sh) out(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV_SH1));
+    outS(Pm(P_SPEC_ILLUM_PREV));
+    outD(Pm(P_DIFF_ILLUM_PREV));
+    outS(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV));
+    outD(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV));
+    if (sh) outS(Pm(P_SPEC_ILLUM_PREV_SH1));
+    if (sh) outD(Pm(P_DIFF_ILLUM_PREV_SH1));
+    if (sh) outS(Pm(P_SPEC_ILLUM_RESPONSIVE_PREV_SH1));
+    if (sh) outD(Pm(P_DIFF_ILLUM_RESPONSIVE_PREV_SH1));
     emit("RELAX_HistoryClamping.cs.hlsl" + sig, 8, 8, kCb);
 
     beginPass(name("Copy"));
-    in(Pm(P_SPEC_ILLUM_PREV));
-    in(Pm(P_DIFF_ILLUM_PREV));
-    out(U(ResourceType::OUT_SPEC_SH0));
-    out(U(ResourceType::OUT_DIFF_SH0));
+    inS(Pm(P_SPEC_ILLUM_PREV));
+    inD(Pm(P_DIFF_ILLUM_PREV));
+    outS(U(ResourceType::OUT_SPEC_SH0));
+    outD(U(ResourceType::OUT_DIFF_SH0));
     emit("RELAX_Copy.cs.hlsl" + sig, 8, 8, kCb);
 
     beginPass(name("Anti-firefly"));
     in(Tr(T_TILES));
     in(U(ResourceType::IN_NORMAL_ROUGHNESS));
     in(U(ResourceType::IN_VIEWZ));
-    in(U(ResourceType::OUT_SPEC_SH0));
-    in(U(ResourceType::OUT_DIFF_SH0));
-    out(Pm(P_SPEC_ILLUM_PREV));
-    out(Pm(P_DIFF_ILLUM_PREV));
+    inS(U(ResourceType::OUT_SPEC_SH0));
+    inD(U(ResourceType::OUT_DIFF_SH0));
+    outS(Pm(P_SPEC_ILLUM_PREV));
+    outD(Pm(P_DIFF_ILLUM_PREV));
     emit("RELAX_AntiFirefly.cs.hlsl" + sig, 8, 8, kCb);
 
     for (int i = 0; i < 2; i++) {
@@ -243,28 +276,28 @@ void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
             in(U(ResourceType::IN_NORMAL_ROUGHNESS));
             in(U(ResourceType::IN_VIEWZ));
             if (smem) {
-                in(Pm(P_SPEC_ILLUM_PREV));
-                in(Pm(P_DIFF_ILLUM_PREV));
+                inS(Pm(P_SPEC_ILLUM_PREV));
+                inD(Pm(P_DIFF_ILLUM_PREV));
             } else {
-                in(even ? Tr(T_SPEC_ILLUM_PONG) : Tr(T_SPEC_ILLUM_PING));
-                in(even ? Tr(T_DIFF_ILLUM_PONG) : Tr(T_DIFF_ILLUM_PING));
+                inS(even ? Tr(T_SPEC_ILLUM_PONG) : Tr(T_SPEC_ILLUM_PING));
+                inD(even ? Tr(T_DIFF_ILLUM_PONG) : Tr(T_DIFF_ILLUM_PING));
             }
-            in(Tr(T_SPEC_REPROJECTION_CONFIDENCE));
-            in(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
-            in(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
+            inS(Tr(T_SPEC_REPROJECTION_CONFIDENCE));
+            inS(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
+            inD(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
             if (smem) {
-                if (sh) in(Pm(P_SPEC_ILLUM_PREV_SH1));
-                if (sh) in(Pm(P_DIFF_ILLUM_PREV_SH1));
+                if (sh) inS(Pm(P_SPEC_ILLUM_PREV_SH1));
+                if (sh) inD(Pm(P_DIFF_ILLUM_PREV_SH1));
             } else {
-                if (sh) in(even ? Tr(T_SPEC_ILLUM_PONG_SH1) : Tr(T_SPEC_ILLUM_PING_SH1));
-                if (sh) in(even ? Tr(T_DIFF_ILLUM_PONG_SH1) : Tr(T_DIFF_ILLUM_PING_SH1));
+                if (sh) inS(even ? Tr(T_SPEC_ILLUM_PONG_SH1) : Tr(T_SPEC_ILLUM_PING_SH1));
+                if (sh) inD(even ? Tr(T_DIFF_ILLUM_PONG_SH1) : Tr(T_DIFF_ILLUM_PING_SH1));
             }
             if (last) {
-                out(U(ResourceType::OUT_SPEC_SH0));
-                out(U(ResourceType::OUT_DIFF_SH0));
+                outS(U(ResourceType::OUT_SPEC_SH0));
+                outD(U(ResourceType::OUT_DIFF_SH0));
             } else {
-                out(even ? Tr(T_SPEC_ILLUM_PING) : Tr(T_SPEC_ILLUM_PONG));
-                out(even ? Tr(T_DIFF_ILLUM_PING) : Tr(T_DIFF_ILLUM_PONG));
+                outS(even ? Tr(T_SPEC_ILLUM_PING) : Tr(T_SPEC_ILLUM_PONG));
+                outD(even ? Tr(T_DIFF_ILLUM_PING) : Tr(T_DIFF_ILLUM_PONG));
             }
             if (smem) {
                 out(Pm(P_NORMAL_ROUGHNESS_PREV));
@@ -272,11 +305,11 @@ void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
                 out(Pm(P_VIEWZ_PREV));
             }
             if (last) {
-                if (sh) out(U(ResourceType::OUT_SPEC_SH1));
-                if (sh) out(U(ResourceType::OUT_DIFF_SH1));
+                if (sh) outS(U(ResourceType::OUT_SPEC_SH1));
+                if (sh) outD(U(ResourceType::OUT_DIFF_SH1));
             } else {
-                if (sh) out(even ? Tr(T_SPEC_ILLUM_PING_SH1) : Tr(T_SPEC_ILLUM_PONG_SH1));
-                if (sh) out(even ? Tr(T_DIFF_ILLUM_PING_SH1) : Tr(T_DIFF_ILLUM_PONG_SH1));
+                if (sh) outS(even ? Tr(T_SPEC_ILLUM_PING_SH1) : Tr(T_SPEC_ILLUM_PONG_SH1));
+                if (sh) outD(even ? Tr(T_DIFF_ILLUM_PING_SH1) : Tr(T_DIFF_ILLUM_PONG_SH1));
             }
             if (smem)
                 emit("RELAX_AtrousSmem.cs.hlsl" + sig, 8, 8, kCb);
@@ -287,14 +320,14 @@ void Graph::buildRelaxDiffuseSpecular(DenoiserState& d, bool sh) {
 
     beginPass(name("Split screen"));
     in(U(ResourceType::IN_VIEWZ));
-    in(U(ResourceType::IN_DIFF_SH0));
-    in(U(ResourceType::IN_SPEC_SH0));
-    if (sh) in(U(ResourceType::IN_DIFF_SH1));
-    if (sh) in(U(ResourceType::IN_SPEC_SH1));
-    out(U(ResourceType::OUT_DIFF_SH0));
-    out(U(ResourceType::OUT_SPEC_SH0));
-    if (sh) out(U(ResourceType::OUT_DIFF_SH1));
-    if (sh) out(U(ResourceType::OUT_SPEC_SH1));
+    inD(U(ResourceType::IN_DIFF_SH0));
+    inS(U(ResourceType::IN_SPEC_SH0));
+    if (sh) inD(U(ResourceType::IN_DIFF_SH1));
+    if (sh) inS(U(ResourceType::IN_SPEC_SH1));
+    outD(U(ResourceType::OUT_DIFF_SH0));
+    outS(U(ResourceType::OUT_SPEC_SH0));
+    if (sh) outD(U(ResourceType::OUT_DIFF_SH1));
+    if (sh) outS(U(ResourceType::OUT_SPEC_SH1));
     emit("RELAX_SplitScreen.cs.hlsl" + sig, 8, 16, kCb);
 
     beginPass(name("Validation"));

@@ -42,6 +42,10 @@ static const Denoiser kSupported[] = {
     Denoiser::REBLUR_DIFFUSE,
     Denoiser::REBLUR_SPECULAR,
     Denoiser::REBLUR_DIFFUSE_SPECULAR,
+    Denoiser::RELAX_DIFFUSE,
+    Denoiser::RELAX_DIFFUSE_SH,
+    Denoiser::RELAX_SPECULAR,
+    Denoiser::RELAX_SPECULAR_SH,
     Denoiser::RELAX_DIFFUSE_SPECULAR,
     Denoiser::RELAX_DIFFUSE_SPECULAR_SH,
     Denoiser::SIGMA_SHADOW,
@@ -164,8 +168,12 @@ Result Graph::create(const InstanceCreationDesc& desc) {
             case Denoiser::SIGMA_SHADOW: buildSigmaShadow(d, false); break;
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: buildSigmaShadow(d, true); break;
             case Denoiser::REFERENCE: buildReference(d); break;
-            case Denoiser::RELAX_DIFFUSE_SPECULAR_SH: buildRelaxDiffuseSpecular(d, true); break;
-            case Denoiser::RELAX_DIFFUSE_SPECULAR: buildRelaxDiffuseSpecular(d, false); break;
+            case Denoiser::RELAX_DIFFUSE: buildRelax(d, true, false, false); break;
+            case Denoiser::RELAX_DIFFUSE_SH: buildRelax(d, true, false, true); break;
+            case Denoiser::RELAX_SPECULAR: buildRelax(d, false, true, false); break;
+            case Denoiser::RELAX_SPECULAR_SH: buildRelax(d, false, true, true); break;
+            case Denoiser::RELAX_DIFFUSE_SPECULAR: buildRelax(d, true, true, false); break;
+            case Denoiser::RELAX_DIFFUSE_SPECULAR_SH: buildRelax(d, true, true, true); break;
             default: return Result::INVALID_ARGUMENT;
         }
         d.swapNum = m_swaps.size() - d.firstSwap;
@@ -464,6 +472,10 @@ Result Graph::getComputeDispatches(const Identifier* ids, uint32_t idsNum, const
             case Denoiser::SIGMA_SHADOW:
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: updateSigma(d); break;
             case Denoiser::REFERENCE: updateReference(d); break;
+            case Denoiser::RELAX_DIFFUSE:
+            case Denoiser::RELAX_DIFFUSE_SH:
+            case Denoiser::RELAX_SPECULAR:
+            case Denoiser::RELAX_SPECULAR_SH:
             case Denoiser::RELAX_DIFFUSE_SPECULAR_SH:
             case Denoiser::RELAX_DIFFUSE_SPECULAR: updateRelax(d); break;
             default: break;

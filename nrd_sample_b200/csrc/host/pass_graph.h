@@ -120,7 +120,7 @@ private:
     void buildSigmaShadow(DenoiserState& d, bool translucency);
     void updateSigma(const DenoiserState& d);
     void fillSigmaConstants(const SigmaSettings& s, void* dst);
-    void buildRelaxDiffuseSpecular(DenoiserState& d, bool sh);
+    void buildRelax(DenoiserState& d, bool diff, bool spec, bool sh);
     void updateRelax(const DenoiserState& d);
     void* fillRelaxConstants(const RelaxSettings& s, void* dst);
     void buildReference(DenoiserState& d);

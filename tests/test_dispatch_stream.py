@@ -37,12 +37,21 @@ CASES = [
     ("relax_sh_8_iterations", api.Denoiser.RELAX_DIFFUSE_SPECULAR_SH, 640, 360, "relax_8"),
     ("relax_1440p", api.Denoiser.RELAX_DIFFUSE_SPECULAR, 2560, 1440, None),
     ("relax_odd_firefly_recon", api.Denoiser.RELAX_DIFFUSE_SPECULAR, 1000, 562, "relax_firefly_recon"),
+    ("relax_diffuse_1080p", api.Denoiser.RELAX_DIFFUSE, 1920, 1080, None),
+    ("relax_diffuse_firefly_recon", api.Denoiser.RELAX_DIFFUSE, 1000, 562, "relax_firefly_recon"),
+    ("relax_diffuse_sh_cb_guides_split", api.Denoiser.RELAX_DIFFUSE_SH, 1280, 720, "relax_cb_guides_split"),
+    ("relax_diffuse_sh_8_iterations", api.Denoiser.RELAX_DIFFUSE_SH, 640, 360, "relax_8"),
+    ("relax_specular_1080p", api.Denoiser.RELAX_SPECULAR, 1920, 1080, None),
+    ("relax_specular_cb_guides_split", api.Denoiser.RELAX_SPECULAR, 1280, 720, "relax_cb_guides_split"),
+    ("relax_specular_sh_firefly_recon", api.Denoiser.RELAX_SPECULAR_SH, 1000, 562, "relax_firefly_recon"),
+    ("relax_specular_sh_8_iterations", api.Denoiser.RELAX_SPECULAR_SH, 640, 360, "relax_8"),
 ]
 
 
 # CommonSettings overrides per case kind; "static" freezes the camera so the REFERENCE frame counter advances
 COMMON = {
     "reblur_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.4),
+    "relax_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.4),
     "split_only": dict(splitScreen=1.0),
     "reference": dict(splitScreen=0.25),
 }
@@ -64,6 +73,8 @@ def _settings(kind):
     if kind == "relax_firefly_recon":
         return api.RelaxSettings(enableAntiFirefly=True, hitDistanceReconstructionMode=2, atrousIterationNum=4, diffuseMinLuminanceWeight=0.1, specularLobeAngleSlack=0.3,
                                  diffuseMaxAccumulatedFrameNum=40, historyFixFrameNum=2)
+    if kind == "relax_cb_guides_split":
+        return api.RelaxSettings(checkerboardMode=1, enableAntiFirefly=True)
     if kind == "relax_8":
         return api.RelaxSettings(atrousIterationNum=8, diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0, enableRoughnessEdgeStopping=False)
     return None
