@@ -59,8 +59,8 @@ NRD_DEV float customWeightsFloat(float s00, float s10, float s01, float s11, flo
     return sum < 0.0001f ? 0.0f : o * (1.0f / sum);
 }
 // SH = false is RELAX_DIFFUSE_SPECULAR ( NRD_MODE = RADIANCE ): the SH1 textures are not bound, every access to them compiles away
-template <bool SH>
-NRD_DEV float3 customWeightsSH(const TexRGBA16F& t, int x, int y, float4 w) {
+template <bool SH, class TEX>
+NRD_DEV float3 customWeightsSH(const TEX& t, int x, int y, float4 w) {
     if constexpr (!SH) return f3(0.0f);
     float3 o = xyz(t.load(x, y)) * w.x;
     o += xyz(t.load(x + 1, y)) * w.y;
@@ -123,33 +123,75 @@ NRD_DEV float2 clampUvToViewport(const RelaxConstants& cb, float2 uv) {
     return min2(uv * scale, scale - 0.5f * make_float2(cb.resourceSizeInv[0], cb.resourceSizeInv[1]));
 }
 NRD_DEV float4 gatherR32(const TexR32F& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
-NRD_DEV float4 gatherR8(const TexR8& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
-NRD_DEV float4 gatherR16(const TexR16F& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
-template <bool SH> NRD_DEV void storeSh(const TexRGBA16F& t, int x, int y, float3 v) { if constexpr (SH) t.store(x, y, f4(v, 0.0f)); }
-template <bool SH> NRD_DEV float3 loadSh(const TexRGBA16F& t, int x, int y) { if constexpr (SH) return xyz(t.load(x, y)); else return f3(0.0f); }
-template <bool SH> NRD_DEV float3 sampleNearestSh(const TexRGBA16F& t, float2 uv) { if constexpr (SH) return xyz(t.sampleNearest(uv)); else return f3(0.0f); }
+template <class TEX> NRD_DEV float4 gatherR8(const TEX& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
+template <class TEX> NRD_DEV float4 gatherR16(const TEX& t, int x0, int y0) { return make_float4(t.fetchClamped(x0, y0), t.fetchClamped(x0 + 1, y0), t.fetchClamped(x0, y0 + 1), t.fetchClamped(x0 + 1, y0 + 1)); }
+template <bool SH, class TEX> NRD_DEV void storeSh(const TEX& t, int x, int y, float3 v) { if constexpr (SH) t.store(x, y, f4(v, 0.0f)); }
+template <bool SH, class TEX> NRD_DEV float3 loadSh(const TEX& t, int x, int y) { if constexpr (SH) return xyz(t.load(x, y)); else return f3(0.0f); }
+template <bool SH, class TEX> NRD_DEV float3 sampleNearestSh(const TEX& t, float2 uv) { if constexpr (SH) return xyz(t.sampleNearest(uv)); else return f3(0.0f); }
 
-// ---- parameter blocks (member order = DispatchDesc::resources order) ------------------------------------------------------------
+// ---- NRD_SIGNAL ( DIFF / SPEC / BOTH ) ------------------------------------------------------------------------------------------
+// RELAX_DIFFUSE( _SH ) and RELAX_SPECULAR( _SH ) are the two-lobe shaders with the other lobe's `#if( NRD_DIFF )` / `#if( NRD_SPEC )` blocks removed
+// ( the only two-lobe expression is TA's history cap, handled where it occurs ). The kernels get that for free from the type system: the
+// parameter blocks are templates on SIGNAL, and the texture members of a lobe the denoiser does not have become DeadTex — same layout, every
+// read is a compile-time zero, every write a no-op — so the compiler removes the whole lobe ( loads, taps, weights, stores ) from that instantiation.
+template <class T> struct DeadTex : TexView {
+    using R = decltype(std::declval<const T&>().load(0, 0));
+    NRD_DEV R load(int, int) const { return R{}; }
+    NRD_DEV R fetch(int, int) const { return R{}; }
+    NRD_DEV R fetchClamped(int, int) const { return R{}; }
+    NRD_DEV R sampleNearest(float2) const { return R{}; }
+    NRD_DEV R sampleLinear(float2) const { return R{}; }
+    NRD_DEV void store(int, int, R) const {}
+    NRD_DEV int cx(int) const { return 0; }
+    NRD_DEV int cy(int) const { return 0; }
+};
+template <> struct DeadTex<TexAnyX> : TexView {  // TexAnyX carries two more words
+    uint32_t kind, bytesPerTexel;
+    NRD_DEV float load(int, int) const { return 0.0f; }
+    NRD_DEV float fetch(int, int) const { return 0.0f; }
+    NRD_DEV float sampleLinear(float2) const { return 0.0f; }
+};
+template <class T, int SIGNAL> using SpecTex = std::conditional_t<(SIGNAL & SIGNAL_SPEC) != 0, T, DeadTex<T>>;
+template <class T, int SIGNAL> using DiffTex = std::conditional_t<(SIGNAL & SIGNAL_DIFF) != 0, T, DeadTex<T>>;
+static_assert(sizeof(DeadTex<TexRGBA16F>) == sizeof(TexRGBA16F) && sizeof(DeadTex<TexAnyX>) == sizeof(TexAnyX), "dead views keep the layout of the parameter blocks");
+
+// ---- parameter blocks (member order = DispatchDesc::resources order of the two-lobe denoiser; the executor fills the <SIGNAL_BOTH> block) ----
+#define S16 SpecTex<TexRGBA16F, SIGNAL>
+#define D16 DiffTex<TexRGBA16F, SIGNAL>
 struct RelaxClassifyParams { TexR32F viewZ; TexR8 outTiles; };
-struct RelaxPrePassParams { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, specSh, diffSh, outSpec, outDiff, outSpecSh, outDiffSh; };
-struct RelaxTaParams {
+template <int SIGNAL> struct RelaxPrePassParamsT { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; S16 spec; D16 diff; S16 specSh; D16 diffSh; S16 outSpec; D16 outDiff; S16 outSpecSh; D16 outDiffSh; };
+template <int SIGNAL> struct RelaxTaParamsT {
     TexR8 tiles; TexRGBA16F mv; TexNR normalRoughness; TexR32F viewZ; TexAnyX mixDummy; TexRGBA8 prevNormalRoughness; TexR32F prevViewZ; TexR8 prevHistoryLength, prevMaterialID;
-    TexRGBA16F spec, diff, historySpecFast, historyDiffFast, historySpec, historyDiff; TexR16F prevSpecHitDist; TexAnyX specConfDummy, diffConfDummy;
-    TexRGBA16F specSh, diffSh, historySpecShFast, historyDiffShFast, historySpecSh, historyDiffSh;
-    TexR8 outHistoryLength; TexRGBA16F outSpec, outDiff, outSpecFast, outDiffFast; TexR16F outSpecHitDist; TexR8 outSpecReprojectionConfidence;
-    TexRGBA16F outSpecSh, outDiffSh, outSpecShFast, outDiffShFast;
+    S16 spec; D16 diff; S16 historySpecFast; D16 historyDiffFast; S16 historySpec; D16 historyDiff; SpecTex<TexR16F, SIGNAL> prevSpecHitDist; SpecTex<TexAnyX, SIGNAL> specConfDummy;
+    DiffTex<TexAnyX, SIGNAL> diffConfDummy;
+    S16 specSh; D16 diffSh; S16 historySpecShFast; D16 historyDiffShFast; S16 historySpecSh; D16 historyDiffSh;
+    TexR8 outHistoryLength; S16 outSpec; D16 outDiff; S16 outSpecFast; D16 outDiffFast; SpecTex<TexR16F, SIGNAL> outSpecHitDist; SpecTex<TexR8, SIGNAL> outSpecReprojectionConfidence;
+    S16 outSpecSh; D16 outDiffSh; S16 outSpecShFast; D16 outDiffShFast;
 };
-struct RelaxHistoryFixParams { TexR8 tiles, historyLength; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, specSh, diffSh, outSpec, outDiff, outSpecSh, outDiffSh; };
-struct RelaxHistoryClampingParams {
-    TexR8 tiles; TexR32F viewZ; TexR8 historyLength; TexRGBA16F specNoisy, diffNoisy, spec, diff, specFast, diffFast, specSh, diffSh, specShFast, diffShFast;
-    TexR8 outHistoryLength; TexRGBA16F outSpec, outDiff, outSpecFast, outDiffFast, outSpecSh, outDiffSh, outSpecShFast, outDiffShFast;
+template <int SIGNAL> struct RelaxHistoryFixParamsT { TexR8 tiles, historyLength; TexNR normalRoughness; TexR32F viewZ; S16 spec; D16 diff; S16 specSh; D16 diffSh; S16 outSpec; D16 outDiff; S16 outSpecSh; D16 outDiffSh; };
+template <int SIGNAL> struct RelaxHistoryClampingParamsT {
+    TexR8 tiles; TexR32F viewZ; TexR8 historyLength; S16 specNoisy; D16 diffNoisy; S16 spec; D16 diff; S16 specFast; D16 diffFast; S16 specSh; D16 diffSh; S16 specShFast; D16 diffShFast;
+    TexR8 outHistoryLength; S16 outSpec; D16 outDiff; S16 outSpecFast; D16 outDiffFast; S16 outSpecSh; D16 outDiffSh; S16 outSpecShFast; D16 outDiffShFast;
 };
-struct RelaxCopyParams { TexRGBA16F spec, diff, outSpec, outDiff; };
-struct RelaxAntiFireflyParams { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, outSpec, outDiff; };
-struct RelaxAtrousParams {
-    TexR8 tiles, historyLength; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff; TexR8 specReprojectionConfidence; TexAnyX specConfDummy, diffConfDummy; TexRGBA16F specSh, diffSh;
-    TexRGBA16F outSpec, outDiff; TexRGBA8 outNormalRoughness; TexR8 outMaterialID; TexR32F outViewZ; TexRGBA16F outSpecSh, outDiffSh;
+template <int SIGNAL> struct RelaxCopyParamsT { S16 spec; D16 diff; S16 outSpec; D16 outDiff; };
+template <int SIGNAL> struct RelaxAntiFireflyParamsT { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; S16 spec; D16 diff; S16 outSpec; D16 outDiff; };
+template <int SIGNAL> struct RelaxAtrousParamsT {
+    TexR8 tiles, historyLength; TexNR normalRoughness; TexR32F viewZ; S16 spec; D16 diff; SpecTex<TexR8, SIGNAL> specReprojectionConfidence; SpecTex<TexAnyX, SIGNAL> specConfDummy;
+    DiffTex<TexAnyX, SIGNAL> diffConfDummy; S16 specSh; D16 diffSh;
+    S16 outSpec; D16 outDiff; TexRGBA8 outNormalRoughness; TexR8 outMaterialID; TexR32F outViewZ; S16 outSpecSh; D16 outDiffSh;
 };
+using RelaxPrePassParams = RelaxPrePassParamsT<SIGNAL_BOTH>;
+using RelaxTaParams = RelaxTaParamsT<SIGNAL_BOTH>;
+using RelaxHistoryFixParams = RelaxHistoryFixParamsT<SIGNAL_BOTH>;
+using RelaxHistoryClampingParams = RelaxHistoryClampingParamsT<SIGNAL_BOTH>;
+using RelaxCopyParams = RelaxCopyParamsT<SIGNAL_BOTH>;
+using RelaxAntiFireflyParams = RelaxAntiFireflyParamsT<SIGNAL_BOTH>;
+using RelaxAtrousParams = RelaxAtrousParamsT<SIGNAL_BOTH>;
+// the <SIGNAL> view of the block the executor filled ( identical layout, see DeadTex )
+template <template <int> class P, int SIGNAL> const P<SIGNAL>& lobeView(const P<SIGNAL_BOTH>& p, std::integral_constant<int, SIGNAL>) {
+    static_assert(sizeof(P<SIGNAL>) == sizeof(P<SIGNAL_BOTH>), "layout");
+    return reinterpret_cast<const P<SIGNAL>&>(p);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxClassifyParams p) {
@@ -162,7 +204,7 @@ __global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_con
 // ---------------------------------------------------------------------------------------------------------------
 // Confidence-driven relaxation of the a-trous edge stopping ( RELAX_AtrousSmem.cs.hlsl:201-215, 239-251; RELAX_Atrous.cs.hlsl:67-80, 107-119 ):
 // returns { r for the normal weights, r for the luminance weight }
-NRD_DEV float2 confidenceDrivenRelaxation(const RelaxConstants& cb, const TexAnyX& confidence, float2 pixelUv) {
+template <class TEX> NRD_DEV float2 confidenceDrivenRelaxation(const RelaxConstants& cb, const TEX& confidence, float2 pixelUv) {
     const float relaxation = saturate(cb.confidenceDrivenRelaxationMultiplier * (1.0f - saturate(confidence.sampleLinear(pixelUv))));
     return make_float2(saturate(relaxation * cb.confidenceDrivenNormalEdgeStoppingRelaxation), saturate(relaxation * cb.confidenceDrivenLuminanceEdgeStoppingRelaxation));
 }
@@ -178,8 +220,8 @@ NRD_DEV float2 applyCheckerboardShift(float2 pos, uint32_t mode, int counter, ui
 }
 
 // CB: checkerboarded inputs ( CheckerboardMode::BLACK / WHITE ): the traced pixels sit in the left half of the input textures
-template <bool SH, bool CB>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxPrePassParams p) {
+template <bool SH, bool CB, int SIGNAL>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxPrePassParamsT<SIGNAL> p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
@@ -215,7 +257,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
         cbX1 >>= 1;
     }
     // the traced row neighbours of a pixel the checkerboard skipped this frame ( :101-125, 238-262 )
-    auto resolve = [&](const TexRGBA16F& tex, const TexRGBA16F& texSh, float minMaterial, float4& illumination, float3& sh) {
+    auto resolve = [&](const auto& tex, const auto& texSh, float minMaterial, float4& illumination, float3& sh) {
         float2 wc = resolveWeights;
         wc.x *= compareMaterials(centerMaterialID, materialID0, minMaterial) ? 1.0f : 0.0f;
         wc.y *= compareMaterials(centerMaterialID, materialID1, minMaterial) ? 1.0f : 0.0f;
@@ -362,8 +404,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
 #define RELAX_TA_MIN_BLOCKS 4  // 64 regs: 612 us vs 652 us at 80 regs (3 CTAs) and 714 us at 128 regs (2 CTAs) per 1440p frame
 #endif
 // OPT: checkerboard resolve speed-up and the application's guide textures ( confidence, threshold mix ); compiled out of the plain kernel
-template <bool SH, bool OPT>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParams p) {
+template <bool SH, bool OPT, int SIGNAL>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParamsT<SIGNAL> p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float currentLinearZ = relaxViewZ(cb, p.viewZ.load(px, py));
@@ -519,7 +561,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
     footprintQuality *= lerp(0.1f, 1.0f, saturate(sizeQuality + fabsf(cb.orthoMode)));
     if (footprintQuality < 1.0f) historyLength = fmaxf(historyLength * sqrtf(footprintQuality), 1.0f);
     historyLength = cb.resetHistory != 0 ? 1.0f : historyLength;
-    historyLength = fminf(historyLength, 1.0f + fmaxf(cb.diffMaxAccumulatedFrameNum, cb.specMaxAccumulatedFrameNum));
+    // TA:582-588: the cap is the longer of the two lobes' histories, or the only lobe's
+    historyLength = fminf(historyLength, 1.0f + (SIGNAL == SIGNAL_BOTH ? fmaxf(cb.diffMaxAccumulatedFrameNum, cb.specMaxAccumulatedFrameNum)
+                                                                     : (SIGNAL == SIGNAL_DIFF ? cb.diffMaxAccumulatedFrameNum : cb.specMaxAccumulatedFrameNum)));
 
     // ---- diffuse ----
     {
@@ -765,8 +809,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <bool SH>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryFixParams p) {
+template <bool SH, int SIGNAL>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryFixParamsT<SIGNAL> p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
@@ -834,10 +878,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const 
 constexpr int HC_BORDER = 2, HC_TILE_W = BLOCK_W + 2 * HC_BORDER, HC_TILE_H = BLOCK_H + 2 * HC_BORDER;
 
 // One lobe (the specular and diffuse halves of the shader differ in three constants only)
-template <bool SPEC, bool SH>
+template <bool SPEC, bool SH, class TEX>
 NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)[HC_TILE_W], const float4 (*sNoisy)[HC_TILE_W], int px, int py, float historyLength,
-                                 const TexRGBA16F& slowTex, const TexRGBA16F& fastTex, const TexRGBA16F& shTex, const TexRGBA16F& shFastTex, const TexRGBA16F& outSlow,
-                                 const TexRGBA16F& outFast, const TexRGBA16F& outSh, const TexRGBA16F& outShFast, float maxFast, float maxSlow) {
+                                 const TEX& slowTex, const TEX& fastTex, const TEX& shTex, const TEX& shFastTex, const TEX& outSlow,
+                                 const TEX& outFast, const TEX& outSh, const TEX& outShFast, float maxFast, float maxSlow) {
     const int sx = threadIdx.x + HC_BORDER, sy = threadIdx.y + HC_BORDER;
     float3 m1 = f3(0.0f), m2 = f3(0.0f), noisyM1 = f3(0.0f);
     float noisyM2 = 0.0f, sum = 0.0f;
@@ -918,8 +962,8 @@ NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)
     storeSh<SH>(outShFast, px, py, shFast);
 }
 
-template <bool SH>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParams p) {
+template <bool SH, int SIGNAL>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParamsT<SIGNAL> p) {
     __shared__ float4 sSpecFast[HC_TILE_H][HC_TILE_W], sSpecNoisy[HC_TILE_H][HC_TILE_W], sDiffFast[HC_TILE_H][HC_TILE_W], sDiffNoisy[HC_TILE_H][HC_TILE_W];
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     // the CTA covers two 16x16 tiles of one tile row
@@ -952,15 +996,17 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(c
     p.outHistoryLength.store(px, py, historyLength / 255.0f);
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxCopyKernel(const __grid_constant__ RelaxCopyParams p) {
+template <int SIGNAL>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxCopyKernel(const __grid_constant__ RelaxCopyParamsT<SIGNAL> p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
-    if (!p.outSpec.inside(px, py)) return;
-    *p.outSpec.ptrw<uint2>(px, py) = p.spec.inside(px, py) ? p.spec.fetchRaw(px, py) : make_uint2(0u, 0u);
-    *p.outDiff.ptrw<uint2>(px, py) = p.diff.inside(px, py) ? p.diff.fetchRaw(px, py) : make_uint2(0u, 0u);
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0)
+        if (p.outSpec.inside(px, py)) *p.outSpec.template ptrw<uint2>(px, py) = p.spec.inside(px, py) ? p.spec.fetchRaw(px, py) : make_uint2(0u, 0u);
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0)
+        if (p.outDiff.inside(px, py)) *p.outDiff.template ptrw<uint2>(px, py) = p.diff.inside(px, py) ? p.diff.fetchRaw(px, py) : make_uint2(0u, 0u);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-NRD_DEV float4 rcrs(const RelaxConstants& cb, const TexNR& normalRoughness, const TexRGBA16F& tex, int px, int py, float minMaterial, float centerMaterialID) {
+template <class TEX> NRD_DEV float4 rcrs(const RelaxConstants& cb, const TexNR& normalRoughness, const TEX& tex, int px, int py, float minMaterial, float centerMaterialID) {
     const float4 center = tex.load(px, py);
     const float centerL = luminance(xyz(center));
     float maxL = -1.0f, minL = 1.0e6f;
@@ -983,7 +1029,8 @@ NRD_DEV float4 rcrs(const RelaxConstants& cb, const TexNR& normalRoughness, cons
     return f4(xyz(tex.load(sx, sy)), center.w);
 }
 
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAntiFireflyParams p) {
+template <int SIGNAL>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAntiFireflyParamsT<SIGNAL> p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     if (!relaxInRange(cb, relaxViewZ(cb, p.viewZ.load(px, py)))) return;
@@ -1090,8 +1137,8 @@ struct AtrousTexel {
     float3 specSh, diffSh, worldPos;
     float materialID;
 };
-template <bool SH>
-NRD_DEV AtrousTexel atrousFetch(const RelaxConstants& cb, const RelaxAtrousParams& p, int x, int y) {
+template <bool SH, class PARAMS>
+NRD_DEV AtrousTexel atrousFetch(const RelaxConstants& cb, const PARAMS& p, int x, int y) {
     const int gx = clampi(x, 0, cb.rectSize[0] - 1), gy = clampi(y, 0, cb.rectSize[1] - 1);
     AtrousTexel r;
     r.spec = p.spec.load(gx, gy);
@@ -1107,8 +1154,8 @@ constexpr int AT_BORDER = 2, AT_TILE_W = BLOCK_W + 2 * AT_BORDER, AT_TILE_H = BL
 #ifndef RELAX_ATROUS_SMEM_MIN_BLOCKS
 #define RELAX_ATROUS_SMEM_MIN_BLOCKS 4
 #endif
-template <bool SH>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParams p) {
+template <bool SH, int SIGNAL>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p) {
     // the reference's groupshared tile: 36x12 texels of { illumination + 2nd moment, SH1, normal + roughness, world position + material }
     __shared__ float4 sSpec[AT_TILE_H][AT_TILE_W], sDiff[AT_TILE_H][AT_TILE_W], sNr[AT_TILE_H][AT_TILE_W], sPosMat[AT_TILE_H][AT_TILE_W];
     __shared__ float4 sSpecSh[SH ? AT_TILE_H : 1][SH ? AT_TILE_W : 1], sDiffSh[SH ? AT_TILE_H : 1][SH ? AT_TILE_W : 1];
@@ -1298,8 +1345,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
     }
 }
 
-template <bool SH>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParams p) {
+template <bool SH, int SIGNAL>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
@@ -1504,11 +1551,19 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
     const Format F16 = Format::RGBA16_SFLOAT, R8 = Format::R8_UNORM, R32 = Format::R32_SFLOAT, NR = Format::R10_G10_B10_A2_UNORM;
     const dim3 block(BLOCK_W, BLOCK_H);
     const dim3 pixelGrid((cb.rectSize[0] + BLOCK_W - 1) / BLOCK_W, (cb.rectSize[1] + BLOCK_H - 1) / BLOCK_H);
-    // "|NRD_SIGNAL=BOTH|NRD_MODE=SH" ( RELAX_DIFFUSE_SPECULAR_SH ) or "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE" ( RELAX_DIFFUSE_SPECULAR: same passes, no SH1 textures )
+    // "|NRD_SIGNAL=<DIFF|SPEC|BOTH>|NRD_MODE=<SH|RADIANCE>": the six RELAX denoisers run the same kernels; RADIANCE has no SH1 textures, a single-lobe
+    // denoiser binds only its own lobe ( the parameter block keeps the two-lobe layout, the other lobe's views stay empty and are dead code in the kernel )
     const bool sh = id.find("|NRD_MODE=SH") != std::string::npos;
-    const std::string sig = sh ? "|NRD_SIGNAL=BOTH|NRD_MODE=SH" : "|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE";
-    auto takeSh = [&](TexRGBA16F& t) { if (sh) t = b.take<TexRGBA16F>(F16); else t = TexRGBA16F(); };
-    const uint32_t noSh = sh ? 0u : 1u;   // multiplies the number of SH1 bindings a pass loses
+    const int signal = id.find("|NRD_SIGNAL=DIFF") != std::string::npos ? SIGNAL_DIFF : (id.find("|NRD_SIGNAL=SPEC") != std::string::npos ? SIGNAL_SPEC : SIGNAL_BOTH);
+    const bool hasDiff = (signal & SIGNAL_DIFF) != 0, hasSpec = (signal & SIGNAL_SPEC) != 0;
+    const std::string sigSignal = std::string("|NRD_SIGNAL=") + (signal == SIGNAL_BOTH ? "BOTH" : (hasDiff ? "DIFF" : "SPEC"));
+    const std::string sig = sigSignal + (sh ? "|NRD_MODE=SH" : "|NRD_MODE=RADIANCE");
+    const uint32_t lobes = (hasDiff ? 1u : 0u) + (hasSpec ? 1u : 0u);
+    auto takeS = [&](TexRGBA16F& t) { t = hasSpec ? b.take<TexRGBA16F>(F16) : TexRGBA16F(); };
+    auto takeD = [&](TexRGBA16F& t) { t = hasDiff ? b.take<TexRGBA16F>(F16) : TexRGBA16F(); };
+    auto takeShS = [&](TexRGBA16F& t) { t = (sh && hasSpec) ? b.take<TexRGBA16F>(F16) : TexRGBA16F(); };
+    auto takeShD = [&](TexRGBA16F& t) { t = (sh && hasDiff) ? b.take<TexRGBA16F>(F16) : TexRGBA16F(); };
+    const uint32_t shOn = sh ? 1u : 0u;
 
     if (id == "RELAX_ClassifyTiles.cs.hlsl") {
         RelaxClassifyParams p;
@@ -1521,19 +1576,19 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.tiles = b.take<TexR8>(R8);
         p.normalRoughness = b.take<TexNR>(NR);
         p.viewZ = b.take<TexR32F>(R32);
-        p.spec = b.take<TexRGBA16F>(F16);
-        p.diff = b.take<TexRGBA16F>(F16);
-        takeSh(p.specSh);
-        takeSh(p.diffSh);
-        p.outSpec = b.take<TexRGBA16F>(F16);
-        p.outDiff = b.take<TexRGBA16F>(F16);
-        takeSh(p.outSpecSh);
-        takeSh(p.outDiffSh);
-        if (bad(11 - 4 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        takeS(p.spec);
+        takeD(p.diff);
+        takeShS(p.specSh);
+        takeShD(p.diffSh);
+        takeS(p.outSpec);
+        takeD(p.outDiff);
+        takeShS(p.outSpecSh);
+        takeShD(p.outDiffSh);
+        if (bad(3 + (2 + 2 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (checkerboarded) {
-            if (sh) relaxPrePassKernel<true, true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxPrePassKernel<false, true><<<pixelGrid, block, 0, stream>>>(cb, p);
+            if (sh) withSignal(signal, [&](auto sig_) { relaxPrePassKernel<true, true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxPrePassKernel<false, true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
         } else {
-            if (sh) relaxPrePassKernel<true, false><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxPrePassKernel<false, false><<<pixelGrid, block, 0, stream>>>(cb, p);
+            if (sh) withSignal(signal, [&](auto sig_) { relaxPrePassKernel<true, false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxPrePassKernel<false, false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
         }
     } else if (id == "RELAX_TemporalAccumulation.cs.hlsl" + sig) {
         RelaxTaParams p;
@@ -1546,37 +1601,37 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.prevViewZ = b.take<TexR32F>(R32);
         p.prevHistoryLength = b.take<TexR8>(R8);
         p.prevMaterialID = b.take<TexR8>(R8);
-        p.spec = b.take<TexRGBA16F>(F16);
-        p.diff = b.take<TexRGBA16F>(F16);
-        p.historySpecFast = b.take<TexRGBA16F>(F16);
-        p.historyDiffFast = b.take<TexRGBA16F>(F16);
-        p.historySpec = b.take<TexRGBA16F>(F16);
-        p.historyDiff = b.take<TexRGBA16F>(F16);
-        p.prevSpecHitDist = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.specConfDummy = b.takeGuide();
-        p.diffConfDummy = b.takeGuide();
-        takeSh(p.specSh);
-        takeSh(p.diffSh);
-        takeSh(p.historySpecShFast);
-        takeSh(p.historyDiffShFast);
-        takeSh(p.historySpecSh);
-        takeSh(p.historyDiffSh);
+        takeS(p.spec);
+        takeD(p.diff);
+        takeS(p.historySpecFast);
+        takeD(p.historyDiffFast);
+        takeS(p.historySpec);
+        takeD(p.historyDiff);
+        if (hasSpec) p.prevSpecHitDist = b.take<TexR16F>(Format::R16_SFLOAT);
+        if (hasSpec) p.specConfDummy = b.takeGuide();
+        if (hasDiff) p.diffConfDummy = b.takeGuide();
+        takeShS(p.specSh);
+        takeShD(p.diffSh);
+        takeShS(p.historySpecShFast);
+        takeShD(p.historyDiffShFast);
+        takeShS(p.historySpecSh);
+        takeShD(p.historyDiffSh);
         p.outHistoryLength = b.take<TexR8>(R8);
-        p.outSpec = b.take<TexRGBA16F>(F16);
-        p.outDiff = b.take<TexRGBA16F>(F16);
-        p.outSpecFast = b.take<TexRGBA16F>(F16);
-        p.outDiffFast = b.take<TexRGBA16F>(F16);
-        p.outSpecHitDist = b.take<TexR16F>(Format::R16_SFLOAT);
-        p.outSpecReprojectionConfidence = b.take<TexR8>(R8);
-        takeSh(p.outSpecSh);
-        takeSh(p.outDiffSh);
-        takeSh(p.outSpecShFast);
-        takeSh(p.outDiffShFast);
-        if (bad(35 - 10 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        takeS(p.outSpec);
+        takeD(p.outDiff);
+        takeS(p.outSpecFast);
+        takeD(p.outDiffFast);
+        if (hasSpec) p.outSpecHitDist = b.take<TexR16F>(Format::R16_SFLOAT);
+        if (hasSpec) p.outSpecReprojectionConfidence = b.take<TexR8>(R8);
+        takeShS(p.outSpecSh);
+        takeShD(p.outDiffSh);
+        takeShS(p.outSpecShFast);
+        takeShD(p.outDiffShFast);
+        if (bad(10 + (6 + 5 * shOn) * lobes + (hasSpec ? 3 : 0) + 0 * shOn)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (checkerboarded || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix) {
-            if (sh) relaxTemporalAccumulationKernel<true, true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxTemporalAccumulationKernel<false, true><<<pixelGrid, block, 0, stream>>>(cb, p);
+            if (sh) withSignal(signal, [&](auto sig_) { relaxTemporalAccumulationKernel<true, true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxTemporalAccumulationKernel<false, true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
         } else {
-            if (sh) relaxTemporalAccumulationKernel<true, false><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxTemporalAccumulationKernel<false, false><<<pixelGrid, block, 0, stream>>>(cb, p);
+            if (sh) withSignal(signal, [&](auto sig_) { relaxTemporalAccumulationKernel<true, false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxTemporalAccumulationKernel<false, false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
         }
     } else if (id == "RELAX_HistoryFix.cs.hlsl" + sig) {
         RelaxHistoryFixParams p;
@@ -1584,42 +1639,42 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.historyLength = b.take<TexR8>(R8);
         p.normalRoughness = b.take<TexNR>(NR);
         p.viewZ = b.take<TexR32F>(R32);
-        p.spec = b.take<TexRGBA16F>(F16);
-        p.diff = b.take<TexRGBA16F>(F16);
-        takeSh(p.specSh);
-        takeSh(p.diffSh);
-        p.outSpec = b.take<TexRGBA16F>(F16);
-        p.outDiff = b.take<TexRGBA16F>(F16);
-        takeSh(p.outSpecSh);
-        takeSh(p.outDiffSh);
-        if (bad(12 - 4 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) relaxHistoryFixKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxHistoryFixKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+        takeS(p.spec);
+        takeD(p.diff);
+        takeShS(p.specSh);
+        takeShD(p.diffSh);
+        takeS(p.outSpec);
+        takeD(p.outDiff);
+        takeShS(p.outSpecSh);
+        takeShD(p.outDiffSh);
+        if (bad(4 + (2 + 2 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (sh) withSignal(signal, [&](auto sig_) { relaxHistoryFixKernel<true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxHistoryFixKernel<false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
     } else if (id == "RELAX_HistoryClamping.cs.hlsl" + sig) {
         RelaxHistoryClampingParams p;
         p.tiles = b.take<TexR8>(R8);
         p.viewZ = b.take<TexR32F>(R32);
         p.historyLength = b.take<TexR8>(R8);
         TexRGBA16F* ins[6] = {&p.specNoisy, &p.diffNoisy, &p.spec, &p.diff, &p.specFast, &p.diffFast};
-        for (TexRGBA16F* t : ins) *t = b.take<TexRGBA16F>(F16);
+        for (int i = 0; i < 6; i++) (i & 1) ? takeD(*ins[i]) : takeS(*ins[i]);
         TexRGBA16F* insSh[4] = {&p.specSh, &p.diffSh, &p.specShFast, &p.diffShFast};
-        for (TexRGBA16F* t : insSh) takeSh(*t);
+        for (int i = 0; i < 4; i++) (i & 1) ? takeShD(*insSh[i]) : takeShS(*insSh[i]);
         p.outHistoryLength = b.take<TexR8>(R8);
         TexRGBA16F* outs[4] = {&p.outSpec, &p.outDiff, &p.outSpecFast, &p.outDiffFast};
-        for (TexRGBA16F* t : outs) *t = b.take<TexRGBA16F>(F16);
+        for (int i = 0; i < 4; i++) (i & 1) ? takeD(*outs[i]) : takeS(*outs[i]);
         TexRGBA16F* outsSh[4] = {&p.outSpecSh, &p.outDiffSh, &p.outSpecShFast, &p.outDiffShFast};
-        for (TexRGBA16F* t : outsSh) takeSh(*t);
-        if (bad(22 - 8 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) relaxHistoryClampingKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxHistoryClampingKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
-    } else if (id == "RELAX_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=0" || id == "RELAX_HitDistReconstruction.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=RADIANCE|MODE_5X5=1") {
+        for (int i = 0; i < 4; i++) (i & 1) ? takeShD(*outsSh[i]) : takeShS(*outsSh[i]);
+        if (bad(4 + (5 + 4 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
+        if (sh) withSignal(signal, [&](auto sig_) { relaxHistoryClampingKernel<true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxHistoryClampingKernel<false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
+    } else if (id == "RELAX_HitDistReconstruction.cs.hlsl" + sigSignal + "|NRD_MODE=RADIANCE|MODE_5X5=0" || id == "RELAX_HitDistReconstruction.cs.hlsl" + sigSignal + "|NRD_MODE=RADIANCE|MODE_5X5=1") {
         RelaxHitDistReconstructionParams p;
         p.tiles = b.take<TexR8>(R8);
         p.normalRoughness = b.take<TexNR>(NR);
         p.viewZ = b.take<TexR32F>(R32);
-        p.spec = b.take<TexRGBA16F>(F16);
-        p.diff = b.take<TexRGBA16F>(F16);
-        p.outSpec = b.take<TexRGBA16F>(F16);
-        p.outDiff = b.take<TexRGBA16F>(F16);
-        if (bad(7)) return (uint32_t)Result::INVALID_ARGUMENT;
+        takeS(p.spec);
+        takeD(p.diff);
+        takeS(p.outSpec);
+        takeD(p.outDiff);
+        if (bad(3 + 2 * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (id.back() == '1')
             relaxHitDistReconstructionKernel<2><<<pixelGrid, block, 0, stream>>>(cb, p);
         else
@@ -1627,35 +1682,35 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
     } else if (id == "RELAX_SplitScreen.cs.hlsl" + sig) {
         RelaxSplitScreenParams p;
         p.viewZ = b.take<TexR32F>(R32);
-        p.diff = b.take<TexRGBA16F>(F16);
-        p.spec = b.take<TexRGBA16F>(F16);
-        takeSh(p.diffSh);
-        takeSh(p.specSh);
-        p.outDiff = b.take<TexRGBA16F>(F16);
-        p.outSpec = b.take<TexRGBA16F>(F16);
-        takeSh(p.outDiffSh);
-        takeSh(p.outSpecSh);
-        if (bad(9 - 4 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        takeD(p.diff);
+        takeS(p.spec);
+        takeShD(p.diffSh);
+        takeShS(p.specSh);
+        takeD(p.outDiff);
+        takeS(p.outSpec);
+        takeShD(p.outDiffSh);
+        takeShS(p.outSpecSh);
+        if (bad(1 + (2 + 2 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (sh) relaxSplitScreenKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxSplitScreenKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
     } else if (id == "RELAX_Copy.cs.hlsl" + sig) {
         RelaxCopyParams p;
-        p.spec = b.take<TexRGBA16F>(F16);
-        p.diff = b.take<TexRGBA16F>(F16);
-        p.outSpec = b.take<TexRGBA16F>(F16);
-        p.outDiff = b.take<TexRGBA16F>(F16);
-        if (bad(4)) return (uint32_t)Result::INVALID_ARGUMENT;
-        relaxCopyKernel<<<pixelGrid, block, 0, stream>>>(p);
+        takeS(p.spec);
+        takeD(p.diff);
+        takeS(p.outSpec);
+        takeD(p.outDiff);
+        if (bad(2 * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
+        withSignal(signal, [&](auto sig_) { relaxCopyKernel<decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(lobeView(p, sig_)); });
     } else if (id == "RELAX_AntiFirefly.cs.hlsl" + sig) {
         RelaxAntiFireflyParams p;
         p.tiles = b.take<TexR8>(R8);
         p.normalRoughness = b.take<TexNR>(NR);
         p.viewZ = b.take<TexR32F>(R32);
-        p.spec = b.take<TexRGBA16F>(F16);
-        p.diff = b.take<TexRGBA16F>(F16);
-        p.outSpec = b.take<TexRGBA16F>(F16);
-        p.outDiff = b.take<TexRGBA16F>(F16);
-        if (bad(7)) return (uint32_t)Result::INVALID_ARGUMENT;
-        relaxAntiFireflyKernel<<<pixelGrid, block, 0, stream>>>(cb, p);
+        takeS(p.spec);
+        takeD(p.diff);
+        takeS(p.outSpec);
+        takeD(p.outDiff);
+        if (bad(3 + 2 * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
+        withSignal(signal, [&](auto sig_) { relaxAntiFireflyKernel<decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
     } else if (id == "RELAX_AtrousSmem.cs.hlsl" + sig || id == "RELAX_Atrous.cs.hlsl" + sig) {
         const bool smem = id == "RELAX_AtrousSmem.cs.hlsl" + sig;
         RelaxAtrousParams p = {};
@@ -1663,27 +1718,27 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.historyLength = b.take<TexR8>(R8);
         p.normalRoughness = b.take<TexNR>(NR);
         p.viewZ = b.take<TexR32F>(R32);
-        p.spec = b.take<TexRGBA16F>(F16);
-        p.diff = b.take<TexRGBA16F>(F16);
-        p.specReprojectionConfidence = b.take<TexR8>(R8);
-        p.specConfDummy = b.takeGuide();
-        p.diffConfDummy = b.takeGuide();
-        takeSh(p.specSh);
-        takeSh(p.diffSh);
-        p.outSpec = b.take<TexRGBA16F>(F16);
-        p.outDiff = b.take<TexRGBA16F>(F16);
+        takeS(p.spec);
+        takeD(p.diff);
+        if (hasSpec) p.specReprojectionConfidence = b.take<TexR8>(R8);
+        if (hasSpec) p.specConfDummy = b.takeGuide();
+        if (hasDiff) p.diffConfDummy = b.takeGuide();
+        takeShS(p.specSh);
+        takeShD(p.diffSh);
+        takeS(p.outSpec);
+        takeD(p.outDiff);
         if (smem) {
             p.outNormalRoughness = b.take<TexRGBA8>(Format::RGBA8_UNORM);
             p.outMaterialID = b.take<TexR8>(R8);
             p.outViewZ = b.take<TexR32F>(R32);
         }
-        takeSh(p.outSpecSh);
-        takeSh(p.outDiffSh);
-        if (bad((smem ? 18 : 15) - 4 * noSh)) return (uint32_t)Result::INVALID_ARGUMENT;
+        takeShS(p.outSpecSh);
+        takeShD(p.outDiffSh);
+        if (bad(4 + (smem ? 3 : 0) + (3 + 2 * shOn) * lobes + (hasSpec ? 1 : 0))) return (uint32_t)Result::INVALID_ARGUMENT;
         if (smem) {
-            if (sh) relaxAtrousSmemKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxAtrousSmemKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+            if (sh) withSignal(signal, [&](auto sig_) { relaxAtrousSmemKernel<true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxAtrousSmemKernel<false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
         } else {
-            if (sh) relaxAtrousKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxAtrousKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
+            if (sh) withSignal(signal, [&](auto sig_) { relaxAtrousKernel<true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxAtrousKernel<false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
         }
     } else {
         err = "no CUDA kernel for shader '" + id + "'";

@@ -70,6 +70,10 @@ IDENTIFIERS = [
     ("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=0"), ("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), ("REBLUR_PrePass.cs.hlsl", ""),
     ("REBLUR_TemporalAccumulation.cs.hlsl", ""), ("REBLUR_HistoryFix.cs.hlsl", ""), ("REBLUR_Blur.cs.hlsl", ""), ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0"),
     ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1"), ("REBLUR_TemporalStabilization.cs.hlsl", ""), ("REBLUR_SplitScreen.cs.hlsl", ""))] + [
+    # RELAX_DIFFUSE / RELAX_DIFFUSE_SH / RELAX_SPECULAR / RELAX_SPECULAR_SH
+] + [f"RELAX_HitDistReconstruction.cs.hlsl|NRD_SIGNAL={sig}|NRD_MODE=RADIANCE|MODE_5X5={m}" for sig in ("DIFF", "SPEC") for m in (0, 1)] + [
+    f"RELAX_{f}.cs.hlsl|NRD_SIGNAL={sig}|NRD_MODE={mode}" for sig in ("DIFF", "SPEC") for mode in ("RADIANCE", "SH")
+    for f in ("PrePass", "TemporalAccumulation", "HistoryFix", "HistoryClamping", "Copy", "AntiFirefly", "AtrousSmem", "Atrous", "SplitScreen")] + [
     # REFERENCE
     "REFERENCE_TemporalAccumulation.cs.hlsl", "REFERENCE_Copy.cs.hlsl",
     # ours: calls the application-side functions of the reference's NRD.hlsli ( oracle/ref_shim/Shaders/NRD_FrontEndProbe.cs.hlsl )

@@ -44,12 +44,27 @@ CASES["reblur_diff"] = (api.Denoiser.REBLUR_DIFFUSE, "reblur_frame_diff", ("OUT_
 CASES["reblur_spec"] = (api.Denoiser.REBLUR_SPECULAR, "reblur_frame_spec", ("OUT_SPEC_RADIANCE_HITDIST",), "reblur")
 CASES["reblur_diff_cb_guides"] = (api.Denoiser.REBLUR_DIFFUSE, "reblur_frame_diff_cb_guides", ("OUT_DIFF_RADIANCE_HITDIST",), "reblur")
 CASES["reblur_spec_recon_nots"] = (api.Denoiser.REBLUR_SPECULAR, "reblur_frame_spec_holes", ("OUT_SPEC_RADIANCE_HITDIST",), "reblur")
-SETTINGS = {"reblur_diff_cb_guides": lambda: api.ReblurSettings(checkerboardMode=2),
+# RELAX_DIFFUSE / RELAX_DIFFUSE_SH / RELAX_SPECULAR / RELAX_SPECULAR_SH ( NRD_SIGNAL = DIFF / SPEC ): plain, and the way NRDSample would drive them
+# ( checkerboard WHITE + confidence + anti-firefly ) resp. with hit-distance reconstruction and a split screen
+CASES["relax_diff"] = (api.Denoiser.RELAX_DIFFUSE, "relax_frame_diff_nosh", ("OUT_DIFF_RADIANCE_HITDIST",), "reblur")
+CASES["relax_spec"] = (api.Denoiser.RELAX_SPECULAR, "relax_frame_spec_nosh", ("OUT_SPEC_RADIANCE_HITDIST",), "reblur")
+CASES["relax_diff_sh_cb_guides"] = (api.Denoiser.RELAX_DIFFUSE_SH, "relax_frame_diff_cb_guides", ("OUT_DIFF_SH0", "OUT_DIFF_SH1"), "reblur")
+CASES["relax_spec_sh_cb_guides"] = (api.Denoiser.RELAX_SPECULAR_SH, "relax_frame_spec_cb_guides", ("OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur")
+CASES["relax_diff_recon_split"] = (api.Denoiser.RELAX_DIFFUSE, "relax_frame_diff_nosh_holes", ("OUT_DIFF_RADIANCE_HITDIST",), "reblur")
+CASES["relax_spec_sh_recon_split"] = (api.Denoiser.RELAX_SPECULAR_SH, "relax_frame_spec_holes", ("OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur")
+SETTINGS = {"relax_diff_sh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True),
+            "relax_spec_sh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True),
+            "relax_diff_recon_split": lambda: api.RelaxSettings(hitDistanceReconstructionMode=2),
+            "relax_spec_sh_recon_split": lambda: api.RelaxSettings(hitDistanceReconstructionMode=1),
+            "reblur_diff_cb_guides": lambda: api.ReblurSettings(checkerboardMode=2),
             "reblur_spec_recon_nots": lambda: api.ReblurSettings(hitDistanceReconstructionMode=1, maxStabilizedFrameNum=0),
             "relax_nosh_recon5x5": lambda: api.RelaxSettings(hitDistanceReconstructionMode=2), "relax_recon3x3": lambda: api.RelaxSettings(hitDistanceReconstructionMode=1),
             "relax_cb_guides_split": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True), "relax_nosh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2),
             "reblur_split": lambda: api.ReblurSettings(checkerboardMode=2), "reference": lambda: api.ReferenceSettings(maxAccumulatedFrameNum=5), "reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_guides_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
-COMMON = {"reblur_diff_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
+COMMON = {"relax_diff_sh_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
+          "relax_spec_sh_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
+          "relax_diff_recon_split": dict(splitScreen=0.3), "relax_spec_sh_recon_split": dict(splitScreen=0.3),
+          "reblur_diff_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
           "relax_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.3),
           "relax_nosh_cb_guides": dict(isHistoryConfidenceAvailable=True),
           "reblur_guides_cb": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True), "reblur_split": dict(splitScreen=0.35),
@@ -73,6 +88,10 @@ def frame_of(name, f, w, h):
         if name.startswith(f"reblur_frame_{lobe}"):
             kw = dict(checkerboard=2, guides=True) if name.endswith("_cb_guides") else (dict(holes=True) if name.endswith("_holes") else {})
             return {k: v for k, v in synth.reblur_frame(f, w, h, **kw).items() if other not in k}
+    for lobe, other in (("diff", "_SPEC_"), ("spec", "_DIFF_")):
+        if name.startswith(f"relax_frame_{lobe}"):
+            kw = dict(checkerboard=2, guides=True) if name.endswith("_cb_guides") else (dict(holes=True) if name.endswith("_holes") else {})
+            return {k: v for k, v in synth.relax_frame(f, w, h, sh="_nosh" not in name, **kw).items() if other not in k}
     if name == "relax_frame_nosh":
         return synth.relax_frame(f, w, h, sh=False)
     if name == "relax_frame_holes":
@@ -91,7 +110,8 @@ def frame_of(name, f, w, h):
         return synth.sigma_frame(f, w, h, translucency=True)
     return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"reblur_diff": (3e-2, 45.0), "reblur_spec": (3e-2, 45.0), "reblur_diff_cb_guides": (3e-2, 45.0), "reblur_spec_recon_nots": (3e-2, 45.0), "reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0), "reblur_split": (3e-2, 45.0), "reference": (1e-3, 80.0), "relax_cb_guides_split": (2e-3, 60.0), "relax_nosh_cb_guides": (2e-3, 60.0), "relax_nosh_recon5x5": (2e-3, 60.0), "relax_recon3x3": (2e-3, 60.0)}
+LIMITS = {"relax_diff": (2e-3, 60.0), "relax_spec": (2e-3, 60.0), "relax_diff_sh_cb_guides": (2e-3, 60.0), "relax_spec_sh_cb_guides": (2e-3, 60.0),
+          "relax_diff_recon_split": (2e-3, 60.0), "relax_spec_sh_recon_split": (2e-3, 60.0), "reblur_diff": (3e-2, 45.0), "reblur_spec": (3e-2, 45.0), "reblur_diff_cb_guides": (3e-2, 45.0), "reblur_spec_recon_nots": (3e-2, 45.0), "reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0), "reblur_split": (3e-2, 45.0), "reference": (1e-3, 80.0), "relax_cb_guides_split": (2e-3, 60.0), "relax_nosh_cb_guides": (2e-3, 60.0), "relax_nosh_recon5x5": (2e-3, 60.0), "relax_recon3x3": (2e-3, 60.0)}
 
 
 @pytest.fixture(scope="module")
