@@ -139,12 +139,17 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
     Binder b{tex, n, 0, true, &err, id.c_str()};
     // "<file>|NRD_SIGNAL=<DIFF|SPEC|BOTH>|NRD_MODE=RADIANCE<suffix>" (InstanceImpl.h:59-67). REBLUR_DIFFUSE / REBLUR_SPECULAR bind only their own lobe's
     // textures (REBLUR_*.resources.hlsli): takeD / takeS consume a binding only when the permutation has that lobe
+    // "|NRD_MODE=SH" ( REBLUR_DIFFUSE_SH / REBLUR_SPECULAR_SH / REBLUR_DIFFUSE_SPECULAR_SH ): each lobe binds a second RGBA16F next to the first
+    // ( takeShD / takeShS below, in the order of the REBLUR_*.resources.hlsli lists ); the launchers pick the SH instantiation when those views are bound
     int signal = 0;
+    bool sh = false;
     std::string kSig;
-    for (int k = 1; k <= 3 && !signal; k++) {
-        const std::string candidate = std::string("|NRD_SIGNAL=") + (k == 1 ? "DIFF" : (k == 2 ? "SPEC" : "BOTH")) + "|NRD_MODE=RADIANCE";
+    for (int k = 1; k <= 6 && !signal; k++) {
+        const int sg = (k - 1) % 3 + 1;
+        const std::string candidate = std::string("|NRD_SIGNAL=") + (sg == 1 ? "DIFF" : (sg == 2 ? "SPEC" : "BOTH")) + (k > 3 ? "|NRD_MODE=SH" : "|NRD_MODE=RADIANCE");
         if (id.find(candidate) != std::string::npos) {
-            signal = k;
+            signal = sg;
+            sh = k > 3;
             kSig = candidate;
         }
     }
@@ -157,6 +162,21 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
     };
     auto takeD16 = [&]() { return hasDiff ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
     auto takeS16 = [&]() { return hasSpec ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
+    auto takeShD = [&]() { return (hasDiff && sh) ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
+    auto takeShS = [&]() { return (hasSpec && sh) ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
+    const uint32_t shLobes = sh ? lobes : 0u;
+    // the sky-tile mask: R8_UNORM, or the full-resolution RGBA16F that REBLUR_DIFFUSE_SPECULAR_SH's pool table puts under TILES ( see TexTiles )
+    auto takeTiles = [&]() {
+        TexTiles v{};
+        if (b.next < n && tex[b.next].format == (uint32_t)Format::RGBA16_SFLOAT) {
+            static_cast<TexView&>(v) = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+            v.texelBytes = 8u;
+        } else {
+            static_cast<TexView&>(v) = b.take<TexR8>(Format::R8_UNORM);
+            v.texelBytes = 1u;
+        }
+        return v;
+    };
     auto takeDF = [&]() { return hasDiff ? b.take<TexR16F>(Format::R16_SFLOAT) : TexR16F{}; };
     auto takeSF = [&]() { return hasSpec ? b.take<TexR16F>(Format::R16_SFLOAT) : TexR16F{}; };
     // data1: RG8_UNORM for two lobes, R8_UNORM for one (Reblur.cpp: DATA1 format); P has `data1` + `data1R8` or `outData1` + `outData1R8`
@@ -168,13 +188,13 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
     if (id == "REBLUR_ClassifyTiles.cs.hlsl") {
         ClassifyTilesParams p = {};
         p.inViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
-        p.outTiles = b.take<TexR8>(Format::R8_UNORM);
+        p.outTiles = takeTiles();
         uint32_t r = done(2);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurClassifyTiles(cb, p, rows, stream);
     } else if (is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=0") || is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1")) {
         HitDistReconstructionParams p = {};
-        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.inDiff = takeD16();
@@ -189,27 +209,35 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.inDiff = takeD16();
         p.inSpec = takeS16();
+        p.inDiffSh = takeShD();
+        p.inSpecSh = takeShS();
         p.outDiff = takeD16();
         p.outSpec = takeS16();
-        uint32_t r = done(1 + 2 * lobes);
+        p.outDiffSh = takeShD();
+        p.outSpecSh = takeShS();
+        uint32_t r = done(1 + 2 * lobes + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurSplitScreen(cb, p, signal, rows, stream);
     } else if (is("REBLUR_PrePass.cs.hlsl")) {
         PrePassParams p = {};
-        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.inDiff = takeD16();
         p.inSpec = takeS16();
+        p.inDiffSh = takeShD();
+        p.inSpecSh = takeShS();
         p.outDiff = takeD16();
         p.outSpec = takeS16();
         p.outSpecHitDistForTracking = takeSF();
-        uint32_t r = done(3 + 2 * lobes + (hasSpec ? 1 : 0));
+        p.outDiffSh = takeShD();
+        p.outSpecSh = takeShS();
+        uint32_t r = done(3 + 2 * lobes + (hasSpec ? 1 : 0) + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurPrePass(cb, p, signal, kflags, rows, stream);
     } else if (is("REBLUR_TemporalAccumulation.cs.hlsl")) {
         TemporalAccumulationParams p = {};
-        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.mv = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
@@ -227,6 +255,10 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.historySpecFast = takeSF();
         p.prevSpecHitDistForTracking = takeSF();
         p.inSpecHitDistForTracking = takeSF();
+        p.inDiffSh = takeShD();
+        p.inSpecSh = takeShS();
+        p.historyDiffSh = takeShD();
+        p.historySpecSh = takeShS();
         takeData1(p.outData1, p.outData1R8);
         p.outDiff = takeD16();
         p.outSpec = takeS16();
@@ -235,12 +267,14 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecHitDistForTracking = takeSF();
         if (hasSpec) p.outData2 = b.take<TexR32U>(Format::R32_UINT);
         else p.outData2R8 = b.take<TexR8U>(Format::R8_UINT);
-        uint32_t r = done(10 + 6 * lobes + (hasSpec ? 3 : 0));
+        p.outDiffSh = takeShD();
+        p.outSpecSh = takeShS();
+        uint32_t r = done(10 + 6 * lobes + (hasSpec ? 3 : 0) + 3 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurTemporalAccumulation(cb, p, signal, rows, stream);
     } else if (is("REBLUR_HistoryFix.cs.hlsl")) {
         HistoryFixParams p = {};
-        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         takeData1(p.data1, p.data1R8);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
@@ -249,36 +283,46 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.inDiffFast = takeDF();
         p.inSpecFast = takeSF();
         p.specHitDistForTracking = takeSF();
+        p.inDiffSh = takeShD();
+        p.inSpecSh = takeShS();
         p.outDiff = takeD16();
         p.outSpec = takeS16();
         p.outDiffFast = takeDF();
         p.outSpecFast = takeSF();
-        uint32_t r = done(4 + 4 * lobes + (hasSpec ? 1 : 0));
+        p.outDiffSh = takeShD();
+        p.outSpecSh = takeShS();
+        uint32_t r = done(4 + 4 * lobes + (hasSpec ? 1 : 0) + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurHistoryFix(cb, p, signal, quads, rows, stream);
     } else if (is("REBLUR_Blur.cs.hlsl")) {
         BlurParams p = {};
-        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         takeData1(p.data1, p.data1R8);
         p.inDiff = takeD16();
         p.inSpec = takeS16();
+        p.inDiffSh = takeShD();
+        p.inSpecSh = takeShS();
         p.outViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.outDiff = takeD16();
         p.outSpec = takeS16();
-        uint32_t r = done(5 + 2 * lobes);
+        p.outDiffSh = takeShD();
+        p.outSpecSh = takeShS();
+        uint32_t r = done(5 + 2 * lobes + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurBlur(cb, p, signal, kflags, rows, stream);
     } else if (is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1") || is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0")) {
         const bool ts = is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1");
         PostBlurParams p = {};
-        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         takeData1(p.data1, p.data1R8);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.inDiff = takeD16();
         p.inSpec = takeS16();
+        p.inDiffSh = takeShD();
+        p.inSpecSh = takeShS();
         p.outNormalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.outDiff = takeD16();
         p.outSpec = takeS16();
@@ -286,13 +330,17 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
             p.outInternalData = b.take<TexR16U>(Format::R16_UINT);
             p.outDiffCopy = takeD16();
             p.outSpecCopy = takeS16();
+            p.outDiffShCopy = takeShD();
+            p.outSpecShCopy = takeShS();
         }
-        uint32_t r = done(ts ? 5 + 2 * lobes : 6 + 3 * lobes);
+        p.outDiffSh = takeShD();  // the SH history comes last ( Reblur_DiffuseSpecularSh.hpp:268-281 )
+        p.outSpecSh = takeShS();
+        uint32_t r = done(ts ? 5 + 2 * lobes + 2 * shLobes : 6 + 3 * lobes + 3 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurPostBlur(cb, p, signal, ts, kflags, rows, stream);
     } else if (is("REBLUR_TemporalStabilization.cs.hlsl")) {
         TemporalStabilizationParams p = {};
-        p.tiles = b.take<TexR8>(Format::R8_UNORM);
+        p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         takeData1(p.data1, p.data1R8);
@@ -303,13 +351,17 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.inSpec = takeS16();
         p.historyDiffLuma = takeDF();
         p.historySpecLuma = takeSF();
+        p.inDiffSh = takeShD();  // the SH history written by the post-blur
+        p.inSpecSh = takeShS();
         p.mv = b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
         p.outInternalData = b.take<TexR16U>(Format::R16_UINT);
         p.outDiff = takeD16();
         p.outSpec = takeS16();
         p.outDiffLuma = takeDF();
         p.outSpecLuma = takeSF();
-        uint32_t r = done(7 + 4 * lobes + (hasSpec ? 1 : 0));
+        p.outDiffSh = takeShD();
+        p.outSpecSh = takeShS();
+        uint32_t r = done(7 + 4 * lobes + (hasSpec ? 1 : 0) + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurTemporalStabilization(cb, p, signal, rows, stream);
     } else {

@@ -26,8 +26,12 @@ enum PassIndex : uint32_t {
 
 const uint32_t kCb = sizeof(ReblurConstants);
 
-bool hasDiffuse(Denoiser d) { return d == Denoiser::REBLUR_DIFFUSE || d == Denoiser::REBLUR_DIFFUSE_SPECULAR; }
-bool hasSpecular(Denoiser d) { return d == Denoiser::REBLUR_SPECULAR || d == Denoiser::REBLUR_DIFFUSE_SPECULAR; }
+bool hasDiffuse(Denoiser d) {
+    return d == Denoiser::REBLUR_DIFFUSE || d == Denoiser::REBLUR_DIFFUSE_SPECULAR || d == Denoiser::REBLUR_DIFFUSE_SH || d == Denoiser::REBLUR_DIFFUSE_SPECULAR_SH;
+}
+bool hasSpecular(Denoiser d) {
+    return d == Denoiser::REBLUR_SPECULAR || d == Denoiser::REBLUR_DIFFUSE_SPECULAR || d == Denoiser::REBLUR_SPECULAR_SH || d == Denoiser::REBLUR_DIFFUSE_SPECULAR_SH;
+}
 
 }  // namespace
 
@@ -36,7 +40,10 @@ bool hasSpecular(Denoiser d) { return d == Denoiser::REBLUR_SPECULAR || d == Den
 // Pool layout: permanent = prev viewZ / normal+roughness / internal data, then per lobe { history, fast history, stabilized luma ping / pong },
 // then the specular hit-distance-for-tracking ping / pong; transient = data1 (RG8 for both lobes, R8 for one), data2 (R32_UINT, R8_UINT without
 // specular), hit distance for tracking (specular), per lobe { tmp2, fast history }, tiles.
-void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
+// sh: REBLUR_DIFFUSE_SH / REBLUR_SPECULAR_SH / REBLUR_DIFFUSE_SPECULAR_SH (NRD_MODE = SH; Reblur_DiffuseSh.hpp, Reblur_SpecularSh.hpp,
+// Reblur_DiffuseSpecularSh.hpp): the same graph over IN / OUT_*_SH0 with a second RGBA16F per lobe ( SH1 ) carried through every pass — the
+// user's OUT_*_SH1 as "SH_TEMP1", one more permanent ( SH history, after the lobe's stabilized pair ) and transient ( SH_TMP2, after the lobe's fast history ).
+void Graph::buildReblur(DenoiserState& d, bool diff, bool spec, bool sh) {
     new (&d.settings.reblur) ReblurSettings();
     d.settingsSize = sizeof(ReblurSettings);
 
@@ -48,18 +55,21 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
     const uint16_t P_PREV_NORMAL_ROUGHNESS = perm(Format::R10_G10_B10_A2_UNORM);  // must match the IN_NORMAL_ROUGHNESS encoding
     const uint16_t P_PREV_INTERNAL_DATA = perm(Format::R16_UINT);                 // 6b diff frames | 6b spec frames | 4b material
     uint16_t P_DIFF_HISTORY = 0, P_DIFF_FAST_HISTORY = 0, P_DIFF_STABILIZED_PING = 0, P_DIFF_STABILIZED_PONG = 0;
+    uint16_t P_DIFF_SH_HISTORY = 0, P_SPEC_SH_HISTORY = 0, T_DIFF_SH_TMP2 = 0, T_SPEC_SH_TMP2 = 0;
     uint16_t P_SPEC_HISTORY = 0, P_SPEC_FAST_HISTORY = 0, P_SPEC_STABILIZED_PING = 0, P_SPEC_STABILIZED_PONG = 0, P_SPEC_HITDIST_TRACKING_PING = 0, P_SPEC_HITDIST_TRACKING_PONG = 0;
     if (diff) {
         P_DIFF_HISTORY = perm(kRadiance);
         P_DIFF_FAST_HISTORY = perm(kFast);
         P_DIFF_STABILIZED_PING = perm(Format::R16_SFLOAT);
         P_DIFF_STABILIZED_PONG = perm(Format::R16_SFLOAT);
+        if (sh) P_DIFF_SH_HISTORY = perm(kRadiance);
     }
     if (spec) {
         P_SPEC_HISTORY = perm(kRadiance);
         P_SPEC_FAST_HISTORY = perm(kFast);
         P_SPEC_STABILIZED_PING = perm(Format::R16_SFLOAT);
         P_SPEC_STABILIZED_PONG = perm(Format::R16_SFLOAT);
+        if (sh) P_SPEC_SH_HISTORY = perm(kRadiance);
         P_SPEC_HITDIST_TRACKING_PING = perm(Format::R16_SFLOAT);
         P_SPEC_HITDIST_TRACKING_PONG = perm(Format::R16_SFLOAT);
     }
@@ -71,28 +81,49 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
     if (diff) {
         T_DIFF_TMP2 = tran(kRadiance);
         T_DIFF_FAST = tran(kFast);
+        if (sh) T_DIFF_SH_TMP2 = tran(kRadiance);
     }
     if (spec) {
         T_SPEC_TMP2 = tran(kRadiance);
         T_SPEC_FAST = tran(kFast);
+        if (sh) T_SPEC_SH_TMP2 = tran(kRadiance);
     }
-    const uint16_t T_TILES = tran(Format::R8_UNORM, 16);
+    // Reblur_DiffuseSpecularSh.hpp:59-82 adds ELEVEN transient textures for its ten names: a third RGBA16F sits where the enum says TILES, and the
+    // R8 texture at 1/16 resolution that follows is never bound. The passes therefore keep their sky-tile mask in the top-left corner of a
+    // full-resolution RGBA16F texture. Kept as is: pool sizes and binding indices are part of the stream an integration sees.
+    uint16_t T_TILES;
+    if (diff && spec && sh) {
+        T_TILES = tran(kRadiance);
+        tran(Format::R8_UNORM, 16);
+    } else {
+        T_TILES = tran(Format::R8_UNORM, 16);
+    }
 
     auto U = [](ResourceType t) { return Slot::user(t); };
     auto Pm = [](uint16_t i) { return Slot::perm(i); };
     auto Tr = [](uint16_t i) { return Slot::tran(i); };
     // The user's output textures double as scratch ("TEMP1") between passes
-    const Slot diffTemp1 = U(ResourceType::OUT_DIFF_RADIANCE_HITDIST), specTemp1 = U(ResourceType::OUT_SPEC_RADIANCE_HITDIST);
+    const ResourceType inDiff = sh ? ResourceType::IN_DIFF_SH0 : ResourceType::IN_DIFF_RADIANCE_HITDIST, inSpec = sh ? ResourceType::IN_SPEC_SH0 : ResourceType::IN_SPEC_RADIANCE_HITDIST;
+    const ResourceType outDiff = sh ? ResourceType::OUT_DIFF_SH0 : ResourceType::OUT_DIFF_RADIANCE_HITDIST, outSpec = sh ? ResourceType::OUT_SPEC_SH0 : ResourceType::OUT_SPEC_RADIANCE_HITDIST;
+    const Slot diffTemp1 = U(outDiff), specTemp1 = U(outSpec);
     const Slot diffTemp2 = Tr(T_DIFF_TMP2), specTemp2 = Tr(T_SPEC_TMP2);
+    const Slot diffShTemp1 = U(ResourceType::OUT_DIFF_SH1), specShTemp1 = U(ResourceType::OUT_SPEC_SH1), diffShTemp2 = Tr(T_DIFF_SH_TMP2), specShTemp2 = Tr(T_SPEC_SH_TMP2);
     const Slot dummy = U(ResourceType::IN_VIEWZ);  // bound where an optional input is absent
-    const std::string sig = std::string("|NRD_SIGNAL=") + (diff && spec ? "BOTH" : (diff ? "DIFF" : "SPEC")) + "|NRD_MODE=RADIANCE";
-    const std::string prefix = std::string("REBLUR_") + (diff && spec ? "DiffuseSpecular" : (diff ? "Diffuse" : "Specular")) + " - ";
+    const std::string sigSignal = std::string("|NRD_SIGNAL=") + (diff && spec ? "BOTH" : (diff ? "DIFF" : "SPEC"));
+    const std::string sig = sigSignal + (sh ? "|NRD_MODE=SH" : "|NRD_MODE=RADIANCE");
+    // Reblur_DiffuseSh.hpp never defines DENOISER_NAME ( the other files do ), so its pass names carry the macro's own name
+    const std::string prefix = (sh && diff && !spec) ? std::string("DENOISER_NAME - ")
+                                                     : std::string("REBLUR_") + (diff && spec ? "DiffuseSpecular" : (diff ? "Diffuse" : "Specular")) + (sh ? "Sh - " : " - ");
     auto name = [&](const char* pass) { return intern(prefix + pass); };
     // bind helpers: a lobe's binding exists only when the denoiser has that lobe
     auto inD = [&](Slot s, Slot swap = Slot()) { if (diff) in(s, swap); };
     auto inS = [&](Slot s, Slot swap = Slot()) { if (spec) in(s, swap); };
     auto outD = [&](Slot s, Slot swap = Slot()) { if (diff) out(s, swap); };
     auto outS = [&](Slot s, Slot swap = Slot()) { if (spec) out(s, swap); };
+    auto inShD = [&](Slot s) { if (diff && sh) in(s); };
+    auto inShS = [&](Slot s) { if (spec && sh) in(s); };
+    auto outShD = [&](Slot s) { if (diff && sh) out(s); };
+    auto outShS = [&](Slot s) { if (spec && sh) out(s); };
 
     beginPass(name("Classify tiles"));
     in(U(ResourceType::IN_VIEWZ));
@@ -105,11 +136,11 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(U(ResourceType::IN_VIEWZ));
-        inD(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
-        inS(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+        inD(U(inDiff));
+        inS(U(inSpec));
         outD(prepassFollows ? diffTemp2 : diffTemp1);
         outS(prepassFollows ? specTemp2 : specTemp1);
-        emit("REBLUR_HitDistReconstruction.cs.hlsl" + sig + (is5x5 ? "|MODE_5X5=1" : "|MODE_5X5=0"), 8, 16, kCb);
+        emit("REBLUR_HitDistReconstruction.cs.hlsl" + sigSignal + "|NRD_MODE=RADIANCE" + (is5x5 ? "|MODE_5X5=1" : "|MODE_5X5=0"), 8, 16, kCb);
     }
 
     for (int i = 0; i < 2; i++) {
@@ -118,11 +149,15 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
         in(Tr(T_TILES));
         in(U(ResourceType::IN_NORMAL_ROUGHNESS));
         in(U(ResourceType::IN_VIEWZ));
-        inD(afterReconstruction ? diffTemp2 : U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
-        inS(afterReconstruction ? specTemp2 : U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+        inD(afterReconstruction ? diffTemp2 : U(inDiff));
+        inS(afterReconstruction ? specTemp2 : U(inSpec));
+        inShD(U(ResourceType::IN_DIFF_SH1));
+        inShS(U(ResourceType::IN_SPEC_SH1));
         outD(diffTemp1);
         outS(specTemp1);
         outS(Tr(T_SPEC_HITDIST_TRACKING));
+        outShD(diffShTemp1);
+        outShS(specShTemp1);
         emit("REBLUR_PrePass.cs.hlsl" + sig, 16, 16, kCb);
     }
 
@@ -139,14 +174,18 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
         in(hasMix ? U(ResourceType::IN_DISOCCLUSION_THRESHOLD_MIX) : dummy);
         inD(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
         inS(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
-        inD(afterPrepass ? diffTemp1 : U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
-        inS(afterPrepass ? specTemp1 : U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
+        inD(afterPrepass ? diffTemp1 : U(inDiff));
+        inS(afterPrepass ? specTemp1 : U(inSpec));
         inD(Pm(P_DIFF_HISTORY));
         inS(Pm(P_SPEC_HISTORY));
         inD(Pm(P_DIFF_FAST_HISTORY));
         inS(Pm(P_SPEC_FAST_HISTORY));
         inS(Pm(P_SPEC_HITDIST_TRACKING_PING), Pm(P_SPEC_HITDIST_TRACKING_PONG));
         inS(Tr(T_SPEC_HITDIST_TRACKING));
+        inShD(afterPrepass ? diffShTemp1 : U(ResourceType::IN_DIFF_SH1));
+        inShS(afterPrepass ? specShTemp1 : U(ResourceType::IN_SPEC_SH1));
+        inShD(Pm(P_DIFF_SH_HISTORY));
+        inShS(Pm(P_SPEC_SH_HISTORY));
         out(Tr(T_DATA1));
         outD(diffTemp2);
         outS(specTemp2);
@@ -154,6 +193,8 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
         outS(Tr(T_SPEC_FAST));
         outS(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
         out(Tr(T_DATA2));
+        outShD(diffShTemp2);
+        outShS(specShTemp2);
         emit("REBLUR_TemporalAccumulation.cs.hlsl" + sig, 8, 16, kCb);
     }
 
@@ -167,10 +208,14 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
     inD(Tr(T_DIFF_FAST));
     inS(Tr(T_SPEC_FAST));
     inS(Pm(P_SPEC_HITDIST_TRACKING_PONG), Pm(P_SPEC_HITDIST_TRACKING_PING));
+    inShD(diffShTemp2);
+    inShS(specShTemp2);
     outD(diffTemp1);
     outS(specTemp1);
     outD(Pm(P_DIFF_FAST_HISTORY));
     outS(Pm(P_SPEC_FAST_HISTORY));
+    outShD(diffShTemp1);
+    outShS(specShTemp1);
     emit("REBLUR_HistoryFix.cs.hlsl" + sig, 8, 16, kCb);
 
     beginPass(name("Blur"));
@@ -180,9 +225,13 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
     in(Tr(T_DATA1));
     inD(diffTemp1);
     inS(specTemp1);
+    inShD(diffShTemp1);
+    inShS(specShTemp1);
     out(Pm(P_PREV_VIEWZ));
     outD(diffTemp2);
     outS(specTemp2);
+    outShD(diffShTemp2);
+    outShS(specShTemp2);
     emit("REBLUR_Blur.cs.hlsl" + sig, 8, 16, kCb);
 
     for (int i = 0; i < 2; i++) {
@@ -194,14 +243,20 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
         in(Pm(P_PREV_VIEWZ));
         inD(diffTemp2);
         inS(specTemp2);
+        inShD(diffShTemp2);
+        inShS(specShTemp2);
         out(Pm(P_PREV_NORMAL_ROUGHNESS));
         outD(Pm(P_DIFF_HISTORY));
         outS(Pm(P_SPEC_HISTORY));
         if (!stabilizationFollows) {
             out(Pm(P_PREV_INTERNAL_DATA));
-            outD(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
-            outS(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
+            outD(U(outDiff));
+            outS(U(outSpec));
+            outShD(U(ResourceType::OUT_DIFF_SH1));
+            outShS(U(ResourceType::OUT_SPEC_SH1));
         }
+        outShD(Pm(P_DIFF_SH_HISTORY));
+        outShS(Pm(P_SPEC_SH_HISTORY));
         emit("REBLUR_PostBlur.cs.hlsl" + sig + (stabilizationFollows ? "|TEMPORAL_STABILIZATION=1" : "|TEMPORAL_STABILIZATION=0"), 8, 16, kCb);
     }
 
@@ -216,20 +271,28 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
     inS(Pm(P_SPEC_HISTORY));
     inD(Pm(P_DIFF_STABILIZED_PING), Pm(P_DIFF_STABILIZED_PONG));
     inS(Pm(P_SPEC_STABILIZED_PING), Pm(P_SPEC_STABILIZED_PONG));
+    inShD(Pm(P_DIFF_SH_HISTORY));
+    inShS(Pm(P_SPEC_SH_HISTORY));
     out(U(ResourceType::IN_MV));  // bound read-write by the reference; only read by this pass
     out(Pm(P_PREV_INTERNAL_DATA));
-    outD(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
-    outS(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
+    outD(U(outDiff));
+    outS(U(outSpec));
     outD(Pm(P_DIFF_STABILIZED_PONG), Pm(P_DIFF_STABILIZED_PING));
     outS(Pm(P_SPEC_STABILIZED_PONG), Pm(P_SPEC_STABILIZED_PING));
+    outShD(U(ResourceType::OUT_DIFF_SH1));
+    outShS(U(ResourceType::OUT_SPEC_SH1));
     emit("REBLUR_TemporalStabilization.cs.hlsl" + sig, 8, 16, kCb);
 
     beginPass(name("Split screen"));
     in(U(ResourceType::IN_VIEWZ));
-    inD(U(ResourceType::IN_DIFF_RADIANCE_HITDIST));
-    inS(U(ResourceType::IN_SPEC_RADIANCE_HITDIST));
-    outD(U(ResourceType::OUT_DIFF_RADIANCE_HITDIST));
-    outS(U(ResourceType::OUT_SPEC_RADIANCE_HITDIST));
+    inD(U(inDiff));
+    inS(U(inSpec));
+    inShD(U(ResourceType::IN_DIFF_SH1));
+    inShS(U(ResourceType::IN_SPEC_SH1));
+    outD(U(outDiff));
+    outS(U(outSpec));
+    outShD(U(ResourceType::OUT_DIFF_SH1));
+    outShS(U(ResourceType::OUT_SPEC_SH1));
     emit("REBLUR_SplitScreen.cs.hlsl" + sig, 8, 16, kCb);
 
     // REBLUR_ADD_VALIDATION_DISPATCH (Reblur.cpp:65-78): a single-lobe denoiser binds its input in both lobe slots
@@ -239,8 +302,8 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec) {
     in(U(ResourceType::IN_MV));
     in(Tr(T_DATA1));
     in(Tr(T_DATA2));
-    in(U(diff ? ResourceType::IN_DIFF_RADIANCE_HITDIST : ResourceType::IN_SPEC_RADIANCE_HITDIST));
-    in(U(spec ? ResourceType::IN_SPEC_RADIANCE_HITDIST : ResourceType::IN_DIFF_RADIANCE_HITDIST));
+    in(U(diff ? inDiff : inSpec));
+    in(U(spec ? inSpec : inDiff));
     out(U(ResourceType::OUT_VALIDATION));
     emit("REBLUR_Validation.cs.hlsl", 8, 16, kCb, GRID_FROM_RESOURCE, 1);
 }

@@ -42,6 +42,9 @@ static const Denoiser kSupported[] = {
     Denoiser::REBLUR_DIFFUSE,
     Denoiser::REBLUR_SPECULAR,
     Denoiser::REBLUR_DIFFUSE_SPECULAR,
+    Denoiser::REBLUR_DIFFUSE_SH,
+    Denoiser::REBLUR_SPECULAR_SH,
+    Denoiser::REBLUR_DIFFUSE_SPECULAR_SH,
     Denoiser::RELAX_DIFFUSE,
     Denoiser::RELAX_DIFFUSE_SH,
     Denoiser::RELAX_SPECULAR,
@@ -165,6 +168,9 @@ Result Graph::create(const InstanceCreationDesc& desc) {
             case Denoiser::REBLUR_DIFFUSE: buildReblur(d, true, false); break;
             case Denoiser::REBLUR_SPECULAR: buildReblur(d, false, true); break;
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: buildReblur(d, true, true); break;
+            case Denoiser::REBLUR_DIFFUSE_SH: buildReblur(d, true, false, true); break;
+            case Denoiser::REBLUR_SPECULAR_SH: buildReblur(d, false, true, true); break;
+            case Denoiser::REBLUR_DIFFUSE_SPECULAR_SH: buildReblur(d, true, true, true); break;
             case Denoiser::SIGMA_SHADOW: buildSigmaShadow(d, false); break;
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: buildSigmaShadow(d, true); break;
             case Denoiser::REFERENCE: buildReference(d); break;
@@ -468,6 +474,9 @@ Result Graph::getComputeDispatches(const Identifier* ids, uint32_t idsNum, const
         switch (d.desc.denoiser) {
             case Denoiser::REBLUR_DIFFUSE:
             case Denoiser::REBLUR_SPECULAR:
+            case Denoiser::REBLUR_DIFFUSE_SH:
+            case Denoiser::REBLUR_SPECULAR_SH:
+            case Denoiser::REBLUR_DIFFUSE_SPECULAR_SH:
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: updateReblur(d); break;
             case Denoiser::SIGMA_SHADOW:
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: updateSigma(d); break;

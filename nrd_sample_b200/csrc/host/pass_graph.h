@@ -114,7 +114,7 @@ private:
     void flipPingPong(const DenoiserState& d);
 
     // graph_reblur.cpp / graph_sigma.cpp / graph_relax.cpp
-    void buildReblur(DenoiserState& d, bool diff, bool spec);
+    void buildReblur(DenoiserState& d, bool diff, bool spec, bool sh = false);
     void updateReblur(const DenoiserState& d);
     void fillReblurConstants(const ReblurSettings& s, void* dst);
     void buildSigmaShadow(DenoiserState& d, bool translucency);

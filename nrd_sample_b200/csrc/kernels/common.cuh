@@ -141,6 +141,24 @@ struct TexNR : TexView {
     }
 };
 
+// The sky-tile mask ( 0 or 1 per 16x16 tile ). R8_UNORM everywhere except REBLUR_DIFFUSE_SPECULAR_SH, whose pool table hands the passes a
+// full-resolution RGBA16F texture under the TILES index ( Reblur_DiffuseSpecularSh.hpp:59-82: eleven textures for ten names ); graphics
+// hardware converts on access, here the view does: `texelBytes` = 1 or 8, the mask lives in .x ( readers only ask "!= 0" ).
+struct TexTiles : TexView {
+    uint32_t texelBytes;
+    NRD_DEV float load(int x, int y) const {
+        if (!inside(x, y)) return 0.0f;
+        const uint8_t* at = data + (size_t)(y * pitch + x) * texelBytes;
+        return texelBytes == 1u ? (float)__ldg(at) : (float)__ldg(reinterpret_cast<const unsigned short*>(at));  // half bits of .x: zero iff the value is +0
+    }
+    NRD_DEV void store(int x, int y, float v) const {
+        if (!inside(x, y)) return;
+        uint8_t* at = data + (size_t)(y * pitch + x) * texelBytes;
+        if (texelBytes == 1u) *at = (uint8_t)unormQ(v, 255.0f);
+        else *reinterpret_cast<uint2*>(at) = make_uint2((uint32_t)__half_as_ushort(__float2half_rn(v)), 0u);  // a scalar store to a 4-channel UAV: ( v, 0, 0, 0 )
+    }
+};
+
 struct TexR8 : TexView {  // R8_UNORM
     NRD_DEV float fetch(int x, int y) const { return (float)__ldg(ptr<uint8_t>(x, y)) / 255.0f; }
     NRD_DEV float load(int x, int y) const { return inside(x, y) ? fetch(x, y) : 0.0f; }

@@ -92,6 +92,8 @@ NRD_DEV float4 mixHistoryAndCurrent(const ReblurConstants& cb, float4 history, f
     float fw = fmaxf(f, minHitDistAccumSpeed(cb, roughness));
     return make_float4(lerp(history.x, current.x, f), lerp(history.y, current.y, f), lerp(history.z, current.z, f), lerp(history.w, current.w, fw));
 }
+// REBLUR_SH_TYPE sh; sh *= GetLumaScale( length( sh ), luma )
+NRD_DEV float4 rescaleSh(float4 sh, float newLuma) { return sh * lumaScale(sqrtf(dot(sh, sh)), newLuma); }
 NRD_DEV float4 changeLuma(float4 c, float newLuma) {
     float s = lumaScale(c.x, newLuma);
     return make_float4(c.x * s, c.y * s, c.z * s, c.w);
@@ -182,6 +184,15 @@ struct HistoryFilter {
         }
         return sum < 0.0001f ? c * 0.0f : c / sum;
     }
+    // _BilinearFilterWithCustomWeights_Color on a four-channel texture ( the SH history, REBLUR_Common.hlsli:351-371 )
+    NRD_DEV float4 bilinear4(const TexRGBA16F& tex) const {
+        float4 c = tex.load(ox, oy) * custom.x;
+        c += tex.load(ox + 1, oy) * custom.y;
+        c += tex.load(ox, oy + 1) * custom.z;
+        c += tex.load(ox + 1, oy + 1) * custom.w;
+        float s = sum4(custom);
+        return s < 0.0001f ? f4(0.0f) : c / s;
+    }
     NRD_DEV float bilinear(const TexR16F& tex) const {
         float c = tex.load(ox, oy) * custom.x;
         c += tex.load(ox + 1, oy) * custom.y;
@@ -195,49 +206,56 @@ struct HistoryFilter {
 // ---- launch parameter blocks (member order = shader register order = DispatchDesc::resources order) ----------
 struct ClassifyTilesParams {
     TexR32F inViewZ;
-    TexR8 outTiles;
+    TexTiles outTiles;
 };
 struct SplitScreenParams {
     TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexRGBA16F outDiff, outSpec;
+    TexRGBA16F inDiffSh, inSpecSh, outDiffSh, outSpecSh;  // NRD_MODE = SH only ( unbound = null views otherwise ): the second RGBA16F of each lobe
 };
 struct HitDistReconstructionParams {
-    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
+    TexTiles tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexRGBA16F outDiff, outSpec;
 };
 struct PrePassParams {
-    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
+    TexTiles tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexRGBA16F outDiff, outSpec; TexR16F outSpecHitDistForTracking;
+    TexRGBA16F inDiffSh, inSpecSh, outDiffSh, outSpecSh;  // NRD_MODE = SH only
 };
 // `data1R8` / `data2R8` / `outData1R8` / `outData2R8`: the single-lobe formats of data1 / data2 (bound instead of the two-lobe view)
 struct BlurParams {
-    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRG8 data1; TexRGBA16F inDiff, inSpec;
+    TexTiles tiles; TexNR normalRoughness; TexR32F viewZ; TexRG8 data1; TexRGBA16F inDiff, inSpec;
     TexR32F outViewZ; TexRGBA16F outDiff, outSpec;
     TexR8 data1R8;
+    TexRGBA16F inDiffSh, inSpecSh, outDiffSh, outSpecSh;  // NRD_MODE = SH only
 };
 struct PostBlurParams {
-    TexR8 tiles; TexNR normalRoughness; TexRG8 data1; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
+    TexTiles tiles; TexNR normalRoughness; TexRG8 data1; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexNR outNormalRoughness; TexRGBA16F outDiff, outSpec;
     TexR16U outInternalData; TexRGBA16F outDiffCopy, outSpecCopy;  // only bound when TEMPORAL_STABILIZATION = 0
     TexR8 data1R8;
+    TexRGBA16F inDiffSh, inSpecSh, outDiffSh, outSpecSh, outDiffShCopy, outSpecShCopy;  // NRD_MODE = SH only ( out*Sh = the SH history )
 };
 struct TemporalAccumulationParams {
-    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F mv; TexR32F prevViewZ; TexNR prevNormalRoughness; TexR16U prevInternalData;
+    TexTiles tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F mv; TexR32F prevViewZ; TexNR prevNormalRoughness; TexR16U prevInternalData;
     TexAnyX disocclusionThresholdMix, diffConfidence, specConfidence;  // dummies (IN_VIEWZ) unless the optional inputs are enabled
     TexRGBA16F inDiff, inSpec, historyDiff, historySpec; TexR16F historyDiffFast, historySpecFast, prevSpecHitDistForTracking, inSpecHitDistForTracking;
     TexRG8 outData1; TexRGBA16F outDiff, outSpec; TexR16F outDiffFast, outSpecFast, outSpecHitDistForTracking; TexR32U outData2;
     TexR8 outData1R8; TexR8U outData2R8;
+    TexRGBA16F inDiffSh, inSpecSh, historyDiffSh, historySpecSh, outDiffSh, outSpecSh;  // NRD_MODE = SH only
 };
 struct HistoryFixParams {
-    TexR8 tiles; TexNR normalRoughness; TexRG8 data1; TexR32F viewZ; TexRGBA16F inDiff, inSpec; TexR16F inDiffFast, inSpecFast, specHitDistForTracking;
+    TexTiles tiles; TexNR normalRoughness; TexRG8 data1; TexR32F viewZ; TexRGBA16F inDiff, inSpec; TexR16F inDiffFast, inSpecFast, specHitDistForTracking;
     TexRGBA16F outDiff, outSpec; TexR16F outDiffFast, outSpecFast;
     TexR8 data1R8;
+    TexRGBA16F inDiffSh, inSpecSh, outDiffSh, outSpecSh;  // NRD_MODE = SH only
 };
 struct TemporalStabilizationParams {
-    TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRG8 data1; TexR32U data2; TexR16F specHitDistForTracking; TexRGBA16F inDiff, inSpec;
+    TexTiles tiles; TexNR normalRoughness; TexR32F viewZ; TexRG8 data1; TexR32U data2; TexR16F specHitDistForTracking; TexRGBA16F inDiff, inSpec;
     TexR16F historyDiffLuma, historySpecLuma;
     TexRGBA16F mv; TexR16U outInternalData; TexRGBA16F outDiff, outSpec; TexR16F outDiffLuma, outSpecLuma;
     TexR8 data1R8; TexR8U data2R8;
+    TexRGBA16F inDiffSh, inSpecSh, outDiffSh, outSpecSh;  // NRD_MODE = SH only ( in*Sh = the SH history )
 };
 
 }  // namespace nrdk

@@ -25,7 +25,8 @@ namespace {
 constexpr int HF_BORDER = 4;  // REBLUR_ANTI_FIREFLY_FILTER_RADIUS
 constexpr int HF_TILE_W = BLOCK_W + 2 * HF_BORDER, HF_TILE_H = BLOCK_H + 2 * HF_BORDER;
 
-template <int LOBE, int SIGNAL>
+// SH ( NRD_MODE = SH ): the lobe's second RGBA16F is reconstructed with the same weights and rescaled to the clamped luma ( REBLUR_HistoryFix.cs.hlsl:106-108, 135-137, 194-207, 286-294 )
+template <int LOBE, int SIGNAL, bool SH>
 NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p, const float (*sLuma)[HF_TILE_W], const float2 (*sRow)[HF_TILE_H][BLOCK_W], bool tileHasSky,
                             int px, int py, float strideIn, float frameNum,
                             float frameNumAvgNorm, float viewZ, float materialID, float3 N, float roughness, float3 Nv, float3 Xv, float frustumSize, float2 pixelUv) {
@@ -37,6 +38,8 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
     const float2 rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
 
     float4 v = in.load(px, py);
+    float4 sh = f4(0.0f);
+    if constexpr (SH) sh = (LOBE == DIFF ? p.inDiffSh : p.inSpecSh).load(px, py);
     const float smc = LOBE == DIFF ? 1.0f : specMagicCurve(roughness);
     const float nonLinearAccumSpeed = 1.0f / (1.0f + frameNum);
 
@@ -59,6 +62,7 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
 
         float sum = 1.0f + frameNum;
         v *= sum;
+        sh *= sum;
 
         for (int j = -2; j <= 2; j++)
             for (int i = -2; i <= 2; i++) {
@@ -91,8 +95,14 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
 
                 sum += w;
                 v += smp * w;
+                if constexpr (SH) {
+                    float4 shs = (LOBE == DIFF ? p.inDiffSh : p.inSpecSh).load(tx, ty);
+                    shs = w == 0.0f ? f4(0.0f) : shs;
+                    sh += shs * w;
+                }
             }
         v *= positiveRcp(sum);
+        sh *= positiveRcp(sum);
     }
 
     float luma = v.x;
@@ -162,13 +172,14 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
     }
 
     out.store(px, py, changeLuma(v, luma));
+    if constexpr (SH) (LOBE == DIFF ? p.outDiffSh : p.outSpecSh).store(px, py, rescaleSh(sh, luma));
 }
 }  // namespace
 
 #ifndef HF_MIN_BLOCKS
 #    define HF_MIN_BLOCKS 3  // 512-thread CTAs: 40 regs (3 CTAs / SM) 153 us vs 156 us at 57 regs (2 CTAs)
 #endif
-template <int SIGNAL>
+template <int SIGNAL, bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, HF_MIN_BLOCKS) reblurHistoryFixKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HistoryFixParams p, int quads, int ctaY0) {
     constexpr bool HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0, HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0;
     __shared__ float sDiffLuma[HAS_DIFF ? HF_TILE_H : 1][HF_TILE_W];
@@ -246,8 +257,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, HF_MIN_BLOCKS) reblurHistory
     stride *= 2.0f / 2.0f;
     stride *= materialID == cb.historyFixAlternatePixelStrideMaterialID ? cb.historyFixAlternatePixelStride : cb.historyFixBasePixelStride;
 
-    if constexpr (HAS_DIFF) historyFixLobe<DIFF, SIGNAL>(cb, p, sDiffLuma, sDiffRow, tileHasSky, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
-    if constexpr (HAS_SPEC) historyFixLobe<SPEC, SIGNAL>(cb, p, sSpecLuma, sSpecRow, tileHasSky, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+    if constexpr (HAS_DIFF) historyFixLobe<DIFF, SIGNAL, SH>(cb, p, sDiffLuma, sDiffRow, tileHasSky, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+    if constexpr (HAS_SPEC) historyFixLobe<SPEC, SIGNAL, SH>(cb, p, sSpecLuma, sSpecRow, tileHasSky, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
 }
 
 // ===============================================================================================================
@@ -281,7 +292,7 @@ NRD_DEV void lumaMoments3x3(const float (*sLuma)[TS_TILE_W], float& luma, float&
 #ifndef TS_MIN_BLOCKS
 #    define TS_MIN_BLOCKS 3  // 512-thread CTAs: 40 regs + a small spill (3 CTAs / SM) beats 64 regs (2 CTAs) by 12 % on B200
 #endif
-template <int SIGNAL>
+template <int SIGNAL, bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTemporalStabilizationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                        const __grid_constant__ TemporalStabilizationParams p, int ctaY0) {
     constexpr bool HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0, HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0;
@@ -374,6 +385,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
         diff.w = cb.returnHistoryLengthInsteadOfOcclusion ? data1.x : diff.w;
         p.outDiff.store(px, py, diff);
         p.outDiffLuma.store(px, py, lumaStabilized);
+        if constexpr (SH) p.outDiffSh.store(px, py, rescaleSh(p.inDiffSh.load(px, py), lumaStabilized));  // REBLUR_TemporalStabilization.cs.hlsl:175-187
     }
 
     // ---- Specular ----
@@ -428,6 +440,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
         spec.w = cb.returnHistoryLengthInsteadOfOcclusion ? data1.y : spec.w;
         p.outSpec.store(px, py, spec);
         p.outSpecLuma.store(px, py, lumaStabilized);
+        if constexpr (SH) p.outSpecSh.store(px, py, rescaleSh(p.inSpecSh.load(px, py), lumaStabilized));  // REBLUR_TemporalStabilization.cs.hlsl:302-314
     }
 
     p.outInternalData.store(px, py, packInternalData(cb, data1.x, data1.y, materialID));
@@ -456,13 +469,21 @@ void launchReblurHistoryFix(const ReblurConstants& cb, const HistoryFixParams& p
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    withSignal(signal, [&](auto sig) { reblurHistoryFixKernel<decltype(sig)::value><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0); });
+    const bool sh = p.inDiffSh.data || p.inSpecSh.data;  // bound by the executor for "|NRD_MODE=SH" only
+    withSignal(signal, [&](auto sig) {
+        if (sh) reblurHistoryFixKernel<decltype(sig)::value, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
+        else reblurHistoryFixKernel<decltype(sig)::value, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
+    });
 }
 void launchReblurTemporalStabilization(const ReblurConstants& cb, const TemporalStabilizationParams& p, int signal, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    withSignal(signal, [&](auto sig) { reblurTemporalStabilizationKernel<decltype(sig)::value><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0); });
+    const bool sh = p.inDiffSh.data || p.inSpecSh.data;
+    withSignal(signal, [&](auto sig) {
+        if (sh) reblurTemporalStabilizationKernel<decltype(sig)::value, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+        else reblurTemporalStabilizationKernel<decltype(sig)::value, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+    });
 }
 
 }  // namespace nrdk

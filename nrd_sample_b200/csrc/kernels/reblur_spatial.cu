@@ -83,10 +83,12 @@ NRD_DEV P2 exponentialWeight2(P2 y) {
 
 // One lobe of one spatial pass for one pixel
 // CB: checkerboard input (pre-pass only): `input` is half width, holds the pixels whose parity equals `cbMode` this frame
-template <int PASS, int LOBE, bool CB = false>
+// SH ( NRD_MODE = SH ): a second RGBA16F per lobe rides along with the weights of the first ( REBLUR_Common_SpatialFilter.hlsli:67-69, 268-280, 307-335 )
+struct ShIo { const TexRGBA16F *in, *out, *outCopy; };
+template <int PASS, int LOBE, bool CB = false, bool SH = false>
 NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const TexR32F& viewZTex, const TexNR& nrTex, const TexRGBA16F& input,
                            const TexRGBA16F& output, const TexR16F* outSpecHitDistForTracking, const TexRGBA16F* outputCopy, bool temporalStabilization, bool robustMirrorTest,
-                           const Resolve* resolve = nullptr) {
+                           const Resolve* resolve = nullptr, ShIo shIo = ShIo()) {
     static_assert(!CB || PASS == PRE_PASS, "only the pre-pass reads checkerboarded input");
     const uint32_t cbMode = CB ? (LOBE == DIFF ? cb.diffCheckerboard : cb.specCheckerboard) : 2u;
     const float ROUGHNESS = LOBE == DIFF ? 1.0f : s.roughness;
@@ -99,9 +101,12 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
 
     float sum = 1.0f;
     float4 result = input.load(CB ? s.px >> 1 : s.px, s.py);
+    float4 resultSh = f4(0.0f);
+    if constexpr (SH) resultSh = shIo.in->load(CB ? s.px >> 1 : s.px, s.py);
     if (CB && resolve->checkerboard != cbMode) {
         sum = 0.0f;
         result = f4(0.0f);
+        resultSh = f4(0.0f);
     }
 
     if (PASS != PRE_PASS || MAX_BLUR_RADIUS != 0.0f) {
@@ -189,6 +194,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
         float hitDistForTracking = hitDist == 0.0f ? NRD_INF : hitDist;
         P2 sum2(0.0f);
         P2 accX(0.0f), accY(0.0f), accZ(0.0f), accW(0.0f);
+        P2 shX(0.0f), shY(0.0f), shZ(0.0f), shW(0.0f);
 
 #pragma unroll
         for (int pair = 0; pair < 4; pair++) {
@@ -253,6 +259,11 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             const float zRawA = viewZTex.fetch(txa, tya), zRawB = viewZTex.fetch(txb, tyb);
             const uint32_t nrA = nrTex.fetchRaw(txa, tya), nrB = nrTex.fetchRaw(txb, tyb);
             uint2 rawA = input.fetchRaw(ixa, tya), rawB = input.fetchRaw(ixb, tyb);
+            uint2 rawShA = make_uint2(0u, 0u), rawShB = make_uint2(0u, 0u);
+            if constexpr (SH) {
+                rawShA = shIo.in->fetchRaw(ixa, tya);
+                rawShB = shIo.in->fetchRaw(ixb, tyb);
+            }
 
             P2 zs = absMul2(P2(zRawA, zRawB), fabsf(cb.viewZScale));  // UnpackViewZ: | z * scale |
             P2 rx = fma2(fx, rayMulX, rayAddX), ry = fma2(fy, rayMulY, rayAddY);
@@ -320,11 +331,24 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             accY = fma2(P2(smpA.y, smpB.y), w, accY);
             accZ = fma2(P2(smpA.z, smpB.z), w, accZ);
             accW = fma2(sw, w, accW);
+            if constexpr (SH) {
+                if (w.a() == 0.0f) rawShA = make_uint2(0u, 0u);  // Denanify by the FINAL weight ( :268-272 )
+                if (w.b() == 0.0f) rawShB = make_uint2(0u, 0u);
+                const float4 a4 = TexRGBA16F::decode(rawShA), b4 = TexRGBA16F::decode(rawShB);
+                shX = fma2(P2(a4.x, b4.x), w, shX);
+                shY = fma2(P2(a4.y, b4.y), w, shY);
+                shZ = fma2(P2(a4.z, b4.z), w, shZ);
+                shW = fma2(P2(a4.w, b4.w), w, shW);
+            }
         }
 
         sum += sum2.a() + sum2.b();
         result += make_float4(accX.a() + accX.b(), accY.a() + accY.b(), accZ.a() + accZ.b(), accW.a() + accW.b());
         result *= positiveRcp(sum);
+        if constexpr (SH) {
+            resultSh += make_float4(shX.a() + shX.b(), shY.a() + shY.b(), shZ.a() + shZ.b(), shW.a() + shW.b());
+            resultSh *= positiveRcp(sum);
+        }
         if (PASS != PRE_PASS) result.w = hitDist / hitDistScale;
         if (PASS == PRE_PASS && LOBE == SPEC) outSpecHitDistForTracking->store(s.px, s.py, hitDistForTracking == NRD_INF ? 0.0f : hitDistForTracking);
     }
@@ -335,13 +359,21 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
         if (resolve->wc.x == 0.0f) s0 = f4(0.0f);
         if (resolve->wc.y == 0.0f) s1 = f4(0.0f);
         result = s0 * resolve->wc.x + s1 * resolve->wc.y;
+        if constexpr (SH) {
+            float4 sh0 = shIo.in->load(resolve->x0, s.py), sh1 = shIo.in->load(resolve->x1, s.py);
+            if (resolve->wc.x == 0.0f) sh0 = f4(0.0f);
+            if (resolve->wc.y == 0.0f) sh1 = f4(0.0f);
+            resultSh = sh0 * resolve->wc.x + sh1 * resolve->wc.y;
+        }
     }
 
     output.store(s.px, s.py, result);
+    if constexpr (SH) shIo.out->store(s.px, s.py, resultSh);
 
     if (PASS == POST_BLUR && !temporalStabilization) {
         result.w = cb.returnHistoryLengthInsteadOfOcclusion ? (LOBE == DIFF ? s.data1.x : s.data1.y) : result.w;
         outputCopy->store(s.px, s.py, result);
+        if constexpr (SH) shIo.outCopy->store(s.px, s.py, resultSh);
     }
 }
 
@@ -357,7 +389,7 @@ __global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_co
     if (threadIdx.x == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
 }
 
-template <bool CB, int SIGNAL>
+template <bool CB, int SIGNAL, bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags, int ctaY0) {
     const bool robust = (flags & 2) != 0;
     Center s;
@@ -383,8 +415,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPr
         r.x0 = x0 >> 1;
         r.x1 = x1 >> 1;
     }
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<PRE_PASS, DIFF, CB>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r);
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<PRE_PASS, SPEC, CB>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r);
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<PRE_PASS, DIFF, CB, SH>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<PRE_PASS, SPEC, CB, SH>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
 }
 
 // Non-linear accumulation speed with the quad-neighbour smoothing of REBLUR_Blur.cs.hlsl:40-59 (lanes x^1, x^2 of the row)
@@ -400,7 +432,7 @@ NRD_DEV float2 quadSmoothedAccumSpeed(const ReblurConstants& cb, float2 data1, f
     return n;
 }
 
-template <int SIGNAL>
+template <int SIGNAL, bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
@@ -420,11 +452,11 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBl
     if (skyTile || !inDenoisingRange(cb, s.viewZ) || s.px > cb.rectSizeMinusOne[0] || s.py > cb.rectSizeMinusOne[1]) return;
 
     setupCenter(cb, s, p.normalRoughness, cb.rotator);
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<BLUR, DIFF>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust);
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<BLUR, SPEC>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust);
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<BLUR, DIFF, false, SH>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<BLUR, SPEC, false, SH>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
 }
 
-template <bool TEMPORAL_STABILIZATION, int SIGNAL>
+template <bool TEMPORAL_STABILIZATION, int SIGNAL, bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
@@ -443,8 +475,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPo
     p.outNormalRoughness.storeRaw(s.px, s.py, p.normalRoughness.loadRaw(s.px, s.py));
     if (!TEMPORAL_STABILIZATION) p.outInternalData.store(s.px, s.py, packInternalData(cb, s.data1.x, s.data1.y, s.materialID));
 
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<POST_BLUR, DIFF>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust);
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<POST_BLUR, SPEC>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust);
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<POST_BLUR, DIFF, false, SH>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, &p.outDiffShCopy});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<POST_BLUR, SPEC, false, SH>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, &p.outSpecShCopy});
 }
 
 // REBLUR_SplitScreen.cs.hlsl:21-56: the noisy input (range-masked) left of CommonSettings::splitScreen
@@ -455,6 +487,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurSplitScreenKernel(cons
     const float inRange = inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.load(px, py))) ? 1.0f : 0.0f;
     if (signal & SIGNAL_DIFF) p.outDiff.store(px, py, p.inDiff.load(px >> (cb.diffCheckerboard != 2u ? 1 : 0), py) * inRange);
     if (signal & SIGNAL_SPEC) p.outSpec.store(px, py, p.inSpec.load(px >> (cb.specCheckerboard != 2u ? 1 : 0), py) * inRange);
+    // NRD_MODE = SH ( :44-52 ): the SH1 inputs, same addressing
+    if ((signal & SIGNAL_DIFF) && p.inDiffSh.data) p.outDiffSh.store(px, py, p.inDiffSh.load(px >> (cb.diffCheckerboard != 2u ? 1 : 0), py) * inRange);
+    if ((signal & SIGNAL_SPEC) && p.inSpecSh.data) p.outSpecSh.store(px, py, p.inSpecSh.load(px >> (cb.specCheckerboard != 2u ? 1 : 0), py) * inRange);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -474,19 +509,27 @@ void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int 
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
+    const bool cbOn = cb.diffCheckerboard != 2u || cb.specCheckerboard != 2u;  // CheckerboardMode::BLACK / WHITE set both (Reblur.cpp:301-313)
+    const bool sh = p.inDiffSh.data || p.inSpecSh.data;                        // bound by the executor for "|NRD_MODE=SH" only
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        if (cb.diffCheckerboard != 2u || cb.specCheckerboard != 2u)  // CheckerboardMode::BLACK / WHITE set both (Reblur.cpp:301-313)
-            reblurPrePassKernel<true, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
-        else
-            reblurPrePassKernel<false, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        if (sh) {
+            if (cbOn) reblurPrePassKernel<true, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+            else reblurPrePassKernel<false, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        } else {
+            if (cbOn) reblurPrePassKernel<true, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+            else reblurPrePassKernel<false, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        }
     });
 }
 void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int signal, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
+    const bool sh = p.inDiffSh.data || p.inSpecSh.data;
+    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
     withSignal(signal, [&](auto sig) {
-        reblurBlurKernel<decltype(sig)::value><<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        if (sh) reblurBlurKernel<decltype(sig)::value, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        else reblurBlurKernel<decltype(sig)::value, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
     });
 }
 void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, int signal, bool temporalStabilization, int flags, Rows rows, cudaStream_t stream) {
@@ -495,10 +538,14 @@ void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, in
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        if (temporalStabilization)
-            reblurPostBlurKernel<true, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
-        else
-            reblurPostBlurKernel<false, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        const bool sh = p.inDiffSh.data || p.inSpecSh.data;
+        if (sh) {
+            if (temporalStabilization) reblurPostBlurKernel<true, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+            else reblurPostBlurKernel<false, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        } else {
+            if (temporalStabilization) reblurPostBlurKernel<true, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+            else reblurPostBlurKernel<false, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        }
     });
 }
 

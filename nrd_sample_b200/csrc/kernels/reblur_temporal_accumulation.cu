@@ -43,7 +43,9 @@ NRD_DEV uint4 gather4(const TexR16U& t, int x0, int y0) {
 #    define TA_MIN_BLOCKS 4  // 64 regs (4 CTAs / SM): 383 us vs 401 us at 80 regs (3 CTAs) and 467 us at 128 regs (2 CTAs) for a 1440p frame on B200
 #endif
 // OPTIONAL: checkerboard resolve speed-up and the application's guide textures (confidence, threshold mix); compiled out of the plain kernel
-template <bool OPTIONAL, int SIGNAL>
+// SH ( NRD_MODE = SH ): the lobe's second RGBA16F accumulates with the lobe's speed from a bilinear ( custom weights ) history fetch and follows the
+// firefly clamp of the luma ( REBLUR_TemporalAccumulation.cs.hlsl:781-783, 801-804, 819-821, 831-833, 923-925, 940-943, 957-959, 968-970 )
+template <bool OPTIONAL, int SIGNAL, bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTemporalAccumulationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                       const __grid_constant__ TemporalAccumulationParams p, int ctaY0) {
     __shared__ float4 sNormalHitDist[TILE_H][TILE_W];
@@ -493,6 +495,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         // Sample history
         float4 specHistory;
         float specFastHistory;
+        float4 specShHistory = f4(0.0f);
         {
             float2 uv = lerp(smbPixelUv, vmbPixelUv, virtualHistoryAmount);
             float4 occlusionWeights = lerp(smbOcclusionWeights, vmbOcclusionWeights, virtualHistoryAmount);
@@ -500,6 +503,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
             HistoryFilter hf(saturate(uv) * rectSizePrev, resourceSizeInvPrev, occlusionWeights, allowCatRom);
             specHistory = clampNegativeToZero(hf.color(p.historySpec));
             specFastHistory = fmaxf(hf.bilinear(p.historySpecFast), 0.0f);
+            if constexpr (SH) specShHistory = hf.bilinear4(p.historySpecSh);
         }
 
         // Accumulation
@@ -508,6 +512,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         const float specNonLinearAccumSpeed = checkerboardResolveAccumSpeed(cb, 1.0f / (1.0f + specAccumSpeed), specHasData);
 
         float4 specResult = mixHistoryAndCurrent(cb, specHistory, spec, specNonLinearAccumSpeed, roughness);
+        float4 specShResult = f4(0.0f);
+        if constexpr (SH) specShResult = lerp(specShHistory, p.inSpecSh.load(px, py), specNonLinearAccumSpeed);
 
         // Firefly suppressor
         const float specMaxRelativeIntensity = cb.fireflySuppressorMinRelativeScale + 38.0f / (specAccumSpeed + 1.0f);
@@ -518,11 +524,13 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
             float lumaClamped = fminf(lumaResult, specHistory.x * specMaxRelativeIntensity);
             lumaClamped = lerp(lumaResult, lumaClamped, specAntifireflyFactor);
             specResult = changeLuma(specResult, lumaClamped);
+            if constexpr (SH) specShResult = rescaleSh(specShResult, lumaClamped);
 
             float hitDistMaxRelativeIntensity = 1.2f + 1.0f / (specAccumSpeed + 1.0f);
             specResult.w = lerp(specResult.w, fminf(specResult.w, specHistory.w * hitDistMaxRelativeIntensity), specAntifireflyFactor);
         }
         p.outSpec.store(px, py, specResult);
+        if constexpr (SH) p.outSpecSh.store(px, py, specShResult);
 
         {  // Fast history
             float maxFastAccumulatedFrameNum = cb.maxFastAccumulatedFrameNum;
@@ -552,9 +560,12 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         HistoryFilter hf(saturate(smbPixelUv) * rectSizePrev, resourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom);
         const float4 diffHistory = clampNegativeToZero(hf.color(p.historyDiff));
         const float diffFastHistory = fmaxf(hf.bilinear(p.historyDiffFast), 0.0f);
+        float4 diffShResult = f4(0.0f);
+        if constexpr (SH) diffShResult = hf.bilinear4(p.historyDiffSh);
 
         const float diffNonLinearAccumSpeed = checkerboardResolveAccumSpeed(cb, 1.0f / (1.0f + diffAccumSpeed), diffHasData);
         float4 diffResult = mixHistoryAndCurrent(cb, diffHistory, diff, diffNonLinearAccumSpeed);
+        if constexpr (SH) diffShResult = lerp(diffShResult, p.inDiffSh.load(px, py), diffNonLinearAccumSpeed);
 
         const float diffMaxRelativeIntensity = cb.fireflySuppressorMinRelativeScale + 38.0f / (diffAccumSpeed + 1.0f);
         float diffAntifireflyFactor = diffAccumSpeed * cb.maxBlurRadius * 0.1f;
@@ -564,10 +575,12 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         float lumaClamped = fminf(lumaResult, diffHistory.x * diffMaxRelativeIntensity);
         lumaClamped = lerp(lumaResult, lumaClamped, diffAntifireflyFactor);
         diffResult = changeLuma(diffResult, lumaClamped);
+        if constexpr (SH) diffShResult = rescaleSh(diffShResult, lumaClamped);
 
         float hitDistMaxRelativeIntensity = 1.2f + 1.0f / (diffAccumSpeed + 1.0f);
         diffResult.w = lerp(diffResult.w, fminf(diffResult.w, diffHistory.w * hitDistMaxRelativeIntensity), diffAntifireflyFactor);
         p.outDiff.store(px, py, diffResult);
+        if constexpr (SH) p.outDiffSh.store(px, py, diffShResult);
 
         float fastNonLinearAccumSpeed = checkerboardResolveAccumSpeed(cb, 1.0f / (1.0f + fminf(diffAccumSpeed, cb.maxFastAccumulatedFrameNum)), diffHasData);
         float fastResult = lerp(diffFastHistory, diff.x, fastNonLinearAccumSpeed);
@@ -585,10 +598,15 @@ void launchReblurTemporalAccumulation(const ReblurConstants& cb, const TemporalA
     dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        if (cb.specCheckerboard != 2u || cb.diffCheckerboard != 2u || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix)
-            reblurTemporalAccumulationKernel<true, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
-        else
-            reblurTemporalAccumulationKernel<false, S><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+        const bool optional = cb.specCheckerboard != 2u || cb.diffCheckerboard != 2u || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix;
+        const bool sh = p.inDiffSh.data || p.inSpecSh.data;  // bound by the executor for "|NRD_MODE=SH" only
+        if (sh) {
+            if (optional) reblurTemporalAccumulationKernel<true, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+            else reblurTemporalAccumulationKernel<false, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+        } else {
+            if (optional) reblurTemporalAccumulationKernel<true, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+            else reblurTemporalAccumulationKernel<false, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+        }
     });
 }
 

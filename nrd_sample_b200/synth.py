@@ -247,7 +247,7 @@ def checkerboard_pack(full: torch.Tensor, mode: int, frame_index: int) -> torch.
 
 
 def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, with_clean: bool = False, holes: bool = False,
-                 checkerboard: int = 0, guides: bool = False) -> Dict[str, torch.Tensor]:
+                 checkerboard: int = 0, guides: bool = False, sh: bool = False) -> Dict[str, torch.Tensor]:
     """All user inputs of REBLUR_DIFFUSE_SPECULAR for one frame, in their API storage formats. `holes`: probabilistic lobe sampling as in
     NRDSample — every pixel traced only one lobe this frame (checkerboard flipping per frame), the other lobe has hit distance 0 and
     relies on ReblurSettings::hitDistanceReconstructionMode."""
@@ -327,10 +327,28 @@ def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period
         conf_s = (rnd() * 1.3).clamp(0, 1)
         out["IN_SPEC_CONFIDENCE"] = (conf_s * 255.0 + 0.5).to(torch.uint8).contiguous()
         out["IN_DISOCCLUSION_THRESHOLD_MIX"] = (rough > 0.3).to(torch.float16).contiguous()
-    if checkerboard:   # nrd::CheckerboardMode: 1 = BLACK, 2 = WHITE
+    if sh:
+        # REBLUR_DIFFUSE_SPECULAR_SH ( NRD_MODE = SH ), REBLUR_FrontEnd_PackSh ( NRD.hlsli:831-849 ): SH0 = the same { Y, Co, Cg, normHitDist }, SH1 =
+        # { direction * Y, 0 }. Directions as in `relax_frame` ( around N / the mirror direction ), from their own generator so that the
+        # RADIANCE inputs of a frame do not depend on `sh`.
+        gen_sh = torch.Generator(device=device)
+        gen_sh.manual_seed(SEED_BASE + 0x5348 + frame_index)
+
+        def around(axis, spread):
+            d = axis + spread.unsqueeze(-1) * (torch.rand(height, width, 3, device=device, generator=gen_sh) * 2.0 - 1.0)
+            return d / d.norm(dim=-1, keepdim=True).clamp_min(1e-6)
+
+        for lobe, axis, spread in (("DIFF", N, torch.full_like(rough, 0.8)), ("SPEC", R, rough * 0.7 + 0.02)):
+            sh0 = out.pop(f"IN_{lobe}_RADIANCE_HITDIST")
+            out[f"IN_{lobe}_SH0"] = sh0
+            sh1 = torch.cat([around(axis, spread) * sh0[..., :1].float(), torch.zeros(height, width, 1, device=device)], -1).to(torch.float16)
+            out[f"IN_{lobe}_SH1"] = torch.where(hit[..., None], sh1, zero4).contiguous()
+    if checkerboard:   # nrd::CheckerboardMode: 1 = BLACK, 2 = WHITE; SH1 travels with its SH0
         diff_mode, spec_mode = (0, 1) if checkerboard == 1 else (1, 0)
-        out["IN_DIFF_RADIANCE_HITDIST"] = checkerboard_pack(out["IN_DIFF_RADIANCE_HITDIST"], diff_mode, frame_index)
-        out["IN_SPEC_RADIANCE_HITDIST"] = checkerboard_pack(out["IN_SPEC_RADIANCE_HITDIST"], spec_mode, frame_index)
+        for k in (("IN_DIFF_SH0", "IN_DIFF_SH1") if sh else ("IN_DIFF_RADIANCE_HITDIST",)):
+            out[k] = checkerboard_pack(out[k], diff_mode, frame_index)
+        for k in (("IN_SPEC_SH0", "IN_SPEC_SH1") if sh else ("IN_SPEC_RADIANCE_HITDIST",)):
+            out[k] = checkerboard_pack(out[k], spec_mode, frame_index)
     if with_clean:
         out["_clean_diff"] = diff_clean
         out["_clean_spec"] = spec_clean

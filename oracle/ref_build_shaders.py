@@ -74,6 +74,11 @@ IDENTIFIERS = [
 ] + [f"RELAX_HitDistReconstruction.cs.hlsl|NRD_SIGNAL={sig}|NRD_MODE=RADIANCE|MODE_5X5={m}" for sig in ("DIFF", "SPEC") for m in (0, 1)] + [
     f"RELAX_{f}.cs.hlsl|NRD_SIGNAL={sig}|NRD_MODE={mode}" for sig in ("DIFF", "SPEC") for mode in ("RADIANCE", "SH")
     for f in ("PrePass", "TemporalAccumulation", "HistoryFix", "HistoryClamping", "Copy", "AntiFirefly", "AtrousSmem", "Atrous", "SplitScreen")] + [
+    # REBLUR_DIFFUSE_SH / REBLUR_SPECULAR_SH / REBLUR_DIFFUSE_SPECULAR_SH ( hit-distance reconstruction runs the RADIANCE permutation )
+] + [f"{f}|NRD_SIGNAL={sig}|NRD_MODE=SH{suffix}" for sig in ("DIFF", "SPEC", "BOTH") for f, suffix in (
+    ("REBLUR_PrePass.cs.hlsl", ""), ("REBLUR_TemporalAccumulation.cs.hlsl", ""), ("REBLUR_HistoryFix.cs.hlsl", ""), ("REBLUR_Blur.cs.hlsl", ""),
+    ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0"), ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1"), ("REBLUR_TemporalStabilization.cs.hlsl", ""),
+    ("REBLUR_SplitScreen.cs.hlsl", ""))] + [
     # REFERENCE
     "REFERENCE_TemporalAccumulation.cs.hlsl", "REFERENCE_Copy.cs.hlsl",
     # ours: calls the application-side functions of the reference's NRD.hlsli ( oracle/ref_shim/Shaders/NRD_FrontEndProbe.cs.hlsl )

@@ -28,6 +28,13 @@ CASES = [
     ("reblur_specular_1080p", api.Denoiser.REBLUR_SPECULAR, 1920, 1080, None),
     ("reblur_specular_cb_guides_split", api.Denoiser.REBLUR_SPECULAR, 1280, 720, "reblur_cb_guides_split"),
     ("reblur_specular_noprepass", api.Denoiser.REBLUR_SPECULAR, 640, 360, "noprepass"),
+    ("reblur_sh_1440p", api.Denoiser.REBLUR_DIFFUSE_SPECULAR_SH, 2560, 1440, None),
+    ("reblur_sh_cb_guides_split", api.Denoiser.REBLUR_DIFFUSE_SPECULAR_SH, 1280, 720, "reblur_cb_guides_split"),
+    ("reblur_sh_recon_nots", api.Denoiser.REBLUR_DIFFUSE_SPECULAR_SH, 1000, 562, "recon_nots"),
+    ("reblur_diffuse_sh_1080p", api.Denoiser.REBLUR_DIFFUSE_SH, 1920, 1080, None),
+    ("reblur_diffuse_sh_noprepass", api.Denoiser.REBLUR_DIFFUSE_SH, 640, 360, "noprepass"),
+    ("reblur_specular_sh_recon_nots", api.Denoiser.REBLUR_SPECULAR_SH, 1280, 720, "recon_nots"),
+    ("reblur_specular_sh_cb_guides_split", api.Denoiser.REBLUR_SPECULAR_SH, 1000, 562, "reblur_cb_guides_split"),
     ("sigma_512", api.Denoiser.SIGMA_SHADOW, 512, 512, "sigma"),
     ("sigma_nostab", api.Denoiser.SIGMA_SHADOW, 640, 360, "sigma_nostab"),
     ("sigma_translucency_1080p", api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, 1920, 1080, "sigma"),

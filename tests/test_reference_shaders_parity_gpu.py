@@ -52,7 +52,17 @@ CASES["relax_diff_sh_cb_guides"] = (api.Denoiser.RELAX_DIFFUSE_SH, "relax_frame_
 CASES["relax_spec_sh_cb_guides"] = (api.Denoiser.RELAX_SPECULAR_SH, "relax_frame_spec_cb_guides", ("OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur")
 CASES["relax_diff_recon_split"] = (api.Denoiser.RELAX_DIFFUSE, "relax_frame_diff_nosh_holes", ("OUT_DIFF_RADIANCE_HITDIST",), "reblur")
 CASES["relax_spec_sh_recon_split"] = (api.Denoiser.RELAX_SPECULAR_SH, "relax_frame_spec_holes", ("OUT_SPEC_SH0", "OUT_SPEC_SH1"), "reblur")
-SETTINGS = {"relax_diff_sh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True),
+# REBLUR_DIFFUSE_SH / REBLUR_SPECULAR_SH / REBLUR_DIFFUSE_SPECULAR_SH ( NRD_MODE = SH ): plain; checkerboard WHITE + guides + split screen; reconstruction without
+# stabilization. The two-lobe denoiser keeps its tile mask in a full-resolution RGBA16F texture ( DESIGN.md "reference warts" ).
+SH4 = ("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1")
+CASES["reblur_sh"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR_SH, "reblur_frame_sh", SH4, "reblur")
+CASES["reblur_sh_cb_guides_split"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR_SH, "reblur_frame_sh_cb_guides", SH4, "reblur")
+CASES["reblur_sh_recon_nots"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR_SH, "reblur_frame_sh_holes", SH4, "reblur")
+CASES["reblur_diff_sh"] = (api.Denoiser.REBLUR_DIFFUSE_SH, "reblur_frame_diff_sh", SH4[:2], "reblur")
+CASES["reblur_spec_sh_cb_guides"] = (api.Denoiser.REBLUR_SPECULAR_SH, "reblur_frame_spec_sh_cb_guides", SH4[2:], "reblur")
+SETTINGS = {"reblur_sh_cb_guides_split": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_spec_sh_cb_guides": lambda: api.ReblurSettings(checkerboardMode=2),
+            "reblur_sh_recon_nots": lambda: api.ReblurSettings(hitDistanceReconstructionMode=1, maxStabilizedFrameNum=0),
+            "relax_diff_sh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True),
             "relax_spec_sh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True),
             "relax_diff_recon_split": lambda: api.RelaxSettings(hitDistanceReconstructionMode=2),
             "relax_spec_sh_recon_split": lambda: api.RelaxSettings(hitDistanceReconstructionMode=1),
@@ -61,7 +71,9 @@ SETTINGS = {"relax_diff_sh_cb_guides": lambda: api.RelaxSettings(checkerboardMod
             "relax_nosh_recon5x5": lambda: api.RelaxSettings(hitDistanceReconstructionMode=2), "relax_recon3x3": lambda: api.RelaxSettings(hitDistanceReconstructionMode=1),
             "relax_cb_guides_split": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True), "relax_nosh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2),
             "reblur_split": lambda: api.ReblurSettings(checkerboardMode=2), "reference": lambda: api.ReferenceSettings(maxAccumulatedFrameNum=5), "reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_guides_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
-COMMON = {"relax_diff_sh_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
+COMMON = {"reblur_sh_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.35),
+          "reblur_spec_sh_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
+          "relax_diff_sh_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
           "relax_spec_sh_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
           "relax_diff_recon_split": dict(splitScreen=0.3), "relax_spec_sh_recon_split": dict(splitScreen=0.3),
           "reblur_diff_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
@@ -84,10 +96,10 @@ def out_format(which, o, runner):
 
 
 def frame_of(name, f, w, h):
-    for lobe, other in (("diff", "_SPEC_"), ("spec", "_DIFF_")):   # single-lobe denoisers: the other lobe's inputs do not exist
+    for lobe, other in (("diff", "_SPEC_"), ("spec", "_DIFF_"), ("sh", "~")):   # single-lobe denoisers: the other lobe's inputs do not exist
         if name.startswith(f"reblur_frame_{lobe}"):
             kw = dict(checkerboard=2, guides=True) if name.endswith("_cb_guides") else (dict(holes=True) if name.endswith("_holes") else {})
-            return {k: v for k, v in synth.reblur_frame(f, w, h, **kw).items() if other not in k}
+            return {k: v for k, v in synth.reblur_frame(f, w, h, sh="_sh" in name, **kw).items() if other not in k}
     for lobe, other in (("diff", "_SPEC_"), ("spec", "_DIFF_")):
         if name.startswith(f"relax_frame_{lobe}"):
             kw = dict(checkerboard=2, guides=True) if name.endswith("_cb_guides") else (dict(holes=True) if name.endswith("_holes") else {})
@@ -110,7 +122,8 @@ def frame_of(name, f, w, h):
         return synth.sigma_frame(f, w, h, translucency=True)
     return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"relax_diff": (2e-3, 60.0), "relax_spec": (2e-3, 60.0), "relax_diff_sh_cb_guides": (2e-3, 60.0), "relax_spec_sh_cb_guides": (2e-3, 60.0),
+LIMITS = {"reblur_sh": (3e-2, 45.0), "reblur_sh_cb_guides_split": (3e-2, 45.0), "reblur_sh_recon_nots": (3e-2, 45.0), "reblur_diff_sh": (3e-2, 45.0),
+          "reblur_spec_sh_cb_guides": (3e-2, 45.0), "relax_diff": (2e-3, 60.0), "relax_spec": (2e-3, 60.0), "relax_diff_sh_cb_guides": (2e-3, 60.0), "relax_spec_sh_cb_guides": (2e-3, 60.0),
           "relax_diff_recon_split": (2e-3, 60.0), "relax_spec_sh_recon_split": (2e-3, 60.0), "reblur_diff": (3e-2, 45.0), "reblur_spec": (3e-2, 45.0), "reblur_diff_cb_guides": (3e-2, 45.0), "reblur_spec_recon_nots": (3e-2, 45.0), "reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0), "reblur_split": (3e-2, 45.0), "reference": (1e-3, 80.0), "relax_cb_guides_split": (2e-3, 60.0), "relax_nosh_cb_guides": (2e-3, 60.0), "relax_nosh_recon5x5": (2e-3, 60.0), "relax_recon3x3": (2e-3, 60.0)}
 
 
@@ -176,7 +189,9 @@ def test_each_dispatch_against_the_reference_shaders(ex, runner, which):
             # the reference's tap weight is 1 instead of the Gaussian when any( uv != MirrorUv( uv ) ), which is decided by the last mantissa bit
             # of the tap position ( DESIGN.md "chaotic predicates" ): an FMA-contracting GPU flips it on a third of the taps, so texel-wise
             # agreement is not defined for these passes in faithful mode — the image is ( measured: 60-74 dB )
-            assert r["psnr"] >= 55.0, f"{key}: {r}"
+            # NRD_MODE = SH: the SH1 textures ( direction * luma, signed, a smaller peak than the radiance ) see the same flipped taps — the SH0
+            # numbers equal the RADIANCE ones to the digit — and land 3 dB lower against their own peak ( measured: 54.2 dB and up )
+            assert r["psnr"] >= (50.0 if "_sh" in which else 55.0), f"{key}: {r}"
             continue
         lim = 5e-2 if (which.startswith("reblur") and key[2] == "R32_UINT") else limit   # data2's fp16 curvature on the static first frame, see test_reblur_parity_gpu
         assert r["frac_bad"] <= lim, f"{key}: {r}"
