@@ -44,6 +44,11 @@ WORKLOADS = {
     "reblur": dict(denoiser="REBLUR_DIFFUSE_SPECULAR", frame="reblur_frame", metric=METRIC, published_ms=2.55,
                    outputs=(("OUT_DIFF_RADIANCE_HITDIST", "RGBA16_SFLOAT"), ("OUT_SPEC_RADIANCE_HITDIST", "RGBA16_SFLOAT")),
                    pass_bytes=PASS_BYTES_PER_PIXEL, what="REBLUR_DIFFUSE_SPECULAR full pass chain, {w}x{h}, synthetic 1spp noisy radiance + G-buffer"),
+    # NRD_MODE = SH: a second RGBA16F per lobe through every pass ( +8 B/px per lobe per texture read or written; no published number )
+    "reblur_sh": dict(denoiser="REBLUR_DIFFUSE_SPECULAR_SH", frame="reblur_frame_sh", metric="denoised Mpixels/s (REBLUR diff+spec SH, 1440p)", published_ms=None,
+                      outputs=(("OUT_DIFF_SH0", "RGBA16_SFLOAT"), ("OUT_DIFF_SH1", "RGBA16_SFLOAT"), ("OUT_SPEC_SH0", "RGBA16_SFLOAT"), ("OUT_SPEC_SH1", "RGBA16_SFLOAT")),
+                      pass_bytes={"Classify tiles": 4, "Pre-pass": 74, "Temporal accumulation": 142, "History fix": 84, "Blur": 78, "Post-blur": 78, "Temporal stabilization": 98},
+                      what="REBLUR_DIFFUSE_SPECULAR_SH full pass chain, {w}x{h}, synthetic 1spp noisy SH radiance + G-buffer"),
     "relax": dict(denoiser="RELAX_DIFFUSE_SPECULAR_SH", frame="relax_frame", metric="denoised Mpixels/s (RELAX diff+spec SH, 1440p)", published_ms=4.80,
                   outputs=(("OUT_DIFF_SH0", "RGBA16_SFLOAT"), ("OUT_DIFF_SH1", "RGBA16_SFLOAT"), ("OUT_SPEC_SH0", "RGBA16_SFLOAT"), ("OUT_SPEC_SH1", "RGBA16_SFLOAT")),
                   pass_bytes={"Classify tiles": 4, "Pre-pass": 72, "Temporal accumulation": 200, "History fix": 5, "History clamping": 150, "A-trous (SMEM)": 83, "A-trous": 74},
@@ -299,14 +304,15 @@ def run_product(args):
                         "note": "the chains are FP32-issue bound on B200 (30-40 FLOP per algorithmic byte vs a ~10 FLOP/B fp32 ridge); see DESIGN.md"}
         line = {
             "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / world / (3.6864 / (wl["published_ms"] * 1e-3)) if (W, H) == (2560, 1440) else None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / world / (3.6864 / (wl["published_ms"] * 1e-3)) if (W, H) == (2560, 1440) and wl["published_ms"] else None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["what"].format(w=W, h=H), "denoiser": wl["denoiser"],
                        "resolution": [W, H],
                        "settings": "library defaults" if not recon else f"library defaults + hitDistanceReconstructionMode = AREA_{args.hitdist_reconstruction.upper()} (the NRD README's setting), one lobe traced per pixel",
                        "streams_per_gpu": 1, "parallelism": f"replicas x{world} (independent frame streams, no collective)",
                        "l2_policy": f"ring of {RING} distinct frames: {RING * in_bytes // 2**20} MiB of inputs + pools > 126 MB L2",
-                       "baseline_note": f"vs_baseline = per-GPU value / ({wl['published_ms']} ms per 1440p frame on an RTX 4080, NRD README)"},
+                       "baseline_note": (f"vs_baseline = per-GPU value / ({wl['published_ms']} ms per 1440p frame on an RTX 4080, NRD README)" if wl["published_ms"]
+                                         else "no published number for this denoiser")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_pipe / args.steps,
                     "call": "nrdcuDenoiseHostPipelined: pinned host inputs -> H2D -> chain -> D2H of the outputs every step, uploads / downloads of neighbouring steps overlap the kernels",
                     "serial": {"value": e2e_serial, "ms_per_step": ms_host / args.steps, "call": "nrdcuDenoiseHost: the same copies and kernels back to back on one stream"}},

@@ -356,6 +356,11 @@ def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period
     return out
 
 
+def reblur_frame_sh(frame_index: int, width: int, height: int, device="cpu", period: int = 0) -> Dict[str, torch.Tensor]:
+    """The inputs of REBLUR_DIFFUSE_SPECULAR_SH ( `reblur_frame( sh = True )` ) under a name `bench.py --denoiser reblur_sh` can look up."""
+    return reblur_frame(frame_index, width, height, device, period, sh=True)
+
+
 def reference_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0) -> Dict[str, torch.Tensor]:
     """IN_SIGNAL of the REFERENCE denoiser: the noisy diffuse radiance of `reblur_frame` as an RGBA16F image (NRDSample feeds its composed frame)."""
     return {"IN_SIGNAL": reblur_frame(frame_index, width, height, device, period)["IN_DIFF_RADIANCE_HITDIST"]}
