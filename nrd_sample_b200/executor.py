@@ -324,3 +324,9 @@ def backend_unpack_radiance(mode: int, texture: torch.Tensor) -> torch.Tensor:
     rc = L.nrdcuBackEndUnpackRadiance(mode, C.byref(tex), out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     _frontend_check(rc, "nrdcuBackEndUnpackRadiance")
     return out
+
+
+def host_library():
+    """nrd_api.NrdLibrary over the product library (the nrd:: entry points live in the same .so as the executor)."""
+    from . import nrd_api
+    return nrd_api.NrdLibrary(_build.build() if not os.environ.get("NRD_B200_LIB") else os.environ["NRD_B200_LIB"])

@@ -34,24 +34,110 @@ import torch.distributed as dist
 TILE = 16
 HALO_ROWS = 64
 
-# Rows of apron each written texture needs on the neighbour, by (pass, binding index in DispatchDesc::resources). The default is
-# HALO_ROWS; entries below are smaller because every later reader of that texture stays closer to its own pixel:
-#   0  = only ever read at the pixel itself (or not at all: the final outputs, IN_MV which temporal stabilisation binds read-write)
-#   2  = read through a 1-texel shared-memory border,  8 = 9x9 luma window of history fix,
-#   32 = history-fix 5x5 taps with stride <= 14 (2 x 14 = 28) and blur taps (maxBlurRadius = 30).
-# Post-blur reaches 2 x 30 = 60 rows and everything that survives into the next frame is fetched at pixel + motion: HALO_ROWS.
-HALO_TABLE = {
-    "Classify tiles": {1: 0},
-    "Pre-pass": {5: 0, 6: 0, 7: 2},
-    "Temporal accumulation": {19: 32, 20: 32, 21: 8, 22: 8, 24: 0},
-    "History fix": {9: 32, 10: 32},
-    "Temporal stabilization": {10: 0, 12: 0, 13: 0},
-}
+# Rows of apron each written texture needs on the neighbour: derived per denoiser from WHO READS the texture later (this frame or the
+# next one) and how far that reader reaches from its own pixel. Keyed by the reader's pass name ( "<denoiser> - <pass>" -> "<pass>" ) and the
+# format class of the texture it reads:
+#   0  = only ever read at the pixel itself,  2 = read through a 1-texel shared-memory border,
+#   history fix: 5x5 taps with stride <= historyFixBasePixelStride (2 x 14 + 4 = 32, data1 rides along with the taps),
+#   blur: maxBlurRadius + 2, post-blur: 2 x maxBlurRadius + 2, pre-pass: the larger pre-pass radius + 2,
+#   anything read by the NEXT frame is fetched at pixel + motion: the default.
+_DATA2 = ("R32_UINT", "R8_UINT")
+_DATA1 = ("RG8_UNORM", "R8_UNORM")
 
 
-def halo_rows_for(pass_name: str, binding: int, default: int = HALO_ROWS) -> int:
+def reader_reach(pass_name: str, fmt_name: str, same_frame: bool, default: int, max_blur_radius: float = 30.0, prepass_radius: float = 50.0, history_fix_stride: float = 14.0) -> int:
+    """Rows a REBLUR pass reaches beyond its own pixel into an input texture of format `fmt_name` written `same_frame` or last frame."""
+    if not same_frame:
+        return default
+    name = pass_name.split(" - ")[-1]
+    data = fmt_name in _DATA1 or fmt_name in _DATA2
+    if name == "Pre-pass":
+        r = int(prepass_radius + 0.999) + 2
+    elif name == "Temporal accumulation":
+        r = 0 if data else 2
+    elif name == "History fix":
+        r = 0 if fmt_name in _DATA2 else int(2.0 * history_fix_stride + 0.999) + 4
+    elif name == "Blur":
+        r = 0 if data else int(max_blur_radius + 0.999) + 2
+    elif name == "Post-blur":
+        r = 0 if data else int(2.0 * max_blur_radius + 0.999) + 2
+    elif name == "Temporal stabilization":
+        r = 0 if data else 2
+    elif name in ("Split screen", "Classify tiles"):
+        r = 0
+    else:
+        r = default
+    return min(default, r)
+
+
+def derive_halo_table(host_lib, denoiser: int, width: int, height: int, default: int = HALO_ROWS, settings=None, common_kw=None) -> dict:
+    """{(pass name, binding index): apron rows} for every storage binding of a steady-state frame of `denoiser`, from the dispatch streams
+    of two consecutive frames ( the pools ping-pong with period 2 ) of a scratch nrd::Instance: a texture written by dispatch i needs as many
+    rows on the neighbour as the farthest-reaching dispatch that reads it before it is written again. Works for every REBLUR denoiser
+    ( binding indices differ between REBLUR_DIFFUSE / _SPECULAR / _DIFFUSE_SPECULAR and their SH variants; the readers do not )."""
+    from . import nrd_api as api, synth
+    inst = api.NrdInstance(host_lib, [(0, denoiser)])
+    assert inst.result == api.Result.SUCCESS, inst.result
+    perm, tran = inst.pools()
+    fmt_of_pool = {int(api.ResourceType.PERMANENT_POOL): perm, int(api.ResourceType.TRANSIENT_POOL): tran}
+    kw = {}
+    if settings is not None:
+        assert inst.set_denoiser_settings(0, settings) == api.Result.SUCCESS
+        for src, dst in (("maxBlurRadius", "max_blur_radius"), ("historyFixBasePixelStride", "history_fix_stride")):
+            if hasattr(settings, src):
+                kw[dst] = float(getattr(settings, src))
+        if hasattr(settings, "diffusePrepassBlurRadius"):
+            kw["prepass_radius"] = max(float(settings.diffusePrepassBlurRadius), float(settings.specularPrepassBlurRadius))
+    streams = []
+    for f in range(4):
+        assert inst.set_common_settings(synth.common_settings(f, width, height, **(common_kw or {}))) == api.Result.SUCCESS
+        r, d = inst.get_compute_dispatches([0])
+        assert r == api.Result.SUCCESS
+        streams.append(d)
+    inst.destroy()
+
+    def key(b):
+        return (b.type, b.index if b.type in fmt_of_pool else 0)
+
+    def fmt_name(b):
+        if b.type in fmt_of_pool:
+            return api.Format(fmt_of_pool[b.type][b.index][0]).name
+        return "RGBA16_SFLOAT"   # user outputs ( radiance / SH ): the widest class
+
+    storage = int(api.DescriptorType.STORAGE_TEXTURE)
+    table = {}
+    for a, nxt in ((streams[2], streams[3]), (streams[3], streams[2])):   # steady state: no clears, both ping-pong phases
+        seq = [(d, True) for d in a] + [(d, False) for d in nxt]
+        for i, d in enumerate(a):
+            for j, b in enumerate(d.bindings):
+                if b.descriptor != storage:
+                    continue
+                rows = 0
+                # ( REBLUR_DIFFUSE_SPECULAR_SH keeps the mask in a full-resolution texture, DESIGN.md "reference warts": same access pattern )
+                if d.name.endswith("Classify tiles") or (b.type in fmt_of_pool and fmt_of_pool[b.type][b.index][1] > 1):
+                    table[(d.name.split(" - ")[-1], j)] = 0   # the 1/16-resolution tile mask: read at ( pixel >> 4 ) by the strip that classified it
+                    continue
+                # IN_MV is bound read-write by temporal stabilisation but only written on clear frames: it stays a ( full-frame ) input
+                for r, same in (seq[i + 1:] if b.type != int(api.ResourceType.IN_MV) else []):
+                    rd, wr = False, False
+                    for x in r.bindings:
+                        if key(x) == key(b):
+                            if x.descriptor == storage:
+                                wr = True
+                            else:
+                                rd = True
+                    if rd:
+                        rows = max(rows, reader_reach(r.name, fmt_name(b), same, default, **kw))
+                    if wr:
+                        break
+                k = (d.name.split(" - ")[-1], j)
+                table[k] = max(table.get(k, 0), rows)
+    return table
+
+
+def halo_rows_for(table: dict, pass_name: str, binding: int, default: int = HALO_ROWS) -> int:
     """Apron rows for output `binding` of the pass called '<denoiser> - <pass_name>' (never more than `default`)."""
-    return min(default, HALO_TABLE.get(pass_name.split(" - ")[-1], {}).get(binding, default))
+    return min(default, table.get((pass_name.split(" - ")[-1], binding), default))
 
 
 def strip_rows(height: int, world: int, weights: Optional[Sequence[float]] = None, min_rows: int = 0) -> List[Tuple[int, int]]:
@@ -108,7 +194,8 @@ def _scaled(rows: Tuple[int, int], halo: int, tex_height: int, full_height: int)
     """Strip rows and halo in the row units of a texture that may be downsampled (tiles: 1/16)."""
     if tex_height == full_height:
         return rows[0], rows[1], halo
-    ds = (full_height + tex_height - 1) // tex_height
+    ds = TILE   # the only downsampled textures are the 1/16 tile masks ( re-deriving the factor from the two heights is wrong for e.g. 130 rows -> 9 tile rows )
+    assert tex_height == (full_height + TILE - 1) // TILE, (tex_height, full_height)
     return rows[0] // ds, min((rows[1] + ds - 1) // ds, tex_height), (halo + ds - 1) // ds
 
 
@@ -172,7 +259,7 @@ class TiledDenoiser:
     Construct on every rank of an initialised process group (backend nccl); call `denoise()` in lockstep."""
 
     def __init__(self, denoiser: int, width: int, height: int, rank: int, world: int, device: int = 0, halo_rows: int = HALO_ROWS, flags: Optional[int] = None,
-                 group: Optional[dist.ProcessGroup] = None, use_table: bool = True, mode: str = "peer", row_weights: Optional[Sequence[float]] = None):
+                 group: Optional[dist.ProcessGroup] = None, use_table: bool = True, mode: str = "peer", row_weights: Optional[Sequence[float]] = None, settings=None):
         from . import executor as ex
         self.ex = ex
         self.rank, self.world, self.height, self.width, self.halo, self.group = rank, world, height, width, halo_rows, group
@@ -181,6 +268,11 @@ class TiledDenoiser:
         if world > 1 and min(b - a for a, b in self.strips) < halo_rows:
             raise ValueError(f"strips of {min(b - a for a, b in self.strips)} rows are shorter than the {halo_rows}-row halo")
         self.den = ex.CudaDenoiser(denoiser, width, height, device=device, flags=ex.FLAG_QUAD_INTRINSICS if flags is None else flags)
+        self.denoiser, self._settings = denoiser, settings
+        # per-texture aprons of THIS denoiser ( binding indices differ between the REBLUR variants ); use_table=False -> `halo_rows` everywhere
+        self.table = derive_halo_table(ex.host_library(), denoiser, width, height, halo_rows, settings) if use_table else {}
+        if settings is not None:
+            self.den.set_denoiser_settings(settings)
         self.device = device
         self.bytes_sent = 0
         self.use_table = use_table
@@ -195,7 +287,7 @@ class TiledDenoiser:
     def _after_dispatch(self, user, index, name, textures, is_storage, n):
         # pools ping-pong between two bindings at most, so the send / recv list of a (pass, pointers) pair is built once
         pass_name = name.decode() if name else ""
-        wanted = [(i, halo_rows_for(pass_name, i, self.halo) if self.use_table else self.halo) for i in range(n) if is_storage[i]]
+        wanted = [(i, halo_rows_for(self.table, pass_name, i, self.halo) if self.use_table else self.halo) for i in range(n) if is_storage[i]]
         wanted = [(i, h) for i, h in wanted if h > 0]
         key = (name, tuple(textures[i].data for i, _ in wanted))
         plan = self._plans.get(key)
@@ -234,9 +326,8 @@ class TiledDenoiser:
             return
         ex, L = self.ex, self.ex.load()
         if self.use_table:
-            for pass_name, table in HALO_TABLE.items():
-                for binding, rows in table.items():
-                    ex._check(L.nrdcuTileSetHalo(self.den.ctx, pass_name.encode(), binding, min(rows, self.halo)), "nrdcuTileSetHalo")
+            for (pass_name, binding), rows in self.table.items():
+                ex._check(L.nrdcuTileSetHalo(self.den.ctx, pass_name.encode(), binding, min(rows, self.halo)), "nrdcuTileSetHalo")
         ex._check(L.nrdcuTileSetHalo(self.den.ctx, None, 0, self.halo), "nrdcuTileSetHalo")
         size = L.nrdcuTileExportSize(self.den.ctx)
         blob = C.create_string_buffer(size)
@@ -254,6 +345,15 @@ class TiledDenoiser:
         b, e = C.c_uint64(), C.c_uint32()
         self.ex._check(self.ex.load().nrdcuTileGetStatus(self.den.ctx, C.byref(b), C.byref(e)), "nrdcuTileGetStatus")
         return int(b.value), int(e.value)
+
+    def set_denoiser_settings(self, settings):
+        """Blur radii / history-fix stride change how far passes reach: the apron table follows the settings ( before attach_peers in peer mode )."""
+        if self.use_table and self.world > 1:
+            if self._attached:
+                raise RuntimeError("TiledDenoiser.set_denoiser_settings after attach_peers: pass `settings=` to the constructor instead")
+            self.table = derive_halo_table(self.ex.host_library(), self.denoiser, self.width, self.height, self.halo, settings)
+            self._plans.clear()
+        self.den.set_denoiser_settings(settings)
 
     def __getattr__(self, item):  # set_user_texture, set_common_settings, set_denoiser_settings, pool_texture, profiling ...
         return getattr(self.den, item)

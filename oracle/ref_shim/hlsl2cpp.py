@@ -8,6 +8,7 @@ hlsl_cpu.h. Purely lexical: HLSL spellings that C++ lacks are rewritten, the alg
     scalar swizzles  s.xxx                     -> hlsl_splat3( s )
     groupshared                                -> static thread_local ( one OS thread executes a group )
     per-thread mutable statics of ml.hlsli     -> per-fiber state
+    any( uv != mirrorUv )                      -> hlsl::probeMirror( ... ) ( counts the branch, value unchanged )
     uint2( GetUint( ), GetUint( ) )            -> uint2{ ... } ( left-to-right argument evaluation, as DXC does )
 The output is piped into g++ by oracle/ref_build_shaders.py and never written into the repository."""
 import re
@@ -73,6 +74,11 @@ def transform(text: str, identifier: str, namespace: str) -> str:
         raise SystemExit(f"{identifier}: unparsed groupshared declaration")
     # ( Type )0 zero-initialisation of structs
     text = re.sub(r"=\s*\(\s*([A-Z]\w*)\s*\)\s*0\s*;", r"= \1();", text)
+
+    # test probe ( tests/test_parity_at_baseline_sizes_gpu.py ): count how often the spatial passes take the "tap was mirrored" branch of
+    # REBLUR_Common_SpatialFilter.hlsli:198 — the predicate hangs on the last mantissa bit of the tap position ( DESIGN.md "chaotic predicates" ),
+    # so the CUDA kernels are compared on its RATE. The value of the expression is passed through unchanged.
+    text = re.sub(r"any\s*\(\s*uv\s*!=\s*mirrorUv\s*\)", "hlsl::probeMirror( any( uv != mirrorUv ) )", text)
 
     use_fibers = bool(re.search(r"\bGroupMemoryBarrier(WithGroupSync)?\b|\bQuadRead\w+\b", text))
     x, y, z = (threads + [1, 1])[:3]

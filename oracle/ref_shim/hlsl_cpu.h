@@ -497,4 +497,5 @@ struct ShaderEntry {
     const char* identifier; ShaderModule* module; void (*entry)(uint3, uint3, uint3, uint); uint32_t gx, gy, gz; bool useFibers;
 };
 void registerShader(const ShaderEntry& e);
+bool probeMirror(bool mirrored);   // hlsl_runtime.cpp: branch counter behind nrd_refshader_probe
 }  // namespace hlsl

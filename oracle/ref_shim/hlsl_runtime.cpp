@@ -12,6 +12,16 @@ namespace hlsl {
 static std::map<std::string, ShaderEntry>& registry() { static std::map<std::string, ShaderEntry> r; return r; }
 void registerShader(const ShaderEntry& e) { registry()[e.identifier] = e; }
 
+// probeMirror: [0] taps seen, [1] taps that took the "mirrored" branch; per OS thread, folded by nrd_refshader_probe
+static constexpr int kMaxProbeThreads = 512;
+static uint64_t g_probe[kMaxProbeThreads][8];
+bool probeMirror(bool mirrored) {
+    uint64_t* c = g_probe[omp_get_thread_num() % kMaxProbeThreads];
+    c[0]++;
+    c[1] += mirrored ? 1u : 0u;
+    return mirrored;
+}
+
 static thread_local GroupRun t_group;
 GroupRun& groupRun() { return t_group; }
 
@@ -90,5 +100,11 @@ __attribute__((visibility("default"))) int nrd_refshader_dispatch(const char* sh
 }
 __attribute__((visibility("default"))) int nrd_refshader_count() { return (int)registry().size(); }
 __attribute__((visibility("default"))) const char* nrd_refshader_name(int i) { for (auto& kv : registry()) if (i-- == 0) return kv.second.identifier; return nullptr; }
+// out[0] = taps whose mirror predicate was evaluated since the last reset, out[1] = how many of them were "mirrored"
+__attribute__((visibility("default"))) void nrd_refshader_probe(uint64_t* out, int reset) {
+    uint64_t a = 0, b = 0;
+    for (int i = 0; i < kMaxProbeThreads; i++) { a += g_probe[i][0]; b += g_probe[i][1]; if (reset) g_probe[i][0] = g_probe[i][1] = 0; }
+    if (out) { out[0] = a; out[1] = b; }
+}
 __attribute__((visibility("default"))) void nrd_refshader_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
 }

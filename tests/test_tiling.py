@@ -49,22 +49,43 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _reference_run(w, h, frames):
+# denoiser -> ( outputs, the other lobe's input marker to drop, SH inputs, CPU engine ): the hand-written oracle covers the RADIANCE denoisers; the
+# SH one runs on the reference's own shaders ( oracle/_ref/libnrd_refshaders.so, skipped when it was not built )
+VARIANTS = {
+    "REBLUR_DIFFUSE_SPECULAR": (("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"), "~", False, "oracle"),
+    "REBLUR_DIFFUSE": (("OUT_DIFF_RADIANCE_HITDIST",), "_SPEC_", False, "oracle"),
+    "REBLUR_SPECULAR": (("OUT_SPEC_RADIANCE_HITDIST",), "_DIFF_", False, "oracle"),
+    "REBLUR_DIFFUSE_SPECULAR_SH": (("OUT_DIFF_SH0", "OUT_DIFF_SH1", "OUT_SPEC_SH0", "OUT_SPEC_SH1"), "~", True, "reference"),
+}
+
+
+def _frame(name, f, w, h):
+    _, drop, sh, _ = VARIANTS[name]
+    return {k: v for k, v in synth.reblur_frame(f, w, h, sh=sh).items() if drop not in k}
+
+
+def _make(name, w, h):
     from oracle import runner
-    den = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.REBLUR_DIFFUSE_SPECULAR, w, h, robust_mirror_test=True)
-    od, os_ = runner.alloc_texture(F16, w, h), runner.alloc_texture(F16, w, h)
-    den.set_user_texture(RT.OUT_DIFF_RADIANCE_HITDIST, od)
-    den.set_user_texture(RT.OUT_SPEC_RADIANCE_HITDIST, os_)
-    outs = []
+    outputs, _, _, engine = VARIANTS[name]
+    den = runner.OracleDenoiser(runner.default_host_library(), getattr(api.Denoiser, name), w, h, robust_mirror_test=True, engine=engine)
+    outs = [runner.alloc_texture(F16, w, h) for _ in outputs]
+    for o, t in zip(outputs, outs):
+        den.set_user_texture(getattr(RT, o), t)
+    return den, outs
+
+
+def _reference_run(w, h, frames, name="REBLUR_DIFFUSE_SPECULAR"):
+    den, outs = _make(name, w, h)
+    res = []
     for f in range(frames):
-        for k, v in synth.reblur_frame(f, w, h).items():
+        for k, v in _frame(name, f, w, h).items():
             den.set_user_texture(getattr(RT, k), v)
         den.denoise(synth.common_settings(f, w, h))
-        outs.append((od.clone(), os_.clone()))
-    return outs
+        res.append(tuple(t.clone() for t in outs))
+    return res
 
 
-def _rank_main(rank, world, port, w, h, frames, halo, result_dir):
+def _rank_main(rank, world, port, w, h, frames, halo, result_dir, name="REBLUR_DIFFUSE_SPECULAR"):
     from oracle import runner
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -72,14 +93,14 @@ def _rank_main(rank, world, port, w, h, frames, halo, result_dir):
         runner.lib().nrd_oracle_set_threads(2)
         strips = tiling.strip_rows(h, world)
         y0, y1 = strips[rank]
-        den = runner.OracleDenoiser(runner.default_host_library(), api.Denoiser.REBLUR_DIFFUSE_SPECULAR, w, h, robust_mirror_test=True)
-        od, os_ = runner.alloc_texture(F16, w, h), runner.alloc_texture(F16, w, h)
-        den.set_user_texture(RT.OUT_DIFF_RADIANCE_HITDIST, od)
-        den.set_user_texture(RT.OUT_SPEC_RADIANCE_HITDIST, os_)
+        den, outs_t = _make(name, w, h)
+        table = tiling.derive_halo_table(runner.default_host_library(), getattr(api.Denoiser, name), w, h, halo)   # per-denoiser aprons ( tiling.py )
 
         def after(i, d, keys, self):
             if d.shader.startswith("Clear"):
                 return  # every rank clears its whole copy
+            if d.name.endswith("Classify tiles"):
+                return  # the tile mask is strip-local ( read at pixel >> 4 ); REBLUR_DIFFUSE_SPECULAR_SH keeps it in a full-resolution texture whose rows do not map to strips
             planes, halos = [], []
             for j, (b, k) in enumerate(zip(d.bindings, keys)):
                 if b.descriptor != int(api.DescriptorType.STORAGE_TEXTURE):
@@ -91,15 +112,15 @@ def _rank_main(rank, world, port, w, h, frames, halo, result_dir):
                     p[:ty0] = 0xFF          # poison: 0xFFFF is a NaN in fp16, 255 in UNORM, an impossible history word
                     p[ty1:] = 0xFF
                 planes.append(p)
-                halos.append(tiling.halo_rows_for(d.name, j, halo))   # the per-texture table of tiling.py, capped by `halo`
+                halos.append(tiling.halo_rows_for(table, d.name, j, halo))   # the derived per-texture table, capped by `halo`
             tiling.exchange_halos(planes, strips, rank, h, halos)
 
         outs = []
         for f in range(frames):
-            for k, v in synth.reblur_frame(f, w, h).items():
+            for k, v in _frame(name, f, w, h).items():
                 den.set_user_texture(getattr(RT, k), v)
             den.denoise(synth.common_settings(f, w, h), on_dispatch=after)
-            outs.append((od[y0:y1].clone(), os_[y0:y1].clone()))
+            outs.append(tuple(t[y0:y1].clone() for t in outs_t))
         torch.save(outs, os.path.join(result_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -122,3 +143,41 @@ def test_strips_with_halo_exchange_reproduce_the_single_process_frame(tmp_path, 
                 equal &= same
     if not expect_equal:
         assert not equal, "a 16-row halo cannot cover 30-60 px blur radii: the poison must have leaked into the strips"
+
+
+def test_halo_table_is_derived_per_denoiser():
+    """The apron of a written texture follows its READERS, not a binding index: the same role gets the same rows in every REBLUR variant."""
+    from oracle import runner
+    lib = runner.default_host_library()
+    rows = {}
+    for name in ("REBLUR_DIFFUSE_SPECULAR", "REBLUR_DIFFUSE", "REBLUR_SPECULAR", "REBLUR_DIFFUSE_SH", "REBLUR_SPECULAR_SH", "REBLUR_DIFFUSE_SPECULAR_SH"):
+        t = tiling.derive_halo_table(lib, getattr(api.Denoiser, name), 96, 160)
+        assert t and all(0 <= v <= tiling.HALO_ROWS for v in t.values())
+        by_pass = {}
+        for (p, _), v in t.items():
+            by_pass.setdefault(p, []).append(v)
+        rows[name] = by_pass
+        assert 32 in by_pass["Temporal accumulation"] and 0 in by_pass["Temporal accumulation"]          # radiance -> history fix taps; data2 -> at the pixel
+        assert by_pass["Classify tiles"] == [0]
+        assert max(by_pass["Blur"]) == 64                                                                # post-blur reaches 2 x 30 rows; PREV_VIEWZ survives the frame
+        assert 32 in by_pass["History fix"] and max(by_pass["Temporal stabilization"]) == 64
+        assert 0 in by_pass["Temporal stabilization"]                                                    # the final outputs / IN_MV
+    # larger radii -> taller aprons
+    big = tiling.derive_halo_table(lib, api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 96, 160, 128, api.ReblurSettings(maxBlurRadius=50.0))
+    assert max(v for (p, _), v in big.items() if p == "Blur") >= 102
+
+
+@pytest.mark.parametrize("name", ["REBLUR_DIFFUSE", "REBLUR_SPECULAR", "REBLUR_DIFFUSE_SPECULAR_SH"])
+def test_strips_of_the_other_reblur_denoisers(tmp_path, name):
+    """the binding-index table only fitted REBLUR_DIFFUSE_SPECULAR; the derived table must hold for the other variants."""
+    from oracle import runner
+    if VARIANTS[name][3] == "reference" and runner.ref_shaders() is None:
+        pytest.skip("oracle/_ref/libnrd_refshaders.so was not shipped")
+    world, w, h, frames, halo = 2, 96, 160, 3, 64
+    ref = _reference_run(w, h, frames, name)
+    mp.spawn(_rank_main, args=(world, _free_port(), w, h, frames, halo, str(tmp_path), name), nprocs=world, join=True)
+    for r, (y0, y1) in enumerate(tiling.strip_rows(h, world)):
+        outs = torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"))
+        for f in range(frames):
+            for got, want in zip(outs[f], ref[f]):
+                assert torch.equal(got.view(torch.int16), want[y0:y1].view(torch.int16)), f"{name} rank {r} frame {f}: strip differs from the single-process frame"
