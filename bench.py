@@ -1,19 +1,27 @@
 #!/usr/bin/env python
 """Headline benchmark: denoised Mpixels/s of the REBLUR_DIFFUSE_SPECULAR pass chain at 2560x1440 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--width 2560 --height 1440]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--width 2560 --height 1440] [--denoiser reblur|reblur_sh|relax|sigma]
 
-A "step" is one nrdcuDenoise of one synthetic frame (7 passes: classify tiles, pre-pass, temporal accumulation,
-history fix, blur, post-blur, temporal stabilisation) in steady state. `value` times K steps with the frame's inputs
-already in HBM (CUDA events on the launch stream, barrier + synchronize on both sides, max over ranks); `e2e` times the
-same K steps through the host-buffer entry point nrdcuDenoiseHostPipelined: pinned host inputs -> H2D -> 7 kernels -> D2H of both
-denoised outputs, every step, with the uploads / downloads of neighbouring steps overlapping the kernels (`e2e.serial` = the same
-through nrdcuDenoiseHost, everything back to back on one stream). N > 1 (torchrun): every rank denoises its own independent stream of frames (replicas, no
-data-path collective — REBLUR frames shard as independent streams, BASELINE.json config 5), `value` is the aggregate.
+A "step" is one nrdcuDenoise of one synthetic frame (7 passes: classify tiles, pre-pass, temporal accumulation, history fix, blur,
+post-blur, temporal stabilisation) in steady state.
 
-`--impl reference`: the reference has no CPU (or CUDA) implementation of this path — its HLSL cannot be built or run
-here — so this arm times the oracle's CPU restatement of the same chain (oracle/, "port") on all host cores, on a
-bounded sample of the workload (a 1280x720 stream of the same synthetic scene), rank 0 only.
+* `value`: K steps with the frame's inputs already in HBM (CUDA events on the launch stream, barrier + synchronize on both sides, max
+  over ranks).
+* `e2e`: the same K steps through the host-frame entry point nrdcuDenoiseHostFrames — the renderer-facing staging blocks in pinned,
+  NUMA-local host memory -> ONE H2D copy -> 7 kernels -> ONE D2H copy of both denoised outputs, every step, uploads / downloads of
+  neighbouring steps overlapping the kernels. `e2e.per_texture` is the older nrdcuDenoiseHostPipelined (one 2D copy per texture from
+  caller-owned pinned buffers), `e2e.serial` nrdcuDenoiseHost (everything back to back on one stream).
+* `vs_baseline`: the NRD README's 2.55 ms per 1440p frame (RTX 4080) was taken with HitDistanceReconstructionMode::AREA_3X3, so the ratio
+  is computed from a second timed leg with that setting on inputs with one traced lobe per pixel (`baseline_leg`), not from `value`.
+* N > 1 (torchrun): every rank denoises its own independent stream of frames (replicas, no data-path collective — BASELINE.json
+  config 4, "64 independent 1440p frames"), `value` is the aggregate; in the same run the ranks then denoise ONE 3840x2160 frame as N strips
+  with seam rows pushed over NVLink peer memory (BASELINE.json config 3) and the line carries it as `tiled_4k`.
+
+`--impl reference`: the reference's denoisers are HLSL compute shaders with no CPU or CUDA path; this arm executes the reference's OWN
+shaders compiled as C++ (oracle/_ref/libnrd_refshaders.so, built in the build container from /root/reference) on all host threads, driven
+by the reference's OWN host library (oracle/_ref/libnrd_ref.so), at the SAME resolution and settings, rank 0 only. Falls back to the
+oracle port (and says so) when those libraries were not shipped.
 """
 from __future__ import annotations
 
@@ -34,12 +42,10 @@ UNIT = "Mpixels/s"
 PASS_BYTES_PER_PIXEL = {
     "Classify tiles": 4, "Pre-pass": 42, "Temporal accumulation": 94, "History fix": 52, "Blur": 46, "Post-blur": 46, "Temporal stabilization": 66,
 }
-CHAIN_BYTES_PER_PIXEL = sum(PASS_BYTES_PER_PIXEL.values())  # 350
-PUBLISHED_MPX_S = 3.6864 / 2.55e-3  # NRD/README.md:30: REBLUR_DIFFUSE_SPECULAR 2.55 ms @1440p on RTX 4080
 RING = 4  # distinct frames cycled through (4 x 118 MB of inputs at 1440p >> 126 MB L2)
 
-# Secondary workloads (`--denoiser relax|sigma`): BASELINE.json configs 2 and 0/1', same harness, own metric name. Compulsory bytes per pixel per
-# pass from SURVEY.md App. B; published RTX 4080 times from External/NRD/README.md:32,34.
+# Secondary workloads (`--denoiser relax|sigma`): BASELINE.json configs 2 and 0, same harness, own metric name. Compulsory bytes per pixel per
+# pass from SURVEY.md App. B; published RTX 4080 times from External/NRD/README.md:30-34.
 WORKLOADS = {
     "reblur": dict(denoiser="REBLUR_DIFFUSE_SPECULAR", frame="reblur_frame", metric=METRIC, published_ms=2.55,
                    outputs=(("OUT_DIFF_RADIANCE_HITDIST", "RGBA16_SFLOAT"), ("OUT_SPEC_RADIANCE_HITDIST", "RGBA16_SFLOAT")),
@@ -74,14 +80,25 @@ def usable_cores() -> int:
     return max(1, n)
 
 
-def measured_peak_gbs():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def config_of(args, world):
+    """The `config` object both arms print: same workload, resolution, settings and keys, so the driver's same-config check compares like with like."""
+    wl = WORKLOADS[args.denoiser]
+    recon = args.hitdist_reconstruction
+    return {"workload": wl["what"].format(w=args.width, h=args.height), "denoiser": wl["denoiser"], "resolution": [args.width, args.height],
+            "settings": "library defaults" if recon == "off" else f"library defaults + hitDistanceReconstructionMode = AREA_{recon.upper()} (the NRD README's setting), one lobe traced per pixel",
+            "streams_per_gpu": 1, "parallelism": f"replicas x{world} (independent frame streams, no collective)",
+            "l2_policy": f"ring of {RING} distinct frames of inputs + the pools: larger than the 126 MB L2 at 1440p"}
 
 
 class ClockSampler(threading.Thread):
@@ -113,34 +130,49 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
 
 
-def run_reference(args):
-    """Reference arm: the reference's OWN compute shaders (External/NRD/Shaders/*.cs.hlsl compiled as C++ into oracle/_ref/libnrd_refshaders.so
-    in the build container) executing the chain on the host cores; falls back to the oracle port when that library was not
-    shipped. The reference has no CPU path of its own: this is the closest thing to "the reference on this box's CPU"."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def cpu_denoiser(which: str, W: int, H: int, recon: int, prefer_reference: bool):
+    """A CPU engine for the workload: the reference's shaders driven by the reference's host library when both were shipped
+    (oracle/_ref, `prefer_reference`), else the oracle port driven by the product's host library. Returns (denoiser, step, kind, what, threads)."""
     import torch  # noqa: F401
     from nrd_sample_b200 import nrd_api as api, synth
     from oracle import runner
 
-    W, H = 960, 540  # bounded sample: a smaller stream of the same scene (cost per pixel is resolution independent)
     threads = usable_cores()
     runner.lib().nrd_oracle_set_threads(threads)
-    engine = "reference" if runner.ref_shaders() is not None else "oracle"
-    if engine == "reference":
+    wl = WORKLOADS[which]
+    use_ref = prefer_reference and runner.ref_shaders() is not None
+    if use_ref:
         runner.ref_shaders().nrd_refshader_set_threads(threads)
-    wl = WORKLOADS[args.denoiser]
-    den = runner.OracleDenoiser(runner.default_host_library(), getattr(api.Denoiser, wl["denoiser"]), W, H, engine=engine)
+    ref_host = use_ref and os.path.exists(runner.REF_LIB_PATH)
+    host = api.NrdLibrary(runner.REF_LIB_PATH) if ref_host else runner.default_host_library()
+    den = runner.OracleDenoiser(host, getattr(api.Denoiser, wl["denoiser"]), W, H, engine="reference" if use_ref else "oracle")
     for name, fmt in wl["outputs"]:
         den.set_user_texture(getattr(api.ResourceType, name), runner.alloc_texture(getattr(api.Format, fmt), W, H))
-    frames = [getattr(synth, wl["frame"])(i, W, H, period=RING) for i in range(RING)]
+    extra = {"holes": True} if recon else {}
+    frames = [getattr(synth, wl["frame"])(i, W, H, period=RING, **extra) for i in range(RING)]
+    settings = api.ReblurSettings(hitDistanceReconstructionMode=recon) if recon else None
 
     def step(i):
         for k, v in frames[i % RING].items():
             den.set_user_texture(getattr(api.ResourceType, k), v)
-        den.denoise(synth.common_settings(i, W, H, period=RING))
+        den.denoise(synth.common_settings(i, W, H, period=RING), settings=settings if i == 0 else None)
 
+    if use_ref:
+        what = ("the reference's compute shaders compiled as C++ (oracle/_ref/libnrd_refshaders.so), thread groups spread over the host threads, dispatch stream from "
+                + ("the reference's host library (oracle/_ref/libnrd_ref.so)" if ref_host else "the product's host library (libnrd_ref.so was not shipped)"))
+    else:
+        what = "oracle/ CPU restatement, OpenMP over rows" + (" (libnrd_refshaders.so was not shipped)" if prefer_reference else "")
+    return den, step, ("reference" if use_ref else "port"), what, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W, H = args.width, args.height
+    recon = {"off": 0, "3x3": 1, "5x5": 2}[args.hitdist_reconstruction]
+    den, step, kind, what, threads = cpu_denoiser(args.denoiser, W, H, recon, prefer_reference=True)
+    wl = WORKLOADS[args.denoiser]
     for i in range(args.warmup):
         step(i)
     t0 = time.perf_counter()
@@ -148,20 +180,43 @@ def run_reference(args):
         step(i)
     dt = time.perf_counter() - t0
     value = W * H * args.steps / dt / 1e6
-    kind = "reference" if engine == "reference" else "port"
-    what = ("the reference's compute shaders compiled as C++ (oracle/_ref/libnrd_refshaders.so), thread groups spread over the host threads" if engine == "reference"
-            else "oracle/ CPU restatement (libnrd_refshaders.so was not shipped)")
     line = {
         "impl": "reference", "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["what"].format(w=args.width, h=args.height), "denoiser": wl["denoiser"], "resolution": [args.width, args.height], "settings": "library defaults"},
+        "config": config_of(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": f"{args.steps} steady-state frames of a {W}x{H} stream of the same synthetic scene: {what}"},
+                         "sample": f"{args.steps} steady-state frames of the {W}x{H} stream itself (every step is one whole frame): {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference's denoisers are HLSL compute shaders with no CPU or CUDA path; this arm executes those shaders on the CPU through oracle/ref_shim/hlsl_cpu.h",
     }
     print(json.dumps(line))
+
+
+def cpu_baseline(which="reblur"):
+    """The oracle port on this box's host cores, bounded sample (N = 1 only)."""
+    W, H, warm, steps = 1280, 720, 4, 8
+    den, step, kind, what, threads = cpu_denoiser(which, W, H, 0, prefer_reference=False)
+    t0 = 0.0
+    for i in range(warm + steps):
+        if i == warm:
+            t0 = time.perf_counter()
+        step(i)
+    dt = time.perf_counter() - t0
+    return {"value": W * H * steps / dt / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{steps} steady-state frames of a {W}x{H} stream of the same synthetic scene ({what})"}
+
+
+def profile_numbers(denoiser_key: str, W: int, H: int):
+    """DRAM traffic and executed warp-instructions per launch from the committed ncu captures (profiles/dram_traffic.json, profiles/inst_counts.json)."""
+    out = {}
+    for name in ("dram_traffic", "inst_counts"):
+        p = os.path.join(ROOT, "profiles", f"{name}.json")
+        try:
+            out[name] = json.load(open(p)).get(f"{W}x{H}" if denoiser_key == "reblur" else f"{denoiser_key} {W}x{H}", {})
+        except Exception:
+            out[name] = {}
+    return out
 
 
 def run_product(args):
@@ -173,7 +228,7 @@ def run_product(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the denoiser has no CPU fallback (use --impl reference for the CPU oracle arm)")
+        raise SystemExit("bench.py: no CUDA device — the denoiser has no CPU fallback (use --impl reference for the CPU reference arm)")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
@@ -188,57 +243,49 @@ def run_product(args):
     def fmt_of(name):
         return getattr(api.Format, INPUT_FORMATS.get(name, "RGBA16_SFLOAT"))
 
-    # every rank gets its own stream of frames (different seeds per rank via the frame index offset)
     recon = {"off": 0, "3x3": 1, "5x5": 2}[args.hitdist_reconstruction]
-    extra = {"holes": True} if recon else {}
     if recon:
         assert args.denoiser == "reblur", "--hitdist-reconstruction applies to the REBLUR workload"
         pass_bytes = dict(pass_bytes, **{"Hit distance reconstruction": 40})
-    frames = [getattr(synth, wl["frame"])(i + 1000 * rank, W, H, device=dev, period=RING, **extra) for i in range(RING)]
-    host_frames = [{k: v.cpu().pin_memory() for k, v in f.items()} for f in frames]
-    outs = [(getattr(RT, name), getattr(api.Format, fmt), ex.alloc_texture(getattr(api.Format, fmt), W, H, dev)) for name, fmt in wl["outputs"]]
-    host_outs = [torch.zeros_like(t, device="cpu").pin_memory() for _, _, t in outs]
-    in_bytes = sum(v.numel() * v.element_size() for v in frames[0].values())
-    out_bytes = sum(t.numel() * t.element_size() for _, _, t in outs)
-
-    den = ex.CudaDenoiser(getattr(api.Denoiser, wl["denoiser"]), W, H, device=local)
-    if recon:
-        den.set_denoiser_settings(api.ReblurSettings(hitDistanceReconstructionMode=recon))
     stream = torch.cuda.current_stream()
-
-    def settings(i):
-        return synth.common_settings(i + 1000 * rank, W, H, period=RING)
-
-    def step_device(i):
-        for k, v in frames[i % RING].items():
-            den.set_user_texture(getattr(RT, k), v, fmt_of(k))
-        for rt, fmt, t in outs:
-            den.set_user_texture(rt, t, fmt)
-        den.set_common_settings(settings(i))
-        den.denoise(stream)
-
-    def step_host(i):
-        for k, v in host_frames[i % RING].items():
-            den.set_host_texture(getattr(RT, k), v, fmt_of(k), is_output=False)
-        for (rt, fmt, _), h in zip(outs, host_outs):
-            den.set_host_texture(rt, h, fmt, is_output=True)
-        den.set_common_settings(settings(i))
-        den.denoise_host(stream)
-
-    def step_host_pipelined(i):
-        for k, v in host_frames[i % RING].items():
-            den.set_host_texture(getattr(RT, k), v, fmt_of(k), is_output=False)
-        for (rt, fmt, _), h in zip(outs, host_outs):
-            den.set_host_texture(rt, h, fmt, is_output=True)
-        den.set_common_settings(settings(i))
-        den.denoise_host_pipelined(stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, first, profile=False, finish=None):
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    class Leg:
+        """One denoiser instance + a ring of frames; every rank gets its own stream of frames (seeds offset by the rank)."""
+
+        def __init__(self, recon_mode):
+            extra = {"holes": True} if recon_mode else {}
+            self.frames = [getattr(synth, wl["frame"])(i + 1000 * rank, W, H, device=dev, period=RING, **extra) for i in range(RING)]
+            self.outs = [(getattr(RT, name), getattr(api.Format, fmt), ex.alloc_texture(getattr(api.Format, fmt), W, H, dev)) for name, fmt in wl["outputs"]]
+            self.den = ex.CudaDenoiser(getattr(api.Denoiser, wl["denoiser"]), W, H, device=local)
+            if recon_mode:
+                self.den.set_denoiser_settings(api.ReblurSettings(hitDistanceReconstructionMode=recon_mode))
+            self.in_bytes = sum(v.numel() * v.element_size() for v in self.frames[0].values())
+            self.out_bytes = sum(t.numel() * t.element_size() for _, _, t in self.outs)
+
+        def settings(self, i):
+            return synth.common_settings(i + 1000 * rank, W, H, period=RING)
+
+        def step_device(self, i):
+            for k, v in self.frames[i % RING].items():
+                self.den.set_user_texture(getattr(RT, k), v, fmt_of(k))
+            for rt, fmt, t in self.outs:
+                self.den.set_user_texture(rt, t, fmt)
+            self.den.set_common_settings(self.settings(i))
+            self.den.denoise(stream)
+
+    def timed(den, step_fn, first, profile=False, finish=None):
         for i in range(first, first + args.warmup):
             step_fn(i)
         barrier()
@@ -258,26 +305,96 @@ def run_product(args):
         launches = ex.launch_count() - launches0
         prof = den.profile() if profile else {}
         den.set_profiling(False)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches, prof
+        return max_over_ranks(ms), launches, prof
 
+    # ---- leg 1: device-resident ( `value`, per-pass roofline ) --------------------------------------------------------------------
+    leg = Leg(recon)
+    den = leg.den
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_dev, launches, prof = timed(step_device, 0, profile=True)
+    ms_dev, launches, prof = timed(den, leg.step_device, 0, profile=True)
     clocks = sampler.stop() if sampler else None
-    ms_host, _, _ = timed(step_host, args.warmup + args.steps)
-    ms_pipe, _, _ = timed(step_host_pipelined, 2 * (args.warmup + args.steps), finish=lambda: den.host_flush(stream))
+
+    # ---- leg 2: host buffers ( `e2e` ) ------------------------------------------------------------------------------------------
+    host_frames = [{k: v.cpu().pin_memory() for k, v in f.items()} for f in leg.frames]
+    host_outs = [torch.zeros_like(t, device="cpu").pin_memory() for _, _, t in leg.outs]
+
+    def step_host(pipelined):
+        def fn(i):
+            for k, v in host_frames[i % RING].items():
+                den.set_host_texture(getattr(RT, k), v, fmt_of(k), is_output=False)
+            for (rt, fmt, _), h in zip(leg.outs, host_outs):
+                den.set_host_texture(rt, h, fmt, is_output=True)
+            den.set_common_settings(leg.settings(i))
+            (den.denoise_host_pipelined if pipelined else den.denoise_host)(stream)
+        return fn
+
+    ms_host, _, _ = timed(den, step_host(False), args.warmup + args.steps)
+    ms_pipe, _, _ = timed(den, step_host(True), 2 * (args.warmup + args.steps), finish=lambda: den.host_flush(stream))
+    den.host_flush(stream)
+    torch.cuda.synchronize()
+
+    # host frames: the renderer-facing staging blocks ( own instance: its user slots point into the executor's device blocks )
+    fden = ex.CudaDenoiser(getattr(api.Denoiser, wl["denoiser"]), W, H, device=local)
+    if recon:
+        fden.set_denoiser_settings(api.ReblurSettings(hitDistanceReconstructionMode=recon))
+    for k in leg.frames[0]:
+        fden.declare_host_texture(getattr(RT, k), fmt_of(k), is_output=False)
+    for rt, fmt, _ in leg.outs:
+        fden.declare_host_texture(rt, fmt, is_output=True)
+    in_frames = [fden.host_frame(False) for _ in range(RING)]
+    out_frame = fden.host_frame(True)
+    for hf, f in zip(in_frames, leg.frames):
+        for k, v in f.items():
+            hf.tensor(getattr(RT, k)).copy_(v.cpu())   # the "renderer" writes its frame straight into the staging block
+
+    def step_frames(i):
+        fden.set_common_settings(leg.settings(i))
+        fden.denoise_host_frames(in_frames[i % RING], out_frame, stream)
+
+    ms_frames, _, _ = timed(fden, step_frames, 3 * (args.warmup + args.steps), finish=lambda: fden.host_flush(stream))
+    fden.host_flush(stream)
+    torch.cuda.synchronize()
+    numa_node = in_frames[0].numa_node
+    for hf in in_frames + [out_frame]:
+        hf.close()
+    fden.close()
+    del host_frames, host_outs
+
+    # ---- leg 3 ( REBLUR at 1440p ): the README's setting, for vs_baseline ---------------------------------------------------------
+    baseline_leg = None
+    if args.denoiser == "reblur" and (W, H) == (2560, 1440) and wl["published_ms"]:
+        if recon == 1:
+            ms_b = ms_dev
+        else:
+            den.close()
+            den = None
+            legb = Leg(1)
+            ms_b, _, _ = timed(legb.den, legb.step_device, 0)
+            legb.den.close()
+            del legb
+        baseline_leg = {"ms_per_step": ms_b / args.steps, "value": px * args.steps * world / (ms_b * 1e-3) / 1e6, "settings": "hitDistanceReconstructionMode = AREA_3X3, one lobe traced per pixel",
+                        "published": f"{wl['published_ms']} ms per 1440p frame on an RTX 4080 (External/NRD/README.md:30)"}
+    if den is not None:
+        den.close()
+    del leg
+    torch.cuda.empty_cache()
+
+    # ---- leg 4 ( N > 1, REBLUR ): ONE 3840x2160 frame as N strips ( BASELINE.json config 3 ) -----------------------------------------
+    tiled = None
+    if world > 1 and args.denoiser == "reblur" and not args.no_tiled:
+        try:
+            tiled = tiled_4k(args, ex, api, synth, dist, torch, rank, world, local, barrier, max_over_ranks)
+        except Exception as e:   # a failed strip run must not take the replica numbers with it
+            tiled = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
+        peak, peak_src, sm_mhz = measured_peaks()
         total_px = px * args.steps * world
         value = total_px / (ms_dev * 1e-3) / 1e6
-        e2e_value = total_px / (ms_pipe * 1e-3) / 1e6
-        e2e_serial = total_px / (ms_host * 1e-3) / 1e6
+        numbers = profile_numbers(args.denoiser, W, H)
+        issue_peak = 148 * 4 * (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else sm_mhz) * 1e6   # warp-instructions per second: 148 SMs x 4 schedulers x clock
         passes = {}
         for name, (tot, cnt) in prof.items():
             short = name.split(" - ")[-1]
@@ -286,70 +403,127 @@ def run_product(args):
                 gbs = pass_bytes[short] * px / (avg_ms * 1e-3) / 1e9
                 passes[short] = {"avg_us": round(avg_ms * 1e3, 2), "launches_per_step": cnt // args.steps, "alg_bytes_per_px": pass_bytes[short], "achieved_gbs": round(gbs, 1),
                                  "frac": round(gbs / peak, 4)}
-        dom = max(passes, key=lambda k: passes[k]["avg_us"]) if passes else None
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-        if dom and os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(f"{W}x{H}" if args.denoiser == "reblur" else f"{args.denoiser} {W}x{H}", {}).get(dom)
-            except Exception:
-                traffic = None
+                inst = numbers["inst_counts"].get(short)
+                if inst:   # executed warp-instructions per launch ( ncu smsp__inst_executed.sum ) over what the schedulers could issue in the measured time
+                    passes[short]["issue_frac"] = round(inst / (avg_ms * 1e-3 * issue_peak), 4)
+        dom = max(passes, key=lambda k: passes[k]["avg_us"] * passes[k]["launches_per_step"]) if passes else None
         chain_bytes = sum(pass_bytes[k] * v["launches_per_step"] for k, v in passes.items())
         chain_gbs = chain_bytes * px / (ms_dev / args.steps * 1e-3) / 1e9
+        chain_inst = sum(numbers["inst_counts"].get(k, 0) * v["launches_per_step"] for k, v in passes.items())
         roofline = None
         if dom:
-            roofline = {"bound": "hbm", "kernel": dom, "achieved": passes[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": passes[dom]["frac"], "traffic": traffic,
-                        "peak_source": peak_src, "alg_bytes_per_launch": pass_bytes[dom] * px,
-                        "chain": {"alg_bytes_per_px": chain_bytes, "achieved": round(chain_gbs, 1), "frac": round(chain_gbs / peak, 4)}, "passes": passes,
-                        "note": "the chains are FP32-issue bound on B200 (30-40 FLOP per algorithmic byte vs a ~10 FLOP/B fp32 ridge); see DESIGN.md"}
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": passes[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": passes[dom]["frac"],
+                        "traffic": numbers["dram_traffic"].get(dom), "peak_source": peak_src, "alg_bytes_per_launch": pass_bytes[dom] * px,
+                        "issue_frac": passes[dom].get("issue_frac"),
+                        "chain": {"alg_bytes_per_px": chain_bytes, "achieved": round(chain_gbs, 1), "frac": round(chain_gbs / peak, 4),
+                                  "issue_frac": round(chain_inst / (ms_dev / args.steps * 1e-3 * issue_peak), 4) if chain_inst else None},
+                        "passes": passes,
+                        "note": "the chains are FP32-issue bound on B200 (30-40 FLOP per algorithmic byte vs a ~10 FLOP/B fp32 ridge): issue_frac = executed warp-instructions (ncu, profiles/inst_counts.json) / (time x 148 SMs x 4 schedulers x SM clock); see DESIGN.md"}
+        cfg = config_of(args, world)
+        cfg["baseline_note"] = ("vs_baseline = per-GPU Mpixels/s of baseline_leg (AREA_3X3, like the published run) / (3.6864 Mpixels / 2.55 ms on an RTX 4080, NRD README)" if baseline_leg
+                                else (f"vs_baseline = per-GPU value / ({wl['published_ms']} ms per 1440p frame on an RTX 4080, NRD README)" if wl["published_ms"] and (W, H) == (2560, 1440)
+                                      else "no published number for this denoiser / resolution"))
+        if baseline_leg:
+            vs_baseline = baseline_leg["value"] / world / (3.6864 / (wl["published_ms"] * 1e-3))
+        elif wl["published_ms"] and (W, H) == (2560, 1440):
+            vs_baseline = value / world / (3.6864 / (wl["published_ms"] * 1e-3))
+        else:
+            vs_baseline = None
+
+        def mpx(ms):
+            return total_px / (ms * 1e-3) / 1e6
+
+        e2e_ms = ms_frames / args.steps
         line = {
             "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / world / (3.6864 / (wl["published_ms"] * 1e-3)) if (W, H) == (2560, 1440) and wl["published_ms"] else None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": wl["what"].format(w=W, h=H), "denoiser": wl["denoiser"],
-                       "resolution": [W, H],
-                       "settings": "library defaults" if not recon else f"library defaults + hitDistanceReconstructionMode = AREA_{args.hitdist_reconstruction.upper()} (the NRD README's setting), one lobe traced per pixel",
-                       "streams_per_gpu": 1, "parallelism": f"replicas x{world} (independent frame streams, no collective)",
-                       "l2_policy": f"ring of {RING} distinct frames: {RING * in_bytes // 2**20} MiB of inputs + pools > 126 MB L2",
-                       "baseline_note": (f"vs_baseline = per-GPU value / ({wl['published_ms']} ms per 1440p frame on an RTX 4080, NRD README)" if wl["published_ms"]
-                                         else "no published number for this denoiser")},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_pipe / args.steps,
-                    "call": "nrdcuDenoiseHostPipelined: pinned host inputs -> H2D -> chain -> D2H of the outputs every step, uploads / downloads of neighbouring steps overlap the kernels",
-                    "serial": {"value": e2e_serial, "ms_per_step": ms_host / args.steps, "call": "nrdcuDenoiseHost: the same copies and kernels back to back on one stream"}},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": vs_baseline, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": mpx(ms_frames), "unit": UNIT, "h2d_bytes_per_step": leg_in_bytes(W, H, wl, recon, api), "d2h_bytes_per_step": leg_out_bytes(W, H, wl, api), "ms_per_step": e2e_ms,
+                    "call": "nrdcuDenoiseHostFrames: renderer-facing staging blocks in pinned NUMA-local host memory -> ONE H2D copy -> chain -> ONE D2H copy every step, copies of neighbouring steps overlap the kernels",
+                    "pcie_gbs_per_gpu": {"h2d": round(leg_in_bytes(W, H, wl, recon, api) / (e2e_ms * 1e-3) / 1e9, 1), "d2h": round(leg_out_bytes(W, H, wl, api) / (e2e_ms * 1e-3) / 1e9, 1)},
+                    "host_numa_node_rank0": numa_node,
+                    "per_texture": {"value": mpx(ms_pipe), "ms_per_step": ms_pipe / args.steps, "call": "nrdcuDenoiseHostPipelined: one 2D copy per texture from caller-owned pinned buffers, pipelined"},
+                    "serial": {"value": mpx(ms_host), "ms_per_step": ms_host / args.steps, "call": "nrdcuDenoiseHost: the same copies and kernels back to back on one stream"}},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
         }
+        if baseline_leg:
+            line["baseline_leg"] = baseline_leg
+        if tiled is not None:
+            line["tiled_4k"] = tiled
         # CPU baseline: the oracle port on this box's host cores, bounded sample (N=1 only)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.denoiser)
         print(json.dumps(line))
-    den.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(which="reblur"):
-    import torch  # noqa: F401
-    from nrd_sample_b200 import nrd_api as api, synth
-    from oracle import runner
+def leg_in_bytes(W, H, wl, recon, api):
+    from nrd_sample_b200 import synth
+    names = list(getattr(synth, wl["frame"])(0, 32, 32).keys())
+    return sum(W * H * api.FORMAT_BYTES[getattr(api.Format, INPUT_FORMATS.get(k, "RGBA16_SFLOAT"))] for k in names)
 
-    W, H, warm, steps = 1280, 720, 4, 8
-    threads = usable_cores()
-    runner.lib().nrd_oracle_set_threads(threads)
-    wl = WORKLOADS[which]
-    den = runner.OracleDenoiser(runner.default_host_library(), getattr(api.Denoiser, wl["denoiser"]), W, H)
-    for name, fmt in wl["outputs"]:
-        den.set_user_texture(getattr(api.ResourceType, name), runner.alloc_texture(getattr(api.Format, fmt), W, H))
-    frames = [getattr(synth, wl["frame"])(i, W, H, period=RING) for i in range(RING)]
-    t0 = 0.0
-    for i in range(warm + steps):
-        if i == warm:
-            t0 = time.perf_counter()
-        for k, v in frames[i % RING].items():
-            den.set_user_texture(getattr(api.ResourceType, k), v)
-        den.denoise(synth.common_settings(i, W, H, period=RING))
-    dt = time.perf_counter() - t0
-    return {"value": W * H * steps / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{steps} steady-state frames of a {W}x{H} stream of the same synthetic scene (oracle/ CPU restatement, OpenMP over rows)"}
+
+def leg_out_bytes(W, H, wl, api):
+    return sum(W * H * api.FORMAT_BYTES[getattr(api.Format, fmt)] for _, fmt in wl["outputs"])
+
+
+def tiled_4k(args, ex, api, synth, dist, torch, rank, world, local, barrier, max_over_ranks):
+    """BASELINE.json config 3: ONE 3840x2160 REBLUR_DIFFUSE_SPECULAR frame per step, rank r computing strip r of every pass (cuts balanced by
+    denoising-range pixels), seam rows pushed into the neighbours' HBM over NVLink peer memory after each pass (nrd_sample_b200/tiling.py,
+    csrc/kernels/peer_halo.cu). Strong scaling: `speedup_vs_1` = whole-frame time on one GPU (rank 0 measures it in the same run) / strip time."""
+    from nrd_sample_b200 import tiling
+    W, H = 3840, 2160
+    dev = f"cuda:{local}"
+    RT, F16 = api.ResourceType, api.Format.RGBA16_SFLOAT
+    fmt = {"IN_VIEWZ": api.Format.R32_SFLOAT, "IN_NORMAL_ROUGHNESS": api.Format.R10_G10_B10_A2_UNORM}
+    frames = [synth.reblur_frame(i, W, H, device=dev, period=RING) for i in range(RING)]
+    stream = torch.cuda.current_stream()
+    steps, warm = args.steps, max(args.warmup, 6)
+
+    def run(den):
+        def step(i):
+            for k, v in frames[i % RING].items():
+                den.set_user_texture(getattr(RT, k), v, fmt.get(k, F16))   # IN_MV is bound read-write by temporal stabilisation but only written on clear frames
+            den.set_common_settings(synth.common_settings(i, W, H, period=RING))
+            den.denoise()
+        for i in range(warm):
+            step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(warm, warm + steps):
+            step(i)
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1) / steps
+
+    # one GPU, whole frame ( every rank runs it so that the barriers inside run() stay matched; rank 0's time is the reference )
+    whole = ex.CudaDenoiser(api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, device=local)
+    keep = [ex.alloc_texture(F16, W, H, dev), ex.alloc_texture(F16, W, H, dev)]
+    whole.set_user_texture(RT.OUT_DIFF_RADIANCE_HITDIST, keep[0], F16)
+    whole.set_user_texture(RT.OUT_SPEC_RADIANCE_HITDIST, keep[1], F16)
+    ms_one = run(whole)
+    whole.close()
+    t = torch.tensor([ms_one], device=dev)
+    dist.broadcast(t, 0)
+    ms_one = float(t.item())
+
+    weights = tiling.tile_row_weights(frames[0]["IN_VIEWZ"])   # the same on every rank: all hold the full input frame
+    den = tiling.TiledDenoiser(api.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, rank, world, local, mode="peer", row_weights=weights)
+    outs = [den.shared_texture(RT.OUT_DIFF_RADIANCE_HITDIST, F16), den.shared_texture(RT.OUT_SPEC_RADIANCE_HITDIST, F16)]   # in the context, so the neighbours can map them
+    den.attach_peers()
+    sent0 = den.status()[0]
+    ms = max_over_ranks(run(den))
+    sent, wait_error = den.status()
+    per_frame = (sent - sent0) // (steps + warm)
+    tb = torch.tensor([float(per_frame)], device=dev)
+    dist.all_reduce(tb)
+    out = {"ms_per_frame": ms, "ms_per_frame_1gpu": ms_one, "speedup_vs_1": ms_one / ms, "mpixels_per_s": W * H / ms / 1e3, "halo_bytes": int(tb.item()),
+           "halo_bytes_note": "seam bytes pushed per frame, summed over all strips", "mode": "peer stores over NVLink (CUDA IPC), work-balanced cuts",
+           "strips": den.strips, "halo_rows": den.halo, "max_vertical_motion_rows": den.halo - 2, "wait_error": wait_error, "resolution": [W, H], "steps": steps}
+    den.close()
+    del outs
+    return out
 
 
 def main():
@@ -361,6 +535,7 @@ def main():
     ap.add_argument("--width", type=int, default=2560)
     ap.add_argument("--height", type=int, default=1440)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tiled", action="store_true", help="N > 1: skip the 3840x2160 strip run (tiled_4k)")
     ap.add_argument("--hitdist-reconstruction", default="off", choices=["off", "3x3", "5x5"],
                     help="REBLUR only: run with ReblurSettings::hitDistanceReconstructionMode (the README's 2.55 ms was taken with 3x3) on inputs with one lobe per pixel")
     ap.add_argument("--denoiser", default="reblur", choices=sorted(WORKLOADS), help="reblur = the headline workload (default); relax / sigma = BASELINE.json configs 2 and 0")

@@ -46,6 +46,8 @@ enum {
     NRDCU_FLAG_CUDA_GRAPH = 1u << 1,      /* reserved, ignored: every pass takes new constants each frame, so a replayed graph would need all of its
                                              kernel nodes patched per frame — no gain over 7-10 launches while the chains are GPU-bound */
     NRDCU_FLAG_ROBUST_MIRROR_TEST = 1u << 2, /* DEBUG: spatial taps use "left the screen" instead of the reference's bit-fragile any(uv != MirrorUv(uv)) */
+    NRDCU_FLAG_PROBE_MIRROR = 1u << 3,       /* DEBUG: the REBLUR_DIFFUSE_SPECULAR spatial passes count their taps and how many took the "mirrored" branch
+                                                of REBLUR_Common_SpatialFilter.hlsli:198 ( read with nrdcuGetMirrorProbe ) */
 };
 #define NRDCU_DEFAULT_FLAGS (NRDCU_FLAG_QUAD_INTRINSICS)
 
@@ -115,6 +117,21 @@ NRDCU_API uint32_t nrdcuDenoiseHost(nrdcuContext* ctx, const uint32_t* identifie
 NRDCU_API uint32_t nrdcuDenoiseHostPipelined(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, void* stream);
 NRDCU_API uint32_t nrdcuHostFlush(nrdcuContext* ctx, void* stream);
 
+/* Host frames: the plugin path without per-texture copies. A host frame is ONE pinned host block holding every host resource of one
+ * direction ( declared with nrdcuSetHostResource( ..., hostData = NULL, ... ) ), laid out exactly like the executor's device block
+ * ( 256-byte row pitch ), allocated on the NUMA node the GPU hangs off ( mbind + cudaHostRegister; falls back to cudaHostAlloc ). The
+ * renderer writes its G-buffer / radiance straight into the views nrdcuHostFrameGetTexture returns ( `data` is a HOST pointer there ) and
+ * reads the denoised outputs from an output frame, so a frame costs ONE cudaMemcpyAsync up and ONE down, pipelined like
+ * nrdcuDenoiseHostPipelined ( upload of call i + 1 and download of call i - 1 overlap the kernels of call i; nrdcuHostFlush as there ).
+ * Any number of frames may exist per direction ( e.g. a ring the renderer fills ahead ). */
+typedef struct nrdcuHostFrame nrdcuHostFrame;
+NRDCU_API uint32_t nrdcuHostFrameCreate(nrdcuContext* ctx, int direction, nrdcuHostFrame** out);
+NRDCU_API uint32_t nrdcuHostFrameGetTexture(nrdcuHostFrame* frame, uint32_t resourceType, nrdcuTexture* outHostView);
+NRDCU_API uint32_t nrdcuHostFrameGetInfo(nrdcuHostFrame* frame, uint64_t* bytes, int* numaNode /* -1: unknown / not bound */);
+NRDCU_API void nrdcuHostFrameDestroy(nrdcuHostFrame* frame);
+NRDCU_API uint32_t nrdcuDenoiseHostFrames(nrdcuContext* ctx, const uint32_t* identifiers, uint32_t identifiersNum, nrdcuHostFrame* inputs, nrdcuHostFrame* outputs,
+                                          void* stream);
+
 /* ---- per-pass timing -----------------------------------------------------------------------------------------
  * With profiling on, nrdcuDenoise brackets every dispatch with CUDA events on `stream`; nrdcuResolveProfile
  * synchronises and accumulates them per pass name (DispatchDesc::name). Used by bench.py for the live roofline. */
@@ -144,6 +161,8 @@ NRDCU_API const char* nrdcuFrontEndGetLastError(void);
 NRDCU_API const char* nrdcuGetLastError(void);
 NRDCU_API uint64_t nrdcuGetLaunchCount(void);           /* kernels launched by this library since load (all contexts) */
 NRDCU_API uint64_t nrdcuGetPoolBytes(nrdcuContext* ctx); /* device bytes held by the pools (README memory table analogue) */
+/* NRDCU_FLAG_PROBE_MIRROR counters of the current device: out[0] = taps, out[1] = taps whose weight took the "mirrored" branch; reset != 0 clears them */
+NRDCU_API uint32_t nrdcuGetMirrorProbe(uint64_t* out, int reset);
 
 #ifdef __cplusplus
 }

@@ -379,6 +379,9 @@ void Graph::fillReblurConstants(const ReblurSettings& s, void* dst) {
         k.viewVectorWorldPrev[i] = f.viewDirectionPrev[i];
         k.mvScale[i] = c.motionVectorScale[i];
     }
+    // the reference negates the whole SSE register of the matrix column ( InstanceImpl.cpp:434-435 ): .w = -( 0 ) = -0.0f, never read by a shader
+    k.viewVectorWorld[3] = -f.viewToWorld.m[11];
+    k.viewVectorWorldPrev[3] = -f.viewToWorldPrev.m[11];
     k.hitDistSettings[0] = s.hitDistanceParameters.A;
     k.hitDistSettings[1] = s.hitDistanceParameters.B;
     k.hitDistSettings[2] = s.hitDistanceParameters.C;

@@ -145,6 +145,7 @@ void Graph::fillSigmaConstants(const SigmaSettings& s, void* dst) {
     memcpy(k.rotatorPost, f.rotatorPost, 16);
     memcpy(k.frustum, f.frustum, 16);
     memcpy(k.frustumPrev, f.frustumPrev, 16);
+    k.viewVectorWorld[3] = -f.viewToWorld.m[11];   // the reference negates the whole SSE register ( InstanceImpl.cpp:434 ): -0.0f
     for (int i = 0; i < 3; i++) {
         k.viewVectorWorld[i] = f.viewDirection[i];
         k.cameraDelta[i] = f.cameraDelta[i];

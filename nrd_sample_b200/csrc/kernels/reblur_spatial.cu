@@ -85,7 +85,11 @@ NRD_DEV P2 exponentialWeight2(P2 y) {
 // CB: checkerboard input (pre-pass only): `input` is half width, holds the pixels whose parity equals `cbMode` this frame
 // SH ( NRD_MODE = SH ): a second RGBA16F per lobe rides along with the weights of the first ( REBLUR_Common_SpatialFilter.hlsli:67-69, 268-280, 307-335 )
 struct ShIo { const TexRGBA16F *in, *out, *outCopy; };
-template <int PASS, int LOBE, bool CB = false, bool SH = false>
+// PROBE ( NRDCU_FLAG_PROBE_MIRROR, tests only ): counts the taps and how many of them took the "mirrored" branch of the Gaussian weight
+// ( REBLUR_Common_SpatialFilter.hlsli:198 ) into g_mirrorProbe — the predicate is decided by the last mantissa bit of the tap position, so
+// parity with the reference is stated on its RATE ( tests/test_parity_at_baseline_sizes_gpu.py ). Compiled out of every other instantiation.
+__device__ unsigned long long g_mirrorProbe[2];
+template <int PASS, int LOBE, bool CB = false, bool SH = false, bool PROBE = false>
 NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const TexR32F& viewZTex, const TexNR& nrTex, const TexRGBA16F& input,
                            const TexRGBA16F& output, const TexR16F* outSpecHitDistForTracking, const TexRGBA16F* outputCopy, bool temporalStabilization, bool robustMirrorTest,
                            const Resolve* resolve = nullptr, ShIo shIo = ShIo()) {
@@ -192,6 +196,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
         const bool perspective = cb.orthoMode == 0.0f;
 
         float hitDistForTracking = hitDist == 0.0f ? NRD_INF : hitDist;
+        unsigned probeMirrored = 0u;
         P2 sum2(0.0f);
         P2 accX(0.0f), accY(0.0f), accZ(0.0f), accW(0.0f);
         P2 shX(0.0f), shY(0.0f), shZ(0.0f), shW(0.0f);
@@ -232,6 +237,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
                 mirB = ux.b() != mx.b() || uy.b() != my.b();
             }
             P2 w(mirA ? 1.0f : kGaussOuter, mirB ? 1.0f : kGaussInner);
+            if constexpr (PROBE) probeMirrored += (mirA ? 1u : 0u) + (mirB ? 1u : 0u);
 
             // texel coordinates: mirrorUv() < 1 keeps every tap inside the rect, so fetches need no bounds checks
             P2 fx = floor2(mx * rectSize.x), fy = floor2(my * rectSize.y);
@@ -342,6 +348,14 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             }
         }
 
+        if constexpr (PROBE) {
+            const unsigned active = __activemask();
+            const unsigned mirrored = __reduce_add_sync(active, probeMirrored);
+            if ((threadIdx.x & 31) == __ffs(active) - 1) {
+                atomicAdd(&g_mirrorProbe[0], 8ull * __popc(active));
+                atomicAdd(&g_mirrorProbe[1], (unsigned long long)mirrored);
+            }
+        }
         sum += sum2.a() + sum2.b();
         result += make_float4(accX.a() + accX.b(), accY.a() + accY.b(), accZ.a() + accZ.b(), accW.a() + accW.b());
         result *= positiveRcp(sum);
@@ -389,7 +403,7 @@ __global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_co
     if (threadIdx.x == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
 }
 
-template <bool CB, int SIGNAL, bool SH>
+template <bool CB, int SIGNAL, bool SH, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags, int ctaY0) {
     const bool robust = (flags & 2) != 0;
     Center s;
@@ -415,8 +429,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPr
         r.x0 = x0 >> 1;
         r.x1 = x1 >> 1;
     }
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<PRE_PASS, DIFF, CB, SH>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<PRE_PASS, SPEC, CB, SH>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<PRE_PASS, DIFF, CB, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<PRE_PASS, SPEC, CB, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
 }
 
 // Non-linear accumulation speed with the quad-neighbour smoothing of REBLUR_Blur.cs.hlsl:40-59 (lanes x^1, x^2 of the row)
@@ -432,7 +446,7 @@ NRD_DEV float2 quadSmoothedAccumSpeed(const ReblurConstants& cb, float2 data1, f
     return n;
 }
 
-template <int SIGNAL, bool SH>
+template <int SIGNAL, bool SH, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
@@ -452,11 +466,11 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBl
     if (skyTile || !inDenoisingRange(cb, s.viewZ) || s.px > cb.rectSizeMinusOne[0] || s.py > cb.rectSizeMinusOne[1]) return;
 
     setupCenter(cb, s, p.normalRoughness, cb.rotator);
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<BLUR, DIFF, false, SH>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<BLUR, SPEC, false, SH>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<BLUR, DIFF, false, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<BLUR, SPEC, false, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
 }
 
-template <bool TEMPORAL_STABILIZATION, int SIGNAL, bool SH>
+template <bool TEMPORAL_STABILIZATION, int SIGNAL, bool SH, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
@@ -475,8 +489,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPo
     p.outNormalRoughness.storeRaw(s.px, s.py, p.normalRoughness.loadRaw(s.px, s.py));
     if (!TEMPORAL_STABILIZATION) p.outInternalData.store(s.px, s.py, packInternalData(cb, s.data1.x, s.data1.y, s.materialID));
 
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<POST_BLUR, DIFF, false, SH>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, &p.outDiffShCopy});
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<POST_BLUR, SPEC, false, SH>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, &p.outSpecShCopy});
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<POST_BLUR, DIFF, false, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, &p.outDiffShCopy});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<POST_BLUR, SPEC, false, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, &p.outSpecShCopy});
 }
 
 // REBLUR_SplitScreen.cs.hlsl:21-56: the noisy input (range-masked) left of CommonSettings::splitScreen
@@ -490,6 +504,13 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurSplitScreenKernel(cons
     // NRD_MODE = SH ( :44-52 ): the SH1 inputs, same addressing
     if ((signal & SIGNAL_DIFF) && p.inDiffSh.data) p.outDiffSh.store(px, py, p.inDiffSh.load(px >> (cb.diffCheckerboard != 2u ? 1 : 0), py) * inRange);
     if ((signal & SIGNAL_SPEC) && p.inSpecSh.data) p.outSpecSh.store(px, py, p.inSpecSh.load(px >> (cb.specCheckerboard != 2u ? 1 : 0), py) * inRange);
+}
+
+// Reads ( and optionally clears ) g_mirrorProbe: out[0] = taps, out[1] = taps that took the "mirrored" branch
+bool readMirrorProbe(unsigned long long* out, bool reset) {
+    unsigned long long zero[2] = {0ull, 0ull};
+    if (out && cudaMemcpyFromSymbol(out, g_mirrorProbe, sizeof(zero)) != cudaSuccess) return false;
+    return !reset || cudaMemcpyToSymbol(g_mirrorProbe, zero, sizeof(zero)) == cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -511,6 +532,10 @@ void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int 
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
     const bool cbOn = cb.diffCheckerboard != 2u || cb.specCheckerboard != 2u;  // CheckerboardMode::BLACK / WHITE set both (Reblur.cpp:301-313)
     const bool sh = p.inDiffSh.data || p.inSpecSh.data;                        // bound by the executor for "|NRD_MODE=SH" only
+    if ((flags & 4) && signal == SIGNAL_BOTH && !sh && !cbOn) {  // NRDCU_FLAG_PROBE_MIRROR
+        reblurPrePassKernel<false, SIGNAL_BOTH, false, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        return;
+    }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
         if (sh) {
@@ -527,6 +552,10 @@ void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int signal
     if (!g.count) return;
     const bool sh = p.inDiffSh.data || p.inSpecSh.data;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
+    if ((flags & 4) && signal == SIGNAL_BOTH && !sh) {
+        reblurBlurKernel<SIGNAL_BOTH, false, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        return;
+    }
     withSignal(signal, [&](auto sig) {
         if (sh) reblurBlurKernel<decltype(sig)::value, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
         else reblurBlurKernel<decltype(sig)::value, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
@@ -536,6 +565,10 @@ void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, in
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
+    if ((flags & 4) && signal == SIGNAL_BOTH && !(p.inDiffSh.data || p.inSpecSh.data) && temporalStabilization) {
+        reblurPostBlurKernel<true, SIGNAL_BOTH, false, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        return;
+    }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
         const bool sh = p.inDiffSh.data || p.inSpecSh.data;

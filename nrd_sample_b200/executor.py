@@ -23,11 +23,13 @@ class CuTexture(C.Structure):
 FLAG_QUAD_INTRINSICS = 1
 FLAG_CUDA_GRAPH = 2
 FLAG_ROBUST_MIRROR_TEST = 4
+FLAG_PROBE_MIRROR = 8
 
 NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdcuAllocSharedTexture", "nrdcuTileExportSize", "nrdcuTileExport", "nrdcuTileAttach",
                  "nrdcuTileSetHalo", "nrdcuTileGetStatus", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
                  "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuDenoiseHostPipelined", "nrdcuHostFlush", "nrdcuGetLastError", "nrdcuGetLaunchCount",
-                 "nrdcuGetPoolBytes", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile",
+                 "nrdcuHostFrameCreate", "nrdcuHostFrameGetTexture", "nrdcuHostFrameGetInfo", "nrdcuHostFrameDestroy", "nrdcuDenoiseHostFrames",
+                 "nrdcuGetPoolBytes", "nrdcuGetMirrorProbe", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile",
                  "nrdcuFrontEndPackNormalRoughness", "nrdcuFrontEndPackRadianceHitDist", "nrdcuBackEndUnpackRadiance", "nrdcuFrontEndProbe", "nrdcuFrontEndGetLastError")
 
 # nrd::Format -> (torch dtype, channels) for tensors handed to / returned by the executor
@@ -110,6 +112,18 @@ def load() -> C.CDLL:
         L.nrdcuGetProfileEntry.restype = C.c_uint32
         L.nrdcuResetProfile.argtypes = [C.c_void_p]
         L.nrdcuResetProfile.restype = None
+        L.nrdcuHostFrameCreate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.nrdcuHostFrameCreate.restype = C.c_uint32
+        L.nrdcuHostFrameGetTexture.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(CuTexture)]
+        L.nrdcuHostFrameGetTexture.restype = C.c_uint32
+        L.nrdcuHostFrameGetInfo.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        L.nrdcuHostFrameGetInfo.restype = C.c_uint32
+        L.nrdcuHostFrameDestroy.argtypes = [C.c_void_p]
+        L.nrdcuHostFrameDestroy.restype = None
+        L.nrdcuDenoiseHostFrames.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nrdcuDenoiseHostFrames.restype = C.c_uint32
+        L.nrdcuGetMirrorProbe.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+        L.nrdcuGetMirrorProbe.restype = C.c_uint32
         _lib = L
     return _lib
 
@@ -125,6 +139,13 @@ def _check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().nrdcuGetLaunchCount())
+
+
+def mirror_probe(reset: bool = False):
+    """(taps, taps that took the "mirrored" weight branch) counted by the spatial passes of contexts created with FLAG_PROBE_MIRROR."""
+    out = (C.c_uint64 * 2)()
+    _check(load().nrdcuGetMirrorProbe(out, 1 if reset else 0), "nrdcuGetMirrorProbe")
+    return int(out[0]), int(out[1])
 
 
 def texture_of(t: torch.Tensor, fmt: int) -> CuTexture:
@@ -217,6 +238,19 @@ class CudaDenoiser:
         s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
         _check(load().nrdcuHostFlush(self.ctx, C.c_void_p(s)), "nrdcuHostFlush")
 
+    # ---- host frames: one pinned, NUMA-local host block per direction, one copy up and one down per call ------------------------------------
+    def declare_host_texture(self, rtype: int, fmt: int, is_output: bool, width: Optional[int] = None, height: Optional[int] = None):
+        """Make `rtype` part of the host frames of its direction ( call for every host resource before the first host_frame() )."""
+        _check(load().nrdcuSetHostResource(self.ctx, int(rtype), None, width or self.width, height or self.height, 0, int(fmt), 1 if is_output else 0), "nrdcuSetHostResource")
+
+    def host_frame(self, is_output: bool) -> "HostFrame":
+        return HostFrame(self, is_output)
+
+    def denoise_host_frames(self, inputs: "HostFrame", outputs: "HostFrame", stream: Optional[torch.cuda.Stream] = None):
+        """Upload `inputs` ( one copy ), run the chain, download into `outputs` ( one copy ), pipelined across calls; host_flush() before reading."""
+        s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        _check(load().nrdcuDenoiseHostFrames(self.ctx, self._ids, 1, inputs.handle, outputs.handle, C.c_void_p(s)), "nrdcuDenoiseHostFrames")
+
     def pool_texture(self, permanent: bool, index: int) -> torch.Tensor:
         """Copy of a pool texture (debug / parity tap)."""
         tex = CuTexture()
@@ -247,6 +281,33 @@ class CudaDenoiser:
 
     def pool_bytes(self) -> int:
         return int(load().nrdcuGetPoolBytes(self.ctx))
+
+
+class HostFrame:
+    """nrdcuHostFrame: the renderer-facing staging block. `tensor( rtype )` is a CPU tensor VIEW ( H, W[, C] ) of the resource inside the pinned
+    block ( rows are 256-byte aligned: the view may be strided )."""
+
+    def __init__(self, den: CudaDenoiser, is_output: bool):
+        self.den, self.is_output = den, is_output
+        h = C.c_void_p()
+        _check(load().nrdcuHostFrameCreate(den.ctx, 1 if is_output else 0, C.byref(h)), "nrdcuHostFrameCreate")
+        self.handle = h
+        b, n = C.c_uint64(), C.c_int()
+        _check(load().nrdcuHostFrameGetInfo(h, C.byref(b), C.byref(n)), "nrdcuHostFrameGetInfo")
+        self.bytes, self.numa_node = int(b.value), int(n.value)
+
+    def tensor(self, rtype: int) -> torch.Tensor:
+        tex = CuTexture()
+        _check(load().nrdcuHostFrameGetTexture(self.handle, int(rtype), C.byref(tex)), "nrdcuHostFrameGetTexture")
+        dtype, ch = FORMAT_STORAGE[api.Format(tex.format)]
+        raw = torch.frombuffer((C.c_uint8 * (tex.pitchBytes * tex.height)).from_address(tex.data), dtype=torch.uint8).view(dtype)
+        pitch = tex.pitchBytes // raw.element_size()
+        return raw.as_strided((tex.height, tex.width, ch), (pitch, ch, 1)) if ch > 1 else raw.as_strided((tex.height, tex.width), (pitch, 1))
+
+    def close(self):
+        if self.handle:
+            load().nrdcuHostFrameDestroy(self.handle)
+            self.handle = None
 
 
 def _as_byte_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:

@@ -77,7 +77,17 @@ def ref_shaders() -> Optional[C.CDLL]:
         _ref_shaders.nrd_refshader_name.restype = C.c_char_p
         _ref_shaders.nrd_refshader_name.argtypes = [C.c_int]
         _ref_shaders.nrd_refshader_set_threads.argtypes = [C.c_int]
+        if hasattr(_ref_shaders, "nrd_refshader_probe"):
+            _ref_shaders.nrd_refshader_probe.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+            _ref_shaders.nrd_refshader_probe.restype = None
     return _ref_shaders
+
+
+def ref_mirror_probe(reset: bool = False):
+    """(taps, taps that took the "mirrored" branch of REBLUR_Common_SpatialFilter.hlsli:198) counted by the reference shaders since the last reset."""
+    out = (C.c_uint64 * 2)()
+    ref_shaders().nrd_refshader_probe(out, 1 if reset else 0)
+    return int(out[0]), int(out[1])
 
 
 def ref_shader_names() -> List[str]:
