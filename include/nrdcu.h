@@ -161,7 +161,11 @@ NRDCU_API const char* nrdcuFrontEndGetLastError(void);
 NRDCU_API const char* nrdcuGetLastError(void);
 NRDCU_API uint64_t nrdcuGetLaunchCount(void);           /* kernels launched by this library since load (all contexts) */
 NRDCU_API uint64_t nrdcuGetPoolBytes(nrdcuContext* ctx); /* device bytes held by the pools (README memory table analogue) */
-/* NRDCU_FLAG_PROBE_MIRROR counters of the current device: out[0] = taps, out[1] = taps whose weight took the "mirrored" branch; reset != 0 clears them */
+/* The split NRDIntegration.h:266-277 reports: permanent pool ( history, survives the frame ), transient pool ( aliasable between denoisers and with the
+ * application's own per-frame memory ), plus what this executor keeps for itself ( REBLUR's geometry plane ). Any pointer may be NULL. */
+NRDCU_API uint32_t nrdcuGetMemoryUsage(nrdcuContext* ctx, uint64_t* persistentBytes, uint64_t* aliasableBytes, uint64_t* privateBytes);
+/* NRDCU_FLAG_PROBE_MIRROR counters of the current device, 14 values: out[0] = taps, out[1] = taps whose weight took the "mirrored" branch, then the same pair
+ * per ( pass, lobe ) at out[2 + 2 * slot], slot = pass * 2 + lobe ( pass 0 pre-pass / 1 blur / 2 post-blur; lobe 0 diffuse / 1 specular ); reset != 0 clears them */
 NRDCU_API uint32_t nrdcuGetMirrorProbe(uint64_t* out, int reset);
 
 #ifdef __cplusplus

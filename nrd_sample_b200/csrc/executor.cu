@@ -7,6 +7,7 @@
 #include <sys/syscall.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -24,6 +25,7 @@ namespace nrdk {
 // kernels/*.cu
 void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t stream);
 void launchReblurClassifyTiles(const ReblurConstants&, const ClassifyTilesParams&, Rows, cudaStream_t);
+void launchReblurGeometryPlane(const ReblurConstants&, const GeometryPlaneParams&, int row0, int row1, cudaStream_t);
 void launchReblurHitDistReconstruction(const ReblurConstants&, const HitDistReconstructionParams&, int signal, bool is5x5, Rows, cudaStream_t);
 void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int signal, int flags, Rows, cudaStream_t);
 void launchReblurSplitScreen(const ReblurConstants&, const SplitScreenParams&, int signal, Rows, cudaStream_t);
@@ -45,6 +47,17 @@ namespace {
 
 thread_local std::string g_lastError;
 std::atomic<uint64_t> g_launchCount{0};
+
+// The geometry plane of the frame being denoised ( kernels/reblur_spatial.cu: { normal, |viewZ| } decoded once per texel for the 48 spatial taps per
+// pixel ). nrdcuDenoiseRows points g_plane at its context's plane for the duration of the call; the context-less nrdcuDispatch builds a
+// stream-ordered temporary instead.
+struct GeomPlane {
+    nrdcuTexture tex = {};
+    const void *fromNormalRoughness = nullptr, *fromViewZ = nullptr;   // what it was decoded from ...
+    int row0 = 0, row1 = 0;                                             // ... and for which rows; row1 == 0: not decoded this frame
+    uint32_t margin = 64;                                               // rows beyond the strip the taps may reach ( strips only )
+};
+thread_local GeomPlane* g_plane = nullptr;
 
 uint32_t fail(Result r, const char* fmt, ...) {
     char buf[512];
@@ -189,6 +202,45 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         else single = b.take<TexR8>(Format::R8_UNORM);
     };
 
+    // the geometry plane for a spatial pass reading ( normalRoughness, viewZ ): decoded at most once per frame and row range
+    void* tempPlane = nullptr;
+    auto acquirePlane = [&](const TexNR& nr, const TexR32F& z, TexGeom& out) -> bool {
+        const int rectH = cb.rectSizeMinusOne[1] + 1;
+        const bool strip = rows.begin > 0 || rows.end < rectH;
+        const int margin = g_plane ? (int)g_plane->margin : 64;
+        const int r0 = strip ? std::max(rows.begin - margin, 0) : 0, r1 = strip ? std::min(rows.end + margin, rectH) : rectH;
+        nrdcuTexture t = {};
+        bool decode = true;
+        if (g_plane) {
+            if (!g_plane->tex.data) return false;
+            t = g_plane->tex;
+            decode = !(g_plane->fromNormalRoughness == nr.data && g_plane->fromViewZ == z.data && g_plane->row1 > g_plane->row0 && g_plane->row0 <= r0 && g_plane->row1 >= r1);
+            if (decode) {
+                g_plane->fromNormalRoughness = nr.data;
+                g_plane->fromViewZ = z.data;
+                g_plane->row0 = r0;
+                g_plane->row1 = r1;
+            }
+        } else {
+            const uint32_t pitch = ((uint32_t)nr.w * 16u + 255u) & ~255u;
+            if (cudaMallocAsync(&tempPlane, (size_t)pitch * nr.h, stream) != cudaSuccess) return false;
+            t = {tempPlane, (uint32_t)nr.w, (uint32_t)nr.h, pitch, (uint32_t)Format::RGBA32_SFLOAT};
+        }
+        out.data = (uint8_t*)t.data;
+        out.w = (int)t.width;
+        out.h = (int)t.height;
+        out.pitch = (int)(t.pitchBytes / 16u);
+        if (decode) {
+            GeometryPlaneParams gp = {nr, z, out};
+            launchReblurGeometryPlane(cb, gp, r0, r1, stream);
+            g_launchCount.fetch_add(1, std::memory_order_relaxed);
+        }
+        return true;
+    };
+    auto releasePlane = [&]() {
+        if (tempPlane) cudaFreeAsync(tempPlane, stream);
+    };
+
     if (id == "REBLUR_ClassifyTiles.cs.hlsl") {
         ClassifyTilesParams p = {};
         p.inViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
@@ -238,7 +290,9 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecSh = takeShS();
         uint32_t r = done(3 + 2 * lobes + (hasSpec ? 1 : 0) + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
+        if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
         launchReblurPrePass(cb, p, signal, kflags, rows, stream);
+        releasePlane();
     } else if (is("REBLUR_TemporalAccumulation.cs.hlsl")) {
         TemporalAccumulationParams p = {};
         p.tiles = takeTiles();
@@ -315,7 +369,9 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecSh = takeShS();
         uint32_t r = done(5 + 2 * lobes + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
+        if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
         launchReblurBlur(cb, p, signal, kflags, rows, stream);
+        releasePlane();
     } else if (is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1") || is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0")) {
         const bool ts = is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1");
         PostBlurParams p = {};
@@ -341,7 +397,9 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecSh = takeShS();
         uint32_t r = done(ts ? 5 + 2 * lobes + 2 * shLobes : 6 + 3 * lobes + 3 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
+        if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
         launchReblurPostBlur(cb, p, signal, ts, kflags, rows, stream);
+        releasePlane();
     } else if (is("REBLUR_TemporalStabilization.cs.hlsl")) {
         TemporalStabilizationParams p = {};
         p.tiles = takeTiles();
@@ -389,9 +447,9 @@ extern "C" {
 NRDCU_API const char* nrdcuGetLastError(void) { return g_lastError.c_str(); }
 NRDCU_API uint64_t nrdcuGetLaunchCount(void) { return g_launchCount.load(); }
 NRDCU_API uint32_t nrdcuGetMirrorProbe(uint64_t* out, int reset) {
-    unsigned long long v[2] = {0ull, 0ull};
+    unsigned long long v[14] = {};
     if (!nrdk::readMirrorProbe(v, reset != 0)) return fail(Result::FAILURE, "nrdcuGetMirrorProbe: %s", cudaGetErrorString(cudaGetLastError()));
-    if (out) { out[0] = v[0]; out[1] = v[1]; }
+    if (out) for (int i = 0; i < 14; i++) out[i] = v[i];
     return 0;
 }
 
@@ -470,6 +528,7 @@ struct nrdcuContext {
     uint16_t width = 0, height = 0;
     std::vector<nrdcuTexture> permanent, transient;
     std::vector<uint32_t> permanentDs, transientDs;   // TextureDesc::downsampleFactor of each pool texture
+    GeomPlane plane;                                  // REBLUR's per-frame geometry plane ( allocated when the instance holds a REBLUR denoiser )
     std::vector<DenoiserDesc> denoisers;              // ( identifier, denoiser ) pairs of the instance
     std::vector<uint8_t> checkerboard;                // per denoiser: its settings ask for half-width ( checkerboarded ) radiance inputs
     bool halfWidthInputs = false;
@@ -744,6 +803,12 @@ NRDCU_API uint32_t nrdcuCreate(const void* instanceCreationDesc, uint16_t resour
         nrdcuDestroy(ctx);
         return (uint32_t)Result::FAILURE;
     }
+    for (const DenoiserDesc& dn : ctx->denoisers)
+        if (dn.denoiser <= Denoiser::REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION && !ctx->plane.tex.data &&
+            !allocTexture(ctx, (uint32_t)Format::RGBA32_SFLOAT, resourceWidth, resourceHeight, ctx->plane.tex, true)) {
+            nrdcuDestroy(ctx);
+            return (uint32_t)Result::FAILURE;
+        }
     *out = ctx;
     return (uint32_t)Result::SUCCESS;
 }
@@ -774,6 +839,16 @@ NRDCU_API void nrdcuDestroy(nrdcuContext* ctx) {
 }
 
 NRDCU_API void* nrdcuGetInstance(nrdcuContext* ctx) { return ctx ? ctx->instance : nullptr; }
+NRDCU_API uint32_t nrdcuGetMemoryUsage(nrdcuContext* ctx, uint64_t* persistentBytes, uint64_t* aliasableBytes, uint64_t* privateBytes) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuGetMemoryUsage: null context");
+    uint64_t perm = 0, tran = 0;
+    for (const nrdcuTexture& t : ctx->permanent) perm += (uint64_t)t.pitchBytes * t.height;
+    for (const nrdcuTexture& t : ctx->transient) tran += (uint64_t)t.pitchBytes * t.height;
+    if (persistentBytes) *persistentBytes = perm;
+    if (aliasableBytes) *aliasableBytes = tran;
+    if (privateBytes) *privateBytes = ctx->poolBytes - perm - tran;   // the geometry plane: not part of the reference's pools
+    return 0;
+}
 NRDCU_API uint64_t nrdcuGetPoolBytes(nrdcuContext* ctx) { return ctx ? ctx->poolBytes : 0; }
 
 NRDCU_API uint32_t nrdcuSetCommonSettings(nrdcuContext* ctx, const void* commonSettings) {
@@ -831,6 +906,13 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
     Result r = GetComputeDispatches(*ctx->instance, identifiers, identifiersNum, dispatches, n);
     if (r != Result::SUCCESS) return fail(r, "nrd::GetComputeDispatches failed (%u)", (uint32_t)r);
     const InstanceDesc& d = *GetInstanceDesc(*ctx->instance);
+    // new frame, new G-buffer: the geometry plane is decoded again by the first spatial pass that needs it
+    ctx->plane.row0 = ctx->plane.row1 = 0;
+    ctx->plane.margin = ctx->tile.defaultHalo;
+    struct PlaneScope {
+        PlaneScope(GeomPlane* p) { g_plane = p; }
+        ~PlaneScope() { g_plane = nullptr; }
+    } planeScope(&ctx->plane);
     for (uint32_t i = 0; i < n; i++) {
         const DispatchDesc& dd = dispatches[i];
         ctx->scratch.resize(dd.resourcesNum);

@@ -141,6 +141,13 @@ struct TexNR : TexView {
     }
 };
 
+// Executor-private geometry plane ( RGBA32F ): { world-space normal as unpackNormalRoughness returns it, | viewZ * viewZScale | } per texel of the
+// current frame's IN_NORMAL_ROUGHNESS / IN_VIEWZ, written once per frame by reblurGeometryPlaneKernel and gathered by the spatial passes
+struct TexGeom : TexView {
+    NRD_DEV float4 fetch(int x, int y) const { return __ldg(ptr<float4>(x, y)); }
+    NRD_DEV void store(int x, int y, float4 v) const { if (inside(x, y)) *ptrw<float4>(x, y) = v; }
+};
+
 // The sky-tile mask ( 0 or 1 per 16x16 tile ). R8_UNORM everywhere except REBLUR_DIFFUSE_SPECULAR_SH, whose pool table hands the passes a
 // full-resolution RGBA16F texture under the TILES index ( Reblur_DiffuseSpecularSh.hpp:59-82: eleven textures for ten names ); graphics
 // hardware converts on access, here the view does: `texelBytes` = 1 or 8, the mask lives in .x ( readers only ask "!= 0" ).

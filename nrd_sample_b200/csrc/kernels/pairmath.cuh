@@ -35,6 +35,14 @@ NRD_DEV P2 operator-(float x, P2 y) { return fma2(y, -1.0f, x); }
 NRD_DEV P2 operator*(P2 x, float y) { return x * P2(y); }
 NRD_DEV P2 operator*(float x, P2 y) { return P2(x) * y; }
 
+// x * y rounded to fp32 and only THEN + z ( two roundings, as an IEEE engine without contraction does ). Neither the __fmul2_rn / __fadd2_rn intrinsics nor
+// explicit mul.rn.f32x2 / add.rn.f32x2 PTX keep the packed pair apart under -use_fast_math ( measured: one FFMA2 either way ); the scalar __fadd_rn is
+// documented never to fuse, so the addition is issued per lane.
+NRD_DEV P2 mulThenAdd2(P2 x, P2 y, float z) {
+    const P2 p = x * y;
+    return P2(__fadd_rn(p.v.x, z), __fadd_rn(p.v.y, z));
+}
+
 // scalar-per-lane steps, each written so that one instruction per lane suffices
 NRD_DEV float satOneMinus(float x) {  // saturate( 1 - x ) as ONE FADD.SAT (nvcc otherwise emits 1 - x and the saturate separately)
     float d;
@@ -43,8 +51,14 @@ NRD_DEV float satOneMinus(float x) {  // saturate( 1 - x ) as ONE FADD.SAT (nvcc
 }
 NRD_DEV P2 sat2(P2 x) { return P2(__saturatef(x.v.x), __saturatef(x.v.y)); }                    // FADD.SAT
 NRD_DEV P2 satOneMinus2(P2 x) { return P2(satOneMinus(x.v.x), satOneMinus(x.v.y)); }            // FADD.SAT 1, -x
-// saturate( 1 - |x| ) = 1 - min( |x|, 1 ): FMNMX takes the |.| modifier, the subtraction is packed
-NRD_DEV P2 oneMinusAbsSat2(P2 x) { return fma2(P2(fminf(fabsf(x.v.x), 1.0f), fminf(fabsf(x.v.y), 1.0f)), -1.0f, 1.0f); }
+// saturate( 1 - |x| ): ONE FADD.SAT per lane with the |.| and negate modifiers folded in ( 2 instructions per pair; 1 - min( |x|, 1 ) as two FMNMX and a
+// packed subtraction is 3 and gives the same bits )
+NRD_DEV float satOneMinusAbs(float x) {
+    float d;
+    asm("{\n\t.reg .f32 t;\n\tabs.f32 t, %1;\n\tsub.sat.ftz.f32 %0, 0f3F800000, t;\n\t}" : "=f"(d) : "f"(x));
+    return d;
+}
+NRD_DEV P2 oneMinusAbsSat2(P2 x) { return P2(satOneMinusAbs(x.v.x), satOneMinusAbs(x.v.y)); }
 NRD_DEV P2 absMul2(P2 x, float k) { return P2(fabsf(x.v.x) * k, fabsf(x.v.y) * k); }                                         // FMUL |x|, k
 NRD_DEV P2 mulSat2(P2 x, P2 y) { return P2(__saturatef(x.v.x * y.v.x), __saturatef(x.v.y * y.v.y)); }                        // FMUL.SAT
 NRD_DEV P2 abs2(P2 x) { return P2(fabsf(x.v.x), fabsf(x.v.y)); }

@@ -4,6 +4,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "pairmath.cuh"
 
 namespace nrdk {
 
@@ -184,6 +185,43 @@ struct HistoryFilter {
         }
         return sum < 0.0001f ? c * 0.0f : c / sum;
     }
+    // The same filter on an RGBA16F texture with Blackwell's packed fp32x2 pipe: a texel decodes into two register pairs ( .xy, .zw ) for free, so
+    // every lerp / weight / sum is one FFMA2-class instruction per pair — half the issue slots of the four-channel scalar form above.
+    struct Px { P2 lo, hi; };
+    static NRD_DEV Px px(const TexRGBA16F& tex, int x, int y) {
+        const uint2 raw = tex.fetchRaw(x, y);
+        return {P2(__half22float2(*reinterpret_cast<const __half2*>(&raw.x))), P2(__half22float2(*reinterpret_cast<const __half2*>(&raw.y)))};
+    }
+    static NRD_DEV Px lerpPx(Px a, Px b, float t) { return {fma2(b.lo - a.lo, t, a.lo), fma2(b.hi - a.hi, t, a.hi)}; }
+    NRD_DEV float4 color(const TexRGBA16F& tex) const {
+        const int x0 = tex.cx(ox), x1 = tex.cx(ox + 1), y0 = tex.cy(oy), y1 = tex.cy(oy + 1);
+        Px c;
+        if (bicubic) {
+            const int xm = tex.cx(ox - 1), x2 = tex.cx(ox + 2), ym = tex.cy(oy - 1), y2 = tex.cy(oy + 2);
+            Px t = lerpPx(px(tex, x0, ym), px(tex, x1, ym), tc.x);
+            c = {t.lo * w.x, t.hi * w.x};
+            t = lerpPx(px(tex, xm, y0), px(tex, xm, y1), tc.y);
+            c = {fma2(t.lo, w.y, c.lo), fma2(t.hi, w.y, c.hi)};
+            t = lerpPx(lerpPx(px(tex, x0, y0), px(tex, x1, y0), tc.x), lerpPx(px(tex, x0, y1), px(tex, x1, y1), tc.x), tc.y);
+            c = {fma2(t.lo, w.z, c.lo), fma2(t.hi, w.z, c.hi)};
+            t = lerpPx(px(tex, x2, y0), px(tex, x2, y1), tc.y);
+            c = {fma2(t.lo, w.w, c.lo), fma2(t.hi, w.w, c.hi)};
+            t = lerpPx(px(tex, x0, y2), px(tex, x1, y2), tc.x);
+            c = {fma2(t.lo, w4, c.lo), fma2(t.hi, w4, c.hi)};
+        } else {
+            Px t = px(tex, x0, y0);
+            c = {t.lo * w.x, t.hi * w.x};
+            t = px(tex, x1, y0);
+            c = {fma2(t.lo, w.y, c.lo), fma2(t.hi, w.y, c.hi)};
+            t = px(tex, x0, y1);
+            c = {fma2(t.lo, w.z, c.lo), fma2(t.hi, w.z, c.hi)};
+            t = px(tex, x1, y1);
+            c = {fma2(t.lo, w.w, c.lo), fma2(t.hi, w.w, c.hi)};
+        }
+        const float k = sum < 0.0001f ? 0.0f : 1.0f / sum;
+        c = {c.lo * k, c.hi * k};
+        return make_float4(c.lo.a(), c.lo.b(), c.hi.a(), c.hi.b());
+    }
     // _BilinearFilterWithCustomWeights_Color on a four-channel texture ( the SH history, REBLUR_Common.hlsli:351-371 )
     NRD_DEV float4 bilinear4(const TexRGBA16F& tex) const {
         float4 c = tex.load(ox, oy) * custom.x;
@@ -221,6 +259,11 @@ struct PrePassParams {
     TexTiles tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexRGBA16F outDiff, outSpec; TexR16F outSpecHitDistForTracking;
     TexRGBA16F inDiffSh, inSpecSh, outDiffSh, outSpecSh;  // NRD_MODE = SH only
+    TexGeom geom;                                          // not a shader binding: the executor's geometry plane of ( normalRoughness, viewZ )
+};
+// what the geometry plane is decoded from, and the rows it has to cover ( a strip plus the reach of its taps )
+struct GeometryPlaneParams {
+    TexNR normalRoughness; TexR32F viewZ; TexGeom out;
 };
 // `data1R8` / `data2R8` / `outData1R8` / `outData2R8`: the single-lobe formats of data1 / data2 (bound instead of the two-lobe view)
 struct BlurParams {
@@ -228,6 +271,7 @@ struct BlurParams {
     TexR32F outViewZ; TexRGBA16F outDiff, outSpec;
     TexR8 data1R8;
     TexRGBA16F inDiffSh, inSpecSh, outDiffSh, outSpecSh;  // NRD_MODE = SH only
+    TexGeom geom;
 };
 struct PostBlurParams {
     TexTiles tiles; TexNR normalRoughness; TexRG8 data1; TexR32F viewZ; TexRGBA16F inDiff, inSpec;
@@ -235,6 +279,7 @@ struct PostBlurParams {
     TexR16U outInternalData; TexRGBA16F outDiffCopy, outSpecCopy;  // only bound when TEMPORAL_STABILIZATION = 0
     TexR8 data1R8;
     TexRGBA16F inDiffSh, inSpecSh, outDiffSh, outSpecSh, outDiffShCopy, outSpecShCopy;  // NRD_MODE = SH only ( out*Sh = the SH history )
+    TexGeom geom;
 };
 struct TemporalAccumulationParams {
     TexTiles tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F mv; TexR32F prevViewZ; TexNR prevNormalRoughness; TexR16U prevInternalData;

@@ -88,9 +88,9 @@ struct ShIo { const TexRGBA16F *in, *out, *outCopy; };
 // PROBE ( NRDCU_FLAG_PROBE_MIRROR, tests only ): counts the taps and how many of them took the "mirrored" branch of the Gaussian weight
 // ( REBLUR_Common_SpatialFilter.hlsli:198 ) into g_mirrorProbe — the predicate is decided by the last mantissa bit of the tap position, so
 // parity with the reference is stated on its RATE ( tests/test_parity_at_baseline_sizes_gpu.py ). Compiled out of every other instantiation.
-__device__ unsigned long long g_mirrorProbe[2];
+__device__ unsigned long long g_mirrorProbe[6][2];   // [ pass * 2 + lobe ][ taps, mirrored ]
 template <int PASS, int LOBE, bool CB = false, bool SH = false, bool PROBE = false>
-NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const TexR32F& viewZTex, const TexNR& nrTex, const TexRGBA16F& input,
+NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const TexGeom& geom, const TexNR& nrTex, const TexRGBA16F& input,
                            const TexRGBA16F& output, const TexR16F* outSpecHitDistForTracking, const TexRGBA16F* outputCopy, bool temporalStabilization, bool robustMirrorTest,
                            const Resolve* resolve = nullptr, ShIo shIo = ShIo()) {
     static_assert(!CB || PASS == PRE_PASS, "only the pre-pass reads checkerboarded input");
@@ -196,6 +196,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
         const bool perspective = cb.orthoMode == 0.0f;
 
         float hitDistForTracking = hitDist == 0.0f ? NRD_INF : hitDist;
+        const float mirrorEps = robustMirrorTest ? 1e-6f : 0.0f;
         unsigned probeMirrored = 0u;
         P2 sum2(0.0f);
         P2 accX(0.0f), accY(0.0f), accZ(0.0f), accW(0.0f);
@@ -216,33 +217,37 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
                 P2 cx = fma2(oy, clipB.x, fma2(ox, clipA.x, P2(clipC.x)));
                 P2 cy = fma2(oy, clipB.y, fma2(ox, clipA.y, P2(clipC.y)));
                 P2 cw = fma2(oy, clipB.z, fma2(ox, clipA.z, P2(clipC.z)));
+                // Geometry::GetScreenUv ( ml.hlsli:659-672 ): clip.xy / clip.w * ( 0.5, -0.5 ) + 0.5. The product is ROUNDED before 0.5 is added, as in the
+                // reference: a tap at uv < 0.25 is then an exact sum with trailing zero mantissa bits, which is what the reference's mirror predicate
+                // ( uv != MirrorUv( uv ), decided by those bits ) sees. A fused multiply-add here took the "mirrored" branch 12 % more often than the
+                // reference's shaders at 1080p ( 0.42 against 0.31 in the specular lobes of blur / post-blur; tests/test_parity_at_baseline_sizes_gpu.py
+                // measures the rate of both engines per pass and lobe ).
                 P2 iw = rcp2(cw) * 0.5f;
-                ux = fma2(cx, iw, 0.5f);
-                uy = fma2(cy * -1.0f, iw, 0.5f);
+                ux = mulThenAdd2(cx, iw, 0.5f);
+                uy = mulThenAdd2(cy * -1.0f, iw, 0.5f);
             }
 
             // MirrorUv (Common.hlsli:312-318): 1 - | 1 - frac( uv / 2 ) * 2 |, capped below 1
             P2 hx = ux * 0.5f, hy = uy * 0.5f;
             P2 mx = min2(oneMinusAbsSat2(fma2(hx - floor2(hx), -2.0f, 1.0f)), 0.99999f);
             P2 my = min2(oneMinusAbsSat2(fma2(hy - floor2(hy), -2.0f, 1.0f)), 0.99999f);
-            // Reference predicate: any( uv != mirrorUv ). For in-screen taps mirrorUv = 1 - ( 1 - uv ) re-rounds uv, so the
-            // outcome hangs on the last mantissa bits of uv (DESIGN.md "chaotic predicates"); the robust variant (debug
-            // flag, used by the strict parity tests) asks the intended question: did the tap leave the screen?
-            bool mirA, mirB;
-            if (robustMirrorTest) {
-                mirA = ux.a() < 0.0f || uy.a() < 0.0f || ux.a() >= 1.0f || uy.a() >= 1.0f;
-                mirB = ux.b() < 0.0f || uy.b() < 0.0f || ux.b() >= 1.0f || uy.b() >= 1.0f;
-            } else {
-                mirA = ux.a() != mx.a() || uy.a() != my.a();
-                mirB = ux.b() != mx.b() || uy.b() != my.b();
-            }
+            // Reference predicate: any( uv != mirrorUv ). For in-screen taps mirrorUv = 1 - ( 1 - uv ) re-rounds uv, so the outcome hangs on the last
+            // mantissa bits of uv (DESIGN.md "chaotic predicates"); the robust variant (debug flag, used by the strict parity tests) asks the intended
+            // question — did mirroring MOVE the tap? — as | uv - mirrorUv | > 1e-6 ( re-rounding moves it by <= 2^-24 ). One code path for both:
+            // the threshold is 0 for the reference's predicate.
+            const P2 dux = ux - mx, duy = uy - my;
+            const bool mirA = fabsf(dux.a()) > mirrorEps || fabsf(duy.a()) > mirrorEps;
+            const bool mirB = fabsf(dux.b()) > mirrorEps || fabsf(duy.b()) > mirrorEps;
             P2 w(mirA ? 1.0f : kGaussOuter, mirB ? 1.0f : kGaussInner);
             if constexpr (PROBE) probeMirrored += (mirA ? 1u : 0u) + (mirB ? 1u : 0u);
 
-            // texel coordinates: mirrorUv() < 1 keeps every tap inside the rect, so fetches need no bounds checks
-            P2 fx = floor2(mx * rectSize.x), fy = floor2(my * rectSize.y);
-            int txa = (int)fx.a(), txb = (int)fx.b();
-            const int tya = (int)fy.a(), tyb = (int)fy.b();
+            // texel coordinates: mirrorUv() < 1 keeps every tap inside the rect, so fetches need no bounds checks. F2I.FLOOR gives the texel, the
+            // float copy the view ray needs comes back through I2FP ( ALU pipe ) instead of a second rounding on the quarter-rate XU pipe
+            const P2 sx = mx * rectSize.x, sy = my * rectSize.y;
+            int txa = __float2int_rd(sx.a()), txb = __float2int_rd(sx.b());
+            const int tya = __float2int_rd(sy.a()), tyb = __float2int_rd(sy.b());
+            P2 fx((float)txa, (float)txb);
+            const P2 fy((float)tya, (float)tyb);
             int ixa = txa, ixb = txb;  // x in the (possibly half-width) input
             if (CB) {
                 // Move to a pixel that was traced this frame: taps n = pair (even / odd) and n + 4 share the shift direction
@@ -262,8 +267,9 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
                 ixb = clampi(ixb, 0, input.w - 1);
             }
 
-            const float zRawA = viewZTex.fetch(txa, tya), zRawB = viewZTex.fetch(txb, tyb);
-            const uint32_t nrA = nrTex.fetchRaw(txa, tya), nrB = nrTex.fetchRaw(txb, tyb);
+            // One 128-bit fetch per tap from the geometry plane ( reblurGeometryPlaneKernel ): { world-space normal, |viewZ| } decoded ONCE per texel
+            // per frame instead of once per tap — 48 taps per pixel and frame read it back ( NRD.hlsli:387-400, 656-684; Common.hlsli:261 )
+            const float4 gA = geom.fetch(txa, tya), gB = geom.fetch(txb, tyb);
             uint2 rawA = input.fetchRaw(ixa, tya), rawB = input.fetchRaw(ixb, tyb);
             uint2 rawShA = make_uint2(0u, 0u), rawShB = make_uint2(0u, 0u);
             if constexpr (SH) {
@@ -271,28 +277,26 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
                 rawShB = shIo.in->fetchRaw(ixb, tyb);
             }
 
-            P2 zs = absMul2(P2(zRawA, zRawB), fabsf(cb.viewZScale));  // UnpackViewZ: | z * scale |
+            const P2 zs(gA.w, gB.w);
             P2 rx = fma2(fx, rayMulX, rayAddX), ry = fma2(fy, rayMulY, rayAddY);
             P2 sxy = perspective ? zs : P2(cb.orthoMode);
+            // dot( N, Ns ): scalar FFMAs straight from the two fetched quads into one register pair ( pairing x / y / z across the taps first would cost moves )
+            const P2 cosa(fmaf(gA.z, s.N.z, fmaf(gA.y, s.N.y, gA.x * s.N.x)), fmaf(gB.z, s.N.z, fmaf(gB.y, s.N.y, gB.x * s.N.x)));
 
-            // normal + roughness + material of both taps (NRD.hlsli:387-400, 656-684)
-            P2 px10((float)(nrA & 1023u), (float)(nrB & 1023u)), py10((float)((nrA >> 10) & 1023u), (float)((nrB >> 10) & 1023u));
-            P2 pz10((float)((nrA >> 20) & 1023u), (float)((nrB >> 20) & 1023u));
-            px10 = px10 * (1.0f / 1023.0f);
-            py10 = py10 * (1.0f / 1023.0f);
-            P2 t = fma2(pz10, 2.0f / 1023.0f, -1.0f);
-            P2 nx = px10 - py10, ny = (px10 + py10) + -1.0f;
-            // ( 1 - |nx| ) - |ny| with the sign of t: scalar FADDs so the |.| modifiers fold into the instructions
-            const float nzA = (1.0f - fabsf(nx.a())) - fabsf(ny.a()), nzB = (1.0f - fabsf(nx.b())) - fabsf(ny.b());
-            P2 nz(t.a() < 0.0f ? -nzA : nzA, t.b() < 0.0f ? -nzB : nzB);
-            P2 invLen = rsqrt2(fma2(nz, nz, fma2(ny, ny, fma2(nx, nx, 1e-9f))));
-            P2 cosa = fma2(nz, s.N.z, fma2(ny, s.N.y, nx * s.N.x)) * invLen;
-            P2 roughS = abs2(t);
+            // roughness ( specular lobe ) and material ID still come from the raw 10:10:10:2 texel: 3 instructions per tap, only where they are used
+            P2 roughS(0.0f);
             bool matchA = true, matchB = true;
-            if (!materialsAlwaysMatch) {
-                const uint32_t ka = nrA >> 30, kb = nrB >> 30;
-                matchA = ka == centerK || (float)max(ka, centerK) <= MIN_MATERIAL;
-                matchB = kb == centerK || (float)max(kb, centerK) <= MIN_MATERIAL;
+            if (LOBE == SPEC || !materialsAlwaysMatch) {
+                const uint32_t nrA = nrTex.fetchRaw(txa, tya), nrB = nrTex.fetchRaw(txb, tyb);
+                if (LOBE == SPEC) {
+                    const P2 pz10((float)((nrA >> 20) & 1023u), (float)((nrB >> 20) & 1023u));
+                    roughS = abs2(fma2(pz10, 2.0f / 1023.0f, -1.0f));
+                }
+                if (!materialsAlwaysMatch) {
+                    const uint32_t ka = nrA >> 30, kb = nrB >> 30;
+                    matchA = ka == centerK || (float)max(ka, centerK) <= MIN_MATERIAL;
+                    matchB = kb == centerK || (float)max(kb, centerK) <= MIN_MATERIAL;
+                }
             }
 
             // Math::AcosApproxPositive
@@ -352,8 +356,8 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             const unsigned active = __activemask();
             const unsigned mirrored = __reduce_add_sync(active, probeMirrored);
             if ((threadIdx.x & 31) == __ffs(active) - 1) {
-                atomicAdd(&g_mirrorProbe[0], 8ull * __popc(active));
-                atomicAdd(&g_mirrorProbe[1], (unsigned long long)mirrored);
+                atomicAdd(&g_mirrorProbe[PASS * 2 + LOBE][0], 8ull * __popc(active));
+                atomicAdd(&g_mirrorProbe[PASS * 2 + LOBE][1], (unsigned long long)mirrored);
             }
         }
         sum += sum2.a() + sum2.b();
@@ -403,6 +407,15 @@ __global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_co
     if (threadIdx.x == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
 }
 
+// Decodes IN_NORMAL_ROUGHNESS + IN_VIEWZ into the geometry plane, one thread per texel. Same arithmetic as the centre set-up of the passes
+// ( unpackNormalRoughness, |viewZ * scale| ), so a tap that lands on the centre texel sees the centre's own normal.
+__global__ void __launch_bounds__(256) reblurGeometryPlaneKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ GeometryPlaneParams p, int row0, int row1) {
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (px > cb.rectSizeMinusOne[0] || py >= row1) return;
+    const float4 nr = unpackNormalRoughness(p.normalRoughness.fetchRaw(px, py));
+    p.out.store(px, py, make_float4(nr.x, nr.y, nr.z, fabsf(p.viewZ.fetch(px, py)) * fabsf(cb.viewZScale)));
+}
+
 template <bool CB, int SIGNAL, bool SH, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags, int ctaY0) {
     const bool robust = (flags & 2) != 0;
@@ -429,8 +442,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPr
         r.x0 = x0 >> 1;
         r.x1 = x1 >> 1;
     }
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<PRE_PASS, DIFF, CB, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<PRE_PASS, SPEC, CB, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<PRE_PASS, DIFF, CB, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<PRE_PASS, SPEC, CB, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
 }
 
 // Non-linear accumulation speed with the quad-neighbour smoothing of REBLUR_Blur.cs.hlsl:40-59 (lanes x^1, x^2 of the row)
@@ -466,8 +479,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBl
     if (skyTile || !inDenoisingRange(cb, s.viewZ) || s.px > cb.rectSizeMinusOne[0] || s.py > cb.rectSizeMinusOne[1]) return;
 
     setupCenter(cb, s, p.normalRoughness, cb.rotator);
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<BLUR, DIFF, false, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<BLUR, SPEC, false, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<BLUR, DIFF, false, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<BLUR, SPEC, false, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
 }
 
 template <bool TEMPORAL_STABILIZATION, int SIGNAL, bool SH, bool PROBE = false>
@@ -489,8 +502,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPo
     p.outNormalRoughness.storeRaw(s.px, s.py, p.normalRoughness.loadRaw(s.px, s.py));
     if (!TEMPORAL_STABILIZATION) p.outInternalData.store(s.px, s.py, packInternalData(cb, s.data1.x, s.data1.y, s.materialID));
 
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<POST_BLUR, DIFF, false, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, &p.outDiffShCopy});
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<POST_BLUR, SPEC, false, SH, PROBE>(cb, s, p.viewZ, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, &p.outSpecShCopy});
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<POST_BLUR, DIFF, false, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, &p.outDiffShCopy});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<POST_BLUR, SPEC, false, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, &p.outSpecShCopy});
 }
 
 // REBLUR_SplitScreen.cs.hlsl:21-56: the noisy input (range-masked) left of CommonSettings::splitScreen
@@ -506,10 +519,20 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurSplitScreenKernel(cons
     if ((signal & SIGNAL_SPEC) && p.inSpecSh.data) p.outSpecSh.store(px, py, p.inSpecSh.load(px >> (cb.specCheckerboard != 2u ? 1 : 0), py) * inRange);
 }
 
-// Reads ( and optionally clears ) g_mirrorProbe: out[0] = taps, out[1] = taps that took the "mirrored" branch
+// Reads ( and optionally clears ) g_mirrorProbe: out[0] = taps, out[1] = taps that took the "mirrored" branch, then the same pair per ( pass, lobe )
+// slot at out[2 + 2 * slot] ( 14 values; slot = pass * 2 + lobe, pass 0 pre-pass / 1 blur / 2 post-blur, lobe 0 diffuse / 1 specular )
 bool readMirrorProbe(unsigned long long* out, bool reset) {
-    unsigned long long zero[2] = {0ull, 0ull};
-    if (out && cudaMemcpyFromSymbol(out, g_mirrorProbe, sizeof(zero)) != cudaSuccess) return false;
+    unsigned long long v[6][2], zero[6][2] = {};
+    if (cudaMemcpyFromSymbol(v, g_mirrorProbe, sizeof(v)) != cudaSuccess) return false;
+    if (out) {
+        out[0] = out[1] = 0ull;
+        for (int k = 0; k < 6; k++) {
+            out[0] += v[k][0];
+            out[1] += v[k][1];
+            out[2 + 2 * k] = v[k][0];
+            out[3 + 2 * k] = v[k][1];
+        }
+    }
     return !reset || cudaMemcpyToSymbol(g_mirrorProbe, zero, sizeof(zero)) == cudaSuccess;
 }
 
@@ -520,6 +543,13 @@ void launchReblurClassifyTiles(const ReblurConstants& cb, const ClassifyTilesPar
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, 16);
     if (!g.count) return;
     reblurClassifyTilesKernel<<<dim3((cb.rectSizeMinusOne[0] + 16) / 16, g.count), 256, 0, stream>>>(cb, p, g.ctaY0);
+}
+// rows [ row0, row1 ) of the plane ( clamped to the rect )
+void launchReblurGeometryPlane(const ReblurConstants& cb, const GeometryPlaneParams& p, int row0, int row1, cudaStream_t stream) {
+    row0 = row0 < 0 ? 0 : row0;
+    row1 = row1 > cb.rectSizeMinusOne[1] + 1 ? cb.rectSizeMinusOne[1] + 1 : row1;
+    if (row1 <= row0) return;
+    reblurGeometryPlaneKernel<<<dim3((cb.rectSizeMinusOne[0] + 32) / 32, (row1 - row0 + 7) / 8), 256, 0, stream>>>(cb, p, row0, row1);
 }
 void launchReblurSplitScreen(const ReblurConstants& cb, const SplitScreenParams& p, int signal, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);

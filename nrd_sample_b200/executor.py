@@ -29,7 +29,7 @@ NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdc
                  "nrdcuTileSetHalo", "nrdcuTileGetStatus", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
                  "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuDenoiseHostPipelined", "nrdcuHostFlush", "nrdcuGetLastError", "nrdcuGetLaunchCount",
                  "nrdcuHostFrameCreate", "nrdcuHostFrameGetTexture", "nrdcuHostFrameGetInfo", "nrdcuHostFrameDestroy", "nrdcuDenoiseHostFrames",
-                 "nrdcuGetPoolBytes", "nrdcuGetMirrorProbe", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile",
+                 "nrdcuGetPoolBytes", "nrdcuGetMemoryUsage", "nrdcuGetMirrorProbe", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile",
                  "nrdcuFrontEndPackNormalRoughness", "nrdcuFrontEndPackRadianceHitDist", "nrdcuBackEndUnpackRadiance", "nrdcuFrontEndProbe", "nrdcuFrontEndGetLastError")
 
 # nrd::Format -> (torch dtype, channels) for tensors handed to / returned by the executor
@@ -143,9 +143,16 @@ def launch_count() -> int:
 
 def mirror_probe(reset: bool = False):
     """(taps, taps that took the "mirrored" weight branch) counted by the spatial passes of contexts created with FLAG_PROBE_MIRROR."""
-    out = (C.c_uint64 * 2)()
+    out = (C.c_uint64 * 14)()
     _check(load().nrdcuGetMirrorProbe(out, 1 if reset else 0), "nrdcuGetMirrorProbe")
     return int(out[0]), int(out[1])
+
+
+def mirror_probe_detail():
+    """{(pass, lobe): (taps, mirrored)} of the same counters; pass in ("Pre-pass", "Blur", "Post-blur"), lobe in ("diff", "spec")."""
+    out = (C.c_uint64 * 14)()
+    _check(load().nrdcuGetMirrorProbe(out, 0), "nrdcuGetMirrorProbe")
+    return {(p, l): (int(out[2 + 2 * (i * 2 + j)]), int(out[3 + 2 * (i * 2 + j)])) for i, p in enumerate(("Pre-pass", "Blur", "Post-blur")) for j, l in enumerate(("diff", "spec"))}
 
 
 def texture_of(t: torch.Tensor, fmt: int) -> CuTexture:

@@ -164,7 +164,8 @@ static void spatialFilter(const ReblurCtx& c, const SpatialCommon& s, const Tex&
             float2 mirrorUv = MirrorUv(uv);
             // any( uv != mirrorUv ) is bit-fragile for in-screen taps ( 1 - ( 1 - uv ) re-rounds uv ); flag bit1 of
             // nrd_oracle_dispatch swaps in the intended "tap left the screen" test for the strict parity runs
-            bool mirrored = robustMirrorTest ? (uv.x < 0.0f || uv.y < 0.0f || uv.x >= 1.0f || uv.y >= 1.0f) : (uv.x != mirrorUv.x || uv.y != mirrorUv.y);
+            // ( "did mirroring MOVE the tap?": re-rounding moves an in-screen tap by <= 2^-24, leaving the screen by twice the overshoot )
+            bool mirrored = robustMirrorTest ? (fabsf(uv.x - mirrorUv.x) > 1e-6f || fabsf(uv.y - mirrorUv.y) > 1e-6f) : (uv.x != mirrorUv.x || uv.y != mirrorUv.y);
             float w = mirrored ? 1.0f : GetGaussianWeight(offset.z);
 
             float2 posf = mirrorUv * cb.gRectSize;

@@ -455,6 +455,7 @@ struct Fiber {
     uint3 groupThreadID; uint groupIndex = 0;
     uint8_t xchg[64]; uint32_t xchgSeq = 0;
     uint rngHashState = 0; uint2 rngTeaState;
+    uint32_t probeCalls = 0;   // probeMirror calls of this thread so far: taps 0-7 are the first lobe's, 8-15 the second's
 };
 struct GroupRun {
     std::vector<Fiber> fibers; ucontext_t sched; int current = -1; bool useFibers = false;

@@ -12,11 +12,17 @@ namespace hlsl {
 static std::map<std::string, ShaderEntry>& registry() { static std::map<std::string, ShaderEntry> r; return r; }
 void registerShader(const ShaderEntry& e) { registry()[e.identifier] = e; }
 
-// probeMirror: [0] taps seen, [1] taps that took the "mirrored" branch; per OS thread, folded by nrd_refshader_probe
-static constexpr int kMaxProbeThreads = 512;
-static uint64_t g_probe[kMaxProbeThreads][8];
+// probeMirror: per OS thread, per ( spatial pass, lobe ): [0] taps seen, [1] taps that took the "mirrored" branch; folded by nrd_refshader_probe
+static constexpr int kMaxProbeThreads = 512, kProbeSlots = 6;   // slot = pass * 2 + lobe, pass 0 pre-pass / 1 blur / 2 post-blur
+static uint64_t g_probe[kMaxProbeThreads][kProbeSlots][2];
+static int g_probePass = 0;          // set per dispatch from the shader identifier
+static bool g_probeTwoLobes = true;  // NRD_SIGNAL=BOTH: the first 8 taps of a thread are the diffuse lobe's
+static bool g_probeSpecOnly = false;
 bool probeMirror(bool mirrored) {
-    uint64_t* c = g_probe[omp_get_thread_num() % kMaxProbeThreads];
+    Fiber& f = currentFiber();
+    const int lobe = g_probeTwoLobes ? (int)((f.probeCalls >> 3) & 1u) : (g_probeSpecOnly ? 1 : 0);
+    f.probeCalls++;
+    uint64_t* c = g_probe[omp_get_thread_num() % kMaxProbeThreads][g_probePass * 2 + lobe];
     c[0]++;
     c[1] += mirrored ? 1u : 0u;
     return mirrored;
@@ -45,6 +51,7 @@ void runGroup(const ShaderModule& module, void (*entry)(uint3, uint3, uint3, uin
         g.current = 0;
         for (uint z = 0; z < groupSize.z; z++) for (uint y = 0; y < groupSize.y; y++) for (uint x = 0; x < groupSize.x; x++) {
             uint3 t(x, y, z);
+            g.fibers[0].probeCalls = 0;
             entry(t, groupID, uint3(groupID * groupSize + t), (z * groupSize.y + y) * groupSize.x + x);
         }
         return;
@@ -59,7 +66,7 @@ void runGroup(const ShaderModule& module, void (*entry)(uint3, uint3, uint3, uin
         getcontext(&f.ctx);
         f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = kStackBytes; f.ctx.uc_link = &g.sched;
         makecontext(&f.ctx, fiberMain, 0);
-        f.state = 0; f.xchgSeq = 0; f.groupIndex = (uint)i;
+        f.state = 0; f.xchgSeq = 0; f.probeCalls = 0; f.groupIndex = (uint)i;
         f.groupThreadID = uint3((uint)i % groupSize.x, ((uint)i / groupSize.x) % groupSize.y, (uint)i / (groupSize.x * groupSize.y));
     }
     for (;;) {
@@ -92,6 +99,10 @@ __attribute__((visibility("default"))) int nrd_refshader_dispatch(const char* sh
         t->data = (uint8_t*)textures[i].data; t->w = (int)textures[i].width; t->h = (int)textures[i].height; t->pitch = (int)textures[i].pitchBytes; t->fmt = textures[i].format;
     }
     if (!m.constants.empty() && constantsSize && !loadConstants(m, constants, constantsSize)) { fprintf(stderr, "refshader %s: constant buffer of %u bytes does not match the declared layout\n", e.identifier, constantsSize); return 2; }
+    const std::string ident = shaderIdentifier;
+    g_probePass = ident.find("REBLUR_PostBlur") == 0 ? 2 : (ident.find("REBLUR_Blur") == 0 ? 1 : 0);
+    g_probeTwoLobes = ident.find("NRD_SIGNAL=BOTH") != std::string::npos;
+    g_probeSpecOnly = ident.find("NRD_SIGNAL=SPEC") != std::string::npos;
     const uint3 gs(e.gx, e.gy, e.gz);
     const long groups = (long)gridW * (long)gridH;
 #pragma omp parallel for schedule(dynamic, 1)
@@ -100,11 +111,17 @@ __attribute__((visibility("default"))) int nrd_refshader_dispatch(const char* sh
 }
 __attribute__((visibility("default"))) int nrd_refshader_count() { return (int)registry().size(); }
 __attribute__((visibility("default"))) const char* nrd_refshader_name(int i) { for (auto& kv : registry()) if (i-- == 0) return kv.second.identifier; return nullptr; }
-// out[0] = taps whose mirror predicate was evaluated since the last reset, out[1] = how many of them were "mirrored"
+// out[0] = taps whose mirror predicate was evaluated since the last reset, out[1] = how many of them were "mirrored"; then the same pair per
+// ( pass, lobe ) slot: out[2 + 2 * slot], out[3 + 2 * slot], slot = pass * 2 + lobe ( 14 values in all )
 __attribute__((visibility("default"))) void nrd_refshader_probe(uint64_t* out, int reset) {
-    uint64_t a = 0, b = 0;
-    for (int i = 0; i < kMaxProbeThreads; i++) { a += g_probe[i][0]; b += g_probe[i][1]; if (reset) g_probe[i][0] = g_probe[i][1] = 0; }
-    if (out) { out[0] = a; out[1] = b; }
+    uint64_t v[2 + 2 * kProbeSlots] = {};
+    for (int i = 0; i < kMaxProbeThreads; i++)
+        for (int k = 0; k < kProbeSlots; k++) {
+            v[0] += g_probe[i][k][0]; v[1] += g_probe[i][k][1];
+            v[2 + 2 * k] += g_probe[i][k][0]; v[3 + 2 * k] += g_probe[i][k][1];
+            if (reset) g_probe[i][k][0] = g_probe[i][k][1] = 0;
+        }
+    if (out) memcpy(out, v, sizeof(v));
 }
 __attribute__((visibility("default"))) void nrd_refshader_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
 }

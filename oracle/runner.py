@@ -85,9 +85,16 @@ def ref_shaders() -> Optional[C.CDLL]:
 
 def ref_mirror_probe(reset: bool = False):
     """(taps, taps that took the "mirrored" branch of REBLUR_Common_SpatialFilter.hlsli:198) counted by the reference shaders since the last reset."""
-    out = (C.c_uint64 * 2)()
+    out = (C.c_uint64 * 14)()
     ref_shaders().nrd_refshader_probe(out, 1 if reset else 0)
     return int(out[0]), int(out[1])
+
+
+def ref_mirror_probe_detail():
+    """{(pass, lobe): (taps, mirrored)} of the same counters ( see executor.mirror_probe_detail )."""
+    out = (C.c_uint64 * 14)()
+    ref_shaders().nrd_refshader_probe(out, 0)
+    return {(p, l): (int(out[2 + 2 * (i * 2 + j)]), int(out[3 + 2 * (i * 2 + j)])) for i, p in enumerate(("Pre-pass", "Blur", "Post-blur")) for j, l in enumerate(("diff", "spec"))}
 
 
 def ref_shader_names() -> List[str]:

@@ -4,6 +4,8 @@ import ctypes as C
 import os
 import re
 
+import pytest
+
 from nrd_sample_b200 import executor, nrd_api as api
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -73,3 +75,39 @@ def test_executor_fails_loudly_without_gpu(product_lib):
         assert "no CUDA device" in str(e)
     else:
         raise AssertionError("nrdcuCreate must fail without a CUDA device (no CPU fallback)")
+
+
+def _build_integration_twin(tmp_path):
+    """g++ the NRDSample-shaped call sequence of tests/integration_twin_main.cpp against include/NRDIntegrationCuda.h and the product library."""
+    import subprocess
+    from nrd_sample_b200 import build
+    lib = build.build()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "integration_twin")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(root, "tests", "integration_twin_main.cpp"), "-o", exe, lib, "-L", os.path.join(cuda, "lib64"), "-lcudart", f"-Wl,-rpath,{os.path.dirname(lib)}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_integration_twin_compiles_and_fails_loudly_without_a_device(tmp_path):
+    """include/NRDIntegrationCuda.h mirrors nrd::Integration ( NRDIntegration.h:211-277: Recreate / NewFrame / SetCommonSettings / SetDenoiserSettings /
+    Denoise / Destroy + the memory getters ). It must compile warning-free as plain C++17, and with no CUDA device Recreate reports FAILURE — no CPU path."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the gpu-marked twin test covers this box")
+    exe = _build_integration_twin(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "no CUDA device" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_integration_twin_denoises_on_the_device(tmp_path):
+    import subprocess
+    exe = _build_integration_twin(tmp_path)
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0 and "denoised 2 frames" in r.stdout, r.stdout + r.stderr
+    assert "persistent" in r.stdout
