@@ -46,6 +46,8 @@ enum {
     NRDCU_FLAG_CUDA_GRAPH = 1u << 1,      /* reserved, ignored: every pass takes new constants each frame, so a replayed graph would need all of its
                                              kernel nodes patched per frame — no gain over 7-10 launches while the chains are GPU-bound */
     NRDCU_FLAG_ROBUST_MIRROR_TEST = 1u << 2, /* DEBUG: spatial taps use "left the screen" instead of the reference's bit-fragile any(uv != MirrorUv(uv)) */
+    NRDCU_FLAG_NO_SEAM_OVERLAP = 1u << 4,    /* strips over peer memory: do NOT split each pass into "seam rows first, interior second" ( the push of the seam rows then
+                                                follows the whole pass instead of overlapping its interior ); for A/B timing */
     NRDCU_FLAG_PROBE_MIRROR = 1u << 3,       /* DEBUG: the REBLUR_DIFFUSE_SPECULAR spatial passes count their taps and how many took the "mirrored" branch
                                                 of REBLUR_Common_SpatialFilter.hlsli:198 ( read with nrdcuGetMirrorProbe ) */
 };

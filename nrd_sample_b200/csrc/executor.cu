@@ -54,8 +54,10 @@ std::atomic<uint64_t> g_launchCount{0};
 struct GeomPlane {
     nrdcuTexture tex = {};
     const void *fromNormalRoughness = nullptr, *fromViewZ = nullptr;   // what it was decoded from ...
+    const void* viewZCopy = nullptr;                                    // ... and the copy of that viewZ the blur pass wrote ( PREV_VIEWZ: what post-blur binds )
     int row0 = 0, row1 = 0;                                             // ... and for which rows; row1 == 0: not decoded this frame
     uint32_t margin = 64;                                               // rows beyond the strip the taps may reach ( strips only )
+    int stripRow0 = 0, stripRow1 = 0x7FFFFFFF;                          // the strip this context computes ( a pass may arrive as several row ranges of it )
 };
 thread_local GeomPlane* g_plane = nullptr;
 
@@ -206,18 +208,21 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
     void* tempPlane = nullptr;
     auto acquirePlane = [&](const TexNR& nr, const TexR32F& z, TexGeom& out) -> bool {
         const int rectH = cb.rectSizeMinusOne[1] + 1;
-        const bool strip = rows.begin > 0 || rows.end < rectH;
+        const int begin = g_plane ? std::min(rows.begin, g_plane->stripRow0) : rows.begin, end = g_plane ? std::max(std::min(rows.end, rectH), std::min(g_plane->stripRow1, rectH)) : rows.end;
+        const bool strip = begin > 0 || end < rectH;
         const int margin = g_plane ? (int)g_plane->margin : 64;
-        const int r0 = strip ? std::max(rows.begin - margin, 0) : 0, r1 = strip ? std::min(rows.end + margin, rectH) : rectH;
+        const int r0 = strip ? std::max(begin - margin, 0) : 0, r1 = strip ? std::min(end + margin, rectH) : rectH;
         nrdcuTexture t = {};
         bool decode = true;
         if (g_plane) {
             if (!g_plane->tex.data) return false;
             t = g_plane->tex;
-            decode = !(g_plane->fromNormalRoughness == nr.data && g_plane->fromViewZ == z.data && g_plane->row1 > g_plane->row0 && g_plane->row0 <= r0 && g_plane->row1 >= r1);
+            const bool sameZ = g_plane->fromViewZ == z.data || (g_plane->viewZCopy && g_plane->viewZCopy == z.data);
+            decode = !(g_plane->fromNormalRoughness == nr.data && sameZ && g_plane->row1 > g_plane->row0 && g_plane->row0 <= r0 && g_plane->row1 >= r1);
             if (decode) {
                 g_plane->fromNormalRoughness = nr.data;
                 g_plane->fromViewZ = z.data;
+                g_plane->viewZCopy = nullptr;
                 g_plane->row0 = r0;
                 g_plane->row1 = r1;
             }
@@ -372,6 +377,8 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
         launchReblurBlur(cb, p, signal, kflags, rows, stream);
         releasePlane();
+        // the blur pass copies viewZ ( sky included ) into PREV_VIEWZ, which is what post-blur binds as its viewZ: same texels, same plane
+        if (g_plane && g_plane->fromViewZ == p.viewZ.data) g_plane->viewZCopy = p.outViewZ.data;
     } else if (is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1") || is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0")) {
         const bool ts = is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1");
         PostBlurParams p = {};
@@ -560,6 +567,9 @@ struct nrdcuContext {
         uint32_t* peerFlags[2] = {nullptr, nullptr};
         uint32_t* hostError = nullptr;        // pinned, mapped: set by the wait kernel on timeout
         uint32_t seq = 0, defaultHalo = 64;
+        cudaStream_t seamStream = nullptr;    // seam rows first: their push overlaps the interior of the same pass
+        cudaEvent_t seamsDone = nullptr, pushed = nullptr;
+        bool overlap = true;
         std::vector<HaloRule> rules;
         uint64_t bytesPushed = 0;
     } tile;
@@ -600,7 +610,26 @@ bool allocTexture(nrdcuContext* ctx, uint32_t fmt, uint32_t w, uint32_t h, nrdcu
 // Seam traffic of one dispatch in peer mode: rows of every written texture that the neighbours' later passes reach into go straight
 // into the neighbours' copies, then flag + wait (kernels/peer_halo.cu). Every dispatch signals and waits, with or without rows to
 // push: that keeps neighbouring strips within one pass of each other, which is what makes writing into their aprons safe.
-uint32_t pushHalos(nrdcuContext* ctx, const DispatchDesc& dd, uint32_t rowBegin, uint32_t rowEnd, cudaStream_t stream) {
+// rows of apron the written textures of `dd` need on the neighbours ( the largest over its storage bindings; 0 for clears )
+uint32_t maxHaloRows(const nrdcuContext* ctx, const DispatchDesc& dd) {
+    const nrdcuContext::Tile& t = ctx->tile;
+    if (!strncmp(dd.name, "Clear", 5)) return 0;
+    const char* dash = strstr(dd.name, " - ");
+    const char* passName = dash ? dash + 3 : dd.name;
+    uint32_t most = 0;
+    for (uint32_t k = 0; k < dd.resourcesNum; k++) {
+        if (dd.resources[k].descriptorType != DescriptorType::STORAGE_TEXTURE) continue;
+        uint32_t halo = t.defaultHalo;
+        for (const auto& r : t.rules)
+            if (r.binding == k && r.pass == passName) halo = r.rows < t.defaultHalo ? r.rows : t.defaultHalo;
+        most = std::max(most, halo);
+    }
+    return most;
+}
+
+// `pushStream`: where the seam rows are stored into the neighbours and the flag is raised ( the launch stream, or the context's seam stream when the
+// pass was split into seam rows first / interior second ); the wait for the neighbours' flags always goes onto the launch stream
+uint32_t pushHalos(nrdcuContext* ctx, const DispatchDesc& dd, uint32_t rowBegin, uint32_t rowEnd, cudaStream_t stream, cudaStream_t pushStream) {
     nrdcuContext::Tile& t = ctx->tile;
     const uint32_t fullH = ctx->height;
     const uint32_t y0 = rowBegin, y1 = rowEnd < fullH ? rowEnd : fullH;
@@ -637,8 +666,12 @@ uint32_t pushHalos(nrdcuContext* ctx, const DispatchDesc& dd, uint32_t rowBegin,
         }
     }
     t.seq++;
-    nrdk::launchHaloPush(segs, stream);
-    nrdk::launchHaloSignal(t.peerFlags[0] ? t.peerFlags[0] + 1 : nullptr, t.peerFlags[1] ? t.peerFlags[1] + 0 : nullptr, t.seq, stream);
+    nrdk::launchHaloPush(segs, pushStream);
+    nrdk::launchHaloSignal(t.peerFlags[0] ? t.peerFlags[0] + 1 : nullptr, t.peerFlags[1] ? t.peerFlags[1] + 0 : nullptr, t.seq, pushStream);
+    if (pushStream != stream) {   // the next pass may overwrite what is being pushed ( TEMP1 / TEMP2 alternate ): it starts after the push has left
+        cudaEventRecord(t.pushed, pushStream);
+        cudaStreamWaitEvent(stream, t.pushed, 0);
+    }
     nrdk::launchHaloWait(t.flags, t.seq, t.peerFlags[0] != nullptr, t.peerFlags[1] != nullptr, t.hostError, stream);
     if (!checkLaunch("halo push")) return (uint32_t)Result::FAILURE;
     return 0;
@@ -746,6 +779,15 @@ NRDCU_API uint32_t nrdcuTileAttach(nrdcuContext* ctx, const void* blobAbove, con
                 t.peerFlags[d] = (uint32_t*)mapped;
         }
     }
+    if (!t.seamStream) {
+        // highest priority: the block scheduler hands freed SM slots to the push kernel first, so the seam rows leave while the interior still runs
+        int leastPriority = 0, greatestPriority = 0;
+        cudaDeviceGetStreamPriorityRange(&leastPriority, &greatestPriority);
+        cudaStreamCreateWithPriority(&t.seamStream, cudaStreamNonBlocking, greatestPriority);
+        cudaEventCreateWithFlags(&t.seamsDone, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&t.pushed, cudaEventDisableTiming);
+    }
+    t.overlap = !(ctx->flags & NRDCU_FLAG_NO_SEAM_OVERLAP);
     t.attached = true;
     return 0;
 }
@@ -823,6 +865,11 @@ NRDCU_API void nrdcuDestroy(nrdcuContext* ctx) {
         if (ctx->tile.peerFlags[d]) cudaIpcCloseMemHandle(ctx->tile.peerFlags[d]);
     }
     if (ctx->tile.hostError) cudaFreeHost(ctx->tile.hostError);
+    if (ctx->tile.seamStream) {
+        cudaStreamDestroy(ctx->tile.seamStream);
+        cudaEventDestroy(ctx->tile.seamsDone);
+        cudaEventDestroy(ctx->tile.pushed);
+    }
     if (ctx->pipe.h2d) {
         cudaStreamDestroy(ctx->pipe.h2d);
         cudaStreamDestroy(ctx->pipe.d2h);
@@ -908,7 +955,10 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
     const InstanceDesc& d = *GetInstanceDesc(*ctx->instance);
     // new frame, new G-buffer: the geometry plane is decoded again by the first spatial pass that needs it
     ctx->plane.row0 = ctx->plane.row1 = 0;
+    ctx->plane.viewZCopy = nullptr;
     ctx->plane.margin = ctx->tile.defaultHalo;
+    ctx->plane.stripRow0 = (int)rowBegin;
+    ctx->plane.stripRow1 = rowEnd > 0x7FFFFFFFu ? 0x7FFFFFFF : (int)rowEnd;
     struct PlaneScope {
         PlaneScope(GeomPlane* p) { g_plane = p; }
         ~PlaneScope() { g_plane = nullptr; }
@@ -946,15 +996,35 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
             evStop = grab();
             cudaEventRecord(evStart, (cudaStream_t)stream);
         }
-        uint32_t rc = nrdcuDispatchRows(d.pipelines[dd.pipelineIndex].shaderIdentifier, dd.constantBufferData, dd.constantBufferDataSize, ctx->scratch.data(),
-                                        dd.resourcesNum, ctx->flags, stream, rowBegin, rowEnd);
+        const char* shader = d.pipelines[dd.pipelineIndex].shaderIdentifier;
+        auto run = [&](uint32_t r0, uint32_t r1) {
+            return r1 > r0 ? nrdcuDispatchRows(shader, dd.constantBufferData, dd.constantBufferDataSize, ctx->scratch.data(), dd.resourcesNum, ctx->flags, stream, r0, r1) : 0u;
+        };
+        // Strips over peer memory: the rows the neighbours need are computed FIRST, their push ( own stream ) then overlaps the interior of the same pass
+        const uint32_t stripEnd = std::min<uint32_t>(rowEnd, ctx->height);
+        uint32_t edge = ctx->tile.attached && ctx->tile.overlap ? (maxHaloRows(ctx, dd) + 15u) & ~15u : 0u;
+        if (edge && stripEnd - rowBegin < 2u * edge + 32u) edge = 0;   // strip too short to have an interior worth a second launch
+        uint32_t rc = 0;
+        if (edge) {
+            const uint32_t topEnd = ctx->tile.peerFlags[0] ? rowBegin + edge : rowBegin;
+            const uint32_t bottomBegin = ctx->tile.peerFlags[1] ? ((stripEnd - edge) & ~15u) : stripEnd;
+            rc = run(rowBegin, topEnd);
+            if (!rc) rc = run(bottomBegin, rowEnd);
+            if (!rc) {
+                cudaEventRecord(ctx->tile.seamsDone, (cudaStream_t)stream);
+                cudaStreamWaitEvent(ctx->tile.seamStream, ctx->tile.seamsDone, 0);
+                // ( the push + flag go onto the seam stream in pushHalos below; it waits for nothing but the seam rows )
+            }
+            if (!rc) rc = run(topEnd, bottomBegin);
+        } else
+            rc = run(rowBegin, rowEnd);
         if (ctx->profiling) {
             cudaEventRecord(evStop, (cudaStream_t)stream);
             ctx->pending.push_back({dd.name, evStart, evStop});   // kept on the error path too: nrdcuResolveProfile recycles the events
         }
         if (rc != 0) return rc;
         if (ctx->tile.attached) {
-            rc = pushHalos(ctx, dd, rowBegin, rowEnd, (cudaStream_t)stream);
+            rc = pushHalos(ctx, dd, rowBegin, rowEnd, (cudaStream_t)stream, edge ? ctx->tile.seamStream : (cudaStream_t)stream);
             if (rc != 0) return rc;
         }
         if (afterDispatch) {

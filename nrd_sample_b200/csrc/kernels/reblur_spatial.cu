@@ -309,7 +309,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             // plane distance: NoX = dot( Nv, Xvs ), Xvs = ( ray.xy * sxy, zs )
             P2 NoX = fma2(zs, s.Nv.z, sxy * fma2(ry, s.Nv.y, rx * s.Nv.x));
             w = w * nonExponentialWeight2(fma2(NoX, geomParams.x, geomParams.y));
-            w = sel2(zs.a() < cb.denoisingRange, zs.b() < cb.denoisingRange, w, P2(0.0f));
+            // ( taps beyond the denoising range: zs = +INF in the plane, the plane-distance weight above is 0 for them )
 
             // Denanify, on the packed fp16 words (2 selects per tap instead of 4)
             if (w.a() == 0.0f) rawA = make_uint2(0u, 0u);
@@ -413,7 +413,10 @@ __global__ void __launch_bounds__(256) reblurGeometryPlaneKernel(const __grid_co
     const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
     if (px > cb.rectSizeMinusOne[0] || py >= row1) return;
     const float4 nr = unpackNormalRoughness(p.normalRoughness.fetchRaw(px, py));
-    p.out.store(px, py, make_float4(nr.x, nr.y, nr.z, fabsf(p.viewZ.fetch(px, py)) * fabsf(cb.viewZScale)));
+    // texels outside the denoising range carry +INF: every tap weight includes the plane-distance term sat( 1 - | NoX a + b | ) with NoX proportional
+    // to this value, so such a tap weighs exactly 0 ( INF or NaN -> FADD.SAT -> 0 ) without a per-tap range compare ( Common.hlsli:567-572 )
+    const float zs = fabsf(p.viewZ.fetch(px, py)) * fabsf(cb.viewZScale);
+    p.out.store(px, py, make_float4(nr.x, nr.y, nr.z, zs < cb.denoisingRange ? zs : __int_as_float(0x7F800000)));
 }
 
 template <bool CB, int SIGNAL, bool SH, bool PROBE = false>

@@ -24,6 +24,7 @@ FLAG_QUAD_INTRINSICS = 1
 FLAG_CUDA_GRAPH = 2
 FLAG_ROBUST_MIRROR_TEST = 4
 FLAG_PROBE_MIRROR = 8
+FLAG_NO_SEAM_OVERLAP = 16
 
 NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdcuAllocSharedTexture", "nrdcuTileExportSize", "nrdcuTileExport", "nrdcuTileAttach",
                  "nrdcuTileSetHalo", "nrdcuTileGetStatus", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
