@@ -26,14 +26,14 @@ namespace nrdk {
 void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t stream);
 void launchReblurClassifyTiles(const ReblurConstants&, const ClassifyTilesParams&, Rows, cudaStream_t);
 void launchReblurGeometryPlane(const ReblurConstants&, const GeometryPlaneParams&, int row0, int row1, cudaStream_t);
-void launchReblurHitDistReconstruction(const ReblurConstants&, const HitDistReconstructionParams&, int signal, bool is5x5, Rows, cudaStream_t);
+void launchReblurHitDistReconstruction(const ReblurConstants&, const HitDistReconstructionParams&, int signal, bool occlusion, bool is5x5, Rows, cudaStream_t);
 void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int signal, int flags, Rows, cudaStream_t);
 void launchReblurSplitScreen(const ReblurConstants&, const SplitScreenParams&, int signal, Rows, cudaStream_t);
 void launchReblurBlur(const ReblurConstants&, const BlurParams&, int signal, int flags, Rows, cudaStream_t);
 void launchReblurPostBlur(const ReblurConstants&, const PostBlurParams&, int signal, bool temporalStabilization, int flags, Rows, cudaStream_t);
-void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccumulationParams&, int signal, Rows, cudaStream_t);
-void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, int signal, bool quads, Rows, cudaStream_t);
-void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, int signal, Rows, cudaStream_t);
+void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccumulationParams&, int signal, int mode, Rows, cudaStream_t);
+void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, int signal, int mode, bool quads, Rows, cudaStream_t);
+void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, int signal, int mode, Rows, cudaStream_t);
 bool readMirrorProbe(unsigned long long* out, bool reset);
 uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
 uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
@@ -74,9 +74,9 @@ uint32_t fail(Result r, const char* fmt, ...) {
 uint32_t bytesPerTexel(uint32_t fmt) {
     switch ((Format)fmt) {
         case Format::R8_UNORM: case Format::R8_UINT: return 1;
-        case Format::RG8_UNORM: case Format::R16_UINT: case Format::R16_SFLOAT: return 2;
+        case Format::RG8_UNORM: case Format::R16_UINT: case Format::R16_SFLOAT: case Format::R16_UNORM: return 2;
         case Format::RGBA8_UNORM: case Format::RG16_SFLOAT: case Format::R32_UINT: case Format::R32_SFLOAT: case Format::R10_G10_B10_A2_UNORM: return 4;
-        case Format::RGBA16_SFLOAT: return 8;
+        case Format::RGBA16_SFLOAT: case Format::RGBA16_SNORM: case Format::RGBA16_UNORM: return 8;
         case Format::RGBA32_SFLOAT: return 16;
         default: return 0;
     }
@@ -108,6 +108,36 @@ struct Binder {
         v.w = (int)x.width;
         v.h = (int)x.height;
         v.pitch = (int)(x.pitchBytes / (bytesPerTexel(x.format) ? bytesPerTexel(x.format) : 1u));  // in texels (see TexView)
+        v.fmt = x.format;
+        next++;
+        return v;
+    }
+    // NRD_MODE = OCCLUSION / DO: the lobe's signal ( and fast history ) lives in 16 / 8-bit UNORM / SNORM pool textures, while the application may hand over
+    // anything from R8 to RGBA16F for IN / OUT_*_HITDIST ( NRDSample binds its RGBA16F textures, Source/NRDSample.cpp:489-500 ): the kernels read the format
+    // from the view ( reblur_common.cuh Sig< MODE > ), so any of the listed formats is accepted here
+    template <class V> V takeAny(const std::initializer_list<Format>& accepted) {
+        V v{};
+        if (next >= n) {
+            ok = false;
+            return v;
+        }
+        const nrdcuTexture& x = t[next];
+        bool known = false;
+        for (Format f : accepted) known |= x.format == (uint32_t)f;
+        const uint32_t bpp = bytesPerTexel(x.format);
+        if (!known || !bpp || !x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
+            if (ok) {
+                char buf[256];
+                snprintf(buf, sizeof(buf), "%s: binding %u has format %u pitch %u, which this mode cannot read", shader, next, x.format, x.pitchBytes);
+                *err = buf;
+            }
+            ok = false;
+        }
+        v.data = (uint8_t*)x.data;
+        v.w = (int)x.width;
+        v.h = (int)x.height;
+        v.pitch = (int)(x.pitchBytes / (bpp ? bpp : 1u));
+        v.fmt = x.format;
         next++;
         return v;
     }
@@ -160,18 +190,20 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
     // textures (REBLUR_*.resources.hlsli): takeD / takeS consume a binding only when the permutation has that lobe
     // "|NRD_MODE=SH" ( REBLUR_DIFFUSE_SH / REBLUR_SPECULAR_SH / REBLUR_DIFFUSE_SPECULAR_SH ): each lobe binds a second RGBA16F next to the first
     // ( takeShD / takeShS below, in the order of the REBLUR_*.resources.hlsli lists ); the launchers pick the SH instantiation when those views are bound
-    int signal = 0;
-    bool sh = false;
+    int signal = 0, mode = MODE_RADIANCE;
     std::string kSig;
-    for (int k = 1; k <= 6 && !signal; k++) {
-        const int sg = (k - 1) % 3 + 1;
-        const std::string candidate = std::string("|NRD_SIGNAL=") + (sg == 1 ? "DIFF" : (sg == 2 ? "SPEC" : "BOTH")) + (k > 3 ? "|NRD_MODE=SH" : "|NRD_MODE=RADIANCE");
-        if (id.find(candidate) != std::string::npos) {
-            signal = sg;
-            sh = k > 3;
-            kSig = candidate;
+    static const char* const kModes[4] = {"RADIANCE", "SH", "OCCLUSION", "DO"};   // MODE_* of kernels/reblur_common.cuh
+    for (int m = 0; m < 4 && !signal; m++)
+        for (int sg = 1; sg <= 3 && !signal; sg++) {
+            const std::string candidate = std::string("|NRD_SIGNAL=") + (sg == 1 ? "DIFF" : (sg == 2 ? "SPEC" : "BOTH")) + "|NRD_MODE=" + kModes[m];
+            if (id.find(candidate) != std::string::npos) {
+                signal = sg;
+                mode = m;
+                kSig = candidate;
+            }
         }
-    }
+    const bool sh = mode == MODE_SH, occlusion = mode == MODE_OCCLUSION, polymorphicMode = mode == MODE_OCCLUSION || mode == MODE_DO;
+    const int kflagsMode = kflags | (mode << 4);
     const bool hasDiff = (signal & 1) != 0, hasSpec = (signal & 2) != 0;
     const uint32_t lobes = (hasDiff ? 1u : 0u) + (hasSpec ? 1u : 0u);
     auto is = [&](const char* file, const char* suffix = "") { return signal != 0 && id == std::string(file) + kSig + suffix; };
@@ -179,8 +211,16 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         if (!b.ok || b.next != expected || n != expected) return fail(Result::INVALID_ARGUMENT, "%s", err.empty() ? (id + ": wrong number of textures").c_str() : err.c_str());
         return 0xFFFFFFFFu;
     };
-    auto takeD16 = [&]() { return hasDiff ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
-    auto takeS16 = [&]() { return hasSpec ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
+    // the lobe's signal texture: RGBA16F in the RADIANCE / SH modes; anything the format-polymorphic accessors read in the occlusion modes and in the two
+    // RADIANCE permutations the occlusion denoisers share ( hit-distance reconstruction of DO, split screen ): R16_UNORM / RGBA16_SNORM pools, application formats
+    bool anySignalFormat = polymorphicMode;
+    auto takeSig = [&]() {
+        if (!anySignalFormat) return b.take<TexRGBA16F>(Format::RGBA16_SFLOAT);
+        return b.takeAny<TexRGBA16F>({Format::R8_UNORM, Format::R16_UNORM, Format::R16_SFLOAT, Format::R32_SFLOAT, Format::RGBA8_UNORM, Format::RGBA16_UNORM, Format::RGBA16_SNORM,
+                                      Format::RGBA16_SFLOAT, Format::RGBA32_SFLOAT});
+    };
+    auto takeD16 = [&]() { return hasDiff ? takeSig() : TexRGBA16F{}; };
+    auto takeS16 = [&]() { return hasSpec ? takeSig() : TexRGBA16F{}; };
     auto takeShD = [&]() { return (hasDiff && sh) ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
     auto takeShS = [&]() { return (hasSpec && sh) ? b.take<TexRGBA16F>(Format::RGBA16_SFLOAT) : TexRGBA16F{}; };
     const uint32_t shLobes = sh ? lobes : 0u;
@@ -196,8 +236,10 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         }
         return v;
     };
-    auto takeDF = [&]() { return hasDiff ? b.take<TexR16F>(Format::R16_SFLOAT) : TexR16F{}; };
-    auto takeSF = [&]() { return hasSpec ? b.take<TexR16F>(Format::R16_SFLOAT) : TexR16F{}; };
+    auto takeFast = [&]() { return polymorphicMode ? b.takeAny<TexR16F>({Format::R8_UNORM, Format::R16_UNORM, Format::R16_SFLOAT}) : b.take<TexR16F>(Format::R16_SFLOAT); };
+    auto takeDF = [&]() { return hasDiff ? takeFast() : TexR16F{}; };                                             // fast history ( REBLUR_FAST_TYPE )
+    auto takeSF = [&]() { return hasSpec ? b.take<TexR16F>(Format::R16_SFLOAT) : TexR16F{}; };                    // hit distance for tracking: always R16F
+    auto takeSFast = [&]() { return hasSpec ? takeFast() : TexR16F{}; };
     // data1: RG8_UNORM for two lobes, R8_UNORM for one (Reblur.cpp: DATA1 format); P has `data1` + `data1R8` or `outData1` + `outData1R8`
     auto takeData1 = [&](TexRG8& both, TexR8& single) {
         if (lobes == 2) both = b.take<TexRG8>(Format::RG8_UNORM);
@@ -254,6 +296,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         if (r != 0xFFFFFFFFu) return r;
         launchReblurClassifyTiles(cb, p, rows, stream);
     } else if (is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=0") || is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1")) {
+        anySignalFormat = true;
         HitDistReconstructionParams p = {};
         p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
@@ -264,8 +307,9 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpec = takeS16();
         uint32_t r = done(3 + 2 * lobes);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurHitDistReconstruction(cb, p, signal, is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), rows, stream);
+        launchReblurHitDistReconstruction(cb, p, signal, occlusion, is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), rows, stream);
     } else if (is("REBLUR_SplitScreen.cs.hlsl")) {
+        anySignalFormat = true;
         SplitScreenParams p = {};
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.inDiff = takeD16();
@@ -296,7 +340,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         uint32_t r = done(3 + 2 * lobes + (hasSpec ? 1 : 0) + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
-        launchReblurPrePass(cb, p, signal, kflags, rows, stream);
+        launchReblurPrePass(cb, p, signal, kflagsMode, rows, stream);
         releasePlane();
     } else if (is("REBLUR_TemporalAccumulation.cs.hlsl")) {
         TemporalAccumulationParams p = {};
@@ -315,9 +359,9 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.historyDiff = takeD16();
         p.historySpec = takeS16();
         p.historyDiffFast = takeDF();
-        p.historySpecFast = takeSF();
+        p.historySpecFast = takeSFast();
         p.prevSpecHitDistForTracking = takeSF();
-        p.inSpecHitDistForTracking = takeSF();
+        if (!occlusion) p.inSpecHitDistForTracking = takeSF();   // no pre-pass in front of the occlusion denoisers ( REBLUR_TemporalAccumulation.resources.hlsli:39-41 )
         p.inDiffSh = takeShD();
         p.inSpecSh = takeShS();
         p.historyDiffSh = takeShD();
@@ -326,15 +370,17 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outDiff = takeD16();
         p.outSpec = takeS16();
         p.outDiffFast = takeDF();
-        p.outSpecFast = takeSF();
+        p.outSpecFast = takeSFast();
         p.outSpecHitDistForTracking = takeSF();
-        if (hasSpec) p.outData2 = b.take<TexR32U>(Format::R32_UINT);
-        else p.outData2R8 = b.take<TexR8U>(Format::R8_UINT);
+        if (!occlusion) {   // the occlusion denoisers write no data2 ( :63-65 )
+            if (hasSpec) p.outData2 = b.take<TexR32U>(Format::R32_UINT);
+            else p.outData2R8 = b.take<TexR8U>(Format::R8_UINT);
+        }
         p.outDiffSh = takeShD();
         p.outSpecSh = takeShS();
-        uint32_t r = done(10 + 6 * lobes + (hasSpec ? 3 : 0) + 3 * shLobes);
+        uint32_t r = done((occlusion ? 9 : 10) + 6 * lobes + (hasSpec ? (occlusion ? 2 : 3) : 0) + 3 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurTemporalAccumulation(cb, p, signal, rows, stream);
+        launchReblurTemporalAccumulation(cb, p, signal, mode, rows, stream);
     } else if (is("REBLUR_HistoryFix.cs.hlsl")) {
         HistoryFixParams p = {};
         p.tiles = takeTiles();
@@ -344,19 +390,19 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.inDiff = takeD16();
         p.inSpec = takeS16();
         p.inDiffFast = takeDF();
-        p.inSpecFast = takeSF();
-        p.specHitDistForTracking = takeSF();
+        p.inSpecFast = takeSFast();
+        if (!occlusion) p.specHitDistForTracking = takeSF();   // REBLUR_HistoryFix.resources.hlsli:30-32
         p.inDiffSh = takeShD();
         p.inSpecSh = takeShS();
         p.outDiff = takeD16();
         p.outSpec = takeS16();
         p.outDiffFast = takeDF();
-        p.outSpecFast = takeSF();
+        p.outSpecFast = takeSFast();
         p.outDiffSh = takeShD();
         p.outSpecSh = takeShS();
-        uint32_t r = done(4 + 4 * lobes + (hasSpec ? 1 : 0) + 2 * shLobes);
+        uint32_t r = done(4 + 4 * lobes + (hasSpec && !occlusion ? 1 : 0) + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurHistoryFix(cb, p, signal, quads, rows, stream);
+        launchReblurHistoryFix(cb, p, signal, mode, quads, rows, stream);
     } else if (is("REBLUR_Blur.cs.hlsl")) {
         BlurParams p = {};
         p.tiles = takeTiles();
@@ -375,7 +421,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         uint32_t r = done(5 + 2 * lobes + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
-        launchReblurBlur(cb, p, signal, kflags, rows, stream);
+        launchReblurBlur(cb, p, signal, kflagsMode, rows, stream);
         releasePlane();
         // the blur pass copies viewZ ( sky included ) into PREV_VIEWZ, which is what post-blur binds as its viewZ: same texels, same plane
         if (g_plane && g_plane->fromViewZ == p.viewZ.data) g_plane->viewZCopy = p.outViewZ.data;
@@ -405,7 +451,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         uint32_t r = done(ts ? 5 + 2 * lobes + 2 * shLobes : 6 + 3 * lobes + 3 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
-        launchReblurPostBlur(cb, p, signal, ts, kflags, rows, stream);
+        launchReblurPostBlur(cb, p, signal, ts, kflagsMode, rows, stream);
         releasePlane();
     } else if (is("REBLUR_TemporalStabilization.cs.hlsl")) {
         TemporalStabilizationParams p = {};
@@ -432,7 +478,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecSh = takeShS();
         uint32_t r = done(7 + 4 * lobes + (hasSpec ? 1 : 0) + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurTemporalStabilization(cb, p, signal, rows, stream);
+        launchReblurTemporalStabilization(cb, p, signal, mode, rows, stream);
     } else {
         return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", id.c_str());
     }

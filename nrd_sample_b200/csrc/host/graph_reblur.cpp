@@ -26,12 +26,27 @@ enum PassIndex : uint32_t {
 
 const uint32_t kCb = sizeof(ReblurConstants);
 
+// g_ReblurProps ( Reblur.cpp:85-96 )
 bool hasDiffuse(Denoiser d) {
-    return d == Denoiser::REBLUR_DIFFUSE || d == Denoiser::REBLUR_DIFFUSE_SPECULAR || d == Denoiser::REBLUR_DIFFUSE_SH || d == Denoiser::REBLUR_DIFFUSE_SPECULAR_SH;
+    return d == Denoiser::REBLUR_DIFFUSE || d == Denoiser::REBLUR_DIFFUSE_SPECULAR || d == Denoiser::REBLUR_DIFFUSE_SH || d == Denoiser::REBLUR_DIFFUSE_SPECULAR_SH ||
+           d == Denoiser::REBLUR_DIFFUSE_OCCLUSION || d == Denoiser::REBLUR_DIFFUSE_SPECULAR_OCCLUSION || d == Denoiser::REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION;
 }
 bool hasSpecular(Denoiser d) {
-    return d == Denoiser::REBLUR_SPECULAR || d == Denoiser::REBLUR_DIFFUSE_SPECULAR || d == Denoiser::REBLUR_SPECULAR_SH || d == Denoiser::REBLUR_DIFFUSE_SPECULAR_SH;
+    return d == Denoiser::REBLUR_SPECULAR || d == Denoiser::REBLUR_DIFFUSE_SPECULAR || d == Denoiser::REBLUR_SPECULAR_SH || d == Denoiser::REBLUR_DIFFUSE_SPECULAR_SH ||
+           d == Denoiser::REBLUR_SPECULAR_OCCLUSION || d == Denoiser::REBLUR_DIFFUSE_SPECULAR_OCCLUSION;
 }
+
+// Pass indices of the occlusion denoisers ( Update_ReblurOcclusion, Reblur.cpp:204-215 ): no pre-pass, no stabilization
+enum OcclusionPassIndex : uint32_t {
+    OCC_CLASSIFY_TILES = 0,
+    OCC_HITDIST_RECONSTRUCTION = 1,  // 2 permutations: bit0 = 5x5
+    OCC_TEMPORAL_ACCUMULATION = 3,   // 8: bit0 = after reconstruction, bit1 = confidence inputs, bit2 = threshold mix
+    OCC_HISTORY_FIX = 11,
+    OCC_BLUR = 12,
+    OCC_POST_BLUR = 13,
+    OCC_SPLIT_SCREEN = 14,
+    OCC_VALIDATION = 15,
+};
 
 }  // namespace
 
@@ -43,11 +58,13 @@ bool hasSpecular(Denoiser d) {
 // sh: REBLUR_DIFFUSE_SH / REBLUR_SPECULAR_SH / REBLUR_DIFFUSE_SPECULAR_SH (NRD_MODE = SH; Reblur_DiffuseSh.hpp, Reblur_SpecularSh.hpp,
 // Reblur_DiffuseSpecularSh.hpp): the same graph over IN / OUT_*_SH0 with a second RGBA16F per lobe ( SH1 ) carried through every pass — the
 // user's OUT_*_SH1 as "SH_TEMP1", one more permanent ( SH history, after the lobe's stabilized pair ) and transient ( SH_TMP2, after the lobe's fast history ).
-void Graph::buildReblur(DenoiserState& d, bool diff, bool spec, bool sh) {
+// directional: REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION ( NRD_MODE = DO, Reblur_DiffuseDirectionalOcclusion.hpp ): the diffuse-only graph over IN / OUT_DIFF_DIRECTION_HITDIST
+// with 16-bit SNORM signal textures and an 8-bit UNORM fast history ( Reblur.cpp:38-39 ); reconstruction and split screen keep the RADIANCE permutation.
+void Graph::buildReblur(DenoiserState& d, bool diff, bool spec, bool sh, bool directional) {
     new (&d.settings.reblur) ReblurSettings();
     d.settingsSize = sizeof(ReblurSettings);
 
-    const Format kRadiance = Format::RGBA16_SFLOAT, kFast = Format::R16_SFLOAT;
+    const Format kRadiance = directional ? Format::RGBA16_SNORM : Format::RGBA16_SFLOAT, kFast = directional ? Format::R8_UNORM : Format::R16_SFLOAT;
     uint16_t nPerm = 0, nTran = 0;
     auto perm = [&](Format f) { addPermanent(f); return nPerm++; };
     auto tran = [&](Format f, uint16_t ds = 1) { addTransient(f, ds); return nTran++; };
@@ -103,16 +120,16 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec, bool sh) {
     auto Pm = [](uint16_t i) { return Slot::perm(i); };
     auto Tr = [](uint16_t i) { return Slot::tran(i); };
     // The user's output textures double as scratch ("TEMP1") between passes
-    const ResourceType inDiff = sh ? ResourceType::IN_DIFF_SH0 : ResourceType::IN_DIFF_RADIANCE_HITDIST, inSpec = sh ? ResourceType::IN_SPEC_SH0 : ResourceType::IN_SPEC_RADIANCE_HITDIST;
-    const ResourceType outDiff = sh ? ResourceType::OUT_DIFF_SH0 : ResourceType::OUT_DIFF_RADIANCE_HITDIST, outSpec = sh ? ResourceType::OUT_SPEC_SH0 : ResourceType::OUT_SPEC_RADIANCE_HITDIST;
+    const ResourceType inDiff = directional ? ResourceType::IN_DIFF_DIRECTION_HITDIST : (sh ? ResourceType::IN_DIFF_SH0 : ResourceType::IN_DIFF_RADIANCE_HITDIST), inSpec = sh ? ResourceType::IN_SPEC_SH0 : ResourceType::IN_SPEC_RADIANCE_HITDIST;
+    const ResourceType outDiff = directional ? ResourceType::OUT_DIFF_DIRECTION_HITDIST : (sh ? ResourceType::OUT_DIFF_SH0 : ResourceType::OUT_DIFF_RADIANCE_HITDIST), outSpec = sh ? ResourceType::OUT_SPEC_SH0 : ResourceType::OUT_SPEC_RADIANCE_HITDIST;
     const Slot diffTemp1 = U(outDiff), specTemp1 = U(outSpec);
     const Slot diffTemp2 = Tr(T_DIFF_TMP2), specTemp2 = Tr(T_SPEC_TMP2);
     const Slot diffShTemp1 = U(ResourceType::OUT_DIFF_SH1), specShTemp1 = U(ResourceType::OUT_SPEC_SH1), diffShTemp2 = Tr(T_DIFF_SH_TMP2), specShTemp2 = Tr(T_SPEC_SH_TMP2);
     const Slot dummy = U(ResourceType::IN_VIEWZ);  // bound where an optional input is absent
     const std::string sigSignal = std::string("|NRD_SIGNAL=") + (diff && spec ? "BOTH" : (diff ? "DIFF" : "SPEC"));
-    const std::string sig = sigSignal + (sh ? "|NRD_MODE=SH" : "|NRD_MODE=RADIANCE");
+    const std::string sig = sigSignal + (directional ? "|NRD_MODE=DO" : (sh ? "|NRD_MODE=SH" : "|NRD_MODE=RADIANCE"));
     // Reblur_DiffuseSh.hpp never defines DENOISER_NAME ( the other files do ), so its pass names carry the macro's own name
-    const std::string prefix = (sh && diff && !spec) ? std::string("DENOISER_NAME - ")
+    const std::string prefix = directional ? std::string("REBLUR_DirectionalOcclusion - ") : (sh && diff && !spec) ? std::string("DENOISER_NAME - ")
                                                      : std::string("REBLUR_") + (diff && spec ? "DiffuseSpecular" : (diff ? "Diffuse" : "Specular")) + (sh ? "Sh - " : " - ");
     auto name = [&](const char* pass) { return intern(prefix + pass); };
     // bind helpers: a lobe's binding exists only when the denoiser has that lobe
@@ -293,7 +310,7 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec, bool sh) {
     outS(U(outSpec));
     outShD(U(ResourceType::OUT_DIFF_SH1));
     outShS(U(ResourceType::OUT_SPEC_SH1));
-    emit("REBLUR_SplitScreen.cs.hlsl" + sig, 8, 16, kCb);
+    emit("REBLUR_SplitScreen.cs.hlsl" + (directional ? sigSignal + "|NRD_MODE=RADIANCE" : sig), 8, 16, kCb);
 
     // REBLUR_ADD_VALIDATION_DISPATCH (Reblur.cpp:65-78): a single-lobe denoiser binds its input in both lobe slots
     beginPass(name("Validation"));
@@ -306,6 +323,191 @@ void Graph::buildReblur(DenoiserState& d, bool diff, bool spec, bool sh) {
     in(U(spec ? inSpec : inDiff));
     out(U(ResourceType::OUT_VALIDATION));
     emit("REBLUR_Validation.cs.hlsl", 8, 16, kCb, GRID_FROM_RESOURCE, 1);
+}
+
+// REBLUR_DIFFUSE_OCCLUSION / REBLUR_SPECULAR_OCCLUSION / REBLUR_DIFFUSE_SPECULAR_OCCLUSION ( NRD_MODE = OCCLUSION; Reblur_DiffuseOcclusion.hpp,
+// Reblur_SpecularOcclusion.hpp, Reblur_DiffuseSpecularOcclusion.hpp ): hit distance only — one 16-bit UNORM channel per lobe ( 8-bit fast history ), no pre-pass,
+// no data2, no stabilization; the post-blur writes history, internal data and the user's OUT_*_HITDIST. Permanent pool: prev viewZ / normal+roughness / internal
+// data, the histories of the lobes, the fast histories of the lobes, the specular tracking ping / pong; transient: data1, per lobe { tmp2, fast history }, tiles.
+void Graph::buildReblurOcclusion(DenoiserState& d, bool diff, bool spec) {
+    new (&d.settings.reblur) ReblurSettings();
+    d.settingsSize = sizeof(ReblurSettings);
+
+    const Format kOcclusion = Format::R16_UNORM, kFast = Format::R8_UNORM;
+    uint16_t nPerm = 0, nTran = 0;
+    auto perm = [&](Format f) { addPermanent(f); return nPerm++; };
+    auto tran = [&](Format f, uint16_t ds = 1) { addTransient(f, ds); return nTran++; };
+    const uint16_t P_PREV_VIEWZ = perm(Format::R32_SFLOAT);
+    const uint16_t P_PREV_NORMAL_ROUGHNESS = perm(Format::R10_G10_B10_A2_UNORM);
+    const uint16_t P_PREV_INTERNAL_DATA = perm(Format::R16_UINT);
+    uint16_t P_DIFF_HISTORY = 0, P_SPEC_HISTORY = 0, P_DIFF_FAST_HISTORY = 0, P_SPEC_FAST_HISTORY = 0, P_TRACKING_PING = 0, P_TRACKING_PONG = 0;
+    if (diff) P_DIFF_HISTORY = perm(kOcclusion);
+    if (spec) P_SPEC_HISTORY = perm(kOcclusion);
+    if (diff) P_DIFF_FAST_HISTORY = perm(kFast);
+    if (spec) P_SPEC_FAST_HISTORY = perm(kFast);
+    if (spec) {
+        P_TRACKING_PING = perm(Format::R16_SFLOAT);
+        P_TRACKING_PONG = perm(Format::R16_SFLOAT);
+    }
+    const uint16_t T_DATA1 = tran(diff && spec ? Format::RG8_UNORM : Format::R8_UNORM);
+    uint16_t T_DIFF_TMP2 = 0, T_DIFF_FAST = 0, T_SPEC_TMP2 = 0, T_SPEC_FAST = 0;
+    if (diff) {
+        T_DIFF_TMP2 = tran(kOcclusion);
+        T_DIFF_FAST = tran(kFast);
+    }
+    if (spec) {
+        T_SPEC_TMP2 = tran(kOcclusion);
+        T_SPEC_FAST = tran(kFast);
+    }
+    const uint16_t T_TILES = tran(Format::R8_UNORM, 16);
+
+    auto U = [](ResourceType t) { return Slot::user(t); };
+    auto Pm = [](uint16_t i) { return Slot::perm(i); };
+    auto Tr = [](uint16_t i) { return Slot::tran(i); };
+    const Slot inDiff = U(ResourceType::IN_DIFF_HITDIST), inSpec = U(ResourceType::IN_SPEC_HITDIST);
+    const Slot diffTemp1 = U(ResourceType::OUT_DIFF_HITDIST), specTemp1 = U(ResourceType::OUT_SPEC_HITDIST);   // the user's outputs double as scratch
+    const Slot diffTemp2 = Tr(T_DIFF_TMP2), specTemp2 = Tr(T_SPEC_TMP2);
+    const Slot dummy = U(ResourceType::IN_VIEWZ);
+    const std::string sigSignal = std::string("|NRD_SIGNAL=") + (diff && spec ? "BOTH" : (diff ? "DIFF" : "SPEC"));
+    const std::string sig = sigSignal + "|NRD_MODE=OCCLUSION";
+    const std::string prefix = std::string("REBLUR_") + (diff && spec ? "DiffuseSpecular" : (diff ? "Diffuse" : "Specular")) + "Occlusion - ";
+    auto name = [&](const char* pass) { return intern(prefix + pass); };
+    auto inD = [&](Slot s, Slot swap = Slot()) { if (diff) in(s, swap); };
+    auto inS = [&](Slot s, Slot swap = Slot()) { if (spec) in(s, swap); };
+    auto outD = [&](Slot s, Slot swap = Slot()) { if (diff) out(s, swap); };
+    auto outS = [&](Slot s, Slot swap = Slot()) { if (spec) out(s, swap); };
+
+    beginPass(name("Classify tiles"));
+    in(U(ResourceType::IN_VIEWZ));
+    out(Tr(T_TILES));
+    emit("REBLUR_ClassifyTiles.cs.hlsl", 16, 16, kCb);
+
+    for (int i = 0; i < 2; i++) {
+        beginPass(name("Hit distance reconstruction"));
+        in(Tr(T_TILES));
+        in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+        in(U(ResourceType::IN_VIEWZ));
+        inD(inDiff);
+        inS(inSpec);
+        outD(diffTemp1);
+        outS(specTemp1);
+        emit("REBLUR_HitDistReconstruction.cs.hlsl" + sig + (i ? "|MODE_5X5=1" : "|MODE_5X5=0"), 8, 16, kCb);
+    }
+
+    for (int i = 0; i < 8; i++) {
+        const bool hasMix = (i >> 2) & 1, hasConfidence = (i >> 1) & 1, afterReconstruction = i & 1;
+        beginPass(name("Temporal accumulation"));
+        in(Tr(T_TILES));
+        in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+        in(U(ResourceType::IN_VIEWZ));
+        in(U(ResourceType::IN_MV));
+        in(Pm(P_PREV_VIEWZ));
+        in(Pm(P_PREV_NORMAL_ROUGHNESS));
+        in(Pm(P_PREV_INTERNAL_DATA));
+        in(hasMix ? U(ResourceType::IN_DISOCCLUSION_THRESHOLD_MIX) : dummy);
+        inD(hasConfidence ? U(ResourceType::IN_DIFF_CONFIDENCE) : dummy);
+        inS(hasConfidence ? U(ResourceType::IN_SPEC_CONFIDENCE) : dummy);
+        inD(afterReconstruction ? diffTemp1 : inDiff);
+        inS(afterReconstruction ? specTemp1 : inSpec);
+        inD(Pm(P_DIFF_HISTORY));
+        inS(Pm(P_SPEC_HISTORY));
+        inD(Pm(P_DIFF_FAST_HISTORY));
+        inS(Pm(P_SPEC_FAST_HISTORY));
+        inS(Pm(P_TRACKING_PING), Pm(P_TRACKING_PONG));
+        out(Tr(T_DATA1));
+        outD(diffTemp2);
+        outS(specTemp2);
+        outD(Tr(T_DIFF_FAST));
+        outS(Tr(T_SPEC_FAST));
+        outS(Pm(P_TRACKING_PONG), Pm(P_TRACKING_PING));
+        emit("REBLUR_TemporalAccumulation.cs.hlsl" + sig, 8, 16, kCb);
+    }
+
+    beginPass(name("History fix"));
+    in(Tr(T_TILES));
+    in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+    in(Tr(T_DATA1));
+    in(U(ResourceType::IN_VIEWZ));
+    inD(diffTemp2);
+    inS(specTemp2);
+    inD(Tr(T_DIFF_FAST));
+    inS(Tr(T_SPEC_FAST));
+    outD(diffTemp1);
+    outS(specTemp1);
+    outD(Pm(P_DIFF_FAST_HISTORY));
+    outS(Pm(P_SPEC_FAST_HISTORY));
+    emit("REBLUR_HistoryFix.cs.hlsl" + sig, 8, 16, kCb);
+
+    beginPass(name("Blur"));
+    in(Tr(T_TILES));
+    in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+    in(U(ResourceType::IN_VIEWZ));
+    in(Tr(T_DATA1));
+    inD(diffTemp1);
+    inS(specTemp1);
+    out(Pm(P_PREV_VIEWZ));
+    outD(diffTemp2);
+    outS(specTemp2);
+    emit("REBLUR_Blur.cs.hlsl" + sig, 8, 16, kCb);
+
+    beginPass(name("Post-blur"));
+    in(Tr(T_TILES));
+    in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+    in(Tr(T_DATA1));
+    in(Pm(P_PREV_VIEWZ));
+    inD(diffTemp2);
+    inS(specTemp2);
+    out(Pm(P_PREV_NORMAL_ROUGHNESS));
+    outD(Pm(P_DIFF_HISTORY));
+    outS(Pm(P_SPEC_HISTORY));
+    out(Pm(P_PREV_INTERNAL_DATA));
+    outD(U(ResourceType::OUT_DIFF_HITDIST));
+    outS(U(ResourceType::OUT_SPEC_HITDIST));
+    emit("REBLUR_PostBlur.cs.hlsl" + sig + "|TEMPORAL_STABILIZATION=0", 8, 16, kCb);
+
+    beginPass(name("Split screen"));
+    in(U(ResourceType::IN_VIEWZ));
+    inD(inDiff);
+    inS(inSpec);
+    outD(U(ResourceType::OUT_DIFF_HITDIST));
+    outS(U(ResourceType::OUT_SPEC_HITDIST));
+    emit("REBLUR_SplitScreen.cs.hlsl" + sigSignal + "|NRD_MODE=RADIANCE", 8, 16, kCb);
+
+    // REBLUR_ADD_VALIDATION_DISPATCH( Transient::DATA1, ... ): there is no data2, data1 is bound in its slot too
+    beginPass(name("Validation"));
+    in(U(ResourceType::IN_NORMAL_ROUGHNESS));
+    in(U(ResourceType::IN_VIEWZ));
+    in(U(ResourceType::IN_MV));
+    in(Tr(T_DATA1));
+    in(Tr(T_DATA1));
+    in(diff ? inDiff : inSpec);
+    in(spec ? inSpec : inDiff);
+    out(U(ResourceType::OUT_VALIDATION));
+    emit("REBLUR_Validation.cs.hlsl", 8, 16, kCb, GRID_FROM_RESOURCE, 1);
+}
+
+// Update_ReblurOcclusion ( Reblur.cpp:203-277 )
+void Graph::updateReblurOcclusion(const DenoiserState& d) {
+    const ReblurSettings& s = d.settings.reblur;
+    const bool reconstruct = s.hitDistanceReconstructionMode != HitDistanceReconstructionMode::OFF && s.checkerboardMode == CheckerboardMode::OFF;
+    auto push = [&](uint32_t pass) { fillReblurConstants(s, pushDispatch(d, pass)); };
+    if (m_common.splitScreen >= 1.0f) {
+        push(OCC_SPLIT_SCREEN);
+        return;
+    }
+    push(OCC_CLASSIFY_TILES);
+    if (reconstruct) push(OCC_HITDIST_RECONSTRUCTION + (s.hitDistanceReconstructionMode == HitDistanceReconstructionMode::AREA_5X5 ? 1 : 0));
+    push(OCC_TEMPORAL_ACCUMULATION + (m_common.isDisocclusionThresholdMixAvailable ? 4 : 0) + (m_common.isHistoryConfidenceAvailable ? 2 : 0) + (reconstruct ? 1 : 0));
+    push(OCC_HISTORY_FIX);
+    push(OCC_BLUR);
+    push(OCC_POST_BLUR);
+    if (m_common.splitScreen > 0.0f) push(OCC_SPLIT_SCREEN);
+    if (m_common.enableValidation) {
+        uint8_t* cb = (uint8_t*)pushDispatch(d, OCC_VALIDATION);
+        fillReblurConstants(s, cb);
+        uint32_t flags[2] = {hasDiffuse(d.desc.denoiser) ? 1u : 0u, hasSpecular(d.desc.denoiser) ? 1u : 0u};
+        memcpy(cb + offsetof(ReblurConstants, _pad), flags, sizeof(flags));
+    }
 }
 
 void Graph::updateReblur(const DenoiserState& d) {

@@ -45,6 +45,10 @@ static const Denoiser kSupported[] = {
     Denoiser::REBLUR_DIFFUSE_SH,
     Denoiser::REBLUR_SPECULAR_SH,
     Denoiser::REBLUR_DIFFUSE_SPECULAR_SH,
+    Denoiser::REBLUR_DIFFUSE_OCCLUSION,
+    Denoiser::REBLUR_SPECULAR_OCCLUSION,
+    Denoiser::REBLUR_DIFFUSE_SPECULAR_OCCLUSION,
+    Denoiser::REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION,
     Denoiser::RELAX_DIFFUSE,
     Denoiser::RELAX_DIFFUSE_SH,
     Denoiser::RELAX_SPECULAR,
@@ -171,6 +175,10 @@ Result Graph::create(const InstanceCreationDesc& desc) {
             case Denoiser::REBLUR_DIFFUSE_SH: buildReblur(d, true, false, true); break;
             case Denoiser::REBLUR_SPECULAR_SH: buildReblur(d, false, true, true); break;
             case Denoiser::REBLUR_DIFFUSE_SPECULAR_SH: buildReblur(d, true, true, true); break;
+            case Denoiser::REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION: buildReblur(d, true, false, false, true); break;
+            case Denoiser::REBLUR_DIFFUSE_OCCLUSION: buildReblurOcclusion(d, true, false); break;
+            case Denoiser::REBLUR_SPECULAR_OCCLUSION: buildReblurOcclusion(d, false, true); break;
+            case Denoiser::REBLUR_DIFFUSE_SPECULAR_OCCLUSION: buildReblurOcclusion(d, true, true); break;
             case Denoiser::SIGMA_SHADOW: buildSigmaShadow(d, false); break;
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: buildSigmaShadow(d, true); break;
             case Denoiser::REFERENCE: buildReference(d); break;
@@ -477,7 +485,11 @@ Result Graph::getComputeDispatches(const Identifier* ids, uint32_t idsNum, const
             case Denoiser::REBLUR_DIFFUSE_SH:
             case Denoiser::REBLUR_SPECULAR_SH:
             case Denoiser::REBLUR_DIFFUSE_SPECULAR_SH:
+            case Denoiser::REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION:
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: updateReblur(d); break;
+            case Denoiser::REBLUR_DIFFUSE_OCCLUSION:
+            case Denoiser::REBLUR_SPECULAR_OCCLUSION:
+            case Denoiser::REBLUR_DIFFUSE_SPECULAR_OCCLUSION: updateReblurOcclusion(d); break;
             case Denoiser::SIGMA_SHADOW:
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: updateSigma(d); break;
             case Denoiser::REFERENCE: updateReference(d); break;

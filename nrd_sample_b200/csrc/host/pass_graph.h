@@ -114,8 +114,10 @@ private:
     void flipPingPong(const DenoiserState& d);
 
     // graph_reblur.cpp / graph_sigma.cpp / graph_relax.cpp
-    void buildReblur(DenoiserState& d, bool diff, bool spec, bool sh = false);
+    void buildReblur(DenoiserState& d, bool diff, bool spec, bool sh = false, bool directional = false);
     void updateReblur(const DenoiserState& d);
+    void buildReblurOcclusion(DenoiserState& d, bool diff, bool spec);
+    void updateReblurOcclusion(const DenoiserState& d);
     void fillReblurConstants(const ReblurSettings& s, void* dst);
     void buildSigmaShadow(DenoiserState& d, bool translucency);
     void updateSigma(const DenoiserState& d);

@@ -58,6 +58,7 @@ inline RowGrid rowGrid(Rows r, int rectHeight, int blockHeight) {
 struct TexView {
     uint8_t* data;
     int w, h, pitch;  // pitch in TEXELS (the executor divides the byte pitch by the texel size): address = base + (y * pitch + x) * sizeof(T)
+    uint32_t fmt;     // nrd::Format of the bound texture ( sits in the struct's tail padding ): only the format-polymorphic accessors of the occlusion modes read it
     NRD_DEV bool inside(int x, int y) const { return (unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h; }
     // one 32-bit IMAD for the texel index + one IMAD.WIDE for the address (textures are < 2^31 texels)
     template <class T> NRD_DEV const T* ptr(int x, int y) const { return reinterpret_cast<const T*>(data) + (y * pitch + x); }

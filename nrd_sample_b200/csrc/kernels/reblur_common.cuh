@@ -24,6 +24,92 @@ template <class F> inline void withSignal(int signal, F&& call) {
     else call(std::integral_constant<int, SIGNAL_BOTH>());
 }
 
+// NRD_MODE of a permutation ( NRD.hlsli ): RADIANCE and SH carry YCoCg radiance + hit distance in RGBA16F; OCCLUSION carries the normalized hit distance alone
+// ( REBLUR_TYPE = float, REBLUR_Config.hlsli:103-107 ), DO a direction in .xyz + the hit distance in .w ( Reblur.cpp:36-39: R16_UNORM / RGBA16_SNORM pools,
+// R8_UNORM fast history ). In registers every mode is a float4 with the hit distance in .w ( zeros in .xyz for OCCLUSION ).
+enum : int { MODE_RADIANCE = 0, MODE_SH = 1, MODE_OCCLUSION = 2, MODE_DO = 3 };
+
+// Format-polymorphic texel access for the occlusion modes: one uniform switch on the bound texture's nrd::Format ( pool textures are R16_UNORM /
+// RGBA16_SNORM / R8_UNORM, application textures whatever the application owns ). RADIANCE / SH keep their fixed-width RGBA16F / R16F paths.
+NRD_DEV float4 anyFetch4(const TexView& t, int x, int y) {
+    const size_t i = (size_t)(y * t.pitch + x);
+    switch ((nrd::Format)t.fmt) {
+        case nrd::Format::R8_UNORM: return make_float4((float)__ldg(t.data + i) / 255.0f, 0.0f, 0.0f, 0.0f);
+        case nrd::Format::R16_UNORM: return make_float4((float)__ldg(reinterpret_cast<const unsigned short*>(t.data) + i) / 65535.0f, 0.0f, 0.0f, 0.0f);
+        case nrd::Format::R16_SFLOAT: return make_float4(__half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(t.data) + i))), 0.0f, 0.0f, 0.0f);
+        case nrd::Format::R32_SFLOAT: return make_float4(__ldg(reinterpret_cast<const float*>(t.data) + i), 0.0f, 0.0f, 0.0f);
+        case nrd::Format::RGBA8_UNORM: {
+            const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(t.data) + i);
+            return make_float4((float)v.x / 255.0f, (float)v.y / 255.0f, (float)v.z / 255.0f, (float)v.w / 255.0f);
+        }
+        case nrd::Format::RGBA16_UNORM: {
+            const ushort4 v = __ldg(reinterpret_cast<const ushort4*>(t.data) + i);
+            return make_float4((float)v.x / 65535.0f, (float)v.y / 65535.0f, (float)v.z / 65535.0f, (float)v.w / 65535.0f);
+        }
+        case nrd::Format::RGBA16_SNORM: {
+            const short4 v = __ldg(reinterpret_cast<const short4*>(t.data) + i);
+            return make_float4(fmaxf((float)v.x / 32767.0f, -1.0f), fmaxf((float)v.y / 32767.0f, -1.0f), fmaxf((float)v.z / 32767.0f, -1.0f), fmaxf((float)v.w / 32767.0f, -1.0f));
+        }
+        case nrd::Format::RGBA32_SFLOAT: return __ldg(reinterpret_cast<const float4*>(t.data) + i);
+        default: return TexRGBA16F::decode(__ldg(reinterpret_cast<const uint2*>(t.data) + i));   // RGBA16_SFLOAT
+    }
+}
+NRD_DEV int snormQ(float v) { v = fminf(fmaxf(v, -1.0f), 1.0f) * 32767.0f; return (int)(v + (v >= 0.0f ? 0.5f : -0.5f)); }   // NaN -> 0
+NRD_DEV void anyStore4(const TexView& t, int x, int y, float4 v) {
+    if (!t.inside(x, y)) return;
+    const size_t i = (size_t)(y * t.pitch + x);
+    switch ((nrd::Format)t.fmt) {
+        case nrd::Format::R8_UNORM: t.data[i] = (uint8_t)unormQ(v.x, 255.0f); break;
+        case nrd::Format::R16_UNORM: reinterpret_cast<unsigned short*>(t.data)[i] = (unsigned short)unormQ(v.x, 65535.0f); break;
+        case nrd::Format::R16_SFLOAT: reinterpret_cast<__half*>(t.data)[i] = __float2half_rn(v.x); break;
+        case nrd::Format::R32_SFLOAT: reinterpret_cast<float*>(t.data)[i] = v.x; break;
+        case nrd::Format::RGBA8_UNORM:
+            reinterpret_cast<uchar4*>(t.data)[i] = make_uchar4((unsigned char)unormQ(v.x, 255.0f), (unsigned char)unormQ(v.y, 255.0f), (unsigned char)unormQ(v.z, 255.0f), (unsigned char)unormQ(v.w, 255.0f));
+            break;
+        case nrd::Format::RGBA16_UNORM:
+            reinterpret_cast<ushort4*>(t.data)[i] = make_ushort4((unsigned short)unormQ(v.x, 65535.0f), (unsigned short)unormQ(v.y, 65535.0f), (unsigned short)unormQ(v.z, 65535.0f), (unsigned short)unormQ(v.w, 65535.0f));
+            break;
+        case nrd::Format::RGBA16_SNORM: reinterpret_cast<short4*>(t.data)[i] = make_short4((short)snormQ(v.x), (short)snormQ(v.y), (short)snormQ(v.z), (short)snormQ(v.w)); break;
+        case nrd::Format::RGBA32_SFLOAT: reinterpret_cast<float4*>(t.data)[i] = v; break;
+        default: {
+            const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+            reinterpret_cast<uint2*>(t.data)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+    }
+}
+
+// The lobe's signal texture ( bound through a TexRGBA16F-typed member in every mode ) and its fast history ( TexR16F-typed member )
+template <int MODE> struct Sig {
+    static constexpr bool FIXED = MODE == MODE_RADIANCE || MODE == MODE_SH;
+    // OCCLUSION: Texture2D< float > reads .x of whatever is bound; in registers the value travels in .w
+    static NRD_DEV float4 fromTexel(float4 v) { return MODE == MODE_OCCLUSION ? make_float4(0.0f, 0.0f, 0.0f, v.x) : v; }
+    static NRD_DEV float4 toTexel(float4 v) { return MODE == MODE_OCCLUSION ? make_float4(v.w, 0.0f, 0.0f, 0.0f) : v; }
+    static NRD_DEV float4 fetch(const TexRGBA16F& t, int x, int y) {
+        if constexpr (FIXED) return t.fetch(x, y);
+        else return fromTexel(anyFetch4(t, x, y));
+    }
+    static NRD_DEV float4 load(const TexRGBA16F& t, int x, int y) { return t.inside(x, y) ? fetch(t, x, y) : f4(0.0f); }
+    static NRD_DEV float4 fetchClamped(const TexRGBA16F& t, int x, int y) { return fetch(t, t.cx(x), t.cy(y)); }
+    static NRD_DEV void store(const TexRGBA16F& t, int x, int y, float4 v) {
+        if constexpr (FIXED) t.store(x, y, v);
+        else anyStore4(t, x, y, toTexel(v));
+    }
+    // REBLUR_Common.hlsli:147-238
+    static NRD_DEV float luma(float4 c) { return FIXED ? c.x : c.w; }
+};
+template <int MODE> struct FastSig {   // REBLUR_FAST_TYPE: R16F luma, or the R8_UNORM hit distance of the occlusion modes
+    static NRD_DEV float fetch(const TexR16F& t, int x, int y) {
+        if constexpr (Sig<MODE>::FIXED) return t.fetch(x, y);
+        else return anyFetch4(t, x, y).x;
+    }
+    static NRD_DEV float load(const TexR16F& t, int x, int y) { return t.inside(x, y) ? fetch(t, x, y) : 0.0f; }
+    static NRD_DEV float fetchClamped(const TexR16F& t, int x, int y) { return fetch(t, t.cx(x), t.cy(y)); }
+    static NRD_DEV void store(const TexR16F& t, int x, int y, float v) {
+        if constexpr (Sig<MODE>::FIXED) t.store(x, y, v);
+        else anyStore4(t, x, y, make_float4(v, 0.0f, 0.0f, 0.0f));
+    }
+};
+
 NRD_DEV float unpackViewZ(const ReblurConstants& cb, float z) { return fabsf(z * cb.viewZScale); }
 NRD_DEV bool inDenoisingRange(const ReblurConstants& cb, float z) { return z < cb.denoisingRange; }
 NRD_DEV float applyGeometryWeightLast(const ReblurConstants& cb, float w, float z, float NoX, float2 p) {
@@ -100,6 +186,20 @@ NRD_DEV float4 changeLuma(float4 c, float newLuma) {
     return make_float4(c.x * s, c.y * s, c.z * s, c.w);
 }
 NRD_DEV float4 clampNegativeToZero(float4 c) { return f4(linearToYCoCg(yCoCgToLinear(xyz(c))), saturate(c.w)); }
+// GetLuma / ChangeLuma / ClampNegativeToZero per NRD_MODE ( REBLUR_Common.hlsli:147-238 ): "luma" is the hit distance in the occlusion modes
+template <int MODE> NRD_DEV float lumaOf(float4 c) { return Sig<MODE>::luma(c); }
+template <int MODE> NRD_DEV float4 changeLumaM(float4 c, float newLuma) {
+    if constexpr (MODE == MODE_OCCLUSION) return make_float4(0.0f, 0.0f, 0.0f, newLuma);
+    else if constexpr (MODE == MODE_DO) {
+        const float s = lumaScale(c.w, newLuma);
+        return make_float4(c.x * s, c.y * s, c.z * s, newLuma);
+    } else return changeLuma(c, newLuma);
+}
+template <int MODE> NRD_DEV float4 clampNegativeToZeroM(float4 c) {
+    if constexpr (MODE == MODE_OCCLUSION) return make_float4(0.0f, 0.0f, 0.0f, saturate(c.w));
+    else if constexpr (MODE == MODE_DO) return changeLumaM<MODE_DO>(c, saturate(c.w));
+    else return clampNegativeToZero(c);
+}
 NRD_DEV float computeAntilag(const ReblurConstants& cb, float h, float a, float sigma, float accumSpeed) {
     float s = sigma * cb.antilagSettings[0];
     float magic = cb.antilagSettings[1] * cb.framerateScale * cb.framerateScale;
@@ -184,6 +284,33 @@ struct HistoryFilter {
             c += tex.fetch(x1, y1) * w.w;
         }
         return sum < 0.0001f ? c * 0.0f : c / sum;
+    }
+    // The filter on the signal / fast-history texture of an occlusion mode: same taps through the format-polymorphic accessors ( A = Sig< MODE > or FastSig< MODE > )
+    template <class A, class TEX> NRD_DEV auto colorAny(const TEX& tex) const -> decltype(A::fetch(tex, 0, 0)) {
+        const int x0 = tex.cx(ox), x1 = tex.cx(ox + 1), y0 = tex.cy(oy), y1 = tex.cy(oy + 1);
+        decltype(A::fetch(tex, 0, 0)) c;
+        if (bicubic) {
+            const int xm = tex.cx(ox - 1), x2 = tex.cx(ox + 2), ym = tex.cy(oy - 1), y2 = tex.cy(oy + 2);
+            c = lerp(A::fetch(tex, x0, ym), A::fetch(tex, x1, ym), tc.x) * w.x;
+            c += lerp(A::fetch(tex, xm, y0), A::fetch(tex, xm, y1), tc.y) * w.y;
+            c += lerp(lerp(A::fetch(tex, x0, y0), A::fetch(tex, x1, y0), tc.x), lerp(A::fetch(tex, x0, y1), A::fetch(tex, x1, y1), tc.x), tc.y) * w.z;
+            c += lerp(A::fetch(tex, x2, y0), A::fetch(tex, x2, y1), tc.y) * w.w;
+            c += lerp(A::fetch(tex, x0, y2), A::fetch(tex, x1, y2), tc.x) * w4;
+        } else {
+            c = A::fetch(tex, x0, y0) * w.x;
+            c += A::fetch(tex, x1, y0) * w.y;
+            c += A::fetch(tex, x0, y1) * w.z;
+            c += A::fetch(tex, x1, y1) * w.w;
+        }
+        return sum < 0.0001f ? c * 0.0f : c / sum;
+    }
+    template <class A> NRD_DEV float bilinearAny(const TexR16F& tex) const {
+        float c = A::load(tex, ox, oy) * custom.x;
+        c += A::load(tex, ox + 1, oy) * custom.y;
+        c += A::load(tex, ox, oy + 1) * custom.z;
+        c += A::load(tex, ox + 1, oy + 1) * custom.w;
+        float s = sum4(custom);
+        return s < 0.0001f ? 0.0f : c / s;
     }
     // The same filter on an RGBA16F texture with Blackwell's packed fp32x2 pipe: a texel decodes into two register pairs ( .xy, .zw ) for free, so
     // every lerp / weight / sum is one FFMA2-class instruction per pair — half the issue slots of the four-channel scalar form above.

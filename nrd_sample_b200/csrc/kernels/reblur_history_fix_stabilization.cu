@@ -26,7 +26,9 @@ constexpr int HF_BORDER = 4;  // REBLUR_ANTI_FIREFLY_FILTER_RADIUS
 constexpr int HF_TILE_W = BLOCK_W + 2 * HF_BORDER, HF_TILE_H = BLOCK_H + 2 * HF_BORDER;
 
 // SH ( NRD_MODE = SH ): the lobe's second RGBA16F is reconstructed with the same weights and rescaled to the clamped luma ( REBLUR_HistoryFix.cs.hlsl:106-108, 135-137, 194-207, 286-294 )
-template <int LOBE, int SIGNAL, bool SH>
+// MODE ( NRD_MODE ): OCCLUSION / DO go through the format-polymorphic Sig / FastSig, their "luma" is the hit distance, there is no anti-firefly clamp
+// ( NRD_SUPPORTS_ANTIFIREFLY = 0 ) and OCCLUSION has no hit-distance-for-tracking texture ( REBLUR_HistoryFix.cs.hlsl:311-314 )
+template <int LOBE, int SIGNAL, int MODE>
 NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p, const float (*sLuma)[HF_TILE_W], const float2 (*sRow)[HF_TILE_H][BLOCK_W], bool tileHasSky,
                             int px, int py, float strideIn, float frameNum,
                             float frameNumAvgNorm, float viewZ, float materialID, float3 N, float roughness, float3 Nv, float3 Xv, float frustumSize, float2 pixelUv) {
@@ -37,7 +39,8 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
     const float2 rectSize = make_float2(cb.rectSize[0], cb.rectSize[1]);
     const float2 rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
 
-    float4 v = in.load(px, py);
+    constexpr bool SH = MODE == MODE_SH, FIXED = Sig<MODE>::FIXED;
+    float4 v = Sig<MODE>::load(in, px, py);
     float4 sh = f4(0.0f);
     if constexpr (SH) sh = (LOBE == DIFF ? p.inDiffSh : p.inSpecSh).load(px, py);
     const float smc = LOBE == DIFF ? 1.0f : specMagicCurve(roughness);
@@ -45,7 +48,7 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
 
     const float hitDistScale = hitDistanceNormalization(viewZ, cb.hitDistSettings, LOBE == DIFF ? 1.0f : roughness);
     float hitDist = v.w * hitDistScale;
-    if (LOBE == SPEC) hitDist = lerp(p.specHitDistForTracking.load(px, py), hitDist, smc);
+    if (LOBE == SPEC && MODE != MODE_OCCLUSION) hitDist = lerp(p.specHitDistForTracking.load(px, py), hitDist, smc);
     const float hdFactor = hitDistFactor(hitDist, frustumSize);
     hitDist = LOBE == DIFF ? v.w : saturate(hitDist / hitDistScale);
 
@@ -89,7 +92,7 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
                 w *= 1.0f + (LOBE == DIFF ? fn.x : fn.y);
                 w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
 
-                float4 smp = in.load(tx, ty);
+                float4 smp = Sig<MODE>::load(in, tx, ty);
                 smp = w == 0.0f ? f4(0.0f) : smp;
                 w *= exponentialWeight(smp.w, hitDistParams.x, hitDistParams.y);
 
@@ -105,14 +108,14 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
         sh *= positiveRcp(sum);
     }
 
-    float luma = v.x;
+    float luma = lumaOf<MODE>(v);
 
     float f = frameNumAvgNorm;
     if (LOBE == SPEC) f = lerp(1.0f, f, smc);
 
     const int sx = threadIdx.x + HF_BORDER, sy = threadIdx.y + HF_BORDER;
     float fastCenter = lerp(luma, sLuma[sy][sx], f);
-    outFast.store(px, py, fastCenter);
+    FastSig<MODE>::store(outFast, px, py, fastCenter);
 
     // Local variance: 5x5 for the fast-history clamp, 9x9 minus the central 3x3 for the anti-firefly clamp
     float fastM1 = fastCenter, fastM2 = fastCenter * fastCenter;
@@ -154,7 +157,7 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
             }
     }
 
-    if (cb.antiFirefly != 0.0f) {
+    if (FIXED && cb.antiFirefly != 0.0f) {
         const float invNorm = 1.0f / ((HF_BORDER * 2 + 1) * (HF_BORDER * 2 + 1) - 3 * 3);
         antiFireflyM1 *= invNorm;
         antiFireflyM2 *= invNorm;
@@ -171,7 +174,7 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
         luma = lerp(lumaClamped, luma, 1.0f / (1.0f + (cb.maxFastAccumulatedFrameNum < cb.maxAccumulatedFrameNum ? 1.0f : 0.0f) * frameNum * 2.0f));
     }
 
-    out.store(px, py, changeLuma(v, luma));
+    Sig<MODE>::store(out, px, py, changeLumaM<MODE>(v, luma));
     if constexpr (SH) (LOBE == DIFF ? p.outDiffSh : p.outSpecSh).store(px, py, rescaleSh(sh, luma));
 }
 }  // namespace
@@ -179,7 +182,7 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
 #ifndef HF_MIN_BLOCKS
 #    define HF_MIN_BLOCKS 3  // 512-thread CTAs: 40 regs (3 CTAs / SM) 153 us vs 156 us at 57 regs (2 CTAs)
 #endif
-template <int SIGNAL, bool SH>
+template <int SIGNAL, int MODE>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, HF_MIN_BLOCKS) reblurHistoryFixKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HistoryFixParams p, int quads, int ctaY0) {
     constexpr bool HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0, HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0;
     __shared__ float sDiffLuma[HAS_DIFF ? HF_TILE_H : 1][HF_TILE_W];
@@ -199,8 +202,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, HF_MIN_BLOCKS) reblurHistory
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
             // the coordinates are clamped to the rect: plain fetches, issued together with the viewZ load instead of behind its sky test
             float dFast = 0.0f, sFast = 0.0f;
-            if constexpr (HAS_DIFF) dFast = p.inDiffFast.fetch(gx, gy);
-            if constexpr (HAS_SPEC) sFast = p.inSpecFast.fetch(gx, gy);
+            if constexpr (HAS_DIFF) dFast = FastSig<MODE>::fetch(p.inDiffFast, gx, gy);
+            if constexpr (HAS_SPEC) sFast = FastSig<MODE>::fetch(p.inSpecFast, gx, gy);
             bool sky = !inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.fetch(gx, gy)));
             sawSky |= sky ? 1 : 0;
             if constexpr (HAS_DIFF) sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : dFast;
@@ -257,8 +260,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, HF_MIN_BLOCKS) reblurHistory
     stride *= 2.0f / 2.0f;
     stride *= materialID == cb.historyFixAlternatePixelStrideMaterialID ? cb.historyFixAlternatePixelStride : cb.historyFixBasePixelStride;
 
-    if constexpr (HAS_DIFF) historyFixLobe<DIFF, SIGNAL, SH>(cb, p, sDiffLuma, sDiffRow, tileHasSky, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
-    if constexpr (HAS_SPEC) historyFixLobe<SPEC, SIGNAL, SH>(cb, p, sSpecLuma, sSpecRow, tileHasSky, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+    if constexpr (HAS_DIFF) historyFixLobe<DIFF, SIGNAL, MODE>(cb, p, sDiffLuma, sDiffRow, tileHasSky, px, py, stride.x, frameNum.x, frameNumAvgNorm.x, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
+    if constexpr (HAS_SPEC) historyFixLobe<SPEC, SIGNAL, MODE>(cb, p, sSpecLuma, sSpecRow, tileHasSky, px, py, stride.y, frameNum.y, frameNumAvgNorm.y, viewZ, materialID, N, roughness, Nv, Xv, frustumSize, pixelUv);
 }
 
 // ===============================================================================================================
@@ -292,12 +295,14 @@ NRD_DEV void lumaMoments3x3(const float (*sLuma)[TS_TILE_W], float& luma, float&
 #ifndef TS_MIN_BLOCKS
 #    define TS_MIN_BLOCKS 3  // 512-thread CTAs: 40 regs + a small spill (3 CTAs / SM) beats 64 regs (2 CTAs) by 12 % on B200
 #endif
-template <int SIGNAL, bool SH>
+// MODE: RADIANCE / SH / DO ( the occlusion denoisers have no stabilization pass ); DO stabilizes the hit distance in .w as its "luma"
+template <int SIGNAL, int MODE>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTemporalStabilizationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                        const __grid_constant__ TemporalStabilizationParams p, int ctaY0) {
     constexpr bool HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0, HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0;
     __shared__ float sDiffLuma[HAS_DIFF ? TS_TILE_H : 1][TS_TILE_W];
     __shared__ float sSpecLuma[HAS_SPEC ? TS_TILE_H : 1][TS_TILE_W];
+    constexpr bool SH = MODE == MODE_SH, FIXED = Sig<MODE>::FIXED;
 
     const int2 cta = ctaTile<5>(ctaY0);
     const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
@@ -309,8 +314,13 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
             // clamped coordinates: plain fetches of the luma half-words, issued together with the viewZ load
             float dLuma = 0.0f, sLuma = 0.0f;
-            if constexpr (HAS_DIFF) dLuma = __half2float(__ushort_as_half(__ldg(p.inDiff.template ptr<unsigned short>(gx * 4, gy * 4) )));
-            if constexpr (HAS_SPEC) sLuma = __half2float(__ushort_as_half(__ldg(p.inSpec.template ptr<unsigned short>(gx * 4, gy * 4) )));
+            if constexpr (FIXED) {
+                if constexpr (HAS_DIFF) dLuma = __half2float(__ushort_as_half(__ldg(p.inDiff.template ptr<unsigned short>(gx * 4, gy * 4) )));
+                if constexpr (HAS_SPEC) sLuma = __half2float(__ushort_as_half(__ldg(p.inSpec.template ptr<unsigned short>(gx * 4, gy * 4) )));
+            } else {
+                if constexpr (HAS_DIFF) dLuma = lumaOf<MODE>(Sig<MODE>::fetch(p.inDiff, gx, gy));
+                if constexpr (HAS_SPEC) sLuma = lumaOf<MODE>(Sig<MODE>::fetch(p.inSpec, gx, gy));
+            }
             bool sky = !inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.fetch(gx, gy)));
             if constexpr (HAS_DIFF) sDiffLuma[sy][sx] = sky ? REBLUR_INVALID : dLuma;
             if constexpr (HAS_SPEC) sSpecLuma[sy][sx] = sky ? REBLUR_INVALID : sLuma;
@@ -381,9 +391,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
         lumaHistory = clampf(lumaHistory, m1 - s, m1 + s);
         float lumaStabilized = lerp(luma, lumaHistory, fminf(historyWeight, cb.stabilizationStrength));
 
-        float4 diff = changeLuma(p.inDiff.load(px, py), lumaStabilized);
+        float4 diff = changeLumaM<MODE>(Sig<MODE>::load(p.inDiff, px, py), lumaStabilized);
         diff.w = cb.returnHistoryLengthInsteadOfOcclusion ? data1.x : diff.w;
-        p.outDiff.store(px, py, diff);
+        Sig<MODE>::store(p.outDiff, px, py, diff);
         p.outDiffLuma.store(px, py, lumaStabilized);
         if constexpr (SH) p.outDiffSh.store(px, py, rescaleSh(p.inDiffSh.load(px, py), lumaStabilized));  // REBLUR_TemporalStabilization.cs.hlsl:175-187
     }
@@ -436,9 +446,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
         lumaHistory = clampf(lumaHistory, m1 - s, m1 + s);
         float lumaStabilized = lerp(luma, lumaHistory, fminf(historyWeight, cb.stabilizationStrength));
 
-        float4 spec = changeLuma(p.inSpec.load(px, py), lumaStabilized);
+        float4 spec = changeLumaM<MODE>(Sig<MODE>::load(p.inSpec, px, py), lumaStabilized);
         spec.w = cb.returnHistoryLengthInsteadOfOcclusion ? data1.y : spec.w;
-        p.outSpec.store(px, py, spec);
+        Sig<MODE>::store(p.outSpec, px, py, spec);
         p.outSpecLuma.store(px, py, lumaStabilized);
         if constexpr (SH) p.outSpecSh.store(px, py, rescaleSh(p.inSpecSh.load(px, py), lumaStabilized));  // REBLUR_TemporalStabilization.cs.hlsl:302-314
     }
@@ -465,24 +475,33 @@ void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t s
     clearKernel<<<dim3(blocksX, height), 256, 0, stream>>>((uint8_t*)data, rowBytes, height, pitch);
 }
 
-void launchReblurHistoryFix(const ReblurConstants& cb, const HistoryFixParams& p, int signal, bool quads, Rows rows, cudaStream_t stream) {
+void launchReblurHistoryFix(const ReblurConstants& cb, const HistoryFixParams& p, int signal, int mode, bool quads, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    const bool sh = p.inDiffSh.data || p.inSpecSh.data;  // bound by the executor for "|NRD_MODE=SH" only
+    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
+    if (mode == MODE_DO) {
+        reblurHistoryFixKernel<SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
+        return;
+    }
     withSignal(signal, [&](auto sig) {
-        if (sh) reblurHistoryFixKernel<decltype(sig)::value, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
-        else reblurHistoryFixKernel<decltype(sig)::value, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
+        constexpr int S = decltype(sig)::value;
+        if (mode == MODE_SH) reblurHistoryFixKernel<S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
+        else if (mode == MODE_OCCLUSION) reblurHistoryFixKernel<S, MODE_OCCLUSION><<<grid, block, 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
+        else reblurHistoryFixKernel<S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
     });
 }
-void launchReblurTemporalStabilization(const ReblurConstants& cb, const TemporalStabilizationParams& p, int signal, Rows rows, cudaStream_t stream) {
+void launchReblurTemporalStabilization(const ReblurConstants& cb, const TemporalStabilizationParams& p, int signal, int mode, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    const bool sh = p.inDiffSh.data || p.inSpecSh.data;
+    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
+    if (mode == MODE_DO) {
+        reblurTemporalStabilizationKernel<SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        return;
+    }
     withSignal(signal, [&](auto sig) {
-        if (sh) reblurTemporalStabilizationKernel<decltype(sig)::value, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
-        else reblurTemporalStabilizationKernel<decltype(sig)::value, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+        constexpr int S = decltype(sig)::value;
+        if (mode == MODE_SH) reblurTemporalStabilizationKernel<S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        else reblurTemporalStabilizationKernel<S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
     });
 }
 

@@ -13,7 +13,20 @@ constexpr int BLOCK_W = 32, BLOCK_H = 8;
 
 template <int BORDER>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHitDistReconstructionKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HitDistReconstructionParams p,
-                                                                                     int signal, int ctaY0) {
+                                                                                     int signal, int occlusion, int ctaY0) {
+    // Texel access by bound format ( a uniform branch; this pass is bandwidth-bound ): the NRD_MODE = OCCLUSION permutation carries the hit distance alone
+    // ( Texture2D< float >: .x of whatever is bound, REBLUR_HitDistReconstruction.cs.hlsl:151-166 ), and the RADIANCE permutation also serves
+    // REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, whose textures are RGBA16_SNORM or the application's own format
+    auto ld = [&](const TexRGBA16F& t, int x, int y) -> float4 {
+        if (!t.inside(x, y)) return f4(0.0f);
+        if (t.fmt == (uint32_t)nrd::Format::RGBA16_SFLOAT && !occlusion) return t.fetch(x, y);
+        const float4 v = anyFetch4(t, x, y);
+        return occlusion ? make_float4(0.0f, 0.0f, 0.0f, v.x) : v;
+    };
+    auto st = [&](const TexRGBA16F& t, int x, int y, float4 v) {
+        if (t.fmt == (uint32_t)nrd::Format::RGBA16_SFLOAT && !occlusion) t.store(x, y, v);
+        else anyStore4(t, x, y, occlusion ? make_float4(v.w, 0.0f, 0.0f, 0.0f) : v);
+    };
     const bool hasDiff = (signal & SIGNAL_DIFF) != 0, hasSpec = (signal & SIGNAL_SPEC) != 0;
     constexpr int TW = BLOCK_W + 2 * BORDER, TH = BLOCK_H + 2 * BORDER;
     __shared__ float4 sNormalRoughness[TH][TW];
@@ -31,7 +44,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHitDistReconstructionK
             const float viewZ = unpackViewZ(cb, p.viewZ.load(gx, gy));
             sNormalRoughness[ty][tx] = unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy));
             const bool inRange = inDenoisingRange(cb, viewZ);
-            sHitDistViewZ[ty][tx] = make_float4(inRange && hasDiff ? p.inDiff.load(gx, gy).w : 0.0f, inRange && hasSpec ? p.inSpec.load(gx, gy).w : 0.0f, viewZ, 0.0f);
+            sHitDistViewZ[ty][tx] = make_float4(inRange && hasDiff ? ld(p.inDiff, gx, gy).w : 0.0f, inRange && hasSpec ? ld(p.inSpec, gx, gy).w : 0.0f, viewZ, 0.0f);
         }
     }
     __syncthreads();
@@ -87,24 +100,24 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHitDistReconstructionK
     acc.y /= fmaxf(sum.y, NRD_EPS);
 
     if (hasDiff) {
-        const float4 diff = p.inDiff.load(px, py);
-        p.outDiff.store(px, py, make_float4(diff.x, diff.y, diff.z, acc.x));
+        const float4 diff = ld(p.inDiff, px, py);
+        st(p.outDiff, px, py, make_float4(diff.x, diff.y, diff.z, acc.x));
     }
     if (hasSpec) {
-        const float4 spec = p.inSpec.load(px, py);
-        p.outSpec.store(px, py, make_float4(spec.x, spec.y, spec.z, acc.y));
+        const float4 spec = ld(p.inSpec, px, py);
+        st(p.outSpec, px, py, make_float4(spec.x, spec.y, spec.z, acc.y));
     }
 }
 }  // namespace
 
-void launchReblurHitDistReconstruction(const ReblurConstants& cb, const HitDistReconstructionParams& p, int signal, bool is5x5, Rows rows, cudaStream_t stream) {
+void launchReblurHitDistReconstruction(const ReblurConstants& cb, const HitDistReconstructionParams& p, int signal, bool occlusion, bool is5x5, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
     if (is5x5)
-        reblurHitDistReconstructionKernel<2><<<grid, block, 0, stream>>>(cb, p, signal, g.ctaY0);
+        reblurHitDistReconstructionKernel<2><<<grid, block, 0, stream>>>(cb, p, signal, occlusion ? 1 : 0, g.ctaY0);
     else
-        reblurHitDistReconstructionKernel<1><<<grid, block, 0, stream>>>(cb, p, signal, g.ctaY0);
+        reblurHitDistReconstructionKernel<1><<<grid, block, 0, stream>>>(cb, p, signal, occlusion ? 1 : 0, g.ctaY0);
 }
 
 }  // namespace nrdk

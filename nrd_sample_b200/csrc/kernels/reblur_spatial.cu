@@ -89,11 +89,14 @@ struct ShIo { const TexRGBA16F *in, *out, *outCopy; };
 // ( REBLUR_Common_SpatialFilter.hlsli:198 ) into g_mirrorProbe — the predicate is decided by the last mantissa bit of the tap position, so
 // parity with the reference is stated on its RATE ( tests/test_parity_at_baseline_sizes_gpu.py ). Compiled out of every other instantiation.
 __device__ unsigned long long g_mirrorProbe[6][2];   // [ pass * 2 + lobe ][ taps, mirrored ]
-template <int PASS, int LOBE, bool CB = false, bool SH = false, bool PROBE = false>
+// MODE: NRD_MODE of the permutation ( reblur_common.cuh ). OCCLUSION / DO read and write their signal through the format-polymorphic Sig< MODE >, keep
+// minHitDistWeight unscaled and filter the hit distance like any other channel ( REBLUR_Common_SpatialFilter.hlsli:140-142, 283-285, 327-329 ).
+template <int PASS, int LOBE, bool CB = false, int MODE = MODE_RADIANCE, bool PROBE = false>
 NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const TexGeom& geom, const TexNR& nrTex, const TexRGBA16F& input,
                            const TexRGBA16F& output, const TexR16F* outSpecHitDistForTracking, const TexRGBA16F* outputCopy, bool temporalStabilization, bool robustMirrorTest,
                            const Resolve* resolve = nullptr, ShIo shIo = ShIo()) {
     static_assert(!CB || PASS == PRE_PASS, "only the pre-pass reads checkerboarded input");
+    constexpr bool SH = MODE == MODE_SH, FIXED = Sig<MODE>::FIXED;
     const uint32_t cbMode = CB ? (LOBE == DIFF ? cb.diffCheckerboard : cb.specCheckerboard) : 2u;
     const float ROUGHNESS = LOBE == DIFF ? 1.0f : s.roughness;
     const float NLAS = LOBE == DIFF ? s.nonLinearAccumSpeed.x : s.nonLinearAccumSpeed.y;
@@ -104,7 +107,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
     const float2 rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
 
     float sum = 1.0f;
-    float4 result = input.load(CB ? s.px >> 1 : s.px, s.py);
+    float4 result = Sig<MODE>::load(input, CB ? s.px >> 1 : s.px, s.py);
     float4 resultSh = f4(0.0f);
     if constexpr (SH) resultSh = shIo.in->load(CB ? s.px >> 1 : s.px, s.py);
     if (CB && resolve->checkerboard != cbMode) {
@@ -151,7 +154,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
         const float2 roughParams = roughnessWeightParams(ROUGHNESS, cb.roughnessFraction * fractionScale);
         const float2 hitDistParams = hitDistanceWeightParams(result.w, NLAS);
         float minHitDistWeight = cb.minHitDistanceWeight * fractionScale * smc;
-        if (PASS != PRE_PASS) minHitDistWeight *= NLAS;
+        if (PASS != PRE_PASS && FIXED) minHitDistWeight *= NLAS;
         // CompareMaterials( m0, m, minm ) = max( m0, minm ) == max( m, minm ) on the 2-bit IDs k0, k in 0..3 is
         // ( k == k0 ) || max( k, k0 ) <= minm: integer compares, and no work at all when minm >= 3 (the default is 4)
         const uint32_t centerK = (uint32_t)(s.materialID + 0.5f);
@@ -270,7 +273,15 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             // One 128-bit fetch per tap from the geometry plane ( reblurGeometryPlaneKernel ): { world-space normal, |viewZ| } decoded ONCE per texel
             // per frame instead of once per tap — 48 taps per pixel and frame read it back ( NRD.hlsli:387-400, 656-684; Common.hlsli:261 )
             const float4 gA = geom.fetch(txa, tya), gB = geom.fetch(txb, tyb);
-            uint2 rawA = input.fetchRaw(ixa, tya), rawB = input.fetchRaw(ixb, tyb);
+            uint2 rawA = make_uint2(0u, 0u), rawB = make_uint2(0u, 0u);
+            float4 smpA = f4(0.0f), smpB = f4(0.0f);
+            if constexpr (FIXED) {
+                rawA = input.fetchRaw(ixa, tya);
+                rawB = input.fetchRaw(ixb, tyb);
+            } else {
+                smpA = Sig<MODE>::fetch(input, ixa, tya);
+                smpB = Sig<MODE>::fetch(input, ixb, tyb);
+            }
             uint2 rawShA = make_uint2(0u, 0u), rawShB = make_uint2(0u, 0u);
             if constexpr (SH) {
                 rawShA = shIo.in->fetchRaw(ixa, tya);
@@ -312,9 +323,15 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             // ( taps beyond the denoising range: zs = +INF in the plane, the plane-distance weight above is 0 for them )
 
             // Denanify, on the packed fp16 words (2 selects per tap instead of 4)
-            if (w.a() == 0.0f) rawA = make_uint2(0u, 0u);
-            if (w.b() == 0.0f) rawB = make_uint2(0u, 0u);
-            const float4 smpA = TexRGBA16F::decode(rawA), smpB = TexRGBA16F::decode(rawB);
+            if constexpr (FIXED) {
+                if (w.a() == 0.0f) rawA = make_uint2(0u, 0u);
+                if (w.b() == 0.0f) rawB = make_uint2(0u, 0u);
+                smpA = TexRGBA16F::decode(rawA);
+                smpB = TexRGBA16F::decode(rawB);
+            } else {
+                if (w.a() == 0.0f) smpA = f4(0.0f);
+                if (w.b() == 0.0f) smpB = f4(0.0f);
+            }
             P2 sw(smpA.w, smpB.w);
 
             if (PASS == PRE_PASS && LOBE == SPEC) {
@@ -367,13 +384,13 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
             resultSh += make_float4(shX.a() + shX.b(), shY.a() + shY.b(), shZ.a() + shZ.b(), shW.a() + shW.b());
             resultSh *= positiveRcp(sum);
         }
-        if (PASS != PRE_PASS) result.w = hitDist / hitDistScale;
+        if (PASS != PRE_PASS && FIXED) result.w = hitDist / hitDistScale;
         if (PASS == PRE_PASS && LOBE == SPEC) outSpecHitDistForTracking->store(s.px, s.py, hitDistForTracking == NRD_INF ? 0.0f : hitDistForTracking);
     }
 
     // Checkerboard resolve ( if the pre-pass found nothing ): the traced row neighbours, REBLUR_Common_SpatialFilter.hlsli:294-316
     if (CB && sum == 0.0f) {
-        float4 s0 = input.load(resolve->x0, s.py), s1 = input.load(resolve->x1, s.py);
+        float4 s0 = Sig<MODE>::load(input, resolve->x0, s.py), s1 = Sig<MODE>::load(input, resolve->x1, s.py);
         if (resolve->wc.x == 0.0f) s0 = f4(0.0f);
         if (resolve->wc.y == 0.0f) s1 = f4(0.0f);
         result = s0 * resolve->wc.x + s1 * resolve->wc.y;
@@ -385,12 +402,12 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
         }
     }
 
-    output.store(s.px, s.py, result);
+    Sig<MODE>::store(output, s.px, s.py, result);
     if constexpr (SH) shIo.out->store(s.px, s.py, resultSh);
 
     if (PASS == POST_BLUR && !temporalStabilization) {
-        result.w = cb.returnHistoryLengthInsteadOfOcclusion ? (LOBE == DIFF ? s.data1.x : s.data1.y) : result.w;
-        outputCopy->store(s.px, s.py, result);
+        if (FIXED) result.w = cb.returnHistoryLengthInsteadOfOcclusion ? (LOBE == DIFF ? s.data1.x : s.data1.y) : result.w;
+        Sig<MODE>::store(*outputCopy, s.px, s.py, result);
         if constexpr (SH) shIo.outCopy->store(s.px, s.py, resultSh);
     }
 }
@@ -419,7 +436,7 @@ __global__ void __launch_bounds__(256) reblurGeometryPlaneKernel(const __grid_co
     p.out.store(px, py, make_float4(nr.x, nr.y, nr.z, zs < cb.denoisingRange ? zs : __int_as_float(0x7F800000)));
 }
 
-template <bool CB, int SIGNAL, bool SH, bool PROBE = false>
+template <bool CB, int SIGNAL, int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags, int ctaY0) {
     const bool robust = (flags & 2) != 0;
     Center s;
@@ -445,8 +462,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPr
         r.x0 = x0 >> 1;
         r.x1 = x1 >> 1;
     }
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<PRE_PASS, DIFF, CB, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<PRE_PASS, SPEC, CB, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<PRE_PASS, DIFF, CB, MODE, PROBE>(cb, s, p.geom, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, &r, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<PRE_PASS, SPEC, CB, MODE, PROBE>(cb, s, p.geom, p.normalRoughness, p.inSpec, p.outSpec, &p.outSpecHitDistForTracking, nullptr, true, robust, &r, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
 }
 
 // Non-linear accumulation speed with the quad-neighbour smoothing of REBLUR_Blur.cs.hlsl:40-59 (lanes x^1, x^2 of the row)
@@ -462,7 +479,7 @@ NRD_DEV float2 quadSmoothedAccumSpeed(const ReblurConstants& cb, float2 data1, f
     return n;
 }
 
-template <int SIGNAL, bool SH, bool PROBE = false>
+template <int SIGNAL, int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
@@ -482,11 +499,11 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBl
     if (skyTile || !inDenoisingRange(cb, s.viewZ) || s.px > cb.rectSizeMinusOne[0] || s.py > cb.rectSizeMinusOne[1]) return;
 
     setupCenter(cb, s, p.normalRoughness, cb.rotator);
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<BLUR, DIFF, false, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<BLUR, SPEC, false, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<BLUR, DIFF, false, MODE, PROBE>(cb, s, p.geom, p.normalRoughness, p.inDiff, p.outDiff, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, nullptr});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<BLUR, SPEC, false, MODE, PROBE>(cb, s, p.geom, p.normalRoughness, p.inSpec, p.outSpec, nullptr, nullptr, true, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, nullptr});
 }
 
-template <bool TEMPORAL_STABILIZATION, int SIGNAL, bool SH, bool PROBE = false>
+template <bool TEMPORAL_STABILIZATION, int SIGNAL, int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags, int ctaY0) {
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
@@ -505,8 +522,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPo
     p.outNormalRoughness.storeRaw(s.px, s.py, p.normalRoughness.loadRaw(s.px, s.py));
     if (!TEMPORAL_STABILIZATION) p.outInternalData.store(s.px, s.py, packInternalData(cb, s.data1.x, s.data1.y, s.materialID));
 
-    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<POST_BLUR, DIFF, false, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, &p.outDiffShCopy});
-    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<POST_BLUR, SPEC, false, SH, PROBE>(cb, s, p.geom, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, &p.outSpecShCopy});
+    if constexpr ((SIGNAL & SIGNAL_DIFF) != 0) spatialFilter<POST_BLUR, DIFF, false, MODE, PROBE>(cb, s, p.geom, p.normalRoughness, p.inDiff, p.outDiff, nullptr, &p.outDiffCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inDiffSh, &p.outDiffSh, &p.outDiffShCopy});
+    if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) spatialFilter<POST_BLUR, SPEC, false, MODE, PROBE>(cb, s, p.geom, p.normalRoughness, p.inSpec, p.outSpec, nullptr, &p.outSpecCopy, TEMPORAL_STABILIZATION, robust, nullptr, ShIo{&p.inSpecSh, &p.outSpecSh, &p.outSpecShCopy});
 }
 
 // REBLUR_SplitScreen.cs.hlsl:21-56: the noisy input (range-masked) left of CommonSettings::splitScreen
@@ -515,8 +532,15 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurSplitScreenKernel(cons
     const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
     if (u > cb.splitScreen || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1]) return;
     const float inRange = inDenoisingRange(cb, unpackViewZ(cb, p.viewZ.load(px, py))) ? 1.0f : 0.0f;
-    if (signal & SIGNAL_DIFF) p.outDiff.store(px, py, p.inDiff.load(px >> (cb.diffCheckerboard != 2u ? 1 : 0), py) * inRange);
-    if (signal & SIGNAL_SPEC) p.outSpec.store(px, py, p.inSpec.load(px >> (cb.specCheckerboard != 2u ? 1 : 0), py) * inRange);
+    // the RADIANCE permutation serves the occlusion denoisers too ( Reblur_DiffuseSpecularOcclusion.hpp:215-226 ): their textures are single-channel or SNORM,
+    // a graphics API converts on access, here the views carry the format
+    auto copy = [&](const TexRGBA16F& src, const TexRGBA16F& dst, uint32_t checkerboard) {
+        const int sx = px >> (checkerboard != 2u ? 1 : 0);
+        if (src.fmt == (uint32_t)nrd::Format::RGBA16_SFLOAT && dst.fmt == (uint32_t)nrd::Format::RGBA16_SFLOAT) dst.store(px, py, src.load(sx, py) * inRange);
+        else anyStore4(dst, px, py, (src.inside(sx, py) ? anyFetch4(src, sx, py) : f4(0.0f)) * inRange);
+    };
+    if (signal & SIGNAL_DIFF) copy(p.inDiff, p.outDiff, cb.diffCheckerboard);
+    if (signal & SIGNAL_SPEC) copy(p.inSpec, p.outSpec, cb.specCheckerboard);
     // NRD_MODE = SH ( :44-52 ): the SH1 inputs, same addressing
     if ((signal & SIGNAL_DIFF) && p.inDiffSh.data) p.outDiffSh.store(px, py, p.inDiffSh.load(px >> (cb.diffCheckerboard != 2u ? 1 : 0), py) * inRange);
     if ((signal & SIGNAL_SPEC) && p.inSpecSh.data) p.outSpecSh.store(px, py, p.inSpecSh.load(px >> (cb.specCheckerboard != 2u ? 1 : 0), py) * inRange);
@@ -559,58 +583,76 @@ void launchReblurSplitScreen(const ReblurConstants& cb, const SplitScreenParams&
     if (!g.count) return;
     reblurSplitScreenKernel<<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, signal, g.ctaY0);
 }
+// `flags`: bit 0 quad smoothing, bit 1 robust mirror test, bit 2 mirror probe, bits 4-5 NRD_MODE of the permutation ( MODE_* )
 void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int signal, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
+    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
     const bool cbOn = cb.diffCheckerboard != 2u || cb.specCheckerboard != 2u;  // CheckerboardMode::BLACK / WHITE set both (Reblur.cpp:301-313)
-    const bool sh = p.inDiffSh.data || p.inSpecSh.data;                        // bound by the executor for "|NRD_MODE=SH" only
-    if ((flags & 4) && signal == SIGNAL_BOTH && !sh && !cbOn) {  // NRDCU_FLAG_PROBE_MIRROR
-        reblurPrePassKernel<false, SIGNAL_BOTH, false, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    const int mode = (flags >> 4) & 3;
+    if ((flags & 4) && signal == SIGNAL_BOTH && mode == MODE_RADIANCE && !cbOn) {  // NRDCU_FLAG_PROBE_MIRROR
+        reblurPrePassKernel<false, SIGNAL_BOTH, MODE_RADIANCE, true><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        return;
+    }
+    if (mode == MODE_DO) {   // REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION: the only denoiser of this mode has one lobe ( the occlusion denoisers have no pre-pass )
+        if (cbOn) reblurPrePassKernel<true, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        else reblurPrePassKernel<false, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
         return;
     }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        if (sh) {
-            if (cbOn) reblurPrePassKernel<true, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
-            else reblurPrePassKernel<false, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        if (mode == MODE_SH) {
+            if (cbOn) reblurPrePassKernel<true, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+            else reblurPrePassKernel<false, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
         } else {
-            if (cbOn) reblurPrePassKernel<true, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
-            else reblurPrePassKernel<false, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+            if (cbOn) reblurPrePassKernel<true, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+            else reblurPrePassKernel<false, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
         }
     });
 }
 void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int signal, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    const bool sh = p.inDiffSh.data || p.inSpecSh.data;
-    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    if ((flags & 4) && signal == SIGNAL_BOTH && !sh) {
-        reblurBlurKernel<SIGNAL_BOTH, false, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    const int mode = (flags >> 4) & 3;
+    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
+    if ((flags & 4) && signal == SIGNAL_BOTH && mode == MODE_RADIANCE) {
+        reblurBlurKernel<SIGNAL_BOTH, MODE_RADIANCE, true><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        return;
+    }
+    if (mode == MODE_DO) {
+        reblurBlurKernel<SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
         return;
     }
     withSignal(signal, [&](auto sig) {
-        if (sh) reblurBlurKernel<decltype(sig)::value, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
-        else reblurBlurKernel<decltype(sig)::value, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        constexpr int S = decltype(sig)::value;
+        if (mode == MODE_SH) reblurBlurKernel<S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        else if (mode == MODE_OCCLUSION) reblurBlurKernel<S, MODE_OCCLUSION><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        else reblurBlurKernel<S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
     });
 }
 void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, int signal, bool temporalStabilization, int flags, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
-    if ((flags & 4) && signal == SIGNAL_BOTH && !(p.inDiffSh.data || p.inSpecSh.data) && temporalStabilization) {
-        reblurPostBlurKernel<true, SIGNAL_BOTH, false, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+    const int mode = (flags >> 4) & 3;
+    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
+    if ((flags & 4) && signal == SIGNAL_BOTH && mode == MODE_RADIANCE && temporalStabilization) {
+        reblurPostBlurKernel<true, SIGNAL_BOTH, MODE_RADIANCE, true><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        return;
+    }
+    if (mode == MODE_DO) {
+        if (temporalStabilization) reblurPostBlurKernel<true, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        else reblurPostBlurKernel<false, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
         return;
     }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        const bool sh = p.inDiffSh.data || p.inSpecSh.data;
-        if (sh) {
-            if (temporalStabilization) reblurPostBlurKernel<true, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
-            else reblurPostBlurKernel<false, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+        if (mode == MODE_OCCLUSION) reblurPostBlurKernel<false, S, MODE_OCCLUSION><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);   // the occlusion graph has no stabilization pass
+        else if (mode == MODE_SH) {
+            if (temporalStabilization) reblurPostBlurKernel<true, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+            else reblurPostBlurKernel<false, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
         } else {
-            if (temporalStabilization) reblurPostBlurKernel<true, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
-            else reblurPostBlurKernel<false, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, flags, g.ctaY0);
+            if (temporalStabilization) reblurPostBlurKernel<true, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+            else reblurPostBlurKernel<false, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
         }
     });
 }

@@ -45,10 +45,14 @@ NRD_DEV uint4 gather4(const TexR16U& t, int x0, int y0) {
 // OPTIONAL: checkerboard resolve speed-up and the application's guide textures (confidence, threshold mix); compiled out of the plain kernel
 // SH ( NRD_MODE = SH ): the lobe's second RGBA16F accumulates with the lobe's speed from a bilinear ( custom weights ) history fetch and follows the
 // firefly clamp of the luma ( REBLUR_TemporalAccumulation.cs.hlsl:781-783, 801-804, 819-821, 831-833, 923-925, 940-943, 957-959, 968-970 )
-template <bool OPTIONAL, int SIGNAL, bool SH>
+// MODE ( NRD_MODE ): OCCLUSION / DO read and write their signal and fast history through the format-polymorphic Sig / FastSig, skip the firefly suppressor
+// ( NRD_SUPPORTS_ANTIFIREFLY = 0, REBLUR_Config.hlsli:38-41 ); OCCLUSION additionally has no pre-pass in front of it — it reads the ( possibly half-width,
+// checkerboarded ) input itself and resolves the missing pixels from their row neighbours ( TA:331-345, 359-378, 893-912 ) — and writes no data2.
+template <bool OPTIONAL, int SIGNAL, int MODE>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTemporalAccumulationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                       const __grid_constant__ TemporalAccumulationParams p, int ctaY0) {
     __shared__ float4 sNormalHitDist[TILE_H][TILE_W];
+    constexpr bool SH = MODE == MODE_SH, FIXED = Sig<MODE>::FIXED, OCC = MODE == MODE_OCCLUSION;
 
     const int2 cta = ctaTile<1>(ctaY0);
     const int px = cta.x * BLOCK_W + threadIdx.x, py = cta.y * BLOCK_H + threadIdx.y;
@@ -68,7 +72,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
             int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
             float3 N = xyz(unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy)));
             if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) {
-                float hitDist = cb.specPrepassBlurRadius == 0.0f ? p.inSpec.load(gx, gy).w : p.inSpecHitDistForTracking.load(gx, gy);
+                float hitDist;
+                if constexpr (OCC) hitDist = Sig<MODE>::load(p.inSpec, gx >> (cb.specCheckerboard != 2u ? 1 : 0), gy).w;   // TA:46-55
+                else hitDist = cb.specPrepassBlurRadius == 0.0f ? Sig<MODE>::load(p.inSpec, gx, gy).w : p.inSpecHitDistForTracking.load(gx, gy);
                 float z = unpackViewZ(cb, p.viewZ.load(gx, gy));
                 sNormalHitDist[sy][sx] = f4(N, (hitDist == 0.0f || !inDenoisingRange(cb, z)) ? NRD_INF : hitDist);
             } else
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
 
     hitDistForTracking = hitDistForTracking == NRD_INF ? 0.0f : hitDistForTracking;
     const float hitDistNormalization = hitDistanceNormalization(viewZ, cb.hitDistSettings, roughness);
-    hitDistForTracking *= cb.specPrepassBlurRadius == 0.0f ? hitDistNormalization : 1.0f;
+    hitDistForTracking *= (OCC || cb.specPrepassBlurRadius == 0.0f) ? hitDistNormalization : 1.0f;   // TA:135-139
     if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) p.outSpecHitDistForTracking.store(px, py, hitDistForTracking);
 
     // Previous position and surface motion uv
@@ -226,6 +232,35 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
     smbFootprintQuality = sqrt01(smbFootprintQuality);
     smbFootprintQuality *= sizeQuality;
 
+    // Checkerboard resolve of the occlusion mode ( TA:331-345 ): the traced row neighbours and their disocclusion weights
+    int cbX0 = 0, cbX1 = 0;
+    float2 wc = f2(0.0f);
+    if constexpr (OCC) {
+        const int x0 = max(px - 1, 0), x1 = min(px + 1, cb.rectSizeMinusOne[0]);
+        const float viewZ0 = unpackViewZ(cb, p.viewZ.load(x0, py)), viewZ1 = unpackViewZ(cb, p.viewZ.load(x1, py));
+        const float threshold = disocclusionThresholdAt(0.02f, frustumSize, NoV);  // NRD_DISOCCLUSION_THRESHOLD
+        wc = make_float2(threshold >= fabsf(viewZ0 - viewZ) ? 1.0f : 0.0f, threshold >= fabsf(viewZ1 - viewZ) ? 1.0f : 0.0f);
+        if (!inDenoisingRange(cb, viewZ0) || px < 1) wc.x = 0.0f;
+        if (!inDenoisingRange(cb, viewZ1) || px >= cb.rectSizeMinusOne[0]) wc.y = 0.0f;
+        wc = wc * positiveRcp(wc.x + wc.y);
+        cbX0 = x0 >> 1;
+        cbX1 = x1 >> 1;
+    }
+    // the lobe's input of this pixel: full width after a pre-pass, half width and resolved here in the occlusion mode
+    auto currentSignal = [&](const TexRGBA16F& tex, uint32_t checkerboard, bool hasData) {
+        if constexpr (!OCC) return Sig<MODE>::load(tex, px, py);
+        else {
+            float4 v = Sig<MODE>::load(tex, px >> (checkerboard != 2u ? 1 : 0), py);
+            if (!hasData) {
+                float4 s0 = Sig<MODE>::load(tex, cbX0, py), s1 = Sig<MODE>::load(tex, cbX1, py);
+                if (wc.x == 0.0f) s0 = f4(0.0f);
+                if (wc.y == 0.0f) s1 = f4(0.0f);
+                v = s0 * wc.x + s1 * wc.y;
+            }
+            return v;
+        }
+    };
+
     // =============================================================================================== Specular
     float specAccumSpeedCorrected = 0.0f, curvature = 0.0f, virtualHistoryAmount = 0.0f;  // what a diffuse-only denoiser packs (TA:869-873)
     if constexpr ((SIGNAL & SIGNAL_SPEC) != 0) {
@@ -235,7 +270,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
 
         // Checkerboard ( RADIANCE mode: the pre-pass has already resolved the half-width input, only the accumulation speed changes; TA:329-357 )
         const bool specHasData = !OPTIONAL || cb.specCheckerboard == 2u || (((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u) == cb.specCheckerboard;
-        const float4 spec = p.inSpec.load(px, py);
+        const float4 spec = currentSignal(p.inSpec, cb.specCheckerboard, specHasData);
 
         // Curvature estimation along predicted motion (TA:387-467)
         curvature = 0.0f;
@@ -453,7 +488,17 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         {
             float a = atanf(smbParallaxInPixelsMax * pixelSize / length(X));
             float nonLinearAccumSpeed = 1.0f / (1.0f + smbSpecAccumSpeed);
-            float hPrev = p.historySpec.sampleLinear(smbPixelUv * resolutionScalePrev).w;
+            float hPrev;
+            if constexpr (FIXED) hPrev = p.historySpec.sampleLinear(smbPixelUv * resolutionScalePrev).w;
+            else {   // the same clamped bilinear fetch through the polymorphic accessor
+                const float2 uvp = smbPixelUv * resolutionScalePrev;
+                const float tx = uvp.x * (float)p.historySpec.w - 0.5f, ty = uvp.y * (float)p.historySpec.h - 0.5f;
+                const float fx = floorf(tx), fy = floorf(ty);
+                const int x0 = (int)fx, y0 = (int)fy;
+                const float a = Sig<MODE>::fetchClamped(p.historySpec, x0, y0).w, b = Sig<MODE>::fetchClamped(p.historySpec, x0 + 1, y0).w;
+                const float c = Sig<MODE>::fetchClamped(p.historySpec, x0, y0 + 1).w, d = Sig<MODE>::fetchClamped(p.historySpec, x0 + 1, y0 + 1).w;
+                hPrev = lerp(lerp(a, b, tx - fx), lerp(c, d, tx - fx), ty - fy);
+            }
             float h = lerp(hPrev, spec.w, nonLinearAccumSpeed) * hitDistNormalization;
 
             float tana0 = specularLobeTanHalfAngle(roughnessModified, NRD_MAX_PERCENT_OF_LOBE_VOLUME);
@@ -501,8 +546,13 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
             float4 occlusionWeights = lerp(smbOcclusionWeights, vmbOcclusionWeights, virtualHistoryAmount);
             bool allowCatRom = virtualHistoryAmount < 0.5f ? smbAllowCatRom : vmbAllowCatRom;
             HistoryFilter hf(saturate(uv) * rectSizePrev, resourceSizeInvPrev, occlusionWeights, allowCatRom);
-            specHistory = clampNegativeToZero(hf.color(p.historySpec));
-            specFastHistory = fmaxf(hf.bilinear(p.historySpecFast), 0.0f);
+            if constexpr (FIXED) {
+                specHistory = clampNegativeToZero(hf.color(p.historySpec));
+                specFastHistory = fmaxf(hf.bilinear(p.historySpecFast), 0.0f);
+            } else {
+                specHistory = clampNegativeToZeroM<MODE>(hf.template colorAny<Sig<MODE>>(p.historySpec));
+                specFastHistory = fmaxf(hf.template bilinearAny<FastSig<MODE>>(p.historySpecFast), 0.0f);
+            }
             if constexpr (SH) specShHistory = hf.bilinear4(p.historySpecSh);
         }
 
@@ -519,7 +569,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         const float specMaxRelativeIntensity = cb.fireflySuppressorMinRelativeScale + 38.0f / (specAccumSpeed + 1.0f);
         float specAntifireflyFactor = specAccumSpeed * cb.maxBlurRadius * 0.1f;
         specAntifireflyFactor /= 1.0f + specAntifireflyFactor;
-        {
+        if constexpr (FIXED) {
             float lumaResult = specResult.x;
             float lumaClamped = fminf(lumaResult, specHistory.x * specMaxRelativeIntensity);
             lumaClamped = lerp(lumaResult, lumaClamped, specAntifireflyFactor);
@@ -529,7 +579,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
             float hitDistMaxRelativeIntensity = 1.2f + 1.0f / (specAccumSpeed + 1.0f);
             specResult.w = lerp(specResult.w, fminf(specResult.w, specHistory.w * hitDistMaxRelativeIntensity), specAntifireflyFactor);
         }
-        p.outSpec.store(px, py, specResult);
+        Sig<MODE>::store(p.outSpec, px, py, specResult);
         if constexpr (SH) p.outSpecSh.store(px, py, specShResult);
 
         {  // Fast history
@@ -538,14 +588,16 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
 
             float specHistoryConfidence = lerp(surfaceHistoryConfidence, virtualHistoryConfidence, virtualHistoryAmount);
             float fastNonLinearAccumSpeed = nonLinearAccumSpeedFast(cb, specAccumSpeed, maxFastAccumulatedFrameNum, specHistoryConfidence, specHasData);
-            float fastResult = lerp(specFastHistory, spec.x, fastNonLinearAccumSpeed);
-            float fastClamped = fminf(fastResult, specHistory.x * specMaxRelativeIntensity * 4.0f);
-            fastResult = lerp(fastResult, fastClamped, specAntifireflyFactor);
-            p.outSpecFast.store(px, py, fastResult);
+            float fastResult = lerp(specFastHistory, lumaOf<MODE>(spec), fastNonLinearAccumSpeed);
+            if constexpr (FIXED) {
+                float fastClamped = fminf(fastResult, specHistory.x * specMaxRelativeIntensity * 4.0f);
+                fastResult = lerp(fastResult, fastClamped, specAntifireflyFactor);
+            }
+            FastSig<MODE>::store(p.outSpecFast, px, py, fastResult);
         }
     }
 
-    storeData2<SIGNAL>(p, px, py, fbits, curvature, virtualHistoryAmount, smbAllowCatRom);
+    if constexpr (!OCC) storeData2<SIGNAL>(p, px, py, fbits, curvature, virtualHistoryAmount, smbAllowCatRom);   // TA:873-877
 
     // =============================================================================================== Diffuse
     if constexpr ((SIGNAL & SIGNAL_DIFF) == 0) diffAccumSpeed = 0.0f;  // TA:972-974
@@ -555,11 +607,18 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         diffAccumSpeed *= lerp(diffHistoryConfidence, 1.0f, 1.0f / (1.0f + diffAccumSpeed));
 
         const bool diffHasData = !OPTIONAL || cb.diffCheckerboard == 2u || (((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u) == cb.diffCheckerboard;
-        const float4 diff = p.inDiff.load(px, py);
+        const float4 diff = currentSignal(p.inDiff, cb.diffCheckerboard, diffHasData);
 
         HistoryFilter hf(saturate(smbPixelUv) * rectSizePrev, resourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom);
-        const float4 diffHistory = clampNegativeToZero(hf.color(p.historyDiff));
-        const float diffFastHistory = fmaxf(hf.bilinear(p.historyDiffFast), 0.0f);
+        float4 diffHistory;
+        float diffFastHistory;
+        if constexpr (FIXED) {
+            diffHistory = clampNegativeToZero(hf.color(p.historyDiff));
+            diffFastHistory = fmaxf(hf.bilinear(p.historyDiffFast), 0.0f);
+        } else {
+            diffHistory = clampNegativeToZeroM<MODE>(hf.template colorAny<Sig<MODE>>(p.historyDiff));
+            diffFastHistory = fmaxf(hf.template bilinearAny<FastSig<MODE>>(p.historyDiffFast), 0.0f);
+        }
         float4 diffShResult = f4(0.0f);
         if constexpr (SH) diffShResult = hf.bilinear4(p.historyDiffSh);
 
@@ -571,41 +630,49 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
         float diffAntifireflyFactor = diffAccumSpeed * cb.maxBlurRadius * 0.1f;
         diffAntifireflyFactor /= 1.0f + diffAntifireflyFactor;
 
-        float lumaResult = diffResult.x;
-        float lumaClamped = fminf(lumaResult, diffHistory.x * diffMaxRelativeIntensity);
-        lumaClamped = lerp(lumaResult, lumaClamped, diffAntifireflyFactor);
-        diffResult = changeLuma(diffResult, lumaClamped);
-        if constexpr (SH) diffShResult = rescaleSh(diffShResult, lumaClamped);
+        if constexpr (FIXED) {
+            float lumaResult = diffResult.x;
+            float lumaClamped = fminf(lumaResult, diffHistory.x * diffMaxRelativeIntensity);
+            lumaClamped = lerp(lumaResult, lumaClamped, diffAntifireflyFactor);
+            diffResult = changeLuma(diffResult, lumaClamped);
+            if constexpr (SH) diffShResult = rescaleSh(diffShResult, lumaClamped);
 
-        float hitDistMaxRelativeIntensity = 1.2f + 1.0f / (diffAccumSpeed + 1.0f);
-        diffResult.w = lerp(diffResult.w, fminf(diffResult.w, diffHistory.w * hitDistMaxRelativeIntensity), diffAntifireflyFactor);
-        p.outDiff.store(px, py, diffResult);
+            float hitDistMaxRelativeIntensity = 1.2f + 1.0f / (diffAccumSpeed + 1.0f);
+            diffResult.w = lerp(diffResult.w, fminf(diffResult.w, diffHistory.w * hitDistMaxRelativeIntensity), diffAntifireflyFactor);
+        }
+        Sig<MODE>::store(p.outDiff, px, py, diffResult);
         if constexpr (SH) p.outDiffSh.store(px, py, diffShResult);
 
         float fastNonLinearAccumSpeed = checkerboardResolveAccumSpeed(cb, 1.0f / (1.0f + fminf(diffAccumSpeed, cb.maxFastAccumulatedFrameNum)), diffHasData);
-        float fastResult = lerp(diffFastHistory, diff.x, fastNonLinearAccumSpeed);
-        float fastClamped = fminf(fastResult, diffHistory.x * diffMaxRelativeIntensity * 4.0f);
-        fastResult = lerp(fastResult, fastClamped, diffAntifireflyFactor);
-        p.outDiffFast.store(px, py, fastResult);
+        float fastResult = lerp(diffFastHistory, lumaOf<MODE>(diff), fastNonLinearAccumSpeed);
+        if constexpr (FIXED) {
+            float fastClamped = fminf(fastResult, diffHistory.x * diffMaxRelativeIntensity * 4.0f);
+            fastResult = lerp(fastResult, fastClamped, diffAntifireflyFactor);
+        }
+        FastSig<MODE>::store(p.outDiffFast, px, py, fastResult);
     }
 
     storeData1<SIGNAL>(p, px, py, diffAccumSpeed, specAccumSpeedCorrected);
 }
 
-void launchReblurTemporalAccumulation(const ReblurConstants& cb, const TemporalAccumulationParams& p, int signal, Rows rows, cudaStream_t stream) {
+void launchReblurTemporalAccumulation(const ReblurConstants& cb, const TemporalAccumulationParams& p, int signal, int mode, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count);
+    const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
+    const bool optional = cb.specCheckerboard != 2u || cb.diffCheckerboard != 2u || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix;
+    if (mode == MODE_DO) {   // one denoiser, one lobe
+        reblurTemporalAccumulationKernel<true, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        return;
+    }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        const bool optional = cb.specCheckerboard != 2u || cb.diffCheckerboard != 2u || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix;
-        const bool sh = p.inDiffSh.data || p.inSpecSh.data;  // bound by the executor for "|NRD_MODE=SH" only
-        if (sh) {
-            if (optional) reblurTemporalAccumulationKernel<true, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
-            else reblurTemporalAccumulationKernel<false, S, true><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+        if (mode == MODE_OCCLUSION) reblurTemporalAccumulationKernel<true, S, MODE_OCCLUSION><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        else if (mode == MODE_SH) {
+            if (optional) reblurTemporalAccumulationKernel<true, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+            else reblurTemporalAccumulationKernel<false, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
         } else {
-            if (optional) reblurTemporalAccumulationKernel<true, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
-            else reblurTemporalAccumulationKernel<false, S, false><<<grid, dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, g.ctaY0);
+            if (optional) reblurTemporalAccumulationKernel<true, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+            else reblurTemporalAccumulationKernel<false, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
         }
     });
 }

@@ -77,6 +77,7 @@ bool bindAny4(const nrdcuTexture& t, TexAny4& v) {
     v.w = (int)t.width;
     v.h = (int)t.height;
     v.pitch = (int)(t.pitchBytes / bpp);
+    v.fmt = t.format;
     return true;
 }
 

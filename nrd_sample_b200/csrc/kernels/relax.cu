@@ -1500,6 +1500,7 @@ struct RelaxBinder {
         v.w = (int)x.width;
         v.h = (int)x.height;
         v.pitch = (int)(x.pitchBytes / bpp);
+        v.fmt = x.format;
         next++;
         return v;
     }

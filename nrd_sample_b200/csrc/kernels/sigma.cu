@@ -449,6 +449,7 @@ struct SigmaBinder {
         v.w = (int)x.width;
         v.h = (int)x.height;
         v.pitch = (int)(x.pitchBytes / bpp);
+        v.fmt = x.format;
         next++;
         return v;
     }

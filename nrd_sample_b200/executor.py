@@ -41,6 +41,8 @@ FORMAT_STORAGE = {
     api.Format.RGBA8_UNORM: (torch.uint8, 4),
     api.Format.R16_UINT: (torch.int16, 1),
     api.Format.R16_SFLOAT: (torch.float16, 1),
+    api.Format.R16_UNORM: (torch.int16, 1),
+    api.Format.RGBA16_SNORM: (torch.int16, 4),
     api.Format.RGBA16_SFLOAT: (torch.float16, 4),
     api.Format.R32_UINT: (torch.int32, 1),
     api.Format.R32_SFLOAT: (torch.float32, 1),

@@ -82,9 +82,11 @@ class Format(enum.IntEnum):
     R8_UINT = 2
     RG8_UNORM = 4
     RGBA8_UNORM = 8
+    R16_UNORM = 13
     R16_UINT = 15
     R16_SFLOAT = 17
     RG16_SFLOAT = 22
+    RGBA16_SNORM = 24
     RGBA16_SFLOAT = 27
     R32_UINT = 28
     R32_SFLOAT = 30
@@ -95,7 +97,7 @@ class Format(enum.IntEnum):
 
 FORMAT_BYTES = {
     Format.R8_UNORM: 1, Format.R8_UINT: 1, Format.RG8_UNORM: 2, Format.RGBA8_UNORM: 4, Format.R16_UINT: 2, Format.R16_SFLOAT: 2,
-    Format.RG16_SFLOAT: 4, Format.RGBA16_SFLOAT: 8, Format.R32_UINT: 4, Format.R32_SFLOAT: 4, Format.R10_G10_B10_A2_UNORM: 4, Format.RGBA32_SFLOAT: 16,
+    Format.RG16_SFLOAT: 4, Format.RGBA16_SFLOAT: 8, Format.R16_UNORM: 2, Format.RGBA16_SNORM: 8, Format.R32_UINT: 4, Format.R32_SFLOAT: 4, Format.R10_G10_B10_A2_UNORM: 4, Format.RGBA32_SFLOAT: 16,
 }
 
 

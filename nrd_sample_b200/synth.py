@@ -356,6 +356,38 @@ def reblur_frame(frame_index: int, width: int, height: int, device="cpu", period
     return out
 
 
+def occlusion_frame(frame_index: int, width: int, height: int, device="cpu", period: int = 0, lobes: str = "both", directional: bool = False, checkerboard: int = 0,
+                    guides: bool = False, holes: bool = False, rgba16f: bool = False) -> Dict[str, torch.Tensor]:
+    """User inputs of the REBLUR occlusion denoisers: the G-buffer and motion of `reblur_frame` with the normalized hit distance alone.
+    REBLUR_*_OCCLUSION: IN_DIFF_HITDIST / IN_SPEC_HITDIST as R16_UNORM ( int16 storage ), or — `rgba16f`, what NRDSample binds ( Source/NRDSample.cpp:495-500 ) —
+    as RGBA16F with the value in .x. REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION ( `directional` ): IN_DIFF_DIRECTION_HITDIST RGBA16F = { direction * hitDist, hitDist },
+    the shape of REBLUR_FrontEnd_PackDirectionalOcclusion ( NRD.hlsli:853-864 ). Checkerboarded inputs are half width in the left half, as for `reblur_frame`."""
+    base = reblur_frame(frame_index, width, height, device, period, holes=holes, guides=guides)
+    out = {k: v for k, v in base.items() if "RADIANCE" not in k}
+    nhd = {"DIFF": base["IN_DIFF_RADIANCE_HITDIST"][..., 3].float(), "SPEC": base["IN_SPEC_RADIANCE_HITDIST"][..., 3].float()}
+    if directional:
+        cam = make_camera(frame_index, width, height, period)
+        n = _raycast(cam, width, height, torch.device(device))["N"]
+        d = torch.cat([n * nhd["DIFF"].unsqueeze(-1), nhd["DIFF"].unsqueeze(-1)], -1).to(torch.float16)
+        out["IN_DIFF_DIRECTION_HITDIST"] = (checkerboard_pack(d, 0 if checkerboard == 1 else 1, frame_index) if checkerboard else d).contiguous()
+        return out
+    diff_mode, spec_mode = (0, 1) if checkerboard == 1 else (1, 0)
+    for lobe, mode in (("DIFF", diff_mode), ("SPEC", spec_mode)):
+        if lobes != "both" and lobes.upper() != lobe[:4]:
+            continue
+        v = nhd[lobe].clamp(0, 1)
+        if rgba16f:
+            t = torch.stack([v, torch.zeros_like(v), torch.zeros_like(v), torch.ones_like(v)], -1).to(torch.float16)
+        else:
+            t = (v * 65535.0 + 0.5).to(torch.int32).clamp(0, 65535).to(torch.uint16).view(torch.int16)
+        out[f"IN_{lobe}_HITDIST"] = (checkerboard_pack(t, mode, frame_index) if checkerboard else t).contiguous()
+    if lobes == "diff":
+        out.pop("IN_SPEC_CONFIDENCE", None)
+    if lobes == "spec":
+        out.pop("IN_DIFF_CONFIDENCE", None)
+    return out
+
+
 def reblur_frame_sh(frame_index: int, width: int, height: int, device="cpu", period: int = 0) -> Dict[str, torch.Tensor]:
     """The inputs of REBLUR_DIFFUSE_SPECULAR_SH ( `reblur_frame( sh = True )` ) under a name `bench.py --denoiser reblur_sh` can look up."""
     return reblur_frame(frame_index, width, height, device, period, sh=True)

@@ -79,6 +79,13 @@ IDENTIFIERS = [
     ("REBLUR_PrePass.cs.hlsl", ""), ("REBLUR_TemporalAccumulation.cs.hlsl", ""), ("REBLUR_HistoryFix.cs.hlsl", ""), ("REBLUR_Blur.cs.hlsl", ""),
     ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0"), ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1"), ("REBLUR_TemporalStabilization.cs.hlsl", ""),
     ("REBLUR_SplitScreen.cs.hlsl", ""))] + [
+    # REBLUR_*_OCCLUSION ( NRD_MODE = OCCLUSION: no pre-pass, no stabilization ) and REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION ( NRD_MODE = DO, diffuse only )
+] + [f"{f}|NRD_SIGNAL={sig}|NRD_MODE=OCCLUSION{suffix}" for sig in ("DIFF", "SPEC", "BOTH") for f, suffix in (
+    ("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=0"), ("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), ("REBLUR_TemporalAccumulation.cs.hlsl", ""),
+    ("REBLUR_HistoryFix.cs.hlsl", ""), ("REBLUR_Blur.cs.hlsl", ""), ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0"))] + [
+    f"{f}|NRD_SIGNAL=DIFF|NRD_MODE=DO{suffix}" for f, suffix in (
+        ("REBLUR_PrePass.cs.hlsl", ""), ("REBLUR_TemporalAccumulation.cs.hlsl", ""), ("REBLUR_HistoryFix.cs.hlsl", ""), ("REBLUR_Blur.cs.hlsl", ""),
+        ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0"), ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1"), ("REBLUR_TemporalStabilization.cs.hlsl", ""))] + [
     # REFERENCE
     "REFERENCE_TemporalAccumulation.cs.hlsl", "REFERENCE_Copy.cs.hlsl",
     # ours: calls the application-side functions of the reference's NRD.hlsli ( oracle/ref_shim/Shaders/NRD_FrontEndProbe.cs.hlsl )

@@ -301,14 +301,14 @@ template <class A, class B, class = std::enable_if_t<Tr<A>::num && Tr<B>::num>> 
 
 // ------------------------------------------------------------------------------------------------ textures
 enum Format : uint32_t {  // numeric values = nrd::Format ( NRDDescs.h )
-    R8_UNORM = 0, R8_UINT = 2, RG8_UNORM = 4, RGBA8_UNORM = 8, R16_UINT = 15, R16_SFLOAT = 17, RG16_SFLOAT = 22, RGBA16_SFLOAT = 27, R32_UINT = 28, R32_SFLOAT = 30, RGBA32_SFLOAT = 39, R10_G10_B10_A2_UNORM = 40,
+    R8_UNORM = 0, R8_UINT = 2, RG8_UNORM = 4, RGBA8_UNORM = 8, R16_UNORM = 13, R16_UINT = 15, R16_SFLOAT = 17, RG16_SFLOAT = 22, RGBA16_SNORM = 24, RGBA16_SFLOAT = 27, R32_UINT = 28, R32_SFLOAT = 30, RGBA32_SFLOAT = 39, R10_G10_B10_A2_UNORM = 40,
 };
 struct HostTexture { void* data; uint32_t width, height, pitchBytes, format; };   // same layout as the oracle's OracleTexture
 
 struct TexData {
     uint8_t* data = nullptr; int w = 0, h = 0, pitch = 0; uint32_t fmt = 0;
     bool inside(int x, int y) const { return x >= 0 && y >= 0 && x < w && y < h; }
-    int bpp() const { switch (fmt) { case R8_UNORM: case R8_UINT: return 1; case RG8_UNORM: case R16_UINT: case R16_SFLOAT: return 2; case RGBA16_SFLOAT: return 8; case RGBA32_SFLOAT: return 16; default: return 4; } }
+    int bpp() const { switch (fmt) { case R8_UNORM: case R8_UINT: return 1; case RG8_UNORM: case R16_UINT: case R16_SFLOAT: case R16_UNORM: return 2; case RGBA16_SFLOAT: case RGBA16_SNORM: return 8; case RGBA32_SFLOAT: return 16; default: return 4; } }
     uint8_t* at(int x, int y) const { return data + (size_t)y * pitch + (size_t)x * bpp(); }
     float4 fetch(int x, int y) const {
         const uint8_t* p = at(x, y);
@@ -317,6 +317,8 @@ struct TexData {
             case RG8_UNORM: return float4(p[0] / 255.0f, p[1] / 255.0f, 0, 1);
             case RGBA8_UNORM: return float4(p[0] / 255.0f, p[1] / 255.0f, p[2] / 255.0f, p[3] / 255.0f);
             case R16_SFLOAT: { uint16_t v; memcpy(&v, p, 2); return float4(halfToFloat(v), 0, 0, 1); }
+            case R16_UNORM: { uint16_t v; memcpy(&v, p, 2); return float4(v / 65535.0f, 0, 0, 1); }
+            case RGBA16_SNORM: { int16_t v[4]; memcpy(v, p, 8); return float4(std::fmax(v[0] / 32767.0f, -1.0f), std::fmax(v[1] / 32767.0f, -1.0f), std::fmax(v[2] / 32767.0f, -1.0f), std::fmax(v[3] / 32767.0f, -1.0f)); }
             case RG16_SFLOAT: { uint16_t v[2]; memcpy(v, p, 4); return float4(halfToFloat(v[0]), halfToFloat(v[1]), 0, 1); }
             case RGBA16_SFLOAT: { uint16_t v[4]; memcpy(v, p, 8); return float4(halfToFloat(v[0]), halfToFloat(v[1]), halfToFloat(v[2]), halfToFloat(v[3])); }
             case R32_SFLOAT: { float v; memcpy(&v, p, 4); return float4(v, 0, 0, 1); }
@@ -337,6 +339,8 @@ struct TexData {
             case RG8_UNORM: p[0] = (uint8_t)unorm(v.x, 255.0f); p[1] = (uint8_t)unorm(v.y, 255.0f); break;
             case RGBA8_UNORM: for (int i = 0; i < 4; i++) p[i] = (uint8_t)unorm(v.d[i], 255.0f); break;
             case R16_SFLOAT: { uint16_t q = (uint16_t)halfBits(v.x); memcpy(p, &q, 2); break; }
+            case R16_UNORM: { uint16_t q = (uint16_t)unorm(v.x, 65535.0f); memcpy(p, &q, 2); break; }
+            case RGBA16_SNORM: { int16_t q[4]; for (int i = 0; i < 4; i++) { float s = std::fmin(std::fmax(v.d[i], -1.0f), 1.0f) * 32767.0f; q[i] = (int16_t)(int)(s + (s >= 0.0f ? 0.5f : -0.5f)); } memcpy(p, q, 8); break; }
             case RG16_SFLOAT: { uint16_t q[2] = {(uint16_t)halfBits(v.x), (uint16_t)halfBits(v.y)}; memcpy(p, q, 4); break; }
             case RGBA16_SFLOAT: { uint16_t q[4] = {(uint16_t)halfBits(v.x), (uint16_t)halfBits(v.y), (uint16_t)halfBits(v.z), (uint16_t)halfBits(v.w)}; memcpy(p, q, 8); break; }
             case R32_SFLOAT: memcpy(p, &v.x, 4); break;

@@ -110,6 +110,8 @@ FORMAT_STORAGE = {
     api.Format.RGBA8_UNORM: (torch.uint8, 4),
     api.Format.R16_UINT: (torch.int16, 1),
     api.Format.R16_SFLOAT: (torch.float16, 1),
+    api.Format.R16_UNORM: (torch.int16, 1),
+    api.Format.RGBA16_SNORM: (torch.int16, 4),
     api.Format.RGBA16_SFLOAT: (torch.float16, 4),
     api.Format.R32_UINT: (torch.int32, 1),
     api.Format.R32_SFLOAT: (torch.float32, 1),
@@ -126,6 +128,12 @@ USER_FORMATS = {
     api.ResourceType.IN_SPEC_RADIANCE_HITDIST: api.Format.RGBA16_SFLOAT,
     api.ResourceType.OUT_DIFF_RADIANCE_HITDIST: api.Format.RGBA16_SFLOAT,
     api.ResourceType.OUT_SPEC_RADIANCE_HITDIST: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.IN_DIFF_HITDIST: api.Format.R16_UNORM,            # "R8+" ( NRDDescs.h:77-80 ); NRDSample binds RGBA16F ( pass fmt= explicitly )
+    api.ResourceType.IN_SPEC_HITDIST: api.Format.R16_UNORM,
+    api.ResourceType.OUT_DIFF_HITDIST: api.Format.R16_UNORM,
+    api.ResourceType.OUT_SPEC_HITDIST: api.Format.R16_UNORM,
+    api.ResourceType.IN_DIFF_DIRECTION_HITDIST: api.Format.RGBA16_SFLOAT,
+    api.ResourceType.OUT_DIFF_DIRECTION_HITDIST: api.Format.RGBA16_SFLOAT,
     api.ResourceType.IN_DIFF_SH0: api.Format.RGBA16_SFLOAT,
     api.ResourceType.IN_DIFF_SH1: api.Format.RGBA16_SFLOAT,
     api.ResourceType.IN_SPEC_SH0: api.Format.RGBA16_SFLOAT,

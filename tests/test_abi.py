@@ -50,9 +50,11 @@ def test_library_desc_and_strings(host_library):
 
 
 def test_error_behaviour(host_library):
-    # unsupported denoiser -> UNSUPPORTED (InstanceImpl.cpp:95-102); duplicate identifiers -> NON_UNIQUE_IDENTIFIER (:104-108)
-    inst = api.NrdInstance(host_library, [(0, api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION)])
+    # a denoiser outside LibraryDesc::supportedDenoisers -> UNSUPPORTED (InstanceImpl.cpp:95-102); all 19 of the reference are supported, so: an id past the enum
+    assert sorted(host_library.supported_denoisers()) == list(range(19))
+    inst = api.NrdInstance(host_library, [(0, 19)])
     assert inst.result == api.Result.UNSUPPORTED
+    # duplicate identifiers -> NON_UNIQUE_IDENTIFIER (:104-108)
     inst = api.NrdInstance(host_library, [(3, api.Denoiser.REBLUR_DIFFUSE_SPECULAR), (3, api.Denoiser.SIGMA_SHADOW)])
     assert inst.result == api.Result.NON_UNIQUE_IDENTIFIER
     inst = api.NrdInstance(host_library, [(1, api.Denoiser.REBLUR_DIFFUSE_SPECULAR)])

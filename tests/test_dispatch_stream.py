@@ -35,6 +35,17 @@ CASES = [
     ("reblur_diffuse_sh_noprepass", api.Denoiser.REBLUR_DIFFUSE_SH, 640, 360, "noprepass"),
     ("reblur_specular_sh_recon_nots", api.Denoiser.REBLUR_SPECULAR_SH, 1280, 720, "recon_nots"),
     ("reblur_specular_sh_cb_guides_split", api.Denoiser.REBLUR_SPECULAR_SH, 1000, 562, "reblur_cb_guides_split"),
+    # NRD_MODE = OCCLUSION ( hit distance only: R16_UNORM / R8_UNORM pools, no pre-pass, no stabilization ) and NRD_MODE = DO ( RGBA16_SNORM )
+    ("reblur_occlusion_1080p", api.Denoiser.REBLUR_DIFFUSE_SPECULAR_OCCLUSION, 1920, 1080, None),
+    ("reblur_occlusion_cb_guides_split", api.Denoiser.REBLUR_DIFFUSE_SPECULAR_OCCLUSION, 1280, 720, "reblur_cb_guides_split"),
+    ("reblur_occlusion_recon", api.Denoiser.REBLUR_DIFFUSE_SPECULAR_OCCLUSION, 1000, 562, "recon_nots"),
+    ("reblur_diffuse_occlusion_720p", api.Denoiser.REBLUR_DIFFUSE_OCCLUSION, 1280, 720, None),
+    ("reblur_diffuse_occlusion_recon", api.Denoiser.REBLUR_DIFFUSE_OCCLUSION, 640, 360, "recon_nots"),
+    ("reblur_specular_occlusion_720p", api.Denoiser.REBLUR_SPECULAR_OCCLUSION, 1280, 720, None),
+    ("reblur_specular_occlusion_cb_guides_split", api.Denoiser.REBLUR_SPECULAR_OCCLUSION, 1000, 562, "reblur_cb_guides_split"),
+    ("reblur_directional_occlusion_1080p", api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, 1920, 1080, None),
+    ("reblur_directional_occlusion_recon_nots", api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, 1000, 562, "recon_nots"),
+    ("reblur_directional_occlusion_cb_guides_split", api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, 1280, 720, "reblur_cb_guides_split"),
     ("sigma_512", api.Denoiser.SIGMA_SHADOW, 512, 512, "sigma"),
     ("sigma_nostab", api.Denoiser.SIGMA_SHADOW, 640, 360, "sigma_nostab"),
     ("sigma_translucency_1080p", api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, 1920, 1080, "sigma"),

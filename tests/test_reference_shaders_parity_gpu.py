@@ -60,7 +60,21 @@ CASES["reblur_sh_cb_guides_split"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR_SH, "
 CASES["reblur_sh_recon_nots"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR_SH, "reblur_frame_sh_holes", SH4, "reblur")
 CASES["reblur_diff_sh"] = (api.Denoiser.REBLUR_DIFFUSE_SH, "reblur_frame_diff_sh", SH4[:2], "reblur")
 CASES["reblur_spec_sh_cb_guides"] = (api.Denoiser.REBLUR_SPECULAR_SH, "reblur_frame_spec_sh_cb_guides", SH4[2:], "reblur")
-SETTINGS = {"reblur_sh_cb_guides_split": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_spec_sh_cb_guides": lambda: api.ReblurSettings(checkerboardMode=2),
+# REBLUR_*_OCCLUSION ( NRD_MODE = OCCLUSION: R16_UNORM / R8_UNORM pools, no pre-pass, no stabilization ) and REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION ( NRD_MODE = DO:
+# RGBA16_SNORM pools ): plain; checkerboard WHITE + guides + split screen; hit-distance reconstruction; the application's textures as R16_UNORM and — what NRDSample
+# binds ( Source/NRDSample.cpp:489-500 ) — as RGBA16F
+OCC2 = ("OUT_DIFF_HITDIST", "OUT_SPEC_HITDIST")
+CASES["reblur_occ"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR_OCCLUSION, "occ_frame", OCC2, "reblur")
+CASES["reblur_occ_cb_guides_split"] = (api.Denoiser.REBLUR_DIFFUSE_SPECULAR_OCCLUSION, "occ_frame_cb_guides", OCC2, "reblur")
+CASES["reblur_occ_diff_recon"] = (api.Denoiser.REBLUR_DIFFUSE_OCCLUSION, "occ_frame_diff_holes", OCC2[:1], "reblur")
+CASES["reblur_occ_spec_rgba16f"] = (api.Denoiser.REBLUR_SPECULAR_OCCLUSION, "occ_frame_spec_rgba16f", OCC2[1:], "reblur")
+CASES["reblur_do"] = (api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, "occ_frame_do", ("OUT_DIFF_DIRECTION_HITDIST",), "reblur")
+CASES["reblur_do_cb_guides_split"] = (api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, "occ_frame_do_cb_guides", ("OUT_DIFF_DIRECTION_HITDIST",), "reblur")
+CASES["reblur_do_recon_nots"] = (api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, "occ_frame_do_holes", ("OUT_DIFF_DIRECTION_HITDIST",), "reblur")
+SETTINGS = {"reblur_occ_cb_guides_split": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_occ_diff_recon": lambda: api.ReblurSettings(hitDistanceReconstructionMode=2),
+            "reblur_do_cb_guides_split": lambda: api.ReblurSettings(checkerboardMode=2),
+            "reblur_do_recon_nots": lambda: api.ReblurSettings(hitDistanceReconstructionMode=1, maxStabilizedFrameNum=0),
+            "reblur_sh_cb_guides_split": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_spec_sh_cb_guides": lambda: api.ReblurSettings(checkerboardMode=2),
             "reblur_sh_recon_nots": lambda: api.ReblurSettings(hitDistanceReconstructionMode=1, maxStabilizedFrameNum=0),
             "relax_diff_sh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True),
             "relax_spec_sh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True),
@@ -71,7 +85,9 @@ SETTINGS = {"reblur_sh_cb_guides_split": lambda: api.ReblurSettings(checkerboard
             "relax_nosh_recon5x5": lambda: api.RelaxSettings(hitDistanceReconstructionMode=2), "relax_recon3x3": lambda: api.RelaxSettings(hitDistanceReconstructionMode=1),
             "relax_cb_guides_split": lambda: api.RelaxSettings(checkerboardMode=2, enableAntiFirefly=True), "relax_nosh_cb_guides": lambda: api.RelaxSettings(checkerboardMode=2),
             "reblur_split": lambda: api.ReblurSettings(checkerboardMode=2), "reference": lambda: api.ReferenceSettings(maxAccumulatedFrameNum=5), "reblur_cb": lambda: api.ReblurSettings(checkerboardMode=2), "reblur_guides_cb": lambda: api.ReblurSettings(checkerboardMode=2)}
-COMMON = {"reblur_sh_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.35),
+COMMON = {"reblur_occ_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.35),
+          "reblur_do_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.35),
+          "reblur_sh_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.35),
           "reblur_spec_sh_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
           "relax_diff_sh_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
           "relax_spec_sh_cb_guides": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True),
@@ -88,7 +104,12 @@ def common_of(which, f, w, h):
     cs = synth.common_settings(0 if which in STATIC_CAMERA else f, w, h, **COMMON.get(which, {}))
     cs.frameIndex = f
     return cs
-OUTPUT_FORMATS = {"sigma_tr": {"OUT_SHADOW_TRANSLUCENCY": api.Format.RGBA8_UNORM}}
+OUTPUT_FORMATS = {"sigma_tr": {"OUT_SHADOW_TRANSLUCENCY": api.Format.RGBA8_UNORM}, "reblur_occ_spec_rgba16f": {"OUT_SPEC_HITDIST": api.Format.RGBA16_SFLOAT}}
+INPUT_FORMATS = {"reblur_occ_spec_rgba16f": {"IN_SPEC_HITDIST": api.Format.RGBA16_SFLOAT}}
+
+
+def in_format(which, k, runner):
+    return INPUT_FORMATS.get(which, {}).get(k, runner.USER_FORMATS[getattr(RT, k)])
 
 
 def out_format(which, o, runner):
@@ -96,6 +117,16 @@ def out_format(which, o, runner):
 
 
 def frame_of(name, f, w, h):
+    if name.startswith("occ_frame"):
+        kw = dict(directional="_do" in name, rgba16f=name.endswith("_rgba16f"), holes=name.endswith("_holes"))
+        if name.endswith("_cb_guides"):
+            kw.update(checkerboard=2, guides=True)
+        if "_diff" in name or "_spec" in name:
+            kw["lobes"] = "diff" if "_diff" in name else "spec"
+        frame = synth.occlusion_frame(f, w, h, **kw)
+        if "_do" in name:
+            frame.pop("IN_SPEC_CONFIDENCE", None)
+        return frame
     for lobe, other in (("diff", "_SPEC_"), ("spec", "_DIFF_"), ("sh", "~")):   # single-lobe denoisers: the other lobe's inputs do not exist
         if name.startswith(f"reblur_frame_{lobe}"):
             kw = dict(checkerboard=2, guides=True) if name.endswith("_cb_guides") else (dict(holes=True) if name.endswith("_holes") else {})
@@ -122,7 +153,9 @@ def frame_of(name, f, w, h):
         return synth.sigma_frame(f, w, h, translucency=True)
     return getattr(synth, name)(f, w, h)
 # worst accepted fraction of texels outside the format tolerance of tests/util.compare, per dispatch, and closed-loop PSNR floor [dB]
-LIMITS = {"reblur_sh": (3e-2, 45.0), "reblur_sh_cb_guides_split": (3e-2, 45.0), "reblur_sh_recon_nots": (3e-2, 45.0), "reblur_diff_sh": (3e-2, 45.0),
+LIMITS = {"reblur_occ": (3e-2, 45.0), "reblur_occ_cb_guides_split": (3e-2, 45.0), "reblur_occ_diff_recon": (3e-2, 45.0), "reblur_occ_spec_rgba16f": (3e-2, 45.0),
+          "reblur_do": (3e-2, 45.0), "reblur_do_cb_guides_split": (3e-2, 45.0), "reblur_do_recon_nots": (3e-2, 45.0),
+          "reblur_sh": (3e-2, 45.0), "reblur_sh_cb_guides_split": (3e-2, 45.0), "reblur_sh_recon_nots": (3e-2, 45.0), "reblur_diff_sh": (3e-2, 45.0),
           "reblur_spec_sh_cb_guides": (3e-2, 45.0), "relax_diff": (2e-3, 60.0), "relax_spec": (2e-3, 60.0), "relax_diff_sh_cb_guides": (2e-3, 60.0), "relax_spec_sh_cb_guides": (2e-3, 60.0),
           "relax_diff_recon_split": (2e-3, 60.0), "relax_spec_sh_recon_split": (2e-3, 60.0), "reblur_diff": (3e-2, 45.0), "reblur_spec": (3e-2, 45.0), "reblur_diff_cb_guides": (3e-2, 45.0), "reblur_spec_recon_nots": (3e-2, 45.0), "reblur": (3e-2, 45.0), "sigma": (1e-3, 60.0), "relax": (2e-3, 60.0), "relax_nosh": (2e-3, 60.0), "sigma_tr": (1e-3, 60.0), "reblur_cb": (3e-2, 45.0), "reblur_guides_cb": (3e-2, 45.0), "reblur_split": (3e-2, 45.0), "reference": (1e-3, 80.0), "relax_cb_guides_split": (2e-3, 60.0), "relax_nosh_cb_guides": (2e-3, 60.0), "relax_nosh_recon5x5": (2e-3, 60.0), "relax_recon3x3": (2e-3, 60.0)}
 
@@ -176,7 +209,7 @@ def test_each_dispatch_against_the_reference_shaders(ex, runner, which):
 
     for f in range(frames):
         for k, v in frame_of(CASES[which][1], f, w, h).items():
-            ref.set_user_texture(getattr(RT, k), v)
+            ref.set_user_texture(getattr(RT, k), v, in_format(which, k, runner))
         ref.denoise(common_of(which, f, w, h), settings=SETTINGS[which]() if which in SETTINGS else None, before_dispatch=before, on_dispatch=after)
 
     os.makedirs("gpurun_out", exist_ok=True)
@@ -185,13 +218,17 @@ def test_each_dispatch_against_the_reference_shaders(ex, runner, which):
     limit = LIMITS[which][0]
     for key, r in worst.items():
         spatial = which.startswith("reblur") and any(p in key[0] for p in ("Pre-pass", "Blur", "Post-blur"))
-        if spatial and key[2] == "RGBA16_SFLOAT":
+        if spatial and key[2] in ("RGBA16_SFLOAT", "R16_UNORM", "RGBA16_SNORM"):
             # the reference's tap weight is 1 instead of the Gaussian when any( uv != MirrorUv( uv ) ), which is decided by the last mantissa bit
             # of the tap position ( DESIGN.md "chaotic predicates" ): an FMA-contracting GPU flips it on a third of the taps, so texel-wise
             # agreement is not defined for these passes in faithful mode — the image is ( measured: 60-74 dB )
             # NRD_MODE = SH: the SH1 textures ( direction * luma, signed, a smaller peak than the radiance ) see the same flipped taps — the SH0
             # numbers equal the RADIANCE ones to the digit — and land 3 dB lower against their own peak ( measured: 54.2 dB and up )
-            assert r["psnr"] >= (50.0 if "_sh" in which else 55.0), f"{key}: {r}"
+            # NRD_MODE = OCCLUSION / DO: the filtered signal IS the 1-spp hit distance ( uniform noise, no smooth radiance around it ), so the same flipped taps
+            # move the result further: measured 46.4 dB ( DO pre-pass on reconstructed hit distances ) and 47.5 dB ( specular blur ) and up; every
+            # non-spatial pass of these denoisers agrees with the reference shaders texel for texel ( frac_bad = 0 )
+            floor = 45.0 if ("_occ" in which or "_do" in which) else (50.0 if "_sh" in which else 55.0)
+            assert r["psnr"] >= floor, f"{key}: {r}"
             continue
         lim = 5e-2 if (which.startswith("reblur") and key[2] == "R32_UINT") else limit   # data2's fp16 curvature on the static first frame, see test_reblur_parity_gpu
         assert r["frac_bad"] <= lim, f"{key}: {r}"
@@ -212,9 +249,9 @@ def test_closed_loop_against_the_reference_shaders(ex, runner, which):
     for f in range(frames):
         for k, v in frame_of(frame_fn, f, w, h).items():
             rt = getattr(RT, k)
-            ref.set_user_texture(rt, v)
+            ref.set_user_texture(rt, v, in_format(which, k, runner))
             keep[k] = v.to("cuda:0")
-            cud.set_user_texture(rt, keep[k], runner.USER_FORMATS[rt])
+            cud.set_user_texture(rt, keep[k], in_format(which, k, runner))
         cs = common_of(which, f, w, h)
         ref.denoise(cs, settings=SETTINGS[which]() if which in SETTINGS else None)
         cud.set_common_settings(cs)
@@ -232,4 +269,110 @@ def test_closed_loop_against_the_reference_shaders(ex, runner, which):
             assert r["psnr"] >= LIMITS[which][1], f"{which} frame {f} {o}: {r}"
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(log, open(f"gpurun_out/refshader_closed_loop_{which}.json", "w"))
+    cud.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------------
+# Dynamic resolution ( CommonSettings::rectSize < resourceSize, changing from frame to frame; NRDSettings.h:121-124, 171; Common.hlsli:226-248 ): the
+# application renders into the top-left rectSize part of its resourceSize textures ( NRDSample does whenever DLSS or its resolution scale is on ).
+# rectOrigin stays 0: the reference build has NRD_SUPPORTS_VIEWPORT_OFFSET = 0 and rejects anything else ( InstanceImpl.cpp:320-321 ).
+DYNRES = ["reblur", "relax", "sigma", "relax_nosh", "reblur_sh", "reblur_occ"]
+DYNRES_RESOURCE = (224, 128)
+DYNRES_RECTS = [(176, 96), (176, 96), (144, 80), (208, 120), (208, 120), (160, 112)]
+
+
+def dynres_frame(which, f):
+    W, H = DYNRES_RESOURCE
+    rw, rh = DYNRES_RECTS[f]
+    out = {}
+    for k, v in frame_of(CASES[which][1], f, rw, rh).items():
+        full = torch.zeros((H, W) + tuple(v.shape[2:]), dtype=v.dtype)
+        full[:rh, :rw] = v
+        out[k] = full.contiguous()
+    return out
+
+
+def dynres_common(which, f):
+    W, H = DYNRES_RESOURCE
+    rw, rh = DYNRES_RECTS[f]
+    pw, ph = DYNRES_RECTS[max(f - 1, 0)]
+    cs = common_of(which, f, rw, rh)   # camera with the rect's aspect ratio, motion vectors in rect pixels
+    cs.resourceSize[0], cs.resourceSize[1], cs.resourceSizePrev[0], cs.resourceSizePrev[1] = W, H, W, H
+    cs.rectSize[0], cs.rectSize[1], cs.rectSizePrev[0], cs.rectSizePrev[1] = rw, rh, pw, ph
+    return cs
+
+
+@pytest.mark.parametrize("which", DYNRES)
+def test_dynamic_resolution_each_dispatch(ex, runner, which):
+    W, H = DYNRES_RESOURCE
+    ref = reference_engine(runner, which, W, H)
+    flags = ex.FLAG_QUAD_INTRINSICS
+    snap, worst = {}, {}
+
+    def before(i, d, keys, den):
+        snap["t"] = [den.textures[k].clone() for k in keys]
+
+    def after(i, d, keys, den):
+        gpu = [t.to("cuda:0") for t in snap["t"]]
+        ex.dispatch(d.shader, d.constants, [ex.texture_of(g, den.formats[k]) for g, k in zip(gpu, keys)], flags=flags)
+        torch.cuda.synchronize()
+        for j, (b, k) in enumerate(zip(d.bindings, keys)):
+            if b.descriptor != int(api.DescriptorType.STORAGE_TEXTURE):
+                continue
+            fmt = den.formats[k]
+            r = compare(gpu[j], den.textures[k], fmt, layout=CASES[which][3])
+            key = (d.name, j, api.Format(fmt).name)
+            if key not in worst or r["frac_bad"] > worst[key]["frac_bad"]:
+                worst[key] = r
+
+    for f in range(len(DYNRES_RECTS)):
+        for k, v in dynres_frame(which, f).items():
+            ref.set_user_texture(getattr(RT, k), v, in_format(which, k, runner))
+        ref.denoise(dynres_common(which, f), settings=SETTINGS[which]() if which in SETTINGS else None, before_dispatch=before, on_dispatch=after)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump({" | ".join(map(str, k)): {"frac_bad": v["frac_bad"], "psnr": v["psnr"], "max_abs": v["max_abs"]} for k, v in worst.items()},
+              open(f"gpurun_out/refshader_dynres_per_dispatch_{which}.json", "w"), indent=1)
+    limit = LIMITS[which][0]
+    for key, r in worst.items():
+        spatial = which.startswith("reblur") and any(p in key[0] for p in ("Pre-pass", "Blur", "Post-blur"))
+        if spatial and key[2] in ("RGBA16_SFLOAT", "R16_UNORM", "RGBA16_SNORM"):
+            assert r["psnr"] >= 50.0, f"{key}: {r}"   # the mirror predicate, as in test_each_dispatch_against_the_reference_shaders
+            continue
+        lim = 5e-2 if (which.startswith("reblur") and key[2] == "R32_UINT") else limit
+        assert r["frac_bad"] <= lim, f"{key}: {r}"
+
+
+@pytest.mark.parametrize("which", DYNRES)
+def test_dynamic_resolution_closed_loop(ex, runner, which):
+    W, H = DYNRES_RESOURCE
+    den_id, _, outputs, _ = CASES[which]
+    ref = reference_engine(runner, which, W, H)
+    cud = ex.CudaDenoiser(den_id, W, H, flags=ex.FLAG_QUAD_INTRINSICS)
+    gout = {}
+    for o in outputs:
+        fmt = out_format(which, o, runner)
+        gout[o] = ex.alloc_texture(fmt, W, H, "cuda:0")
+        cud.set_user_texture(getattr(RT, o), gout[o], fmt)
+    keep = {}
+    for f in range(len(DYNRES_RECTS)):
+        rw, rh = DYNRES_RECTS[f]
+        for k, v in dynres_frame(which, f).items():
+            rt = getattr(RT, k)
+            ref.set_user_texture(rt, v, in_format(which, k, runner))
+            keep[k] = v.to("cuda:0")
+            cud.set_user_texture(rt, keep[k], in_format(which, k, runner))
+        cs = dynres_common(which, f)
+        ref.denoise(cs, settings=SETTINGS[which]() if which in SETTINGS else None)
+        cud.set_common_settings(cs)
+        if which in SETTINGS:
+            cud.set_denoiser_settings(SETTINGS[which]())
+        cud.denoise()
+        torch.cuda.synchronize()
+        for o in outputs:
+            fmt = out_format(which, o, runner)
+            g, c = gout[o][:rh, :rw], ref.textures[(int(getattr(RT, o)), 0)][:rh, :rw]   # the denoised rect
+            if o.endswith("SH1"):
+                g, c = g[..., :3], c[..., :3]
+            r = compare(g, c, fmt, layout=CASES[which][3])
+            assert r["psnr"] >= LIMITS[which][1], f"{which} frame {f} rect {rw}x{rh} {o}: {r}"
     cud.close()

@@ -20,6 +20,10 @@ def decode(t: torch.Tensor, fmt: int, layout: str = "reblur") -> torch.Tensor:
     if f == api.Format.R10_G10_B10_A2_UNORM:
         v = t.to(torch.int64) & 0xFFFFFFFF
         return torch.stack([(v & 1023), (v >> 10) & 1023, (v >> 20) & 1023, (v >> 30) & 3], -1).float()
+    if f == api.Format.R16_UNORM:
+        return ((t.to(torch.int64) & 0xFFFF).float() / 65535.0).unsqueeze(-1)
+    if f == api.Format.RGBA16_SNORM:
+        return (t.float() / 32767.0).clamp_min(-1.0)
     if f == api.Format.R16_UINT:
         v = t.to(torch.int64) & 0xFFFF
         return torch.stack([v & 63, (v >> 6) & 63, (v >> 12) & 15], -1).float()
@@ -42,6 +46,10 @@ def compare(a: torch.Tensor, b: torch.Tensor, fmt: int, atol=1e-3, rtol=2 ** -9,
     diff = (da - db).abs()
     if f in (api.Format.R8_UNORM, api.Format.RG8_UNORM, api.Format.RGBA8_UNORM, api.Format.R10_G10_B10_A2_UNORM):
         bad = diff > 1.0
+    elif f == api.Format.R16_UNORM:
+        bad = diff > 16.5 / 65535.0       # 12 bits of a 16-bit UNORM: the weights upstream are fast-math fp32 against IEEE fp32, amplified by the spatial passes
+    elif f == api.Format.RGBA16_SNORM:
+        bad = diff > 8.5 / 32767.0
     elif f in (api.Format.R16_UINT, api.Format.R8_UINT):
         bad = diff > 0.0
     elif f == api.Format.R32_UINT and layout == "sigma":
