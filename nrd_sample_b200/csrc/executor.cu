@@ -178,8 +178,8 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
     if (constantsSize != sizeof(ReblurConstants) || !constants) return fail(Result::INVALID_ARGUMENT, "%s: expected %zu constant bytes, got %u", id.c_str(), sizeof(ReblurConstants), constantsSize);
     ReblurConstants cb;
     memcpy(&cb, constants, sizeof(cb));
-    if (cb.resolutionScale[0] != 1.0f || cb.resolutionScale[1] != 1.0f || cb.resolutionScalePrev[0] != 1.0f || cb.resolutionScalePrev[1] != 1.0f || cb.isRectChanged)
-        return fail(Result::UNSUPPORTED, "%s: dynamic resolution (rectSize != resourceSize) is not implemented", id.c_str());
+    // dynamic resolution ( rectSize < resourceSize, CommonSettings ): the kernels work in rect pixels and scale uv by gResolutionScale( Prev ) wherever the
+    // reference samples a resource-sized texture; rectOrigin is always 0 ( NRD_SUPPORTS_VIEWPORT_OFFSET = 0: the host library rejects anything else )
     if ((cb.diffCheckerboard == 2) != (cb.specCheckerboard == 2)) return fail(Result::INVALID_ARGUMENT, "%s: checkerboard constants %u / %u", id.c_str(), cb.diffCheckerboard, cb.specCheckerboard);
 
     const bool quads = flags & NRDCU_FLAG_QUAD_INTRINSICS;

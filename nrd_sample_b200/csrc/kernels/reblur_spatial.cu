@@ -488,8 +488,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBl
     s.py = cta.y * BLOCK_H + threadIdx.y;
 
     // viewZ (sky included) is copied for the next pass and the next frame
+    // ( by every thread of the reference's 8x16 groups: up to the rect rounded up to 8 x 16; with dynamic resolution the texels beyond belong to nobody )
     float viewZpacked = p.viewZ.load(s.px, s.py);
-    p.outViewZ.store(s.px, s.py, viewZpacked);
+    if (s.px < ((cb.rectSizeMinusOne[0] + 8) & ~7) && s.py < ((cb.rectSizeMinusOne[1] + 16) & ~15)) p.outViewZ.store(s.px, s.py, viewZpacked);
 
     // No lane leaves before the quad exchange; lanes of sky tiles / outside the rect only feed their own quads
     bool skyTile = p.tiles.load(s.px >> 4, s.py >> 4) != 0.0f;
@@ -611,7 +612,8 @@ void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int 
     });
 }
 void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int signal, int flags, Rows rows, cudaStream_t stream) {
-    const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
+    // the grid covers the rect rounded up to the reference's 16-row groups: their threads below the rect still copy viewZ
+    const RowGrid g = rowGrid(rows, (cb.rectSizeMinusOne[1] + 16) & ~15, BLOCK_H);
     if (!g.count) return;
     const int mode = (flags >> 4) & 3;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);

@@ -18,16 +18,17 @@ namespace {
 constexpr int BLOCK_W = 32, BLOCK_H = 8, BORDER = 1;
 constexpr int TILE_W = BLOCK_W + 2 * BORDER, TILE_H = BLOCK_H + 2 * BORDER;
 
-// Requires rng.init( pixelPos, frameIndex ): picks ONE texel of the bilinear footprint (REBLUR_USE_STF = 1)
-NRD_DEV void stochasticBilinearTexel(Rng& rng, float2 uv, float2 texSize, int& tx, int& ty) {
-    Bilinear f = getBilinearFilter(uv, texSize);
+// Requires rng.init( pixelPos, frameIndex ): picks ONE texel of the bilinear footprint (REBLUR_USE_STF = 1). The reference turns ( origin + 0.5 ) / filterSize
+// back into a texel through a nearest sampler ( clamp addressing ) of a texture that is `texW x texH` texels ( the RESOURCE size: with dynamic resolution
+// the rect the filter works in is smaller ), after scaling the uv by `scale` ( gResolutionScalePrev for the previous frame, TA:665; 1 for the current one, TA:440 )
+NRD_DEV void stochasticBilinearTexel(Rng& rng, float2 uv, float2 filterSize, float2 scale, int texW, int texH, int& tx, int& ty) {
+    Bilinear f = getBilinearFilter(uv, filterSize);
     float r0 = rng.next();
     float r1 = rng.next();
     float ox = f.origin.x + step(r0, f.weights.x), oy = f.origin.y + step(r1, f.weights.y);
-    // the reference turns (origin + 0.5) / texSize back into a texel through a nearest sampler (clamp addressing)
-    float2 uvq = make_float2((ox + 0.5f) / texSize.x, (oy + 0.5f) / texSize.y);
-    tx = (int)floorf(uvq.x * texSize.x);
-    ty = (int)floorf(uvq.y * texSize.y);
+    float2 uvq = make_float2((ox + 0.5f) / filterSize.x, (oy + 0.5f) / filterSize.y) * scale;
+    tx = (int)floorf(uvq.x * (float)texW);
+    ty = (int)floorf(uvq.y * (float)texH);
 }
 
 NRD_DEV float4 gather4(const TexR32F& t, int x0, int y0) {
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
                 float3 xHigh = rotate(cb.viewToWorld, reconstructViewPosition(motionUvHigh, cb.frustum, zHigh, cb.orthoMode));
 
                 int tx, ty;
-                stochasticBilinearTexel(rng, uvScaled, rectSize, tx, ty);
+                stochasticBilinearTexel(rng, uvScaled, rectSize, f2(1.0f), p.normalRoughness.w, p.normalRoughness.h, tx, ty);
                 float3 nHigh = xyz(unpackNormalRoughness(p.normalRoughness.fetchRawClamped(tx, ty)));
 
                 float2 gp = geometryWeightParams(0.04f, frustumSize, X, N);
@@ -470,8 +471,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTempora
             float2 vmbPixelUvPrev = vmbPixelUv + vmbDelta * stepBetweenTaps;
 
             int tx, ty;
-            stochasticBilinearTexel(rng, vmbPixelUvPrev, rectSizePrev, tx, ty);
-            // nearest sampler after "* gResolutionScalePrev" (== 1 while rect == resource)
+            stochasticBilinearTexel(rng, vmbPixelUvPrev, rectSizePrev, resolutionScalePrev, p.prevNormalRoughness.w, p.prevNormalRoughness.h, tx, ty);
             float4 prevNR = unpackNormalRoughness(p.prevNormalRoughness.fetchRawClamped(tx, ty));
 
             float w = encodingAwareNormalWeight(xyz(vmbN), xyz(prevNR), lobeHalfAngle, curvatureAngle * (1.0f + stepBetweenTaps), 0.0f);

@@ -1163,7 +1163,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
     const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
     const float isSky = threadIdx.x < 16 ? skyL : skyR;
     const float viewZpacked = p.viewZ.load(px, py);
-    p.outViewZ.store(px, py, viewZpacked);
+    // the prev-frame planes are written by EVERY thread of the reference's 8x8 groups, i.e. up to the rect rounded up to 8 ( this CTA is 32 wide: with
+    // dynamic resolution the texels beyond that belong to nobody and stay untouched, as in the reference )
+    const bool inReferenceGrid = px < ((cb.rectSize[0] + 7) & ~7);
+    if (inReferenceGrid) p.outViewZ.store(px, py, viewZpacked);
     const bool skipTile = skyL != 0.0f && skyR != 0.0f;  // nothing to filter in this CTA: only the prev-frame planes are written
     if (!skipTile) {
         const int baseX = blockIdx.x * BLOCK_W - AT_BORDER, baseY = blockIdx.y * BLOCK_H - AT_BORDER;
@@ -1202,10 +1205,10 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
     float4 normalRoughness = ctr.nr;
     const float centerViewZ = relaxViewZ(cb, viewZpacked);
     if (!relaxInRange(cb, centerViewZ)) normalRoughness = f4(1.0f / 255.0f);
-    p.outNormalRoughness.store(px, py, packPrevNormalRoughness(normalRoughness));
+    if (inReferenceGrid) p.outNormalRoughness.store(px, py, packPrevNormalRoughness(normalRoughness));
     const float3 centerWorldPos = ctr.worldPos;
     const float centerMaterialID = ctr.materialID;
-    p.outMaterialID.store(px, py, centerMaterialID / 255.0f);
+    if (inReferenceGrid) p.outMaterialID.store(px, py, centerMaterialID / 255.0f);
 
     if (isSky != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     if (!relaxInRange(cb, centerViewZ)) return;
@@ -1533,10 +1536,9 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
     }
     RelaxConstants cb;
     memcpy(&cb, constants, sizeof(cb));
-    if (cb.resolutionScale[0] != 1.0f || cb.resolutionScale[1] != 1.0f || cb.rectOrigin[0] || cb.rectOrigin[1] || cb.rectSizePrev[0] != (float)cb.rectSize[0] ||
-        cb.rectSizePrev[1] != (float)cb.rectSize[1]) {
-        err = id + ": dynamic resolution (rectSize != resourceSize) is not implemented";
-        return (uint32_t)Result::UNSUPPORTED;
+    if (cb.rectOrigin[0] || cb.rectOrigin[1]) {   // NRD_SUPPORTS_VIEWPORT_OFFSET = 0; dynamic resolution ( rectSize < resourceSize ) itself is supported
+        err = id + ": rectOrigin must be 0";
+        return (uint32_t)Result::INVALID_ARGUMENT;
     }
     if ((cb.diffCheckerboard == 2) != (cb.specCheckerboard == 2)) {
         err = id + ": inconsistent checkerboard constants";

@@ -91,6 +91,8 @@ template <class ST>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaCopyParams<ST> p) {
     using Raw = typename std::conditional<std::is_same<ST, TexR8>::value, uint8_t, uint32_t>::type;
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    // the reference dispatches this pass over the PREVIOUS frame's rect ( Sigma_Shadow.hpp: "USE_PREV_DIMS" ) in 8x16 groups
+    if (px >= (((int)cb.rectSizePrev[0] + 7) & ~7) || py >= (((int)cb.rectSizePrev[1] + 15) & ~15)) return;
     const float isSky = p.tiles.load(px >> 4, py >> 4).x;
     if ((isSky != 0.0f && !cb.isRectChanged) || !p.history.inside(px, py)) return;
     *p.outHistory.template ptrw<Raw>(px, py) = __ldg(p.history.template ptr<Raw>(px, py));
@@ -465,9 +467,9 @@ uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t co
     }
     SigmaConstants cb;
     memcpy(&cb, constants, sizeof(cb));
-    if (cb.resolutionScale[0] != 1.0f || cb.resolutionScale[1] != 1.0f || cb.isRectChanged || cb.rectOrigin[0] || cb.rectOrigin[1]) {
-        err = id + ": dynamic resolution (rectSize != resourceSize) is not implemented";
-        return (uint32_t)Result::UNSUPPORTED;
+    if (cb.rectOrigin[0] || cb.rectOrigin[1]) {   // NRD_SUPPORTS_VIEWPORT_OFFSET = 0; dynamic resolution ( rectSize < resourceSize ) itself is supported
+        err = id + ": rectOrigin must be 0";
+        return (uint32_t)Result::INVALID_ARGUMENT;
     }
     SigmaBinder b{tex, n, 0, true, &err, &id};
     auto bad = [&](uint32_t expected) {
@@ -510,7 +512,8 @@ uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t co
             p.outHistory = b.take<typename SG::Tex>(SG::format);
             p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
             if (bad(5)) return false;
-            sigmaCopyKernel<typename SG::Tex><<<pixelGrid, block, 0, stream>>>(cb, p);
+            const dim3 prevGrid(((int)cb.rectSizePrev[0] + BLOCK_W - 1) / BLOCK_W, (((int)cb.rectSizePrev[1] + 15) / 16 * 16 + BLOCK_H - 1) / BLOCK_H);
+            sigmaCopyKernel<typename SG::Tex><<<prevGrid, block, 0, stream>>>(cb, p);
             return true;
         };
         if (!(wide ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
