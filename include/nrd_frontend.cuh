@@ -82,20 +82,20 @@ NRDFE_FN F3 _NRD_EncodeNormalRoughness101010(F3 n, float roughness) {           
     r.y = n.y * 0.5f + 0.5f;
     r.x = n.x * 0.5f + r.y;
     r.y -= n.x * 0.5f;
-    roughness = fmaxf(roughness, 1.5f / 512.0f);  // can't be 0 to not ruin the "n.z" sign bit
+    roughness = fmaxf(roughness, 1.5f / 512.0f);  // the sign of the stored value carries sign( n.z ): keep it away from +-0
     float s = n.z < 0.0f ? -roughness : roughness;
     r.z = s * 0.5f + 0.5f;
     return r;
 }
 NRDFE_FN F4 _NRD_DecodeNormalRoughness101010(F3 p) {                                                // :387-400
-    float t = p.z * 2.0f - 1.0f;  // signed roughness
+    float t = p.z * 2.0f - 1.0f;  // [ -1, 1 ]: magnitude = roughness, sign = sign( n.z )
     F4 r;
     r.x = p.x - p.y;
     r.y = p.x + p.y - 1.0f;
     r.z = t < 0.0f ? -1.0f : 1.0f;
     r.z *= 1.0f - fabsf(r.x) - fabsf(r.y);
     r.w = fabsf(t);
-    return r;  // "r.xyz" gets normalized later
+    return r;  // un-normalised; the caller normalises
 }
 NRDFE_FN float _NRD_Luminance(F3 c) { return dot(c, f3(0.2126f, 0.7152f, 0.0722f)); }                // :403-406
 NRDFE_FN F3 _NRD_LinearToYCoCg(F3 c) {                                                              // :409-416
@@ -141,7 +141,7 @@ NRDFE_FN float _NRD_GeometryTerm(float roughness, float NoL, float NoV) {       
     return 0.5f / (a + b);
 }
 NRDFE_FN float _NRD_DiffuseTerm(float roughness, float NoL, float NoV, float VoH) {                 // :486-494
-    float f = 2.0f * VoH * VoH * roughness - 0.5f;  // yes, linear roughness
+    float f = 2.0f * VoH * VoH * roughness - 0.5f;  // Burley diffuse on LINEAR roughness, as the application front end expects
     float FdV = f * _NRD_Pow5(NoV) + 1.0f;
     float FdL = f * _NRD_Pow5(NoL) + 1.0f;
     float d = FdV * FdL;
@@ -150,14 +150,14 @@ NRDFE_FN float _NRD_DiffuseTerm(float roughness, float NoL, float NoV, float VoH
 NRDFE_FN F2 _NRD_ComputeBrdfs(F3 Ld, F3 Ls, F3 N, F3 V, float roughness) {                          // :497-526
     F2 result;
     float NoV = fabsf(dot(N, V));
-    {  // Diffuse
+    {  // lobe 0
         F3 H = normalize(Ld + V);
         float NoL = saturate(dot(N, Ld));
         float VoH = fabsf(dot(V, H));
         float Kdiff = _NRD_DiffuseTerm(roughness, NoL, NoV, VoH);
         result.x = Kdiff * NoL;
     }
-    {  // Specular
+    {  // lobe 1
         F3 H = normalize(Ls + V);
         float NoL = saturate(dot(N, Ls));
         float NoH = saturate(dot(N, H));
@@ -166,7 +166,7 @@ NRDFE_FN F2 _NRD_ComputeBrdfs(F3 Ld, F3 Ls, F3 N, F3 V, float roughness) {      
         float Kspec = D * Gmod;
         result.y = Kspec * NoL;
     }
-    return result;  // no F, because it's already demodulated
+    return result;  // Fresnel left out: the material demodulation has divided it away
 }
 NRDFE_FN F3 _NRD_EnvironmentTerm_Rtg(F3 Rf0, float NoV, float roughness) {                          // :529-556 ( "Ray Tracing Gems", ch. 32 )
     float m = saturate(roughness * roughness);
@@ -211,7 +211,7 @@ NRDFE_FN NRD_SG _NRD_SG_Create(F3 radiance, F3 direction, float normHitDist) {  
     sg.chroma = f2(YCoCg.y, YCoCg.z);
     sg.c1 = direction * YCoCg.x;
     sg.normHitDist = normHitDist;
-    sg.sharpness = 0.0f;  // computed in resolve
+    sg.sharpness = 0.0f;  // the resolve functions fill this in
     return sg;
 }
 NRDFE_FN float _NRD_SG_InnerProduct(NRD_SG a, NRD_SG b) {                                           // :619-631
@@ -383,7 +383,7 @@ NRDFE_FN F3 NRD_SG_ResolveDiffuse(NRD_SG sg, F3 N, F3 V, float roughness) {     
     float NoL = saturate(dot(N, L));
     NRD_SG light = {};
     light.sharpness = 2.0f;
-    light.c0 = sg.c0 * light.sharpness;  // with normalization
+    light.c0 = sg.c0 * light.sharpness;  // amplitude scaled so that the lobe integrates to c0
     light.c1 = L;
     NRD_SG ndf = {};
     ndf.c0 = 1.0f;
@@ -408,19 +408,19 @@ NRDFE_FN F3 NRD_SG_ResolveSpecular(NRD_SG sg, F3 N, F3 V, float roughness) {    
     F3 H = normalize(L + V);
     float NoV = fabsf(dot(N, V));
     float VoH = fabsf(dot(V, H));
-    NoV = lerp(0.02f, 1.0f, NoV);  // fix energy increase on the horizon / silhouette
+    NoV = lerp(0.02f, 1.0f, NoV);  // grazing view angles would otherwise brighten the result
     NRD_SG light = {};
     light.sharpness = 2.0f / m2;
-    light.c0 = sg.c0 * light.sharpness;  // with normalization
+    light.c0 = sg.c0 * light.sharpness;  // amplitude scaled so that the lobe integrates to c0
     light.c1 = L;
     float ndfSharpness = 0.5f / fmaxf(m2 * VoH, 1e-8f);
     NRD_SG warpedNdf = {};
     warpedNdf.c0 = 1.0f;
-    warpedNdf.c1 = L;  // same as "reflect( -V, H )"
+    warpedNdf.c1 = L;  // = V mirrored about the half vector
     warpedNdf.sharpness = ndfSharpness;
     float Y = _NRD_SG_InnerProduct(warpedNdf, light);
     float Gmod = _NRD_GeometryTerm(roughness, NoL, NoV);
-    Y *= Gmod * NoL;  // F applied in demodulation
+    Y *= Gmod * NoL;  // no Fresnel here, see _NRD_ComputeBrdfs
     Y *= lerp(lerp(0.1f, 0.4f, m2), 0.8f, NoV);
     Y = fmaxf(Y, sg.c0 / NRDFE_PI);
     return _NRD_YCoCgToLinear_Corrected(Y, sg.c0, sg.chroma);
@@ -456,7 +456,7 @@ NRDFE_FN F3 NRD_SH_ResolveSpecular(NRD_SG sh, F3 N, F3 V, float roughness) {    
     float NoV = fabsf(dot(N, V));
     float f = _NRD_GetSpecularDominantFactor(NoV, roughness);
     F3 D = _NRD_GetSpecularDominantDirection(N, V, f);
-    float Y = sh.c0 * k0 + dot(sh.c1, D) * k1;  // suboptimal, use SG resolve instead
+    float Y = sh.c0 * k0 + dot(sh.c1, D) * k1;  // linear SH evaluation; NRD_SG_ResolveSpecular is the better estimator
     return _NRD_YCoCgToLinear_Corrected(Y, sh.c0, sh.chroma);
 }
 
@@ -472,13 +472,13 @@ NRDFE_FN float _NRD_AcosApproxSphere(float x) {                                 
 NRDFE_FN float _NRD_CosDifference(float cosA, float cosB) {                                                          // :1213-1219
     float sqSinA = saturate(1.0f - cosA * cosA);
     float sqSinB = saturate(1.0f - cosB * cosB);
-    return cosA * cosB + sqrtf(sqSinA * sqSinB);  // cos( A - B )
+    return cosA * cosB + sqrtf(sqSinA * sqSinB);  // angle-difference identity
 }
 NRDFE_FN F3 _NRD_RotateTowards(F3 a, F3 b, float cosAngle) {                                                         // :1221-1230
     float cosTheta = dot(a, b);
     float sinAngle = sqrtf(saturate(1.0f - cosAngle * cosAngle));
     float sinTheta = sqrtf(saturate(1.0f - cosTheta * cosTheta));
-    float sinDiff = sinTheta * cosAngle - sinAngle * cosTheta;  // sin( theta - angle )
+    float sinDiff = sinTheta * cosAngle - sinAngle * cosTheta;  // angle-difference identity
     F3 rotated = (sinDiff * a + sinAngle * b) * (1.0f / sinTheta);
     return sinTheta < NRDFE_EPS ? a : rotated;
 }

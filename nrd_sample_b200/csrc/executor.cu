@@ -25,6 +25,7 @@ namespace nrdk {
 // kernels/*.cu
 void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t stream);
 void launchReblurClassifyTiles(const ReblurConstants&, const ClassifyTilesParams&, Rows, cudaStream_t);
+void launchReblurValidation(const ReblurConstants&, const ReblurValidationParams&, cudaStream_t);
 void launchReblurGeometryPlane(const ReblurConstants&, const GeometryPlaneParams&, int row0, int row1, cudaStream_t);
 void launchReblurHitDistReconstruction(const ReblurConstants&, const HitDistReconstructionParams&, int signal, bool occlusion, bool is5x5, Rows, cudaStream_t);
 void launchReblurPrePass(const ReblurConstants&, const PrePassParams&, int signal, int flags, Rows, cudaStream_t);
@@ -288,7 +289,27 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         if (tempPlane) cudaFreeAsync(tempPlane, stream);
     };
 
-    if (id == "REBLUR_ClassifyTiles.cs.hlsl") {
+    if (id == "REBLUR_Validation.cs.hlsl") {
+        // REBLUR_Validation.resources.hlsli:22-34: bound by whatever format each texture has ( data1 RG8 / R8, data2 R32_UINT / R8_UINT or data1 again, the lobe
+        // inputs of the denoiser, OUT_VALIDATION "RGBA8+" )
+        auto takeView = [&]() {
+            TexView v = b.takeAny<TexView>({Format::R8_UNORM, Format::R8_UINT, Format::RG8_UNORM, Format::RGBA8_UNORM, Format::R16_UNORM, Format::R16_SFLOAT, Format::R16_UINT,
+                                            Format::RG16_SFLOAT, Format::RGBA16_UNORM, Format::RGBA16_SNORM, Format::RGBA16_SFLOAT, Format::R32_UINT, Format::R32_SFLOAT, Format::RGBA32_SFLOAT});
+            return v;
+        };
+        ReblurValidationParams p = {};
+        p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
+        p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
+        p.mv = takeView();
+        p.data1 = takeView();
+        p.data2 = takeView();
+        p.diff = takeView();
+        p.spec = takeView();
+        p.out = takeView();
+        uint32_t r = done(8);
+        if (r != 0xFFFFFFFFu) return r;
+        launchReblurValidation(cb, p, stream);
+    } else if (id == "REBLUR_ClassifyTiles.cs.hlsl") {
         ClassifyTilesParams p = {};
         p.inViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.outTiles = takeTiles();

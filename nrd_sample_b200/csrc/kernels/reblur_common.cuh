@@ -373,6 +373,11 @@ struct ClassifyTilesParams {
     TexR32F inViewZ;
     TexTiles outTiles;
 };
+// REBLUR_Validation.resources.hlsli:22-34; bound by format, not by type: data1 is RG8 or R8, data2 R32_UINT / R8_UINT ( or data1 again for the occlusion denoisers ),
+// the lobe inputs whatever the denoiser's inputs are, OUT_VALIDATION "RGBA8+"
+struct ReblurValidationParams {
+    TexNR normalRoughness; TexR32F viewZ; TexView mv, data1, data2, diff, spec, out;
+};
 struct SplitScreenParams {
     TexR32F viewZ; TexRGBA16F inDiff, inSpec;
     TexRGBA16F outDiff, outSpec;

@@ -14,7 +14,7 @@
 
 #include "../../../include/nrd_b200.h"
 #include "../../../include/nrdcu.h"
-#include "reblur_common.cuh"  // HistoryFilter
+#include "debug_overlay.cuh"  // HistoryFilter
 
 namespace nrdk {
 
@@ -1473,6 +1473,95 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __gr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// RELAX validation overlay ( RELAX_Validation.cs.hlsl:31-212 ): the viewports of the REBLUR overlay that RELAX has data for — normals, roughness, viewZ,
+// motion-vector error, world units + jitter, accumulated frames. See kernels/debug_overlay.cuh for the grid and the captions.
+struct RelaxValidationParams {
+    TexNR normalRoughness; TexR32F viewZ; TexView mv; TexR8 historyLength; TexView out;
+};
+__global__ void __launch_bounds__(256) relaxValidationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxValidationParams p) {
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (!p.out.inside(px, py)) return;
+    if (cb.resetHistory != 0u) {
+        anyStore4(p.out, px, py, f4(0.0f));
+        return;
+    }
+    const float2 resourceSize = make_float2(cb.resourceSize[0], cb.resourceSize[1]);
+    const OverlayCell cell = overlayCell(px, py, resourceSize);
+    const float2 uvScaled = cell.uv * make_float2(cb.resolutionScale[0], cb.resolutionScale[1]);
+    const float4 nr = unpackNormalRoughness(p.normalRoughness.sampleNearestRaw(uvScaled));
+    const float viewZ = relaxViewZ(cb, p.viewZ.sampleNearest(uvScaled));
+    const float4 mvRaw = anyFetch4(p.mv, p.mv.cx((int)floorf(uvScaled.x * (float)p.mv.w)), p.mv.cy((int)floorf(uvScaled.y * (float)p.mv.h)));
+    const float3 mv = make_float3(mvRaw.x * cb.mvScale[0], mvRaw.y * cb.mvScale[1], mvRaw.z * cb.mvScale[2]);
+    const float historyLength = 255.0f * p.historyLength.sampleNearest(uvScaled) - 1.0f;
+    const float3 X = currentWorldPosClip(cb, cell.uv * 2.0f - 1.0f, viewZ);
+    const bool isInf = !relaxInRange(cb, viewZ);
+    const bool checker = ((((unsigned)px >> 2) ^ ((unsigned)py >> 2)) & 1u) != 0u;
+    const float notInf = isInf ? 0.0f : 1.0f;
+
+    Caption text(px, py, cell.captionX, cell.captionY);
+    float4 result = anyFetch4(p.out, px, py);
+    auto set = [&](float3 c) { result = f4(c, 1.0f); };
+    switch (cell.index) {
+        case 0:
+            text.print("NORMALS");
+            text.nextChar();
+            text.printUint(2u);
+            set(xyz(nr) * 0.5f + 0.5f);
+            break;
+        case 1:
+            text.print("ROUGHNESS");
+            text.nextChar();
+            text.printUint(1u);
+            set(f3(nr.w));
+            break;
+        case 2: {
+            text.print("Z");
+            const float f = 0.1f * viewZ / (1.0f + 0.1f * viewZ);
+            set(isInf ? make_float3(1.0f, 0.0f, 0.0f) : make_float3(0.0f, f, 0.0f));
+            break;
+        }
+        case 3: {
+            text.print("MV");
+            const float2 expected = screenUv(cb.worldToClipPrev, X);
+            float2 prev = cell.uv + xy(mv);
+            if (cb.mvScale[3] != 0.0f) prev = screenUv(cb.worldToClipPrev, X + mv);
+            const float2 delta = (prev - expected) * make_float2((float)cb.rectSize[0], (float)cb.rectSize[1]);
+            set(isInScreenNearest(prev) ? make_float3(fabsf(delta.x), fabsf(delta.y), 0.0f) : make_float3(0.0f, 0.0f, 1.0f));
+            break;
+        }
+        case 4: {
+            text.print("UNITS & JITTER");
+            const float2 dim = make_float2(0.5f * resourceSize.y / resourceSize.x, 0.5f);
+            const float2 remapped = (cell.uv - (1.0f - dim)) / dim;
+            if (remapped.x > 0.0f && remapped.y > 0.0f) {
+                const float2 dimInPixels = resourceSize * 0.25f * dim;
+                const float2 uv = make_float2(cb.jitter[0], cb.jitter[1]) + 0.5f;
+                const bool valid = saturate(uv.x) == uv.x && saturate(uv.y) == uv.y;
+                const int ax = (int)(saturate(uv.x) * dimInPixels.x), ay = (int)(saturate(uv.y) * dimInPixels.y);
+                const int bx = (int)(remapped.x * dimInPixels.x), by = (int)(remapped.y * dimInPixels.y);
+                float3 rgb = xyz(result);
+                if (abs(ax - bx) <= 1 && abs(ay - by) <= 1 && valid) rgb = f3(0.66f);
+                if (abs(ax - bx) <= 3 && abs(ay - by) <= 3 && !valid) rgb = make_float3(1.0f, 0.0f, 0.0f);
+                result = f4(rgb, 1.0f);
+            } else {
+                const float3 shifted = X + viewZ * 0.001f;
+                set(make_float3(frac(shifted.x), frac(shifted.y), frac(shifted.z)) * notInf);
+            }
+            break;
+        }
+        case 8: {
+            text.print("DIFF-SPEC FRAMES");
+            float f = 1.0f - saturate(historyLength / fmaxf(fmaxf(cb.diffMaxAccumulatedFrameNum, cb.specMaxAccumulatedFrameNum), 1.0f));
+            if (checker && historyLength < 2.0f) f = 0.75f;
+            set(colorizeZucconi(cell.uv.y > 0.95f ? 1.0f - cell.uv.x : f * notInf));
+            break;
+        }
+        default: break;
+    }
+    anyStore4(p.out, px, py, f4(applyCaption(xyz(result), text.foreground), result.w));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 uint32_t bytesOf(nrd::Format f) {
     switch (f) {
         case nrd::Format::R8_UNORM: return 1;
@@ -1497,6 +1586,28 @@ struct RelaxBinder {
         const uint32_t bpp = bytesOf(expect);
         if (x.format != (uint32_t)expect || !x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
             if (ok) *err = *id + ": binding " + std::to_string(next) + " has format " + std::to_string(x.format) + " (expected " + std::to_string((uint32_t)expect) + ")";
+            ok = false;
+        }
+        v.data = (uint8_t*)x.data;
+        v.w = (int)x.width;
+        v.h = (int)x.height;
+        v.pitch = (int)(x.pitchBytes / bpp);
+        v.fmt = x.format;
+        next++;
+        return v;
+    }
+    // any bound format the polymorphic accessors read ( validation overlay: IN_MV and OUT_VALIDATION are the application's choice )
+    TexView takeView() {
+        TexView v{};
+        if (next >= n) {
+            ok = false;
+            return v;
+        }
+        const nrdcuTexture& x = t[next];
+        const uint32_t bpp = x.format == (uint32_t)nrd::Format::RGBA32_SFLOAT ? 16u : (x.format == (uint32_t)nrd::Format::RGBA16_UNORM || x.format == (uint32_t)nrd::Format::RGBA16_SNORM) ? 8u
+                                                                                      : (x.format == (uint32_t)nrd::Format::R16_UNORM ? 2u : bytesOf((nrd::Format)x.format));
+        if (!x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
+            if (ok) *err = *id + ": binding " + std::to_string(next) + " has a pitch that does not fit its format";
             ok = false;
         }
         v.data = (uint8_t*)x.data;
@@ -1568,7 +1679,16 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
     auto takeShD = [&](TexRGBA16F& t) { t = (sh && hasDiff) ? b.take<TexRGBA16F>(F16) : TexRGBA16F(); };
     const uint32_t shOn = sh ? 1u : 0u;
 
-    if (id == "RELAX_ClassifyTiles.cs.hlsl") {
+    if (id == "RELAX_Validation.cs.hlsl") {
+        RelaxValidationParams p;
+        p.normalRoughness = b.take<TexNR>(NR);
+        p.viewZ = b.take<TexR32F>(R32);
+        p.mv = b.takeView();
+        p.historyLength = b.take<TexR8>(R8);
+        p.out = b.takeView();
+        if (bad(5)) return (uint32_t)Result::INVALID_ARGUMENT;
+        relaxValidationKernel<<<dim3((p.out.w + 31) / 32, (p.out.h + 7) / 8), 256, 0, stream>>>(cb, p);
+    } else if (id == "RELAX_ClassifyTiles.cs.hlsl") {
         RelaxClassifyParams p;
         p.viewZ = b.take<TexR32F>(R32);
         p.outTiles = b.take<TexR8>(R8);

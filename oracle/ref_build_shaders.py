@@ -86,6 +86,8 @@ IDENTIFIERS = [
     f"{f}|NRD_SIGNAL=DIFF|NRD_MODE=DO{suffix}" for f, suffix in (
         ("REBLUR_PrePass.cs.hlsl", ""), ("REBLUR_TemporalAccumulation.cs.hlsl", ""), ("REBLUR_HistoryFix.cs.hlsl", ""), ("REBLUR_Blur.cs.hlsl", ""),
         ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0"), ("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1"), ("REBLUR_TemporalStabilization.cs.hlsl", ""))] + [
+    # validation overlays ( CommonSettings::enableValidation )
+    "REBLUR_Validation.cs.hlsl", "RELAX_Validation.cs.hlsl",
     # REFERENCE
     "REFERENCE_TemporalAccumulation.cs.hlsl", "REFERENCE_Copy.cs.hlsl",
     # ours: calls the application-side functions of the reference's NRD.hlsli ( oracle/ref_shim/Shaders/NRD_FrontEndProbe.cs.hlsl )

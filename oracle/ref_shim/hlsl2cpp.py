@@ -80,6 +80,9 @@ def transform(text: str, identifier: str, namespace: str) -> str:
     # so the CUDA kernels are compared on its RATE. The value of the expression is passed through unchanged.
     text = re.sub(r"any\s*\(\s*uv\s*!=\s*mirrorUv\s*\)", "hlsl::probeMirror( any( uv != mirrorUv ) )", text)
 
+    # HLSL promotes `uint % float` to a float remainder ( REBLUR_Validation.cs.hlsl:215 ); C++ has no such operator
+    text = re.sub(r"\(\s*gFrameIndex\s*>>\s*2\s*\)\s*%\s*gMaxAccumulatedFrameNum", "uint( fmod( float( gFrameIndex >> 2 ), gMaxAccumulatedFrameNum ) )", text)
+
     use_fibers = bool(re.search(r"\bGroupMemoryBarrier(WithGroupSync)?\b|\bQuadRead\w+\b", text))
     x, y, z = (threads + [1, 1])[:3]
     return f"""#include "hlsl_cpu.h"

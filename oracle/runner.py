@@ -145,6 +145,7 @@ USER_FORMATS = {
     api.ResourceType.IN_PENUMBRA: api.Format.R16_SFLOAT,
     api.ResourceType.OUT_SHADOW_TRANSLUCENCY: api.Format.R8_UNORM,   # RGBA8_UNORM for SIGMA_SHADOW_TRANSLUCENCY ( pass fmt= explicitly )
     api.ResourceType.IN_TRANSLUCENCY: api.Format.RGBA8_UNORM,
+    api.ResourceType.OUT_VALIDATION: api.Format.RGBA8_UNORM,   # "RGBA8+", .w = transparency ( NRDDescs.h:142-144 )
     api.ResourceType.IN_SIGNAL: api.Format.RGBA16_SFLOAT,    # NRDSample's "Composed" ( Source/NRDSample.cpp:484-485, 2944 )
     api.ResourceType.OUT_SIGNAL: api.Format.RGBA16_SFLOAT,
     # the application's choice ( Texture2D<float> in the shaders ); these are what synth.reblur_frame( guides=True ) makes

@@ -214,7 +214,7 @@ def test_missing_resource_and_bad_format_are_reported(ex):
     with pytest.raises(ex.NrdcuError):
         ex.dispatch("REBLUR_ClassifyTiles.cs.hlsl", b"\0" * 864, [ex.texture_of(t, api.Format.R32_SFLOAT), ex.texture_of(t, api.Format.R32_SFLOAT)])  # tiles must be R8
     with pytest.raises(ex.NrdcuError, match="UNSUPPORTED"):
-        ex.dispatch("REBLUR_Validation.cs.hlsl", b"\0" * 864, [])   # the debug overlay has no CUDA kernel
+        ex.dispatch("REBLUR_NoSuchPass.cs.hlsl", b"\0" * 864, [])   # a shader identifier without a kernel
     cud.close()
 
 

@@ -376,3 +376,54 @@ def test_dynamic_resolution_closed_loop(ex, runner, which):
             r = compare(g, c, fmt, layout=CASES[which][3])
             assert r["psnr"] >= LIMITS[which][1], f"{which} frame {f} rect {rw}x{rh} {o}: {r}"
     cud.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------------
+# Validation overlay ( CommonSettings::enableValidation, NRDSettings.h:193; REBLUR_Validation.cs.hlsl / RELAX_Validation.cs.hlsl ): the 4 x 4 grid of debug
+# viewports in OUT_VALIDATION. Compared with the reference shaders texel by texel EXCEPT the caption bands: the layout of the captions is the reference's, the
+# 5x6 glyph bitmaps are this repository's own ( kernels/debug_overlay.cuh ).
+@pytest.mark.parametrize("which", ["reblur", "reblur_diff", "reblur_occ", "relax", "relax_diff"])
+def test_validation_overlay(ex, runner, which):
+    w, h, frames = 256, 160, 4
+    den_id, frame_fn, outputs, _ = CASES[which]
+    ref = reference_engine(runner, which, w, h)
+    val_ref = runner.alloc_texture(api.Format.RGBA8_UNORM, w, h)
+    ref.set_user_texture(RT.OUT_VALIDATION, val_ref, api.Format.RGBA8_UNORM)
+    seen = []
+    snap = {}
+
+    def before(i, d, keys, den):
+        snap["t"] = [den.textures[k].clone() for k in keys] if d.name.endswith("Validation") else None
+
+    def after(i, d, keys, den):
+        if snap["t"] is None:
+            return
+        gpu = [t.to("cuda:0") for t in snap["t"]]
+        ex.dispatch(d.shader, d.constants, [ex.texture_of(g, den.formats[k]) for g, k in zip(gpu, keys)], flags=ex.FLAG_QUAD_INTRINSICS)
+        torch.cuda.synchronize()
+        got, want = gpu[-1].cpu().int(), den.textures[keys[-1]].int()
+        mask = torch.ones(h, w, dtype=torch.bool)
+        for cy in range(4):
+            y0 = int(cy * h * 0.25 + 5.0)
+            mask[y0:y0 + 6, :] = False            # the caption rows of this row of viewports
+        diff = (got - want).abs().amax(-1)
+        bad = ((diff > 1) & mask).float().sum().item() / mask.float().sum().item()
+        wrong = (diff > 1) & mask
+        cells = {cy * 4 + cx: int(wrong[cy * h // 4:(cy + 1) * h // 4, cx * w // 4:(cx + 1) * w // 4].sum()) for cy in range(4) for cx in range(4)}
+        seen.append((d.name, bad, int(((got != want).any(-1) & ~mask).sum()), {k: v for k, v in cells.items() if v}))
+        if bad > 2e-3:   # the box is remote: leave what a post-mortem needs
+            os.makedirs("gpurun_out", exist_ok=True)
+            torch.save({"got": got, "want": want, "inputs": [t.cpu() for t in snap["t"]], "formats": [int(den.formats[k]) for k in keys], "constants": bytes(d.constants)},
+                       f"gpurun_out/validation_debug_{which}.pt")
+        assert bad <= 2e-3, f"{d.name}: {bad:.4%} of the texels outside the captions differ by more than 1 LSB; per viewport {seen[-1][3]}"
+
+    for f in range(frames):
+        for k, v in frame_of(frame_fn, f, w, h).items():
+            ref.set_user_texture(getattr(RT, k), v, in_format(which, k, runner))
+        cs = common_of(which, f, w, h)
+        cs.enableValidation = True
+        ref.denoise(cs, settings=SETTINGS[which]() if which in SETTINGS else None, before_dispatch=before, on_dispatch=after)
+    assert len(seen) == frames, seen                                          # one validation dispatch per frame
+    assert val_ref[..., :3].float().std() > 10.0                               # the overlay shows something
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(seen, open(f"gpurun_out/validation_overlay_{which}.json", "w"))
