@@ -43,8 +43,10 @@ typedef struct nrdcuTexture {
 /* Flags of nrdcuCreate / nrdcuDispatch */
 enum {
     NRDCU_FLAG_QUAD_INTRINSICS = 1u << 0, /* replay SM6.0 quad smoothing (NRD_SUPPORTS_QUAD_INTRINSICS=1, the reference default) */
-    NRDCU_FLAG_CUDA_GRAPH = 1u << 1,      /* reserved, ignored: every pass takes new constants each frame, so a replayed graph would need all of its
-                                             kernel nodes patched per frame — no gain over 7-10 launches while the chains are GPU-bound */
+    NRDCU_FLAG_CUDA_GRAPH = 1u << 1,      /* nrdcuDenoise keeps each distinct frame ( the chain of kernels and the memory it binds: odd / even ping-pong, the
+                                             first frame with its clears ) as an instantiated CUDA graph; later frames of the same shape only patch the kernel
+                                             nodes' parameters ( constants ) and launch the graph once. Pays where the frame is launch-bound ( small frames );
+                                             ignored with strips over peer memory, profiling, row ranges and per-dispatch callbacks */
     NRDCU_FLAG_ROBUST_MIRROR_TEST = 1u << 2, /* DEBUG: spatial taps use "left the screen" instead of the reference's bit-fragile any(uv != MirrorUv(uv)) */
     NRDCU_FLAG_NO_SEAM_OVERLAP = 1u << 4,    /* strips over peer memory: do NOT split each pass into "seam rows first, interior second" ( the push of the seam rows then
                                                 follows the whole pass instead of overlapping its interior ); for A/B timing */
@@ -166,6 +168,8 @@ NRDCU_API uint64_t nrdcuGetPoolBytes(nrdcuContext* ctx); /* device bytes held by
 /* The split NRDIntegration.h:266-277 reports: permanent pool ( history, survives the frame ), transient pool ( aliasable between denoisers and with the
  * application's own per-frame memory ), plus what this executor keeps for itself ( REBLUR's geometry plane ). Any pointer may be NULL. */
 NRDCU_API uint32_t nrdcuGetMemoryUsage(nrdcuContext* ctx, uint64_t* persistentBytes, uint64_t* aliasableBytes, uint64_t* privateBytes);
+/* NRDCU_FLAG_CUDA_GRAPH bookkeeping: frames captured into a new graph, frames replayed from a cached one, graphs currently cached */
+NRDCU_API uint32_t nrdcuGetGraphStats(nrdcuContext* ctx, uint64_t* captures, uint64_t* replays, uint32_t* cached);
 /* NRDCU_FLAG_PROBE_MIRROR counters of the current device, 14 values: out[0] = taps, out[1] = taps whose weight took the "mirrored" branch, then the same pair
  * per ( pass, lobe ) at out[2 + 2 * slot], slot = pass * 2 + lobe ( pass 0 pre-pass / 1 blur / 2 post-blur; lobe 0 diffuse / 1 specular ); reset != 0 clears them */
 NRDCU_API uint32_t nrdcuGetMirrorProbe(uint64_t* out, int reset);

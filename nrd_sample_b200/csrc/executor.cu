@@ -17,6 +17,7 @@
 
 #include "../../include/nrd_b200.h"
 #include "../../include/nrdcu.h"
+#include "pipeline_key.h"
 #include "kernels/reblur_common.cuh"
 #include "kernels/peer_halo.cuh"
 #include "kernels/sigma_common.cuh"
@@ -36,9 +37,9 @@ void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccu
 void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, int signal, int mode, bool quads, Rows, cudaStream_t);
 void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, int signal, int mode, Rows, cudaStream_t);
 bool readMirrorProbe(unsigned long long* out, bool reset);
-uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
-uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, cudaStream_t stream, std::string& err);
-uint32_t dispatchReference(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, uint32_t gridW, uint32_t gridH, cudaStream_t stream,
+uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, Rows rows, cudaStream_t stream, std::string& err);
+uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, Rows rows, cudaStream_t stream, std::string& err);
+uint32_t dispatchReference(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, uint32_t gridW, uint32_t gridH, cudaStream_t stream,
                            std::string& err);
 }  // namespace nrdk
 
@@ -173,43 +174,32 @@ bool checkLaunch(const char* what) {
     return true;
 }
 
-uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, uint32_t flags, nrdk::Rows rows,
+uint32_t dispatchReblur(const nrdk::PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, uint32_t flags, nrdk::Rows rows,
                         cudaStream_t stream) {
     using namespace nrdk;
-    if (constantsSize != sizeof(ReblurConstants) || !constants) return fail(Result::INVALID_ARGUMENT, "%s: expected %zu constant bytes, got %u", id.c_str(), sizeof(ReblurConstants), constantsSize);
+    const char* const id = key.id;
+    if (constantsSize != sizeof(ReblurConstants) || !constants) return fail(Result::INVALID_ARGUMENT, "%s: expected %zu constant bytes, got %u", id, sizeof(ReblurConstants), constantsSize);
     ReblurConstants cb;
     memcpy(&cb, constants, sizeof(cb));
     // dynamic resolution ( rectSize < resourceSize, CommonSettings ): the kernels work in rect pixels and scale uv by gResolutionScale( Prev ) wherever the
     // reference samples a resource-sized texture; rectOrigin is always 0 ( NRD_SUPPORTS_VIEWPORT_OFFSET = 0: the host library rejects anything else )
-    if ((cb.diffCheckerboard == 2) != (cb.specCheckerboard == 2)) return fail(Result::INVALID_ARGUMENT, "%s: checkerboard constants %u / %u", id.c_str(), cb.diffCheckerboard, cb.specCheckerboard);
+    if ((cb.diffCheckerboard == 2) != (cb.specCheckerboard == 2)) return fail(Result::INVALID_ARGUMENT, "%s: checkerboard constants %u / %u", id, cb.diffCheckerboard, cb.specCheckerboard);
 
     const bool quads = flags & NRDCU_FLAG_QUAD_INTRINSICS;
     const int kflags = (quads ? 1 : 0) | ((flags & NRDCU_FLAG_ROBUST_MIRROR_TEST) ? 2 : 0) | ((flags & NRDCU_FLAG_PROBE_MIRROR) ? 4 : 0);
     std::string err;
-    Binder b{tex, n, 0, true, &err, id.c_str()};
-    // "<file>|NRD_SIGNAL=<DIFF|SPEC|BOTH>|NRD_MODE=RADIANCE<suffix>" (InstanceImpl.h:59-67). REBLUR_DIFFUSE / REBLUR_SPECULAR bind only their own lobe's
-    // textures (REBLUR_*.resources.hlsli): takeD / takeS consume a binding only when the permutation has that lobe
-    // "|NRD_MODE=SH" ( REBLUR_DIFFUSE_SH / REBLUR_SPECULAR_SH / REBLUR_DIFFUSE_SPECULAR_SH ): each lobe binds a second RGBA16F next to the first
-    // ( takeShD / takeShS below, in the order of the REBLUR_*.resources.hlsli lists ); the launchers pick the SH instantiation when those views are bound
-    int signal = 0, mode = MODE_RADIANCE;
-    std::string kSig;
-    static const char* const kModes[4] = {"RADIANCE", "SH", "OCCLUSION", "DO"};   // MODE_* of kernels/reblur_common.cuh
-    for (int m = 0; m < 4 && !signal; m++)
-        for (int sg = 1; sg <= 3 && !signal; sg++) {
-            const std::string candidate = std::string("|NRD_SIGNAL=") + (sg == 1 ? "DIFF" : (sg == 2 ? "SPEC" : "BOTH")) + "|NRD_MODE=" + kModes[m];
-            if (id.find(candidate) != std::string::npos) {
-                signal = sg;
-                mode = m;
-                kSig = candidate;
-            }
-        }
+    Binder b{tex, n, 0, true, &err, id};
+    // "<file>|NRD_SIGNAL=<DIFF|SPEC|BOTH>|NRD_MODE=<RADIANCE|SH|OCCLUSION|DO><suffix>" (InstanceImpl.h:59-67), parsed into `key` when the pipeline was
+    // resolved. REBLUR_DIFFUSE / REBLUR_SPECULAR bind only their own lobe's textures (REBLUR_*.resources.hlsli): takeD / takeS consume a binding only when
+    // the permutation has that lobe. NRD_MODE=SH ( REBLUR_DIFFUSE_SH / REBLUR_SPECULAR_SH / REBLUR_DIFFUSE_SPECULAR_SH ): each lobe binds a second RGBA16F
+    // next to the first ( takeShD / takeShS below, in the order of the REBLUR_*.resources.hlsli lists )
+    const int signal = key.signal, mode = key.mode;
     const bool sh = mode == MODE_SH, occlusion = mode == MODE_OCCLUSION, polymorphicMode = mode == MODE_OCCLUSION || mode == MODE_DO;
     const int kflagsMode = kflags | (mode << 4);
     const bool hasDiff = (signal & 1) != 0, hasSpec = (signal & 2) != 0;
     const uint32_t lobes = (hasDiff ? 1u : 0u) + (hasSpec ? 1u : 0u);
-    auto is = [&](const char* file, const char* suffix = "") { return signal != 0 && id == std::string(file) + kSig + suffix; };
     auto done = [&](uint32_t expected) -> uint32_t {
-        if (!b.ok || b.next != expected || n != expected) return fail(Result::INVALID_ARGUMENT, "%s", err.empty() ? (id + ": wrong number of textures").c_str() : err.c_str());
+        if (!b.ok || b.next != expected || n != expected) return fail(Result::INVALID_ARGUMENT, "%s", err.empty() ? (std::string(id) + ": wrong number of textures").c_str() : err.c_str());
         return 0xFFFFFFFFu;
     };
     // the lobe's signal texture: RGBA16F in the RADIANCE / SH modes; anything the format-polymorphic accessors read in the occlusion modes and in the two
@@ -289,7 +279,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         if (tempPlane) cudaFreeAsync(tempPlane, stream);
     };
 
-    if (id == "REBLUR_Validation.cs.hlsl") {
+    if (key.pass == REBLUR_VALIDATION) {
         // REBLUR_Validation.resources.hlsli:22-34: bound by whatever format each texture has ( data1 RG8 / R8, data2 R32_UINT / R8_UINT or data1 again, the lobe
         // inputs of the denoiser, OUT_VALIDATION "RGBA8+" )
         auto takeView = [&]() {
@@ -309,14 +299,14 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         uint32_t r = done(8);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurValidation(cb, p, stream);
-    } else if (id == "REBLUR_ClassifyTiles.cs.hlsl") {
+    } else if (key.pass == REBLUR_CLASSIFY_TILES) {
         ClassifyTilesParams p = {};
         p.inViewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.outTiles = takeTiles();
         uint32_t r = done(2);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurClassifyTiles(cb, p, rows, stream);
-    } else if (is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=0") || is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1")) {
+    } else if (key.pass == REBLUR_HITDIST_RECONSTRUCTION) {
         anySignalFormat = true;
         HitDistReconstructionParams p = {};
         p.tiles = takeTiles();
@@ -328,8 +318,8 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpec = takeS16();
         uint32_t r = done(3 + 2 * lobes);
         if (r != 0xFFFFFFFFu) return r;
-        launchReblurHitDistReconstruction(cb, p, signal, occlusion, is("REBLUR_HitDistReconstruction.cs.hlsl", "|MODE_5X5=1"), rows, stream);
-    } else if (is("REBLUR_SplitScreen.cs.hlsl")) {
+        launchReblurHitDistReconstruction(cb, p, signal, occlusion, key.mode5x5, rows, stream);
+    } else if (key.pass == REBLUR_SPLIT_SCREEN) {
         anySignalFormat = true;
         SplitScreenParams p = {};
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
@@ -344,7 +334,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         uint32_t r = done(1 + 2 * lobes + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurSplitScreen(cb, p, signal, rows, stream);
-    } else if (is("REBLUR_PrePass.cs.hlsl")) {
+    } else if (key.pass == REBLUR_PREPASS) {
         PrePassParams p = {};
         p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
@@ -360,10 +350,10 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecSh = takeShS();
         uint32_t r = done(3 + 2 * lobes + (hasSpec ? 1 : 0) + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
-        if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
+        if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id);
         launchReblurPrePass(cb, p, signal, kflagsMode, rows, stream);
         releasePlane();
-    } else if (is("REBLUR_TemporalAccumulation.cs.hlsl")) {
+    } else if (key.pass == REBLUR_TEMPORAL_ACCUMULATION) {
         TemporalAccumulationParams p = {};
         p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
@@ -402,7 +392,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         uint32_t r = done((occlusion ? 9 : 10) + 6 * lobes + (hasSpec ? (occlusion ? 2 : 3) : 0) + 3 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurTemporalAccumulation(cb, p, signal, mode, rows, stream);
-    } else if (is("REBLUR_HistoryFix.cs.hlsl")) {
+    } else if (key.pass == REBLUR_HISTORY_FIX) {
         HistoryFixParams p = {};
         p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
@@ -424,7 +414,7 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         uint32_t r = done(4 + 4 * lobes + (hasSpec && !occlusion ? 1 : 0) + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
         launchReblurHistoryFix(cb, p, signal, mode, quads, rows, stream);
-    } else if (is("REBLUR_Blur.cs.hlsl")) {
+    } else if (key.pass == REBLUR_BLUR) {
         BlurParams p = {};
         p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
@@ -441,13 +431,13 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecSh = takeShS();
         uint32_t r = done(5 + 2 * lobes + 2 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
-        if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
+        if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id);
         launchReblurBlur(cb, p, signal, kflagsMode, rows, stream);
         releasePlane();
         // the blur pass copies viewZ ( sky included ) into PREV_VIEWZ, which is what post-blur binds as its viewZ: same texels, same plane
         if (g_plane && g_plane->fromViewZ == p.viewZ.data) g_plane->viewZCopy = p.outViewZ.data;
-    } else if (is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1") || is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=0")) {
-        const bool ts = is("REBLUR_PostBlur.cs.hlsl", "|TEMPORAL_STABILIZATION=1");
+    } else if (key.pass == REBLUR_POST_BLUR) {
+        const bool ts = key.temporalStabilization;
         PostBlurParams p = {};
         p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
@@ -471,10 +461,10 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         p.outSpecSh = takeShS();
         uint32_t r = done(ts ? 5 + 2 * lobes + 2 * shLobes : 6 + 3 * lobes + 3 * shLobes);
         if (r != 0xFFFFFFFFu) return r;
-        if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id.c_str());
+        if (!acquirePlane(p.normalRoughness, p.viewZ, p.geom)) return fail(Result::FAILURE, "%s: no memory for the geometry plane", id);
         launchReblurPostBlur(cb, p, signal, ts, kflagsMode, rows, stream);
         releasePlane();
-    } else if (is("REBLUR_TemporalStabilization.cs.hlsl")) {
+    } else if (key.pass == REBLUR_TEMPORAL_STABILIZATION) {
         TemporalStabilizationParams p = {};
         p.tiles = takeTiles();
         p.normalRoughness = b.take<TexNR>(Format::R10_G10_B10_A2_UNORM);
@@ -501,15 +491,55 @@ uint32_t dispatchReblur(const std::string& id, const void* constants, uint32_t c
         if (r != 0xFFFFFFFFu) return r;
         launchReblurTemporalStabilization(cb, p, signal, mode, rows, stream);
     } else {
-        return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", id.c_str());
+        return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", id);
     }
-    if (!checkLaunch(id.c_str())) return (uint32_t)Result::FAILURE;
+    if (!checkLaunch(id)) return (uint32_t)Result::FAILURE;
     return (uint32_t)Result::SUCCESS;
+}
+
+// One dispatch of an already resolved pipeline: no text is looked at from here on
+uint32_t dispatchResolved(const nrdk::PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures, uint32_t texturesNum, uint32_t flags,
+                          cudaStream_t s, uint32_t rowBegin, uint32_t rowEnd) {
+    if (rowBegin % 16u) return fail(Result::INVALID_ARGUMENT, "nrdcuDispatchRows: rowBegin %u is not a multiple of 16", rowBegin);
+    // a ragged rowEnd inside the frame would let the last CTA row ( 8 or 16 pixels tall ) store past it, into the neighbouring strip's rows
+    if (rowEnd != 0xFFFFFFFFu && rowEnd % 16u) {
+        uint32_t frameH = 0;
+        for (uint32_t k = 0; k < texturesNum; k++) frameH = textures[k].height > frameH ? textures[k].height : frameH;
+        if (rowEnd < frameH) return fail(Result::INVALID_ARGUMENT, "nrdcuDispatchRows: rowEnd %u is inside the frame and not a multiple of 16", rowEnd);
+    }
+    nrdk::Rows rows;
+    rows.begin = (int)rowBegin;
+    rows.end = rowEnd > 0x7FFFFFFFu ? 0x7FFFFFFF : (int)rowEnd;
+    const bool partial = rowBegin != 0 || rowEnd != 0xFFFFFFFFu;
+    std::string err;
+    uint32_t r = 0;
+    switch (key.family) {
+        case nrdk::FAMILY_CLEAR: {  // clears always cover the whole texture (frame 0 only)
+            if (texturesNum != 1 || !textures[0].data) return fail(Result::INVALID_ARGUMENT, "Clear: exactly one texture expected");
+            const nrdcuTexture& t = textures[0];
+            uint32_t bpp = bytesPerTexel(t.format);
+            if (!bpp) return fail(Result::UNSUPPORTED, "Clear: unsupported format %u", t.format);
+            nrdk::launchClear(t.data, (int)(t.width * bpp), (int)t.height, (int)t.pitchBytes, s);
+            return checkLaunch("Clear") ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
+        }
+        case nrdk::FAMILY_REBLUR: return dispatchReblur(key, constants, constantsSize, textures, texturesNum, flags, rows, s);
+        case nrdk::FAMILY_SIGMA: r = nrdk::dispatchSigma(key, constants, constantsSize, textures, texturesNum, rows, s, err); break;
+        case nrdk::FAMILY_RELAX: r = nrdk::dispatchRelax(key, constants, constantsSize, textures, texturesNum, rows, s, err); break;
+        case nrdk::FAMILY_REFERENCE:
+            if (partial) return fail(Result::UNSUPPORTED, "%s: the REFERENCE denoiser has no row ranges (multi-GPU strips)", key.id);
+            r = nrdk::dispatchReference(key, constants, constantsSize, textures, texturesNum, 0u, 0u, s, err);
+            break;
+        default: return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", key.id);
+    }
+    if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
+    return checkLaunch(key.id) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
 }
 
 }  // namespace
 
 namespace nrdk {
+thread_local GraphReplay* g_graphReplay = nullptr;
+thread_local GraphRecord* g_graphRecord = nullptr;
 void countLaunch() { g_launchCount.fetch_add(1, std::memory_order_relaxed); }  // kernels launched by frontend.cu
 }
 
@@ -530,50 +560,8 @@ NRDCU_API uint32_t nrdcuGetMirrorProbe(uint64_t* out, int reset) {
 NRDCU_API uint32_t nrdcuDispatchRows(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures, uint32_t texturesNum,
                                      uint32_t flags, void* stream, uint32_t rowBegin, uint32_t rowEnd) {
     if (!shaderIdentifier || (!textures && texturesNum)) return fail(Result::INVALID_ARGUMENT, "nrdcuDispatch: null argument");
-    if (rowBegin % 16u) return fail(Result::INVALID_ARGUMENT, "nrdcuDispatchRows: rowBegin %u is not a multiple of 16", rowBegin);
-    // a ragged rowEnd inside the frame would let the last CTA row ( 8 or 16 pixels tall ) store past it, into the neighbouring strip's rows
-    if (rowEnd != 0xFFFFFFFFu && rowEnd % 16u) {
-        uint32_t frameH = 0;
-        for (uint32_t k = 0; k < texturesNum; k++) frameH = textures[k].height > frameH ? textures[k].height : frameH;
-        if (rowEnd < frameH) return fail(Result::INVALID_ARGUMENT, "nrdcuDispatchRows: rowEnd %u is inside the frame and not a multiple of 16", rowEnd);
-    }
-    const std::string id = shaderIdentifier;
-    cudaStream_t s = (cudaStream_t)stream;
-    nrdk::Rows rows;
-    rows.begin = (int)rowBegin;
-    rows.end = rowEnd > 0x7FFFFFFFu ? 0x7FFFFFFF : (int)rowEnd;
-    const bool partial = rowBegin != 0 || rowEnd != 0xFFFFFFFFu;
-    if (id.rfind("Clear.cs.hlsl", 0) == 0) {  // clears always cover the whole texture (frame 0 only)
-        if (texturesNum != 1 || !textures[0].data) return fail(Result::INVALID_ARGUMENT, "Clear: exactly one texture expected");
-        const nrdcuTexture& t = textures[0];
-        uint32_t bpp = bytesPerTexel(t.format);
-        if (!bpp) return fail(Result::UNSUPPORTED, "Clear: unsupported format %u", t.format);
-        nrdk::launchClear(t.data, (int)(t.width * bpp), (int)t.height, (int)t.pitchBytes, s);
-        return checkLaunch("Clear") ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
-    }
-    if (id.rfind("REBLUR_", 0) == 0) return dispatchReblur(id, constants, constantsSize, textures, texturesNum, flags, rows, s);
-    if (id.rfind("SIGMA_", 0) == 0) {
-        if (partial) return fail(Result::UNSUPPORTED, "%s: row ranges (multi-GPU strips) are implemented for REBLUR only", shaderIdentifier);
-        std::string err;
-        uint32_t r = nrdk::dispatchSigma(id, constants, constantsSize, textures, texturesNum, s, err);
-        if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
-        return checkLaunch(id.c_str()) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
-    }
-    if (id.rfind("RELAX_", 0) == 0) {
-        if (partial) return fail(Result::UNSUPPORTED, "%s: row ranges (multi-GPU strips) are implemented for REBLUR only", shaderIdentifier);
-        std::string err;
-        uint32_t r = nrdk::dispatchRelax(id, constants, constantsSize, textures, texturesNum, s, err);
-        if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
-        return checkLaunch(id.c_str()) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
-    }
-    if (id.rfind("REFERENCE_", 0) == 0) {
-        if (partial) return fail(Result::UNSUPPORTED, "%s: row ranges (multi-GPU strips) are implemented for REBLUR only", shaderIdentifier);
-        std::string err;
-        uint32_t r = nrdk::dispatchReference(id, constants, constantsSize, textures, texturesNum, 0u, 0u, s, err);
-        if (r != (uint32_t)Result::SUCCESS) return fail((Result)r, "%s", err.c_str());
-        return checkLaunch(id.c_str()) ? (uint32_t)Result::SUCCESS : (uint32_t)Result::FAILURE;
-    }
-    return fail(Result::UNSUPPORTED, "no CUDA kernel for shader '%s'", shaderIdentifier);
+    // the context-less entry resolves the identifier on every call; a context ( nrdcuCreate ) does it once per pipeline
+    return dispatchResolved(nrdk::resolvePipeline(shaderIdentifier), constants, constantsSize, textures, texturesNum, flags, (cudaStream_t)stream, rowBegin, rowEnd);
 }
 
 NRDCU_API uint32_t nrdcuDispatch(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures, uint32_t texturesNum,
@@ -603,6 +591,7 @@ struct nrdcuContext {
     std::vector<nrdcuTexture> permanent, transient;
     std::vector<uint32_t> permanentDs, transientDs;   // TextureDesc::downsampleFactor of each pool texture
     GeomPlane plane;                                  // REBLUR's per-frame geometry plane ( allocated when the instance holds a REBLUR denoiser )
+    std::vector<nrdk::PipelineKey> pipelines;         // InstanceDesc::pipelines resolved to kernels at creation
     std::vector<DenoiserDesc> denoisers;              // ( identifier, denoiser ) pairs of the instance
     std::vector<uint8_t> checkerboard;                // per denoiser: its settings ask for half-width ( checkerboarded ) radiance inputs
     bool halfWidthInputs = false;
@@ -640,6 +629,17 @@ struct nrdcuContext {
         std::vector<HaloRule> rules;
         uint64_t bytesPushed = 0;
     } tile;
+    // NRDCU_FLAG_CUDA_GRAPH: frames kept as instantiated graphs, keyed by what they bind ( ping-pong parity, frame 0 with its clears, ... )
+    struct FrameGraph {
+        uint64_t signature = 0, lastUse = 0;
+        cudaGraph_t graph = nullptr;          // kept alive: the node handles below belong to it
+        cudaGraphExec_t exec = nullptr;
+        std::vector<cudaGraphNode_t> nodes;   // kernel nodes in launch order
+        std::vector<const void*> funcs;       // ... and the kernel each one runs
+    };
+    std::vector<FrameGraph> graphs;
+    cudaStream_t captureStream = nullptr;     // frames are captured on a stream of the library's own ( the caller's may be the legacy default stream )
+    uint64_t graphClock = 0, graphCaptures = 0, graphReplays = 0;
     // per-dispatch CUDA-event timing (bench.py's live roofline measurement)
     struct ProfileEntry { const char* name; double totalMs = 0; uint64_t count = 0; };
     struct PendingTiming { const char* name; cudaEvent_t start, stop; };
@@ -898,6 +898,17 @@ NRDCU_API uint32_t nrdcuCreate(const void* instanceCreationDesc, uint16_t resour
     ctx->denoisers.assign(icd.denoisers, icd.denoisers + icd.denoisersNum);
     ctx->checkerboard.assign(icd.denoisersNum, 0);
     const InstanceDesc& d = *GetInstanceDesc(*ctx->instance);
+    // pipelines are picked HERE, once ( the reference integration creates its pipeline objects in Recreate, NRDIntegration.hpp:199-239 ): every
+    // shaderIdentifier of the instance becomes a PipelineKey, and an identifier without a kernel fails the creation instead of the first frame
+    ctx->pipelines.resize(d.pipelinesNum);
+    for (uint32_t i = 0; i < d.pipelinesNum; i++) {
+        ctx->pipelines[i] = nrdk::resolvePipeline(d.pipelines[i].shaderIdentifier);
+        if (ctx->pipelines[i].family == nrdk::FAMILY_UNKNOWN) {
+            const std::string id = d.pipelines[i].shaderIdentifier;
+            nrdcuDestroy(ctx);
+            return fail(Result::UNSUPPORTED, "nrdcuCreate: no CUDA kernel for pipeline %u '%s'", i, id.c_str());
+        }
+    }
     auto makePool = [&](const TextureDesc* descs, uint32_t n, std::vector<nrdcuTexture>& pool, std::vector<uint32_t>& dsOut) {
         pool.resize(n);
         dsOut.resize(n);
@@ -931,6 +942,11 @@ NRDCU_API void nrdcuDestroy(nrdcuContext* ctx) {
             if (p) cudaIpcCloseMemHandle(p);
         if (ctx->tile.peerFlags[d]) cudaIpcCloseMemHandle(ctx->tile.peerFlags[d]);
     }
+    for (nrdcuContext::FrameGraph& fg : ctx->graphs) {
+        cudaGraphExecDestroy(fg.exec);
+        cudaGraphDestroy(fg.graph);
+    }
+    if (ctx->captureStream) cudaStreamDestroy(ctx->captureStream);
     if (ctx->tile.hostError) cudaFreeHost(ctx->tile.hostError);
     if (ctx->tile.seamStream) {
         cudaStreamDestroy(ctx->tile.seamStream);
@@ -1019,7 +1035,6 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
     uint32_t n = 0;
     Result r = GetComputeDispatches(*ctx->instance, identifiers, identifiersNum, dispatches, n);
     if (r != Result::SUCCESS) return fail(r, "nrd::GetComputeDispatches failed (%u)", (uint32_t)r);
-    const InstanceDesc& d = *GetInstanceDesc(*ctx->instance);
     // new frame, new G-buffer: the geometry plane is decoded again by the first spatial pass that needs it
     ctx->plane.row0 = ctx->plane.row1 = 0;
     ctx->plane.viewZCopy = nullptr;
@@ -1030,6 +1045,8 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
         PlaneScope(GeomPlane* p) { g_plane = p; }
         ~PlaneScope() { g_plane = nullptr; }
     } planeScope(&ctx->plane);
+    // the frame: every dispatch of the list, in order, onto `stream`
+    auto runFrame = [&](void* stream) -> uint32_t {
     for (uint32_t i = 0; i < n; i++) {
         const DispatchDesc& dd = dispatches[i];
         ctx->scratch.resize(dd.resourcesNum);
@@ -1063,9 +1080,9 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
             evStop = grab();
             cudaEventRecord(evStart, (cudaStream_t)stream);
         }
-        const char* shader = d.pipelines[dd.pipelineIndex].shaderIdentifier;
+        const nrdk::PipelineKey& pipeline = ctx->pipelines[dd.pipelineIndex];
         auto run = [&](uint32_t r0, uint32_t r1) {
-            return r1 > r0 ? nrdcuDispatchRows(shader, dd.constantBufferData, dd.constantBufferDataSize, ctx->scratch.data(), dd.resourcesNum, ctx->flags, stream, r0, r1) : 0u;
+            return r1 > r0 ? dispatchResolved(pipeline, dd.constantBufferData, dd.constantBufferDataSize, ctx->scratch.data(), dd.resourcesNum, ctx->flags, (cudaStream_t)stream, r0, r1) : 0u;
         };
         // Strips over peer memory: the rows the neighbours need are computed FIRST, their push ( own stream ) then overlaps the interior of the same pass
         const uint32_t stripEnd = std::min<uint32_t>(rowEnd, ctx->height);
@@ -1102,7 +1119,144 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
         }
     }
     return 0;
+    };
+    auto resetPlane = [&]() {
+        ctx->plane.row0 = ctx->plane.row1 = 0;
+        ctx->plane.viewZCopy = nullptr;
+    };
+    const bool graphMode = (ctx->flags & NRDCU_FLAG_CUDA_GRAPH) && n != 0 && !ctx->tile.attached && !ctx->profiling && !afterDispatch && rowBegin == 0 && rowEnd == 0xFFFFFFFFu;
+    if (!graphMode) return runFrame(stream);
+
+    // ---- NRDCU_FLAG_CUDA_GRAPH ------------------------------------------------------------------------------------------------------------------
+    // What decides the chain of kernels and everything in their parameters that is not a constant: which pipelines run and which memory they bind
+    uint64_t signature = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { signature = (signature ^ v) * 1099511628211ull; };
+    mix(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const DispatchDesc& dd = dispatches[i];
+        mix(dd.pipelineIndex);
+        mix(dd.resourcesNum);
+        for (uint32_t k = 0; k < dd.resourcesNum; k++) {
+            const ResourceDesc& res = dd.resources[k];
+            const nrdcuTexture& t = res.type == ResourceType::PERMANENT_POOL ? ctx->permanent[res.indexInPool] : (res.type == ResourceType::TRANSIENT_POOL ? ctx->transient[res.indexInPool] : ctx->user[(uint32_t)res.type]);
+            mix((uint64_t)(uintptr_t)t.data);
+            mix(((uint64_t)t.width << 32) | t.height);
+            mix(((uint64_t)t.pitchBytes << 32) | t.format);
+        }
+    }
+    ctx->graphClock++;
+    for (size_t g = 0; g < ctx->graphs.size(); g++) {
+        nrdcuContext::FrameGraph& fg = ctx->graphs[g];
+        if (fg.signature != signature) continue;
+        // same chain as a frame seen before: run the host side of every dispatch with the launches redirected into the graph's kernel nodes
+        nrdk::GraphReplay replay;
+        replay.exec = fg.exec;
+        replay.nodes = fg.nodes.data();
+        replay.funcs = fg.funcs.data();
+        replay.count = (uint32_t)fg.nodes.size();
+        nrdk::g_graphReplay = &replay;
+        uint32_t rc = runFrame(stream);
+        nrdk::g_graphReplay = nullptr;
+        if (rc != 0) return rc;
+        if (!replay.failed && replay.cursor == replay.count) {
+            cudaError_t ge = cudaGraphLaunch(fg.exec, (cudaStream_t)stream);
+            if (ge != cudaSuccess) return fail(Result::FAILURE, "cudaGraphLaunch: %s", cudaGetErrorString(ge));
+            fg.lastUse = ctx->graphClock;
+            ctx->graphReplays++;
+            return 0;
+        }
+        // the settings changed which kernels run ( another template instance, another number of launches ): forget this graph, capture again
+        cudaGraphExecDestroy(fg.exec);
+        cudaGraphDestroy(fg.graph);
+        ctx->graphs.erase(ctx->graphs.begin() + (long)g);
+        resetPlane();
+        break;
+    }
+    if (!ctx->captureStream && (e = cudaStreamCreateWithFlags(&ctx->captureStream, cudaStreamNonBlocking)) != cudaSuccess) return fail(Result::FAILURE, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    nrdk::GraphRecord record;
+    if ((e = cudaStreamBeginCapture(ctx->captureStream, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) return fail(Result::FAILURE, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+    nrdk::g_graphRecord = &record;
+    uint32_t rc = runFrame(ctx->captureStream);
+    nrdk::g_graphRecord = nullptr;
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(ctx->captureStream, &graph);
+    if (rc != 0) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (e != cudaSuccess || !graph) return fail(Result::FAILURE, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    nrdcuContext::FrameGraph fg;
+    fg.signature = signature;
+    fg.lastUse = ctx->graphClock;
+    // the captured graph is one chain of kernel nodes: walk it from its root
+    bool chain = !record.overflow;
+    {
+        size_t roots = 0, total = 0;
+        cudaGraphGetNodes(graph, nullptr, &total);
+        cudaGraphGetRootNodes(graph, nullptr, &roots);
+        cudaGraphNode_t node = nullptr;
+        if (roots == 1) {
+            size_t one = 1;
+            cudaGraphGetRootNodes(graph, &node, &one);
+        } else
+            chain = false;
+        while (chain && node) {
+            cudaGraphNodeType type;
+            if (cudaGraphNodeGetType(node, &type) != cudaSuccess || type != cudaGraphNodeTypeKernel) chain = false;
+            fg.nodes.push_back(node);
+            size_t next = 0;
+            cudaGraphNodeGetDependentNodes(node, nullptr, &next);
+            if (next > 1) chain = false;
+            cudaGraphNode_t nextNode = nullptr;
+            if (next == 1) {
+                size_t one = 1;
+                cudaGraphNodeGetDependentNodes(node, &nextNode, &one);
+            }
+            node = nextNode;
+        }
+        if (fg.nodes.size() != total || fg.nodes.size() != record.count) chain = false;
+    }
+    e = cudaGraphInstantiate(&fg.exec, graph, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return fail(Result::FAILURE, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    fg.graph = graph;
+    e = cudaGraphLaunch(fg.exec, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cudaGraphExecDestroy(fg.exec);
+        cudaGraphDestroy(graph);
+        return fail(Result::FAILURE, "cudaGraphLaunch: %s", cudaGetErrorString(e));
+    }
+    ctx->graphCaptures++;
+    if (!chain) {   // not a plain chain of kernels: run it this once, keep nothing
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaGraphExecDestroy(fg.exec);
+        cudaGraphDestroy(graph);
+        return 0;
+    }
+    fg.funcs.assign(record.funcs, record.funcs + record.count);
+    if (ctx->graphs.size() >= 8) {   // least recently used out
+        size_t victim = 0;
+        for (size_t g = 1; g < ctx->graphs.size(); g++)
+            if (ctx->graphs[g].lastUse < ctx->graphs[victim].lastUse) victim = g;
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaGraphExecDestroy(ctx->graphs[victim].exec);
+        cudaGraphDestroy(ctx->graphs[victim].graph);
+        ctx->graphs.erase(ctx->graphs.begin() + (long)victim);
+    }
+    ctx->graphs.push_back(std::move(fg));
+    return 0;
 }
+
+NRDCU_API uint32_t nrdcuGetGraphStats(nrdcuContext* ctx, uint64_t* captures, uint64_t* replays, uint32_t* cached) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuGetGraphStats: null context");
+    if (captures) *captures = ctx->graphCaptures;
+    if (replays) *replays = ctx->graphReplays;
+    if (cached) *cached = (uint32_t)ctx->graphs.size();
+    return 0;
+}
+
 
 NRDCU_API uint32_t nrdcuSetProfiling(nrdcuContext* ctx, int enabled) {
     if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuSetProfiling: null context");

@@ -14,6 +14,10 @@
 #include "../host/constants.h"
 #include "vecmath.cuh"
 
+#include <tuple>
+#include <type_traits>
+#include <utility>
+
 namespace nrdk {
 
 using nrdb::Mat4;
@@ -51,6 +55,67 @@ inline RowGrid rowGrid(Rows r, int rectHeight, int blockHeight) {
     if (e <= b) return {0, 0u};
     return {b / blockHeight, (unsigned)((e - b + blockHeight - 1) / blockHeight)};
 }
+
+// =================================================================================================================
+// Kernel launches. Every kernel of the denoiser chains goes through launchK, which does one of two things:
+//  - normally: kernel<<< grid, block, smem, stream >>>( args... );
+//  - while the executor REPLAYS a frame it holds as a CUDA graph ( NRDCU_FLAG_CUDA_GRAPH ): the launch that would have happened becomes the new parameter
+//    set of the graph's next kernel node ( constants and views change every frame, the chain of kernels does not ). A launch that does not match the
+//    recorded chain — another kernel, or more launches than nodes — marks the replay as failed and the executor captures the frame afresh.
+// While a frame is being captured the launched functions are also recorded, so that a later replay can tell whether it still is the same chain.
+// =================================================================================================================
+struct GraphReplay {
+    cudaGraphExec_t exec = nullptr;
+    const cudaGraphNode_t* nodes = nullptr;
+    const void* const* funcs = nullptr;
+    uint32_t count = 0, cursor = 0;
+    bool failed = false;
+};
+struct GraphRecord {
+    static constexpr uint32_t kMax = 64;
+    const void* funcs[kMax];
+    uint32_t count = 0;
+    bool overflow = false;
+};
+extern thread_local GraphReplay* g_graphReplay;   // executor.cu
+extern thread_local GraphRecord* g_graphRecord;
+
+#ifdef __CUDACC__
+template <class Tuple, size_t... I> inline void launchParamPointers(Tuple& values, void** out, std::index_sequence<I...>) { ((out[I] = (void*)&std::get<I>(values)), ...); }
+
+template <class... P, class... A> inline void launchK(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const A&... args) {
+    static_assert(sizeof...(P) == sizeof...(A), "launchK: argument count does not match the kernel's parameter list");
+    GraphReplay* replay = g_graphReplay;
+    if (!replay) {
+        if (GraphRecord* rec = g_graphRecord) {
+            if (rec->count < GraphRecord::kMax) rec->funcs[rec->count++] = (const void*)kernel;
+            else rec->overflow = true;
+        }
+        kernel<<<grid, block, smem, stream>>>(args...);
+        return;
+    }
+    if (replay->failed) return;
+    if (replay->cursor >= replay->count || replay->funcs[replay->cursor] != (const void*)kernel) {
+        replay->failed = true;
+        return;
+    }
+    std::tuple<std::remove_cv_t<std::remove_reference_t<P>>...> values(args...);   // the kernel's own parameter types, by value
+    void* pointers[sizeof...(P)];
+    launchParamPointers(values, pointers, std::index_sequence_for<P...>());
+    cudaKernelNodeParams np = {};
+    np.func = (void*)kernel;
+    np.gridDim = grid;
+    np.blockDim = block;
+    np.sharedMemBytes = (unsigned)smem;
+    np.kernelParams = pointers;
+    if (cudaGraphExecKernelNodeSetParams(replay->exec, replay->nodes[replay->cursor], &np) != cudaSuccess) {
+        (void)cudaGetLastError();
+        replay->failed = true;
+        return;
+    }
+    replay->cursor++;
+}
+#endif
 
 // =================================================================================================================
 // Texture views. One struct per storage format so every access compiles to a single fixed-width LDG/STG.

@@ -472,7 +472,7 @@ void launchClear(void* data, int rowBytes, int height, int pitch, cudaStream_t s
     int blocksX = (rowBytes / 16 + 255) / 256;
     if (blocksX < 1) blocksX = 1;
     if (blocksX > 8) blocksX = 8;
-    clearKernel<<<dim3(blocksX, height), 256, 0, stream>>>((uint8_t*)data, rowBytes, height, pitch);
+    launchK(clearKernel, dim3(blocksX, height), 256, 0, stream, (uint8_t*)data, rowBytes, height, pitch);
 }
 
 void launchReblurHistoryFix(const ReblurConstants& cb, const HistoryFixParams& p, int signal, int mode, bool quads, Rows rows, cudaStream_t stream) {
@@ -480,14 +480,14 @@ void launchReblurHistoryFix(const ReblurConstants& cb, const HistoryFixParams& p
     if (!g.count) return;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
     if (mode == MODE_DO) {
-        reblurHistoryFixKernel<SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
+        launchK(reblurHistoryFixKernel<SIGNAL_DIFF, MODE_DO>, grid, block, 0, stream, cb, p, quads ? 1 : 0, g.ctaY0);
         return;
     }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        if (mode == MODE_SH) reblurHistoryFixKernel<S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
-        else if (mode == MODE_OCCLUSION) reblurHistoryFixKernel<S, MODE_OCCLUSION><<<grid, block, 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
-        else reblurHistoryFixKernel<S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, quads ? 1 : 0, g.ctaY0);
+        if (mode == MODE_SH) launchK(reblurHistoryFixKernel<S, MODE_SH>, grid, block, 0, stream, cb, p, quads ? 1 : 0, g.ctaY0);
+        else if (mode == MODE_OCCLUSION) launchK(reblurHistoryFixKernel<S, MODE_OCCLUSION>, grid, block, 0, stream, cb, p, quads ? 1 : 0, g.ctaY0);
+        else launchK(reblurHistoryFixKernel<S, MODE_RADIANCE>, grid, block, 0, stream, cb, p, quads ? 1 : 0, g.ctaY0);
     });
 }
 void launchReblurTemporalStabilization(const ReblurConstants& cb, const TemporalStabilizationParams& p, int signal, int mode, Rows rows, cudaStream_t stream) {
@@ -495,13 +495,13 @@ void launchReblurTemporalStabilization(const ReblurConstants& cb, const Temporal
     if (!g.count) return;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
     if (mode == MODE_DO) {
-        reblurTemporalStabilizationKernel<SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        launchK(reblurTemporalStabilizationKernel<SIGNAL_DIFF, MODE_DO>, grid, block, 0, stream, cb, p, g.ctaY0);
         return;
     }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        if (mode == MODE_SH) reblurTemporalStabilizationKernel<S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
-        else reblurTemporalStabilizationKernel<S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        if (mode == MODE_SH) launchK(reblurTemporalStabilizationKernel<S, MODE_SH>, grid, block, 0, stream, cb, p, g.ctaY0);
+        else launchK(reblurTemporalStabilizationKernel<S, MODE_RADIANCE>, grid, block, 0, stream, cb, p, g.ctaY0);
     });
 }
 

@@ -115,9 +115,9 @@ void launchReblurHitDistReconstruction(const ReblurConstants& cb, const HitDistR
     if (!g.count) return;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
     if (is5x5)
-        reblurHitDistReconstructionKernel<2><<<grid, block, 0, stream>>>(cb, p, signal, occlusion ? 1 : 0, g.ctaY0);
+        launchK(reblurHitDistReconstructionKernel<2>, grid, block, 0, stream, cb, p, signal, occlusion ? 1 : 0, g.ctaY0);
     else
-        reblurHitDistReconstructionKernel<1><<<grid, block, 0, stream>>>(cb, p, signal, occlusion ? 1 : 0, g.ctaY0);
+        launchK(reblurHitDistReconstructionKernel<1>, grid, block, 0, stream, cb, p, signal, occlusion ? 1 : 0, g.ctaY0);
 }
 
 }  // namespace nrdk

@@ -570,19 +570,19 @@ bool readMirrorProbe(unsigned long long* out, bool reset) {
 void launchReblurClassifyTiles(const ReblurConstants& cb, const ClassifyTilesParams& p, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, 16);
     if (!g.count) return;
-    reblurClassifyTilesKernel<<<dim3((cb.rectSizeMinusOne[0] + 16) / 16, g.count), 256, 0, stream>>>(cb, p, g.ctaY0);
+    launchK(reblurClassifyTilesKernel, dim3((cb.rectSizeMinusOne[0] + 16) / 16, g.count), 256, 0, stream, cb, p, g.ctaY0);
 }
 // rows [ row0, row1 ) of the plane ( clamped to the rect )
 void launchReblurGeometryPlane(const ReblurConstants& cb, const GeometryPlaneParams& p, int row0, int row1, cudaStream_t stream) {
     row0 = row0 < 0 ? 0 : row0;
     row1 = row1 > cb.rectSizeMinusOne[1] + 1 ? cb.rectSizeMinusOne[1] + 1 : row1;
     if (row1 <= row0) return;
-    reblurGeometryPlaneKernel<<<dim3((cb.rectSizeMinusOne[0] + 32) / 32, (row1 - row0 + 7) / 8), 256, 0, stream>>>(cb, p, row0, row1);
+    launchK(reblurGeometryPlaneKernel, dim3((cb.rectSizeMinusOne[0] + 32) / 32, (row1 - row0 + 7) / 8), 256, 0, stream, cb, p, row0, row1);
 }
 void launchReblurSplitScreen(const ReblurConstants& cb, const SplitScreenParams& p, int signal, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
     if (!g.count) return;
-    reblurSplitScreenKernel<<<dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream>>>(cb, p, signal, g.ctaY0);
+    launchK(reblurSplitScreenKernel, dim3((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), dim3(BLOCK_W, BLOCK_H), 0, stream, cb, p, signal, g.ctaY0);
 }
 // `flags`: bit 0 quad smoothing, bit 1 robust mirror test, bit 2 mirror probe, bits 4-5 NRD_MODE of the permutation ( MODE_* )
 void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int signal, int flags, Rows rows, cudaStream_t stream) {
@@ -592,22 +592,22 @@ void launchReblurPrePass(const ReblurConstants& cb, const PrePassParams& p, int 
     const bool cbOn = cb.diffCheckerboard != 2u || cb.specCheckerboard != 2u;  // CheckerboardMode::BLACK / WHITE set both (Reblur.cpp:301-313)
     const int mode = (flags >> 4) & 3;
     if ((flags & 4) && signal == SIGNAL_BOTH && mode == MODE_RADIANCE && !cbOn) {  // NRDCU_FLAG_PROBE_MIRROR
-        reblurPrePassKernel<false, SIGNAL_BOTH, MODE_RADIANCE, true><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        launchK(reblurPrePassKernel<false, SIGNAL_BOTH, MODE_RADIANCE, true>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         return;
     }
     if (mode == MODE_DO) {   // REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION: the only denoiser of this mode has one lobe ( the occlusion denoisers have no pre-pass )
-        if (cbOn) reblurPrePassKernel<true, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
-        else reblurPrePassKernel<false, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        if (cbOn) launchK(reblurPrePassKernel<true, SIGNAL_DIFF, MODE_DO>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
+        else launchK(reblurPrePassKernel<false, SIGNAL_DIFF, MODE_DO>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         return;
     }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
         if (mode == MODE_SH) {
-            if (cbOn) reblurPrePassKernel<true, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
-            else reblurPrePassKernel<false, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+            if (cbOn) launchK(reblurPrePassKernel<true, S, MODE_SH>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
+            else launchK(reblurPrePassKernel<false, S, MODE_SH>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         } else {
-            if (cbOn) reblurPrePassKernel<true, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
-            else reblurPrePassKernel<false, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+            if (cbOn) launchK(reblurPrePassKernel<true, S, MODE_RADIANCE>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
+            else launchK(reblurPrePassKernel<false, S, MODE_RADIANCE>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         }
     });
 }
@@ -618,18 +618,18 @@ void launchReblurBlur(const ReblurConstants& cb, const BlurParams& p, int signal
     const int mode = (flags >> 4) & 3;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
     if ((flags & 4) && signal == SIGNAL_BOTH && mode == MODE_RADIANCE) {
-        reblurBlurKernel<SIGNAL_BOTH, MODE_RADIANCE, true><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        launchK(reblurBlurKernel<SIGNAL_BOTH, MODE_RADIANCE, true>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         return;
     }
     if (mode == MODE_DO) {
-        reblurBlurKernel<SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        launchK(reblurBlurKernel<SIGNAL_DIFF, MODE_DO>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         return;
     }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        if (mode == MODE_SH) reblurBlurKernel<S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
-        else if (mode == MODE_OCCLUSION) reblurBlurKernel<S, MODE_OCCLUSION><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
-        else reblurBlurKernel<S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        if (mode == MODE_SH) launchK(reblurBlurKernel<S, MODE_SH>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
+        else if (mode == MODE_OCCLUSION) launchK(reblurBlurKernel<S, MODE_OCCLUSION>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
+        else launchK(reblurBlurKernel<S, MODE_RADIANCE>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
     });
 }
 void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, int signal, bool temporalStabilization, int flags, Rows rows, cudaStream_t stream) {
@@ -638,23 +638,23 @@ void launchReblurPostBlur(const ReblurConstants& cb, const PostBlurParams& p, in
     const int mode = (flags >> 4) & 3;
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
     if ((flags & 4) && signal == SIGNAL_BOTH && mode == MODE_RADIANCE && temporalStabilization) {
-        reblurPostBlurKernel<true, SIGNAL_BOTH, MODE_RADIANCE, true><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        launchK(reblurPostBlurKernel<true, SIGNAL_BOTH, MODE_RADIANCE, true>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         return;
     }
     if (mode == MODE_DO) {
-        if (temporalStabilization) reblurPostBlurKernel<true, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
-        else reblurPostBlurKernel<false, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+        if (temporalStabilization) launchK(reblurPostBlurKernel<true, SIGNAL_DIFF, MODE_DO>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
+        else launchK(reblurPostBlurKernel<false, SIGNAL_DIFF, MODE_DO>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         return;
     }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        if (mode == MODE_OCCLUSION) reblurPostBlurKernel<false, S, MODE_OCCLUSION><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);   // the occlusion graph has no stabilization pass
+        if (mode == MODE_OCCLUSION) launchK(reblurPostBlurKernel<false, S, MODE_OCCLUSION>, grid, block, 0, stream, cb, p, flags, g.ctaY0);   // the occlusion graph has no stabilization pass
         else if (mode == MODE_SH) {
-            if (temporalStabilization) reblurPostBlurKernel<true, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
-            else reblurPostBlurKernel<false, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+            if (temporalStabilization) launchK(reblurPostBlurKernel<true, S, MODE_SH>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
+            else launchK(reblurPostBlurKernel<false, S, MODE_SH>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         } else {
-            if (temporalStabilization) reblurPostBlurKernel<true, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
-            else reblurPostBlurKernel<false, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, flags, g.ctaY0);
+            if (temporalStabilization) launchK(reblurPostBlurKernel<true, S, MODE_RADIANCE>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
+            else launchK(reblurPostBlurKernel<false, S, MODE_RADIANCE>, grid, block, 0, stream, cb, p, flags, g.ctaY0);
         }
     });
 }

@@ -661,18 +661,18 @@ void launchReblurTemporalAccumulation(const ReblurConstants& cb, const TemporalA
     const dim3 grid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, g.count), block(BLOCK_W, BLOCK_H);
     const bool optional = cb.specCheckerboard != 2u || cb.diffCheckerboard != 2u || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix;
     if (mode == MODE_DO) {   // one denoiser, one lobe
-        reblurTemporalAccumulationKernel<true, SIGNAL_DIFF, MODE_DO><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        launchK(reblurTemporalAccumulationKernel<true, SIGNAL_DIFF, MODE_DO>, grid, block, 0, stream, cb, p, g.ctaY0);
         return;
     }
     withSignal(signal, [&](auto sig) {
         constexpr int S = decltype(sig)::value;
-        if (mode == MODE_OCCLUSION) reblurTemporalAccumulationKernel<true, S, MODE_OCCLUSION><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+        if (mode == MODE_OCCLUSION) launchK(reblurTemporalAccumulationKernel<true, S, MODE_OCCLUSION>, grid, block, 0, stream, cb, p, g.ctaY0);
         else if (mode == MODE_SH) {
-            if (optional) reblurTemporalAccumulationKernel<true, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
-            else reblurTemporalAccumulationKernel<false, S, MODE_SH><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+            if (optional) launchK(reblurTemporalAccumulationKernel<true, S, MODE_SH>, grid, block, 0, stream, cb, p, g.ctaY0);
+            else launchK(reblurTemporalAccumulationKernel<false, S, MODE_SH>, grid, block, 0, stream, cb, p, g.ctaY0);
         } else {
-            if (optional) reblurTemporalAccumulationKernel<true, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
-            else reblurTemporalAccumulationKernel<false, S, MODE_RADIANCE><<<grid, block, 0, stream>>>(cb, p, g.ctaY0);
+            if (optional) launchK(reblurTemporalAccumulationKernel<true, S, MODE_RADIANCE>, grid, block, 0, stream, cb, p, g.ctaY0);
+            else launchK(reblurTemporalAccumulationKernel<false, S, MODE_RADIANCE>, grid, block, 0, stream, cb, p, g.ctaY0);
         }
     });
 }

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) reblurValidationKernel(const __grid_const
 }  // namespace
 
 void launchReblurValidation(const ReblurConstants& cb, const ReblurValidationParams& p, cudaStream_t stream) {
-    reblurValidationKernel<<<dim3((p.out.w + 31) / 32, (p.out.h + 7) / 8), 256, 0, stream>>>(cb, p);
+    launchK(reblurValidationKernel, dim3((p.out.w + 31) / 32, (p.out.h + 7) / 8), 256, 0, stream, cb, p);
 }
 
 }  // namespace nrdk

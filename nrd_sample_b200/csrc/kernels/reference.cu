@@ -7,6 +7,7 @@
 
 #include "../../../include/nrd_b200.h"
 #include "../../../include/nrdcu.h"
+#include "../pipeline_key.h"
 #include "common.cuh"
 
 namespace nrdk {
@@ -85,15 +86,16 @@ bool bindAny4(const nrdcuTexture& t, TexAny4& v) {
 
 // Dispatch by shader identifier (called by the executor). `gridW` x `gridH`: the 16x16 groups of the DispatchDesc (the constants of
 // the accumulation pass carry no rect size); 0 = cover the whole history texture.
-uint32_t dispatchReference(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, uint32_t gridW, uint32_t gridH,
+uint32_t dispatchReference(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, uint32_t gridW, uint32_t gridH,
                            cudaStream_t stream, std::string& err) {
     using nrd::Result;
+    const std::string id = key.id;   // ( short: fits the small-string buffer; used by the messages only )
     TexAny4 a, b;
     if (n != 2 || !bindAny4(tex[0], a) || !bindAny4(tex[1], b)) {
         err = id + ": expects an input and an output in RGBA8 / RGBA16F / RGBA32F";
         return (uint32_t)Result::INVALID_ARGUMENT;
     }
-    if (id == "REFERENCE_TemporalAccumulation.cs.hlsl") {
+    if (key.pass == REFERENCE_TEMPORAL_ACCUMULATION) {
         if (constantsSize != sizeof(ReferenceAccumulateConstants) || !constants) {
             err = id + ": expected 16 constant bytes";
             return (uint32_t)Result::INVALID_ARGUMENT;
@@ -101,8 +103,8 @@ uint32_t dispatchReference(const std::string& id, const void* constants, uint32_
         ReferenceAccumulateConstants cb;
         memcpy(&cb, constants, sizeof(cb));
         const int w = gridW ? min((int)gridW * 16, b.w) : b.w, h = gridH ? min((int)gridH * 16, b.h) : b.h;
-        referenceTemporalAccumulationKernel<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, stream>>>(cb, a, b);
-    } else if (id == "REFERENCE_Copy.cs.hlsl") {
+        launchK(referenceTemporalAccumulationKernel, dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, stream, cb, a, b);
+    } else if (key.pass == REFERENCE_COPY) {
         if (constantsSize != sizeof(ReferenceCopyConstants) || !constants) {
             err = id + ": expected 24 constant bytes";
             return (uint32_t)Result::INVALID_ARGUMENT;
@@ -113,7 +115,7 @@ uint32_t dispatchReference(const std::string& id, const void* constants, uint32_
         int w = min(b.w, (int)(1.0f / cb.rectSizeInv[0] + 0.5f)), h = min(b.h, (int)(1.0f / cb.rectSizeInv[1] + 0.5f));
         if (gridW) w = min(w, (int)gridW * 16);
         if (gridH) h = min(h, (int)gridH * 16);
-        referenceCopyKernel<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, stream>>>(cb, a, b, w, h);
+        launchK(referenceCopyKernel, dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, stream, cb, a, b, w, h);
     } else {
         err = "no CUDA kernel for shader '" + id + "'";
         return (uint32_t)Result::UNSUPPORTED;

@@ -14,6 +14,7 @@
 
 #include "../../../include/nrd_b200.h"
 #include "../../../include/nrdcu.h"
+#include "../pipeline_key.h"
 #include "debug_overlay.cuh"  // HistoryFilter
 
 namespace nrdk {
@@ -1575,7 +1576,7 @@ struct RelaxBinder {
     uint32_t n, next;
     bool ok;
     std::string* err;
-    const std::string* id;
+    const char* id;
     template <class V> V take(nrd::Format expect) {
         V v{};
         if (next >= n) {
@@ -1585,7 +1586,7 @@ struct RelaxBinder {
         const nrdcuTexture& x = t[next];
         const uint32_t bpp = bytesOf(expect);
         if (x.format != (uint32_t)expect || !x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
-            if (ok) *err = *id + ": binding " + std::to_string(next) + " has format " + std::to_string(x.format) + " (expected " + std::to_string((uint32_t)expect) + ")";
+            if (ok) *err = std::string(id) + ": binding " + std::to_string(next) + " has format " + std::to_string(x.format) + " (expected " + std::to_string((uint32_t)expect) + ")";
             ok = false;
         }
         v.data = (uint8_t*)x.data;
@@ -1607,7 +1608,7 @@ struct RelaxBinder {
         const uint32_t bpp = x.format == (uint32_t)nrd::Format::RGBA32_SFLOAT ? 16u : (x.format == (uint32_t)nrd::Format::RGBA16_UNORM || x.format == (uint32_t)nrd::Format::RGBA16_SNORM) ? 8u
                                                                                       : (x.format == (uint32_t)nrd::Format::R16_UNORM ? 2u : bytesOf((nrd::Format)x.format));
         if (!x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
-            if (ok) *err = *id + ": binding " + std::to_string(next) + " has a pitch that does not fit its format";
+            if (ok) *err = std::string(id) + ": binding " + std::to_string(next) + " has a pitch that does not fit its format";
             ok = false;
         }
         v.data = (uint8_t*)x.data;
@@ -1627,7 +1628,7 @@ struct RelaxBinder {
         }
         const nrdcuTexture& x = t[next];
         if (!bindGuide(x.format, x.data, x.width, x.height, x.pitchBytes, v)) {
-            if (ok) *err = *id + ": binding " + std::to_string(next) + " (single-channel guide) has unsupported format " + std::to_string(x.format);
+            if (ok) *err = std::string(id) + ": binding " + std::to_string(next) + " (single-channel guide) has unsupported format " + std::to_string(x.format);
             ok = false;
         }
         next++;
@@ -1638,28 +1639,33 @@ struct RelaxBinder {
 }  // namespace
 
 // Dispatch by shader identifier (called by the executor). Returns an nrd::Result; `err` explains a failure.
-uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, cudaStream_t stream, std::string& err) {
+uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, Rows rows, cudaStream_t stream, std::string& err) {
     using nrd::Format;
     using nrd::Result;
+    const char* const id = key.id;
+    if (rows.begin != 0 || rows.end != 0x7FFFFFFF) {
+        err = std::string(id) + ": row ranges (multi-GPU strips) are implemented for REBLUR only";
+        return (uint32_t)Result::UNSUPPORTED;
+    }
     if (constantsSize != sizeof(RelaxConstants) || !constants) {
-        err = id + ": expected " + std::to_string(sizeof(RelaxConstants)) + " constant bytes";
+        err = std::string(id) + ": expected " + std::to_string(sizeof(RelaxConstants)) + " constant bytes";
         return (uint32_t)Result::INVALID_ARGUMENT;
     }
     RelaxConstants cb;
     memcpy(&cb, constants, sizeof(cb));
     if (cb.rectOrigin[0] || cb.rectOrigin[1]) {   // NRD_SUPPORTS_VIEWPORT_OFFSET = 0; dynamic resolution ( rectSize < resourceSize ) itself is supported
-        err = id + ": rectOrigin must be 0";
+        err = std::string(id) + ": rectOrigin must be 0";
         return (uint32_t)Result::INVALID_ARGUMENT;
     }
     if ((cb.diffCheckerboard == 2) != (cb.specCheckerboard == 2)) {
-        err = id + ": inconsistent checkerboard constants";
+        err = std::string(id) + ": inconsistent checkerboard constants";
         return (uint32_t)Result::INVALID_ARGUMENT;
     }
     const bool checkerboarded = cb.diffCheckerboard != 2;
-    RelaxBinder b{tex, n, 0, true, &err, &id};
+    RelaxBinder b{tex, n, 0, true, &err, id};
     auto bad = [&](uint32_t expected) {
         if (b.ok && b.next == expected && n == expected) return false;
-        if (err.empty()) err = id + ": wrong number of textures";
+        if (err.empty()) err = std::string(id) + ": wrong number of textures";
         return true;
     };
     const Format F16 = Format::RGBA16_SFLOAT, R8 = Format::R8_UNORM, R32 = Format::R32_SFLOAT, NR = Format::R10_G10_B10_A2_UNORM;
@@ -1667,11 +1673,9 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
     const dim3 pixelGrid((cb.rectSize[0] + BLOCK_W - 1) / BLOCK_W, (cb.rectSize[1] + BLOCK_H - 1) / BLOCK_H);
     // "|NRD_SIGNAL=<DIFF|SPEC|BOTH>|NRD_MODE=<SH|RADIANCE>": the six RELAX denoisers run the same kernels; RADIANCE has no SH1 textures, a single-lobe
     // denoiser binds only its own lobe ( the parameter block keeps the two-lobe layout, the other lobe's views stay empty and are dead code in the kernel )
-    const bool sh = id.find("|NRD_MODE=SH") != std::string::npos;
-    const int signal = id.find("|NRD_SIGNAL=DIFF") != std::string::npos ? SIGNAL_DIFF : (id.find("|NRD_SIGNAL=SPEC") != std::string::npos ? SIGNAL_SPEC : SIGNAL_BOTH);
+    const bool sh = key.mode == 1;
+    const int signal = key.signal == 1 ? SIGNAL_DIFF : (key.signal == 2 ? SIGNAL_SPEC : SIGNAL_BOTH);
     const bool hasDiff = (signal & SIGNAL_DIFF) != 0, hasSpec = (signal & SIGNAL_SPEC) != 0;
-    const std::string sigSignal = std::string("|NRD_SIGNAL=") + (signal == SIGNAL_BOTH ? "BOTH" : (hasDiff ? "DIFF" : "SPEC"));
-    const std::string sig = sigSignal + (sh ? "|NRD_MODE=SH" : "|NRD_MODE=RADIANCE");
     const uint32_t lobes = (hasDiff ? 1u : 0u) + (hasSpec ? 1u : 0u);
     auto takeS = [&](TexRGBA16F& t) { t = hasSpec ? b.take<TexRGBA16F>(F16) : TexRGBA16F(); };
     auto takeD = [&](TexRGBA16F& t) { t = hasDiff ? b.take<TexRGBA16F>(F16) : TexRGBA16F(); };
@@ -1679,7 +1683,7 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
     auto takeShD = [&](TexRGBA16F& t) { t = (sh && hasDiff) ? b.take<TexRGBA16F>(F16) : TexRGBA16F(); };
     const uint32_t shOn = sh ? 1u : 0u;
 
-    if (id == "RELAX_Validation.cs.hlsl") {
+    if (key.pass == RELAX_VALIDATION) {
         RelaxValidationParams p;
         p.normalRoughness = b.take<TexNR>(NR);
         p.viewZ = b.take<TexR32F>(R32);
@@ -1687,14 +1691,14 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         p.historyLength = b.take<TexR8>(R8);
         p.out = b.takeView();
         if (bad(5)) return (uint32_t)Result::INVALID_ARGUMENT;
-        relaxValidationKernel<<<dim3((p.out.w + 31) / 32, (p.out.h + 7) / 8), 256, 0, stream>>>(cb, p);
-    } else if (id == "RELAX_ClassifyTiles.cs.hlsl") {
+        launchK(relaxValidationKernel, dim3((p.out.w + 31) / 32, (p.out.h + 7) / 8), 256, 0, stream, cb, p);
+    } else if (key.pass == RELAX_CLASSIFY_TILES) {
         RelaxClassifyParams p;
         p.viewZ = b.take<TexR32F>(R32);
         p.outTiles = b.take<TexR8>(R8);
         if (bad(2)) return (uint32_t)Result::INVALID_ARGUMENT;
-        relaxClassifyTilesKernel<<<dim3((cb.rectSize[0] + 15) / 16, (cb.rectSize[1] + 15) / 16), 256, 0, stream>>>(cb, p);
-    } else if (id == "RELAX_PrePass.cs.hlsl" + sig) {
+        launchK(relaxClassifyTilesKernel, dim3((cb.rectSize[0] + 15) / 16, (cb.rectSize[1] + 15) / 16), 256, 0, stream, cb, p);
+    } else if (key.pass == RELAX_PREPASS) {
         RelaxPrePassParams p;
         p.tiles = b.take<TexR8>(R8);
         p.normalRoughness = b.take<TexNR>(NR);
@@ -1709,11 +1713,11 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         takeShD(p.outDiffSh);
         if (bad(3 + (2 + 2 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (checkerboarded) {
-            if (sh) withSignal(signal, [&](auto sig_) { relaxPrePassKernel<true, true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxPrePassKernel<false, true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<true, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<false, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
         } else {
-            if (sh) withSignal(signal, [&](auto sig_) { relaxPrePassKernel<true, false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxPrePassKernel<false, false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<true, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<false, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
         }
-    } else if (id == "RELAX_TemporalAccumulation.cs.hlsl" + sig) {
+    } else if (key.pass == RELAX_TEMPORAL_ACCUMULATION) {
         RelaxTaParams p;
         p.tiles = b.take<TexR8>(R8);
         p.mv = b.take<TexRGBA16F>(F16);
@@ -1752,11 +1756,11 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         takeShD(p.outDiffShFast);
         if (bad(10 + (6 + 5 * shOn) * lobes + (hasSpec ? 3 : 0) + 0 * shOn)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (checkerboarded || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix) {
-            if (sh) withSignal(signal, [&](auto sig_) { relaxTemporalAccumulationKernel<true, true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxTemporalAccumulationKernel<false, true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<true, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<false, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
         } else {
-            if (sh) withSignal(signal, [&](auto sig_) { relaxTemporalAccumulationKernel<true, false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxTemporalAccumulationKernel<false, false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<true, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<false, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
         }
-    } else if (id == "RELAX_HistoryFix.cs.hlsl" + sig) {
+    } else if (key.pass == RELAX_HISTORY_FIX) {
         RelaxHistoryFixParams p;
         p.tiles = b.take<TexR8>(R8);
         p.historyLength = b.take<TexR8>(R8);
@@ -1771,8 +1775,8 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         takeShS(p.outSpecSh);
         takeShD(p.outDiffSh);
         if (bad(4 + (2 + 2 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) withSignal(signal, [&](auto sig_) { relaxHistoryFixKernel<true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxHistoryFixKernel<false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
-    } else if (id == "RELAX_HistoryClamping.cs.hlsl" + sig) {
+        if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxHistoryFixKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxHistoryFixKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+    } else if (key.pass == RELAX_HISTORY_CLAMPING) {
         RelaxHistoryClampingParams p;
         p.tiles = b.take<TexR8>(R8);
         p.viewZ = b.take<TexR32F>(R32);
@@ -1787,8 +1791,8 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         TexRGBA16F* outsSh[4] = {&p.outSpecSh, &p.outDiffSh, &p.outSpecShFast, &p.outDiffShFast};
         for (int i = 0; i < 4; i++) (i & 1) ? takeShD(*outsSh[i]) : takeShS(*outsSh[i]);
         if (bad(4 + (5 + 4 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) withSignal(signal, [&](auto sig_) { relaxHistoryClampingKernel<true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxHistoryClampingKernel<false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
-    } else if (id == "RELAX_HitDistReconstruction.cs.hlsl" + sigSignal + "|NRD_MODE=RADIANCE|MODE_5X5=0" || id == "RELAX_HitDistReconstruction.cs.hlsl" + sigSignal + "|NRD_MODE=RADIANCE|MODE_5X5=1") {
+        if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+    } else if (key.pass == RELAX_HITDIST_RECONSTRUCTION) {
         RelaxHitDistReconstructionParams p;
         p.tiles = b.take<TexR8>(R8);
         p.normalRoughness = b.take<TexNR>(NR);
@@ -1798,11 +1802,11 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         takeS(p.outSpec);
         takeD(p.outDiff);
         if (bad(3 + 2 * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (id.back() == '1')
-            relaxHitDistReconstructionKernel<2><<<pixelGrid, block, 0, stream>>>(cb, p);
+        if (key.mode5x5)
+            launchK(relaxHitDistReconstructionKernel<2>, pixelGrid, block, 0, stream, cb, p);
         else
-            relaxHitDistReconstructionKernel<1><<<pixelGrid, block, 0, stream>>>(cb, p);
-    } else if (id == "RELAX_SplitScreen.cs.hlsl" + sig) {
+            launchK(relaxHitDistReconstructionKernel<1>, pixelGrid, block, 0, stream, cb, p);
+    } else if (key.pass == RELAX_SPLIT_SCREEN) {
         RelaxSplitScreenParams p;
         p.viewZ = b.take<TexR32F>(R32);
         takeD(p.diff);
@@ -1814,16 +1818,16 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         takeShD(p.outDiffSh);
         takeShS(p.outSpecSh);
         if (bad(1 + (2 + 2 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) relaxSplitScreenKernel<true><<<pixelGrid, block, 0, stream>>>(cb, p); else relaxSplitScreenKernel<false><<<pixelGrid, block, 0, stream>>>(cb, p);
-    } else if (id == "RELAX_Copy.cs.hlsl" + sig) {
+        if (sh) launchK(relaxSplitScreenKernel<true>, pixelGrid, block, 0, stream, cb, p); else launchK(relaxSplitScreenKernel<false>, pixelGrid, block, 0, stream, cb, p);
+    } else if (key.pass == RELAX_COPY) {
         RelaxCopyParams p;
         takeS(p.spec);
         takeD(p.diff);
         takeS(p.outSpec);
         takeD(p.outDiff);
         if (bad(2 * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        withSignal(signal, [&](auto sig_) { relaxCopyKernel<decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(lobeView(p, sig_)); });
-    } else if (id == "RELAX_AntiFirefly.cs.hlsl" + sig) {
+        withSignal(signal, [&](auto sig_) { launchK(relaxCopyKernel<decltype(sig_)::value>, pixelGrid, block, 0, stream, lobeView(p, sig_)); });
+    } else if (key.pass == RELAX_ANTI_FIREFLY) {
         RelaxAntiFireflyParams p;
         p.tiles = b.take<TexR8>(R8);
         p.normalRoughness = b.take<TexNR>(NR);
@@ -1833,9 +1837,9 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         takeS(p.outSpec);
         takeD(p.outDiff);
         if (bad(3 + 2 * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        withSignal(signal, [&](auto sig_) { relaxAntiFireflyKernel<decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
-    } else if (id == "RELAX_AtrousSmem.cs.hlsl" + sig || id == "RELAX_Atrous.cs.hlsl" + sig) {
-        const bool smem = id == "RELAX_AtrousSmem.cs.hlsl" + sig;
+        withSignal(signal, [&](auto sig_) { launchK(relaxAntiFireflyKernel<decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+    } else if (key.pass == RELAX_ATROUS_SMEM || key.pass == RELAX_ATROUS) {
+        const bool smem = key.pass == RELAX_ATROUS_SMEM;
         RelaxAtrousParams p = {};
         p.tiles = b.take<TexR8>(R8);
         p.historyLength = b.take<TexR8>(R8);
@@ -1859,12 +1863,12 @@ uint32_t dispatchRelax(const std::string& id, const void* constants, uint32_t co
         takeShD(p.outDiffSh);
         if (bad(4 + (smem ? 3 : 0) + (3 + 2 * shOn) * lobes + (hasSpec ? 1 : 0))) return (uint32_t)Result::INVALID_ARGUMENT;
         if (smem) {
-            if (sh) withSignal(signal, [&](auto sig_) { relaxAtrousSmemKernel<true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxAtrousSmemKernel<false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
         } else {
-            if (sh) withSignal(signal, [&](auto sig_) { relaxAtrousKernel<true, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { relaxAtrousKernel<false, decltype(sig_)::value><<<pixelGrid, block, 0, stream>>>(cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxAtrousKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxAtrousKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
         }
     } else {
-        err = "no CUDA kernel for shader '" + id + "'";
+        err = std::string("no CUDA kernel for shader '") + id + "'";
         return (uint32_t)Result::UNSUPPORTED;
     }
     return (uint32_t)Result::SUCCESS;

@@ -11,6 +11,7 @@
 
 #include "../../../include/nrd_b200.h"
 #include "../../../include/nrdcu.h"
+#include "../pipeline_key.h"
 #include "sigma_common.cuh"
 
 namespace nrdk {
@@ -434,7 +435,7 @@ struct SigmaBinder {
     uint32_t n, next;
     bool ok;
     std::string* err;
-    const std::string* id;
+    const char* id;
     template <class V> V take(nrd::Format expect) {
         V v{};
         if (next >= n) {
@@ -444,7 +445,7 @@ struct SigmaBinder {
         const nrdcuTexture& x = t[next];
         const uint32_t bpp = bytesOf(expect);
         if (x.format != (uint32_t)expect || !x.data || (x.pitchBytes % bpp) != 0 || x.pitchBytes < x.width * bpp) {
-            if (ok) *err = *id + ": binding " + std::to_string(next) + " has format " + std::to_string(x.format) + " (expected " + std::to_string((uint32_t)expect) + ")";
+            if (ok) *err = std::string(id) + ": binding " + std::to_string(next) + " has format " + std::to_string(x.format) + " (expected " + std::to_string((uint32_t)expect) + ")";
             ok = false;
         }
         v.data = (uint8_t*)x.data;
@@ -458,32 +459,36 @@ struct SigmaBinder {
 };
 }  // namespace
 
-uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, cudaStream_t stream, std::string& err) {
+uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, Rows rows, cudaStream_t stream, std::string& err) {
     using nrd::Format;
     using nrd::Result;
+    const char* const id = key.id;
     if (constantsSize != sizeof(SigmaConstants) || !constants) {
-        err = id + ": expected " + std::to_string(sizeof(SigmaConstants)) + " constant bytes";
+        err = std::string(id) + ": expected " + std::to_string(sizeof(SigmaConstants)) + " constant bytes";
         return (uint32_t)Result::INVALID_ARGUMENT;
+    }
+    if (rows.begin != 0 || rows.end != 0x7FFFFFFF) {
+        err = std::string(id) + ": row ranges (multi-GPU strips) are implemented for REBLUR only";
+        return (uint32_t)Result::UNSUPPORTED;
     }
     SigmaConstants cb;
     memcpy(&cb, constants, sizeof(cb));
     if (cb.rectOrigin[0] || cb.rectOrigin[1]) {   // NRD_SUPPORTS_VIEWPORT_OFFSET = 0; dynamic resolution ( rectSize < resourceSize ) itself is supported
-        err = id + ": rectOrigin must be 0";
+        err = std::string(id) + ": rectOrigin must be 0";
         return (uint32_t)Result::INVALID_ARGUMENT;
     }
-    SigmaBinder b{tex, n, 0, true, &err, &id};
+    SigmaBinder b{tex, n, 0, true, &err, id};
     auto bad = [&](uint32_t expected) {
         if (b.ok && b.next == expected && n == expected) return false;
-        if (err.empty()) err = id + ": wrong number of textures";
+        if (err.empty()) err = std::string(id) + ": wrong number of textures";
         return true;
     };
     const dim3 block(BLOCK_W, BLOCK_H);
     const dim3 pixelGrid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, (cb.rectSizeMinusOne[1] + BLOCK_H) / BLOCK_H);
     const int tilesW = cb.tilesSizeMinusOne[0] + 1, tilesH = cb.tilesSizeMinusOne[1] + 1;
 
-    const bool tr = id.find("|TRANSLUCENCY=1") != std::string::npos;
-    auto is = [&](const char* file, const char* suffix = "") { return id == std::string(file) + (tr ? "|TRANSLUCENCY=1" : "|TRANSLUCENCY=0") + suffix; };
-    if (is("SIGMA_ClassifyTiles.cs.hlsl")) {
+    const bool tr = key.translucency;
+    if (key.pass == SIGMA_CLASSIFY_TILES) {
         SigmaClassifyTilesParams p = {};
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
         p.penumbra = b.take<TexR16F>(Format::R16_SFLOAT);
@@ -491,16 +496,16 @@ uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t co
         p.outTiles = b.take<TexRGBA8>(Format::RGBA8_UNORM);
         if (bad(tr ? 4 : 3)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (tr)
-            sigmaClassifyTilesKernel<true><<<dim3(tilesW, tilesH), 256, 0, stream>>>(cb, p);
+            launchK(sigmaClassifyTilesKernel<true>, dim3(tilesW, tilesH), 256, 0, stream, cb, p);
         else
-            sigmaClassifyTilesKernel<false><<<dim3(tilesW, tilesH), 256, 0, stream>>>(cb, p);
-    } else if (id == "SIGMA_SmoothTiles.cs.hlsl") {
+            launchK(sigmaClassifyTilesKernel<false>, dim3(tilesW, tilesH), 256, 0, stream, cb, p);
+    } else if (key.pass == SIGMA_SMOOTH_TILES) {
         SigmaSmoothTilesParams p;
         p.tiles = b.take<TexRGBA8>(Format::RGBA8_UNORM);
         p.outTiles = b.take<TexRG8>(Format::RG8_UNORM);
         if (bad(2)) return (uint32_t)Result::INVALID_ARGUMENT;
-        sigmaSmoothTilesKernel<<<dim3((tilesW + 15) / 16, (tilesH + 15) / 16), 256, 0, stream>>>(cb, p);
-    } else if (id == "SIGMA_Copy.cs.hlsl") {
+        launchK(sigmaSmoothTilesKernel, dim3((tilesW + 15) / 16, (tilesH + 15) / 16), 256, 0, stream, cb, p);
+    } else if (key.pass == SIGMA_COPY) {
         // one shader for both variants (gIn_History is declared float4): the history's own format picks the texel width
         const bool wide = n > 1 && tex[1].format == (uint32_t)Format::RGBA8_UNORM;
         auto run = [&](auto sig) -> bool {
@@ -513,12 +518,12 @@ uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t co
             p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
             if (bad(5)) return false;
             const dim3 prevGrid(((int)cb.rectSizePrev[0] + BLOCK_W - 1) / BLOCK_W, (((int)cb.rectSizePrev[1] + 15) / 16 * 16 + BLOCK_H - 1) / BLOCK_H);
-            sigmaCopyKernel<typename SG::Tex><<<prevGrid, block, 0, stream>>>(cb, p);
+            launchK(sigmaCopyKernel<typename SG::Tex>, prevGrid, block, 0, stream, cb, p);
             return true;
         };
         if (!(wide ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
-    } else if (is("SIGMA_Blur.cs.hlsl", "|FIRST_PASS=1") || is("SIGMA_Blur.cs.hlsl", "|FIRST_PASS=0")) {
-        const bool first = is("SIGMA_Blur.cs.hlsl", "|FIRST_PASS=1");
+    } else if (key.pass == SIGMA_BLUR) {
+        const bool first = key.firstPass;
         auto run = [&](auto sig) -> bool {
             using SG = decltype(sig);
             constexpr bool TR = std::is_same<SG, SigmaSignal<true>>::value;
@@ -533,13 +538,13 @@ uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t co
             p.outShadow = b.take<typename SG::Tex>(SG::format);
             if (bad(hasShadow ? 7 : 6)) return false;
             if (first)
-                sigmaBlurKernel<true, TR><<<pixelGrid, block, 0, stream>>>(cb, p);
+                launchK(sigmaBlurKernel<true, TR>, pixelGrid, block, 0, stream, cb, p);
             else
-                sigmaBlurKernel<false, TR><<<pixelGrid, block, 0, stream>>>(cb, p);
+                launchK(sigmaBlurKernel<false, TR>, pixelGrid, block, 0, stream, cb, p);
             return true;
         };
         if (!(tr ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
-    } else if (is("SIGMA_TemporalStabilization.cs.hlsl")) {
+    } else if (key.pass == SIGMA_TEMPORAL_STABILIZATION) {
         auto run = [&](auto sig) -> bool {
             using SG = decltype(sig);
             constexpr bool TR = std::is_same<SG, SigmaSignal<true>>::value;
@@ -554,11 +559,11 @@ uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t co
             p.outShadow = b.take<typename SG::Tex>(SG::format);
             p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
             if (bad(9)) return false;
-            sigmaTemporalStabilizationKernel<TR><<<pixelGrid, block, 0, stream>>>(cb, p);
+            launchK(sigmaTemporalStabilizationKernel<TR>, pixelGrid, block, 0, stream, cb, p);
             return true;
         };
         if (!(tr ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
-    } else if (is("SIGMA_SplitScreen.cs.hlsl")) {
+    } else if (key.pass == SIGMA_SPLIT_SCREEN) {
         auto run = [&](auto sig) -> bool {
             using SG = decltype(sig);
             constexpr bool TR = std::is_same<SG, SigmaSignal<true>>::value;
@@ -568,12 +573,12 @@ uint32_t dispatchSigma(const std::string& id, const void* constants, uint32_t co
             if (TR) p.translucency = b.take<typename SG::Tex>(SG::format);
             p.outShadow = b.take<typename SG::Tex>(SG::format);
             if (bad(TR ? 4 : 3)) return false;
-            sigmaSplitScreenKernel<TR><<<pixelGrid, block, 0, stream>>>(cb, p);
+            launchK(sigmaSplitScreenKernel<TR>, pixelGrid, block, 0, stream, cb, p);
             return true;
         };
         if (!(tr ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
     } else {
-        err = "no CUDA kernel for shader '" + id + "'";
+        err = std::string("no CUDA kernel for shader '") + id + "'";
         return (uint32_t)Result::UNSUPPORTED;
     }
     return (uint32_t)Result::SUCCESS;

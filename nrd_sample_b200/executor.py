@@ -30,7 +30,7 @@ NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdc
                  "nrdcuTileSetHalo", "nrdcuTileGetStatus", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
                  "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuDenoiseHostPipelined", "nrdcuHostFlush", "nrdcuGetLastError", "nrdcuGetLaunchCount",
                  "nrdcuHostFrameCreate", "nrdcuHostFrameGetTexture", "nrdcuHostFrameGetInfo", "nrdcuHostFrameDestroy", "nrdcuDenoiseHostFrames",
-                 "nrdcuGetPoolBytes", "nrdcuGetMemoryUsage", "nrdcuGetMirrorProbe", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile",
+                 "nrdcuGetPoolBytes", "nrdcuGetMemoryUsage", "nrdcuGetGraphStats", "nrdcuGetMirrorProbe", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile",
                  "nrdcuFrontEndPackNormalRoughness", "nrdcuFrontEndPackRadianceHitDist", "nrdcuBackEndUnpackRadiance", "nrdcuFrontEndProbe", "nrdcuFrontEndGetLastError")
 
 # nrd::Format -> (torch dtype, channels) for tensors handed to / returned by the executor
@@ -107,6 +107,8 @@ def load() -> C.CDLL:
         L.nrdcuGetLaunchCount.restype = C.c_uint64
         L.nrdcuGetPoolBytes.argtypes = [C.c_void_p]
         L.nrdcuGetPoolBytes.restype = C.c_uint64
+        L.nrdcuGetGraphStats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.nrdcuGetGraphStats.restype = C.c_uint32
         L.nrdcuSetProfiling.argtypes = [C.c_void_p, C.c_int]
         L.nrdcuSetProfiling.restype = C.c_uint32
         L.nrdcuResolveProfile.argtypes = [C.c_void_p]
@@ -291,6 +293,12 @@ class CudaDenoiser:
 
     def pool_bytes(self) -> int:
         return int(load().nrdcuGetPoolBytes(self.ctx))
+
+    def graph_stats(self) -> dict:
+        """FLAG_CUDA_GRAPH bookkeeping: frames captured into a new graph, frames replayed from a cached one, graphs cached."""
+        cap, rep, cached = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        _check(load().nrdcuGetGraphStats(self.ctx, C.byref(cap), C.byref(rep), C.byref(cached)), "nrdcuGetGraphStats")
+        return {"captures": cap.value, "replays": rep.value, "cached": cached.value}
 
 
 class HostFrame:

@@ -46,6 +46,14 @@ CASES = [
     ("reblur_directional_occlusion_1080p", api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, 1920, 1080, None),
     ("reblur_directional_occlusion_recon_nots", api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, 1000, 562, "recon_nots"),
     ("reblur_directional_occlusion_cb_guides_split", api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, 1280, 720, "reblur_cb_guides_split"),
+    # CommonSettings::enableValidation: one more dispatch at the end of the frame ( REBLUR_ADD_VALIDATION_DISPATCH / RELAX_ADD_VALIDATION_DISPATCH )
+    ("reblur_validation", api.Denoiser.REBLUR_DIFFUSE_SPECULAR, 1280, 720, "validation"),
+    ("reblur_specular_validation", api.Denoiser.REBLUR_SPECULAR, 640, 360, "validation"),
+    ("reblur_diffuse_sh_validation", api.Denoiser.REBLUR_DIFFUSE_SH, 640, 360, "validation"),
+    ("reblur_occlusion_validation", api.Denoiser.REBLUR_DIFFUSE_SPECULAR_OCCLUSION, 1000, 562, "validation"),
+    ("reblur_directional_occlusion_validation", api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, 640, 360, "validation"),
+    ("relax_validation", api.Denoiser.RELAX_DIFFUSE_SPECULAR, 1280, 720, "validation"),
+    ("relax_specular_sh_validation", api.Denoiser.RELAX_SPECULAR_SH, 640, 360, "validation"),
     ("sigma_512", api.Denoiser.SIGMA_SHADOW, 512, 512, "sigma"),
     ("sigma_nostab", api.Denoiser.SIGMA_SHADOW, 640, 360, "sigma_nostab"),
     ("sigma_translucency_1080p", api.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, 1920, 1080, "sigma"),
@@ -71,6 +79,7 @@ COMMON = {
     "reblur_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.4),
     "relax_cb_guides_split": dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, splitScreen=0.4),
     "split_only": dict(splitScreen=1.0),
+    "validation": dict(enableValidation=True),
     "reference": dict(splitScreen=0.25),
 }
 

@@ -427,3 +427,44 @@ def test_validation_overlay(ex, runner, which):
     assert val_ref[..., :3].float().std() > 10.0                               # the overlay shows something
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(seen, open(f"gpurun_out/validation_overlay_{which}.json", "w"))
+
+
+@pytest.mark.parametrize("which", ["reblur", "relax"])
+def test_validation_overlay_through_the_product_api(ex, runner, which):
+    """The same overlay end to end: CommonSettings::enableValidation + OUT_VALIDATION on a CudaDenoiser ( the product's own pass graph emits the dispatch ) against the
+    reference engine's OUT_VALIDATION after 3 frames. The captions are masked as above; the rest inherits the closed-loop tolerance of the denoiser's internal data."""
+    w, h = 256, 160
+    den_id, frame_fn, outputs, _ = CASES[which]
+    ref = reference_engine(runner, which, w, h)
+    cud = ex.CudaDenoiser(den_id, w, h, flags=ex.FLAG_QUAD_INTRINSICS)
+    val_ref = runner.alloc_texture(api.Format.RGBA8_UNORM, w, h)
+    val_gpu = ex.alloc_texture(api.Format.RGBA8_UNORM, w, h, "cuda:0")
+    ref.set_user_texture(RT.OUT_VALIDATION, val_ref, api.Format.RGBA8_UNORM)
+    cud.set_user_texture(RT.OUT_VALIDATION, val_gpu, api.Format.RGBA8_UNORM)
+    gout, keep = {}, {}
+    for o in outputs:
+        fmt = out_format(which, o, runner)
+        gout[o] = ex.alloc_texture(fmt, w, h, "cuda:0")
+        cud.set_user_texture(getattr(RT, o), gout[o], fmt)
+    for f in range(3):
+        for k, v in frame_of(frame_fn, f, w, h).items():
+            ref.set_user_texture(getattr(RT, k), v, in_format(which, k, runner))
+            keep[k] = v.to("cuda:0")
+            cud.set_user_texture(getattr(RT, k), keep[k], in_format(which, k, runner))
+        cs = common_of(which, f, w, h)
+        cs.enableValidation = True
+        ref.denoise(cs, settings=SETTINGS[which]() if which in SETTINGS else None)
+        cud.set_common_settings(cs)
+        if which in SETTINGS:
+            cud.set_denoiser_settings(SETTINGS[which]())
+        cud.denoise()
+    torch.cuda.synchronize()
+    got, want = val_gpu.cpu().int(), val_ref.int()
+    mask = torch.ones(h, w, dtype=torch.bool)
+    for cy in range(4):
+        y0 = int(cy * h * 0.25 + 5.0)
+        mask[y0:y0 + 6, :] = False
+    bad = (((got - want).abs().amax(-1) > 2) & mask).float().sum().item() / mask.float().sum().item()
+    assert want[..., :3].float().std() > 10.0
+    assert bad <= 1e-2, f"{which}: {bad:.3%} of the overlay differs by more than 2 LSB"
+    cud.close()
