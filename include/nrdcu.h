@@ -101,13 +101,19 @@ NRDCU_API void* nrdcuGetInstance(nrdcuContext* ctx);
  *   2. every rank: nrdcuTileExport -> a blob of IPC handles; ranks trade blobs (torch.distributed / MPI / a pipe: plumbing)
  *   3. every rank: nrdcuTileAttach(blob of the rank above, blob of the rank below)  (NULL at the top / bottom of the frame)
  *   4. per frame, in lockstep: nrdcuDenoiseRows(ctx, ..., rowBegin, rowEnd, NULL, NULL)
- * nrdcuTileGetStatus: bytes pushed so far and a non-zero error if a wait for a neighbour timed out (~4 s). */
+ * nrdcuTileGetStatus: bytes pushed so far and a non-zero error if a wait for a neighbour timed out (~4 s).
+ * Row ranges work for every denoiser ( REBLUR, RELAX, SIGMA; REFERENCE has none ): SIGMA's two tile passes ignore the range and cover the whole frame. */
 NRDCU_API uint32_t nrdcuAllocSharedTexture(nrdcuContext* ctx, uint32_t format, uint32_t width, uint32_t height, nrdcuTexture* out);
 NRDCU_API uint32_t nrdcuTileExportSize(nrdcuContext* ctx);
 NRDCU_API uint32_t nrdcuTileExport(nrdcuContext* ctx, void* blob, uint32_t blobSize);
 NRDCU_API uint32_t nrdcuTileAttach(nrdcuContext* ctx, const void* blobAbove, const void* blobBelow, uint32_t blobSize);
 NRDCU_API uint32_t nrdcuTileSetHalo(nrdcuContext* ctx, const char* passName /* NULL: set the default */, uint32_t binding, uint32_t rows);
 NRDCU_API uint32_t nrdcuTileGetStatus(nrdcuContext* ctx, uint64_t* bytesPushed, uint32_t* error);
+/* The temporal passes fetch history at pixel + motion, and a strip only holds `halo` rows of its neighbours: vertical motion of more than
+ * *boundRows ( = halo - 2 ) rows per frame reads rows that were never delivered. nrdcuDenoiseRows checks every strip frame on the device ( 2D / 2.5D motion
+ * vectors; one pass over the strip's IN_MV ): *worstExcessRows is the largest overshoot seen so far, 0 = every fetch stayed inside the apron. A renderer
+ * that sees it non-zero needs a taller halo ( nrdcuTileSetHalo( ctx, NULL, 0, rows ) before nrdcuTileExport ) for that camera speed. */
+NRDCU_API uint32_t nrdcuTileGetMotionBound(nrdcuContext* ctx, uint32_t* boundRows, uint32_t* worstExcessRows);
 
 /* Host-buffer convenience used by plugin-style callers (the `e2e` path of bench.py): uploads the user inputs that
  * were registered with nrdcuSetHostResource from pinned/pageable host memory, runs nrdcuDenoise, downloads the outputs.

@@ -642,6 +642,11 @@ struct nrdcuContext {
     std::vector<FrameGraph> graphs;
     cudaStream_t captureStream = nullptr;     // frames are captured on a stream of the library's own ( the caller's may be the legacy default stream )
     uint64_t graphClock = 0, graphCaptures = 0, graphReplays = 0;
+    // strips: history is fetched at pixel + motion, the apron covers `defaultHalo - 2` rows of it. Checked on the device every frame ( kernels/peer_halo.cu )
+    float motionScaleYRows = 0.0f;
+    bool motionIsWorldSpace = false;
+    uint32_t rectHeight = 0;
+    uint32_t* motionExcess = nullptr;        // pinned, mapped: the worst number of rows a history fetch landed beyond the apron, over all frames so far
     // per-dispatch CUDA-event timing (bench.py's live roofline measurement)
     struct ProfileEntry { const char* name; double totalMs = 0; uint64_t count = 0; };
     struct PendingTiming { const char* name; cudaEvent_t start, stop; };
@@ -877,6 +882,13 @@ NRDCU_API uint32_t nrdcuTileGetStatus(nrdcuContext* ctx, uint64_t* bytesPushed, 
     return 0;
 }
 
+NRDCU_API uint32_t nrdcuTileGetMotionBound(nrdcuContext* ctx, uint32_t* boundRows, uint32_t* worstExcessRows) {
+    if (!ctx) return fail(Result::INVALID_ARGUMENT, "nrdcuTileGetMotionBound: null context");
+    if (boundRows) *boundRows = ctx->tile.defaultHalo >= 2 ? ctx->tile.defaultHalo - 2 : 0u;
+    if (worstExcessRows) *worstExcessRows = ctx->motionExcess ? *(volatile uint32_t*)ctx->motionExcess : 0u;
+    return 0;
+}
+
 NRDCU_API uint32_t nrdcuCreate(const void* instanceCreationDesc, uint16_t resourceWidth, uint16_t resourceHeight, int device, uint32_t flags, nrdcuContext** out) {
     if (!instanceCreationDesc || !out || !resourceWidth || !resourceHeight) return fail(Result::INVALID_ARGUMENT, "nrdcuCreate: null or zero argument");
     *out = nullptr;
@@ -950,6 +962,7 @@ NRDCU_API void nrdcuDestroy(nrdcuContext* ctx) {
     }
     if (ctx->captureStream) cudaStreamDestroy(ctx->captureStream);
     if (ctx->tile.hostError) cudaFreeHost(ctx->tile.hostError);
+    if (ctx->motionExcess) cudaFreeHost(ctx->motionExcess);
     if (ctx->tile.seamStream) {
         cudaStreamDestroy(ctx->tile.seamStream);
         cudaEventDestroy(ctx->tile.seamsDone);
@@ -989,6 +1002,11 @@ NRDCU_API uint32_t nrdcuSetCommonSettings(nrdcuContext* ctx, const void* commonS
     if (cs.resourceSize[0] != ctx->width || cs.resourceSize[1] != ctx->height)
         return fail(Result::INVALID_ARGUMENT, "resourceSize %ux%u does not match the pools created at %ux%u", cs.resourceSize[0], cs.resourceSize[1], ctx->width, ctx->height);
     Result r = SetCommonSettings(*ctx->instance, cs);
+    if (r == Result::SUCCESS) {   // what the strips' motion bound check needs ( nrdcuDenoiseRows )
+        ctx->motionScaleYRows = cs.motionVectorScale[1] * (float)cs.rectSize[1];
+        ctx->motionIsWorldSpace = cs.isMotionVectorInWorldSpace;
+        ctx->rectHeight = cs.rectSize[1];
+    }
     return r == Result::SUCCESS ? 0u : fail(r, "nrd::SetCommonSettings rejected the settings");
 }
 
@@ -1052,6 +1070,17 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
         SigmaFusionScope(bool on) { nrdk::sigmaSetCopyFusion(on); }
         ~SigmaFusionScope() { nrdk::sigmaSetCopyFusion(false); }
     } sigmaFusionScope(!afterDispatch && !ctx->tile.attached && rowBegin == 0 && rowEnd == 0xFFFFFFFFu);
+    // a strip: does any history fetch of this frame leave the apron? ( 2D / 2.5D motion; world-space motion would need the reprojection itself )
+    if ((rowBegin != 0 || rowEnd < ctx->height) && !ctx->motionIsWorldSpace && ctx->user[(uint32_t)ResourceType::IN_MV].data && ctx->tile.defaultHalo >= 2) {
+        if (!ctx->motionExcess) {
+            if (cudaHostAlloc((void**)&ctx->motionExcess, sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess) return fail(Result::FAILURE, "nrdcuDenoiseRows: cudaHostAlloc failed");
+            *ctx->motionExcess = 0;
+        }
+        const nrdcuTexture& mv = ctx->user[(uint32_t)ResourceType::IN_MV];
+        const int frameH = (int)(ctx->rectHeight ? ctx->rectHeight : ctx->height);
+        nrdk::launchMotionBoundCheck(mv.data, mv.pitchBytes, mv.format, (int)std::min<uint32_t>(mv.width, ctx->width), (int)rowBegin, (int)std::min<uint32_t>(rowEnd, (uint32_t)frameH), frameH,
+                                     ctx->motionScaleYRows, (int)ctx->tile.defaultHalo - 2, ctx->motionExcess, (cudaStream_t)stream);
+    }
     // the frame: every dispatch of the list, in order, onto `stream`
     auto runFrame = [&](void* stream) -> uint32_t {
     for (uint32_t i = 0; i < n; i++) {

@@ -5,6 +5,7 @@
 // release-store of the pass sequence number into a flag word in the neighbour's memory; before the next pass starts
 // each GPU spins (one thread) on its own flag words until both neighbours have delivered. No host round trip, no
 // collective library: three tiny launches per pass on the stream that runs the denoiser.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -48,6 +49,30 @@ __global__ void haloWaitKernel(const uint32_t* slots, uint32_t seq, int waitUp, 
     }
 }
 
+// KIND: 0 = RGBA16F, 1 = RG16F, 2 = RGBA32F, 3 = RG32F — only .y is read
+template <int KIND>
+__global__ void __launch_bounds__(256) motionBoundKernel(const uint8_t* __restrict__ mv, uint32_t pitchBytes, int width, int y0, int y1, int frameHeight, float scaleYRows, int bound,
+                                                         uint32_t* worstExcessRows) {
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    float excess = 0.0f;
+    if (px < width && py < y1) {
+        const uint8_t* row = mv + (size_t)py * pitchBytes;
+        float my;
+        if (KIND == 0) my = __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(row) + px * 4 + 1)));
+        else if (KIND == 1) my = __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(row) + px * 2 + 1)));
+        else if (KIND == 2) my = __ldg(reinterpret_cast<const float*>(row) + px * 4 + 1);
+        else my = __ldg(reinterpret_cast<const float*>(row) + px * 2 + 1);
+        const float prevRow = (float)py + 0.5f + my * scaleYRows;
+        if (prevRow >= 0.0f && prevRow < (float)frameHeight) {   // history outside the screen is not fetched
+            const float lo = (float)(y0 - bound), hi = (float)(y1 + bound);
+            excess = fmaxf(lo - prevRow, prevRow - hi);
+        }
+    }
+    const uint32_t rows = excess > 0.0f ? (uint32_t)ceilf(excess) : 0u;
+    const uint32_t warpWorst = __reduce_max_sync(0xFFFFFFFFu, rows);
+    if (warpWorst && (threadIdx.x & 31) == 0) atomicMax_system(worstExcessRows, warpWorst);
+}
+
 }  // namespace
 
 void launchHaloPush(const HaloSegments& segs, cudaStream_t stream) {
@@ -62,4 +87,20 @@ void launchHaloWait(const uint32_t* slots, uint32_t seq, bool waitUp, bool waitD
     haloWaitKernel<<<1, 1, 0, stream>>>(slots, seq, waitUp ? 1 : 0, waitDown ? 1 : 0, hostError, 8000000000ll);
 }
 
+}  // namespace nrdk
+
+namespace nrdk {
+bool launchMotionBoundCheck(const void* mv, uint32_t pitchBytes, uint32_t format, int width, int y0, int y1, int frameHeight, float scaleYRows, int bound, uint32_t* worstExcessRows,
+                            cudaStream_t stream) {
+    if (y1 <= y0 || !mv) return false;
+    const dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);
+    const uint8_t* p = (const uint8_t*)mv;
+    switch (format) {
+        case 27: motionBoundKernel<0><<<grid, 256, 0, stream>>>(p, pitchBytes, width, y0, y1, frameHeight, scaleYRows, bound, worstExcessRows); return true;   // RGBA16_SFLOAT
+        case 22: motionBoundKernel<1><<<grid, 256, 0, stream>>>(p, pitchBytes, width, y0, y1, frameHeight, scaleYRows, bound, worstExcessRows); return true;   // RG16_SFLOAT
+        case 39: motionBoundKernel<2><<<grid, 256, 0, stream>>>(p, pitchBytes, width, y0, y1, frameHeight, scaleYRows, bound, worstExcessRows); return true;   // RGBA32_SFLOAT
+        case 33: motionBoundKernel<3><<<grid, 256, 0, stream>>>(p, pitchBytes, width, y0, y1, frameHeight, scaleYRows, bound, worstExcessRows); return true;   // RG32_SFLOAT
+        default: return false;
+    }
+}
 }  // namespace nrdk

@@ -195,8 +195,8 @@ template <template <int> class P, int SIGNAL> const P<SIGNAL>& lobeView(const P<
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxClassifyParams p) {
-    const int tx = blockIdx.x, ty = blockIdx.y;
+__global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxClassifyParams p, int ctaY0) {
+    const int tx = blockIdx.x, ty = (blockIdx.y + ctaY0);
     const int px = tx * 16 + (threadIdx.x & 15), py = ty * 16 + (threadIdx.x >> 4);
     const int sky = __syncthreads_count(!relaxInRange(cb, fabsf(p.viewZ.load(px, py))));
     if (threadIdx.x == 0) p.outTiles.store(tx, ty, sky == 256 ? 1.0f : 0.0f);
@@ -222,8 +222,8 @@ NRD_DEV float2 applyCheckerboardShift(float2 pos, uint32_t mode, int counter, ui
 
 // CB: checkerboarded inputs ( CheckerboardMode::BLACK / WHITE ): the traced pixels sit in the left half of the input textures
 template <bool SH, bool CB, int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxPrePassParamsT<SIGNAL> p) {
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxPrePassParamsT<SIGNAL> p, int ctaY0) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
     if (!relaxInRange(cb, centerViewZ)) return;
@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
 #endif
 // OPT: checkerboard resolve speed-up and the application's guide textures ( confidence, threshold mix ); compiled out of the plain kernel
 template <bool SH, bool OPT, int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParamsT<SIGNAL> p) {
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParamsT<SIGNAL> p, int ctaY0) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float currentLinearZ = relaxViewZ(cb, p.viewZ.load(px, py));
     const uint32_t checkerboard = ((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u;
@@ -811,8 +811,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
 
 // ---------------------------------------------------------------------------------------------------------------
 template <bool SH, int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryFixParamsT<SIGNAL> p) {
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryFixParamsT<SIGNAL> p, int ctaY0) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
     const float historyLength = 255.0f * p.historyLength.load(px, py);
@@ -964,14 +964,14 @@ NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)
 }
 
 template <bool SH, int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParamsT<SIGNAL> p) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParamsT<SIGNAL> p, int ctaY0) {
     __shared__ float4 sSpecFast[HC_TILE_H][HC_TILE_W], sSpecNoisy[HC_TILE_H][HC_TILE_W], sDiffFast[HC_TILE_H][HC_TILE_W], sDiffNoisy[HC_TILE_H][HC_TILE_W];
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     // the CTA covers two 16x16 tiles of one tile row
     const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
     if (skyL != 0.0f && skyR != 0.0f) return;
     {
-        const int baseX = blockIdx.x * BLOCK_W - HC_BORDER, baseY = blockIdx.y * BLOCK_H - HC_BORDER;
+        const int baseX = blockIdx.x * BLOCK_W - HC_BORDER, baseY = (blockIdx.y + ctaY0) * BLOCK_H - HC_BORDER;
         const int maxX = cb.rectSize[0] - 1, maxY = cb.rectSize[1] - 1;
         for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < HC_TILE_W * HC_TILE_H; i += BLOCK_W * BLOCK_H) {
             const int tx = i % HC_TILE_W, ty = i / HC_TILE_W;
@@ -998,8 +998,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(c
 }
 
 template <int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxCopyKernel(const __grid_constant__ RelaxCopyParamsT<SIGNAL> p) {
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxCopyKernel(const __grid_constant__ RelaxCopyParamsT<SIGNAL> p, int ctaY0) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if constexpr ((SIGNAL & SIGNAL_SPEC) != 0)
         if (p.outSpec.inside(px, py)) *p.outSpec.template ptrw<uint2>(px, py) = p.spec.inside(px, py) ? p.spec.fetchRaw(px, py) : make_uint2(0u, 0u);
     if constexpr ((SIGNAL & SIGNAL_DIFF) != 0)
@@ -1031,8 +1031,8 @@ template <class TEX> NRD_DEV float4 rcrs(const RelaxConstants& cb, const TexNR& 
 }
 
 template <int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAntiFireflyParamsT<SIGNAL> p) {
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAntiFireflyParamsT<SIGNAL> p, int ctaY0) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     if (!relaxInRange(cb, relaxViewZ(cb, p.viewZ.load(px, py)))) return;
     const float centerMaterialID = materialFromRaw(p.normalRoughness.loadRaw(px, py));
@@ -1046,15 +1046,15 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const
 // staged in shared memory, normals decoded once per texel. One permutation serves SH and RADIANCE ( only .w of the SH0 textures changes ).
 struct RelaxHitDistReconstructionParams { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, outSpec, outDiff; };
 template <int BORDER>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHitDistReconstructionKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHitDistReconstructionParams p) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHitDistReconstructionKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHitDistReconstructionParams p, int ctaY0) {
     constexpr int TW = BLOCK_W + 2 * BORDER, TH = BLOCK_H + 2 * BORDER;
     __shared__ float3 sNormal[TH][TW];
     __shared__ float3 sHitDistViewZ[TH][TW];
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
     if (skyL != 0.0f && skyR != 0.0f) return;
     {
-        const int baseX = blockIdx.x * BLOCK_W - BORDER, baseY = blockIdx.y * BLOCK_H - BORDER;
+        const int baseX = blockIdx.x * BLOCK_W - BORDER, baseY = (blockIdx.y + ctaY0) * BLOCK_H - BORDER;
         for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < TW * TH; i += BLOCK_W * BLOCK_H) {
             const int tx = i % TW, ty = i / TW;
             const int gx = clampi(baseX + tx, 0, cb.rectSize[0] - 1), gy = clampi(baseY + ty, 0, cb.rectSize[1] - 1);
@@ -1116,8 +1116,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHitDistReconstructionKe
 // RELAX_SplitScreen.cs.hlsl:21-62: the noisy input (range-masked; radiance converted to YCoCg in SH mode) left of CommonSettings::splitScreen
 struct RelaxSplitScreenParams { TexR32F viewZ; TexRGBA16F diff, spec, diffSh, specSh, outDiff, outSpec, outDiffSh, outSpecSh; };
 template <bool SH>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxSplitScreenKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxSplitScreenParams p) {
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxSplitScreenKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxSplitScreenParams p, int ctaY0) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
     if (u > cb.splitScreen || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float inRange = relaxInRange(cb, relaxViewZ(cb, p.viewZ.load(px, py))) ? 1.0f : 0.0f;
@@ -1156,11 +1156,11 @@ constexpr int AT_BORDER = 2, AT_TILE_W = BLOCK_W + 2 * AT_BORDER, AT_TILE_H = BL
 #define RELAX_ATROUS_SMEM_MIN_BLOCKS 4
 #endif
 template <bool SH, int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
     // the reference's groupshared tile: 36x12 texels of { illumination + 2nd moment, SH1, normal + roughness, world position + material }
     __shared__ float4 sSpec[AT_TILE_H][AT_TILE_W], sDiff[AT_TILE_H][AT_TILE_W], sNr[AT_TILE_H][AT_TILE_W], sPosMat[AT_TILE_H][AT_TILE_W];
     __shared__ float4 sSpecSh[SH ? AT_TILE_H : 1][SH ? AT_TILE_W : 1], sDiffSh[SH ? AT_TILE_H : 1][SH ? AT_TILE_W : 1];
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
     const float isSky = threadIdx.x < 16 ? skyL : skyR;
     const float viewZpacked = p.viewZ.load(px, py);
@@ -1170,7 +1170,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
     if (inReferenceGrid) p.outViewZ.store(px, py, viewZpacked);
     const bool skipTile = skyL != 0.0f && skyR != 0.0f;  // nothing to filter in this CTA: only the prev-frame planes are written
     if (!skipTile) {
-        const int baseX = blockIdx.x * BLOCK_W - AT_BORDER, baseY = blockIdx.y * BLOCK_H - AT_BORDER;
+        const int baseX = blockIdx.x * BLOCK_W - AT_BORDER, baseY = (blockIdx.y + ctaY0) * BLOCK_H - AT_BORDER;
         for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < AT_TILE_W * AT_TILE_H; i += BLOCK_W * BLOCK_H) {
             const int tx = i % AT_TILE_W, ty = i / AT_TILE_W;
             const AtrousTexel t = atrousFetch<SH>(cb, p, baseX + tx, baseY + ty);
@@ -1350,8 +1350,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
 }
 
 template <bool SH, int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p) {
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
     if (!relaxInRange(cb, centerViewZ)) return;
@@ -1643,10 +1643,6 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
     using nrd::Format;
     using nrd::Result;
     const char* const id = key.id;
-    if (rows.begin != 0 || rows.end != 0x7FFFFFFF) {
-        err = std::string(id) + ": row ranges (multi-GPU strips) are implemented for REBLUR only";
-        return (uint32_t)Result::UNSUPPORTED;
-    }
     if (constantsSize != sizeof(RelaxConstants) || !constants) {
         err = std::string(id) + ": expected " + std::to_string(sizeof(RelaxConstants)) + " constant bytes";
         return (uint32_t)Result::INVALID_ARGUMENT;
@@ -1670,7 +1666,11 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
     };
     const Format F16 = Format::RGBA16_SFLOAT, R8 = Format::R8_UNORM, R32 = Format::R32_SFLOAT, NR = Format::R10_G10_B10_A2_UNORM;
     const dim3 block(BLOCK_W, BLOCK_H);
-    const dim3 pixelGrid((cb.rectSize[0] + BLOCK_W - 1) / BLOCK_W, (cb.rectSize[1] + BLOCK_H - 1) / BLOCK_H);
+    // rows [ begin, end ) of the rect ( multi-GPU strips, nrdcuDenoiseRows ): every pass covers only the CTA rows of the strip ( begin is a multiple of 16 )
+    const RowGrid rg = rowGrid(rows, (int)cb.rectSize[1], BLOCK_H);
+    const int ctaY0 = rg.ctaY0;
+    const dim3 pixelGrid((cb.rectSize[0] + BLOCK_W - 1) / BLOCK_W, rg.count);
+    if (rg.count == 0 && key.pass != RELAX_VALIDATION) return (uint32_t)Result::SUCCESS;
     // "|NRD_SIGNAL=<DIFF|SPEC|BOTH>|NRD_MODE=<SH|RADIANCE>": the six RELAX denoisers run the same kernels; RADIANCE has no SH1 textures, a single-lobe
     // denoiser binds only its own lobe ( the parameter block keeps the two-lobe layout, the other lobe's views stay empty and are dead code in the kernel )
     const bool sh = key.mode == 1;
@@ -1697,7 +1697,8 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         p.viewZ = b.take<TexR32F>(R32);
         p.outTiles = b.take<TexR8>(R8);
         if (bad(2)) return (uint32_t)Result::INVALID_ARGUMENT;
-        launchK(relaxClassifyTilesKernel, dim3((cb.rectSize[0] + 15) / 16, (cb.rectSize[1] + 15) / 16), 256, 0, stream, cb, p);
+        const RowGrid tg = rowGrid(rows, (int)cb.rectSize[1], 16);
+        launchK(relaxClassifyTilesKernel, dim3((cb.rectSize[0] + 15) / 16, tg.count), 256, 0, stream, cb, p, tg.ctaY0);
     } else if (key.pass == RELAX_PREPASS) {
         RelaxPrePassParams p;
         p.tiles = b.take<TexR8>(R8);
@@ -1713,9 +1714,9 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         takeShD(p.outDiffSh);
         if (bad(3 + (2 + 2 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (checkerboarded) {
-            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<true, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<false, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<true, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<false, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
         } else {
-            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<true, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<false, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<true, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxPrePassKernel<false, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
         }
     } else if (key.pass == RELAX_TEMPORAL_ACCUMULATION) {
         RelaxTaParams p;
@@ -1756,9 +1757,9 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         takeShD(p.outDiffShFast);
         if (bad(10 + (6 + 5 * shOn) * lobes + (hasSpec ? 3 : 0) + 0 * shOn)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (checkerboarded || cb.hasHistoryConfidence || cb.hasDisocclusionThresholdMix) {
-            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<true, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<false, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<true, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<false, true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
         } else {
-            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<true, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<false, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<true, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxTemporalAccumulationKernel<false, false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
         }
     } else if (key.pass == RELAX_HISTORY_FIX) {
         RelaxHistoryFixParams p;
@@ -1775,7 +1776,7 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         takeShS(p.outSpecSh);
         takeShD(p.outDiffSh);
         if (bad(4 + (2 + 2 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxHistoryFixKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxHistoryFixKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+        if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxHistoryFixKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxHistoryFixKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
     } else if (key.pass == RELAX_HISTORY_CLAMPING) {
         RelaxHistoryClampingParams p;
         p.tiles = b.take<TexR8>(R8);
@@ -1791,7 +1792,7 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         TexRGBA16F* outsSh[4] = {&p.outSpecSh, &p.outDiffSh, &p.outSpecShFast, &p.outDiffShFast};
         for (int i = 0; i < 4; i++) (i & 1) ? takeShD(*outsSh[i]) : takeShS(*outsSh[i]);
         if (bad(4 + (5 + 4 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+        if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
     } else if (key.pass == RELAX_HITDIST_RECONSTRUCTION) {
         RelaxHitDistReconstructionParams p;
         p.tiles = b.take<TexR8>(R8);
@@ -1803,9 +1804,9 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         takeD(p.outDiff);
         if (bad(3 + 2 * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
         if (key.mode5x5)
-            launchK(relaxHitDistReconstructionKernel<2>, pixelGrid, block, 0, stream, cb, p);
+            launchK(relaxHitDistReconstructionKernel<2>, pixelGrid, block, 0, stream, cb, p, ctaY0);
         else
-            launchK(relaxHitDistReconstructionKernel<1>, pixelGrid, block, 0, stream, cb, p);
+            launchK(relaxHitDistReconstructionKernel<1>, pixelGrid, block, 0, stream, cb, p, ctaY0);
     } else if (key.pass == RELAX_SPLIT_SCREEN) {
         RelaxSplitScreenParams p;
         p.viewZ = b.take<TexR32F>(R32);
@@ -1818,7 +1819,7 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         takeShD(p.outDiffSh);
         takeShS(p.outSpecSh);
         if (bad(1 + (2 + 2 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) launchK(relaxSplitScreenKernel<true>, pixelGrid, block, 0, stream, cb, p); else launchK(relaxSplitScreenKernel<false>, pixelGrid, block, 0, stream, cb, p);
+        if (sh) launchK(relaxSplitScreenKernel<true>, pixelGrid, block, 0, stream, cb, p, ctaY0); else launchK(relaxSplitScreenKernel<false>, pixelGrid, block, 0, stream, cb, p, ctaY0);
     } else if (key.pass == RELAX_COPY) {
         RelaxCopyParams p;
         takeS(p.spec);
@@ -1826,7 +1827,7 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         takeS(p.outSpec);
         takeD(p.outDiff);
         if (bad(2 * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        withSignal(signal, [&](auto sig_) { launchK(relaxCopyKernel<decltype(sig_)::value>, pixelGrid, block, 0, stream, lobeView(p, sig_)); });
+        withSignal(signal, [&](auto sig_) { launchK(relaxCopyKernel<decltype(sig_)::value>, pixelGrid, block, 0, stream, lobeView(p, sig_), ctaY0); });
     } else if (key.pass == RELAX_ANTI_FIREFLY) {
         RelaxAntiFireflyParams p;
         p.tiles = b.take<TexR8>(R8);
@@ -1837,7 +1838,7 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         takeS(p.outSpec);
         takeD(p.outDiff);
         if (bad(3 + 2 * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        withSignal(signal, [&](auto sig_) { launchK(relaxAntiFireflyKernel<decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+        withSignal(signal, [&](auto sig_) { launchK(relaxAntiFireflyKernel<decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
     } else if (key.pass == RELAX_ATROUS_SMEM || key.pass == RELAX_ATROUS) {
         const bool smem = key.pass == RELAX_ATROUS_SMEM;
         RelaxAtrousParams p = {};
@@ -1863,9 +1864,9 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         takeShD(p.outDiffSh);
         if (bad(4 + (smem ? 3 : 0) + (3 + 2 * shOn) * lobes + (hasSpec ? 1 : 0))) return (uint32_t)Result::INVALID_ARGUMENT;
         if (smem) {
-            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
         } else {
-            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxAtrousKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); }); else withSignal(signal, [&](auto sig_) { launchK(relaxAtrousKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_)); });
+            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxAtrousKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxAtrousKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
         }
     } else {
         err = std::string("no CUDA kernel for shader '") + id + "'";

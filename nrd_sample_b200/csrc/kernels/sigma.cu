@@ -122,9 +122,9 @@ __global__ void __launch_bounds__(256) sigmaSmoothTilesKernel(const __grid_const
 }
 
 template <class ST>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaCopyParams<ST> p) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaCopyParams<ST> p, int ctaY0) {
     using Raw = typename std::conditional<std::is_same<ST, TexR8>::value, uint8_t, uint32_t>::type;
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     // the reference dispatches this pass over the PREVIOUS frame's rect ( Sigma_Shadow.hpp: "USE_PREV_DIMS" ) in 8x16 groups
     if (px >= (((int)cb.rectSizePrev[0] + 7) & ~7) || py >= (((int)cb.rectSizePrev[1] + 15) & ~15)) return;
     const float isSky = p.tiles.load(px >> 4, py >> 4).x;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid
 // tap's uv: the per-column and per-row terms are hoisted out of the loop. ( The sums are the reference's, regrouped: differences are rounding-level. )
 template <bool FIRST_PASS, bool TR>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid_constant__ SigmaConstants cb,
-                                                                   const __grid_constant__ SigmaBlurParams<typename SigmaSignal<TR>::Tex> p) {
+                                                                   const __grid_constant__ SigmaBlurParams<typename SigmaSignal<TR>::Tex> p, int ctaY0) {
     using SG = SigmaSignal<TR>;
     using S = typename SG::T;
     constexpr bool SHADOW_FROM_PENUMBRA = FIRST_PASS && !TR;  // s = IsLit( penumbra ): no shadow texture bound (SIGMA_Blur.cs.hlsl:35-39)
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid
     __shared__ S sShadow[SHADOW_FROM_PENUMBRA ? 1 : TILE_H][SHADOW_FROM_PENUMBRA ? 1 : TILE_W];
 
     // CTA order: first pass default, post-blur reversed (SIGMA_Blur.cs.hlsl:51-55)
-    const int bx = FIRST_PASS ? (int)blockIdx.x : (int)(gridDim.x - 1u - blockIdx.x), by = FIRST_PASS ? (int)blockIdx.y : (int)(gridDim.y - 1u - blockIdx.y);
+    const int bx = FIRST_PASS ? (int)blockIdx.x : (int)(gridDim.x - 1u - blockIdx.x), by = FIRST_PASS ? (int)(blockIdx.y + ctaY0) : (int)(gridDim.y - 1u - blockIdx.y) + ctaY0;
     const int px = bx * BLOCK_W + threadIdx.x, py = by * BLOCK_H + threadIdx.y;
 
     // The CTA covers two 16x16 tiles of one tile row
@@ -332,13 +332,13 @@ NRD_DEV uint32_t packViewZAndHistoryLength(float viewZ, float historyLength) {
 
 template <bool TR>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H)
-    sigmaTemporalStabilizationKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaTemporalStabilizationParams<typename SigmaSignal<TR>::Tex> p) {
+    sigmaTemporalStabilizationKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaTemporalStabilizationParams<typename SigmaSignal<TR>::Tex> p, int ctaY0) {
     using SG = SigmaSignal<TR>;
     using S = typename SG::T;
     __shared__ S sShadow[TILE_H][TILE_W];
     __shared__ float sPenumbra[TILE_H][TILE_W];
 
-    const int bx = blockIdx.x, by = blockIdx.y;  // NRD_CTA_ORDER_DEFAULT
+    const int bx = blockIdx.x, by = blockIdx.y + ctaY0;  // NRD_CTA_ORDER_DEFAULT
     const int px = bx * BLOCK_W + threadIdx.x, py = by * BLOCK_H + threadIdx.y;
     const float skyL = p.tiles.load((bx * BLOCK_W) >> 4, py >> 4).x, skyR = p.tiles.load((bx * BLOCK_W + 16) >> 4, py >> 4).x;
     if (skyL != 0.0f && skyR != 0.0f) return;
@@ -462,9 +462,9 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H)
 
 template <bool TR>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaSplitScreenKernel(const __grid_constant__ SigmaConstants cb,
-                                                                          const __grid_constant__ SigmaSplitScreenParams<typename SigmaSignal<TR>::Tex> p) {
+                                                                          const __grid_constant__ SigmaSplitScreenParams<typename SigmaSignal<TR>::Tex> p, int ctaY0) {
     using SG = SigmaSignal<TR>;
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = blockIdx.y * BLOCK_H + threadIdx.y;
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
     if (u > cb.splitScreen || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1]) return;
     const float viewZ = sigmaUnpackViewZ(cb, p.viewZ.load(px, py));
@@ -523,6 +523,7 @@ struct SigmaBinder {
 // blur pass, which does the copy for its own pixels. Anything else arriving first, or the end of the frame, launches it on its own.
 struct PendingCopy {
     bool armed = false, wide = false;
+    Rows rows;
     SigmaConstants cb;
     SigmaCopyParams<TexR8> narrowParams;
     SigmaCopyParams<TexRGBA8> wideParams;
@@ -530,16 +531,18 @@ struct PendingCopy {
 thread_local PendingCopy g_pendingCopy;
 thread_local bool g_fuseCopy = false;
 
-static void launchCopy(const SigmaConstants& cb, bool wide, const SigmaCopyParams<TexR8>& pn, const SigmaCopyParams<TexRGBA8>& pw, cudaStream_t stream) {
+static void launchCopy(const SigmaConstants& cb, bool wide, const SigmaCopyParams<TexR8>& pn, const SigmaCopyParams<TexRGBA8>& pw, Rows rows, cudaStream_t stream) {
     const dim3 block(BLOCK_W, BLOCK_H);
-    const dim3 prevGrid(((int)cb.rectSizePrev[0] + BLOCK_W - 1) / BLOCK_W, (((int)cb.rectSizePrev[1] + 15) / 16 * 16 + BLOCK_H - 1) / BLOCK_H);
-    if (wide) launchK(sigmaCopyKernel<TexRGBA8>, prevGrid, block, 0, stream, cb, pw);
-    else launchK(sigmaCopyKernel<TexR8>, prevGrid, block, 0, stream, cb, pn);
+    const RowGrid g = rowGrid(rows, ((int)cb.rectSizePrev[1] + 15) / 16 * 16, BLOCK_H);   // the previous rect, rounded to the reference's 8x16 groups
+    if (!g.count) return;
+    const dim3 prevGrid(((int)cb.rectSizePrev[0] + BLOCK_W - 1) / BLOCK_W, g.count);
+    if (wide) launchK(sigmaCopyKernel<TexRGBA8>, prevGrid, block, 0, stream, cb, pw, g.ctaY0);
+    else launchK(sigmaCopyKernel<TexR8>, prevGrid, block, 0, stream, cb, pn, g.ctaY0);
 }
 void sigmaFlushPendingCopy(cudaStream_t stream) {
     if (!g_pendingCopy.armed) return;
     g_pendingCopy.armed = false;
-    launchCopy(g_pendingCopy.cb, g_pendingCopy.wide, g_pendingCopy.narrowParams, g_pendingCopy.wideParams, stream);
+    launchCopy(g_pendingCopy.cb, g_pendingCopy.wide, g_pendingCopy.narrowParams, g_pendingCopy.wideParams, g_pendingCopy.rows, stream);
 }
 void sigmaSetCopyFusion(bool on) {
     g_fuseCopy = on;
@@ -554,10 +557,6 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
         err = std::string(id) + ": expected " + std::to_string(sizeof(SigmaConstants)) + " constant bytes";
         return (uint32_t)Result::INVALID_ARGUMENT;
     }
-    if (rows.begin != 0 || rows.end != 0x7FFFFFFF) {
-        err = std::string(id) + ": row ranges (multi-GPU strips) are implemented for REBLUR only";
-        return (uint32_t)Result::UNSUPPORTED;
-    }
     SigmaConstants cb;
     memcpy(&cb, constants, sizeof(cb));
     if (cb.rectOrigin[0] || cb.rectOrigin[1]) {   // NRD_SUPPORTS_VIEWPORT_OFFSET = 0; dynamic resolution ( rectSize < resourceSize ) itself is supported
@@ -571,8 +570,15 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
         return true;
     };
     const dim3 block(BLOCK_W, BLOCK_H);
-    const dim3 pixelGrid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, (cb.rectSizeMinusOne[1] + BLOCK_H) / BLOCK_H);
+    // rows [ begin, end ) of the rect ( multi-GPU strips, nrdcuDenoiseRows ): the per-pixel passes cover only the CTA rows of the strip; the two tile passes
+    // always run over the whole frame ( every strip holds the full-frame inputs they read, and the bicubic tile lookup of the blur passes reaches two tile
+    // rows past the strip: 12 us of redundant work per frame instead of a seam trade of the tile masks )
+    const RowGrid rg = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, BLOCK_H);
+    const int ctaY0 = rg.ctaY0;
+    const dim3 pixelGrid((cb.rectSizeMinusOne[0] + BLOCK_W) / BLOCK_W, rg.count);
+    const bool wholeFrame = rows.begin <= 0 && rows.end > cb.rectSizeMinusOne[1];
     const int tilesW = cb.tilesSizeMinusOne[0] + 1, tilesH = cb.tilesSizeMinusOne[1] + 1;
+    if (rg.count == 0 && key.pass != SIGMA_CLASSIFY_TILES && key.pass != SIGMA_SMOOTH_TILES && key.pass != SIGMA_COPY) return (uint32_t)Result::SUCCESS;
 
     const bool tr = key.translucency;
     if (!(key.pass == SIGMA_BLUR && key.firstPass) && key.pass != SIGMA_COPY) sigmaFlushPendingCopy(stream);
@@ -617,11 +623,12 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
             const bool sameGrid = !cb.isRectChanged && (int)cb.rectSizePrev[0] == p.history.w && (int)cb.rectSizePrev[1] == p.history.h && cb.rectSizeMinusOne[0] + 1 == p.history.w &&
                                   cb.rectSizeMinusOne[1] + 1 == p.history.h;
             g_pendingCopy.cb = cb;
+            g_pendingCopy.rows = rows;
             g_pendingCopy.wide = std::is_same<SG, SigmaSignal<true>>::value;
             if constexpr (std::is_same<SG, SigmaSignal<true>>::value) g_pendingCopy.wideParams = p;
             else g_pendingCopy.narrowParams = p;
             g_pendingCopy.armed = true;
-            if (!(g_fuseCopy && sameGrid)) sigmaFlushPendingCopy(stream);
+            if (!(g_fuseCopy && sameGrid && wholeFrame)) sigmaFlushPendingCopy(stream);
             return true;
         };
         if (!(wide ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
@@ -655,9 +662,9 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
                     sigmaFlushPendingCopy(stream);
             }
             if (first)
-                launchK(sigmaBlurKernel<true, TR>, pixelGrid, block, 0, stream, cb, p);
+                launchK(sigmaBlurKernel<true, TR>, pixelGrid, block, 0, stream, cb, p, ctaY0);
             else
-                launchK(sigmaBlurKernel<false, TR>, pixelGrid, block, 0, stream, cb, p);
+                launchK(sigmaBlurKernel<false, TR>, pixelGrid, block, 0, stream, cb, p, ctaY0);
             return true;
         };
         if (!(tr ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
@@ -676,7 +683,7 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
             p.outShadow = b.take<typename SG::Tex>(SG::format);
             p.outHistoryLength = b.take<TexR32U>(Format::R32_UINT);
             if (bad(9)) return false;
-            launchK(sigmaTemporalStabilizationKernel<TR>, pixelGrid, block, 0, stream, cb, p);
+            launchK(sigmaTemporalStabilizationKernel<TR>, pixelGrid, block, 0, stream, cb, p, ctaY0);
             return true;
         };
         if (!(tr ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;
@@ -690,7 +697,7 @@ uint32_t dispatchSigma(const PipelineKey& key, const void* constants, uint32_t c
             if (TR) p.translucency = b.take<typename SG::Tex>(SG::format);
             p.outShadow = b.take<typename SG::Tex>(SG::format);
             if (bad(TR ? 4 : 3)) return false;
-            launchK(sigmaSplitScreenKernel<TR>, pixelGrid, block, 0, stream, cb, p);
+            launchK(sigmaSplitScreenKernel<TR>, pixelGrid, block, 0, stream, cb, p, ctaY0);
             return true;
         };
         if (!(tr ? run(SigmaSignal<true>()) : run(SigmaSignal<false>()))) return (uint32_t)Result::INVALID_ARGUMENT;

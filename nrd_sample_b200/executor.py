@@ -27,7 +27,7 @@ FLAG_PROBE_MIRROR = 8
 FLAG_NO_SEAM_OVERLAP = 16
 
 NRDCU_SYMBOLS = ("nrdcuDispatch", "nrdcuDispatchRows", "nrdcuDenoiseRows", "nrdcuAllocSharedTexture", "nrdcuTileExportSize", "nrdcuTileExport", "nrdcuTileAttach",
-                 "nrdcuTileSetHalo", "nrdcuTileGetStatus", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
+                 "nrdcuTileSetHalo", "nrdcuTileGetStatus", "nrdcuTileGetMotionBound", "nrdcuCreate", "nrdcuDestroy", "nrdcuSetCommonSettings", "nrdcuSetDenoiserSettings", "nrdcuSetResource", "nrdcuDenoise",
                  "nrdcuGetPoolTexture", "nrdcuGetInstance", "nrdcuSetHostResource", "nrdcuDenoiseHost", "nrdcuDenoiseHostPipelined", "nrdcuHostFlush", "nrdcuGetLastError", "nrdcuGetLaunchCount",
                  "nrdcuHostFrameCreate", "nrdcuHostFrameGetTexture", "nrdcuHostFrameGetInfo", "nrdcuHostFrameDestroy", "nrdcuDenoiseHostFrames",
                  "nrdcuGetPoolBytes", "nrdcuGetMemoryUsage", "nrdcuGetGraphStats", "nrdcuGetMirrorProbe", "nrdcuSetProfiling", "nrdcuResolveProfile", "nrdcuGetProfileEntry", "nrdcuResetProfile",
@@ -79,6 +79,8 @@ def load() -> C.CDLL:
         L.nrdcuTileSetHalo.restype = C.c_uint32
         L.nrdcuTileGetStatus.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.nrdcuTileGetStatus.restype = C.c_uint32
+        L.nrdcuTileGetMotionBound.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.nrdcuTileGetMotionBound.restype = C.c_uint32
         L.nrdcuCreate.argtypes = [C.c_void_p, C.c_uint16, C.c_uint16, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
         L.nrdcuCreate.restype = C.c_uint32
         L.nrdcuDestroy.argtypes = [C.c_void_p]

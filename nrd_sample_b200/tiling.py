@@ -21,7 +21,8 @@ same rows through torch.distributed batched send/recv from a per-dispatch callba
 the gloo CPU tests exercise), ~0.1 ms slower per pass.
 
 Bound on temporal reach: history is fetched at pixel + motion; HALO_ROWS - 2 = 62 rows of vertical motion per frame
-are covered, beyond that a strip would need a taller halo (`halo_rows=`).
+are covered, beyond that a strip needs a taller halo (`halo_rows=`). The bound is CHECKED: every strip frame the executor
+scans the strip's motion vectors on the device and keeps the worst overshoot (`TiledDenoiser.motion_bound()`).
 """
 from __future__ import annotations
 
@@ -45,9 +46,16 @@ _DATA2 = ("R32_UINT", "R8_UINT")
 _DATA1 = ("RG8_UNORM", "R8_UNORM")
 
 
-def reader_reach(pass_name: str, fmt_name: str, same_frame: bool, default: int, max_blur_radius: float = 30.0, prepass_radius: float = 50.0, history_fix_stride: float = 14.0) -> int:
+def reader_reach(pass_name: str, fmt_name: str, same_frame: bool, default: int, max_blur_radius: float = 30.0, prepass_radius: float = 50.0, history_fix_stride: float = 14.0,
+                 reblur: bool = True) -> int:
     """Rows a REBLUR pass reaches beyond its own pixel into an input texture of format `fmt_name` written `same_frame` or last frame."""
     if not same_frame:
+        return default
+    # the per-pass rules below are REBLUR's. SIGMA and RELAX share some pass NAMES with other access patterns ( SIGMA's temporal stabilization reads a history copy
+    # written the same frame, at pixel + motion ): every texture of theirs gets the full apron — their reaches ( SIGMA blur 32 + 2, RELAX a-trous strides <= 16 + 1,
+    # pre-pass 50 + 2 ) all fit, and the extra seam bytes are small against REBLUR's
+    # ( decided by the denoiser, not by the name's prefix: REBLUR_DIFFUSE_SH's passes are called "DENOISER_NAME - ...", a wart of the reference kept as is )
+    if not reblur:
         return default
     name = pass_name.split(" - ")[-1]
     data = fmt_name in _DATA1 or fmt_name in _DATA2
@@ -80,7 +88,7 @@ def derive_halo_table(host_lib, denoiser: int, width: int, height: int, default:
     assert inst.result == api.Result.SUCCESS, inst.result
     perm, tran = inst.pools()
     fmt_of_pool = {int(api.ResourceType.PERMANENT_POOL): perm, int(api.ResourceType.TRANSIENT_POOL): tran}
-    kw = {}
+    kw = {"reblur": int(denoiser) <= int(api.Denoiser.REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION)}
     if settings is not None:
         assert inst.set_denoiser_settings(0, settings) == api.Result.SUCCESS
         for src, dst in (("maxBlurRadius", "max_blur_radius"), ("historyFixBasePixelStride", "history_fix_stride")):
@@ -345,6 +353,13 @@ class TiledDenoiser:
         b, e = C.c_uint64(), C.c_uint32()
         self.ex._check(self.ex.load().nrdcuTileGetStatus(self.den.ctx, C.byref(b), C.byref(e)), "nrdcuTileGetStatus")
         return int(b.value), int(e.value)
+
+    def motion_bound(self):
+        """(rows of vertical motion per frame the apron covers, worst overshoot any history fetch of this strip has had so far: 0 = fine).
+        The executor checks every strip frame on the device ( nrdcuTileGetMotionBound ); reading the pair costs nothing."""
+        bound, worst = C.c_uint32(), C.c_uint32()
+        self.ex._check(self.ex.load().nrdcuTileGetMotionBound(self.den.ctx, C.byref(bound), C.byref(worst)), "nrdcuTileGetMotionBound")
+        return int(bound.value), int(worst.value)
 
     def set_denoiser_settings(self, settings):
         """Blur radii / history-fix stride change how far passes reach: the apron table follows the settings ( before attach_peers in peer mode )."""

@@ -181,3 +181,16 @@ def test_strips_of_the_other_reblur_denoisers(tmp_path, name):
         for f in range(frames):
             for got, want in zip(outs[f], ref[f]):
                 assert torch.equal(got.view(torch.int16), want[y0:y1].view(torch.int16)), f"{name} rank {r} frame {f}: strip differs from the single-process frame"
+
+
+def test_sigma_and_relax_get_the_full_apron():
+    """REBLUR's per-pass reach rules must not leak onto SIGMA / RELAX passes of the same name ( SIGMA's temporal stabilization reads a history copy written the same
+    frame at pixel + motion; its history length is R32_UINT like REBLUR's at-the-pixel data2 ): every full-resolution texture they write gets the default apron."""
+    from oracle import runner
+    lib = runner.default_host_library()
+    for name in ("SIGMA_SHADOW", "SIGMA_SHADOW_TRANSLUCENCY", "RELAX_DIFFUSE_SPECULAR_SH", "RELAX_DIFFUSE"):
+        t = tiling.derive_halo_table(lib, getattr(api.Denoiser, name), 96, 160)
+        full = {k: v for k, v in t.items() if k[0] not in ("Classify tiles", "Smooth tiles")}
+        assert full and all(v in (0, tiling.HALO_ROWS) for v in full.values()), (name, t)      # 0: written, never read again before the next write ( final outputs )
+        assert sum(1 for v in full.values() if v == tiling.HALO_ROWS) >= 4, (name, t)
+        assert all(v == 0 for k, v in t.items() if k[0] in ("Classify tiles", "Smooth tiles")), (name, t)
