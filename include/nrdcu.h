@@ -62,7 +62,8 @@ enum {
 NRDCU_API uint32_t nrdcuDispatch(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures,
                                  uint32_t texturesNum, uint32_t flags, void* stream);
 /* Same, restricted to the rect rows [rowBegin, rowEnd) (rowBegin a multiple of 16; rowEnd is clamped to the rect). Every texture is
- * still the whole frame: a strip reads rows outside its range (the halo) and writes only rows inside it. REBLUR passes only. */
+ * still the whole frame: a strip reads rows outside its range (the halo) and writes only rows inside it. Every REBLUR, RELAX and SIGMA pass takes a
+ * range ( SIGMA's two 1/16-resolution tile passes ignore it and cover the frame ); REFERENCE and the validation overlays are whole-frame only. */
 NRDCU_API uint32_t nrdcuDispatchRows(const char* shaderIdentifier, const void* constants, uint32_t constantsSize, const nrdcuTexture* textures,
                                      uint32_t texturesNum, uint32_t flags, void* stream, uint32_t rowBegin, uint32_t rowEnd);
 

@@ -390,8 +390,9 @@ NRD_DEV float2 screenUv(const Mat4& worldToClip, float3 X) {  // Geometry::GetSc
 // Math
 // =================================================================================================================
 NRD_DEV float linearStep(float a, float b, float x) { return saturate((x - a) / (b - a)); }
-NRD_DEV float smoothStep01(float x) { x = saturate(x); return x * x * (3.0f - x * 2.0f); }
-NRD_DEV float smoothStep(float a, float b, float x) { x = linearStep(a, b, x); return x * x * (3.0f - x * 2.0f); }
+// ( 3 - 2 x as one FFMA: x * 2 is exact, so the bits are those of 3.0f - x * 2.0f; nvcc otherwise emits x + x and a subtraction )
+NRD_DEV float smoothStep01(float x) { x = saturate(x); return (x * x) * fmaf(x, -2.0f, 3.0f); }
+NRD_DEV float smoothStep(float a, float b, float x) { x = linearStep(a, b, x); return (x * x) * fmaf(x, -2.0f, 3.0f); }
 NRD_DEV float pow01(float x, float y) { return powf(saturate(x), y); }
 NRD_DEV float sqrt01(float x) { return sqrtf(saturate(x)); }
 NRD_DEV float rsqrtSafe(float x) { return 1.0f / sqrtf(fmaxf(x, ML_SMALL_EPS)); }
@@ -586,7 +587,7 @@ NRD_DEV float2 relaxedRoughnessWeightParams(float m, float fraction = 1.0f, floa
 NRD_DEV float expApprox(float x) { return 1.0f / (x * x - x + 1.0f); }
 NRD_DEV float exponentialWeight(float x, float px, float py) { return expApprox(-3.0f * fabsf(x * px + py)); }
 // Math::SmoothStep( 1, 0, |x px + py| ): ( t - 1 ) / ( 0 - 1 ) is exactly 1 - t, so the division is dropped
-NRD_DEV float nonExponentialWeight(float x, float px, float py) { float s = saturate(1.0f - fabsf(x * px + py)); return s * s * (3.0f - s * 2.0f); }
+NRD_DEV float nonExponentialWeight(float x, float px, float py) { float s = satOneMinusAbs(x * px + py); return (s * s) * fmaf(s, -2.0f, 3.0f); }
 NRD_DEV float gaussianWeight(float r) { return expf(-0.66f * r * r); }
 NRD_DEV float encodingAwareNormalWeight(float3 Ncurr, float3 Nprev, float maxAngle, float curvatureAngle, float thresholdAngle) {
     float angle = acosApproxPositive(dot(Ncurr, Nprev));

@@ -51,13 +51,7 @@ NRD_DEV float satOneMinus(float x) {  // saturate( 1 - x ) as ONE FADD.SAT (nvcc
 }
 NRD_DEV P2 sat2(P2 x) { return P2(__saturatef(x.v.x), __saturatef(x.v.y)); }                    // FADD.SAT
 NRD_DEV P2 satOneMinus2(P2 x) { return P2(satOneMinus(x.v.x), satOneMinus(x.v.y)); }            // FADD.SAT 1, -x
-// saturate( 1 - |x| ): ONE FADD.SAT per lane with the |.| and negate modifiers folded in ( 2 instructions per pair; 1 - min( |x|, 1 ) as two FMNMX and a
-// packed subtraction is 3 and gives the same bits )
-NRD_DEV float satOneMinusAbs(float x) {
-    float d;
-    asm("{\n\t.reg .f32 t;\n\tabs.f32 t, %1;\n\tsub.sat.ftz.f32 %0, 0f3F800000, t;\n\t}" : "=f"(d) : "f"(x));
-    return d;
-}
+// ( satOneMinusAbs: vecmath.cuh — 2 instructions per pair; 1 - min( |x|, 1 ) as two FMNMX and a packed subtraction is 3 and gives the same bits )
 NRD_DEV P2 oneMinusAbsSat2(P2 x) { return P2(satOneMinusAbs(x.v.x), satOneMinusAbs(x.v.y)); }
 NRD_DEV P2 absMul2(P2 x, float k) { return P2(fabsf(x.v.x) * k, fabsf(x.v.y) * k); }                                         // FMUL |x|, k
 NRD_DEV P2 mulSat2(P2 x, P2 y) { return P2(__saturatef(x.v.x * y.v.x), __saturatef(x.v.y * y.v.y)); }                        // FMUL.SAT

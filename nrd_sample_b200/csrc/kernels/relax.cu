@@ -1350,7 +1350,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
 }
 
 template <bool SH, int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));

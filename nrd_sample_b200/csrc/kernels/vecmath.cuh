@@ -82,6 +82,18 @@ NRD_DEV float3 normalize(float3 a) { return a / length(a); }
 NRD_DEV float3 cross(float3 a, float3 b) { return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 NRD_DEV float3 reflect(float3 i, float3 n) { return i - 2.0f * n * dot(i, n); }
 
+// saturate( 1 - |x| ) as ONE FADD.SAT with the |.| and negate modifiers folded in. Written in C, nvcc emits a separate FADD for the absolute value ( the
+// .ftz flavour of abs cannot be a source modifier ) and another for the subtraction before the saturate: 3 instructions for the same bits.
+#ifdef __CUDA_ARCH__
+NRD_DEV float satOneMinusAbs(float x) {
+    float d;
+    asm("{\n\t.reg .f32 t;\n\tabs.f32 t, %1;\n\tsub.sat.ftz.f32 %0, 0f3F800000, t;\n\t}" : "=f"(d) : "f"(x));
+    return d;
+}
+#else
+NRD_DEV float satOneMinusAbs(float x) { return fminf(fmaxf(1.0f - fabsf(x), 0.0f), 1.0f); }
+#endif
+
 NRD_DEV float comp(float4 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 }  // namespace nrdk
