@@ -102,32 +102,61 @@ def config_of(args, world):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons, sampled every 200 ms while the timed region runs."""
+    """SM clock + throttle reasons of the GPU, sampled while the timed region runs: through NVML every 5 ms ( the timed region of a short chain is a few tens of
+    milliseconds: spawning nvidia-smi every 200 ms caught one sample of it ), falling back to nvidia-smi when the NVML binding is not importable."""
 
-    def __init__(self, index: int):
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))   # nvmlClocksEventReason* bits
+
+    def __init__(self, index: int, uuid: str = None):
         super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.index, self.uuid, self.samples, self._halt, self.source = index, uuid, [], threading.Event(), "nvml"
 
-    def run(self):
+    def _nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+            except Exception:
+                h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._halt.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = int(get_reasons(h))
+            self.samples.append((sm, mx, [n for n, b in self.REASONS if bits & b]))
+            self._halt.wait(0.005)
+
+    def _smi(self):
+        self.source = "nvidia-smi"
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 7:
-                    self.samples.append(f)
+                    self.samples.append((int(float(f[0])), int(float(f[1])), [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
+
+    def run(self):
+        try:
+            self._nvml()
+        except Exception:
+            self._smi()
 
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({n for s in self.samples for n in s[2]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 def cpu_denoiser(which: str, W: int, H: int, recon: int, prefer_reference: bool):
@@ -310,7 +339,11 @@ def run_product(args):
     # ---- leg 1: device-resident ( `value`, per-pass roofline ) --------------------------------------------------------------------
     leg = Leg(recon)
     den = leg.den
-    sampler = ClockSampler(local) if rank == 0 else None
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local, gpu_uuid) if rank == 0 else None
     if sampler:
         sampler.start()
     ms_dev, launches, _ = timed(den, leg.step_device, 0)

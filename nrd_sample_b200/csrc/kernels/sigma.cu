@@ -139,8 +139,11 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid
 // denoising range and not umbra-vs-penumbra mismatched with a centre that got this far, i.e. penumbra != 0 ) and "is in penumbra" ( not lit ) go into shared
 // memory next to { penumbra, viewZ } as 0 / 1 factors, so the 24 dense taps are branch- and select-free multiply-adds. dot( Nv, Xv( tap ) ) is affine in the
 // tap's uv: the per-column and per-row terms are hoisted out of the loop. ( The sums are the reference's, regrouped: differences are rounding-level. )
+#ifndef SIGMA_BLUR_MIN_BLOCKS
+#define SIGMA_BLUR_MIN_BLOCKS 5   // <= 51 registers: five CTAs per SM. The first pass ( with the folded copy ) sat at 54 registers = 4 CTAs, 46 % occupancy, top stall long_scoreboard
+#endif
 template <bool FIRST_PASS, bool TR>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaBlurKernel(const __grid_constant__ SigmaConstants cb,
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SIGMA_BLUR_MIN_BLOCKS) sigmaBlurKernel(const __grid_constant__ SigmaConstants cb,
                                                                    const __grid_constant__ SigmaBlurParams<typename SigmaSignal<TR>::Tex> p, int ctaY0) {
     using SG = SigmaSignal<TR>;
     using S = typename SG::T;

@@ -11,7 +11,7 @@ timeout 900 python bench.py --denoiser reblur_sh --steps 20 --warmup 5 --no-cpu-
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
 timeout 120 tools/frame_latency.bin > $O/frame_latency.json 2> $O/frame_latency.err
 # the ncu launch list of the bench command ( per-launch times are cold-cache and serialised: shares, not absolutes )
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/bench_launches_ncu.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"reblur|clearKernel" -c 400 --csv --log-file $O/bench_launches_ncu.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:reblur -s 32 -c 16 -f -o /tmp/reblur_full python tools/profile_frame.py 2560 1440 6 > $O/ncu_reblur.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:relax -s 40 -c 20 -f -o /tmp/relax_full python tools/profile_frame.py 2560 1440 6 relax > $O/ncu_relax.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:sigma -s 20 -c 10 -f -o /tmp/sigma_full python tools/profile_frame.py 2560 1440 6 sigma > $O/ncu_sigma.log 2>&1
