@@ -587,7 +587,11 @@ NRD_DEV float2 relaxedRoughnessWeightParams(float m, float fraction = 1.0f, floa
 NRD_DEV float expApprox(float x) { return 1.0f / (x * x - x + 1.0f); }
 NRD_DEV float exponentialWeight(float x, float px, float py) { return expApprox(-3.0f * fabsf(x * px + py)); }
 // Math::SmoothStep( 1, 0, |x px + py| ): ( t - 1 ) / ( 0 - 1 ) is exactly 1 - t, so the division is dropped
+#ifdef NRD_B200_PLAIN_HELPERS   // experiments ( tools/build_variant.py ): the C forms nvcc turns into three + four instructions
+NRD_DEV float nonExponentialWeight(float x, float px, float py) { float s = saturate(1.0f - fabsf(x * px + py)); return s * s * (3.0f - s * 2.0f); }
+#else
 NRD_DEV float nonExponentialWeight(float x, float px, float py) { float s = satOneMinusAbs(x * px + py); return (s * s) * fmaf(s, -2.0f, 3.0f); }
+#endif
 NRD_DEV float gaussianWeight(float r) { return expf(-0.66f * r * r); }
 NRD_DEV float encodingAwareNormalWeight(float3 Ncurr, float3 Nprev, float maxAngle, float curvatureAngle, float thresholdAngle) {
     float angle = acosApproxPositive(dot(Ncurr, Nprev));

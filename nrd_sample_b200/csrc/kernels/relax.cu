@@ -29,9 +29,13 @@ constexpr float RELAX_MAX_ACCUM_FRAME_NUM = 255.0f;
 constexpr float RELAX_ANTILAG_ACCELERATION_AMOUNT_SCALE = 10.0f;
 constexpr float NRD_FP16_MAX_F = 65504.0f;
 
-__constant__ float3 kPoisson8[8] = {{-0.4706069f, -0.4427112f, +0.6461146f}, {-0.9057375f, +0.3003471f, +0.9542373f}, {-0.3487388f, +0.4037880f, +0.5335386f},
-                                    {+0.1023042f, +0.6439373f, +0.6520134f}, {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
-                                    {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
+// g_Poisson8 ( Common.hlsli:194-205 ): { offset.xy, distance } and GetGaussianWeight( distance ) = exp( -0.66 d^2 ) ( the fp32 values expf gives ) as compile-time
+// constants: the unrolled tap loops fold them into immediates instead of loading the offsets from constant memory and evaluating an exponential per tap
+__device__ constexpr float kPoisson8[8][3] = {{-0.4706069f, -0.4427112f, +0.6461146f}, {-0.9057375f, +0.3003471f, +0.9542373f}, {-0.3487388f, +0.4037880f, +0.5335386f},
+                                              {+0.1023042f, +0.6439373f, +0.6520134f}, {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
+                                              {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
+__device__ constexpr float kPoisson8Gauss[8] = {0.7591724991798401f, 0.5482766032218933f, 0.8287158608436584f, 0.755345344543457f,
+                                                0.7438870072364807f, 0.9366368055343628f, 0.5931912064552307f, 0.6313964128494263f};
 
 // ---- small helpers ------------------------------------------------------------------------------------------------
 NRD_DEV float luminance(float3 x) { return dot(x, make_float3(0.2126f, 0.7152f, 0.0722f)); }
@@ -129,6 +133,7 @@ template <class TEX> NRD_DEV float4 gatherR16(const TEX& t, int x0, int y0) { re
 template <bool SH, class TEX> NRD_DEV void storeSh(const TEX& t, int x, int y, float3 v) { if constexpr (SH) t.store(x, y, f4(v, 0.0f)); }
 template <bool SH, class TEX> NRD_DEV float3 loadSh(const TEX& t, int x, int y) { if constexpr (SH) return xyz(t.load(x, y)); else return f3(0.0f); }
 template <bool SH, class TEX> NRD_DEV float3 sampleNearestSh(const TEX& t, float2 uv) { if constexpr (SH) return xyz(t.sampleNearest(uv)); else return f3(0.0f); }
+template <bool SH, class TEX> NRD_DEV float3 fetchSh(const TEX& t, int x, int y) { if constexpr (SH) return xyz(t.fetch(x, y)); else return f3(0.0f); }   // in-bounds coordinates
 
 // ---- NRD_SIGNAL ( DIFF / SPEC / BOTH ) ------------------------------------------------------------------------------------------
 // RELAX_DIFFUSE( _SH ) and RELAX_SPECULAR( _SH ) are the two-lobe shaders with the other lobe's `#if( NRD_DIFF )` / `#if( NRD_SPEC )` blocks removed
@@ -220,6 +225,48 @@ NRD_DEV float2 applyCheckerboardShift(float2 pos, uint32_t mode, int counter, ui
     return pos;
 }
 
+// One Poisson tap of the pre-pass ( RELAX_PrePass.cs.hlsl:139-176 ): the position is snapped to a pixel centre, so every texture of the pass is point-sampled
+// at the SAME integer texel — floor( uv * rectSize ), clamped to the rect: scaling the snapped uv by gResolutionScale, clamping it to the viewport and
+// multiplying by the texture size lands exactly there. Without checkerboarding that texel is computed once ( one F2I per axis instead of two conversions and
+// two multiplies per texture ); with it the inputs are addressed through their own uv as in the reference.
+struct PrePassTap {
+    float2 uv, uvScaled, uvInput;
+    int x, y;
+    bool inScreen, byTexel;
+    NRD_DEV uint32_t fetchRaw(const TexNR& t) const { return byTexel ? t.fetchRaw(x, y) : t.sampleNearestRaw(uvScaled); }
+    NRD_DEV float fetch(const TexR32F& t) const { return byTexel ? t.fetch(x, y) : t.sampleNearest(uvScaled); }
+    template <class TEX> NRD_DEV float4 fetchInput(const TEX& t) const { return byTexel ? t.fetch(x, y) : t.sampleNearest(uvInput); }
+    template <bool SH, class TEX> NRD_DEV float3 fetchInputSh(const TEX& t) const {
+        if constexpr (SH) return xyz(byTexel ? t.fetch(x, y) : t.sampleNearest(uvInput));
+        else return f3(0.0f);
+    }
+};
+template <bool CB> NRD_DEV PrePassTap prePassTap(const RelaxConstants& cb, float2 pixelUv, float2 rectSize, float2 rectSizeInv, float4 rotator, int i, float blurRadius, uint32_t lobeCheckerboard,
+                                                 bool lobeIsCheckerboarded) {
+    PrePassTap t;
+    float2 uv = pixelUv * rectSize + rotate2(rotator, make_float2(kPoisson8[i][0], kPoisson8[i][1])) * blurRadius;
+    if constexpr (!CB) {
+        const int kx = __float2int_rd(uv.x), ky = __float2int_rd(uv.y);
+        t.uv = make_float2(((float)kx + 0.5f) * rectSizeInv.x, ((float)ky + 0.5f) * rectSizeInv.y);
+        t.inScreen = (unsigned)kx < (unsigned)cb.rectSize[0] && (unsigned)ky < (unsigned)cb.rectSize[1];   // IsInScreenNearest: 0 < ( k + 0.5 ) / size < 1
+        t.x = clampi(kx, 0, cb.rectSize[0] - 1);
+        t.y = clampi(ky, 0, cb.rectSize[1] - 1);
+        t.byTexel = true;
+        t.uvScaled = t.uvInput = t.uv;   // unused
+    } else {
+        uv = floor2(uv) + 0.5f;
+        uv = applyCheckerboardShift(uv, lobeCheckerboard, i, cb.frameIndex);
+        uv = uv * rectSizeInv;
+        t.uv = uv;
+        t.uvScaled = clampUvToViewport(cb, uv);
+        t.uvInput = make_float2(lobeIsCheckerboarded ? t.uvScaled.x * 0.5f : t.uvScaled.x, t.uvScaled.y);
+        t.inScreen = isInScreenNearest(uv);
+        t.x = t.y = 0;
+        t.byTexel = false;
+    }
+    return t;
+}
+
 // CB: checkerboarded inputs ( CheckerboardMode::BLACK / WHITE ): the traced pixels sit in the left half of the input textures
 template <bool SH, bool CB, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxPrePassParamsT<SIGNAL> p, int ctaY0) {
@@ -286,33 +333,27 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
         float weightSum = 1.0f;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const float3 offset = kPoisson8[i];
-            float2 uv = pixelUv * rectSize + rotate2(rotator, make_float2(offset.x, offset.y)) * blurRadius;
-            uv = floor2(uv) + 0.5f;
-            if (CB) uv = applyCheckerboardShift(uv, cb.diffCheckerboard, i, cb.frameIndex);
-            uv = uv * rectSizeInv;
-            const float2 uvScaled = clampUvToViewport(cb, uv);
-            const float2 uvInput = make_float2(diffCb ? uvScaled.x * 0.5f : uvScaled.x, uvScaled.y);
-
+            const PrePassTap tap = prePassTap<CB>(cb, pixelUv, rectSize, rectSizeInv, rotator, i, blurRadius, cb.diffCheckerboard, diffCb);
+            const float2 uv = tap.uv;
             float sampleMaterialID;
-            const float3 sampleNormal = xyz(unpackNormalRoughness(p.normalRoughness.sampleNearestRaw(uvScaled), sampleMaterialID));
-            const float sampleViewZ = relaxViewZ(cb, p.viewZ.sampleNearest(uvScaled));
+            const float3 sampleNormal = xyz(unpackNormalRoughness(tap.fetchRaw(p.normalRoughness), sampleMaterialID));
+            const float sampleViewZ = relaxViewZ(cb, tap.fetch(p.viewZ));
             const float3 sampleWorldPos = currentWorldPosClip(cb, uv * 2.0f - 1.0f, sampleViewZ);
 
-            float sampleWeight = isInScreenNearest(uv) ? 1.0f : 0.0f;
+            float sampleWeight = tap.inScreen ? 1.0f : 0.0f;
             sampleWeight *= relaxInRange(cb, sampleViewZ) ? 1.0f : 0.0f;
             sampleWeight *= compareMaterials(centerMaterialID, sampleMaterialID, cb.diffMinMaterial) ? 1.0f : 0.0f;
             sampleWeight *= planeDistanceWeight(centerWorldPos, centerNormal, planeZ, sampleWorldPos, cb.depthThreshold);
             sampleWeight *= computeWeight(acosApproxPositive(dot(centerNormal, sampleNormal)), normalWeightParam, 0.0f);
 
-            float4 sampleDiffuse = p.diff.sampleNearest(uvInput);
+            float4 sampleDiffuse = tap.fetchInput(p.diff);
             if (sampleWeight == 0.0f) sampleDiffuse = f4(0.0f);
             sampleWeight *= lerp(cb.minHitDistanceWeight, 1.0f, exponentialWeight(sampleDiffuse.w, hitDistanceWeightP.x, hitDistanceWeightP.y));
-            sampleWeight *= gaussianWeight(offset.z);
+            sampleWeight *= kPoisson8Gauss[i];
 
             weightSum += sampleWeight;
             diffuseIllumination += sampleDiffuse * sampleWeight;
-            float3 sampleSH = sampleNearestSh<SH>(p.diffSh, uvInput);
+            float3 sampleSH = tap.template fetchInputSh<SH>(p.diffSh);
             if (sampleWeight == 0.0f) sampleSH = f3(0.0f);
             diffuseSH += sampleSH * sampleWeight;
         }
@@ -354,20 +395,14 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
         const float roughnessLerp = linearStep(0.5f, 1.0f, centerRoughness);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const float3 offset = kPoisson8[i];
-            float2 uv = pixelUv * rectSize + rotate2(rotator, make_float2(offset.x, offset.y)) * blurRadius;
-            uv = floor2(uv) + 0.5f;
-            if (CB) uv = applyCheckerboardShift(uv, cb.specCheckerboard, i, cb.frameIndex);
-            uv = uv * rectSizeInv;
-            const float2 uvScaled = clampUvToViewport(cb, uv);
-            const float2 uvInput = make_float2(specCb ? uvScaled.x * 0.5f : uvScaled.x, uvScaled.y);
-
+            const PrePassTap tap = prePassTap<CB>(cb, pixelUv, rectSize, rectSizeInv, rotator, i, blurRadius, cb.specCheckerboard, specCb);
+            const float2 uv = tap.uv;
             float sampleMaterialID;
-            const float4 sampleNormalRoughness = unpackNormalRoughness(p.normalRoughness.sampleNearestRaw(uvScaled), sampleMaterialID);
+            const float4 sampleNormalRoughness = unpackNormalRoughness(tap.fetchRaw(p.normalRoughness), sampleMaterialID);
             const float3 sampleNormal = xyz(sampleNormalRoughness);
-            const float sampleViewZ = relaxViewZ(cb, p.viewZ.sampleNearest(uvScaled));
+            const float sampleViewZ = relaxViewZ(cb, tap.fetch(p.viewZ));
 
-            float sampleWeight = isInScreenNearest(uv) ? 1.0f : 0.0f;
+            float sampleWeight = tap.inScreen ? 1.0f : 0.0f;
             sampleWeight *= relaxInRange(cb, sampleViewZ) ? 1.0f : 0.0f;
             sampleWeight *= compareMaterials(centerMaterialID, sampleMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
             sampleWeight *= computeWeight(sampleNormalRoughness.w, roughnessWeightP.x, roughnessWeightP.y);
@@ -375,12 +410,12 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
             const float3 sampleWorldPos = currentWorldPosClip(cb, uv * 2.0f - 1.0f, sampleViewZ);
             sampleWeight *= planeDistanceWeight(centerWorldPos, centerNormal, planeZ, sampleWorldPos, cb.depthThreshold);
 
-            float4 sampleSpecular = p.spec.sampleNearest(uvInput);
+            float4 sampleSpecular = tap.fetchInput(p.spec);
             if (sampleWeight == 0.0f) sampleSpecular = f4(0.0f);
             if (rng.next() < sampleWeight * NoV) minHitT = fminf(minHitT, sampleSpecular.w == 0.0f ? NRD_INF : sampleSpecular.w);
 
             sampleWeight *= lerp(specMinHitDistanceWeight, 1.0f, exponentialWeight(sampleSpecular.w, hitDistanceWeightP.x, hitDistanceWeightP.y));
-            sampleWeight *= gaussianWeight(offset.z);
+            sampleWeight *= kPoisson8Gauss[i];
             const float d = length(sampleWorldPos - centerWorldPos);
             const float t = sampleSpecular.w / (specularIllumination.w + d);
             sampleWeight *= lerp(saturate(t), 1.0f, roughnessLerp);
@@ -389,7 +424,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
             specularIllumination.x += sampleSpecular.x * sampleWeight;
             specularIllumination.y += sampleSpecular.y * sampleWeight;
             specularIllumination.z += sampleSpecular.z * sampleWeight;
-            float3 sampleSH = sampleNearestSh<SH>(p.specSh, uvInput);
+            float3 sampleSH = tap.template fetchInputSh<SH>(p.specSh);
             if (sampleWeight == 0.0f) sampleSH = f3(0.0f);
             specularSH += sampleSH * sampleWeight;
         }
