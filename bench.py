@@ -110,25 +110,34 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int, uuid: str = None):
         super().__init__(daemon=True)
         self.index, self.uuid, self.samples, self._halt, self.source = index, uuid, [], threading.Event(), "nvml"
+        self._nv = None
+        try:   # NVML is initialised HERE, before the timed region: nvmlInit alone takes longer than a short chain's 40 steps
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self._nv = (pynvml, h, pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM), get_reasons)
+        except Exception:
+            self._nv = None
+
+    def _sample_nvml(self):
+        pynvml, h, mx, get_reasons = self._nv
+        bits = int(get_reasons(h))
+        self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx, [n for n, b in self.REASONS if bits & b]))
 
     def _nvml(self):
-        import pynvml
-        pynvml.nvmlInit()
-        h = None
-        if self.uuid:
-            try:
-                h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
-            except Exception:
-                h = None
-        if h is None:
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        if self._nv is None:
+            raise RuntimeError("no NVML")
         while not self._halt.is_set():
-            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-            bits = int(get_reasons(h))
-            self.samples.append((sm, mx, [n for n, b in self.REASONS if bits & b]))
-            self._halt.wait(0.005)
+            self._sample_nvml()
+            self._halt.wait(0.002)
 
     def _smi(self):
         self.source = "nvidia-smi"
@@ -151,6 +160,11 @@ class ClockSampler(threading.Thread):
             self._smi()
 
     def stop(self):
+        if self._nv is not None and not self.samples:   # the region was shorter than the thread's start-up: one sample while the GPU is still under load
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
         self._halt.set()
         self.join(timeout=3)
         sm = sorted(s[0] for s in self.samples)

@@ -150,6 +150,24 @@ struct TexR32F : TexView {
     }
 };
 
+// Sky-tile classification ( *_ClassifyTiles.cs.hlsl ): is every pixel of the 16x16 tile ( tx, ty ) outside the denoising range? One WARP per tile: each lane takes 8
+// consecutive pixels of a row as two 128-bit loads ( rows 16-byte aligned and the tile inside the texture; pixel by pixel with out-of-bounds = 0 otherwise ), the
+// verdict is one warp vote — no shared memory, no barrier, 8 tiles per 256-thread CTA. `isSky( rawViewZ )` is the denoiser's own range test.
+template <class IsSky> NRD_DEV bool tileIsSkyWarp(const TexR32F& viewZ, int tx, int ty, IsSky isSky) {
+    const int lane = threadIdx.x & 31;
+    const int px0 = tx * 16 + (lane & 1) * 8, py = ty * 16 + (lane >> 1);
+    bool sky = true;
+    const bool vec = (((uintptr_t)viewZ.data | ((size_t)viewZ.pitch * 4u)) & 15u) == 0 && px0 + 8 <= viewZ.w && py < viewZ.h;
+    if (vec) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(viewZ.ptr<float>(px0, py))), b = __ldg(reinterpret_cast<const float4*>(viewZ.ptr<float>(px0 + 4, py)));
+        sky = isSky(a.x) && isSky(a.y) && isSky(a.z) && isSky(a.w) && isSky(b.x) && isSky(b.y) && isSky(b.z) && isSky(b.w);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) sky = sky && isSky(viewZ.load(px0 + i, py));
+    }
+    return __all_sync(0xFFFFFFFFu, sky);
+}
+
 struct TexR16F : TexView {
     NRD_DEV float fetch(int x, int y) const { return __half2float(__ushort_as_half(__ldg(ptr<unsigned short>(x, y)))); }
     NRD_DEV float load(int x, int y) const { return inside(x, y) ? fetch(x, y) : 0.0f; }

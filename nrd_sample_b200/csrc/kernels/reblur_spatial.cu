@@ -415,13 +415,12 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
-// One CTA of 256 threads per 16x16 tile: each thread tests one pixel, the verdict is a block-wide AND.
-__global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ ClassifyTilesParams p, int ctaY0) {
-    int tx = blockIdx.x, ty = ctaY0 + blockIdx.y;
-    int px = tx * 16 + (threadIdx.x & 15), py = ty * 16 + (threadIdx.x >> 4);
-    float viewZ = unpackViewZ(cb, p.inViewZ.load(px, py));
-    int allSky = __syncthreads_and(!inDenoisingRange(cb, viewZ));
-    if (threadIdx.x == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
+// One warp per 16x16 tile, 8 tiles per CTA ( tileIsSkyWarp, common.cuh )
+__global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ ClassifyTilesParams p, int ctaY0, int tilesW) {
+    const int tx = blockIdx.x * 8 + (threadIdx.x >> 5), ty = ctaY0 + blockIdx.y;
+    if (tx >= tilesW) return;
+    const bool allSky = tileIsSkyWarp(p.inViewZ, tx, ty, [&](float z) { return !inDenoisingRange(cb, unpackViewZ(cb, z)); });
+    if ((threadIdx.x & 31) == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
 }
 
 // Decodes IN_NORMAL_ROUGHNESS + IN_VIEWZ into the geometry plane, one thread per texel. Same arithmetic as the centre set-up of the passes
@@ -570,7 +569,8 @@ bool readMirrorProbe(unsigned long long* out, bool reset) {
 void launchReblurClassifyTiles(const ReblurConstants& cb, const ClassifyTilesParams& p, Rows rows, cudaStream_t stream) {
     const RowGrid g = rowGrid(rows, cb.rectSizeMinusOne[1] + 1, 16);
     if (!g.count) return;
-    launchK(reblurClassifyTilesKernel, dim3((cb.rectSizeMinusOne[0] + 16) / 16, g.count), 256, 0, stream, cb, p, g.ctaY0);
+    const int tilesW = (cb.rectSizeMinusOne[0] + 16) / 16;
+    launchK(reblurClassifyTilesKernel, dim3((tilesW + 7) / 8, g.count), 256, 0, stream, cb, p, g.ctaY0, tilesW);
 }
 // rows [ row0, row1 ) of the plane ( clamped to the rect )
 void launchReblurGeometryPlane(const ReblurConstants& cb, const GeometryPlaneParams& p, int row0, int row1, cudaStream_t stream) {

@@ -200,11 +200,12 @@ template <template <int> class P, int SIGNAL> const P<SIGNAL>& lobeView(const P<
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxClassifyParams p, int ctaY0) {
-    const int tx = blockIdx.x, ty = (blockIdx.y + ctaY0);
-    const int px = tx * 16 + (threadIdx.x & 15), py = ty * 16 + (threadIdx.x >> 4);
-    const int sky = __syncthreads_count(!relaxInRange(cb, fabsf(p.viewZ.load(px, py))));
-    if (threadIdx.x == 0) p.outTiles.store(tx, ty, sky == 256 ? 1.0f : 0.0f);
+// One warp per 16x16 tile, 8 tiles per CTA ( tileIsSkyWarp, common.cuh )
+__global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxClassifyParams p, int ctaY0, int tilesW) {
+    const int tx = blockIdx.x * 8 + (threadIdx.x >> 5), ty = blockIdx.y + ctaY0;
+    if (tx >= tilesW) return;
+    const bool allSky = tileIsSkyWarp(p.viewZ, tx, ty, [&](float z) { return !relaxInRange(cb, fabsf(z)); });
+    if ((threadIdx.x & 31) == 0) p.outTiles.store(tx, ty, allSky ? 1.0f : 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1733,7 +1734,8 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         p.outTiles = b.take<TexR8>(R8);
         if (bad(2)) return (uint32_t)Result::INVALID_ARGUMENT;
         const RowGrid tg = rowGrid(rows, (int)cb.rectSize[1], 16);
-        launchK(relaxClassifyTilesKernel, dim3((cb.rectSize[0] + 15) / 16, tg.count), 256, 0, stream, cb, p, tg.ctaY0);
+        const int tilesW = (cb.rectSize[0] + 15) / 16;
+        launchK(relaxClassifyTilesKernel, dim3((tilesW + 7) / 8, tg.count), 256, 0, stream, cb, p, tg.ctaY0, tilesW);
     } else if (key.pass == RELAX_PREPASS) {
         RelaxPrePassParams p;
         p.tiles = b.take<TexR8>(R8);
