@@ -1509,6 +1509,164 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
     p.outDiff.store(px, py, filteredDiffuse);
 }
 
+// The same pass for the small strides ( STEP = 2, 4 ) with the neighbourhood staged in shared memory: a 32x8 CTA needs ( 32 + 2 STEP ) x ( 8 + 2 STEP ) texels, 1.7x / 2.5x
+// its own pixels, and every one of them is fetched, unpacked ( normal + roughness + material ) and turned into a world position ONCE instead of once per tap that
+// lands on it ( 8 taps per pixel ): ~80 of the ~360 instructions of a tap are that decode. The radiance / SH texels are staged as the raw fp16 words ( converted per
+// tap exactly where the gathering kernel converts what it loaded ), so the tile is 68 B per texel: 29 KB ( STEP 2 ) / 43 KB ( STEP 4 ). The arithmetic per tap is the
+// gathering kernel's, character for character: results are bit-identical. Strides 8 and 16 ( 4.5x / 10x the pixels, random tap offsets ) keep gathering.
+template <bool SH, int SIGNAL, int STEP>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousTiledKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
+    constexpr bool HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0, HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0;
+    constexpr int TW = BLOCK_W + 2 * STEP, TH = BLOCK_H + 2 * STEP;
+    __shared__ float4 sNr[TH][TW], sPosMat[TH][TW];   // { normal, roughness }, { world position, material }
+    __shared__ float sZ[TH][TW];
+    __shared__ uint2 sSpec[HAS_SPEC ? TH : 1][HAS_SPEC ? TW : 1], sDiff[HAS_DIFF ? TH : 1][HAS_DIFF ? TW : 1];
+    __shared__ uint2 sSpecSh[(HAS_SPEC && SH) ? TH : 1][(HAS_SPEC && SH) ? TW : 1], sDiffSh[(HAS_DIFF && SH) ? TH : 1][(HAS_DIFF && SH) ? TW : 1];
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
+    // the CTA covers two 16x16 tiles of one tile row
+    const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
+    if (skyL != 0.0f && skyR != 0.0f) return;
+    {
+        const int baseX = blockIdx.x * BLOCK_W - STEP, baseY = (blockIdx.y + ctaY0) * BLOCK_H - STEP;
+        for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < TW * TH; i += BLOCK_W * BLOCK_H) {
+            const int tx = i % TW, ty = i / TW;
+            // clamped to the rect: a tap outside it has weight 0 and never reads what is staged here for it
+            const int gx = clampi(baseX + tx, 0, cb.rectSize[0] - 1), gy = clampi(baseY + ty, 0, cb.rectSize[1] - 1);
+            float materialID;
+            const float4 nr = unpackNormalRoughness(p.normalRoughness.fetchRaw(gx, gy), materialID);
+            const float z = relaxViewZ(cb, p.viewZ.fetch(gx, gy));
+            sNr[ty][tx] = nr;
+            sZ[ty][tx] = z;
+            sPosMat[ty][tx] = f4(currentWorldPosPixel(cb, gx, gy, z), materialID);
+            if constexpr (HAS_SPEC) sSpec[ty][tx] = p.spec.fetchRaw(gx, gy);
+            if constexpr (HAS_DIFF) sDiff[ty][tx] = p.diff.fetchRaw(gx, gy);
+            if constexpr (HAS_SPEC && SH) sSpecSh[ty][tx] = p.specSh.fetchRaw(gx, gy);
+            if constexpr (HAS_DIFF && SH) sDiffSh[ty][tx] = p.diffSh.fetchRaw(gx, gy);
+        }
+    }
+    __syncthreads();
+    if ((threadIdx.x < 16 ? skyL : skyR) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    const int smx = threadIdx.x + STEP, smy = threadIdx.y + STEP;
+    const float centerViewZ = sZ[smy][smx];
+    if (!relaxInRange(cb, centerViewZ)) return;
+    // the staged texel of a tap / of the centre, decoded like the gathering kernel decodes its loads
+    auto tapSpec = [&](int y, int x) -> float4 { if constexpr (HAS_SPEC) return TexRGBA16F::decode(sSpec[y][x]); else return f4(0.0f); };
+    auto tapDiff = [&](int y, int x) -> float4 { if constexpr (HAS_DIFF) return TexRGBA16F::decode(sDiff[y][x]); else return f4(0.0f); };
+    auto tapSpecSh = [&](int y, int x) -> float3 { if constexpr (HAS_SPEC && SH) return xyz(TexRGBA16F::decode(sSpecSh[y][x])); else return f3(0.0f); };
+    auto tapDiffSh = [&](int y, int x) -> float3 { if constexpr (HAS_DIFF && SH) return xyz(TexRGBA16F::decode(sDiffSh[y][x])); else return f3(0.0f); };
+
+    const float4 centerPosMat = sPosMat[smy][smx];
+    const float centerMaterialID = centerPosMat.w;
+    const float4 centerNormalRoughness = sNr[smy][smx];
+    const float3 centerNormal = xyz(centerNormalRoughness);
+    const float centerRoughness = centerNormalRoughness.w;
+    const float historyLength = 255.0f * p.historyLength.load(px, py);
+    const float stepSize = (float)cb.stepSize;
+    const float kGauss[2] = {0.44198f, 0.27901f};
+
+    float diffuseLobeAngleFraction = (SH ? 1.0f : cb.lobeAngleFraction) / sqrtf(stepSize);  // RELAX_Atrous.cs.hlsl:46-49
+    diffuseLobeAngleFraction = lerp(0.99f, diffuseLobeAngleFraction, saturate(historyLength / 5.0f));
+
+    const float4 centerSpecular = tapSpec(smy, smx);
+    const float centerSpecularLuminance = luminance(xyz(centerSpecular));
+    const float specularPhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, cb.specPhiLuminance * sqrtf(centerSpecular.w));
+    const float2 roughnessWeightP = roughnessWeightParams(centerRoughness, cb.roughnessFraction);
+    const float specularReprojectionConfidence = p.specReprojectionConfidence.load(px, py);
+    float specularLuminanceWeightRelaxation = 1.0f;
+    if (cb.stepSize <= 4) specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, cb.luminanceEdgeStoppingRelaxation);
+    float diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = diffuseLobeAngleFraction, specularLobeAngleFraction = cb.lobeAngleFraction;
+    float diffuseLuminanceWeightRelaxation = 1.0f;
+    if (cb.hasHistoryConfidence) {
+        const float2 pixelUv = make_float2((float)px + 0.5f, (float)py + 0.5f) * make_float2(cb.rectSizeInv[0], cb.rectSizeInv[1]);
+        const float2 rs = confidenceDrivenRelaxation(cb, p.specConfDummy, pixelUv), rd = confidenceDrivenRelaxation(cb, p.diffConfDummy, pixelUv);
+        diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = lerp(diffuseLobeAngleFraction, 1.0f, rs.x);
+        specularLobeAngleFraction = lerp(specularLobeAngleFraction, 1.0f, rs.x);
+        specularLuminanceWeightRelaxation *= 1.0f - rs.y;
+        diffuseLobeAngleFraction = lerp(diffuseLobeAngleFraction, 1.0f, rd.x);
+        diffuseLuminanceWeightRelaxation = 1.0f - rd.y;
+    }
+    const float specularNormalWeightParamSimplified = normalWeightParam2(1.0f, diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight);
+    const float2 specularNormalWeightP = normalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, cb.normalEdgeStoppingRelaxation, specularLobeAngleFraction,
+                                                                  cb.specLobeAngleSlack);
+    float sumWSpecular = 0.44198f * 0.44198f;
+    float4 sumSpecular = centerSpecular * make_float4(sumWSpecular, sumWSpecular, sumWSpecular, sumWSpecular * sumWSpecular);
+    float3 sumSpecularSH = tapSpecSh(smy, smx) * sumWSpecular;
+
+    const float4 centerDiffuse = tapDiff(smy, smx);
+    const float centerDiffuseLuminance = luminance(xyz(centerDiffuse));
+    const float diffusePhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, cb.diffPhiLuminance * sqrtf(centerDiffuse.w));
+    const float diffuseNormalWeightParam = normalWeightParam2(1.0f, diffuseLobeAngleFraction);
+    float sumWDiffuse = 0.44198f * 0.44198f;
+    float4 sumDiffuse = centerDiffuse * make_float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse);
+    float3 sumDiffuseSH = tapDiffSh(smy, smx) * sumWDiffuse;
+
+    const float3 centerWorldPos = xyz(centerPosMat);
+    const float3 centerV = -normalize(centerWorldPos);
+    const float depthThreshold = cb.depthThreshold * (cb.orthoMode == 0.0f ? centerViewZ : 1.0f);
+
+#pragma unroll
+    for (int j = -1; j <= 1; j++)
+#pragma unroll
+        for (int i = -1; i <= 1; i++) {
+            if (i == 0 && j == 0) continue;
+            const int x = px + i * STEP, y = py + j * STEP;
+            const int tx = smx + i * STEP, ty = smy + j * STEP;
+            const bool isInside = x >= 0 && y >= 0 && x < cb.rectSize[0] && y < cb.rectSize[1];
+            const float kernelW = kGauss[i < 0 ? -i : i] * kGauss[j < 0 ? -j : j];
+
+            const float4 samplePosMat = sPosMat[ty][tx];
+            const float sampleMaterialID = samplePosMat.w;
+            const float4 sampleNormalRoughness = sNr[ty][tx];
+            const float3 sampleNormal = xyz(sampleNormalRoughness);
+            const float sampleViewZ = sZ[ty][tx];
+            const float3 sampleWorldPos = xyz(samplePosMat);
+            float geometryW = planeDistanceWeightAtrous(centerWorldPos, centerNormal, sampleWorldPos, depthThreshold);
+            geometryW *= kernelW;
+            geometryW *= (isInside && relaxInRange(cb, sampleViewZ)) ? 1.0f : 0.0f;
+
+            const float3 sampleV = -normalize(sampleWorldPos + cb.roughnessEdgeStoppingRelaxation * centerWorldPos);
+            const float angles = acosApproxPositive(dot(centerNormal, sampleNormal));
+            const float normalWSpecularSimplified = computeWeight(angles, specularNormalWeightParamSimplified, 0.0f);
+            const float normalWSpecular = specularNormalWeightAtrous(specularNormalWeightP, centerNormal, sampleNormal, centerV, sampleV);
+            const float roughnessWSpecular = computeWeight(sampleNormalRoughness.w, roughnessWeightP.x, roughnessWeightP.y);
+            float wSpecular = geometryW * (cb.roughnessEdgeStoppingEnabled ? (normalWSpecular * roughnessWSpecular) : normalWSpecularSimplified);
+            wSpecular *= compareMaterials(sampleMaterialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
+            if (wSpecular > 1e-4f) {
+                const float4 s = tapSpec(ty, tx);
+                float lw = fabsf(centerSpecularLuminance - luminance(xyz(s))) * specularPhiLIlluminationInv;
+                lw = fminf(cb.specMaxLuminanceRelativeDifference, lw);
+                lw *= specularLuminanceWeightRelaxation;
+                wSpecular *= expf(-lw);
+                sumWSpecular += wSpecular;
+                sumSpecular += make_float4(wSpecular, wSpecular, wSpecular, wSpecular * wSpecular) * s;
+                sumSpecularSH += tapSpecSh(ty, tx) * wSpecular;
+            }
+
+            const float normalWDiffuse = computeWeight(angles, diffuseNormalWeightParam, 0.0f);
+            float wDiffuse = geometryW * normalWDiffuse;
+            wDiffuse *= compareMaterials(sampleMaterialID, centerMaterialID, cb.diffMinMaterial) ? 1.0f : 0.0f;
+            if (wDiffuse > 1e-4f) {
+                const float4 s = tapDiff(ty, tx);
+                float lw = fabsf(centerDiffuseLuminance - luminance(xyz(s))) * diffusePhiLIlluminationInv;
+                lw = fminf(cb.diffMaxLuminanceRelativeDifference, lw);
+                lw *= diffuseLuminanceWeightRelaxation;
+                wDiffuse *= expf(-lw);
+                sumWDiffuse += wDiffuse;
+                sumDiffuse += make_float4(wDiffuse, wDiffuse, wDiffuse, wDiffuse * wDiffuse) * s;
+                sumDiffuseSH += tapDiffSh(ty, tx) * wDiffuse;
+            }
+        }
+    const float currHistoryLength = fmaxf(historyLength - 1.0f, 0.0f);
+    float4 filteredSpecular = sumSpecular / make_float4(sumWSpecular, sumWSpecular, sumWSpecular, sumWSpecular * sumWSpecular);
+    if (cb.isLastPass == 1) filteredSpecular = f4(SH ? linearToYCoCg(xyz(filteredSpecular)) : xyz(filteredSpecular), currHistoryLength);   // YCoCg output in SH mode only
+    storeSh<SH>(p.outSpecSh, px, py, sumSpecularSH / sumWSpecular);
+    p.outSpec.store(px, py, filteredSpecular);
+    float4 filteredDiffuse = sumDiffuse / make_float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse);
+    if (cb.isLastPass == 1) filteredDiffuse = f4(SH ? linearToYCoCg(xyz(filteredDiffuse)) : xyz(filteredDiffuse), currHistoryLength);
+    storeSh<SH>(p.outDiffSh, px, py, sumDiffuseSH / sumWDiffuse);
+    p.outDiff.store(px, py, filteredDiffuse);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // RELAX validation overlay ( RELAX_Validation.cs.hlsl:31-212 ): the viewports of the REBLUR overlay that RELAX has data for — normals, roughness, viewZ,
 // motion-vector error, world units + jitter, accumulated frames. See kernels/debug_overlay.cuh for the grid and the captions.
@@ -1903,7 +2061,15 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         if (smem) {
             if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
         } else {
-            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxAtrousKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxAtrousKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
+            // strides 2 and 4: the neighbourhood is staged in shared memory ( relaxAtrousTiledKernel ); larger strides gather
+            auto launchAtrous = [&](auto sh_, auto sig_) {
+                constexpr bool SH_ = decltype(sh_)::value;
+                constexpr int SIG_ = decltype(sig_)::value;
+                if (cb.stepSize == 2) launchK(relaxAtrousTiledKernel<SH_, SIG_, 2>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
+                else if (cb.stepSize == 4) launchK(relaxAtrousTiledKernel<SH_, SIG_, 4>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
+                else launchK(relaxAtrousKernel<SH_, SIG_>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
+            };
+            if (sh) withSignal(signal, [&](auto sig_) { launchAtrous(std::true_type(), sig_); }); else withSignal(signal, [&](auto sig_) { launchAtrous(std::false_type(), sig_); });
         }
     } else {
         err = std::string("no CUDA kernel for shader '") + id + "'";

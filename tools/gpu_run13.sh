@@ -1,6 +1,6 @@
 #!/bin/bash
-mkdir -p gpurun_out/ev3
-O=gpurun_out/ev3
+mkdir -p gpurun_out/ev5
+O=gpurun_out/ev5
 timeout 1200 python -m pytest tests/test_relax_parity_gpu.py tests/test_strips_sigma_relax_gpu.py -q -m gpu > $O/relax_tests.log 2>&1; echo "rc=$?" >> $O/relax_tests.log
 timeout 1200 python -m pytest tests/test_reference_shaders_parity_gpu.py -q -m gpu -k "relax" >> $O/relax_tests.log 2>&1; echo "rc=$?" >> $O/relax_tests.log
 timeout 600 python bench.py --denoiser relax --steps 20 --warmup 5 > $O/bench_relax.json 2> $O/bench_relax.err
@@ -14,4 +14,3 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:rela
 python tools/ncu_summary.py /tmp/relax_full.ncu-rep "relax(TemporalAccumulation|Atrous|PrePass)" > $O/relax_1440p_ncu_summary.txt 2>&1
 python tools/ncu_to_json.py /tmp/relax_full.ncu-rep relax 2560x1440 > $O/ncu_to_json.log 2>&1
 cp profiles/dram_traffic.json profiles/inst_counts.json $O/
-cat $O/ncu_to_json.log
