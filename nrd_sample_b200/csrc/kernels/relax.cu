@@ -10,6 +10,10 @@
 // History clamping and the first a-trous pass stage their 5x5 neighbourhoods in shared memory like the reference (36x12 texels per
 // 32x8 CTA, colour-space conversions / normal decode / world positions done once per texel); the 3x3 of temporal accumulation and
 // anti-firefly go through L1. The arithmetic follows the shaders statement by statement.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "../../../include/nrd_b200.h"
@@ -443,8 +447,26 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
 // OPT: checkerboard resolve speed-up and the application's guide textures ( confidence, threshold mix ); compiled out of the plain kernel
 template <bool SH, bool OPT, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParamsT<SIGNAL> p, int ctaY0) {
+    // Preload( ) of the shader ( RELAX_TemporalAccumulation.cs.hlsl: s_Normal_SpecHitT ): { normal, spec hitT } at the rect-clamped positions of the CTA's 34x10
+    // neighbourhood, unpacked ONCE per texel into shared memory like the reference's group-shared tile. Every pixel reads 11 of them ( the 3x3 plus the two
+    // curvature neighbours again ); decoding per read was ~12 % of the kernel's instructions.
+    constexpr int TA_TILE_W = BLOCK_W + 2, TA_TILE_H = BLOCK_H + 2;
+    __shared__ float4 sNormalHitT[TA_TILE_H][TA_TILE_W];
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
-    if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
+    const int maxX = cb.rectSize[0] - 1, maxY = cb.rectSize[1] - 1;
+    // the CTA covers two 16x16 tiles of one tile row: nothing to do ( and nothing to stage ) when both are sky
+    const float skyL = p.tiles.load((px - (int)threadIdx.x) >> 4, py >> 4), skyR = p.tiles.load((px - (int)threadIdx.x + 16) >> 4, py >> 4);
+    if (skyL != 0.0f && skyR != 0.0f) return;
+    {
+        const int baseX = px - (int)threadIdx.x - 1, baseY = py - (int)threadIdx.y - 1;
+        for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < TA_TILE_W * TA_TILE_H; i += BLOCK_W * BLOCK_H) {
+            const int sx = i % TA_TILE_W, sy = i / TA_TILE_W;
+            const int gx = clampi(baseX + sx, 0, maxX), gy = clampi(baseY + sy, 0, maxY);
+            sNormalHitT[sy][sx] = f4(xyz(unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy))), p.spec.load(gx, gy).w);
+        }
+    }
+    __syncthreads();
+    if ((threadIdx.x < 16 ? skyL : skyR) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float currentLinearZ = relaxViewZ(cb, p.viewZ.load(px, py));
     const uint32_t checkerboard = ((uint32_t)(px ^ py) ^ cb.frameIndex) & 1u;
     if (!relaxInRange(cb, currentLinearZ)) return;
@@ -454,12 +476,8 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
     const float2 resolutionScalePrev = rectSizePrev * resourceSizeInvPrev;
     const float3 cameraDelta = make_float3(cb.cameraDelta[0], cb.cameraDelta[1], cb.cameraDelta[2]);
     const float minRectDim = (float)min(cb.rectSize[0], cb.rectSize[1]);
-    const int maxX = cb.rectSize[0] - 1, maxY = cb.rectSize[1] - 1;
-    // Preload( ) of the shader: { normal, spec hitT } at the rect-clamped position
-    auto preload = [&](int x, int y) -> float4 {
-        const int gx = clampi(x, 0, maxX), gy = clampi(y, 0, maxY);
-        return f4(xyz(unpackNormalRoughness(p.normalRoughness.loadRaw(gx, gy))), p.spec.load(gx, gy).w);
-    };
+    // ( px + dx, py + dy ) with dx, dy in -1..1: the staged texel ( clamped to the rect while staging, like the per-read clamp it replaces )
+    auto preload = [&](int x, int y) -> float4 { return sNormalHitT[y - py + (int)threadIdx.y + 1][x - px + (int)threadIdx.x + 1]; };
 
     float currentMaterialID;
     const float4 currentNormalRoughness = unpackNormalRoughness(p.normalRoughness.loadRaw(px, py), currentMaterialID);
@@ -1509,25 +1527,98 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
     p.outDiff.store(px, py, filteredDiffuse);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA ( cp.async.bulk.tensor ) for the tiles that are staged RAW. The radiance / SH neighbourhoods of the tiled a-trous kernel are the textures' own fp16 words
+// ( they are converted per tap, where the gathering kernel converts what it loaded ), so one elected thread asks the TMA unit for the ( 32 + 2 STEP ) x ( 8 + 2 STEP )
+// box of each of the four RGBA16F textures and the other 255 threads spend no LDG / address / STS instructions on them; the boxes land while the CTA decodes the
+// { normal, roughness } / { world position, material } / viewZ arrays, which cannot come from TMA ( they are computed, not copied ). Texels of a box outside the
+// texture are zero-filled instead of clamped: a tap outside the rect has weight 0 and never reads them. A tensor map describes one texture as 2 x width uint32
+// elements per row ( an RGBA16F texel = two of them ); it is a kernel PARAMETER like the views, so cached CUDA graphs patch it per frame like everything else.
+struct alignas(64) RelaxAtrousTma { CUtensorMap spec, diff, specSh, diffSh; };
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn tensorMapEncoder() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            f = nullptr;
+        }
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+// false: the texture cannot be described ( base not 16-byte aligned, pitch not a multiple of 16 bytes ) or the driver has no encoder — the caller keeps the LDG staging
+inline bool encodeRgba16fBox(CUtensorMap& map, const TexView& t, int boxW, int boxH) {
+    EncodeTiledFn encode = tensorMapEncoder();
+    if (!encode || !t.data || ((uintptr_t)t.data & 15u) != 0 || ((size_t)t.pitch * 8u) % 16u != 0 || t.w <= 0 || t.h <= 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)t.w * 2u, (cuuint64_t)t.h};
+    const cuuint64_t strides[1] = {(cuuint64_t)t.pitch * 8u};
+    const cuuint32_t box[2] = {(cuuint32_t)boxW * 2u, (cuuint32_t)boxH}, elem[2] = {1u, 1u};
+    return encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, t.data, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+NRD_DEV uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+NRD_DEV void mbarrierInit(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // the async proxy ( TMA ) must see the initialised barrier
+}
+NRD_DEV void mbarrierExpectTx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory"); }
+NRD_DEV void mbarrierWait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred done;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
+        "@done bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smemAddr(bar)), "r"(parity)
+        : "memory");
+}
+// box of `map` whose first element is ( x, y ) — in uint32 elements / rows, may be negative or reach past the texture — into shared memory at dst ( 128-byte aligned )
+NRD_DEV void tmaLoadBox2D(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smemAddr(dst)), "l"(map), "r"(smemAddr(bar)), "r"(x), "r"(y)
+                 : "memory");
+}
+
 // The same pass for the small strides ( STEP = 2, 4 ) with the neighbourhood staged in shared memory: a 32x8 CTA needs ( 32 + 2 STEP ) x ( 8 + 2 STEP ) texels, 1.7x / 2.5x
 // its own pixels, and every one of them is fetched, unpacked ( normal + roughness + material ) and turned into a world position ONCE instead of once per tap that
 // lands on it ( 8 taps per pixel ): ~80 of the ~360 instructions of a tap are that decode. The radiance / SH texels are staged as the raw fp16 words ( converted per
 // tap exactly where the gathering kernel converts what it loaded ), so the tile is 68 B per texel: 29 KB ( STEP 2 ) / 43 KB ( STEP 4 ). The arithmetic per tap is the
 // gathering kernel's, character for character: results are bit-identical. Strides 8 and 16 ( 4.5x / 10x the pixels, random tap offsets ) keep gathering.
-template <bool SH, int SIGNAL, int STEP>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousTiledKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
+// TMA: the four raw planes arrive through cp.async.bulk.tensor ( above ) instead of LDG + STS
+template <bool SH, int SIGNAL, int STEP, bool TMA>
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousTiledKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0,
+                                                                                                      const __grid_constant__ RelaxAtrousTma tma) {
     constexpr bool HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0, HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0;
     constexpr int TW = BLOCK_W + 2 * STEP, TH = BLOCK_H + 2 * STEP;
+    static_assert((TW * TH * 8) % 128 == 0, "a TMA box lands on a 128-byte aligned address");
     __shared__ float4 sNr[TH][TW], sPosMat[TH][TW];   // { normal, roughness }, { world position, material }
     __shared__ float sZ[TH][TW];
-    __shared__ uint2 sSpec[HAS_SPEC ? TH : 1][HAS_SPEC ? TW : 1], sDiff[HAS_DIFF ? TH : 1][HAS_DIFF ? TW : 1];
-    __shared__ uint2 sSpecSh[(HAS_SPEC && SH) ? TH : 1][(HAS_SPEC && SH) ? TW : 1], sDiffSh[(HAS_DIFF && SH) ? TH : 1][(HAS_DIFF && SH) ? TW : 1];
+    __shared__ alignas(128) uint2 sSpec[HAS_SPEC ? TH : 1][HAS_SPEC ? TW : 1];
+    __shared__ alignas(128) uint2 sDiff[HAS_DIFF ? TH : 1][HAS_DIFF ? TW : 1];
+    __shared__ alignas(128) uint2 sSpecSh[(HAS_SPEC && SH) ? TH : 1][(HAS_SPEC && SH) ? TW : 1];
+    __shared__ alignas(128) uint2 sDiffSh[(HAS_DIFF && SH) ? TH : 1][(HAS_DIFF && SH) ? TW : 1];
+    __shared__ uint64_t sTmaBar;
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     // the CTA covers two 16x16 tiles of one tile row
     const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
     if (skyL != 0.0f && skyR != 0.0f) return;
     {
         const int baseX = blockIdx.x * BLOCK_W - STEP, baseY = (blockIdx.y + ctaY0) * BLOCK_H - STEP;
+        if constexpr (TMA) {
+            if (threadIdx.x == 0 && threadIdx.y == 0) {
+                constexpr uint32_t kPlanes = (HAS_SPEC ? 1u : 0u) + (HAS_DIFF ? 1u : 0u) + ((HAS_SPEC && SH) ? 1u : 0u) + ((HAS_DIFF && SH) ? 1u : 0u);
+                mbarrierInit(&sTmaBar, 1u);
+                mbarrierExpectTx(&sTmaBar, kPlanes * (uint32_t)(TW * TH * 8));
+                if constexpr (HAS_SPEC) tmaLoadBox2D(&sSpec[0][0], &tma.spec, baseX * 2, baseY, &sTmaBar);
+                if constexpr (HAS_DIFF) tmaLoadBox2D(&sDiff[0][0], &tma.diff, baseX * 2, baseY, &sTmaBar);
+                if constexpr (HAS_SPEC && SH) tmaLoadBox2D(&sSpecSh[0][0], &tma.specSh, baseX * 2, baseY, &sTmaBar);
+                if constexpr (HAS_DIFF && SH) tmaLoadBox2D(&sDiffSh[0][0], &tma.diffSh, baseX * 2, baseY, &sTmaBar);
+            }
+        }
         for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < TW * TH; i += BLOCK_W * BLOCK_H) {
             const int tx = i % TW, ty = i / TW;
             // clamped to the rect: a tap outside it has weight 0 and never reads what is staged here for it
@@ -1538,13 +1629,17 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
             sNr[ty][tx] = nr;
             sZ[ty][tx] = z;
             sPosMat[ty][tx] = f4(currentWorldPosPixel(cb, gx, gy, z), materialID);
-            if constexpr (HAS_SPEC) sSpec[ty][tx] = p.spec.fetchRaw(gx, gy);
-            if constexpr (HAS_DIFF) sDiff[ty][tx] = p.diff.fetchRaw(gx, gy);
-            if constexpr (HAS_SPEC && SH) sSpecSh[ty][tx] = p.specSh.fetchRaw(gx, gy);
-            if constexpr (HAS_DIFF && SH) sDiffSh[ty][tx] = p.diffSh.fetchRaw(gx, gy);
+            if constexpr (!TMA) {
+                if constexpr (HAS_SPEC) sSpec[ty][tx] = p.spec.fetchRaw(gx, gy);
+                if constexpr (HAS_DIFF) sDiff[ty][tx] = p.diff.fetchRaw(gx, gy);
+                if constexpr (HAS_SPEC && SH) sSpecSh[ty][tx] = p.specSh.fetchRaw(gx, gy);
+                if constexpr (HAS_DIFF && SH) sDiffSh[ty][tx] = p.diffSh.fetchRaw(gx, gy);
+            }
         }
     }
     __syncthreads();
+    // every thread waits for the boxes, also the ones about to return: the CTA's shared memory must not be handed to the next CTA with a copy in flight
+    if constexpr (TMA) mbarrierWait(&sTmaBar, 0u);
     if ((threadIdx.x < 16 ? skyL : skyR) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const int smx = threadIdx.x + STEP, smy = threadIdx.y + STEP;
     const float centerViewZ = sZ[smy][smx];
@@ -2065,8 +2160,24 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
             auto launchAtrous = [&](auto sh_, auto sig_) {
                 constexpr bool SH_ = decltype(sh_)::value;
                 constexpr int SIG_ = decltype(sig_)::value;
-                if (cb.stepSize == 2) launchK(relaxAtrousTiledKernel<SH_, SIG_, 2>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
-                else if (cb.stepSize == 4) launchK(relaxAtrousTiledKernel<SH_, SIG_, 4>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
+                if (cb.stepSize == 2 || cb.stepSize == 4) {
+                    // the raw planes through TMA when every bound plane can be described by a tensor map ( NRD_B200_RELAX_TMA=0: A/B switch of the benchmarks )
+                    constexpr bool HAS_SPEC_ = (SIG_ & SIGNAL_SPEC) != 0, HAS_DIFF_ = (SIG_ & SIGNAL_DIFF) != 0;
+                    static const bool tmaWanted = !(getenv("NRD_B200_RELAX_TMA") && getenv("NRD_B200_RELAX_TMA")[0] == '0');
+                    const int step = (int)cb.stepSize, boxW = BLOCK_W + 2 * step, boxH = BLOCK_H + 2 * step;
+                    RelaxAtrousTma tma;
+                    memset(&tma, 0, sizeof(tma));
+                    bool useTma = tmaWanted;
+                    if (useTma && HAS_SPEC_) useTma = encodeRgba16fBox(tma.spec, p.spec, boxW, boxH) && (!SH_ || encodeRgba16fBox(tma.specSh, p.specSh, boxW, boxH));
+                    if (useTma && HAS_DIFF_) useTma = encodeRgba16fBox(tma.diff, p.diff, boxW, boxH) && (!SH_ || encodeRgba16fBox(tma.diffSh, p.diffSh, boxW, boxH));
+                    if (step == 2) {
+                        if (useTma) launchK(relaxAtrousTiledKernel<SH_, SIG_, 2, true>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
+                        else launchK(relaxAtrousTiledKernel<SH_, SIG_, 2, false>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
+                    } else {
+                        if (useTma) launchK(relaxAtrousTiledKernel<SH_, SIG_, 4, true>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
+                        else launchK(relaxAtrousTiledKernel<SH_, SIG_, 4, false>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
+                    }
+                }
                 else launchK(relaxAtrousKernel<SH_, SIG_>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
             };
             if (sh) withSignal(signal, [&](auto sig_) { launchAtrous(std::true_type(), sig_); }); else withSignal(signal, [&](auto sig_) { launchAtrous(std::false_type(), sig_); });
