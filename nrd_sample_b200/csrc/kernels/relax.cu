@@ -12,6 +12,7 @@
 // anti-firefly go through L1. The arithmetic follows the shaders statement by statement.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -930,31 +931,53 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const 
 // ---------------------------------------------------------------------------------------------------------------
 // History clamping: the 5x5 neighbourhood of { responsive history in YCoCg, validity } and { noisy input, luminance^2 } lives in shared
 // memory (36x12 texels per 32x8 CTA), converted once per texel instead of once per tap.
-constexpr int HC_BORDER = 2, HC_TILE_W = BLOCK_W + 2 * HC_BORDER, HC_TILE_H = BLOCK_H + 2 * HC_BORDER;
+// The pass is bound by shared-memory bandwidth, not by arithmetic or DRAM: 25 taps x 2 lobes x 2 LDS.128 per pixel are ~160 us of LDS wavefronts per 1440p frame on
+// their own. So a thread owns HC_ROWS vertically adjacent pixels: their 5x5 windows overlap in 5 x ( HC_ROWS + 4 ) texels, every staged texel is read once per
+// thread and added to the sums of each pixel whose window holds it ( 30 tap reads instead of 50 for two pixels ). Each pixel still adds its 25 taps in the
+// shader's order ( dx outer, dy inner ), so its sums — and everything after them — are bit for bit what one thread per pixel computed.
+constexpr int HC_BORDER = 2, HC_ROWS = 2, HC_PIXELS_H = BLOCK_H * HC_ROWS, HC_TILE_W = BLOCK_W + 2 * HC_BORDER, HC_TILE_H = HC_PIXELS_H + 2 * HC_BORDER;
 
-// One lobe (the specular and diffuse halves of the shader differ in three constants only)
+// One lobe (the specular and diffuse halves of the shader differ in three constants only) for the HC_ROWS pixels ( px, py0 + r ) of a thread; active[ r ]: the
+// pixel is processed ( inside the rect / strip, not sky, in range )
 template <bool SPEC, bool SH, class TEX>
-NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)[HC_TILE_W], const float4 (*sNoisy)[HC_TILE_W], int px, int py, float historyLength,
+NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)[HC_TILE_W], const float4 (*sNoisy)[HC_TILE_W], int px, int py0, const bool* active, const float* historyLengths,
                                  const TEX& slowTex, const TEX& fastTex, const TEX& shTex, const TEX& shFastTex, const TEX& outSlow,
                                  const TEX& outFast, const TEX& outSh, const TEX& outShFast, float maxFast, float maxSlow) {
-    const int sx = threadIdx.x + HC_BORDER, sy = threadIdx.y + HC_BORDER;
-    float3 m1 = f3(0.0f), m2 = f3(0.0f), noisyM1 = f3(0.0f);
-    float noisyM2 = 0.0f, sum = 0.0f;
+    const int sx = threadIdx.x + HC_BORDER, sy0 = threadIdx.y * HC_ROWS + HC_BORDER;
+    float3 m1s[HC_ROWS], m2s[HC_ROWS], noisyM1s[HC_ROWS];
+    float noisyM2s[HC_ROWS], sums[HC_ROWS];
+#pragma unroll
+    for (int r = 0; r < HC_ROWS; r++) {
+        m1s[r] = m2s[r] = noisyM1s[r] = f3(0.0f);
+        noisyM2s[r] = sums[r] = 0.0f;
+    }
 #pragma unroll
     for (int dx = -2; dx <= 2; dx++)
 #pragma unroll
-        for (int dy = -2; dy <= 2; dy++) {
-            const float4 f = sFast[sy + dy][sx + dx];
+        for (int row = -2; row <= HC_ROWS + 1; row++) {   // tile row sy0 + row: tap dy = row - r of pixel r
+            const float4 f = sFast[sy0 + row][sx + dx];
+            const float4 n = sNoisy[sy0 + row][sx + dx];
             if (f.w != 0.0f) {
-                const float3 c = xyz(f);
-                m1 += c;
-                m2 += c * c;
-                const float4 n = sNoisy[sy + dy][sx + dx];
-                noisyM1 += xyz(n);
-                noisyM2 += n.w;
-                sum += 1.0f;
+                const float3 c = xyz(f), c2 = c * c;
+#pragma unroll
+                for (int r = 0; r < HC_ROWS; r++)
+                    if (row - r >= -2 && row - r <= 2) {
+                        m1s[r] += c;
+                        m2s[r] += c2;
+                        noisyM1s[r] += xyz(n);
+                        noisyM2s[r] += n.w;
+                        sums[r] += 1.0f;
+                    }
             }
         }
+#pragma unroll
+    for (int r = 0; r < HC_ROWS; r++) {
+    if (!active[r]) continue;
+    const int py = py0 + r, sy = sy0 + r;
+    const float historyLength = historyLengths[r];
+    float3 m1 = m1s[r], m2 = m2s[r], noisyM1 = noisyM1s[r];
+    float noisyM2 = noisyM2s[r];
+    const float sum = sums[r];
     m1 = m1 / sum;
     m2 = m2 / sum;
     noisyM1 = noisyM1 / sum;
@@ -1015,17 +1038,19 @@ NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)
     const float3 sh = loadSh<SH>(shTex, px, py), shFast = loadSh<SH>(shFastTex, px, py);
     storeSh<SH>(outSh, px, py, lerp(sh, shFast, clampingFactor));
     storeSh<SH>(outShFast, px, py, shFast);
+    }
 }
 
+// ctaY0: first CTA row in units of HC_PIXELS_H ( = 16 ) pixel rows; rowEnd: end of the strip ( or of the rect )
 template <bool SH, int SIGNAL>
-__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParamsT<SIGNAL> p, int ctaY0) {
+__global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParamsT<SIGNAL> p, int ctaY0, int rowEnd) {
     __shared__ float4 sSpecFast[HC_TILE_H][HC_TILE_W], sSpecNoisy[HC_TILE_H][HC_TILE_W], sDiffFast[HC_TILE_H][HC_TILE_W], sDiffNoisy[HC_TILE_H][HC_TILE_W];
-    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
+    const int px = blockIdx.x * BLOCK_W + threadIdx.x, py0 = (blockIdx.y + ctaY0) * HC_PIXELS_H + threadIdx.y * HC_ROWS;
     // the CTA covers two 16x16 tiles of one tile row
-    const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py >> 4);
+    const float skyL = p.tiles.load((blockIdx.x * BLOCK_W) >> 4, py0 >> 4), skyR = p.tiles.load((blockIdx.x * BLOCK_W + 16) >> 4, py0 >> 4);
     if (skyL != 0.0f && skyR != 0.0f) return;
     {
-        const int baseX = blockIdx.x * BLOCK_W - HC_BORDER, baseY = (blockIdx.y + ctaY0) * BLOCK_H - HC_BORDER;
+        const int baseX = blockIdx.x * BLOCK_W - HC_BORDER, baseY = (blockIdx.y + ctaY0) * HC_PIXELS_H - HC_BORDER;
         const int maxX = cb.rectSize[0] - 1, maxY = cb.rectSize[1] - 1;
         for (int i = threadIdx.y * BLOCK_W + threadIdx.x; i < HC_TILE_W * HC_TILE_H; i += BLOCK_W * BLOCK_H) {
             const int tx = i % HC_TILE_W, ty = i / HC_TILE_W;
@@ -1041,14 +1066,25 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(c
     }
     __syncthreads();
     const float isSky = threadIdx.x < 16 ? skyL : skyR;
-    if (isSky != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
-    if (sSpecFast[threadIdx.y + HC_BORDER][threadIdx.x + HC_BORDER].w == 0.0f) return;
-    const float historyLength = 255.0f * p.historyLength.load(px, py);
-    historyClampingLobe<true, SH>(cb, sSpecFast, sSpecNoisy, px, py, historyLength, p.spec, p.specFast, p.specSh, p.specShFast, p.outSpec, p.outSpecFast, p.outSpecSh, p.outSpecShFast,
+    if (isSky != 0.0f || px >= cb.rectSize[0]) return;
+    bool active[HC_ROWS];
+    float historyLengths[HC_ROWS];
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < HC_ROWS; r++) {
+        // ( the validity flag of the staged centre texel: viewZ in the denoising range )
+        active[r] = py0 + r < rowEnd && py0 + r < cb.rectSize[1] && sSpecFast[threadIdx.y * HC_ROWS + r + HC_BORDER][threadIdx.x + HC_BORDER].w != 0.0f;
+        historyLengths[r] = active[r] ? 255.0f * p.historyLength.load(px, py0 + r) : 0.0f;
+        any = any || active[r];
+    }
+    if (!any) return;
+    historyClampingLobe<true, SH>(cb, sSpecFast, sSpecNoisy, px, py0, active, historyLengths, p.spec, p.specFast, p.specSh, p.specShFast, p.outSpec, p.outSpecFast, p.outSpecSh, p.outSpecShFast,
                               cb.specMaxFastAccumulatedFrameNum, cb.specMaxAccumulatedFrameNum);
-    historyClampingLobe<false, SH>(cb, sDiffFast, sDiffNoisy, px, py, historyLength, p.diff, p.diffFast, p.diffSh, p.diffShFast, p.outDiff, p.outDiffFast, p.outDiffSh, p.outDiffShFast,
+    historyClampingLobe<false, SH>(cb, sDiffFast, sDiffNoisy, px, py0, active, historyLengths, p.diff, p.diffFast, p.diffSh, p.diffShFast, p.outDiff, p.outDiffFast, p.outDiffSh, p.outDiffShFast,
                                cb.diffMaxFastAccumulatedFrameNum, cb.diffMaxAccumulatedFrameNum);
-    p.outHistoryLength.store(px, py, historyLength / 255.0f);
+#pragma unroll
+    for (int r = 0; r < HC_ROWS; r++)
+        if (active[r]) p.outHistoryLength.store(px, py0 + r, historyLengths[r] / 255.0f);
 }
 
 template <int SIGNAL>
@@ -2082,7 +2118,11 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         TexRGBA16F* outsSh[4] = {&p.outSpecSh, &p.outDiffSh, &p.outSpecShFast, &p.outDiffShFast};
         for (int i = 0; i < 4; i++) (i & 1) ? takeShD(*outsSh[i]) : takeShS(*outsSh[i]);
         if (bad(4 + (5 + 4 * shOn) * lobes)) return (uint32_t)Result::INVALID_ARGUMENT;
-        if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
+        // 32x16 pixels per CTA ( two rows per thread ); strips begin on multiples of 16 rows
+        const RowGrid rgHc = rowGrid(rows, (int)cb.rectSize[1], HC_PIXELS_H);
+        const dim3 gridHc(pixelGrid.x, rgHc.count);
+        const int rowEnd = std::min(rows.end, (int)cb.rectSize[1]);
+        if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<true, decltype(sig_)::value>, gridHc, block, 0, stream, cb, lobeView(p, sig_), rgHc.ctaY0, rowEnd); }); else withSignal(signal, [&](auto sig_) { launchK(relaxHistoryClampingKernel<false, decltype(sig_)::value>, gridHc, block, 0, stream, cb, lobeView(p, sig_), rgHc.ctaY0, rowEnd); });
     } else if (key.pass == RELAX_HITDIST_RECONSTRUCTION) {
         RelaxHitDistReconstructionParams p;
         p.tiles = b.take<TexR8>(R8);
