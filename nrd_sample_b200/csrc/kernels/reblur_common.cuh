@@ -270,6 +270,29 @@ struct HistoryFilter {
     template <class TEX> NRD_DEV auto color(const TEX& tex) const -> decltype(tex.fetchClamped(0, 0)) {
         const int x0 = tex.cx(ox), x1 = tex.cx(ox + 1), y0 = tex.cy(oy), y1 = tex.cy(oy + 1);
         decltype(tex.fetchClamped(0, 0)) c;
+#ifdef HF_FETCH_ALL
+        {
+            // all 12 texels are requested before the filter is chosen ( see the RGBA16F overload )
+            using T = decltype(tex.fetchClamped(0, 0));
+            const int xm = tex.cx(ox - 1), x2 = tex.cx(ox + 2), ym = tex.cy(oy - 1), y2 = tex.cy(oy + 2);
+            const T t00 = tex.fetch(x0, y0), t10 = tex.fetch(x1, y0), t01 = tex.fetch(x0, y1), t11 = tex.fetch(x1, y1);
+            const T a0 = tex.fetch(x0, ym), a1 = tex.fetch(x1, ym), b0 = tex.fetch(xm, y0), b1 = tex.fetch(xm, y1);
+            const T d0 = tex.fetch(x2, y0), d1 = tex.fetch(x2, y1), e0 = tex.fetch(x0, y2), e1 = tex.fetch(x1, y2);
+            if (bicubic) {
+                c = lerp(a0, a1, tc.x) * w.x;
+                c += lerp(b0, b1, tc.y) * w.y;
+                c += lerp(lerp(t00, t10, tc.x), lerp(t01, t11, tc.x), tc.y) * w.z;
+                c += lerp(d0, d1, tc.y) * w.w;
+                c += lerp(e0, e1, tc.x) * w4;
+            } else {
+                c = t00 * w.x;
+                c += t10 * w.y;
+                c += t01 * w.z;
+                c += t11 * w.w;
+            }
+            return sum < 0.0001f ? c * 0.0f : c / sum;
+        }
+#endif
         if (bicubic) {
             const int xm = tex.cx(ox - 1), x2 = tex.cx(ox + 2), ym = tex.cy(oy - 1), y2 = tex.cy(oy + 2);
             c = lerp(tex.fetch(x0, ym), tex.fetch(x1, ym), tc.x) * w.x;
@@ -323,6 +346,42 @@ struct HistoryFilter {
     NRD_DEV float4 color(const TexRGBA16F& tex) const {
         const int x0 = tex.cx(ox), x1 = tex.cx(ox + 1), y0 = tex.cy(oy), y1 = tex.cy(oy + 1);
         Px c;
+#ifdef HF_FETCH_ALL
+        {
+            // The 12 texels of the Catmull-Rom footprint are requested BEFORE the filter is chosen: with the loads inside the two branches nothing of a later
+            // fetch could be issued until the branch of the one before it had been taken ( the kernels that call this wait on memory latency ). The bilinear
+            // fallback ( disoccluded footprints, a few percent of the pixels ) reads 8 texels it does not use; the arithmetic of both branches is unchanged.
+            const int xm = tex.cx(ox - 1), x2 = tex.cx(ox + 2), ym = tex.cy(oy - 1), y2 = tex.cy(oy + 2);
+            const uint2 r00 = tex.fetchRaw(x0, y0), r10 = tex.fetchRaw(x1, y0), r01 = tex.fetchRaw(x0, y1), r11 = tex.fetchRaw(x1, y1);
+            const uint2 ra0 = tex.fetchRaw(x0, ym), ra1 = tex.fetchRaw(x1, ym), rb0 = tex.fetchRaw(xm, y0), rb1 = tex.fetchRaw(xm, y1);
+            const uint2 rd0 = tex.fetchRaw(x2, y0), rd1 = tex.fetchRaw(x2, y1), re0 = tex.fetchRaw(x0, y2), re1 = tex.fetchRaw(x1, y2);
+            auto dec = [](uint2 raw) -> Px { return {P2(__half22float2(*reinterpret_cast<const __half2*>(&raw.x))), P2(__half22float2(*reinterpret_cast<const __half2*>(&raw.y)))}; };
+            if (bicubic) {
+                Px t = lerpPx(dec(ra0), dec(ra1), tc.x);
+                c = {t.lo * w.x, t.hi * w.x};
+                t = lerpPx(dec(rb0), dec(rb1), tc.y);
+                c = {fma2(t.lo, w.y, c.lo), fma2(t.hi, w.y, c.hi)};
+                t = lerpPx(lerpPx(dec(r00), dec(r10), tc.x), lerpPx(dec(r01), dec(r11), tc.x), tc.y);
+                c = {fma2(t.lo, w.z, c.lo), fma2(t.hi, w.z, c.hi)};
+                t = lerpPx(dec(rd0), dec(rd1), tc.y);
+                c = {fma2(t.lo, w.w, c.lo), fma2(t.hi, w.w, c.hi)};
+                t = lerpPx(dec(re0), dec(re1), tc.x);
+                c = {fma2(t.lo, w4, c.lo), fma2(t.hi, w4, c.hi)};
+            } else {
+                Px t = dec(r00);
+                c = {t.lo * w.x, t.hi * w.x};
+                t = dec(r10);
+                c = {fma2(t.lo, w.y, c.lo), fma2(t.hi, w.y, c.hi)};
+                t = dec(r01);
+                c = {fma2(t.lo, w.z, c.lo), fma2(t.hi, w.z, c.hi)};
+                t = dec(r11);
+                c = {fma2(t.lo, w.w, c.lo), fma2(t.hi, w.w, c.hi)};
+            }
+            const float k = sum < 0.0001f ? 0.0f : 1.0f / sum;
+            c = {c.lo * k, c.hi * k};
+            return make_float4(c.lo.a(), c.lo.b(), c.hi.a(), c.hi.b());
+        }
+#endif
         if (bicubic) {
             const int xm = tex.cx(ox - 1), x2 = tex.cx(ox + 2), ym = tex.cy(oy - 1), y2 = tex.cy(oy + 2);
             Px t = lerpPx(px(tex, x0, ym), px(tex, x1, ym), tc.x);
