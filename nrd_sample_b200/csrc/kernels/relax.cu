@@ -12,6 +12,8 @@
 // anti-firefly go through L1. The arithmetic follows the shaders statement by statement.
 #include <cuda.h>
 
+#define HF_FETCH_ALL   // reblur_common.cuh: HistoryFilter requests the whole footprint before it branches ( measured neutral for REBLUR / SIGMA, -8 us here )
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -736,8 +738,11 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
                                              tapValid(1, 1, zr.w, thr.w, prevMaterialIDs.w));
         const bool anyValid = tapsValid.x != 0.0f || tapsValid.y != 0.0f || tapsValid.z != 0.0f || tapsValid.w != 0.0f;
         const bool allValid = tapsValid.x != 0.0f && tapsValid.y != 0.0f && tapsValid.z != 0.0f && tapsValid.w != 0.0f;
-#ifdef RELAX_TA_VMB_UNCOND
-        constexpr bool kVmbAlways = true;   // fetch the virtual-motion history with the validity gathers in flight; an invalid footprint falls back to the defaults below
+        // The virtual-motion history is fetched with the validity gathers still in flight instead of behind their outcome ( the shader's `if( any valid )` ): an
+        // invalid footprint takes the defaults below, as before. With the history filter requesting its 12 texels ahead of its bicubic / bilinear choice
+        // ( HF_FETCH_ALL ) one memory round trip leaves the dependent chain: 556 -> 543 us per 1440p frame, results unchanged.
+#ifndef RELAX_TA_VMB_COND
+        constexpr bool kVmbAlways = true;
 #else
         constexpr bool kVmbAlways = false;
 #endif
@@ -2226,9 +2231,10 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
                 constexpr bool SH_ = decltype(sh_)::value;
                 constexpr int SIG_ = decltype(sig_)::value;
                 if (cb.stepSize == 2 || cb.stepSize == 4) {
-                    // the raw planes through TMA when every bound plane can be described by a tensor map ( NRD_B200_RELAX_TMA=0: A/B switch of the benchmarks )
+                    // the raw planes through TMA when every bound plane can be described by a tensor map ( NRD_B200_RELAX_TMA=0: A/B switch of the benchmarks and of tests/test_relax_tma_gpu.py )
                     constexpr bool HAS_SPEC_ = (SIG_ & SIGNAL_SPEC) != 0, HAS_DIFF_ = (SIG_ & SIGNAL_DIFF) != 0;
-                    static const bool tmaWanted = !(getenv("NRD_B200_RELAX_TMA") && getenv("NRD_B200_RELAX_TMA")[0] == '0');
+                    const char* tmaEnv = getenv("NRD_B200_RELAX_TMA");   // read per dispatch: tests flip it inside one process
+                    const bool tmaWanted = !(tmaEnv && tmaEnv[0] == '0');
                     const int step = (int)cb.stepSize, boxW = BLOCK_W + 2 * step, boxH = BLOCK_H + 2 * step;
                     RelaxAtrousTma tma;
                     memset(&tma, 0, sizeof(tma));
