@@ -7,9 +7,10 @@
 // RELAX_Copy.cs.hlsl:21-34, RELAX_AntiFirefly.cs.hlsl:21-216, RELAX_AtrousSmem.cs.hlsl:21-484, RELAX_Atrous.cs.hlsl:21-260,
 // RELAX_SplitScreen.cs.hlsl:21-62, helpers RELAX_Common.hlsli:11-185. Build switches of the reference's default build
 // (NRD_USE_PREV_WORLD_SPACE_MATRIX = 0); checkerboard modes, history-confidence and disocclusion-threshold-mix inputs included.
-// History clamping and the first a-trous pass stage their 5x5 neighbourhoods in shared memory like the reference (36x12 texels per
-// 32x8 CTA, colour-space conversions / normal decode / world positions done once per texel); the 3x3 of temporal accumulation and
-// anti-firefly go through L1. The arithmetic follows the shaders statement by statement.
+// History clamping ( 36x20 texels per 32x16 pixels, two rows per thread ), the first a-trous pass ( 36x12 ) and the a-trous passes of strides 2 and 4 stage
+// their neighbourhoods in shared memory like the reference — colour-space conversions / normal decode / world positions done once per texel, the raw fp16 planes
+// of the tiled a-trous passes through TMA — and so does temporal accumulation for its 3x3 of { normal, hitT } ( 34x10 ); anti-firefly goes through L1. The
+// arithmetic follows the shaders statement by statement.
 #include <cuda.h>
 
 #define HF_FETCH_ALL   // reblur_common.cuh: HistoryFilter requests the whole footprint before it branches ( measured neutral for REBLUR / SIGMA, -8 us here )
