@@ -542,6 +542,7 @@ uint32_t dispatchResolved(const nrdk::PipelineKey& key, const void* constants, u
 namespace nrdk {
 thread_local GraphReplay* g_graphReplay = nullptr;
 thread_local GraphRecord* g_graphRecord = nullptr;
+thread_local bool g_pdlAllowed = false;   // launchK may launch with programmatic stream serialization: whole frames of a context that is not a strip of a tiled frame
 void countLaunch() { g_launchCount.fetch_add(1, std::memory_order_relaxed); }  // kernels launched by frontend.cu
 }
 
@@ -1065,6 +1066,12 @@ NRDCU_API uint32_t nrdcuDenoiseRows(nrdcuContext* ctx, const uint32_t* identifie
         PlaneScope(GeomPlane* p) { g_plane = p; }
         ~PlaneScope() { g_plane = nullptr; }
     } planeScope(&ctx->plane);
+    // programmatic dependent launches for the frame of a stand-alone context; strips ( seam kernels on a second stream, flag / wait kernels of the peer exchange
+    // between the passes ) and the context-less nrdcuDispatch keep plain stream serialization
+    struct PdlScope {
+        PdlScope(bool on) { nrdk::g_pdlAllowed = on; }
+        ~PdlScope() { nrdk::g_pdlAllowed = false; }
+    } pdlScope(!ctx->tile.attached);
     // SIGMA's Copy pass rides in its first blur pass while a context runs the frame ( kernels/sigma.cu ); per-dispatch callers and strips get every pass on its own
     struct SigmaFusionScope {
         SigmaFusionScope(bool on) { nrdk::sigmaSetCopyFusion(on); }

@@ -10,6 +10,7 @@
 // Texture semantics: Load out of bounds -> 0, store out of bounds dropped, samplers clamp to edge,
 // bilinear weights exact fp32, UNORM stores round to nearest, FP16 stores round to nearest even.
 #pragma once
+#include <cstdlib>
 #include "../../../include/nrd_b200.h"
 #include "../host/constants.h"
 #include "vecmath.cuh"
@@ -79,8 +80,19 @@ struct GraphRecord {
 };
 extern thread_local GraphReplay* g_graphReplay;   // executor.cu
 extern thread_local GraphRecord* g_graphRecord;
+extern thread_local bool g_pdlAllowed;
 
 #ifdef __CUDACC__
+// First statement of every kernel launched through launchK ( tests/test_abi.py checks the sources ): let the next kernel of the stream be scheduled as this grid's
+// CTAs retire ( griddepcontrol.launch_dependents ), then wait until the previous kernel has completed and its writes are visible ( griddepcontrol.wait ). Both are
+// no-ops for a launch without the programmatic-serialization attribute.
+#ifndef NRD_B200_PDL_DEFAULT
+#define NRD_B200_PDL_DEFAULT true
+#endif
+__device__ __forceinline__ void pdlEntry() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 template <class Tuple, size_t... I> inline void launchParamPointers(Tuple& values, void** out, std::index_sequence<I...>) { ((out[I] = (void*)&std::get<I>(values)), ...); }
 
 template <class... P, class... A> inline void launchK(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const A&... args) {
@@ -90,6 +102,25 @@ template <class... P, class... A> inline void launchK(void (*kernel)(P...), dim3
         if (GraphRecord* rec = g_graphRecord) {
             if (rec->count < GraphRecord::kMax) rec->funcs[rec->count++] = (const void*)kernel;
             else rec->overflow = true;
+        }
+        // Programmatic dependent launch: a chain kernel may be SCHEDULED while its predecessor in the stream is still draining ( every chain kernel starts with
+        // pdlEntry( ), which lets its own successor in and then blocks until the predecessor has completed and flushed — so the launch latency and the ramp-down
+        // of one pass overlap the ramp-up of the next, nothing else ). Not while a frame is captured into a CUDA graph: the executor walks the captured chain
+        // through plain dependency edges, and a replayed graph has no launch gaps to hide. Only whole frames of a stand-alone context ( g_pdlAllowed, set by the executor ): strips of a tiled frame and nrdcuDispatch keep plain serialization. NRD_B200_PDL=0 switches it off ( A/B of the benchmarks ).
+        static const bool pdl = getenv("NRD_B200_PDL") ? getenv("NRD_B200_PDL")[0] != '0' : NRD_B200_PDL_DEFAULT;
+        if (pdl && g_pdlAllowed && !g_graphRecord) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid;
+            cfg.blockDim = block;
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+            return;
         }
         kernel<<<grid, block, smem, stream>>>(args...);
         return;

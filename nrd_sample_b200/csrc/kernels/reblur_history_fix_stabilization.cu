@@ -184,6 +184,7 @@ NRD_DEV void historyFixLobe(const ReblurConstants& cb, const HistoryFixParams& p
 #endif
 template <int SIGNAL, int MODE>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, HF_MIN_BLOCKS) reblurHistoryFixKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HistoryFixParams p, int quads, int ctaY0) {
+    pdlEntry();
     constexpr bool HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0, HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0;
     __shared__ float sDiffLuma[HAS_DIFF ? HF_TILE_H : 1][HF_TILE_W];
     __shared__ float sSpecLuma[HAS_SPEC ? HF_TILE_H : 1][HF_TILE_W];
@@ -299,6 +300,7 @@ NRD_DEV void lumaMoments3x3(const float (*sLuma)[TS_TILE_W], float& luma, float&
 template <int SIGNAL, int MODE>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTemporalStabilizationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                        const __grid_constant__ TemporalStabilizationParams p, int ctaY0) {
+    pdlEntry();
     constexpr bool HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0, HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0;
     __shared__ float sDiffLuma[HAS_DIFF ? TS_TILE_H : 1][TS_TILE_W];
     __shared__ float sSpecLuma[HAS_SPEC ? TS_TILE_H : 1][TS_TILE_W];
@@ -460,6 +462,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TS_MIN_BLOCKS) reblurTempora
 // Clear: zero a whole texture (any format) with 16-byte stores where the row allows it
 // ===============================================================================================================
 __global__ void clearKernel(uint8_t* data, int rowBytes, int height, int pitch) {
+    pdlEntry();
     const int y = blockIdx.y;
     uint8_t* row = data + (size_t)y * pitch;
     const int vecs = (((uintptr_t)row & 15) == 0) ? rowBytes / 16 : 0;

@@ -14,6 +14,7 @@ constexpr int BLOCK_W = 32, BLOCK_H = 8;
 template <int BORDER>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurHitDistReconstructionKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ HitDistReconstructionParams p,
                                                                                      int signal, int occlusion, int ctaY0) {
+    pdlEntry();
     // Texel access by bound format ( a uniform branch; this pass is bandwidth-bound ): the NRD_MODE = OCCLUSION permutation carries the hit distance alone
     // ( Texture2D< float >: .x of whatever is bound, REBLUR_HitDistReconstruction.cs.hlsl:151-166 ), and the RADIANCE permutation also serves
     // REBLUR_DIFFUSE_DIRECTIONAL_OCCLUSION, whose textures are RGBA16_SNORM or the application's own format

@@ -417,6 +417,7 @@ NRD_DEV void spatialFilter(const ReblurConstants& cb, const Center& s, const Tex
 // ---------------------------------------------------------------------------------------------------------------
 // One warp per 16x16 tile, 8 tiles per CTA ( tileIsSkyWarp, common.cuh )
 __global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ ClassifyTilesParams p, int ctaY0, int tilesW) {
+    pdlEntry();
     const int tx = blockIdx.x * 8 + (threadIdx.x >> 5), ty = ctaY0 + blockIdx.y;
     if (tx >= tilesW) return;
     const bool allSky = tileIsSkyWarp(p.inViewZ, tx, ty, [&](float z) { return !inDenoisingRange(cb, unpackViewZ(cb, z)); });
@@ -426,6 +427,7 @@ __global__ void __launch_bounds__(256) reblurClassifyTilesKernel(const __grid_co
 // Decodes IN_NORMAL_ROUGHNESS + IN_VIEWZ into the geometry plane, one thread per texel. Same arithmetic as the centre set-up of the passes
 // ( unpackNormalRoughness, |viewZ * scale| ), so a tap that lands on the centre texel sees the centre's own normal.
 __global__ void __launch_bounds__(256) reblurGeometryPlaneKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ GeometryPlaneParams p, int row0, int row1) {
+    pdlEntry();
     const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
     if (px > cb.rectSizeMinusOne[0] || py >= row1) return;
     const float4 nr = unpackNormalRoughness(p.normalRoughness.fetchRaw(px, py));
@@ -437,6 +439,7 @@ __global__ void __launch_bounds__(256) reblurGeometryPlaneKernel(const __grid_co
 
 template <bool CB, int SIGNAL, int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPrePassKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PrePassParams p, int flags, int ctaY0) {
+    pdlEntry();
     const bool robust = (flags & 2) != 0;
     Center s;
     const int2 cta = ctaTile<0>(ctaY0);
@@ -480,6 +483,7 @@ NRD_DEV float2 quadSmoothedAccumSpeed(const ReblurConstants& cb, float2 data1, f
 
 template <int SIGNAL, int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ BlurParams p, int flags, int ctaY0) {
+    pdlEntry();
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
     const int2 cta = ctaTile<3>(ctaY0);
@@ -505,6 +509,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurBl
 
 template <bool TEMPORAL_STABILIZATION, int SIGNAL, int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPostBlurKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ PostBlurParams p, int flags, int ctaY0) {
+    pdlEntry();
     const bool quads = (flags & 1) != 0, robust = (flags & 2) != 0;
     Center s;
     const int2 cta = ctaTile<4>(ctaY0);
@@ -528,6 +533,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SPATIAL_MIN_BLOCKS) reblurPo
 
 // REBLUR_SplitScreen.cs.hlsl:21-56: the noisy input (range-masked) left of CommonSettings::splitScreen
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) reblurSplitScreenKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ SplitScreenParams p, int signal, int ctaY0) {
+    pdlEntry();
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (ctaY0 + blockIdx.y) * BLOCK_H + threadIdx.y;
     const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
     if (u > cb.splitScreen || px > cb.rectSizeMinusOne[0] || py > cb.rectSizeMinusOne[1]) return;

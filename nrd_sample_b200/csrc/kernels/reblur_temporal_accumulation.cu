@@ -52,6 +52,7 @@ NRD_DEV uint4 gather4(const TexR16U& t, int x0, int y0) {
 template <bool OPTIONAL, int SIGNAL, int MODE>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, TA_MIN_BLOCKS) reblurTemporalAccumulationKernel(const __grid_constant__ ReblurConstants cb,
                                                                                       const __grid_constant__ TemporalAccumulationParams p, int ctaY0) {
+    pdlEntry();
     __shared__ float4 sNormalHitDist[TILE_H][TILE_W];
     constexpr bool SH = MODE == MODE_SH, FIXED = Sig<MODE>::FIXED, OCC = MODE == MODE_OCCLUSION;
 

@@ -36,6 +36,7 @@ NRD_DEV float4 nearestAny(const TexView& t, float2 uv) {
 }
 
 __global__ void __launch_bounds__(256) reblurValidationKernel(const __grid_constant__ ReblurConstants cb, const __grid_constant__ ReblurValidationParams p) {
+    pdlEntry();
     const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (!p.out.inside(px, py)) return;
     if (cb.resetHistory != 0u) {

@@ -52,6 +52,7 @@ struct TexAny4 : TexView {
 
 __global__ void __launch_bounds__(256) referenceTemporalAccumulationKernel(const __grid_constant__ ReferenceAccumulateConstants cb, const __grid_constant__ TexAny4 input,
                                                                           const __grid_constant__ TexAny4 history) {
+    pdlEntry();
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     const float4 in = input.load(x, y), h = history.load(x, y);
     history.store(x, y, lerp(h, in, cb.accumSpeed));
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(256) referenceTemporalAccumulationKernel(const
 
 __global__ void __launch_bounds__(256) referenceCopyKernel(const __grid_constant__ ReferenceCopyConstants cb, const __grid_constant__ TexAny4 input, const __grid_constant__ TexAny4 output,
                                                           int w, int h) {
+    pdlEntry();
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if (x >= w || y >= h) return;
     const float u = ((float)x + 0.5f) * cb.rectSizeInv[0];

@@ -210,6 +210,7 @@ template <template <int> class P, int SIGNAL> const P<SIGNAL>& lobeView(const P<
 // ---------------------------------------------------------------------------------------------------------------
 // One warp per 16x16 tile, 8 tiles per CTA ( tileIsSkyWarp, common.cuh )
 __global__ void __launch_bounds__(256) relaxClassifyTilesKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxClassifyParams p, int ctaY0, int tilesW) {
+    pdlEntry();
     const int tx = blockIdx.x * 8 + (threadIdx.x >> 5), ty = blockIdx.y + ctaY0;
     if (tx >= tilesW) return;
     const bool allSky = tileIsSkyWarp(p.viewZ, tx, ty, [&](float z) { return !relaxInRange(cb, fabsf(z)); });
@@ -279,6 +280,7 @@ template <bool CB> NRD_DEV PrePassTap prePassTap(const RelaxConstants& cb, float
 // CB: checkerboarded inputs ( CheckerboardMode::BLACK / WHITE ): the traced pixels sit in the left half of the input textures
 template <bool SH, bool CB, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxPrePassParamsT<SIGNAL> p, int ctaY0) {
+    pdlEntry();
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
@@ -451,6 +453,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxPrePassKernel(const __g
 // OPT: checkerboard resolve speed-up and the application's guide textures ( confidence, threshold mix ); compiled out of the plain kernel
 template <bool SH, bool OPT, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTemporalAccumulationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxTaParamsT<SIGNAL> p, int ctaY0) {
+    pdlEntry();
     // Preload( ) of the shader ( RELAX_TemporalAccumulation.cs.hlsl: s_Normal_SpecHitT ): { normal, spec hitT } at the rect-clamped positions of the CTA's 34x10
     // neighbourhood, unpacked ONCE per texel into shared memory like the reference's group-shared tile. Every pixel reads 11 of them ( the 3x3 plus the two
     // curvature neighbours again ); decoding per read was ~12 % of the kernel's instructions.
@@ -885,6 +888,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_TA_MIN_BLOCKS) relaxTe
 // ---------------------------------------------------------------------------------------------------------------
 template <bool SH, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryFixKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryFixParamsT<SIGNAL> p, int ctaY0) {
+    pdlEntry();
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
@@ -1062,6 +1066,7 @@ NRD_DEV void historyClampingLobe(const RelaxConstants& cb, const float4 (*sFast)
 // ctaY0: first CTA row in units of HC_PIXELS_H ( = 16 ) pixel rows; rowEnd: end of the strip ( or of the rect )
 template <bool SH, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHistoryClampingParamsT<SIGNAL> p, int ctaY0, int rowEnd) {
+    pdlEntry();
     __shared__ float4 sSpecFast[HC_TILE_H][HC_TILE_W], sSpecNoisy[HC_TILE_H][HC_TILE_W], sDiffFast[HC_TILE_H][HC_TILE_W], sDiffNoisy[HC_TILE_H][HC_TILE_W];
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py0 = (blockIdx.y + ctaY0) * HC_PIXELS_H + threadIdx.y * HC_ROWS;
     // the CTA covers two 16x16 tiles of one tile row
@@ -1107,6 +1112,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHistoryClampingKernel(c
 
 template <int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxCopyKernel(const __grid_constant__ RelaxCopyParamsT<SIGNAL> p, int ctaY0) {
+    pdlEntry();
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if constexpr ((SIGNAL & SIGNAL_SPEC) != 0)
         if (p.outSpec.inside(px, py)) *p.outSpec.template ptrw<uint2>(px, py) = p.spec.inside(px, py) ? p.spec.fetchRaw(px, py) : make_uint2(0u, 0u);
@@ -1140,6 +1146,7 @@ template <class TEX> NRD_DEV float4 rcrs(const RelaxConstants& cb, const TexNR& 
 
 template <int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAntiFireflyParamsT<SIGNAL> p, int ctaY0) {
+    pdlEntry();
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     if (!relaxInRange(cb, relaxViewZ(cb, p.viewZ.load(px, py)))) return;
@@ -1155,6 +1162,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxAntiFireflyKernel(const
 struct RelaxHitDistReconstructionParams { TexR8 tiles; TexNR normalRoughness; TexR32F viewZ; TexRGBA16F spec, diff, outSpec, outDiff; };
 template <int BORDER>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHitDistReconstructionKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxHitDistReconstructionParams p, int ctaY0) {
+    pdlEntry();
     constexpr int TW = BLOCK_W + 2 * BORDER, TH = BLOCK_H + 2 * BORDER;
     __shared__ float3 sNormal[TH][TW];
     __shared__ float3 sHitDistViewZ[TH][TW];
@@ -1225,6 +1233,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxHitDistReconstructionKe
 struct RelaxSplitScreenParams { TexR32F viewZ; TexRGBA16F diff, spec, diffSh, specSh, outDiff, outSpec, outDiffSh, outSpecSh; };
 template <bool SH>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) relaxSplitScreenKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxSplitScreenParams p, int ctaY0) {
+    pdlEntry();
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];
     if (u > cb.splitScreen || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
@@ -1265,6 +1274,7 @@ constexpr int AT_BORDER = 2, AT_TILE_W = BLOCK_W + 2 * AT_BORDER, AT_TILE_H = BL
 #endif
 template <bool SH, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
+    pdlEntry();
     // the reference's groupshared tile: 36x12 texels of { illumination + 2nd moment, SH1, normal + roughness, world position + material }
     __shared__ float4 sSpec[AT_TILE_H][AT_TILE_W], sDiff[AT_TILE_H][AT_TILE_W], sNr[AT_TILE_H][AT_TILE_W], sPosMat[AT_TILE_H][AT_TILE_W];
     __shared__ float4 sSpecSh[SH ? AT_TILE_H : 1][SH ? AT_TILE_W : 1], sDiffSh[SH ? AT_TILE_H : 1][SH ? AT_TILE_W : 1];
@@ -1462,6 +1472,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
 #endif
 template <bool SH, int SIGNAL>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_GATHER_MIN_BLOCKS) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
+    pdlEntry();
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     if (p.tiles.load(px >> 4, py >> 4) != 0.0f || px >= cb.rectSize[0] || py >= cb.rectSize[1]) return;
     const float centerViewZ = relaxViewZ(cb, p.viewZ.load(px, py));
@@ -1659,6 +1670,7 @@ NRD_DEV void tmaLoadBox2D(void* dst, const CUtensorMap* map, int x, int y, uint6
 template <bool SH, int SIGNAL, int STEP, bool TMA>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousTiledKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0,
                                                                                                       const __grid_constant__ RelaxAtrousTma tma) {
+    pdlEntry();
     constexpr bool HAS_SPEC = (SIGNAL & SIGNAL_SPEC) != 0, HAS_DIFF = (SIGNAL & SIGNAL_DIFF) != 0;
     constexpr int TW = BLOCK_W + 2 * STEP, TH = BLOCK_H + 2 * STEP;
     static_assert((TW * TH * 8) % 128 == 0, "a TMA box lands on a 128-byte aligned address");
@@ -1836,6 +1848,7 @@ struct RelaxValidationParams {
     TexNR normalRoughness; TexR32F viewZ; TexView mv; TexR8 historyLength; TexView out;
 };
 __global__ void __launch_bounds__(256) relaxValidationKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxValidationParams p) {
+    pdlEntry();
     const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (!p.out.inside(px, py)) return;
     if (cb.resetHistory != 0u) {

@@ -47,6 +47,7 @@ NRD_DEV float applyGeometryWeightLast(const SigmaConstants& cb, float w, float z
 // textures are 16-byte aligned ( decided on the host ); otherwise, and for the tiles hanging over the edge of the frame, the pixels are read one by one.
 template <bool TR, bool VEC>
 __global__ void __launch_bounds__(256) sigmaClassifyTilesKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaClassifyTilesParams p, int tilesW, int tilesH) {
+    pdlEntry();
     const int lane = threadIdx.x & 31;
     const int tx = blockIdx.x * 8 + (threadIdx.x >> 5), ty = blockIdx.y;
     if (tx >= tilesW) return;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(256) sigmaClassifyTilesKernel(const __grid_con
 
 // One thread per tile texel
 __global__ void __launch_bounds__(256) sigmaSmoothTilesKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaSmoothTilesParams p) {
+    pdlEntry();
     const int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
     const float4 center = p.tiles.load(x, y);
     const float k = 1.01f / (center.y + 0.01f);
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(256) sigmaSmoothTilesKernel(const __grid_const
 
 template <class ST>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaCopyParams<ST> p, int ctaY0) {
+    pdlEntry();
     using Raw = typename std::conditional<std::is_same<ST, TexR8>::value, uint8_t, uint32_t>::type;
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     // the reference dispatches this pass over the PREVIOUS frame's rect ( Sigma_Shadow.hpp: "USE_PREV_DIMS" ) in 8x16 groups
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaCopyKernel(const __grid
 template <bool FIRST_PASS, bool TR>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, SIGMA_BLUR_MIN_BLOCKS) sigmaBlurKernel(const __grid_constant__ SigmaConstants cb,
                                                                    const __grid_constant__ SigmaBlurParams<typename SigmaSignal<TR>::Tex> p, int ctaY0) {
+    pdlEntry();
     using SG = SigmaSignal<TR>;
     using S = typename SG::T;
     constexpr bool SHADOW_FROM_PENUMBRA = FIRST_PASS && !TR;  // s = IsLit( penumbra ): no shadow texture bound (SIGMA_Blur.cs.hlsl:35-39)
@@ -336,6 +340,7 @@ NRD_DEV uint32_t packViewZAndHistoryLength(float viewZ, float historyLength) {
 template <bool TR>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H)
     sigmaTemporalStabilizationKernel(const __grid_constant__ SigmaConstants cb, const __grid_constant__ SigmaTemporalStabilizationParams<typename SigmaSignal<TR>::Tex> p, int ctaY0) {
+    pdlEntry();
     using SG = SigmaSignal<TR>;
     using S = typename SG::T;
     __shared__ S sShadow[TILE_H][TILE_W];
@@ -466,6 +471,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H)
 template <bool TR>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H) sigmaSplitScreenKernel(const __grid_constant__ SigmaConstants cb,
                                                                           const __grid_constant__ SigmaSplitScreenParams<typename SigmaSignal<TR>::Tex> p, int ctaY0) {
+    pdlEntry();
     using SG = SigmaSignal<TR>;
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
     const float u = ((float)px + 0.5f) * cb.rectSizeInv[0];

@@ -131,3 +131,31 @@ def test_every_pipeline_of_every_denoiser_resolves_to_a_kernel(host_library, pro
     for bogus in ("REBLUR_Blur.cs.hlsl|NRD_SIGNAL=FOO|NRD_MODE=SH", "REBLUR_Blur.cs.hlsl", "RELAX_Atrous.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=OCCLUSION", "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=1",
                   "REBLUR_PrePass.cs.hlsl|NRD_SIGNAL=BOTH|NRD_MODE=SH|MODE_5X5=1", "Unknown.cs.hlsl", "SIGMA_Blur.cs.hlsl|TRANSLUCENCY=2|FIRST_PASS=0"):
         assert lib.nrdcuDispatch(bogus.encode(), None, 0, None, 0, 0, None) == int(api.Result.UNSUPPORTED), bogus
+
+
+def test_every_chain_kernel_starts_with_the_dependency_wait():
+    """launchK ( csrc/kernels/common.cuh ) launches with programmatic stream serialization: a kernel that did not begin with pdlEntry( ) — griddepcontrol.wait —
+    could read what its predecessor has not written yet. Every __global__ function of the files that launch through launchK must start with it."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nrd_sample_b200", "csrc")
+    checked = 0
+    for path in sorted(glob.glob(os.path.join(root, "kernels", "*.cu")) + glob.glob(os.path.join(root, "*.cu"))):
+        src = open(path).read()
+        if "launchK(" not in src:
+            continue
+        for m in re.finditer(r"__global__", src):
+            i, depth = m.end(), 0
+            while not (src[i] in "{;" and depth == 0):
+                depth += {"(": 1, ")": -1}.get(src[i], 0)
+                i += 1
+            if src[i] == ";":
+                continue
+            assert src[i + 1:].lstrip().startswith("pdlEntry();"), f"{os.path.basename(path)}: kernel at offset {m.start()} does not start with pdlEntry()"
+            checked += 1
+    assert checked >= 30
+    for path in glob.glob(os.path.join(root, "kernels", "*.cu")):   # and nothing else goes through launchK
+        src = open(path).read()
+        if "launchK(" not in src:
+            assert "pdlEntry" not in src
