@@ -1272,7 +1272,9 @@ constexpr int AT_BORDER = 2, AT_TILE_W = BLOCK_W + 2 * AT_BORDER, AT_TILE_H = BL
 #ifndef RELAX_ATROUS_SMEM_MIN_BLOCKS
 #define RELAX_ATROUS_SMEM_MIN_BLOCKS 4
 #endif
-template <bool SH, int SIGNAL>
+// RES ( all three a-trous kernels ): RelaxSettings::enableRoughnessEdgeStopping, a compile-time switch — the taps evaluate only the specular weight the setting
+// selects ( with the constant-buffer flag tested per tap both forms were computed and one discarded: ~4 % of the instructions of these issue-bound launches )
+template <bool SH, int SIGNAL, bool RES>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousSmemKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
     pdlEntry();
     // the reference's groupshared tile: 36x12 texels of { illumination + 2nd moment, SH1, normal + roughness, world position + material }
@@ -1402,7 +1404,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
                 specularLuminanceW = fminf(cb.specMaxLuminanceRelativeDifference, specularLuminanceW);
                 specularLuminanceW *= specularLuminanceWeightRelaxation;
                 float wSpecular = geometryW * expf(-specularLuminanceW);
-                wSpecular *= cb.roughnessEdgeStoppingEnabled ? (normalWSpecular * roughnessWSpecular) : normalWSpecularSimplified;
+                wSpecular *= RES ? (normalWSpecular * roughnessWSpecular) : normalWSpecularSimplified;
                 wSpecular *= compareMaterials(s.materialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
                 wSpecular = isCenter ? kernelW : wSpecular;
                 sumWSpecular += wSpecular;
@@ -1470,7 +1472,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
 #ifndef RELAX_ATROUS_GATHER_MIN_BLOCKS
 #define RELAX_ATROUS_GATHER_MIN_BLOCKS 4
 #endif
-template <bool SH, int SIGNAL>
+template <bool SH, int SIGNAL, bool RES>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_GATHER_MIN_BLOCKS) relaxAtrousKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0) {
     pdlEntry();
     const int px = blockIdx.x * BLOCK_W + threadIdx.x, py = (blockIdx.y + ctaY0) * BLOCK_H + threadIdx.y;
@@ -1557,7 +1559,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_GATHER_MIN_BLOC
             const float normalWSpecularSimplified = computeWeight(angles, specularNormalWeightParamSimplified, 0.0f);
             const float normalWSpecular = specularNormalWeightAtrous(specularNormalWeightP, centerNormal, sampleNormal, centerV, sampleV);
             const float roughnessWSpecular = computeWeight(sampleNormalRoughness.w, roughnessWeightP.x, roughnessWeightP.y);
-            float wSpecular = geometryW * (cb.roughnessEdgeStoppingEnabled ? (normalWSpecular * roughnessWSpecular) : normalWSpecularSimplified);
+            float wSpecular = geometryW * (RES ? (normalWSpecular * roughnessWSpecular) : normalWSpecularSimplified);
             wSpecular *= compareMaterials(sampleMaterialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
             // The shader reads a tap's radiance / SH only `if( w > 1e-4 )`. Here the four texels are requested together with the tap's geometry and a skipped tap
             // contributes exact zeros instead: nothing waits for a weight before its loads go out, so the loads of all eight taps overlap. The gathering
@@ -1667,7 +1669,7 @@ NRD_DEV void tmaLoadBox2D(void* dst, const CUtensorMap* map, int x, int y, uint6
 // tap exactly where the gathering kernel converts what it loaded ), so the tile is 68 B per texel: 29 KB ( STEP 2 ) / 43 KB ( STEP 4 ). The arithmetic per tap is the
 // gathering kernel's, character for character: results are bit-identical. Strides 8 and 16 ( 4.5x / 10x the pixels, random tap offsets ) keep gathering.
 // TMA: the four raw planes arrive through cp.async.bulk.tensor ( above ) instead of LDG + STS
-template <bool SH, int SIGNAL, int STEP, bool TMA>
+template <bool SH, int SIGNAL, int STEP, bool TMA, bool RES>
 __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS) relaxAtrousTiledKernel(const __grid_constant__ RelaxConstants cb, const __grid_constant__ RelaxAtrousParamsT<SIGNAL> p, int ctaY0,
                                                                                                       const __grid_constant__ RelaxAtrousTma tma) {
     pdlEntry();
@@ -1803,7 +1805,7 @@ __global__ void __launch_bounds__(BLOCK_W* BLOCK_H, RELAX_ATROUS_SMEM_MIN_BLOCKS
             const float normalWSpecularSimplified = computeWeight(angles, specularNormalWeightParamSimplified, 0.0f);
             const float normalWSpecular = specularNormalWeightAtrous(specularNormalWeightP, centerNormal, sampleNormal, centerV, sampleV);
             const float roughnessWSpecular = computeWeight(sampleNormalRoughness.w, roughnessWeightP.x, roughnessWeightP.y);
-            float wSpecular = geometryW * (cb.roughnessEdgeStoppingEnabled ? (normalWSpecular * roughnessWSpecular) : normalWSpecularSimplified);
+            float wSpecular = geometryW * (RES ? (normalWSpecular * roughnessWSpecular) : normalWSpecularSimplified);
             wSpecular *= compareMaterials(sampleMaterialID, centerMaterialID, cb.specMinMaterial) ? 1.0f : 0.0f;
             if (wSpecular > 1e-4f) {
                 const float4 s = tapSpec(ty, tx);
@@ -2238,11 +2240,17 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
         takeShD(p.outDiffSh);
         if (bad(4 + (smem ? 3 : 0) + (3 + 2 * shOn) * lobes + (hasSpec ? 1 : 0))) return (uint32_t)Result::INVALID_ARGUMENT;
         if (smem) {
-            if (sh) withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<true, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); }); else withSignal(signal, [&](auto sig_) { launchK(relaxAtrousSmemKernel<false, decltype(sig_)::value>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0); });
+            auto launchSmem = [&](auto sh_, auto sig_) {
+                constexpr bool SH_ = decltype(sh_)::value;
+                constexpr int SIG_ = decltype(sig_)::value;
+                if (cb.roughnessEdgeStoppingEnabled) launchK(relaxAtrousSmemKernel<SH_, SIG_, true>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
+                else launchK(relaxAtrousSmemKernel<SH_, SIG_, false>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
+            };
+            if (sh) withSignal(signal, [&](auto sig_) { launchSmem(std::true_type(), sig_); }); else withSignal(signal, [&](auto sig_) { launchSmem(std::false_type(), sig_); });
         } else {
             // strides 2 and 4: the neighbourhood is staged in shared memory ( relaxAtrousTiledKernel ); larger strides gather
-            auto launchAtrous = [&](auto sh_, auto sig_) {
-                constexpr bool SH_ = decltype(sh_)::value;
+            auto launchAtrous = [&](auto sh_, auto sig_, auto res_) {
+                constexpr bool SH_ = decltype(sh_)::value, RES_ = decltype(res_)::value;
                 constexpr int SIG_ = decltype(sig_)::value;
                 if (cb.stepSize == 2 || cb.stepSize == 4) {
                     // the raw planes through TMA when every bound plane can be described by a tensor map ( NRD_B200_RELAX_TMA=0: A/B switch of the benchmarks and of tests/test_relax_tma_gpu.py )
@@ -2256,16 +2264,19 @@ uint32_t dispatchRelax(const PipelineKey& key, const void* constants, uint32_t c
                     if (useTma && HAS_SPEC_) useTma = encodeRgba16fBox(tma.spec, p.spec, boxW, boxH) && (!SH_ || encodeRgba16fBox(tma.specSh, p.specSh, boxW, boxH));
                     if (useTma && HAS_DIFF_) useTma = encodeRgba16fBox(tma.diff, p.diff, boxW, boxH) && (!SH_ || encodeRgba16fBox(tma.diffSh, p.diffSh, boxW, boxH));
                     if (step == 2) {
-                        if (useTma) launchK(relaxAtrousTiledKernel<SH_, SIG_, 2, true>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
-                        else launchK(relaxAtrousTiledKernel<SH_, SIG_, 2, false>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
+                        if (useTma) launchK(relaxAtrousTiledKernel<SH_, SIG_, 2, true, RES_>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
+                        else launchK(relaxAtrousTiledKernel<SH_, SIG_, 2, false, RES_>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
                     } else {
-                        if (useTma) launchK(relaxAtrousTiledKernel<SH_, SIG_, 4, true>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
-                        else launchK(relaxAtrousTiledKernel<SH_, SIG_, 4, false>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
+                        if (useTma) launchK(relaxAtrousTiledKernel<SH_, SIG_, 4, true, RES_>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
+                        else launchK(relaxAtrousTiledKernel<SH_, SIG_, 4, false, RES_>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0, tma);
                     }
                 }
-                else launchK(relaxAtrousKernel<SH_, SIG_>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
+                else launchK(relaxAtrousKernel<SH_, SIG_, RES_>, pixelGrid, block, 0, stream, cb, lobeView(p, sig_), ctaY0);
             };
-            if (sh) withSignal(signal, [&](auto sig_) { launchAtrous(std::true_type(), sig_); }); else withSignal(signal, [&](auto sig_) { launchAtrous(std::false_type(), sig_); });
+            auto launchAtrousSh = [&](auto sh_, auto sig_) {
+                if (cb.roughnessEdgeStoppingEnabled) launchAtrous(sh_, sig_, std::true_type()); else launchAtrous(sh_, sig_, std::false_type());
+            };
+            if (sh) withSignal(signal, [&](auto sig_) { launchAtrousSh(std::true_type(), sig_); }); else withSignal(signal, [&](auto sig_) { launchAtrousSh(std::false_type(), sig_); });
         }
     } else {
         err = std::string("no CUDA kernel for shader '") + id + "'";
